@@ -1,0 +1,129 @@
+"""Oracle (TEST INFRASTRUCTURE ONLY): the multigrid solve the reference CONFIGURES in PETSc,
+restated with scipy.sparse in fp64.
+
+PARITY UNPINNED BY THE REFERENCE (arithmetic lives in PETSc 3.20.2, pinned at
+contrib/scripts/install_petsc.sh:12, not installed here; the reference holds no golden vectors
+for it).  Restates, with paths relative to /root/reference/src:
+
+  08_equations/00_stationary/LinearImplicitSystem.cpp:347-370     Galerkin chain A_{l-1} = P^T A_l P
+  08_algebra.../LinearEquationSolverPetsc.cpp:53-90, 428-436      BuildBdcIndex, SetPenalty
+                                                                   (MatZeroRows, diag 1, pattern kept)
+  .../LinearEquationSolverPetsc.cpp:185-290                       PCMG multiplicative V, Richardson+Jacobi
+  .../LinearEquationSolverPetsc.cpp:294-353, 417-424              MGSolve: RES[bdc]=0, cycle, RESC=A EPSC,
+                                                                   RES-=RESC, EPS+=EPSC
+  06_solution/00_single_level/00_definition/Solution.cpp:595-628  UpdateRes (zeros where Bdc<=1.1)
+  08_equations/00_stationary/LinearImplicitSystem.cpp:415-449     HasLinearConverged: ||Res||_2
+
+The outer Krylov solver is PREONLY (as applications/MGAMR/ex5/ex5.cpp:141-204 sets it), so one
+MGSolve is exactly one V-cycle; the coarse solver is a sparse LU (the reference: MUMPS).
+"""
+import numpy as np
+import scipy.sparse as sp
+import scipy.sparse.linalg as spla
+
+from . import mesh_box as mb
+
+
+def penalty(A, bdc_idx):
+    """MatZeroRows(A, idx, 1.0) keeping the nonzero pattern: rows zeroed, diagonal 1."""
+    A = A.tocsr(copy=True)
+    for r in bdc_idx:
+        A.data[A.indptr[r]:A.indptr[r + 1]] = 0.0
+    A = A.tolil()
+    for r in bdc_idx:
+        A[r, r] = 1.0
+    A = A.tocsr()
+    A.sort_indices()
+    return A
+
+
+def penalty_fast(A, bdc_idx):
+    A = A.tocsr(copy=True)
+    A.sort_indices()
+    mask = np.zeros(A.shape[0], dtype=bool)
+    mask[bdc_idx] = True
+    rows = np.repeat(np.arange(A.shape[0]), np.diff(A.indptr))
+    isd = mask[rows]
+    A.data[isd] = 0.0
+    A.data[isd & (A.indices == rows)] = 1.0
+    return A
+
+
+def on_pattern(A, rowptr, col):
+    """Copy A's entries onto the (larger) CSR pattern (rowptr, col); missing entries become
+    explicit zeros.  Every entry of A must lie in the pattern."""
+    A = A.tocoo()
+    n = A.shape[1]
+    rows = np.repeat(np.arange(len(rowptr) - 1, dtype=np.int64), np.diff(rowptr))
+    keys = rows * n + col.astype(np.int64)
+    ka = A.row.astype(np.int64) * n + A.col.astype(np.int64)
+    pos = np.searchsorted(keys, ka)
+    assert np.array_equal(keys[pos], ka), "entry outside the pattern"
+    vals = np.zeros(col.shape[0])
+    np.add.at(vals, pos, A.data)
+    return sp.csr_matrix((vals, col.copy(), rowptr.copy()), shape=A.shape)
+
+
+class Hierarchy:
+    """Per-level operators exactly as the reference sets them up for one MGsolve."""
+
+    def __init__(self, levels, order, fsrc=1.0, dirichlet_faces=(1, 2, 3, 4, 5, 6)):
+        self.levels = levels
+        self.order = order
+        nl = len(levels)
+        self.bdc = [mb.bdc_flags(L, order, dirichlet_faces) for L in levels]
+        self.bdc_idx = [np.nonzero(b < 1.5)[0] for b in self.bdc]
+        # prolongators with Dirichlet rows/cols zeroed (built at init(), before assembly)
+        self.P = [None] * nl
+        for l in range(1, nl):
+            P = mb.prolongator(levels[l - 1], levels[l], order)
+            self.P[l] = mb.zero_dirichlet(P, self.bdc[l], self.bdc[l - 1])
+        # assembly on the finest level (V_CYCLE: only the top level is assembled)
+        self.A_raw = [None] * nl
+        self.A_raw[-1], self.rhs = mb.assemble(levels[-1], order, None, fsrc)
+        # Galerkin chain on the un-penalised matrices
+        for l in range(nl - 1, 0, -1):
+            Ac = (self.P[l].T @ self.A_raw[l] @ self.P[l]).tocsr()
+            # result pattern = coarse element coupling pattern (explicit zeros kept)
+            rp, ci = mb.sparsity(levels[l - 1], order)
+            self.A_raw[l - 1] = on_pattern(Ac, rp, ci)
+        # MGSetLevel: penalty on every level
+        self.A = [penalty_fast(self.A_raw[l], self.bdc_idx[l]) for l in range(nl)]
+        self.dinv = [1.0 / A.diagonal() for A in self.A]
+        self.lu = spla.splu(self.A[0].tocsc())
+
+    def smooth(self, l, x, b, nsweeps, omega):
+        """KSPRICHARDSON (scale omega) + PCJACOBI: x <- x + omega D^-1 (b - A x)."""
+        for _ in range(nsweeps):
+            x = x + omega * (self.dinv[l] * (b - self.A[l] @ x))
+        return x
+
+    def vcycle(self, l, b, npre=1, npost=1, omega=0.5):
+        """PCMG multiplicative V-cycle, zero initial guess on every level."""
+        if l == 0:
+            return self.lu.solve(b)
+        x = np.zeros_like(b)
+        x = self.smooth(l, x, b, npre, omega)
+        r = b - self.A[l] @ x
+        bc = self.P[l].T @ r
+        xc = self.vcycle(l - 1, bc, npre, npost, omega)
+        x = x + self.P[l] @ xc
+        x = self.smooth(l, x, b, npost, omega)
+        return x
+
+    def mg_solve_trace(self, ncycles, npre=1, npost=1, omega=0.5):
+        """Vcycle() of LinearImplicitSystem.cpp:468-497 with outer PREONLY: returns the list of
+        ||_Res||_2 after each MGSolve+UpdateRes, and the final EPS."""
+        top = len(self.levels) - 1
+        res = self.rhs.copy()
+        eps = np.zeros_like(res)
+        free = self.bdc[top] > 1.1
+        trace = []
+        for _ in range(ncycles):
+            res[self.bdc_idx[top]] = 0.0                      # ZerosBoundaryResiduals
+            epsc = self.vcycle(top, res, npre, npost, omega)
+            resc = self.A[top] @ epsc
+            res = res - resc
+            eps = eps + epsc
+            trace.append(float(np.linalg.norm(np.where(free, res, 0.0))))
+        return trace, eps
