@@ -1,0 +1,480 @@
+"""ctypes binding of include/femus_b200.h -- the harness side of the C ABI (tests, bench, smoke).
+
+The product is the shared library; this module only loads it, declares the prototypes and wraps
+handles in small Python classes.  It fails loudly when the library is missing: there is no CPU
+fallback anywhere in femus_b200."""
+import ctypes
+import os
+import re
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libfemus_b200.so")
+HEADER = os.path.join(os.path.dirname(HERE), "include", "femus_b200.h")
+
+_lib = None
+
+vp, ci, cd, i64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_int64
+
+_PROTOS = {
+    # name: (restype, argtypes)
+    "b2_last_error": (ctypes.c_char_p, []),
+    "b2_version": (ci, []),
+    "b2_ctx_create": (ci, [ci, vp]),
+    "b2_ctx_destroy": (ci, [vp]),
+    "b2_ctx_sync": (ci, [vp]),
+    "b2_ctx_stream": (vp, [vp]),
+    "b2_ctx_device": (ci, [vp]),
+    "b2_nccl_unique_id": (ci, [vp]),
+    "b2_ctx_comm_init": (ci, [vp, ci, ci, vp]),
+    "b2_ctx_nranks": (ci, [vp]),
+    "b2_ctx_rank": (ci, [vp]),
+    "b2_ctx_bytes_in_use": (i64, [vp]),
+    "b2_ctx_launch_count": (i64, [vp, ci]),
+    "b2_timer_start": (ci, [vp]),
+    "b2_timer_stop_ms": (ci, [vp, vp]),
+    "b2_ctx_flush_l2": (ci, [vp]),
+    "b2_vec_create": (ci, [vp, i64, vp]),
+    "b2_vec_destroy": (ci, [vp]),
+    "b2_vec_size": (i64, [vp]),
+    "b2_vec_device_ptr": (vp, [vp]),
+    "b2_vec_zero": (ci, [vp]),
+    "b2_vec_fill": (ci, [vp, cd]),
+    "b2_vec_put": (ci, [vp, vp, i64]),
+    "b2_vec_get": (ci, [vp, vp, i64]),
+    "b2_vec_copy": (ci, [vp, vp]),
+    "b2_vec_axpy": (ci, [vp, cd, vp]),
+    "b2_vec_aypx": (ci, [vp, cd, vp]),
+    "b2_vec_scale": (ci, [vp, cd]),
+    "b2_vec_add_scalar": (ci, [vp, cd]),
+    "b2_vec_pointwise_mult": (ci, [vp, vp, vp]),
+    "b2_vec_dot": (ci, [vp, vp, vp]),
+    "b2_vec_norm": (ci, [vp, ci, vp]),
+    "b2_vec_sum": (ci, [vp, vp]),
+    "b2_vec_minmax": (ci, [vp, vp, vp]),
+    "b2_vec_set_indexed": (ci, [vp, vp, vp, i64]),
+    "b2_vec_add_indexed": (ci, [vp, vp, vp, i64]),
+    "b2_vec_fill_indexed": (ci, [vp, vp, i64, cd]),
+    "b2_vec_get_indexed": (ci, [vp, vp, vp, i64]),
+    "b2_vec_copy_masked": (ci, [vp, vp, vp, cd]),
+    "b2_csr_create": (ci, [vp, i64, i64, vp, vp, vp, vp]),
+    "b2_csr_create_from_elements": (ci, [vp, i64, i64, ci, vp, vp]),
+    "b2_csr_destroy": (ci, [vp]),
+    "b2_csr_nrows": (i64, [vp]),
+    "b2_csr_ncols": (i64, [vp]),
+    "b2_csr_nnz": (i64, [vp]),
+    "b2_csr_get": (ci, [vp, vp, vp, vp]),
+    "b2_csr_put_vals": (ci, [vp, vp]),
+    "b2_csr_zero": (ci, [vp]),
+    "b2_csr_copy_vals": (ci, [vp, vp]),
+    "b2_csr_add_blocks": (ci, [vp, i64, ci, ci, vp, vp, vp]),
+    "b2_csr_set_rows": (ci, [vp, i64, vp, vp, vp, vp]),
+    "b2_csr_zero_rows": (ci, [vp, vp, i64, cd]),
+    "b2_csr_zero_cols": (ci, [vp, vp, i64]),
+    "b2_csr_diag": (ci, [vp, vp]),
+    "b2_csr_transpose": (ci, [vp, vp]),
+    "b2_csr_spmv": (ci, [vp, vp, vp]),
+    "b2_csr_spmv_add": (ci, [vp, vp, vp]),
+    "b2_csr_spmv_t": (ci, [vp, vp, vp]),
+    "b2_csr_resid": (ci, [vp, vp, vp, vp]),
+    "b2_csr_jacobi_sweep": (ci, [vp, vp, vp, vp, vp, cd]),
+    "b2_csr_ptap": (ci, [vp, vp, vp]),
+    "b2_csr_last_kernel_ms": (cd, [vp]),
+    "b2_mesh_create": (ci, [vp, i64, i64, vp, vp, vp]),
+    "b2_mesh_destroy": (ci, [vp]),
+    "b2_asm_create": (ci, [vp, vp, ci, vp, ci, vp, vp, vp, vp, vp, vp]),
+    "b2_asm_destroy": (ci, [vp]),
+    "b2_asm_poisson": (ci, [vp, vp, vp, cd, cd]),
+    "b2_asm_last_kernel_ms": (cd, [vp]),
+    "b2_mg_create": (ci, [vp, ci, vp]),
+    "b2_mg_set_level": (ci, [vp, ci, vp, vp, vp, i64, ci, ci, cd]),
+    "b2_mg_set_coarse": (ci, [vp, cd, ci]),
+    "b2_mg_vcycle": (ci, [vp, vp, vp]),
+    "b2_mg_solve": (ci, [vp, vp, vp]),
+    "b2_mg_coarse_iterations": (ci, [vp]),
+    "b2_mg_destroy": (ci, [vp]),
+}
+
+
+def header_symbols():
+    """Every function name include/femus_b200.h declares."""
+    txt = open(HEADER).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(b2_[a-z0-9_]+)\s*\(", txt)))
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} is missing: build it with `python -m femus_b200.build` "
+                               "(femus_b200 has no CPU fallback)")
+        L = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _PROTOS.items():
+            f = getattr(L, name)
+            f.restype = res
+            f.argtypes = args
+        _lib = L
+    return _lib
+
+
+class B2Error(RuntimeError):
+    pass
+
+
+def check(status):
+    if status != 0:
+        raise B2Error(lib().b2_last_error().decode())
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(vp)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _i64(a):
+    return np.ascontiguousarray(a, dtype=np.int64)
+
+
+class Context:
+    def __init__(self, device=0):
+        self.L = lib()
+        h = vp()
+        check(self.L.b2_ctx_create(device, ctypes.byref(h)))
+        self.h = h
+
+    def close(self):
+        if self.h:
+            self.L.b2_ctx_destroy(self.h)
+            self.h = None
+
+    def sync(self):
+        check(self.L.b2_ctx_sync(self.h))
+
+    def stream(self):
+        return self.L.b2_ctx_stream(self.h)
+
+    def comm_init(self, nranks, rank, uid_bytes):
+        buf = (ctypes.c_char * 128).from_buffer_copy(uid_bytes)
+        check(self.L.b2_ctx_comm_init(self.h, nranks, rank, buf))
+
+    @staticmethod
+    def nccl_unique_id():
+        buf = (ctypes.c_char * 128)()
+        check(lib().b2_nccl_unique_id(buf))
+        return bytes(buf)
+
+    def launches(self, reset=False):
+        return int(self.L.b2_ctx_launch_count(self.h, 1 if reset else 0))
+
+    def bytes_in_use(self):
+        return int(self.L.b2_ctx_bytes_in_use(self.h))
+
+    def timer_start(self):
+        check(self.L.b2_timer_start(self.h))
+
+    def timer_stop_ms(self):
+        ms = cd()
+        check(self.L.b2_timer_stop_ms(self.h, ctypes.byref(ms)))
+        return ms.value
+
+    def flush_l2(self):
+        check(self.L.b2_ctx_flush_l2(self.h))
+
+    # factories
+    def vector(self, n_or_array):
+        return Vector(self, n_or_array)
+
+    def csr(self, nrows, ncols, rowptr, col, vals=None):
+        return Csr.from_host(self, nrows, ncols, rowptr, col, vals)
+
+    def csr_from_scipy(self, A):
+        A = A.tocsr()
+        A.sort_indices()
+        return Csr.from_host(self, A.shape[0], A.shape[1], A.indptr, A.indices, A.data)
+
+
+class Vector:
+    def __init__(self, ctx, n_or_array):
+        self.ctx, self.L = ctx, ctx.L
+        h = vp()
+        if np.isscalar(n_or_array):
+            n = int(n_or_array)
+            check(self.L.b2_vec_create(ctx.h, n, ctypes.byref(h)))
+            self.h = h
+        else:
+            a = _f64(n_or_array)
+            check(self.L.b2_vec_create(ctx.h, a.shape[0], ctypes.byref(h)))
+            self.h = h
+            self.put(a)
+
+    def __del__(self):
+        try:
+            if self.h and self.ctx.h:
+                self.L.b2_vec_destroy(self.h)
+        except Exception:
+            pass
+
+    @property
+    def n(self):
+        return int(self.L.b2_vec_size(self.h))
+
+    def put(self, a):
+        a = _f64(a)
+        check(self.L.b2_vec_put(self.h, _ptr(a), a.shape[0]))
+
+    def get(self):
+        out = np.empty(self.n)
+        check(self.L.b2_vec_get(self.h, _ptr(out), out.shape[0]))
+        return out
+
+    def zero(self):
+        check(self.L.b2_vec_zero(self.h))
+
+    def fill(self, a):
+        check(self.L.b2_vec_fill(self.h, float(a)))
+
+    def copy_from(self, x):
+        check(self.L.b2_vec_copy(self.h, x.h))
+
+    def axpy(self, a, x):
+        check(self.L.b2_vec_axpy(self.h, float(a), x.h))
+
+    def aypx(self, a, x):
+        check(self.L.b2_vec_aypx(self.h, float(a), x.h))
+
+    def scale(self, a):
+        check(self.L.b2_vec_scale(self.h, float(a)))
+
+    def add_scalar(self, a):
+        check(self.L.b2_vec_add_scalar(self.h, float(a)))
+
+    def pointwise_mult(self, x, y):
+        check(self.L.b2_vec_pointwise_mult(self.h, x.h, y.h))
+
+    def dot(self, y):
+        out = cd()
+        check(self.L.b2_vec_dot(self.h, y.h, ctypes.byref(out)))
+        return out.value
+
+    def norm(self, kind=2):
+        out = cd()
+        check(self.L.b2_vec_norm(self.h, kind, ctypes.byref(out)))
+        return out.value
+
+    def sum(self):
+        out = cd()
+        check(self.L.b2_vec_sum(self.h, ctypes.byref(out)))
+        return out.value
+
+    def minmax(self):
+        a, b = cd(), cd()
+        check(self.L.b2_vec_minmax(self.h, ctypes.byref(a), ctypes.byref(b)))
+        return a.value, b.value
+
+    def set_indexed(self, idx, vals):
+        idx, vals = _i32(idx), _f64(vals)
+        check(self.L.b2_vec_set_indexed(self.h, _ptr(idx), _ptr(vals), idx.shape[0]))
+
+    def add_indexed(self, idx, vals):
+        idx, vals = _i32(idx), _f64(vals)
+        check(self.L.b2_vec_add_indexed(self.h, _ptr(idx), _ptr(vals), idx.shape[0]))
+
+    def fill_indexed(self, idx, a):
+        idx = _i32(idx)
+        check(self.L.b2_vec_fill_indexed(self.h, _ptr(idx), idx.shape[0], float(a)))
+
+    def get_indexed(self, idx):
+        idx = _i32(idx)
+        out = np.empty(idx.shape[0])
+        check(self.L.b2_vec_get_indexed(self.h, _ptr(idx), _ptr(out), idx.shape[0]))
+        return out
+
+    def copy_masked(self, src, mask, thr):
+        check(self.L.b2_vec_copy_masked(self.h, src.h, mask.h, float(thr)))
+
+
+class Csr:
+    def __init__(self, ctx, h):
+        self.ctx, self.L, self.h = ctx, ctx.L, h
+
+    @classmethod
+    def from_host(cls, ctx, nrows, ncols, rowptr, col, vals=None):
+        rowptr, col = _i64(rowptr), _i32(col)
+        vals = None if vals is None else _f64(vals)
+        h = vp()
+        check(ctx.L.b2_csr_create(ctx.h, nrows, ncols, _ptr(rowptr), _ptr(col), _ptr(vals), ctypes.byref(h)))
+        return cls(ctx, h)
+
+    @classmethod
+    def from_elements(cls, ctx, nrows, dof):
+        dof = _i32(dof)
+        h = vp()
+        check(ctx.L.b2_csr_create_from_elements(ctx.h, nrows, dof.shape[0], dof.shape[1], _ptr(dof), ctypes.byref(h)))
+        return cls(ctx, h)
+
+    def __del__(self):
+        try:
+            if self.h and self.ctx.h:
+                self.L.b2_csr_destroy(self.h)
+        except Exception:
+            pass
+
+    @property
+    def shape(self):
+        return int(self.L.b2_csr_nrows(self.h)), int(self.L.b2_csr_ncols(self.h))
+
+    @property
+    def nnz(self):
+        return int(self.L.b2_csr_nnz(self.h))
+
+    def get(self, structure=True, values=True):
+        n, nnz = self.shape[0], self.nnz
+        rp = np.empty(n + 1, dtype=np.int64) if structure else None
+        ci_ = np.empty(nnz, dtype=np.int32) if structure else None
+        v = np.empty(nnz) if values else None
+        check(self.L.b2_csr_get(self.h, _ptr(rp), _ptr(ci_), _ptr(v)))
+        return rp, ci_, v
+
+    def to_scipy(self):
+        import scipy.sparse as sp
+        rp, ci_, v = self.get()
+        return sp.csr_matrix((v, ci_, rp), shape=self.shape)
+
+    def put_vals(self, v):
+        v = _f64(v)
+        assert v.shape[0] == self.nnz
+        check(self.L.b2_csr_put_vals(self.h, _ptr(v)))
+
+    def zero(self):
+        check(self.L.b2_csr_zero(self.h))
+
+    def copy_vals_from(self, other):
+        check(self.L.b2_csr_copy_vals(self.h, other.h))
+
+    def add_blocks(self, rows, cols, vals):
+        rows, cols, vals = _i32(rows), _i32(cols), _f64(vals)
+        nblk, nrow = rows.shape
+        ncol = cols.shape[1]
+        check(self.L.b2_csr_add_blocks(self.h, nblk, nrow, ncol, _ptr(rows), _ptr(cols), _ptr(vals)))
+
+    def set_rows(self, rows, ptr, cols, vals):
+        rows, ptr, cols, vals = _i32(rows), _i64(ptr), _i32(cols), _f64(vals)
+        check(self.L.b2_csr_set_rows(self.h, rows.shape[0], _ptr(rows), _ptr(ptr), _ptr(cols), _ptr(vals)))
+
+    def zero_rows(self, rows, diag):
+        rows = _i32(rows)
+        check(self.L.b2_csr_zero_rows(self.h, _ptr(rows), rows.shape[0], float(diag)))
+
+    def zero_cols(self, cols):
+        cols = _i32(cols)
+        check(self.L.b2_csr_zero_cols(self.h, _ptr(cols), cols.shape[0]))
+
+    def diag(self, d):
+        check(self.L.b2_csr_diag(self.h, d.h))
+
+    def transpose(self):
+        h = vp()
+        check(self.L.b2_csr_transpose(self.h, ctypes.byref(h)))
+        return Csr(self.ctx, h)
+
+    def spmv(self, x, y):
+        check(self.L.b2_csr_spmv(self.h, x.h, y.h))
+
+    def spmv_add(self, x, y):
+        check(self.L.b2_csr_spmv_add(self.h, x.h, y.h))
+
+    def spmv_t(self, x, y):
+        check(self.L.b2_csr_spmv_t(self.h, x.h, y.h))
+
+    def resid(self, b, x, r):
+        check(self.L.b2_csr_resid(self.h, b.h, x.h, r.h))
+
+    def jacobi_sweep(self, dinv, b, xin, xout, omega):
+        check(self.L.b2_csr_jacobi_sweep(self.h, dinv.h, b.h, xin.h, xout.h, float(omega)))
+
+    def ptap(self, P, A):
+        """self = P^T A P (numeric, onto self's pattern)."""
+        check(self.L.b2_csr_ptap(P.h, A.h, self.h))
+
+
+class Mesh:
+    def __init__(self, ctx, xyz, conn):
+        self.ctx, self.L = ctx, ctx.L
+        xyz, conn = _f64(xyz), _i32(conn)
+        assert xyz.shape[0] == 3 and conn.shape[1] == 27
+        h = vp()
+        check(self.L.b2_mesh_create(ctx.h, xyz.shape[1], conn.shape[0], _ptr(xyz), _ptr(conn), ctypes.byref(h)))
+        self.h = h
+        self.nel, self.nnode = conn.shape[0], xyz.shape[1]
+
+    def __del__(self):
+        try:
+            if self.h and self.ctx.h:
+                self.L.b2_mesh_destroy(self.h)
+        except Exception:
+            pass
+
+
+class Assembler:
+    def __init__(self, mesh, A, dof, tables):
+        """tables = (phi, dxi, deta, dzeta, w) with phi.shape = [ngauss, nve]."""
+        self.ctx, self.L, self.mesh, self.A = mesh.ctx, mesh.ctx.L, mesh, A
+        dof = _i32(dof)
+        phi, dxi, deta, dzeta, w = [_f64(t) for t in tables]
+        h = vp()
+        check(self.L.b2_asm_create(mesh.h, A.h, dof.shape[1], _ptr(dof), phi.shape[0], _ptr(phi), _ptr(dxi),
+                                   _ptr(deta), _ptr(dzeta), _ptr(w), ctypes.byref(h)))
+        self.h = h
+
+    def __del__(self):
+        try:
+            if self.h and self.ctx.h:
+                self.L.b2_asm_destroy(self.h)
+        except Exception:
+            pass
+
+    def poisson(self, u=None, rhs=None, nu=1.0, fsrc=1.0):
+        check(self.L.b2_asm_poisson(self.h, u.h if u is not None else None, rhs.h if rhs is not None else None,
+                                    float(nu), float(fsrc)))
+
+
+class Multigrid:
+    def __init__(self, ctx, nlevels):
+        self.ctx, self.L = ctx, ctx.L
+        h = vp()
+        check(self.L.b2_mg_create(ctx.h, nlevels, ctypes.byref(h)))
+        self.h = h
+        self._keep = []
+
+    def __del__(self):
+        try:
+            if self.h and self.ctx.h:
+                self.L.b2_mg_destroy(self.h)
+        except Exception:
+            pass
+
+    def set_level(self, level, A, P, bdc_idx, npre=1, npost=1, omega=0.5):
+        bdc_idx = _i32(bdc_idx)
+        self._keep.append((A, P))
+        check(self.L.b2_mg_set_level(self.h, level, A.h, P.h if P is not None else None, _ptr(bdc_idx),
+                                     bdc_idx.shape[0], npre, npost, float(omega)))
+
+    def set_coarse(self, rtol=1e-14, maxit=5000):
+        check(self.L.b2_mg_set_coarse(self.h, float(rtol), int(maxit)))
+
+    def vcycle(self, rhs, x):
+        check(self.L.b2_mg_vcycle(self.h, rhs.h, x.h))
+
+    def solve(self, res, eps):
+        check(self.L.b2_mg_solve(self.h, res.h, eps.h))
+
+    def coarse_iterations(self):
+        return int(self.L.b2_mg_coarse_iterations(self.h))

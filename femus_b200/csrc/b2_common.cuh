@@ -1,0 +1,121 @@
+// Internal declarations shared by the femus_b200 CUDA translation units (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "../../include/femus_b200.h"
+
+void b2_set_error(const char* fmt, ...);
+
+#define B2_CUDA(call)                                                                        \
+  do {                                                                                       \
+    cudaError_t e__ = (call);                                                                \
+    if (e__ != cudaSuccess) {                                                                \
+      b2_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__));   \
+      return 1;                                                                              \
+    }                                                                                        \
+  } while (0)
+
+#define B2_CHECK(cond, ...)              \
+  do {                                   \
+    if (!(cond)) {                       \
+      b2_set_error(__VA_ARGS__);         \
+      return 1;                          \
+    }                                    \
+  } while (0)
+
+#define B2_TRY(call)        \
+  do {                      \
+    int s__ = (call);       \
+    if (s__) return s__;    \
+  } while (0)
+
+// every kernel launch of the library goes through this macro: counts the launch and checks it
+#define B2_LAUNCH(ctx, kernel, grid, block, smem, ...)                         \
+  do {                                                                         \
+    kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);           \
+    (ctx)->launches++;                                                         \
+    B2_CUDA(cudaGetLastError());                                               \
+  } while (0)
+
+struct b2_ctx {
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  int64_t bytes = 0;
+  int64_t launches = 0;
+  // scratch for reductions: partial sums + result (device) and a pinned host mirror
+  double* red_partial = nullptr;    // [kRedBlocks * 2]
+  double* red_result = nullptr;     // [8]
+  unsigned int* red_counter = nullptr;
+  double* h_result = nullptr;       // pinned [8]
+  void* flush_buf = nullptr;
+  size_t flush_bytes = 0;
+  // multi-GPU
+  int nranks = 1, rank = 0;
+  void* nccl_comm = nullptr;
+};
+
+static constexpr int kRedBlocks = 1184;   // 148 SMs x 8
+
+struct b2_vec {
+  b2_ctx* ctx;
+  int64_t n;
+  double* d;
+};
+
+struct b2_csr {
+  b2_ctx* ctx;
+  int64_t nrows, ncols, nnz;
+  int64_t* rowptr;   // [nrows+1]
+  int32_t* col;      // [nnz]
+  double* val;       // [nnz]
+  int tpr;           // threads per row chosen for the SpMV family (power of two <= 32)
+  int max_row;       // longest row
+  double last_ms;
+};
+
+template <class T>
+int b2_malloc(b2_ctx* c, T** p, size_t count) {
+  *p = nullptr;
+  if (count == 0) count = 1;
+  B2_CUDA(cudaMalloc((void**)p, count * sizeof(T)));
+  c->bytes += (int64_t)(count * sizeof(T));
+  return 0;
+}
+template <class T>
+void b2_free(b2_ctx* c, T* p, size_t count) {
+  if (!p) return;
+  cudaFree((void*)p);
+  if (count == 0) count = 1;
+  c->bytes -= (int64_t)(count * sizeof(T));
+}
+template <class T>
+int b2_upload(b2_ctx* c, T* dst, const T* src, size_t count) {
+  if (count) B2_CUDA(cudaMemcpyAsync(dst, src, count * sizeof(T), cudaMemcpyHostToDevice, c->stream));
+  B2_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+template <class T>
+int b2_download(b2_ctx* c, T* dst, const T* src, size_t count) {
+  if (count) B2_CUDA(cudaMemcpyAsync(dst, src, count * sizeof(T), cudaMemcpyDeviceToHost, c->stream));
+  B2_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+static inline int b2_grid_for(b2_ctx* c, int64_t work_items, int per_block, int blocks_per_sm) {
+  int64_t need = (work_items + per_block - 1) / per_block;
+  int64_t cap = (int64_t)c->sm_count * blocks_per_sm;
+  if (need < 1) need = 1;
+  return (int)(need < cap ? need : cap);
+}
+
+// internal cross-TU helpers
+int b2_csr_alloc(b2_ctx* c, int64_t nrows, int64_t ncols, int64_t nnz, b2_csr** out);
+int b2_csr_finalize(b2_csr* A);   // row statistics -> tpr / max_row
+int b2_dev_dot(b2_ctx* c, const double* x, const double* y, int64_t n, double* d_out);   // result stays on device
+int b2_allreduce_sum(b2_ctx* c, double* d_buf, int64_t n);

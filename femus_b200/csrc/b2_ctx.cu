@@ -1,0 +1,177 @@
+// Context: device, stream, timers, reduction scratch, NCCL communicator (one rank per GPU).
+// Replaces FemusInit/PetscInitialize + MPI_COMM_WORLD of the reference
+// (src/00_utils/00_application_initialization/FemusInit.cpp:46-73).
+#include "b2_common.cuh"
+#include <cstdarg>
+#include <dlfcn.h>
+
+static thread_local char g_err[1024] = "";
+
+void b2_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+// ---- NCCL through dlopen: the launcher (torch.distributed) usually has libnccl.so.2 loaded
+// already, in which case dlopen hands back that very copy.
+namespace {
+struct NcclApi {
+  void* h = nullptr;
+  void* get_uid = nullptr;
+  void* init_rank = nullptr;
+  void* all_reduce = nullptr;
+  void* destroy = nullptr;
+  void* err_string = nullptr;
+  void* send = nullptr;
+  void* recv = nullptr;
+  void* group_start = nullptr;
+  void* group_end = nullptr;
+} g_nccl;
+struct Uid { char b[128]; };
+
+int load_nccl() {
+  if (g_nccl.h) return 0;
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char* n : names) {
+    g_nccl.h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (g_nccl.h) break;
+  }
+  B2_CHECK(g_nccl.h, "cannot dlopen libnccl.so.2: %s", dlerror());
+  g_nccl.get_uid = dlsym(g_nccl.h, "ncclGetUniqueId");
+  g_nccl.init_rank = dlsym(g_nccl.h, "ncclCommInitRank");
+  g_nccl.all_reduce = dlsym(g_nccl.h, "ncclAllReduce");
+  g_nccl.destroy = dlsym(g_nccl.h, "ncclCommDestroy");
+  g_nccl.err_string = dlsym(g_nccl.h, "ncclGetErrorString");
+  g_nccl.send = dlsym(g_nccl.h, "ncclSend");
+  g_nccl.recv = dlsym(g_nccl.h, "ncclRecv");
+  g_nccl.group_start = dlsym(g_nccl.h, "ncclGroupStart");
+  g_nccl.group_end = dlsym(g_nccl.h, "ncclGroupEnd");
+  B2_CHECK(g_nccl.get_uid && g_nccl.init_rank && g_nccl.all_reduce && g_nccl.send && g_nccl.recv,
+           "libnccl lacks expected symbols");
+  return 0;
+}
+const char* nccl_err(int r) {
+  if (!g_nccl.err_string) return "?";
+  return ((const char* (*)(int))g_nccl.err_string)(r);
+}
+}  // namespace
+
+extern "C" {
+
+const char* b2_last_error(void) { return g_err; }
+int b2_version(void) { return 100; }
+
+int b2_ctx_create(int device, b2_ctx** out) {
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  B2_CHECK(e == cudaSuccess && ndev > 0, "no CUDA device visible (%s): femus_b200 has no CPU fallback",
+           cudaGetErrorString(e));
+  B2_CHECK(device >= 0 && device < ndev, "device %d out of range (%d visible)", device, ndev);
+  B2_CUDA(cudaSetDevice(device));
+  b2_ctx* c = new b2_ctx();
+  c->device = device;
+  cudaDeviceProp prop;
+  B2_CUDA(cudaGetDeviceProperties(&prop, device));
+  c->sm_count = prop.multiProcessorCount;
+  B2_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  B2_CUDA(cudaEventCreate(&c->ev0));
+  B2_CUDA(cudaEventCreate(&c->ev1));
+  B2_TRY(b2_malloc(c, &c->red_partial, (size_t)kRedBlocks * 2));
+  B2_TRY(b2_malloc(c, &c->red_result, 8));
+  B2_TRY(b2_malloc(c, &c->red_counter, 1));
+  B2_CUDA(cudaMemsetAsync(c->red_counter, 0, sizeof(unsigned int), c->stream));
+  B2_CUDA(cudaMallocHost((void**)&c->h_result, 8 * sizeof(double)));
+  B2_CUDA(cudaStreamSynchronize(c->stream));
+  *out = c;
+  return 0;
+}
+
+int b2_ctx_destroy(b2_ctx* c) {
+  if (!c) return 0;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  if (c->nccl_comm && g_nccl.destroy) ((int (*)(void*))g_nccl.destroy)(c->nccl_comm);
+  b2_free(c, c->red_partial, (size_t)kRedBlocks * 2);
+  b2_free(c, c->red_result, 8);
+  b2_free(c, c->red_counter, 1);
+  if (c->flush_buf) cudaFree(c->flush_buf);
+  cudaFreeHost(c->h_result);
+  cudaEventDestroy(c->ev0);
+  cudaEventDestroy(c->ev1);
+  cudaStreamDestroy(c->stream);
+  delete c;
+  return 0;
+}
+
+int b2_ctx_sync(b2_ctx* c) {
+  B2_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+void* b2_ctx_stream(b2_ctx* c) { return (void*)c->stream; }
+int b2_ctx_device(b2_ctx* c) { return c->device; }
+int b2_ctx_nranks(b2_ctx* c) { return c->nranks; }
+int b2_ctx_rank(b2_ctx* c) { return c->rank; }
+int64_t b2_ctx_bytes_in_use(b2_ctx* c) { return c->bytes; }
+int64_t b2_ctx_launch_count(b2_ctx* c, int reset) {
+  int64_t n = c->launches;
+  if (reset) c->launches = 0;
+  return n;
+}
+
+int b2_timer_start(b2_ctx* c) {
+  B2_CUDA(cudaEventRecord(c->ev0, c->stream));
+  return 0;
+}
+int b2_timer_stop_ms(b2_ctx* c, double* ms) {
+  B2_CUDA(cudaEventRecord(c->ev1, c->stream));
+  B2_CUDA(cudaEventSynchronize(c->ev1));
+  float f = 0.f;
+  B2_CUDA(cudaEventElapsedTime(&f, c->ev0, c->ev1));
+  *ms = (double)f;
+  return 0;
+}
+
+int b2_ctx_flush_l2(b2_ctx* c) {
+  if (!c->flush_buf) {
+    c->flush_bytes = (size_t)256 << 20;   // 256 MiB > 126 MB L2
+    B2_CUDA(cudaMalloc(&c->flush_buf, c->flush_bytes));
+  }
+  B2_CUDA(cudaMemsetAsync(c->flush_buf, 0, c->flush_bytes, c->stream));
+  return 0;
+}
+
+int b2_nccl_unique_id(void* id128) {
+  B2_TRY(load_nccl());
+  int r = ((int (*)(void*))g_nccl.get_uid)(id128);
+  B2_CHECK(r == 0, "ncclGetUniqueId: %s", nccl_err(r));
+  return 0;
+}
+
+int b2_ctx_comm_init(b2_ctx* c, int nranks, int rank, const void* id128) {
+  B2_CHECK(nranks >= 1 && rank >= 0 && rank < nranks, "bad rank %d / %d", rank, nranks);
+  c->nranks = nranks;
+  c->rank = rank;
+  if (nranks == 1) return 0;
+  B2_TRY(load_nccl());
+  B2_CUDA(cudaSetDevice(c->device));
+  Uid uid;
+  memcpy(uid.b, id128, 128);
+  int r = ((int (*)(void**, int, Uid, int))g_nccl.init_rank)(&c->nccl_comm, nranks, uid, rank);
+  B2_CHECK(r == 0, "ncclCommInitRank: %s", nccl_err(r));
+  return 0;
+}
+
+}  // extern "C"
+
+// sum-allreduce of n doubles in place on the library stream (ncclDouble = 8, ncclSum = 0)
+int b2_allreduce_sum(b2_ctx* c, double* d_buf, int64_t n) {
+  if (c->nranks == 1 || n == 0) return 0;
+  B2_CHECK(c->nccl_comm, "communicator not initialised");
+  typedef int (*ar_t)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+  int r = ((ar_t)g_nccl.all_reduce)(d_buf, d_buf, (size_t)n, /*ncclDouble*/ 8, /*ncclSum*/ 0, c->nccl_comm, c->stream);
+  B2_CHECK(r == 0, "ncclAllReduce: %s", nccl_err(r));
+  return 0;
+}

@@ -1,0 +1,173 @@
+/* femus_b200 -- C ABI of the B200 (sm_100a) backend for the FEMuS assembly + geometric-multigrid
+ * hot path.  This is the drop-in boundary: everything the FEMuS algebra plugin surface
+ * (NumericVector / SparseMatrix / LinearEquationSolver, reference src/03_algebra and
+ * src/08_algebra.../03_solvers_with_preconditioner) needs from a backend, as plain C.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; b2_last_error() gives the text.
+ *     (The reference aborts on error -- PetscMacro CHKERRABORT; the C++ adapters in
+ *     femus_b200/host/ turn a non-zero status into abort() to keep that behaviour.)
+ *   - handles are opaque and owned by the library; host arrays passed in are copied.
+ *   - indices: 32-bit columns / dof ids (the reference asserts sizeof(PetscInt)==sizeof(int),
+ *     PetscVector.hpp:536), 64-bit row pointers (256^3 Hex27 has 8.6e9 nonzeros).
+ *   - all device work is issued on the context's stream; calls that return a scalar or copy to
+ *     the host synchronise that stream, nothing else does.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails.
+ *
+ * Each group names the reference interface it replaces (paths relative to the reference root).
+ */
+#ifndef FEMUS_B200_H
+#define FEMUS_B200_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct b2_ctx b2_ctx;
+typedef struct b2_vec b2_vec;
+typedef struct b2_csr b2_csr;
+typedef struct b2_mesh b2_mesh;
+typedef struct b2_asm b2_asm;
+typedef struct b2_mg b2_mg;
+
+const char* b2_last_error(void);
+int b2_version(void);
+
+/* ---- context: replaces FemusInit / PetscInitialize + MPI_COMM_WORLD
+ *      (src/00_utils/00_application_initialization/FemusInit.cpp:46-73) ------------------- */
+int b2_ctx_create(int device, b2_ctx** out);
+int b2_ctx_destroy(b2_ctx* c);
+int b2_ctx_sync(b2_ctx* c);
+void* b2_ctx_stream(b2_ctx* c);                 /* cudaStream_t the library launches on */
+int b2_ctx_device(b2_ctx* c);
+/* one rank per GPU; id = 128-byte ncclUniqueId made by b2_nccl_unique_id on rank 0 and sent to
+ * the other ranks by the launcher (torch.distributed / MPI / a file). */
+int b2_nccl_unique_id(void* id128);
+int b2_ctx_comm_init(b2_ctx* c, int nranks, int rank, const void* id128);
+int b2_ctx_nranks(b2_ctx* c);
+int b2_ctx_rank(b2_ctx* c);
+/* bytes currently allocated by the library on the device */
+int64_t b2_ctx_bytes_in_use(b2_ctx* c);
+/* number of kernels launched by the library since the last reset */
+int64_t b2_ctx_launch_count(b2_ctx* c, int reset);
+/* CUDA-event timing on the library stream: b2_timer_start / b2_timer_stop_ms */
+int b2_timer_start(b2_ctx* c);
+int b2_timer_stop_ms(b2_ctx* c, double* ms);
+/* write `bytes` of device memory (>= L2 size) to evict the L2 between timed iterations */
+int b2_ctx_flush_l2(b2_ctx* c);
+
+/* ---- vectors: replaces PetscVector (src/03_algebra/00_vectors/PetscVector.{hpp,cpp}) --------
+ * A vector has n_local owned entries followed by n_ghost halo entries (0 in serial). */
+int b2_vec_create(b2_ctx* c, int64_t n, b2_vec** out);                 /* NumericVector::init */
+int b2_vec_destroy(b2_vec* v);
+int64_t b2_vec_size(const b2_vec* v);
+void* b2_vec_device_ptr(b2_vec* v);
+int b2_vec_zero(b2_vec* v);                                            /* zero()      VecSet(0)        PetscVector.cpp:361 */
+int b2_vec_fill(b2_vec* v, double a);                                  /* operator=(double)            :449 */
+int b2_vec_put(b2_vec* v, const double* host, int64_t n);              /* operator=(std::vector)       :477 */
+int b2_vec_get(const b2_vec* v, double* host, int64_t n);              /* localize / get               :627 */
+int b2_vec_copy(b2_vec* dst, const b2_vec* src);                       /* operator=(NumericVector)     :429 */
+int b2_vec_axpy(b2_vec* y, double a, const b2_vec* x);                 /* add(a,V)    VecAXPY          :303 */
+int b2_vec_aypx(b2_vec* y, double a, const b2_vec* x);                 /* y = x + a y VecAYPX */
+int b2_vec_scale(b2_vec* v, double a);                                 /* scale       VecScale         :378 */
+int b2_vec_add_scalar(b2_vec* v, double a);                            /* add(double) VecShift         :283 */
+int b2_vec_pointwise_mult(b2_vec* w, const b2_vec* x, const b2_vec* y);/* pointwise_mult               :782 */
+int b2_vec_dot(const b2_vec* x, const b2_vec* y, double* out);         /* dot         VecDot           :399 */
+int b2_vec_norm(const b2_vec* x, int kind /*1: l1, 2: l2, 0: linf*/, double* out); /* l1/l2/linfty_norm :43-87 */
+int b2_vec_sum(const b2_vec* x, double* out);                          /* sum         VecSum */
+int b2_vec_minmax(const b2_vec* x, double* mn, double* mx);            /* min/max     PetscVector.hpp:777-796 */
+/* staged set()/add() of PetscVector (VecSetValues INSERT/ADD, PetscVector.cpp:96-141) flushed as
+ * one batch: idx/vals are host arrays. */
+int b2_vec_set_indexed(b2_vec* v, const int32_t* idx, const double* vals, int64_t n);
+int b2_vec_add_indexed(b2_vec* v, const int32_t* idx, const double* vals, int64_t n);
+int b2_vec_fill_indexed(b2_vec* v, const int32_t* idx, int64_t n, double a); /* ZerosBoundaryResiduals LinearEquationSolverPetsc.cpp:417-424 */
+int b2_vec_get_indexed(const b2_vec* v, const int32_t* idx, double* vals, int64_t n); /* get(idx,vals) */
+/* dst[i] = mask[i] > thr ? src[i] : 0  -- Solution::UpdateRes (Solution.cpp:595-628) */
+int b2_vec_copy_masked(b2_vec* dst, const b2_vec* src, const b2_vec* mask, double thr);
+
+/* ---- CSR matrices: replaces PetscMatrix (src/03_algebra/01_matrices/PetscMatrix.{hpp,cpp}) --- */
+/* init(m,n,...,n_nz,n_oz) + pattern: rowptr[nrows+1] (int64), col[nnz] (int32, sorted per row);
+ * vals may be NULL (zeros). */
+int b2_csr_create(b2_ctx* c, int64_t nrows, int64_t ncols, const int64_t* rowptr, const int32_t* col,
+                  const double* vals, b2_csr** out);
+/* Pattern from element->dof lists (every (i,j) pair of every element, zeros included): replaces
+ * LinearEquation::GetSparsityPatternSize + SparseMatrix::init (LinearEquation.cpp:407-548, 334-335).
+ * dof[nel][nve] host array. */
+int b2_csr_create_from_elements(b2_ctx* c, int64_t nrows, int64_t nel, int nve, const int32_t* dof, b2_csr** out);
+int b2_csr_destroy(b2_csr* A);
+int64_t b2_csr_nrows(const b2_csr* A);
+int64_t b2_csr_ncols(const b2_csr* A);
+int64_t b2_csr_nnz(const b2_csr* A);
+int b2_csr_get(const b2_csr* A, int64_t* rowptr, int32_t* col, double* vals);   /* any may be NULL */
+int b2_csr_put_vals(b2_csr* A, const double* vals);
+int b2_csr_zero(b2_csr* A);                                             /* zero()  MatZeroEntries */
+int b2_csr_copy_vals(b2_csr* dst, const b2_csr* src);                   /* same pattern */
+/* add_matrix_blocked (PetscMatrix.cpp:699-729): nblk dense blocks, block b adds
+ * vals[b][i*ncol+j] at (rows[b*nrow+i], cols[b*ncol+j]); host arrays, staged by the adapter
+ * until close(). */
+int b2_csr_add_blocks(b2_csr* A, int64_t nblk, int nrow, int ncol, const int32_t* rows, const int32_t* cols,
+                      const double* vals);
+/* insert_row (PetscMatrix.cpp:683-695), batched: row r gets vals at cols (INSERT). */
+int b2_csr_set_rows(b2_csr* A, int64_t nset, const int32_t* rows, const int64_t* ptr, const int32_t* cols,
+                    const double* vals);
+/* mat_zero_rows / MatZeroRows keeping the pattern (PetscMatrix.cpp:1073-1077;
+ * SetPenalty LinearEquationSolverPetsc.cpp:428-436) */
+int b2_csr_zero_rows(b2_csr* A, const int32_t* rows, int64_t n, double diag);
+/* zero the listed columns (ZeroInterpolatorDirichletNodes does it through two transposes,
+ * LinearImplicitSystem.cpp:1090-1112) */
+int b2_csr_zero_cols(b2_csr* A, const int32_t* cols, int64_t n);
+int b2_csr_diag(const b2_csr* A, b2_vec* d);                            /* MatGetDiagonal PetscMatrix.cpp:1019-1027 */
+int b2_csr_transpose(const b2_csr* A, b2_csr** At);                     /* get_transpose  :1031-1070 */
+int b2_csr_spmv(const b2_csr* A, const b2_vec* x, b2_vec* y);           /* matrix_mult    PetscVector.cpp:203-212 */
+int b2_csr_spmv_add(const b2_csr* A, const b2_vec* x, b2_vec* y);       /* MatMultAdd     :243-247 */
+int b2_csr_spmv_t(const b2_csr* A, const b2_vec* x, b2_vec* y);         /* matrix_mult_transpose :219-228 */
+int b2_csr_resid(const b2_csr* A, const b2_vec* b, const b2_vec* x, b2_vec* r); /* resid: r = b - A x  :232-247 */
+/* one Richardson(omega)+Jacobi sweep  xout = xin + omega * dinv .* (b - A xin)
+ * (KSPRICHARDSON + PCJACOBI, LinearEquationSolverPetsc.cpp:516-519, PetscPreconditioner.cpp:209-212) */
+int b2_csr_jacobi_sweep(const b2_csr* A, const b2_vec* dinv, const b2_vec* b, const b2_vec* xin, b2_vec* xout,
+                        double omega);
+/* matrix_PtAP (PetscMatrix.cpp:733-751): C = P^T A P, numeric phase onto C's existing pattern
+ * (the coarse element-coupling pattern). */
+int b2_csr_ptap(const b2_csr* P, const b2_csr* A, b2_csr* C);
+double b2_csr_last_kernel_ms(const b2_csr* A);
+
+/* ---- mesh + assembly: replaces the element loop of applications/001_Poisson/main.cpp:346-605
+ *      (+ elem_type_3D::Jacobian, ElemType.hpp:1438-1537; MatSetValuesBlocked, VecSetValues) ---- */
+/* xyz[3][nnode] (SoA), conn[nel][27] node ids of the HEX27 elements owned by this rank. */
+int b2_mesh_create(b2_ctx* c, int64_t nnode, int64_t nel, const double* xyz, const int32_t* conn, b2_mesh** out);
+int b2_mesh_destroy(b2_mesh* m);
+/* Assembly plan for one unknown on one mesh: nve = 8 (trilinear) or 27 (triquadratic);
+ * dof[nel][nve] = matrix row of each local node (GetSystemDof, LinearEquation.cpp:76-85);
+ * tables phi/dxi/deta/dzeta [ngauss][nve] and weights[ngauss] as elem_type_3D holds them
+ * (ElemType.cpp:637-740).  Builds the element->CSR slot map for A. */
+int b2_asm_create(b2_mesh* m, b2_csr* A, int nve, const int32_t* dof, int ngauss, const double* phi,
+                  const double* dxi, const double* deta, const double* dzeta, const double* weights,
+                  b2_asm** out);
+int b2_asm_destroy(b2_asm* p);
+/* A += sum_e B_e, rhs += sum_e F_e with B_ij = nu * int grad phi_i . grad phi_j,
+ * F_i = int (fsrc phi_i - nu grad phi_i . grad u).  A and rhs are NOT zeroed here (the app calls
+ * myKK->zero() / SetResZero() first, main.cpp:346, LinearImplicitSystem.cpp:322). */
+int b2_asm_poisson(b2_asm* p, const b2_vec* u, b2_vec* rhs, double nu, double fsrc);
+double b2_asm_last_kernel_ms(const b2_asm* p);
+
+/* ---- geometric multigrid: replaces LinearEquationSolverPetsc::{MGInit,MGSetLevel,MGSolve,MGClear}
+ *      and PETSc PCMG (LinearEquationSolverPetsc.cpp:185-353) ------------------------------- */
+int b2_mg_create(b2_ctx* c, int nlevels, b2_mg** out);                   /* MGInit */
+/* MGSetLevel: level operator A (penalised in place: rows bdc_idx -> identity), prolongator P from
+ * level-1 (NULL on level 0), Dirichlet row list, smoothing steps and Richardson scale. */
+int b2_mg_set_level(b2_mg* mg, int level, b2_csr* A, b2_csr* P, const int32_t* bdc_idx, int64_t nbdc,
+                    int npre, int npost, double omega);
+/* coarse solver: Jacobi-PCG to ||r|| <= rtol ||b|| (the reference: PREONLY + MUMPS LU,
+ * PetscPreconditioner.cpp:147-160) */
+int b2_mg_set_coarse(b2_mg* mg, double rtol, int maxit);
+int b2_mg_vcycle(b2_mg* mg, const b2_vec* rhs, b2_vec* x);               /* one PCMG multiplicative V */
+/* MGSolve with outer PREONLY: RES[bdc]=0; EPSC = Vcycle(RES); RESC = A EPSC; RES -= RESC; EPS += EPSC */
+int b2_mg_solve(b2_mg* mg, b2_vec* res, b2_vec* eps);
+int b2_mg_coarse_iterations(const b2_mg* mg);
+int b2_mg_destroy(b2_mg* mg);                                            /* MGClear */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,321 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle on the same
+seeded inputs.  Bar: integer structure bit-exact; fp64 values within the stated tolerance
+(differences come only from summation order / FMA contraction)."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from femus_b200 import capi
+from oracle import fe_hex, mesh_box as mb, mg
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-12        # north-star: matrix entries / residuals to 1e-12 relative
+
+
+def relerr(a, b):
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+# ------------------------------------------------------------------------------ vectors
+@pytest.mark.parametrize("n", [1, 2, 31, 1000, 100003])
+def test_vector_ops(ctx, n):
+    rng = np.random.default_rng(n)
+    x, y = rng.standard_normal(n), rng.standard_normal(n)
+    X, Y, W = ctx.vector(x), ctx.vector(y), ctx.vector(n)
+    Y.axpy(0.75, X)
+    ref = y + 0.75 * x
+    assert relerr(Y.get(), ref) < 1e-15
+    Y.aypx(-2.0, X)
+    ref = x - 2.0 * ref
+    assert relerr(Y.get(), ref) < 1e-15
+    Y.scale(3.0)
+    ref *= 3.0
+    Y.add_scalar(0.5)
+    ref += 0.5
+    assert relerr(Y.get(), ref) < 1e-15
+    W.pointwise_mult(X, Y)
+    assert relerr(W.get(), x * ref) < 1e-15
+    assert abs(X.dot(Y) - x @ ref) <= 1e-13 * np.abs(x * ref).sum()
+    assert abs(X.norm(2) - np.linalg.norm(x)) <= 1e-14 * np.linalg.norm(x)
+    assert abs(X.norm(1) - np.abs(x).sum()) <= 1e-14 * np.abs(x).sum()
+    assert X.norm(0) == np.abs(x).max()
+    assert abs(X.sum() - x.sum()) <= 1e-13 * np.abs(x).sum()
+    assert X.minmax() == (x.min(), x.max())
+    W.fill(2.5)
+    assert np.all(W.get() == 2.5)
+    W.zero()
+    assert np.all(W.get() == 0.0)
+    W.copy_from(X)
+    assert np.array_equal(W.get(), x)
+    mask = ctx.vector((rng.random(n) > 0.5) * 2.0)
+    W.copy_masked(X, mask, 1.1)
+    assert np.array_equal(W.get(), np.where(mask.get() > 1.1, x, 0.0))
+
+
+def test_vector_indexed(ctx):
+    n = 5000
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal(n)
+    X = ctx.vector(x)
+    idx = rng.permutation(n)[:700].astype(np.int32)
+    v = rng.standard_normal(700)
+    X.set_indexed(idx, v)
+    x[idx] = v
+    assert np.array_equal(X.get(), x)
+    idx2 = rng.integers(0, n, 3000).astype(np.int32)      # duplicates: add semantics
+    v2 = rng.standard_normal(3000)
+    X.add_indexed(idx2, v2)
+    np.add.at(x, idx2, v2)
+    assert relerr(X.get(), x) < 1e-14
+    X.fill_indexed(idx, 0.0)
+    x[idx] = 0.0
+    assert relerr(X.get(), x) < 1e-14
+    assert np.array_equal(X.get_indexed(idx2), X.get()[idx2])
+
+
+def test_empty_vector(ctx):
+    X = ctx.vector(0)
+    X.zero()
+    X.scale(2.0)
+    assert X.get().shape == (0,)
+
+
+# ------------------------------------------------------------------------------ CSR algebra
+def random_csr(rng, m, n, density):
+    A = sp.random(m, n, density=density, random_state=np.random.RandomState(int(rng.integers(1 << 30))), format="csr")
+    A.sort_indices()
+    return A
+
+
+@pytest.mark.parametrize("m,n,density", [(1, 1, 1.0), (50, 70, 0.02), (3000, 3000, 0.001), (2000, 1500, 0.05), (400, 400, 0.4)])
+def test_spmv_family(ctx, m, n, density):
+    rng = np.random.default_rng(m * 7 + n)
+    A = random_csr(rng, m, n, density)
+    # ragged input: some empty rows
+    A = A.tolil()
+    if m > 10:
+        A[3, :] = 0
+    A = A.tocsr()
+    A.eliminate_zeros()
+    A.sort_indices()
+    dA = ctx.csr_from_scipy(A)
+    x, b = rng.standard_normal(n), rng.standard_normal(m)
+    X, Bv, Y = ctx.vector(x), ctx.vector(b), ctx.vector(m)
+    scale = np.abs(A) @ np.abs(x) + 1e-300
+    dA.spmv(X, Y)
+    assert np.all(np.abs(Y.get() - A @ x) <= 4e-16 * scale * 8)
+    Y.put(b)
+    dA.spmv_add(X, Y)
+    assert np.all(np.abs(Y.get() - (b + A @ x)) <= 1e-14 * (scale + np.abs(b)))
+    dA.resid(Bv, X, Y)
+    assert np.all(np.abs(Y.get() - (b - A @ x)) <= 1e-14 * (scale + np.abs(b)))
+    xt = rng.standard_normal(m)
+    XT, YT = ctx.vector(xt), ctx.vector(n)
+    dA.spmv_t(XT, YT)
+    assert np.all(np.abs(YT.get() - A.T @ xt) <= 1e-13 * (np.abs(A.T) @ np.abs(xt) + 1e-300))
+
+
+def test_transpose_zero_rows_cols_diag(ctx):
+    rng = np.random.default_rng(5)
+    A = random_csr(rng, 700, 500, 0.03)
+    dA = ctx.csr_from_scipy(A)
+    T = dA.transpose().to_scipy()
+    At = A.T.tocsr()
+    At.sort_indices()
+    assert np.array_equal(T.indptr, At.indptr) and np.array_equal(T.indices, At.indices)
+    assert np.array_equal(T.data, At.data)
+    S = random_csr(rng, 600, 600, 0.02) + sp.identity(600, format="csr") * 3.0
+    S = S.tocsr()
+    S.sort_indices()
+    dS = ctx.csr_from_scipy(S)
+    d = ctx.vector(600)
+    dS.diag(d)
+    assert np.array_equal(d.get(), S.diagonal())
+    rows = np.sort(rng.permutation(600)[:50]).astype(np.int32)
+    dS.zero_rows(rows, 1.0)
+    ref = mg.penalty_fast(S, rows)
+    got = dS.to_scipy()
+    assert np.array_equal(got.indices, ref.indices) and np.array_equal(got.data, ref.data)
+    cols = np.sort(rng.permutation(500)[:40]).astype(np.int32)
+    dA.zero_cols(cols)
+    ref = A.copy()
+    ref.data[np.isin(ref.indices, cols)] = 0.0
+    assert np.array_equal(dA.to_scipy().data, ref.data)
+
+
+def test_add_blocks_and_set_rows(ctx):
+    """Compat path of add_matrix_blocked / insert_row against the oracle's scatter."""
+    lv = mb.build_hierarchy(2, 2, 2, 1)
+    L = lv[0]
+    d = mb.system_dof(L, "biquadratic")
+    rp, ci = mb.sparsity(L, "biquadratic")
+    A = ctx.csr(rp.shape[0] - 1, rp.shape[0] - 1, rp, ci)
+    X = L.xyz[:, L.conn].transpose(1, 0, 2)
+    F, B = fe_hex.poisson_elements("biquadratic", X, np.zeros((L.nel, 27)))
+    A.add_blocks(d, d, B.reshape(L.nel, -1))
+    ref, _ = mb.assemble(L, "biquadratic")
+    got = A.to_scipy()
+    assert np.array_equal(got.indices, ref.indices)
+    assert np.abs(got.data - ref.data).max() <= RTOL * np.abs(ref.data).max()
+    with pytest.raises(capi.B2Error):
+        bad = d.copy()
+        A2 = ctx.csr(3, 3, np.array([0, 1, 2, 3]), np.array([0, 1, 2]))
+        A2.add_blocks(np.array([[0, 1]]), np.array([[0, 1]]), np.ones((1, 4)))
+    # insert_row
+    P = mb.prolongator(lv[0], mb.refine(lv[0]), "linear").tocsr()
+    dP = ctx.csr(P.shape[0], P.shape[1], P.indptr, P.indices)
+    rows = np.arange(P.shape[0], dtype=np.int32)
+    dP.set_rows(rows, P.indptr, P.indices, P.data)
+    assert np.array_equal(dP.to_scipy().data, P.data)
+
+
+# ------------------------------------------------------------------------------ pattern + assembly
+@pytest.mark.parametrize("order,shape", [("linear", (3, 2, 4)), ("biquadratic", (3, 2, 2)), ("biquadratic", (4, 4, 4))])
+def test_pattern_from_elements_bit_exact(ctx, order, shape):
+    L = mb.build_box(*shape)
+    d = mb.system_dof(L, order)
+    rp, ci = mb.sparsity(L, order)
+    A = capi.Csr.from_elements(ctx, mb.ndofs(L, order), d)
+    grp, gci, _ = A.get(values=False)
+    assert np.array_equal(grp, rp)
+    assert np.array_equal(gci, ci)
+
+
+def distorted(L, amp, seed):
+    """Smoothly distorted copy of the box so that the Jacobian varies inside every element."""
+    x, y, z = L.xyz
+    rng = np.random.default_rng(seed)
+    a = rng.uniform(0.5, 1.5, 3)
+    out = L.xyz.copy()
+    out[0] += amp * np.sin(a[0] * np.pi * y) * np.sin(np.pi * z) * x * (1 - x)
+    out[1] += amp * np.sin(a[1] * np.pi * z) * np.sin(np.pi * x) * y * (1 - y)
+    out[2] += amp * np.sin(a[2] * np.pi * x) * np.sin(np.pi * y) * z * (1 - z)
+    return out
+
+
+@pytest.mark.parametrize("order", ["linear", "biquadratic"])
+@pytest.mark.parametrize("amp", [0.0, 0.08])
+def test_assembly_matches_oracle(ctx, order, amp):
+    lv = mb.build_hierarchy(2, 3, 2, 2)
+    L = lv[-1]
+    L.xyz = distorted(L, amp, 3)
+    n = mb.ndofs(L, order)
+    d = mb.system_dof(L, order)
+    rng = np.random.default_rng(11)
+    u = rng.standard_normal(n)
+    Aref, rhs_ref = mb.assemble(L, order, u, fsrc=1.5)
+    A = capi.Csr.from_elements(ctx, n, d)
+    mesh = capi.Mesh(ctx, L.xyz, L.conn)
+    asm = capi.Assembler(mesh, A, d, fe_hex.tables(order))
+    U, R = ctx.vector(u), ctx.vector(n)
+    asm.poisson(U, R, nu=1.0, fsrc=1.5)
+    got = A.to_scipy()
+    assert np.array_equal(got.indptr, Aref.indptr) and np.array_equal(got.indices, Aref.indices)
+    assert np.abs(got.data - Aref.data).max() <= RTOL * np.abs(Aref.data).max()
+    # residual: tolerance relative to the magnitude of the summed terms
+    mag = np.abs(Aref) @ np.abs(u) + np.abs(rhs_ref)
+    assert np.all(np.abs(R.get() - rhs_ref) <= RTOL * mag.max())
+    # accumulate semantics: a second pass doubles the matrix (the app zeroes it first)
+    asm.poisson(U, None, nu=1.0, fsrc=1.5)
+    assert np.abs(A.to_scipy().data - 2 * Aref.data).max() <= 2 * RTOL * np.abs(Aref.data).max()
+
+
+def test_assembly_golden_elements(ctx):
+    """Single elements of the committed golden fixture (values of the compiled reference)."""
+    import os
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden", "fe_hex_ref.npz"))
+    for order, nve in (("linear", 8), ("biquadratic", 27)):
+        for k in range(G[f"{order}_X"].shape[0]):
+            X = G[f"{order}_X"][k]
+            xyz = np.zeros((3, 27))
+            xyz[:, :nve] = X
+            conn = np.arange(27, dtype=np.int32)[None, :]
+            d = np.arange(nve, dtype=np.int32)[None, :]
+            A = capi.Csr.from_elements(ctx, nve, d)
+            asm = capi.Assembler(capi.Mesh(ctx, xyz, conn), A, d, fe_hex.tables(order))
+            U, R = ctx.vector(G[f"{order}_U"][k]), ctx.vector(nve)
+            asm.poisson(U, R, 1.0, 1.0)
+            B = A.to_scipy().toarray()
+            Bref, Fref = G[f"{order}_B"][k], G[f"{order}_F"][k]
+            assert np.abs(B - Bref).max() <= RTOL * np.abs(Bref).max()
+            assert np.abs(R.get() - Fref).max() <= RTOL * (np.abs(Bref) @ np.abs(G[f"{order}_U"][k])).max()
+
+
+# ------------------------------------------------------------------------------ Galerkin + V-cycle
+@pytest.mark.parametrize("order", ["linear", "biquadratic"])
+def test_ptap_matches_oracle(ctx, order):
+    lv = mb.build_hierarchy(2, 2, 3, 3)
+    H = mg.Hierarchy(lv, order)
+    for l in (2, 1):
+        A = ctx.csr_from_scipy(H.A_raw[l])
+        P = ctx.csr_from_scipy(H.P[l])
+        rp, ci = mb.sparsity(lv[l - 1], order)
+        C = ctx.csr(rp.shape[0] - 1, rp.shape[0] - 1, rp, ci)
+        C.ptap(P, A)
+        got = C.to_scipy()
+        ref = H.A_raw[l - 1]
+        assert np.array_equal(got.indices, ref.indices)
+        assert np.abs(got.data - ref.data).max() <= RTOL * np.abs(ref.data).max()
+
+
+def build_device_hierarchy(ctx, lv, order, fsrc=1.0, npre=1, npost=1, omega=0.5):
+    """Mirror of LinearImplicitSystem::MGsolve on the device through the C ABI."""
+    nl = len(lv)
+    H = mg.Hierarchy(lv, order, fsrc)          # oracle: used for P (host-side setup) and as the checker
+    top = lv[-1]
+    n = mb.ndofs(top, order)
+    d = mb.system_dof(top, order)
+    A = [None] * nl
+    A[-1] = capi.Csr.from_elements(ctx, n, d)
+    asm = capi.Assembler(capi.Mesh(ctx, top.xyz, top.conn), A[-1], d, fe_hex.tables(order))
+    res = ctx.vector(n)
+    asm.poisson(None, res, 1.0, fsrc)
+    P = [None] + [ctx.csr_from_scipy(H.P[l]) for l in range(1, nl)]
+    for l in range(nl - 1, 0, -1):
+        A[l - 1] = capi.Csr.from_elements(ctx, mb.ndofs(lv[l - 1], order), mb.system_dof(lv[l - 1], order))
+        A[l - 1].ptap(P[l], A[l])
+    M = capi.Multigrid(ctx, nl)
+    for l in range(nl):
+        M.set_level(l, A[l], P[l], H.bdc_idx[l], npre, npost, omega)
+    M.set_coarse(1e-15, 5000)
+    return H, M, A, res
+
+
+@pytest.mark.parametrize("order,shape,nl", [("linear", (2, 2, 2), 3), ("biquadratic", (2, 2, 2), 3), ("biquadratic", (2, 3, 2), 2)])
+def test_vcycle_residual_trace(ctx, order, shape, nl):
+    lv = mb.build_hierarchy(*shape, nl)
+    H, M, A, res = build_device_hierarchy(ctx, lv, order)
+    # level operators after Galerkin + penalty
+    for l in range(nl):
+        got, ref = A[l].to_scipy(), H.A[l]
+        assert np.array_equal(got.indices, ref.indices)
+        assert np.abs(got.data - ref.data).max() <= RTOL * np.abs(ref.data).max()
+    ncyc = 6
+    trace_ref, eps_ref = H.mg_solve_trace(ncyc)
+    n = res.n
+    eps = ctx.vector(n)
+    free = ctx.vector(H.bdc[-1])
+    masked = ctx.vector(n)
+    trace = []
+    for _ in range(ncyc):
+        M.solve(res, eps)
+        masked.copy_masked(res, free, 1.1)              # UpdateRes
+        trace.append(masked.norm(2))
+    assert M.coarse_iterations() > 0
+    for a, b in zip(trace, trace_ref):
+        assert abs(a - b) <= RTOL * trace_ref[0], (trace, trace_ref)
+    assert np.abs(eps.get() - eps_ref).max() <= 1e-11 * np.abs(eps_ref).max()
+
+
+def test_single_level_is_a_direct_solve(ctx):
+    """BASELINE config 1 (1 level): MGSolve degenerates to the coarse solver (reference: LU)."""
+    lv = mb.build_hierarchy(4, 4, 4, 1)
+    H, M, A, res = build_device_hierarchy(ctx, lv, "linear")
+    n = res.n
+    eps = ctx.vector(n)
+    M.solve(res, eps)
+    rhs = H.rhs.copy()
+    rhs[H.bdc_idx[0]] = 0.0
+    ref = H.lu.solve(rhs)
+    assert np.abs(eps.get() - ref).max() <= 1e-12 * np.abs(ref).max()

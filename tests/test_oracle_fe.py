@@ -1,0 +1,84 @@
+"""CPU: pin the numpy FE oracle (oracle/fe_hex.py) against the reference's own FE kernel --
+the committed golden fixture (generated from oracle/_ref by tests/golden/make_fe_golden.py) and,
+when the compiled reference is present, oracle/_ref itself."""
+import os
+import numpy as np
+import pytest
+
+from oracle import fe_hex, ref
+
+GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "fe_hex_ref.npz"))
+ORDERS = ("linear", "biquadratic")
+
+
+@pytest.mark.parametrize("order", ORDERS)
+def test_gauss_and_tables_bit_exact(order):
+    w, xi = fe_hex.gauss_hex("seventh")
+    assert np.array_equal(w, GOLD[f"{order}_gauss_w"])
+    assert np.array_equal(xi, GOLD[f"{order}_gauss_xi"])
+    phi, dxi, deta, dzeta, _ = fe_hex.tables(order)
+    for a, k in ((phi, "phi"), (dxi, "dxi"), (deta, "deta"), (dzeta, "dzeta")):
+        assert np.array_equal(a, GOLD[f"{order}_{k}"]), k
+
+
+@pytest.mark.parametrize("order", ORDERS)
+def test_jacobian_bit_exact(order):
+    X = GOLD[f"{order}_X"]
+    tabs = fe_hex.tables(order)
+    for ig in range(64):
+        w, _, g = fe_hex.jacobian(order, X, ig, tabs)
+        assert np.array_equal(w, GOLD[f"{order}_weight"][:, ig])
+        assert np.array_equal(g, GOLD[f"{order}_gradphi"][:, ig])
+
+
+@pytest.mark.parametrize("order", ORDERS)
+def test_poisson_element_bit_exact(order):
+    F, B = fe_hex.poisson_elements(order, GOLD[f"{order}_X"], GOLD[f"{order}_U"], 1.0)
+    assert np.array_equal(B, GOLD[f"{order}_B"])
+    assert np.array_equal(F, GOLD[f"{order}_F"])
+
+
+@pytest.mark.parametrize("order", ORDERS)
+def test_local_prolongator(order):
+    P = fe_hex.local_prolongator(order)
+    pts = fe_hex.fine_points(order)
+    lut = {tuple(p): i for i, p in enumerate(pts)}
+    Pg, pos = GOLD[f"{order}_prol"], GOLD[f"{order}_prol_pos2"]
+    assert Pg.shape == P.shape
+    for i in range(Pg.shape[0]):
+        assert np.array_equal(P[lut[tuple(pos[i])]], Pg[i])
+    assert int((P != 0).sum()) == {"linear": 64, "biquadratic": 729}[order]
+
+
+def test_survey_known_answers():
+    """Numbers measured from the compiled reference and recorded in SURVEY.md section 8c."""
+    n = 27
+    for N, vol, b00, b01, b2626, fro in ((128, 4.7683715820312267e-07, 0.00097222222222222198,
+                                          -0.00011574074074074252, 0.035555555555555, 0.048678499916971554),
+                                         (256, None, 0.00048611111111111099, None, None, 0.024339249958485777)):
+        X = (fe_hex.XC[:n].T + 1.0) * (0.5 / N)
+        F, B = fe_hex.poisson_elements("biquadratic", X[None], np.zeros((1, n)), 1.0)
+        assert abs(B[0, 0, 0] - b00) < 1e-17
+        assert abs(np.linalg.norm(B[0]) - fro) < 1e-15
+        if vol is not None:
+            assert abs(F[0].sum() - vol) < 1e-20
+            assert abs(B[0, 0, 1] - b01) < 1e-17
+            assert abs(B[0, 26, 26] - b2626) < 1e-14
+    X = (fe_hex.XC[:8].T + 1.0) * (0.5 / 32)
+    F, B = fe_hex.poisson_elements("linear", X[None], np.zeros((1, 8)), 1.0)
+    assert abs(F[0].sum() - 3.0517578124999851e-05) < 1e-19
+    assert abs(B[0, 0, 0] - 0.010416666666666642) < 1e-16
+    assert abs(np.linalg.norm(B[0]) - 0.032940392293420523) < 1e-15
+
+
+@pytest.mark.skipif(not ref.available(), reason="oracle/_ref not built (no /root/reference here)")
+@pytest.mark.parametrize("order", ORDERS)
+def test_against_compiled_reference(order):
+    R = ref.RefHex(order)
+    rng = np.random.default_rng(7)
+    n = R.n
+    X = (fe_hex.XC[:n].T * 0.1 + 0.5) + rng.standard_normal((3, n)) * 0.01
+    U = rng.standard_normal(n)
+    Fr, Br = R.poisson_element(X, U, 2.5)
+    Fo, Bo = fe_hex.poisson_elements(order, X[None], U[None], 2.5)
+    assert np.array_equal(Br, Bo[0]) and np.array_equal(Fr, Fo[0])
