@@ -1,0 +1,329 @@
+#!/usr/bin/env python
+"""Benchmark of the FEMuS hot path on B200: per-element Poisson assembly + geometric-multigrid
+V-cycle (BASELINE.json: "DOF/sec assembled + V-cycle SpMV GB/s (fp64)").
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+A step = one pass of the hot path over the mesh: SetResZero, element assembly of the finest-level
+matrix and residual, Galerkin chain P^T A P down the hierarchy, MGSetLevel on every level
+(Dirichlet penalty, Jacobi diagonal), one MGSolve (= one multiplicative V-cycle, outer PREONLY).
+`value` = finest-level DOFs / step time with all inputs resident in HBM; `e2e` = the same with the
+mesh (coordinates, connectivity) and the current solution copied from pinned host memory and the
+correction EPS + residual norm copied back inside the timed region.
+
+Workload at N=1: BASELINE configs[1] (3-D Poisson, Hex27, 128^3 elements, 4-level MG).  N>1: the
+box grows with N (weak scaling, z-slab partition) up to configs[2] (256^3 on 8 GPUs).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "dof_per_sec_assembly_plus_vcycle"
+UNIT = "DOF/s"
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get("hbm_gbs", None), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device=0):
+        self.device = device
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.device)], stdout=open(self.path, "w"),
+                                         stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if not self.proc:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for line in open(self.path):
+            f = [t.strip() for t in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.path)
+        if sm:
+            out["sm_mhz"] = float(np.median(sm))
+            out["sm_max_mhz"] = float(max(mx))
+            out["samples"] = len(sm)
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+# ---------------------------------------------------------------------------------------------
+def cpu_reference_problem(n0, nlevels, order, nthreads):
+    """Setup (untimed) of the CPU sample: oracle meshes, patterns, prolongators."""
+    from oracle import mesh_box as mb, mg, ref, cpu_port, fe_hex
+    lv = mb.build_hierarchy(n0, n0, n0, nlevels)
+    top = lv[-1]
+    rp, ci = mb.sparsity(top, order)
+    dof = mb.system_dof(top, order)
+    kind = "reference" if ref.available() else "port"
+    R = ref.RefHex(order) if kind == "reference" else None
+    state = dict(lv=lv, top=top, rp=rp, ci=ci, dof=dof, kind=kind, R=R, order=order, nthreads=nthreads)
+    state["skeleton"] = None
+    return state
+
+
+def cpu_reference_step(st):
+    """One pass of the hot path on the host cores: assembly by the reference's own FE kernel
+    (oracle/_ref, OpenMP over elements) or the numpy port, Galerkin chain (scipy SpGEMM), level
+    setup, one V-cycle with the OpenMP C port of the CSR kernels."""
+    import scipy.sparse as sp
+    from oracle import mesh_box as mb, mg, cpu_port
+    top, order, nt = st["top"], st["order"], st["nthreads"]
+    n = mb.ndofs(top, order)
+    t0 = time.perf_counter()
+    if st["kind"] == "reference":
+        vals, rhs, _ = st["R"].assemble_csr(top.conn, st["dof"], top.xyz, np.zeros(n), st["rp"], st["ci"], 1.0, nt)
+        A = sp.csr_matrix((vals, st["ci"], st["rp"]), shape=(n, n))
+    else:
+        A, rhs = mb.assemble(top, order)
+    t1 = time.perf_counter()
+    H = mg.Hierarchy(st["lv"], order, A_top=A, rhs=rhs, coarse_lu=False)      # Galerkin + penalty
+    t2 = time.perf_counter()
+    M = cpu_port.PortMG(H, nt)
+    t3 = time.perf_counter()
+    res, eps = M.mg_solve(rhs.copy(), np.zeros(n))
+    t4 = time.perf_counter()
+    return dict(total=(t1 - t0) + (t2 - t1) + (t4 - t3), assembly=t1 - t0, galerkin_setup=t2 - t1, vcycle=t4 - t3,
+                ndofs=n, nel=top.nel, resnorm=float(np.linalg.norm(res)))
+
+
+def run_cpu_sample(n0, nlevels, order, steps, warmup):
+    nthreads = os.cpu_count() or 1
+    st = cpu_reference_problem(n0, nlevels, order, nthreads)
+    for _ in range(warmup):
+        cpu_reference_step(st)
+    rs = [cpu_reference_step(st) for _ in range(steps)]
+    tot = float(np.mean([r["total"] for r in rs]))
+    nve = 27 if order == "biquadratic" else 8
+    out = {
+        "value": rs[0]["ndofs"] / tot, "unit": UNIT, "cores": nthreads, "kind": st["kind"],
+        "sample": (f"{n0 * 2 ** (nlevels - 1)}^3 {'Hex27' if nve == 27 else 'Hex8'} elements, {nlevels}-level MG, "
+                   f"{rs[0]['ndofs']} dofs: assembly by "
+                   f"{'the compiled reference FE kernel (oracle/_ref, OpenMP)' if st['kind'] == 'reference' else 'the numpy port'}"
+                   f", Galerkin by scipy SpGEMM (1 thread), V-cycle by the OpenMP C port; {steps} step(s)"),
+        "ms_per_step": tot * 1e3,
+        "assembly_elem_dof_per_s": rs[0]["nel"] * nve / float(np.mean([r["assembly"] for r in rs])),
+        "assembly_ms": float(np.mean([r["assembly"] for r in rs])) * 1e3,
+        "galerkin_setup_ms": float(np.mean([r["galerkin_setup"] for r in rs])) * 1e3,
+        "vcycle_ms": float(np.mean([r["vcycle"] for r in rs])) * 1e3,
+    }
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+def workload_for(ngpus, n0, nlevels):
+    """Weak scaling: per-GPU work fixed at n0^3 coarse elements; boxes 1:(n,n,n) 2:(n,n,2n)
+    4:(n,2n,2n) 8:(2n,2n,2n) -> 128^3 at N=1 and 256^3 at N=8 for n0=16, 4 levels."""
+    mul = {1: (1, 1, 1), 2: (1, 1, 2), 4: (1, 2, 2), 8: (2, 2, 2)}[ngpus]
+    return n0 * mul[0], n0 * mul[1], n0 * mul[2]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n0", type=int, default=16, help="coarsest-level elements per side per GPU")
+    ap.add_argument("--levels", type=int, default=4)
+    ap.add_argument("--order", default="biquadratic", choices=["linear", "biquadratic"])
+    ap.add_argument("--cpu-n0", type=int, default=4, help="coarsest-level size of the CPU baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    W = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    nve = 27 if args.order == "biquadratic" else 8
+    nx, ny, nz = workload_for(args.gpus, args.n0, args.levels)
+    f = 2 ** (args.levels - 1)
+    workload = (f"3D Poisson, {'Hex27' if nve == 27 else 'Hex8 (Q1 on Hex27 geometry)'}, {nx * f}x{ny * f}x{nz * f} elements, "
+                f"{args.levels}-level geometric MG V-cycle (Richardson 0.5 + Jacobi, 1 pre / 1 post, coarse Jacobi-PCG), fp64")
+    config = {"workload": workload, "coarse_box": [nx, ny, nz], "levels": args.levels, "fe_order": args.order,
+              "partition": "single GPU" if args.gpus == 1 else f"z-slabs over {args.gpus} GPUs",
+              "l2": "inputs larger than L2 (finest CSR >> 126 MB); no flush needed"}
+
+    # ------------------------------------------------------------------ reference arm (CPU)
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        r = run_cpu_sample(args.cpu_n0, args.levels, args.order, max(args.steps, 1), args.warmup)
+        line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+                "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "assembly_elem_dof_per_s": r["assembly_elem_dof_per_s"], "assembly_ms": r["assembly_ms"],
+                "galerkin_setup_ms": r["galerkin_setup_ms"], "vcycle_ms": r["vcycle_ms"], "gpu_launches": 0}
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------ B200 arm
+    import torch
+    import torch.distributed as dist
+    from femus_b200 import capi
+    from femus_b200.poisson import PoissonMG
+
+    if world > 1:
+        raise SystemExit("multi-GPU bench path: see bench_multi (not wired in this build)")
+    torch.cuda.set_device(local_rank)
+    ctx = capi.Context(local_rank)
+    t_setup = time.time()
+    pb = PoissonMG(ctx, nx, ny, nz, args.levels, args.order)
+    ctx.sync()
+    t_setup = time.time() - t_setup
+    top = pb.hier.levels[-1]
+    n, nel = pb.n, pb.nel
+
+    # pinned host copies of the per-step inputs / outputs for the end-to-end leg
+    def pinned(a):
+        t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        return t
+    h_xyz, h_conn = pinned(top.xyz), pinned(top.conn)
+    h_sol = torch.zeros(n, dtype=torch.float64).pin_memory()
+    h_eps = torch.zeros(n, dtype=torch.float64).pin_memory()
+    h2d = h_xyz.numel() * 8 + h_conn.numel() * 4 + n * 8
+    d2h = n * 8 + 8
+
+    def step_resident():
+        pb.step()
+
+    def step_e2e():
+        pb.mesh.update(h_xyz.data_ptr(), h_conn.data_ptr())
+        pb.SOL.put_async(h_sol.data_ptr(), n)
+        pb.step()
+        pb.EPS.get_async(h_eps.data_ptr(), n)
+        return pb.residual_norm()          # D2H of the scalar, synchronises
+
+    # ---- warm-up
+    for _ in range(W):
+        step_resident()
+    ctx.sync()
+    Afine = pb.KK[-1]
+
+    # ---- timed region: K steps, device time on the library stream
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ctx.profile_only(Afine)
+    ctx.launches(reset=True)
+    ctx.sync()
+    ctx.timer_start()
+    for _ in range(args.steps):
+        step_resident()
+    ms_total = ctx.timer_stop_ms()
+    launches = ctx.launches(reset=True)
+    nsp, ms_sp = ctx.profile_read(Afine)
+    ctx.profile_only(None)
+    # phase breakdown (separate passes, same data)
+    phases = {}
+    for name, fn in (("assembly", pb.assemble), ("galerkin", pb.galerkin), ("mg_set_levels", pb.mg_set_levels),
+                     ("vcycle", pb.mg_solve)):
+        ts = []
+        for _ in range(3):
+            ctx.sync()
+            ctx.timer_start()
+            fn()
+            ts.append(ctx.timer_stop_ms())
+        phases[name] = float(np.median(ts))
+    # ---- end-to-end: host buffers in, host buffers out
+    for _ in range(2):
+        step_e2e()
+    ctx.sync()
+    ctx.timer_start()
+    for _ in range(args.steps):
+        resnorm = step_e2e()
+    ms_e2e = ctx.timer_stop_ms()
+    clocks = sampler.stop()
+    # residual trace of a short solve (sanity: the timed path really converges)
+    pb.EPS.zero()
+    pb.assemble(); pb.galerkin(); pb.mg_set_levels()
+    trace = []
+    for _ in range(4):
+        pb.mg_solve()
+        trace.append(pb.residual_norm())
+
+    ms_step = ms_total / args.steps
+    value = n / (ms_step * 1e-3)
+    e2e_value = n / (ms_e2e / args.steps * 1e-3)
+    # ---- roofline of the dominant kernel: finest-level CSR SpMV family (3 launches per step:
+    # 2 x r = b - A x, 1 x Jacobi sweep); algorithmic bytes per launch, BASELINE.md section 4
+    peak, peak_src = measured_peaks()
+    b_y = pb.spmv_bytes(-1)
+    bytes_per_launch = (2 * (b_y + 8 * n) + (b_y + 24 * n)) / 3.0
+    ach = bytes_per_launch / (ms_sp / max(nsp, 1) * 1e-3) / 1e9 if nsp else None
+    roofline = {"bound": "hbm", "kernel": "spmv_kernel<16,*> on the finest-level CSR (resid / Jacobi sweep)",
+                "achieved": ach, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+                "frac": (ach / peak) if ach else None, "traffic": None,
+                "algorithmic_bytes_per_launch": bytes_per_launch, "launches_timed": nsp,
+                "avg_launch_ms": ms_sp / max(nsp, 1), "share_of_step": ms_sp / ms_total}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": W,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": config,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+            "assembly_elem_dof_per_s": nel * nve / (phases["assembly"] * 1e-3),
+            "spmv_gbs": ach, "phases_ms": phases, "finest_dofs": n, "finest_nnz": Afine.nnz, "elements": nel,
+            "setup_s": t_setup, "residual_trace": trace, "coarse_pcg_iterations": pb.mg.coarse_iterations(),
+            "device_bytes": ctx.bytes_in_use()}
+    if not args.no_cpu_baseline:
+        try:
+            line["cpu_baseline"] = {k: v for k, v in run_cpu_sample(args.cpu_n0, args.levels, args.order, 2, 1).items()}
+        except Exception as e:      # the baseline is reported, never required for the GPU number
+            line["cpu_baseline"] = {"error": repr(e)}
+    print(json.dumps(line))
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -52,7 +52,7 @@ def build(force=False, verbose=False):
 
     def run(job):
         src, obj = job
-        extra = ["-x", "cu"] if src.endswith(".cpp") else []
+        extra = []
         r = subprocess.run([NVCC] + FLAGS + extra + ["-c", src, "-o", obj], capture_output=True, text=True)
         log = r.stdout + r.stderr
         with open(obj + ".log", "w") as f:

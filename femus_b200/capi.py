@@ -34,6 +34,13 @@ _PROTOS = {
     "b2_timer_start": (ci, [vp]),
     "b2_timer_stop_ms": (ci, [vp, vp]),
     "b2_ctx_flush_l2": (ci, [vp]),
+    "b2_ctx_profile": (ci, [vp, ci]),
+    "b2_ctx_profile_only": (ci, [vp, vp]),
+    "b2_ctx_profile_read": (ci, [vp, vp, vp, vp]),
+    "b2_ctx_profile_clear": (ci, [vp]),
+    "b2_vec_put_async": (ci, [vp, vp, i64]),
+    "b2_vec_get_async": (ci, [vp, vp, i64]),
+    "b2_mesh_update": (ci, [vp, vp, vp]),
     "b2_vec_create": (ci, [vp, i64, vp]),
     "b2_vec_destroy": (ci, [vp]),
     "b2_vec_size": (i64, [vp]),
@@ -188,6 +195,21 @@ class Context:
     def flush_l2(self):
         check(self.L.b2_ctx_flush_l2(self.h))
 
+    def profile(self, on):
+        check(self.L.b2_ctx_profile(self.h, 1 if on else 0))
+
+    def profile_only(self, obj):
+        check(self.L.b2_ctx_profile_only(self.h, obj.h if obj is not None else None))
+
+    def profile_read(self, obj):
+        """(launch count, total ms) of the profiled launches of a Csr / Assembler; consumed."""
+        n, ms = ci(), cd()
+        check(self.L.b2_ctx_profile_read(self.h, obj.h, ctypes.byref(n), ctypes.byref(ms)))
+        return n.value, ms.value
+
+    def profile_clear(self):
+        check(self.L.b2_ctx_profile_clear(self.h))
+
     # factories
     def vector(self, n_or_array):
         return Vector(self, n_or_array)
@@ -234,6 +256,12 @@ class Vector:
         out = np.empty(self.n)
         check(self.L.b2_vec_get(self.h, _ptr(out), out.shape[0]))
         return out
+
+    def put_async(self, host_ptr, n):
+        check(self.L.b2_vec_put_async(self.h, host_ptr, n))
+
+    def get_async(self, host_ptr, n):
+        check(self.L.b2_vec_get_async(self.h, host_ptr, n))
 
     def zero(self):
         check(self.L.b2_vec_zero(self.h))
@@ -414,6 +442,10 @@ class Mesh:
         check(self.L.b2_mesh_create(ctx.h, xyz.shape[1], conn.shape[0], _ptr(xyz), _ptr(conn), ctypes.byref(h)))
         self.h = h
         self.nel, self.nnode = conn.shape[0], xyz.shape[1]
+
+    def update(self, xyz_ptr=None, conn_ptr=None):
+        """Asynchronous re-upload from (pinned) host pointers."""
+        check(self.L.b2_mesh_update(self.h, xyz_ptr, conn_ptr))
 
     def __del__(self):
         try:

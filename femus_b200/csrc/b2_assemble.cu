@@ -258,6 +258,7 @@ int build_slots(b2_asm* p) {
 template <int NVE, typename SlotT>
 int launch_assemble(b2_asm* p, const b2_vec* u, b2_vec* rhs, double nu, double fsrc) {
   b2_ctx* c = p->mesh->ctx;
+  b2_prof_scope prof(c, p);
   auto kern = assemble_poisson_kernel<NVE, SlotT>;
   const size_t smem = SmemLayout<NVE>::bytes;
   B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -281,6 +282,12 @@ int b2_mesh_create(b2_ctx* c, int64_t nnode, int64_t nel, const double* xyz, con
   B2_TRY(b2_upload(c, m->xyz, xyz, (size_t)3 * nnode));
   B2_TRY(b2_upload(c, m->conn, conn, (size_t)27 * nel));
   *out = m;
+  return 0;
+}
+int b2_mesh_update(b2_mesh* m, const double* xyz, const int32_t* conn) {
+  // asynchronous re-upload (pinned host memory makes it a true async copy)
+  if (xyz) B2_CUDA(cudaMemcpyAsync(m->xyz, xyz, (size_t)3 * m->nnode * sizeof(double), cudaMemcpyHostToDevice, m->ctx->stream));
+  if (conn) B2_CUDA(cudaMemcpyAsync(m->conn, conn, (size_t)27 * m->nel * sizeof(int32_t), cudaMemcpyHostToDevice, m->ctx->stream));
   return 0;
 }
 int b2_mesh_destroy(b2_mesh* m) {

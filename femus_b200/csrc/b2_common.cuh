@@ -58,6 +58,22 @@ struct b2_ctx {
   // multi-GPU
   int nranks = 1, rank = 0;
   void* nccl_comm = nullptr;
+  // optional per-launch event timing of the SpMV family / assembly (b2_ctx_profile)
+  bool profiling = false;
+  const void* prof_only = nullptr;   // when set, only launches tagged with this handle are timed
+  struct ProfRec { const void* tag; cudaEvent_t e0, e1; };
+  std::vector<ProfRec> prof;
+};
+
+// brackets one launch with events when profiling is on
+struct b2_prof_scope {
+  b2_ctx* c; const void* tag; cudaEvent_t e0 = nullptr, e1 = nullptr;
+  b2_prof_scope(b2_ctx* c_, const void* tag_) : c(c_), tag(tag_) {
+    if (c->profiling && (!c->prof_only || c->prof_only == tag)) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, c->stream); }
+  }
+  ~b2_prof_scope() {
+    if (e0) { cudaEventRecord(e1, c->stream); c->prof.push_back({tag, e0, e1}); }
+  }
 };
 
 static constexpr int kRedBlocks = 1184;   // 148 SMs x 8

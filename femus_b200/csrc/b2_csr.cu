@@ -67,6 +67,7 @@ int launch_spmv(const b2_csr* A, const double* x, const double* b, const double*
   b2_ctx* c = A->ctx;
   if (A->nrows == 0) return 0;
   const int tpr = A->tpr;
+  b2_prof_scope prof(c, A);
   const int64_t threads = A->nrows * tpr;
   const int grid = b2_grid_for(c, threads, kBlock, 8 * 4);
 #define B2_SPMV_CASE(T)                                                                                    \

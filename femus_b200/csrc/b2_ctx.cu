@@ -143,6 +143,47 @@ int b2_ctx_flush_l2(b2_ctx* c) {
   return 0;
 }
 
+int b2_ctx_profile(b2_ctx* c, int on) {
+  c->profiling = on != 0;
+  c->prof_only = nullptr;
+  return 0;
+}
+int b2_ctx_profile_only(b2_ctx* c, const void* handle) {
+  c->profiling = handle != nullptr;
+  c->prof_only = handle;
+  return 0;
+}
+// total device time and launch count of the profiled launches tagged with `handle`
+// (a b2_csr* or b2_asm*); the records are consumed.
+int b2_ctx_profile_read(b2_ctx* c, const void* handle, int* count, double* total_ms) {
+  B2_CUDA(cudaStreamSynchronize(c->stream));
+  int n = 0;
+  double t = 0.;
+  std::vector<b2_ctx::ProfRec> keep;
+  for (auto& r : c->prof) {
+    if (r.tag == handle) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, r.e0, r.e1);
+      t += ms;
+      n++;
+      cudaEventDestroy(r.e0);
+      cudaEventDestroy(r.e1);
+    } else {
+      keep.push_back(r);
+    }
+  }
+  c->prof.swap(keep);
+  *count = n;
+  *total_ms = t;
+  return 0;
+}
+int b2_ctx_profile_clear(b2_ctx* c) {
+  B2_CUDA(cudaStreamSynchronize(c->stream));
+  for (auto& r : c->prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+  c->prof.clear();
+  return 0;
+}
+
 int b2_nccl_unique_id(void* id128) {
   B2_TRY(load_nccl());
   int r = ((int (*)(void*))g_nccl.get_uid)(id128);

@@ -193,6 +193,7 @@ int b2_mg_set_level(b2_mg* mg, int level, b2_csr* A, b2_csr* P, const int32_t* b
   B2_CHECK(level == 0 || (P && P->nrows == A->nrows), "b2_mg_set_level: prolongator shape mismatch");
   b2_ctx* c = mg->ctx;
   b2_mg_level& L = mg->L[level];
+  const bool newP = (level > 0) && (L.P != P || !L.R);
   L.A = A;
   L.P = level ? P : nullptr;
   L.npre = npre;
@@ -220,7 +221,7 @@ int b2_mg_set_level(b2_mg* mg, int level, b2_csr* A, b2_csr* P, const int32_t* b
   }
   B2_TRY(b2_csr_diag(A, L.dinv));
   B2_LAUNCH(c, recip_kernel, vec_grid(c, n), kBlock, 0, n, L.dinv->d, L.dinv->d);
-  if (level > 0) {
+  if (newP) {   // the explicit restriction R = P^T is rebuilt only when P changes
     if (L.R) { b2_csr_destroy(L.R); L.R = nullptr; }
     B2_TRY(b2_csr_transpose(P, &L.R));
   }

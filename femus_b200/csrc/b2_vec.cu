@@ -193,6 +193,16 @@ int b2_vec_get(const b2_vec* v, double* host, int64_t n) {
   B2_CHECK(n <= v->n, "b2_vec_get: %lld > size %lld", (long long)n, (long long)v->n);
   return b2_download(v->ctx, host, v->d, (size_t)n);
 }
+int b2_vec_put_async(b2_vec* v, const double* host, int64_t n) {
+  B2_CHECK(n <= v->n, "b2_vec_put_async: too long");
+  B2_CUDA(cudaMemcpyAsync(v->d, host, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, v->ctx->stream));
+  return 0;
+}
+int b2_vec_get_async(const b2_vec* v, double* host, int64_t n) {
+  B2_CHECK(n <= v->n, "b2_vec_get_async: too long");
+  B2_CUDA(cudaMemcpyAsync(host, v->d, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, v->ctx->stream));
+  return 0;
+}
 int b2_vec_copy(b2_vec* dst, const b2_vec* src) {
   B2_CHECK(dst->n == src->n, "b2_vec_copy: size mismatch");
   B2_CUDA(cudaMemcpyAsync(dst->d, src->d, (size_t)src->n * sizeof(double), cudaMemcpyDeviceToDevice, dst->ctx->stream));

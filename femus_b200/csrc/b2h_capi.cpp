@@ -1,0 +1,88 @@
+// C entry points of the HOST layer (mesh hierarchy, dof maps, Dirichlet flags, prolongators, FE
+// tables) so that the Python harness can drive and inspect it.  Pure CPU code: no CUDA calls.
+#include <cstring>
+#include <memory>
+#include "../host/BoxMesh.hpp"
+#include "../../include/femus_b200_host.h"
+
+using namespace femus_b200;
+
+struct b2h_hier {
+  std::vector<MeshLevel> levels;
+};
+struct b2h_csr {
+  HostCsr m;
+};
+
+extern "C" {
+
+b2h_hier* b2h_hier_create(int nx, int ny, int nz, int nlevels, const double* bounds6, int nprocs) {
+  if (nx < 1 || ny < 1 || nz < 1 || nlevels < 1 || nprocs < 1) return nullptr;
+  b2h_hier* h = new b2h_hier();
+  const double unit[6] = {0., 1., 0., 1., 0., 1.};
+  const double* b = bounds6 ? bounds6 : unit;
+  std::vector<int32_t> part;
+  if (nprocs > 1) part = SlabPartition(nx, ny, nz, nprocs);
+  h->levels.reserve(nlevels);
+  h->levels.push_back(GenerateCoarseBoxMesh(nx, ny, nz, b[0], b[1], b[2], b[3], b[4], b[5], nprocs > 1 ? &part : nullptr, nprocs));
+  for (int l = 1; l < nlevels; l++) h->levels.push_back(RefineMesh(h->levels.back()));
+  return h;
+}
+void b2h_hier_destroy(b2h_hier* h) { delete h; }
+int b2h_hier_nlevels(const b2h_hier* h) { return (int)h->levels.size(); }
+int b2h_hier_nprocs(const b2h_hier* h) { return h->levels[0].nprocs; }
+int64_t b2h_level_nel(const b2h_hier* h, int l) { return h->levels[l].nel; }
+int64_t b2h_level_nnode(const b2h_hier* h, int l) { return h->levels[l].nnode; }
+const int32_t* b2h_level_conn(const b2h_hier* h, int l) { return h->levels[l].conn.data(); }
+const int32_t* b2h_level_face(const b2h_hier* h, int l) { return h->levels[l].face.data(); }
+const int32_t* b2h_level_part(const b2h_hier* h, int l) { return h->levels[l].part.data(); }
+const double* b2h_level_xyz(const b2h_hier* h, int l) { return h->levels[l].xyz.data(); }
+const int32_t* b2h_level_child_el(const b2h_hier* h, int l) {
+  return h->levels[l].child_el.empty() ? nullptr : h->levels[l].child_el.data();
+}
+void b2h_level_offsets(const b2h_hier* h, int l, int64_t* elem_offset, int64_t* dof_offset3) {
+  const MeshLevel& L = h->levels[l];
+  const int np1 = L.nprocs + 1;
+  std::copy(L.elem_offset.begin(), L.elem_offset.end(), elem_offset);
+  for (int k = 0; k < 3; k++) std::copy(L.dof_offset[k].begin(), L.dof_offset[k].end(), dof_offset3 + k * np1);
+}
+int64_t b2h_level_ndofs(const b2h_hier* h, int l, int family) { return h->levels[l].ndofs(family); }
+void b2h_level_system_dofs(const b2h_hier* h, int l, int family, int32_t* out) {
+  std::vector<int32_t> d = h->levels[l].system_dofs(family);
+  std::copy(d.begin(), d.end(), out);
+}
+void b2h_level_bdc(const b2h_hier* h, int l, int family, const int* dirichlet_faces7, double* out) {
+  bool f[7];
+  for (int i = 0; i < 7; i++) f[i] = dirichlet_faces7[i] != 0;
+  std::vector<double> b = h->levels[l].GenerateBdc(family, f);
+  std::copy(b.begin(), b.end(), out);
+}
+
+b2h_csr* b2h_prolongator_create(const b2h_hier* h, int lfine, int family) {
+  if (lfine < 1 || lfine >= (int)h->levels.size()) return nullptr;
+  b2h_csr* p = new b2h_csr();
+  p->m = BuildProlongator(h->levels[lfine - 1], h->levels[lfine], family);
+  return p;
+}
+void b2h_csr_destroy(b2h_csr* p) { delete p; }
+int64_t b2h_csr_nrows(const b2h_csr* p) { return p->m.nrows; }
+int64_t b2h_csr_ncols(const b2h_csr* p) { return p->m.ncols; }
+int64_t b2h_csr_nnz(const b2h_csr* p) { return (int64_t)p->m.col.size(); }
+const int64_t* b2h_csr_rowptr(const b2h_csr* p) { return p->m.rowptr.data(); }
+const int32_t* b2h_csr_col(const b2h_csr* p) { return p->m.col.data(); }
+const double* b2h_csr_val(const b2h_csr* p) { return p->m.val.data(); }
+
+int b2h_hex_nve(int family) { return HexElement::nve(family); }
+void b2h_hex_tables(int family, double* phi, double* dxi, double* deta, double* dzeta, double* w) {
+  HexElement::Tables t = HexElement::tables(family);
+  std::copy(t.phi.begin(), t.phi.end(), phi);
+  std::copy(t.dxi.begin(), t.dxi.end(), dxi);
+  std::copy(t.deta.begin(), t.deta.end(), deta);
+  std::copy(t.dzeta.begin(), t.dzeta.end(), dzeta);
+  std::copy(t.w.begin(), t.w.end(), w);
+}
+int b2h_hex_prolongator_row(int family, int a, int b, int c, int* idx, double* val) {
+  return HexElement::prolongator_row(family, a, b, c, idx, val);
+}
+
+}  // extern "C"

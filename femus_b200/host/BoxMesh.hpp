@@ -1,0 +1,361 @@
+// Host-side mesh layer of the backend: structured HEX27 box generation, FEMuS element / node
+// numbering, uniform refinement, dof maps, Dirichlet flags and prolongators.  Integer results must
+// be bit-identical to what FEMuS produces on the same mesh, because they define the DOF->row map
+// and the CSR structure.  Restates (paths relative to the reference's src/):
+//   06_mesh/00_single_level/01_input/02_from_implemented_code/MeshGeneration.cpp:790-849, 976-1071
+//   06_mesh/00_single_level/00_definition/Mesh.cpp:517-559 (node renumbering), :589-616 (element
+//     reorder by rank), :706-853 (dof offsets), :1021-1074 (GetSolutionDof)
+//   06_mesh/00_single_level/03_refinement/MeshRefinement.cpp:188-507, :513-621
+//   06_mesh/00_single_level/02_partitioning/MeshMetisPartitioning.cpp:143-155 (children inherit rank)
+//   06_solution/01_multiple_levels/00_definition/MultiLevelSolution.cpp:725-840 (GenerateBdc)
+//   08_equations/00_stationary/LinearImplicitSystem.cpp:761-909 (BuildProlongatorMatrix)
+// Refinement is topological (works on any conforming HEX27 mesh, not only boxes): a new node is
+// identified by the pair (lowest-numbered corner, opposite corner) of the coarse edge / face
+// quadrant / cell octant it is the centre of.
+#pragma once
+#include <algorithm>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <numeric>
+#include <vector>
+#include "HexElement.hpp"
+
+namespace femus_b200 {
+
+struct HostCsr {
+  int64_t nrows = 0, ncols = 0;
+  std::vector<int64_t> rowptr;
+  std::vector<int32_t> col;
+  std::vector<double> val;
+};
+
+class MeshLevel {
+ public:
+  int level = 0;
+  int nprocs = 1;
+  int64_t nel = 0, nnode = 0;
+  std::vector<int32_t> conn;            // [nel][27] node ids in FEMuS numbering
+  std::vector<int32_t> face;            // [nel][6] faceElementIndex: -1 interior/unset, < -1 boundary
+  std::vector<int32_t> part;            // [nel] owning rank
+  std::vector<int64_t> elem_offset;     // [nprocs+1]
+  std::vector<int64_t> dof_offset[3];   // [family][nprocs+1]
+  std::vector<double> xyz;              // [3][nnode]
+  std::vector<int32_t> child_el;        // [nel][8] fine element of (element, child) once refined
+
+  int32_t node(int64_t iel, int i) const { return conn[iel * 27 + i]; }
+
+  int owner_of_node(int32_t nd) const {
+    const std::vector<int64_t>& o = dof_offset[2];
+    return (int)(std::upper_bound(o.begin(), o.end(), (int64_t)nd) - o.begin()) - 1;
+  }
+  // Mesh::GetSolutionDof (Mesh.cpp:1021-1074), uniform meshes (no "owned ghost" nodes)
+  int32_t GetSolutionDof(int i, int64_t iel, int family) const {
+    const int32_t nd = node(iel, i);
+    if (family == BIQUADRATIC) return nd;
+    const int p = owner_of_node(nd);
+    return (int32_t)((nd - dof_offset[2][p]) + dof_offset[family][p]);
+  }
+  int64_t ndofs(int family) const { return dof_offset[family][nprocs]; }
+
+  // [nel][nve] system dofs of a single-variable system (LinearEquation::GetSystemDof,
+  // LinearEquation.cpp:76-85: KKoffset[0][p] == dofOffset[family][p])
+  std::vector<int32_t> system_dofs(int family) const {
+    const int nve = HexElement::nve(family);
+    std::vector<int32_t> d((size_t)nel * nve);
+    for (int64_t e = 0; e < nel; e++)
+      for (int i = 0; i < nve; i++) d[e * nve + i] = GetSolutionDof(i, e, family);
+    return d;
+  }
+
+  // MultiLevelSolution::GenerateBdc: 2 = free, 0 = Dirichlet on every exterior face whose boundary
+  // index (1..6 = -(faceElementIndex+1), Elem.cpp:361-364) is flagged in dirichlet_faces[1..6].
+  std::vector<double> GenerateBdc(int family, const bool dirichlet_faces[7]) const {
+    std::vector<double> bdc((size_t)ndofs(family), 2.0);
+    const int nfd = HexElement::face_ndofs(family);
+    for (int64_t e = 0; e < nel; e++)
+      for (int f = 0; f < 6; f++) {
+        const int bidx = -(face[e * 6 + f] + 1);
+        if (bidx > 0 && bidx <= 6 && dirichlet_faces[bidx])
+          for (int iv = 0; iv < nfd; iv++) bdc[GetSolutionDof(HexElement::face_nodes()[f][iv], e, family)] = 0.0;
+      }
+    return bdc;
+  }
+
+  // Mesh::FillISvectorDofMapAllFEFamilies: element reorder by rank (stable) and node renumbering
+  // by first visit over (rank, family k, element, local node in [nve(k-1), nve(k))).
+  // `conn` holds temporary node ids in [0, nnode) on entry.  Returns the node map old -> new.
+  std::vector<int32_t> FillISvectorDofMapAllFEFamilies(const std::vector<int32_t>& partition, int nprocs_) {
+    nprocs = nprocs_;
+    // --- elements by rank (Mesh.cpp:589-616); material/group are uniform on box meshes, so the
+    // second sort (Mesh.cpp:621-702) leaves the order unchanged
+    std::vector<int64_t> order(nel);
+    std::iota(order.begin(), order.end(), (int64_t)0);
+    std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) { return partition[a] < partition[b]; });
+    bool identity = true;
+    for (int64_t e = 0; e < nel && identity; e++) identity = (order[e] == e);
+    part.resize(nel);
+    if (identity) {
+      part = partition;
+    } else {
+      std::vector<int32_t> c2(conn.size()), f2(face.size());
+      for (int64_t e = 0; e < nel; e++) {
+        std::copy(conn.begin() + order[e] * 27, conn.begin() + order[e] * 27 + 27, c2.begin() + e * 27);
+        std::copy(face.begin() + order[e] * 6, face.begin() + order[e] * 6 + 6, f2.begin() + e * 6);
+        part[e] = partition[order[e]];
+      }
+      conn.swap(c2);
+      face.swap(f2);
+    }
+    elem_order.assign(order.begin(), order.end());
+    elem_offset.assign(nprocs + 1, 0);
+    for (int64_t e = 0; e < nel; e++) elem_offset[part[e] + 1]++;
+    for (int p = 0; p < nprocs; p++) elem_offset[p + 1] += elem_offset[p];
+    // --- node renumbering (Mesh.cpp:517-559)
+    std::vector<int32_t> map(nnode, -1);
+    std::vector<std::vector<int64_t>> own(3, std::vector<int64_t>(nprocs, 0));
+    int32_t counter = 0;
+    for (int p = 0; p < nprocs; p++)
+      for (int k = 0; k < 3; k++) {
+        const int lo = k == 0 ? 0 : HexElement::nve(k - 1), hi = HexElement::nve(k);
+        for (int64_t e = elem_offset[p]; e < elem_offset[p + 1]; e++)
+          for (int i = lo; i < hi; i++) {
+            const int32_t ii = conn[e * 27 + i];
+            if (map[ii] < 0) {
+              map[ii] = counter++;
+              for (int j = k; j < 3; j++) own[j][p]++;
+            }
+          }
+      }
+    if (counter != nnode) { std::fprintf(stderr, "femus_b200: mesh has %lld unreferenced nodes\n", (long long)(nnode - counter)); std::abort(); }
+    for (auto& c : conn) c = map[c];
+    for (int k = 0; k < 3; k++) {
+      dof_offset[k].assign(nprocs + 1, 0);
+      for (int p = 0; p < nprocs; p++) dof_offset[k][p + 1] = dof_offset[k][p] + own[k][p];
+    }
+    return map;
+  }
+  std::vector<int64_t> elem_order;      // position -> element index before the rank reorder
+};
+
+// z-slab partition of the level-0 box (elements in k, j, i order)
+inline std::vector<int32_t> SlabPartition(int nx, int ny, int nz, int nprocs) {
+  std::vector<int32_t> p((size_t)nx * ny * nz);
+  for (int k = 0; k < nz; k++)
+    for (int64_t t = 0; t < (int64_t)nx * ny; t++) p[(int64_t)k * nx * ny + t] = (int32_t)(((int64_t)k * nprocs) / nz);
+  return p;
+}
+
+// MeshTools::Generation::BuildBox, HEX27 branch
+inline MeshLevel GenerateCoarseBoxMesh(int nx, int ny, int nz, double xmin, double xmax, double ymin, double ymax,
+                                       double zmin, double zmax, const std::vector<int32_t>* partition = nullptr,
+                                       int nprocs = 1) {
+  MeshLevel L;
+  L.level = 0;
+  L.nel = (int64_t)nx * ny * nz;
+  const int64_t sx = 2 * nx + 1, sy = 2 * ny + 1, sz = 2 * nz + 1;
+  L.nnode = sx * sy * sz;
+  L.conn.resize(L.nel * 27);
+  L.face.assign(L.nel * 6, -1);
+  int64_t iel = 0;
+  for (int k = 0; k < 2 * nz; k += 2)
+    for (int j = 0; j < 2 * ny; j += 2)
+      for (int i = 0; i < 2 * nx; i += 2, iel++) {
+        for (int n = 0; n < 27; n++) {
+          const int* o = HexElement::xc()[n];
+          L.conn[iel * 27 + n] = (int32_t)((i + o[0] + 1) + sx * ((j + o[1] + 1) + sy * (k + o[2] + 1)));
+        }
+        if (k == 0) L.face[iel * 6 + 4] = -2;               // bottom
+        if (k == 2 * (nz - 1)) L.face[iel * 6 + 5] = -7;    // top
+        if (j == 0) L.face[iel * 6 + 0] = -3;               // front
+        if (j == 2 * (ny - 1)) L.face[iel * 6 + 2] = -5;    // behind
+        if (i == 0) L.face[iel * 6 + 3] = -6;               // left
+        if (i == 2 * (nx - 1)) L.face[iel * 6 + 1] = -4;    // right
+      }
+  std::vector<int32_t> part = partition ? *partition : std::vector<int32_t>((size_t)L.nel, 0);
+  std::vector<int32_t> map = L.FillISvectorDofMapAllFEFamilies(part, nprocs);
+  L.xyz.resize(3 * L.nnode);
+  for (int64_t k = 0; k < sz; k++)
+    for (int64_t j = 0; j < sy; j++)
+      for (int64_t i = 0; i < sx; i++) {
+        const int64_t nd = map[i + sx * (j + sy * k)];
+        L.xyz[nd] = (static_cast<double>(i) / static_cast<double>(2 * nx)) * (xmax - xmin) + xmin;
+        L.xyz[L.nnode + nd] = (static_cast<double>(j) / static_cast<double>(2 * ny)) * (ymax - ymin) + ymin;
+        L.xyz[2 * L.nnode + nd] = (static_cast<double>(k) / static_cast<double>(2 * nz)) * (zmax - zmin) + zmin;
+      }
+  return L;
+}
+
+namespace detail {
+
+// open-addressing map uint64 -> int32
+class PairMap {
+ public:
+  explicit PairMap(size_t expected) {
+    size_t cap = 64;
+    while (cap < expected * 2) cap <<= 1;
+    keys_.assign(cap, ~0ull);
+    vals_.assign(cap, -1);
+    mask_ = cap - 1;
+  }
+  // returns the stored value, inserting `fresh` if the key is new (inserted = true)
+  int32_t get_or_insert(uint64_t key, int32_t fresh, bool& inserted) {
+    size_t h = (size_t)((key * 0x9E3779B97F4A7C15ull) >> 17) & mask_;
+    while (true) {
+      if (keys_[h] == key) { inserted = false; return vals_[h]; }
+      if (keys_[h] == ~0ull) { keys_[h] = key; vals_[h] = fresh; inserted = true; return fresh; }
+      h = (h + 1) & mask_;
+    }
+  }
+ private:
+  std::vector<uint64_t> keys_;
+  std::vector<int32_t> vals_;
+  size_t mask_;
+};
+
+// The 125 points of a parent's 5x5x5 fine lattice: for each, one (child, local node) that sits
+// there, and the corner structure used to name new nodes.
+struct FinePointTable {
+  int child[125], node[125];
+  int ncorner[125];
+  int corner[125][8];      // parent local nodes at the corners of the sub-entity
+  int opposite[125][8];    // index (into corner[]) of the diagonally opposite corner
+  int pos_of_child_node[8][27];
+  FinePointTable() {
+    for (int q = 0; q < 125; q++) child[q] = -1;
+    for (int j = 0; j < 8; j++) {
+      // child j is the octant at parent vertex j: origin = parent lattice position of that octant
+      const int* v = HexElement::xc()[j];
+      const int o[3] = {v[0] + 1, v[1] + 1, v[2] + 1};     // 0 or 2 on the 5-lattice
+      for (int n = 0; n < 27; n++) {
+        const int* x = HexElement::xc()[n];
+        const int a = o[0] + x[0] + 1, b = o[1] + x[1] + 1, c = o[2] + x[2] + 1;
+        const int q = a + 5 * (b + 5 * c);
+        pos_of_child_node[j][n] = q;
+        if (child[q] < 0 || n < node[q]) { child[q] = j; node[q] = n; }
+      }
+    }
+    for (int c = 0; c < 5; c++)
+      for (int b = 0; b < 5; b++)
+        for (int a = 0; a < 5; a++) {
+          const int q = a + 5 * (b + 5 * c);
+          const int p[3] = {a, b, c};
+          int odd[3], nodd = 0;
+          for (int d = 0; d < 3; d++) if (p[d] & 1) odd[nodd++] = d;
+          ncorner[q] = 1 << nodd;
+          for (int m = 0; m < (1 << nodd); m++) {
+            int cp[3] = {a >> 1, b >> 1, c >> 1};
+            for (int t = 0; t < nodd; t++) if (m & (1 << t)) cp[odd[t]] += 1;
+            corner[q][m] = HexElement::node_at(cp[0], cp[1], cp[2]);
+            opposite[q][m] = ((1 << nodd) - 1) ^ m;
+          }
+        }
+  }
+};
+inline const FinePointTable& fine_points() {
+  static const FinePointTable t;
+  return t;
+}
+
+}  // namespace detail
+
+// Element prolongator scattered to global ids: P of `family` from level C to its refinement F
+// (LinearImplicitSystem::BuildProlongatorMatrix; rows are INSERTED, identical from every
+// neighbouring coarse element, so the first visit defines the row).
+inline HostCsr BuildProlongator(const MeshLevel& C, const MeshLevel& F, int family) {
+  const detail::FinePointTable& T = detail::fine_points();
+  const int nve = HexElement::nve(family);
+  HostCsr P;
+  P.nrows = F.ndofs(family);
+  P.ncols = C.ndofs(family);
+  // local rows
+  int lidx[125][27], lcnt[125];
+  double lval[125][27];
+  bool used[125];
+  for (int q = 0; q < 125; q++) {
+    used[q] = T.node[q] < nve;
+    lcnt[q] = used[q] ? HexElement::prolongator_row(family, q % 5, (q / 5) % 5, q / 25, lidx[q], lval[q]) : 0;
+  }
+  std::vector<int32_t> len((size_t)P.nrows, -1);
+  for (int64_t E = 0; E < C.nel; E++)
+    for (int q = 0; q < 125; q++)
+      if (used[q]) {
+        const int32_t r = F.GetSolutionDof(T.node[q], C.child_el[E * 8 + T.child[q]], family);
+        if (len[r] < 0) len[r] = lcnt[q];
+      }
+  P.rowptr.assign(P.nrows + 1, 0);
+  for (int64_t r = 0; r < P.nrows; r++) P.rowptr[r + 1] = P.rowptr[r] + (len[r] > 0 ? len[r] : 0);
+  P.col.resize(P.rowptr[P.nrows]);
+  P.val.resize(P.rowptr[P.nrows]);
+  std::vector<char> done((size_t)P.nrows, 0);
+  std::vector<std::pair<int32_t, double>> tmp(27);
+  for (int64_t E = 0; E < C.nel; E++) {
+    int32_t cd[27];
+    for (int j = 0; j < nve; j++) cd[j] = C.GetSolutionDof(j, E, family);
+    for (int q = 0; q < 125; q++)
+      if (used[q]) {
+        const int32_t r = F.GetSolutionDof(T.node[q], C.child_el[E * 8 + T.child[q]], family);
+        if (done[r]) continue;
+        done[r] = 1;
+        for (int k = 0; k < lcnt[q]; k++) tmp[k] = {cd[lidx[q][k]], lval[q][k]};
+        std::sort(tmp.begin(), tmp.begin() + lcnt[q]);
+        for (int k = 0; k < lcnt[q]; k++) { P.col[P.rowptr[r] + k] = tmp[k].first; P.val[P.rowptr[r] + k] = tmp[k].second; }
+      }
+  }
+  return P;
+}
+
+// MeshRefinement::RefineMesh, uniform: children 8*iel+j in coarse element order, child j = octant
+// at parent vertex j, boundary faces inherited, partition inherited, then the same renumbering
+// as on level 0; coordinates by biquadratic prolongation of the coarse ones (:470-472).
+inline MeshLevel RefineMesh(MeshLevel& C) {
+  const detail::FinePointTable& T = detail::fine_points();
+  MeshLevel F;
+  F.level = C.level + 1;
+  F.nel = C.nel * 8;
+  F.conn.resize(F.nel * 27);
+  F.face.assign(F.nel * 6, -1);
+  std::vector<int32_t> part(F.nel);
+  detail::PairMap map((size_t)C.nnode * 8 + 1024);
+  int32_t next = (int32_t)C.nnode;
+  for (int64_t E = 0; E < C.nel; E++) {
+    const int32_t* cn = &C.conn[E * 27];
+    int32_t fid[125];
+    for (int q = 0; q < 125; q++) {
+      const int nc = T.ncorner[q];
+      if (nc == 1) { fid[q] = cn[T.corner[q][0]]; continue; }
+      int best = 0;
+      for (int m = 1; m < nc; m++) if (cn[T.corner[q][m]] < cn[T.corner[q][best]]) best = m;
+      const uint64_t key = ((uint64_t)(uint32_t)cn[T.corner[q][best]] << 32) | (uint32_t)cn[T.corner[q][T.opposite[q][best]]];
+      bool ins;
+      fid[q] = map.get_or_insert(key, next, ins);
+      if (ins) next++;
+    }
+    for (int j = 0; j < 8; j++) {
+      const int64_t fe = E * 8 + j;
+      for (int n = 0; n < 27; n++) F.conn[fe * 27 + n] = fid[T.pos_of_child_node[j][n]];
+      part[fe] = C.part[E];
+      for (int f = 0; f < 6; f++) {
+        const int* fn = HexElement::face_nodes()[f];
+        if ((fn[0] == j || fn[1] == j || fn[2] == j || fn[3] == j) && C.face[E * 6 + f] < -1) F.face[fe * 6 + f] = C.face[E * 6 + f];
+      }
+    }
+  }
+  F.nnode = next;
+  F.FillISvectorDofMapAllFEFamilies(part, C.nprocs);
+  // SetChildElement: (coarse element, child) -> fine element after the reorder
+  C.child_el.resize(C.nel * 8);
+  for (int64_t pos = 0; pos < F.nel; pos++) C.child_el[F.elem_order[pos]] = (int32_t)pos;
+  // coordinates: x_f = P_biquadratic x_c, each row summed in ascending coarse-node order
+  HostCsr P = BuildProlongator(C, F, BIQUADRATIC);
+  F.xyz.assign(3 * F.nnode, 0.0);
+  for (int d = 0; d < 3; d++)
+    for (int64_t r = 0; r < P.nrows; r++) {
+      double s = 0.0;
+      for (int64_t k = P.rowptr[r]; k < P.rowptr[r + 1]; k++) s += P.val[k] * C.xyz[d * C.nnode + P.col[k]];
+      F.xyz[d * F.nnode + r] = s;
+    }
+  return F;
+}
+
+}  // namespace femus_b200

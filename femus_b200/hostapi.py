@@ -1,0 +1,153 @@
+"""ctypes binding of include/femus_b200_host.h: the C++ host layer (mesh hierarchy, dof maps,
+Dirichlet flags, prolongators, FE tables) as numpy arrays.  Harness only."""
+import ctypes
+import numpy as np
+
+from .capi import lib
+
+vp, ci, i64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64
+LINEAR, SERENDIPITY, BIQUADRATIC = 0, 1, 2
+FAMILY = {"linear": 0, "quadratic": 1, "biquadratic": 2}
+
+_ready = False
+
+
+def _L():
+    global _ready
+    L = lib()
+    if not _ready:
+        P = {
+            "b2h_hier_create": (vp, [ci, ci, ci, ci, vp, ci]),
+            "b2h_hier_destroy": (None, [vp]),
+            "b2h_hier_nlevels": (ci, [vp]),
+            "b2h_hier_nprocs": (ci, [vp]),
+            "b2h_level_nel": (i64, [vp, ci]),
+            "b2h_level_nnode": (i64, [vp, ci]),
+            "b2h_level_conn": (vp, [vp, ci]),
+            "b2h_level_face": (vp, [vp, ci]),
+            "b2h_level_part": (vp, [vp, ci]),
+            "b2h_level_xyz": (vp, [vp, ci]),
+            "b2h_level_child_el": (vp, [vp, ci]),
+            "b2h_level_offsets": (None, [vp, ci, vp, vp]),
+            "b2h_level_ndofs": (i64, [vp, ci, ci]),
+            "b2h_level_system_dofs": (None, [vp, ci, ci, vp]),
+            "b2h_level_bdc": (None, [vp, ci, ci, vp, vp]),
+            "b2h_prolongator_create": (vp, [vp, ci, ci]),
+            "b2h_csr_destroy": (None, [vp]),
+            "b2h_csr_nrows": (i64, [vp]),
+            "b2h_csr_ncols": (i64, [vp]),
+            "b2h_csr_nnz": (i64, [vp]),
+            "b2h_csr_rowptr": (vp, [vp]),
+            "b2h_csr_col": (vp, [vp]),
+            "b2h_csr_val": (vp, [vp]),
+            "b2h_hex_nve": (ci, [ci]),
+            "b2h_hex_tables": (None, [ci, vp, vp, vp, vp, vp]),
+            "b2h_hex_prolongator_row": (ci, [ci, ci, ci, ci, vp, vp]),
+        }
+        for n, (r, a) in P.items():
+            f = getattr(L, n)
+            f.restype, f.argtypes = r, a
+        _ready = True
+    return L
+
+
+def _view(ptr, shape, dtype):
+    n = int(np.prod(shape))
+    if n == 0 or not ptr:
+        return np.zeros(shape, dtype=dtype)
+    buf = (ctypes.c_char * (n * np.dtype(dtype).itemsize)).from_address(ptr)
+    return np.frombuffer(buf, dtype=dtype).reshape(shape)
+
+
+def _fam(f):
+    return FAMILY[f] if isinstance(f, str) else int(f)
+
+
+class HostLevel:
+    def __init__(self, hier, l):
+        L, h = hier.L, hier.h
+        self.hier, self.l = hier, l
+        self.nel = int(L.b2h_level_nel(h, l))
+        self.nnode = int(L.b2h_level_nnode(h, l))
+        self.conn = _view(L.b2h_level_conn(h, l), (self.nel, 27), np.int32)
+        self.face = _view(L.b2h_level_face(h, l), (self.nel, 6), np.int32)
+        self.part = _view(L.b2h_level_part(h, l), (self.nel,), np.int32)
+        self.xyz = _view(L.b2h_level_xyz(h, l), (3, self.nnode), np.float64)
+        np1 = hier.nprocs + 1
+        eo = np.zeros(np1, dtype=np.int64)
+        do = np.zeros((3, np1), dtype=np.int64)
+        L.b2h_level_offsets(h, l, eo.ctypes.data_as(vp), do.ctypes.data_as(vp))
+        self.elem_offset, self.dof_offset = eo, do
+
+    @property
+    def child_el(self):
+        p = self.hier.L.b2h_level_child_el(self.hier.h, self.l)
+        return _view(p, (self.nel, 8), np.int32) if p else None
+
+    def ndofs(self, family):
+        return int(self.hier.L.b2h_level_ndofs(self.hier.h, self.l, _fam(family)))
+
+    def system_dofs(self, family):
+        f = _fam(family)
+        out = np.zeros((self.nel, self.hier.L.b2h_hex_nve(f)), dtype=np.int32)
+        self.hier.L.b2h_level_system_dofs(self.hier.h, self.l, f, out.ctypes.data_as(vp))
+        return out
+
+    def bdc(self, family, dirichlet_faces=(1, 2, 3, 4, 5, 6)):
+        flags = np.zeros(7, dtype=np.int32)
+        flags[list(dirichlet_faces)] = 1
+        out = np.zeros(self.ndofs(family))
+        self.hier.L.b2h_level_bdc(self.hier.h, self.l, _fam(family), flags.ctypes.data_as(vp), out.ctypes.data_as(vp))
+        return out
+
+
+class HostHierarchy:
+    """MultiLevelMesh of the host layer: GenerateCoarseBoxMesh + RefineMesh."""
+
+    def __init__(self, nx, ny, nz, nlevels, bounds=None, nprocs=1):
+        self.L = _L()
+        b = None if bounds is None else np.ascontiguousarray(bounds, dtype=np.float64)
+        self.h = self.L.b2h_hier_create(nx, ny, nz, nlevels, None if b is None else b.ctypes.data_as(vp), nprocs)
+        if not self.h:
+            raise ValueError("b2h_hier_create failed")
+        self.nprocs = nprocs
+        self.nlevels = nlevels
+        self.levels = [HostLevel(self, l) for l in range(nlevels)]
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.levels = []
+                self.L.b2h_hier_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def prolongator(self, lfine, family):
+        """(rowptr, col, val, shape) of P from level lfine-1 to lfine; arrays are copies."""
+        p = self.L.b2h_prolongator_create(self.h, lfine, _fam(family))
+        if not p:
+            raise ValueError("bad level")
+        n, m, nnz = int(self.L.b2h_csr_nrows(p)), int(self.L.b2h_csr_ncols(p)), int(self.L.b2h_csr_nnz(p))
+        rp = _view(self.L.b2h_csr_rowptr(p), (n + 1,), np.int64).copy()
+        ci_ = _view(self.L.b2h_csr_col(p), (nnz,), np.int32).copy()
+        v = _view(self.L.b2h_csr_val(p), (nnz,), np.float64).copy()
+        self.L.b2h_csr_destroy(p)
+        return rp, ci_, v, (n, m)
+
+
+def hex_tables(family):
+    L = _L()
+    f = _fam(family)
+    nve = L.b2h_hex_nve(f)
+    t = [np.zeros((64, nve)) for _ in range(4)] + [np.zeros(64)]
+    L.b2h_hex_tables(f, *[a.ctypes.data_as(vp) for a in t])
+    return tuple(t)
+
+
+def hex_prolongator_row(family, a, b, c):
+    L = _L()
+    idx = np.zeros(27, dtype=np.int32)
+    val = np.zeros(27)
+    n = L.b2h_hex_prolongator_row(_fam(family), a, b, c, idx.ctypes.data_as(vp), val.ctypes.data_as(vp))
+    return idx[:n].copy(), val[:n].copy()

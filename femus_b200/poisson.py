@@ -1,0 +1,103 @@
+"""Harness-side mirror of the reference's driver for the in-scope application: the sequence
+applications/001_Poisson/main.cpp performs through MultiLevelMesh / MultiLevelSolution /
+LinearImplicitSystem, expressed as calls into the C++ host layer and the device C ABI.
+
+    GenerateCoarseBoxMesh + RefineMesh          main.cpp:133-141
+    AddSolution / GenerateBdc("All")            main.cpp:149-184
+    system.init()                               LinearImplicitSystem.cpp:138-282
+        per-level _KK with exact sparsity       LinearEquation.cpp:196-342
+        BuildProlongatorMatrix, ZeroInterpolatorDirichletNodes   :826-909, :1032-1120
+    system.MGsolve()                            LinearImplicitSystem.cpp:288-411
+        SetResZero, assemble, PtAP chain, MGInit, MGSetLevel, Vcycle
+
+No arithmetic happens here: every number is produced by libfemus_b200.so."""
+import numpy as np
+
+from . import capi, hostapi
+
+
+class PoissonMG:
+    def __init__(self, ctx, nx, ny, nz, nlevels, order="biquadratic", bounds=None, npre=1, npost=1, omega=0.5,
+                 dirichlet_faces=(1, 2, 3, 4, 5, 6), fsrc=1.0, coarse_rtol=1e-14, hier=None):
+        self.ctx = ctx
+        self.order = order
+        self.fam = hostapi.FAMILY[order]
+        self.nlevels = nlevels
+        self.npre, self.npost, self.omega, self.fsrc = npre, npost, omega, fsrc
+        self.hier = hier if hier is not None else hostapi.HostHierarchy(nx, ny, nz, nlevels, bounds)
+        lv = self.hier.levels
+        top = lv[-1]
+        self.ndofs = [L.ndofs(order) for L in lv]
+        self.n = self.ndofs[-1]
+        self.nel = top.nel
+        self.nve = 27 if order == "biquadratic" else 8
+        # --- system.init(): per-level matrices with the exact element-coupling pattern
+        self.dofs = [L.system_dofs(order) for L in lv]
+        self.KK = [capi.Csr.from_elements(ctx, self.ndofs[l], self.dofs[l]) for l in range(nlevels)]
+        self.bdc = [L.bdc(order, dirichlet_faces) for L in lv]
+        self.bdc_idx = [np.nonzero(b < 1.5)[0].astype(np.int32) for b in self.bdc]
+        # --- prolongators, Dirichlet rows (fine) and columns (coarse) zeroed
+        self.PP = [None] * nlevels
+        for l in range(1, nlevels):
+            rp, ci, v, shp = self.hier.prolongator(l, order)
+            P = ctx.csr(shp[0], shp[1], rp, ci, v)
+            P.zero_rows(self.bdc_idx[l], 0.0)
+            P.zero_cols(self.bdc_idx[l - 1])
+            self.PP[l] = P
+        # --- finest-level mesh + assembly plan
+        self.mesh = capi.Mesh(ctx, top.xyz, top.conn)
+        self.tables = hostapi.hex_tables(order)
+        self.asm = capi.Assembler(self.mesh, self.KK[-1], self.dofs[-1], self.tables)
+        # --- vectors of the finest LinearEquation: _RES, _EPS; solution Sol and its Bdc mask
+        self.RES = ctx.vector(self.n)
+        self.EPS = ctx.vector(self.n)
+        self.SOL = ctx.vector(self.n)
+        self.BDC = ctx.vector(self.bdc[-1])
+        self.RESM = ctx.vector(self.n)
+        self.mg = capi.Multigrid(ctx, nlevels)
+        self.mg.set_coarse(coarse_rtol, 10000)
+
+    # ---- pieces of MGsolve -----------------------------------------------------------------
+    def assemble(self):
+        """SetResZero + the assembly callback (KK->zero(); element loop; close())."""
+        self.RES.zero()
+        self.KK[-1].zero()
+        self.asm.poisson(self.SOL, self.RES, 1.0, self.fsrc)
+
+    def galerkin(self):
+        """A_{l-1} = P_l^T A_l P_l down the hierarchy, on the un-penalised matrices."""
+        for l in range(self.nlevels - 1, 0, -1):
+            self.KK[l - 1].ptap(self.PP[l], self.KK[l])
+
+    def mg_set_levels(self):
+        """MGInit + MGSetLevel on every level (SetPenalty, smoother setup)."""
+        for l in range(self.nlevels):
+            self.mg.set_level(l, self.KK[l], self.PP[l], self.bdc_idx[l], self.npre, self.npost, self.omega)
+
+    def mg_solve(self):
+        """One MGSolve (outer PREONLY => one V-cycle) + UpdateRes; returns nothing (no sync)."""
+        self.mg.solve(self.RES, self.EPS)
+
+    def residual_norm(self):
+        """||_Res||_2 after UpdateRes (zeros where Bdc <= 1.1); synchronises."""
+        self.RESM.copy_masked(self.RES, self.BDC, 1.1)
+        return self.RESM.norm(2)
+
+    def step(self):
+        """One pass of the hot path: assembly, Galerkin chain, level setup, one V-cycle."""
+        self.EPS.zero()
+        self.assemble()
+        self.galerkin()
+        self.mg_set_levels()
+        self.mg_solve()
+
+    def update_sol(self):
+        """UpdateSol: Sol += EPS."""
+        self.SOL.axpy(1.0, self.EPS)
+
+    # algorithmic bytes of one y = A x on level l
+    def spmv_bytes(self, l=-1):
+        A = self.KK[l]
+        n, nnz = A.shape[0], A.nnz
+        w = 4 if nnz < 2 ** 31 else 8
+        return nnz * 12 + n * (16 + w)

@@ -54,7 +54,13 @@ int64_t b2_ctx_launch_count(b2_ctx* c, int reset);
 /* CUDA-event timing on the library stream: b2_timer_start / b2_timer_stop_ms */
 int b2_timer_start(b2_ctx* c);
 int b2_timer_stop_ms(b2_ctx* c, double* ms);
-/* write `bytes` of device memory (>= L2 size) to evict the L2 between timed iterations */
+/* per-launch CUDA-event timing of the SpMV family (tag: the b2_csr) and of the assembly kernel
+ * (tag: the b2_asm); b2_ctx_profile_read sums and consumes the records of one tag */
+int b2_ctx_profile(b2_ctx* c, int on);
+int b2_ctx_profile_only(b2_ctx* c, const void* handle);   /* time only this handle's launches */
+int b2_ctx_profile_read(b2_ctx* c, const void* handle, int* count, double* total_ms);
+int b2_ctx_profile_clear(b2_ctx* c);
+/* write 256 MiB of device memory (> L2 size) to evict the L2 between timed iterations */
 int b2_ctx_flush_l2(b2_ctx* c);
 
 /* ---- vectors: replaces PetscVector (src/03_algebra/00_vectors/PetscVector.{hpp,cpp}) --------
@@ -67,6 +73,9 @@ int b2_vec_zero(b2_vec* v);                                            /* zero()
 int b2_vec_fill(b2_vec* v, double a);                                  /* operator=(double)            :449 */
 int b2_vec_put(b2_vec* v, const double* host, int64_t n);              /* operator=(std::vector)       :477 */
 int b2_vec_get(const b2_vec* v, double* host, int64_t n);              /* localize / get               :627 */
+/* asynchronous variants on the library stream (host buffer should be pinned) */
+int b2_vec_put_async(b2_vec* v, const double* host, int64_t n);
+int b2_vec_get_async(const b2_vec* v, double* host, int64_t n);
 int b2_vec_copy(b2_vec* dst, const b2_vec* src);                       /* operator=(NumericVector)     :429 */
 int b2_vec_axpy(b2_vec* y, double a, const b2_vec* x);                 /* add(a,V)    VecAXPY          :303 */
 int b2_vec_aypx(b2_vec* y, double a, const b2_vec* x);                 /* y = x + a y VecAYPX */
@@ -136,6 +145,9 @@ double b2_csr_last_kernel_ms(const b2_csr* A);
  *      (+ elem_type_3D::Jacobian, ElemType.hpp:1438-1537; MatSetValuesBlocked, VecSetValues) ---- */
 /* xyz[3][nnode] (SoA), conn[nel][27] node ids of the HEX27 elements owned by this rank. */
 int b2_mesh_create(b2_ctx* c, int64_t nnode, int64_t nel, const double* xyz, const int32_t* conn, b2_mesh** out);
+/* re-upload coordinates / connectivity into the existing device buffers, asynchronously on the
+ * library stream (either may be NULL) */
+int b2_mesh_update(b2_mesh* m, const double* xyz, const int32_t* conn);
 int b2_mesh_destroy(b2_mesh* m);
 /* Assembly plan for one unknown on one mesh: nve = 8 (trilinear) or 27 (triquadratic);
  * dof[nel][nve] = matrix row of each local node (GetSystemDof, LinearEquation.cpp:76-85);

@@ -1,0 +1,60 @@
+/* femus_b200_host -- C view of the backend's HOST layer (femus_b200/host): the pieces of FEMuS
+ * layers L2/L6/L8 that produce the integer inputs of the device kernels.  Used by the harness
+ * (tests/bench) to drive and inspect the C++ classes; a FEMuS application would use its own
+ * Mesh / MultiLevelSolution / LinearImplicitSystem objects and only the device ABI
+ * (femus_b200.h).  Each entry names the reference interface it mirrors (paths relative to the
+ * reference's src/).  Pure CPU: no GPU needed. */
+#ifndef FEMUS_B200_HOST_H
+#define FEMUS_B200_HOST_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct b2h_hier b2h_hier;   /* MultiLevelMesh: levels 0..nlevels-1 */
+typedef struct b2h_csr b2h_csr;     /* host CSR matrix */
+
+/* MultiLevelMesh::GenerateCoarseBoxMesh(nx,ny,nz,...,HEX27,"seventh") + RefineMesh(nlevels,...)
+ * (06_mesh/01_multiple_levels/00_definition/MultiLevelMesh.cpp; MeshGeneration.cpp:790-1071;
+ * MeshRefinement.cpp:188-507).  bounds6 = xmin,xmax,ymin,ymax,zmin,zmax (NULL: unit cube).
+ * nprocs > 1: z-slab partition of level 0, children inherit (MeshMetisPartitioning.cpp:143-155). */
+b2h_hier* b2h_hier_create(int nx, int ny, int nz, int nlevels, const double* bounds6, int nprocs);
+void b2h_hier_destroy(b2h_hier* h);
+int b2h_hier_nlevels(const b2h_hier* h);
+int b2h_hier_nprocs(const b2h_hier* h);
+int64_t b2h_level_nel(const b2h_hier* h, int l);                 /* Mesh::GetNumberOfElements */
+int64_t b2h_level_nnode(const b2h_hier* h, int l);               /* Mesh::GetNumberOfNodes */
+const int32_t* b2h_level_conn(const b2h_hier* h, int l);         /* elem::GetElementDofIndex, [nel][27] */
+const int32_t* b2h_level_face(const b2h_hier* h, int l);         /* elem::GetFaceElementIndex, [nel][6] */
+const int32_t* b2h_level_part(const b2h_hier* h, int l);         /* element -> rank */
+const double* b2h_level_xyz(const b2h_hier* h, int l);           /* Mesh::GetTopology()->_Sol[0..2], [3][nnode] */
+const int32_t* b2h_level_child_el(const b2h_hier* h, int l);     /* elem::GetChildElement, [nel][8] or NULL */
+/* Mesh::_elementOffset [nprocs+1] and _dofOffset[k=0..2][nprocs+1] (Mesh.cpp:706-853) */
+void b2h_level_offsets(const b2h_hier* h, int l, int64_t* elem_offset, int64_t* dof_offset3);
+int64_t b2h_level_ndofs(const b2h_hier* h, int l, int family);
+/* LinearEquation::GetSystemDof for a single-variable system (LinearEquation.cpp:76-85), [nel][nve] */
+void b2h_level_system_dofs(const b2h_hier* h, int l, int family, int32_t* out);
+/* MultiLevelSolution::GenerateBdc (MultiLevelSolution.cpp:725-840): dirichlet_faces7[1..6] */
+void b2h_level_bdc(const b2h_hier* h, int l, int family, const int* dirichlet_faces7, double* out);
+
+/* LinearImplicitSystem::BuildProlongatorMatrix (LinearImplicitSystem.cpp:826-909), before the
+ * Dirichlet rows/columns are zeroed */
+b2h_csr* b2h_prolongator_create(const b2h_hier* h, int lfine, int family);
+void b2h_csr_destroy(b2h_csr* p);
+int64_t b2h_csr_nrows(const b2h_csr* p);
+int64_t b2h_csr_ncols(const b2h_csr* p);
+int64_t b2h_csr_nnz(const b2h_csr* p);
+const int64_t* b2h_csr_rowptr(const b2h_csr* p);
+const int32_t* b2h_csr_col(const b2h_csr* p);
+const double* b2h_csr_val(const b2h_csr* p);
+
+/* elem_type_3D("hex", family, "seventh"): tables [64][nve] and weights[64] (ElemType.cpp:637-740),
+ * element prolongator row of the fine point (a,b,c) of the 5x5x5 lattice (ElemType.cpp:439-532) */
+int b2h_hex_nve(int family);
+void b2h_hex_tables(int family, double* phi, double* dxi, double* deta, double* dzeta, double* w);
+int b2h_hex_prolongator_row(int family, int a, int b, int c, int* idx, double* val);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -67,7 +67,8 @@ def on_pattern(A, rowptr, col):
 class Hierarchy:
     """Per-level operators exactly as the reference sets them up for one MGsolve."""
 
-    def __init__(self, levels, order, fsrc=1.0, dirichlet_faces=(1, 2, 3, 4, 5, 6)):
+    def __init__(self, levels, order, fsrc=1.0, dirichlet_faces=(1, 2, 3, 4, 5, 6), A_top=None, rhs=None,
+                 coarse_lu=True):
         self.levels = levels
         self.order = order
         nl = len(levels)
@@ -80,7 +81,10 @@ class Hierarchy:
             self.P[l] = mb.zero_dirichlet(P, self.bdc[l], self.bdc[l - 1])
         # assembly on the finest level (V_CYCLE: only the top level is assembled)
         self.A_raw = [None] * nl
-        self.A_raw[-1], self.rhs = mb.assemble(levels[-1], order, None, fsrc)
+        if A_top is None:
+            self.A_raw[-1], self.rhs = mb.assemble(levels[-1], order, None, fsrc)
+        else:                                   # assembled elsewhere (e.g. by oracle/_ref)
+            self.A_raw[-1], self.rhs = A_top, rhs
         # Galerkin chain on the un-penalised matrices
         for l in range(nl - 1, 0, -1):
             Ac = (self.P[l].T @ self.A_raw[l] @ self.P[l]).tocsr()
@@ -90,7 +94,7 @@ class Hierarchy:
         # MGSetLevel: penalty on every level
         self.A = [penalty_fast(self.A_raw[l], self.bdc_idx[l]) for l in range(nl)]
         self.dinv = [1.0 / A.diagonal() for A in self.A]
-        self.lu = spla.splu(self.A[0].tocsc())
+        self.lu = spla.splu(self.A[0].tocsc()) if coarse_lu else None
 
     def smooth(self, l, x, b, nsweeps, omega):
         """KSPRICHARDSON (scale omega) + PCJACOBI: x <- x + omega D^-1 (b - A x)."""
