@@ -87,6 +87,9 @@ _PROTOS = {
     "b2_csr_jacobi_sweep": (ci, [vp, vp, vp, vp, vp, cd]),
     "b2_csr_ptap": (ci, [vp, vp, vp]),
     "b2_csr_last_kernel_ms": (cd, [vp]),
+    "b2_galerkin_create": (ci, [vp, vp, i64, ci, ci, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "b2_galerkin_apply": (ci, [vp]),
+    "b2_galerkin_destroy": (ci, [vp]),
     "b2_mesh_create": (ci, [vp, i64, i64, vp, vp, vp]),
     "b2_mesh_destroy": (ci, [vp]),
     "b2_asm_create": (ci, [vp, vp, ci, vp, ci, vp, vp, vp, vp, vp, vp]),
@@ -431,6 +434,35 @@ class Csr:
     def ptap(self, P, A):
         """self = P^T A P (numeric, onto self's pattern)."""
         check(self.L.b2_csr_ptap(P.h, A.h, self.h))
+
+
+class Galerkin:
+    """Element-gather Galerkin product Ac = P^T Af P (b2_galerkin_*)."""
+
+    def __init__(self, Af, Ac, fine_dofs, coarse_dofs, ploc, fine_entity, valence, fine_mask=None, coarse_mask=None):
+        self.ctx, self.L, self.Af, self.Ac = Af.ctx, Af.ctx.L, Af, Ac
+        fine_dofs, coarse_dofs, ploc = _i32(fine_dofs), _i32(coarse_dofs), _f64(ploc)
+        u8 = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.uint8)
+        fine_entity, valence, fine_mask, coarse_mask = u8(fine_entity), u8(valence), u8(fine_mask), u8(coarse_mask)
+        assert fine_dofs.shape[0] == coarse_dofs.shape[0] == valence.shape[0] and valence.shape[1] == 27
+        assert ploc.shape == (fine_dofs.shape[1], coarse_dofs.shape[1])
+        assert fine_mask is None or fine_mask.shape[0] == Af.shape[0]
+        assert coarse_mask is None or coarse_mask.shape[0] == Ac.shape[0]
+        h = vp()
+        check(self.L.b2_galerkin_create(Af.h, Ac.h, fine_dofs.shape[0], fine_dofs.shape[1], coarse_dofs.shape[1],
+                                        _ptr(fine_dofs), _ptr(coarse_dofs), _ptr(ploc), _ptr(fine_entity), _ptr(valence),
+                                        _ptr(fine_mask), _ptr(coarse_mask), ctypes.byref(h)))
+        self.h = h
+
+    def apply(self):
+        check(self.L.b2_galerkin_apply(self.h))
+
+    def __del__(self):
+        try:
+            if self.h and self.ctx.h:
+                self.L.b2_galerkin_destroy(self.h)
+        except Exception:
+            pass
 
 
 class Mesh:

@@ -72,6 +72,21 @@ const int64_t* b2h_csr_rowptr(const b2h_csr* p) { return p->m.rowptr.data(); }
 const int32_t* b2h_csr_col(const b2h_csr* p) { return p->m.col.data(); }
 const double* b2h_csr_val(const b2h_csr* p) { return p->m.val.data(); }
 
+int b2h_galerkin_nf(int family) { return BuildGalerkinElement(family).nf; }
+void b2h_galerkin_element(int family, double* ploc, uint8_t* fine_entity) {
+  const GalerkinElement g = BuildGalerkinElement(family);
+  std::copy(g.ploc.begin(), g.ploc.end(), ploc);
+  std::copy(g.entity.begin(), g.entity.end(), fine_entity);
+}
+int b2h_galerkin_maps(const b2h_hier* h, int lcoarse, int family, int64_t e0, int64_t e1, int32_t* fine_dofs,
+                      uint8_t* valence) {
+  if (lcoarse < 0 || lcoarse + 1 >= (int)h->levels.size()) return 1;
+  const MeshLevel& C = h->levels[lcoarse];
+  if (e0 < 0 || e1 > C.nel || e0 > e1) return 1;
+  BuildGalerkinMaps(C, h->levels[lcoarse + 1], family, e0, e1, fine_dofs, valence);
+  return 0;
+}
+
 int b2h_hex_nve(int family) { return HexElement::nve(family); }
 void b2h_hex_tables(int family, double* phi, double* dxi, double* deta, double* dzeta, double* w) {
   HexElement::Tables t = HexElement::tables(family);

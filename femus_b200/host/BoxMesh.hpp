@@ -358,4 +358,54 @@ inline MeshLevel RefineMesh(MeshLevel& C) {
   return F;
 }
 
+// Per-coarse-element maps of the element-gather Galerkin product (device kernel b2_galerkin.cu):
+// the fine dofs of every coarse element in lattice order, the entity code of every fine lattice
+// point, the valence (number of elements in [e0,e1)) of the 27 sub-entities of every element, and
+// the dense element prolongator P_loc[nf][nc] (ElemType.cpp:439-532).  Fine lattice: 5 points per
+// direction for the biquadratic family (125 fine dofs), the 3 even ones for the linear family (27).
+struct GalerkinElement {
+  int nf = 0, nc = 0;
+  std::vector<int> q;                 // lattice point (0..124) of local fine dof a
+  std::vector<uint8_t> entity;        // [nf] 3-trit code: per direction 0 = low face, 1 = interior, 2 = high face
+  std::vector<double> ploc;           // [nf][nc]
+};
+inline GalerkinElement BuildGalerkinElement(int family) {
+  const detail::FinePointTable& T = detail::fine_points();
+  GalerkinElement g;
+  g.nc = HexElement::nve(family);
+  for (int q = 0; q < 125; q++)
+    if (T.node[q] < g.nc) g.q.push_back(q);
+  g.nf = (int)g.q.size();
+  g.entity.resize(g.nf);
+  g.ploc.assign((size_t)g.nf * g.nc, 0.0);
+  for (int a = 0; a < g.nf; a++) {
+    const int q = g.q[a], p[3] = {q % 5, (q / 5) % 5, q / 25};
+    int code = 0, mul = 1;
+    for (int d = 0; d < 3; d++) { code += (p[d] == 0 ? 0 : (p[d] == 4 ? 2 : 1)) * mul; mul *= 3; }
+    g.entity[a] = (uint8_t)code;
+    int idx[27];
+    double val[27];
+    const int n = HexElement::prolongator_row(family, p[0], p[1], p[2], idx, val);
+    for (int k = 0; k < n; k++) g.ploc[(size_t)a * g.nc + idx[k]] = val[k];
+  }
+  return g;
+}
+// fine_dofs[(e1-e0)][nf], valence[(e1-e0)][27] for the coarse elements [e0, e1) of C (F = its refinement)
+inline void BuildGalerkinMaps(const MeshLevel& C, const MeshLevel& F, int family, int64_t e0, int64_t e1,
+                              int32_t* fine_dofs, uint8_t* valence) {
+  const detail::FinePointTable& T = detail::fine_points();
+  const GalerkinElement g = BuildGalerkinElement(family);
+  std::vector<uint8_t> count((size_t)C.nnode, 0);
+  for (int64_t E = e0; E < e1; E++)
+    for (int n = 0; n < 27; n++) count[C.conn[E * 27 + n]]++;
+  for (int64_t E = e0; E < e1; E++) {
+    for (int a = 0; a < g.nf; a++) {
+      const int q = g.q[a];
+      fine_dofs[(E - e0) * g.nf + a] = F.GetSolutionDof(T.node[q], C.child_el[E * 8 + T.child[q]], family);
+    }
+    for (int code = 0; code < 27; code++)
+      valence[(E - e0) * 27 + code] = count[C.conn[E * 27 + HexElement::node_at(code % 3, (code / 3) % 3, code / 9)]];
+  }
+}
+
 }  // namespace femus_b200

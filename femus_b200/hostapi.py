@@ -40,6 +40,9 @@ def _L():
             "b2h_csr_rowptr": (vp, [vp]),
             "b2h_csr_col": (vp, [vp]),
             "b2h_csr_val": (vp, [vp]),
+            "b2h_galerkin_nf": (ci, [ci]),
+            "b2h_galerkin_element": (None, [ci, vp, vp]),
+            "b2h_galerkin_maps": (ci, [vp, ci, ci, i64, i64, vp, vp]),
             "b2h_hex_nve": (ci, [ci]),
             "b2h_hex_tables": (None, [ci, vp, vp, vp, vp, vp]),
             "b2h_hex_prolongator_row": (ci, [ci, ci, ci, ci, vp, vp]),
@@ -123,6 +126,18 @@ class HostHierarchy:
         except Exception:
             pass
 
+    def galerkin_maps(self, lcoarse, family, e0=0, e1=None):
+        """(fine_dofs[ne][nf], valence[ne][27]) of the coarse elements [e0, e1) of level lcoarse."""
+        f = _fam(family)
+        nelc = self.levels[lcoarse].nel
+        e1 = nelc if e1 is None else e1
+        nf = self.L.b2h_galerkin_nf(f)
+        fd = np.zeros((e1 - e0, nf), dtype=np.int32)
+        val = np.zeros((e1 - e0, 27), dtype=np.uint8)
+        if self.L.b2h_galerkin_maps(self.h, lcoarse, f, e0, e1, fd.ctypes.data_as(vp), val.ctypes.data_as(vp)):
+            raise ValueError("b2h_galerkin_maps: bad level or element range")
+        return fd, val
+
     def prolongator(self, lfine, family):
         """(rowptr, col, val, shape) of P from level lfine-1 to lfine; arrays are copies."""
         p = self.L.b2h_prolongator_create(self.h, lfine, _fam(family))
@@ -134,6 +149,17 @@ class HostHierarchy:
         v = _view(self.L.b2h_csr_val(p), (nnz,), np.float64).copy()
         self.L.b2h_csr_destroy(p)
         return rp, ci_, v, (n, m)
+
+
+def galerkin_element(family):
+    """(ploc[nf][nc], fine_entity[nf]) of the element-gather Galerkin product."""
+    L = _L()
+    f = _fam(family)
+    nf, nc = L.b2h_galerkin_nf(f), L.b2h_hex_nve(f)
+    ploc = np.zeros((nf, nc))
+    ent = np.zeros(nf, dtype=np.uint8)
+    L.b2h_galerkin_element(f, ploc.ctypes.data_as(vp), ent.ctypes.data_as(vp))
+    return ploc, ent
 
 
 def hex_tables(family):

@@ -44,6 +44,13 @@ class PoissonMG:
             P.zero_rows(self.bdc_idx[l], 0.0)
             P.zero_cols(self.bdc_idx[l - 1])
             self.PP[l] = P
+        # --- Galerkin plans: element-gather P^T A P per level pair (fast path of matrix_PtAP)
+        ploc, fent = hostapi.galerkin_element(order)
+        self.gal = [None] * nlevels
+        for l in range(1, nlevels):
+            fd, val = self.hier.galerkin_maps(l - 1, order)
+            self.gal[l] = capi.Galerkin(self.KK[l], self.KK[l - 1], fd, self.dofs[l - 1], ploc, fent, val,
+                                        self.bdc[l] < 1.5, self.bdc[l - 1] < 1.5)
         # --- finest-level mesh + assembly plan
         self.mesh = capi.Mesh(ctx, top.xyz, top.conn)
         self.tables = hostapi.hex_tables(order)
@@ -64,10 +71,14 @@ class PoissonMG:
         self.KK[-1].zero()
         self.asm.poisson(self.SOL, self.RES, 1.0, self.fsrc)
 
-    def galerkin(self):
-        """A_{l-1} = P_l^T A_l P_l down the hierarchy, on the un-penalised matrices."""
+    def galerkin(self, algebraic=False):
+        """A_{l-1} = P_l^T A_l P_l down the hierarchy, on the un-penalised matrices: element-gather
+        plans by default, the general sparse triple product (b2_csr_ptap) on request."""
         for l in range(self.nlevels - 1, 0, -1):
-            self.KK[l - 1].ptap(self.PP[l], self.KK[l])
+            if algebraic:
+                self.KK[l - 1].ptap(self.PP[l], self.KK[l])
+            else:
+                self.gal[l].apply()
 
     def mg_set_levels(self):
         """MGInit + MGSetLevel on every level (SetPenalty, smoother setup)."""

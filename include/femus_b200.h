@@ -30,6 +30,7 @@ typedef struct b2_csr b2_csr;
 typedef struct b2_mesh b2_mesh;
 typedef struct b2_asm b2_asm;
 typedef struct b2_mg b2_mg;
+typedef struct b2_galerkin b2_galerkin;
 
 const char* b2_last_error(void);
 int b2_version(void);
@@ -140,6 +141,22 @@ int b2_csr_jacobi_sweep(const b2_csr* A, const b2_vec* dinv, const b2_vec* b, co
  * (the coarse element-coupling pattern). */
 int b2_csr_ptap(const b2_csr* P, const b2_csr* A, b2_csr* C);
 double b2_csr_last_kernel_ms(const b2_csr* A);
+/* Fast path of matrix_PtAP for the geometric prolongators of BuildProlongatorMatrix
+ * (LinearImplicitSystem.cpp:826-909, Dirichlet rows/columns zeroed by :1032-1120): the product is
+ * formed coarse element by coarse element, C = sum_E P_E^T (W_E o A|_E) P_E, from
+ *   fine_dofs[nelc][nf]   rows of Af of the fine dofs of coarse element E (lattice order),
+ *   coarse_dofs[nelc][nc] rows of Ac of its coarse dofs (GetSystemDof order),
+ *   ploc[nf][nc]          element prolongator (ElemType.cpp:439-532), fine_entity[nf] the 3-trit
+ *                         code (low/interior/high per direction) of the sub-entity each fine point lies on,
+ *   valence[nelc][27]     number of coarse elements sharing each of the 27 sub-entities of E,
+ *   fine_mask / coarse_mask (may be NULL): 1 where the row / column of P is zeroed (Bdc < 1.5).
+ * Equal to b2_csr_ptap(P, Af, Ac) up to summation order.  nf/nc: 125/27 or 27/8 (hexahedra). */
+int b2_galerkin_create(b2_csr* Af, b2_csr* Ac, int64_t nelc, int nf, int nc, const int32_t* fine_dofs,
+                       const int32_t* coarse_dofs, const double* ploc, const uint8_t* fine_entity,
+                       const uint8_t* valence, const uint8_t* fine_mask, const uint8_t* coarse_mask,
+                       b2_galerkin** out);
+int b2_galerkin_apply(b2_galerkin* g);       /* Ac = P^T Af P (Ac is overwritten) */
+int b2_galerkin_destroy(b2_galerkin* g);
 
 /* ---- mesh + assembly: replaces the element loop of applications/001_Poisson/main.cpp:346-605
  *      (+ elem_type_3D::Jacobian, ElemType.hpp:1438-1537; MatSetValuesBlocked, VecSetValues) ---- */

@@ -48,6 +48,17 @@ const int64_t* b2h_csr_rowptr(const b2h_csr* p);
 const int32_t* b2h_csr_col(const b2h_csr* p);
 const double* b2h_csr_val(const b2h_csr* p);
 
+/* Maps of the element-gather Galerkin product (b2_galerkin_create in femus_b200.h): number of
+ * fine dofs of a coarse element (125 biquadratic / 27 linear), the dense element prolongator
+ * ploc[nf][nc] (ElemType.cpp:439-532) with the entity code of every fine lattice point, and for
+ * the coarse elements [e0,e1) of level lcoarse their fine dofs [nf] (through elem::GetChildElement
+ * and Mesh::GetSolutionDof, as LinearImplicitSystem.cpp:761-811 walks them) and the number of
+ * elements of that range at each of their 27 nodes. */
+int b2h_galerkin_nf(int family);
+void b2h_galerkin_element(int family, double* ploc, uint8_t* fine_entity);
+int b2h_galerkin_maps(const b2h_hier* h, int lcoarse, int family, int64_t e0, int64_t e1, int32_t* fine_dofs,
+                      uint8_t* valence);
+
 /* elem_type_3D("hex", family, "seventh"): tables [64][nve] and weights[64] (ElemType.cpp:637-740),
  * element prolongator row of the fine point (a,b,c) of the 5x5x5 lattice (ElemType.cpp:439-532) */
 int b2h_hex_nve(int family);

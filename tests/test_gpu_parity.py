@@ -259,6 +259,40 @@ def test_ptap_matches_oracle(ctx, order):
         assert np.abs(got.data - ref.data).max() <= RTOL * np.abs(ref.data).max()
 
 
+@pytest.mark.parametrize("order", ["linear", "biquadratic"])
+@pytest.mark.parametrize("shape", [(2, 2, 3), (1, 1, 1), (3, 1, 2)])
+def test_galerkin_element_gather_matches_oracle(ctx, order, shape):
+    """Fast path of matrix_PtAP (coarse-element gather) against the oracle's scipy P^T A P and
+    against the general device triple product, with the Dirichlet rows/columns of P zeroed."""
+    from femus_b200 import hostapi
+    nl = 3
+    hh = hostapi.HostHierarchy(*shape, nl)
+    lv = mb.build_hierarchy(*shape, nl)
+    H = mg.Hierarchy(lv, order)
+    ploc, fent = hostapi.galerkin_element(order)
+    for l in (2, 1):
+        A = ctx.csr_from_scipy(H.A_raw[l])
+        rp, ci = mb.sparsity(lv[l - 1], order)
+        C = ctx.csr(rp.shape[0] - 1, rp.shape[0] - 1, rp, ci)
+        fd, val = hh.galerkin_maps(l - 1, order)
+        # host layer == oracle on the element -> dof maps the plan is built from
+        assert np.array_equal(hh.levels[l - 1].system_dofs(order), mb.system_dof(lv[l - 1], order))
+        G = capi.Galerkin(A, C, fd, mb.system_dof(lv[l - 1], order), ploc, fent, val, H.bdc[l] < 1.5, H.bdc[l - 1] < 1.5)
+        G.apply()
+        got, ref = C.to_scipy(), H.A_raw[l - 1]
+        assert np.array_equal(got.indices, ref.indices)
+        assert np.abs(got.data - ref.data).max() <= RTOL * np.abs(ref.data).max()
+        G.apply()                                   # overwrite semantics (MAT_REUSE_MATRIX)
+        assert np.abs(C.to_scipy().data - ref.data).max() <= RTOL * np.abs(ref.data).max()
+        # without masks: plain P (no Dirichlet zeroing)
+        Pfull = mb.prolongator(lv[l - 1], lv[l], order).tocsr()
+        ref2 = (Pfull.T @ H.A_raw[l] @ Pfull).tocsr()
+        G2 = capi.Galerkin(A, C, fd, mb.system_dof(lv[l - 1], order), ploc, fent, val)
+        G2.apply()
+        got2 = C.to_scipy()
+        assert np.abs((got2 - ref2)).max() <= RTOL * np.abs(ref2.data).max()
+
+
 def build_device_hierarchy(ctx, lv, order, fsrc=1.0, npre=1, npost=1, omega=0.5):
     """Mirror of LinearImplicitSystem::MGsolve on the device through the C ABI."""
     nl = len(lv)
