@@ -213,41 +213,72 @@ def main():
     from femus_b200 import capi
     from femus_b200.poisson import PoissonMG
 
-    if world > 1:
-        raise SystemExit("multi-GPU bench path: see bench_multi (not wired in this build)")
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} needs {args.gpus} ranks (torchrun --nproc-per-node {args.gpus}), got WORLD_SIZE={world}")
     torch.cuda.set_device(local_rank)
     ctx = capi.Context(local_rank)
+    dist_arg = None
+    if world > 1:
+        # one rank per GPU: torch.distributed carries the rendezvous, the library owns its NCCL communicator
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        uid = [capi.Context.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        ctx.comm_init(world, rank, uid[0])
+        from femus_b200.dist import torch_allgather
+        dist_arg = (rank, world, torch_allgather())
+
+    def barrier():
+        ctx.sync()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
     t_setup = time.time()
-    pb = PoissonMG(ctx, nx, ny, nz, args.levels, args.order)
+    pb = PoissonMG(ctx, nx, ny, nz, args.levels, args.order, dist=dist_arg)
     ctx.sync()
     t_setup = time.time() - t_setup
     top = pb.hier.levels[-1]
-    n, nel = pb.n, pb.nel
+    n_loc = pb.n
+    n, nel = pb.n_global, int(sum_over_ranks(pb.nel))
 
     # pinned host copies of the per-step inputs / outputs for the end-to-end leg
     def pinned(a):
         t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
         return t
     h_xyz, h_conn = pinned(top.xyz), pinned(top.conn)
-    h_sol = torch.zeros(n, dtype=torch.float64).pin_memory()
-    h_eps = torch.zeros(n, dtype=torch.float64).pin_memory()
-    h2d = h_xyz.numel() * 8 + h_conn.numel() * 4 + n * 8
-    d2h = n * 8 + 8
+    h_sol = torch.zeros(n_loc, dtype=torch.float64).pin_memory()
+    h_eps = torch.zeros(n_loc, dtype=torch.float64).pin_memory()
+    h2d = sum_over_ranks(h_xyz.numel() * 8 + h_conn.numel() * 4 + n_loc * 8)
+    d2h = sum_over_ranks(n_loc * 8 + 8)
 
     def step_resident():
         pb.step()
 
     def step_e2e():
         pb.mesh.update(h_xyz.data_ptr(), h_conn.data_ptr())
-        pb.SOL.put_async(h_sol.data_ptr(), n)
+        pb.SOL.put_async(h_sol.data_ptr(), n_loc)
         pb.step()
-        pb.EPS.get_async(h_eps.data_ptr(), n)
+        pb.EPS.get_async(h_eps.data_ptr(), n_loc)
         return pb.residual_norm()          # D2H of the scalar, synchronises
 
     # ---- warm-up
     for _ in range(W):
         step_resident()
-    ctx.sync()
+    barrier()
     Afine = pb.KK[-1]
 
     # ---- timed region: K steps, device time on the library stream
@@ -255,12 +286,14 @@ def main():
     sampler.start()
     ctx.profile_only(Afine)
     ctx.launches(reset=True)
-    ctx.sync()
+    barrier()
     ctx.timer_start()
     for _ in range(args.steps):
         step_resident()
-    ms_total = ctx.timer_stop_ms()
-    launches = ctx.launches(reset=True)
+    ms_total_local = ctx.timer_stop_ms()
+    barrier()
+    ms_total = max_over_ranks(ms_total_local)          # device time, max over ranks
+    launches = int(sum_over_ranks(ctx.launches(reset=True)))
     nsp, ms_sp = ctx.profile_read(Afine)
     ctx.profile_only(None)
     # phase breakdown (separate passes, same data)
@@ -277,11 +310,13 @@ def main():
     # ---- end-to-end: host buffers in, host buffers out
     for _ in range(2):
         step_e2e()
-    ctx.sync()
+    barrier()
     ctx.timer_start()
     for _ in range(args.steps):
         resnorm = step_e2e()
     ms_e2e = ctx.timer_stop_ms()
+    barrier()
+    ms_e2e = max_over_ranks(ms_e2e)
     clocks = sampler.stop()
     # residual trace of a short solve (sanity: the timed path really converges)
     pb.EPS.zero()
@@ -298,13 +333,15 @@ def main():
     # 2 x r = b - A x, 1 x Jacobi sweep); algorithmic bytes per launch, BASELINE.md section 4
     peak, peak_src = measured_peaks()
     b_y = pb.spmv_bytes(-1)
-    bytes_per_launch = (2 * (b_y + 8 * n) + (b_y + 24 * n)) / 3.0
+    bytes_per_launch = (2 * (b_y + 8 * n_loc) + (b_y + 24 * n_loc)) / 3.0 if world == 1 else b_y + 16 * n_loc
     ach = bytes_per_launch / (ms_sp / max(nsp, 1) * 1e-3) / 1e9 if nsp else None
     roofline = {"bound": "hbm", "kernel": "spmv_kernel<16,*> on the finest-level CSR (resid / Jacobi sweep)",
                 "achieved": ach, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                 "frac": (ach / peak) if ach else None, "traffic": None,
                 "algorithmic_bytes_per_launch": bytes_per_launch, "launches_timed": nsp,
-                "avg_launch_ms": ms_sp / max(nsp, 1), "share_of_step": ms_sp / ms_total}
+                "avg_launch_ms": ms_sp / max(nsp, 1), "share_of_step": ms_sp / ms_total_local}
+    if world > 1:
+        roofline["kernel"] = "spmv_kernel on rank 0's finest-level partial CSR (weighted resid x3 per step)"
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": W,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
@@ -315,8 +352,13 @@ def main():
             "assembly_elem_dof_per_s": nel * nve / (phases["assembly"] * 1e-3),
             "spmv_gbs": ach, "phases_ms": phases, "finest_dofs": n, "finest_nnz": Afine.nnz, "elements": nel,
             "setup_s": t_setup, "residual_trace": trace, "coarse_pcg_iterations": pb.mg.coarse_iterations(),
-            "device_bytes": ctx.bytes_in_use()}
-    if not args.no_cpu_baseline:
+            "device_bytes": ctx.bytes_in_use(), "dofs_per_rank": n_loc}
+    if world > 1:
+        barrier()
+        dist.destroy_process_group()
+        if rank != 0:
+            return 0
+    if not args.no_cpu_baseline and world == 1:
         try:
             line["cpu_baseline"] = {k: v for k, v in run_cpu_sample(args.cpu_n0, args.levels, args.order, 2, 1).items()}
         except Exception as e:      # the baseline is reported, never required for the GPU number

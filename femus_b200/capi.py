@@ -99,6 +99,13 @@ _PROTOS = {
     "b2_mg_create": (ci, [vp, ci, vp]),
     "b2_mg_set_level": (ci, [vp, ci, vp, vp, vp, i64, ci, ci, cd]),
     "b2_mg_set_coarse": (ci, [vp, cd, ci]),
+    "b2_mg_set_level_halo": (ci, [vp, ci, vp]),
+    "b2_halo_create": (ci, [vp, i64, i64, vp, vp, i64, vp, vp, vp]),
+    "b2_halo_destroy": (ci, [vp]),
+    "b2_halo_owned_count": (i64, [vp]),
+    "b2_halo_interface_count": (i64, [vp]),
+    "b2_halo_sum": (ci, [vp, vp]),
+    "b2_vec_set_halo": (ci, [vp, vp]),
     "b2_mg_vcycle": (ci, [vp, vp, vp]),
     "b2_mg_solve": (ci, [vp, vp, vp]),
     "b2_mg_coarse_iterations": (ci, [vp]),
@@ -328,6 +335,10 @@ class Vector:
         check(self.L.b2_vec_get_indexed(self.h, _ptr(idx), _ptr(out), idx.shape[0]))
         return out
 
+    def set_halo(self, halo):
+        self._halo = halo
+        check(self.L.b2_vec_set_halo(self.h, halo.h if halo is not None else None))
+
     def copy_masked(self, src, mask, thr):
         check(self.L.b2_vec_copy_masked(self.h, src.h, mask.h, float(thr)))
 
@@ -436,6 +447,35 @@ class Csr:
         check(self.L.b2_csr_ptap(P.h, A.h, self.h))
 
 
+class Halo:
+    """Distributed layout of a rank-local vector (b2_halo_*)."""
+
+    def __init__(self, ctx, n_local, local_idx, packed_pos, n_packed, owned, mult):
+        self.ctx, self.L = ctx, ctx.L
+        local_idx, packed_pos = _i32(local_idx), _i32(packed_pos)
+        owned = np.ascontiguousarray(owned, dtype=np.uint8)
+        mult = np.ascontiguousarray(mult, dtype=np.uint8)
+        assert owned.shape[0] == n_local and mult.shape[0] == n_local and local_idx.shape == packed_pos.shape
+        h = vp()
+        check(self.L.b2_halo_create(ctx.h, n_local, local_idx.shape[0], _ptr(local_idx), _ptr(packed_pos), n_packed,
+                                    _ptr(owned), _ptr(mult), ctypes.byref(h)))
+        self.h = h
+        self.n_local = n_local
+
+    def sum(self, v):
+        check(self.L.b2_halo_sum(self.h, v.h))
+
+    def owned_count(self):
+        return int(self.L.b2_halo_owned_count(self.h))
+
+    def __del__(self):
+        try:
+            if self.h and self.ctx.h:
+                self.L.b2_halo_destroy(self.h)
+        except Exception:
+            pass
+
+
 class Galerkin:
     """Element-gather Galerkin product Ac = P^T Af P (b2_galerkin_*)."""
 
@@ -530,6 +570,10 @@ class Multigrid:
         self._keep.append((A, P))
         check(self.L.b2_mg_set_level(self.h, level, A.h, P.h if P is not None else None, _ptr(bdc_idx),
                                      bdc_idx.shape[0], npre, npost, float(omega)))
+
+    def set_level_halo(self, level, halo):
+        self._keep.append(halo)
+        check(self.L.b2_mg_set_level_halo(self.h, level, halo.h if halo is not None else None))
 
     def set_coarse(self, rtol=1e-14, maxit=5000):
         check(self.L.b2_mg_set_coarse(self.h, float(rtol), int(maxit)))

@@ -78,10 +78,27 @@ struct b2_prof_scope {
 
 static constexpr int kRedBlocks = 1184;   // 148 SMs x 8
 
+struct b2_halo;
 struct b2_vec {
   b2_ctx* ctx;
   int64_t n;
   double* d;
+  const b2_halo* halo;   // distributed layout (owned mask for reductions) or null
+};
+
+// Layout of a rank-local vector whose entries on the partition interface are shared with other
+// ranks (every rank holds ALL dofs of its own elements): interface sum through one packed
+// ncclAllReduce, ownership mask (lowest rank owns, Mesh.cpp:530-553) for reductions.
+struct b2_halo {
+  b2_ctx* ctx;
+  int64_t n_local, n_if, n_packed;
+  int32_t* idx;        // [n_if] local dof of interface entry k
+  int32_t* pos;        // [n_if] its position in the packed interface vector (same on every rank)
+  double* send;        // [n_packed] zero except at own positions
+  double* recv;        // [n_packed]
+  uint8_t* owned;      // [n_local] 1 if this rank owns the dof
+  double* invmult;     // [n_local] 1 / (number of ranks holding the dof)
+  int64_t n_owned;
 };
 
 struct b2_csr {
@@ -133,5 +150,10 @@ static inline int b2_grid_for(b2_ctx* c, int64_t work_items, int per_block, int 
 // internal cross-TU helpers
 int b2_csr_alloc(b2_ctx* c, int64_t nrows, int64_t ncols, int64_t nnz, b2_csr** out);
 int b2_csr_finalize(b2_csr* A);   // row statistics -> tpr / max_row
-int b2_dev_dot(b2_ctx* c, const double* x, const double* y, int64_t n, double* d_out);   // result stays on device
+int b2_csr_resid_w(const b2_csr* A, const double* b, const double* w, const double* x, double* r);   // r = w.*b - A x
+int b2_csr_zero_cols_notowned(b2_csr* A, const uint8_t* d_owned);
+int b2_csr_zero_rows_dev(b2_csr* A, const int32_t* d_rows, int64_t n, double diag, const uint8_t* d_owned);
+// result stays on device; owned != null restricts the sum to entries with owned[i] != 0
+int b2_dev_dot(b2_ctx* c, const double* x, const double* y, int64_t n, double* d_out, const uint8_t* owned = nullptr);
 int b2_allreduce_sum(b2_ctx* c, double* d_buf, int64_t n);
+int b2_allreduce_op(b2_ctx* c, double* d_buf, int64_t n, int op);   // 2 = max, 3 = min

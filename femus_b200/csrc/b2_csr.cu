@@ -17,7 +17,9 @@ constexpr int kBlock = 256;
 //   RESID  y = b - A x        (resid)
 //   JACOBI y = x + omega * dinv * (b - A x)   (Richardson + Jacobi sweep, x != y)
 // Streaming operands (val/col) bypass L1 allocation; x stays on the cached path.
-enum SpmvMode { Y_AX, Y_ADD, RESID, JACOBI };
+//   RESID_W y = w .* b - A x  (distributed residual: A is this rank's partial matrix, w = 1/multiplicity,
+//                              so that the interface sum over ranks gives b - A x)
+enum SpmvMode { Y_AX, Y_ADD, RESID, JACOBI, RESID_W };
 
 __device__ __forceinline__ double ld_stream(const double* p) {
   double v;
@@ -57,6 +59,7 @@ __global__ void __launch_bounds__(kBlock) spmv_kernel(int64_t nrows, const int64
       if (MODE == Y_AX) y[row] = acc;
       else if (MODE == Y_ADD) y[row] += acc;
       else if (MODE == RESID) y[row] = b[row] - acc;
+      else if (MODE == RESID_W) y[row] = fma(dinv[row], b[row], -acc);
       else y[row] = fma(omega * dinv[row], b[row] - acc, x[row]);
     }
   }
@@ -307,6 +310,45 @@ int inclusive_scan_u64(b2_ctx* c, unsigned long long* d, int64_t n) {
 }
 
 }  // namespace
+
+int b2_csr_resid_w(const b2_csr* A, const double* b, const double* w, const double* x, double* r) {
+  return launch_spmv<RESID_W>(A, x, b, w, r, 0.);
+}
+
+__global__ void zero_cols_notowned_kernel(int64_t nnz, const int32_t* __restrict__ col, double* __restrict__ val,
+                                          const uint8_t* __restrict__ owned) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < nnz; k += stride)
+    if (!owned[col[k]]) val[k] = 0.0;
+}
+int b2_csr_zero_cols_notowned(b2_csr* A, const uint8_t* d_owned) {
+  if (A->nnz == 0) return 0;
+  b2_ctx* c = A->ctx;
+  B2_LAUNCH(c, zero_cols_notowned_kernel, b2_grid_for(c, A->nnz, kBlock, 8), kBlock, 0, A->nnz, A->col, A->val, d_owned);
+  return 0;
+}
+// rows[i] -> zero, diagonal = diag where the row is owned by this rank, 0 otherwise (the owner's
+// 1 completes the identity row in the interface sum)
+__global__ void zero_rows_owned_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                                       double* __restrict__ val, const int32_t* __restrict__ rows, int64_t n, double diag,
+                                       const uint8_t* __restrict__ owned) {
+  const int lane = threadIdx.x & 31;
+  const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t i = w; i < n; i += nw) {
+    const int32_t r = rows[i];
+    const double d = owned[r] ? diag : 0.0;
+    for (int64_t k = rowptr[r] + lane; k < rowptr[r + 1]; k += 32) val[k] = (col[k] == r) ? d : 0.0;
+  }
+}
+int b2_csr_zero_rows_dev(b2_csr* A, const int32_t* d_rows, int64_t n, double diag, const uint8_t* d_owned) {
+  if (n == 0) return 0;
+  b2_ctx* c = A->ctx;
+  const int grid = b2_grid_for(c, n * 32, kBlock, 8);
+  if (d_owned) B2_LAUNCH(c, zero_rows_owned_kernel, grid, kBlock, 0, A->rowptr, A->col, A->val, d_rows, n, diag, d_owned);
+  else B2_LAUNCH(c, zero_rows_kernel, grid, kBlock, 0, A->rowptr, A->col, A->val, d_rows, n, diag);
+  return 0;
+}
 
 int b2_csr_alloc(b2_ctx* c, int64_t nrows, int64_t ncols, int64_t nnz, b2_csr** out) {
   b2_csr* A = new b2_csr();

@@ -207,6 +207,26 @@ int b2_ctx_comm_init(b2_ctx* c, int nranks, int rank, const void* id128) {
 
 }  // extern "C"
 
+// sum-allreduce from a send buffer into a receive buffer
+int b2_allreduce_into(b2_ctx* c, const double* d_send, double* d_recv, int64_t n) {
+  if (n == 0) return 0;
+  B2_CHECK(c->nranks > 1 && c->nccl_comm, "communicator not initialised");
+  typedef int (*ar_t)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+  int r = ((ar_t)g_nccl.all_reduce)(d_send, d_recv, (size_t)n, /*ncclDouble*/ 8, /*ncclSum*/ 0, c->nccl_comm, c->stream);
+  B2_CHECK(r == 0, "ncclAllReduce: %s", nccl_err(r));
+  c->launches++;
+  return 0;
+}
+// max (op 2) / min (op 3) allreduce in place
+int b2_allreduce_op(b2_ctx* c, double* d_buf, int64_t n, int op) {
+  if (c->nranks == 1 || n == 0) return 0;
+  B2_CHECK(c->nccl_comm, "communicator not initialised");
+  typedef int (*ar_t)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+  int r = ((ar_t)g_nccl.all_reduce)(d_buf, d_buf, (size_t)n, /*ncclDouble*/ 8, op, c->nccl_comm, c->stream);
+  B2_CHECK(r == 0, "ncclAllReduce: %s", nccl_err(r));
+  return 0;
+}
+
 // sum-allreduce of n doubles in place on the library stream (ncclDouble = 8, ncclSum = 0)
 int b2_allreduce_sum(b2_ctx* c, double* d_buf, int64_t n) {
   if (c->nranks == 1 || n == 0) return 0;

@@ -1,0 +1,114 @@
+// Distributed layout of rank-local vectors (one rank per GPU, mesh sharded by element).
+// Replaces what PETSc does behind PetscVector / PetscMatrix for an MPI run of the reference:
+//   - VecSetValues(ADD_VALUES) + VecAssemblyBegin/End: off-process contributions summed into the
+//     owner (PetscVector.cpp:132-141, PetscVector.hpp:595-602),
+//   - VecGhostUpdateBegin/End inside close() (PetscVector.hpp:604-609) and the VecScatter inside
+//     MatMult: ghost values refreshed from the owner,
+//   - VecDot / VecNorm over the owned entries + MPI_Allreduce (PetscVector.cpp:43-87, 399-410).
+// Here every rank keeps ALL dofs of its own elements (its matrices are the sums over its own
+// elements only), so "assemble off-process contributions" and "refresh ghosts" collapse into ONE
+// operation: sum the interface entries over the ranks that hold them.  The interface dofs of all
+// ranks are laid out in one packed vector (position = rank-independent, computed by the host from
+// the lattice names of the nodes); each rank writes its partial values at its own positions of a
+// send buffer that is zero elsewhere, one ncclAllReduce(sum) over NVLink/NVSwitch completes them,
+// and the rank reads back its own positions.
+#include "b2_common.cuh"
+
+namespace {
+constexpr int kBlock = 256;
+
+__global__ void halo_pack_kernel(int64_t n, const int32_t* __restrict__ idx, const int32_t* __restrict__ pos,
+                                 const double* __restrict__ v, double* __restrict__ send) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) send[pos[k]] = v[idx[k]];
+}
+__global__ void halo_unpack_kernel(int64_t n, const int32_t* __restrict__ idx, const int32_t* __restrict__ pos,
+                                   const double* __restrict__ recv, double* __restrict__ v) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) v[idx[k]] = recv[pos[k]];
+}
+__global__ void halo_invmult_kernel(int64_t n, const uint8_t* __restrict__ mult, double* __restrict__ inv) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) inv[i] = 1.0 / (double)mult[i];
+}
+}  // namespace
+
+int b2_allreduce_into(b2_ctx* c, const double* d_send, double* d_recv, int64_t n);   // b2_ctx.cu
+
+extern "C" {
+
+int b2_halo_create(b2_ctx* c, int64_t n_local, int64_t n_if, const int32_t* local_idx, const int32_t* packed_pos,
+                   int64_t n_packed, const uint8_t* owned, const uint8_t* mult, b2_halo** out) {
+  *out = nullptr;
+  B2_CHECK(c && n_local >= 0 && n_if >= 0 && n_packed >= n_if && owned && mult, "b2_halo_create: bad arguments");
+  B2_CHECK(n_if == 0 || (local_idx && packed_pos), "b2_halo_create: null index arrays");
+  for (int64_t k = 0; k < n_if; k++)
+    B2_CHECK(local_idx[k] >= 0 && local_idx[k] < n_local && packed_pos[k] >= 0 && packed_pos[k] < n_packed,
+             "b2_halo_create: interface entry %lld out of range", (long long)k);
+  b2_halo* h = new b2_halo();
+  h->ctx = c;
+  h->n_local = n_local;
+  h->n_if = n_if;
+  h->n_packed = n_packed;
+  h->n_owned = 0;
+  for (int64_t i = 0; i < n_local; i++) {
+    B2_CHECK(mult[i] >= 1, "b2_halo_create: multiplicity of dof %lld is zero", (long long)i);
+    h->n_owned += owned[i] ? 1 : 0;
+  }
+  B2_TRY(b2_malloc(c, &h->idx, (size_t)n_if));
+  B2_TRY(b2_malloc(c, &h->pos, (size_t)n_if));
+  B2_TRY(b2_malloc(c, &h->send, (size_t)n_packed));
+  B2_TRY(b2_malloc(c, &h->recv, (size_t)n_packed));
+  B2_TRY(b2_malloc(c, &h->owned, (size_t)n_local));
+  B2_TRY(b2_malloc(c, &h->invmult, (size_t)n_local));
+  uint8_t* d_mult = nullptr;
+  B2_TRY(b2_malloc(c, &d_mult, (size_t)n_local));
+  B2_TRY(b2_upload(c, h->idx, local_idx, (size_t)n_if));
+  B2_TRY(b2_upload(c, h->pos, packed_pos, (size_t)n_if));
+  B2_TRY(b2_upload(c, h->owned, owned, (size_t)n_local));
+  B2_TRY(b2_upload(c, d_mult, mult, (size_t)n_local));
+  B2_CUDA(cudaMemsetAsync(h->send, 0, (size_t)(n_packed ? n_packed : 1) * sizeof(double), c->stream));
+  B2_CUDA(cudaMemsetAsync(h->recv, 0, (size_t)(n_packed ? n_packed : 1) * sizeof(double), c->stream));
+  if (n_local) B2_LAUNCH(c, halo_invmult_kernel, b2_grid_for(c, n_local, kBlock, 8), kBlock, 0, n_local, d_mult, h->invmult);
+  B2_CUDA(cudaStreamSynchronize(c->stream));
+  b2_free(c, d_mult, (size_t)n_local);
+  *out = h;
+  return 0;
+}
+
+int b2_halo_destroy(b2_halo* h) {
+  if (!h) return 0;
+  b2_ctx* c = h->ctx;
+  cudaStreamSynchronize(c->stream);
+  b2_free(c, h->idx, (size_t)h->n_if);
+  b2_free(c, h->pos, (size_t)h->n_if);
+  b2_free(c, h->send, (size_t)h->n_packed);
+  b2_free(c, h->recv, (size_t)h->n_packed);
+  b2_free(c, h->owned, (size_t)h->n_local);
+  b2_free(c, h->invmult, (size_t)h->n_local);
+  delete h;
+  return 0;
+}
+
+int64_t b2_halo_owned_count(const b2_halo* h) { return h->n_owned; }
+int64_t b2_halo_interface_count(const b2_halo* h) { return h->n_if; }
+
+/* v[interface] <- sum over the ranks holding each interface dof of their v[interface] */
+int b2_halo_sum(b2_halo* h, b2_vec* v) {
+  B2_CHECK(v->n >= h->n_local, "b2_halo_sum: vector shorter than the layout");
+  b2_ctx* c = h->ctx;
+  if (c->nranks == 1 || h->n_packed == 0) return 0;
+  if (h->n_if) B2_LAUNCH(c, halo_pack_kernel, b2_grid_for(c, h->n_if, kBlock, 8), kBlock, 0, h->n_if, h->idx, h->pos, v->d, h->send);
+  B2_TRY(b2_allreduce_into(c, h->send, h->recv, h->n_packed));
+  if (h->n_if) B2_LAUNCH(c, halo_unpack_kernel, b2_grid_for(c, h->n_if, kBlock, 8), kBlock, 0, h->n_if, h->idx, h->pos, h->recv, v->d);
+  return 0;
+}
+
+/* reductions of v run over the owned entries only once a layout is attached (NULL detaches) */
+int b2_vec_set_halo(b2_vec* v, const b2_halo* h) {
+  B2_CHECK(!h || v->n >= h->n_local, "b2_vec_set_halo: vector shorter than the layout");
+  v->halo = h;
+  return 0;
+}
+
+}  // extern "C"

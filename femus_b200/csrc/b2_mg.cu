@@ -16,6 +16,7 @@ struct b2_mg_level {
   b2_vec *dinv = nullptr, *x = nullptr, *t = nullptr, *b = nullptr, *r = nullptr;
   int32_t* bdc = nullptr;   // device copy of the Dirichlet row list
   int64_t nbdc = 0;
+  b2_halo* halo = nullptr;  // borrowed: distributed layout of this level's vectors (null: single rank)
   int npre = 1, npost = 1;
   double omega = 0.5;
 };
@@ -90,7 +91,27 @@ __global__ void pcg_dir_kernel(int64_t n, const double* __restrict__ scal, int c
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) p[i] = fma(beta, p[i], z[i]);
 }
 
+// x += omega * dinv .* r   (second half of a distributed Richardson-Jacobi sweep)
+__global__ void jacobi_update_kernel(int64_t n, const double* __restrict__ dinv, const double* __restrict__ r,
+                                     double* __restrict__ x, double omega) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) x[i] = fma(omega * dinv[i], r[i], x[i]);
+}
+
 int vec_grid(b2_ctx* c, int64_t n) { return b2_grid_for(c, n, kBlock, 8); }
+
+// r = b - A x with every entry complete on every rank that holds it
+int level_resid(b2_mg_level& L, const b2_vec* b, const b2_vec* x, b2_vec* r) {
+  if (!L.halo) return b2_csr_resid(L.A, b, x, r);
+  B2_TRY(b2_csr_resid_w(L.A, b->d, L.halo->invmult, x->d, r->d));
+  return b2_halo_sum(L.halo, r);
+}
+// y = A x, complete
+int level_spmv(b2_mg_level& L, const b2_vec* x, b2_vec* y) {
+  B2_TRY(b2_csr_spmv(L.A, x, y));
+  return L.halo ? b2_halo_sum(L.halo, y) : 0;
+}
+const uint8_t* owned(const b2_mg_level& L) { return L.halo ? L.halo->owned : nullptr; }
 
 int smooth(b2_mg* mg, int l, int nsweeps, bool zero_guess) {
   b2_mg_level& L = mg->L[l];
@@ -104,8 +125,13 @@ int smooth(b2_mg* mg, int l, int nsweeps, bool zero_guess) {
     B2_TRY(b2_vec_zero(L.x));
   }
   for (; done < nsweeps; done++) {
-    B2_TRY(b2_csr_jacobi_sweep(L.A, L.dinv, L.b, L.x, L.t, L.omega));
-    std::swap(L.x, L.t);
+    if (L.halo) {      // interface rows need the other ranks' part of A x before the update
+      B2_TRY(level_resid(L, L.b, L.x, L.t));
+      B2_LAUNCH(c, jacobi_update_kernel, vec_grid(c, n), kBlock, 0, n, L.dinv->d, L.t->d, L.x->d, L.omega);
+    } else {
+      B2_TRY(b2_csr_jacobi_sweep(L.A, L.dinv, L.b, L.x, L.t, L.omega));
+      std::swap(L.x, L.t);
+    }
   }
   return 0;
 }
@@ -120,14 +146,14 @@ int coarse_solve(b2_mg* mg) {
   // x0 = b on Dirichlet rows (identity rows), 0 elsewhere; r = b - A x0
   B2_TRY(b2_vec_zero(L.x));
   if (L.nbdc) B2_LAUNCH(c, copy_idx_kernel, vec_grid(c, L.nbdc), kBlock, 0, L.x->d, L.b->d, L.bdc, L.nbdc);
-  B2_TRY(b2_csr_resid(L.A, L.b, L.x, L.r));
-  B2_TRY(b2_dev_dot(c, L.b->d, L.b->d, n, s + 4));
-  B2_TRY(b2_allreduce_sum(c, s + 4, 1));
+  B2_TRY(level_resid(L, L.b, L.x, L.r));
+  const uint8_t* own = owned(L);
+  B2_TRY(b2_dev_dot(c, L.b->d, L.b->d, n, s + 4, own));
   B2_LAUNCH(c, pcg_start_kernel, g, kBlock, 0, n, L.dinv->d, L.r->d, mg->z->d, mg->p->d);
-  B2_TRY(b2_dev_dot(c, L.r->d, mg->z->d, n, s + 0));
+  B2_TRY(b2_dev_dot(c, L.r->d, mg->z->d, n, s + 0, own));
+  B2_TRY(b2_dev_dot(c, L.r->d, L.r->d, n, s + 3, own));
+  B2_TRY(b2_allreduce_sum(c, s + 3, 2));    // slots 3 (rr) and 4 (bb) together
   B2_TRY(b2_allreduce_sum(c, s + 0, 1));
-  B2_TRY(b2_dev_dot(c, L.r->d, L.r->d, n, s + 3));
-  B2_TRY(b2_allreduce_sum(c, s + 3, 1));
   double h[8];
   B2_TRY(b2_download(c, h, s, 8));
   const double bb = h[4];
@@ -136,17 +162,17 @@ int coarse_solve(b2_mg* mg) {
   int cur = 0;
   const int check_every = 8;
   for (int it = 1; it <= mg->coarse_maxit; it++) {
-    B2_TRY(b2_csr_spmv(L.A, mg->p, mg->q));
-    B2_TRY(b2_dev_dot(c, mg->p->d, mg->q->d, n, s + 1));
+    B2_TRY(level_spmv(L, mg->p, mg->q));
+    B2_TRY(b2_dev_dot(c, mg->p->d, mg->q->d, n, s + 1, own));
     B2_TRY(b2_allreduce_sum(c, s + 1, 1));
     B2_LAUNCH(c, pcg_update_kernel, g, kBlock, 0, n, s, cur, L.dinv->d, mg->p->d, mg->q->d, L.x->d, L.r->d, mg->z->d);
-    B2_TRY(b2_dev_dot(c, L.r->d, mg->z->d, n, s + (cur ^ 2)));
+    B2_TRY(b2_dev_dot(c, L.r->d, mg->z->d, n, s + (cur ^ 2), own));
     B2_TRY(b2_allreduce_sum(c, s + (cur ^ 2), 1));
     B2_LAUNCH(c, pcg_dir_kernel, g, kBlock, 0, n, s, cur, mg->z->d, mg->p->d);
     cur ^= 2;
     mg->coarse_its = it;
     if (it % check_every == 0) {
-      B2_TRY(b2_dev_dot(c, L.r->d, L.r->d, n, s + 3));
+      B2_TRY(b2_dev_dot(c, L.r->d, L.r->d, n, s + 3, own));
       B2_TRY(b2_allreduce_sum(c, s + 3, 1));
       B2_TRY(b2_download(c, h, s, 8));
       if (!(h[3] > mg->coarse_rtol * mg->coarse_rtol * bb)) break;   // also leaves on NaN
@@ -160,9 +186,10 @@ int vcycle(b2_mg* mg, int l) {
   b2_mg_level& L = mg->L[l];
   if (l == 0) return coarse_solve(mg);
   B2_TRY(smooth(mg, l, L.npre, true));
-  B2_TRY(b2_csr_resid(L.A, L.b, L.x, L.r));
+  B2_TRY(level_resid(L, L.b, L.x, L.r));
   b2_mg_level& C = mg->L[l - 1];
-  B2_TRY(b2_csr_spmv(L.R, L.r, C.b));
+  B2_TRY(b2_csr_spmv(L.R, L.r, C.b));        // R = P^T restricted to the fine rows this rank owns
+  if (C.halo) B2_TRY(b2_halo_sum(C.halo, C.b));
   B2_TRY(vcycle(mg, l - 1));
   B2_TRY(b2_csr_spmv_add(L.P, C.x, L.x));
   B2_TRY(smooth(mg, l, L.npost, false));
@@ -214,17 +241,28 @@ int b2_mg_set_level(b2_mg* mg, int level, b2_csr* A, b2_csr* P, const int32_t* b
   }
   if (L.bdc) { b2_free(c, L.bdc, (size_t)L.nbdc); L.bdc = nullptr; }
   L.nbdc = nbdc;
+  B2_CHECK(!L.halo || L.halo->n_local == n, "b2_mg_set_level: layout of level %d has %lld dofs, operator %lld", level,
+           (long long)(L.halo ? L.halo->n_local : 0), (long long)n);
   if (nbdc) {
     B2_TRY(b2_malloc(c, &L.bdc, (size_t)nbdc));
     B2_TRY(b2_upload(c, L.bdc, bdc_idx, (size_t)nbdc));
-    B2_TRY(b2_csr_zero_rows(A, bdc_idx, nbdc, 1.0));     // SetPenalty
+    B2_TRY(b2_csr_zero_rows_dev(A, L.bdc, nbdc, 1.0, owned(L)));     // SetPenalty
   }
   B2_TRY(b2_csr_diag(A, L.dinv));
+  if (L.halo) B2_TRY(b2_halo_sum(L.halo, L.dinv));       // diagonal of the summed operator
   B2_LAUNCH(c, recip_kernel, vec_grid(c, n), kBlock, 0, n, L.dinv->d, L.dinv->d);
   if (newP) {   // the explicit restriction R = P^T is rebuilt only when P changes
     if (L.R) { b2_csr_destroy(L.R); L.R = nullptr; }
     B2_TRY(b2_csr_transpose(P, &L.R));
+    if (L.halo) B2_TRY(b2_csr_zero_cols_notowned(L.R, L.halo->owned));   // shared fine rows restrict once
   }
+  return 0;
+}
+
+int b2_mg_set_level_halo(b2_mg* mg, int level, b2_halo* halo) {
+  B2_CHECK(level >= 0 && level < mg->nlevels, "b2_mg_set_level_halo: bad level %d", level);
+  B2_CHECK(!mg->L[level].R, "b2_mg_set_level_halo: call it before b2_mg_set_level");
+  mg->L[level].halo = halo;
   return 0;
 }
 
@@ -256,7 +294,7 @@ int b2_mg_solve(b2_mg* mg, b2_vec* res, b2_vec* eps) {
   B2_CUDA(cudaMemcpyAsync(L.b->d, res->d, (size_t)L.A->nrows * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
   B2_TRY(vcycle(mg, top));
   // RES -= A EPSC ; EPS += EPSC
-  B2_TRY(b2_csr_resid(L.A, res, L.x, res));
+  B2_TRY(level_resid(L, res, L.x, res));
   B2_TRY(b2_vec_axpy(eps, 1.0, L.x));
   return 0;
 }

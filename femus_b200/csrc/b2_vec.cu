@@ -61,10 +61,12 @@ __device__ __forceinline__ void red_combine(double& a0, double& a1, double b0, d
 template <int OP>
 __global__ void __launch_bounds__(kBlock) vec_reduce_kernel(const double* __restrict__ x, const double* __restrict__ y,
                                                             int64_t n, double* __restrict__ partial,
-                                                            double* __restrict__ result, unsigned int* counter) {
+                                                            double* __restrict__ result, unsigned int* counter,
+                                                            const uint8_t* __restrict__ owned) {
   double a0 = (OP == RED_MINMAX) ? INFINITY : 0.0, a1 = -INFINITY;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    if (owned && !owned[i]) continue;       // entries owned by another rank are counted there
     const double v = x[i];
     if (OP == RED_DOT) a0 = fma(v, y[i], a0);
     else if (OP == RED_SUM) a0 += v;
@@ -140,12 +142,14 @@ int launch_map(b2_vec* y, const b2_vec* x, const b2_vec* z, double a) {
 }
 
 template <int OP>
-int launch_reduce(b2_ctx* c, const double* x, const double* y, int64_t n, double* d_result) {
+int launch_reduce(b2_ctx* c, const double* x, const double* y, int64_t n, double* d_result,
+                  const uint8_t* owned = nullptr) {
   int grid = b2_grid_for(c, n, kBlock * 4, 8);
   if (grid > kRedBlocks) grid = kRedBlocks;
-  B2_LAUNCH(c, vec_reduce_kernel<OP>, grid, kBlock, 0, x, y, n, c->red_partial, d_result, c->red_counter);
+  B2_LAUNCH(c, vec_reduce_kernel<OP>, grid, kBlock, 0, x, y, n, c->red_partial, d_result, c->red_counter, owned);
   return 0;
 }
+inline const uint8_t* owned_of(const b2_vec* v) { return v->halo ? v->halo->owned : nullptr; }
 
 int fetch_result(b2_ctx* c, int count) {
   B2_CUDA(cudaMemcpyAsync(c->h_result, c->red_result, count * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
@@ -155,8 +159,8 @@ int fetch_result(b2_ctx* c, int count) {
 
 }  // namespace
 
-int b2_dev_dot(b2_ctx* c, const double* x, const double* y, int64_t n, double* d_out) {
-  return launch_reduce<RED_DOT>(c, x, y, n, d_out);
+int b2_dev_dot(b2_ctx* c, const double* x, const double* y, int64_t n, double* d_out, const uint8_t* owned) {
+  return launch_reduce<RED_DOT>(c, x, y, n, d_out, owned);
 }
 
 extern "C" {
@@ -164,7 +168,7 @@ extern "C" {
 int b2_vec_create(b2_ctx* c, int64_t n, b2_vec** out) {
   *out = nullptr;
   B2_CHECK(c && n >= 0, "b2_vec_create: bad arguments");
-  b2_vec* v = new b2_vec{c, n, nullptr};
+  b2_vec* v = new b2_vec{c, n, nullptr, nullptr};
   B2_TRY(b2_malloc(c, &v->d, (size_t)n + 2));
   B2_CUDA(cudaMemsetAsync(v->d, 0, ((size_t)n + 2) * sizeof(double), c->stream));
   *out = v;
@@ -230,7 +234,7 @@ int b2_vec_copy_masked(b2_vec* dst, const b2_vec* src, const b2_vec* mask, doubl
 int b2_vec_dot(const b2_vec* x, const b2_vec* y, double* out) {
   B2_CHECK(x->n == y->n, "b2_vec_dot: size mismatch");
   b2_ctx* c = x->ctx;
-  B2_TRY(launch_reduce<RED_DOT>(c, x->d, y->d, x->n, c->red_result));
+  B2_TRY(launch_reduce<RED_DOT>(c, x->d, y->d, x->n, c->red_result, owned_of(x)));
   B2_TRY(b2_allreduce_sum(c, c->red_result, 1));
   B2_TRY(fetch_result(c, 1));
   *out = c->h_result[0];
@@ -239,18 +243,18 @@ int b2_vec_dot(const b2_vec* x, const b2_vec* y, double* out) {
 int b2_vec_norm(const b2_vec* x, int kind, double* out) {
   b2_ctx* c = x->ctx;
   if (kind == 2) {
-    B2_TRY(launch_reduce<RED_DOT>(c, x->d, x->d, x->n, c->red_result));
+    B2_TRY(launch_reduce<RED_DOT>(c, x->d, x->d, x->n, c->red_result, owned_of(x)));
     B2_TRY(b2_allreduce_sum(c, c->red_result, 1));
     B2_TRY(fetch_result(c, 1));
     *out = sqrt(c->h_result[0]);
   } else if (kind == 1) {
-    B2_TRY(launch_reduce<RED_L1>(c, x->d, nullptr, x->n, c->red_result));
+    B2_TRY(launch_reduce<RED_L1>(c, x->d, nullptr, x->n, c->red_result, owned_of(x)));
     B2_TRY(b2_allreduce_sum(c, c->red_result, 1));
     B2_TRY(fetch_result(c, 1));
     *out = c->h_result[0];
   } else if (kind == 0) {
-    B2_CHECK(c->nranks == 1, "linf norm across ranks not wired yet");
     B2_TRY(launch_reduce<RED_LINF>(c, x->d, nullptr, x->n, c->red_result));
+    B2_TRY(b2_allreduce_op(c, c->red_result, 1, 2));
     B2_TRY(fetch_result(c, 1));
     *out = c->h_result[0];
   } else {
@@ -260,7 +264,7 @@ int b2_vec_norm(const b2_vec* x, int kind, double* out) {
 }
 int b2_vec_sum(const b2_vec* x, double* out) {
   b2_ctx* c = x->ctx;
-  B2_TRY(launch_reduce<RED_SUM>(c, x->d, nullptr, x->n, c->red_result));
+  B2_TRY(launch_reduce<RED_SUM>(c, x->d, nullptr, x->n, c->red_result, owned_of(x)));
   B2_TRY(b2_allreduce_sum(c, c->red_result, 1));
   B2_TRY(fetch_result(c, 1));
   *out = c->h_result[0];
@@ -268,8 +272,9 @@ int b2_vec_sum(const b2_vec* x, double* out) {
 }
 int b2_vec_minmax(const b2_vec* x, double* mn, double* mx) {
   b2_ctx* c = x->ctx;
-  B2_CHECK(c->nranks == 1, "min/max across ranks not wired yet");
   B2_TRY(launch_reduce<RED_MINMAX>(c, x->d, nullptr, x->n, c->red_result));
+  B2_TRY(b2_allreduce_op(c, c->red_result, 1, 3));
+  B2_TRY(b2_allreduce_op(c, c->red_result + 1, 1, 2));
   B2_TRY(fetch_result(c, 2));
   if (mn) *mn = c->h_result[0];
   if (mx) *mx = c->h_result[1];

@@ -28,7 +28,26 @@ b2h_hier* b2h_hier_create(int nx, int ny, int nz, int nlevels, const double* bou
   for (int l = 1; l < nlevels; l++) h->levels.push_back(RefineMesh(h->levels.back()));
   return h;
 }
+b2h_hier* b2h_hier_create_local(int nx, int ny, int nz, int nlevels, const double* bounds6, int nprocs, int rank) {
+  if (nx < 1 || ny < 1 || nz < 1 || nlevels < 1 || nprocs < 1 || rank < 0 || rank >= nprocs) return nullptr;
+  const double unit[6] = {0., 1., 0., 1., 0., 1.};
+  const double* b = bounds6 ? bounds6 : unit;
+  std::vector<int32_t> part = SlabPartition(nx, ny, nz, nprocs);
+  MeshLevel G = GenerateCoarseBoxMesh(nx, ny, nz, b[0], b[1], b[2], b[3], b[4], b[5], &part, nprocs);
+  if (G.elem_offset[rank + 1] == G.elem_offset[rank]) return nullptr;      // more ranks than z-layers
+  b2h_hier* h = new b2h_hier();
+  h->levels.reserve(nlevels);
+  h->levels.push_back(ExtractRankSubmesh(G, rank));
+  for (int l = 1; l < nlevels; l++) h->levels.push_back(RefineMesh(h->levels.back()));
+  return h;
+}
 void b2h_hier_destroy(b2h_hier* h) { delete h; }
+const int32_t* b2h_level_ijk(const b2h_hier* h, int l) { return h->levels[l].ijk.data(); }
+int64_t b2h_level_interface_nodes(const b2h_hier* h, int l, int32_t* out) {
+  const std::vector<int32_t> v = InterfaceNodes(h->levels[l]);
+  if (out) std::copy(v.begin(), v.end(), out);
+  return (int64_t)v.size();
+}
 int b2h_hier_nlevels(const b2h_hier* h) { return (int)h->levels.size(); }
 int b2h_hier_nprocs(const b2h_hier* h) { return h->levels[0].nprocs; }
 int64_t b2h_level_nel(const b2h_hier* h, int l) { return h->levels[l].nel; }

@@ -42,6 +42,9 @@ class MeshLevel {
   std::vector<int64_t> dof_offset[3];   // [family][nprocs+1]
   std::vector<double> xyz;              // [3][nnode]
   std::vector<int32_t> child_el;        // [nel][8] fine element of (element, child) once refined
+  std::vector<int32_t> ijk;             // [3][nnode] integer lattice coordinates of the nodes on this level's
+                                        // (2*nx_l+1)(2*ny_l+1)(2*nz_l+1) lattice: a rank-independent name of a node,
+                                        // used to match interface nodes between the sub-meshes of different ranks
 
   int32_t node(int64_t iel, int i) const { return conn[iel * 27 + i]; }
 
@@ -175,10 +178,14 @@ inline MeshLevel GenerateCoarseBoxMesh(int nx, int ny, int nz, double xmin, doub
   std::vector<int32_t> part = partition ? *partition : std::vector<int32_t>((size_t)L.nel, 0);
   std::vector<int32_t> map = L.FillISvectorDofMapAllFEFamilies(part, nprocs);
   L.xyz.resize(3 * L.nnode);
+  L.ijk.resize(3 * L.nnode);
   for (int64_t k = 0; k < sz; k++)
     for (int64_t j = 0; j < sy; j++)
       for (int64_t i = 0; i < sx; i++) {
         const int64_t nd = map[i + sx * (j + sy * k)];
+        L.ijk[nd] = (int32_t)i;
+        L.ijk[L.nnode + nd] = (int32_t)j;
+        L.ijk[2 * L.nnode + nd] = (int32_t)k;
         L.xyz[nd] = (static_cast<double>(i) / static_cast<double>(2 * nx)) * (xmax - xmin) + xmin;
         L.xyz[L.nnode + nd] = (static_cast<double>(j) / static_cast<double>(2 * ny)) * (ymax - ymin) + ymin;
         L.xyz[2 * L.nnode + nd] = (static_cast<double>(k) / static_cast<double>(2 * nz)) * (zmax - zmin) + zmin;
@@ -318,6 +325,16 @@ inline MeshLevel RefineMesh(MeshLevel& C) {
   std::vector<int32_t> part(F.nel);
   detail::PairMap map((size_t)C.nnode * 8 + 1024);
   int32_t next = (int32_t)C.nnode;
+  // lattice coordinates in temporary numbering: a coarse node doubles its coordinates, a new node
+  // sits at the sum of the coordinates of the two opposite corners it is the centre of
+  const bool lattice = !C.ijk.empty();
+  std::vector<int32_t> tijk[3];
+  if (lattice)
+    for (int d = 0; d < 3; d++) {
+      tijk[d].reserve((size_t)C.nnode * 8);
+      tijk[d].resize(C.nnode);
+      for (int64_t n = 0; n < C.nnode; n++) tijk[d][n] = 2 * C.ijk[d * C.nnode + n];
+    }
   for (int64_t E = 0; E < C.nel; E++) {
     const int32_t* cn = &C.conn[E * 27];
     int32_t fid[125];
@@ -326,10 +343,15 @@ inline MeshLevel RefineMesh(MeshLevel& C) {
       if (nc == 1) { fid[q] = cn[T.corner[q][0]]; continue; }
       int best = 0;
       for (int m = 1; m < nc; m++) if (cn[T.corner[q][m]] < cn[T.corner[q][best]]) best = m;
-      const uint64_t key = ((uint64_t)(uint32_t)cn[T.corner[q][best]] << 32) | (uint32_t)cn[T.corner[q][T.opposite[q][best]]];
+      const int32_t na = cn[T.corner[q][best]], nb = cn[T.corner[q][T.opposite[q][best]]];
+      const uint64_t key = ((uint64_t)(uint32_t)na << 32) | (uint32_t)nb;
       bool ins;
       fid[q] = map.get_or_insert(key, next, ins);
-      if (ins) next++;
+      if (ins) {
+        next++;
+        if (lattice)
+          for (int d = 0; d < 3; d++) tijk[d].push_back(C.ijk[d * C.nnode + na] + C.ijk[d * C.nnode + nb]);
+      }
     }
     for (int j = 0; j < 8; j++) {
       const int64_t fe = E * 8 + j;
@@ -342,7 +364,12 @@ inline MeshLevel RefineMesh(MeshLevel& C) {
     }
   }
   F.nnode = next;
-  F.FillISvectorDofMapAllFEFamilies(part, C.nprocs);
+  const std::vector<int32_t> nmap = F.FillISvectorDofMapAllFEFamilies(part, C.nprocs);
+  if (lattice) {
+    F.ijk.resize(3 * F.nnode);
+    for (int d = 0; d < 3; d++)
+      for (int64_t n = 0; n < F.nnode; n++) F.ijk[d * F.nnode + nmap[n]] = tijk[d][n];
+  }
   // SetChildElement: (coarse element, child) -> fine element after the reorder
   C.child_el.resize(C.nel * 8);
   for (int64_t pos = 0; pos < F.nel; pos++) C.child_el[F.elem_order[pos]] = (int32_t)pos;
@@ -356,6 +383,53 @@ inline MeshLevel RefineMesh(MeshLevel& C) {
       F.xyz[d * F.nnode + r] = s;
     }
   return F;
+}
+
+// Sub-mesh of one rank: the elements [elem_offset[rank], elem_offset[rank+1]) of G with their nodes
+// renumbered locally by the same first-visit rule (one "rank").  This is what one GPU holds: it is
+// refined locally with RefineMesh (children inherit the parent's rank in the reference too,
+// MeshMetisPartitioning.cpp:143-155), so no rank ever builds the global fine mesh.  Nodes shared
+// with other ranks are found again through their lattice coordinates `ijk`.
+inline MeshLevel ExtractRankSubmesh(const MeshLevel& G, int rank) {
+  MeshLevel L;
+  L.level = G.level;
+  const int64_t e0 = G.elem_offset[rank], e1 = G.elem_offset[rank + 1];
+  L.nel = e1 - e0;
+  L.conn.resize(L.nel * 27);
+  L.face.assign(G.face.begin() + e0 * 6, G.face.begin() + e1 * 6);
+  std::vector<int32_t> g2t((size_t)G.nnode, -1), t2g;
+  for (int64_t e = e0; e < e1; e++)
+    for (int n = 0; n < 27; n++) {
+      const int32_t g = G.conn[e * 27 + n];
+      if (g2t[g] < 0) { g2t[g] = (int32_t)t2g.size(); t2g.push_back(g); }
+      L.conn[(e - e0) * 27 + n] = g2t[g];
+    }
+  L.nnode = (int64_t)t2g.size();
+  const std::vector<int32_t> part((size_t)L.nel, 0);
+  const std::vector<int32_t> nmap = L.FillISvectorDofMapAllFEFamilies(part, 1);
+  L.xyz.resize(3 * L.nnode);
+  L.ijk.resize(3 * L.nnode);
+  for (int64_t t = 0; t < L.nnode; t++)
+    for (int d = 0; d < 3; d++) {
+      L.xyz[d * L.nnode + nmap[t]] = G.xyz[d * G.nnode + t2g[t]];
+      L.ijk[d * L.nnode + nmap[t]] = G.ijk[d * G.nnode + t2g[t]];
+    }
+  return L;
+}
+
+// Nodes of L on faces that are neither on the domain boundary nor shared by two elements of L:
+// the interface with the sub-meshes of other ranks (sorted).  Empty for a complete mesh.
+inline std::vector<int32_t> InterfaceNodes(const MeshLevel& L) {
+  std::vector<uint8_t> cnt((size_t)L.nnode, 0), mark((size_t)L.nnode, 0);
+  for (int64_t e = 0; e < L.nel; e++)
+    for (int f = 0; f < 6; f++) cnt[L.conn[e * 27 + 20 + f]]++;
+  for (int64_t e = 0; e < L.nel; e++)
+    for (int f = 0; f < 6; f++)
+      if (L.face[e * 6 + f] == -1 && cnt[L.conn[e * 27 + 20 + f]] == 1)
+        for (int iv = 0; iv < 9; iv++) mark[L.conn[e * 27 + HexElement::face_nodes()[f][iv]]] = 1;
+  std::vector<int32_t> out;
+  for (int64_t n = 0; n < L.nnode; n++) if (mark[n]) out.push_back((int32_t)n);
+  return out;
 }
 
 // Per-coarse-element maps of the element-gather Galerkin product (device kernel b2_galerkin.cu):

@@ -18,7 +18,10 @@ def _L():
     if not _ready:
         P = {
             "b2h_hier_create": (vp, [ci, ci, ci, ci, vp, ci]),
+            "b2h_hier_create_local": (vp, [ci, ci, ci, ci, vp, ci, ci]),
             "b2h_hier_destroy": (None, [vp]),
+            "b2h_level_ijk": (vp, [vp, ci]),
+            "b2h_level_interface_nodes": (i64, [vp, ci, vp]),
             "b2h_hier_nlevels": (ci, [vp]),
             "b2h_hier_nprocs": (ci, [vp]),
             "b2h_level_nel": (i64, [vp, ci]),
@@ -76,6 +79,7 @@ class HostLevel:
         self.face = _view(L.b2h_level_face(h, l), (self.nel, 6), np.int32)
         self.part = _view(L.b2h_level_part(h, l), (self.nel,), np.int32)
         self.xyz = _view(L.b2h_level_xyz(h, l), (3, self.nnode), np.float64)
+        self.ijk = _view(L.b2h_level_ijk(h, l), (3, self.nnode), np.int32)
         np1 = hier.nprocs + 1
         eo = np.zeros(np1, dtype=np.int64)
         do = np.zeros((3, np1), dtype=np.int64)
@@ -89,6 +93,20 @@ class HostLevel:
 
     def ndofs(self, family):
         return int(self.hier.L.b2h_level_ndofs(self.hier.h, self.l, _fam(family)))
+
+    def interface_nodes(self):
+        """Sorted nodes on faces shared with the sub-meshes of other ranks (empty on a complete mesh)."""
+        n = int(self.hier.L.b2h_level_interface_nodes(self.hier.h, self.l, None))
+        out = np.zeros(n, dtype=np.int32)
+        if n:
+            self.hier.L.b2h_level_interface_nodes(self.hier.h, self.l, out.ctypes.data_as(vp))
+        return out
+
+    def lattice_key(self, nodes=None):
+        """Rank-independent int64 name of the nodes: i + SX (j + SY k) on the level's global lattice."""
+        sx, sy, _ = self.hier.lattice_dims(self.l)
+        ijk = self.ijk if nodes is None else self.ijk[:, nodes]
+        return ijk[0].astype(np.int64) + sx * (ijk[1].astype(np.int64) + sy * ijk[2].astype(np.int64))
 
     def system_dofs(self, family):
         f = _fam(family)
@@ -107,13 +125,21 @@ class HostLevel:
 class HostHierarchy:
     """MultiLevelMesh of the host layer: GenerateCoarseBoxMesh + RefineMesh."""
 
-    def __init__(self, nx, ny, nz, nlevels, bounds=None, nprocs=1):
+    def __init__(self, nx, ny, nz, nlevels, bounds=None, nprocs=1, local_rank=None):
+        """local_rank=None: the complete mesh (numbered for `nprocs` ranks, z-slabs).
+        local_rank=r: only rank r's sub-mesh of that partition, locally numbered and refined."""
         self.L = _L()
         b = None if bounds is None else np.ascontiguousarray(bounds, dtype=np.float64)
-        self.h = self.L.b2h_hier_create(nx, ny, nz, nlevels, None if b is None else b.ctypes.data_as(vp), nprocs)
+        bp = None if b is None else b.ctypes.data_as(vp)
+        self.box = (nx, ny, nz)
+        if local_rank is None:
+            self.h = self.L.b2h_hier_create(nx, ny, nz, nlevels, bp, nprocs)
+            self.nprocs = nprocs
+        else:
+            self.h = self.L.b2h_hier_create_local(nx, ny, nz, nlevels, bp, nprocs, local_rank)
+            self.nprocs = 1
         if not self.h:
             raise ValueError("b2h_hier_create failed")
-        self.nprocs = nprocs
         self.nlevels = nlevels
         self.levels = [HostLevel(self, l) for l in range(nlevels)]
 
@@ -125,6 +151,11 @@ class HostHierarchy:
                 self.h = None
         except Exception:
             pass
+
+    def lattice_dims(self, l):
+        nx, ny, nz = self.box
+        f = 2 ** (l + 1)
+        return nx * f + 1, ny * f + 1, nz * f + 1
 
     def galerkin_maps(self, lcoarse, family, e0=0, e1=None):
         """(fine_dofs[ne][nf], valence[ne][27]) of the coarse elements [e0, e1) of level lcoarse."""

@@ -14,17 +14,28 @@ No arithmetic happens here: every number is produced by libfemus_b200.so."""
 import numpy as np
 
 from . import capi, hostapi
+from . import dist as distlayout
 
 
 class PoissonMG:
+    """dist=None: the whole mesh on one GPU.  dist=(rank, world, allgather): this rank's z-slab of
+    the mesh (local hierarchy, partial matrices, interface sums through b2_halo); the context must
+    already hold the NCCL communicator (Context.comm_init)."""
+
     def __init__(self, ctx, nx, ny, nz, nlevels, order="biquadratic", bounds=None, npre=1, npost=1, omega=0.5,
-                 dirichlet_faces=(1, 2, 3, 4, 5, 6), fsrc=1.0, coarse_rtol=1e-14, hier=None):
+                 dirichlet_faces=(1, 2, 3, 4, 5, 6), fsrc=1.0, coarse_rtol=1e-14, hier=None, dist=None):
         self.ctx = ctx
         self.order = order
         self.fam = hostapi.FAMILY[order]
         self.nlevels = nlevels
         self.npre, self.npost, self.omega, self.fsrc = npre, npost, omega, fsrc
-        self.hier = hier if hier is not None else hostapi.HostHierarchy(nx, ny, nz, nlevels, bounds)
+        self.dist = dist
+        if hier is not None:
+            self.hier = hier
+        elif dist is None:
+            self.hier = hostapi.HostHierarchy(nx, ny, nz, nlevels, bounds)
+        else:
+            self.hier = hostapi.HostHierarchy(nx, ny, nz, nlevels, bounds, nprocs=dist[1], local_rank=dist[0])
         lv = self.hier.levels
         top = lv[-1]
         self.ndofs = [L.ndofs(order) for L in lv]
@@ -63,6 +74,20 @@ class PoissonMG:
         self.RESM = ctx.vector(self.n)
         self.mg = capi.Multigrid(ctx, nlevels)
         self.mg.set_coarse(coarse_rtol, 10000)
+        # --- distributed layout: interface dofs of every level, ownership; reductions over owned dofs
+        self.layout = [None] * nlevels
+        self.halo = [None] * nlevels
+        self.n_global = self.n
+        if dist is not None:
+            rank, world, gather = dist
+            for l in range(nlevels):
+                lay = distlayout.level_layout(lv[l], self.ndofs[l], rank, gather)
+                self.layout[l] = lay
+                self.halo[l] = capi.Halo(ctx, lay.n_local, lay.idx, lay.pos, lay.n_packed, lay.owned, lay.mult)
+                self.mg.set_level_halo(l, self.halo[l])
+            self.n_global = int(sum(gather(self.layout[-1].n_owned)))
+            for v in (self.RES, self.EPS, self.SOL, self.RESM):
+                v.set_halo(self.halo[-1])
 
     # ---- pieces of MGsolve -----------------------------------------------------------------
     def assemble(self):
@@ -70,6 +95,8 @@ class PoissonMG:
         self.RES.zero()
         self.KK[-1].zero()
         self.asm.poisson(self.SOL, self.RES, 1.0, self.fsrc)
+        if self.halo[-1] is not None:          # close(): contributions of the other ranks' elements
+            self.halo[-1].sum(self.RES)
 
     def galerkin(self, algebraic=False):
         """A_{l-1} = P_l^T A_l P_l down the hierarchy, on the un-penalised matrices: element-gather

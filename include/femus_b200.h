@@ -31,6 +31,7 @@ typedef struct b2_mesh b2_mesh;
 typedef struct b2_asm b2_asm;
 typedef struct b2_mg b2_mg;
 typedef struct b2_galerkin b2_galerkin;
+typedef struct b2_halo b2_halo;
 
 const char* b2_last_error(void);
 int b2_version(void);
@@ -95,6 +96,25 @@ int b2_vec_fill_indexed(b2_vec* v, const int32_t* idx, int64_t n, double a); /* 
 int b2_vec_get_indexed(const b2_vec* v, const int32_t* idx, double* vals, int64_t n); /* get(idx,vals) */
 /* dst[i] = mask[i] > thr ? src[i] : 0  -- Solution::UpdateRes (Solution.cpp:595-628) */
 int b2_vec_copy_masked(b2_vec* dst, const b2_vec* src, const b2_vec* mask, double thr);
+
+/* ---- distributed layout: replaces the MPI side of PetscVector/PetscMatrix -- off-process
+ *      ADD_VALUES assembly (PetscVector.cpp:132-141, PetscMatrix.cpp:699-729 + close()), ghost update
+ *      (PetscVector.hpp:604-609) and owned-entry reductions.  One rank per GPU holds all dofs of its
+ *      own elements; dofs on the partition interface are held by several ranks.
+ *      local_idx[n_if]  : local dof of interface entry k,
+ *      packed_pos[n_if] : its position in the packed interface vector of n_packed entries, the same
+ *                         on every rank that holds the dof,
+ *      owned[n_local]   : 1 if this rank owns the dof (lowest rank holding it, Mesh.cpp:530-553),
+ *      mult[n_local]    : number of ranks holding the dof (>= 1). */
+int b2_halo_create(b2_ctx* c, int64_t n_local, int64_t n_if, const int32_t* local_idx, const int32_t* packed_pos,
+                   int64_t n_packed, const uint8_t* owned, const uint8_t* mult, b2_halo** out);
+int b2_halo_destroy(b2_halo* h);
+int64_t b2_halo_owned_count(const b2_halo* h);
+int64_t b2_halo_interface_count(const b2_halo* h);
+/* v[interface] <- sum over the ranks holding each dof (pack, ncclAllReduce over NVLink, unpack) */
+int b2_halo_sum(b2_halo* h, b2_vec* v);
+/* attach a layout: dot / norms / sum of v then run over owned entries + allreduce (NULL detaches) */
+int b2_vec_set_halo(b2_vec* v, const b2_halo* h);
 
 /* ---- CSR matrices: replaces PetscMatrix (src/03_algebra/01_matrices/PetscMatrix.{hpp,cpp}) --- */
 /* init(m,n,...,n_nz,n_oz) + pattern: rowptr[nrows+1] (int64), col[nnz] (int32, sorted per row);
@@ -187,6 +207,9 @@ int b2_mg_create(b2_ctx* c, int nlevels, b2_mg** out);                   /* MGIn
  * level-1 (NULL on level 0), Dirichlet row list, smoothing steps and Richardson scale. */
 int b2_mg_set_level(b2_mg* mg, int level, b2_csr* A, b2_csr* P, const int32_t* bdc_idx, int64_t nbdc,
                     int npre, int npost, double omega);
+/* distributed run: layout of the level's vectors; A is then this rank's partial operator (sum over
+ * its own elements), P its local prolongator.  Call before b2_mg_set_level. */
+int b2_mg_set_level_halo(b2_mg* mg, int level, b2_halo* halo);
 /* coarse solver: Jacobi-PCG to ||r|| <= rtol ||b|| (the reference: PREONLY + MUMPS LU,
  * PetscPreconditioner.cpp:147-160) */
 int b2_mg_set_coarse(b2_mg* mg, double rtol, int maxit);

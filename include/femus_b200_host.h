@@ -19,7 +19,15 @@ typedef struct b2h_csr b2h_csr;     /* host CSR matrix */
  * MeshRefinement.cpp:188-507).  bounds6 = xmin,xmax,ymin,ymax,zmin,zmax (NULL: unit cube).
  * nprocs > 1: z-slab partition of level 0, children inherit (MeshMetisPartitioning.cpp:143-155). */
 b2h_hier* b2h_hier_create(int nx, int ny, int nz, int nlevels, const double* bounds6, int nprocs);
+/* The same hierarchy restricted to ONE rank of the z-slab partition: the rank's level-0 elements
+ * (Mesh::_elementOffset[rank] .. [rank+1]) with locally renumbered nodes, refined locally (children
+ * inherit the parent's rank, MeshMetisPartitioning.cpp:143-155).  Inside, nprocs == 1. */
+b2h_hier* b2h_hier_create_local(int nx, int ny, int nz, int nlevels, const double* bounds6, int nprocs, int rank);
 void b2h_hier_destroy(b2h_hier* h);
+/* integer lattice coordinates [3][nnode] of the nodes (rank-independent node names) */
+const int32_t* b2h_level_ijk(const b2h_hier* h, int l);
+/* nodes on faces shared with other ranks' sub-meshes, sorted (out may be NULL: count only) */
+int64_t b2h_level_interface_nodes(const b2h_hier* h, int l, int32_t* out);
 int b2h_hier_nlevels(const b2h_hier* h);
 int b2h_hier_nprocs(const b2h_hier* h);
 int64_t b2h_level_nel(const b2h_hier* h, int l);                 /* Mesh::GetNumberOfElements */
