@@ -34,6 +34,7 @@ _PROTOS = {
     "b2_timer_start": (ci, [vp]),
     "b2_timer_stop_ms": (ci, [vp, vp]),
     "b2_ctx_flush_l2": (ci, [vp]),
+    "b2_ctx_set_option": (ci, [vp, ctypes.c_char_p, ci]),
     "b2_ctx_profile": (ci, [vp, ci]),
     "b2_ctx_profile_only": (ci, [vp, vp]),
     "b2_ctx_profile_read": (ci, [vp, vp, vp, vp]),
@@ -201,6 +202,9 @@ class Context:
         ms = cd()
         check(self.L.b2_timer_stop_ms(self.h, ctypes.byref(ms)))
         return ms.value
+
+    def set_option(self, name, value):
+        check(self.L.b2_ctx_set_option(self.h, name.encode(), int(value)))
 
     def flush_l2(self):
         check(self.L.b2_ctx_flush_l2(self.h))

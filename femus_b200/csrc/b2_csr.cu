@@ -1,96 +1,13 @@
 // Device CSR matrix (fp64 values, int32 columns, int64 row pointers): storage, setup kernels
 // (pattern from element lists, transpose, row/column zeroing, diagonal, staged block adds) and
-// the SpMV family.  Replaces PetscMatrix + the MatMult calls of PetscVector
-// (reference src/03_algebra/01_matrices/PetscMatrix.cpp, 00_vectors/PetscVector.cpp:193-247).
+// the row chunking consumed by the SpMV family (b2_spmv.cu).  Replaces PetscMatrix
+// (reference src/03_algebra/01_matrices/PetscMatrix.cpp).
 #include "b2_common.cuh"
 #include <cub/cub.cuh>
 
 namespace {
 
 constexpr int kBlock = 256;
-
-// ------------------------------------------------------------------------------------------
-// SpMV family.  One sub-warp of TPR lanes per row; values and columns of a row are contiguous,
-// so a sub-warp reads 8*TPR contiguous bytes of values per step.  The epilogue selects
-//   Y_AX   y = A x            (MatMult)
-//   Y_ADD  y += A x           (MatMultAdd)
-//   RESID  y = b - A x        (resid)
-//   JACOBI y = x + omega * dinv * (b - A x)   (Richardson + Jacobi sweep, x != y)
-// Streaming operands (val/col) bypass L1 allocation; x stays on the cached path.
-//   RESID_W y = w .* b - A x  (distributed residual: A is this rank's partial matrix, w = 1/multiplicity,
-//                              so that the interface sum over ranks gives b - A x)
-enum SpmvMode { Y_AX, Y_ADD, RESID, JACOBI, RESID_W };
-
-__device__ __forceinline__ double ld_stream(const double* p) {
-  double v;
-  asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
-  return v;
-}
-__device__ __forceinline__ int ld_stream(const int* p) {
-  int v;
-  asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
-  return v;
-}
-
-template <int TPR, int MODE>
-__global__ void __launch_bounds__(kBlock) spmv_kernel(int64_t nrows, const int64_t* __restrict__ rowptr,
-                                                      const int32_t* __restrict__ col,
-                                                      const double* __restrict__ val, const double* __restrict__ x,
-                                                      const double* __restrict__ b, const double* __restrict__ dinv,
-                                                      double* __restrict__ y, double omega) {
-  const int lane = threadIdx.x & (TPR - 1);
-  const int64_t sub = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / TPR;
-  const int64_t nsub = ((int64_t)gridDim.x * blockDim.x) / TPR;
-  for (int64_t row = sub; row < nrows; row += nsub) {
-    const int64_t s = rowptr[row], e = rowptr[row + 1];
-    double acc0 = 0., acc1 = 0.;
-    int64_t k = s + lane;
-    for (; k + TPR < e; k += 2 * TPR) {
-      const double v0 = ld_stream(val + k), v1 = ld_stream(val + k + TPR);
-      const int c0 = ld_stream(col + k), c1 = ld_stream(col + k + TPR);
-      acc0 = fma(v0, x[c0], acc0);
-      acc1 = fma(v1, x[c1], acc1);
-    }
-    if (k < e) acc0 = fma(ld_stream(val + k), x[ld_stream(col + k)], acc0);
-    double acc = acc0 + acc1;
-#pragma unroll
-    for (int o = TPR / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o, TPR);
-    if (lane == 0) {
-      if (MODE == Y_AX) y[row] = acc;
-      else if (MODE == Y_ADD) y[row] += acc;
-      else if (MODE == RESID) y[row] = b[row] - acc;
-      else if (MODE == RESID_W) y[row] = fma(dinv[row], b[row], -acc);
-      else y[row] = fma(omega * dinv[row], b[row] - acc, x[row]);
-    }
-  }
-}
-
-template <int MODE>
-int launch_spmv(const b2_csr* A, const double* x, const double* b, const double* dinv, double* y, double omega) {
-  b2_ctx* c = A->ctx;
-  if (A->nrows == 0) return 0;
-  const int tpr = A->tpr;
-  b2_prof_scope prof(c, A);
-  const int64_t threads = A->nrows * tpr;
-  const int grid = b2_grid_for(c, threads, kBlock, 8 * 4);
-#define B2_SPMV_CASE(T)                                                                                    \
-  case T:                                                                                                  \
-    B2_LAUNCH(c, (spmv_kernel<T, MODE>), grid, kBlock, 0, A->nrows, A->rowptr, A->col, A->val, x, b, dinv, \
-              y, omega);                                                                                   \
-    break;
-  switch (tpr) {
-    B2_SPMV_CASE(1)
-    B2_SPMV_CASE(2)
-    B2_SPMV_CASE(4)
-    B2_SPMV_CASE(8)
-    B2_SPMV_CASE(16)
-    B2_SPMV_CASE(32)
-    default:
-      B2_CHECK(false, "bad tpr %d", tpr);
-  }
-#undef B2_SPMV_CASE
-  return 0;
-}
 
 // ------------------------------------------------------------------------------------------
 __global__ void row_stats_kernel(int64_t nrows, const int64_t* __restrict__ rowptr, int* max_row) {
@@ -311,10 +228,6 @@ int inclusive_scan_u64(b2_ctx* c, unsigned long long* d, int64_t n) {
 
 }  // namespace
 
-int b2_csr_resid_w(const b2_csr* A, const double* b, const double* w, const double* x, double* r) {
-  return launch_spmv<RESID_W>(A, x, b, w, r, 0.);
-}
-
 __global__ void zero_cols_notowned_kernel(int64_t nnz, const int32_t* __restrict__ col, double* __restrict__ val,
                                           const uint8_t* __restrict__ owned) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -359,7 +272,9 @@ int b2_csr_alloc(b2_ctx* c, int64_t nrows, int64_t ncols, int64_t nnz, b2_csr** 
   A->tpr = 8;
   A->max_row = 0;
   A->last_ms = 0.;
-  B2_TRY(b2_malloc(c, &A->rowptr, (size_t)nrows + 1));
+  A->chunk_row = nullptr;
+  A->nchunks = 0;
+  B2_TRY(b2_malloc(c, &A->rowptr, (size_t)nrows + 3));
   B2_TRY(b2_malloc(c, &A->col, (size_t)nnz + 4));
   B2_TRY(b2_malloc(c, &A->val, (size_t)nnz + 4));
   *out = A;
@@ -381,6 +296,7 @@ int b2_csr_finalize(b2_csr* A) {
   int tpr = 1;
   while (tpr < 32 && tpr * 3 < mean) tpr <<= 1;   // ~3+ entries per lane
   A->tpr = tpr;
+  B2_TRY(b2_csr_build_chunks(A));
   return 0;
 }
 
@@ -456,7 +372,8 @@ int b2_csr_create_from_elements(b2_ctx* c, int64_t nrows, int64_t nel, int nve, 
 int b2_csr_destroy(b2_csr* A) {
   if (!A) return 0;
   cudaStreamSynchronize(A->ctx->stream);
-  b2_free(A->ctx, A->rowptr, (size_t)A->nrows + 1);
+  b2_free(A->ctx, A->rowptr, (size_t)A->nrows + 3);
+  if (A->chunk_row) b2_free(A->ctx, A->chunk_row, (size_t)A->nchunks + 1);
   b2_free(A->ctx, A->col, (size_t)A->nnz + 4);
   b2_free(A->ctx, A->val, (size_t)A->nnz + 4);
   delete A;
@@ -627,25 +544,6 @@ int b2_csr_transpose(const b2_csr* A, b2_csr** out) {
   B2_TRY(b2_csr_finalize(T));
   *out = T;
   return 0;
-}
-
-int b2_csr_spmv(const b2_csr* A, const b2_vec* x, b2_vec* y) {
-  B2_CHECK(x->n >= A->ncols && y->n >= A->nrows && x != y, "b2_csr_spmv: bad operands");
-  return launch_spmv<Y_AX>(A, x->d, nullptr, nullptr, y->d, 0.);
-}
-int b2_csr_spmv_add(const b2_csr* A, const b2_vec* x, b2_vec* y) {
-  B2_CHECK(x->n >= A->ncols && y->n >= A->nrows && x != y, "b2_csr_spmv_add: bad operands");
-  return launch_spmv<Y_ADD>(A, x->d, nullptr, nullptr, y->d, 0.);
-}
-int b2_csr_resid(const b2_csr* A, const b2_vec* b, const b2_vec* x, b2_vec* r) {
-  B2_CHECK(x->n >= A->ncols && r->n >= A->nrows && b->n >= A->nrows && x != r, "b2_csr_resid: bad operands");
-  return launch_spmv<RESID>(A, x->d, b->d, nullptr, r->d, 0.);
-}
-int b2_csr_jacobi_sweep(const b2_csr* A, const b2_vec* dinv, const b2_vec* b, const b2_vec* xin, b2_vec* xout,
-                        double omega) {
-  B2_CHECK(A->nrows == A->ncols && xin != xout && xin->n >= A->nrows && xout->n >= A->nrows,
-           "b2_csr_jacobi_sweep: bad operands");
-  return launch_spmv<JACOBI>(A, xin->d, b->d, dinv->d, xout->d, omega);
 }
 
 }  // extern "C"

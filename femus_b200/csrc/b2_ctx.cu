@@ -76,6 +76,7 @@ int b2_ctx_create(int device, b2_ctx** out) {
   cudaDeviceProp prop;
   B2_CUDA(cudaGetDeviceProperties(&prop, device));
   c->sm_count = prop.multiProcessorCount;
+  if (const char* v = getenv("B2_SPMV_VARIANT")) c->spmv_variant = atoi(v);
   B2_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   B2_CUDA(cudaEventCreate(&c->ev0));
   B2_CUDA(cudaEventCreate(&c->ev1));
@@ -141,6 +142,15 @@ int b2_ctx_flush_l2(b2_ctx* c) {
   }
   B2_CUDA(cudaMemsetAsync(c->flush_buf, 0, c->flush_bytes, c->stream));
   return 0;
+}
+
+int b2_ctx_set_option(b2_ctx* c, const char* name, int value) {
+  if (!strcmp(name, "spmv_variant")) {
+    B2_CHECK(value == 0 || value == 2 || value == 3 || value == 4 || value == 6, "spmv_variant %d (0, 2, 3, 4, 6)", value);
+    c->spmv_variant = value;
+    return 0;
+  }
+  B2_CHECK(false, "b2_ctx_set_option: unknown option '%s'", name);
 }
 
 int b2_ctx_profile(b2_ctx* c, int on) {
