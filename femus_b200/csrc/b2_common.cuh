@@ -55,8 +55,10 @@ struct b2_ctx {
   double* h_result = nullptr;       // pinned [8]
   void* flush_buf = nullptr;
   size_t flush_bytes = 0;
-  // SpMV kernel: 0 = register-streaming, 2/3/4/6 = TMA-staged ring with that many stages (B2_SPMV_VARIANT)
-  int spmv_variant = 3;
+  // SpMV kernel: 0 = register-streaming, 1 = TMA-staged ring (default), 2 = staged + software-pipelined
+  // gathers (B2_SPMV_VARIANT)
+  int spmv_variant = 1;
+  int spmv_timing = 0;     // diagnostic: y = A x prints the consumer phase cycles of CTA 0
   // multi-GPU
   int nranks = 1, rank = 0;
   void* nccl_comm = nullptr;
@@ -109,8 +111,13 @@ struct b2_csr {
   int64_t* rowptr;   // [nrows+1]
   int32_t* col;      // [nnz]
   double* val;       // [nnz]
-  int32_t* chunk_row;  // [nchunks+1] row cuts of the TMA-staged SpMV (b2_spmv.cu), null: streaming kernel
-  int64_t nchunks;
+  // SpMV plan (b2_spmv.cu), null: streaming kernel
+  int32_t* chunk_row;        // [nchunks+1] row cuts
+  int64_t* cdesc;            // [nchunks+1][4] packed {first nonzero, dictionary start, first row, 0} per chunk
+  int64_t* dict_ptr;         // [nchunks+1] start of every chunk's column dictionary (multiples of 4)
+  int32_t* dict;             // [dict_total] distinct columns of every chunk, sorted
+  unsigned short* lidx;      // [nnz] position of each nonzero's column in its chunk's dictionary
+  int64_t nchunks, dict_total, dict_cap;   // dict_cap: largest chunk dictionary (sizes the shared memory)
   int tpr;           // threads per row of the streaming SpMV kernel (power of two <= 32)
   int max_row;       // longest row
   double last_ms;
@@ -155,6 +162,7 @@ static inline int b2_grid_for(b2_ctx* c, int64_t work_items, int per_block, int 
 int b2_csr_alloc(b2_ctx* c, int64_t nrows, int64_t ncols, int64_t nnz, b2_csr** out);
 int b2_csr_finalize(b2_csr* A);   // row statistics -> tpr / max_row, SpMV row chunks
 int b2_csr_build_chunks(b2_csr* A);
+void b2_csr_free_plan(b2_csr* A);
 int b2_csr_resid_w(const b2_csr* A, const double* b, const double* w, const double* x, double* r);   // r = w.*b - A x
 int b2_csr_zero_cols_notowned(b2_csr* A, const uint8_t* d_owned);
 int b2_csr_zero_rows_dev(b2_csr* A, const int32_t* d_rows, int64_t n, double diag, const uint8_t* d_owned);

@@ -273,10 +273,16 @@ int b2_csr_alloc(b2_ctx* c, int64_t nrows, int64_t ncols, int64_t nnz, b2_csr** 
   A->max_row = 0;
   A->last_ms = 0.;
   A->chunk_row = nullptr;
+  A->dict_ptr = nullptr;
+  A->cdesc = nullptr;
+  A->dict = nullptr;
+  A->lidx = nullptr;
   A->nchunks = 0;
+  A->dict_total = 0;
+  A->dict_cap = 0;
   B2_TRY(b2_malloc(c, &A->rowptr, (size_t)nrows + 3));
-  B2_TRY(b2_malloc(c, &A->col, (size_t)nnz + 4));
-  B2_TRY(b2_malloc(c, &A->val, (size_t)nnz + 4));
+  B2_TRY(b2_malloc(c, &A->col, (size_t)nnz + 16));
+  B2_TRY(b2_malloc(c, &A->val, (size_t)nnz + 16));
   *out = A;
   return 0;
 }
@@ -373,9 +379,9 @@ int b2_csr_destroy(b2_csr* A) {
   if (!A) return 0;
   cudaStreamSynchronize(A->ctx->stream);
   b2_free(A->ctx, A->rowptr, (size_t)A->nrows + 3);
-  if (A->chunk_row) b2_free(A->ctx, A->chunk_row, (size_t)A->nchunks + 1);
-  b2_free(A->ctx, A->col, (size_t)A->nnz + 4);
-  b2_free(A->ctx, A->val, (size_t)A->nnz + 4);
+  b2_csr_free_plan(A);
+  b2_free(A->ctx, A->col, (size_t)A->nnz + 16);
+  b2_free(A->ctx, A->val, (size_t)A->nnz + 16);
   delete A;
   return 0;
 }

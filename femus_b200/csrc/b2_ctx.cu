@@ -146,8 +146,12 @@ int b2_ctx_flush_l2(b2_ctx* c) {
 
 int b2_ctx_set_option(b2_ctx* c, const char* name, int value) {
   if (!strcmp(name, "spmv_variant")) {
-    B2_CHECK(value == 0 || value == 2 || value == 3 || value == 4 || value == 6, "spmv_variant %d (0, 2, 3, 4, 6)", value);
+    B2_CHECK(value >= 0 && value <= 2, "spmv_variant %d (0, 1, 2)", value);
     c->spmv_variant = value;
+    return 0;
+  }
+  if (!strcmp(name, "spmv_timing")) {
+    c->spmv_timing = value;
     return 0;
   }
   B2_CHECK(false, "b2_ctx_set_option: unknown option '%s'", name);

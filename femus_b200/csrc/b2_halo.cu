@@ -60,7 +60,7 @@ int b2_halo_create(b2_ctx* c, int64_t n_local, int64_t n_if, const int32_t* loca
   B2_TRY(b2_malloc(c, &h->send, (size_t)n_packed));
   B2_TRY(b2_malloc(c, &h->recv, (size_t)n_packed));
   B2_TRY(b2_malloc(c, &h->owned, (size_t)n_local));
-  B2_TRY(b2_malloc(c, &h->invmult, (size_t)n_local));
+  B2_TRY(b2_malloc(c, &h->invmult, (size_t)n_local + 4));   // +4: the SpMV stages 16-byte aligned slices
   uint8_t* d_mult = nullptr;
   B2_TRY(b2_malloc(c, &d_mult, (size_t)n_local));
   B2_TRY(b2_upload(c, h->idx, local_idx, (size_t)n_if));
@@ -85,7 +85,7 @@ int b2_halo_destroy(b2_halo* h) {
   b2_free(c, h->send, (size_t)h->n_packed);
   b2_free(c, h->recv, (size_t)h->n_packed);
   b2_free(c, h->owned, (size_t)h->n_local);
-  b2_free(c, h->invmult, (size_t)h->n_local);
+  b2_free(c, h->invmult, (size_t)h->n_local + 4);
   delete h;
   return 0;
 }

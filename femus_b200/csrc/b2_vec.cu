@@ -169,15 +169,15 @@ int b2_vec_create(b2_ctx* c, int64_t n, b2_vec** out) {
   *out = nullptr;
   B2_CHECK(c && n >= 0, "b2_vec_create: bad arguments");
   b2_vec* v = new b2_vec{c, n, nullptr, nullptr};
-  B2_TRY(b2_malloc(c, &v->d, (size_t)n + 2));
-  B2_CUDA(cudaMemsetAsync(v->d, 0, ((size_t)n + 2) * sizeof(double), c->stream));
+  B2_TRY(b2_malloc(c, &v->d, (size_t)n + 4));
+  B2_CUDA(cudaMemsetAsync(v->d, 0, ((size_t)n + 4) * sizeof(double), c->stream));
   *out = v;
   return 0;
 }
 int b2_vec_destroy(b2_vec* v) {
   if (!v) return 0;
   cudaStreamSynchronize(v->ctx->stream);
-  b2_free(v->ctx, v->d, (size_t)v->n + 2);
+  b2_free(v->ctx, v->d, (size_t)v->n + 4);
   delete v;
   return 0;
 }

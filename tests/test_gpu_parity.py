@@ -116,6 +116,55 @@ def test_spmv_family(ctx, m, n, density):
     assert np.all(np.abs(YT.get() - A.T @ xt) <= 1e-13 * (np.abs(A.T) @ np.abs(xt) + 1e-300))
 
 
+@pytest.mark.parametrize("variant", [0, 1, 2])
+@pytest.mark.parametrize("kind", ["fe_like", "long_rows", "mostly_empty", "short_rows"])
+def test_spmv_kernels_and_edge_shapes(ctx, variant, kind):
+    """Every SpMV kernel (register-streaming, TMA-staged, staged + pipelined gathers) on shapes that
+    stress the row chunking: FE-like banded rows, rows too long to stage (streaming fallback), long
+    runs of empty rows, very short rows; all epilogues including r aliased with b (MGSolve does it)."""
+    rng = np.random.default_rng(11)
+    if kind == "fe_like":
+        m = n = 6000
+        offs = sorted(set(int(o) for o in rng.integers(-300, 300, 60)))
+        A = sp.dia_matrix((rng.standard_normal((len(offs), n)), offs), shape=(m, n)).tocsr()
+    elif kind == "long_rows":
+        m, n = 40, 5000
+        A = random_csr(rng, m, n, 0.5)                      # ~2500 entries per row
+    elif kind == "mostly_empty":
+        m, n = 5000, 300
+        A = sp.lil_matrix((m, n))
+        for r in (0, 7, 2500, 2501, 4999):
+            A[r, rng.integers(0, n, 40)] = rng.standard_normal(40)
+        A = A.tocsr()
+    else:
+        m, n = 20000, 9000
+        A = random_csr(rng, m, n, 3.0 / n)
+    A = A.tocsr()
+    A.sort_indices()
+    ctx.set_option("spmv_variant", variant)
+    try:
+        dA = ctx.csr_from_scipy(A)
+        x, b, dinv = rng.standard_normal(n), rng.standard_normal(m), rng.random(m) + 0.5
+        X, Bv, Y = ctx.vector(x), ctx.vector(b), ctx.vector(m)
+        scale = np.abs(A) @ np.abs(x) + np.abs(b) + 1e-300
+        dA.spmv(X, Y)
+        assert np.all(np.abs(Y.get() - A @ x) <= 1e-14 * scale)
+        Y.put(b)
+        dA.spmv_add(X, Y)
+        assert np.all(np.abs(Y.get() - (b + A @ x)) <= 1e-14 * scale)
+        dA.resid(Bv, X, Y)
+        assert np.all(np.abs(Y.get() - (b - A @ x)) <= 1e-14 * scale)
+        R = ctx.vector(b)
+        dA.resid(R, X, R)                                   # r aliased with b
+        assert np.all(np.abs(R.get() - (b - A @ x)) <= 1e-14 * scale)
+        if m == n:
+            D = ctx.vector(dinv)
+            dA.jacobi_sweep(D, Bv, X, Y, 0.5)
+            assert np.all(np.abs(Y.get() - (x + 0.5 * dinv * (b - A @ x))) <= 1e-14 * (scale + np.abs(x)))
+    finally:
+        ctx.set_option("spmv_variant", 1)
+
+
 def test_transpose_zero_rows_cols_diag(ctx):
     rng = np.random.default_rng(5)
     A = random_csr(rng, 700, 500, 0.03)

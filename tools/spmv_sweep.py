@@ -25,7 +25,7 @@ ref = {}
 ctx.set_option("spmv_variant", 0)
 for name, (f, _) in ops.items():
     f(yref); ref[name] = yref.get()
-for var in (0, 2, 3, 4, 6):
+for var in (0, 1, 2):
     ctx.set_option("spmv_variant", var)
     for name, (f, nbytes) in ops.items():
         f(y)
@@ -35,11 +35,14 @@ for var in (0, 2, 3, 4, 6):
             ctx.timer_start(); f(y); ts.append(ctx.timer_stop_ms())
         t = float(np.median(ts))
         print(f"variant {var} {name:8s} {t:7.3f} ms  {nbytes / t / 1e6:7.1f} GB/s  relerr {err:.2e}", flush=True)
+if os.environ.get('SPMV_TIMING'):
+    for var in (1, 2):
+        ctx.set_option('spmv_variant', var); ctx.set_option('spmv_timing', 1); A.spmv(x, y); ctx.set_option('spmv_timing', 0)
 # P / R
 if nl > 1:
     P = pb.PP[-1]; R = P.transpose()
     xc = ctx.vector(rng.standard_normal(P.shape[1])); yf = ctx.vector(P.shape[0]); yc = ctx.vector(P.shape[1])
-    for var in (0, 3):
+    for var in (0, 1):
         ctx.set_option("spmv_variant", var)
         for name, f, M in (("P", lambda: P.spmv(xc, yf), P), ("R", lambda: R.spmv(yf, yc), R)):
             ts = []
@@ -50,7 +53,7 @@ if nl > 1:
             print(f"variant {var} {name} spmv {t:7.3f} ms {nb / t / 1e6:7.1f} GB/s  sum {yf.sum() if name=='P' else yc.sum():.12e}", flush=True)
 for l in range(nl - 1):
     Al = pb.KK[l]; xx = ctx.vector(rng.standard_normal(Al.shape[0])); yy = ctx.vector(Al.shape[0])
-    for var in (0, 3):
+    for var in (0, 1):
         ctx.set_option("spmv_variant", var)
         ts = []
         for _ in range(8):
