@@ -96,6 +96,7 @@ _PROTOS = {
     "b2_asm_create": (ci, [vp, vp, ci, vp, ci, vp, vp, vp, vp, vp, vp]),
     "b2_asm_destroy": (ci, [vp]),
     "b2_asm_poisson": (ci, [vp, vp, vp, cd, cd]),
+    "b2_asm_poisson_galerkin": (ci, [vp, vp, vp, vp, cd, cd]),
     "b2_asm_last_kernel_ms": (cd, [vp]),
     "b2_mg_create": (ci, [vp, ci, vp]),
     "b2_mg_set_level": (ci, [vp, ci, vp, vp, vp, i64, ci, ci, cd]),
@@ -552,6 +553,11 @@ class Assembler:
     def poisson(self, u=None, rhs=None, nu=1.0, fsrc=1.0):
         check(self.L.b2_asm_poisson(self.h, u.h if u is not None else None, rhs.h if rhs is not None else None,
                                     float(nu), float(fsrc)))
+
+    def poisson_galerkin(self, gal, u=None, rhs=None, nu=1.0, fsrc=1.0):
+        """Assembly fused with the Galerkin product of `gal` (Ac = P^T A P from the element matrices)."""
+        check(self.L.b2_asm_poisson_galerkin(self.h, gal.h, u.h if u is not None else None,
+                                             rhs.h if rhs is not None else None, float(nu), float(fsrc)))
 
 
 class Multigrid:

@@ -35,7 +35,23 @@ struct b2_asm {
   int slot_bytes;  // 1 or 2
   size_t slot_count;
   double last_ms;
+  // fused Galerkin plan (b2_asm_poisson_galerkin): per-child element prolongators of the plan `gal`
+  const b2_galerkin* gal;
+  void* gal_tab;          // device: GalTables<nve>
 };
+
+// what the fused kernel needs from a Galerkin plan (b2_galerkin.cu)
+struct b2_galerkin_view {
+  b2_csr *Af, *Ac;
+  int64_t nelc;
+  int nf, nc;
+  const int32_t *fd, *cd;
+  const double* ploc;
+  const uint8_t *fmask, *cmask;
+  const void* slot;
+  int slot_bytes;
+};
+int b2_galerkin_get_view(const b2_galerkin* g, b2_galerkin_view* v);
 
 namespace {
 
@@ -47,20 +63,49 @@ template <int NVE> struct Tile;
 template <> struct Tile<27> { static constexpr int TI = 7, TJ = 4; };   // 4 x 7 lane grid, 28 lanes busy
 template <> struct Tile<8> { static constexpr int TI = 2, TJ = 1; };    // 4 x 8 lane grid
 
+// Element prolongator of each of the 8 children of a refined hexahedron, restricted to the child's
+// own NVE nodes: Pc[j][n][J] = ploc[lattice(j, n)][J].  Stored twice, by rows (fine node n -> coarse
+// J) and by columns, as compressed lists; exact zeros dropped (Q2: 125 entries per child).
+template <int NVE>
+struct GalTables {
+  static constexpr int MAXNNZ = NVE == 27 ? 128 : 64;
+  int rowptr[8][NVE + 1];
+  int colptr[8][NVE + 1];
+  unsigned char rcol[8][MAXNNZ];   // by rows: coarse index J
+  unsigned char crow[8][MAXNNZ];   // by columns: fine node n
+  double rval[8][MAXNNZ];
+  double cval[8][MAXNNZ];
+};
+
+struct GalArgs {
+  const void* tab;            // GalTables<NVE> (device)
+  const int32_t* cd;          // [nelc][NVE] coarse dofs
+  const void* cslot;          // [nelc][NVE*NVE] slot of (I,J) inside row cd_I of the coarse matrix
+  const uint8_t* fmask;       // fine Dirichlet rows of P (may be null)
+  const uint8_t* cmask;       // coarse Dirichlet columns of P (may be null)
+  const int64_t* Cp;          // coarse rowptr
+  double* Cv;                 // coarse values
+};
+
 template <int NVE>
 struct SmemLayout {
   static constexpr int tab_doubles = 4 * NG * NVE + NG;
   // per warp: X[3][GP], U[GP], geo[10][NG], G[2][3][GP]
   static constexpr int warp_doubles = 3 * GP + GP + 10 * NG + 2 * 3 * GP;
   static constexpr size_t bytes = (size_t)(tab_doubles + kWarps * warp_doubles) * sizeof(double);
+  static constexpr size_t bytes_gal = bytes + sizeof(GalTables<NVE>);
+  // the per-warp geometry + gradient buffers (10*NG + 6*GP doubles) are reused for the element matrix
+  static_assert(10 * NG + 2 * 3 * GP >= NVE * NVE, "element matrix does not fit the reused buffers");
 };
 
-template <int NVE, typename SlotT>
+// GAL: additionally forms the Galerkin coarse operator C = P^T A P of the next-coarser level from
+// the element matrices while they are still on chip (see the header of this file).
+template <int NVE, typename SlotT, bool GAL, typename CSlotT>
 __global__ void __launch_bounds__(kWarps * 32, 1)
 assemble_poisson_kernel(int64_t nel, int64_t nnode, const double* __restrict__ xyz, const int32_t* __restrict__ conn,
                         const int32_t* __restrict__ dof, const double* __restrict__ tab,
                         const SlotT* __restrict__ slot, const int64_t* __restrict__ rowptr, double* __restrict__ Aval,
-                        const double* __restrict__ u, double* __restrict__ rhs, double nu, double fsrc) {
+                        const double* __restrict__ u, double* __restrict__ rhs, double nu, double fsrc, const GalArgs ga) {
   constexpr int TI = Tile<NVE>::TI, TJ = Tile<NVE>::TJ;
   extern __shared__ double smem[];
   double* s_phi = smem;
@@ -77,11 +122,21 @@ assemble_poisson_kernel(int64_t nel, int64_t nnode, const double* __restrict__ x
 
   for (int t = threadIdx.x; t < SmemLayout<NVE>::tab_doubles; t += blockDim.x) smem[t] = tab[t];
   for (int t = lane; t < 2 * 3 * GP; t += 32) sG[t] = 0.0;     // padding nodes stay zero forever
+  const GalTables<NVE>* gt = nullptr;
+  if (GAL) {
+    int* dst = reinterpret_cast<int*>(smem + SmemLayout<NVE>::tab_doubles + kWarps * SmemLayout<NVE>::warp_doubles);
+    const int* src = reinterpret_cast<const int*>(ga.tab);
+    for (int t = threadIdx.x; t < (int)(sizeof(GalTables<NVE>) / 4); t += blockDim.x) dst[t] = src[t];
+    gt = reinterpret_cast<const GalTables<NVE>*>(dst);
+  }
   __syncthreads();
 
   const int rg = lane & 3, cg = lane >> 2;                      // row group / column group of the tile
   const int i0 = rg * TI, j0 = cg * TJ;
 
+  // In one trip the 8 warps of a group hold the 8 children of ONE coarse element (kWarps
+  // consecutive elements per CTA and trip; GAL requires nel to be a multiple of 8, so a group is
+  // either complete or absent and its named barrier below is always reached by all 8 warps).
   for (int64_t e = (int64_t)blockIdx.x * kWarps + wib; e < nel; e += (int64_t)gridDim.x * kWarps) {
     // ---- gather: node ids (coalesced), coordinates, dofs, current solution
     int mydof = 0;
@@ -201,6 +256,102 @@ assemble_poisson_kernel(int64_t nel, int64_t nnode, const double* __restrict__ x
       }
     }
     __syncwarp();
+
+    if (GAL) {
+      // ---- D = Pc^T (nu B) Pc for this child; the element matrix goes to shared memory (geometry
+      //      and gradient buffers are dead now), rows/columns of Dirichlet fine dofs dropped
+      double* Bs = sGeo;                       // [NVE][NVE]
+      const int child = (int)(e & 7);
+      const int fm = (lane < NVE && ga.fmask) ? (int)ga.fmask[mydof] : 0;
+#pragma unroll
+      for (int a = 0; a < TI; a++) {
+        const int i = i0 + a;
+        const int fi = __shfl_sync(0xffffffffu, fm, i < NVE ? i : 0);
+#pragma unroll
+        for (int b = 0; b < TJ; b++) {
+          const int j = j0 + b;
+          const int fj = __shfl_sync(0xffffffffu, fm, j < NVE ? j : 0);
+          if (i < NVE && j < NVE) Bs[i * NVE + j] = (fi | fj) ? 0.0 : nu * B[a][b];
+        }
+      }
+      __syncwarp();
+      // T = Bs Pc.  Lane J walks the compressed column J of Pc (<= 8 entries); for every entry
+      // (n, v) it updates its whole column T[0..NVE)[J] += Bs[.][n] v: NVE independent FMAs per
+      // step, registers with static indices.
+      double R[NVE];
+#pragma unroll
+      for (int i = 0; i < NVE; i++) R[i] = 0.0;
+      if (lane < NVE) {
+#pragma unroll 1
+        for (int q = gt->colptr[child][lane]; q < gt->colptr[child][lane + 1]; q++) {
+          const int n = gt->crow[child][q];
+          const double v = gt->cval[child][q];
+#pragma unroll
+          for (int i = 0; i < NVE; i++) R[i] = fma(Bs[i * NVE + n], v, R[i]);
+        }
+      }
+      __syncwarp();
+      if (lane < NVE) {
+#pragma unroll
+        for (int i = 0; i < NVE; i++) Bs[i * NVE + lane] = R[i];      // Bs now holds T
+      }
+      __syncwarp();
+      // D = Pc^T T.  Lane I walks the compressed column I of Pc; for every entry (i, v) it updates
+      // its whole row D[I][0..NVE) += v T[i][.]
+#pragma unroll
+      for (int j = 0; j < NVE; j++) R[j] = 0.0;
+      if (lane < NVE) {
+#pragma unroll 1
+        for (int q = gt->colptr[child][lane]; q < gt->colptr[child][lane + 1]; q++) {
+          const int i = gt->crow[child][q];
+          const double v = gt->cval[child][q];
+#pragma unroll
+          for (int j = 0; j < NVE; j++) R[j] = fma(v, Bs[i * NVE + j], R[j]);
+        }
+      }
+      __syncwarp();
+      if (lane < NVE) {
+#pragma unroll
+        for (int j = 0; j < NVE; j++) Bs[lane * NVE + j] = R[j];      // Bs now holds D
+      }
+      // ---- the 8 children of a coarse element sit in the 8 warps of a group: sum their D and
+      //      scatter once per coarse element (one atomic per entry instead of eight).  Named
+      //      barrier per group: the other group keeps running.
+      const int grp = wib >> 3;
+      asm volatile("bar.sync %0, 256;" ::"r"(grp + 1) : "memory");
+      {
+        const int64_t E = e >> 3;
+        const CSlotT* cslot = reinterpret_cast<const CSlotT*>(ga.cslot) + (size_t)E * (NVE * NVE);
+        const double* D0 = s_w + NG + (size_t)(8 * grp) * SmemLayout<NVE>::warp_doubles + (3 * GP + GP);
+        for (int idx = threadIdx.x & 255; idx < NVE * NVE; idx += 256) {
+          double v = 0.0;
+#pragma unroll
+          for (int w = 0; w < 8; w++) v += D0[(size_t)w * SmemLayout<NVE>::warp_doubles + idx];
+          if (v == 0.0) continue;
+          const int I = idx / NVE, J = idx - I * NVE;
+          const int32_t dI = ga.cd[E * NVE + I];
+          if (ga.cmask) {
+            const int32_t dJ = ga.cd[E * NVE + J];
+            if (ga.cmask[dI] || ga.cmask[dJ]) continue;
+          }
+          atomicAdd(&ga.Cv[ga.Cp[dI] + (int64_t)cslot[idx]], v);
+        }
+      }
+      asm volatile("bar.sync %0, 256;" ::"r"(grp + 1) : "memory");
+    }
+  }
+}
+
+// host-side check of the fused plan: fine element 8E+j must be child j of coarse element E with its
+// local node n at lattice point lat[j][n] of E
+__global__ void gal_check_kernel(int64_t nelc, int nve, int nf, const int32_t* __restrict__ dof,
+                                 const int32_t* __restrict__ fd, const unsigned char* __restrict__ lat, int* err) {
+  const int64_t total = nelc * 8 * nve;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+    const int64_t E = t / (8 * nve);
+    const int jn = (int)(t - E * 8 * nve);
+    if (dof[(E * 8) * nve + jn] != fd[E * nf + lat[jn]]) atomicExch(err, 1);
   }
 }
 
@@ -259,13 +410,106 @@ template <int NVE, typename SlotT>
 int launch_assemble(b2_asm* p, const b2_vec* u, b2_vec* rhs, double nu, double fsrc) {
   b2_ctx* c = p->mesh->ctx;
   b2_prof_scope prof(c, p);
-  auto kern = assemble_poisson_kernel<NVE, SlotT>;
+  auto kern = assemble_poisson_kernel<NVE, SlotT, false, uint8_t>;
   const size_t smem = SmemLayout<NVE>::bytes;
   B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int grid = (int)((p->mesh->nel + kWarps - 1) / kWarps);
   if (grid > c->sm_count) grid = c->sm_count;
+  GalArgs ga = {};
   B2_LAUNCH(c, kern, grid, kWarps * 32, smem, p->mesh->nel, p->mesh->nnode, p->mesh->xyz, p->mesh->conn, p->dof,
-            p->tab, (const SlotT*)p->slot, p->A->rowptr, p->A->val, u ? u->d : nullptr, rhs ? rhs->d : nullptr, nu, fsrc);
+            p->tab, (const SlotT*)p->slot, p->A->rowptr, p->A->val, u ? u->d : nullptr, rhs ? rhs->d : nullptr, nu, fsrc, ga);
+  return 0;
+}
+
+template <int NVE, typename SlotT, typename CSlotT>
+int launch_assemble_gal(b2_asm* p, const b2_galerkin_view& g, const b2_vec* u, b2_vec* rhs, double nu, double fsrc) {
+  b2_ctx* c = p->mesh->ctx;
+  b2_prof_scope prof(c, p);
+  auto kern = assemble_poisson_kernel<NVE, SlotT, true, CSlotT>;
+  const size_t smem = SmemLayout<NVE>::bytes_gal;
+  B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int grid = (int)((p->mesh->nel + kWarps - 1) / kWarps);
+  if (grid > c->sm_count) grid = c->sm_count;
+  GalArgs ga = {p->gal_tab, g.cd, g.slot, g.fmask, g.cmask, g.Ac->rowptr, g.Ac->val};
+  B2_LAUNCH(c, kern, grid, kWarps * 32, smem, p->mesh->nel, p->mesh->nnode, p->mesh->xyz, p->mesh->conn, p->dof,
+            p->tab, (const SlotT*)p->slot, p->A->rowptr, p->A->val, u ? u->d : nullptr, rhs ? rhs->d : nullptr, nu, fsrc, ga);
+  return 0;
+}
+
+// Per-child prolongator tables of a Galerkin plan and the check that the fine elements are the
+// children of the plan's coarse elements in the reference's order (children 8*iel + j,
+// MeshRefinement.cpp:188-507; local nodes through fine2CoarseVertexMapping, Hexahedron.cpp:75-83).
+template <int NVE>
+int build_gal_tables(b2_asm* p, const b2_galerkin* gal, const b2_galerkin_view& g) {
+  b2_ctx* c = p->mesh->ctx;
+  const int nf = g.nf, nc = g.nc;
+  B2_CHECK(nc == NVE && p->nve == NVE, "fused Galerkin: coarse and fine unknowns must be of the same family");
+  B2_CHECK(p->mesh->nel == 8 * g.nelc, "fused Galerkin: %lld fine elements are not 8 x %lld coarse elements",
+           (long long)p->mesh->nel, (long long)g.nelc);
+  B2_CHECK(g.Af == p->A, "fused Galerkin: the plan's fine matrix is not the assembled matrix");
+  std::vector<int32_t> hdof(8 * NVE), hfd(nf);
+  std::vector<double> hp((size_t)nf * nc);
+  B2_TRY(b2_download(c, hdof.data(), p->dof, (size_t)8 * NVE));
+  B2_TRY(b2_download(c, hfd.data(), g.fd, (size_t)nf));
+  B2_TRY(b2_download(c, hp.data(), g.ploc, (size_t)nf * nc));
+  std::vector<unsigned char> lat(8 * NVE);
+  for (int jn = 0; jn < 8 * NVE; jn++) {
+    int a = -1;
+    for (int t = 0; t < nf; t++)
+      if (hfd[t] == hdof[jn]) { a = t; break; }
+    B2_CHECK(a >= 0, "fused Galerkin: fine element %d is not a child of coarse element 0", jn / NVE);
+    lat[jn] = (unsigned char)a;
+  }
+  unsigned char* d_lat = nullptr;
+  int* d_err = nullptr;
+  B2_TRY(b2_malloc(c, &d_lat, lat.size()));
+  B2_TRY(b2_malloc(c, &d_err, 1));
+  B2_TRY(b2_upload(c, d_lat, lat.data(), lat.size()));
+  B2_CUDA(cudaMemsetAsync(d_err, 0, sizeof(int), c->stream));
+  B2_LAUNCH(c, gal_check_kernel, b2_grid_for(c, g.nelc * 8 * NVE, 256, 8), 256, 0, g.nelc, NVE, nf, p->dof, g.fd, d_lat, d_err);
+  int err = 0;
+  B2_TRY(b2_download(c, &err, d_err, 1));
+  b2_free(c, d_lat, lat.size());
+  b2_free(c, d_err, 1);
+  B2_CHECK(err == 0, "fused Galerkin: the fine elements are not ordered as children 8*E+j of the coarse elements");
+  auto* T = new GalTables<NVE>();
+  memset(T, 0, sizeof(*T));
+  for (int j = 0; j < 8; j++) {
+    int q = 0;
+    for (int n = 0; n < NVE; n++) {
+      T->rowptr[j][n] = q;
+      for (int J = 0; J < NVE; J++) {
+        const double v = hp[(size_t)lat[j * NVE + n] * nc + J];
+        if (v != 0.0) {
+          if (q >= GalTables<NVE>::MAXNNZ) { delete T; B2_CHECK(false, "fused Galerkin: child prolongator too dense"); }
+          T->rcol[j][q] = (unsigned char)J;
+          T->rval[j][q] = v;
+          q++;
+        }
+      }
+    }
+    T->rowptr[j][NVE] = q;
+    q = 0;
+    for (int J = 0; J < NVE; J++) {
+      T->colptr[j][J] = q;
+      for (int n = 0; n < NVE; n++) {
+        const double v = hp[(size_t)lat[j * NVE + n] * nc + J];
+        if (v != 0.0) {
+          T->crow[j][q] = (unsigned char)n;
+          T->cval[j][q] = v;
+          q++;
+        }
+      }
+    }
+    T->colptr[j][NVE] = q;
+  }
+  GalTables<NVE>* d_T = nullptr;
+  int s = b2_malloc(c, &d_T, 1);
+  if (!s) s = b2_upload(c, d_T, T, 1);
+  delete T;
+  B2_TRY(s);
+  p->gal = gal;
+  p->gal_tab = d_T;
   return 0;
 }
 
@@ -313,6 +557,8 @@ int b2_asm_create(b2_mesh* m, b2_csr* A, int nve, const int32_t* dof, int ngauss
   p->nve = nve;
   p->ngauss = ngauss;
   p->last_ms = 0.;
+  p->gal = nullptr;
+  p->gal_tab = nullptr;
   B2_TRY(b2_malloc(c, &p->dof, (size_t)m->nel * nve));
   B2_TRY(b2_upload(c, p->dof, dof, (size_t)m->nel * nve));
   const size_t tn = (size_t)ngauss * nve;
@@ -342,6 +588,10 @@ int b2_asm_destroy(b2_asm* p) {
   b2_free(c, p->tab, (size_t)4 * p->ngauss * p->nve + p->ngauss);
   if (p->slot_bytes == 1) b2_free(c, (uint8_t*)p->slot, p->slot_count);
   else b2_free(c, (uint16_t*)p->slot, p->slot_count);
+  if (p->gal_tab) {
+    if (p->nve == 27) b2_free(c, (GalTables<27>*)p->gal_tab, 1);
+    else b2_free(c, (GalTables<8>*)p->gal_tab, 1);
+  }
   delete p;
   return 0;
 }
@@ -355,6 +605,36 @@ int b2_asm_poisson(b2_asm* p, const b2_vec* u, b2_vec* rhs, double nu, double fs
   }
   if (p->slot_bytes == 1) return launch_assemble<8, uint8_t>(p, u, rhs, nu, fsrc);
   return launch_assemble<8, uint16_t>(p, u, rhs, nu, fsrc);
+}
+int b2_asm_poisson_galerkin(b2_asm* p, b2_galerkin* gal, const b2_vec* u, b2_vec* rhs, double nu, double fsrc) {
+  B2_CHECK(p && gal, "b2_asm_poisson_galerkin: null argument");
+  B2_CHECK(!u || u->n >= p->A->nrows, "b2_asm_poisson_galerkin: solution vector too short");
+  B2_CHECK(!rhs || rhs->n >= p->A->nrows, "b2_asm_poisson_galerkin: rhs vector too short");
+  b2_ctx* c = p->mesh->ctx;
+  b2_galerkin_view g;
+  B2_TRY(b2_galerkin_get_view(gal, &g));
+  if (p->gal != gal) {
+    if (p->gal_tab) {
+      if (p->nve == 27) b2_free(c, (GalTables<27>*)p->gal_tab, 1);
+      else b2_free(c, (GalTables<8>*)p->gal_tab, 1);
+      p->gal_tab = nullptr;
+      p->gal = nullptr;
+    }
+    if (p->nve == 27) B2_TRY(build_gal_tables<27>(p, gal, g));
+    else B2_TRY(build_gal_tables<8>(p, gal, g));
+  }
+  B2_CUDA(cudaMemsetAsync(g.Ac->val, 0, (size_t)g.Ac->nnz * sizeof(double), c->stream));
+  const bool s1 = p->slot_bytes == 1, c1 = g.slot_bytes == 1;
+  if (p->nve == 27) {
+    if (s1 && c1) return launch_assemble_gal<27, uint8_t, uint8_t>(p, g, u, rhs, nu, fsrc);
+    if (s1) return launch_assemble_gal<27, uint8_t, uint16_t>(p, g, u, rhs, nu, fsrc);
+    if (c1) return launch_assemble_gal<27, uint16_t, uint8_t>(p, g, u, rhs, nu, fsrc);
+    return launch_assemble_gal<27, uint16_t, uint16_t>(p, g, u, rhs, nu, fsrc);
+  }
+  if (s1 && c1) return launch_assemble_gal<8, uint8_t, uint8_t>(p, g, u, rhs, nu, fsrc);
+  if (s1) return launch_assemble_gal<8, uint8_t, uint16_t>(p, g, u, rhs, nu, fsrc);
+  if (c1) return launch_assemble_gal<8, uint16_t, uint8_t>(p, g, u, rhs, nu, fsrc);
+  return launch_assemble_gal<8, uint16_t, uint16_t>(p, g, u, rhs, nu, fsrc);
 }
 double b2_asm_last_kernel_ms(const b2_asm* p) { return p->last_ms; }
 

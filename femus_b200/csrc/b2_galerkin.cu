@@ -312,6 +312,23 @@ int launch_galerkin(b2_galerkin* g) {
 
 }  // namespace
 
+// read-only view of a plan for the fused assembly kernel (b2_assemble.cu)
+struct b2_galerkin_view {
+  b2_csr *Af, *Ac;
+  int64_t nelc;
+  int nf, nc;
+  const int32_t *fd, *cd;
+  const double* ploc;
+  const uint8_t *fmask, *cmask;
+  const void* slot;
+  int slot_bytes;
+};
+int b2_galerkin_get_view(const b2_galerkin* g, b2_galerkin_view* v) {
+  B2_CHECK(g && v, "b2_galerkin_get_view: null argument");
+  *v = b2_galerkin_view{g->Af, g->Ac, g->nelc, g->nf, g->nc, g->fd, g->cd, g->ploc, g->fmask, g->cmask, g->slot, g->slot_bytes};
+  return 0;
+}
+
 extern "C" {
 
 int b2_galerkin_create(b2_csr* Af, b2_csr* Ac, int64_t nelc, int nf, int nc, const int32_t* fine_dofs,

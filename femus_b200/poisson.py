@@ -23,13 +23,15 @@ class PoissonMG:
     already hold the NCCL communicator (Context.comm_init)."""
 
     def __init__(self, ctx, nx, ny, nz, nlevels, order="biquadratic", bounds=None, npre=1, npost=1, omega=0.5,
-                 dirichlet_faces=(1, 2, 3, 4, 5, 6), fsrc=1.0, coarse_rtol=1e-14, hier=None, dist=None):
+                 dirichlet_faces=(1, 2, 3, 4, 5, 6), fsrc=1.0, coarse_rtol=1e-14, hier=None, dist=None, fused=True):
         self.ctx = ctx
         self.order = order
         self.fam = hostapi.FAMILY[order]
         self.nlevels = nlevels
         self.npre, self.npost, self.omega, self.fsrc = npre, npost, omega, fsrc
         self.dist = dist
+        # fused: the finest Galerkin product is formed inside the assembly kernel (b2_asm_poisson_galerkin)
+        self.fused = fused and nlevels > 1
         if hier is not None:
             self.hier = hier
         elif dist is None:
@@ -94,14 +96,20 @@ class PoissonMG:
         """SetResZero + the assembly callback (KK->zero(); element loop; close())."""
         self.RES.zero()
         self.KK[-1].zero()
-        self.asm.poisson(self.SOL, self.RES, 1.0, self.fsrc)
+        if self.fused:
+            self.asm.poisson_galerkin(self.gal[-1], self.SOL, self.RES, 1.0, self.fsrc)
+        else:
+            self.asm.poisson(self.SOL, self.RES, 1.0, self.fsrc)
         if self.halo[-1] is not None:          # close(): contributions of the other ranks' elements
             self.halo[-1].sum(self.RES)
 
     def galerkin(self, algebraic=False):
         """A_{l-1} = P_l^T A_l P_l down the hierarchy, on the un-penalised matrices: element-gather
         plans by default, the general sparse triple product (b2_csr_ptap) on request."""
-        for l in range(self.nlevels - 1, 0, -1):
+        top = self.nlevels - 1
+        for l in range(top, 0, -1):
+            if l == top and self.fused and not algebraic:
+                continue            # already formed by the fused assembly
             if algebraic:
                 self.KK[l - 1].ptap(self.PP[l], self.KK[l])
             else:

@@ -201,6 +201,14 @@ int b2_asm_destroy(b2_asm* p);
  * F_i = int (fsrc phi_i - nu grad phi_i . grad u).  A and rhs are NOT zeroed here (the app calls
  * myKK->zero() / SetResZero() first, main.cpp:346, LinearImplicitSystem.cpp:322). */
 int b2_asm_poisson(b2_asm* p, const b2_vec* u, b2_vec* rhs, double nu, double fsrc);
+/* Fused fast path of "assemble, then matrix_PtAP" (LinearImplicitSystem.cpp:326 + 347-370): the same
+ * assembly, and in the same pass gal's coarse matrix Ac = P^T A P is formed from the element matrices
+ * while they are on chip, C = sum_e Pc(e)^T B_e Pc(e) with Pc(e) the element prolongator of the child
+ * (ElemType.cpp:439-532) with Dirichlet rows/columns dropped as in ZeroInterpolatorDirichletNodes --
+ * equal to b2_galerkin_apply(gal) after b2_asm_poisson up to summation order, without re-reading
+ * the fine matrix.  gal must have been created on this plan's matrix; Ac is overwritten, A is not zeroed.
+ * Fails (no fallback) if the fine elements are not the children 8*E+j of gal's coarse elements. */
+int b2_asm_poisson_galerkin(b2_asm* p, b2_galerkin* gal, const b2_vec* u, b2_vec* rhs, double nu, double fsrc);
 double b2_asm_last_kernel_ms(const b2_asm* p);
 
 /* ---- geometric multigrid: replaces LinearEquationSolverPetsc::{MGInit,MGSetLevel,MGSolve,MGClear}

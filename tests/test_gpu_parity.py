@@ -165,6 +165,40 @@ def test_spmv_kernels_and_edge_shapes(ctx, variant, kind):
         ctx.set_option("spmv_variant", 1)
 
 
+@pytest.mark.parametrize("order,shape,nl", [("biquadratic", (2, 2, 2), 2), ("biquadratic", (3, 2, 4), 3), ("linear", (2, 3, 2), 3)])
+def test_fused_assembly_galerkin_matches_separate(ctx, order, shape, nl):
+    """b2_asm_poisson_galerkin: same fine matrix and residual as b2_asm_poisson, and its coarse matrix
+    equals both the element-gather product and the oracle's scipy P^T A P (Dirichlet rows/columns of
+    P zeroed), on a deformed mesh with a non-zero solution."""
+    from femus_b200.poisson import PoissonMG
+    from oracle import mesh_box as mb, mg
+    pf = PoissonMG(ctx, *shape, nl, order, fused=True)
+    ps = PoissonMG(ctx, *shape, nl, order, fused=False)
+    rng = np.random.default_rng(3)
+    sol = rng.standard_normal(pf.n)
+    for pb in (pf, ps):
+        pb.SOL.put(sol)
+        pb.assemble()
+        pb.galerkin()
+    Af, As = pf.KK[-1].to_scipy(), ps.KK[-1].to_scipy()
+    # (fp64 atomics: the order of the element contributions differs from run to run)
+    assert np.array_equal(Af.indices, As.indices)
+    assert np.abs(Af.data - As.data).max() <= 1e-14 * np.abs(As.data).max()
+    assert np.abs(pf.RES.get() - ps.RES.get()).max() <= 1e-13 * np.abs(ps.RES.get()).max()
+    for l in range(nl - 1):
+        Cf, Cs = pf.KK[l].to_scipy(), ps.KK[l].to_scipy()
+        assert np.array_equal(Cf.indices, Cs.indices)
+        assert np.abs(Cf.data - Cs.data).max() <= 1e-13 * np.abs(Cs.data).max()
+    # oracle: P^T A P with scipy on the oracle's own hierarchy
+    lv = mb.build_hierarchy(*shape, nl)
+    H = mg.Hierarchy(lv, order, A_top=As, rhs=np.zeros(pf.n), coarse_lu=False)
+    for l in range(nl - 1):
+        C, Co = pf.KK[l].to_scipy(), H.A_raw[l]
+        assert np.array_equal(C.indptr, Co.indptr) and np.array_equal(C.indices, Co.indices)
+        assert np.abs(C.data - Co.data).max() <= 1e-12 * np.abs(Co.data).max()
+    del pf, ps
+
+
 def test_transpose_zero_rows_cols_diag(ctx):
     rng = np.random.default_rng(5)
     A = random_csr(rng, 700, 500, 0.03)
