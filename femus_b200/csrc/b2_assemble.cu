@@ -31,9 +31,10 @@ struct b2_asm {
   int nve, ngauss;
   int32_t* dof;    // [nel][nve]
   double* tab;     // phi, dxi, deta, dzeta [ng][nve] each, then w[ng]
-  void* slot;      // [nel][TI*TJ][32] uint8 or uint16: position of (i,j) inside row dof_i
+  void* slot;      // [nel][TI*TJ][32] uint8 or uint16: position of (i,j) inside row dof_i (tile kernel)
+  void* nslot;     // [nel][nve*nve] the same in natural (i,j) order (tensor-core kernel, nve = 27)
   int slot_bytes;  // 1 or 2
-  size_t slot_count;
+  size_t slot_count, nslot_count;
   double last_ms;
   // fused Galerkin plan (b2_asm_poisson_galerkin): per-child element prolongators of the plan `gal`
   const b2_galerkin* gal;
@@ -342,6 +343,283 @@ assemble_poisson_kernel(int64_t nel, int64_t nnode, const double* __restrict__ x
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Triquadratic elements on the FP64 tensor cores.  B = sum_g w_g G_g G_g^T (G_g: 27 x 3 gradients at
+// Gauss point g) is a 27 x 27 x 192 GEMM per element; per Gauss point it is one k-step of
+// mma.sync.m8n8k4.f64 (K = 3 padded to 4) on the 4 x 4 grid of 8 x 8 output tiles, of which only the
+// 10 upper ones are formed (B is symmetric).  Against the CUDA-core tile kernel above this needs 8
+// shared-memory fragment loads per lane and Gauss point instead of 33 (that kernel is bound by
+// shared-memory wavefronts, ncu: l1tex data pipe 94 %, fp64 pipe 57 %).  The element matrix is then
+// written to shared memory once; residual, scatter and the fused Galerkin product read it from there,
+// so the scatter uses a slot map in natural (i, j) order.
+constexpr int MS = 36;            // column stride of the fragment buffers: conflict-free 8-byte fragment loads
+struct MmaSmem {
+  static constexpr int tab_doubles = 3 * NG * 27 + NG;                   // dxi, deta, dzeta, weights
+  // per warp: X[3][GP], U[GP], rowbase[GP] (int64), geo[10][NG], M[2][4][MS]
+  static constexpr int warp_doubles = 3 * GP + GP + GP + 10 * NG + 2 * 4 * MS;
+  static constexpr size_t bytes = (size_t)(tab_doubles + kWarps * warp_doubles) * sizeof(double);
+  static constexpr size_t bytes_gal = bytes + sizeof(GalTables<27>);
+  static_assert(10 * NG + 2 * 4 * MS >= 27 * 27, "element matrix does not fit the reused buffers");
+};
+
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+template <typename SlotT, bool GAL, typename CSlotT>
+__global__ void __launch_bounds__(kWarps * 32, 1)
+assemble_q2_mma_kernel(int64_t nel, int64_t nnode, const double* __restrict__ xyz, const int32_t* __restrict__ conn,
+                       const int32_t* __restrict__ dof, const double* __restrict__ tab, const SlotT* __restrict__ nslot,
+                       const int64_t* __restrict__ rowptr, double* __restrict__ Aval, const double* __restrict__ u,
+                       double* __restrict__ rhs, double nu, double fsrc, const GalArgs ga) {
+  constexpr int NVE = 27;
+  extern __shared__ double smem[];
+  double* s_dx = smem;
+  double* s_dy = s_dx + NG * NVE;
+  double* s_dz = s_dy + NG * NVE;
+  double* s_w = s_dz + NG * NVE;
+  const double* g_phi = tab;          // the shape-value table is only needed for the source term: read through L1
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  double* wbase = s_w + NG + wib * MmaSmem::warp_doubles;
+  double* sX = wbase;                                   // [3][GP]
+  double* sU = sX + 3 * GP;                             // [GP]
+  long long* sRow = reinterpret_cast<long long*>(sU + GP);   // [GP] rowptr[dof_i]
+  double* sGeo = reinterpret_cast<double*>(sRow + GP);  // [10][NG]: J^-1 (9, row-major), weight
+  double* sM = sGeo + 10 * NG;                          // [2][4][MS]: G and w*G, column-major (component, node)
+  double* Bs = sGeo;                                    // [27][27] element matrix, reuses geo + M
+
+  for (int t = threadIdx.x; t < MmaSmem::tab_doubles; t += blockDim.x) smem[t] = tab[NG * NVE + t];
+  const GalTables<NVE>* gt = nullptr;
+  if (GAL) {
+    int* dst = reinterpret_cast<int*>(smem + MmaSmem::tab_doubles + kWarps * MmaSmem::warp_doubles);
+    const int* src = reinterpret_cast<const int*>(ga.tab);
+    for (int t = threadIdx.x; t < (int)(sizeof(GalTables<NVE>) / 4); t += blockDim.x) dst[t] = src[t];
+    gt = reinterpret_cast<const GalTables<NVE>*>(dst);
+  }
+  __syncthreads();
+
+  // fragment coordinates of this lane: row l/4 of an 8-row tile, k-column l%4; outputs (l/4, 2(l%4)+{0,1})
+  const int fr = lane >> 2, fk = lane & 3;
+
+  for (int64_t e = (int64_t)blockIdx.x * kWarps + wib; e < nel; e += (int64_t)gridDim.x * kWarps) {
+    // ---- gather: node ids (coalesced), coordinates, dofs, current solution, row starts
+    int mydof = 0;
+    if (lane < NVE) {
+      const int64_t nd = conn[e * 27 + lane];
+      sX[0 * GP + lane] = xyz[nd];
+      sX[1 * GP + lane] = xyz[nnode + nd];
+      sX[2 * GP + lane] = xyz[2 * nnode + nd];
+      mydof = dof[e * NVE + lane];
+      sU[lane] = u ? u[mydof] : 0.0;
+      sRow[lane] = rowptr[mydof];
+    }
+    for (int t = lane; t < 2 * 4 * MS; t += 32) sM[t] = 0.0;      // padding rows 27..31 and the k = 3 column stay zero
+    __syncwarp();
+
+    // ---- A. geometry at the Gauss points owned by this lane
+#pragma unroll 1
+    for (int g = lane; g < NG; g += 32) {
+      double J00 = 0, J01 = 0, J02 = 0, J10 = 0, J11 = 0, J12 = 0, J20 = 0, J21 = 0, J22 = 0;
+      const double* dx = s_dx + g * NVE;
+      const double* dy = s_dy + g * NVE;
+      const double* dz = s_dz + g * NVE;
+#pragma unroll 9
+      for (int n = 0; n < NVE; n++) {
+        const double x0 = sX[n], x1 = sX[GP + n], x2 = sX[2 * GP + n];
+        const double a = dx[n], b = dy[n], c = dz[n];
+        J00 = fma(a, x0, J00); J01 = fma(a, x1, J01); J02 = fma(a, x2, J02);
+        J10 = fma(b, x0, J10); J11 = fma(b, x1, J11); J12 = fma(b, x2, J12);
+        J20 = fma(c, x0, J20); J21 = fma(c, x1, J21); J22 = fma(c, x2, J22);
+      }
+      const double det = J00 * (J11 * J22 - J12 * J21) + J01 * (J12 * J20 - J10 * J22) + J02 * (J10 * J21 - J11 * J20);
+      const double id = 1.0 / det;
+      sGeo[0 * NG + g] = (-J12 * J21 + J11 * J22) * id;
+      sGeo[1 * NG + g] = (J02 * J21 - J01 * J22) * id;
+      sGeo[2 * NG + g] = (-J02 * J11 + J01 * J12) * id;
+      sGeo[3 * NG + g] = (J12 * J20 - J10 * J22) * id;
+      sGeo[4 * NG + g] = (-J02 * J20 + J00 * J22) * id;
+      sGeo[5 * NG + g] = (J02 * J10 - J00 * J12) * id;
+      sGeo[6 * NG + g] = (-J11 * J20 + J10 * J21) * id;
+      sGeo[7 * NG + g] = (J01 * J20 - J00 * J21) * id;
+      sGeo[8 * NG + g] = (-J01 * J10 + J00 * J11) * id;
+      sGeo[9 * NG + g] = det * s_w[g];
+    }
+    __syncwarp();
+
+    // ---- B. stiffness on the tensor cores: 10 upper 8x8 tiles, 2 accumulators per lane and tile
+    double C[10][2];
+#pragma unroll
+    for (int t = 0; t < 10; t++) C[t][0] = C[t][1] = 0.0;
+    double src = 0.0;
+#pragma unroll 1
+    for (int g = 0; g < NG; g++) {
+      const double wg = sGeo[9 * NG + g];
+      if (lane < NVE) {
+        const double a = s_dx[g * NVE + lane], b = s_dy[g * NVE + lane], c = s_dz[g * NVE + lane];
+        const double g0 = fma(c, sGeo[2 * NG + g], fma(b, sGeo[1 * NG + g], a * sGeo[0 * NG + g]));
+        const double g1 = fma(c, sGeo[5 * NG + g], fma(b, sGeo[4 * NG + g], a * sGeo[3 * NG + g]));
+        const double g2 = fma(c, sGeo[8 * NG + g], fma(b, sGeo[7 * NG + g], a * sGeo[6 * NG + g]));
+        sM[0 * MS + lane] = g0;
+        sM[1 * MS + lane] = g1;
+        sM[2 * MS + lane] = g2;
+        sM[4 * MS + 0 * MS + lane] = g0 * wg;
+        sM[4 * MS + 1 * MS + lane] = g1 * wg;
+        sM[4 * MS + 2 * MS + lane] = g2 * wg;
+        if (rhs) src = fma(__ldg(g_phi + g * NVE + lane), wg, src);
+      }
+      __syncwarp();
+      double fa[4], fb[4];
+#pragma unroll
+      for (int T = 0; T < 4; T++) {
+        fa[T] = sM[fk * MS + 8 * T + fr];               // G[8T + l/4][l%4]
+        fb[T] = sM[4 * MS + fk * MS + 8 * T + fr];      // (w G)[8T + l/4][l%4]
+      }
+      int t = 0;
+#pragma unroll
+      for (int I = 0; I < 4; I++)
+#pragma unroll
+        for (int Jt = I; Jt < 4; Jt++) {
+          dmma(C[t][0], C[t][1], fa[I], fb[Jt]);
+          t++;
+        }
+      __syncwarp();
+    }
+
+    // ---- C. element matrix -> shared memory (both triangles), scaled by nu
+    {
+      int t = 0;
+#pragma unroll
+      for (int I = 0; I < 4; I++)
+#pragma unroll
+        for (int Jt = I; Jt < 4; Jt++) {
+          const int i = 8 * I + fr;
+#pragma unroll
+          for (int r = 0; r < 2; r++) {
+            const int j = 8 * Jt + 2 * fk + r;
+            if (i < NVE && j < NVE) {
+              const double v = nu * C[t][r];
+              Bs[i * NVE + j] = v;
+              if (I != Jt) Bs[j * NVE + i] = v;
+            }
+          }
+          t++;
+        }
+    }
+    __syncwarp();
+
+    // ---- residual F_i = fsrc * sum_g phi_i w_g - (B u)_i
+    if (rhs && lane < NVE) {
+      double s = 0.0;
+#pragma unroll 9
+      for (int j = 0; j < NVE; j++) s = fma(Bs[lane * NVE + j], sU[j], s);
+      atomicAdd(&rhs[mydof], fsrc * src - s);
+    }
+    // ---- scatter: natural (i, j) order through the slot map
+    {
+      const SlotT* sl = nslot + (size_t)e * (NVE * NVE);
+      for (int idx = lane; idx < NVE * NVE; idx += 32) {
+        const int i = idx / NVE;
+        atomicAdd(&Aval[sRow[i] + (long long)sl[idx]], Bs[idx]);
+      }
+    }
+    __syncwarp();
+
+    if (GAL) {
+      const int child = (int)(e & 7);
+      // rows/columns of Dirichlet fine dofs do not take part in the Galerkin product
+      if (ga.fmask) {
+        const int fm = lane < NVE ? (int)ga.fmask[mydof] : 0;
+        const unsigned mask = __ballot_sync(0xffffffffu, fm != 0);
+        if (mask) {
+          for (int idx = lane; idx < NVE * NVE; idx += 32) {
+            const int i = idx / NVE, j = idx - i * NVE;
+            if (((mask >> i) | (mask >> j)) & 1u) Bs[idx] = 0.0;
+          }
+          __syncwarp();
+        }
+      }
+      double R[NVE];
+#pragma unroll
+      for (int i = 0; i < NVE; i++) R[i] = 0.0;
+      if (lane < NVE) {
+#pragma unroll 1
+        for (int q = gt->colptr[child][lane]; q < gt->colptr[child][lane + 1]; q++) {
+          const int n = gt->crow[child][q];
+          const double v = gt->cval[child][q];
+#pragma unroll
+          for (int i = 0; i < NVE; i++) R[i] = fma(Bs[i * NVE + n], v, R[i]);
+        }
+      }
+      __syncwarp();
+      if (lane < NVE) {
+#pragma unroll
+        for (int i = 0; i < NVE; i++) Bs[i * NVE + lane] = R[i];      // Bs now holds T = B Pc
+      }
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < NVE; j++) R[j] = 0.0;
+      if (lane < NVE) {
+#pragma unroll 1
+        for (int q = gt->colptr[child][lane]; q < gt->colptr[child][lane + 1]; q++) {
+          const int i = gt->crow[child][q];
+          const double v = gt->cval[child][q];
+#pragma unroll
+          for (int j = 0; j < NVE; j++) R[j] = fma(v, Bs[i * NVE + j], R[j]);
+        }
+      }
+      __syncwarp();
+      if (lane < NVE) {
+#pragma unroll
+        for (int j = 0; j < NVE; j++) Bs[lane * NVE + j] = R[j];      // Bs now holds D = Pc^T B Pc
+      }
+      const int grp = wib >> 3;
+      asm volatile("bar.sync %0, 256;" ::"r"(grp + 1) : "memory");
+      {
+        const int64_t E = e >> 3;
+        const CSlotT* cslot = reinterpret_cast<const CSlotT*>(ga.cslot) + (size_t)E * (NVE * NVE);
+        const double* D0 = s_w + NG + (size_t)(8 * grp) * MmaSmem::warp_doubles + (3 * GP + GP + GP);
+        for (int idx = threadIdx.x & 255; idx < NVE * NVE; idx += 256) {
+          double v = 0.0;
+#pragma unroll
+          for (int w = 0; w < 8; w++) v += D0[(size_t)w * MmaSmem::warp_doubles + idx];
+          if (v == 0.0) continue;
+          const int I = idx / NVE, J = idx - I * NVE;
+          const int32_t dI = ga.cd[E * NVE + I];
+          if (ga.cmask) {
+            const int32_t dJ = ga.cd[E * NVE + J];
+            if (ga.cmask[dI] || ga.cmask[dJ]) continue;
+          }
+          atomicAdd(&ga.Cv[ga.Cp[dI] + (int64_t)cslot[idx]], v);
+        }
+      }
+      asm volatile("bar.sync %0, 256;" ::"r"(grp + 1) : "memory");
+    }
+  }
+}
+
+// element -> CSR slot map in natural (i, j) order
+template <typename SlotT>
+__global__ void natural_slot_kernel(int64_t total, int nve, const int32_t* __restrict__ dof, const int64_t* __restrict__ rowptr,
+                                    const int32_t* __restrict__ col, SlotT* __restrict__ slot, int* err) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int nn = nve * nve;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+    const int64_t e = t / nn;
+    const int idx = (int)(t - e * nn);
+    const int i = idx / nve, j = idx - i * nve;
+    const int32_t r = dof[e * nve + i], c = dof[e * nve + j];
+    const int64_t s = rowptr[r], en = rowptr[r + 1];
+    int64_t lo = s, hi = en;
+    while (lo < hi) {
+      const int64_t mid = (lo + hi) >> 1;
+      if (col[mid] < c) lo = mid + 1;
+      else hi = mid;
+    }
+    if (lo >= en || col[lo] != c) atomicExch(err, 1);
+    slot[t] = (SlotT)(lo - s);
+  }
+}
+
 // host-side check of the fused plan: fine element 8E+j must be child j of coarse element E with its
 // local node n at lattice point lat[j][n] of E
 __global__ void gal_check_kernel(int64_t nelc, int nve, int nf, const int32_t* __restrict__ dof,
@@ -403,6 +681,40 @@ int build_slots(b2_asm* p) {
   B2_TRY(b2_download(c, &err, d_err, 1));
   b2_free(c, d_err, 1);
   B2_CHECK(err == 0, "b2_asm_create: an element couples dofs outside the matrix pattern");
+  return 0;
+}
+
+template <typename SlotT>
+int build_natural_slots(b2_asm* p) {
+  b2_ctx* c = p->mesh->ctx;
+  const int64_t total = p->mesh->nel * p->nve * p->nve;
+  p->nslot_count = (size_t)total;
+  SlotT* s = nullptr;
+  B2_TRY(b2_malloc(c, &s, p->nslot_count));
+  p->nslot = s;
+  int* d_err = nullptr;
+  B2_TRY(b2_malloc(c, &d_err, 1));
+  B2_CUDA(cudaMemsetAsync(d_err, 0, sizeof(int), c->stream));
+  B2_LAUNCH(c, natural_slot_kernel<SlotT>, b2_grid_for(c, total, 256, 8), 256, 0, total, p->nve, p->dof, p->A->rowptr,
+            p->A->col, s, d_err);
+  int err = 0;
+  B2_TRY(b2_download(c, &err, d_err, 1));
+  b2_free(c, d_err, 1);
+  B2_CHECK(err == 0, "b2_asm_create: an element couples dofs outside the matrix pattern");
+  return 0;
+}
+
+template <typename SlotT, bool GAL, typename CSlotT>
+int launch_assemble_mma(b2_asm* p, const GalArgs& ga, const b2_vec* u, b2_vec* rhs, double nu, double fsrc) {
+  b2_ctx* c = p->mesh->ctx;
+  b2_prof_scope prof(c, p);
+  auto kern = assemble_q2_mma_kernel<SlotT, GAL, CSlotT>;
+  const size_t smem = GAL ? MmaSmem::bytes_gal : MmaSmem::bytes;
+  B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int grid = (int)((p->mesh->nel + kWarps - 1) / kWarps);
+  if (grid > c->sm_count) grid = c->sm_count;
+  B2_LAUNCH(c, kern, grid, kWarps * 32, smem, p->mesh->nel, p->mesh->nnode, p->mesh->xyz, p->mesh->conn, p->dof, p->tab,
+            (const SlotT*)p->nslot, p->A->rowptr, p->A->val, u ? u->d : nullptr, rhs ? rhs->d : nullptr, nu, fsrc, ga);
   return 0;
 }
 
@@ -569,9 +881,13 @@ int b2_asm_create(b2_mesh* m, b2_csr* A, int nve, const int32_t* dof, int ngauss
   B2_TRY(b2_upload(c, p->tab + 3 * tn, dzeta, tn));
   B2_TRY(b2_upload(c, p->tab + 4 * tn, weights, (size_t)ngauss));
   p->slot_bytes = A->max_row <= 256 ? 1 : 2;
+  p->nslot = nullptr;
+  p->nslot_count = 0;
   if (nve == 27) {
     if (p->slot_bytes == 1) B2_TRY((build_slots<27, uint8_t>(p)));
     else B2_TRY((build_slots<27, uint16_t>(p)));
+    if (p->slot_bytes == 1) B2_TRY(build_natural_slots<uint8_t>(p));
+    else B2_TRY(build_natural_slots<uint16_t>(p));
   } else {
     if (p->slot_bytes == 1) B2_TRY((build_slots<8, uint8_t>(p)));
     else B2_TRY((build_slots<8, uint16_t>(p)));
@@ -588,6 +904,10 @@ int b2_asm_destroy(b2_asm* p) {
   b2_free(c, p->tab, (size_t)4 * p->ngauss * p->nve + p->ngauss);
   if (p->slot_bytes == 1) b2_free(c, (uint8_t*)p->slot, p->slot_count);
   else b2_free(c, (uint16_t*)p->slot, p->slot_count);
+  if (p->nslot) {
+    if (p->slot_bytes == 1) b2_free(c, (uint8_t*)p->nslot, p->nslot_count);
+    else b2_free(c, (uint16_t*)p->nslot, p->nslot_count);
+  }
   if (p->gal_tab) {
     if (p->nve == 27) b2_free(c, (GalTables<27>*)p->gal_tab, 1);
     else b2_free(c, (GalTables<8>*)p->gal_tab, 1);
@@ -599,6 +919,11 @@ int b2_asm_destroy(b2_asm* p) {
 int b2_asm_poisson(b2_asm* p, const b2_vec* u, b2_vec* rhs, double nu, double fsrc) {
   B2_CHECK(!u || u->n >= p->A->nrows, "b2_asm_poisson: solution vector too short");
   B2_CHECK(!rhs || rhs->n >= p->A->nrows, "b2_asm_poisson: rhs vector too short");
+  if (p->nve == 27 && p->mesh->ctx->asm_variant == 1) {      // FP64 tensor-core kernel
+    GalArgs ga = {};
+    if (p->slot_bytes == 1) return launch_assemble_mma<uint8_t, false, uint8_t>(p, ga, u, rhs, nu, fsrc);
+    return launch_assemble_mma<uint16_t, false, uint8_t>(p, ga, u, rhs, nu, fsrc);
+  }
   if (p->nve == 27) {
     if (p->slot_bytes == 1) return launch_assemble<27, uint8_t>(p, u, rhs, nu, fsrc);
     return launch_assemble<27, uint16_t>(p, u, rhs, nu, fsrc);
@@ -625,6 +950,13 @@ int b2_asm_poisson_galerkin(b2_asm* p, b2_galerkin* gal, const b2_vec* u, b2_vec
   }
   B2_CUDA(cudaMemsetAsync(g.Ac->val, 0, (size_t)g.Ac->nnz * sizeof(double), c->stream));
   const bool s1 = p->slot_bytes == 1, c1 = g.slot_bytes == 1;
+  if (p->nve == 27 && c->asm_variant == 1) {      // FP64 tensor-core kernel
+    GalArgs ga = {p->gal_tab, g.cd, g.slot, g.fmask, g.cmask, g.Ac->rowptr, g.Ac->val};
+    if (s1 && c1) return launch_assemble_mma<uint8_t, true, uint8_t>(p, ga, u, rhs, nu, fsrc);
+    if (s1) return launch_assemble_mma<uint8_t, true, uint16_t>(p, ga, u, rhs, nu, fsrc);
+    if (c1) return launch_assemble_mma<uint16_t, true, uint8_t>(p, ga, u, rhs, nu, fsrc);
+    return launch_assemble_mma<uint16_t, true, uint16_t>(p, ga, u, rhs, nu, fsrc);
+  }
   if (p->nve == 27) {
     if (s1 && c1) return launch_assemble_gal<27, uint8_t, uint8_t>(p, g, u, rhs, nu, fsrc);
     if (s1) return launch_assemble_gal<27, uint8_t, uint16_t>(p, g, u, rhs, nu, fsrc);

@@ -58,7 +58,9 @@ struct b2_ctx {
   // SpMV kernel: 0 = register-streaming, 1 = TMA-staged ring (default), 2 = staged + software-pipelined
   // gathers (B2_SPMV_VARIANT)
   int spmv_variant = 1;
-  int spmv_timing = 0;     // diagnostic: y = A x prints the consumer phase cycles of CTA 0
+  int spmv_timing = 0;
+  // assembly kernel for triquadratic elements: 1 = FP64 tensor cores (mma.sync m8n8k4), 0 = CUDA-core tiles
+  int asm_variant = 1;     // diagnostic: y = A x prints the consumer phase cycles of CTA 0
   // multi-GPU
   int nranks = 1, rank = 0;
   void* nccl_comm = nullptr;

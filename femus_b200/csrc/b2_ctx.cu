@@ -77,6 +77,7 @@ int b2_ctx_create(int device, b2_ctx** out) {
   B2_CUDA(cudaGetDeviceProperties(&prop, device));
   c->sm_count = prop.multiProcessorCount;
   if (const char* v = getenv("B2_SPMV_VARIANT")) c->spmv_variant = atoi(v);
+  if (const char* v = getenv("B2_ASM_VARIANT")) c->asm_variant = atoi(v);
   B2_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   B2_CUDA(cudaEventCreate(&c->ev0));
   B2_CUDA(cudaEventCreate(&c->ev1));
@@ -148,6 +149,11 @@ int b2_ctx_set_option(b2_ctx* c, const char* name, int value) {
   if (!strcmp(name, "spmv_variant")) {
     B2_CHECK(value >= 0 && value <= 2, "spmv_variant %d (0, 1, 2)", value);
     c->spmv_variant = value;
+    return 0;
+  }
+  if (!strcmp(name, "asm_variant")) {
+    B2_CHECK(value == 0 || value == 1, "asm_variant %d (0, 1)", value);
+    c->asm_variant = value;
     return 0;
   }
   if (!strcmp(name, "spmv_timing")) {

@@ -63,7 +63,8 @@ int b2_ctx_profile_only(b2_ctx* c, const void* handle);   /* time only this hand
 int b2_ctx_profile_read(b2_ctx* c, const void* handle, int* count, double* total_ms);
 int b2_ctx_profile_clear(b2_ctx* c);
 /* tuning knobs: "spmv_variant" = 0 (register-streaming SpMV) | 1 (TMA-staged ring, default) | 2 (staged +
- * software-pipelined gathers); "spmv_timing" = 1 makes y = A x print the consumer phase cycles of CTA 0 */
+ * software-pipelined gathers); "spmv_timing" = 1 makes y = A x print the consumer phase cycles of CTA 0;
+ * "asm_variant" = 1 (triquadratic assembly on the FP64 tensor cores, default) | 0 (CUDA-core register tiles) */
 int b2_ctx_set_option(b2_ctx* c, const char* name, int value);
 /* write 256 MiB of device memory (> L2 size) to evict the L2 between timed iterations */
 int b2_ctx_flush_l2(b2_ctx* c);

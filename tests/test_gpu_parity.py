@@ -166,7 +166,7 @@ def test_spmv_kernels_and_edge_shapes(ctx, variant, kind):
 
 
 @pytest.mark.parametrize("order,shape,nl", [("biquadratic", (2, 2, 2), 2), ("biquadratic", (3, 2, 4), 3), ("linear", (2, 3, 2), 3)])
-def test_fused_assembly_galerkin_matches_separate(ctx, order, shape, nl):
+def test_fused_assembly_galerkin_matches_separate(ctx, order, shape, nl, asm_variant):
     """b2_asm_poisson_galerkin: same fine matrix and residual as b2_asm_poisson, and its coarse matrix
     equals both the element-gather product and the oracle's scipy P^T A P (Dirichlet rows/columns of
     P zeroed), on a deformed mesh with a non-zero solution."""
@@ -277,9 +277,17 @@ def distorted(L, amp, seed):
     return out
 
 
+@pytest.fixture(params=[1, 0], ids=["tensorcore", "cudacore"])
+def asm_variant(request, ctx):
+    """Both triquadratic assembly kernels: FP64 tensor cores (default) and CUDA-core register tiles."""
+    ctx.set_option("asm_variant", request.param)
+    yield request.param
+    ctx.set_option("asm_variant", 1)
+
+
 @pytest.mark.parametrize("order", ["linear", "biquadratic"])
 @pytest.mark.parametrize("amp", [0.0, 0.08])
-def test_assembly_matches_oracle(ctx, order, amp):
+def test_assembly_matches_oracle(ctx, order, amp, asm_variant):
     lv = mb.build_hierarchy(2, 3, 2, 2)
     L = lv[-1]
     L.xyz = distorted(L, amp, 3)
@@ -304,7 +312,7 @@ def test_assembly_matches_oracle(ctx, order, amp):
     assert np.abs(A.to_scipy().data - 2 * Aref.data).max() <= 2 * RTOL * np.abs(Aref.data).max()
 
 
-def test_assembly_golden_elements(ctx):
+def test_assembly_golden_elements(ctx, asm_variant):
     """Single elements of the committed golden fixture (values of the compiled reference)."""
     import os
     G = np.load(os.path.join(os.path.dirname(__file__), "golden", "fe_hex_ref.npz"))
