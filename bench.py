@@ -296,17 +296,25 @@ def main():
     launches = int(sum_over_ranks(ctx.launches(reset=True)))
     nsp, ms_sp = ctx.profile_read(Afine)
     ctx.profile_only(None)
-    # phase breakdown (separate passes, same data)
+    # phase breakdown (separate passes, same data); the assembly kernel is event-timed on its own
     phases = {}
+    kernel_ms = {}
     for name, fn in (("assembly", pb.assemble), ("galerkin", pb.galerkin), ("mg_set_levels", pb.mg_set_levels),
                      ("vcycle", pb.mg_solve)):
         ts = []
         for _ in range(3):
             ctx.sync()
+            if name == "assembly":
+                ctx.profile_only(pb.asm)
             ctx.timer_start()
             fn()
             ts.append(ctx.timer_stop_ms())
+            if name == "assembly":
+                nk, msk = ctx.profile_read(pb.asm)
+                ctx.profile_only(None)
+                kernel_ms.setdefault("assembly", []).append(msk / max(nk, 1))
         phases[name] = float(np.median(ts))
+    asm_kernel_ms = float(np.median(kernel_ms["assembly"]))
     # ---- end-to-end: host buffers in, host buffers out
     for _ in range(2):
         step_e2e()
@@ -335,20 +343,38 @@ def main():
     b_y = pb.spmv_bytes(-1)
     bytes_per_launch = (2 * (b_y + 8 * n_loc) + (b_y + 24 * n_loc)) / 3.0 if world == 1 else b_y + 16 * n_loc
     ach = bytes_per_launch / (ms_sp / max(nsp, 1) * 1e-3) / 1e9 if nsp else None
-    roofline = {"bound": "hbm", "kernel": "spmv_kernel<16,*> on the finest-level CSR (resid / Jacobi sweep)",
+    # DRAM traffic per launch of the same kernel from the ncu --set full capture of this round
+    # (profiles/r1_ncu_summary.md: dram__bytes_read.sum + dram__bytes_write.sum, mean of resid x2 + Jacobi x1)
+    traffic = 12.77e9 if (world == 1 and args.n0 == 16 and args.levels == 4 and args.order == "biquadratic") else None
+    roofline = {"bound": "hbm", "kernel": "spmv_tma_kernel on the finest-level CSR (2 x r = b - A x, 1 x Jacobi sweep per step)",
                 "achieved": ach, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-                "frac": (ach / peak) if ach else None, "traffic": None,
+                "frac": (ach / peak) if ach else None, "traffic": traffic,
                 "algorithmic_bytes_per_launch": bytes_per_launch, "launches_timed": nsp,
                 "avg_launch_ms": ms_sp / max(nsp, 1), "share_of_step": ms_sp / ms_total_local}
     if world > 1:
-        roofline["kernel"] = "spmv_kernel on rank 0's finest-level partial CSR (weighted resid x3 per step)"
+        roofline["kernel"] = "spmv_tma_kernel on rank 0's finest-level partial CSR (weighted resid x3 per step)"
+    # the kernel with the largest share of the step is the (fused) assembly: FP64 tensor-core / shared-memory
+    # bound, not HBM bound.  Algorithmic work per Q2 element: 4.5e5 flop, 7020 B.
+    nel_loc = pb.nel
+    flop_el = 4.5e5 if nve == 27 else 4.5e5 * (8 * 8) / (27 * 27)
+    bytes_el = (27 * 3 * 8 + 27 * 4 + nve * 8) + (nve * nve + nve) * 8
+    asm_roof = {"kernel": "assemble_q2_mma_kernel (assembly fused with the finest Galerkin product)" if nve == 27
+                else "assemble_poisson_kernel", "avg_launch_ms": asm_kernel_ms, "share_of_step": asm_kernel_ms / ms_step,
+                "bound": "tensor", "unit": "TFLOP/s", "achieved": nel_loc * flop_el / (asm_kernel_ms * 1e-3) / 1e12,
+                "peak": 40.0, "peak_source": "nominal B200 fp64 (MEASURED_PEAKS.json carries no fp64 figure)",
+                "algorithmic_flop_per_launch": nel_loc * flop_el,
+                "hbm_view": {"algorithmic_bytes_per_launch": nel_loc * bytes_el,
+                             "achieved_gbs": nel_loc * bytes_el / (asm_kernel_ms * 1e-3) / 1e9, "peak_gbs": peak,
+                             "traffic": 28.25e9 if traffic else None},
+                "limiters_ncu": "l1tex data pipe (shared-memory wavefronts) 66-69 %, fp64 tensor pipe 33-44 % (profiles/r1_ncu_summary.md)"}
+    asm_roof["frac"] = asm_roof["achieved"] / asm_roof["peak"]
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": W,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": config,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "roofline_assembly": asm_roof,
             "assembly_elem_dof_per_s": nel * nve / (phases["assembly"] * 1e-3),
             "spmv_gbs": ach, "phases_ms": phases, "finest_dofs": n, "finest_nnz": Afine.nnz, "elements": nel,
             "setup_s": t_setup, "residual_trace": trace, "coarse_pcg_iterations": pb.mg.coarse_iterations(),

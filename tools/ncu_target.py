@@ -51,6 +51,10 @@ if "asm" in what:
     pb.KK[-1].zero()
     pb.RES.zero()
     pb.asm.poisson(pb.SOL, pb.RES, 1.0, 1.0)
+if "fused" in what:
+    pb.KK[-1].zero()
+    pb.RES.zero()
+    pb.asm.poisson_galerkin(pb.gal[-1], pb.SOL, pb.RES, 1.0, 1.0)
 if "galerkin" in what:
     pb.gal[-1].apply()
 if "spmv" in what:
