@@ -65,16 +65,13 @@ template <> struct Tile<27> { static constexpr int TI = 7, TJ = 4; };   // 4 x 7
 template <> struct Tile<8> { static constexpr int TI = 2, TJ = 1; };    // 4 x 8 lane grid
 
 // Element prolongator of each of the 8 children of a refined hexahedron, restricted to the child's
-// own NVE nodes: Pc[j][n][J] = ploc[lattice(j, n)][J].  Stored twice, by rows (fine node n -> coarse
-// J) and by columns, as compressed lists; exact zeros dropped (Q2: 125 entries per child).
+// own NVE nodes: Pc[j][n][J] = ploc[lattice(j, n)][J], stored by columns as compressed lists
+// (both products of the fused kernel walk columns); exact zeros dropped (Q2: 125 entries per child).
 template <int NVE>
 struct GalTables {
   static constexpr int MAXNNZ = NVE == 27 ? 128 : 64;
-  int rowptr[8][NVE + 1];
   int colptr[8][NVE + 1];
-  unsigned char rcol[8][MAXNNZ];   // by rows: coarse index J
-  unsigned char crow[8][MAXNNZ];   // by columns: fine node n
-  double rval[8][MAXNNZ];
+  unsigned char crow[8][MAXNNZ];   // fine node n of every entry of column J
   double cval[8][MAXNNZ];
 };
 
@@ -345,9 +342,9 @@ assemble_poisson_kernel(int64_t nel, int64_t nnode, const double* __restrict__ x
 
 // ------------------------------------------------------------------------------------------
 // Triquadratic elements on the FP64 tensor cores.  B = sum_g w_g G_g G_g^T (G_g: 27 x 3 gradients at
-// Gauss point g) is a 27 x 27 x 192 GEMM per element; per Gauss point it is one k-step of
-// mma.sync.m8n8k4.f64 (K = 3 padded to 4) on the 4 x 4 grid of 8 x 8 output tiles, of which only the
-// 10 upper ones are formed (B is symmetric).  Against the CUDA-core tile kernel above this needs 8
+// Gauss point g) is a 27 x 27 x 192 GEMM per element: 48 k-steps of mma.sync.m8n8k4.f64 (DMMA.8x8x4
+// is the only fp64 tensor shape of sm_100a: m16n8k8 compiles to four of them) on the 4 x 4 grid of
+// 8 x 8 output tiles, of which only the 10 upper ones are formed (B is symmetric).  Against the CUDA-core tile kernel above this needs 8
 // shared-memory fragment loads per lane and Gauss point instead of 33 (that kernel is bound by
 // shared-memory wavefronts, ncu: l1tex data pipe 94 %, fp64 pipe 57 %).  The element matrix is then
 // written to shared memory once; residual, scatter and the fused Galerkin product read it from there,
@@ -355,11 +352,11 @@ assemble_poisson_kernel(int64_t nel, int64_t nnode, const double* __restrict__ x
 constexpr int MS = 36;            // column stride of the fragment buffers: conflict-free 8-byte fragment loads
 struct MmaSmem {
   static constexpr int tab_doubles = 3 * NG * 27 + NG;                   // dxi, deta, dzeta, weights
-  // per warp: X[3][GP], U[GP], rowbase[GP] (int64), geo[10][NG], M[2][4][MS]
-  static constexpr int warp_doubles = 3 * GP + GP + GP + 10 * NG + 2 * 4 * MS;
+  // per warp: X[3][GP], U[GP], rowbase[GP] (int64), geo[10][NG], M[2 buffers][2: G, wG][4][MS]
+  static constexpr int warp_doubles = 3 * GP + GP + GP + 10 * NG + 2 * 2 * 4 * MS;
   static constexpr size_t bytes = (size_t)(tab_doubles + kWarps * warp_doubles) * sizeof(double);
   static constexpr size_t bytes_gal = bytes + sizeof(GalTables<27>);
-  static_assert(10 * NG + 2 * 4 * MS >= 27 * 27, "element matrix does not fit the reused buffers");
+  static_assert(10 * NG + 2 * 2 * 4 * MS >= 27 * 27, "element matrix does not fit the reused buffers");
 };
 
 __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
@@ -385,7 +382,7 @@ assemble_q2_mma_kernel(int64_t nel, int64_t nnode, const double* __restrict__ xy
   double* sU = sX + 3 * GP;                             // [GP]
   long long* sRow = reinterpret_cast<long long*>(sU + GP);   // [GP] rowptr[dof_i]
   double* sGeo = reinterpret_cast<double*>(sRow + GP);  // [10][NG]: J^-1 (9, row-major), weight
-  double* sM = sGeo + 10 * NG;                          // [2][4][MS]: G and w*G, column-major (component, node)
+  double* sM = sGeo + 10 * NG;                          // [2][2][4][MS]: double-buffered G and w*G, (component, node)
   double* Bs = sGeo;                                    // [27][27] element matrix, reuses geo + M
 
   for (int t = threadIdx.x; t < MmaSmem::tab_doubles; t += blockDim.x) smem[t] = tab[NG * NVE + t];
@@ -413,7 +410,7 @@ assemble_q2_mma_kernel(int64_t nel, int64_t nnode, const double* __restrict__ xy
       sU[lane] = u ? u[mydof] : 0.0;
       sRow[lane] = rowptr[mydof];
     }
-    for (int t = lane; t < 2 * 4 * MS; t += 32) sM[t] = 0.0;      // padding rows 27..31 and the k = 3 column stay zero
+    for (int t = lane; t < 2 * 2 * 4 * MS; t += 32) sM[t] = 0.0;  // padding rows 27..31 stay zero
     __syncwarp();
 
     // ---- A. geometry at the Gauss points owned by this lane
@@ -451,28 +448,35 @@ assemble_q2_mma_kernel(int64_t nel, int64_t nnode, const double* __restrict__ xy
 #pragma unroll
     for (int t = 0; t < 10; t++) C[t][0] = C[t][1] = 0.0;
     double src = 0.0;
-#pragma unroll 1
-    for (int g = 0; g < NG; g++) {
-      const double wg = sGeo[9 * NG + g];
+    // The GEMM's K dimension is (Gauss point, component) flattened, 192 = 48 k-steps of 4 with no
+    // padding: a Gauss point contributes 3 consecutive columns, so 4 points make 3 k-steps.  The two
+    // halves of the fragment buffer hold alternate k-steps; a half is rewritten only after a
+    // __syncwarp that follows the fragment loads of the k-step it held before (see the order below).
+    auto grad = [&](int g, double& g0, double& g1, double& g2, double& wg) {
+      wg = sGeo[9 * NG + g];
+      g0 = g1 = g2 = 0.0;
       if (lane < NVE) {
         const double a = s_dx[g * NVE + lane], b = s_dy[g * NVE + lane], c = s_dz[g * NVE + lane];
-        const double g0 = fma(c, sGeo[2 * NG + g], fma(b, sGeo[1 * NG + g], a * sGeo[0 * NG + g]));
-        const double g1 = fma(c, sGeo[5 * NG + g], fma(b, sGeo[4 * NG + g], a * sGeo[3 * NG + g]));
-        const double g2 = fma(c, sGeo[8 * NG + g], fma(b, sGeo[7 * NG + g], a * sGeo[6 * NG + g]));
-        sM[0 * MS + lane] = g0;
-        sM[1 * MS + lane] = g1;
-        sM[2 * MS + lane] = g2;
-        sM[4 * MS + 0 * MS + lane] = g0 * wg;
-        sM[4 * MS + 1 * MS + lane] = g1 * wg;
-        sM[4 * MS + 2 * MS + lane] = g2 * wg;
+        g0 = fma(c, sGeo[2 * NG + g], fma(b, sGeo[1 * NG + g], a * sGeo[0 * NG + g]));
+        g1 = fma(c, sGeo[5 * NG + g], fma(b, sGeo[4 * NG + g], a * sGeo[3 * NG + g]));
+        g2 = fma(c, sGeo[8 * NG + g], fma(b, sGeo[7 * NG + g], a * sGeo[6 * NG + g]));
         if (rhs) src = fma(__ldg(g_phi + g * NVE + lane), wg, src);
       }
-      __syncwarp();
+    };
+    auto put = [&](int kstep, int col, double v, double w) {       // column `col` of k-step `kstep`
+      if (lane < NVE) {
+        double* M = sM + (kstep & 1) * (2 * 4 * MS) + col * MS + lane;
+        M[0] = v;
+        M[4 * MS] = v * w;
+      }
+    };
+    auto mma_step = [&](int kstep) {
+      const double* M = sM + (kstep & 1) * (2 * 4 * MS);
       double fa[4], fb[4];
 #pragma unroll
       for (int T = 0; T < 4; T++) {
-        fa[T] = sM[fk * MS + 8 * T + fr];               // G[8T + l/4][l%4]
-        fb[T] = sM[4 * MS + fk * MS + 8 * T + fr];      // (w G)[8T + l/4][l%4]
+        fa[T] = M[fk * MS + 8 * T + fr];               // G[8T + l/4][k]
+        fb[T] = M[4 * MS + fk * MS + 8 * T + fr];      // (w G)[8T + l/4][k]
       }
       int t = 0;
 #pragma unroll
@@ -482,8 +486,29 @@ assemble_q2_mma_kernel(int64_t nel, int64_t nnode, const double* __restrict__ xy
           dmma(C[t][0], C[t][1], fa[I], fb[Jt]);
           t++;
         }
+    };
+#pragma unroll 1
+    for (int q = 0; q < NG / 4; q++) {
+      const int s0 = 3 * q;
+      double g0, g1, g2, wg;
+      grad(4 * q + 0, g0, g1, g2, wg);
+      put(s0, 0, g0, wg); put(s0, 1, g1, wg); put(s0, 2, g2, wg);
       __syncwarp();
+      grad(4 * q + 1, g0, g1, g2, wg);
+      put(s0, 3, g0, wg); put(s0 + 1, 0, g1, wg); put(s0 + 1, 1, g2, wg);
+      __syncwarp();
+      mma_step(s0);
+      grad(4 * q + 2, g0, g1, g2, wg);
+      put(s0 + 1, 2, g0, wg); put(s0 + 1, 3, g1, wg);
+      __syncwarp();
+      mma_step(s0 + 1);
+      put(s0 + 2, 0, g2, wg);          // the half of k-step s0: its fragments were loaded before the last __syncwarp
+      grad(4 * q + 3, g0, g1, g2, wg);
+      put(s0 + 2, 1, g0, wg); put(s0 + 2, 2, g1, wg); put(s0 + 2, 3, g2, wg);
+      __syncwarp();
+      mma_step(s0 + 2);
     }
+    __syncwarp();
 
     // ---- C. element matrix -> shared memory (both triangles), scaled by nu
     {
@@ -788,25 +813,12 @@ int build_gal_tables(b2_asm* p, const b2_galerkin* gal, const b2_galerkin_view& 
   memset(T, 0, sizeof(*T));
   for (int j = 0; j < 8; j++) {
     int q = 0;
-    for (int n = 0; n < NVE; n++) {
-      T->rowptr[j][n] = q;
-      for (int J = 0; J < NVE; J++) {
-        const double v = hp[(size_t)lat[j * NVE + n] * nc + J];
-        if (v != 0.0) {
-          if (q >= GalTables<NVE>::MAXNNZ) { delete T; B2_CHECK(false, "fused Galerkin: child prolongator too dense"); }
-          T->rcol[j][q] = (unsigned char)J;
-          T->rval[j][q] = v;
-          q++;
-        }
-      }
-    }
-    T->rowptr[j][NVE] = q;
-    q = 0;
     for (int J = 0; J < NVE; J++) {
       T->colptr[j][J] = q;
       for (int n = 0; n < NVE; n++) {
         const double v = hp[(size_t)lat[j * NVE + n] * nc + J];
         if (v != 0.0) {
+          if (q >= GalTables<NVE>::MAXNNZ) { delete T; B2_CHECK(false, "fused Galerkin: child prolongator too dense"); }
           T->crow[j][q] = (unsigned char)n;
           T->cval[j][q] = v;
           q++;

@@ -5,7 +5,4 @@ tail -25 gpurun_out/pytest_gpu.log
 if ! grep -q "pytest exit 0" gpurun_out/pytest_gpu.log; then exit 0; fi
 timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench.json 2> gpurun_out/bench.err
 python -c "
-import json; d=json.load(open('gpurun_out/bench.json')); print(d['phases_ms'], d['ms_per_step'], d['value'], d['e2e'], d['residual_trace'], d['assembly_elem_dof_per_s'])"
-B2_ASM_VARIANT=0 timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_v0.json 2> gpurun_out/bench_v0.err
-python -c "
-import json; d=json.load(open('gpurun_out/bench_v0.json')); print('cudacore', d['phases_ms'], d['ms_per_step'])"
+import json; d=json.load(open('gpurun_out/bench.json')); print(d['phases_ms'], d['ms_per_step'], d['value'], d['e2e']['value'], d['residual_trace'], d['roofline_assembly']['avg_launch_ms'])"
