@@ -170,5 +170,6 @@ int b2_csr_zero_cols_notowned(b2_csr* A, const uint8_t* d_owned);
 int b2_csr_zero_rows_dev(b2_csr* A, const int32_t* d_rows, int64_t n, double diag, const uint8_t* d_owned);
 // result stays on device; owned != null restricts the sum to entries with owned[i] != 0
 int b2_dev_dot(b2_ctx* c, const double* x, const double* y, int64_t n, double* d_out, const uint8_t* owned = nullptr);
+int b2_halo_sum_scalars(b2_halo* h, b2_vec* v, double* d_scal, int nscal);   // interface sum + scalars, one collective
 int b2_allreduce_sum(b2_ctx* c, double* d_buf, int64_t n);
 int b2_allreduce_op(b2_ctx* c, double* d_buf, int64_t n, int op);   // 2 = max, 3 = min

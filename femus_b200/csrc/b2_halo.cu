@@ -27,6 +27,23 @@ __global__ void halo_unpack_kernel(int64_t n, const int32_t* __restrict__ idx, c
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) v[idx[k]] = recv[pos[k]];
 }
+// the same with nscal extra scalars appended to the packed vector (one collective for both)
+__global__ void halo_pack_scal_kernel(int64_t n, const int32_t* __restrict__ idx, const int32_t* __restrict__ pos,
+                                      const double* __restrict__ v, double* __restrict__ send, int64_t n_packed,
+                                      const double* __restrict__ scal, int nscal) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t0 < nscal) send[n_packed + t0] = scal[t0];
+  for (int64_t k = t0; k < n; k += stride) send[pos[k]] = v[idx[k]];
+}
+__global__ void halo_unpack_scal_kernel(int64_t n, const int32_t* __restrict__ idx, const int32_t* __restrict__ pos,
+                                        const double* __restrict__ recv, double* __restrict__ v, int64_t n_packed,
+                                        double* __restrict__ scal, int nscal) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t0 < nscal) scal[t0] = recv[n_packed + t0];
+  for (int64_t k = t0; k < n; k += stride) v[idx[k]] = recv[pos[k]];
+}
 __global__ void halo_invmult_kernel(int64_t n, const uint8_t* __restrict__ mult, double* __restrict__ inv) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) inv[i] = 1.0 / (double)mult[i];
@@ -57,8 +74,8 @@ int b2_halo_create(b2_ctx* c, int64_t n_local, int64_t n_if, const int32_t* loca
   }
   B2_TRY(b2_malloc(c, &h->idx, (size_t)n_if));
   B2_TRY(b2_malloc(c, &h->pos, (size_t)n_if));
-  B2_TRY(b2_malloc(c, &h->send, (size_t)n_packed));
-  B2_TRY(b2_malloc(c, &h->recv, (size_t)n_packed));
+  B2_TRY(b2_malloc(c, &h->send, (size_t)n_packed + 8));     // +8: scalars riding with the interface sum
+  B2_TRY(b2_malloc(c, &h->recv, (size_t)n_packed + 8));
   B2_TRY(b2_malloc(c, &h->owned, (size_t)n_local));
   B2_TRY(b2_malloc(c, &h->invmult, (size_t)n_local + 4));   // +4: the SpMV stages 16-byte aligned slices
   uint8_t* d_mult = nullptr;
@@ -67,8 +84,8 @@ int b2_halo_create(b2_ctx* c, int64_t n_local, int64_t n_if, const int32_t* loca
   B2_TRY(b2_upload(c, h->pos, packed_pos, (size_t)n_if));
   B2_TRY(b2_upload(c, h->owned, owned, (size_t)n_local));
   B2_TRY(b2_upload(c, d_mult, mult, (size_t)n_local));
-  B2_CUDA(cudaMemsetAsync(h->send, 0, (size_t)(n_packed ? n_packed : 1) * sizeof(double), c->stream));
-  B2_CUDA(cudaMemsetAsync(h->recv, 0, (size_t)(n_packed ? n_packed : 1) * sizeof(double), c->stream));
+  B2_CUDA(cudaMemsetAsync(h->send, 0, (size_t)(n_packed + 8) * sizeof(double), c->stream));
+  B2_CUDA(cudaMemsetAsync(h->recv, 0, (size_t)(n_packed + 8) * sizeof(double), c->stream));
   if (n_local) B2_LAUNCH(c, halo_invmult_kernel, b2_grid_for(c, n_local, kBlock, 8), kBlock, 0, n_local, d_mult, h->invmult);
   B2_CUDA(cudaStreamSynchronize(c->stream));
   b2_free(c, d_mult, (size_t)n_local);
@@ -82,8 +99,8 @@ int b2_halo_destroy(b2_halo* h) {
   cudaStreamSynchronize(c->stream);
   b2_free(c, h->idx, (size_t)h->n_if);
   b2_free(c, h->pos, (size_t)h->n_if);
-  b2_free(c, h->send, (size_t)h->n_packed);
-  b2_free(c, h->recv, (size_t)h->n_packed);
+  b2_free(c, h->send, (size_t)h->n_packed + 8);
+  b2_free(c, h->recv, (size_t)h->n_packed + 8);
   b2_free(c, h->owned, (size_t)h->n_local);
   b2_free(c, h->invmult, (size_t)h->n_local + 4);
   delete h;
@@ -103,6 +120,23 @@ int b2_halo_sum(b2_halo* h, b2_vec* v) {
   if (h->n_if) B2_LAUNCH(c, halo_unpack_kernel, b2_grid_for(c, h->n_if, kBlock, 8), kBlock, 0, h->n_if, h->idx, h->pos, h->recv, v->d);
   return 0;
 }
+
+}  // extern "C"
+
+// v[interface] <- sum over ranks, and d_scal[0..nscal) <- sum over ranks, in ONE ncclAllReduce
+// (latency-bound solvers: the coarse PCG sends its dot products with the interface values)
+int b2_halo_sum_scalars(b2_halo* h, b2_vec* v, double* d_scal, int nscal) {
+  B2_CHECK(v->n >= h->n_local && nscal >= 0 && nscal <= 8, "b2_halo_sum_scalars: bad arguments");
+  b2_ctx* c = h->ctx;
+  if (c->nranks == 1) return 0;
+  const int grid = b2_grid_for(c, h->n_if > 0 ? h->n_if : 1, kBlock, 8);
+  B2_LAUNCH(c, halo_pack_scal_kernel, grid, kBlock, 0, h->n_if, h->idx, h->pos, v->d, h->send, h->n_packed, d_scal, nscal);
+  B2_TRY(b2_allreduce_into(c, h->send, h->recv, h->n_packed + nscal));
+  B2_LAUNCH(c, halo_unpack_scal_kernel, grid, kBlock, 0, h->n_if, h->idx, h->pos, h->recv, v->d, h->n_packed, d_scal, nscal);
+  return 0;
+}
+
+extern "C" {
 
 /* reductions of v run over the owned entries only once a layout is attached (NULL detaches) */
 int b2_vec_set_halo(b2_vec* v, const b2_halo* h) {

@@ -6,7 +6,9 @@
 // with P^T (PCMGSetRestriction(..., PP), :277), interpolation with P (:276), level operators with
 // Dirichlet rows set to identity (SetPenalty, :428-436).  The coarse solve (reference: PREONLY +
 // MUMPS LU, PetscPreconditioner.cpp:147-160) is a Jacobi-preconditioned CG run to a tight
-// relative residual.
+// relative residual, in the single-reduction form of Chronopoulos and Gear: one operator
+// application and ONE reduction per iteration, and in the sharded run the three scalars of that
+// reduction travel in the same ncclAllReduce as the interface values of the product.
 #include "b2_common.cuh"
 
 struct b2_mg_level {
@@ -29,8 +31,10 @@ struct b2_mg {
   int coarse_maxit = 5000;
   int coarse_its = 0;
   // PCG work vectors on level 0 and device scalars
-  b2_vec *p = nullptr, *q = nullptr, *z = nullptr;
-  double* scal = nullptr;   // [8]: 0 rz, 1 pq, 2 rz_new, 3 rr, 4 bb
+  b2_vec *p = nullptr, *q = nullptr, *z = nullptr, *w = nullptr;
+  double* scal = nullptr;   // [16]: 0 gamma_new (r.u), 1 delta (w.u), 2 rr, 3 bb | 8 gamma, 9 alpha, 10 beta
+  double* dot_partial = nullptr;      // [kRedBlocks][4]
+  unsigned int* dot_counter = nullptr;
 };
 
 namespace {
@@ -57,38 +61,102 @@ __global__ void copy_idx_kernel(double* __restrict__ dst, const double* __restri
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[idx[i]] = src[idx[i]];
 }
 
-// ---- PCG kernels with device-resident scalars -------------------------------------------------
-// z = dinv .* r ; p = z            (start)
-__global__ void pcg_start_kernel(int64_t n, const double* __restrict__ dinv, const double* __restrict__ r,
-                                 double* __restrict__ z, double* __restrict__ p) {
+// ---- single-reduction PCG (Chronopoulos-Gear) kernels, scalars resident on the device ------------
+// out[0] = sum_owned r.u, out[1] = sum_all w.u, out[2] = sum_owned r.r (, out[3] = sum_owned b.b), one pass,
+// deterministic two-level reduction with a ticket counter.  w is this rank's PARTIAL product: since u
+// is complete on every rank that holds a dof, summing w.u over ALL local entries and over the ranks
+// gives the dot product with the completed w -- so it can be formed before the interface sum.
+__global__ void __launch_bounds__(kBlock) cg_dots_kernel(int64_t n, const double* __restrict__ r, const double* __restrict__ u,
+                                                         const double* __restrict__ w, const double* __restrict__ b,
+                                                         const uint8_t* __restrict__ owned, double* __restrict__ partial,
+                                                         double* __restrict__ out, unsigned int* counter) {
+  double a[4] = {0., 0., 0., 0.};
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    const double zi = dinv[i] * r[i];
-    z[i] = zi;
-    p[i] = zi;
+    const double ui = u[i];
+    a[1] = fma(w[i], ui, a[1]);
+    if (!owned || owned[i]) {
+      const double ri = r[i];
+      a[0] = fma(ri, ui, a[0]);
+      a[2] = fma(ri, ri, a[2]);
+      if (b) a[3] = fma(b[i], b[i], a[3]);
+    }
+  }
+  __shared__ double sh[kBlock / 32][4];
+  __shared__ bool last;
+#pragma unroll
+  for (int k = 0; k < 4; k++)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a[k] += __shfl_down_sync(0xffffffffu, a[k], o);
+  const int wi = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0)
+    for (int k = 0; k < 4; k++) sh[wi][k] = a[k];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int k = 0; k < 4; k++) {
+      double t = 0.;
+      for (int ww = 0; ww < kBlock / 32; ww++) t += sh[ww][k];
+      partial[4 * blockIdx.x + k] = t;
+    }
+    __threadfence();
+    last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (last && wi == 0) {
+    double t[4] = {0., 0., 0., 0.};
+    for (int k = l; k < (int)gridDim.x; k += 32)
+      for (int j = 0; j < 4; j++) t[j] += __ldcg(&partial[4 * k + j]);
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) t[j] += __shfl_down_sync(0xffffffffu, t[j], o);
+    if (l == 0) {
+      out[0] = t[0]; out[1] = t[1]; out[2] = t[2];
+      if (b) out[3] = t[3];
+      *counter = 0;
+    }
   }
 }
-// alpha = rz/pq ; x += alpha p ; r -= alpha q ; z = dinv .* r
-__global__ void pcg_update_kernel(int64_t n, const double* __restrict__ scal, int cur, const double* __restrict__ dinv,
-                                  const double* __restrict__ p, const double* __restrict__ q, double* __restrict__ x,
-                                  double* __restrict__ r, double* __restrict__ z) {
-  const double pq = scal[1];
-  const double alpha = pq != 0.0 ? scal[cur] / pq : 0.0;
+// u = dinv .* r
+__global__ void cg_precond_kernel(int64_t n, const double* __restrict__ dinv, const double* __restrict__ r, double* __restrict__ u) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) u[i] = dinv[i] * r[i];
+}
+// scalars of one iteration, by every thread from the reduced values (first: beta = 0, alpha = gamma/delta):
+//   beta = gamma_new / gamma ; alpha = gamma_new / (delta - beta * gamma_new / alpha_old)
+// then  p = u + beta p ; s = w + beta s ; x += alpha p ; r -= alpha s ; u = dinv .* r
+// (thread 0 of block 0 publishes gamma, alpha for the next iteration AFTER a grid-wide read: the
+//  scalars live in two banks selected by `bank`, so no thread can see the new values too early)
+__global__ void cg_step_kernel(int64_t n, double* __restrict__ sc, int bank, int first, const double* __restrict__ dinv,
+                               const double* __restrict__ w, double* __restrict__ u, double* __restrict__ p,
+                               double* __restrict__ s, double* __restrict__ x, double* __restrict__ r) {
+  const double gn = sc[0], delta = sc[1];
+  const double* old = sc + 8 + 4 * bank;          // gamma, alpha of the previous iteration
+  double beta = 0.0, alpha;
+  if (first) {
+    alpha = delta != 0.0 ? gn / delta : 0.0;
+  } else {
+    const double g = old[0], al = old[1];
+    beta = g != 0.0 ? gn / g : 0.0;
+    const double den = delta - (al != 0.0 ? beta * gn / al : 0.0);
+    alpha = den != 0.0 ? gn / den : 0.0;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    double* nw = sc + 8 + 4 * (bank ^ 1);
+    nw[0] = gn;
+    nw[1] = alpha;
+  }
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    x[i] = fma(alpha, p[i], x[i]);
-    const double ri = fma(-alpha, q[i], r[i]);
+    const double pi = fma(beta, p[i], u[i]);
+    const double si = fma(beta, s[i], w[i]);
+    p[i] = pi;
+    s[i] = si;
+    x[i] = fma(alpha, pi, x[i]);
+    const double ri = fma(-alpha, si, r[i]);
     r[i] = ri;
-    z[i] = dinv[i] * ri;
+    u[i] = dinv[i] * ri;
   }
-}
-// beta = rz_new/rz ; p = z + beta p.  r.z is double buffered in slots 0 and 2 (`cur` = current).
-__global__ void pcg_dir_kernel(int64_t n, const double* __restrict__ scal, int cur, const double* __restrict__ z,
-                               double* __restrict__ p) {
-  const double rz = scal[cur], rzn = scal[cur ^ 2];
-  const double beta = rz != 0.0 ? rzn / rz : 0.0;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) p[i] = fma(beta, p[i], z[i]);
 }
 
 // x += omega * dinv .* r   (second half of a distributed Richardson-Jacobi sweep)
@@ -138,45 +206,43 @@ int smooth(b2_mg* mg, int l, int nsweeps, bool zero_guess) {
 
 int coarse_solve(b2_mg* mg) {
   // Jacobi-PCG on level 0: solves A x = b with x, b the level-0 work vectors.
+  // r, u = D^-1 r, w = A u, p, s = A p as in Chronopoulos & Gear; mg->z = u, mg->w = w, mg->p = p, mg->q = s.
   b2_mg_level& L = mg->L[0];
   b2_ctx* c = mg->ctx;
   const int64_t n = L.A->nrows;
   const int g = vec_grid(c, n);
-  double* s = mg->scal;
+  int gd = b2_grid_for(c, n, kBlock * 4, 8);
+  if (gd > kRedBlocks) gd = kRedBlocks;
+  double* sc = mg->scal;
+  const uint8_t* own = owned(L);
   // x0 = b on Dirichlet rows (identity rows), 0 elsewhere; r = b - A x0
   B2_TRY(b2_vec_zero(L.x));
   if (L.nbdc) B2_LAUNCH(c, copy_idx_kernel, vec_grid(c, L.nbdc), kBlock, 0, L.x->d, L.b->d, L.bdc, L.nbdc);
   B2_TRY(level_resid(L, L.b, L.x, L.r));
-  const uint8_t* own = owned(L);
-  B2_TRY(b2_dev_dot(c, L.b->d, L.b->d, n, s + 4, own));
-  B2_LAUNCH(c, pcg_start_kernel, g, kBlock, 0, n, L.dinv->d, L.r->d, mg->z->d, mg->p->d);
-  B2_TRY(b2_dev_dot(c, L.r->d, mg->z->d, n, s + 0, own));
-  B2_TRY(b2_dev_dot(c, L.r->d, L.r->d, n, s + 3, own));
-  B2_TRY(b2_allreduce_sum(c, s + 3, 2));    // slots 3 (rr) and 4 (bb) together
-  B2_TRY(b2_allreduce_sum(c, s + 0, 1));
-  double h[8];
-  B2_TRY(b2_download(c, h, s, 8));
-  const double bb = h[4];
+  B2_TRY(b2_vec_zero(mg->p));
+  B2_TRY(b2_vec_zero(mg->q));
+  B2_LAUNCH(c, cg_precond_kernel, g, kBlock, 0, n, L.dinv->d, L.r->d, mg->z->d);
+  double h[4];
+  double bb = 0.0;
   mg->coarse_its = 0;
-  if (bb == 0.0 || h[3] <= mg->coarse_rtol * mg->coarse_rtol * bb) return 0;
-  int cur = 0;
   const int check_every = 8;
-  for (int it = 1; it <= mg->coarse_maxit; it++) {
-    B2_TRY(level_spmv(L, mg->p, mg->q));
-    B2_TRY(b2_dev_dot(c, mg->p->d, mg->q->d, n, s + 1, own));
-    B2_TRY(b2_allreduce_sum(c, s + 1, 1));
-    B2_LAUNCH(c, pcg_update_kernel, g, kBlock, 0, n, s, cur, L.dinv->d, mg->p->d, mg->q->d, L.x->d, L.r->d, mg->z->d);
-    B2_TRY(b2_dev_dot(c, L.r->d, mg->z->d, n, s + (cur ^ 2), own));
-    B2_TRY(b2_allreduce_sum(c, s + (cur ^ 2), 1));
-    B2_LAUNCH(c, pcg_dir_kernel, g, kBlock, 0, n, s, cur, mg->z->d, mg->p->d);
-    cur ^= 2;
-    mg->coarse_its = it;
-    if (it % check_every == 0) {
-      B2_TRY(b2_dev_dot(c, L.r->d, L.r->d, n, s + 3, own));
-      B2_TRY(b2_allreduce_sum(c, s + 3, 1));
-      B2_TRY(b2_download(c, h, s, 8));
-      if (!(h[3] > mg->coarse_rtol * mg->coarse_rtol * bb)) break;   // also leaves on NaN
+  int bank = 0;
+  for (int it = 0; it <= mg->coarse_maxit; it++) {
+    // w = A u (this rank's part), the three dot products, then ONE collective for interface + scalars
+    B2_TRY(b2_csr_spmv(L.A, mg->z, mg->w));
+    B2_LAUNCH(c, cg_dots_kernel, gd, kBlock, 0, n, L.r->d, mg->z->d, mg->w->d, it == 0 ? L.b->d : (const double*)nullptr, own,
+              mg->dot_partial, sc, mg->dot_counter);
+    if (L.halo) B2_TRY(b2_halo_sum_scalars(L.halo, mg->w, sc, it == 0 ? 4 : 3));
+    if (it == 0 || it % check_every == 0) {      // convergence on ||r||^2 <= rtol^2 ||b||^2 (one small D2H)
+      B2_TRY(b2_download(c, h, sc, 4));
+      if (it == 0) bb = h[3];
+      if (bb == 0.0 || !(h[2] > mg->coarse_rtol * mg->coarse_rtol * bb)) break;      // also leaves on NaN
     }
+    if (it == mg->coarse_maxit) break;
+    B2_LAUNCH(c, cg_step_kernel, g, kBlock, 0, n, sc, bank, it == 0 ? 1 : 0, L.dinv->d, mg->w->d, mg->z->d, mg->p->d, mg->q->d,
+              L.x->d, L.r->d);
+    bank ^= 1;
+    mg->coarse_its = it + 1;
   }
   return 0;
 }
@@ -207,8 +273,11 @@ int b2_mg_create(b2_ctx* c, int nlevels, b2_mg** out) {
   mg->ctx = c;
   mg->nlevels = nlevels;
   mg->L.resize(nlevels);
-  B2_TRY(b2_malloc(c, &mg->scal, 8));
-  B2_CUDA(cudaMemsetAsync(mg->scal, 0, 8 * sizeof(double), c->stream));
+  B2_TRY(b2_malloc(c, &mg->scal, 16));
+  B2_CUDA(cudaMemsetAsync(mg->scal, 0, 16 * sizeof(double), c->stream));
+  B2_TRY(b2_malloc(c, &mg->dot_partial, (size_t)kRedBlocks * 4));
+  B2_TRY(b2_malloc(c, &mg->dot_counter, 1));
+  B2_CUDA(cudaMemsetAsync(mg->dot_counter, 0, sizeof(unsigned int), c->stream));
   *out = mg;
   return 0;
 }
@@ -237,6 +306,7 @@ int b2_mg_set_level(b2_mg* mg, int level, b2_csr* A, b2_csr* P, const int32_t* b
       B2_TRY(b2_vec_create(c, n, &mg->p));
       B2_TRY(b2_vec_create(c, n, &mg->q));
       B2_TRY(b2_vec_create(c, n, &mg->z));
+      B2_TRY(b2_vec_create(c, n, &mg->w));
     }
   }
   if (L.bdc) { b2_free(c, L.bdc, (size_t)L.nbdc); L.bdc = nullptr; }
@@ -317,7 +387,10 @@ int b2_mg_destroy(b2_mg* mg) {
   b2_vec_destroy(mg->p);
   b2_vec_destroy(mg->q);
   b2_vec_destroy(mg->z);
-  b2_free(c, mg->scal, 8);
+  b2_vec_destroy(mg->w);
+  b2_free(c, mg->scal, 16);
+  b2_free(c, mg->dot_partial, (size_t)kRedBlocks * 4);
+  b2_free(c, mg->dot_counter, 1);
   delete mg;
   return 0;
 }
