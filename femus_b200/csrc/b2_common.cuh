@@ -113,6 +113,7 @@ struct b2_csr {
   int64_t* rowptr;   // [nrows+1]
   int32_t* col;      // [nnz]
   double* val;       // [nnz]
+  int32_t* diag_pos; // [nrows] position of the diagonal inside each row (built by the first b2_csr_diag), or null
   // SpMV plan (b2_spmv.cu), null: streaming kernel
   int32_t* chunk_row;        // [nchunks+1] row cuts
   int64_t* cdesc;            // [nchunks+1][4] packed {first nonzero, dictionary start, first row, 0} per chunk

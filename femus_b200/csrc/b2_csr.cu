@@ -56,12 +56,22 @@ __global__ void zero_cols_kernel(int64_t nnz, const int32_t* __restrict__ col, d
     if (mask[col[k]]) val[k] = 0.0;
 }
 
-__global__ void diag_kernel(int64_t nrows, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
-                            const double* __restrict__ val, double* __restrict__ d) {
+// position of the diagonal inside every row (-1: structurally absent): found once per pattern, then
+// MatGetDiagonal is a plain gather
+__global__ void diag_pos_kernel(int64_t nrows, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                                int32_t* __restrict__ pos) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < nrows; r += stride) {
     const int64_t p = find_in_row(col, rowptr[r], rowptr[r + 1], (int32_t)r);
-    d[r] = p >= 0 ? val[p] : 0.0;
+    pos[r] = p >= 0 ? (int32_t)(p - rowptr[r]) : -1;
+  }
+}
+__global__ void diag_gather_kernel(int64_t nrows, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ pos,
+                                   const double* __restrict__ val, double* __restrict__ d) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < nrows; r += stride) {
+    const int32_t p = pos[r];
+    d[r] = p >= 0 ? val[rowptr[r] + p] : 0.0;
   }
 }
 
@@ -272,6 +282,7 @@ int b2_csr_alloc(b2_ctx* c, int64_t nrows, int64_t ncols, int64_t nnz, b2_csr** 
   A->tpr = 8;
   A->max_row = 0;
   A->last_ms = 0.;
+  A->diag_pos = nullptr;
   A->chunk_row = nullptr;
   A->dict_ptr = nullptr;
   A->cdesc = nullptr;
@@ -380,6 +391,7 @@ int b2_csr_destroy(b2_csr* A) {
   cudaStreamSynchronize(A->ctx->stream);
   b2_free(A->ctx, A->rowptr, (size_t)A->nrows + 3);
   b2_csr_free_plan(A);
+  if (A->diag_pos) b2_free(A->ctx, A->diag_pos, (size_t)A->nrows);
   b2_free(A->ctx, A->col, (size_t)A->nnz + 16);
   b2_free(A->ctx, A->val, (size_t)A->nnz + 16);
   delete A;
@@ -504,7 +516,13 @@ int b2_csr_diag(const b2_csr* A, b2_vec* d) {
   B2_CHECK(d->n >= A->nrows, "b2_csr_diag: vector too short");
   b2_ctx* c = A->ctx;
   const int grid = b2_grid_for(c, A->nrows, kBlock, 8);
-  B2_LAUNCH(c, diag_kernel, grid, kBlock, 0, A->nrows, A->rowptr, A->col, A->val, d->d);
+  if (A->nrows == 0) return 0;
+  if (!A->diag_pos) {       // first call on this pattern (the pattern of a b2_csr never changes)
+    b2_csr* M = const_cast<b2_csr*>(A);
+    B2_TRY(b2_malloc(c, &M->diag_pos, (size_t)A->nrows));
+    B2_LAUNCH(c, diag_pos_kernel, grid, kBlock, 0, A->nrows, A->rowptr, A->col, M->diag_pos);
+  }
+  B2_LAUNCH(c, diag_gather_kernel, grid, kBlock, 0, A->nrows, A->rowptr, A->diag_pos, A->val, d->d);
   return 0;
 }
 

@@ -31,6 +31,8 @@ def lib():
         L.port_axpby.argtypes = [i64, cd, vp, cd, vp, ci]
         L.port_pmult.argtypes = [i64, vp, vp, vp, ci]
         L.port_max_threads.restype = ci
+        L.port_ptap.restype = ci
+        L.port_ptap.argtypes = [i64, i64] + [vp] * 12 + [ci]
         _lib = L
     return _lib
 
@@ -126,3 +128,22 @@ class PortMG:
         self.A[top].spmv(epsc, res, 2, b=res.copy())
         eps += epsc
         return res, eps
+
+
+def ptap(P, A, rp, ci_, nthreads):
+    """C = P^T A P on the pattern (rp, ci_) with the OpenMP port (scipy CSR in, scipy CSR out)."""
+    import scipy.sparse as sp
+    L = lib()
+    P = P.tocsr(); A = A.tocsr(); R = P.T.tocsr()
+    for M in (P, A, R):
+        M.sort_indices()
+    f = lambda M: (np.ascontiguousarray(M.indptr, dtype=np.int64), np.ascontiguousarray(M.indices, dtype=np.int32),
+                   np.ascontiguousarray(M.data, dtype=np.float64))
+    Ap, Ai, Ax = f(A); Pp, Pi, Px = f(P); Rp, Ri, Rx = f(R)
+    rp = np.ascontiguousarray(rp, dtype=np.int64); ci_ = np.ascontiguousarray(ci_, dtype=np.int32)
+    Cx = np.zeros(ci_.shape[0])
+    err = L.port_ptap(P.shape[0], P.shape[1], _p(Ap), _p(Ai), _p(Ax), _p(Pp), _p(Pi), _p(Px), _p(Rp), _p(Ri), _p(Rx),
+                      _p(rp), _p(ci_), _p(Cx), int(nthreads))
+    if err:
+        raise RuntimeError(f"port_ptap failed ({err}): product leaves the coarse pattern or out of memory")
+    return sp.csr_matrix((Cx, ci_, rp), shape=(P.shape[1], P.shape[1]))

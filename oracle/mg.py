@@ -68,7 +68,7 @@ class Hierarchy:
     """Per-level operators exactly as the reference sets them up for one MGsolve."""
 
     def __init__(self, levels, order, fsrc=1.0, dirichlet_faces=(1, 2, 3, 4, 5, 6), A_top=None, rhs=None,
-                 coarse_lu=True):
+                 coarse_lu=True, ptap=None):
         self.levels = levels
         self.order = order
         nl = len(levels)
@@ -79,22 +79,31 @@ class Hierarchy:
         for l in range(1, nl):
             P = mb.prolongator(levels[l - 1], levels[l], order)
             self.P[l] = mb.zero_dirichlet(P, self.bdc[l], self.bdc[l - 1])
+        # coarse patterns = coarse element coupling patterns (explicit zeros kept); fixed at init()
+        self.patterns = [mb.sparsity(levels[l], order) for l in range(nl - 1)]
+        self.coarse_lu = coarse_lu
         # assembly on the finest level (V_CYCLE: only the top level is assembled)
-        self.A_raw = [None] * nl
         if A_top is None:
-            self.A_raw[-1], self.rhs = mb.assemble(levels[-1], order, None, fsrc)
-        else:                                   # assembled elsewhere (e.g. by oracle/_ref)
-            self.A_raw[-1], self.rhs = A_top, rhs
-        # Galerkin chain on the un-penalised matrices
+            A_top, rhs = mb.assemble(levels[-1], order, None, fsrc)
+        self.set_operator(A_top, rhs, ptap)
+
+    def set_operator(self, A_top, rhs, ptap=None):
+        """What one MGsolve does with a freshly assembled finest matrix: Galerkin chain on the
+        un-penalised matrices, then MGSetLevel's penalty and the Jacobi diagonal on every level.
+        ptap: optional threaded triple product (oracle.cpu_port.ptap) for the CPU baseline."""
+        nl = len(self.levels)
+        self.A_raw = [None] * nl
+        self.A_raw[-1], self.rhs = A_top, rhs
         for l in range(nl - 1, 0, -1):
+            rp, ci = self.patterns[l - 1]
+            if ptap is not None:
+                self.A_raw[l - 1] = ptap(self.P[l], self.A_raw[l], rp, ci)
+                continue
             Ac = (self.P[l].T @ self.A_raw[l] @ self.P[l]).tocsr()
-            # result pattern = coarse element coupling pattern (explicit zeros kept)
-            rp, ci = mb.sparsity(levels[l - 1], order)
             self.A_raw[l - 1] = on_pattern(Ac, rp, ci)
-        # MGSetLevel: penalty on every level
         self.A = [penalty_fast(self.A_raw[l], self.bdc_idx[l]) for l in range(nl)]
         self.dinv = [1.0 / A.diagonal() for A in self.A]
-        self.lu = spla.splu(self.A[0].tocsc()) if coarse_lu else None
+        self.lu = spla.splu(self.A[0].tocsc()) if self.coarse_lu else None
 
     def smooth(self, l, x, b, nsweeps, omega):
         """KSPRICHARDSON (scale omega) + PCJACOBI: x <- x + omega D^-1 (b - A x)."""
