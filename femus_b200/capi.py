@@ -34,12 +34,18 @@ _PROTOS = {
     "b2_timer_start": (ci, [vp]),
     "b2_timer_stop_ms": (ci, [vp, vp]),
     "b2_ctx_flush_l2": (ci, [vp]),
+    "b2_ctx_measure_fp64_tensor": (ci, [vp, vp]),
     "b2_ctx_set_option": (ci, [vp, ctypes.c_char_p, ci]),
     "b2_ctx_profile": (ci, [vp, ci]),
     "b2_ctx_profile_only": (ci, [vp, vp]),
     "b2_ctx_profile_read": (ci, [vp, vp, vp, vp]),
     "b2_ctx_profile_clear": (ci, [vp]),
     "b2_vec_put_async": (ci, [vp, vp, i64]),
+    "b2_vec_prefetch": (ci, [vp, vp, i64]),
+    "b2_ctx_open_copies": (ci, [vp]),
+    "b2_ctx_join_copies": (ci, [vp]),
+    "b2_mesh_prefetch": (ci, [vp, vp, vp]),
+    "b2_mesh_swap": (ci, [vp]),
     "b2_vec_get_async": (ci, [vp, vp, i64]),
     "b2_mesh_update": (ci, [vp, vp, vp]),
     "b2_vec_create": (ci, [vp, i64, vp]),
@@ -204,6 +210,18 @@ class Context:
         check(self.L.b2_timer_stop_ms(self.h, ctypes.byref(ms)))
         return ms.value
 
+    def open_copies(self):
+        check(self.L.b2_ctx_open_copies(self.h))
+
+    def join_copies(self):
+        check(self.L.b2_ctx_join_copies(self.h))
+
+    def measure_fp64_tensor(self):
+        """Measured fp64 tensor-core (DMMA) peak of this device in TFLOP/s."""
+        t = cd()
+        check(self.L.b2_ctx_measure_fp64_tensor(self.h, ctypes.byref(t)))
+        return t.value
+
     def set_option(self, name, value):
         check(self.L.b2_ctx_set_option(self.h, name.encode(), int(value)))
 
@@ -274,6 +292,9 @@ class Vector:
 
     def put_async(self, host_ptr, n):
         check(self.L.b2_vec_put_async(self.h, host_ptr, n))
+
+    def prefetch(self, host_ptr, n):
+        check(self.L.b2_vec_prefetch(self.h, host_ptr, n))
 
     def get_async(self, host_ptr, n):
         check(self.L.b2_vec_get_async(self.h, host_ptr, n))
@@ -519,6 +540,13 @@ class Mesh:
         check(self.L.b2_mesh_create(ctx.h, xyz.shape[1], conn.shape[0], _ptr(xyz), _ptr(conn), ctypes.byref(h)))
         self.h = h
         self.nel, self.nnode = conn.shape[0], xyz.shape[1]
+
+    def prefetch(self, xyz_ptr=None, conn_ptr=None):
+        """Upload the next step's mesh into the shadow buffers on the copy stream."""
+        check(self.L.b2_mesh_prefetch(self.h, xyz_ptr, conn_ptr))
+
+    def swap(self):
+        check(self.L.b2_mesh_swap(self.h))
 
     def update(self, xyz_ptr=None, conn_ptr=None):
         """Asynchronous re-upload from (pinned) host pointers."""

@@ -23,6 +23,8 @@ struct b2_mesh {
   int64_t nnode, nel;
   double* xyz;     // [3][nnode]
   int32_t* conn;   // [nel][27]
+  double* xyz_shadow;    // second copy of both, allocated by the first b2_mesh_prefetch: the next step's
+  int32_t* conn_shadow;  // mesh is uploaded here while the current step still reads xyz / conn
 };
 
 struct b2_asm {
@@ -839,12 +841,53 @@ int build_gal_tables(b2_asm* p, const b2_galerkin* gal, const b2_galerkin_view& 
 
 }  // namespace
 
+// fp64 tensor-core issue-rate probe: every warp keeps 8 independent DMMA.8x8x4 chains busy
+__global__ void __launch_bounds__(512) dmma_probe_kernel(int iters, double* out) {
+  double c[8][2];
+#pragma unroll
+  for (int t = 0; t < 8; t++) c[t][0] = c[t][1] = 0.0;
+  const double a = 1.0 + 1e-9 * threadIdx.x, b = 1.0 - 1e-9 * threadIdx.x;
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int t = 0; t < 8; t++) dmma(c[t][0], c[t][1], a, b);
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int t = 0; t < 8; t++) s += c[t][0] + c[t][1];
+  if (s == -1.0) out[0] = s;      // never true: keeps the chains alive
+}
+
 extern "C" {
+
+/* measured fp64 tensor-core peak (TFLOP/s) of this device: the denominator next to the assembly
+ * kernel's achieved rate in bench.py (MEASURED_PEAKS.json carries no fp64 figure) */
+int b2_ctx_measure_fp64_tensor(b2_ctx* c, double* tflops) {
+  double* d = nullptr;
+  B2_TRY(b2_malloc(c, &d, 1));
+  const int iters = 20000, grid = c->sm_count * 2;
+  dmma_probe_kernel<<<grid, 512, 0, c->stream>>>(2000, d);       // warm-up
+  cudaEvent_t e0, e1;
+  B2_CUDA(cudaEventCreate(&e0));
+  B2_CUDA(cudaEventCreate(&e1));
+  B2_CUDA(cudaEventRecord(e0, c->stream));
+  dmma_probe_kernel<<<grid, 512, 0, c->stream>>>(iters, d);
+  c->launches += 2;
+  B2_CUDA(cudaEventRecord(e1, c->stream));
+  B2_CUDA(cudaEventSynchronize(e1));
+  float ms = 0.f;
+  B2_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  b2_free(c, d, 1);
+  const double flop = (double)grid * 16.0 * iters * 8.0 * 512.0;     // warps x iterations x chains x (8x8x4 FMA = 512 flop)
+  *tflops = flop / (ms * 1e-3) / 1e12;
+  return 0;
+}
 
 int b2_mesh_create(b2_ctx* c, int64_t nnode, int64_t nel, const double* xyz, const int32_t* conn, b2_mesh** out) {
   *out = nullptr;
   B2_CHECK(c && nnode > 0 && nel > 0 && xyz && conn, "b2_mesh_create: bad arguments");
-  b2_mesh* m = new b2_mesh{c, nnode, nel, nullptr, nullptr};
+  b2_mesh* m = new b2_mesh{c, nnode, nel, nullptr, nullptr, nullptr, nullptr};
   B2_TRY(b2_malloc(c, &m->xyz, (size_t)3 * nnode));
   B2_TRY(b2_malloc(c, &m->conn, (size_t)27 * nel));
   B2_TRY(b2_upload(c, m->xyz, xyz, (size_t)3 * nnode));
@@ -858,9 +901,32 @@ int b2_mesh_update(b2_mesh* m, const double* xyz, const int32_t* conn) {
   if (conn) B2_CUDA(cudaMemcpyAsync(m->conn, conn, (size_t)27 * m->nel * sizeof(int32_t), cudaMemcpyHostToDevice, m->ctx->stream));
   return 0;
 }
+// upload into the shadow buffers on the copy stream (call b2_ctx_open_copies first), then
+// b2_ctx_join_copies + b2_mesh_swap before the step that uses the new mesh
+int b2_mesh_prefetch(b2_mesh* m, const double* xyz, const int32_t* conn) {
+  b2_ctx* c = m->ctx;
+  if (!m->xyz_shadow) {
+    B2_TRY(b2_malloc(c, &m->xyz_shadow, (size_t)3 * m->nnode));
+    B2_TRY(b2_malloc(c, &m->conn_shadow, (size_t)27 * m->nel));
+    B2_CUDA(cudaMemcpyAsync(m->xyz_shadow, m->xyz, (size_t)3 * m->nnode * sizeof(double), cudaMemcpyDeviceToDevice, c->copy_stream));
+    B2_CUDA(cudaMemcpyAsync(m->conn_shadow, m->conn, (size_t)27 * m->nel * sizeof(int32_t), cudaMemcpyDeviceToDevice, c->copy_stream));
+  }
+  if (xyz) B2_CUDA(cudaMemcpyAsync(m->xyz_shadow, xyz, (size_t)3 * m->nnode * sizeof(double), cudaMemcpyHostToDevice, c->copy_stream));
+  if (conn) B2_CUDA(cudaMemcpyAsync(m->conn_shadow, conn, (size_t)27 * m->nel * sizeof(int32_t), cudaMemcpyHostToDevice, c->copy_stream));
+  return 0;
+}
+int b2_mesh_swap(b2_mesh* m) {
+  B2_CHECK(m->xyz_shadow, "b2_mesh_swap: nothing was prefetched");
+  std::swap(m->xyz, m->xyz_shadow);
+  std::swap(m->conn, m->conn_shadow);
+  return 0;
+}
 int b2_mesh_destroy(b2_mesh* m) {
   if (!m) return 0;
   cudaStreamSynchronize(m->ctx->stream);
+  cudaStreamSynchronize(m->ctx->copy_stream);
+  if (m->xyz_shadow) b2_free(m->ctx, m->xyz_shadow, (size_t)3 * m->nnode);
+  if (m->conn_shadow) b2_free(m->ctx, m->conn_shadow, (size_t)27 * m->nel);
   b2_free(m->ctx, m->xyz, (size_t)3 * m->nnode);
   b2_free(m->ctx, m->conn, (size_t)27 * m->nel);
   delete m;

@@ -46,6 +46,10 @@ struct b2_ctx {
   int sm_count = 148;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // second stream for host->device prefetches that overlap the compute of the previous step
+  // (b2_mesh_prefetch / b2_vec_prefetch / b2_ctx_join_copies)
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_copied = nullptr, ev_free = nullptr;
   int64_t bytes = 0;
   int64_t launches = 0;
   // scratch for reductions: partial sums + result (device) and a pinned host mirror

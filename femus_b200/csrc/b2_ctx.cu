@@ -81,6 +81,9 @@ int b2_ctx_create(int device, b2_ctx** out) {
   B2_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   B2_CUDA(cudaEventCreate(&c->ev0));
   B2_CUDA(cudaEventCreate(&c->ev1));
+  B2_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+  B2_CUDA(cudaEventCreateWithFlags(&c->ev_copied, cudaEventDisableTiming));
+  B2_CUDA(cudaEventCreateWithFlags(&c->ev_free, cudaEventDisableTiming));
   B2_TRY(b2_malloc(c, &c->red_partial, (size_t)kRedBlocks * 2));
   B2_TRY(b2_malloc(c, &c->red_result, 8));
   B2_TRY(b2_malloc(c, &c->red_counter, 1));
@@ -104,6 +107,9 @@ int b2_ctx_destroy(b2_ctx* c) {
   cudaEventDestroy(c->ev0);
   cudaEventDestroy(c->ev1);
   cudaStreamDestroy(c->stream);
+  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+  if (c->ev_copied) cudaEventDestroy(c->ev_copied);
+  if (c->ev_free) cudaEventDestroy(c->ev_free);
   delete c;
   return 0;
 }
@@ -142,6 +148,21 @@ int b2_ctx_flush_l2(b2_ctx* c) {
     B2_CUDA(cudaMalloc(&c->flush_buf, c->flush_bytes));
   }
   B2_CUDA(cudaMemsetAsync(c->flush_buf, 0, c->flush_bytes, c->stream));
+  return 0;
+}
+
+// Prefetch protocol (double-buffered inputs): b2_ctx_open_copies makes the copy stream wait for
+// everything enqueued so far on the compute stream (the buffers about to be overwritten may still be
+// read by it); the b2_*_prefetch calls then copy on the copy stream; b2_ctx_join_copies makes the
+// compute stream wait for those copies.
+int b2_ctx_open_copies(b2_ctx* c) {
+  B2_CUDA(cudaEventRecord(c->ev_free, c->stream));
+  B2_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_free, 0));
+  return 0;
+}
+int b2_ctx_join_copies(b2_ctx* c) {
+  B2_CUDA(cudaEventRecord(c->ev_copied, c->copy_stream));
+  B2_CUDA(cudaStreamWaitEvent(c->stream, c->ev_copied, 0));
   return 0;
 }
 

@@ -202,6 +202,12 @@ int b2_vec_put_async(b2_vec* v, const double* host, int64_t n) {
   B2_CUDA(cudaMemcpyAsync(v->d, host, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, v->ctx->stream));
   return 0;
 }
+// host -> device on the copy stream (see b2_ctx_open_copies / b2_ctx_join_copies)
+int b2_vec_prefetch(b2_vec* v, const double* host, int64_t n) {
+  B2_CHECK(n <= v->n, "b2_vec_prefetch: too long");
+  B2_CUDA(cudaMemcpyAsync(v->d, host, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, v->ctx->copy_stream));
+  return 0;
+}
 int b2_vec_get_async(const b2_vec* v, double* host, int64_t n) {
   B2_CHECK(n <= v->n, "b2_vec_get_async: too long");
   B2_CUDA(cudaMemcpyAsync(host, v->d, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, v->ctx->stream));

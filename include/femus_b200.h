@@ -66,6 +66,8 @@ int b2_ctx_profile_clear(b2_ctx* c);
  * software-pipelined gathers); "spmv_timing" = 1 makes y = A x print the consumer phase cycles of CTA 0;
  * "asm_variant" = 1 (triquadratic assembly on the FP64 tensor cores, default) | 0 (CUDA-core register tiles) */
 int b2_ctx_set_option(b2_ctx* c, const char* name, int value);
+/* measured issue-rate peak of mma.sync.m8n8k4.f64 on this device, TFLOP/s (a few ms of DMMA chains) */
+int b2_ctx_measure_fp64_tensor(b2_ctx* c, double* tflops);
 /* write 256 MiB of device memory (> L2 size) to evict the L2 between timed iterations */
 int b2_ctx_flush_l2(b2_ctx* c);
 
@@ -82,6 +84,12 @@ int b2_vec_get(const b2_vec* v, double* host, int64_t n);              /* locali
 /* asynchronous variants on the library stream (host buffer should be pinned) */
 int b2_vec_put_async(b2_vec* v, const double* host, int64_t n);
 int b2_vec_get_async(const b2_vec* v, double* host, int64_t n);
+/* Overlapped input upload (double buffering): b2_ctx_open_copies orders the copy stream after the
+ * compute enqueued so far, b2_vec_prefetch / b2_mesh_prefetch copy on the copy stream into buffers the
+ * running step does not read, b2_ctx_join_copies orders the compute stream after those copies. */
+int b2_ctx_open_copies(b2_ctx* c);
+int b2_ctx_join_copies(b2_ctx* c);
+int b2_vec_prefetch(b2_vec* v, const double* host, int64_t n);
 int b2_vec_copy(b2_vec* dst, const b2_vec* src);                       /* operator=(NumericVector)     :429 */
 int b2_vec_axpy(b2_vec* y, double a, const b2_vec* x);                 /* add(a,V)    VecAXPY          :303 */
 int b2_vec_aypx(b2_vec* y, double a, const b2_vec* x);                 /* y = x + a y VecAYPX */
@@ -189,6 +197,9 @@ int b2_mesh_create(b2_ctx* c, int64_t nnode, int64_t nel, const double* xyz, con
 /* re-upload coordinates / connectivity into the existing device buffers, asynchronously on the
  * library stream (either may be NULL) */
 int b2_mesh_update(b2_mesh* m, const double* xyz, const int32_t* conn);
+/* upload the NEXT step's mesh into shadow buffers on the copy stream; b2_mesh_swap makes them current */
+int b2_mesh_prefetch(b2_mesh* m, const double* xyz, const int32_t* conn);
+int b2_mesh_swap(b2_mesh* m);
 int b2_mesh_destroy(b2_mesh* m);
 /* Assembly plan for one unknown on one mesh: nve = 8 (trilinear) or 27 (triquadratic);
  * dof[nel][nve] = matrix row of each local node (GetSystemDof, LinearEquation.cpp:76-85);
