@@ -343,8 +343,11 @@ assemble_poisson_kernel(int64_t nel, int64_t nnode, const double* __restrict__ x
 }
 
 // ------------------------------------------------------------------------------------------
-// Triquadratic elements on the FP64 tensor cores.  B = sum_g w_g G_g G_g^T (G_g: 27 x 3 gradients at
-// Gauss point g) is a 27 x 27 x 192 GEMM per element: 48 k-steps of mma.sync.m8n8k4.f64 (DMMA.8x8x4
+// Triquadratic elements on the FP64 tensor cores.  With D_g the 27 x 3 REFERENCE gradients at Gauss
+// point g (the same table for every element) and K_g = w_g det_g J_g^-1 J_g^-T (3 x 3, symmetric),
+// B = sum_g D_g K_g D_g^T = D (K D^T) is a 27 x 27 x 192 GEMM per element whose left operand never
+// changes: its fragments are read straight from the table in shared memory, only the right operand
+// D_g K_g (9 FMA per node and point) is formed and staged per element.  The GEMM runs as 48 k-steps of mma.sync.m8n8k4.f64 (DMMA.8x8x4
 // is the only fp64 tensor shape of sm_100a: m16n8k8 compiles to four of them) on the 4 x 4 grid of
 // 8 x 8 output tiles, of which only the 10 upper ones are formed (B is symmetric).  Against the CUDA-core tile kernel above this needs 8
 // shared-memory fragment loads per lane and Gauss point instead of 33 (that kernel is bound by
@@ -352,13 +355,16 @@ assemble_poisson_kernel(int64_t nel, int64_t nnode, const double* __restrict__ x
 // written to shared memory once; residual, scatter and the fused Galerkin product read it from there,
 // so the scatter uses a slot map in natural (i, j) order.
 constexpr int MS = 36;            // column stride of the fragment buffers: conflict-free 8-byte fragment loads
+constexpr int KT = 3 * NG;        // K dimension of the element GEMM: (Gauss point, reference direction)
 struct MmaSmem {
-  static constexpr int tab_doubles = 3 * NG * 27 + NG;                   // dxi, deta, dzeta, weights
-  // per warp: X[3][GP], U[GP], rowbase[GP] (int64), geo[10][NG], M[2 buffers][2: G, wG][4][MS]
-  static constexpr int warp_doubles = 3 * GP + GP + GP + 10 * NG + 2 * 2 * 4 * MS;
+  // reference gradients twice: D[k = 3g + a][node] with row stride MS (fragment loads of the GEMM, rows of
+  // D_g K_g) and [a][g][node] with row stride 27 (geometry phase, lanes = Gauss points: conflict-free), weights
+  static constexpr int tab_doubles = KT * MS + 3 * NG * 27 + NG;
+  // per warp: X[3][GP], U[GP], rowbase[GP] (int64), geo[7][NG], M[2 halves][4][MS]
+  static constexpr int warp_doubles = 3 * GP + GP + GP + 7 * NG + 2 * 4 * MS;
   static constexpr size_t bytes = (size_t)(tab_doubles + kWarps * warp_doubles) * sizeof(double);
   static constexpr size_t bytes_gal = bytes + sizeof(GalTables<27>);
-  static_assert(10 * NG + 2 * 2 * 4 * MS >= 27 * 27, "element matrix does not fit the reused buffers");
+  static_assert(7 * NG + 2 * 4 * MS >= 27 * 27, "element matrix does not fit the reused buffers");
 };
 
 __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
@@ -373,21 +379,26 @@ assemble_q2_mma_kernel(int64_t nel, int64_t nnode, const double* __restrict__ xy
                        double* __restrict__ rhs, double nu, double fsrc, const GalArgs ga) {
   constexpr int NVE = 27;
   extern __shared__ double smem[];
-  double* s_dx = smem;
+  double* sT = smem;                                    // [KT][MS] reference gradients, row k = 3 g + a
+  double* s_dx = sT + KT * MS;                          // [3][NG][27] the same, geometry-phase layout
   double* s_dy = s_dx + NG * NVE;
   double* s_dz = s_dy + NG * NVE;
-  double* s_w = s_dz + NG * NVE;
+  double* s_w = s_dz + NG * NVE;                        // [NG] Gauss weights
   const double* g_phi = tab;          // the shape-value table is only needed for the source term: read through L1
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   double* wbase = s_w + NG + wib * MmaSmem::warp_doubles;
   double* sX = wbase;                                   // [3][GP]
   double* sU = sX + 3 * GP;                             // [GP]
   long long* sRow = reinterpret_cast<long long*>(sU + GP);   // [GP] rowptr[dof_i]
-  double* sGeo = reinterpret_cast<double*>(sRow + GP);  // [10][NG]: J^-1 (9, row-major), weight
-  double* sM = sGeo + 10 * NG;                          // [2][2][4][MS]: double-buffered G and w*G, (component, node)
+  double* sGeo = reinterpret_cast<double*>(sRow + GP);  // [7][NG]: K00 K01 K02 K11 K12 K22, weight
+  double* sM = sGeo + 7 * NG;                           // [2][4][MS]: two k-steps of D K, (k, node)
   double* Bs = sGeo;                                    // [27][27] element matrix, reuses geo + M
 
-  for (int t = threadIdx.x; t < MmaSmem::tab_doubles; t += blockDim.x) smem[t] = tab[NG * NVE + t];
+  for (int t = threadIdx.x; t < KT * MS; t += blockDim.x) {
+    const int k = t / MS, n = t - k * MS, g = k / 3, a = k - 3 * g;
+    sT[t] = n < NVE ? tab[(1 + a) * NG * NVE + g * NVE + n] : 0.0;
+  }
+  for (int t = threadIdx.x; t < 3 * NG * NVE + NG; t += blockDim.x) s_dx[t] = tab[NG * NVE + t];
   const GalTables<NVE>* gt = nullptr;
   if (GAL) {
     int* dst = reinterpret_cast<int*>(smem + MmaSmem::tab_doubles + kWarps * MmaSmem::warp_doubles);
@@ -412,7 +423,7 @@ assemble_q2_mma_kernel(int64_t nel, int64_t nnode, const double* __restrict__ xy
       sU[lane] = u ? u[mydof] : 0.0;
       sRow[lane] = rowptr[mydof];
     }
-    for (int t = lane; t < 2 * 2 * 4 * MS; t += 32) sM[t] = 0.0;  // padding rows 27..31 stay zero
+    for (int t = lane; t < 2 * 4 * MS; t += 32) sM[t] = 0.0;      // padding rows 27..31 stay zero
     __syncwarp();
 
     // ---- A. geometry at the Gauss points owned by this lane
@@ -432,16 +443,19 @@ assemble_q2_mma_kernel(int64_t nel, int64_t nnode, const double* __restrict__ xy
       }
       const double det = J00 * (J11 * J22 - J12 * J21) + J01 * (J12 * J20 - J10 * J22) + J02 * (J10 * J21 - J11 * J20);
       const double id = 1.0 / det;
-      sGeo[0 * NG + g] = (-J12 * J21 + J11 * J22) * id;
-      sGeo[1 * NG + g] = (J02 * J21 - J01 * J22) * id;
-      sGeo[2 * NG + g] = (-J02 * J11 + J01 * J12) * id;
-      sGeo[3 * NG + g] = (J12 * J20 - J10 * J22) * id;
-      sGeo[4 * NG + g] = (-J02 * J20 + J00 * J22) * id;
-      sGeo[5 * NG + g] = (J02 * J10 - J00 * J12) * id;
-      sGeo[6 * NG + g] = (-J11 * J20 + J10 * J21) * id;
-      sGeo[7 * NG + g] = (J01 * J20 - J00 * J21) * id;
-      sGeo[8 * NG + g] = (-J01 * J10 + J00 * J11) * id;
-      sGeo[9 * NG + g] = det * s_w[g];
+      // JacI[d][a] as ElemType.hpp:1478-1486; grad phi_n [d] = sum_a dphi_n/dxi_a JacI[d][a]
+      const double I00 = (-J12 * J21 + J11 * J22) * id, I01 = (J02 * J21 - J01 * J22) * id, I02 = (-J02 * J11 + J01 * J12) * id;
+      const double I10 = (J12 * J20 - J10 * J22) * id, I11 = (-J02 * J20 + J00 * J22) * id, I12 = (J02 * J10 - J00 * J12) * id;
+      const double I20 = (-J11 * J20 + J10 * J21) * id, I21 = (J01 * J20 - J00 * J21) * id, I22 = (-J01 * J10 + J00 * J11) * id;
+      const double wd = det * s_w[g];
+      // K_ab = weight * sum_d JacI[d][a] JacI[d][b]
+      sGeo[0 * NG + g] = wd * fma(I20, I20, fma(I10, I10, I00 * I00));
+      sGeo[1 * NG + g] = wd * fma(I20, I21, fma(I10, I11, I00 * I01));
+      sGeo[2 * NG + g] = wd * fma(I20, I22, fma(I10, I12, I00 * I02));
+      sGeo[3 * NG + g] = wd * fma(I21, I21, fma(I11, I11, I01 * I01));
+      sGeo[4 * NG + g] = wd * fma(I21, I22, fma(I11, I12, I01 * I02));
+      sGeo[5 * NG + g] = wd * fma(I22, I22, fma(I12, I12, I02 * I02));
+      sGeo[6 * NG + g] = wd;
     }
     __syncwarp();
 
@@ -454,31 +468,30 @@ assemble_q2_mma_kernel(int64_t nel, int64_t nnode, const double* __restrict__ xy
     // padding: a Gauss point contributes 3 consecutive columns, so 4 points make 3 k-steps.  The two
     // halves of the fragment buffer hold alternate k-steps; a half is rewritten only after a
     // __syncwarp that follows the fragment loads of the k-step it held before (see the order below).
-    auto grad = [&](int g, double& g0, double& g1, double& g2, double& wg) {
-      wg = sGeo[9 * NG + g];
-      g0 = g1 = g2 = 0.0;
+    auto grad = [&](int g, double& h0, double& h1, double& h2, double& wg) {     // row `lane` of D_g K_g
+      wg = sGeo[6 * NG + g];
+      h0 = h1 = h2 = 0.0;
       if (lane < NVE) {
-        const double a = s_dx[g * NVE + lane], b = s_dy[g * NVE + lane], c = s_dz[g * NVE + lane];
-        g0 = fma(c, sGeo[2 * NG + g], fma(b, sGeo[1 * NG + g], a * sGeo[0 * NG + g]));
-        g1 = fma(c, sGeo[5 * NG + g], fma(b, sGeo[4 * NG + g], a * sGeo[3 * NG + g]));
-        g2 = fma(c, sGeo[8 * NG + g], fma(b, sGeo[7 * NG + g], a * sGeo[6 * NG + g]));
+        const double a = sT[(3 * g + 0) * MS + lane], b = sT[(3 * g + 1) * MS + lane], c = sT[(3 * g + 2) * MS + lane];
+        const double K00 = sGeo[0 * NG + g], K01 = sGeo[1 * NG + g], K02 = sGeo[2 * NG + g];
+        const double K11 = sGeo[3 * NG + g], K12 = sGeo[4 * NG + g], K22 = sGeo[5 * NG + g];
+        h0 = fma(c, K02, fma(b, K01, a * K00));
+        h1 = fma(c, K12, fma(b, K11, a * K01));
+        h2 = fma(c, K22, fma(b, K12, a * K02));
         if (rhs) src = fma(__ldg(g_phi + g * NVE + lane), wg, src);
       }
     };
-    auto put = [&](int kstep, int col, double v, double w) {       // column `col` of k-step `kstep`
-      if (lane < NVE) {
-        double* M = sM + (kstep & 1) * (2 * 4 * MS) + col * MS + lane;
-        M[0] = v;
-        M[4 * MS] = v * w;
-      }
+    auto put = [&](int kstep, int col, double v, double) {       // column `col` of k-step `kstep` of D K
+      if (lane < NVE) sM[(kstep & 1) * (4 * MS) + col * MS + lane] = v;
     };
     auto mma_step = [&](int kstep) {
-      const double* M = sM + (kstep & 1) * (2 * 4 * MS);
+      const double* M = sM + (kstep & 1) * (4 * MS);
+      const double* D = sT + (4 * kstep) * MS;          // rows k = 4 kstep .. 4 kstep + 3 of the reference-gradient table
       double fa[4], fb[4];
 #pragma unroll
       for (int T = 0; T < 4; T++) {
-        fa[T] = M[fk * MS + 8 * T + fr];               // G[8T + l/4][k]
-        fb[T] = M[4 * MS + fk * MS + 8 * T + fr];      // (w G)[8T + l/4][k]
+        fa[T] = D[fk * MS + 8 * T + fr];                // D[8T + l/4][k]
+        fb[T] = M[fk * MS + 8 * T + fr];                // (D K)[8T + l/4][k]
       }
       int t = 0;
 #pragma unroll
