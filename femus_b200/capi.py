@@ -96,6 +96,8 @@ _PROTOS = {
     "b2_csr_last_kernel_ms": (cd, [vp]),
     "b2_galerkin_create": (ci, [vp, vp, i64, ci, ci, vp, vp, vp, vp, vp, vp, vp, vp]),
     "b2_galerkin_apply": (ci, [vp]),
+    "b2_galerkin_record_elements": (ci, [vp, ci]),
+    "b2_galerkin_apply_from_elements": (ci, [vp, vp]),
     "b2_galerkin_destroy": (ci, [vp]),
     "b2_mesh_create": (ci, [vp, i64, i64, vp, vp, vp]),
     "b2_mesh_destroy": (ci, [vp]),
@@ -522,6 +524,13 @@ class Galerkin:
 
     def apply(self):
         check(self.L.b2_galerkin_apply(self.h))
+
+    def record_elements(self, on=True):
+        check(self.L.b2_galerkin_record_elements(self.h, 1 if on else 0))
+
+    def apply_from_elements(self, finer):
+        """Ac = P^T Af P from the element matrices recorded by `finer` (whose coarse matrix is our Af)."""
+        check(self.L.b2_galerkin_apply_from_elements(self.h, finer.h))
 
     def __del__(self):
         try:

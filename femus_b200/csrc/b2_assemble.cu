@@ -53,6 +53,9 @@ struct b2_galerkin_view {
   const uint8_t *fmask, *cmask;
   const void* slot;
   int slot_bytes;
+  double** emat;        // storage slots owned by the plan (element-matrix chain)
+  void** chain_tab;
+  int* chain_tab_nve;
 };
 int b2_galerkin_get_view(const b2_galerkin* g, b2_galerkin_view* v);
 
@@ -85,6 +88,7 @@ struct GalArgs {
   const uint8_t* cmask;       // coarse Dirichlet columns of P (may be null)
   const int64_t* Cp;          // coarse rowptr
   double* Cv;                 // coarse values
+  double* emat;               // [nelc][NVE*NVE] record of every coarse element's Galerkin matrix, or null
 };
 
 template <int NVE>
@@ -327,6 +331,7 @@ assemble_poisson_kernel(int64_t nel, int64_t nnode, const double* __restrict__ x
           double v = 0.0;
 #pragma unroll
           for (int w = 0; w < 8; w++) v += D0[(size_t)w * SmemLayout<NVE>::warp_doubles + idx];
+          if (ga.emat) ga.emat[(size_t)E * (NVE * NVE) + idx] = v;
           if (v == 0.0) continue;
           const int I = idx / NVE, J = idx - I * NVE;
           const int32_t dI = ga.cd[E * NVE + I];
@@ -622,6 +627,7 @@ assemble_q2_mma_kernel(int64_t nel, int64_t nnode, const double* __restrict__ xy
           double v = 0.0;
 #pragma unroll
           for (int w = 0; w < 8; w++) v += D0[(size_t)w * MmaSmem::warp_doubles + idx];
+          if (ga.emat) ga.emat[(size_t)E * (NVE * NVE) + idx] = v;
           if (v == 0.0) continue;
           const int I = idx / NVE, J = idx - I * NVE;
           const int32_t dI = ga.cd[E * NVE + I];
@@ -657,6 +663,105 @@ __global__ void natural_slot_kernel(int64_t total, int nve, const int32_t* __res
     }
     if (lo >= en || col[lo] != c) atomicExch(err, 1);
     slot[t] = (SlotT)(lo - s);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Galerkin product of a COARSER level pair from recorded element matrices.  The fused assembly (and
+// this kernel itself) records, for every element E of level l, its Galerkin element matrix
+// D_E = sum over the 8 children of Pc^T B Pc.  Since A_l = sum_E D_E (scattered), the next operator is
+// A_{l-1} = sum_E Pc(E)^T D_E Pc(E), again 8 children per coarser element: the chain never re-reads
+// an assembled matrix (12 B per nonzero) -- it streams 5.8 KB per element once.
+template <int NVE, typename CSlotT>
+__global__ void __launch_bounds__(kWarps * 32, 1)
+galerkin_from_elements_kernel(int64_t nel, const double* __restrict__ emat_in, const int32_t* __restrict__ dof,
+                              const GalArgs ga) {
+  extern __shared__ double smem[];
+  constexpr int WD = NVE * NVE + 3;                                  // odd stride between the warps' matrices
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  double* Bs = smem + (size_t)wib * WD;
+  const GalTables<NVE>* gt;
+  {
+    int* dst = reinterpret_cast<int*>(smem + (size_t)kWarps * WD);
+    const int* src = reinterpret_cast<const int*>(ga.tab);
+    for (int t = threadIdx.x; t < (int)(sizeof(GalTables<NVE>) / 4); t += blockDim.x) dst[t] = src[t];
+    gt = reinterpret_cast<const GalTables<NVE>*>(dst);
+  }
+  __syncthreads();
+  for (int64_t e = (int64_t)blockIdx.x * kWarps + wib; e < nel; e += (int64_t)gridDim.x * kWarps) {
+    const int child = (int)(e & 7);
+    const double* De = emat_in + (size_t)e * (NVE * NVE);
+    for (int idx = lane; idx < NVE * NVE; idx += 32) Bs[idx] = De[idx];
+    // rows/columns of this level's Dirichlet dofs do not take part (rows of P zeroed)
+    unsigned mask = 0;
+    if (ga.fmask) {
+      const int fm = lane < NVE ? (int)ga.fmask[dof[e * NVE + lane]] : 0;
+      mask = __ballot_sync(0xffffffffu, fm != 0);
+    }
+    __syncwarp();
+    if (mask) {
+      for (int idx = lane; idx < NVE * NVE; idx += 32) {
+        const int i = idx / NVE, j = idx - i * NVE;
+        if (((mask >> i) | (mask >> j)) & 1u) Bs[idx] = 0.0;
+      }
+      __syncwarp();
+    }
+    double R[NVE];
+#pragma unroll
+    for (int i = 0; i < NVE; i++) R[i] = 0.0;
+    if (lane < NVE) {
+#pragma unroll 1
+      for (int q = gt->colptr[child][lane]; q < gt->colptr[child][lane + 1]; q++) {
+        const int n = gt->crow[child][q];
+        const double v = gt->cval[child][q];
+#pragma unroll
+        for (int i = 0; i < NVE; i++) R[i] = fma(Bs[i * NVE + n], v, R[i]);
+      }
+    }
+    __syncwarp();
+    if (lane < NVE) {
+#pragma unroll
+      for (int i = 0; i < NVE; i++) Bs[i * NVE + lane] = R[i];      // T = D Pc
+    }
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < NVE; j++) R[j] = 0.0;
+    if (lane < NVE) {
+#pragma unroll 1
+      for (int q = gt->colptr[child][lane]; q < gt->colptr[child][lane + 1]; q++) {
+        const int i = gt->crow[child][q];
+        const double v = gt->cval[child][q];
+#pragma unroll
+        for (int j = 0; j < NVE; j++) R[j] = fma(v, Bs[i * NVE + j], R[j]);
+      }
+    }
+    __syncwarp();
+    if (lane < NVE) {
+#pragma unroll
+      for (int j = 0; j < NVE; j++) Bs[lane * NVE + j] = R[j];      // Pc^T D Pc
+    }
+    const int grp = wib >> 3;
+    asm volatile("bar.sync %0, 256;" ::"r"(grp + 1) : "memory");
+    {
+      const int64_t E = e >> 3;
+      const CSlotT* cslot = reinterpret_cast<const CSlotT*>(ga.cslot) + (size_t)E * (NVE * NVE);
+      const double* D0 = smem + (size_t)(8 * grp) * WD;
+      for (int idx = threadIdx.x & 255; idx < NVE * NVE; idx += 256) {
+        double v = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; w++) v += D0[(size_t)w * WD + idx];
+        if (ga.emat) ga.emat[(size_t)E * (NVE * NVE) + idx] = v;
+        if (v == 0.0) continue;
+        const int I = idx / NVE, J = idx - I * NVE;
+        const int32_t dI = ga.cd[E * NVE + I];
+        if (ga.cmask) {
+          const int32_t dJ = ga.cd[E * NVE + J];
+          if (ga.cmask[dI] || ga.cmask[dJ]) continue;
+        }
+        atomicAdd(&ga.Cv[ga.Cp[dI] + (int64_t)cslot[idx]], v);
+      }
+    }
+    asm volatile("bar.sync %0, 256;" ::"r"(grp + 1) : "memory");
   }
 }
 
@@ -782,7 +887,7 @@ int launch_assemble_gal(b2_asm* p, const b2_galerkin_view& g, const b2_vec* u, b
   B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int grid = (int)((p->mesh->nel + kWarps - 1) / kWarps);
   if (grid > c->sm_count) grid = c->sm_count;
-  GalArgs ga = {p->gal_tab, g.cd, g.slot, g.fmask, g.cmask, g.Ac->rowptr, g.Ac->val};
+  GalArgs ga = {p->gal_tab, g.cd, g.slot, g.fmask, g.cmask, g.Ac->rowptr, g.Ac->val, *g.emat};
   B2_LAUNCH(c, kern, grid, kWarps * 32, smem, p->mesh->nel, p->mesh->nnode, p->mesh->xyz, p->mesh->conn, p->dof,
             p->tab, (const SlotT*)p->slot, p->A->rowptr, p->A->val, u ? u->d : nullptr, rhs ? rhs->d : nullptr, nu, fsrc, ga);
   return 0;
@@ -792,16 +897,14 @@ int launch_assemble_gal(b2_asm* p, const b2_galerkin_view& g, const b2_vec* u, b
 // children of the plan's coarse elements in the reference's order (children 8*iel + j,
 // MeshRefinement.cpp:188-507; local nodes through fine2CoarseVertexMapping, Hexahedron.cpp:75-83).
 template <int NVE>
-int build_gal_tables(b2_asm* p, const b2_galerkin* gal, const b2_galerkin_view& g) {
-  b2_ctx* c = p->mesh->ctx;
+int make_gal_tables(b2_ctx* c, const int32_t* d_dof, int64_t nel_fine, const b2_galerkin_view& g, GalTables<NVE>** out) {
   const int nf = g.nf, nc = g.nc;
-  B2_CHECK(nc == NVE && p->nve == NVE, "fused Galerkin: coarse and fine unknowns must be of the same family");
-  B2_CHECK(p->mesh->nel == 8 * g.nelc, "fused Galerkin: %lld fine elements are not 8 x %lld coarse elements",
-           (long long)p->mesh->nel, (long long)g.nelc);
-  B2_CHECK(g.Af == p->A, "fused Galerkin: the plan's fine matrix is not the assembled matrix");
+  B2_CHECK(nc == NVE, "Galerkin from element matrices: coarse and fine unknowns must be of the same family");
+  B2_CHECK(nel_fine == 8 * g.nelc, "Galerkin from element matrices: %lld fine elements are not 8 x %lld coarse elements",
+           (long long)nel_fine, (long long)g.nelc);
   std::vector<int32_t> hdof(8 * NVE), hfd(nf);
   std::vector<double> hp((size_t)nf * nc);
-  B2_TRY(b2_download(c, hdof.data(), p->dof, (size_t)8 * NVE));
+  B2_TRY(b2_download(c, hdof.data(), d_dof, (size_t)8 * NVE));
   B2_TRY(b2_download(c, hfd.data(), g.fd, (size_t)nf));
   B2_TRY(b2_download(c, hp.data(), g.ploc, (size_t)nf * nc));
   std::vector<unsigned char> lat(8 * NVE);
@@ -818,7 +921,7 @@ int build_gal_tables(b2_asm* p, const b2_galerkin* gal, const b2_galerkin_view& 
   B2_TRY(b2_malloc(c, &d_err, 1));
   B2_TRY(b2_upload(c, d_lat, lat.data(), lat.size()));
   B2_CUDA(cudaMemsetAsync(d_err, 0, sizeof(int), c->stream));
-  B2_LAUNCH(c, gal_check_kernel, b2_grid_for(c, g.nelc * 8 * NVE, 256, 8), 256, 0, g.nelc, NVE, nf, p->dof, g.fd, d_lat, d_err);
+  B2_LAUNCH(c, gal_check_kernel, b2_grid_for(c, g.nelc * 8 * NVE, 256, 8), 256, 0, g.nelc, NVE, nf, d_dof, g.fd, d_lat, d_err);
   int err = 0;
   B2_TRY(b2_download(c, &err, d_err, 1));
   b2_free(c, d_lat, lat.size());
@@ -843,15 +946,25 @@ int build_gal_tables(b2_asm* p, const b2_galerkin* gal, const b2_galerkin_view& 
     T->colptr[j][NVE] = q;
   }
   GalTables<NVE>* d_T = nullptr;
-  int s = b2_malloc(c, &d_T, 1);
-  if (!s) s = b2_upload(c, d_T, T, 1);
+  int st = b2_malloc(c, &d_T, 1);
+  if (!st) st = b2_upload(c, d_T, T, 1);
   delete T;
-  B2_TRY(s);
+  B2_TRY(st);
+  *out = d_T;
+  return 0;
+}
+
+template <int NVE>
+int build_gal_tables(b2_asm* p, const b2_galerkin* gal, const b2_galerkin_view& g) {
+  b2_ctx* c = p->mesh->ctx;
+  B2_CHECK(p->nve == NVE, "fused Galerkin: coarse and fine unknowns must be of the same family");
+  B2_CHECK(g.Af == p->A, "fused Galerkin: the plan's fine matrix is not the assembled matrix");
+  GalTables<NVE>* d_T = nullptr;
+  B2_TRY(make_gal_tables<NVE>(c, p->dof, p->mesh->nel, g, &d_T));
   p->gal = gal;
   p->gal_tab = d_T;
   return 0;
 }
-
 }  // namespace
 
 // fp64 tensor-core issue-rate probe: every warp keeps 8 independent DMMA.8x8x4 chains busy
@@ -1042,7 +1155,7 @@ int b2_asm_poisson_galerkin(b2_asm* p, b2_galerkin* gal, const b2_vec* u, b2_vec
   B2_CUDA(cudaMemsetAsync(g.Ac->val, 0, (size_t)g.Ac->nnz * sizeof(double), c->stream));
   const bool s1 = p->slot_bytes == 1, c1 = g.slot_bytes == 1;
   if (p->nve == 27 && c->asm_variant == 1) {      // FP64 tensor-core kernel
-    GalArgs ga = {p->gal_tab, g.cd, g.slot, g.fmask, g.cmask, g.Ac->rowptr, g.Ac->val};
+    GalArgs ga = {p->gal_tab, g.cd, g.slot, g.fmask, g.cmask, g.Ac->rowptr, g.Ac->val, *g.emat};
     if (s1 && c1) return launch_assemble_mma<uint8_t, true, uint8_t>(p, ga, u, rhs, nu, fsrc);
     if (s1) return launch_assemble_mma<uint8_t, true, uint16_t>(p, ga, u, rhs, nu, fsrc);
     if (c1) return launch_assemble_mma<uint16_t, true, uint8_t>(p, ga, u, rhs, nu, fsrc);
@@ -1058,6 +1171,62 @@ int b2_asm_poisson_galerkin(b2_asm* p, b2_galerkin* gal, const b2_vec* u, b2_vec
   if (s1) return launch_assemble_gal<8, uint8_t, uint16_t>(p, g, u, rhs, nu, fsrc);
   if (c1) return launch_assemble_gal<8, uint16_t, uint8_t>(p, g, u, rhs, nu, fsrc);
   return launch_assemble_gal<8, uint16_t, uint16_t>(p, g, u, rhs, nu, fsrc);
+}
+/* record the Galerkin element matrices of gal's coarse elements whenever gal is applied by the fused
+ * assembly or from element matrices (needed by b2_galerkin_apply_from_elements of the next plan) */
+int b2_galerkin_record_elements(b2_galerkin* gal, int on) {
+  b2_galerkin_view g;
+  B2_TRY(b2_galerkin_get_view(gal, &g));
+  b2_ctx* c = g.Af->ctx;
+  const size_t n = (size_t)g.nelc * g.nc * g.nc;
+  if (on && !*g.emat) B2_TRY(b2_malloc(c, g.emat, n));
+  if (!on && *g.emat) { cudaStreamSynchronize(c->stream); b2_free(c, *g.emat, n); *g.emat = nullptr; }
+  return 0;
+}
+
+}  // extern "C"
+
+template <int NVE, typename CSlotT>
+static int launch_from_elements(b2_ctx* c, const b2_galerkin_view& g, const b2_galerkin_view& f) {
+  auto kern = galerkin_from_elements_kernel<NVE, CSlotT>;
+  const size_t smem = ((size_t)kWarps * (NVE * NVE + 3)) * sizeof(double) + sizeof(GalTables<NVE>);
+  B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int64_t nel = f.nelc;
+  int grid = (int)((nel + kWarps - 1) / kWarps);
+  if (grid > c->sm_count) grid = c->sm_count;
+  GalArgs ga = {*g.chain_tab, g.cd, g.slot, g.fmask, g.cmask, g.Ac->rowptr, g.Ac->val, *g.emat};
+  B2_LAUNCH(c, kern, grid, kWarps * 32, smem, nel, (const double*)*f.emat, f.cd, ga);
+  return 0;
+}
+
+extern "C" {
+
+/* gal: Ac = P^T Af P formed from the element matrices recorded by `finer` (the plan whose coarse
+ * matrix is gal's fine matrix): A_{l-1} = sum_E Pc(E)^T D_E Pc(E).  Equal to b2_galerkin_apply(gal)
+ * up to summation order, without reading Af. */
+int b2_galerkin_apply_from_elements(b2_galerkin* gal, b2_galerkin* finer) {
+  B2_CHECK(gal && finer, "b2_galerkin_apply_from_elements: null argument");
+  b2_galerkin_view g, f;
+  B2_TRY(b2_galerkin_get_view(gal, &g));
+  B2_TRY(b2_galerkin_get_view(finer, &f));
+  b2_ctx* c = g.Af->ctx;
+  B2_CHECK(f.Ac == g.Af, "b2_galerkin_apply_from_elements: the finer plan's coarse matrix is not this plan's fine matrix");
+  B2_CHECK(*f.emat, "b2_galerkin_apply_from_elements: the finer plan has no recorded element matrices "
+                    "(b2_galerkin_record_elements, then apply it through the fused assembly or from elements)");
+  B2_CHECK(g.nc == f.nc && (g.nc == 27 || g.nc == 8), "b2_galerkin_apply_from_elements: unsupported element family");
+  if (!*g.chain_tab) {
+    if (g.nc == 27) { GalTables<27>* t = nullptr; B2_TRY(make_gal_tables<27>(c, f.cd, f.nelc, g, &t)); *g.chain_tab = t; }
+    else { GalTables<8>* t = nullptr; B2_TRY(make_gal_tables<8>(c, f.cd, f.nelc, g, &t)); *g.chain_tab = t; }
+    *g.chain_tab_nve = g.nc;
+  }
+  B2_CUDA(cudaMemsetAsync(g.Ac->val, 0, (size_t)g.Ac->nnz * sizeof(double), c->stream));
+  b2_prof_scope prof(c, gal);
+  if (g.nc == 27) {
+    if (g.slot_bytes == 1) return launch_from_elements<27, uint8_t>(c, g, f);
+    return launch_from_elements<27, uint16_t>(c, g, f);
+  }
+  if (g.slot_bytes == 1) return launch_from_elements<8, uint8_t>(c, g, f);
+  return launch_from_elements<8, uint16_t>(c, g, f);
 }
 double b2_asm_last_kernel_ms(const b2_asm* p) { return p->last_ms; }
 

@@ -40,6 +40,11 @@ struct b2_galerkin {
   uint8_t* cmask;   // [Ac->nrows] or null
   void* slot;       // [nelc][nc*nc]
   int slot_bytes;
+  // element-matrix chain (b2_assemble.cu): the nc x nc Galerkin matrix of every coarse element of this
+  // plan, recorded when the plan is applied from element matrices; feeds the next-coarser plan
+  double* emat;     // [nelc][nc*nc] or null
+  void* chain_tab;  // per-child prolongator tables for b2_galerkin_apply_from_elements, or null
+  int chain_tab_nve;
 };
 
 namespace {
@@ -322,10 +327,15 @@ struct b2_galerkin_view {
   const uint8_t *fmask, *cmask;
   const void* slot;
   int slot_bytes;
+  double** emat;        // storage slots owned by the plan (element-matrix chain)
+  void** chain_tab;
+  int* chain_tab_nve;
 };
 int b2_galerkin_get_view(const b2_galerkin* g, b2_galerkin_view* v) {
   B2_CHECK(g && v, "b2_galerkin_get_view: null argument");
-  *v = b2_galerkin_view{g->Af, g->Ac, g->nelc, g->nf, g->nc, g->fd, g->cd, g->ploc, g->fmask, g->cmask, g->slot, g->slot_bytes};
+  b2_galerkin* m = const_cast<b2_galerkin*>(g);
+  *v = b2_galerkin_view{g->Af, g->Ac, g->nelc, g->nf, g->nc, g->fd, g->cd, g->ploc, g->fmask, g->cmask, g->slot, g->slot_bytes,
+                        &m->emat, &m->chain_tab, &m->chain_tab_nve};
   return 0;
 }
 
@@ -378,6 +388,9 @@ int b2_galerkin_create(b2_csr* Af, b2_csr* Ac, int64_t nelc, int nf, int nc, con
   B2_TRY(b2_malloc(c, &g->val, (size_t)nelc * 27));
   B2_TRY(b2_upload(c, g->val, valence, (size_t)nelc * 27));
   g->fmask = g->cmask = nullptr;
+  g->emat = nullptr;
+  g->chain_tab = nullptr;
+  g->chain_tab_nve = 0;
   if (fine_mask) {
     B2_TRY(b2_malloc(c, &g->fmask, (size_t)Af->nrows));
     B2_TRY(b2_upload(c, g->fmask, fine_mask, (size_t)Af->nrows));
@@ -419,6 +432,8 @@ int b2_galerkin_destroy(b2_galerkin* g) {
   if (g->fmask) b2_free(c, g->fmask, (size_t)g->Af->nrows);
   if (g->cmask) b2_free(c, g->cmask, (size_t)g->Ac->nrows);
   const size_t ns = (size_t)g->nelc * g->nc * g->nc;
+  if (g->emat) b2_free(c, g->emat, ns);
+  if (g->chain_tab) { cudaFree(g->chain_tab); }
   if (g->slot_bytes == 1) b2_free(c, (uint8_t*)g->slot, ns);
   else b2_free(c, (uint16_t*)g->slot, ns);
   delete g;

@@ -68,6 +68,9 @@ class PoissonMG:
         self.mesh = capi.Mesh(ctx, top.xyz, top.conn)
         self.tables = hostapi.hex_tables(order)
         self.asm = capi.Assembler(self.mesh, self.KK[-1], self.dofs[-1], self.tables)
+        if self.fused:      # element-matrix Galerkin chain: every plan but the coarsest records its element matrices
+            for l in range(2, nlevels):
+                self.gal[l].record_elements(True)
         # --- vectors of the finest LinearEquation: _RES, _EPS; solution Sol and its Bdc mask
         self.RES = ctx.vector(self.n)
         self.EPS = ctx.vector(self.n)
@@ -112,6 +115,8 @@ class PoissonMG:
                 continue            # already formed by the fused assembly
             if algebraic:
                 self.KK[l - 1].ptap(self.PP[l], self.KK[l])
+            elif self.fused:
+                self.gal[l].apply_from_elements(self.gal[l + 1])
             else:
                 self.gal[l].apply()
 

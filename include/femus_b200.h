@@ -221,6 +221,13 @@ int b2_asm_poisson(b2_asm* p, const b2_vec* u, b2_vec* rhs, double nu, double fs
  * the fine matrix.  gal must have been created on this plan's matrix; Ac is overwritten, A is not zeroed.
  * Fails (no fallback) if the fine elements are not the children 8*E+j of gal's coarse elements. */
 int b2_asm_poisson_galerkin(b2_asm* p, b2_galerkin* gal, const b2_vec* u, b2_vec* rhs, double nu, double fsrc);
+/* Element-matrix Galerkin chain for the levels below: with recording on, applying `gal` through
+ * b2_asm_poisson_galerkin (or through b2_galerkin_apply_from_elements) also stores the nc x nc
+ * Galerkin matrix D_E of each of its coarse elements; the next-coarser plan then forms
+ * Ac = sum_E Pc(E)^T D_E Pc(E) from those (5.8 KB streamed per element) instead of gathering rows of
+ * its fine matrix.  Equal to b2_galerkin_apply / matrix_PtAP up to summation order. */
+int b2_galerkin_record_elements(b2_galerkin* gal, int on);
+int b2_galerkin_apply_from_elements(b2_galerkin* gal, b2_galerkin* finer);
 double b2_asm_last_kernel_ms(const b2_asm* p);
 
 /* ---- geometric multigrid: replaces LinearEquationSolverPetsc::{MGInit,MGSetLevel,MGSolve,MGClear}
