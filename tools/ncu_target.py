@@ -55,6 +55,8 @@ if "fused" in what:
     pb.KK[-1].zero()
     pb.RES.zero()
     pb.asm.poisson_galerkin(pb.gal[-1], pb.SOL, pb.RES, 1.0, 1.0)
+if "chain" in what and nl > 2:
+    pb.gal[-2].apply_from_elements(pb.gal[-1])
 if "galerkin" in what:
     pb.gal[-1].apply()
 if "spmv" in what:
