@@ -105,6 +105,7 @@ _PROTOS = {
     "b2_asm_destroy": (ci, [vp]),
     "b2_asm_poisson": (ci, [vp, vp, vp, cd, cd]),
     "b2_asm_poisson_galerkin": (ci, [vp, vp, vp, vp, cd, cd]),
+    "b2_asm_neumann": (ci, [vp, i64, vp, vp, vp, ci, vp, vp, vp, vp, vp, vp]),
     "b2_asm_last_kernel_ms": (cd, [vp]),
     "b2_mg_create": (ci, [vp, ci, vp]),
     "b2_mg_set_level": (ci, [vp, ci, vp, vp, vp, i64, ci, ci, cd]),
@@ -590,6 +591,14 @@ class Assembler:
     def poisson(self, u=None, rhs=None, nu=1.0, fsrc=1.0):
         check(self.L.b2_asm_poisson(self.h, u.h if u is not None else None, rhs.h if rhs is not None else None,
                                     float(nu), float(fsrc)))
+
+    def neumann(self, face_elem, face_local, face_value, face_tables, face_nodes, rhs):
+        """rhs += boundary integrals of a constant flux over the listed faces (b2_asm_neumann)."""
+        fe, fl, fv = _i32(face_elem), _i32(face_local), _f64(face_value)
+        phi, dxi, deta, w = [_f64(t) for t in face_tables]
+        fn = _i32(face_nodes)
+        check(self.L.b2_asm_neumann(self.h, fe.shape[0], _ptr(fe), _ptr(fl), _ptr(fv), phi.shape[1], _ptr(phi), _ptr(dxi),
+                                    _ptr(deta), _ptr(w), _ptr(fn), rhs.h))
 
     def poisson_galerkin(self, gal, u=None, rhs=None, nu=1.0, fsrc=1.0):
         """Assembly fused with the Galerkin product of `gal` (Ac = P^T A P from the element matrices)."""

@@ -967,6 +967,59 @@ int build_gal_tables(b2_asm* p, const b2_galerkin* gal, const b2_galerkin_view& 
 }
 }  // namespace
 
+// Neumann boundary integrals (applications/001_Poisson/main.cpp:495-548 with elem_type_2D::JacobianSur,
+// ElemType.hpp:1330-1379): one warp per boundary face, lanes = the 16 Gauss points of the face rule
+// for the surface Jacobian, then lanes = face dofs for F_i += sum_g phi_i(g) value weight_g.
+__global__ void neumann_kernel(int64_t nfaces, const int32_t* __restrict__ felem, const int32_t* __restrict__ flocal,
+                               const double* __restrict__ fvalue, int nvf, int nve, const double* __restrict__ ftab,
+                               const int32_t* __restrict__ fnodes, int64_t nnode, const double* __restrict__ xyz,
+                               const int32_t* __restrict__ conn, const int32_t* __restrict__ dof, double* __restrict__ rhs) {
+  constexpr int NG2 = 16;
+  __shared__ double sW[8][NG2];
+  __shared__ double sX[8][3][9];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const double* phi = ftab;
+  const double* dxi = phi + NG2 * nvf;
+  const double* deta = dxi + NG2 * nvf;
+  const double* w = deta + NG2 * nvf;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t k = warp; k < nfaces; k += nwarps) {
+    const int64_t e = felem[k];
+    const int f = flocal[k];
+    int loc = 0;
+    if (lane < nvf) {
+      loc = fnodes[f * 9 + lane];                    // element-local node of face dof `lane`
+      const int64_t nd = conn[e * 27 + loc];
+      sX[wib][0][lane] = xyz[nd];
+      sX[wib][1][lane] = xyz[nnode + nd];
+      sX[wib][2][lane] = xyz[2 * nnode + nd];
+    }
+    __syncwarp();
+    if (lane < NG2) {
+      double J00 = 0, J10 = 0, J20 = 0, J01 = 0, J11 = 0, J21 = 0;
+      for (int i = 0; i < nvf; i++) {
+        const double a = dxi[lane * nvf + i], b = deta[lane * nvf + i];
+        J00 = fma(a, sX[wib][0][i], J00); J10 = fma(a, sX[wib][1][i], J10); J20 = fma(a, sX[wib][2][i], J20);
+        J01 = fma(b, sX[wib][0][i], J01); J11 = fma(b, sX[wib][1][i], J11); J21 = fma(b, sX[wib][2][i], J21);
+      }
+      const double nx = J10 * J21 - J11 * J20, ny = J01 * J20 - J21 * J00, nz = J00 * J11 - J01 * J10;
+      const double inv = 1.0 / sqrt(nx * nx + ny * ny + nz * nz);
+      const double n0 = nx * inv, n1 = ny * inv, n2 = nz * inv;
+      // the reference takes the determinant of [t1 t2 n] as the area element
+      const double det = J00 * (J11 * n2 - n1 * J21) + J01 * (n1 * J20 - J10 * n2) + n0 * (J10 * J21 - J11 * J20);
+      sW[wib][lane] = det * w[lane];
+    }
+    __syncwarp();
+    if (lane < nvf) {
+      double s = 0.0;
+      for (int g = 0; g < NG2; g++) s = fma(phi[g * nvf + lane] * fvalue[k], sW[wib][g], s);
+      atomicAdd(&rhs[dof[e * nve + loc]], s);
+    }
+    __syncwarp();
+  }
+}
+
 // fp64 tensor-core issue-rate probe: every warp keeps 8 independent DMMA.8x8x4 chains busy
 __global__ void __launch_bounds__(512) dmma_probe_kernel(int iters, double* out) {
   double c[8][2];
@@ -984,6 +1037,49 @@ __global__ void __launch_bounds__(512) dmma_probe_kernel(int iters, double* out)
 }
 
 extern "C" {
+
+/* rhs += Neumann integrals over the listed boundary faces (host arrays: element, local face, flux value);
+ * ftab = phi, dxi, deta [16][nvf] and weights[16] of the face element, face_nodes[6][9] the local nodes
+ * of the hexahedron's faces.  Face dofs must be element dofs (nvf = 4 with nve = 8, 9 with 27). */
+int b2_asm_neumann(b2_asm* p, int64_t nfaces, const int32_t* face_elem, const int32_t* face_local, const double* face_value,
+                   int nvf, const double* phi, const double* dxi, const double* deta, const double* weights,
+                   const int32_t* face_nodes, b2_vec* rhs) {
+  B2_CHECK(p && rhs && (nfaces == 0 || (face_elem && face_local && face_value)), "b2_asm_neumann: null argument");
+  B2_CHECK((nvf == 4 && p->nve == 8) || (nvf == 9 && p->nve == 27), "b2_asm_neumann: nvf=%d does not match nve=%d", nvf, p->nve);
+  B2_CHECK(rhs->n >= p->A->nrows, "b2_asm_neumann: rhs vector too short");
+  if (nfaces == 0) return 0;
+  b2_ctx* c = p->mesh->ctx;
+  for (int64_t k = 0; k < nfaces; k++)
+    B2_CHECK(face_elem[k] >= 0 && face_elem[k] < p->mesh->nel && face_local[k] >= 0 && face_local[k] < 6,
+             "b2_asm_neumann: face %lld out of range", (long long)k);
+  int32_t *d_e = nullptr, *d_f = nullptr, *d_fn = nullptr;
+  double *d_v = nullptr, *d_t = nullptr;
+  const size_t nt = (size_t)3 * 16 * nvf + 16;
+  std::vector<double> tab(nt);
+  std::copy(phi, phi + 16 * nvf, tab.begin());
+  std::copy(dxi, dxi + 16 * nvf, tab.begin() + 16 * nvf);
+  std::copy(deta, deta + 16 * nvf, tab.begin() + 2 * 16 * nvf);
+  std::copy(weights, weights + 16, tab.begin() + 3 * 16 * nvf);
+  B2_TRY(b2_malloc(c, &d_e, (size_t)nfaces));
+  B2_TRY(b2_malloc(c, &d_f, (size_t)nfaces));
+  B2_TRY(b2_malloc(c, &d_v, (size_t)nfaces));
+  B2_TRY(b2_malloc(c, &d_t, nt));
+  B2_TRY(b2_malloc(c, &d_fn, 54));
+  B2_TRY(b2_upload(c, d_e, face_elem, (size_t)nfaces));
+  B2_TRY(b2_upload(c, d_f, face_local, (size_t)nfaces));
+  B2_TRY(b2_upload(c, d_v, face_value, (size_t)nfaces));
+  B2_TRY(b2_upload(c, d_t, tab.data(), nt));
+  B2_TRY(b2_upload(c, d_fn, face_nodes, 54));
+  B2_LAUNCH(c, neumann_kernel, b2_grid_for(c, nfaces * 32, 256, 8), 256, 0, nfaces, d_e, d_f, d_v, nvf, p->nve, d_t, d_fn,
+            p->mesh->nnode, p->mesh->xyz, p->mesh->conn, p->dof, rhs->d);
+  B2_CUDA(cudaStreamSynchronize(c->stream));
+  b2_free(c, d_e, (size_t)nfaces);
+  b2_free(c, d_f, (size_t)nfaces);
+  b2_free(c, d_v, (size_t)nfaces);
+  b2_free(c, d_t, nt);
+  b2_free(c, d_fn, 54);
+  return 0;
+}
 
 /* measured fp64 tensor-core peak (TFLOP/s) of this device: the denominator next to the assembly
  * kernel's achieved rate in bench.py (MEASURED_PEAKS.json carries no fp64 figure) */

@@ -115,6 +115,29 @@ void b2h_hex_tables(int family, double* phi, double* dxi, double* deta, double* 
   std::copy(t.dzeta.begin(), t.dzeta.end(), dzeta);
   std::copy(t.w.begin(), t.w.end(), w);
 }
+int b2h_face_nvf(int family) { return HexElement::face_ndofs(family); }
+void b2h_face_tables(int family, double* phi, double* dxi, double* deta, double* w) {
+  HexElement::FaceTables t = HexElement::face_tables(family);
+  std::copy(t.phi.begin(), t.phi.end(), phi);
+  std::copy(t.dxi.begin(), t.dxi.end(), dxi);
+  std::copy(t.deta.begin(), t.deta.end(), deta);
+  std::copy(t.w.begin(), t.w.end(), w);
+}
+void b2h_hex_face_nodes(int32_t* out) {
+  for (int f = 0; f < 6; f++)
+    for (int i = 0; i < 9; i++) out[f * 9 + i] = HexElement::face_nodes()[f][i];
+}
+int64_t b2h_level_boundary_faces(const b2h_hier* h, int l, int32_t* elem, int32_t* face, int32_t* bidx) {
+  const MeshLevel& L = h->levels[l];
+  int64_t n = 0;
+  for (int64_t e = 0; e < L.nel; e++)
+    for (int f = 0; f < 6; f++)
+      if (L.face[e * 6 + f] < -1) {
+        if (elem) { elem[n] = (int32_t)e; face[n] = f; bidx[n] = -(L.face[e * 6 + f] + 1); }
+        n++;
+      }
+  return n;
+}
 int b2h_hex_prolongator_row(int family, int a, int b, int c, int* idx, double* val) {
   return HexElement::prolongator_row(family, a, b, c, idx, val);
 }

@@ -86,6 +86,45 @@ struct HexElement {
         }
   }
 
+  // ---- face element (quadrilateral with 4 / 9 nodes: vertices, edge midpoints, centre;
+  //      01_fe/2d/Quadrilateral.cpp:22-31) and its "seventh" rule (quadrature_Quadrangle.cpp:30-33):
+  //      what elem_type_2D::JacobianSur needs for the Neumann integrals of main.cpp:495-548
+  static constexpr int NG2 = 16;
+  static void shape2(int family, int a, const double p[2], double& phi, double g[2]) {
+    static const int ind[9][2] = {{0, 0}, {2, 0}, {2, 2}, {0, 2}, {1, 0}, {2, 1}, {1, 2}, {0, 1}, {1, 1}};
+    if (family == SERENDIPITY) { std::abort(); }
+    double v[2], d[2];
+    for (int k = 0; k < 2; k++) lag1d(family, p[k], ind[a][k], v[k], d[k]);
+    phi = v[0] * v[1];
+    g[0] = d[0] * v[1];
+    g[1] = v[0] * d[1];
+  }
+  struct FaceTables {
+    int nvf = 0;
+    std::vector<double> phi, dxi, deta, w;      // [NG2][nvf] row-major, weights [NG2]
+  };
+  static FaceTables face_tables(int family) {
+    static const double p[4] = {-0.86113631159405, -0.33998104358486, 0.33998104358486, 0.86113631159405};
+    static const double w2[3] = {0.1210029932856, 0.22685185185185, 0.42529330301069};
+    FaceTables t;
+    t.nvf = face_ndofs(family);
+    t.phi.resize(NG2 * t.nvf); t.dxi.resize(NG2 * t.nvf); t.deta.resize(NG2 * t.nvf); t.w.resize(NG2);
+    int g = 0;
+    for (int a = 0; a < 4; a++)
+      for (int b = 0; b < 4; b++, g++) {
+        const double xi[2] = {p[a], p[b]};
+        t.w[g] = w2[(a == 1 || a == 2) + (b == 1 || b == 2)];
+        for (int i = 0; i < t.nvf; i++) {
+          double ph, gr[2];
+          shape2(family, i, xi, ph, gr);
+          t.phi[g * t.nvf + i] = ph;
+          t.dxi[g * t.nvf + i] = gr[0];
+          t.deta[g * t.nvf + i] = gr[1];
+        }
+      }
+    return t;
+  }
+
   // tables [NG][nve] row-major + weights
   struct Tables {
     int nve = 0;

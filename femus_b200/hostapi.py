@@ -49,6 +49,10 @@ def _L():
             "b2h_hex_nve": (ci, [ci]),
             "b2h_hex_tables": (None, [ci, vp, vp, vp, vp, vp]),
             "b2h_hex_prolongator_row": (ci, [ci, ci, ci, ci, vp, vp]),
+            "b2h_face_nvf": (ci, [ci]),
+            "b2h_face_tables": (None, [ci, vp, vp, vp, vp]),
+            "b2h_hex_face_nodes": (None, [vp]),
+            "b2h_level_boundary_faces": (i64, [vp, ci, vp, vp, vp]),
         }
         for n, (r, a) in P.items():
             f = getattr(L, n)
@@ -113,6 +117,14 @@ class HostLevel:
         out = np.zeros((self.nel, self.hier.L.b2h_hex_nve(f)), dtype=np.int32)
         self.hier.L.b2h_level_system_dofs(self.hier.h, self.l, f, out.ctypes.data_as(vp))
         return out
+
+    def boundary_faces(self):
+        """(element, local face, boundary index) of every boundary face of the level."""
+        L, h = self.hier.L, self.hier.h
+        n = L.b2h_level_boundary_faces(h, self.l, None, None, None)
+        e, f, b = (np.zeros(n, dtype=np.int32) for _ in range(3))
+        L.b2h_level_boundary_faces(h, self.l, e.ctypes.data_as(vp), f.ctypes.data_as(vp), b.ctypes.data_as(vp))
+        return e, f, b
 
     def bdc(self, family, dirichlet_faces=(1, 2, 3, 4, 5, 6)):
         flags = np.zeros(7, dtype=np.int32)
@@ -200,6 +212,22 @@ def hex_tables(family):
     t = [np.zeros((64, nve)) for _ in range(4)] + [np.zeros(64)]
     L.b2h_hex_tables(f, *[a.ctypes.data_as(vp) for a in t])
     return tuple(t)
+
+
+def face_tables(family):
+    """(phi, dxi, deta, w) of the face element elem_type_2D("quad", family, "seventh"): [16][nvf], [16]."""
+    L = _L()
+    f = _fam(family)
+    nvf = L.b2h_face_nvf(f)
+    t = [np.zeros((16, nvf)) for _ in range(3)] + [np.zeros(16)]
+    L.b2h_face_tables(f, *[a.ctypes.data_as(vp) for a in t])
+    return tuple(t)
+
+
+def hex_face_nodes():
+    out = np.zeros((6, 9), dtype=np.int32)
+    _L().b2h_hex_face_nodes(out.ctypes.data_as(vp))
+    return out
 
 
 def hex_prolongator_row(family, a, b, c):

@@ -23,13 +23,16 @@ class PoissonMG:
     already hold the NCCL communicator (Context.comm_init)."""
 
     def __init__(self, ctx, nx, ny, nz, nlevels, order="biquadratic", bounds=None, npre=1, npost=1, omega=0.5,
-                 dirichlet_faces=(1, 2, 3, 4, 5, 6), fsrc=1.0, coarse_rtol=1e-14, hier=None, dist=None, fused=True):
+                 dirichlet_faces=(1, 2, 3, 4, 5, 6), fsrc=1.0, coarse_rtol=1e-14, hier=None, dist=None, fused=True,
+                 neumann=None):
         self.ctx = ctx
         self.order = order
         self.fam = hostapi.FAMILY[order]
         self.nlevels = nlevels
         self.npre, self.npost, self.omega, self.fsrc = npre, npost, omega, fsrc
         self.dist = dist
+        # neumann: {boundary index: constant flux} (JSON "bdc_type": "neumann", "bdc_func": value)
+        self.neumann = dict(neumann) if neumann else {}
         # fused: the finest Galerkin product is formed inside the assembly kernel (b2_asm_poisson_galerkin)
         self.fused = fused and nlevels > 1
         if hier is not None:
@@ -68,6 +71,12 @@ class PoissonMG:
         self.mesh = capi.Mesh(ctx, top.xyz, top.conn)
         self.tables = hostapi.hex_tables(order)
         self.asm = capi.Assembler(self.mesh, self.KK[-1], self.dofs[-1], self.tables)
+        if self.neumann:    # Neumann faces of the finest level: (element, local face, flux)
+            fe, fl, fb = top.boundary_faces()
+            sel = np.isin(fb, list(self.neumann))
+            self.nm_faces = (fe[sel], fl[sel], np.array([self.neumann[int(b)] for b in fb[sel]], dtype=np.float64))
+            self.nm_tables = hostapi.face_tables(order)
+            self.nm_face_nodes = hostapi.hex_face_nodes()
         if self.fused:      # element-matrix Galerkin chain: every plan but the coarsest records its element matrices
             for l in range(2, nlevels):
                 self.gal[l].record_elements(True)
@@ -103,6 +112,8 @@ class PoissonMG:
             self.asm.poisson_galerkin(self.gal[-1], self.SOL, self.RES, 1.0, self.fsrc)
         else:
             self.asm.poisson(self.SOL, self.RES, 1.0, self.fsrc)
+        if self.neumann and self.nm_faces[0].size:
+            self.asm.neumann(*self.nm_faces, self.nm_tables, self.nm_face_nodes, self.RES)
         if self.halo[-1] is not None:          # close(): contributions of the other ranks' elements
             self.halo[-1].sum(self.RES)
 

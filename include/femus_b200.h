@@ -213,6 +213,14 @@ int b2_asm_destroy(b2_asm* p);
  * F_i = int (fsrc phi_i - nu grad phi_i . grad u).  A and rhs are NOT zeroed here (the app calls
  * myKK->zero() / SetResZero() first, main.cpp:346, LinearImplicitSystem.cpp:322). */
 int b2_asm_poisson(b2_asm* p, const b2_vec* u, b2_vec* rhs, double nu, double fsrc);
+/* Neumann boundary integrals of the same callback (main.cpp:495-548, elem_type_2D::JacobianSur,
+ * ElemType.hpp:1330-1379): rhs[dof] += sum_g phi_i(g) * value * weight_g over the listed boundary faces
+ * (element, local face 0..5, constant flux value).  phi/dxi/deta [16][nvf] and weights[16] are the tables
+ * of the face element elem_type_2D("quad", family, "seventh"), face_nodes[6][9] the local nodes of the
+ * hexahedron's faces (Elem.hpp `ig` table). */
+int b2_asm_neumann(b2_asm* p, int64_t nfaces, const int32_t* face_elem, const int32_t* face_local, const double* face_value,
+                   int nvf, const double* phi, const double* dxi, const double* deta, const double* weights,
+                   const int32_t* face_nodes, b2_vec* rhs);
 /* Fused fast path of "assemble, then matrix_PtAP" (LinearImplicitSystem.cpp:326 + 347-370): the same
  * assembly, and in the same pass gal's coarse matrix Ac = P^T A P is formed from the element matrices
  * while they are on chip, C = sum_e Pc(e)^T B_e Pc(e) with Pc(e) the element prolongator of the child

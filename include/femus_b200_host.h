@@ -72,6 +72,14 @@ int b2h_galerkin_maps(const b2h_hier* h, int lcoarse, int family, int64_t e0, in
 int b2h_hex_nve(int family);
 void b2h_hex_tables(int family, double* phi, double* dxi, double* deta, double* dzeta, double* w);
 int b2h_hex_prolongator_row(int family, int a, int b, int c, int* idx, double* val);
+/* face element elem_type_2D("quad", family, "seventh") of a hexahedron: tables [16][nvf] and weights[16]
+ * (nvf = 4 or 9), the local nodes of the 6 faces [6][9] (Elem.hpp `ig` table) and the boundary faces
+ * of a level as (element, local face, boundary index = -(faceElementIndex+1), Elem.cpp:361-364);
+ * b2h_level_boundary_faces with NULL arrays only counts. */
+int b2h_face_nvf(int family);
+void b2h_face_tables(int family, double* phi, double* dxi, double* deta, double* w);
+void b2h_hex_face_nodes(int32_t* out);
+int64_t b2h_level_boundary_faces(const b2h_hier* h, int l, int32_t* elem, int32_t* face, int32_t* bidx);
 
 #ifdef __cplusplus
 }

@@ -257,6 +257,32 @@ def assemble(L, order, U=None, fsrc=1.0):
     return A, rhs
 
 
+def neumann_rhs(L, order, neumann):
+    """Boundary part of the residual: for every element face on a boundary whose index is a key of
+    `neumann` (value = constant flux), F[local node] += sum_g phi_i value weight with the face element of
+    the unknown's family on the first nve_face face nodes (applications/001_Poisson/main.cpp:495-548;
+    face -> local nodes: Elem.hpp `ig` table = fe_hex.FACE_NODES; boundary index = -(faceElementIndex+1),
+    Elem.cpp:361-364)."""
+    from . import fe_quad
+    d = system_dof(L, order)
+    n = ndofs(L, order)
+    nvf = fe_quad.NDOFS2[order]
+    tabs = fe_quad.tables2(order)
+    rhs = np.zeros(n)
+    for f in range(6):
+        bidx = -(L.face[:, f] + 1)
+        for e in np.nonzero(L.face[:, f] < -1)[0]:
+            b = int(bidx[e])
+            if b not in neumann:
+                continue
+            loc = fe_hex.FACE_NODES[f][:nvf]
+            X = L.xyz[:, L.conn[e, loc]]
+            Ff = fe_quad.neumann_face(order, X, float(neumann[b]), tabs)
+            # the face's local nodes are element-local nodes < nve for both families (vertices first)
+            np.add.at(rhs, d[e, loc], Ff)
+    return rhs
+
+
 def prolongator(C, F, order):
     """P (fine dofs x coarse dofs) of family `order` from level C to its refinement F
     (LinearImplicitSystem.cpp:761-909; rows inserted, identical from every neighbour)."""

@@ -68,7 +68,7 @@ class Hierarchy:
     """Per-level operators exactly as the reference sets them up for one MGsolve."""
 
     def __init__(self, levels, order, fsrc=1.0, dirichlet_faces=(1, 2, 3, 4, 5, 6), A_top=None, rhs=None,
-                 coarse_lu=True, ptap=None):
+                 coarse_lu=True, ptap=None, neumann=None):
         self.levels = levels
         self.order = order
         nl = len(levels)
@@ -85,6 +85,8 @@ class Hierarchy:
         # assembly on the finest level (V_CYCLE: only the top level is assembled)
         if A_top is None:
             A_top, rhs = mb.assemble(levels[-1], order, None, fsrc)
+            if neumann:
+                rhs = rhs + mb.neumann_rhs(levels[-1], order, neumann)
         self.set_operator(A_top, rhs, ptap)
 
     def set_operator(self, A_top, rhs, ptap=None):

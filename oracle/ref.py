@@ -42,6 +42,14 @@ def lib():
         L.fref_poisson_assemble_csr.restype = cd
         L.fref_poisson_assemble_csr.argtypes = [vp, ctypes.c_long, ctypes.c_long, vp, vp, vp, ctypes.c_long,
                                                 vp, vp, vp, vp, vp, cd, ci]
+        L.fref2_create.restype = vp
+        L.fref2_create.argtypes = [ctypes.c_char_p] * 3
+        L.fref2_destroy.argtypes = [vp]
+        L.fref2_ndofs.argtypes = [vp]
+        L.fref2_ngauss.argtypes = [vp]
+        L.fref2_gauss.argtypes = [vp, vp, vp]
+        L.fref2_tables.argtypes = [vp] * 4
+        L.fref2_jacobian_sur.argtypes = [vp, vp, ci, ci, vp, vp, vp]
         _lib = L
     return _lib
 
@@ -115,3 +123,38 @@ class RefHex:
         sec = self.L.fref_poisson_assemble_csr(self.h, e0, e1, _p(conn), _p(dof), _p(xyz), xyz.shape[1], _p(sol),
                                                _p(rowptr), _p(col), _p(vals), _p(rhs), float(fsrc), int(nthreads))
         return vals, rhs, sec
+
+
+class RefQuad:
+    """elem_type_2D("quad", order, gauss) of the reference: the face element of a hexahedron."""
+
+    def __init__(self, order="biquadratic", gauss="seventh"):
+        self.L = lib()
+        self.h = ctypes.c_void_p(self.L.fref2_create(b"quad", order.encode(), gauss.encode()))
+        self.n = self.L.fref2_ndofs(self.h)
+        self.ng = self.L.fref2_ngauss(self.h)
+
+    def gauss(self):
+        w = np.zeros(self.ng)
+        xi = np.zeros((2, self.ng))
+        self.L.fref2_gauss(self.h, _p(w), _p(xi))
+        return w, xi.T.copy()
+
+    def tables(self):
+        t = [np.zeros((self.ng, self.n)) for _ in range(3)]
+        self.L.fref2_tables(self.h, *[_p(a) for a in t])
+        return t
+
+    def jacobian_sur(self, X, ig):
+        X = np.ascontiguousarray(X, dtype=np.float64)          # [3][n]
+        w = ctypes.c_double()
+        phi = np.zeros(self.n)
+        nrm = np.zeros(3)
+        self.L.fref2_jacobian_sur(self.h, _p(X), X.shape[1], ig, ctypes.byref(w), _p(phi), _p(nrm))
+        return w.value, phi, nrm
+
+    def __del__(self):
+        try:
+            self.L.fref2_destroy(self.h)
+        except Exception:
+            pass

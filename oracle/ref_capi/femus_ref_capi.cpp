@@ -17,6 +17,7 @@
 #include "ElemType.hpp"
 
 using femus::elem_type_3D;
+using femus::elem_type_2D;
 
 extern "C" {
 
@@ -181,6 +182,45 @@ double fref_poisson_assemble_csr(void* h, long e0, long e1, const int* conn, con
   timespec ts1; clock_gettime(CLOCK_MONOTONIC, &ts1);
   return (ts1.tv_sec - ts0.tv_sec) + 1e-9 * (ts1.tv_nsec - ts0.tv_nsec);
 #endif
+}
+
+// ---- boundary faces: the reference's own elem_type_2D ("quad", order, gauss) and JacobianSur
+//      (ElemType.hpp:1330-1379), as applications/001_Poisson/main.cpp:495-594 calls them for the
+//      Neumann integrals
+void* fref2_create(const char* geom, const char* order, const char* gauss) { return new elem_type_2D(geom, order, gauss); }
+void fref2_destroy(void* h) { delete static_cast<elem_type_2D*>(h); }
+int fref2_ndofs(void* h) { return static_cast<elem_type_2D*>(h)->GetNDofs(); }
+int fref2_ngauss(void* h) { return (int)static_cast<elem_type_2D*>(h)->GetGaussPointNumber(); }
+void fref2_gauss(void* h, double* w, double* xi) {
+  auto* e = static_cast<elem_type_2D*>(h);
+  const int ng = (int)e->GetGaussPointNumber();
+  const femus::Gauss* g = e->GetGaussRule();
+  for (int i = 0; i < ng; i++) {
+    w[i] = g->GetGaussWeightsPointer()[i];
+    for (int d = 0; d < 2; d++) xi[d * ng + i] = g->GetGaussCoordinatePointer(d)[i];
+  }
+}
+void fref2_tables(void* h, double* phi, double* dxi, double* deta) {
+  auto* e = static_cast<elem_type_2D*>(h);
+  const int ng = (int)e->GetGaussPointNumber(), n = e->GetNDofs();
+  for (int g = 0; g < ng; g++)
+    for (int i = 0; i < n; i++) {
+      phi[g * n + i] = e->GetPhi(g)[i];
+      dxi[g * n + i] = e->GetDPhiDXi(g)[i];
+      deta[g * n + i] = e->GetDPhiDEta(g)[i];
+    }
+}
+// coords: [3][n]; out: weight, phi[ndofs], normal[3]
+void fref2_jacobian_sur(void* h, const double* coords, int ncoord, int ig, double* weight, double* phi, double* normal) {
+  auto* e = static_cast<elem_type_2D*>(h);
+  std::vector<std::vector<double>> vt(3, std::vector<double>(ncoord));
+  for (int d = 0; d < 3; d++) for (int i = 0; i < ncoord; i++) vt[d][i] = coords[d * ncoord + i];
+  std::vector<double> p, g, nrm;
+  double w;
+  e->JacobianSur(vt, (unsigned)ig, w, p, g, nrm);
+  *weight = w;
+  std::copy(p.begin(), p.end(), phi);
+  std::copy(nrm.begin(), nrm.end(), normal);
 }
 
 }  // extern "C"

@@ -50,3 +50,33 @@ for order in ("linear", "biquadratic"):
     out[f"{order}_prol"], out[f"{order}_prol_pos2"] = P, pos
 np.savez_compressed(os.path.join(ROOT, "tests", "golden", "fe_hex_ref.npz"), **out)
 print("wrote fe_hex_ref.npz", {k: v.shape for k, v in out.items()})
+
+# ---- face element (Neumann integrals): tests/golden/fe_quad_ref.npz
+from oracle import fe_quad  # noqa: E402
+outq = {}
+for order in ("linear", "biquadratic"):
+    Q = ref.RefQuad(order)
+    w, xi = Q.gauss()
+    outq[f"{order}_gauss_w"], outq[f"{order}_gauss_xi"] = w, xi
+    phi, dxi, deta = Q.tables()
+    outq[f"{order}_phi"], outq[f"{order}_dxi"], outq[f"{order}_deta"] = phi, dxi, deta
+    base = np.array([[0, 1, 1, 0, 0.5, 1, 0.5, 0, 0.5], [0, 0, 1, 1, 0, 0.5, 1, 0.5, 0.5], [0.3] * 9])
+    Xs = [base / 128.0, base + 0.07 * rng.standard_normal(base.shape), base[[2, 0, 1]] * 0.3 + 0.02 * rng.standard_normal(base.shape)]
+    Ws, Ns, Fs = [], [], []
+    for X in Xs:
+        wj, nj = [], []
+        F = np.zeros(Q.n)
+        for ig in range(Q.ng):
+            wt, ph, nrm = Q.jacobian_sur(X[:, :Q.n].copy(), ig)
+            wj.append(wt)
+            nj.append(nrm)
+            for i in range(Q.n):
+                F[i] += ph[i] * 0.2 * wt          # main.cpp:541-546 with bdc_func = 0.2
+        Ws.append(wj)
+        Ns.append(nj)
+        Fs.append(F)
+    outq[f"{order}_X"] = np.array(Xs)
+    outq[f"{order}_weight"], outq[f"{order}_normal"], outq[f"{order}_F02"] = np.array(Ws), np.array(Ns), np.array(Fs)
+np.savez_compressed(os.path.join(ROOT, "tests", "golden", "fe_quad_ref.npz"), **outq)
+print("wrote tests/golden/fe_quad_ref.npz")
+

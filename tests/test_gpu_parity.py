@@ -312,6 +312,50 @@ def test_assembly_matches_oracle(ctx, order, amp, asm_variant):
     assert np.abs(A.to_scipy().data - 2 * Aref.data).max() <= 2 * RTOL * np.abs(Aref.data).max()
 
 
+@pytest.mark.parametrize("order", ["linear", "biquadratic"])
+def test_neumann_faces_match_oracle(ctx, order):
+    """b2_asm_neumann on a distorted mesh against the oracle's restatement of main.cpp:495-548
+    (elem_type_2D::JacobianSur pinned bit-exactly to the compiled reference), two flux values."""
+    from femus_b200 import hostapi
+    from femus_b200.poisson import PoissonMG
+    neumann = {3: 0.2, 6: -1.5}
+    pb = PoissonMG(ctx, 2, 3, 2, 2, order, dirichlet_faces=(1,), neumann=neumann, fsrc=0.0)
+    lv = mb.build_hierarchy(2, 3, 2, 2)
+    L = lv[-1]
+    L.xyz = distorted(L, 0.06, 2)
+    xyz_host = np.ascontiguousarray(L.xyz)
+    pb.mesh.update(xyz_host.ctypes.data, None)
+    ctx.sync()
+    pb.assemble()
+    _, rhs0 = mb.assemble(L, order, None, 0.0)
+    ref_rhs = rhs0 + mb.neumann_rhs(L, order, neumann)
+    got = pb.RES.get()
+    assert np.abs(got - ref_rhs).max() <= 1e-13 * np.abs(ref_rhs).max()
+    assert abs(got.sum() - (mb.neumann_rhs(L, order, neumann)).sum()) <= 1e-12
+    del pb
+
+
+@pytest.mark.parametrize("order", ["linear", "biquadratic"])
+def test_vcycle_trace_with_neumann_and_partial_dirichlet(ctx, order):
+    """The shipped 3-D input of applications/001_Poisson (input3D_Hex_first.json): source 0, Dirichlet on
+    "top" only, Neumann flux 0.2 on "right", natural elsewhere; residual trace against the oracle."""
+    from femus_b200.poisson import PoissonMG
+    from oracle import mg
+    neumann, dirichlet = {3: 0.2}, (6,)
+    pb = PoissonMG(ctx, 2, 2, 2, 3, order, dirichlet_faces=dirichlet, neumann=neumann, fsrc=0.0, coarse_rtol=1e-15)
+    pb.assemble(); pb.galerkin(); pb.mg_set_levels()
+    lv = mb.build_hierarchy(2, 2, 2, 3)
+    H = mg.Hierarchy(lv, order, fsrc=0.0, dirichlet_faces=dirichlet, neumann=neumann)
+    trace, eps = H.mg_solve_trace(3)
+    r0 = float(np.linalg.norm(np.where(H.bdc[-1] > 1.1, H.rhs, 0.0)))
+    assert abs(pb.residual_norm() - r0) <= 1e-12 * r0
+    for k in range(3):
+        pb.mg_solve()
+        assert abs(pb.residual_norm() - trace[k]) <= 1e-11 * r0, (k, pb.residual_norm(), trace[k])
+    assert np.abs(pb.EPS.get() - eps).max() <= 1e-10 * np.abs(eps).max()
+    del pb
+
+
 def test_assembly_golden_elements(ctx, asm_variant):
     """Single elements of the committed golden fixture (values of the compiled reference)."""
     import os

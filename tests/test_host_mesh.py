@@ -52,3 +52,18 @@ def test_non_unit_bounds_and_tables():
 def test_bad_arguments():
     with pytest.raises(ValueError):
         hostapi.HostHierarchy(0, 1, 1, 1)
+
+
+def test_face_element_tables_and_boundary_faces():
+    """Host face element (Neumann integrals) bit-exact against the oracle restatement (itself pinned to the
+    reference's elem_type_2D), face-node table, and the boundary-face list against the oracle's face flags."""
+    from oracle import fe_quad, fe_hex
+    for order in ("linear", "biquadratic"):
+        for a, b in zip(hostapi.face_tables(order), fe_quad.tables2(order)):
+            assert np.array_equal(a, b)
+    assert np.array_equal(hostapi.hex_face_nodes(), fe_hex.FACE_NODES)
+    H = hostapi.HostHierarchy(2, 3, 2, 2)
+    lv = mb.build_hierarchy(2, 3, 2, 2)
+    e, f, b = H.levels[-1].boundary_faces()
+    ref = [(int(el), int(fa), int(-(lv[-1].face[el, fa] + 1))) for el in range(lv[-1].nel) for fa in range(6) if lv[-1].face[el, fa] < -1]
+    assert list(zip(e.tolist(), f.tolist(), b.tolist())) == ref

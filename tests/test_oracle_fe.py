@@ -82,3 +82,47 @@ def test_against_compiled_reference(order):
     Fr, Br = R.poisson_element(X, U, 2.5)
     Fo, Bo = fe_hex.poisson_elements(order, X[None], U[None], 2.5)
     assert np.array_equal(Br, Bo[0]) and np.array_equal(Fr, Fo[0])
+
+
+# ---- face element / Neumann boundary integral -----------------------------------------------
+GQ = np.load(os.path.join(os.path.dirname(__file__), "golden", "fe_quad_ref.npz"))
+
+
+@pytest.mark.parametrize("order", ORDERS)
+def test_face_element_bit_exact_vs_golden(order):
+    """oracle/fe_quad.py against the committed values of the reference's elem_type_2D: Gauss rule,
+    tables, JacobianSur weight/normal and the Neumann face vector with bdc_func = 0.2."""
+    from oracle import fe_quad
+    w, xi = fe_quad.gauss_quad()
+    assert np.array_equal(w, GQ[f"{order}_gauss_w"]) and np.array_equal(xi, GQ[f"{order}_gauss_xi"])
+    phi, dxi, deta, _ = fe_quad.tables2(order)
+    assert np.array_equal(phi, GQ[f"{order}_phi"]) and np.array_equal(dxi, GQ[f"{order}_dxi"]) and np.array_equal(deta, GQ[f"{order}_deta"])
+    for k, X in enumerate(GQ[f"{order}_X"]):
+        for ig in range(16):
+            wt, _, nrm = fe_quad.jacobian_sur(order, X, ig)
+            assert wt == GQ[f"{order}_weight"][k, ig] and np.array_equal(nrm, GQ[f"{order}_normal"][k, ig])
+        assert np.array_equal(fe_quad.neumann_face(order, X, 0.2), GQ[f"{order}_F02"][k])
+
+
+@pytest.mark.skipif(not ref.available(), reason="oracle/_ref not built (no /root/reference here)")
+@pytest.mark.parametrize("order", ORDERS)
+def test_face_element_against_compiled_reference(order):
+    from oracle import fe_quad
+    Q = ref.RefQuad(order)
+    rng = np.random.default_rng(2)
+    base = np.array([[0, 1, 1, 0, 0.5, 1, 0.5, 0, 0.5], [0, 0, 1, 1, 0, 0.5, 1, 0.5, 0.5], [0.3] * 9])
+    for _ in range(4):
+        X = base + 0.05 * rng.standard_normal(base.shape)
+        for ig in range(16):
+            a = Q.jacobian_sur(X[:, :Q.n].copy(), ig)
+            b = fe_quad.jacobian_sur(order, X, ig)
+            assert a[0] == b[0] and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+
+
+def test_neumann_rhs_integrates_the_flux():
+    """Sum of the Neumann vector = flux x area of the face set (partition of unity), any family."""
+    from oracle import mesh_box as mb
+    lv = mb.build_hierarchy(2, 3, 2, 2)
+    for order in ORDERS:
+        r = mb.neumann_rhs(lv[-1], order, {3: 0.2, 6: -1.5})
+        assert abs(r.sum() - (0.2 * 1.0 - 1.5 * 1.0)) < 1e-13
