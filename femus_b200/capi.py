@@ -110,6 +110,8 @@ _PROTOS = {
     "b2_mg_create": (ci, [vp, ci, vp]),
     "b2_mg_set_level": (ci, [vp, ci, vp, vp, vp, i64, ci, ci, cd]),
     "b2_mg_set_coarse": (ci, [vp, cd, ci]),
+    "b2_mg_set_smoother": (ci, [vp, ci, ci, cd, cd]),
+    "b2_mg_level_bounds": (ci, [vp, ci, vp, vp]),
     "b2_mg_set_level_halo": (ci, [vp, ci, vp]),
     "b2_halo_create": (ci, [vp, i64, i64, vp, vp, i64, vp, vp, vp]),
     "b2_halo_destroy": (ci, [vp]),
@@ -630,6 +632,15 @@ class Multigrid:
     def set_level_halo(self, level, halo):
         self._keep.append(halo)
         check(self.L.b2_mg_set_level_halo(self.h, level, halo.h if halo is not None else None))
+
+    def set_smoother(self, level, kind, emin=0.0, emax=0.0):
+        """kind: "richardson" (Richardson+Jacobi) or "chebyshev" (Chebyshev+Jacobi; emax <= 0: estimated)."""
+        check(self.L.b2_mg_set_smoother(self.h, level, {"richardson": 0, "chebyshev": 1}[kind], float(emin), float(emax)))
+
+    def level_bounds(self, level):
+        a, b = cd(), cd()
+        check(self.L.b2_mg_level_bounds(self.h, level, ctypes.byref(a), ctypes.byref(b)))
+        return a.value, b.value
 
     def set_coarse(self, rtol=1e-14, maxit=5000):
         check(self.L.b2_mg_set_coarse(self.h, float(rtol), int(maxit)))

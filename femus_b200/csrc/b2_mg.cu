@@ -21,6 +21,11 @@ struct b2_mg_level {
   b2_halo* halo = nullptr;  // borrowed: distributed layout of this level's vectors (null: single rank)
   int npre = 1, npost = 1;
   double omega = 0.5;
+  // smoother: 0 = Richardson(omega) + Jacobi, 1 = Chebyshev + Jacobi on [emin, emax] of D^-1 A
+  int smoother = 0;
+  double emin = 0., emax = 0.;     // bounds in use
+  double emin_user = 0., emax_user = 0.;   // emax_user <= 0: estimated at MGSetLevel (power iteration)
+  b2_vec* d = nullptr;             // Chebyshev direction
 };
 
 struct b2_mg {
@@ -166,6 +171,28 @@ __global__ void jacobi_update_kernel(int64_t n, const double* __restrict__ dinv,
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) x[i] = fma(omega * dinv[i], r[i], x[i]);
 }
 
+// Chebyshev step: d = cd * d + cz * dinv .* r ; x = (zero ? 0 : x) + d
+__global__ void cheb_update_kernel(int64_t n, const double* __restrict__ dinv, const double* __restrict__ r,
+                                   double* __restrict__ d, double* __restrict__ x, double cd, double cz, int zero) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const double di = fma(cz * dinv[i], r[i], cd * d[i]);
+    d[i] = di;
+    x[i] = zero ? di : x[i] + di;
+  }
+}
+// deterministic start vector of the eigenvalue estimate
+__global__ void power_start_kernel(int64_t n, double* __restrict__ v) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) v[i] = 1.0 + 0.5 * sin((double)(i % 1000));
+}
+// v = scale * dinv .* w
+__global__ void scaled_precond_kernel(int64_t n, const double* __restrict__ dinv, const double* __restrict__ w,
+                                      double* __restrict__ v, double scale) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) v[i] = scale * (dinv[i] * w[i]);
+}
+
 int vec_grid(b2_ctx* c, int64_t n) { return b2_grid_for(c, n, kBlock, 8); }
 
 // r = b - A x with every entry complete on every rank that holds it
@@ -181,10 +208,67 @@ int level_spmv(b2_mg_level& L, const b2_vec* x, b2_vec* y) {
 }
 const uint8_t* owned(const b2_mg_level& L) { return L.halo ? L.halo->owned : nullptr; }
 
+// largest eigenvalue of D^-1 A by `its` power iterations from a fixed start vector (our own stated
+// bound: PETSc's KSPCHEBYSHEV estimates it with GMRES on a random vector, which is not reproducible)
+int estimate_emax(b2_mg* mg, b2_mg_level& L, int its, double* out) {
+  b2_ctx* c = mg->ctx;
+  const int64_t n = L.A->nrows;
+  const int g = vec_grid(c, n);
+  double* s = mg->scal + 4;
+  B2_LAUNCH(c, power_start_kernel, g, kBlock, 0, n, L.x->d);
+  if (L.nbdc) B2_LAUNCH(c, fill_idx_kernel, vec_grid(c, L.nbdc), kBlock, 0, L.x->d, L.bdc, L.nbdc, 0.0);
+  if (L.halo) {        // shared dofs carry different local indices on different ranks: average the start values
+    B2_TRY(b2_halo_sum(L.halo, L.x));
+    B2_LAUNCH(c, scaled_precond_kernel, g, kBlock, 0, n, L.halo->invmult, L.x->d, L.t->d, 1.0);
+    std::swap(L.x, L.t);
+  }
+  double lam = 0.0, h = 0.0;
+  for (int it = 0; it <= its; it++) {
+    B2_TRY(b2_dev_dot(c, L.x->d, L.x->d, n, s, owned(L)));
+    B2_TRY(b2_allreduce_sum(c, s, 1));
+    B2_TRY(b2_download(c, &h, s, 1));
+    const double nrm = sqrt(h);
+    if (it > 0) lam = nrm;            // ||D^-1 A v|| with ||v|| = 1
+    if (it == its || nrm == 0.0) break;
+    B2_TRY(b2_vec_scale(L.x, 1.0 / nrm));
+    B2_TRY(level_spmv(L, L.x, L.t));
+    B2_LAUNCH(c, scaled_precond_kernel, g, kBlock, 0, n, L.dinv->d, L.t->d, L.x->d, 1.0);
+  }
+  *out = lam;
+  return 0;
+}
+
+// Chebyshev + Jacobi sweeps on [emin, emax] (Saad, Iterative Methods, alg. 12.1)
+int smooth_chebyshev(b2_mg* mg, b2_mg_level& L, int nsweeps, bool zero_guess) {
+  b2_ctx* c = mg->ctx;
+  const int64_t n = L.A->nrows;
+  if (nsweeps <= 0) return zero_guess ? b2_vec_zero(L.x) : 0;
+  const double theta = 0.5 * (L.emax + L.emin), delta = 0.5 * (L.emax - L.emin), sigma1 = theta / delta;
+  double rho = 1.0 / sigma1;
+  for (int k = 0; k < nsweeps; k++) {
+    const double* r = L.b->d;                       // zero guess: r = b
+    if (!(zero_guess && k == 0)) {
+      B2_TRY(level_resid(L, L.b, L.x, L.t));
+      r = L.t->d;
+    }
+    double cd = 0.0, cz = 1.0 / theta;
+    if (k > 0) {
+      const double rho_new = 1.0 / (2.0 * sigma1 - rho);
+      cd = rho_new * rho;
+      cz = 2.0 * rho_new / delta;
+      rho = rho_new;
+    }
+    B2_LAUNCH(c, cheb_update_kernel, vec_grid(c, n), kBlock, 0, n, L.dinv->d, r, L.d->d, L.x->d, cd, cz,
+              (zero_guess && k == 0) ? 1 : 0);
+  }
+  return 0;
+}
+
 int smooth(b2_mg* mg, int l, int nsweeps, bool zero_guess) {
   b2_mg_level& L = mg->L[l];
   b2_ctx* c = mg->ctx;
   const int64_t n = L.A->nrows;
+  if (L.smoother == 1) return smooth_chebyshev(mg, L, nsweeps, zero_guess);
   int done = 0;
   if (zero_guess && nsweeps > 0) {
     B2_LAUNCH(c, jacobi_first_kernel, vec_grid(c, n), kBlock, 0, n, L.dinv->d, L.b->d, L.x->d, L.omega);
@@ -321,6 +405,18 @@ int b2_mg_set_level(b2_mg* mg, int level, b2_csr* A, b2_csr* P, const int32_t* b
   B2_TRY(b2_csr_diag(A, L.dinv));
   if (L.halo) B2_TRY(b2_halo_sum(L.halo, L.dinv));       // diagonal of the summed operator
   B2_LAUNCH(c, recip_kernel, vec_grid(c, n), kBlock, 0, n, L.dinv->d, L.dinv->d);
+  if (L.smoother == 1 && level > 0) {
+    if (!L.d) B2_TRY(b2_vec_create(c, n, &L.d));
+    if (L.emax_user <= 0.0) {                       // our own stated bounds: [0.1, 1.1] x power-iteration estimate
+      double lam = 0.0;
+      B2_TRY(estimate_emax(mg, L, 10, &lam));
+      L.emax = 1.1 * lam;
+      L.emin = 0.1 * lam;
+    } else {
+      L.emax = L.emax_user;
+      L.emin = L.emin_user;
+    }
+  }
   if (newP) {   // the explicit restriction R = P^T is rebuilt only when P changes
     if (L.R) { b2_csr_destroy(L.R); L.R = nullptr; }
     B2_TRY(b2_csr_transpose(P, &L.R));
@@ -333,6 +429,25 @@ int b2_mg_set_level_halo(b2_mg* mg, int level, b2_halo* halo) {
   B2_CHECK(level >= 0 && level < mg->nlevels, "b2_mg_set_level_halo: bad level %d", level);
   B2_CHECK(!mg->L[level].R, "b2_mg_set_level_halo: call it before b2_mg_set_level");
   mg->L[level].halo = halo;
+  return 0;
+}
+
+/* smoother of one level: kind 0 = Richardson(omega)+Jacobi (KSPRICHARDSON+PCJACOBI), 1 = Chebyshev+Jacobi
+ * (KSPCHEBYSHEV+PCJACOBI, LinearEquationSolverPetsc.cpp:452-536) on the interval [emin, emax] of D^-1 A;
+ * emax <= 0: estimated at b2_mg_set_level by 10 power iterations from a fixed start vector, interval
+ * [0.1, 1.1] x estimate.  Call before b2_mg_set_level. */
+int b2_mg_set_smoother(b2_mg* mg, int level, int kind, double emin, double emax) {
+  B2_CHECK(level >= 0 && level < mg->nlevels && (kind == 0 || kind == 1), "b2_mg_set_smoother: bad arguments");
+  B2_CHECK(kind == 0 || emax <= 0.0 || (emin > 0.0 && emin < emax), "b2_mg_set_smoother: need 0 < emin < emax");
+  mg->L[level].smoother = kind;
+  mg->L[level].emin_user = emin;
+  mg->L[level].emax_user = emax;
+  return 0;
+}
+int b2_mg_level_bounds(const b2_mg* mg, int level, double* emin, double* emax) {
+  B2_CHECK(level >= 0 && level < mg->nlevels, "b2_mg_level_bounds: bad level");
+  *emin = mg->L[level].emin;
+  *emax = mg->L[level].emax;
   return 0;
 }
 
@@ -381,6 +496,7 @@ int b2_mg_destroy(b2_mg* mg) {
     b2_vec_destroy(L.t);
     b2_vec_destroy(L.b);
     b2_vec_destroy(L.r);
+    b2_vec_destroy(L.d);
     if (L.R) b2_csr_destroy(L.R);
     if (L.bdc) b2_free(c, L.bdc, (size_t)L.nbdc);
   }

@@ -24,7 +24,7 @@ class PoissonMG:
 
     def __init__(self, ctx, nx, ny, nz, nlevels, order="biquadratic", bounds=None, npre=1, npost=1, omega=0.5,
                  dirichlet_faces=(1, 2, 3, 4, 5, 6), fsrc=1.0, coarse_rtol=1e-14, hier=None, dist=None, fused=True,
-                 neumann=None):
+                 neumann=None, smoother="richardson"):
         self.ctx = ctx
         self.order = order
         self.fam = hostapi.FAMILY[order]
@@ -88,6 +88,10 @@ class PoissonMG:
         self.RESM = ctx.vector(self.n)
         self.mg = capi.Multigrid(ctx, nlevels)
         self.mg.set_coarse(coarse_rtol, 10000)
+        self.smoother = smoother
+        if smoother != "richardson":
+            for l in range(1, nlevels):
+                self.mg.set_smoother(l, smoother)
         # --- distributed layout: interface dofs of every level, ownership; reductions over owned dofs
         self.layout = [None] * nlevels
         self.halo = [None] * nlevels

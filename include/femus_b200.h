@@ -248,6 +248,13 @@ int b2_mg_set_level(b2_mg* mg, int level, b2_csr* A, b2_csr* P, const int32_t* b
 /* distributed run: layout of the level's vectors; A is then this rank's partial operator (sum over
  * its own elements), P its local prolongator.  Call before b2_mg_set_level. */
 int b2_mg_set_level_halo(b2_mg* mg, int level, b2_halo* halo);
+/* smoother of a level (call before b2_mg_set_level): kind 0 = Richardson(omega)+Jacobi, 1 = Chebyshev+Jacobi
+ * (KSPCHEBYSHEV + PCJACOBI, LinearEquationSolverPetsc.cpp:452-536) on [emin, emax] of D^-1 A.  emax <= 0:
+ * the bounds are OUR OWN stated ones -- [0.1, 1.1] x the largest eigenvalue found by 10 power iterations
+ * from a fixed start vector at b2_mg_set_level (PETSc estimates with GMRES on a random vector, which is
+ * not reproducible); b2_mg_level_bounds returns the interval in use. */
+int b2_mg_set_smoother(b2_mg* mg, int level, int kind, double emin, double emax);
+int b2_mg_level_bounds(const b2_mg* mg, int level, double* emin, double* emax);
 /* coarse solver: Jacobi-PCG to ||r|| <= rtol ||b|| (the reference: PREONLY + MUMPS LU,
  * PetscPreconditioner.cpp:147-160) */
 int b2_mg_set_coarse(b2_mg* mg, double rtol, int maxit);

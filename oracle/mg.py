@@ -68,9 +68,10 @@ class Hierarchy:
     """Per-level operators exactly as the reference sets them up for one MGsolve."""
 
     def __init__(self, levels, order, fsrc=1.0, dirichlet_faces=(1, 2, 3, 4, 5, 6), A_top=None, rhs=None,
-                 coarse_lu=True, ptap=None, neumann=None):
+                 coarse_lu=True, ptap=None, neumann=None, smoother="richardson"):
         self.levels = levels
         self.order = order
+        self.smoother = smoother
         nl = len(levels)
         self.bdc = [mb.bdc_flags(L, order, dirichlet_faces) for L in levels]
         self.bdc_idx = [np.nonzero(b < 1.5)[0] for b in self.bdc]
@@ -106,9 +107,48 @@ class Hierarchy:
         self.A = [penalty_fast(self.A_raw[l], self.bdc_idx[l]) for l in range(nl)]
         self.dinv = [1.0 / A.diagonal() for A in self.A]
         self.lu = spla.splu(self.A[0].tocsc()) if self.coarse_lu else None
+        # Chebyshev bounds: our own stated ones, [0.1, 1.1] x the power-iteration estimate of lambda_max(D^-1 A)
+        self.ebounds = [None] * nl
+        if self.smoother == "chebyshev":
+            for l in range(1, nl):
+                lam = self.estimate_emax(l)
+                self.ebounds[l] = (0.1 * lam, 1.1 * lam)
+
+    def estimate_emax(self, l, its=10):
+        """Largest eigenvalue of D^-1 A by power iteration from the fixed start vector
+        v_i = 1 + 0.5 sin(i mod 1000), zero on Dirichlet rows (b2_mg.cu estimate_emax)."""
+        n = self.A[l].shape[0]
+        v = 1.0 + 0.5 * np.sin((np.arange(n) % 1000).astype(np.float64))
+        v[self.bdc_idx[l]] = 0.0
+        lam = 0.0
+        for it in range(its + 1):
+            nrm = float(np.sqrt(v @ v))
+            if it > 0:
+                lam = nrm
+            if it == its or nrm == 0.0:
+                break
+            v = self.dinv[l] * (self.A[l] @ (v / nrm))
+        return lam
 
     def smooth(self, l, x, b, nsweeps, omega):
-        """KSPRICHARDSON (scale omega) + PCJACOBI: x <- x + omega D^-1 (b - A x)."""
+        """KSPRICHARDSON (scale omega) + PCJACOBI: x <- x + omega D^-1 (b - A x); or Chebyshev + Jacobi
+        on the stated interval (Saad, alg. 12.1), restarted at every call like a PETSc smoother."""
+        if self.smoother == "chebyshev":
+            emin, emax = self.ebounds[l]
+            theta, delta = 0.5 * (emax + emin), 0.5 * (emax - emin)
+            sigma1 = theta / delta
+            rho = 1.0 / sigma1
+            d = None
+            for k in range(nsweeps):
+                z = self.dinv[l] * (b - self.A[l] @ x)
+                if k == 0:
+                    d = z / theta
+                else:
+                    rho_new = 1.0 / (2.0 * sigma1 - rho)
+                    d = (rho_new * rho) * d + (2.0 * rho_new / delta) * z
+                    rho = rho_new
+                x = x + d
+            return x
         for _ in range(nsweeps):
             x = x + omega * (self.dinv[l] * (b - self.A[l] @ x))
         return x

@@ -356,6 +356,33 @@ def test_vcycle_trace_with_neumann_and_partial_dirichlet(ctx, order):
     del pb
 
 
+@pytest.mark.parametrize("order,npre", [("linear", 2), ("biquadratic", 3)])
+def test_vcycle_trace_chebyshev_smoother(ctx, order, npre):
+    """Chebyshev + Jacobi smoothing (KSPCHEBYSHEV + PCJACOBI) with our stated eigenvalue bounds
+    ([0.1, 1.1] x a 10-step power-iteration estimate from a fixed start vector): bounds and V-cycle
+    residual trace against the oracle."""
+    from femus_b200.poisson import PoissonMG
+    from oracle import mg
+    pb = PoissonMG(ctx, 2, 2, 2, 3, order, npre=npre, npost=npre, smoother="chebyshev", coarse_rtol=1e-15)
+    pb.assemble(); pb.galerkin(); pb.mg_set_levels()
+    lv = mb.build_hierarchy(2, 2, 2, 3)
+    H = mg.Hierarchy(lv, order, smoother="chebyshev")
+    for l in (1, 2):
+        a, b = pb.mg.level_bounds(l)
+        assert abs(a - H.ebounds[l][0]) <= 1e-12 * a and abs(b - H.ebounds[l][1]) <= 1e-12 * b
+    trace, eps = H.mg_solve_trace(3, npre, npre)
+    r0 = float(np.linalg.norm(np.where(H.bdc[-1] > 1.1, H.rhs, 0.0)))
+    for k in range(3):
+        pb.mg_solve()
+        assert abs(pb.residual_norm() - trace[k]) <= 1e-11 * r0, (k, pb.residual_norm(), trace[k])
+    assert np.abs(pb.EPS.get() - eps).max() <= 1e-10 * np.abs(eps).max()
+    if order == "biquadratic":      # degree 3 Chebyshev smoothing contracts faster than 3 damped-Jacobi sweeps
+        Hj = mg.Hierarchy(lv, order)
+        tj, _ = Hj.mg_solve_trace(3, npre, npre)
+        assert trace[-1] < tj[-1]
+    del pb
+
+
 def test_assembly_golden_elements(ctx, asm_variant):
     """Single elements of the committed golden fixture (values of the compiled reference)."""
     import os
