@@ -83,26 +83,51 @@ class NumpyRank:
                 x = x + self.omega * self.dinv[l] * self.resid(l, b, x)
         return x
 
+    def halo_sum_scalars(self, l, v, scal):
+        """b2_halo_sum_scalars: interface values and the scalars in ONE all_reduce."""
+        lay = self.lay[l]
+        buf = np.zeros(lay.n_packed + len(scal))
+        buf[lay.pos] = v[lay.idx]
+        buf[lay.n_packed:] = scal
+        buf = self.allreduce(buf)
+        v = v.copy()
+        v[lay.idx] = buf[lay.pos]
+        return v, buf[lay.n_packed:].copy()
+
     def coarse(self, b, rtol=1e-15, maxit=5000):
+        """Single-reduction (Chronopoulos-Gear) Jacobi-PCG as b2_mg.cu coarse_solve: per iteration one
+        partial product w = A u, the local sums (r.u over owned, w.u over ALL local entries -- u is
+        complete on every holder, so the partial w can be used --, r.r over owned) and one collective
+        that completes w on the interface and reduces the three scalars."""
         idx = np.nonzero(self.bdc[0] < 1.5)[0]
+        own = self.lay[0].owned.astype(bool)
         x = np.zeros_like(b)
         x[idx] = b[idx]
         r = self.resid(0, b, x)
-        z = self.dinv[0] * r
-        p = z.copy()
-        rz = self.dot(0, r, z)
-        bb = self.dot(0, b, b)
-        for _ in range(maxit):
-            if self.dot(0, r, r) <= rtol * rtol * bb:
+        u = self.dinv[0] * r
+        p = np.zeros_like(b)
+        s = np.zeros_like(b)
+        gamma = alpha = bb = 0.0
+        for it in range(maxit + 1):
+            w = self.A[0] @ u
+            scal = [r[own] @ u[own], w @ u, r[own] @ r[own]] + ([b[own] @ b[own]] if it == 0 else [])
+            w, red = self.halo_sum_scalars(0, w, scal)
+            gn, delta, rr = red[0], red[1], red[2]
+            if it == 0:
+                bb = red[3]
+            if bb == 0.0 or not (rr > rtol * rtol * bb):
                 break
-            q = self.halo_sum(0, self.A[0] @ p)
-            alpha = rz / self.dot(0, p, q)
+            if it == 0:
+                beta, alpha = 0.0, gn / delta
+            else:
+                beta = gn / gamma
+                alpha = gn / (delta - beta * gn / alpha)
+            gamma = gn
+            p = u + beta * p
+            s = w + beta * s
             x += alpha * p
-            r -= alpha * q
-            z = self.dinv[0] * r
-            rzn = self.dot(0, r, z)
-            p = z + (rzn / rz) * p
-            rz = rzn
+            r -= alpha * s
+            u = self.dinv[0] * r
         return x
 
     def vcycle(self, l, b):
