@@ -1183,9 +1183,9 @@ int b2_asm_create(b2_mesh* m, b2_csr* A, int nve, const int32_t* dof, int ngauss
   p->slot_bytes = A->max_row <= 256 ? 1 : 2;
   p->nslot = nullptr;
   p->nslot_count = 0;
-  if (nve == 27) {
-    if (p->slot_bytes == 1) B2_TRY((build_slots<27, uint8_t>(p)));
-    else B2_TRY((build_slots<27, uint16_t>(p)));
+  p->slot = nullptr;
+  p->slot_count = 0;
+  if (nve == 27) {     // tensor-core kernel: natural-order map; the tile-order map of the CUDA-core kernel is built on demand
     if (p->slot_bytes == 1) B2_TRY(build_natural_slots<uint8_t>(p));
     else B2_TRY(build_natural_slots<uint16_t>(p));
   } else {
@@ -1202,8 +1202,10 @@ int b2_asm_destroy(b2_asm* p) {
   cudaStreamSynchronize(c->stream);
   b2_free(c, p->dof, (size_t)p->mesh->nel * p->nve);
   b2_free(c, p->tab, (size_t)4 * p->ngauss * p->nve + p->ngauss);
-  if (p->slot_bytes == 1) b2_free(c, (uint8_t*)p->slot, p->slot_count);
-  else b2_free(c, (uint16_t*)p->slot, p->slot_count);
+  if (p->slot) {
+    if (p->slot_bytes == 1) b2_free(c, (uint8_t*)p->slot, p->slot_count);
+    else b2_free(c, (uint16_t*)p->slot, p->slot_count);
+  }
   if (p->nslot) {
     if (p->slot_bytes == 1) b2_free(c, (uint8_t*)p->nslot, p->nslot_count);
     else b2_free(c, (uint16_t*)p->nslot, p->nslot_count);
@@ -1225,6 +1227,10 @@ int b2_asm_poisson(b2_asm* p, const b2_vec* u, b2_vec* rhs, double nu, double fs
     return launch_assemble_mma<uint16_t, false, uint8_t>(p, ga, u, rhs, nu, fsrc);
   }
   if (p->nve == 27) {
+    if (!p->slot) {      // first use of the CUDA-core kernel on this plan
+      if (p->slot_bytes == 1) B2_TRY((build_slots<27, uint8_t>(p)));
+      else B2_TRY((build_slots<27, uint16_t>(p)));
+    }
     if (p->slot_bytes == 1) return launch_assemble<27, uint8_t>(p, u, rhs, nu, fsrc);
     return launch_assemble<27, uint16_t>(p, u, rhs, nu, fsrc);
   }
@@ -1258,6 +1264,10 @@ int b2_asm_poisson_galerkin(b2_asm* p, b2_galerkin* gal, const b2_vec* u, b2_vec
     return launch_assemble_mma<uint16_t, true, uint16_t>(p, ga, u, rhs, nu, fsrc);
   }
   if (p->nve == 27) {
+    if (!p->slot) {
+      if (s1) B2_TRY((build_slots<27, uint8_t>(p)));
+      else B2_TRY((build_slots<27, uint16_t>(p)));
+    }
     if (s1 && c1) return launch_assemble_gal<27, uint8_t, uint8_t>(p, g, u, rhs, nu, fsrc);
     if (s1) return launch_assemble_gal<27, uint8_t, uint16_t>(p, g, u, rhs, nu, fsrc);
     if (c1) return launch_assemble_gal<27, uint16_t, uint8_t>(p, g, u, rhs, nu, fsrc);

@@ -49,3 +49,12 @@ if nl > 1:
     P = pb.PP[-1]
     xc = ctx.vector(P.shape[1]); yf = ctx.vector(P.shape[0])
     timed(lambda: P.spmv(xc, yf), "P spmv", 5)
+# explicit teardown: library objects must go before the context (and before interpreter shutdown)
+del x, y, A
+try:
+    del Al, xx, yy, P, xc, yf
+except NameError:
+    pass
+del pb
+ctx.close()
+
