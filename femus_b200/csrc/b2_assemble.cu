@@ -1,21 +1,26 @@
 // Element assembly of the 3-D Poisson stiffness matrix / residual on HEX27 meshes, one warp per
 // element.  Replaces the element loop of applications/001_Poisson/main.cpp:350-602 together with
 // elem_type_3D::Jacobian_type (src/02_reference_geom_elements/03_fe_evaluations_at_quadrature/
-// ElemType.hpp:1438-1537), MatSetValuesBlocked (PetscMatrix.cpp:699-729) and VecSetValues
-// (PetscVector.cpp:132-141).
+// ElemType.hpp:1438-1537), MatSetValuesBlocked (PetscMatrix.cpp:699-729), VecSetValues
+// (PetscVector.cpp:132-141), the Neumann face integrals (main.cpp:495-548, elem_type_2D::JacobianSur)
+// and -- fused -- the first Galerkin product of LinearImplicitSystem.cpp:347-370.
 //
-// Per element (warp):
+// Kernels in this file
+//   assemble_q2_mma_kernel      triquadratic elements, element matrix on the FP64 tensor cores (default)
+//   assemble_poisson_kernel     CUDA-core register tiles: trilinear elements, and triquadratic on request
+//   galerkin_from_elements_kernel   coarser Galerkin products from recorded element matrices
+//   neumann_kernel              boundary faces
+//
+// Common structure per element (warp):
 //   A. lanes = Gauss points (2 each for the 64-point rule): J = sum_n dphi[g][n] x[n] with the
-//      shape-derivative tables staged in shared memory once per CTA, then det, J^-1 and
-//      weight = det * w_g, kept in shared memory (10 doubles per point).
-//   B. for every Gauss point: lanes < nve form grad phi_n = J^-1 dphi_n (3 doubles each, shared
-//      memory, double buffered), then every lane updates its TI x TJ register tile of
-//      B_ij += (grad phi_i . grad phi_j) weight.
-//   C. residual F_i = fsrc * sum_g phi_i weight - (B u)_i (row sums reduced with shuffles),
-//      scatter: fp64 atomicAdd into the CSR through a precomputed element->slot map, and into rhs.
+//      shape-derivative tables staged in shared memory once per CTA, then det, J^-1, weight.
+//   B. element matrix B_ij = sum_g w_g grad phi_i . grad phi_j (tensor-core GEMM or register tiles).
+//   C. residual F_i = fsrc * sum_g phi_i weight - (B u)_i, scatter: fp64 atomicAdd into the CSR
+//      through a precomputed element->slot map (no searches), and into rhs.
+//   D. (fused Galerkin) D_e = Pc^T B Pc, summed over the 8 children of a coarse element, scattered
+//      to the coarse matrix and recorded for the element-matrix chain.
 // The geometry map uses the unknown's own family and its first nve nodes, like the reference
-// (ElemType.hpp:1462).  The kernel is FP64-FMA bound (~1.7e5 FMA per triquadratic element); the
-// only HBM traffic is 27 node ids + 81 coordinates in and 729 atomics out.
+// (ElemType.hpp:1462).  HBM traffic: 27 node ids + 81 coordinates in, 729 atomics out per element.
 #include "b2_common.cuh"
 
 struct b2_mesh {
