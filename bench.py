@@ -277,25 +277,28 @@ def main():
     # pinned host memory and its outputs (correction EPS, residual norm) go back to the host, all inside
     # the timed region.  The inputs are double buffered on the device: step k+1's upload runs on the
     # copy stream while step k computes (b2_ctx_open_copies / b2_mesh_prefetch / b2_vec_prefetch).
-    sol_shadow = ctx.vector(n_loc)
+    sol_shadow, eps_shadow = ctx.vector(n_loc), ctx.vector(n_loc)
     if pb.halo[-1] is not None:
         sol_shadow.set_halo(pb.halo[-1])
-    e2e_state = {"shadow": sol_shadow}
+        eps_shadow.set_halo(pb.halo[-1])
+    e2e_state = {"shadow": sol_shadow, "eps_shadow": eps_shadow}
 
     def upload_next():
         ctx.open_copies()
         pb.mesh.prefetch(h_xyz.data_ptr(), h_conn.data_ptr())
         e2e_state["shadow"].prefetch(h_sol.data_ptr(), n_loc)
+        ctx.mark_copies()
 
     def step_e2e(more):
-        ctx.join_copies()                  # the compute stream waits for this step's inputs
+        ctx.wait_marked()                  # the compute stream waits for this step's inputs (not for the last download)
         pb.mesh.swap()
         pb.SOL, e2e_state["shadow"] = e2e_state["shadow"], pb.SOL
         if more:
             upload_next()                  # next step's inputs, behind this step's compute
+        pb.EPS, e2e_state["eps_shadow"] = e2e_state["eps_shadow"], pb.EPS     # the other buffer may still be downloading
         pb.step()
-        pb.EPS.get_async(h_eps.data_ptr(), n_loc)
-        return pb.residual_norm()          # D2H of the scalar, synchronises
+        pb.EPS.fetch(h_eps.data_ptr(), n_loc)      # copy stream: overlaps the next step's assembly
+        return pb.residual_norm()          # D2H of the scalar, synchronises the compute stream
 
     # ---- warm-up
     for _ in range(W):
@@ -341,11 +344,13 @@ def main():
     upload_next()
     for k in range(2):
         step_e2e(k < 1)
+    ctx.join_copies()
     barrier()
     ctx.timer_start()
     upload_next()
     for k in range(args.steps):
         resnorm = step_e2e(k + 1 < args.steps)
+    ctx.join_copies()                      # the last correction has reached the host inside the timed region
     ms_e2e = ctx.timer_stop_ms()
     barrier()
     ms_e2e = max_over_ranks(ms_e2e)

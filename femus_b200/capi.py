@@ -42,8 +42,11 @@ _PROTOS = {
     "b2_ctx_profile_clear": (ci, [vp]),
     "b2_vec_put_async": (ci, [vp, vp, i64]),
     "b2_vec_prefetch": (ci, [vp, vp, i64]),
+    "b2_vec_fetch": (ci, [vp, vp, i64]),
     "b2_ctx_open_copies": (ci, [vp]),
     "b2_ctx_join_copies": (ci, [vp]),
+    "b2_ctx_mark_copies": (ci, [vp]),
+    "b2_ctx_wait_marked": (ci, [vp]),
     "b2_mesh_prefetch": (ci, [vp, vp, vp]),
     "b2_mesh_swap": (ci, [vp]),
     "b2_vec_get_async": (ci, [vp, vp, i64]),
@@ -221,6 +224,12 @@ class Context:
     def join_copies(self):
         check(self.L.b2_ctx_join_copies(self.h))
 
+    def mark_copies(self):
+        check(self.L.b2_ctx_mark_copies(self.h))
+
+    def wait_marked(self):
+        check(self.L.b2_ctx_wait_marked(self.h))
+
     def measure_fp64_tensor(self):
         """Measured fp64 tensor-core (DMMA) peak of this device in TFLOP/s."""
         t = cd()
@@ -300,6 +309,10 @@ class Vector:
 
     def prefetch(self, host_ptr, n):
         check(self.L.b2_vec_prefetch(self.h, host_ptr, n))
+
+    def fetch(self, host_ptr, n):
+        """D2H on the copy stream, ordered after the compute enqueued so far."""
+        check(self.L.b2_vec_fetch(self.h, host_ptr, n))
 
     def get_async(self, host_ptr, n):
         check(self.L.b2_vec_get_async(self.h, host_ptr, n))

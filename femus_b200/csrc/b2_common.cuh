@@ -49,7 +49,7 @@ struct b2_ctx {
   // second stream for host->device prefetches that overlap the compute of the previous step
   // (b2_mesh_prefetch / b2_vec_prefetch / b2_ctx_join_copies)
   cudaStream_t copy_stream = nullptr;
-  cudaEvent_t ev_copied = nullptr, ev_free = nullptr;
+  cudaEvent_t ev_copied = nullptr, ev_free = nullptr, ev_marked = nullptr;
   int64_t bytes = 0;
   int64_t launches = 0;
   // scratch for reductions: partial sums + result (device) and a pinned host mirror

@@ -84,6 +84,7 @@ int b2_ctx_create(int device, b2_ctx** out) {
   B2_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
   B2_CUDA(cudaEventCreateWithFlags(&c->ev_copied, cudaEventDisableTiming));
   B2_CUDA(cudaEventCreateWithFlags(&c->ev_free, cudaEventDisableTiming));
+  B2_CUDA(cudaEventCreateWithFlags(&c->ev_marked, cudaEventDisableTiming));
   B2_TRY(b2_malloc(c, &c->red_partial, (size_t)kRedBlocks * 2));
   B2_TRY(b2_malloc(c, &c->red_result, 8));
   B2_TRY(b2_malloc(c, &c->red_counter, 1));
@@ -110,6 +111,7 @@ int b2_ctx_destroy(b2_ctx* c) {
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   if (c->ev_copied) cudaEventDestroy(c->ev_copied);
   if (c->ev_free) cudaEventDestroy(c->ev_free);
+  if (c->ev_marked) cudaEventDestroy(c->ev_marked);
   delete c;
   return 0;
 }
@@ -160,9 +162,19 @@ int b2_ctx_open_copies(b2_ctx* c) {
   B2_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_free, 0));
   return 0;
 }
-int b2_ctx_join_copies(b2_ctx* c) {
+int b2_ctx_join_copies(b2_ctx* c) {      // the compute stream waits for EVERYTHING issued on the copy stream so far
   B2_CUDA(cudaEventRecord(c->ev_copied, c->copy_stream));
   B2_CUDA(cudaStreamWaitEvent(c->stream, c->ev_copied, 0));
+  return 0;
+}
+// mark the end of a batch of prefetches; b2_ctx_wait_marked makes the compute stream wait for that
+// batch only (later copies, e.g. a result download of the previous step, keep overlapping)
+int b2_ctx_mark_copies(b2_ctx* c) {
+  B2_CUDA(cudaEventRecord(c->ev_marked, c->copy_stream));
+  return 0;
+}
+int b2_ctx_wait_marked(b2_ctx* c) {
+  B2_CUDA(cudaStreamWaitEvent(c->stream, c->ev_marked, 0));
   return 0;
 }
 

@@ -208,6 +208,16 @@ int b2_vec_prefetch(b2_vec* v, const double* host, int64_t n) {
   B2_CUDA(cudaMemcpyAsync(v->d, host, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, v->ctx->copy_stream));
   return 0;
 }
+// device -> host on the copy stream, ordered after everything enqueued so far on the compute stream
+// (the result of the step just issued); b2_ctx_join_copies / b2_ctx_sync make it visible to the host
+int b2_vec_fetch(const b2_vec* v, double* host, int64_t n) {
+  B2_CHECK(n <= v->n, "b2_vec_fetch: too long");
+  b2_ctx* c = v->ctx;
+  B2_CUDA(cudaEventRecord(c->ev_free, c->stream));
+  B2_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_free, 0));
+  B2_CUDA(cudaMemcpyAsync(host, v->d, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, c->copy_stream));
+  return 0;
+}
 int b2_vec_get_async(const b2_vec* v, double* host, int64_t n) {
   B2_CHECK(n <= v->n, "b2_vec_get_async: too long");
   B2_CUDA(cudaMemcpyAsync(host, v->d, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, v->ctx->stream));

@@ -89,7 +89,13 @@ int b2_vec_get_async(const b2_vec* v, double* host, int64_t n);
  * running step does not read, b2_ctx_join_copies orders the compute stream after those copies. */
 int b2_ctx_open_copies(b2_ctx* c);
 int b2_ctx_join_copies(b2_ctx* c);
+/* b2_ctx_mark_copies closes a batch of prefetches; b2_ctx_wait_marked makes the compute stream wait for
+ * that batch only, so that a later b2_vec_fetch keeps overlapping the next step */
+int b2_ctx_mark_copies(b2_ctx* c);
+int b2_ctx_wait_marked(b2_ctx* c);
 int b2_vec_prefetch(b2_vec* v, const double* host, int64_t n);
+/* device -> host on the copy stream, after the compute enqueued so far (overlaps the next step) */
+int b2_vec_fetch(const b2_vec* v, double* host, int64_t n);
 int b2_vec_copy(b2_vec* dst, const b2_vec* src);                       /* operator=(NumericVector)     :429 */
 int b2_vec_axpy(b2_vec* y, double a, const b2_vec* x);                 /* add(a,V)    VecAXPY          :303 */
 int b2_vec_aypx(b2_vec* y, double a, const b2_vec* x);                 /* y = x + a y VecAYPX */

@@ -1,4 +1,8 @@
 #!/bin/bash
 mkdir -p gpurun_out
 timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
-tail -12 gpurun_out/pytest_gpu.log
+tail -4 gpurun_out/pytest_gpu.log
+timeout 900 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err
+tail -3 gpurun_out/bench.err
+python -c "
+import json; d=json.load(open('gpurun_out/bench.json')); print(d['phases_ms'], d['ms_per_step'], d['value'], d['e2e'], d['cpu_baseline']['value'])"
