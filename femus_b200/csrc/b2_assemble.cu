@@ -512,7 +512,7 @@ assemble_q2_mma_kernel(int64_t nel, int64_t nnode, const double* __restrict__ xy
           t++;
         }
     };
-#pragma unroll 1
+#pragma unroll 2
     for (int q = 0; q < NG / 4; q++) {
       const int s0 = 3 * q;
       double g0, g1, g2, wg;
