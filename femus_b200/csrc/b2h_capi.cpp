@@ -3,6 +3,7 @@
 #include <cstring>
 #include <memory>
 #include "../host/BoxMesh.hpp"
+#include "../host/GambitIO.hpp"
 #include "../../include/femus_b200_host.h"
 
 using namespace femus_b200;
@@ -41,8 +42,16 @@ b2h_hier* b2h_hier_create_local(int nx, int ny, int nz, int nlevels, const doubl
   for (int l = 1; l < nlevels; l++) h->levels.push_back(RefineMesh(h->levels.back()));
   return h;
 }
+b2h_hier* b2h_hier_create_from_neu(const char* path, int nlevels, double Lref) {
+  if (!path || nlevels < 1 || Lref <= 0.) return nullptr;
+  b2h_hier* h = new b2h_hier();
+  h->levels.reserve(nlevels);
+  h->levels.push_back(ReadGambitHex27(path, Lref));
+  for (int l = 1; l < nlevels; l++) h->levels.push_back(RefineMesh(h->levels.back()));
+  return h;
+}
 void b2h_hier_destroy(b2h_hier* h) { delete h; }
-const int32_t* b2h_level_ijk(const b2h_hier* h, int l) { return h->levels[l].ijk.data(); }
+const int32_t* b2h_level_ijk(const b2h_hier* h, int l) { return h->levels[l].ijk.empty() ? nullptr : h->levels[l].ijk.data(); }
 int64_t b2h_level_interface_nodes(const b2h_hier* h, int l, int32_t* out) {
   const std::vector<int32_t> v = InterfaceNodes(h->levels[l]);
   if (out) std::copy(v.begin(), v.end(), out);

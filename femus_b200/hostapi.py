@@ -19,6 +19,7 @@ def _L():
         P = {
             "b2h_hier_create": (vp, [ci, ci, ci, ci, vp, ci]),
             "b2h_hier_create_local": (vp, [ci, ci, ci, ci, vp, ci, ci]),
+            "b2h_hier_create_from_neu": (vp, [ctypes.c_char_p, ci, ctypes.c_double]),
             "b2h_hier_destroy": (None, [vp]),
             "b2h_level_ijk": (vp, [vp, ci]),
             "b2h_level_interface_nodes": (i64, [vp, ci, vp]),
@@ -83,7 +84,8 @@ class HostLevel:
         self.face = _view(L.b2h_level_face(h, l), (self.nel, 6), np.int32)
         self.part = _view(L.b2h_level_part(h, l), (self.nel,), np.int32)
         self.xyz = _view(L.b2h_level_xyz(h, l), (3, self.nnode), np.float64)
-        self.ijk = _view(L.b2h_level_ijk(h, l), (3, self.nnode), np.int32)
+        p_ijk = L.b2h_level_ijk(h, l)      # lattice names of the nodes: box meshes only
+        self.ijk = _view(p_ijk, (3, self.nnode), np.int32) if p_ijk else None
         np1 = hier.nprocs + 1
         eo = np.zeros(np1, dtype=np.int64)
         do = np.zeros((3, np1), dtype=np.int64)
@@ -154,6 +156,20 @@ class HostHierarchy:
             raise ValueError("b2h_hier_create failed")
         self.nlevels = nlevels
         self.levels = [HostLevel(self, l) for l in range(nlevels)]
+
+    @classmethod
+    def from_neu(cls, path, nlevels, Lref=1.0):
+        """MultiLevelMesh::ReadCoarseMesh on a Gambit .neu file of 27-node hexahedra + RefineMesh."""
+        self = cls.__new__(cls)
+        self.L = _L()
+        self.box = None
+        self.nprocs = 1
+        self.h = self.L.b2h_hier_create_from_neu(str(path).encode(), nlevels, float(Lref))
+        if not self.h:
+            raise ValueError("b2h_hier_create_from_neu failed")
+        self.nlevels = nlevels
+        self.levels = [HostLevel(self, l) for l in range(nlevels)]
+        return self
 
     def __del__(self):
         try:

@@ -23,6 +23,9 @@ b2h_hier* b2h_hier_create(int nx, int ny, int nz, int nlevels, const double* bou
  * (Mesh::_elementOffset[rank] .. [rank+1]) with locally renumbered nodes, refined locally (children
  * inherit the parent's rank, MeshMetisPartitioning.cpp:143-155).  Inside, nprocs == 1. */
 b2h_hier* b2h_hier_create_local(int nx, int ny, int nz, int nlevels, const double* bounds6, int nprocs, int rank);
+/* MultiLevelMesh::ReadCoarseMesh(name, "seventh", Lref) for a Gambit .neu file of 27-node hexahedra
+ * (GambitIO.cpp:92-352) + RefineMesh; aborts on anything else, like the reference on bad input */
+b2h_hier* b2h_hier_create_from_neu(const char* path, int nlevels, double Lref);
 void b2h_hier_destroy(b2h_hier* h);
 /* integer lattice coordinates [3][nnode] of the nodes (rank-independent node names) */
 const int32_t* b2h_level_ijk(const b2h_hier* h, int l);

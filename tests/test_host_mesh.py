@@ -1,5 +1,6 @@
 """CPU: the product's C++ host layer (topological refinement, femus_b200/host/BoxMesh.hpp) against
 the independent lattice-based numpy oracle: integer results bit-exact, coordinates bit-exact."""
+import os
 import numpy as np
 import pytest
 
@@ -67,3 +68,25 @@ def test_face_element_tables_and_boundary_faces():
     e, f, b = H.levels[-1].boundary_faces()
     ref = [(int(el), int(fa), int(-(lv[-1].face[el, fa] + 1))) for el in range(lv[-1].nel) for fa in range(6) if lv[-1].face[el, fa] < -1]
     assert list(zip(e.tolist(), f.tolist(), b.tolist())) == ref
+
+
+NEU = os.path.join(os.path.dirname(__file__), "golden", "cube_Hex.neu")
+
+
+def test_gambit_reader_matches_oracle_reader():
+    """Host .neu reader (GambitIO.cpp:92-352) against the independent numpy reader: connectivity in FEMuS
+    local order and first-visit numbering, boundary flags, coordinates, dof maps and Dirichlet flags,
+    bit-exact; the refined levels stay conforming (node counts of a 2x2x2 cube: 5^3, 9^3, 17^3)."""
+    from oracle import gambit
+    H = hostapi.HostHierarchy.from_neu(NEU, 3)
+    L = gambit.read_hex27(NEU)
+    h = H.levels[0]
+    assert np.array_equal(h.conn, L.conn) and np.array_equal(h.face, L.face) and np.array_equal(h.xyz, L.xyz)
+    for order in ("linear", "biquadratic"):
+        assert np.array_equal(h.system_dofs(order), mb.system_dof(L, order))
+        assert np.array_equal(h.bdc(order), mb.bdc_flags(L, order))
+    assert [lv.nnode for lv in H.levels] == [125, 729, 4913] and [lv.nel for lv in H.levels] == [8, 64, 512]
+    for lv in H.levels:                      # six boundary sets with the same number of faces each
+        b = -(lv.face[lv.face < -1] + 1)
+        assert np.array_equal(np.bincount(b)[1:], np.full(6, lv.nel ** (2 / 3) + 0.5, dtype=int))
+        assert lv.xyz.min() == 0.0 and lv.xyz.max() == 1.0
