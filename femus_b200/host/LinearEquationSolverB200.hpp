@@ -17,7 +17,7 @@
 namespace femus {
 
 enum MgSmootherType { FULL = 0, MULTIPLICATIVE, ADDITIVE, KASKADE };      // 00_enums MgTypeEnum.hpp
-enum B200SolverType { RICHARDSON_B200 = 0, PREONLY_B200 };                // the subset of SolvertypeEnum.hpp in scope
+enum B200SolverType { RICHARDSON_B200 = 0, CHEBYSHEV_B200, PREONLY_B200 }; // the subset of SolvertypeEnum.hpp in scope
 
 class LinearEquationSolverB200 {
  public:
@@ -89,6 +89,10 @@ class LinearEquationSolverB200 {
       Pm.close();
       P = Pm.handle();
     }
+    // level smoother: set_solver_type(RICHARDSON) -> Richardson(scale)+Jacobi, set_solver_type(CHEBYSHEV) ->
+    // Chebyshev+Jacobi with the backend's stated eigenvalue bounds (KSPSetType switch, :452-536)
+    B2_ABORT_IF(b2_mg_set_smoother(LinSolver->_mg, (int)_level, _levelSolverType == CHEBYSHEV_B200 ? 1 : 0, 0., 0.),
+                "b2_mg_set_smoother");
     // SetPenalty (:428-436) happens inside: Dirichlet rows -> identity, pattern kept
     B2_ABORT_IF(b2_mg_set_level(LinSolver->_mg, (int)_level, _KK->handle(), P, _bdcIndex.data(), (int64_t)_bdcIndex.size(), (int)npre,
                                 (int)npost, _richardsonScaleFactor),
