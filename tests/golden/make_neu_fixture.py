@@ -1,0 +1,65 @@
+"""Generate tests/golden/cube_hex27_2x2x2.neu from the reference's shipped coarse mesh
+applications/001_Poisson/input/cube_Hex.neu: the same nodes, elements, group and boundary sets,
+re-serialised in Gambit neutral format by this script (free-format numbers, own header), because
+/root/reference does not exist on the GPU box.  Run in the build container:
+    python tests/golden/make_neu_fixture.py"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+SRC = "/root/reference/applications/001_Poisson/input/cube_Hex.neu"
+DST = os.path.join(ROOT, "tests", "golden", "cube_hex27_2x2x2.neu")
+
+
+def parse(path):
+    lines = open(path).read().split("\n")
+
+    def section(title, start=0):
+        i = next(k for k in range(start, len(lines)) if lines[k].strip().startswith(title))
+        j = next(k for k in range(i, len(lines)) if lines[k].strip() == "ENDOFSECTION")
+        return i, lines[i + 1:j]
+
+    hdr = next(k for k, l in enumerate(lines) if "NUMNP" in l)
+    nvt, nel, ngroup, nbcd, dim, dimn = [int(t) for t in lines[hdr + 1].split()]
+    nodes = [[float(t) for t in l.split()[1:4]] for l in section("NODAL COORDINATES")[1]]
+    toks = " ".join(section("ELEMENTS/CELLS")[1]).split()
+    elems, p = [], 0
+    for _ in range(nel):
+        nve = int(toks[p + 2])
+        elems.append((int(toks[p + 1]), [int(t) for t in toks[p + 3:p + 3 + nve]]))
+        p += 3 + nve
+    _, grp = section("ELEMENT GROUP")
+    gh = grp[0].split()
+    group = dict(material=int(gh[gh.index("MATERIAL:") + 1]), name=grp[1].strip(), elems=[int(t) for t in " ".join(grp[3:]).split()])
+    bsets, start = [], 0
+    for _ in range(nbcd):
+        i, body = section("BOUNDARY CONDITIONS", start)
+        head = body[0].split()
+        bsets.append((int(head[0]), [[int(t) for t in l.split()] for l in body[1:1 + int(head[2])]]))
+        start = i + 1
+    return nvt, nel, dim, dimn, nodes, elems, group, bsets
+
+
+def write(path, nvt, nel, dim, dimn, nodes, elems, group, bsets):
+    out = ["CONTROL INFO 2.3.16", "** GAMBIT NEUTRAL FILE", "cube_hex27_2x2x2 (femus_b200 test fixture)",
+           "PROGRAM: femus_b200/tests/golden/make_neu_fixture.py VERSION: 1", "re-serialised from the reference's cube_Hex.neu",
+           "NUMNP NELEM NGRPS NBSETS NDFCD NDFVL", f"{nvt} {nel} 1 {len(bsets)} {dim} {dimn}", "ENDOFSECTION",
+           "NODAL COORDINATES 2.3.16"]
+    out += [f"{i + 1} {x!r} {y!r} {z!r}" for i, (x, y, z) in enumerate(nodes)]
+    out += ["ENDOFSECTION", "ELEMENTS/CELLS 2.3.16"]
+    out += [f"{i + 1} {t} {len(n)} " + " ".join(str(v) for v in n) for i, (t, n) in enumerate(elems)]
+    out += ["ENDOFSECTION", "ELEMENT GROUP 2.3.16",
+            f"GROUP: 1 ELEMENTS: {len(group['elems'])} MATERIAL: {group['material']} NFLAGS: 1", group["name"], "0",
+            " ".join(str(v) for v in group["elems"]), "ENDOFSECTION"]
+    for name, faces in bsets:
+        out += ["BOUNDARY CONDITIONS 2.3.16", f"{name} 1 {len(faces)} 0 6"]
+        out += [" ".join(str(v) for v in f) for f in faces]
+        out += ["ENDOFSECTION"]
+    open(path, "w").write("\n".join(out) + "\n")
+
+
+if __name__ == "__main__":
+    if not os.path.exists(SRC):
+        sys.exit("reference mesh not present: " + SRC)
+    write(DST, *parse(SRC))
+    print("wrote", DST)

@@ -576,13 +576,13 @@ def test_full_size_properties(ctx):
     del pb
 
 
-NEU = __import__("os").path.join(__import__("os").path.dirname(__file__), "golden", "cube_Hex.neu")
+NEU = __import__("os").path.join(__import__("os").path.dirname(__file__), "golden", "cube_hex27_2x2x2.neu")
 
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("order", ["linear", "biquadratic"])
 def test_neu_mesh_single_level_matches_oracle(ctx, order):
-    """The reference's shipped coarse mesh (cube_Hex.neu, unstructured element order and orientations):
+    """The reference's shipped coarse mesh (cube_hex27_2x2x2.neu, unstructured element order and orientations):
     pattern bit-exact, matrix and residual to 1e-12, single-level solve against a sparse direct solve."""
     import scipy.sparse.linalg as spla
     from femus_b200 import hostapi
@@ -608,7 +608,7 @@ def test_neu_mesh_single_level_matches_oracle(ctx, order):
 
 @pytest.mark.gpu
 def test_neu_mesh_multilevel_solution_equals_box_solution(ctx):
-    """3 levels refined from cube_Hex.neu by the host's topological refinement, fused assembly + element-
+    """3 levels refined from cube_hex27_2x2x2.neu by the host's topological refinement, fused assembly + element-
     matrix Galerkin chain + V-cycles to convergence: the discrete solution must coincide, node by node
     (matched through coordinates), with the oracle's solution on the generated 2x2x2 box hierarchy --
     same FE space, different element order, orientations and numbering."""

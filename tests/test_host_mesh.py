@@ -70,7 +70,7 @@ def test_face_element_tables_and_boundary_faces():
     assert list(zip(e.tolist(), f.tolist(), b.tolist())) == ref
 
 
-NEU = os.path.join(os.path.dirname(__file__), "golden", "cube_Hex.neu")
+NEU = os.path.join(os.path.dirname(__file__), "golden", "cube_hex27_2x2x2.neu")
 
 
 def test_gambit_reader_matches_oracle_reader():
