@@ -36,6 +36,7 @@ struct b2_asm {
   b2_mesh* mesh;
   b2_csr* A;
   int nve, ngauss;
+  bool general;    // not a hexahedron with the 64-point rule: table-driven kernel
   int32_t* dof;    // [nel][nve]
   double* tab;     // phi, dxi, deta, dzeta [ng][nve] each, then w[ng]
   void* slot;      // [nel][TI*TJ][32] uint8 or uint16: position of (i,j) inside row dof_i (tile kernel)
@@ -970,6 +971,167 @@ int build_gal_tables(b2_asm* p, const b2_galerkin* gal, const b2_galerkin_view& 
   p->gal_tab = d_T;
   return 0;
 }
+
+// ------------------------------------------------------------------------------------------
+// Table-driven assembly for ANY Lagrange family elem_type_3D can build (tetrahedra 4/10/15, wedges
+// 6/15/21, hexahedra with another quadrature rule ...): the kernel only sees nve <= 27 dofs per element,
+// ng <= 64 Gauss points and the four tables of ElemType.cpp:637-740, exactly what
+// elem_type_3D::Jacobian_type (ElemType.hpp:1438-1537) works from -- the per-element-type dispatch of the
+// reference is the choice of tables.  One warp per element:
+//   A. lanes = Gauss points: J, det, J^-1, weight (node-order sums as the reference's :1462-1472);
+//   B. per Gauss point the nve physical gradients go to a double-buffered shared tile; lane l owns the
+//      entries l, l+32, ... of the row-major nve x nve element matrix in registers;
+//   C. element matrix to shared memory, residual F_i = fsrc sum_g phi_i w_g - nu (B u)_i by lane i,
+//      fp64 atomicAdd scatter through the natural-order slot map (coalesced slot reads, no searches).
+// CUDA cores only: these element matrices are 4x4 ... 21x21 with 5-45 Gauss points, too small and too
+// ragged for the DMMA tiling of the Hex27 kernel.  HBM traffic per element: nve node ids + 3 nve
+// coordinates + nve dofs + nve^2 slots in, nve^2 + nve atomics out.
+constexpr int kGenWarps = 8;
+constexpr int kGenMaxNg = 64;
+constexpr int kGenAcc = (27 * 27 + 31) / 32;      // 23 entries per lane at most
+
+struct GenSmem {
+  // per warp: X[3][32], U[32], dofs[32] (as int), G[2][3][32], Geo[10][ng], B[nve*nve rounded up to 8]
+  static int warp_doubles(int nve, int ng) { return 3 * 32 + 32 + 16 + 2 * 3 * 32 + 10 * ng + ((nve * nve + 7) & ~7); }
+  static size_t bytes(int nve, int ng) { return (size_t)(4 * ng * nve + ng + kGenWarps * warp_doubles(nve, ng)) * sizeof(double); }
+};
+
+template <typename SlotT>
+__global__ void __launch_bounds__(kGenWarps * 32)
+assemble_general_kernel(int64_t nel, int64_t nnode, int nve, int ng, const double* __restrict__ xyz,
+                        const int32_t* __restrict__ conn, const int32_t* __restrict__ dof, const double* __restrict__ tab,
+                        const SlotT* __restrict__ slot, const int64_t* __restrict__ rowptr, double* __restrict__ Aval,
+                        const double* __restrict__ u, double* __restrict__ rhs, double nu, double fsrc) {
+  extern __shared__ double smem[];
+  const int tn = ng * nve;
+  double* s_phi = smem;
+  double* s_dx = s_phi + tn;
+  double* s_dy = s_dx + tn;
+  double* s_dz = s_dy + tn;
+  double* s_w = s_dz + tn;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  double* wbase = s_w + ng + wib * (336 + 10 * ng + ((nve * nve + 7) & ~7));
+  double* sX = wbase;                                  // [3][32]
+  double* sU = sX + 96;                                // [32]
+  int* sDof = reinterpret_cast<int*>(sU + 32);         // [32] ints in 16 doubles
+  double* sG = sU + 32 + 16;                           // [2][3][32]
+  double* sGeo = sG + 192;                             // [10][ng]
+  double* sB = sGeo + 10 * ng;                         // [nve][nve]
+  for (int t = threadIdx.x; t < 4 * tn + ng; t += blockDim.x) smem[t] = tab[t];
+  __syncthreads();
+
+  const int nn = nve * nve;
+  // (i, j) of the entries this lane owns, packed i * 32 + j
+  int ij[kGenAcc];
+#pragma unroll
+  for (int k = 0; k < kGenAcc; k++) {
+    const int e = lane + 32 * k;
+    const int i = e < nn ? e / nve : 0;
+    ij[k] = i * 32 + (e < nn ? e - i * nve : 0);
+  }
+
+  for (int64_t el = (int64_t)blockIdx.x * kGenWarps + wib; el < nel; el += (int64_t)gridDim.x * kGenWarps) {
+    if (lane < nve) {
+      const int64_t nd = conn[el * 27 + lane];
+      sX[lane] = xyz[nd];
+      sX[32 + lane] = xyz[nnode + nd];
+      sX[64 + lane] = xyz[2 * nnode + nd];
+      const int d = dof[el * nve + lane];
+      sDof[lane] = d;
+      sU[lane] = u ? u[d] : 0.0;
+    }
+    __syncwarp();
+
+    // ---- A. geometry at the Gauss points owned by this lane
+    for (int g = lane; g < ng; g += 32) {
+      double J00 = 0, J01 = 0, J02 = 0, J10 = 0, J11 = 0, J12 = 0, J20 = 0, J21 = 0, J22 = 0;
+      const double* dx = s_dx + g * nve;
+      const double* dy = s_dy + g * nve;
+      const double* dz = s_dz + g * nve;
+      for (int n = 0; n < nve; n++) {
+        const double x0 = sX[n], x1 = sX[32 + n], x2 = sX[64 + n];
+        const double a = dx[n], b = dy[n], c = dz[n];
+        J00 = fma(a, x0, J00); J01 = fma(a, x1, J01); J02 = fma(a, x2, J02);
+        J10 = fma(b, x0, J10); J11 = fma(b, x1, J11); J12 = fma(b, x2, J12);
+        J20 = fma(c, x0, J20); J21 = fma(c, x1, J21); J22 = fma(c, x2, J22);
+      }
+      const double det = J00 * (J11 * J22 - J12 * J21) + J01 * (J12 * J20 - J10 * J22) + J02 * (J10 * J21 - J11 * J20);
+      const double id = 1.0 / det;
+      sGeo[0 * ng + g] = (-J12 * J21 + J11 * J22) * id;
+      sGeo[1 * ng + g] = (J02 * J21 - J01 * J22) * id;
+      sGeo[2 * ng + g] = (-J02 * J11 + J01 * J12) * id;
+      sGeo[3 * ng + g] = (J12 * J20 - J10 * J22) * id;
+      sGeo[4 * ng + g] = (-J02 * J20 + J00 * J22) * id;
+      sGeo[5 * ng + g] = (J02 * J10 - J00 * J12) * id;
+      sGeo[6 * ng + g] = (-J11 * J20 + J10 * J21) * id;
+      sGeo[7 * ng + g] = (J01 * J20 - J00 * J21) * id;
+      sGeo[8 * ng + g] = (-J01 * J10 + J00 * J11) * id;
+      sGeo[9 * ng + g] = det * s_w[g];
+    }
+    __syncwarp();
+
+    // ---- B. element matrix, entries lane + 32 k in registers
+    double acc[kGenAcc];
+#pragma unroll
+    for (int k = 0; k < kGenAcc; k++) acc[k] = 0.0;
+    for (int g = 0; g < ng; g++) {
+      double* G = sG + (g & 1) * 96;
+      if (lane < nve) {
+        const double a = s_dx[g * nve + lane], b = s_dy[g * nve + lane], c = s_dz[g * nve + lane];
+        G[lane] = fma(c, sGeo[2 * ng + g], fma(b, sGeo[1 * ng + g], a * sGeo[0 * ng + g]));
+        G[32 + lane] = fma(c, sGeo[5 * ng + g], fma(b, sGeo[4 * ng + g], a * sGeo[3 * ng + g]));
+        G[64 + lane] = fma(c, sGeo[8 * ng + g], fma(b, sGeo[7 * ng + g], a * sGeo[6 * ng + g]));
+      }
+      __syncwarp();
+      const double wg = sGeo[9 * ng + g];
+#pragma unroll
+      for (int k = 0; k < kGenAcc; k++) {
+        if (32 * k < nn) {      // warp-uniform: skips the unused register rows of small elements
+          const int i = ij[k] >> 5, j = ij[k] & 31;
+          const double d = fma(G[64 + i], G[64 + j], fma(G[32 + i], G[32 + j], G[i] * G[j]));
+          acc[k] = fma(d, wg, acc[k]);
+        }
+      }
+    }
+
+    // ---- C. element matrix to shared memory, residual, scatter
+#pragma unroll
+    for (int k = 0; k < kGenAcc; k++) {
+      const int e = lane + 32 * k;
+      if (e < nn) sB[e] = acc[k];
+    }
+    __syncwarp();
+    if (rhs && lane < nve) {
+      double src = 0.0, bu = 0.0;
+      for (int g = 0; g < ng; g++) src = fma(s_phi[g * nve + lane], sGeo[9 * ng + g], src);
+      for (int j = 0; j < nve; j++) bu = fma(sB[lane * nve + j], sU[j], bu);
+      atomicAdd(&rhs[sDof[lane]], fsrc * src - nu * bu);
+    }
+    const SlotT* sl = slot + (size_t)el * nn;
+#pragma unroll
+    for (int k = 0; k < kGenAcc; k++) {
+      const int e = lane + 32 * k;
+      if (e < nn) atomicAdd(&Aval[rowptr[sDof[ij[k] >> 5]] + (int64_t)sl[e]], nu * acc[k]);
+    }
+    __syncwarp();      // the next element overwrites X, U, dofs, Geo, B
+  }
+}
+
+template <typename SlotT>
+int launch_assemble_general(b2_asm* p, const b2_vec* u, b2_vec* rhs, double nu, double fsrc) {
+  b2_ctx* c = p->mesh->ctx;
+  b2_prof_scope prof(c, p);
+  auto kern = assemble_general_kernel<SlotT>;
+  const size_t smem = GenSmem::bytes(p->nve, p->ngauss);
+  B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = (int)((size_t)220 * 1024 / (smem + 1024));      // CTAs one SM's shared memory holds
+  per_sm = per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm);
+  const int grid = b2_grid_for(c, p->mesh->nel, kGenWarps, per_sm);
+  B2_LAUNCH(c, kern, grid, kGenWarps * 32, smem, p->mesh->nel, p->mesh->nnode, p->nve, p->ngauss, p->mesh->xyz, p->mesh->conn,
+            p->dof, p->tab, (const SlotT*)p->nslot, p->A->rowptr, p->A->val, u ? u->d : nullptr, rhs ? rhs->d : nullptr, nu,
+            fsrc);
+  return 0;
+}
 }  // namespace
 
 // Neumann boundary integrals (applications/001_Poisson/main.cpp:495-548 with elem_type_2D::JacobianSur,
@@ -1164,8 +1326,12 @@ int b2_asm_create(b2_mesh* m, b2_csr* A, int nve, const int32_t* dof, int ngauss
                   const double* dxi, const double* deta, const double* dzeta, const double* weights, b2_asm** out) {
   *out = nullptr;
   B2_CHECK(m && A && dof && phi && dxi && deta && dzeta && weights, "b2_asm_create: null argument");
-  B2_CHECK(nve == 8 || nve == 27, "b2_asm_create: nve=%d (supported: 8 trilinear, 27 triquadratic)", nve);
-  B2_CHECK(ngauss == NG, "b2_asm_create: ngauss=%d (supported: 64, the 'seventh' hex rule)", ngauss);
+  // hexahedra with the 64-point rule run the specialised kernels; every other family / rule of
+  // elem_type_3D (tetrahedra, wedges, other quadrature orders) runs the table-driven kernel
+  const bool general = !((nve == 8 || nve == 27) && ngauss == NG);
+  B2_CHECK(nve >= 1 && nve <= 27, "b2_asm_create: nve=%d (1..27 dofs per element)", nve);
+  B2_CHECK(ngauss >= 1 && ngauss <= kGenMaxNg, "b2_asm_create: ngauss=%d (1..%d Gauss points)", ngauss, kGenMaxNg);
+  B2_CHECK(GenSmem::bytes(nve, ngauss) <= (size_t)227 * 1024, "b2_asm_create: tables of %d x %d do not fit shared memory", ngauss, nve);
   B2_CHECK(A->max_row <= 65536, "b2_asm_create: rows longer than 65536 entries");
   b2_ctx* c = m->ctx;
   b2_asm* p = new b2_asm();
@@ -1176,6 +1342,7 @@ int b2_asm_create(b2_mesh* m, b2_csr* A, int nve, const int32_t* dof, int ngauss
   p->last_ms = 0.;
   p->gal = nullptr;
   p->gal_tab = nullptr;
+  p->general = general;
   B2_TRY(b2_malloc(c, &p->dof, (size_t)m->nel * nve));
   B2_TRY(b2_upload(c, p->dof, dof, (size_t)m->nel * nve));
   const size_t tn = (size_t)ngauss * nve;
@@ -1190,7 +1357,7 @@ int b2_asm_create(b2_mesh* m, b2_csr* A, int nve, const int32_t* dof, int ngauss
   p->nslot_count = 0;
   p->slot = nullptr;
   p->slot_count = 0;
-  if (nve == 27) {     // tensor-core kernel: natural-order map; the tile-order map of the CUDA-core kernel is built on demand
+  if (nve == 27 || general) {     // natural-order map (tensor-core and table-driven kernels); the tile-order map of the CUDA-core kernel is built on demand
     if (p->slot_bytes == 1) B2_TRY(build_natural_slots<uint8_t>(p));
     else B2_TRY(build_natural_slots<uint16_t>(p));
   } else {
@@ -1226,6 +1393,14 @@ int b2_asm_destroy(b2_asm* p) {
 int b2_asm_poisson(b2_asm* p, const b2_vec* u, b2_vec* rhs, double nu, double fsrc) {
   B2_CHECK(!u || u->n >= p->A->nrows, "b2_asm_poisson: solution vector too short");
   B2_CHECK(!rhs || rhs->n >= p->A->nrows, "b2_asm_poisson: rhs vector too short");
+  if (p->general || p->mesh->ctx->asm_variant == 2) {       // table-driven kernel (any family)
+    if (!p->nslot) {
+      if (p->slot_bytes == 1) B2_TRY(build_natural_slots<uint8_t>(p));
+      else B2_TRY(build_natural_slots<uint16_t>(p));
+    }
+    if (p->slot_bytes == 1) return launch_assemble_general<uint8_t>(p, u, rhs, nu, fsrc);
+    return launch_assemble_general<uint16_t>(p, u, rhs, nu, fsrc);
+  }
   if (p->nve == 27 && p->mesh->ctx->asm_variant == 1) {      // FP64 tensor-core kernel
     GalArgs ga = {};
     if (p->slot_bytes == 1) return launch_assemble_mma<uint8_t, false, uint8_t>(p, ga, u, rhs, nu, fsrc);
@@ -1246,6 +1421,7 @@ int b2_asm_poisson_galerkin(b2_asm* p, b2_galerkin* gal, const b2_vec* u, b2_vec
   B2_CHECK(p && gal, "b2_asm_poisson_galerkin: null argument");
   B2_CHECK(!u || u->n >= p->A->nrows, "b2_asm_poisson_galerkin: solution vector too short");
   B2_CHECK(!rhs || rhs->n >= p->A->nrows, "b2_asm_poisson_galerkin: rhs vector too short");
+  B2_CHECK(!p->general, "b2_asm_poisson_galerkin: the fused Galerkin product is for refined hexahedra (8 or 27 dofs, 64 Gauss points)");
   b2_ctx* c = p->mesh->ctx;
   b2_galerkin_view g;
   B2_TRY(b2_galerkin_get_view(gal, &g));

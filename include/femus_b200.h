@@ -64,7 +64,8 @@ int b2_ctx_profile_read(b2_ctx* c, const void* handle, int* count, double* total
 int b2_ctx_profile_clear(b2_ctx* c);
 /* tuning knobs: "spmv_variant" = 0 (register-streaming SpMV) | 1 (TMA-staged ring, default) | 2 (staged +
  * software-pipelined gathers); "spmv_timing" = 1 makes y = A x print the consumer phase cycles of CTA 0;
- * "asm_variant" = 1 (triquadratic assembly on the FP64 tensor cores, default) | 0 (CUDA-core register tiles) */
+ * "asm_variant" = 1 (triquadratic assembly on the FP64 tensor cores, default) | 0 (CUDA-core register tiles) |
+ * 2 (the table-driven kernel of the non-hexahedral families, also for hexahedra) */
 int b2_ctx_set_option(b2_ctx* c, const char* name, int value);
 /* measured issue-rate peak of mma.sync.m8n8k4.f64 on this device, TFLOP/s (a few ms of DMMA chains) */
 int b2_ctx_measure_fp64_tensor(b2_ctx* c, double* tflops);
@@ -207,10 +208,13 @@ int b2_mesh_update(b2_mesh* m, const double* xyz, const int32_t* conn);
 int b2_mesh_prefetch(b2_mesh* m, const double* xyz, const int32_t* conn);
 int b2_mesh_swap(b2_mesh* m);
 int b2_mesh_destroy(b2_mesh* m);
-/* Assembly plan for one unknown on one mesh: nve = 8 (trilinear) or 27 (triquadratic);
- * dof[nel][nve] = matrix row of each local node (GetSystemDof, LinearEquation.cpp:76-85);
+/* Assembly plan for one unknown on one mesh: nve dofs per element (<= 27), local nodes 0..nve-1 of every
+ * conn row; dof[nel][nve] = matrix row of each local node (GetSystemDof, LinearEquation.cpp:76-85);
  * tables phi/dxi/deta/dzeta [ngauss][nve] and weights[ngauss] as elem_type_3D holds them
- * (ElemType.cpp:637-740).  Builds the element->CSR slot map for A. */
+ * (ElemType.cpp:637-740), ngauss <= 64.  The tables ARE the element type (the reference dispatches on
+ * _finiteElement[ielGeom][solType], main.cpp:438): hexahedra with 8 or 27 dofs and the 64-point rule run
+ * the specialised kernels, every other family of elem_type_3D (tetrahedra 4/10/15, wedges 6/15/21, other
+ * rules; conn rows padded to 27) the table-driven one.  Builds the element->CSR slot map for A. */
 int b2_asm_create(b2_mesh* m, b2_csr* A, int nve, const int32_t* dof, int ngauss, const double* phi,
                   const double* dxi, const double* deta, const double* dzeta, const double* weights,
                   b2_asm** out);

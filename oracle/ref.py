@@ -58,12 +58,12 @@ def _p(a):
     return a.ctypes.data_as(ctypes.c_void_p)
 
 
-class RefHex:
-    """elem_type_3D("hex", order, gauss) of the reference."""
+class RefElem:
+    """elem_type_3D(geom, order, gauss) of the reference; geom = "hex" | "tet" | "wedge"."""
 
-    def __init__(self, order="biquadratic", gauss="seventh"):
+    def __init__(self, geom="hex", order="biquadratic", gauss="seventh"):
         self.L = lib()
-        self.h = ctypes.c_void_p(self.L.fref_create(b"hex", order.encode(), gauss.encode()))
+        self.h = ctypes.c_void_p(self.L.fref_create(geom.encode(), order.encode(), gauss.encode()))
         self.n = self.L.fref_ndofs(self.h)
         self.ng = self.L.fref_ngauss(self.h)
         self.nf = self.L.fref_ndofs_fine(self.h)
@@ -123,6 +123,20 @@ class RefHex:
         sec = self.L.fref_poisson_assemble_csr(self.h, e0, e1, _p(conn), _p(dof), _p(xyz), xyz.shape[1], _p(sol),
                                                _p(rowptr), _p(col), _p(vals), _p(rhs), float(fsrc), int(nthreads))
         return vals, rhs, sec
+
+
+class RefHex(RefElem):
+    """elem_type_3D("hex", order, gauss) of the reference."""
+
+    def __init__(self, order="biquadratic", gauss="seventh"):
+        super().__init__("hex", order, gauss)
+
+
+class RefTet(RefElem):
+    """elem_type_3D("tet", order, gauss) of the reference (order: linear 4, quadratic 10, biquadratic 15)."""
+
+    def __init__(self, order="quadratic", gauss="seventh"):
+        super().__init__("tet", order, gauss)
 
 
 class RefQuad:

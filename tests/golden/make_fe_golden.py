@@ -80,3 +80,47 @@ for order in ("linear", "biquadratic"):
 np.savez_compressed(os.path.join(ROOT, "tests", "golden", "fe_quad_ref.npz"), **outq)
 print("wrote tests/golden/fe_quad_ref.npz")
 
+
+# ---- tetrahedra (4 / 10 / 15 dofs, 31-point rule): tests/golden/fe_tet_ref.npz
+from oracle import fe_tet  # noqa: E402
+outt = {}
+for order in ("linear", "quadratic", "biquadratic"):
+    R = ref.RefTet(order)
+    w, xi = R.gauss()
+    outt[f"{order}_gauss_w"], outt[f"{order}_gauss_xi"] = w, xi
+    phi, dxi, deta, dzeta = R.tables()
+    outt[f"{order}_phi"], outt[f"{order}_dxi"], outt[f"{order}_deta"], outt[f"{order}_dzeta"] = phi, dxi, deta, dzeta
+    n = R.n
+    # the reference tetrahedron scaled to a 1/64 box cell, and three distorted / rotated ones
+    Xs = [fe_tet.XC[:n].T / 64.0]
+    for _ in range(3):
+        M = np.eye(3) + 0.2 * rng.standard_normal((3, 3))
+        if np.linalg.det(M) < 0:
+            M[:, 0] = -M[:, 0]
+        Xs.append(M @ fe_tet.XC[:n].T * 0.2 + 0.3 + rng.standard_normal((3, n)) * 0.001)
+    Xs = np.array(Xs)
+    Us = rng.standard_normal((Xs.shape[0], n))
+    Fs, Bs, Ws, Gs = [], [], [], []
+    for X, U in zip(Xs, Us):
+        F, B = R.poisson_element(X, U, 1.0)
+        Fs.append(F)
+        Bs.append(B)
+        wj, gj = [], []
+        for ig in range(R.ng):
+            wt, _, g = R.jacobian(X, ig)
+            wj.append(wt)
+            gj.append(g)
+        Ws.append(wj)
+        Gs.append(gj)
+    outt[f"{order}_X"], outt[f"{order}_U"] = Xs, Us
+    outt[f"{order}_F"], outt[f"{order}_B"] = np.array(Fs), np.array(Bs)
+    outt[f"{order}_weight"], outt[f"{order}_gradphi"] = np.array(Ws), np.array(Gs)
+    rows = R.prolongator()                       # fine dof i -> (child, child-local node), coarse columns
+    P = np.zeros((R.nf, n))
+    kv = np.zeros((R.nf, 2), dtype=np.int64)
+    for i, (ch, nd, idx, val) in enumerate(rows):
+        P[i, idx] = val
+        kv[i] = (ch, nd)
+    outt[f"{order}_prol"], outt[f"{order}_prol_kvert"] = P, kv
+np.savez_compressed(os.path.join(ROOT, "tests", "golden", "fe_tet_ref.npz"), **outt)
+print("wrote tests/golden/fe_tet_ref.npz")

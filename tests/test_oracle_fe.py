@@ -126,3 +126,70 @@ def test_neumann_rhs_integrates_the_flux():
     for order in ORDERS:
         r = mb.neumann_rhs(lv[-1], order, {3: 0.2, 6: -1.5})
         assert abs(r.sum() - (0.2 * 1.0 - 1.5 * 1.0)) < 1e-13
+
+
+# ------------------------------------------------------------------------------ tetrahedra
+from oracle import fe_tet  # noqa: E402
+
+GOLD_TET = np.load(os.path.join(os.path.dirname(__file__), "golden", "fe_tet_ref.npz"))
+TET_ORDERS = ("linear", "quadratic", "biquadratic")
+TET_ULP = 2e-15      # fe_tet.py restates the mathematics, not the reference's operation order
+
+
+@pytest.mark.parametrize("order", TET_ORDERS)
+def test_tet_gauss_and_tables(order):
+    """31-point rule bit-exact (data), shape tables to a few ulp; partition of unity; Kronecker property."""
+    w, xi = fe_tet.gauss_tet("seventh")
+    assert np.array_equal(w, GOLD_TET[f"{order}_gauss_w"]) and np.array_equal(xi, GOLD_TET[f"{order}_gauss_xi"])
+    phi, dxi, deta, dzeta, _ = fe_tet.tables(order)
+    for a, k in ((phi, "phi"), (dxi, "dxi"), (deta, "deta"), (dzeta, "dzeta")):
+        assert np.abs(a - GOLD_TET[f"{order}_{k}"]).max() <= TET_ULP, k
+    assert np.abs(phi.sum(axis=1) - 1.0).max() < 1e-14
+    n = fe_tet.NDOFS[order]
+    assert np.abs(fe_tet.shape(order, fe_tet.XC[:n])[0] - np.eye(n)).max() < 1e-14
+
+
+@pytest.mark.parametrize("order", TET_ORDERS)
+def test_tet_jacobian_and_poisson_element(order):
+    X, U = GOLD_TET[f"{order}_X"], GOLD_TET[f"{order}_U"]
+    tabs = fe_tet.tables(order)
+    for ig in range(31):
+        w, _, g = fe_hex.jacobian(order, X, ig, tabs)
+        assert np.abs(w - GOLD_TET[f"{order}_weight"][:, ig]).max() <= 1e-14 * np.abs(GOLD_TET[f"{order}_weight"]).max()
+        gr = GOLD_TET[f"{order}_gradphi"][:, ig]
+        assert np.abs(g - gr).max() <= 1e-13 * np.abs(gr).max()
+    F, B = fe_hex.poisson_elements(order, X, U, 1.0, tabs)
+    Br, Fr = GOLD_TET[f"{order}_B"], GOLD_TET[f"{order}_F"]
+    for k in range(X.shape[0]):
+        assert np.abs(B[k] - Br[k]).max() <= 1e-13 * np.abs(Br[k]).max()
+        assert np.abs(F[k] - Fr[k]).max() <= 1e-13 * (np.abs(Br[k]) @ np.abs(U[k])).max()
+
+
+@pytest.mark.parametrize("order", TET_ORDERS)
+def test_tet_local_prolongator(order):
+    """Element prolongator of the 8 children: same non-zero structure as the reference's, values to an ulp;
+    fine-dof counts 10 / 35 / 67 and nnz 16 / 116 / 447 as measured from the compiled reference."""
+    P = fe_tet.local_prolongator(order)
+    Pg, kv = GOLD_TET[f"{order}_prol"], GOLD_TET[f"{order}_prol_kvert"]
+    for i in range(Pg.shape[0]):
+        mine = P[kv[i, 0], kv[i, 1]]
+        assert np.array_equal(mine != 0, Pg[i] != 0)
+        assert np.abs(mine - Pg[i]).max() <= 4e-16
+    assert (Pg.shape[0], int((Pg != 0).sum())) == {"linear": (10, 16), "quadratic": (35, 116), "biquadratic": (67, 447)}[order]
+    # every (child, node) pair maps to one of the nf distinct fine points
+    pts = fe_tet.child_points(order).reshape(-1, 3)
+    assert len({tuple(np.round(p * 24).astype(int)) for p in pts}) == Pg.shape[0]
+
+
+@pytest.mark.skipif(not ref.available(), reason="compiled reference (oracle/_ref) not present")
+@pytest.mark.parametrize("order", TET_ORDERS)
+def test_tet_against_compiled_reference(order):
+    R = ref.RefTet(order)
+    rng = np.random.default_rng(5)
+    n = R.n
+    X = (np.eye(3) + 0.2 * rng.standard_normal((3, 3))) @ fe_tet.XC[:n].T + 0.01 * rng.standard_normal((3, n))
+    U = rng.standard_normal(n)
+    Fr, Br = R.poisson_element(X, U, 2.5)
+    F, B = fe_hex.poisson_elements(order, X[None], U[None], 2.5, fe_tet.tables(order))
+    assert np.abs(B[0] - Br).max() <= 1e-13 * np.abs(Br).max()
+    assert np.abs(F[0] - Fr).max() <= 1e-13 * (np.abs(Br) @ np.abs(U) + 2.5).max()

@@ -1,0 +1,130 @@
+"""GPU parity of the table-driven assembly kernel (b2_assemble.cu: assemble_general_kernel) -- the path of
+every element family that is not a hexahedron with the 64-point rule (tetrahedra) --
+against the CPU oracle on the same seeded inputs, through the C ABI.  Bar: CSR structure bit-exact,
+values / residuals to 1e-12 relative."""
+import os
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from femus_b200 import capi
+from oracle import fe_hex, fe_tet, mesh_box as mb
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-12
+GOLD_TET = np.load(os.path.join(os.path.dirname(__file__), "golden", "fe_tet_ref.npz"))
+
+
+def oracle_assemble(xyz, conn, dof, n, U, fsrc, tabs):
+    nve = dof.shape[1]
+    X = xyz[:, conn[:, :nve]].transpose(1, 0, 2)
+    F, B = fe_hex.poisson_elements(None, X, U[dof], fsrc, tabs)
+    rows = np.repeat(dof, nve, axis=1).ravel()
+    cols = np.tile(dof, (1, nve)).ravel()
+    A = sp.csr_matrix((B.ravel(), (rows, cols)), shape=(n, n))
+    A.sum_duplicates()
+    A.sort_indices()
+    rhs = np.zeros(n)
+    np.add.at(rhs, dof.ravel(), F.ravel())
+    return A, rhs
+
+
+def tet_soup(rng, nel, nnode, order):
+    """Random conforming-agnostic 'soup': every element is a distorted copy of the reference tetrahedron,
+    elements share dofs at random (what the kernel sees is only conn / dof / xyz)."""
+    nve = fe_tet.NDOFS[order]
+    conn = np.full((nel, 27), -1, dtype=np.int32)
+    xyz = np.zeros((3, nnode + 15 * nel))
+    dof = np.zeros((nel, nve), dtype=np.int32)
+    ndof = max(nve, nnode)
+    for e in range(nel):
+        M = np.eye(3) + 0.2 * rng.standard_normal((3, 3))
+        if np.linalg.det(M) < 0:
+            M[:, 0] = -M[:, 0]
+        ids = nnode + 15 * e + np.arange(15)
+        xyz[:, ids] = M @ fe_tet.XC.T * 0.1 + rng.uniform(0, 1, (3, 1)) + 0.0005 * rng.standard_normal((3, 15))
+        conn[e, :15] = ids
+        dof[e] = rng.choice(ndof, nve, replace=False)
+    conn[conn < 0] = 0           # padding entries of the 27-wide rows are never read
+    return xyz, conn, dof, ndof
+
+
+@pytest.mark.parametrize("order", ["linear", "quadratic", "biquadratic"])
+@pytest.mark.parametrize("nel", [1, 7, 400])
+def test_tet_assembly_matches_oracle(ctx, order, nel):
+    rng = np.random.default_rng(100 + nel)
+    xyz, conn, dof, n = tet_soup(rng, nel, 60, order)
+    tabs = fe_tet.tables(order)
+    u = rng.standard_normal(n)
+    Aref, rhs_ref = oracle_assemble(xyz, conn, dof, n, u, 1.5, tabs)
+    A = capi.Csr.from_elements(ctx, n, dof)
+    asm = capi.Assembler(capi.Mesh(ctx, xyz, conn), A, dof, tabs)
+    U, R = ctx.vector(u), ctx.vector(n)
+    asm.poisson(U, R, nu=1.0, fsrc=1.5)
+    got = A.to_scipy()
+    assert np.array_equal(got.indptr, Aref.indptr) and np.array_equal(got.indices, Aref.indices)
+    assert np.abs(got.data - Aref.data).max() <= RTOL * np.abs(Aref.data).max()
+    mag = np.abs(Aref) @ np.abs(u) + np.abs(rhs_ref)
+    assert np.abs(R.get() - rhs_ref).max() <= RTOL * mag.max()
+    # accumulate semantics and nu scaling: a second pass with nu = 2 adds twice the matrix
+    asm.poisson(U, None, nu=2.0, fsrc=1.5)
+    assert np.abs(A.to_scipy().data - 3 * Aref.data).max() <= 3 * RTOL * np.abs(Aref.data).max()
+
+
+def test_tet_golden_elements(ctx):
+    """Single tetrahedra of the committed fixture: element matrices / residuals of the compiled reference."""
+    for order in ("linear", "quadratic", "biquadratic"):
+        nve = fe_tet.NDOFS[order]
+        tabs = fe_tet.tables(order)
+        for k in range(GOLD_TET[f"{order}_X"].shape[0]):
+            xyz = np.zeros((3, 27))
+            xyz[:, :nve] = GOLD_TET[f"{order}_X"][k]
+            conn = np.arange(27, dtype=np.int32)[None, :]
+            d = np.arange(nve, dtype=np.int32)[None, :]
+            A = capi.Csr.from_elements(ctx, nve, d)
+            asm = capi.Assembler(capi.Mesh(ctx, xyz, conn), A, d, tabs)
+            Uk = GOLD_TET[f"{order}_U"][k]
+            U, R = ctx.vector(Uk), ctx.vector(nve)
+            asm.poisson(U, R, 1.0, 1.0)
+            B = A.to_scipy().toarray()
+            Bref, Fref = GOLD_TET[f"{order}_B"][k], GOLD_TET[f"{order}_F"][k]
+            assert np.abs(B - Bref).max() <= RTOL * np.abs(Bref).max()
+            assert np.abs(R.get() - Fref).max() <= RTOL * (np.abs(Bref) @ np.abs(Uk)).max()
+
+
+@pytest.mark.parametrize("order", ["linear", "biquadratic"])
+def test_general_kernel_on_hexahedra(ctx, order):
+    """asm_variant 2 sends hexahedra through the table-driven kernel too: same oracle, same bar as the
+    specialised kernels (tests/test_gpu_parity.py::test_assembly_matches_oracle)."""
+    lv = mb.build_hierarchy(2, 3, 2, 2)
+    L = lv[-1]
+    x, y, z = L.xyz
+    L.xyz = L.xyz + 0.05 * np.stack([np.sin(np.pi * y) * x * (1 - x), np.sin(np.pi * z) * y * (1 - y), np.sin(np.pi * x) * z * (1 - z)])
+    n = mb.ndofs(L, order)
+    d = mb.system_dof(L, order)
+    u = np.random.default_rng(3).standard_normal(n)
+    Aref, rhs_ref = mb.assemble(L, order, u, fsrc=0.7)
+    ctx.set_option("asm_variant", 2)
+    try:
+        A = capi.Csr.from_elements(ctx, n, d)
+        asm = capi.Assembler(capi.Mesh(ctx, L.xyz, L.conn), A, d, fe_hex.tables(order))
+        U, R = ctx.vector(u), ctx.vector(n)
+        asm.poisson(U, R, nu=1.0, fsrc=0.7)
+    finally:
+        ctx.set_option("asm_variant", 1)
+    got = A.to_scipy()
+    assert np.array_equal(got.indices, Aref.indices)
+    assert np.abs(got.data - Aref.data).max() <= RTOL * np.abs(Aref.data).max()
+    assert np.abs(R.get() - rhs_ref).max() <= RTOL * (np.abs(Aref) @ np.abs(u) + np.abs(rhs_ref)).max()
+
+
+def test_general_plan_rejects_bad_sizes(ctx):
+    """Error behaviour: tables beyond 64 Gauss points are refused with a status (no silent fallback)."""
+    rng = np.random.default_rng(0)
+    xyz, conn, dof, n = tet_soup(rng, 4, 30, "quadratic")
+    A = capi.Csr.from_elements(ctx, n, dof)
+    mesh = capi.Mesh(ctx, xyz, conn)
+    phi, dxi, deta, dzeta, w = fe_tet.tables("quadratic")
+    big = np.zeros((65, 10))
+    with pytest.raises(capi.B2Error):
+        capi.Assembler(mesh, A, dof, (big, big, big, big, np.zeros(65)))
