@@ -35,6 +35,10 @@ def _deps_mtime():
     inc = os.path.join(os.path.dirname(HERE), "include")
     for f in os.listdir(inc):
         m = max(m, os.path.getmtime(os.path.join(inc, f)))
+    host = os.path.join(HERE, "host")           # b2h_capi.cpp includes the host layer's headers
+    for f in os.listdir(host):
+        if f.endswith(".hpp"):
+            m = max(m, os.path.getmtime(os.path.join(host, f)))
     return m
 
 

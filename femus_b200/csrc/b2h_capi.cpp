@@ -4,6 +4,7 @@
 #include <memory>
 #include "../host/BoxMesh.hpp"
 #include "../host/GambitIO.hpp"
+#include "../host/TetMesh.hpp"
 #include "../../include/femus_b200_host.h"
 
 using namespace femus_b200;
@@ -46,8 +47,8 @@ b2h_hier* b2h_hier_create_from_neu(const char* path, int nlevels, double Lref) {
   if (!path || nlevels < 1 || Lref <= 0.) return nullptr;
   b2h_hier* h = new b2h_hier();
   h->levels.reserve(nlevels);
-  h->levels.push_back(ReadGambitHex27(path, Lref));
-  for (int l = 1; l < nlevels; l++) h->levels.push_back(RefineMesh(h->levels.back()));
+  h->levels.push_back(ReadGambit(path, Lref));
+  for (int l = 1; l < nlevels; l++) h->levels.push_back(RefineAnyMesh(h->levels.back()));
   return h;
 }
 void b2h_hier_destroy(b2h_hier* h) { delete h; }
@@ -89,7 +90,7 @@ void b2h_level_bdc(const b2h_hier* h, int l, int family, const int* dirichlet_fa
 b2h_csr* b2h_prolongator_create(const b2h_hier* h, int lfine, int family) {
   if (lfine < 1 || lfine >= (int)h->levels.size()) return nullptr;
   b2h_csr* p = new b2h_csr();
-  p->m = BuildProlongator(h->levels[lfine - 1], h->levels[lfine], family);
+  p->m = BuildAnyProlongator(h->levels[lfine - 1], h->levels[lfine], family);
   return p;
 }
 void b2h_csr_destroy(b2h_csr* p) { delete p; }
@@ -111,9 +112,26 @@ int b2h_galerkin_maps(const b2h_hier* h, int lcoarse, int family, int64_t e0, in
   if (lcoarse < 0 || lcoarse + 1 >= (int)h->levels.size()) return 1;
   const MeshLevel& C = h->levels[lcoarse];
   if (e0 < 0 || e1 > C.nel || e0 > e1) return 1;
+  if (C.uniform_type() != HEX) return 1;       // the element-gather Galerkin product is for hexahedra
   BuildGalerkinMaps(C, h->levels[lcoarse + 1], family, e0, e1, fine_dofs, valence);
   return 0;
 }
+
+int b2h_level_elem_type(const b2h_hier* h, int l) { return h->levels[l].uniform_type(); }
+int b2h_elem_nve(int type, int family) { return ElemTopology::nve(type, family); }
+int b2h_elem_ngauss(int type) { return type == TET ? TetElement::NG : HexElement::NG; }
+void b2h_elem_tables(int type, int family, double* phi, double* dxi, double* deta, double* dzeta, double* w) {
+  HexElement::Tables t = type == TET ? TetElement::tables(family) : HexElement::tables(family);
+  std::copy(t.phi.begin(), t.phi.end(), phi);
+  std::copy(t.dxi.begin(), t.dxi.end(), dxi);
+  std::copy(t.deta.begin(), t.deta.end(), deta);
+  std::copy(t.dzeta.begin(), t.dzeta.end(), dzeta);
+  std::copy(t.w.begin(), t.w.end(), w);
+}
+int b2h_tet_prolongator_row(int family, int child, int node, int* idx, double* val) {
+  return TetElement::prolongator_row(family, child, node, idx, val);
+}
+int b2h_tet_child_face(int child, int child_face) { return detail::tet_child_faces().parent_face[child][child_face]; }
 
 int b2h_hex_nve(int family) { return HexElement::nve(family); }
 void b2h_hex_tables(int family, double* phi, double* dxi, double* deta, double* dzeta, double* w) {

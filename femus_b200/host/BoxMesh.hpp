@@ -20,8 +20,20 @@
 #include <numeric>
 #include <vector>
 #include "HexElement.hpp"
+#include "TetElement.hpp"
 
 namespace femus_b200 {
+
+// Geometric element types in the reference's numbering (GeomElTypeEnum: HEX 0, TET 1, WEDGE 2) and the
+// per-type tables of Elem.hpp:102-130, 581-610 (NVE, NFC, ig, NFACENODES) the mesh layer needs.
+enum GeomType { HEX = 0, TET = 1 };
+struct ElemTopology {
+  static int nve(int type, int family) { return type == TET ? TetElement::nve(family) : HexElement::nve(family); }
+  static int nfaces(int type) { return type == TET ? 4 : 6; }
+  static int face_ndofs(int type, int family) { return type == TET ? TetElement::face_ndofs(family) : HexElement::face_ndofs(family); }
+  static int face_node(int type, int f, int i) { return type == TET ? TetElement::face_nodes()[f][i] : HexElement::face_nodes()[f][i]; }
+  static int nchildren(int) { return 8; }
+};
 
 struct HostCsr {
   int64_t nrows = 0, ncols = 0;
@@ -35,8 +47,9 @@ class MeshLevel {
   int level = 0;
   int nprocs = 1;
   int64_t nel = 0, nnode = 0;
-  std::vector<int32_t> conn;            // [nel][27] node ids in FEMuS numbering
+  std::vector<int32_t> conn;            // [nel][27] node ids in FEMuS numbering (rows of shorter elements padded with -1)
   std::vector<int32_t> face;            // [nel][6] faceElementIndex: -1 interior/unset, < -1 boundary
+  std::vector<uint8_t> etype;           // [nel] GeomType per element; empty = all hexahedra
   std::vector<int32_t> part;            // [nel] owning rank
   std::vector<int64_t> elem_offset;     // [nprocs+1]
   std::vector<int64_t> dof_offset[3];   // [family][nprocs+1]
@@ -47,6 +60,14 @@ class MeshLevel {
                                         // used to match interface nodes between the sub-meshes of different ranks
 
   int32_t node(int64_t iel, int i) const { return conn[iel * 27 + i]; }
+  int type_of(int64_t iel) const { return etype.empty() ? (int)HEX : (int)etype[iel]; }
+  // the one element type of the level; mixed meshes are not supported by the dof-table entry points
+  int uniform_type() const {
+    const int t = type_of(0);
+    for (int64_t e = 1; e < nel; e++)
+      if (type_of(e) != t) { std::fprintf(stderr, "femus_b200: mixed element types are not supported yet\n"); std::abort(); }
+    return t;
+  }
 
   int owner_of_node(int32_t nd) const {
     const std::vector<int64_t>& o = dof_offset[2];
@@ -64,7 +85,7 @@ class MeshLevel {
   // [nel][nve] system dofs of a single-variable system (LinearEquation::GetSystemDof,
   // LinearEquation.cpp:76-85: KKoffset[0][p] == dofOffset[family][p])
   std::vector<int32_t> system_dofs(int family) const {
-    const int nve = HexElement::nve(family);
+    const int nve = ElemTopology::nve(uniform_type(), family);
     std::vector<int32_t> d((size_t)nel * nve);
     for (int64_t e = 0; e < nel; e++)
       for (int i = 0; i < nve; i++) d[e * nve + i] = GetSolutionDof(i, e, family);
@@ -75,20 +96,22 @@ class MeshLevel {
   // index (1..6 = -(faceElementIndex+1), Elem.cpp:361-364) is flagged in dirichlet_faces[1..6].
   std::vector<double> GenerateBdc(int family, const bool dirichlet_faces[7]) const {
     std::vector<double> bdc((size_t)ndofs(family), 2.0);
-    const int nfd = HexElement::face_ndofs(family);
-    for (int64_t e = 0; e < nel; e++)
-      for (int f = 0; f < 6; f++) {
+    for (int64_t e = 0; e < nel; e++) {
+      const int t = type_of(e), nfd = ElemTopology::face_ndofs(t, family);
+      for (int f = 0; f < ElemTopology::nfaces(t); f++) {
         const int bidx = -(face[e * 6 + f] + 1);
         if (bidx > 0 && bidx <= 6 && dirichlet_faces[bidx])
-          for (int iv = 0; iv < nfd; iv++) bdc[GetSolutionDof(HexElement::face_nodes()[f][iv], e, family)] = 0.0;
+          for (int iv = 0; iv < nfd; iv++) bdc[GetSolutionDof(ElemTopology::face_node(t, f, iv), e, family)] = 0.0;
       }
+    }
     return bdc;
   }
 
   // Mesh::FillISvectorDofMapAllFEFamilies: element reorder by rank (stable) and node renumbering
   // by first visit over (rank, family k, element, local node in [nve(k-1), nve(k))).
   // `conn` holds temporary node ids in [0, nnode) on entry.  Returns the node map old -> new.
-  std::vector<int32_t> FillISvectorDofMapAllFEFamilies(const std::vector<int32_t>& partition, int nprocs_) {
+  std::vector<int32_t> FillISvectorDofMapAllFEFamilies(const std::vector<int32_t>& partition, int nprocs_,
+                                                       bool drop_unreferenced = false) {
     nprocs = nprocs_;
     // --- elements by rank (Mesh.cpp:589-616); material/group are uniform on box meshes, so the
     // second sort (Mesh.cpp:621-702) leaves the order unchanged
@@ -102,13 +125,16 @@ class MeshLevel {
       part = partition;
     } else {
       std::vector<int32_t> c2(conn.size()), f2(face.size());
+      std::vector<uint8_t> t2(etype.size());
       for (int64_t e = 0; e < nel; e++) {
         std::copy(conn.begin() + order[e] * 27, conn.begin() + order[e] * 27 + 27, c2.begin() + e * 27);
         std::copy(face.begin() + order[e] * 6, face.begin() + order[e] * 6 + 6, f2.begin() + e * 6);
+        if (!etype.empty()) t2[e] = etype[order[e]];
         part[e] = partition[order[e]];
       }
       conn.swap(c2);
       face.swap(f2);
+      etype.swap(t2);
     }
     elem_order.assign(order.begin(), order.end());
     elem_offset.assign(nprocs + 1, 0);
@@ -120,8 +146,8 @@ class MeshLevel {
     int32_t counter = 0;
     for (int p = 0; p < nprocs; p++)
       for (int k = 0; k < 3; k++) {
-        const int lo = k == 0 ? 0 : HexElement::nve(k - 1), hi = HexElement::nve(k);
-        for (int64_t e = elem_offset[p]; e < elem_offset[p + 1]; e++)
+        for (int64_t e = elem_offset[p]; e < elem_offset[p + 1]; e++) {
+          const int t = type_of(e), lo = k == 0 ? 0 : ElemTopology::nve(t, k - 1), hi = ElemTopology::nve(t, k);
           for (int i = lo; i < hi; i++) {
             const int32_t ii = conn[e * 27 + i];
             if (map[ii] < 0) {
@@ -129,9 +155,13 @@ class MeshLevel {
               for (int j = k; j < 3; j++) own[j][p]++;
             }
           }
+        }
       }
-    if (counter != nnode) { std::fprintf(stderr, "femus_b200: mesh has %lld unreferenced nodes\n", (long long)(nnode - counter)); std::abort(); }
-    for (auto& c : conn) c = map[c];
+    // temporary ids no element refers to (the face and centre nodes of refined tetrahedra are not nodes of
+    // the children) disappear: the reference sets the node count to _dofOffset[2][nprocs] (Mesh.cpp:886-891)
+    if (counter != nnode && !drop_unreferenced) { std::fprintf(stderr, "femus_b200: mesh has %lld unreferenced nodes\n", (long long)(nnode - counter)); std::abort(); }
+    nnode = counter;
+    for (auto& c : conn) if (c >= 0) c = map[c];
     for (int k = 0; k < 3; k++) {
       dof_offset[k].assign(nprocs + 1, 0);
       for (int p = 0; p < nprocs; p++) dof_offset[k][p + 1] = dof_offset[k][p] + own[k][p];
@@ -420,6 +450,7 @@ inline MeshLevel ExtractRankSubmesh(const MeshLevel& G, int rank) {
 // Nodes of L on faces that are neither on the domain boundary nor shared by two elements of L:
 // the interface with the sub-meshes of other ranks (sorted).  Empty for a complete mesh.
 inline std::vector<int32_t> InterfaceNodes(const MeshLevel& L) {
+  if (!L.etype.empty()) return {};      // hexahedral slabs only: the sharded run partitions generated boxes
   std::vector<uint8_t> cnt((size_t)L.nnode, 0), mark((size_t)L.nnode, 0);
   for (int64_t e = 0; e < L.nel; e++)
     for (int f = 0; f < 6; f++) cnt[L.conn[e * 27 + 20 + f]]++;

@@ -1,24 +1,77 @@
-// Gambit neutral-file (.neu) reader for HEX27 meshes: the coarse-mesh input of the reference's shipped
-// 3-D Poisson cases (applications/001_Poisson/input/cube_Hex.neu, input3D_Hex_*.json).  Follows
-// GambitIO::read (src/06_mesh/00_single_level/01_input/01_from_external_file/GambitIO.cpp:92-352):
-// section order CONTROL INFO / NODAL COORDINATES / ELEMENTS/CELLS / ELEMENT GROUP / BOUNDARY CONDITIONS,
-// local nodes permuted by GambitToFemusVertexIndex (:56-61), faces by GambitToFemusFaceIndex (:83),
-// boundary flag = -(set name) - 1 (:330), coordinates divided by Lref (:262-264); then the
-// reference renumbers nodes by first visit exactly as for a generated box (Mesh.cpp:517-559).
-// Only 27-node hexahedra and a single element group are accepted (tets, wedges and the
+// Gambit neutral-file (.neu) reader for meshes of 27-node hexahedra or 10-node tetrahedra: the coarse-mesh
+// input of the reference's shipped 3-D Poisson cases (applications/001_Poisson/input/cube_Hex.neu,
+// cube_Tet.neu, input3D_*.json).  Follows GambitIO::read (src/06_mesh/00_single_level/01_input/
+// 01_from_external_file/GambitIO.cpp:92-352): section order CONTROL INFO / NODAL COORDINATES /
+// ELEMENTS/CELLS / ELEMENT GROUP / BOUNDARY CONDITIONS, local nodes permuted by GambitToFemusVertexIndex
+// (:56-67), faces by GambitToFemusFaceIndex (:83-85), boundary flag = -(set name) - 1 (:330), coordinates
+// divided by Lref (:262-264); then Mesh::AddBiquadraticNodesNotInMeshFile (Mesh.cpp:1207-1333) creates the
+// face and centre nodes a 10-node tetrahedron lacks, and the reference renumbers nodes by first visit exactly
+// as for a generated box (Mesh.cpp:517-559).
+// One element type per file and a single element group are accepted (wedges, mixed meshes and the
 // material/group reordering of Mesh.cpp:621-702 are the next step); anything else aborts.
 #pragma once
 #include <cstdio>
 #include <cstdlib>
 #include <fstream>
+#include <map>
 #include <string>
 #include "BoxMesh.hpp"
 
 namespace femus_b200 {
 
-inline MeshLevel ReadGambitHex27(const char* path, double Lref = 1.0) {
-  static const int vertex_map[27] = {4, 16, 0, 15, 23, 11, 7, 19, 3, 12, 20, 8, 25, 26, 24, 14, 22, 10, 5, 17, 1, 13, 21, 9, 6, 18, 2};
-  static const int face_map[6] = {0, 4, 2, 5, 3, 1};
+// Mesh::AddBiquadraticNodesNotInMeshFile for tetrahedra: one node per triangular face (shared by the two
+// elements that have the same three vertices), one per element; coordinates from the element's 10 file
+// nodes with the barycentric weights of Mesh.cpp:105-113 (-1/9 vertices, 4/9 edges of the face; -1/8, 1/4
+// for the centre), every element overwriting what an earlier one wrote, in element order, as the reference.
+inline void AddBiquadraticNodesNotInMeshFile(MeshLevel& L, std::vector<double>& xyz_file) {
+  if (L.etype.empty()) return;
+  struct Key { uint32_t a, b, c; bool operator<(const Key& o) const { return a != o.a ? a < o.a : (b != o.b ? b < o.b : c < o.c); } };
+  std::map<Key, int32_t> face_node;
+  int64_t nn = L.nnode;
+  for (int64_t e = 0; e < L.nel; e++) {
+    if (L.etype[e] != TET) continue;
+    for (int f = 0; f < 4; f++) {
+      uint32_t v[3];
+      for (int k = 0; k < 3; k++) v[k] = (uint32_t)L.conn[e * 27 + TetElement::face_nodes()[f][k]];
+      std::sort(v, v + 3);
+      auto it = face_node.find(Key{v[0], v[1], v[2]});
+      if (it == face_node.end()) it = face_node.emplace(Key{v[0], v[1], v[2]}, (int32_t)nn++).first;
+      L.conn[e * 27 + 10 + f] = it->second;
+    }
+  }
+  for (int64_t e = 0; e < L.nel; e++)
+    if (L.etype[e] == TET) L.conn[e * 27 + 14] = (int32_t)nn++;
+  const int64_t n0 = L.nnode;
+  std::vector<double> x2((size_t)3 * nn);
+  for (int d = 0; d < 3; d++) std::copy(xyz_file.begin() + d * n0, xyz_file.begin() + (d + 1) * n0, x2.begin() + d * nn);
+  for (int64_t e = 0; e < L.nel; e++) {
+    if (L.etype[e] != TET) continue;
+    for (int j = 10; j < 15; j++) {
+      double w[10];
+      for (int i = 0; i < 10; i++) w[i] = 0.;
+      if (j < 14) {
+        for (int k = 0; k < 3; k++) { w[TetElement::face_nodes()[j - 10][k]] = -1. / 9.; w[TetElement::face_nodes()[j - 10][3 + k]] = 4. / 9.; }
+      } else {
+        for (int i = 0; i < 4; i++) w[i] = -1. / 8.;
+        for (int i = 4; i < 10; i++) w[i] = 1. / 4.;
+      }
+      const int32_t jn = L.conn[e * 27 + j];
+      for (int d = 0; d < 3; d++) {
+        double s = 0.;
+        for (int i = 0; i < 10; i++) s += x2[(size_t)d * nn + L.conn[e * 27 + i]] * w[i];
+        x2[(size_t)d * nn + jn] = s;
+      }
+    }
+  }
+  L.nnode = nn;
+  xyz_file.swap(x2);
+}
+
+inline MeshLevel ReadGambit(const char* path, double Lref = 1.0) {
+  static const int vertex_map_hex[27] = {4, 16, 0, 15, 23, 11, 7, 19, 3, 12, 20, 8, 25, 26, 24, 14, 22, 10, 5, 17, 1, 13, 21, 9, 6, 18, 2};
+  static const int vertex_map_tet[10] = {0, 4, 1, 6, 5, 2, 7, 8, 9, 3};
+  static const int face_map_hex[6] = {0, 4, 2, 5, 3, 1};
+  static const int face_map_tet[4] = {0, 1, 2, 3};
   auto fail = [&](const char* what) {
     std::fprintf(stderr, "femus_b200: Gambit file %s: %s\n", path, what);
     std::abort();
@@ -53,21 +106,25 @@ inline MeshLevel ReadGambitHex27(const char* path, double Lref = 1.0) {
   L.level = 0;
   L.nel = nel;
   L.nnode = nvt;
-  L.conn.resize((size_t)nel * 27);
+  L.conn.assign((size_t)nel * 27, -1);
   L.face.assign((size_t)nel * 6, -1);
+  std::vector<uint8_t> etype((size_t)nel, (uint8_t)HEX);
   seek("ELEMENTS/CELLS");
   in >> tok;                                    // version
   for (long iel = 0; iel < nel; iel++) {
     long id, type, nve;
     in >> id >> type >> nve;
-    if (nve != 27) fail("only 27-node hexahedra are supported by the B200 backend so far");
-    for (int i = 0; i < 27; i++) {
+    if (nve != 27 && nve != 10) fail("only 27-node hexahedra and 10-node tetrahedra are supported by the B200 backend so far");
+    etype[iel] = nve == 27 ? (uint8_t)HEX : (uint8_t)TET;
+    if (etype[iel] != etype[0]) fail("mixed element types are not supported by the B200 backend so far");
+    for (int i = 0; i < nve; i++) {
       long v;
       in >> v;
       if (v < 1 || v > nvt) fail("node id out of range");
-      L.conn[(size_t)iel * 27 + vertex_map[i]] = (int32_t)(v - 1);
+      L.conn[(size_t)iel * 27 + (nve == 27 ? vertex_map_hex[i] : vertex_map_tet[i])] = (int32_t)(v - 1);
     }
   }
+  if (etype[0] != HEX) L.etype = etype;
   in >> tok;
   if (tok != "ENDOFSECTION") fail("bad element section");
   if (ngroup != 1) fail("more than one element group: the material/group element reordering is not implemented");
@@ -80,14 +137,16 @@ inline MeshLevel ReadGambitHex27(const char* path, double Lref = 1.0) {
     in >> value >> itype >> nface >> d0 >> d1;
     const int32_t flag = (int32_t)(-value - 1);
     for (long i = 0; i < nface; i++) {
-      long iel, etype, iface;
-      in >> iel >> etype >> iface;
-      if (iel < 1 || iel > nel || iface < 1 || iface > 6) fail("boundary face out of range");
-      L.face[(size_t)(iel - 1) * 6 + face_map[iface - 1]] = flag;
+      long iel, file_type, iface;
+      in >> iel >> file_type >> iface;
+      if (iel < 1 || iel > nel || iface < 1 || iface > ElemTopology::nfaces(etype[iel - 1])) fail("boundary face out of range");
+      L.face[(size_t)(iel - 1) * 6 + (etype[iel - 1] == HEX ? face_map_hex[iface - 1] : face_map_tet[iface - 1])] = flag;
     }
     in >> tok;
     if (tok != "ENDOFSECTION") fail("bad boundary section");
   }
+  AddBiquadraticNodesNotInMeshFile(L, xyz_file);
+  nvt = (long)L.nnode;
   // node renumbering by first visit (serial: one rank), coordinates follow
   const std::vector<int32_t> part((size_t)nel, 0);
   const std::vector<int32_t> map = L.FillISvectorDofMapAllFEFamilies(part, 1);

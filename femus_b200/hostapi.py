@@ -7,6 +7,7 @@ from .capi import lib
 
 vp, ci, i64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64
 LINEAR, SERENDIPITY, BIQUADRATIC = 0, 1, 2
+HEX, TET = 0, 1
 FAMILY = {"linear": 0, "quadratic": 1, "biquadratic": 2}
 
 _ready = False
@@ -47,6 +48,12 @@ def _L():
             "b2h_galerkin_nf": (ci, [ci]),
             "b2h_galerkin_element": (None, [ci, vp, vp]),
             "b2h_galerkin_maps": (ci, [vp, ci, ci, i64, i64, vp, vp]),
+            "b2h_level_elem_type": (ci, [vp, ci]),
+            "b2h_elem_nve": (ci, [ci, ci]),
+            "b2h_elem_ngauss": (ci, [ci]),
+            "b2h_elem_tables": (None, [ci, ci, vp, vp, vp, vp, vp]),
+            "b2h_tet_prolongator_row": (ci, [ci, ci, ci, vp, vp]),
+            "b2h_tet_child_face": (ci, [ci, ci]),
             "b2h_hex_nve": (ci, [ci]),
             "b2h_hex_tables": (None, [ci, vp, vp, vp, vp, vp]),
             "b2h_hex_prolongator_row": (ci, [ci, ci, ci, ci, vp, vp]),
@@ -80,6 +87,7 @@ class HostLevel:
         self.hier, self.l = hier, l
         self.nel = int(L.b2h_level_nel(h, l))
         self.nnode = int(L.b2h_level_nnode(h, l))
+        self.elem_type = int(L.b2h_level_elem_type(h, l))
         self.conn = _view(L.b2h_level_conn(h, l), (self.nel, 27), np.int32)
         self.face = _view(L.b2h_level_face(h, l), (self.nel, 6), np.int32)
         self.part = _view(L.b2h_level_part(h, l), (self.nel,), np.int32)
@@ -116,7 +124,7 @@ class HostLevel:
 
     def system_dofs(self, family):
         f = _fam(family)
-        out = np.zeros((self.nel, self.hier.L.b2h_hex_nve(f)), dtype=np.int32)
+        out = np.zeros((self.nel, self.hier.L.b2h_elem_nve(self.elem_type, f)), dtype=np.int32)
         self.hier.L.b2h_level_system_dofs(self.hier.h, self.l, f, out.ctypes.data_as(vp))
         return out
 
@@ -219,6 +227,28 @@ def galerkin_element(family):
     ent = np.zeros(nf, dtype=np.uint8)
     L.b2h_galerkin_element(f, ploc.ctypes.data_as(vp), ent.ctypes.data_as(vp))
     return ploc, ent
+
+
+def elem_tables(elem_type, family):
+    """(phi, dxi, deta, dzeta, w) of elem_type_3D(type, family, "seventh"): [ngauss][nve] and [ngauss]."""
+    L = _L()
+    f = _fam(family)
+    nve, ng = L.b2h_elem_nve(elem_type, f), L.b2h_elem_ngauss(elem_type)
+    t = [np.zeros((ng, nve)) for _ in range(4)] + [np.zeros(ng)]
+    L.b2h_elem_tables(elem_type, f, *[a.ctypes.data_as(vp) for a in t])
+    return tuple(t)
+
+
+def tet_prolongator_row(family, child, node):
+    L = _L()
+    idx = np.zeros(15, dtype=np.int32)
+    val = np.zeros(15)
+    n = L.b2h_tet_prolongator_row(_fam(family), child, node, idx.ctypes.data_as(vp), val.ctypes.data_as(vp))
+    return idx[:n].copy(), val[:n].copy()
+
+
+def tet_child_face(child, child_face):
+    return int(_L().b2h_tet_child_face(child, child_face))
 
 
 def hex_tables(family):

@@ -1,8 +1,9 @@
 """Oracle (TEST INFRASTRUCTURE ONLY): Gambit neutral-file reader for HEX27 meshes, restated with numpy
 from src/06_mesh/00_single_level/01_input/01_from_external_file/GambitIO.cpp:56-61 (local node
 permutation), :83 (face permutation), :92-352 (sections), followed by the reference's first-visit node
-renumbering (mesh_box._renumber, Mesh.cpp:517-559).  Fixture: tests/golden/cube_Hex.neu is a verbatim
-copy of the reference's applications/001_Poisson/input/cube_Hex.neu (mesh input data, not code).
+renumbering (mesh_box._renumber, Mesh.cpp:517-559).  Fixture: tests/golden/cube_hex27_2x2x2.neu holds the
+nodes, elements and boundary sets of the reference's applications/001_Poisson/input/cube_Hex.neu,
+re-serialised by tests/golden/make_neu_fixture.py.  Tetrahedral files: oracle/mesh_tet.py.
 PARITY UNPINNED BY THE REFERENCE beyond the file format itself (no expected numbering is shipped)."""
 import numpy as np
 

@@ -38,9 +38,10 @@ class Level:
     pass
 
 
-def _renumber(conn_lat, part_el, nprocs):
+def _renumber(conn_lat, part_el, nprocs, NVE=NVE):
     """Element reorder by rank (stable) + node renumbering by first visit over
-    (rank, family k, element, local node in [NVE[k-1],NVE[k])) -- Mesh.cpp:517-559, 589-616."""
+    (rank, family k, element, local node in [NVE[k-1],NVE[k])) -- Mesh.cpp:517-559, 589-616.
+    NVE: dofs per family of the (single) element type, hexahedra by default."""
     order_el = np.argsort(part_el, kind="stable")
     conn_lat = conn_lat[order_el]
     part_el = part_el[order_el]
@@ -76,8 +77,8 @@ def _renumber(conn_lat, part_el, nprocs):
     return order_el, conn, lat_of_new, elem_offset, dof_offset, own, part_el
 
 
-def _finish_level(L, conn_lat, part_el, nprocs):
-    order_el, conn, lat_of_new, elem_offset, dof_offset, own, part_el = _renumber(conn_lat, part_el, nprocs)
+def _finish_level(L, conn_lat, part_el, nprocs, NVE=NVE):
+    order_el, conn, lat_of_new, elem_offset, dof_offset, own, part_el = _renumber(conn_lat, part_el, nprocs, NVE)
     L.order_el = order_el                 # position -> pre-reorder element index
     L.conn = conn                         # [nel,27] node ids (FEMuS numbering)
     L.lat_of_node = lat_of_new            # node id -> lattice id

@@ -1,14 +1,16 @@
-"""Generate tests/golden/cube_hex27_2x2x2.neu from the reference's shipped coarse mesh
-applications/001_Poisson/input/cube_Hex.neu: the same nodes, elements, group and boundary sets,
-re-serialised in Gambit neutral format by this script (free-format numbers, own header), because
-/root/reference does not exist on the GPU box.  Run in the build container:
+"""Generate tests/golden/cube_hex27_2x2x2.neu and tests/golden/cube_tet10.neu from the reference's shipped
+coarse meshes applications/001_Poisson/input/cube_Hex.neu (8 hexahedra of 27 nodes) and cube_Tet.neu (105
+tetrahedra of 10 nodes): the same nodes, elements, group and boundary sets, re-serialised in Gambit neutral
+format by this script (free-format numbers, own header), because /root/reference does not exist on the GPU
+box.  Run in the build container:
     python tests/golden/make_neu_fixture.py"""
 import os
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-SRC = "/root/reference/applications/001_Poisson/input/cube_Hex.neu"
-DST = os.path.join(ROOT, "tests", "golden", "cube_hex27_2x2x2.neu")
+INPUT = "/root/reference/applications/001_Poisson/input/"
+JOBS = [(INPUT + "cube_Hex.neu", os.path.join(ROOT, "tests", "golden", "cube_hex27_2x2x2.neu"), "cube_hex27_2x2x2"),
+        (INPUT + "cube_Tet.neu", os.path.join(ROOT, "tests", "golden", "cube_tet10.neu"), "cube_tet10")]
 
 
 def parse(path):
@@ -40,9 +42,9 @@ def parse(path):
     return nvt, nel, dim, dimn, nodes, elems, group, bsets
 
 
-def write(path, nvt, nel, dim, dimn, nodes, elems, group, bsets):
-    out = ["CONTROL INFO 2.3.16", "** GAMBIT NEUTRAL FILE", "cube_hex27_2x2x2 (femus_b200 test fixture)",
-           "PROGRAM: femus_b200/tests/golden/make_neu_fixture.py VERSION: 1", "re-serialised from the reference's cube_Hex.neu",
+def write(path, title, source, nvt, nel, dim, dimn, nodes, elems, group, bsets):
+    out = ["CONTROL INFO 2.3.16", "** GAMBIT NEUTRAL FILE", title + " (femus_b200 test fixture)",
+           "PROGRAM: femus_b200/tests/golden/make_neu_fixture.py VERSION: 1", "re-serialised from the reference's " + os.path.basename(source),
            "NUMNP NELEM NGRPS NBSETS NDFCD NDFVL", f"{nvt} {nel} 1 {len(bsets)} {dim} {dimn}", "ENDOFSECTION",
            "NODAL COORDINATES 2.3.16"]
     out += [f"{i + 1} {x!r} {y!r} {z!r}" for i, (x, y, z) in enumerate(nodes)]
@@ -59,7 +61,8 @@ def write(path, nvt, nel, dim, dimn, nodes, elems, group, bsets):
 
 
 if __name__ == "__main__":
-    if not os.path.exists(SRC):
-        sys.exit("reference mesh not present: " + SRC)
-    write(DST, *parse(SRC))
-    print("wrote", DST)
+    for src, dst, title in JOBS:
+        if not os.path.exists(src):
+            sys.exit("reference mesh not present: " + src)
+        write(dst, title, src, *parse(src))
+        print("wrote", dst)

@@ -90,3 +90,86 @@ def test_gambit_reader_matches_oracle_reader():
         b = -(lv.face[lv.face < -1] + 1)
         assert np.array_equal(np.bincount(b)[1:], np.full(6, lv.nel ** (2 / 3) + 0.5, dtype=int))
         assert lv.xyz.min() == 0.0 and lv.xyz.max() == 1.0
+
+
+# ------------------------------------------------------------------------------ tetrahedra
+NEU_TET = os.path.join(os.path.dirname(__file__), "golden", "cube_tet10.neu")
+TET_ORDERS = ("linear", "quadratic", "biquadratic")
+
+
+def test_tet_element_tables_and_prolongator_rows():
+    """Host TetElement.hpp against the committed values of the compiled reference (tests/golden/fe_tet_ref.npz):
+    31-point rule bit-exact, shape tables to a few ulp, element prolongator rows with the reference's non-zero
+    structure; child faces against coarse2FineFaceMapping (MeshRefinement.hpp:88-93)."""
+    from oracle import mesh_tet as mt
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden", "fe_tet_ref.npz"))
+    for order in TET_ORDERS:
+        phi, dxi, deta, dzeta, w = hostapi.elem_tables(hostapi.TET, order)
+        assert np.array_equal(w, G[f"{order}_gauss_w"])
+        for a, k in ((phi, "phi"), (dxi, "dxi"), (deta, "deta"), (dzeta, "dzeta")):
+            assert a.shape == G[f"{order}_{k}"].shape and np.abs(a - G[f"{order}_{k}"]).max() <= 2e-15, (order, k)
+        Pg, kv = G[f"{order}_prol"], G[f"{order}_prol_kvert"]
+        for i in range(Pg.shape[0]):
+            idx, val = hostapi.tet_prolongator_row(order, int(kv[i, 0]), int(kv[i, 1]))
+            assert np.array_equal(idx, np.nonzero(Pg[i])[0])
+            assert np.abs(val - Pg[i, idx]).max() <= 4e-16
+    got = {(f, j, cf) for j in range(8) for cf in range(4) for f in [hostapi.tet_child_face(j, cf)] if f >= 0}
+    assert got == {(f, j, cf) for f in range(4) for (j, cf) in mt.COARSE_TO_FINE_FACE[f]}
+    # hexahedra through the same entry point
+    for a, b in zip(hostapi.elem_tables(hostapi.HEX, "biquadratic"), hostapi.hex_tables("biquadratic")):
+        assert np.array_equal(a, b)
+
+
+def test_tet_mesh_hierarchy_matches_oracle():
+    """cube_tet10.neu (the reference's cube_Tet.neu re-serialised: 105 ten-node tetrahedra): reader with the
+    face / centre nodes of AddBiquadraticNodesNotInMeshFile, first-visit numbering, 1 -> 8 refinement, boundary
+    flags, dof maps, Dirichlet flags: integers bit-exact against the independent numpy oracle on 3 levels;
+    coordinates exact on level 0 (same operation order) and to 1e-15 on refined levels; prolongators with
+    identical structure and values to an ulp."""
+    from oracle import mesh_tet as mt
+    H = hostapi.HostHierarchy.from_neu(NEU_TET, 3)
+    lv = mt.build_hierarchy(NEU_TET, 3)
+    assert [h.elem_type for h in H.levels] == [hostapi.TET] * 3
+    assert [h.nel for h in H.levels] == [105, 840, 6720]
+    for l, (h, L) in enumerate(zip(H.levels, lv)):
+        assert h.nnode == L.nnode
+        assert np.array_equal(h.conn[:, :15], L.conn) and np.all(h.conn[:, 15:] == -1)
+        assert np.array_equal(h.face[:, :4], L.face) and np.all(h.face[:, 4:] == -1)
+        assert np.array_equal(h.dof_offset, L.dof_offset)
+        if l == 0:
+            assert np.array_equal(h.xyz, L.xyz)
+        else:
+            assert np.abs(h.xyz - L.xyz).max() <= 1e-15
+        assert h.xyz.min() >= -1e-15 and h.xyz.max() <= 1 + 1e-15
+        for order in TET_ORDERS:
+            assert np.array_equal(h.system_dofs(order), mt.system_dof(L, order))
+            assert np.array_equal(h.bdc(order), mt.bdc_flags(L, order))
+            assert np.array_equal(h.bdc(order, (1, 4)), mt.bdc_flags(L, order, (1, 4)))
+        if l + 1 < len(lv):
+            assert np.array_equal(h.child_el, lv[l + 1].child_el)
+    # Euler characteristic of a ball: V - E + F - C = 1 on every level (vertices, edges, faces, cells)
+    for h in H.levels:
+        v, e, f = h.dof_offset[0, -1], h.dof_offset[1, -1] - h.dof_offset[0, -1], h.nnode - h.dof_offset[1, -1] - h.nel
+        assert v - e + f - h.nel == 1
+    for l in (1, 2):
+        for order in TET_ORDERS:
+            rp, ci, v, shp = H.prolongator(l, order)
+            P = mt.prolongator(lv[l - 1], lv[l], order)
+            assert shp == P.shape and np.array_equal(rp, P.indptr) and np.array_equal(ci, P.indices)
+            assert np.abs(v - P.data).max() <= 1e-15
+            assert np.abs(P @ np.ones(P.shape[1]) - 1.0).max() < 1e-14          # constants are reproduced
+
+
+def test_tet_refinement_is_nested():
+    """Refined coordinates are the coarse FE geometry evaluated at the child nodes: on this affine mesh every
+    fine vertex that is a coarse node keeps its coordinates and every element volume is 1/8 of its parent's."""
+    H = hostapi.HostHierarchy.from_neu(NEU_TET, 2)
+    C, F = H.levels
+    def vol(L):
+        X = L.xyz[:, L.conn[:, :4]]
+        M = np.stack([X[:, :, k] - X[:, :, 0] for k in (1, 2, 3)], axis=-1)       # [3, nel, 3]
+        return np.abs(np.linalg.det(M.transpose(1, 0, 2))) / 6
+    vc, vf = vol(C), vol(F)
+    assert abs(vc.sum() - 1.0) < 1e-13 and abs(vf.sum() - 1.0) < 1e-13
+    # the file's mid-edge nodes are the edge midpoints only to its 12 printed digits
+    assert np.abs(vf[C.child_el] - vc[:, None] / 8).max() < 1e-10 * vc.max()
