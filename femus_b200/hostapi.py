@@ -229,6 +229,10 @@ def galerkin_element(family):
     return ploc, ent
 
 
+def elem_nve(elem_type, family):
+    return int(_L().b2h_elem_nve(elem_type, _fam(family)))
+
+
 def elem_tables(elem_type, family):
     """(phi, dxi, deta, dzeta, w) of elem_type_3D(type, family, "seventh"): [ngauss][nve] and [ngauss]."""
     L = _L()

@@ -46,7 +46,15 @@ class PoissonMG:
         self.ndofs = [L.ndofs(order) for L in lv]
         self.n = self.ndofs[-1]
         self.nel = top.nel
-        self.nve = 27 if order == "biquadratic" else 8
+        # element type of the mesh (hexahedra from the box generator or a .neu file, tetrahedra from a .neu
+        # file): the reference dispatches on it through _finiteElement[ielGeom][solType] (main.cpp:438)
+        self.elem_type = top.elem_type
+        self.hex = self.elem_type == hostapi.HEX
+        self.nve = hostapi.elem_nve(self.elem_type, order)
+        if not self.hex:       # the element-gather / fused Galerkin products are kernels for refined hexahedra
+            self.fused = False
+            if self.neumann or dist is not None:
+                raise NotImplementedError("Neumann faces and the sharded run are implemented for hexahedra")
         # --- system.init(): per-level matrices with the exact element-coupling pattern
         self.dofs = [L.system_dofs(order) for L in lv]
         self.KK = [capi.Csr.from_elements(ctx, self.ndofs[l], self.dofs[l]) for l in range(nlevels)]
@@ -61,15 +69,17 @@ class PoissonMG:
             P.zero_cols(self.bdc_idx[l - 1])
             self.PP[l] = P
         # --- Galerkin plans: element-gather P^T A P per level pair (fast path of matrix_PtAP)
-        ploc, fent = hostapi.galerkin_element(order)
+        # (hexahedra; other element types use the general triple product b2_csr_ptap, like MatPtAP)
         self.gal = [None] * nlevels
-        for l in range(1, nlevels):
+        if self.hex:
+            ploc, fent = hostapi.galerkin_element(order)
+        for l in range(1, nlevels if self.hex else 0):
             fd, val = self.hier.galerkin_maps(l - 1, order)
             self.gal[l] = capi.Galerkin(self.KK[l], self.KK[l - 1], fd, self.dofs[l - 1], ploc, fent, val,
                                         self.bdc[l] < 1.5, self.bdc[l - 1] < 1.5)
         # --- finest-level mesh + assembly plan
         self.mesh = capi.Mesh(ctx, top.xyz, top.conn)
-        self.tables = hostapi.hex_tables(order)
+        self.tables = hostapi.elem_tables(self.elem_type, order)
         self.asm = capi.Assembler(self.mesh, self.KK[-1], self.dofs[-1], self.tables)
         if self.neumann:    # Neumann faces of the finest level: (element, local face, flux)
             fe, fl, fb = top.boundary_faces()
@@ -125,6 +135,7 @@ class PoissonMG:
         """A_{l-1} = P_l^T A_l P_l down the hierarchy, on the un-penalised matrices: element-gather
         plans by default, the general sparse triple product (b2_csr_ptap) on request."""
         top = self.nlevels - 1
+        algebraic = algebraic or not self.hex
         for l in range(top, 0, -1):
             if l == top and self.fused and not algebraic:
                 continue            # already formed by the fused assembly

@@ -242,5 +242,8 @@ def prolongator(C, F, order):
     return P
 
 
+zero_dirichlet = mb.zero_dirichlet
+
+
 def C_child(C, F, E, j):
     return int(F.child_el[E, j])

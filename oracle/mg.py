@@ -68,7 +68,9 @@ class Hierarchy:
     """Per-level operators exactly as the reference sets them up for one MGsolve."""
 
     def __init__(self, levels, order, fsrc=1.0, dirichlet_faces=(1, 2, 3, 4, 5, 6), A_top=None, rhs=None,
-                 coarse_lu=True, ptap=None, neumann=None, smoother="richardson"):
+                 coarse_lu=True, ptap=None, neumann=None, smoother="richardson", mesh=None):
+        """mesh: the oracle module the levels come from (mesh_box by default, mesh_tet for tetrahedra)."""
+        mb = mesh if mesh is not None else globals()["mb"]
         self.levels = levels
         self.order = order
         self.smoother = smoother

@@ -128,3 +128,92 @@ def test_general_plan_rejects_bad_sizes(ctx):
     big = np.zeros((65, 10))
     with pytest.raises(capi.B2Error):
         capi.Assembler(mesh, A, dof, (big, big, big, big, np.zeros(65)))
+
+
+# ------------------------------------------------------------------------------ tetrahedral meshes end to end
+NEU_TET = os.path.join(os.path.dirname(__file__), "golden", "cube_tet10.neu")
+
+
+@pytest.mark.parametrize("order", ["linear", "quadratic", "biquadratic"])
+def test_tet_mesh_single_level_matches_oracle(ctx, order):
+    """cube_tet10.neu (the reference's cube_Tet.neu, 105 Tet10 elements, re-serialised) through the host reader
+    and the driver sequence of 001_Poisson: pattern bit-exact, matrix and residual to 1e-12 against the oracle,
+    single-level solve (the reference: LU) against a sparse direct solve."""
+    import scipy.sparse.linalg as spla
+    from femus_b200 import hostapi
+    from femus_b200.poisson import PoissonMG
+    from oracle import mesh_tet as mt, mg
+    H = hostapi.HostHierarchy.from_neu(NEU_TET, 1)
+    pb = PoissonMG(ctx, 0, 0, 0, 1, order, hier=H, coarse_rtol=1e-15)
+    pb.assemble()
+    L = mt.read_tet10(NEU_TET)
+    Aref, rhs = mt.assemble(L, order)
+    A = pb.KK[-1].to_scipy()
+    assert np.array_equal(A.indptr, Aref.indptr) and np.array_equal(A.indices, Aref.indices)
+    assert np.abs(A.data - Aref.data).max() <= RTOL * np.abs(Aref.data).max()
+    assert np.abs(pb.RES.get() - rhs).max() <= RTOL * np.abs(rhs).max()
+    pb.galerkin(); pb.mg_set_levels(); pb.mg_solve()
+    idx = np.nonzero(mt.bdc_flags(L, order) < 1.5)[0]
+    Ap = mg.penalty_fast(Aref, idx)
+    b = rhs.copy(); b[idx] = 0.0
+    x = spla.spsolve(Ap.tocsc(), b)
+    assert np.abs(pb.EPS.get() - x).max() <= 1e-10 * np.abs(x).max()
+    del pb
+
+
+@pytest.mark.parametrize("order,nl", [("linear", 3), ("quadratic", 3), ("biquadratic", 2)])
+def test_tet_mesh_vcycle_trace(ctx, order, nl):
+    """Multigrid on refined tetrahedra: assembly on the finest level (table-driven kernel), Galerkin chain by
+    the general triple product (what MatPtAP does), penalised level operators and the residual trace of six
+    V-cycles against the oracle (exact coarse solve), 1e-12 relative."""
+    from femus_b200 import hostapi
+    from femus_b200.poisson import PoissonMG
+    from oracle import mesh_tet as mt, mg
+    H = hostapi.HostHierarchy.from_neu(NEU_TET, nl)
+    pb = PoissonMG(ctx, 0, 0, 0, nl, order, hier=H, coarse_rtol=1e-15)
+    assert not pb.fused and pb.nve == fe_tet.NDOFS[order]
+    pb.assemble(); pb.galerkin(); pb.mg_set_levels()
+    O = mg.Hierarchy(mt.build_hierarchy(NEU_TET, nl), order, mesh=mt)
+    for l in range(nl):
+        got, ref = pb.KK[l].to_scipy(), O.A[l]
+        assert np.array_equal(got.indptr, ref.indptr) and np.array_equal(got.indices, ref.indices)
+        assert np.abs(got.data - ref.data).max() <= RTOL * np.abs(ref.data).max()
+    trace_ref, eps_ref = O.mg_solve_trace(6)
+    trace = []
+    for _ in range(6):
+        pb.mg_solve()
+        trace.append(pb.residual_norm())
+    for a, b in zip(trace, trace_ref):
+        assert abs(a - b) <= RTOL * trace_ref[0], (trace, trace_ref)
+    assert np.abs(pb.EPS.get() - eps_ref).max() <= 1e-11 * np.abs(eps_ref).max()
+    del pb
+
+
+def test_tet_and_hex_solutions_agree(ctx):
+    """The same boundary-value problem (-lap u = 1, u = 0 on the unit cube) on the tetrahedral and on the
+    hexahedral coarse mesh of the reference, two refinements each, quadratic elements, solved to convergence:
+    the two discrete solutions agree at the cube centre and in the mean to discretisation accuracy."""
+    from femus_b200 import hostapi
+    from femus_b200.poisson import PoissonMG
+    vals = []
+    for path, order in ((NEU_TET, "quadratic"), (os.path.join(os.path.dirname(NEU_TET), "cube_hex27_2x2x2.neu"), "biquadratic")):
+        H = hostapi.HostHierarchy.from_neu(path, 3)
+        pb = PoissonMG(ctx, 0, 0, 0, 3, order, hier=H, npre=2, npost=2, coarse_rtol=1e-14)
+        pb.assemble(); pb.galerkin(); pb.mg_set_levels()
+        r0 = pb.residual_norm()
+        for _ in range(200):
+            pb.mg_solve()
+            if pb.residual_norm() <= 1e-10 * r0:
+                break
+        assert pb.residual_norm() <= 1e-10 * r0
+        u = pb.EPS.get()
+        top = H.levels[-1]
+        # one rank: the dofs of a family are the first dof_offset[family] nodes ([vertices][edges][faces, centres])
+        xyz = top.xyz[:, :top.dof_offset[hostapi.FAMILY[order], -1]]
+        c = np.argmin(np.abs(xyz - 0.5).sum(axis=0))
+        assert np.abs(xyz[:, c] - 0.5).max() < 1e-12
+        vals.append(u[c])
+        del pb
+    # u(1/2,1/2,1/2) of the continuous problem is 0.0562128...
+    assert abs(vals[0] - 0.0562128) < 2e-4 and abs(vals[1] - 0.0562128) < 2e-4
+    assert abs(vals[0] - vals[1]) < 2e-4
