@@ -53,6 +53,10 @@ struct HexElement {
       if (i == 0) { v = 0.5 * (1. - x); d = -0.5; }
       else if (i == 2) { v = 0.5 * (1. + x); d = 0.5; }
       else { v = 0.; d = 0.; }
+    } else if (family == SERENDIPITY) {  // 1-D factor of the 20-node element: linear at the ends, bubble in the middle
+      if (i == 0) { v = 0.5 * (1. - x); d = -0.5; }
+      else if (i == 1) { v = (1. - x) * (1. + x); d = -2. * x; }
+      else { v = 0.5 * (1. + x); d = 0.5; }
     } else {  // biquadratic
       if (i == 0) { v = 0.5 * x * (x - 1.); d = x - 0.5; }
       else if (i == 1) { v = (1. - x) * (1. + x); d = -2. * x; }
@@ -61,9 +65,18 @@ struct HexElement {
   }
   // phi_a and its reference gradient at point p
   static void shape(int family, int a, const double p[3], double& phi, double g[3]) {
-    if (family == SERENDIPITY) { std::abort(); }   // 20-node element: not needed by the Poisson path yet
     double v[3], d[3];
     for (int k = 0; k < 3; k++) lag1d(family, p[k], xc()[a][k] + 1, v[k], d[k]);
+    if (family == SERENDIPITY && xc()[a][0] * xc()[a][1] * xc()[a][2] != 0) {
+      // vertex function of the 20-node element: trilinear x (x.xa + y.ya + z.za - 2) (HexQuadratic, Hexahedron.cpp:167-197)
+      const double ix = xc()[a][0], jx = xc()[a][1], kx = xc()[a][2];
+      const double c = -2. + ix * p[0] + jx * p[1] + kx * p[2];
+      phi = c * v[0] * v[1] * v[2];
+      g[0] = v[1] * v[2] * (ix * v[0] + c * d[0]);
+      g[1] = v[0] * v[2] * (jx * v[1] + c * d[1]);
+      g[2] = v[0] * v[1] * (kx * v[2] + c * d[2]);
+      return;
+    }
     phi = v[0] * v[1] * v[2];
     g[0] = d[0] * v[1] * v[2];
     g[1] = v[0] * d[1] * v[2];

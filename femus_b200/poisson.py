@@ -49,12 +49,13 @@ class PoissonMG:
         # element type of the mesh (hexahedra from the box generator or a .neu file, tetrahedra from a .neu
         # file): the reference dispatches on it through _finiteElement[ielGeom][solType] (main.cpp:438)
         self.elem_type = top.elem_type
-        self.hex = self.elem_type == hostapi.HEX
+        # fast Galerkin paths: hexahedra with 8 or 27 dofs (the 20-node family uses the general triple product)
+        self.hex = self.elem_type == hostapi.HEX and order != "quadratic"
         self.nve = hostapi.elem_nve(self.elem_type, order)
         if not self.hex:       # the element-gather / fused Galerkin products are kernels for refined hexahedra
             self.fused = False
             if self.neumann or dist is not None:
-                raise NotImplementedError("Neumann faces and the sharded run are implemented for hexahedra")
+                raise NotImplementedError("Neumann faces and the sharded run are implemented for hexahedra with 8 or 27 dofs")
         # --- system.init(): per-level matrices with the exact element-coupling pattern
         self.dofs = [L.system_dofs(order) for L in lv]
         self.KK = [capi.Csr.from_elements(ctx, self.ndofs[l], self.dofs[l]) for l in range(nlevels)]

@@ -11,8 +11,12 @@ from oracle import ref, fe_hex  # noqa: E402
 assert ref.build(), "oracle/_ref could not be built (is /root/reference present?)"
 out = {}
 rng = np.random.default_rng(20261017)
-for order in ("linear", "biquadratic"):
+rng20 = np.random.default_rng(20261018)      # the 20-node family was added later: own stream, so that nothing else moves
+for order in ("linear", "biquadratic", "quadratic"):
     R = ref.RefHex(order)
+    rng_ = rng
+    if order == "quadratic":
+        rng = rng20
     w, xi = R.gauss()
     out[f"{order}_gauss_w"], out[f"{order}_gauss_xi"] = w, xi
     phi, dxi, deta, dzeta = R.tables()
@@ -48,6 +52,7 @@ for order in ("linear", "biquadratic"):
         P[i, idx] = val
         pos[i] = fe_hex.XC[ch] + fe_hex.XC[nd]
     out[f"{order}_prol"], out[f"{order}_prol_pos2"] = P, pos
+    rng = rng_
 np.savez_compressed(os.path.join(ROOT, "tests", "golden", "fe_hex_ref.npz"), **out)
 print("wrote fe_hex_ref.npz", {k: v.shape for k, v in out.items()})
 

@@ -23,7 +23,7 @@ def test_hierarchy_bit_exact(shape, nl, nprocs):
         assert np.array_equal(a.xyz, b.xyz)
         if l < nl - 1:
             assert np.array_equal(a.child_el, lv[l + 1].child_el)
-        for fam in ("linear", "biquadratic"):
+        for fam in ("linear", "quadratic", "biquadratic"):
             assert np.array_equal(a.system_dofs(fam), mb.system_dof(b, fam))
             assert np.array_equal(a.bdc(fam), mb.bdc_flags(b, fam))
             assert np.array_equal(a.bdc(fam, (3,)), mb.bdc_flags(b, fam, (3,)))
@@ -38,7 +38,7 @@ def test_non_unit_bounds_and_tables():
     H = hostapi.HostHierarchy(2, 2, 2, 2, bounds=(-1., 2., 0., 0.5, 3., 4.))
     lv = mb.build_hierarchy(2, 2, 2, 2, bounds=(-1., 2., 0., 0.5, 3., 4.))
     assert np.array_equal(H.levels[1].xyz, lv[1].xyz)
-    for fam in ("linear", "biquadratic"):
+    for fam in ("linear", "quadratic", "biquadratic"):
         for x, y in zip(hostapi.hex_tables(fam), fe_hex.tables(fam)):
             assert np.array_equal(x, y)
         Pl = fe_hex.local_prolongator(fam)

@@ -217,3 +217,40 @@ def test_tet_and_hex_solutions_agree(ctx):
     # u(1/2,1/2,1/2) of the continuous problem is 0.0562128...
     assert abs(vals[0] - 0.0562128) < 2e-4 and abs(vals[1] - 0.0562128) < 2e-4
     assert abs(vals[0] - vals[1]) < 2e-4
+
+
+# ------------------------------------------------------------------------------ 20-node hexahedra
+@pytest.mark.parametrize("shape,nl", [((2, 3, 2), 2), ((2, 2, 2), 3)])
+def test_hex20_assembly_and_vcycle_trace(ctx, shape, nl):
+    """The serendipity family on hexahedra (fe_order "serendipity" of the reference's input3D_Hex_serendipity.json,
+    20 dofs per element on the 27-node geometry): table-driven assembly, general triple product, V-cycle trace
+    against the oracle, whose 20-node tables are bit-exact with the compiled reference."""
+    from femus_b200 import hostapi
+    from femus_b200.poisson import PoissonMG
+    from oracle import mg
+    order = "quadratic"
+    H = hostapi.HostHierarchy(*shape, nl)
+    pb = PoissonMG(ctx, 0, 0, 0, nl, order, hier=H, coarse_rtol=1e-15)
+    assert pb.nve == 20 and not pb.fused
+    pb.assemble()
+    lv = mb.build_hierarchy(*shape, nl)
+    Aref, rhs = mb.assemble(lv[-1], order)
+    A = pb.KK[-1].to_scipy()
+    assert np.array_equal(A.indptr, Aref.indptr) and np.array_equal(A.indices, Aref.indices)
+    assert np.abs(A.data - Aref.data).max() <= RTOL * np.abs(Aref.data).max()
+    assert np.abs(pb.RES.get() - rhs).max() <= RTOL * np.abs(rhs).max()
+    pb.galerkin(); pb.mg_set_levels()
+    O = mg.Hierarchy(lv, order)
+    for l in range(nl):
+        got, ref = pb.KK[l].to_scipy(), O.A[l]
+        assert np.array_equal(got.indices, ref.indices)
+        assert np.abs(got.data - ref.data).max() <= RTOL * np.abs(ref.data).max()
+    trace_ref, eps_ref = O.mg_solve_trace(6)
+    trace = []
+    for _ in range(6):
+        pb.mg_solve()
+        trace.append(pb.residual_norm())
+    for a, b in zip(trace, trace_ref):
+        assert abs(a - b) <= RTOL * trace_ref[0], (trace, trace_ref)
+    assert np.abs(pb.EPS.get() - eps_ref).max() <= 1e-11 * np.abs(eps_ref).max()
+    del pb
