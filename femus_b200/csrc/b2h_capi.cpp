@@ -4,7 +4,7 @@
 #include <memory>
 #include "../host/BoxMesh.hpp"
 #include "../host/GambitIO.hpp"
-#include "../host/TetMesh.hpp"
+#include "../host/GeneralMesh.hpp"
 #include "../../include/femus_b200_host.h"
 
 using namespace femus_b200;
@@ -119,19 +119,43 @@ int b2h_galerkin_maps(const b2h_hier* h, int lcoarse, int family, int64_t e0, in
 
 int b2h_level_elem_type(const b2h_hier* h, int l) { return h->levels[l].uniform_type(); }
 int b2h_elem_nve(int type, int family) { return ElemTopology::nve(type, family); }
-int b2h_elem_ngauss(int type) { return type == TET ? TetElement::NG : HexElement::NG; }
+int b2h_elem_ngauss(int type) { return ElemTopology::ngauss(type); }
 void b2h_elem_tables(int type, int family, double* phi, double* dxi, double* deta, double* dzeta, double* w) {
-  HexElement::Tables t = type == TET ? TetElement::tables(family) : HexElement::tables(family);
+  HexElement::Tables t = ElemTopology::tables(type, family);
   std::copy(t.phi.begin(), t.phi.end(), phi);
   std::copy(t.dxi.begin(), t.dxi.end(), dxi);
   std::copy(t.deta.begin(), t.deta.end(), deta);
   std::copy(t.dzeta.begin(), t.dzeta.end(), dzeta);
   std::copy(t.w.begin(), t.w.end(), w);
 }
-int b2h_tet_prolongator_row(int family, int child, int node, int* idx, double* val) {
-  return TetElement::prolongator_row(family, child, node, idx, val);
+int b2h_elem_prolongator_row(int type, int family, int child, int node, int* idx, double* val) {
+  return ElemTopology::prolongator_row(type, family, child, node, idx, val);
 }
-int b2h_tet_child_face(int child, int child_face) { return detail::tet_child_faces().parent_face[child][child_face]; }
+int b2h_elem_child_face(int type, int child, int child_face) { return detail::child_faces().parent_face[type][child][child_face]; }
+void b2h_level_elem_types(const b2h_hier* h, int l, uint8_t* out) {
+  const MeshLevel& L = h->levels[l];
+  for (int64_t e = 0; e < L.nel; e++) out[e] = (uint8_t)L.type_of(e);
+}
+void b2h_level_system_dofs27(const b2h_hier* h, int l, int family, int32_t* out) {
+  std::vector<int32_t> d = h->levels[l].system_dofs27(family);
+  std::copy(d.begin(), d.end(), out);
+}
+b2h_csr* b2h_sparsity_create(const b2h_hier* h, int l, int family) {
+  if (l < 0 || l >= (int)h->levels.size()) return nullptr;
+  b2h_csr* p = new b2h_csr();
+  p->m = BuildSparsity(h->levels[l], family);
+  return p;
+}
+/* test hook: the general (any element type) refinement and prolongator on a hexahedral box hierarchy */
+b2h_hier* b2h_hier_create_general(int nx, int ny, int nz, int nlevels) {
+  if (nx < 1 || ny < 1 || nz < 1 || nlevels < 1) return nullptr;
+  b2h_hier* h = new b2h_hier();
+  h->levels.reserve(nlevels);
+  h->levels.push_back(GenerateCoarseBoxMesh(nx, ny, nz, 0., 1., 0., 1., 0., 1., nullptr, 1));
+  h->levels.back().etype.assign((size_t)h->levels.back().nel, (uint8_t)HEX);
+  for (int l = 1; l < nlevels; l++) h->levels.push_back(RefineGeneralMesh(h->levels.back()));
+  return h;
+}
 
 int b2h_hex_nve(int family) { return HexElement::nve(family); }
 void b2h_hex_tables(int family, double* phi, double* dxi, double* deta, double* dzeta, double* w) {

@@ -21,18 +21,56 @@
 #include <vector>
 #include "HexElement.hpp"
 #include "TetElement.hpp"
+#include "WedgeElement.hpp"
 
 namespace femus_b200 {
 
 // Geometric element types in the reference's numbering (GeomElTypeEnum: HEX 0, TET 1, WEDGE 2) and the
-// per-type tables of Elem.hpp:102-130, 581-610 (NVE, NFC, ig, NFACENODES) the mesh layer needs.
-enum GeomType { HEX = 0, TET = 1 };
+// per-type tables of Elem.hpp:102-140, 581-615 (NVE, NFC, ig, NFACENODES), MeshRefinement.hpp:118-135
+// (edge2VerticesMapping) and the bases' fine2CoarseVertexMapping that the mesh layer needs.  Local node
+// classes are the same for every type: [vertices][edge midpoints][face centres][centre], and face f owns the
+// node nve(type, SERENDIPITY) + f.
+enum GeomType { HEX = 0, TET = 1, WEDGE = 2 };
 struct ElemTopology {
-  static int nve(int type, int family) { return type == TET ? TetElement::nve(family) : HexElement::nve(family); }
-  static int nfaces(int type) { return type == TET ? 4 : 6; }
-  static int face_ndofs(int type, int family) { return type == TET ? TetElement::face_ndofs(family) : HexElement::face_ndofs(family); }
-  static int face_node(int type, int f, int i) { return type == TET ? TetElement::face_nodes()[f][i] : HexElement::face_nodes()[f][i]; }
-  static int nchildren(int) { return 8; }
+  static int nve(int type, int family) {
+    return type == TET ? TetElement::nve(family) : (type == WEDGE ? WedgeElement::nve(family) : HexElement::nve(family));
+  }
+  static int nvert(int type) { return nve(type, LINEAR); }
+  static int nedges(int type) { return nve(type, SERENDIPITY) - nve(type, LINEAR); }
+  static int nfaces(int type) { return type == TET ? 4 : (type == WEDGE ? 5 : 6); }
+  static int face_nvert(int type, int f) { return type == TET ? 3 : (type == WEDGE ? WedgeElement::face_nvert(f) : 4); }
+  static int face_ndofs(int type, int f, int family) {
+    return type == TET ? TetElement::face_ndofs(family) : (type == WEDGE ? WedgeElement::face_ndofs(f, family) : HexElement::face_ndofs(family));
+  }
+  static int face_node(int type, int f, int i) {
+    return type == TET ? TetElement::face_nodes()[f][i] : (type == WEDGE ? WedgeElement::face_nodes()[f][i] : HexElement::face_nodes()[f][i]);
+  }
+  static void edge(int type, int e, int& a, int& b) {
+    static const int hex_edges[12][2] = {{0, 1}, {1, 2}, {2, 3}, {3, 0}, {4, 5}, {5, 6}, {6, 7}, {7, 4}, {0, 4}, {1, 5}, {2, 6}, {3, 7}};
+    const int* p = type == TET ? TetElement::edges()[e] : (type == WEDGE ? WedgeElement::edges()[e] : hex_edges[e]);
+    a = p[0];
+    b = p[1];
+  }
+  // vertex v of child j as a parent local node
+  static int child_vertex(int type, int j, int v) {
+    if (type == TET) return TetElement::child_vertices()[j][v];
+    if (type == WEDGE) return WedgeElement::child_vertices()[j][v];
+    const int* a = HexElement::xc()[j];          // child j = octant at parent vertex j: node at (xc[j] + xc[v]) / 2
+    const int* b = HexElement::xc()[v];
+    return HexElement::node_at((a[0] + b[0]) / 2 + 1, (a[1] + b[1]) / 2 + 1, (a[2] + b[2]) / 2 + 1);
+  }
+  // element prolongator row of (child j, child-local node a): coarse functions with |phi| >= 1e-14
+  static int prolongator_row(int type, int family, int j, int a, int* idx, double* val) {
+    if (type == TET) return TetElement::prolongator_row(family, j, a, idx, val);
+    if (type == WEDGE) return WedgeElement::prolongator_row(family, j, a, idx, val);
+    const int* o = HexElement::xc()[j];
+    const int* x = HexElement::xc()[a];
+    return HexElement::prolongator_row(family, o[0] + x[0] + 2, o[1] + x[1] + 2, o[2] + x[2] + 2, idx, val);
+  }
+  static int ngauss(int type) { return type == TET ? TetElement::NG : (type == WEDGE ? WedgeElement::NG : HexElement::NG); }
+  static HexElement::Tables tables(int type, int family) {
+    return type == TET ? TetElement::tables(family) : (type == WEDGE ? WedgeElement::tables(family) : HexElement::tables(family));
+  }
 };
 
 struct HostCsr {
@@ -61,11 +99,11 @@ class MeshLevel {
 
   int32_t node(int64_t iel, int i) const { return conn[iel * 27 + i]; }
   int type_of(int64_t iel) const { return etype.empty() ? (int)HEX : (int)etype[iel]; }
-  // the one element type of the level; mixed meshes are not supported by the dof-table entry points
+  // the one element type of the level, -1 for a mixed mesh
   int uniform_type() const {
     const int t = type_of(0);
     for (int64_t e = 1; e < nel; e++)
-      if (type_of(e) != t) { std::fprintf(stderr, "femus_b200: mixed element types are not supported yet\n"); std::abort(); }
+      if (type_of(e) != t) return -1;
     return t;
   }
 
@@ -85,10 +123,19 @@ class MeshLevel {
   // [nel][nve] system dofs of a single-variable system (LinearEquation::GetSystemDof,
   // LinearEquation.cpp:76-85: KKoffset[0][p] == dofOffset[family][p])
   std::vector<int32_t> system_dofs(int family) const {
-    const int nve = ElemTopology::nve(uniform_type(), family);
+    const int ut = uniform_type();
+    if (ut < 0) { std::fprintf(stderr, "femus_b200: system_dofs on a mixed mesh: use system_dofs27\n"); std::abort(); }
+    const int nve = ElemTopology::nve(ut, family);
     std::vector<int32_t> d((size_t)nel * nve);
     for (int64_t e = 0; e < nel; e++)
       for (int i = 0; i < nve; i++) d[e * nve + i] = GetSolutionDof(i, e, family);
+    return d;
+  }
+  // the same for meshes of several element types: rows of 27, padded with -1 after nve(type, family) entries
+  std::vector<int32_t> system_dofs27(int family) const {
+    std::vector<int32_t> d((size_t)nel * 27, -1);
+    for (int64_t e = 0; e < nel; e++)
+      for (int i = 0; i < ElemTopology::nve(type_of(e), family); i++) d[e * 27 + i] = GetSolutionDof(i, e, family);
     return d;
   }
 
@@ -97,11 +144,11 @@ class MeshLevel {
   std::vector<double> GenerateBdc(int family, const bool dirichlet_faces[7]) const {
     std::vector<double> bdc((size_t)ndofs(family), 2.0);
     for (int64_t e = 0; e < nel; e++) {
-      const int t = type_of(e), nfd = ElemTopology::face_ndofs(t, family);
+      const int t = type_of(e);
       for (int f = 0; f < ElemTopology::nfaces(t); f++) {
         const int bidx = -(face[e * 6 + f] + 1);
         if (bidx > 0 && bidx <= 6 && dirichlet_faces[bidx])
-          for (int iv = 0; iv < nfd; iv++) bdc[GetSolutionDof(ElemTopology::face_node(t, f, iv), e, family)] = 0.0;
+          for (int iv = 0; iv < ElemTopology::face_ndofs(t, f, family); iv++) bdc[GetSolutionDof(ElemTopology::face_node(t, f, iv), e, family)] = 0.0;
       }
     }
     return bdc;

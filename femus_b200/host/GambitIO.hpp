@@ -1,4 +1,5 @@
-// Gambit neutral-file (.neu) reader for meshes of 27-node hexahedra or 10-node tetrahedra: the coarse-mesh
+// Gambit neutral-file (.neu) reader for meshes of 27-node hexahedra, 10-node tetrahedra and 18-node wedges,
+// also mixed (cube_all_shapes_Six_boundary_groups.neu): the coarse-mesh
 // input of the reference's shipped 3-D Poisson cases (applications/001_Poisson/input/cube_Hex.neu,
 // cube_Tet.neu, input3D_*.json).  Follows GambitIO::read (src/06_mesh/00_single_level/01_input/
 // 01_from_external_file/GambitIO.cpp:92-352): section order CONTROL INFO / NODAL COORDINATES /
@@ -7,8 +8,8 @@
 // divided by Lref (:262-264); then Mesh::AddBiquadraticNodesNotInMeshFile (Mesh.cpp:1207-1333) creates the
 // face and centre nodes a 10-node tetrahedron lacks, and the reference renumbers nodes by first visit exactly
 // as for a generated box (Mesh.cpp:517-559).
-// One element type per file and a single element group are accepted (wedges, mixed meshes and the
-// material/group reordering of Mesh.cpp:621-702 are the next step); anything else aborts.
+// A single element group is accepted (the material/group reordering of Mesh.cpp:621-702 is the next step);
+// anything else aborts.
 #pragma once
 #include <cstdio>
 #include <cstdlib>
@@ -19,46 +20,55 @@
 
 namespace femus_b200 {
 
-// Mesh::AddBiquadraticNodesNotInMeshFile for tetrahedra: one node per triangular face (shared by the two
-// elements that have the same three vertices), one per element; coordinates from the element's 10 file
-// nodes with the barycentric weights of Mesh.cpp:105-113 (-1/9 vertices, 4/9 edges of the face; -1/8, 1/4
-// for the centre), every element overwriting what an earlier one wrote, in element order, as the reference.
+// Mesh::AddBiquadraticNodesNotInMeshFile for tetrahedra and wedges: one node per TRIANGULAR face (shared by the
+// two elements, of either type, that have the same three vertices), one per element; coordinates from the
+// element's file nodes with the barycentric weights of Mesh.cpp:105-125 (-1/9 on the three vertices, 4/9 on the
+// three edge nodes of the triangle; tetrahedron centre -1/8, 1/4; wedge centre from its mid-height triangle
+// 12-14 / 15-17), every element overwriting what an earlier one wrote, in element order, as the reference.
 inline void AddBiquadraticNodesNotInMeshFile(MeshLevel& L, std::vector<double>& xyz_file) {
   if (L.etype.empty()) return;
   struct Key { uint32_t a, b, c; bool operator<(const Key& o) const { return a != o.a ? a < o.a : (b != o.b ? b < o.b : c < o.c); } };
   std::map<Key, int32_t> face_node;
   int64_t nn = L.nnode;
   for (int64_t e = 0; e < L.nel; e++) {
-    if (L.etype[e] != TET) continue;
-    for (int f = 0; f < 4; f++) {
+    const int t = L.etype[e];
+    if (t == HEX) continue;
+    for (int f = 0; f < ElemTopology::nfaces(t); f++) {
+      if (ElemTopology::face_nvert(t, f) != 3) continue;
       uint32_t v[3];
-      for (int k = 0; k < 3; k++) v[k] = (uint32_t)L.conn[e * 27 + TetElement::face_nodes()[f][k]];
+      for (int k = 0; k < 3; k++) v[k] = (uint32_t)L.conn[e * 27 + ElemTopology::face_node(t, f, k)];
       std::sort(v, v + 3);
       auto it = face_node.find(Key{v[0], v[1], v[2]});
       if (it == face_node.end()) it = face_node.emplace(Key{v[0], v[1], v[2]}, (int32_t)nn++).first;
-      L.conn[e * 27 + 10 + f] = it->second;
+      L.conn[e * 27 + ElemTopology::nve(t, SERENDIPITY) + f] = it->second;
     }
   }
   for (int64_t e = 0; e < L.nel; e++)
-    if (L.etype[e] == TET) L.conn[e * 27 + 14] = (int32_t)nn++;
+    if (L.etype[e] != HEX) L.conn[e * 27 + ElemTopology::nve(L.etype[e], BIQUADRATIC) - 1] = (int32_t)nn++;
   const int64_t n0 = L.nnode;
   std::vector<double> x2((size_t)3 * nn);
   for (int d = 0; d < 3; d++) std::copy(xyz_file.begin() + d * n0, xyz_file.begin() + (d + 1) * n0, x2.begin() + d * nn);
   for (int64_t e = 0; e < L.nel; e++) {
-    if (L.etype[e] != TET) continue;
-    for (int j = 10; j < 15; j++) {
-      double w[10];
-      for (int i = 0; i < 10; i++) w[i] = 0.;
-      if (j < 14) {
-        for (int k = 0; k < 3; k++) { w[TetElement::face_nodes()[j - 10][k]] = -1. / 9.; w[TetElement::face_nodes()[j - 10][3 + k]] = 4. / 9.; }
-      } else {
+    const int t = L.etype[e];
+    if (t == HEX) continue;
+    const int ndof = ElemTopology::nve(t, BIQUADRATIC), jstart = t == TET ? 10 : 18;
+    for (int j = jstart; j < ndof; j++) {
+      double w[18];
+      for (int i = 0; i < jstart; i++) w[i] = 0.;
+      if (j < ndof - 1) {           // centre of the triangular face that owns node j
+        const int f = j - ElemTopology::nve(t, SERENDIPITY);
+        for (int k = 0; k < 3; k++) { w[ElemTopology::face_node(t, f, k)] = -1. / 9.; w[ElemTopology::face_node(t, f, 3 + k)] = 4. / 9.; }
+      } else if (t == TET) {
         for (int i = 0; i < 4; i++) w[i] = -1. / 8.;
         for (int i = 4; i < 10; i++) w[i] = 1. / 4.;
+      } else {
+        for (int i = 12; i < 15; i++) w[i] = -1. / 9.;
+        for (int i = 15; i < 18; i++) w[i] = 4. / 9.;
       }
       const int32_t jn = L.conn[e * 27 + j];
       for (int d = 0; d < 3; d++) {
         double s = 0.;
-        for (int i = 0; i < 10; i++) s += x2[(size_t)d * nn + L.conn[e * 27 + i]] * w[i];
+        for (int i = 0; i < jstart; i++) s += x2[(size_t)d * nn + L.conn[e * 27 + i]] * w[i];
         x2[(size_t)d * nn + jn] = s;
       }
     }
@@ -70,8 +80,10 @@ inline void AddBiquadraticNodesNotInMeshFile(MeshLevel& L, std::vector<double>& 
 inline MeshLevel ReadGambit(const char* path, double Lref = 1.0) {
   static const int vertex_map_hex[27] = {4, 16, 0, 15, 23, 11, 7, 19, 3, 12, 20, 8, 25, 26, 24, 14, 22, 10, 5, 17, 1, 13, 21, 9, 6, 18, 2};
   static const int vertex_map_tet[10] = {0, 4, 1, 6, 5, 2, 7, 8, 9, 3};
+  static const int vertex_map_wedge[18] = {3, 11, 5, 9, 10, 4, 12, 17, 14, 15, 16, 13, 0, 8, 2, 6, 7, 1};
   static const int face_map_hex[6] = {0, 4, 2, 5, 3, 1};
   static const int face_map_tet[4] = {0, 1, 2, 3};
+  static const int face_map_wedge[5] = {2, 1, 0, 4, 3};
   auto fail = [&](const char* what) {
     std::fprintf(stderr, "femus_b200: Gambit file %s: %s\n", path, what);
     std::abort();
@@ -114,17 +126,19 @@ inline MeshLevel ReadGambit(const char* path, double Lref = 1.0) {
   for (long iel = 0; iel < nel; iel++) {
     long id, type, nve;
     in >> id >> type >> nve;
-    if (nve != 27 && nve != 10) fail("only 27-node hexahedra and 10-node tetrahedra are supported by the B200 backend so far");
-    etype[iel] = nve == 27 ? (uint8_t)HEX : (uint8_t)TET;
-    if (etype[iel] != etype[0]) fail("mixed element types are not supported by the B200 backend so far");
+    if (nve != 27 && nve != 10 && nve != 18) fail("element is not a 27-node hexahedron, 10-node tetrahedron or 18-node wedge (use a second-order mesh)");
+    etype[iel] = nve == 27 ? (uint8_t)HEX : (nve == 10 ? (uint8_t)TET : (uint8_t)WEDGE);
+    const int* vmap = nve == 27 ? vertex_map_hex : (nve == 10 ? vertex_map_tet : vertex_map_wedge);
     for (int i = 0; i < nve; i++) {
       long v;
       in >> v;
       if (v < 1 || v > nvt) fail("node id out of range");
-      L.conn[(size_t)iel * 27 + (nve == 27 ? vertex_map_hex[i] : vertex_map_tet[i])] = (int32_t)(v - 1);
+      L.conn[(size_t)iel * 27 + vmap[i]] = (int32_t)(v - 1);
     }
   }
-  if (etype[0] != HEX) L.etype = etype;
+  bool all_hex = true;
+  for (long iel = 0; iel < nel; iel++) all_hex = all_hex && etype[iel] == HEX;
+  if (!all_hex) L.etype = etype;
   in >> tok;
   if (tok != "ENDOFSECTION") fail("bad element section");
   if (ngroup != 1) fail("more than one element group: the material/group element reordering is not implemented");
@@ -140,7 +154,8 @@ inline MeshLevel ReadGambit(const char* path, double Lref = 1.0) {
       long iel, file_type, iface;
       in >> iel >> file_type >> iface;
       if (iel < 1 || iel > nel || iface < 1 || iface > ElemTopology::nfaces(etype[iel - 1])) fail("boundary face out of range");
-      L.face[(size_t)(iel - 1) * 6 + (etype[iel - 1] == HEX ? face_map_hex[iface - 1] : face_map_tet[iface - 1])] = flag;
+      const int* fmap = etype[iel - 1] == HEX ? face_map_hex : (etype[iel - 1] == TET ? face_map_tet : face_map_wedge);
+      L.face[(size_t)(iel - 1) * 6 + fmap[iface - 1]] = flag;
     }
     in >> tok;
     if (tok != "ENDOFSECTION") fail("bad boundary section");

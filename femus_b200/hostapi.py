@@ -7,7 +7,7 @@ from .capi import lib
 
 vp, ci, i64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64
 LINEAR, SERENDIPITY, BIQUADRATIC = 0, 1, 2
-HEX, TET = 0, 1
+HEX, TET, WEDGE = 0, 1, 2
 FAMILY = {"linear": 0, "quadratic": 1, "biquadratic": 2}
 
 _ready = False
@@ -52,8 +52,12 @@ def _L():
             "b2h_elem_nve": (ci, [ci, ci]),
             "b2h_elem_ngauss": (ci, [ci]),
             "b2h_elem_tables": (None, [ci, ci, vp, vp, vp, vp, vp]),
-            "b2h_tet_prolongator_row": (ci, [ci, ci, ci, vp, vp]),
-            "b2h_tet_child_face": (ci, [ci, ci]),
+            "b2h_elem_prolongator_row": (ci, [ci, ci, ci, ci, vp, vp]),
+            "b2h_elem_child_face": (ci, [ci, ci, ci]),
+            "b2h_level_elem_types": (None, [vp, ci, vp]),
+            "b2h_level_system_dofs27": (None, [vp, ci, ci, vp]),
+            "b2h_sparsity_create": (vp, [vp, ci, ci]),
+            "b2h_hier_create_general": (vp, [ci, ci, ci, ci]),
             "b2h_hex_nve": (ci, [ci]),
             "b2h_hex_tables": (None, [ci, vp, vp, vp, vp, vp]),
             "b2h_hex_prolongator_row": (ci, [ci, ci, ci, ci, vp, vp]),
@@ -87,7 +91,9 @@ class HostLevel:
         self.hier, self.l = hier, l
         self.nel = int(L.b2h_level_nel(h, l))
         self.nnode = int(L.b2h_level_nnode(h, l))
-        self.elem_type = int(L.b2h_level_elem_type(h, l))
+        self.elem_type = int(L.b2h_level_elem_type(h, l))      # -1: several element types (see elem_types)
+        self.elem_types = np.zeros(self.nel, dtype=np.uint8)
+        L.b2h_level_elem_types(h, l, self.elem_types.ctypes.data_as(vp))
         self.conn = _view(L.b2h_level_conn(h, l), (self.nel, 27), np.int32)
         self.face = _view(L.b2h_level_face(h, l), (self.nel, 6), np.int32)
         self.part = _view(L.b2h_level_part(h, l), (self.nel,), np.int32)
@@ -122,8 +128,26 @@ class HostLevel:
         ijk = self.ijk if nodes is None else self.ijk[:, nodes]
         return ijk[0].astype(np.int64) + sx * (ijk[1].astype(np.int64) + sy * ijk[2].astype(np.int64))
 
+    def system_dofs27(self, family):
+        """GetSystemDof of every element in rows of 27, padded with -1 (meshes of several element types)."""
+        out = np.zeros((self.nel, 27), dtype=np.int32)
+        self.hier.L.b2h_level_system_dofs27(self.hier.h, self.l, _fam(family), out.ctypes.data_as(vp))
+        return out
+
+    def sparsity(self, family):
+        """(rowptr, col) of the system matrix, built on the host (GetSparsityPatternSize)."""
+        L = self.hier.L
+        p = L.b2h_sparsity_create(self.hier.h, self.l, _fam(family))
+        n, nnz = int(L.b2h_csr_nrows(p)), int(L.b2h_csr_nnz(p))
+        rp = _view(L.b2h_csr_rowptr(p), (n + 1,), np.int64).copy()
+        ci_ = _view(L.b2h_csr_col(p), (nnz,), np.int32).copy()
+        L.b2h_csr_destroy(p)
+        return rp, ci_
+
     def system_dofs(self, family):
         f = _fam(family)
+        if self.elem_type < 0:
+            raise ValueError("mesh of several element types: use system_dofs27")
         out = np.zeros((self.nel, self.hier.L.b2h_elem_nve(self.elem_type, f)), dtype=np.int32)
         self.hier.L.b2h_level_system_dofs(self.hier.h, self.l, f, out.ctypes.data_as(vp))
         return out
@@ -167,7 +191,8 @@ class HostHierarchy:
 
     @classmethod
     def from_neu(cls, path, nlevels, Lref=1.0):
-        """MultiLevelMesh::ReadCoarseMesh on a Gambit .neu file of 27-node hexahedra + RefineMesh."""
+        """MultiLevelMesh::ReadCoarseMesh on a Gambit .neu file (27-node hexahedra, 10-node tetrahedra, 18-node
+        wedges, also mixed) + RefineMesh."""
         self = cls.__new__(cls)
         self.L = _L()
         self.box = None
@@ -175,6 +200,20 @@ class HostHierarchy:
         self.h = self.L.b2h_hier_create_from_neu(str(path).encode(), nlevels, float(Lref))
         if not self.h:
             raise ValueError("b2h_hier_create_from_neu failed")
+        self.nlevels = nlevels
+        self.levels = [HostLevel(self, l) for l in range(nlevels)]
+        return self
+
+    @classmethod
+    def box_general(cls, nx, ny, nz, nlevels):
+        """Test hook: a generated box of hexahedra refined by the general (any element type) code path."""
+        self = cls.__new__(cls)
+        self.L = _L()
+        self.box = (nx, ny, nz)
+        self.nprocs = 1
+        self.h = self.L.b2h_hier_create_general(nx, ny, nz, nlevels)
+        if not self.h:
+            raise ValueError("b2h_hier_create_general failed")
         self.nlevels = nlevels
         self.levels = [HostLevel(self, l) for l in range(nlevels)]
         return self
@@ -243,16 +282,24 @@ def elem_tables(elem_type, family):
     return tuple(t)
 
 
-def tet_prolongator_row(family, child, node):
+def elem_prolongator_row(elem_type, family, child, node):
     L = _L()
-    idx = np.zeros(15, dtype=np.int32)
-    val = np.zeros(15)
-    n = L.b2h_tet_prolongator_row(_fam(family), child, node, idx.ctypes.data_as(vp), val.ctypes.data_as(vp))
+    idx = np.zeros(27, dtype=np.int32)
+    val = np.zeros(27)
+    n = L.b2h_elem_prolongator_row(elem_type, _fam(family), child, node, idx.ctypes.data_as(vp), val.ctypes.data_as(vp))
     return idx[:n].copy(), val[:n].copy()
 
 
+def elem_child_face(elem_type, child, child_face):
+    return int(_L().b2h_elem_child_face(elem_type, child, child_face))
+
+
+def tet_prolongator_row(family, child, node):
+    return elem_prolongator_row(TET, family, child, node)
+
+
 def tet_child_face(child, child_face):
-    return int(_L().b2h_tet_child_face(child, child_face))
+    return elem_child_face(TET, child, child_face)
 
 
 def hex_tables(family):

@@ -23,10 +23,10 @@ b2h_hier* b2h_hier_create(int nx, int ny, int nz, int nlevels, const double* bou
  * (Mesh::_elementOffset[rank] .. [rank+1]) with locally renumbered nodes, refined locally (children
  * inherit the parent's rank, MeshMetisPartitioning.cpp:143-155).  Inside, nprocs == 1. */
 b2h_hier* b2h_hier_create_local(int nx, int ny, int nz, int nlevels, const double* bounds6, int nprocs, int rank);
-/* MultiLevelMesh::ReadCoarseMesh(name, "seventh", Lref) for a Gambit .neu file of 27-node hexahedra or of
- * 10-node tetrahedra (GambitIO.cpp:92-352; the face and centre nodes of the 15-node tetrahedron are added as
- * Mesh::AddBiquadraticNodesNotInMeshFile does, Mesh.cpp:1207-1333) + RefineMesh; aborts on anything else,
- * like the reference on bad input */
+/* MultiLevelMesh::ReadCoarseMesh(name, "seventh", Lref) for a Gambit .neu file of 27-node hexahedra, 10-node
+ * tetrahedra and 18-node wedges, also mixed (GambitIO.cpp:92-352; the face and centre nodes tetrahedra and
+ * wedges lack are added as Mesh::AddBiquadraticNodesNotInMeshFile does, Mesh.cpp:1207-1333) + RefineMesh;
+ * aborts on anything else, like the reference on bad input */
 b2h_hier* b2h_hier_create_from_neu(const char* path, int nlevels, double Lref);
 void b2h_hier_destroy(b2h_hier* h);
 /* integer lattice coordinates [3][nnode] of the nodes (rank-independent node names) */
@@ -72,19 +72,28 @@ void b2h_galerkin_element(int family, double* ploc, uint8_t* fine_entity);
 int b2h_galerkin_maps(const b2h_hier* h, int lcoarse, int family, int64_t e0, int64_t e1, int32_t* fine_dofs,
                       uint8_t* valence);
 
-/* Element type of a level (GeomElTypeEnum: 0 HEX, 1 TET; one type per mesh so far), dofs per element of a
- * family (Elem.hpp NVE: hex 8/20/27, tet 4/10/15), Gauss points of the "seventh" rule (64 / 31) and
- * elem_type_3D(type, family, "seventh") tables [ngauss][nve], weights[ngauss] (ElemType.cpp:637-740).
- * Tetrahedra: element prolongator row of (child, child-local node) (ElemType.cpp:439-532 with
- * Tetrahedron.cpp:86-95) and the parent face a child face lies on, -1 if interior
- * (coarse2FineFaceMapping, MeshRefinement.hpp:88-93).  For tetrahedral levels conn rows hold 15 nodes
- * (padded with -1 to 27), face rows 4 flags (padded to 6) and child_el the 8 children. */
+/* Element types (GeomElTypeEnum: 0 HEX, 1 TET, 2 WEDGE).  b2h_level_elem_type: the type of a level, -1 if the
+ * mesh mixes types (then b2h_level_elem_types gives the type of every element).  Per type: dofs per element
+ * of a family (Elem.hpp NVE: hex 8/20/27, tet 4/10/15, wedge 6/15/21), Gauss points of the "seventh" rule
+ * (64 / 31 / 52), elem_type_3D(type, family, "seventh") tables [ngauss][nve], weights[ngauss]
+ * (ElemType.cpp:637-740), element prolongator row of (child, child-local node) (ElemType.cpp:439-532 with the
+ * bases' fine2CoarseVertexMapping) and the parent face a child face lies on, -1 if interior
+ * (coarse2FineFaceMapping, MeshRefinement.hpp:79-100).  conn rows hold 27 / 15 / 21 nodes (padded with -1
+ * to 27), face rows 6 / 4 / 5 flags (padded with -1 to 6), child_el the 8 children of every element. */
 int b2h_level_elem_type(const b2h_hier* h, int l);
+void b2h_level_elem_types(const b2h_hier* h, int l, uint8_t* out);
 int b2h_elem_nve(int type, int family);
 int b2h_elem_ngauss(int type);
 void b2h_elem_tables(int type, int family, double* phi, double* dxi, double* deta, double* dzeta, double* w);
-int b2h_tet_prolongator_row(int family, int child, int node, int* idx, double* val);
-int b2h_tet_child_face(int child, int child_face);
+int b2h_elem_prolongator_row(int type, int family, int child, int node, int* idx, double* val);
+int b2h_elem_child_face(int type, int child, int child_face);
+/* GetSystemDof of every element in rows of 27 padded with -1 (meshes of several element types), and the
+ * sparsity pattern of the single-variable system built on the host (LinearEquation::GetSparsityPatternSize,
+ * LinearEquation.cpp:407-548): a b2h_csr with zero values */
+void b2h_level_system_dofs27(const b2h_hier* h, int l, int family, int32_t* out);
+b2h_csr* b2h_sparsity_create(const b2h_hier* h, int l, int family);
+/* test hook: a generated hexahedral box hierarchy refined by the general (any element type) code path */
+b2h_hier* b2h_hier_create_general(int nx, int ny, int nz, int nlevels);
 
 /* elem_type_3D("hex", family, "seventh"): tables [64][nve] and weights[64] (ElemType.cpp:637-740),
  * element prolongator row of the fine point (a,b,c) of the 5x5x5 lattice (ElemType.cpp:439-532) */

@@ -129,3 +129,48 @@ for order in ("linear", "quadratic", "biquadratic"):
     outt[f"{order}_prol"], outt[f"{order}_prol_kvert"] = P, kv
 np.savez_compressed(os.path.join(ROOT, "tests", "golden", "fe_tet_ref.npz"), **outt)
 print("wrote tests/golden/fe_tet_ref.npz")
+
+# ---- wedges (6 / 15 / 21 dofs, 52-point rule): tests/golden/fe_wedge_ref.npz
+from oracle import fe_wedge  # noqa: E402
+rng = np.random.default_rng(20261019)
+outw = {}
+for order in ("linear", "quadratic", "biquadratic"):
+    R = ref.RefElem("wedge", order)
+    w, xi = R.gauss()
+    outw[f"{order}_gauss_w"], outw[f"{order}_gauss_xi"] = w, xi
+    phi, dxi, deta, dzeta = R.tables()
+    outw[f"{order}_phi"], outw[f"{order}_dxi"], outw[f"{order}_deta"], outw[f"{order}_dzeta"] = phi, dxi, deta, dzeta
+    n = R.n
+    # the reference wedge scaled to a 1/64 box cell, and three distorted / rotated ones
+    Xs = [fe_wedge.XC[:n].T / 64.0]
+    for _ in range(3):
+        M = np.eye(3) + 0.2 * rng.standard_normal((3, 3))
+        if np.linalg.det(M) < 0:
+            M[:, 0] = -M[:, 0]
+        Xs.append(M @ fe_wedge.XC[:n].T * 0.2 + 0.3 + rng.standard_normal((3, n)) * 0.001)
+    Xs = np.array(Xs)
+    Us = rng.standard_normal((Xs.shape[0], n))
+    Fs, Bs, Ws, Gs = [], [], [], []
+    for X, U in zip(Xs, Us):
+        F, B = R.poisson_element(X, U, 1.0)
+        Fs.append(F)
+        Bs.append(B)
+        wj, gj = [], []
+        for ig in range(R.ng):
+            wt, _, g = R.jacobian(X, ig)
+            wj.append(wt)
+            gj.append(g)
+        Ws.append(wj)
+        Gs.append(gj)
+    outw[f"{order}_X"], outw[f"{order}_U"] = Xs, Us
+    outw[f"{order}_F"], outw[f"{order}_B"] = np.array(Fs), np.array(Bs)
+    outw[f"{order}_weight"], outw[f"{order}_gradphi"] = np.array(Ws), np.array(Gs)
+    rows = R.prolongator()                       # fine dof i -> (child, child-local node), coarse columns
+    P = np.zeros((R.nf, n))
+    kv = np.zeros((R.nf, 2), dtype=np.int64)
+    for i, (ch, nd, idx, val) in enumerate(rows):
+        P[i, idx] = val
+        kv[i] = (ch, nd)
+    outw[f"{order}_prol"], outw[f"{order}_prol_kvert"] = P, kv
+np.savez_compressed(os.path.join(ROOT, "tests", "golden", "fe_wedge_ref.npz"), **outw)
+print("wrote tests/golden/fe_wedge_ref.npz")

@@ -1,6 +1,7 @@
-"""Generate tests/golden/cube_hex27_2x2x2.neu and tests/golden/cube_tet10.neu from the reference's shipped
-coarse meshes applications/001_Poisson/input/cube_Hex.neu (8 hexahedra of 27 nodes) and cube_Tet.neu (105
-tetrahedra of 10 nodes): the same nodes, elements, group and boundary sets, re-serialised in Gambit neutral
+"""Generate tests/golden/cube_{hex27_2x2x2,tet10,wedge18,mixed}.neu from the reference's shipped
+coarse meshes applications/001_Poisson/input/cube_Hex.neu (8 hexahedra of 27 nodes), cube_Tet.neu (105
+tetrahedra of 10 nodes), cube_Wedge.neu (16 wedges of 18 nodes) and cube_all_shapes_Six_boundary_groups.neu
+(4 hexahedra, 10 tetrahedra, 6 wedges): the same nodes, elements, group and boundary sets, re-serialised in Gambit neutral
 format by this script (free-format numbers, own header), because /root/reference does not exist on the GPU
 box.  Run in the build container:
     python tests/golden/make_neu_fixture.py"""
@@ -10,7 +11,9 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 INPUT = "/root/reference/applications/001_Poisson/input/"
 JOBS = [(INPUT + "cube_Hex.neu", os.path.join(ROOT, "tests", "golden", "cube_hex27_2x2x2.neu"), "cube_hex27_2x2x2"),
-        (INPUT + "cube_Tet.neu", os.path.join(ROOT, "tests", "golden", "cube_tet10.neu"), "cube_tet10")]
+        (INPUT + "cube_Tet.neu", os.path.join(ROOT, "tests", "golden", "cube_tet10.neu"), "cube_tet10"),
+        (INPUT + "cube_Wedge.neu", os.path.join(ROOT, "tests", "golden", "cube_wedge18.neu"), "cube_wedge18"),
+        (INPUT + "cube_all_shapes_Six_boundary_groups.neu", os.path.join(ROOT, "tests", "golden", "cube_mixed.neu"), "cube_mixed")]
 
 
 def parse(path):

@@ -97,27 +97,94 @@ NEU_TET = os.path.join(os.path.dirname(__file__), "golden", "cube_tet10.neu")
 TET_ORDERS = ("linear", "quadratic", "biquadratic")
 
 
-def test_tet_element_tables_and_prolongator_rows():
-    """Host TetElement.hpp against the committed values of the compiled reference (tests/golden/fe_tet_ref.npz):
-    31-point rule bit-exact, shape tables to a few ulp, element prolongator rows with the reference's non-zero
-    structure; child faces against coarse2FineFaceMapping (MeshRefinement.hpp:88-93)."""
-    from oracle import mesh_tet as mt
-    G = np.load(os.path.join(os.path.dirname(__file__), "golden", "fe_tet_ref.npz"))
+@pytest.mark.parametrize("geom", ["tet", "wedge"])
+def test_simplex_element_tables_and_prolongator_rows(geom):
+    """Host TetElement.hpp / WedgeElement.hpp against the committed values of the compiled reference
+    (tests/golden/fe_{tet,wedge}_ref.npz): Gauss rule bit-exact, shape tables to a few ulp, element prolongator
+    rows with the reference's non-zero structure."""
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden", f"fe_{geom}_ref.npz"))
+    et = {"tet": hostapi.TET, "wedge": hostapi.WEDGE}[geom]
     for order in TET_ORDERS:
-        phi, dxi, deta, dzeta, w = hostapi.elem_tables(hostapi.TET, order)
+        phi, dxi, deta, dzeta, w = hostapi.elem_tables(et, order)
         assert np.array_equal(w, G[f"{order}_gauss_w"])
         for a, k in ((phi, "phi"), (dxi, "dxi"), (deta, "deta"), (dzeta, "dzeta")):
-            assert a.shape == G[f"{order}_{k}"].shape and np.abs(a - G[f"{order}_{k}"]).max() <= 2e-15, (order, k)
+            assert a.shape == G[f"{order}_{k}"].shape and np.abs(a - G[f"{order}_{k}"]).max() <= 3e-15, (order, k)
         Pg, kv = G[f"{order}_prol"], G[f"{order}_prol_kvert"]
         for i in range(Pg.shape[0]):
-            idx, val = hostapi.tet_prolongator_row(order, int(kv[i, 0]), int(kv[i, 1]))
+            idx, val = hostapi.elem_prolongator_row(et, order, int(kv[i, 0]), int(kv[i, 1]))
             assert np.array_equal(idx, np.nonzero(Pg[i])[0])
             assert np.abs(val - Pg[i, idx]).max() <= 4e-16
-    got = {(f, j, cf) for j in range(8) for cf in range(4) for f in [hostapi.tet_child_face(j, cf)] if f >= 0}
-    assert got == {(f, j, cf) for f in range(4) for (j, cf) in mt.COARSE_TO_FINE_FACE[f]}
-    # hexahedra through the same entry point
+
+
+def test_child_faces_and_hex_through_the_general_entry_points():
+    """The parent face of every child face, derived geometrically by the host, against coarse2FineFaceMapping
+    (MeshRefinement.hpp:79-100) for the three element types; hexahedral tables / prolongator rows through the
+    per-type entry points equal the specialised ones."""
+    from oracle import mesh_mixed as mm
+    for et in (hostapi.HEX, hostapi.TET, hostapi.WEDGE):
+        nf = mm.NFACES[et]
+        got = {(f, j, cf) for j in range(8) for cf in range(nf) for f in [hostapi.elem_child_face(et, j, cf)] if f >= 0}
+        assert got == {(f, j, cf) for f in range(nf) for (j, cf) in mm.COARSE_TO_FINE_FACE[et][f]}
     for a, b in zip(hostapi.elem_tables(hostapi.HEX, "biquadratic"), hostapi.hex_tables("biquadratic")):
         assert np.array_equal(a, b)
+    for order in ("linear", "quadratic", "biquadratic"):
+        P = mm._local_prolongator(mm.HEX, order)
+        for j in range(8):
+            for a in range(P.shape[1]):
+                idx, val = hostapi.elem_prolongator_row(hostapi.HEX, order, j, a)
+                assert np.array_equal(idx, np.nonzero(P[j, a])[0]) and np.array_equal(val, P[j, a, idx])
+
+
+@pytest.mark.parametrize("name", ["cube_wedge18", "cube_mixed", "cube_tet10", "cube_hex27_2x2x2"])
+def test_unstructured_hierarchies_match_mixed_oracle(name):
+    """The reference's shipped 3-D coarse meshes (re-serialised): 16 wedges; 4 hexahedra + 10 tetrahedra + 6 wedges
+    sharing triangular and quadrilateral faces; 105 tetrahedra; 8 hexahedra.  Reader (+ nodes the file lacks),
+    numbering, 1 -> 8 refinement, boundary flags, dof maps, Dirichlet flags, host sparsity: integers bit-exact
+    against the independent oracle (oracle/mesh_mixed.py) on 3 levels; prolongators identical in structure."""
+    from oracle import mesh_mixed as mm
+    path = os.path.join(os.path.dirname(__file__), "golden", name + ".neu")
+    H = hostapi.HostHierarchy.from_neu(path, 3)
+    lv = mm.build_hierarchy(path, 3)
+    for l, (h, L) in enumerate(zip(H.levels, lv)):
+        assert h.nnode == L.nnode and np.array_equal(h.elem_types, L.etype)
+        assert np.array_equal(h.conn, L.conn) and np.array_equal(h.face, L.face) and np.array_equal(h.dof_offset, L.dof_offset)
+        assert np.abs(h.xyz - L.xyz).max() <= (0.0 if l == 0 else 1e-15)
+        for order in TET_ORDERS:
+            assert np.array_equal(h.system_dofs27(order), mm.system_dofs27(L, order))
+            assert np.array_equal(h.bdc(order), mm.bdc_flags(L, order))
+            assert np.array_equal(h.bdc(order, (2, 5)), mm.bdc_flags(L, order, (2, 5)))
+            rp, ci = h.sparsity(order)
+            rpo, cio = mm.sparsity(L, order)
+            assert np.array_equal(rp, rpo) and np.array_equal(ci, cio)
+        if l + 1 < len(lv):
+            assert np.array_equal(h.child_el, lv[l + 1].child_el)
+        v, e = h.dof_offset[0, -1], h.dof_offset[1, -1] - h.dof_offset[0, -1]
+        nfaces = {0: 6, 1: 4, 2: 5}
+        ncentre = h.nel
+        f = h.nnode - h.dof_offset[1, -1] - ncentre
+        assert v - e + f - h.nel == 1                                   # Euler characteristic of a ball
+    for l in (1, 2):
+        for order in TET_ORDERS:
+            rp, ci, v, shp = H.prolongator(l, order)
+            P = mm.prolongator(lv[l - 1], lv[l], order)
+            assert shp == P.shape and np.array_equal(rp, P.indptr) and np.array_equal(ci, P.indices)
+            assert np.abs(v - P.data).max() <= 1e-15
+            assert np.abs(P @ np.ones(P.shape[1]) - 1.0).max() < 1e-14
+
+
+def test_general_refinement_equals_hexahedral_refinement():
+    """A generated box refined by the general (any element type) code and by the specialised hexahedral code:
+    identical connectivity, numbering, flags, coordinates and prolongators."""
+    A = hostapi.HostHierarchy.box_general(2, 3, 2, 3)
+    B = hostapi.HostHierarchy(2, 3, 2, 3)
+    for l in range(3):
+        a, b = A.levels[l], B.levels[l]
+        assert np.array_equal(a.conn, b.conn) and np.array_equal(a.face, b.face) and np.array_equal(a.dof_offset, b.dof_offset)
+        assert np.array_equal(a.xyz, b.xyz)
+        if l:
+            for order in ("linear", "quadratic", "biquadratic"):
+                pa, pb = A.prolongator(l, order), B.prolongator(l, order)
+                assert all(np.array_equal(x, y) for x, y in zip(pa[:3], pb[:3]))
 
 
 def test_tet_mesh_hierarchy_matches_oracle():

@@ -129,68 +129,83 @@ def test_neumann_rhs_integrates_the_flux():
         assert abs(r.sum() - (0.2 * 1.0 - 1.5 * 1.0)) < 1e-13
 
 
-# ------------------------------------------------------------------------------ tetrahedra
-from oracle import fe_tet  # noqa: E402
+# ------------------------------------------------------------------------------ tetrahedra and wedges
+from oracle import fe_tet, fe_wedge  # noqa: E402
 
-GOLD_TET = np.load(os.path.join(os.path.dirname(__file__), "golden", "fe_tet_ref.npz"))
+GOLD_G = {"tet": np.load(os.path.join(os.path.dirname(__file__), "golden", "fe_tet_ref.npz")),
+          "wedge": np.load(os.path.join(os.path.dirname(__file__), "golden", "fe_wedge_ref.npz"))}
+FE_G = {"tet": fe_tet, "wedge": fe_wedge}
+GEOMS = ("tet", "wedge")
 TET_ORDERS = ("linear", "quadratic", "biquadratic")
-TET_ULP = 2e-15      # fe_tet.py restates the mathematics, not the reference's operation order
+TET_ULP = 3e-15      # fe_tet.py / fe_wedge.py restate the mathematics, not the reference's operation order
 
 
+@pytest.mark.parametrize("geom", GEOMS)
 @pytest.mark.parametrize("order", TET_ORDERS)
-def test_tet_gauss_and_tables(order):
-    """31-point rule bit-exact (data), shape tables to a few ulp; partition of unity; Kronecker property."""
-    w, xi = fe_tet.gauss_tet("seventh")
-    assert np.array_equal(w, GOLD_TET[f"{order}_gauss_w"]) and np.array_equal(xi, GOLD_TET[f"{order}_gauss_xi"])
-    phi, dxi, deta, dzeta, _ = fe_tet.tables(order)
+def test_simplex_gauss_and_tables(geom, order):
+    """31-point (tet) / 52-point (wedge) rule bit-exact (data), shape tables to a few ulp; partition of unity;
+    Kronecker property at the element's own nodes."""
+    fe, G = FE_G[geom], GOLD_G[geom]
+    w, xi = (fe.gauss_tet if geom == "tet" else fe.gauss_wedge)("seventh")
+    assert np.array_equal(w, G[f"{order}_gauss_w"]) and np.array_equal(xi, G[f"{order}_gauss_xi"])
+    phi, dxi, deta, dzeta, _ = fe.tables(order)
     for a, k in ((phi, "phi"), (dxi, "dxi"), (deta, "deta"), (dzeta, "dzeta")):
-        assert np.abs(a - GOLD_TET[f"{order}_{k}"]).max() <= TET_ULP, k
+        assert np.abs(a - G[f"{order}_{k}"]).max() <= TET_ULP, k
     assert np.abs(phi.sum(axis=1) - 1.0).max() < 1e-14
-    n = fe_tet.NDOFS[order]
-    assert np.abs(fe_tet.shape(order, fe_tet.XC[:n])[0] - np.eye(n)).max() < 1e-14
+    n = fe.NDOFS[order]
+    assert np.abs(fe.shape(order, fe.XC[:n])[0] - np.eye(n)).max() < 1e-14
 
 
+@pytest.mark.parametrize("geom", GEOMS)
 @pytest.mark.parametrize("order", TET_ORDERS)
-def test_tet_jacobian_and_poisson_element(order):
-    X, U = GOLD_TET[f"{order}_X"], GOLD_TET[f"{order}_U"]
-    tabs = fe_tet.tables(order)
-    for ig in range(31):
+def test_simplex_jacobian_and_poisson_element(geom, order):
+    fe, G = FE_G[geom], GOLD_G[geom]
+    X, U = G[f"{order}_X"], G[f"{order}_U"]
+    tabs = fe.tables(order)
+    for ig in range(tabs[4].shape[0]):
         w, _, g = fe_hex.jacobian(order, X, ig, tabs)
-        assert np.abs(w - GOLD_TET[f"{order}_weight"][:, ig]).max() <= 1e-14 * np.abs(GOLD_TET[f"{order}_weight"]).max()
-        gr = GOLD_TET[f"{order}_gradphi"][:, ig]
+        assert np.abs(w - G[f"{order}_weight"][:, ig]).max() <= 1e-14 * np.abs(G[f"{order}_weight"]).max()
+        gr = G[f"{order}_gradphi"][:, ig]
         assert np.abs(g - gr).max() <= 1e-13 * np.abs(gr).max()
     F, B = fe_hex.poisson_elements(order, X, U, 1.0, tabs)
-    Br, Fr = GOLD_TET[f"{order}_B"], GOLD_TET[f"{order}_F"]
+    Br, Fr = G[f"{order}_B"], G[f"{order}_F"]
     for k in range(X.shape[0]):
         assert np.abs(B[k] - Br[k]).max() <= 1e-13 * np.abs(Br[k]).max()
         assert np.abs(F[k] - Fr[k]).max() <= 1e-13 * (np.abs(Br[k]) @ np.abs(U[k])).max()
 
 
+@pytest.mark.parametrize("geom", GEOMS)
 @pytest.mark.parametrize("order", TET_ORDERS)
-def test_tet_local_prolongator(order):
+def test_simplex_local_prolongator(geom, order):
     """Element prolongator of the 8 children: same non-zero structure as the reference's, values to an ulp;
-    fine-dof counts 10 / 35 / 67 and nnz 16 / 116 / 447 as measured from the compiled reference."""
-    P = fe_tet.local_prolongator(order)
-    Pg, kv = GOLD_TET[f"{order}_prol"], GOLD_TET[f"{order}_prol_kvert"]
+    fine-dof counts and nnz as measured from the compiled reference (tet 10/35/67 and 16/116/447,
+    wedge 18/57/95 and 36/264/603)."""
+    fe, G = FE_G[geom], GOLD_G[geom]
+    P = fe.local_prolongator(order)
+    Pg, kv = G[f"{order}_prol"], G[f"{order}_prol_kvert"]
     for i in range(Pg.shape[0]):
         mine = P[kv[i, 0], kv[i, 1]]
         assert np.array_equal(mine != 0, Pg[i] != 0)
         assert np.abs(mine - Pg[i]).max() <= 4e-16
-    assert (Pg.shape[0], int((Pg != 0).sum())) == {"linear": (10, 16), "quadratic": (35, 116), "biquadratic": (67, 447)}[order]
+    expect = {"tet": {"linear": (10, 16), "quadratic": (35, 116), "biquadratic": (67, 447)},
+              "wedge": {"linear": (18, 36), "quadratic": (57, 264), "biquadratic": (95, 603)}}
+    assert (Pg.shape[0], int((Pg != 0).sum())) == expect[geom][order]
     # every (child, node) pair maps to one of the nf distinct fine points
-    pts = fe_tet.child_points(order).reshape(-1, 3)
+    pts = fe.child_points(order).reshape(-1, 3)
     assert len({tuple(np.round(p * 24).astype(int)) for p in pts}) == Pg.shape[0]
 
 
 @pytest.mark.skipif(not ref.available(), reason="compiled reference (oracle/_ref) not present")
+@pytest.mark.parametrize("geom", GEOMS)
 @pytest.mark.parametrize("order", TET_ORDERS)
-def test_tet_against_compiled_reference(order):
-    R = ref.RefTet(order)
+def test_simplex_against_compiled_reference(geom, order):
+    fe = FE_G[geom]
+    R = ref.RefElem(geom, order)
     rng = np.random.default_rng(5)
     n = R.n
-    X = (np.eye(3) + 0.2 * rng.standard_normal((3, 3))) @ fe_tet.XC[:n].T + 0.01 * rng.standard_normal((3, n))
+    X = (np.eye(3) + 0.2 * rng.standard_normal((3, 3))) @ fe.XC[:n].T + 0.01 * rng.standard_normal((3, n))
     U = rng.standard_normal(n)
     Fr, Br = R.poisson_element(X, U, 2.5)
-    F, B = fe_hex.poisson_elements(order, X[None], U[None], 2.5, fe_tet.tables(order))
+    F, B = fe_hex.poisson_elements(order, X[None], U[None], 2.5, fe.tables(order))
     assert np.abs(B[0] - Br).max() <= 1e-13 * np.abs(Br).max()
     assert np.abs(F[0] - Fr).max() <= 1e-13 * (np.abs(Br) @ np.abs(U) + 2.5).max()
