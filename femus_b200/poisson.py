@@ -48,17 +48,24 @@ class PoissonMG:
         self.nel = top.nel
         # element type of the mesh (hexahedra from the box generator or a .neu file, tetrahedra from a .neu
         # file): the reference dispatches on it through _finiteElement[ielGeom][solType] (main.cpp:438)
-        self.elem_type = top.elem_type
+        self.elem_type = top.elem_type             # -1: the mesh mixes hexahedra, tetrahedra and wedges
+        self.mixed = self.elem_type < 0
         # fast Galerkin paths: hexahedra with 8 or 27 dofs (the 20-node family uses the general triple product)
         self.hex = self.elem_type == hostapi.HEX and order != "quadratic"
-        self.nve = hostapi.elem_nve(self.elem_type, order)
+        self.nve = None if self.mixed else hostapi.elem_nve(self.elem_type, order)
         if not self.hex:       # the element-gather / fused Galerkin products are kernels for refined hexahedra
             self.fused = False
             if self.neumann or dist is not None:
                 raise NotImplementedError("Neumann faces and the sharded run are implemented for hexahedra with 8 or 27 dofs")
         # --- system.init(): per-level matrices with the exact element-coupling pattern
-        self.dofs = [L.system_dofs(order) for L in lv]
-        self.KK = [capi.Csr.from_elements(ctx, self.ndofs[l], self.dofs[l]) for l in range(nlevels)]
+        # (a mesh of several element types has ragged element rows: pattern built on the host, as the
+        # reference's GetSparsityPatternSize does, LinearEquation.cpp:407-548)
+        if self.mixed:
+            self.dofs = [L.system_dofs27(order) for L in lv]
+            self.KK = [ctx.csr(self.ndofs[l], self.ndofs[l], *lv[l].sparsity(order)) for l in range(nlevels)]
+        else:
+            self.dofs = [L.system_dofs(order) for L in lv]
+            self.KK = [capi.Csr.from_elements(ctx, self.ndofs[l], self.dofs[l]) for l in range(nlevels)]
         self.bdc = [L.bdc(order, dirichlet_faces) for L in lv]
         self.bdc_idx = [np.nonzero(b < 1.5)[0].astype(np.int32) for b in self.bdc]
         # --- prolongators, Dirichlet rows (fine) and columns (coarse) zeroed
@@ -79,9 +86,15 @@ class PoissonMG:
             self.gal[l] = capi.Galerkin(self.KK[l], self.KK[l - 1], fd, self.dofs[l - 1], ploc, fent, val,
                                         self.bdc[l] < 1.5, self.bdc[l - 1] < 1.5)
         # --- finest-level mesh + assembly plan
-        self.mesh = capi.Mesh(ctx, top.xyz, top.conn)
-        self.tables = hostapi.elem_tables(self.elem_type, order)
-        self.asm = capi.Assembler(self.mesh, self.KK[-1], self.dofs[-1], self.tables)
+        # one plan per element type present (the tables are the element type: _finiteElement[ielGeom][solType])
+        self.plans = []
+        for t in ([self.elem_type] if not self.mixed else sorted(set(top.elem_types.tolist()))):
+            sel = slice(None) if not self.mixed else np.nonzero(top.elem_types == t)[0]
+            mesh_t = capi.Mesh(ctx, top.xyz, np.ascontiguousarray(top.conn[sel]))
+            dof_t = self.dofs[-1] if not self.mixed else np.ascontiguousarray(self.dofs[-1][sel][:, :hostapi.elem_nve(t, order)])
+            tables_t = hostapi.elem_tables(t, order)
+            self.plans.append((mesh_t, capi.Assembler(mesh_t, self.KK[-1], dof_t, tables_t), tables_t))
+        self.mesh, self.asm, self.tables = self.plans[0]
         if self.neumann:    # Neumann faces of the finest level: (element, local face, flux)
             fe, fl, fb = top.boundary_faces()
             sel = np.isin(fb, list(self.neumann))
@@ -126,7 +139,8 @@ class PoissonMG:
         if self.fused:
             self.asm.poisson_galerkin(self.gal[-1], self.SOL, self.RES, 1.0, self.fsrc)
         else:
-            self.asm.poisson(self.SOL, self.RES, 1.0, self.fsrc)
+            for _, asm, _ in self.plans:       # one launch per element type, accumulating into KK and RES
+                asm.poisson(self.SOL, self.RES, 1.0, self.fsrc)
         if self.neumann and self.nm_faces[0].size:
             self.asm.neumann(*self.nm_faces, self.nm_tables, self.nm_face_nodes, self.RES)
         if self.halo[-1] is not None:          # close(): contributions of the other ranks' elements

@@ -256,3 +256,92 @@ def test_hex20_assembly_and_vcycle_trace(ctx, shape, nl):
         assert abs(a - b) <= RTOL * trace_ref[0], (trace, trace_ref)
     assert np.abs(pb.EPS.get() - eps_ref).max() <= 1e-11 * np.abs(eps_ref).max()
     del pb
+
+
+# ------------------------------------------------------------------------------ wedges and mixed meshes
+GOLDEN = os.path.dirname(NEU_TET)
+
+
+def test_wedge_golden_elements(ctx):
+    """Single wedges of the committed fixture (element matrices / residuals of the compiled reference,
+    6 / 15 / 21 dofs, 52 Gauss points) through the table-driven kernel."""
+    from oracle import fe_wedge
+    G = np.load(os.path.join(GOLDEN, "fe_wedge_ref.npz"))
+    for order in ("linear", "quadratic", "biquadratic"):
+        nve = fe_wedge.NDOFS[order]
+        tabs = fe_wedge.tables(order)
+        for k in range(G[f"{order}_X"].shape[0]):
+            xyz = np.zeros((3, 27))
+            xyz[:, :nve] = G[f"{order}_X"][k]
+            conn = np.arange(27, dtype=np.int32)[None, :]
+            d = np.arange(nve, dtype=np.int32)[None, :]
+            A = capi.Csr.from_elements(ctx, nve, d)
+            asm = capi.Assembler(capi.Mesh(ctx, xyz, conn), A, d, tabs)
+            Uk = G[f"{order}_U"][k]
+            U, R = ctx.vector(Uk), ctx.vector(nve)
+            asm.poisson(U, R, 1.0, 1.0)
+            B = A.to_scipy().toarray()
+            Bref, Fref = G[f"{order}_B"][k], G[f"{order}_F"][k]
+            assert np.abs(B - Bref).max() <= RTOL * np.abs(Bref).max()
+            assert np.abs(R.get() - Fref).max() <= RTOL * (np.abs(Bref) @ np.abs(Uk)).max()
+
+
+@pytest.mark.parametrize("name", ["cube_wedge18", "cube_mixed"])
+@pytest.mark.parametrize("order", ["linear", "quadratic", "biquadratic"])
+def test_wedge_and_mixed_mesh_single_level(ctx, name, order):
+    """The reference's cube_Wedge.neu (16 wedges) and cube_all_shapes_Six_boundary_groups.neu (4 hexahedra, 10
+    tetrahedra, 6 wedges), re-serialised: one assembly plan per element type accumulating into one matrix;
+    pattern bit-exact, matrix and residual to 1e-12 against the oracle, single-level solve against a sparse
+    direct solve.  The current solution is non-zero, so the residual carries B u of every element type."""
+    import scipy.sparse.linalg as spla
+    from femus_b200 import hostapi
+    from femus_b200.poisson import PoissonMG
+    from oracle import mesh_mixed as mm, mg
+    path = os.path.join(GOLDEN, name + ".neu")
+    H = hostapi.HostHierarchy.from_neu(path, 1)
+    pb = PoissonMG(ctx, 0, 0, 0, 1, order, hier=H, coarse_rtol=1e-15)
+    assert len(pb.plans) == (3 if name == "cube_mixed" else 1)
+    L = mm.read_neu(path)
+    u = np.random.default_rng(4).standard_normal(pb.n)
+    pb.SOL.put(u)
+    pb.assemble()
+    Aref, rhs = mm.assemble(L, order, u)
+    A = pb.KK[-1].to_scipy()
+    assert np.array_equal(A.indptr, Aref.indptr) and np.array_equal(A.indices, Aref.indices)
+    assert np.abs(A.data - Aref.data).max() <= RTOL * np.abs(Aref.data).max()
+    assert np.abs(pb.RES.get() - rhs).max() <= RTOL * (np.abs(Aref) @ np.abs(u) + np.abs(rhs)).max()
+    pb.galerkin(); pb.mg_set_levels(); pb.mg_solve()
+    idx = np.nonzero(mm.bdc_flags(L, order) < 1.5)[0]
+    Ap = mg.penalty_fast(Aref, idx)
+    b = rhs.copy(); b[idx] = 0.0
+    x = spla.spsolve(Ap.tocsc(), b)
+    assert np.abs(pb.EPS.get() - x).max() <= 1e-10 * np.abs(x).max()
+    del pb
+
+
+@pytest.mark.parametrize("name,order,nl", [("cube_wedge18", "linear", 3), ("cube_wedge18", "biquadratic", 3), ("cube_mixed", "quadratic", 3),
+                                           ("cube_mixed", "biquadratic", 2)])
+def test_wedge_and_mixed_mesh_vcycle_trace(ctx, name, order, nl):
+    """Multigrid on refined wedges / mixed meshes: per-type assembly on the finest level, Galerkin chain by the
+    general triple product, penalised level operators and six V-cycles against the oracle (Richardson 0.3)."""
+    from femus_b200 import hostapi
+    from femus_b200.poisson import PoissonMG
+    from oracle import mesh_mixed as mm, mg
+    path = os.path.join(GOLDEN, name + ".neu")
+    H = hostapi.HostHierarchy.from_neu(path, nl)
+    pb = PoissonMG(ctx, 0, 0, 0, nl, order, hier=H, coarse_rtol=1e-15, omega=0.3)
+    pb.assemble(); pb.galerkin(); pb.mg_set_levels()
+    O = mg.Hierarchy(mm.build_hierarchy(path, nl), order, mesh=mm)
+    for l in range(nl):
+        got, ref = pb.KK[l].to_scipy(), O.A[l]
+        assert np.array_equal(got.indptr, ref.indptr) and np.array_equal(got.indices, ref.indices)
+        assert np.abs(got.data - ref.data).max() <= RTOL * np.abs(ref.data).max()
+    trace_ref, eps_ref = O.mg_solve_trace(6, omega=0.3)
+    trace = []
+    for _ in range(6):
+        pb.mg_solve()
+        trace.append(pb.residual_norm())
+    for a, b in zip(trace, trace_ref):
+        assert abs(a - b) <= RTOL * trace_ref[0], (trace, trace_ref)
+    assert np.abs(pb.EPS.get() - eps_ref).max() <= 1e-11 * np.abs(eps_ref).max()
+    del pb
