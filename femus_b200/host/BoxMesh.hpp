@@ -88,6 +88,7 @@ class MeshLevel {
   std::vector<int32_t> conn;            // [nel][27] node ids in FEMuS numbering (rows of shorter elements padded with -1)
   std::vector<int32_t> face;            // [nel][6] faceElementIndex: -1 interior/unset, < -1 boundary
   std::vector<uint8_t> etype;           // [nel] GeomType per element; empty = all hexahedra
+  std::vector<int16_t> material, group; // [nel] element material / group of a mesh file; empty = one group
   std::vector<int32_t> part;            // [nel] owning rank
   std::vector<int64_t> elem_offset;     // [nprocs+1]
   std::vector<int64_t> dof_offset[3];   // [family][nprocs+1]
@@ -160,11 +161,17 @@ class MeshLevel {
   std::vector<int32_t> FillISvectorDofMapAllFEFamilies(const std::vector<int32_t>& partition, int nprocs_,
                                                        bool drop_unreferenced = false) {
     nprocs = nprocs_;
-    // --- elements by rank (Mesh.cpp:589-616); material/group are uniform on box meshes, so the
-    // second sort (Mesh.cpp:621-702) leaves the order unchanged
+    // --- elements by rank (Mesh.cpp:589-616), then inside each rank by (material, group, index) -- the
+    // bubble sort of Mesh.cpp:621-702; one stable sort on the three keys gives the same order
     std::vector<int64_t> order(nel);
     std::iota(order.begin(), order.end(), (int64_t)0);
-    std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) { return partition[a] < partition[b]; });
+    const bool groups = !material.empty();
+    std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) {
+      if (partition[a] != partition[b]) return partition[a] < partition[b];
+      if (!groups) return false;
+      if (material[a] != material[b]) return material[a] < material[b];
+      return group[a] < group[b];
+    });
     bool identity = true;
     for (int64_t e = 0; e < nel && identity; e++) identity = (order[e] == e);
     part.resize(nel);
@@ -173,15 +180,19 @@ class MeshLevel {
     } else {
       std::vector<int32_t> c2(conn.size()), f2(face.size());
       std::vector<uint8_t> t2(etype.size());
+      std::vector<int16_t> m2(material.size()), g2(group.size());
       for (int64_t e = 0; e < nel; e++) {
         std::copy(conn.begin() + order[e] * 27, conn.begin() + order[e] * 27 + 27, c2.begin() + e * 27);
         std::copy(face.begin() + order[e] * 6, face.begin() + order[e] * 6 + 6, f2.begin() + e * 6);
         if (!etype.empty()) t2[e] = etype[order[e]];
+        if (groups) { m2[e] = material[order[e]]; g2[e] = group[order[e]]; }
         part[e] = partition[order[e]];
       }
       conn.swap(c2);
       face.swap(f2);
       etype.swap(t2);
+      material.swap(m2);
+      group.swap(g2);
     }
     elem_order.assign(order.begin(), order.end());
     elem_offset.assign(nprocs + 1, 0);
@@ -399,6 +410,7 @@ inline MeshLevel RefineMesh(MeshLevel& C) {
   F.nel = C.nel * 8;
   F.conn.resize(F.nel * 27);
   F.face.assign(F.nel * 6, -1);
+  if (!C.material.empty()) { F.material.resize(F.nel); F.group.resize(F.nel); }     // children inherit (MeshRefinement.cpp:252-258)
   std::vector<int32_t> part(F.nel);
   detail::PairMap map((size_t)C.nnode * 8 + 1024);
   int32_t next = (int32_t)C.nnode;
@@ -434,6 +446,7 @@ inline MeshLevel RefineMesh(MeshLevel& C) {
       const int64_t fe = E * 8 + j;
       for (int n = 0; n < 27; n++) F.conn[fe * 27 + n] = fid[T.pos_of_child_node[j][n]];
       part[fe] = C.part[E];
+      if (!C.material.empty()) { F.material[fe] = C.material[E]; F.group[fe] = C.group[E]; }
       for (int f = 0; f < 6; f++) {
         const int* fn = HexElement::face_nodes()[f];
         if ((fn[0] == j || fn[1] == j || fn[2] == j || fn[3] == j) && C.face[E * 6 + f] < -1) F.face[fe * 6 + f] = C.face[E * 6 + f];

@@ -8,8 +8,8 @@
 // divided by Lref (:262-264); then Mesh::AddBiquadraticNodesNotInMeshFile (Mesh.cpp:1207-1333) creates the
 // face and centre nodes a 10-node tetrahedron lacks, and the reference renumbers nodes by first visit exactly
 // as for a generated box (Mesh.cpp:517-559).
-// A single element group is accepted (the material/group reordering of Mesh.cpp:621-702 is the next step);
-// anything else aborts.
+// Element groups set the material / group of their elements, by which the reference orders the elements of
+// a rank (Mesh.cpp:621-702).  Anything the reference would reject aborts.
 #pragma once
 #include <cstdio>
 #include <cstdlib>
@@ -141,9 +141,27 @@ inline MeshLevel ReadGambit(const char* path, double Lref = 1.0) {
   if (!all_hex) L.etype = etype;
   in >> tok;
   if (tok != "ENDOFSECTION") fail("bad element section");
-  if (ngroup != 1) fail("more than one element group: the material/group element reordering is not implemented");
-  seek("GROUP:");
-  seek("ENDOFSECTION");
+  // ELEMENT GROUP sections (GambitIO.cpp:290-313): "GROUP: id ELEMENTS: n MATERIAL: mat NFLAGS: k", the group
+  // NAME (an integer in FEMuS meshes), the flags line, then the n element ids; elements start in group 1
+  if (ngroup < 1) fail("no element group");
+  std::vector<int16_t> material((size_t)nel, 0), group((size_t)nel, 1);
+  for (long k = 0; k < ngroup; k++) {
+    seek("GROUP:");
+    long ngel = 0, gr_mat = 0, gr_name = 0;
+    in >> tok >> tok >> ngel >> tok >> gr_mat >> tok >> tok >> gr_name >> tok;
+    if (!in || ngel < 0) fail("bad group header (the group name must be an integer)");
+    for (long i = 0; i < ngel; i++) {
+      long iel;
+      in >> iel;
+      if (iel < 1 || iel > nel) fail("group element out of range");
+      group[iel - 1] = (int16_t)gr_name;
+      material[iel - 1] = (int16_t)gr_mat;
+    }
+    in >> tok;
+    if (tok != "ENDOFSECTION") fail("bad group section");
+  }
+  L.material = material;
+  L.group = group;
   for (long k = 0; k < nbcd; k++) {
     seek("CONDITIONS");
     in >> tok;                                  // version

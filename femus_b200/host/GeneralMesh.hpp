@@ -106,6 +106,7 @@ inline MeshLevel RefineGeneralMesh(MeshLevel& C) {
   F.conn.assign((size_t)F.nel * 27, -1);
   F.face.assign((size_t)F.nel * 6, -1);
   F.etype.assign((size_t)F.nel, (uint8_t)HEX);
+  if (!C.material.empty()) { F.material.resize(F.nel); F.group.resize(F.nel); }     // children inherit (MeshRefinement.cpp:252-258)
   std::vector<int32_t> part(F.nel);
   int32_t next = (int32_t)C.nnode;      // coarse nodes keep their ids in the temporary numbering
   std::map<std::array<int32_t, 2>, int32_t> edge_node;
@@ -120,6 +121,7 @@ inline MeshLevel RefineGeneralMesh(MeshLevel& C) {
       int32_t* fn = &F.conn[fe * 27];
       F.etype[fe] = (uint8_t)t;
       part[fe] = C.part[E];
+      if (!C.material.empty()) { F.material[fe] = C.material[E]; F.group[fe] = C.group[E]; }
       for (int v = 0; v < nv; v++) fn[v] = cn[ElemTopology::child_vertex(t, j, v)];
       for (int e = 0; e < ne; e++) {
         int a, b;

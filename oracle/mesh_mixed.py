@@ -59,13 +59,29 @@ class Level:
     pass
 
 
-def _renumber(L, conn, etype, part, nprocs):
-    """Mesh.cpp:517-559 (+ :589-616): stable element reorder by rank, nodes by first visit over
-    (rank, family, element, local node of that family)."""
+def _renumber(L, conn, etype, part, nprocs, material=None, group=None):
+    """Mesh.cpp:517-559 (+ :589-616, :621-702): stable element reorder by rank, then the reference's bubble sort
+    by (material, group, index) inside each rank; nodes by first visit over (rank, family, element, local node
+    of that family)."""
     order = np.argsort(part, kind="stable")
-    conn, etype, part = conn[order], etype[order], part[order]
     nel = conn.shape[0]
     elem_offset = np.concatenate([[0], np.cumsum(np.bincount(part, minlength=nprocs))])
+    if material is not None:
+        inv = list(order)                                   # inverse_element_mapping
+        for p in range(nprocs):
+            n = elem_offset[p + 1] - elem_offset[p]
+            while n > 1:
+                new_n = 0
+                for j in range(elem_offset[p] + 1, elem_offset[p] + n):
+                    jel, iel = inv[j], inv[j - 1]
+                    if material[jel] < material[iel] or (material[jel] == material[iel] and
+                                                         (group[jel] < group[iel] or (group[jel] == group[iel] and jel < iel))):
+                        inv[j - 1], inv[j] = jel, iel
+                        new_n = j - elem_offset[p]
+                n = new_n
+        order = np.array(inv, dtype=np.int64)
+        L.material, L.group = material[order], group[order]
+    conn, etype, part = conn[order], etype[order], part[order]
     new = {}
     own = np.zeros((3, nprocs), dtype=np.int64)
     for p in range(nprocs):
@@ -146,9 +162,21 @@ def read_neu(path, Lref=1.0):
 
     hdr = next(k for k, l in enumerate(lines) if "NUMNP" in l)
     nvt, nel, ngroup, nbcd, dim, dimn = [int(t) for t in lines[hdr + 1].split()]
-    assert dim == 3 and dimn == 3 and ngroup == 1
+    assert dim == 3 and dimn == 3 and ngroup >= 1
     xyz = np.array([[float(t) for t in l.split()[1:4]] for l in section("NODAL COORDINATES")]).T / Lref
     toks = " ".join(section("ELEMENTS/CELLS")).split()
+    # ELEMENT GROUP sections (GambitIO.cpp:290-313): header, integer group name, flags line, element ids
+    material, group = np.zeros(nel, dtype=np.int64), np.ones(nel, dtype=np.int64)
+    gstarts = [k for k, l in enumerate(lines) if l.strip().startswith("GROUP:")]
+    assert len(gstarts) == ngroup
+    for i in gstarts:
+        head = lines[i].split()
+        ngel, mat = int(head[head.index("ELEMENTS:") + 1]), int(head[head.index("MATERIAL:") + 1])
+        name = int(lines[i + 1].split()[0])
+        j = next(k for k in range(i, len(lines)) if lines[k].strip() == "ENDOFSECTION")
+        ids = np.array(" ".join(lines[i + 3:j]).split(), dtype=np.int64) - 1
+        assert ids.shape[0] == ngel
+        group[ids], material[ids] = name, mat
     conn = np.full((nel, 27), -1, dtype=np.int64)
     etype = np.zeros(nel, dtype=np.int64)
     p = 0
@@ -168,7 +196,7 @@ def read_neu(path, Lref=1.0):
             iel, _, iface = [int(t) for t in l.split()]
             face[iel - 1, GAMBIT_TO_FEMUS_FACE[etype[iel - 1]][iface - 1]] = -value - 1
     conn, xyz_file = _add_biquadratic_nodes(conn, etype, xyz)
-    L = _renumber(Level(), conn, etype, np.zeros(nel, dtype=np.int64), 1)
+    L = _renumber(Level(), conn, etype, np.zeros(nel, dtype=np.int64), 1, material, group)
     L.face = face[L.order_el]
     L.xyz = xyz_file[:, L.old_of_new]
     L.level = 0
@@ -210,7 +238,7 @@ def refine(C):
     for e in range(nelc * 8):
         conn[e, NVE[etype[e]][2] - 1] = nn
         nn += 1
-    F = _renumber(Level(), conn, etype, np.repeat(C.part, 8), C.nprocs)
+    F = _renumber(Level(), conn, etype, np.repeat(C.part, 8), C.nprocs, np.repeat(C.material, 8), np.repeat(C.group, 8))
     F.face = face[F.order_el]
     F.level = C.level + 1
     inv = np.empty(nelc * 8, dtype=np.int64)

@@ -48,14 +48,15 @@ def parse(path):
 def write(path, title, source, nvt, nel, dim, dimn, nodes, elems, group, bsets):
     out = ["CONTROL INFO 2.3.16", "** GAMBIT NEUTRAL FILE", title + " (femus_b200 test fixture)",
            "PROGRAM: femus_b200/tests/golden/make_neu_fixture.py VERSION: 1", "re-serialised from the reference's " + os.path.basename(source),
-           "NUMNP NELEM NGRPS NBSETS NDFCD NDFVL", f"{nvt} {nel} 1 {len(bsets)} {dim} {dimn}", "ENDOFSECTION",
+           "NUMNP NELEM NGRPS NBSETS NDFCD NDFVL", f"{nvt} {nel} {len(group) if isinstance(group, list) else 1} {len(bsets)} {dim} {dimn}", "ENDOFSECTION",
            "NODAL COORDINATES 2.3.16"]
     out += [f"{i + 1} {x!r} {y!r} {z!r}" for i, (x, y, z) in enumerate(nodes)]
     out += ["ENDOFSECTION", "ELEMENTS/CELLS 2.3.16"]
     out += [f"{i + 1} {t} {len(n)} " + " ".join(str(v) for v in n) for i, (t, n) in enumerate(elems)]
-    out += ["ENDOFSECTION", "ELEMENT GROUP 2.3.16",
-            f"GROUP: 1 ELEMENTS: {len(group['elems'])} MATERIAL: {group['material']} NFLAGS: 1", group["name"], "0",
-            " ".join(str(v) for v in group["elems"]), "ENDOFSECTION"]
+    out += ["ENDOFSECTION"]
+    for k, g in enumerate(group if isinstance(group, list) else [group]):
+        out += ["ELEMENT GROUP 2.3.16", f"GROUP: {k + 1} ELEMENTS: {len(g['elems'])} MATERIAL: {g['material']} NFLAGS: 1", g["name"], "0",
+                " ".join(str(v) for v in g["elems"]), "ENDOFSECTION"]
     for name, faces in bsets:
         out += ["BOUNDARY CONDITIONS 2.3.16", f"{name} 1 {len(faces)} 0 6"]
         out += [" ".join(str(v) for v in f) for f in faces]
@@ -69,3 +70,13 @@ if __name__ == "__main__":
             sys.exit("reference mesh not present: " + src)
         write(dst, title, src, *parse(src))
         print("wrote", dst)
+    # the mixed mesh cut into three element groups (names / materials chosen so that the reference's ordering by
+    # (material, group, index), Mesh.cpp:621-702, moves elements): a synthetic multi-group case, no shipped
+    # 3-D Poisson input has more than one group
+    nvt, nel, dim, dimn, nodes, elems, group, bsets = parse(INPUT + "cube_all_shapes_Six_boundary_groups.neu")
+    groups = [dict(material=4, name="3", elems=[e for e in range(1, nel + 1) if e % 3 == 1]),
+              dict(material=2, name="9", elems=[e for e in range(1, nel + 1) if e % 3 == 2]),
+              dict(material=2, name="5", elems=[e for e in range(1, nel + 1) if e % 3 == 0])]
+    dst = os.path.join(ROOT, "tests", "golden", "cube_mixed_3groups.neu")
+    write(dst, "cube_mixed_3groups", "cube_all_shapes_Six_boundary_groups.neu (regrouped)", nvt, nel, dim, dimn, nodes, elems, groups, bsets)
+    print("wrote", dst)

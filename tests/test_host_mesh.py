@@ -135,7 +135,7 @@ def test_child_faces_and_hex_through_the_general_entry_points():
                 assert np.array_equal(idx, np.nonzero(P[j, a])[0]) and np.array_equal(val, P[j, a, idx])
 
 
-@pytest.mark.parametrize("name", ["cube_wedge18", "cube_mixed", "cube_tet10", "cube_hex27_2x2x2"])
+@pytest.mark.parametrize("name", ["cube_wedge18", "cube_mixed", "cube_tet10", "cube_hex27_2x2x2", "cube_mixed_3groups"])
 def test_unstructured_hierarchies_match_mixed_oracle(name):
     """The reference's shipped 3-D coarse meshes (re-serialised): 16 wedges; 4 hexahedra + 10 tetrahedra + 6 wedges
     sharing triangular and quadrilateral faces; 105 tetrahedra; 8 hexahedra.  Reader (+ nodes the file lacks),

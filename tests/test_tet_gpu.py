@@ -286,13 +286,15 @@ def test_wedge_golden_elements(ctx):
             assert np.abs(R.get() - Fref).max() <= RTOL * (np.abs(Bref) @ np.abs(Uk)).max()
 
 
-@pytest.mark.parametrize("name", ["cube_wedge18", "cube_mixed"])
+@pytest.mark.parametrize("name", ["cube_wedge18", "cube_mixed", "cube_mixed_3groups"])
 @pytest.mark.parametrize("order", ["linear", "quadratic", "biquadratic"])
 def test_wedge_and_mixed_mesh_single_level(ctx, name, order):
     """The reference's cube_Wedge.neu (16 wedges) and cube_all_shapes_Six_boundary_groups.neu (4 hexahedra, 10
     tetrahedra, 6 wedges), re-serialised: one assembly plan per element type accumulating into one matrix;
     pattern bit-exact, matrix and residual to 1e-12 against the oracle, single-level solve against a sparse
-    direct solve.  The current solution is non-zero, so the residual carries B u of every element type."""
+    direct solve.  The current solution is non-zero, so the residual carries B u of every element type.
+    cube_mixed_3groups: the same mesh cut into three element groups, which the reference reorders by
+    (material, group, index) (Mesh.cpp:621-702) -- another element order and numbering, same kernels."""
     import scipy.sparse.linalg as spla
     from femus_b200 import hostapi
     from femus_b200.poisson import PoissonMG
@@ -300,7 +302,7 @@ def test_wedge_and_mixed_mesh_single_level(ctx, name, order):
     path = os.path.join(GOLDEN, name + ".neu")
     H = hostapi.HostHierarchy.from_neu(path, 1)
     pb = PoissonMG(ctx, 0, 0, 0, 1, order, hier=H, coarse_rtol=1e-15)
-    assert len(pb.plans) == (3 if name == "cube_mixed" else 1)
+    assert len(pb.plans) == (3 if name.startswith("cube_mixed") else 1)
     L = mm.read_neu(path)
     u = np.random.default_rng(4).standard_normal(pb.n)
     pb.SOL.put(u)
