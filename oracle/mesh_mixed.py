@@ -333,6 +333,27 @@ def assemble(L, order, U=None, fsrc=1.0):
     return A, rhs
 
 
+def neumann_rhs(L, order, neumann):
+    """Boundary part of the residual on a mesh of any element types: for every boundary face whose index is a key
+    of `neumann` (value = constant flux), F[local node] += sum_g phi_i value weight_g with the face element
+    _finiteElement[GetElementFaceType][order] -- triangle or quadrilateral -- on the face's first
+    GetElementFaceDofNumber nodes (applications/001_Poisson/main.cpp:495-548; face -> local nodes: Elem.hpp `ig`)."""
+    from . import fe_face
+    rhs = np.zeros(ndofs(L, order))
+    tabs = {k: fe_face.tables(k, order) for k in ("tri", "quad")}
+    for e in range(L.nel):
+        t = L.etype[e]
+        for f in range(NFACES[t]):
+            b = -(int(L.face[e, f]) + 1)
+            if b <= 0 or b not in neumann:
+                continue
+            kind = fe_face.face_kind(FACE_NVERT[t][f])
+            loc = FACE_NODES[t][f][:fe_face.ndofs(kind, order)]
+            Ff = fe_face.neumann_face(L.xyz[:, L.conn[e, loc]], float(neumann[b]), tabs[kind])
+            np.add.at(rhs, node_dof(L, order, L.conn[e, loc]), Ff)
+    return rhs
+
+
 def _local_prolongator(t, order):
     if t != HEX:
         return FE[t].local_prolongator(order)

@@ -139,12 +139,13 @@ class RefTet(RefElem):
         super().__init__("tet", order, gauss)
 
 
-class RefQuad:
-    """elem_type_2D("quad", order, gauss) of the reference: the face element of a hexahedron."""
+class RefFace:
+    """elem_type_2D(geom, order, gauss) of the reference, geom = "quad" | "tri": the face elements of the 3-D
+    elements (quadrilaterals with 4 / 8 / 9 dofs, triangles with 3 / 6 / 7)."""
 
-    def __init__(self, order="biquadratic", gauss="seventh"):
+    def __init__(self, geom="quad", order="biquadratic", gauss="seventh"):
         self.L = lib()
-        self.h = ctypes.c_void_p(self.L.fref2_create(b"quad", order.encode(), gauss.encode()))
+        self.h = ctypes.c_void_p(self.L.fref2_create(geom.encode(), order.encode(), gauss.encode()))
         self.n = self.L.fref2_ndofs(self.h)
         self.ng = self.L.fref2_ngauss(self.h)
 
@@ -172,3 +173,10 @@ class RefQuad:
             self.L.fref2_destroy(self.h)
         except Exception:
             pass
+
+
+class RefQuad(RefFace):
+    """elem_type_2D("quad", order, gauss) of the reference: the face element of a hexahedron."""
+
+    def __init__(self, order="biquadratic", gauss="seventh"):
+        super().__init__("quad", order, gauss)

@@ -174,3 +174,40 @@ for order in ("linear", "quadratic", "biquadratic"):
     outw[f"{order}_prol"], outw[f"{order}_prol_kvert"] = P, kv
 np.savez_compressed(os.path.join(ROOT, "tests", "golden", "fe_wedge_ref.npz"), **outw)
 print("wrote tests/golden/fe_wedge_ref.npz")
+
+
+# ---- face elements of every 3-D element (triangles 3 / 6 / 7, quadrilaterals 4 / 8 / 9; 13- and 16-point rules):
+#      tests/golden/fe_face_ref.npz.  Own random stream, so that the fixtures above do not move.
+rngf = np.random.default_rng(20261019)
+outf = {}
+REFPTS = {"tri": np.array([[0, 0], [1, 0], [0, 1], [.5, 0], [.5, .5], [0, .5], [1. / 3, 1. / 3]]),
+          "quad": np.array([[-1, -1], [1, -1], [1, 1], [-1, 1], [0, -1], [1, 0], [0, 1], [-1, 0], [0, 0]], dtype=float)}
+for geom in ("tri", "quad"):
+    for order in ("linear", "quadratic", "biquadratic"):
+        Q = ref.RefFace(geom, order)
+        k = f"{geom}_{order}"
+        w, xi = Q.gauss()
+        outf[f"{k}_gauss_w"], outf[f"{k}_gauss_xi"] = w, xi
+        phi, dxi, deta = Q.tables()
+        outf[f"{k}_phi"], outf[f"{k}_dxi"], outf[f"{k}_deta"] = phi, dxi, deta
+        # a flat face of a 1/64 cell, a curved one, a rotated + curved one (face nodes in 3-D)
+        P = REFPTS[geom][:Q.n]
+        flat = np.array([P[:, 0], P[:, 1], 0.3 + 0 * P[:, 0]])
+        Xs = [flat / 64.0, flat + 0.05 * rngf.standard_normal(flat.shape), flat[[2, 0, 1]] * 0.3 + 0.02 * rngf.standard_normal(flat.shape)]
+        Ws, Ns, Fs = [], [], []
+        for X in Xs:
+            wj, nj = [], []
+            F = np.zeros(Q.n)
+            for ig in range(Q.ng):
+                wt, ph, nrm = Q.jacobian_sur(np.ascontiguousarray(X), ig)
+                wj.append(wt)
+                nj.append(nrm)
+                for i in range(Q.n):
+                    F[i] += ph[i] * 0.2 * wt          # main.cpp:541-546 with bdc_func = 0.2
+            Ws.append(wj)
+            Ns.append(nj)
+            Fs.append(F)
+        outf[f"{k}_X"] = np.array(Xs)
+        outf[f"{k}_weight"], outf[f"{k}_normal"], outf[f"{k}_F02"] = np.array(Ws), np.array(Ns), np.array(Fs)
+np.savez_compressed(os.path.join(ROOT, "tests", "golden", "fe_face_ref.npz"), **outf)
+print("wrote tests/golden/fe_face_ref.npz")

@@ -129,6 +129,67 @@ def test_neumann_rhs_integrates_the_flux():
         assert abs(r.sum() - (0.2 * 1.0 - 1.5 * 1.0)) < 1e-13
 
 
+# ---- face elements of tetrahedra and wedges (triangles 3 / 6 / 7, quadrilaterals 4 / 8 / 9) ----------------
+GF = np.load(os.path.join(os.path.dirname(__file__), "golden", "fe_face_ref.npz"))
+FACE_CASES = [(g, o) for g in ("tri", "quad") for o in ("linear", "quadratic", "biquadratic")]
+
+
+@pytest.mark.parametrize("geom,order", FACE_CASES)
+def test_any_face_element_vs_golden(geom, order):
+    """oracle/fe_face.py against the committed values of the reference's elem_type_2D(geom, order, "seventh"):
+    Gauss rule bit-exact; tables, JacobianSur weight / normal and the Neumann face vector (bdc_func = 0.2) to
+    2e-15 (the triangle functions are restated as products of barycentrics, not the reference's expanded
+    polynomials); the 4 / 9-node quadrilaterals stay bit-exact."""
+    from oracle import fe_face
+    k = f"{geom}_{order}"
+    phi, dxi, deta, w = fe_face.tables(geom, order)
+    assert np.array_equal(w, GF[f"{k}_gauss_w"])
+    assert phi.shape == GF[f"{k}_phi"].shape == (13 if geom == "tri" else 16, fe_face.ndofs(geom, order))
+    exact = geom == "quad" and order != "quadratic"
+    tol = 0.0 if exact else 2e-15
+    for a, b in ((phi, GF[f"{k}_phi"]), (dxi, GF[f"{k}_dxi"]), (deta, GF[f"{k}_deta"])):
+        assert np.abs(a - b).max() <= tol
+    for j, X in enumerate(GF[f"{k}_X"]):
+        for ig in range(w.shape[0]):
+            wt, ph, nrm = fe_face.jacobian_sur(X, ig, (phi, dxi, deta, w))
+            assert abs(wt - GF[f"{k}_weight"][j, ig]) <= 1e-14 * abs(GF[f"{k}_weight"][j, ig]) + tol
+            assert np.abs(nrm - GF[f"{k}_normal"][j, ig]).max() <= 1e-14
+        F = fe_face.neumann_face(X, 0.2, (phi, dxi, deta, w))
+        assert np.abs(F - GF[f"{k}_F02"][j]).max() <= 1e-14 * np.abs(GF[f"{k}_F02"][j]).max()
+        if exact:
+            assert np.array_equal(F, GF[f"{k}_F02"][j])
+
+
+@pytest.mark.skipif(not ref.available(), reason="oracle/_ref not built (no /root/reference here)")
+@pytest.mark.parametrize("geom,order", FACE_CASES)
+def test_any_face_element_against_compiled_reference(geom, order):
+    from oracle import fe_face
+    Q = ref.RefFace(geom, order)
+    tabs = fe_face.tables(geom, order)
+    assert (Q.n, Q.ng) == (fe_face.ndofs(geom, order), tabs[3].shape[0])
+    rng = np.random.default_rng(5)
+    base = GF[f"{geom}_{order}_X"][0] * 64.0
+    for _ in range(4):
+        X = base + 0.05 * rng.standard_normal(base.shape)
+        for ig in range(Q.ng):
+            a = Q.jacobian_sur(X.copy(), ig)
+            b = fe_face.jacobian_sur(X, ig, tabs)
+            assert abs(a[0] - b[0]) <= 1e-14 * abs(a[0]) and np.abs(a[1] - b[1]).max() <= 2e-15 and np.abs(a[2] - b[2]).max() <= 1e-14
+
+
+@pytest.mark.parametrize("mesh", ["cube_tet10", "cube_wedge18", "cube_mixed", "cube_hex27_2x2x2"])
+def test_neumann_rhs_on_any_element_type_integrates_the_flux(mesh):
+    """Sum of the Neumann vector = flux x area of the face sets (partition of unity of the face bases) on
+    tetrahedra (triangular faces), wedges (both kinds) and the mixed mesh, every family; on hexahedra the
+    general loop reproduces mesh_box.neumann_rhs's face vectors."""
+    from oracle import mesh_mixed as mm
+    L = mm.build_hierarchy(os.path.join(os.path.dirname(__file__), "golden", mesh + ".neu"), 2)[-1]
+    for order in ("linear", "quadratic", "biquadratic"):
+        r = mm.neumann_rhs(L, order, {1: 0.2, 3: -1.5})
+        assert abs(r.sum() - (0.2 - 1.5)) < 1e-13
+        assert np.count_nonzero(r) > 0
+
+
 # ------------------------------------------------------------------------------ tetrahedra and wedges
 from oracle import fe_tet, fe_wedge  # noqa: E402
 
