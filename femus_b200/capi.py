@@ -109,6 +109,7 @@ _PROTOS = {
     "b2_asm_poisson": (ci, [vp, vp, vp, cd, cd]),
     "b2_asm_poisson_galerkin": (ci, [vp, vp, vp, vp, cd, cd]),
     "b2_asm_neumann": (ci, [vp, i64, vp, vp, vp, ci, vp, vp, vp, vp, vp, vp]),
+    "b2_asm_neumann_faces": (ci, [vp, i64, vp, vp, vp, ci, ci, vp, vp, vp, vp, vp, vp]),
     "b2_asm_last_kernel_ms": (cd, [vp]),
     "b2_mg_create": (ci, [vp, ci, vp]),
     "b2_mg_set_level": (ci, [vp, ci, vp, vp, vp, i64, ci, ci, cd]),
@@ -614,6 +615,15 @@ class Assembler:
         fn = _i32(face_nodes)
         check(self.L.b2_asm_neumann(self.h, fe.shape[0], _ptr(fe), _ptr(fl), _ptr(fv), phi.shape[1], _ptr(phi), _ptr(dxi),
                                     _ptr(deta), _ptr(w), _ptr(fn), rhs.h))
+
+    def neumann_faces(self, face_elem, face_local, face_value, face_tables, face_nodes, rhs):
+        """The same for the faces of any element type, one face kind per call (b2_asm_neumann_faces): face_tables
+        = (phi, dxi, deta [ngf][nvf], w[ngf]) of the triangle or quadrilateral, face_nodes[6][9] of the element type."""
+        fe, fl, fv = _i32(face_elem), _i32(face_local), _f64(face_value)
+        phi, dxi, deta, w = [_f64(t) for t in face_tables]
+        fn = _i32(face_nodes)
+        check(self.L.b2_asm_neumann_faces(self.h, fe.shape[0], _ptr(fe), _ptr(fl), _ptr(fv), phi.shape[1], phi.shape[0],
+                                          _ptr(phi), _ptr(dxi), _ptr(deta), _ptr(w), _ptr(fn), rhs.h))
 
     def poisson_galerkin(self, gal, u=None, rhs=None, nu=1.0, fsrc=1.0):
         """Assembly fused with the Galerkin product of `gal` (Ac = P^T A P from the element matrices)."""

@@ -1135,20 +1135,21 @@ int launch_assemble_general(b2_asm* p, const b2_vec* u, b2_vec* rhs, double nu, 
 }  // namespace
 
 // Neumann boundary integrals (applications/001_Poisson/main.cpp:495-548 with elem_type_2D::JacobianSur,
-// ElemType.hpp:1330-1379): one warp per boundary face, lanes = the 16 Gauss points of the face rule
-// for the surface Jacobian, then lanes = face dofs for F_i += sum_g phi_i(g) value weight_g.
+// ElemType.hpp:1330-1379): one warp per boundary face, lanes = the Gauss points of the face rule (16 on a
+// quadrilateral, 13 on a triangle) for the surface Jacobian, then lanes = face dofs for
+// F_i += sum_g phi_i(g) value weight_g.  The face element is the tables: nvf dofs, ngf points.
 __global__ void neumann_kernel(int64_t nfaces, const int32_t* __restrict__ felem, const int32_t* __restrict__ flocal,
-                               const double* __restrict__ fvalue, int nvf, int nve, const double* __restrict__ ftab,
+                               const double* __restrict__ fvalue, int nvf, int ngf, int nve, const double* __restrict__ ftab,
                                const int32_t* __restrict__ fnodes, int64_t nnode, const double* __restrict__ xyz,
                                const int32_t* __restrict__ conn, const int32_t* __restrict__ dof, double* __restrict__ rhs) {
-  constexpr int NG2 = 16;
+  constexpr int NG2 = 16;                            // most points any face rule has
   __shared__ double sW[8][NG2];
   __shared__ double sX[8][3][9];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const double* phi = ftab;
-  const double* dxi = phi + NG2 * nvf;
-  const double* deta = dxi + NG2 * nvf;
-  const double* w = deta + NG2 * nvf;
+  const double* dxi = phi + ngf * nvf;
+  const double* deta = dxi + ngf * nvf;
+  const double* w = deta + ngf * nvf;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   for (int64_t k = warp; k < nfaces; k += nwarps) {
@@ -1163,7 +1164,7 @@ __global__ void neumann_kernel(int64_t nfaces, const int32_t* __restrict__ felem
       sX[wib][2][lane] = xyz[2 * nnode + nd];
     }
     __syncwarp();
-    if (lane < NG2) {
+    if (lane < ngf) {
       double J00 = 0, J10 = 0, J20 = 0, J01 = 0, J11 = 0, J21 = 0;
       for (int i = 0; i < nvf; i++) {
         const double a = dxi[lane * nvf + i], b = deta[lane * nvf + i];
@@ -1180,7 +1181,7 @@ __global__ void neumann_kernel(int64_t nfaces, const int32_t* __restrict__ felem
     __syncwarp();
     if (lane < nvf) {
       double s = 0.0;
-      for (int g = 0; g < NG2; g++) s = fma(phi[g * nvf + lane] * fvalue[k], sW[wib][g], s);
+      for (int g = 0; g < ngf; g++) s = fma(phi[g * nvf + lane] * fvalue[k], sW[wib][g], s);
       atomicAdd(&rhs[dof[e * nve + loc]], s);
     }
     __syncwarp();
@@ -1205,28 +1206,37 @@ __global__ void __launch_bounds__(512) dmma_probe_kernel(int iters, double* out)
 
 extern "C" {
 
-/* rhs += Neumann integrals over the listed boundary faces (host arrays: element, local face, flux value);
- * ftab = phi, dxi, deta [16][nvf] and weights[16] of the face element, face_nodes[6][9] the local nodes
- * of the hexahedron's faces.  Face dofs must be element dofs (nvf = 4 with nve = 8, 9 with 27). */
-int b2_asm_neumann(b2_asm* p, int64_t nfaces, const int32_t* face_elem, const int32_t* face_local, const double* face_value,
-                   int nvf, const double* phi, const double* dxi, const double* deta, const double* weights,
-                   const int32_t* face_nodes, b2_vec* rhs) {
-  B2_CHECK(p && rhs && (nfaces == 0 || (face_elem && face_local && face_value)), "b2_asm_neumann: null argument");
-  B2_CHECK((nvf == 4 && p->nve == 8) || (nvf == 9 && p->nve == 27), "b2_asm_neumann: nvf=%d does not match nve=%d", nvf, p->nve);
-  B2_CHECK(rhs->n >= p->A->nrows, "b2_asm_neumann: rhs vector too short");
+/* rhs += Neumann integrals over the listed boundary faces (host arrays: element, local face, flux value) of ONE
+ * face kind: the face element is its tables phi, dxi, deta [ngf][nvf] and weights[ngf] (ngf <= 16 Gauss points,
+ * nvf <= 9 dofs: quadrilaterals 4 / 8 / 9 with 16 points, triangles 3 / 6 / 7 with 13), face_nodes[6][9] the
+ * element-local nodes of the element type's faces (rows of unused faces / entries: -1).  Face dofs must be
+ * element dofs: every listed face's first nvf local nodes are < nve. */
+int b2_asm_neumann_faces(b2_asm* p, int64_t nfaces, const int32_t* face_elem, const int32_t* face_local, const double* face_value,
+                         int nvf, int ngf, const double* phi, const double* dxi, const double* deta, const double* weights,
+                         const int32_t* face_nodes, b2_vec* rhs) {
+  B2_CHECK(p && rhs && phi && dxi && deta && weights && face_nodes && (nfaces == 0 || (face_elem && face_local && face_value)),
+           "b2_asm_neumann_faces: null argument");
+  B2_CHECK(nvf >= 1 && nvf <= 9 && ngf >= 1 && ngf <= 16, "b2_asm_neumann_faces: nvf=%d (1..9) or ngf=%d (1..16) out of range", nvf, ngf);
+  B2_CHECK(rhs->n >= p->A->nrows, "b2_asm_neumann_faces: rhs vector too short");
   if (nfaces == 0) return 0;
   b2_ctx* c = p->mesh->ctx;
-  for (int64_t k = 0; k < nfaces; k++)
+  for (int64_t k = 0; k < nfaces; k++) {
     B2_CHECK(face_elem[k] >= 0 && face_elem[k] < p->mesh->nel && face_local[k] >= 0 && face_local[k] < 6,
-             "b2_asm_neumann: face %lld out of range", (long long)k);
+             "b2_asm_neumann_faces: face %lld out of range", (long long)k);
+    for (int i = 0; i < nvf; i++) {
+      const int loc = face_nodes[face_local[k] * 9 + i];
+      B2_CHECK(loc >= 0 && loc < p->nve, "b2_asm_neumann_faces: face %lld (local face %d): face dof %d is local node %d, not one of the element's %d dofs",
+               (long long)k, (int)face_local[k], i, loc, p->nve);
+    }
+  }
   int32_t *d_e = nullptr, *d_f = nullptr, *d_fn = nullptr;
   double *d_v = nullptr, *d_t = nullptr;
-  const size_t nt = (size_t)3 * 16 * nvf + 16;
+  const size_t nt = (size_t)3 * ngf * nvf + ngf;
   std::vector<double> tab(nt);
-  std::copy(phi, phi + 16 * nvf, tab.begin());
-  std::copy(dxi, dxi + 16 * nvf, tab.begin() + 16 * nvf);
-  std::copy(deta, deta + 16 * nvf, tab.begin() + 2 * 16 * nvf);
-  std::copy(weights, weights + 16, tab.begin() + 3 * 16 * nvf);
+  std::copy(phi, phi + ngf * nvf, tab.begin());
+  std::copy(dxi, dxi + ngf * nvf, tab.begin() + ngf * nvf);
+  std::copy(deta, deta + ngf * nvf, tab.begin() + 2 * ngf * nvf);
+  std::copy(weights, weights + ngf, tab.begin() + 3 * ngf * nvf);
   B2_TRY(b2_malloc(c, &d_e, (size_t)nfaces));
   B2_TRY(b2_malloc(c, &d_f, (size_t)nfaces));
   B2_TRY(b2_malloc(c, &d_v, (size_t)nfaces));
@@ -1237,7 +1247,7 @@ int b2_asm_neumann(b2_asm* p, int64_t nfaces, const int32_t* face_elem, const in
   B2_TRY(b2_upload(c, d_v, face_value, (size_t)nfaces));
   B2_TRY(b2_upload(c, d_t, tab.data(), nt));
   B2_TRY(b2_upload(c, d_fn, face_nodes, 54));
-  B2_LAUNCH(c, neumann_kernel, b2_grid_for(c, nfaces * 32, 256, 8), 256, 0, nfaces, d_e, d_f, d_v, nvf, p->nve, d_t, d_fn,
+  B2_LAUNCH(c, neumann_kernel, b2_grid_for(c, nfaces * 32, 256, 8), 256, 0, nfaces, d_e, d_f, d_v, nvf, ngf, p->nve, d_t, d_fn,
             p->mesh->nnode, p->mesh->xyz, p->mesh->conn, p->dof, rhs->d);
   B2_CUDA(cudaStreamSynchronize(c->stream));
   b2_free(c, d_e, (size_t)nfaces);
@@ -1246,6 +1256,16 @@ int b2_asm_neumann(b2_asm* p, int64_t nfaces, const int32_t* face_elem, const in
   b2_free(c, d_t, nt);
   b2_free(c, d_fn, 54);
   return 0;
+}
+
+/* The same for hexahedra with 8 or 27 dofs: ftab = phi, dxi, deta [16][nvf] and weights[16] of the quadrilateral
+ * face element (nvf = 4 with nve = 8, 9 with 27), face_nodes[6][9] the local nodes of the hexahedron's faces. */
+int b2_asm_neumann(b2_asm* p, int64_t nfaces, const int32_t* face_elem, const int32_t* face_local, const double* face_value,
+                   int nvf, const double* phi, const double* dxi, const double* deta, const double* weights,
+                   const int32_t* face_nodes, b2_vec* rhs) {
+  B2_CHECK(p && rhs && (nfaces == 0 || (face_elem && face_local && face_value)), "b2_asm_neumann: null argument");
+  B2_CHECK((nvf == 4 && p->nve == 8) || (nvf == 9 && p->nve == 27), "b2_asm_neumann: nvf=%d does not match nve=%d", nvf, p->nve);
+  return b2_asm_neumann_faces(p, nfaces, face_elem, face_local, face_value, nvf, 16, phi, dxi, deta, weights, face_nodes, rhs);
 }
 
 /* measured fp64 tensor-core peak (TFLOP/s) of this device: the denominator next to the assembly

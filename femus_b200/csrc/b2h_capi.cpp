@@ -3,6 +3,7 @@
 #include <cstring>
 #include <memory>
 #include "../host/BoxMesh.hpp"
+#include "../host/FaceElement.hpp"
 #include "../host/GambitIO.hpp"
 #include "../host/GeneralMesh.hpp"
 #include "../../include/femus_b200_host.h"
@@ -188,6 +189,23 @@ int64_t b2h_level_boundary_faces(const b2h_hier* h, int l, int32_t* elem, int32_
         n++;
       }
   return n;
+}
+int b2h_face_kind_ngauss(int kind) { return FaceElement::ngauss(kind); }
+int b2h_face_kind_ndofs(int kind, int family) { return FaceElement::ndofs(kind, family); }
+void b2h_face_kind_tables(int kind, int family, double* phi, double* dxi, double* deta, double* w) {
+  FaceElement::Tables t = FaceElement::tables(kind, family);
+  std::copy(t.phi.begin(), t.phi.end(), phi);
+  std::copy(t.dxi.begin(), t.dxi.end(), dxi);
+  std::copy(t.deta.begin(), t.deta.end(), deta);
+  std::copy(t.w.begin(), t.w.end(), w);
+}
+void b2h_elem_face_nodes(int type, int32_t* out) {
+  for (int f = 0; f < 6; f++)
+    for (int i = 0; i < 9; i++)
+      out[f * 9 + i] = (f < ElemTopology::nfaces(type) && i < ElemTopology::face_ndofs(type, f, BIQUADRATIC)) ? ElemTopology::face_node(type, f, i) : -1;
+}
+int b2h_elem_face_kind(int type, int f) {
+  return f < ElemTopology::nfaces(type) ? FaceElement::kind_of_nvert(ElemTopology::face_nvert(type, f)) : -1;
 }
 int b2h_hex_prolongator_row(int family, int a, int b, int c, int* idx, double* val) {
   return HexElement::prolongator_row(family, a, b, c, idx, val);

@@ -65,6 +65,11 @@ def _L():
             "b2h_face_tables": (None, [ci, vp, vp, vp, vp]),
             "b2h_hex_face_nodes": (None, [vp]),
             "b2h_level_boundary_faces": (i64, [vp, ci, vp, vp, vp]),
+            "b2h_face_kind_ngauss": (ci, [ci]),
+            "b2h_face_kind_ndofs": (ci, [ci, ci]),
+            "b2h_face_kind_tables": (None, [ci, ci, vp, vp, vp, vp]),
+            "b2h_elem_face_nodes": (None, [ci, vp]),
+            "b2h_elem_face_kind": (ci, [ci, ci]),
         }
         for n, (r, a) in P.items():
             f = getattr(L, n)
@@ -325,6 +330,33 @@ def hex_face_nodes():
     out = np.zeros((6, 9), dtype=np.int32)
     _L().b2h_hex_face_nodes(out.ctypes.data_as(vp))
     return out
+
+
+QUAD_FACE, TRI_FACE = 0, 1
+
+
+def face_kind_tables(kind, family):
+    """(phi, dxi, deta, w) of elem_type_2D("quad" | "tri", family, "seventh"): [ngauss][ndofs], [ngauss]
+    (kind 0: quadrilateral, 4 / 8 / 9 dofs, 16 points; 1: triangle, 3 / 6 / 7 dofs, 13 points)."""
+    L = _L()
+    f = _fam(family)
+    ng, nvf = L.b2h_face_kind_ngauss(kind), L.b2h_face_kind_ndofs(kind, f)
+    t = [np.zeros((ng, nvf)) for _ in range(3)] + [np.zeros(ng)]
+    L.b2h_face_kind_tables(kind, f, *[a.ctypes.data_as(vp) for a in t])
+    return tuple(t)
+
+
+def elem_face_nodes(elem_type):
+    """[6][9] element-local nodes of the faces of an element type, -1 where no face / entry exists."""
+    out = np.zeros((6, 9), dtype=np.int32)
+    _L().b2h_elem_face_nodes(elem_type, out.ctypes.data_as(vp))
+    return out
+
+
+def elem_face_kinds(elem_type):
+    """face kind (0 quadrilateral, 1 triangle) of the 6 local faces, -1 past the last one."""
+    L = _L()
+    return np.array([L.b2h_elem_face_kind(elem_type, f) for f in range(6)], dtype=np.int32)
 
 
 def hex_prolongator_row(family, a, b, c):

@@ -17,6 +17,28 @@ from . import capi, hostapi
 from . import dist as distlayout
 
 
+def neumann_face_groups(level, order, neumann, elem_type, sel, bfaces=None):
+    """Neumann faces of the elements of one assembly plan (element type `elem_type`, rows `sel` of the level's
+    connectivity), one group per face kind: the reference picks the face element per face,
+    _finiteElement[GetElementFaceType(iel, jface)][order_ind] (main.cpp:507-525).  Returns a list of
+    ((plan-local element, local face, flux), face tables, face nodes[6][9]) ready for b2_asm_neumann_faces."""
+    fe, fl, fb = bfaces if bfaces is not None else level.boundary_faces()
+    nm = np.isin(fb, list(neumann))
+    fe, fl, fb = fe[nm], fl[nm], fb[nm]
+    pos = np.full(level.nel, -1, dtype=np.int64)         # element -> row of the plan's connectivity
+    pos[sel] = np.arange(level.nel if isinstance(sel, slice) else len(sel))
+    kinds = hostapi.elem_face_kinds(elem_type)
+    mine = pos[fe] >= 0
+    out = []
+    for kind in (hostapi.QUAD_FACE, hostapi.TRI_FACE):
+        g = mine & (kinds[fl] == kind)
+        if g.any():
+            faces = (pos[fe[g]].astype(np.int32), fl[g].astype(np.int32),
+                     np.array([neumann[int(b)] for b in fb[g]], dtype=np.float64))
+            out.append((faces, hostapi.face_kind_tables(kind, order), hostapi.elem_face_nodes(elem_type)))
+    return out
+
+
 class PoissonMG:
     """dist=None: the whole mesh on one GPU.  dist=(rank, world, allgather): this rank's z-slab of
     the mesh (local hierarchy, partial matrices, interface sums through b2_halo); the context must
@@ -55,8 +77,8 @@ class PoissonMG:
         self.nve = None if self.mixed else hostapi.elem_nve(self.elem_type, order)
         if not self.hex:       # the element-gather / fused Galerkin products are kernels for refined hexahedra
             self.fused = False
-            if self.neumann or dist is not None:
-                raise NotImplementedError("Neumann faces and the sharded run are implemented for hexahedra with 8 or 27 dofs")
+            if dist is not None:
+                raise NotImplementedError("the sharded run is implemented for hexahedra with 8 or 27 dofs")
         # --- system.init(): per-level matrices with the exact element-coupling pattern
         # (a mesh of several element types has ragged element rows: pattern built on the host, as the
         # reference's GetSparsityPatternSize does, LinearEquation.cpp:407-548)
@@ -88,17 +110,23 @@ class PoissonMG:
         # --- finest-level mesh + assembly plan
         # one plan per element type present (the tables are the element type: _finiteElement[ielGeom][solType])
         self.plans = []
+        self.nm_groups = []         # Neumann faces per (plan, face kind): (assembler, faces, tables, face nodes)
+        if self.neumann:
+            fe, fl, fb = top.boundary_faces()
+            nm = np.isin(fb, list(self.neumann))
+            fe, fl, fb = fe[nm], fl[nm], fb[nm]
         for t in ([self.elem_type] if not self.mixed else sorted(set(top.elem_types.tolist()))):
             sel = slice(None) if not self.mixed else np.nonzero(top.elem_types == t)[0]
             mesh_t = capi.Mesh(ctx, top.xyz, np.ascontiguousarray(top.conn[sel]))
             dof_t = self.dofs[-1] if not self.mixed else np.ascontiguousarray(self.dofs[-1][sel][:, :hostapi.elem_nve(t, order)])
             tables_t = hostapi.elem_tables(t, order)
             self.plans.append((mesh_t, capi.Assembler(mesh_t, self.KK[-1], dof_t, tables_t), tables_t))
+            if self.neumann and not self.hex:
+                for faces, tabs, fnodes in neumann_face_groups(top, order, self.neumann, t, sel, (fe, fl, fb)):
+                    self.nm_groups.append((self.plans[-1][1], faces, tabs, fnodes))
         self.mesh, self.asm, self.tables = self.plans[0]
-        if self.neumann:    # Neumann faces of the finest level: (element, local face, flux)
-            fe, fl, fb = top.boundary_faces()
-            sel = np.isin(fb, list(self.neumann))
-            self.nm_faces = (fe[sel], fl[sel], np.array([self.neumann[int(b)] for b in fb[sel]], dtype=np.float64))
+        if self.neumann and self.hex:    # Neumann faces of the finest level: (element, local face, flux)
+            self.nm_faces = (fe, fl, np.array([self.neumann[int(b)] for b in fb], dtype=np.float64))
             self.nm_tables = hostapi.face_tables(order)
             self.nm_face_nodes = hostapi.hex_face_nodes()
         if self.fused:      # element-matrix Galerkin chain: every plan but the coarsest records its element matrices
@@ -141,8 +169,10 @@ class PoissonMG:
         else:
             for _, asm, _ in self.plans:       # one launch per element type, accumulating into KK and RES
                 asm.poisson(self.SOL, self.RES, 1.0, self.fsrc)
-        if self.neumann and self.nm_faces[0].size:
+        if self.neumann and self.hex and self.nm_faces[0].size:
             self.asm.neumann(*self.nm_faces, self.nm_tables, self.nm_face_nodes, self.RES)
+        for asm, faces, tabs, fnodes in self.nm_groups:
+            asm.neumann_faces(*faces, tabs, fnodes, self.RES)
         if self.halo[-1] is not None:          # close(): contributions of the other ranks' elements
             self.halo[-1].sum(self.RES)
 

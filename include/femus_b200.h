@@ -231,6 +231,15 @@ int b2_asm_poisson(b2_asm* p, const b2_vec* u, b2_vec* rhs, double nu, double fs
 int b2_asm_neumann(b2_asm* p, int64_t nfaces, const int32_t* face_elem, const int32_t* face_local, const double* face_value,
                    int nvf, const double* phi, const double* dxi, const double* deta, const double* weights,
                    const int32_t* face_nodes, b2_vec* rhs);
+/* The same for the faces of ANY element type, one face kind per call: the reference selects the face element
+ * _finiteElement[GetElementFaceType(iel, jface)][order_ind] (main.cpp:507-525) -- here it is the tables handed
+ * in: phi/dxi/deta [ngf][nvf], weights[ngf] with ngf <= 16 Gauss points and nvf <= 9 dofs (quadrilaterals
+ * 4 / 8 / 9 dofs and 16 points; triangles 3 / 6 / 7 dofs and 13 points, Triangle.hpp:60-170); face_nodes[6][9]
+ * = GetLocalFaceVertexIndex of the plan's element type, -1 where a face or entry does not exist.  Fails if a
+ * listed face's dof is not an element dof. */
+int b2_asm_neumann_faces(b2_asm* p, int64_t nfaces, const int32_t* face_elem, const int32_t* face_local, const double* face_value,
+                         int nvf, int ngf, const double* phi, const double* dxi, const double* deta, const double* weights,
+                         const int32_t* face_nodes, b2_vec* rhs);
 /* Fused fast path of "assemble, then matrix_PtAP" (LinearImplicitSystem.cpp:326 + 347-370): the same
  * assembly, and in the same pass gal's coarse matrix Ac = P^T A P is formed from the element matrices
  * while they are on chip, C = sum_e Pc(e)^T B_e Pc(e) with Pc(e) the element prolongator of the child

@@ -108,6 +108,16 @@ int b2h_face_nvf(int family);
 void b2h_face_tables(int family, double* phi, double* dxi, double* deta, double* w);
 void b2h_hex_face_nodes(int32_t* out);
 int64_t b2h_level_boundary_faces(const b2h_hier* h, int l, int32_t* elem, int32_t* face, int32_t* bidx);
+/* face elements of every 3-D element: elem_type_2D(kind, family, "seventh"), kind 0 = "quad" (4 / 8 / 9 dofs,
+ * 16 points), 1 = "tri" (3 / 6 / 7 dofs, 13 points; 01_fe/2d/Triangle.hpp:60-170, quadrature_Triangle.cpp) --
+ * what _finiteElement[GetElementFaceType(iel, jface)][order_ind] selects in main.cpp:507-525.  Tables
+ * [ngauss][ndofs], weights[ngauss].  Per element type: local nodes of its faces [6][9] padded with -1
+ * (Elem.hpp `ig` table, GetLocalFaceVertexIndex) and the face kind of face f (-1 past the last face). */
+int b2h_face_kind_ngauss(int kind);
+int b2h_face_kind_ndofs(int kind, int family);
+void b2h_face_kind_tables(int kind, int family, double* phi, double* dxi, double* deta, double* w);
+void b2h_elem_face_nodes(int type, int32_t* out);
+int b2h_elem_face_kind(int type, int f);
 
 #ifdef __cplusplus
 }

@@ -240,3 +240,68 @@ def test_tet_refinement_is_nested():
     assert abs(vc.sum() - 1.0) < 1e-13 and abs(vf.sum() - 1.0) < 1e-13
     # the file's mid-edge nodes are the edge midpoints only to its 12 printed digits
     assert np.abs(vf[C.child_el] - vc[:, None] / 8).max() < 1e-10 * vc.max()
+
+
+# ---- face elements of every element type / Neumann face groups ---------------------------------------------
+def test_face_kind_tables_and_face_nodes_match_oracle():
+    """Host FaceElement (triangles 3/6/7 with 13 points, quadrilaterals 4/8/9 with 16) against oracle/fe_face.py
+    (pinned to the compiled reference): weights bit-exact, 4/9-node quadrilateral tables bit-exact, the others to
+    2e-15; face -> local node tables and face kinds of hexahedra, tetrahedra and wedges."""
+    from oracle import fe_face, mesh_mixed as mm
+    for kind, geom in ((hostapi.QUAD_FACE, "quad"), (hostapi.TRI_FACE, "tri")):
+        for order in ("linear", "quadratic", "biquadratic"):
+            got, want = hostapi.face_kind_tables(kind, order), fe_face.tables(geom, order)
+            assert got[0].shape == want[0].shape and np.array_equal(got[3], want[3])
+            for a, b in zip(got[:3], want[:3]):
+                assert np.abs(a - b).max() <= (0.0 if geom == "quad" and order != "quadratic" else 2e-15)
+            assert np.abs(got[0].sum(axis=1) - 1.0).max() < 1e-14          # partition of unity
+    for t in (mm.HEX, mm.TET, mm.WEDGE):
+        fn, fk = hostapi.elem_face_nodes(t), hostapi.elem_face_kinds(t)
+        for f in range(6):
+            if f >= mm.NFACES[t]:
+                assert fk[f] == -1 and (fn[f] == -1).all()
+                continue
+            assert fk[f] == (hostapi.TRI_FACE if mm.FACE_NVERT[t][f] == 3 else hostapi.QUAD_FACE)
+            nodes = list(mm.FACE_NODES[t][f])
+            n = 7 if mm.FACE_NVERT[t][f] == 3 else 9
+            assert fn[f, :n].tolist() == [int(x) for x in nodes[:n]] and (fn[f, n:] == -1).all()
+
+
+def _neumann_groups_numpy(level, order, neumann):
+    """What the driver hands to b2_asm_neumann_faces, evaluated with numpy in the kernel's operation order."""
+    from femus_b200.poisson import neumann_face_groups
+    mixed = level.elem_type < 0
+    dofs = level.system_dofs27(order)
+    rhs = np.zeros(level.ndofs(order))
+    for t in (sorted(set(level.elem_types.tolist())) if mixed else [level.elem_type]):
+        sel = np.nonzero(level.elem_types == t)[0] if mixed else slice(None)
+        conn, dof = level.conn[sel], dofs[sel]
+        nve = hostapi.elem_nve(t, order)
+        for (fe, fl, fv), (phi, dxi, deta, w), fnodes in neumann_face_groups(level, order, neumann, t, sel):
+            nvf = phi.shape[1]
+            for e, f, v in zip(fe, fl, fv):
+                loc = fnodes[f, :nvf]
+                assert (loc >= 0).all() and (loc < nve).all()
+                X = level.xyz[:, conn[e, loc]]
+                J = np.stack([X @ dxi.T, X @ deta.T], axis=-1)             # [3][ng][2]
+                n = np.cross(J[:, :, 0].T, J[:, :, 1].T)
+                area = np.sqrt((n * n).sum(axis=1))
+                np.add.at(rhs, dof[e, loc], (phi * (v * area * w)[:, None]).sum(axis=0))
+    return rhs
+
+
+@pytest.mark.parametrize("name", ["cube_tet10", "cube_wedge18", "cube_mixed", "cube_hex27_2x2x2"])
+def test_neumann_face_groups_match_oracle(name):
+    """The (plan, face kind) groups of Neumann faces the driver builds for b2_asm_neumann_faces -- plan-local
+    element rows, local faces, host face tables, face-node tables -- reproduce the oracle's boundary vector
+    (oracle/mesh_mixed.neumann_rhs, main.cpp:495-548) on tetrahedra, wedges, the mixed mesh and hexahedra."""
+    from oracle import mesh_mixed as mm
+    path = os.path.join(os.path.dirname(__file__), "golden", name + ".neu")
+    H = hostapi.HostHierarchy.from_neu(path, 2)
+    L = mm.build_hierarchy(path, 2)[-1]
+    neumann = {1: 0.2, 4: -1.5, 6: 0.7}
+    for order in ("linear", "quadratic", "biquadratic"):
+        got = _neumann_groups_numpy(H.levels[-1], order, neumann)
+        want = mm.neumann_rhs(L, order, neumann)
+        assert np.abs(got - want).max() <= 1e-13 * np.abs(want).max()
+        assert abs(got.sum() - (0.2 - 1.5 + 0.7)) < 1e-13
