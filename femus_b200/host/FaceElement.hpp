@@ -6,7 +6,7 @@
 // The 4 / 9-node quadrilateral tables are HexElement's (bit-exact with the reference); the 8-node
 // quadrilateral and the triangles are evaluated from products of affine factors (the triangle terms are the
 // ones the wedge is built from, WedgeElement::tri_terms) and agree with the reference's expanded polynomials to
-// a few ulp (tests/test_host_mesh.py against oracle/fe_face.py, itself pinned to the compiled reference).
+// a few ulp (tests/test_host_mesh.py, against a restatement pinned to the compiled reference).
 #pragma once
 #include <vector>
 #include "HexElement.hpp"
