@@ -115,6 +115,13 @@ _PROTOS = {
     "b2_mg_set_level": (ci, [vp, ci, vp, vp, vp, i64, ci, ci, cd]),
     "b2_mg_set_coarse": (ci, [vp, cd, ci]),
     "b2_mg_set_smoother": (ci, [vp, ci, ci, cd, cd]),
+    "b2_schwarz_create": (ci, [vp, vp, i64, vp, vp, i64, vp, vp, vp]),
+    "b2_schwarz_setup": (ci, [vp]),
+    "b2_schwarz_apply": (ci, [vp, vp, vp]),
+    "b2_schwarz_bytes": (i64, [vp]),
+    "b2_schwarz_groups": (i64, [vp]),
+    "b2_schwarz_destroy": (ci, [vp]),
+    "b2_mg_set_level_schwarz": (ci, [vp, ci, vp]),
     "b2_mg_level_bounds": (ci, [vp, ci, vp, vp]),
     "b2_mg_set_level_halo": (ci, [vp, ci, vp]),
     "b2_halo_create": (ci, [vp, i64, i64, vp, vp, i64, vp, vp, vp]),
@@ -631,6 +638,41 @@ class Assembler:
                                              rhs.h if rhs is not None else None, float(nu), float(fsrc)))
 
 
+class Schwarz:
+    """Element-block multiplicative Schwarz preconditioner on a device operator (b2_schwarz_*): blocks as
+    (blk_ptr, blk_dofs) with sorted dofs, schedule as (group_ptr, group_blocks) -- hostapi.AsmIndex / asm_schedule."""
+
+    def __init__(self, ctx, A, blk_ptr, blk_dofs, group_ptr, group_blocks):
+        self.ctx, self.L, self.A = ctx, ctx.L, A
+        bp, bd = np.ascontiguousarray(blk_ptr, dtype=np.int64), _i32(blk_dofs)
+        gp, gb = np.ascontiguousarray(group_ptr, dtype=np.int64), _i32(group_blocks)
+        h = vp()
+        check(self.L.b2_schwarz_create(ctx.h, A.h, bp.shape[0] - 1, _ptr(bp), _ptr(bd), gp.shape[0] - 1, _ptr(gp), _ptr(gb),
+                                       ctypes.byref(h)))
+        self.h = h
+
+    def __del__(self):
+        try:
+            if self.h and self.ctx.h:
+                self.L.b2_schwarz_destroy(self.h)
+        except Exception:
+            pass
+
+    def setup(self):
+        check(self.L.b2_schwarz_setup(self.h))
+
+    def apply(self, r, y):
+        check(self.L.b2_schwarz_apply(self.h, r.h, y.h))
+
+    @property
+    def nbytes(self):
+        return int(self.L.b2_schwarz_bytes(self.h))
+
+    @property
+    def ngroups(self):
+        return int(self.L.b2_schwarz_groups(self.h))
+
+
 class Multigrid:
     def __init__(self, ctx, nlevels):
         self.ctx, self.L = ctx, ctx.L
@@ -659,6 +701,11 @@ class Multigrid:
     def set_smoother(self, level, kind, emin=0.0, emax=0.0):
         """kind: "richardson" (Richardson+Jacobi) or "chebyshev" (Chebyshev+Jacobi; emax <= 0: estimated)."""
         check(self.L.b2_mg_set_smoother(self.h, level, {"richardson": 0, "chebyshev": 1}[kind], float(emin), float(emax)))
+
+    def set_level_schwarz(self, level, schwarz):
+        """Level smoother = Richardson(omega) + the element-block preconditioner (b2_mg_set_level_schwarz)."""
+        self._keep.append(schwarz)
+        check(self.L.b2_mg_set_level_schwarz(self.h, level, schwarz.h if schwarz is not None else None))
 
     def level_bounds(self, level):
         a, b = cd(), cd()

@@ -166,6 +166,7 @@ static inline int b2_grid_for(b2_ctx* c, int64_t work_items, int per_block, int 
 }
 
 // internal cross-TU helpers
+const b2_csr* b2_schwarz_operator(const b2_schwarz* s);
 int b2_csr_alloc(b2_ctx* c, int64_t nrows, int64_t ncols, int64_t nnz, b2_csr** out);
 int b2_csr_finalize(b2_csr* A);   // row statistics -> tpr / max_row, SpMV row chunks
 int b2_csr_build_chunks(b2_csr* A);

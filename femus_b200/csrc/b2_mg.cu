@@ -21,8 +21,10 @@ struct b2_mg_level {
   b2_halo* halo = nullptr;  // borrowed: distributed layout of this level's vectors (null: single rank)
   int npre = 1, npost = 1;
   double omega = 0.5;
-  // smoother: 0 = Richardson(omega) + Jacobi, 1 = Chebyshev + Jacobi on [emin, emax] of D^-1 A
+  // smoother: 0 = Richardson(omega) + Jacobi, 1 = Chebyshev + Jacobi on [emin, emax] of D^-1 A,
+  // 2 = Richardson(omega) + element-block multiplicative Schwarz (b2_schwarz.cu)
   int smoother = 0;
+  b2_schwarz* schwarz = nullptr;   // borrowed
   double emin = 0., emax = 0.;     // bounds in use
   double emin_user = 0., emax_user = 0.;   // emax_user <= 0: estimated at MGSetLevel (power iteration)
   b2_vec* d = nullptr;             // Chebyshev direction
@@ -264,11 +266,27 @@ int smooth_chebyshev(b2_mg* mg, b2_mg_level& L, int nsweeps, bool zero_guess) {
   return 0;
 }
 
+// Richardson(omega) around the element-block preconditioner: x <- x + omega M^-1 (b - A x)
+int smooth_schwarz(b2_mg* mg, b2_mg_level& L, int nsweeps, bool zero_guess) {
+  if (zero_guess) B2_TRY(b2_vec_zero(L.x));
+  for (int k = 0; k < nsweeps; k++) {
+    const b2_vec* r = L.b;                          // zero guess: r = b
+    if (!(zero_guess && k == 0)) {
+      B2_TRY(level_resid(L, L.b, L.x, L.t));
+      r = L.t;
+    }
+    B2_TRY(b2_schwarz_apply(L.schwarz, r, L.d));
+    B2_TRY(b2_vec_axpy(L.x, L.omega, L.d));
+  }
+  return 0;
+}
+
 int smooth(b2_mg* mg, int l, int nsweeps, bool zero_guess) {
   b2_mg_level& L = mg->L[l];
   b2_ctx* c = mg->ctx;
   const int64_t n = L.A->nrows;
   if (L.smoother == 1) return smooth_chebyshev(mg, L, nsweeps, zero_guess);
+  if (L.smoother == 2) return smooth_schwarz(mg, L, nsweeps, zero_guess);
   int done = 0;
   if (zero_guess && nsweeps > 0) {
     B2_LAUNCH(c, jacobi_first_kernel, vec_grid(c, n), kBlock, 0, n, L.dinv->d, L.b->d, L.x->d, L.omega);
@@ -405,6 +423,12 @@ int b2_mg_set_level(b2_mg* mg, int level, b2_csr* A, b2_csr* P, const int32_t* b
   B2_TRY(b2_csr_diag(A, L.dinv));
   if (L.halo) B2_TRY(b2_halo_sum(L.halo, L.dinv));       // diagonal of the summed operator
   B2_LAUNCH(c, recip_kernel, vec_grid(c, n), kBlock, 0, n, L.dinv->d, L.dinv->d);
+  if (L.smoother == 2 && level > 0) {          // numeric phase of the block smoother on the penalised operator
+    B2_CHECK(!L.halo, "b2_mg_set_level: the element-block smoother runs on one rank only");
+    B2_CHECK(L.schwarz && b2_schwarz_operator(L.schwarz) == A, "b2_mg_set_level: level %d: the block smoother was created on another operator", level);
+    if (!L.d) B2_TRY(b2_vec_create(c, n, &L.d));
+    B2_TRY(b2_schwarz_setup(L.schwarz));
+  }
   if (L.smoother == 1 && level > 0) {
     if (!L.d) B2_TRY(b2_vec_create(c, n, &L.d));
     if (L.emax_user <= 0.0) {                       // our own stated bounds: [0.1, 1.1] x power-iteration estimate
@@ -444,6 +468,13 @@ int b2_mg_set_smoother(b2_mg* mg, int level, int kind, double emin, double emax)
   mg->L[level].emax_user = emax;
   return 0;
 }
+int b2_mg_set_level_schwarz(b2_mg* mg, int level, b2_schwarz* s) {
+  B2_CHECK(mg && level >= 1 && level < mg->nlevels, "b2_mg_set_level_schwarz: bad level %d (the coarsest level has no smoother)", level);
+  mg->L[level].schwarz = s;
+  mg->L[level].smoother = s ? 2 : 0;
+  return 0;
+}
+
 int b2_mg_level_bounds(const b2_mg* mg, int level, double* emin, double* emax) {
   B2_CHECK(level >= 0 && level < mg->nlevels, "b2_mg_level_bounds: bad level");
   *emin = mg->L[level].emin;

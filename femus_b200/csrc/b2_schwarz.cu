@@ -1,0 +1,257 @@
+// Element-block (ASM / Vanka) smoother: the preconditioner LinearEquationSolverPetscAsm configures in PETSc
+// (reference src/08_algebra.../03_solvers_with_preconditioner/petsc_asm/LinearEquationSolverPetscAsm.cpp:266-340,
+// 03_algebra/02_preconditioners/PetscPreconditioner.cpp:179-184): PCASM with the caller's overlapping index sets
+// (BuildASMIndex, :91-262), PC_ASM_BASIC, local type PC_COMPOSITE_MULTIPLICATIVE, overlap 0, exact block solves
+// (MLU_PRECOND on the blocks).  On one rank PCApply_ASM is the multiplicative sweep
+//     y = 0;  for i = 0 .. nblocks-1:   y[B_i] += A[B_i,B_i]^-1 (r - A y)[B_i]
+// which is sequential as written.  Here the blocks arrive with a SCHEDULE: ordered groups of mutually independent
+// blocks (no block of a group reads or writes a dof another block of the group writes).  Blocks of one group
+// commute, so one launch per group -- one CTA per block -- reproduces the sweep in any block order that respects
+// the groups: the reference's own order when the groups are the dependency levels of that order, a coloured order
+// (few groups, the GPU-sized choice) when they are colours (the host layer builds both, host/AsmPartition.hpp).
+//
+// Data: the inverse of every diagonal block A[B_i,B_i], dense fp64 [m_i][m_i] row-major in HBM (125 x 125 for a
+// 2x2x2 block of HEX27 elements = 125 KB).  The apply kernel is HBM-bound on those inverses: per block m^2 x 8 B of
+// inverse + the block's CSR rows (12 B per non-zero) in, m x 8 B out.
+//   schwarz_extract_kernel   A[B,B] -> dense (binary search of every column in the block's sorted dof list)
+//   schwarz_invert_kernel    in-place Gauss-Jordan without pivoting (blocks of the penalised SPD operator), one CTA
+//                            per block, pivot row / column staged in shared memory
+//   schwarz_apply_kernel     t = (r - A y)[B] (warp per row), z = inv . t (warp per row, coalesced), y[B] += z
+#include "b2_common.cuh"
+
+struct b2_schwarz {
+  b2_ctx* ctx = nullptr;
+  b2_csr* A = nullptr;            // borrowed
+  int64_t nblocks = 0, ngroups = 0, ndofs_total = 0, inv_total = 0;
+  int max_m = 0;
+  int64_t* blk_ptr = nullptr;     // [nblocks+1] device
+  int32_t* blk_dofs = nullptr;    // [ndofs_total] device, every block's dofs sorted
+  int64_t* inv_ptr = nullptr;     // [nblocks+1] device: start of every block's inverse
+  double* inv = nullptr;          // [inv_total]
+  int32_t* group_blocks = nullptr;   // [nblocks] device: blocks in schedule order
+  std::vector<int64_t> group_ptr;    // [ngroups+1] host
+  int* err = nullptr;             // device: 1 + first block whose pivot vanished, or 0
+  bool ready = false;
+};
+
+namespace {
+
+constexpr int kApplyThreads = 256;
+constexpr int kInvertThreads = 512;
+
+__global__ void schwarz_extract_kernel(int64_t nblocks, const int64_t* __restrict__ blk_ptr, const int32_t* __restrict__ blk_dofs,
+                                       const int64_t* __restrict__ inv_ptr, const int64_t* __restrict__ rowptr,
+                                       const int32_t* __restrict__ col, const double* __restrict__ val, double* __restrict__ inv) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  for (int64_t b = blockIdx.x; b < nblocks; b += gridDim.x) {
+    const int32_t* D = blk_dofs + blk_ptr[b];
+    const int m = (int)(blk_ptr[b + 1] - blk_ptr[b]);
+    double* M = inv + inv_ptr[b];
+    for (int i = warp; i < m; i += nwarps) {
+      double* row = M + (int64_t)i * m;
+      for (int j = lane; j < m; j += 32) row[j] = 0.0;
+      __syncwarp();
+      const int64_t k0 = rowptr[D[i]], k1 = rowptr[D[i] + 1];
+      for (int64_t k = k0 + lane; k < k1; k += 32) {
+        const int32_t c = col[k];
+        int lo = 0, hi = m;                 // first position with D[pos] >= c
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          if (D[mid] < c) lo = mid + 1; else hi = mid;
+        }
+        if (lo < m && D[lo] == c) row[lo] = val[k];
+      }
+    }
+  }
+}
+
+// In-place Gauss-Jordan: for every pivot k, row k is scaled by 1/pivot (its k-th entry becomes 1/pivot, the image of
+// the identity column) and every other row i gets  M[i][j] = (j == k ? 0 : M[i][j]) - M[i][k] * rowk[j].
+__global__ void __launch_bounds__(kInvertThreads) schwarz_invert_kernel(int64_t nblocks, const int64_t* __restrict__ blk_ptr,
+                                                                         const int64_t* __restrict__ inv_ptr, double* __restrict__ inv,
+                                                                         int max_m, int* __restrict__ err) {
+  extern __shared__ double sh[];
+  double* rowk = sh;
+  double* colk = sh + max_m;
+  for (int64_t b = blockIdx.x; b < nblocks; b += gridDim.x) {
+    const int m = (int)(blk_ptr[b + 1] - blk_ptr[b]);
+    double* M = inv + inv_ptr[b];
+    __syncthreads();                       // the extract launch finished; rowk / colk of the previous block are free
+    for (int k = 0; k < m; k++) {
+      for (int i = threadIdx.x; i < m; i += blockDim.x) {
+        colk[i] = M[(int64_t)i * m + k];
+        rowk[i] = M[(int64_t)k * m + i];
+      }
+      __syncthreads();
+      const double piv = colk[k];
+      if (threadIdx.x == 0 && !(fabs(piv) > 0.0)) atomicCAS(err, 0, (int)(b < 0x7ffffffe ? b + 1 : 0x7fffffff));
+      const double p = 1.0 / piv;
+      __syncthreads();                     // every thread has read the pivot before row k is rewritten
+      for (int j = threadIdx.x; j < m; j += blockDim.x) {
+        const double v = (j == k ? 1.0 : rowk[j]) * p;
+        rowk[j] = v;
+        M[(int64_t)k * m + j] = v;
+      }
+      __syncthreads();
+      const int64_t total = (int64_t)m * m;
+      for (int64_t e = threadIdx.x; e < total; e += blockDim.x) {
+        const int i = (int)(e / m), j = (int)(e - (int64_t)i * m);
+        if (i == k) continue;
+        const double old = (j == k) ? 0.0 : M[e];
+        M[e] = fma(-colk[i], rowk[j], old);
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// One CTA per block of the group.  y is read (columns of the block's rows) and written (the block's own dofs) through
+// the same plain pointer: no other CTA of this launch touches those entries (the schedule's guarantee).
+__global__ void __launch_bounds__(kApplyThreads) schwarz_apply_kernel(int64_t g0, int64_t g1, const int32_t* __restrict__ group_blocks,
+                                                                       const int64_t* __restrict__ blk_ptr, const int32_t* __restrict__ blk_dofs,
+                                                                       const int64_t* __restrict__ inv_ptr, const double* __restrict__ inv,
+                                                                       const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                                                                       const double* __restrict__ val, const double* __restrict__ r,
+                                                                       double* y, int max_m) {
+  extern __shared__ double sh[];
+  double* t = sh;
+  double* z = sh + max_m;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  for (int64_t q = g0 + blockIdx.x; q < g1; q += gridDim.x) {
+    const int64_t b = group_blocks[q];
+    const int32_t* D = blk_dofs + blk_ptr[b];
+    const int m = (int)(blk_ptr[b + 1] - blk_ptr[b]);
+    const double* M = inv + inv_ptr[b];
+    __syncthreads();                       // t / z of the previous block are free
+    for (int i = warp; i < m; i += nwarps) {
+      const int64_t row = D[i];
+      double acc = 0.0;
+      for (int64_t k = rowptr[row] + lane; k < rowptr[row + 1]; k += 32) acc = fma(val[k], y[col[k]], acc);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (lane == 0) t[i] = r[row] - acc;
+    }
+    __syncthreads();
+    for (int i = warp; i < m; i += nwarps) {
+      const double* Mi = M + (int64_t)i * m;
+      double acc = 0.0;
+      for (int j = lane; j < m; j += 32) acc = fma(Mi[j], t[j], acc);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (lane == 0) z[i] = acc;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < m; i += blockDim.x) y[D[i]] += z[i];
+  }
+}
+
+}  // namespace
+
+const b2_csr* b2_schwarz_operator(const b2_schwarz* s) { return s ? s->A : nullptr; }
+
+extern "C" {
+
+int b2_schwarz_create(b2_ctx* c, b2_csr* A, int64_t nblocks, const int64_t* blk_ptr, const int32_t* blk_dofs, int64_t ngroups,
+                      const int64_t* group_ptr, const int32_t* group_blocks, b2_schwarz** out) {
+  B2_CHECK(c && A && out && blk_ptr && blk_dofs && group_ptr && group_blocks, "b2_schwarz_create: null argument");
+  B2_CHECK(A->nrows == A->ncols, "b2_schwarz_create: operator must be square");
+  B2_CHECK(nblocks >= 1 && ngroups >= 1 && ngroups <= nblocks, "b2_schwarz_create: %lld blocks in %lld groups", (long long)nblocks,
+           (long long)ngroups);
+  B2_CHECK(blk_ptr[0] == 0 && group_ptr[0] == 0 && group_ptr[ngroups] == nblocks, "b2_schwarz_create: offsets must start at 0 and the groups hold every block");
+  int max_m = 0;
+  std::vector<int64_t> inv_ptr((size_t)nblocks + 1, 0);
+  for (int64_t b = 0; b < nblocks; b++) {
+    const int64_t m = blk_ptr[b + 1] - blk_ptr[b];
+    B2_CHECK(m >= 1 && m <= 4096, "b2_schwarz_create: block %lld has %lld dofs (1..4096 supported)", (long long)b, (long long)m);
+    for (int64_t k = blk_ptr[b]; k < blk_ptr[b + 1]; k++) {
+      B2_CHECK(blk_dofs[k] >= 0 && blk_dofs[k] < A->nrows, "b2_schwarz_create: block %lld: dof %d outside the operator", (long long)b, (int)blk_dofs[k]);
+      B2_CHECK(k == blk_ptr[b] || blk_dofs[k] > blk_dofs[k - 1], "b2_schwarz_create: block %lld: dofs must be sorted and distinct", (long long)b);
+    }
+    if (m > max_m) max_m = (int)m;
+    inv_ptr[b + 1] = inv_ptr[b] + m * m;
+  }
+  std::vector<uint8_t> seen((size_t)nblocks, 0);
+  for (int64_t g = 0; g < ngroups; g++) B2_CHECK(group_ptr[g + 1] > group_ptr[g], "b2_schwarz_create: group %lld is empty", (long long)g);
+  for (int64_t q = 0; q < nblocks; q++) {
+    B2_CHECK(group_blocks[q] >= 0 && group_blocks[q] < nblocks && !seen[group_blocks[q]], "b2_schwarz_create: the schedule must list every block once");
+    seen[group_blocks[q]] = 1;
+  }
+  b2_schwarz* s = new b2_schwarz();
+  s->ctx = c;
+  s->A = A;
+  s->nblocks = nblocks;
+  s->ngroups = ngroups;
+  s->ndofs_total = blk_ptr[nblocks];
+  s->inv_total = inv_ptr[nblocks];
+  s->max_m = max_m;
+  s->group_ptr.assign(group_ptr, group_ptr + ngroups + 1);
+  *out = s;
+  B2_TRY(b2_malloc(c, &s->blk_ptr, (size_t)nblocks + 1));
+  B2_TRY(b2_malloc(c, &s->blk_dofs, (size_t)s->ndofs_total));
+  B2_TRY(b2_malloc(c, &s->inv_ptr, (size_t)nblocks + 1));
+  B2_TRY(b2_malloc(c, &s->inv, (size_t)s->inv_total));
+  B2_TRY(b2_malloc(c, &s->group_blocks, (size_t)nblocks));
+  B2_TRY(b2_malloc(c, &s->err, 1));
+  B2_TRY(b2_upload(c, s->blk_ptr, blk_ptr, (size_t)nblocks + 1));
+  B2_TRY(b2_upload(c, s->blk_dofs, blk_dofs, (size_t)s->ndofs_total));
+  B2_TRY(b2_upload(c, s->inv_ptr, inv_ptr.data(), (size_t)nblocks + 1));
+  B2_TRY(b2_upload(c, s->group_blocks, group_blocks, (size_t)nblocks));
+  // shared memory of the two kernels: 2 x max_m doubles (<= 64 KB)
+  const int smem = 2 * max_m * (int)sizeof(double);
+  if (smem > 48 * 1024) {
+    B2_CUDA(cudaFuncSetAttribute(schwarz_invert_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    B2_CUDA(cudaFuncSetAttribute(schwarz_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  }
+  return 0;
+}
+
+/* numeric phase: A[B_i,B_i] of the operator's CURRENT values (call it after the penalty rows are set), inverted */
+int b2_schwarz_setup(b2_schwarz* s) {
+  B2_CHECK(s, "b2_schwarz_setup: null handle");
+  b2_ctx* c = s->ctx;
+  const int smem = 2 * s->max_m * (int)sizeof(double);
+  B2_CUDA(cudaMemsetAsync(s->err, 0, sizeof(int), c->stream));
+  B2_LAUNCH(c, schwarz_extract_kernel, b2_grid_for(c, s->nblocks, 1, 8), 256, 0, s->nblocks, s->blk_ptr, s->blk_dofs, s->inv_ptr,
+            s->A->rowptr, s->A->col, s->A->val, s->inv);
+  B2_LAUNCH(c, schwarz_invert_kernel, b2_grid_for(c, s->nblocks, 1, 4), kInvertThreads, smem, s->nblocks, s->blk_ptr, s->inv_ptr, s->inv,
+            s->max_m, s->err);
+  int err = 0;
+  B2_TRY(b2_download(c, &err, s->err, 1));
+  B2_CHECK(err == 0, "b2_schwarz_setup: block %d is singular (zero pivot without pivoting)", err - 1);
+  s->ready = true;
+  return 0;
+}
+
+/* y = M^-1 r: the multiplicative sweep over the schedule's groups, one launch per group */
+int b2_schwarz_apply(b2_schwarz* s, const b2_vec* r, b2_vec* y) {
+  B2_CHECK(s && r && y, "b2_schwarz_apply: null argument");
+  B2_CHECK(s->ready, "b2_schwarz_apply: call b2_schwarz_setup first");
+  B2_CHECK(r->n >= s->A->nrows && y->n >= s->A->nrows && r->d != y->d, "b2_schwarz_apply: vectors too short or aliased");
+  b2_ctx* c = s->ctx;
+  const int smem = 2 * s->max_m * (int)sizeof(double);
+  B2_CUDA(cudaMemsetAsync(y->d, 0, (size_t)s->A->nrows * sizeof(double), c->stream));
+  for (int64_t g = 0; g < s->ngroups; g++) {
+    const int64_t g0 = s->group_ptr[g], g1 = s->group_ptr[g + 1];
+    B2_LAUNCH(c, schwarz_apply_kernel, b2_grid_for(c, g1 - g0, 1, 16), kApplyThreads, smem, g0, g1, s->group_blocks, s->blk_ptr,
+              s->blk_dofs, s->inv_ptr, s->inv, s->A->rowptr, s->A->col, s->A->val, r->d, y->d, s->max_m);
+  }
+  return 0;
+}
+
+int64_t b2_schwarz_bytes(const b2_schwarz* s) { return s ? s->inv_total * (int64_t)sizeof(double) : 0; }
+int64_t b2_schwarz_groups(const b2_schwarz* s) { return s ? s->ngroups : 0; }
+
+int b2_schwarz_destroy(b2_schwarz* s) {
+  if (!s) return 0;
+  b2_ctx* c = s->ctx;
+  b2_free(c, s->blk_ptr, (size_t)s->nblocks + 1);
+  b2_free(c, s->blk_dofs, (size_t)s->ndofs_total);
+  b2_free(c, s->inv_ptr, (size_t)s->nblocks + 1);
+  b2_free(c, s->inv, (size_t)s->inv_total);
+  b2_free(c, s->group_blocks, (size_t)s->nblocks);
+  b2_free(c, s->err, 1);
+  delete s;
+  return 0;
+}
+
+}  // extern "C"

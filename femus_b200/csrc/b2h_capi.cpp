@@ -2,6 +2,8 @@
 // tables) so that the Python harness can drive and inspect it.  Pure CPU code: no CUDA calls.
 #include <cstring>
 #include <memory>
+#include <string>
+#include "../host/AsmPartition.hpp"
 #include "../host/BoxMesh.hpp"
 #include "../host/FaceElement.hpp"
 #include "../host/GambitIO.hpp"
@@ -16,6 +18,10 @@ struct b2h_hier {
 struct b2h_csr {
   HostCsr m;
 };
+struct b2h_asm {
+  AsmIndex ix;
+};
+static thread_local std::string g_b2h_error;
 
 extern "C" {
 
@@ -207,6 +213,39 @@ void b2h_elem_face_nodes(int type, int32_t* out) {
 int b2h_elem_face_kind(int type, int f) {
   return f < ElemTopology::nfaces(type) ? FaceElement::kind_of_nvert(ElemTopology::face_nvert(type, f)) : -1;
 }
+b2h_asm* b2h_asm_create(const b2h_hier* h, int l, int family, int block_elems, int iproc) {
+  try {
+    if (!h || l < 0 || l >= (int)h->levels.size() || family < 0 || family > 2 || block_elems < 1)
+      throw std::invalid_argument("b2h_asm_create: bad level, family or block size");
+    std::unique_ptr<b2h_asm> a(new b2h_asm());
+    a->ix = BuildAsmIndex(h->levels[l], family, (unsigned)block_elems, iproc);
+    return a.release();
+  } catch (const std::exception& e) {
+    g_b2h_error = e.what();
+    return nullptr;
+  }
+}
+void b2h_asm_destroy(b2h_asm* a) { delete a; }
+int64_t b2h_asm_nblocks(const b2h_asm* a) { return a->ix.nblocks(); }
+void b2h_asm_block_type_range(const b2h_asm* a, int64_t* out3) { std::copy(a->ix.block_type_range, a->ix.block_type_range + 3, out3); }
+const int64_t* b2h_asm_elem_ptr(const b2h_asm* a) { return a->ix.elem_ptr.data(); }
+const int32_t* b2h_asm_elems(const b2h_asm* a) { return a->ix.elems.data(); }
+const int64_t* b2h_asm_local_ptr(const b2h_asm* a) { return a->ix.local_ptr.data(); }
+const int32_t* b2h_asm_local(const b2h_asm* a) { return a->ix.local.data(); }
+const int64_t* b2h_asm_overlap_ptr(const b2h_asm* a) { return a->ix.overlap_ptr.data(); }
+const int32_t* b2h_asm_overlap(const b2h_asm* a) { return a->ix.overlap.data(); }
+int64_t b2h_asm_schedule(int64_t n, const int64_t* rowptr, const int32_t* col, int64_t nblocks, const int64_t* blk_ptr,
+                         const int32_t* blk_dofs, int mode, int32_t* group_of_block) {
+  try {
+    if (n < 1 || nblocks < 1 || !rowptr || !col || !blk_ptr || !blk_dofs || !group_of_block)
+      throw std::invalid_argument("b2h_asm_schedule: null or empty argument");
+    return AsmSchedule(n, rowptr, col, nblocks, blk_ptr, blk_dofs, mode, group_of_block);
+  } catch (const std::exception& e) {
+    g_b2h_error = e.what();
+    return -1;
+  }
+}
+const char* b2h_last_error(void) { return g_b2h_error.c_str(); }
 int b2h_hex_prolongator_row(int family, int a, int b, int c, int* idx, double* val) {
   return HexElement::prolongator_row(family, a, b, c, idx, val);
 }

@@ -65,6 +65,18 @@ def _L():
             "b2h_face_tables": (None, [ci, vp, vp, vp, vp]),
             "b2h_hex_face_nodes": (None, [vp]),
             "b2h_level_boundary_faces": (i64, [vp, ci, vp, vp, vp]),
+            "b2h_asm_create": (vp, [vp, ci, ci, ci, ci]),
+            "b2h_asm_destroy": (None, [vp]),
+            "b2h_asm_nblocks": (i64, [vp]),
+            "b2h_asm_block_type_range": (None, [vp, vp]),
+            "b2h_asm_elem_ptr": (vp, [vp]),
+            "b2h_asm_elems": (vp, [vp]),
+            "b2h_asm_local_ptr": (vp, [vp]),
+            "b2h_asm_local": (vp, [vp]),
+            "b2h_asm_overlap_ptr": (vp, [vp]),
+            "b2h_asm_overlap": (vp, [vp]),
+            "b2h_asm_schedule": (i64, [i64, vp, vp, i64, vp, vp, ci, vp]),
+            "b2h_last_error": (ctypes.c_char_p, []),
             "b2h_face_kind_ngauss": (ci, [ci]),
             "b2h_face_kind_ndofs": (ci, [ci, ci]),
             "b2h_face_kind_tables": (None, [ci, ci, vp, vp, vp, vp]),
@@ -333,6 +345,56 @@ def hex_face_nodes():
 
 
 QUAD_FACE, TRI_FACE = 0, 1
+
+
+class AsmIndex:
+    """Element blocks and index sets of the ASM / Vanka smoother on one level for one Lagrange variable without
+    Schur variables (MeshASMPartitioning::DoPartition + LinearEquationSolverPetscAsm::BuildASMIndex): per block
+    its elements, the sorted local and overlapping dof sets, as (ptr[nblocks+1], entries) pairs."""
+
+    def __init__(self, level, family, block_elems, iproc=0):
+        L = level.hier.L
+        h = L.b2h_asm_create(level.hier.h, level.l, _fam(family), int(block_elems), int(iproc))
+        if not h:
+            raise ValueError(L.b2h_last_error().decode())
+        try:
+            nb = int(L.b2h_asm_nblocks(h))
+            self.nblocks = nb
+            rng = np.zeros(3, dtype=np.int64)
+            L.b2h_asm_block_type_range(h, rng.ctypes.data_as(vp))
+            self.block_type_range = rng
+            for name in ("elem", "local", "overlap"):
+                ptr = _view(getattr(L, f"b2h_asm_{name}_ptr")(h), (nb + 1,), np.int64).copy()
+                ent = getattr(L, "b2h_asm_" + {"elem": "elems", "local": "local", "overlap": "overlap"}[name])(h)
+                setattr(self, name + "_ptr", ptr)
+                setattr(self, name, _view(ent, (int(ptr[-1]),), np.int32).copy() if ptr[-1] else np.zeros(0, dtype=np.int32))
+        finally:
+            L.b2h_asm_destroy(h)
+
+    def blocks(self, which="overlap"):
+        ptr, ent = getattr(self, which + "_ptr"), getattr(self, which)
+        return [ent[ptr[b]:ptr[b + 1]] for b in range(self.nblocks)]
+
+
+def asm_schedule(rowptr, col, blk_ptr, blk_dofs, mode="colours"):
+    """Groups of mutually independent blocks for the multiplicative sweep (b2h_asm_schedule): mode "levels" = the
+    dependency levels of the given block order (the reference's sequential sweep exactly), "colours" = greedy
+    colouring.  Returns (group_of_block, group_ptr, group_blocks): blocks in sweep order, cut into groups."""
+    rowptr = np.ascontiguousarray(rowptr, dtype=np.int64)
+    col = np.ascontiguousarray(col, dtype=np.int32)
+    blk_ptr = np.ascontiguousarray(blk_ptr, dtype=np.int64)
+    blk_dofs = np.ascontiguousarray(blk_dofs, dtype=np.int32)
+    nb = blk_ptr.shape[0] - 1
+    grp = np.zeros(nb, dtype=np.int32)
+    L = _L()
+    ng = L.b2h_asm_schedule(rowptr.shape[0] - 1, rowptr.ctypes.data_as(vp), col.ctypes.data_as(vp), nb, blk_ptr.ctypes.data_as(vp),
+                            blk_dofs.ctypes.data_as(vp), {"levels": 0, "colours": 1}[mode], grp.ctypes.data_as(vp))
+    if ng < 0:
+        raise ValueError(L.b2h_last_error().decode())
+    order = np.argsort(grp, kind="stable").astype(np.int32)
+    gptr = np.zeros(ng + 1, dtype=np.int64)
+    np.cumsum(np.bincount(grp, minlength=ng), out=gptr[1:])
+    return grp, gptr, order
 
 
 def face_kind_tables(kind, family):

@@ -46,7 +46,7 @@ class PoissonMG:
 
     def __init__(self, ctx, nx, ny, nz, nlevels, order="biquadratic", bounds=None, npre=1, npost=1, omega=0.5,
                  dirichlet_faces=(1, 2, 3, 4, 5, 6), fsrc=1.0, coarse_rtol=1e-14, hier=None, dist=None, fused=True,
-                 neumann=None, smoother="richardson"):
+                 neumann=None, smoother="richardson", asm_block_elems=8, asm_schedule="colours"):
         self.ctx = ctx
         self.order = order
         self.fam = hostapi.FAMILY[order]
@@ -141,7 +141,23 @@ class PoissonMG:
         self.mg = capi.Multigrid(ctx, nlevels)
         self.mg.set_coarse(coarse_rtol, 10000)
         self.smoother = smoother
-        if smoother != "richardson":
+        self.asm_index = [None] * nlevels
+        self.asm_groups = [None] * nlevels
+        self.schwarz = [None] * nlevels
+        if smoother == "asm":
+            # "smoother": "asm" of 001_Poisson (main.cpp:234-250): element blocks of every level above the coarsest
+            # (DoPartition + BuildASMIndex on the host), swept in `asm_schedule` order: "levels" = the reference's
+            # block order exactly, "colours" = the same sweep with the blocks stably sorted by colour
+            if dist is not None:
+                raise NotImplementedError("the element-block smoother runs on one rank")
+            for l in range(1, nlevels):
+                ix = hostapi.AsmIndex(lv[l], order, asm_block_elems)
+                rp, ci = lv[l].sparsity(order)
+                grp, gptr, gblocks = hostapi.asm_schedule(rp, ci, ix.overlap_ptr, ix.overlap, asm_schedule)
+                self.asm_index[l], self.asm_groups[l] = ix, grp
+                self.schwarz[l] = capi.Schwarz(ctx, self.KK[l], ix.overlap_ptr, ix.overlap, gptr, gblocks)
+                self.mg.set_level_schwarz(l, self.schwarz[l])
+        elif smoother != "richardson":
             for l in range(1, nlevels):
                 self.mg.set_smoother(l, smoother)
         # --- distributed layout: interface dofs of every level, ownership; reductions over owned dofs

@@ -32,6 +32,7 @@ typedef struct b2_asm b2_asm;
 typedef struct b2_mg b2_mg;
 typedef struct b2_galerkin b2_galerkin;
 typedef struct b2_halo b2_halo;
+typedef struct b2_schwarz b2_schwarz;
 
 const char* b2_last_error(void);
 int b2_version(void);
@@ -274,6 +275,31 @@ int b2_mg_set_level_halo(b2_mg* mg, int level, b2_halo* halo);
  * not reproducible); b2_mg_level_bounds returns the interval in use. */
 int b2_mg_set_smoother(b2_mg* mg, int level, int kind, double emin, double emax);
 int b2_mg_level_bounds(const b2_mg* mg, int level, double* emin, double* emax);
+
+/* ---- element-block (ASM / Vanka) smoother: LinearEquationSolverPetscAsm (petsc_asm/LinearEquationSolverPetscAsm.cpp)
+ * What the reference sets (:266-340, PetscPreconditioner.cpp:179-184): PCASM, PC_ASM_BASIC, local type
+ * PC_COMPOSITE_MULTIPLICATIVE, the overlapping index sets of BuildASMIndex (:91-262), overlap 0.  On one rank that is
+ *     y = 0;  for i = 0 .. nblocks-1:   y[B_i] += A[B_i,B_i]^-1 (r - A y)[B_i].
+ * Block solves are exact (MLU_PRECOND on the blocks; stated choice -- 001_Poisson's own sub-preconditioner is one
+ * SSOR sweep).  blk_ptr[nblocks+1] / blk_dofs: every block's dofs, sorted (host arrays; the host layer builds them,
+ * b2h_asm_create).  The SCHEDULE group_ptr[ngroups+1] / group_blocks[nblocks] lists the blocks in sweep order, cut
+ * into groups of mutually independent blocks (one launch per group, one CTA per block): the dependency levels of the
+ * reference's block order reproduce its sweep exactly, a colouring gives few, large groups (b2h_asm_schedule).
+ * The caller guarantees the independence inside a group; everything else is checked.
+ * b2_schwarz_setup: numeric phase (extract and invert the blocks of A's current values).
+ * b2_schwarz_apply: y = M^-1 r.  One rank only (no interface sums). */
+int b2_schwarz_create(b2_ctx* ctx, b2_csr* A, int64_t nblocks, const int64_t* blk_ptr, const int32_t* blk_dofs,
+                      int64_t ngroups, const int64_t* group_ptr, const int32_t* group_blocks, b2_schwarz** out);
+int b2_schwarz_setup(b2_schwarz* s);
+int b2_schwarz_apply(b2_schwarz* s, const b2_vec* r, b2_vec* y);
+int64_t b2_schwarz_bytes(const b2_schwarz* s);      /* HBM held by the block inverses */
+int64_t b2_schwarz_groups(const b2_schwarz* s);
+int b2_schwarz_destroy(b2_schwarz* s);
+/* level smoother = KSPRICHARDSON(scale omega of b2_mg_set_level) + this preconditioner, npre / npost iterations
+ * (LinearEquationSolverPetsc.cpp:516-519 with the PC of LinearEquationSolverPetscAsm::SetPreconditioner).  s must
+ * have been created on the operator handed to b2_mg_set_level for that level; b2_mg_set_level runs its numeric
+ * phase after the penalty.  NULL restores the level's previous smoother kind 0. */
+int b2_mg_set_level_schwarz(b2_mg* mg, int level, b2_schwarz* s);
 /* coarse solver: Jacobi-PCG to ||r|| <= rtol ||b|| (the reference: PREONLY + MUMPS LU,
  * PetscPreconditioner.cpp:147-160) */
 int b2_mg_set_coarse(b2_mg* mg, double rtol, int maxit);

@@ -119,6 +119,32 @@ void b2h_face_kind_tables(int kind, int family, double* phi, double* dxi, double
 void b2h_elem_face_nodes(int type, int32_t* out);
 int b2h_elem_face_kind(int type, int f);
 
+
+/* ---- element-block (ASM / Vanka) smoother, one Lagrange variable, no Schur variable (001_Poisson "asm", main.cpp:234-250)
+ * b2h_asm_create: MeshASMPartitioning::DoPartition (MeshASMPartitioning.cpp:89-148) with block_elems elements per
+ * block, capped by the level's element count (LinearImplicitSystem.cpp:1191-1201), then
+ * LinearEquationSolverPetscAsm::BuildASMIndex (LinearEquationSolverPetscAsm.cpp:91-262) for rank iproc: per block
+ * its elements, the sorted "local" and "overlapping" index sets (CSR-like: ptr[nblocks+1] + entries).  NULL on bad
+ * arguments (b2h_last_error).  block_type_range[3]: _blockTypeRange (solid / porous / fluid block ends).
+ * b2h_asm_schedule: groups of mutually independent blocks for the multiplicative sweep of b2_schwarz_apply on the
+ * operator pattern (rowptr, col): mode 0 = dependency levels of the given block order (the reference's sequential
+ * sweep, exactly), mode 1 = greedy colours (the reference's sweep with the block list stably sorted by colour).
+ * Writes group_of_block[nblocks], returns the number of groups, -1 on bad arguments. */
+typedef struct b2h_asm b2h_asm;
+b2h_asm* b2h_asm_create(const b2h_hier* h, int l, int family, int block_elems, int iproc);
+void b2h_asm_destroy(b2h_asm* a);
+int64_t b2h_asm_nblocks(const b2h_asm* a);
+void b2h_asm_block_type_range(const b2h_asm* a, int64_t* out3);
+const int64_t* b2h_asm_elem_ptr(const b2h_asm* a);
+const int32_t* b2h_asm_elems(const b2h_asm* a);
+const int64_t* b2h_asm_local_ptr(const b2h_asm* a);
+const int32_t* b2h_asm_local(const b2h_asm* a);
+const int64_t* b2h_asm_overlap_ptr(const b2h_asm* a);
+const int32_t* b2h_asm_overlap(const b2h_asm* a);
+int64_t b2h_asm_schedule(int64_t n, const int64_t* rowptr, const int32_t* col, int64_t nblocks, const int64_t* blk_ptr,
+                         const int32_t* blk_dofs, int mode, int32_t* group_of_block);
+const char* b2h_last_error(void);
+
 #ifdef __cplusplus
 }
 #endif

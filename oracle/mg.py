@@ -68,8 +68,12 @@ class Hierarchy:
     """Per-level operators exactly as the reference sets them up for one MGsolve."""
 
     def __init__(self, levels, order, fsrc=1.0, dirichlet_faces=(1, 2, 3, 4, 5, 6), A_top=None, rhs=None,
-                 coarse_lu=True, ptap=None, neumann=None, smoother="richardson", mesh=None):
-        """mesh: the oracle module the levels come from (mesh_box by default, mesh_tet for tetrahedra)."""
+                 coarse_lu=True, ptap=None, neumann=None, smoother="richardson", mesh=None, asm_blocks=None, asm_sub="lu",
+                 asm_orders=None):
+        """mesh: the oracle module the levels come from (mesh_box by default, mesh_tet for tetrahedra).
+        smoother "asm": asm_blocks[l] = the overlapping index sets of level l >= 1 (oracle.asm.level_blocks),
+        asm_orders[l] = the order they are swept in (None: as listed)."""
+        self.asm_blocks, self.asm_sub, self.asm_orders = asm_blocks, asm_sub, asm_orders
         mb = mesh if mesh is not None else globals()["mb"]
         self.levels = levels
         self.order = order
@@ -109,6 +113,12 @@ class Hierarchy:
         self.A = [penalty_fast(self.A_raw[l], self.bdc_idx[l]) for l in range(nl)]
         self.dinv = [1.0 / A.diagonal() for A in self.A]
         self.lu = spla.splu(self.A[0].tocsc()) if self.coarse_lu else None
+        self.asm = [None] * nl
+        if self.smoother == "asm":          # PCASM sub-matrices are extracted from the penalised level operator
+            from . import asm as _asm
+            for l in range(1, nl):
+                self.asm[l] = _asm.BlockSmoother(self.A[l], self.asm_blocks[l], self.asm_sub,
+                                                 self.asm_orders[l] if self.asm_orders else None)
         # Chebyshev bounds: our own stated ones, [0.1, 1.1] x the power-iteration estimate of lambda_max(D^-1 A)
         self.ebounds = [None] * nl
         if self.smoother == "chebyshev":
@@ -135,6 +145,8 @@ class Hierarchy:
     def smooth(self, l, x, b, nsweeps, omega):
         """KSPRICHARDSON (scale omega) + PCJACOBI: x <- x + omega D^-1 (b - A x); or Chebyshev + Jacobi
         on the stated interval (Saad, alg. 12.1), restarted at every call like a PETSc smoother."""
+        if self.smoother == "asm":           # KSPRICHARDSON (scale omega) + PCASM (basic, multiplicative)
+            return self.asm[l].richardson(x, b, nsweeps, omega)
         if self.smoother == "chebyshev":
             emin, emax = self.ebounds[l]
             theta, delta = 0.5 * (emax + emin), 0.5 * (emax - emin)

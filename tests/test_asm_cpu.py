@@ -1,0 +1,143 @@
+"""Element-block (ASM / Vanka) smoother, CPU side: the host layer's index sets (MeshASMPartitioning::DoPartition,
+LinearEquationSolverPetscAsm::BuildASMIndex) bit-exact against the oracle's literal restatement, the sweep
+schedules (dependency levels = the reference's sequential sweep, colours), and the oracle smoother itself."""
+import os
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from femus_b200 import hostapi
+from oracle import asm, mesh_box as mb, mesh_mixed as mm, mg
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _same(ix, be, rng, loc, ovl):
+    assert ix.nblocks == len(be) and ix.block_type_range.tolist() == list(rng)
+    for a, b in zip(ix.blocks("elem"), be):
+        assert a.tolist() == list(b)
+    for a, b in zip(ix.blocks("local"), loc):
+        assert np.array_equal(a, b)
+    for a, b in zip(ix.blocks("overlap"), ovl):
+        assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("nprocs", [1, 2, 3])
+@pytest.mark.parametrize("order", ["linear", "quadratic", "biquadratic"])
+def test_index_sets_bit_exact_on_boxes(nprocs, order):
+    """Blocks of 1, 5, 8, 64 and 'all' elements on two refined levels of a 2x3x3 box, every rank of 1, 2 and 3-rank
+    slab partitions (ghost dofs of other ranks end up in the overlapping sets only)."""
+    H = hostapi.HostHierarchy(2, 3, 3, 3, nprocs=nprocs)
+    lv = mb.build_hierarchy(2, 3, 3, 3, nprocs=nprocs)
+    for l in (1, 2):
+        ed = mb.system_dof(lv[l], order)
+        for nb in (1, 5, 8, 64, 10 ** 6):
+            for iproc in range(nprocs):
+                ix = hostapi.AsmIndex(H.levels[l], order, nb, iproc)
+                _same(ix, *asm.level_blocks(lv[l], ed, mb.FAMILY[order], nb, iproc))
+                if iproc > 0 and nb == 8:        # shared nodes belong to the lowest rank: ranks > 0 see ghosts
+                    d0, d1 = lv[l].dof_offset[mb.FAMILY[order]][iproc:iproc + 2]
+                    assert any(((b < d0) | (b >= d1)).any() for b in ix.blocks("overlap"))
+                    assert all(((b >= d0) & (b < d1)).all() for b in ix.blocks("local"))
+    # every owned dof is in exactly one local set
+    ix = hostapi.AsmIndex(H.levels[2], order, 8, 0)
+    allloc = np.concatenate(ix.blocks("local"))
+    assert len(np.unique(allloc)) == len(allloc) == lv[2].dof_offset[mb.FAMILY[order]][1]
+
+
+@pytest.mark.parametrize("name", ["cube_mixed_3groups", "cube_mixed", "cube_tet10", "cube_wedge18"])
+def test_index_sets_bit_exact_on_unstructured_meshes(name):
+    """Mixed element types and two material classes (cube_mixed_3groups: 7 solid + 13 fluid elements on the coarse
+    level => solid blocks first, _blockTypeRange = [ns, ns, ns + nf])."""
+    path = os.path.join(GOLDEN, name + ".neu")
+    H = hostapi.HostHierarchy.from_neu(path, 2)
+    lv = mm.build_hierarchy(path, 2)
+    for l in (0, 1):
+        for order in ("linear", "quadratic", "biquadratic"):
+            ed = mm.element_dofs(lv[l], order)
+            for nb in (1, 3, 8):
+                ix = hostapi.AsmIndex(H.levels[l], order, nb)
+                be, rng, loc, ovl = asm.level_blocks(lv[l], ed, mm.FAMILY[order], nb)
+                _same(ix, be, rng, loc, ovl)
+                if name == "cube_mixed_3groups":
+                    assert 0 < rng[0] == rng[1] < rng[2]
+
+
+def test_bad_arguments_fail_loudly():
+    H = hostapi.HostHierarchy(2, 2, 2, 2)
+    with pytest.raises(ValueError):
+        hostapi.AsmIndex(H.levels[1], "linear", 0)
+    with pytest.raises(ValueError):
+        hostapi.AsmIndex(H.levels[1], "linear", 8, iproc=3)
+    ix = hostapi.AsmIndex(H.levels[1], "linear", 8)
+    rp, ci = H.levels[1].sparsity("linear")
+    with pytest.raises(ValueError):
+        hostapi.asm_schedule(rp[:5], ci, ix.overlap_ptr, ix.overlap, "levels")      # dofs outside the operator
+
+
+def _independent(A, blocks, members):
+    """no block of `members` writes what another one reads or writes"""
+    pat = sp.csr_matrix(A)
+    written = {}
+    for b in members:
+        for d in blocks[b]:
+            assert written.setdefault(int(d), b) == b
+    for b in members:
+        cols = np.unique(np.concatenate([pat.indices[pat.indptr[r]:pat.indptr[r + 1]] for r in blocks[b]]))
+        for c in cols:
+            assert written.get(int(c), b) == b
+
+
+@pytest.mark.parametrize("order", ["linear", "biquadratic"])
+def test_schedules_reproduce_the_sequential_sweep(order):
+    """levels: groups equal the oracle's dependency levels, blocks of a group are independent, and the sweep in
+    (group, block) order equals the sequential sweep BIT FOR BIT; colours: independent inside a colour, 8 colours on
+    2x2x2-element blocks of a box, and the coloured sweep equals the oracle's sweep over the stably sorted list."""
+    lv = mb.build_hierarchy(2, 2, 2, 3)
+    H = hostapi.HostHierarchy(2, 2, 2, 3)
+    ix = hostapi.AsmIndex(H.levels[2], order, 8)
+    blocks = ix.blocks()
+    O = mg.Hierarchy(lv, order, smoother="asm", asm_blocks=[None, hostapi.AsmIndex(H.levels[1], order, 8).blocks(), blocks])
+    A = O.A[2]
+    rp, ci = H.levels[2].sparsity(order)
+    assert np.array_equal(rp, A.indptr) and np.array_equal(ci, A.indices)
+    grp, gptr, gblocks = hostapi.asm_schedule(rp, ci, ix.overlap_ptr, ix.overlap, "levels")
+    assert np.array_equal(grp, asm.schedule(A, blocks))
+    r = np.random.default_rng(1).standard_normal(A.shape[0])
+    S = O.asm[2]
+    y_seq = S.apply(r)
+    for g in range(len(gptr) - 1):
+        _independent(A, blocks, gblocks[gptr[g]:gptr[g + 1]].tolist())
+    assert np.array_equal(S.apply(r, gblocks), y_seq)
+    assert np.array_equal(S.apply(r, gblocks[::-1][np.argsort(grp[gblocks[::-1]], kind="stable")]), y_seq)   # any order inside a group
+    grp2, gptr2, gblocks2 = hostapi.asm_schedule(rp, ci, ix.overlap_ptr, ix.overlap, "colours")
+    assert len(gptr2) - 1 == 8 and np.array_equal(np.bincount(grp2), np.full(8, 8))
+    for g in range(8):
+        _independent(A, blocks, gblocks2[gptr2[g]:gptr2[g + 1]].tolist())
+    y_col = S.apply(r, gblocks2)
+    assert np.abs(y_col - y_seq).max() > 1e-6 * np.abs(y_seq).max()         # another sweep order: another preconditioner
+    assert np.abs(A @ y_col - r).max() < np.abs(r).max()                      # ... and still a contraction of the residual
+
+
+def test_oracle_block_smoother_properties():
+    """One block holding every dof: M^-1 is the exact inverse.  Blocks = single dofs in order: the sweep is forward
+    Gauss-Seidel.  In the V-cycle the block smoother beats Richardson + Jacobi by orders of magnitude."""
+    lv = mb.build_hierarchy(2, 2, 2, 2)
+    H0 = mg.Hierarchy(lv, "linear")
+    A = H0.A[1]
+    n = A.shape[0]
+    r = np.random.default_rng(2).standard_normal(n)
+    assert np.abs(A @ asm.BlockSmoother(A, [np.arange(n)]).apply(r) - r).max() < 1e-12
+    y = asm.BlockSmoother(A, [np.array([i]) for i in range(n)]).apply(r)
+    Lw = sp.tril(A).tocsr()
+    import scipy.sparse.linalg as spla
+    assert np.abs(y - spla.spsolve_triangular(Lw, r, lower=True)).max() < 1e-12
+    ed = mb.system_dof(lv[1], "linear")
+    _, _, _, ovl = asm.level_blocks(lv[1], ed, 0, 8)
+    Ha = mg.Hierarchy(lv, "linear", smoother="asm", asm_blocks=[None, ovl])
+    ta, _ = Ha.mg_solve_trace(4, omega=1.0)
+    tj, _ = H0.mg_solve_trace(4)
+    assert ta[-1] < 1e-3 * tj[-1]
+    Hs = mg.Hierarchy(lv, "linear", smoother="asm", asm_blocks=[None, ovl], asm_sub="ssor")
+    ts, _ = Hs.mg_solve_trace(4, omega=1.0)
+    assert ts[-1] < tj[-1]

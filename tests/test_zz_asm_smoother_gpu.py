@@ -1,0 +1,115 @@
+"""GPU parity of the element-block (ASM / Vanka) smoother (b2_schwarz.cu, smoother kind 2 of b2_mg.cu) against the
+oracle's restatement of PCASM (basic, multiplicative, exact block solves; oracle/asm.py), through the C ABI.
+Reference: LinearEquationSolverPetscAsm.cpp:91-340, MeshASMPartitioning.cpp:89-148, 001_Poisson main.cpp:234-250.
+Bar: preconditioner application and V-cycle residual traces to 1e-12 relative (block inverses by Gauss-Jordan on the
+GPU, LU in the oracle)."""
+import os
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-12
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _oracle(pb, levels, order, mesh=None, **kw):
+    from oracle import mg
+    blocks = [None] + [pb.asm_index[l].blocks() for l in range(1, pb.nlevels)]
+    orders = [None] + [np.argsort(pb.asm_groups[l], kind="stable") for l in range(1, pb.nlevels)]
+    return mg.Hierarchy(levels, order, smoother="asm", asm_blocks=blocks, asm_orders=orders, mesh=mesh, **kw)
+
+
+@pytest.mark.parametrize("schedule", ["levels", "colours"])
+@pytest.mark.parametrize("order,shape,nb", [("linear", (2, 3, 2), 8), ("biquadratic", (2, 2, 2), 8), ("biquadratic", (2, 3, 2), 5),
+                                            ("quadratic", (2, 2, 2), 8)])
+def test_block_preconditioner_matches_oracle(ctx, schedule, order, shape, nb):
+    """y = M^-1 r on the penalised finest operator of a 3-level box hierarchy: blocks of nb elements in the
+    reference's order ("levels": its sequential sweep exactly) and in coloured order, ragged last block (nb = 5)."""
+    from femus_b200.poisson import PoissonMG
+    from oracle import mesh_box as mb
+    pb = PoissonMG(ctx, *shape, 3, order, smoother="asm", asm_block_elems=nb, asm_schedule=schedule, fused=False)
+    pb.assemble(); pb.galerkin(); pb.mg_set_levels()
+    O = _oracle(pb, mb.build_hierarchy(*shape, 3), order)
+    rng = np.random.default_rng(3)
+    for l in (1, 2):
+        n = pb.ndofs[l]
+        r = rng.standard_normal(n)
+        R, Y = ctx.vector(r), ctx.vector(n)
+        pb.schwarz[l].apply(R, Y)
+        want = O.asm[l].apply(r)
+        assert np.abs(Y.get() - want).max() <= RTOL * np.abs(want).max()
+        if schedule == "colours":
+            assert pb.schwarz[l].ngroups <= 27
+        assert pb.schwarz[l].nbytes == 8 * sum(len(b) ** 2 for b in pb.asm_index[l].blocks())
+    del pb
+
+
+@pytest.mark.parametrize("schedule,order,nl", [("levels", "linear", 3), ("colours", "linear", 3), ("colours", "biquadratic", 3),
+                                               ("levels", "biquadratic", 2)])
+def test_vcycle_trace_with_block_smoother(ctx, schedule, order, nl):
+    """001_Poisson with "smoother": "asm" (Richardson around the block preconditioner, here scale 1): four V-cycles
+    against the oracle, and the smoother's pay-off against Richardson + Jacobi on the same problem."""
+    from femus_b200.poisson import PoissonMG
+    from oracle import mesh_box as mb, mg
+    pb = PoissonMG(ctx, 2, 2, 2, nl, order, smoother="asm", asm_block_elems=8, asm_schedule=schedule, omega=1.0, coarse_rtol=1e-15)
+    pb.assemble(); pb.galerkin(); pb.mg_set_levels()
+    lv = mb.build_hierarchy(2, 2, 2, nl)
+    O = _oracle(pb, lv, order)
+    trace_ref, eps_ref = O.mg_solve_trace(4, omega=1.0)
+    trace = []
+    for _ in range(4):
+        pb.mg_solve()
+        trace.append(pb.residual_norm())
+    for a, b in zip(trace, trace_ref):
+        assert abs(a - b) <= RTOL * trace_ref[0], (trace, trace_ref)
+    assert np.abs(pb.EPS.get() - eps_ref).max() <= 1e-11 * np.abs(eps_ref).max()
+    jac, _ = mg.Hierarchy(lv, order).mg_solve_trace(4)
+    assert trace[-1] < 1e-2 * jac[-1]
+    del pb
+
+
+@pytest.mark.parametrize("name,order", [("cube_tet10", "quadratic"), ("cube_mixed_3groups", "biquadratic")])
+def test_block_smoother_on_unstructured_meshes(ctx, name, order):
+    """Tetrahedra and the mixed mesh with two material classes (solid blocks first): ragged blocks of 3 elements,
+    coloured sweep, V-cycle trace against the oracle."""
+    from femus_b200 import hostapi
+    from femus_b200.poisson import PoissonMG
+    from oracle import mesh_mixed as mm
+    path = os.path.join(GOLDEN, name + ".neu")
+    H = hostapi.HostHierarchy.from_neu(path, 2)
+    pb = PoissonMG(ctx, 0, 0, 0, 2, order, hier=H, smoother="asm", asm_block_elems=3, omega=1.0, coarse_rtol=1e-15)
+    pb.assemble(); pb.galerkin(); pb.mg_set_levels()
+    O = _oracle(pb, mm.build_hierarchy(path, 2), order, mesh=mm)
+    trace_ref, eps_ref = O.mg_solve_trace(4, omega=1.0)
+    trace = []
+    for _ in range(4):
+        pb.mg_solve()
+        trace.append(pb.residual_norm())
+    for a, b in zip(trace, trace_ref):
+        assert abs(a - b) <= RTOL * trace_ref[0], (trace, trace_ref)
+    assert np.abs(pb.EPS.get() - eps_ref).max() <= 1e-11 * np.abs(eps_ref).max()
+    del pb
+
+
+def test_block_smoother_fails_loudly(ctx):
+    from femus_b200 import capi, hostapi
+    H = hostapi.HostHierarchy(2, 2, 2, 2)
+    L = H.levels[1]
+    A = capi.Csr.from_elements(ctx, L.ndofs("linear"), L.system_dofs("linear"))
+    ix = hostapi.AsmIndex(L, "linear", 8)
+    rp, ci = L.sparsity("linear")
+    grp, gptr, gblocks = hostapi.asm_schedule(rp, ci, ix.overlap_ptr, ix.overlap, "colours")
+    bad = gblocks.copy()
+    bad[1] = bad[0]
+    with pytest.raises(RuntimeError):
+        capi.Schwarz(ctx, A, ix.overlap_ptr, ix.overlap, gptr, bad)                 # a block listed twice
+    unsorted = ix.overlap.copy()
+    unsorted[[0, 1]] = unsorted[[1, 0]]
+    with pytest.raises(RuntimeError):
+        capi.Schwarz(ctx, A, ix.overlap_ptr, unsorted, gptr, gblocks)
+    S = capi.Schwarz(ctx, A, ix.overlap_ptr, ix.overlap, gptr, gblocks)
+    r, y = ctx.vector(A.shape[0]), ctx.vector(A.shape[0])
+    with pytest.raises(RuntimeError):
+        S.apply(r, y)                                                               # numeric phase not run
+    with pytest.raises(RuntimeError):
+        S.setup()                                                                   # all-zero operator: singular blocks
