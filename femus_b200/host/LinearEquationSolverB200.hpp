@@ -24,7 +24,7 @@ class LinearEquationSolverB200 {
   LinearEquationSolverB200(const unsigned& igrid) : _KK(nullptr), _RES(nullptr), _EPS(nullptr), _EPSC(nullptr), _RESC(nullptr),
         _level(igrid), _mg(nullptr), _levelMax(0), _richardsonScaleFactor(0.5), _rtol(1.e-5), _abstol(1.e-50), _dtol(1.e+5),
         _maxits(1000), _restart(30), _bdcIndexIsInitialized(false) {}
-  ~LinearEquationSolverB200() { this->MGClear(); this->DeletePde(); }
+  virtual ~LinearEquationSolverB200() { this->MGClear(); this->DeletePde(); }
 
   // ---- LinearEquation::InitPde / DeletePde (LinearEquation.cpp:196-405): level matrix + vectors.
   // dof[nel][nve] are the system dofs of the level's elements (GetSystemDof), bdc[ndofs] the flags
@@ -89,10 +89,7 @@ class LinearEquationSolverB200 {
       Pm.close();
       P = Pm.handle();
     }
-    // level smoother: set_solver_type(RICHARDSON) -> Richardson(scale)+Jacobi, set_solver_type(CHEBYSHEV) ->
-    // Chebyshev+Jacobi with the backend's stated eigenvalue bounds (KSPSetType switch, :452-536)
-    B2_ABORT_IF(b2_mg_set_smoother(LinSolver->_mg, (int)_level, _levelSolverType == CHEBYSHEV_B200 ? 1 : 0, 0., 0.),
-                "b2_mg_set_smoother");
+    this->SetLevelSmoother(LinSolver->_mg);
     // SetPenalty (:428-436) happens inside: Dirichlet rows -> identity, pattern kept
     B2_ABORT_IF(b2_mg_set_level(LinSolver->_mg, (int)_level, _KK->handle(), P, _bdcIndex.data(), (int64_t)_bdcIndex.size(), (int)npre,
                                 (int)npost, _richardsonScaleFactor),
@@ -124,8 +121,16 @@ class LinearEquationSolverB200 {
   B200Matrix* _KK;
   B200Vector *_RES, *_EPS, *_EPSC, *_RESC;
 
- private:
+ protected:
+  // level smoother: set_solver_type(RICHARDSON) -> Richardson(scale)+Jacobi, set_solver_type(CHEBYSHEV) ->
+  // Chebyshev+Jacobi with the backend's stated eigenvalue bounds (KSPSetType switch, :452-536).  The reference's
+  // subclasses override SetPreconditioner (LinearEquationSolverPetscAsm.cpp:266); here they override this.
+  virtual void SetLevelSmoother(b2_mg* mg) {
+    B2_ABORT_IF(b2_mg_set_smoother(mg, (int)_level, _levelSolverType == CHEBYSHEV_B200 ? 1 : 0, 0., 0.), "b2_mg_set_smoother");
+  }
   unsigned _level;
+
+ private:
   b2_mg* _mg;
   unsigned _levelMax;
   B200SolverType _levelSolverType = RICHARDSON_B200, _mgSolverType = PREONLY_B200;

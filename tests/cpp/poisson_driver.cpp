@@ -3,8 +3,11 @@
 // on a box mesh, written against B200Vector / B200Matrix / LinearEquationSolverB200 and the host mesh
 // layer.  tests/test_adapters.py runs it on the GPU and checks what it prints against the oracle.
 //
-//   poisson_driver nx ny nz nlevels family(0 linear | 2 biquadratic) ncycles [compat]
+//   poisson_driver nx ny nz nlevels family(0 linear | 2 biquadratic) ncycles [compat | asm<N> | asmref<N>]
 //
+// "asm<N>" (e.g. asm8) runs the levels through LinearEquationSolverB200Asm: the element-block smoother of
+// "smoother": "asm" (main.cpp:234-250) with N elements per block, Richardson scale 1, coloured sweep; "asmref<N>"
+// sweeps the blocks in the reference's own order.
 // "compat" additionally rebuilds the finest matrix through the slow plugin path (init with counts,
 // add_matrix_blocked per element, close) from the rows of the device-assembled one and checks that
 // both give the same matrix-vector product.
@@ -12,7 +15,8 @@
 #include <cstdlib>
 #include <memory>
 #include "../../femus_b200/host/BoxMesh.hpp"
-#include "../../femus_b200/host/LinearEquationSolverB200.hpp"
+#include <cstring>
+#include "../../femus_b200/host/LinearEquationSolverB200Asm.hpp"
 
 using namespace femus;
 using namespace femus_b200;
@@ -21,7 +25,10 @@ int main(int argc, char** argv) {
   if (argc < 7) { std::fprintf(stderr, "usage: %s nx ny nz nlevels family ncycles [compat]\n", argv[0]); return 2; }
   const int nx = std::atoi(argv[1]), ny = std::atoi(argv[2]), nz = std::atoi(argv[3]), nl = std::atoi(argv[4]);
   const int family = std::atoi(argv[5]), ncycles = std::atoi(argv[6]);
-  const bool compat = argc > 7;
+  const bool use_asm = argc > 7 && std::strncmp(argv[7], "asm", 3) == 0;
+  const bool asm_ref = use_asm && std::strncmp(argv[7], "asmref", 6) == 0;
+  const int asm_blocks = use_asm ? std::atoi(argv[7] + (asm_ref ? 6 : 3)) : 0;
+  const bool compat = argc > 7 && !use_asm;
   const int nve = HexElement::nve(family);
 
   // mlMsh.GenerateCoarseBoxMesh(...); mlMsh.RefineMesh(nl, nl, NULL)            (main.cpp:133-141)
@@ -35,11 +42,20 @@ int main(int argc, char** argv) {
   std::vector<std::unique_ptr<LinearEquationSolverB200>> LinSolver;
   std::vector<std::unique_ptr<B200Matrix>> PP(nl);
   for (int l = 0; l < nl; l++) {
-    LinSolver.emplace_back(new LinearEquationSolverB200((unsigned)l));
+    if (use_asm) {       // system.SetLinearEquationSolverType(FEMuS_ASM); SetNumberOfSchurVariables(0); SetElementBlockNumber(n)
+      LinearEquationSolverB200Asm* s = new LinearEquationSolverB200Asm((unsigned)l);
+      s->SetMesh(&msh[l], family);
+      s->SetNumberOfSchurVariables(0);
+      s->SetElementBlockNumber((unsigned)std::min<int64_t>(asm_blocks, msh[l].nel));      // LinearImplicitSystem.cpp:1198
+      s->SetSweepOrder(asm_ref ? 0 : 1);
+      LinSolver.emplace_back(s);
+    } else {
+      LinSolver.emplace_back(new LinearEquationSolverB200((unsigned)l));
+    }
     const std::vector<int32_t> dof = msh[l].system_dofs(family);
     LinSolver[l]->InitPde((int)msh[l].ndofs(family), msh[l].nel, nve, dof.data(), msh[l].GenerateBdc(family, dirichlet));
     LinSolver[l]->SetTolerances(1.e-10, 1.e-20, 1.e+50, 1, 30);
-    LinSolver[l]->SetRichardsonScaleFactor(0.5);
+    LinSolver[l]->SetRichardsonScaleFactor(use_asm ? 1.0 : 0.5);
   }
   for (int l = 1; l < nl; l++) {      // BuildProlongatorMatrix + ZeroInterpolatorDirichletNodes (:826-909, :1032-1120)
     const HostCsr P = BuildProlongator(msh[l - 1], msh[l], family);

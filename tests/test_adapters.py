@@ -13,8 +13,13 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF = "/root/reference/src"
 
 PROBE = r"""
-#include "femus_b200/host/LinearEquationSolverB200.hpp"
+#include "femus_b200/host/LinearEquationSolverB200Asm.hpp"
 int main() {
+  femus::LinearEquationSolverB200Asm asm_solver(1);     // the element-block level solver (LinearEquationSolverPetscAsm surface)
+  asm_solver.SetNumberOfSchurVariables(0);
+  asm_solver.SetElementBlockNumber(8);
+  femus::LinearEquationSolverB200* base = &asm_solver;
+  (void)base;
   femus::B200Vector v;        // instantiable => every pure virtual of NumericVector is overridden
   femus::B200Matrix m;        // likewise for SparseMatrix
   femus::NumericVector* nv = &v;

@@ -113,3 +113,38 @@ def test_block_smoother_fails_loudly(ctx):
         S.apply(r, y)                                                               # numeric phase not run
     with pytest.raises(RuntimeError):
         S.setup()                                                                   # all-zero operator: singular blocks
+
+
+@pytest.mark.parametrize("mode,shape,nl,order", [("asm8", (2, 2, 2), 3, "biquadratic"), ("asmref8", (2, 2, 2), 3, "linear"),
+                                                 ("asm5", (3, 2, 2), 2, "linear")])
+def test_cpp_driver_with_the_asm_level_solver(mode, shape, nl, order):
+    """tests/cpp/poisson_driver.cpp through LinearEquationSolverB200Asm (the LinearEquationSolverPetscAsm surface:
+    SetNumberOfSchurVariables(0), SetElementBlockNumber(n), MGSetLevel building index sets + preconditioner):
+    residual after every MGsolve cycle and the final solution against the oracle."""
+    import re
+    from femus_b200 import hostapi
+    from oracle import mesh_box as mb, mg
+    from tests.test_adapters import _run_driver
+    fam = {"linear": 0, "biquadratic": 2}[order]
+    nb = int(mode.lstrip("asmref"))
+    ncyc = 3
+    out = _run_driver(list(shape) + [nl, fam, ncyc, mode])
+    res = [float(x) for x in re.findall(r"cycle \d+ residual (\S+)", out)]
+    assert len(res) == ncyc + 1
+    H = hostapi.HostHierarchy(*shape, nl)
+    blocks, orders = [None], [None]
+    for l in range(1, nl):
+        ix = hostapi.AsmIndex(H.levels[l], order, nb)
+        rp, ci = H.levels[l].sparsity(order)
+        grp, _, gblocks = hostapi.asm_schedule(rp, ci, ix.overlap_ptr, ix.overlap, "levels" if mode.startswith("asmref") else "colours")
+        blocks.append(ix.blocks())
+        orders.append(gblocks)
+    O = mg.Hierarchy(mb.build_hierarchy(*shape, nl), order, smoother="asm", asm_blocks=blocks, asm_orders=orders)
+    trace, eps = O.mg_solve_trace(ncyc, omega=1.0)
+    free = O.bdc[-1] > 1.1
+    r0 = float(np.linalg.norm(np.where(free, O.rhs, 0.0)))
+    assert abs(res[0] - r0) <= 1e-12 * r0
+    for k in range(ncyc):
+        assert abs(res[k + 1] - trace[k]) <= 1e-11 * r0, (k, res[k + 1], trace[k])
+    l2 = float(re.search(r"solution l2 (\S+)", out).group(1))
+    assert abs(l2 - np.linalg.norm(eps)) <= 1e-10 * np.linalg.norm(eps)
