@@ -1,0 +1,117 @@
+// Device code of the element-block smoother (b2_schwarz.cu), kept free of host / runtime calls so that the SAME
+// source also compiles for the CPU thread emulator of tests/cpp/cuda_emu.hpp (tests/test_kernel_emulation.py runs
+// these kernels on host threads against the oracle when no GPU is present).  Included inside an anonymous namespace.
+#pragma once
+#ifndef B2_DYN_SHARED
+#define B2_DYN_SHARED(type, name) extern __shared__ type name[]
+#endif
+
+constexpr int kApplyThreads = 256;
+constexpr int kInvertThreads = 512;
+
+__global__ void schwarz_extract_kernel(int64_t nblocks, const int64_t* __restrict__ blk_ptr, const int32_t* __restrict__ blk_dofs,
+                                       const int64_t* __restrict__ inv_ptr, const int64_t* __restrict__ rowptr,
+                                       const int32_t* __restrict__ col, const double* __restrict__ val, double* __restrict__ inv) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  for (int64_t b = blockIdx.x; b < nblocks; b += gridDim.x) {
+    const int32_t* D = blk_dofs + blk_ptr[b];
+    const int m = (int)(blk_ptr[b + 1] - blk_ptr[b]);
+    double* M = inv + inv_ptr[b];
+    for (int i = warp; i < m; i += nwarps) {
+      double* row = M + (int64_t)i * m;
+      for (int j = lane; j < m; j += 32) row[j] = 0.0;
+      __syncwarp();
+      const int64_t k0 = rowptr[D[i]], k1 = rowptr[D[i] + 1];
+      for (int64_t k = k0 + lane; k < k1; k += 32) {
+        const int32_t c = col[k];
+        int lo = 0, hi = m;                 // first position with D[pos] >= c
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          if (D[mid] < c) lo = mid + 1; else hi = mid;
+        }
+        if (lo < m && D[lo] == c) row[lo] = val[k];
+      }
+    }
+  }
+}
+
+// In-place Gauss-Jordan: for every pivot k, row k is scaled by 1/pivot (its k-th entry becomes 1/pivot, the image of
+// the identity column) and every other row i gets  M[i][j] = (j == k ? 0 : M[i][j]) - M[i][k] * rowk[j].
+__global__ void __launch_bounds__(kInvertThreads) schwarz_invert_kernel(int64_t nblocks, const int64_t* __restrict__ blk_ptr,
+                                                                         const int64_t* __restrict__ inv_ptr, double* __restrict__ inv,
+                                                                         int max_m, int* __restrict__ err) {
+  B2_DYN_SHARED(double, sh);
+  double* rowk = sh;
+  double* colk = sh + max_m;
+  for (int64_t b = blockIdx.x; b < nblocks; b += gridDim.x) {
+    const int m = (int)(blk_ptr[b + 1] - blk_ptr[b]);
+    double* M = inv + inv_ptr[b];
+    __syncthreads();                       // the extract launch finished; rowk / colk of the previous block are free
+    for (int k = 0; k < m; k++) {
+      for (int i = threadIdx.x; i < m; i += blockDim.x) {
+        colk[i] = M[(int64_t)i * m + k];
+        rowk[i] = M[(int64_t)k * m + i];
+      }
+      __syncthreads();
+      const double piv = colk[k];
+      if (threadIdx.x == 0 && !(fabs(piv) > 0.0)) atomicCAS(err, 0, (int)(b < 0x7ffffffe ? b + 1 : 0x7fffffff));
+      const double p = 1.0 / piv;
+      __syncthreads();                     // every thread has read the pivot before row k is rewritten
+      for (int j = threadIdx.x; j < m; j += blockDim.x) {
+        const double v = (j == k ? 1.0 : rowk[j]) * p;
+        rowk[j] = v;
+        M[(int64_t)k * m + j] = v;
+      }
+      __syncthreads();
+      const int64_t total = (int64_t)m * m;
+      for (int64_t e = threadIdx.x; e < total; e += blockDim.x) {
+        const int i = (int)(e / m), j = (int)(e - (int64_t)i * m);
+        if (i == k) continue;
+        const double old = (j == k) ? 0.0 : M[e];
+        M[e] = fma(-colk[i], rowk[j], old);
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// One CTA per block of the group.  y is read (columns of the block's rows) and written (the block's own dofs) through
+// the same plain pointer: no other CTA of this launch touches those entries (the schedule's guarantee).
+__global__ void __launch_bounds__(kApplyThreads) schwarz_apply_kernel(int64_t g0, int64_t g1, const int32_t* __restrict__ group_blocks,
+                                                                       const int64_t* __restrict__ blk_ptr, const int32_t* __restrict__ blk_dofs,
+                                                                       const int64_t* __restrict__ inv_ptr, const double* __restrict__ inv,
+                                                                       const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                                                                       const double* __restrict__ val, const double* __restrict__ r,
+                                                                       double* y, int max_m) {
+  B2_DYN_SHARED(double, sh);
+  double* t = sh;
+  double* z = sh + max_m;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  for (int64_t q = g0 + blockIdx.x; q < g1; q += gridDim.x) {
+    const int64_t b = group_blocks[q];
+    const int32_t* D = blk_dofs + blk_ptr[b];
+    const int m = (int)(blk_ptr[b + 1] - blk_ptr[b]);
+    const double* M = inv + inv_ptr[b];
+    __syncthreads();                       // t / z of the previous block are free
+    for (int i = warp; i < m; i += nwarps) {
+      const int64_t row = D[i];
+      double acc = 0.0;
+      for (int64_t k = rowptr[row] + lane; k < rowptr[row + 1]; k += 32) acc = fma(val[k], y[col[k]], acc);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (lane == 0) t[i] = r[row] - acc;
+    }
+    __syncthreads();
+    for (int i = warp; i < m; i += nwarps) {
+      const double* Mi = M + (int64_t)i * m;
+      double acc = 0.0;
+      for (int j = lane; j < m; j += 32) acc = fma(Mi[j], t[j], acc);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (lane == 0) z[i] = acc;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < m; i += blockDim.x) y[D[i]] += z[i];
+  }
+}
+

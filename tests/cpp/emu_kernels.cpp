@@ -1,0 +1,45 @@
+// TEST INFRASTRUCTURE: the device sources femus_b200/csrc/b2_schwarz_kernels.cuh and b2_neumann_kernel.cuh compiled
+// for the CPU thread emulator (cuda_emu.hpp) behind two C entry points that mirror what b2_schwarz_setup /
+// b2_schwarz_apply and b2_asm_neumann_faces launch.  Built and driven by tests/test_kernel_emulation.py.
+#include "cuda_emu.hpp"
+
+namespace {
+#include "../../femus_b200/csrc/b2_schwarz_kernels.cuh"
+}
+#include "../../femus_b200/csrc/b2_neumann_kernel.cuh"
+
+extern "C" {
+
+// extract + invert + the sweep over the schedule's groups; returns the singular-block flag of the invert kernel
+int emu_schwarz(int64_t n, const int64_t* rowptr, const int32_t* col, const double* val, int64_t nblocks, const int64_t* blk_ptr,
+                const int32_t* blk_dofs, int64_t ngroups, const int64_t* group_ptr, const int32_t* group_blocks, const double* r,
+                double* y, double* inv_out, int threads, int grid) {
+  std::vector<int64_t> inv_ptr((size_t)nblocks + 1, 0);
+  int max_m = 0;
+  for (int64_t b = 0; b < nblocks; b++) {
+    const int64_t m = blk_ptr[b + 1] - blk_ptr[b];
+    inv_ptr[b + 1] = inv_ptr[b] + m * m;
+    if (m > max_m) max_m = (int)m;
+  }
+  std::vector<double> inv((size_t)inv_ptr[nblocks], -7.0);          // poisoned: the extract kernel must write every entry
+  int err = 0;
+  const size_t smem = 2 * (size_t)max_m * sizeof(double);
+  emu::launch(schwarz_extract_kernel, (unsigned)grid, (unsigned)threads, 0, nblocks, blk_ptr, blk_dofs, inv_ptr.data(), rowptr, col, val,
+              inv.data());
+  emu::launch(schwarz_invert_kernel, (unsigned)grid, (unsigned)threads, smem, nblocks, blk_ptr, (const int64_t*)inv_ptr.data(), inv.data(),
+              max_m, &err);
+  for (int64_t i = 0; i < n; i++) y[i] = 0.0;
+  for (int64_t g = 0; g < ngroups; g++)
+    emu::launch(schwarz_apply_kernel, (unsigned)grid, (unsigned)threads, smem, group_ptr[g], group_ptr[g + 1], group_blocks, blk_ptr, blk_dofs,
+                (const int64_t*)inv_ptr.data(), (const double*)inv.data(), rowptr, col, val, r, y, max_m);
+  if (inv_out) std::copy(inv.begin(), inv.end(), inv_out);
+  return err;
+}
+
+void emu_neumann(int64_t nfaces, const int32_t* felem, const int32_t* flocal, const double* fvalue, int nvf, int ngf, int nve,
+                 const double* ftab, const int32_t* fnodes, int64_t nnode, const double* xyz, const int32_t* conn, const int32_t* dof,
+                 double* rhs, int grid) {
+  emu::launch(neumann_kernel, (unsigned)grid, 256u, 0, nfaces, felem, flocal, fvalue, nvf, ngf, nve, ftab, fnodes, nnode, xyz, conn, dof, rhs);
+}
+
+}  // extern "C"

@@ -1,0 +1,120 @@
+"""The device sources of the kernels written without a GPU at hand (femus_b200/csrc/b2_schwarz_kernels.cuh,
+b2_neumann_kernel.cuh) executed on the CPU by a thread-per-CUDA-thread emulator (tests/cpp/cuda_emu.hpp: barriers
+for __syncthreads / __syncwarp, warp shuffles, atomics) and compared with the oracle.  This checks the kernels'
+logic -- indexing, the synchronisation protocol, the arithmetic -- on the SAME source nvcc compiles; the GPU parity
+tests (tests/test_tri_faces_gpu.py, tests/test_zz_asm_smoother_gpu.py) remain the gate for the device itself."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from femus_b200 import hostapi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+vp = ctypes.c_void_p
+
+
+@pytest.fixture(scope="module")
+def emu(tmp_path_factory):
+    so = str(tmp_path_factory.mktemp("emu") / "libemu.so")
+    r = subprocess.run(["g++", "-std=c++20", "-O1", "-pthread", "-shared", "-fPIC", "-o", so, os.path.join(ROOT, "tests", "cpp", "emu_kernels.cpp")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    L = ctypes.CDLL(so)
+    L.emu_schwarz.restype = ctypes.c_int
+    L.emu_schwarz.argtypes = [ctypes.c_int64, vp, vp, vp, ctypes.c_int64, vp, vp, ctypes.c_int64, vp, vp, vp, vp, vp, ctypes.c_int, ctypes.c_int]
+    L.emu_neumann.restype = None
+    L.emu_neumann.argtypes = [ctypes.c_int64, vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp, ctypes.c_int64, vp, vp, vp, vp, ctypes.c_int]
+    return L
+
+
+def _p(a):
+    return a.ctypes.data_as(vp)
+
+
+def _run_schwarz(emu, A, ix, gptr, gblocks, r, threads=64, grid=3):
+    rp = np.ascontiguousarray(A.indptr, dtype=np.int64)
+    ci = np.ascontiguousarray(A.indices, dtype=np.int32)
+    va = np.ascontiguousarray(A.data, dtype=np.float64)
+    bp, bd = np.ascontiguousarray(ix.overlap_ptr, dtype=np.int64), np.ascontiguousarray(ix.overlap, dtype=np.int32)
+    gp, gb = np.ascontiguousarray(gptr, dtype=np.int64), np.ascontiguousarray(gblocks, dtype=np.int32)
+    y = np.full(A.shape[0], np.nan)
+    inv = np.zeros(int(sum(len(b) ** 2 for b in ix.blocks())))
+    err = emu.emu_schwarz(A.shape[0], _p(rp), _p(ci), _p(va), ix.nblocks, _p(bp), _p(bd), len(gp) - 1, _p(gp), _p(gb), _p(r), _p(y), _p(inv),
+                          threads, grid)
+    return err, y, inv
+
+
+@pytest.mark.parametrize("order,nb,schedule", [("linear", 8, "levels"), ("linear", 8, "colours"), ("linear", 5, "colours"),
+                                               ("biquadratic", 1, "colours")])
+def test_schwarz_kernels_on_the_emulator(emu, order, nb, schedule):
+    """extract -> Gauss-Jordan inverse -> one launch per group, on the penalised level-1 operator of a 2x2x2 box:
+    block inverses against numpy, the sweep against the oracle's PCASM restatement in the same block order;
+    3 CTAs of 64 threads, so every CTA strides over several blocks of a group."""
+    from oracle import mesh_box as mb, mg
+    shape = (2, 2, 2) if order == "linear" else (1, 2, 1)
+    lv = mb.build_hierarchy(*shape, 2)
+    H = hostapi.HostHierarchy(*shape, 2)
+    ix = hostapi.AsmIndex(H.levels[1], order, nb)
+    rp, ci = H.levels[1].sparsity(order)
+    grp, gptr, gblocks = hostapi.asm_schedule(rp, ci, ix.overlap_ptr, ix.overlap, schedule)
+    O = mg.Hierarchy(lv, order, dirichlet_faces=(1, 3, 6), smoother="asm", asm_blocks=[None, ix.blocks()], asm_orders=[None, gblocks])
+    A = O.A[1]
+    r = np.random.default_rng(7).standard_normal(A.shape[0])
+    err, y, inv = _run_schwarz(emu, A, ix, gptr, gblocks, r)
+    assert err == 0
+    pos = 0
+    for b, M in zip(ix.blocks(), O.asm[1].dense):
+        m = len(b)
+        got = inv[pos:pos + m * m].reshape(m, m)
+        want = np.linalg.inv(M)
+        assert np.abs(got - want).max() <= 1e-12 * np.abs(want).max()
+        pos += m * m
+    want = O.asm[1].apply(r)
+    assert np.abs(y - want).max() <= 1e-12 * np.abs(want).max()
+    if schedule == "levels":        # the reference's own sweep
+        assert np.abs(y - O.asm[1].apply(r, range(ix.nblocks))).max() <= 1e-12 * np.abs(want).max()
+
+
+def test_schwarz_invert_kernel_reports_singular_blocks(emu):
+    import scipy.sparse as sp
+    H = hostapi.HostHierarchy(1, 1, 1, 2)
+    ix = hostapi.AsmIndex(H.levels[1], "linear", 4)
+    rp, ci = H.levels[1].sparsity("linear")
+    grp, gptr, gblocks = hostapi.asm_schedule(rp, ci, ix.overlap_ptr, ix.overlap, "colours")
+    A = sp.csr_matrix((np.zeros(len(ci)), ci, rp))
+    err, _, _ = _run_schwarz(emu, A, ix, gptr, gblocks, np.ones(A.shape[0]), threads=32, grid=1)
+    assert err == 1                 # 1 + index of the first singular block
+
+
+@pytest.mark.parametrize("name,order", [("cube_tet10", "quadratic"), ("cube_wedge18", "biquadratic"), ("cube_mixed", "linear"),
+                                        ("cube_mixed", "quadratic"), ("cube_hex27_2x2x2", "biquadratic")])
+def test_neumann_kernel_on_the_emulator(emu, name, order):
+    """neumann_kernel with the (plan, face kind) groups the driver builds: triangular faces with 13 Gauss points and
+    3 / 6 / 7 dofs, quadrilateral ones with 16 points and 4 / 8 / 9 dofs, against the oracle's boundary vector."""
+    from femus_b200.poisson import neumann_face_groups
+    from oracle import mesh_mixed as mm
+    path = os.path.join(GOLDEN, name + ".neu")
+    level = hostapi.HostHierarchy.from_neu(path, 1).levels[0]
+    neumann = {1: 0.2, 4: -1.5, 6: 0.7}
+    mixed = level.elem_type < 0
+    dofs = level.system_dofs27(order)
+    rhs = np.zeros(level.ndofs(order))
+    xyz = np.ascontiguousarray(level.xyz, dtype=np.float64)
+    ngroups = 0
+    for t in (sorted(set(level.elem_types.tolist())) if mixed else [level.elem_type]):
+        sel = np.nonzero(level.elem_types == t)[0] if mixed else slice(None)
+        nve = hostapi.elem_nve(t, order)
+        conn = np.ascontiguousarray(level.conn[sel], dtype=np.int32)
+        dof = np.ascontiguousarray(dofs[sel][:, :nve], dtype=np.int32)
+        for (fe, fl, fv), (phi, dxi, deta, w), fnodes in neumann_face_groups(level, order, neumann, t, sel):
+            tab = np.concatenate([phi.ravel(), dxi.ravel(), deta.ravel(), w.ravel()])
+            fn = np.ascontiguousarray(fnodes, dtype=np.int32)
+            emu.emu_neumann(len(fe), _p(fe), _p(fl), _p(fv), phi.shape[1], phi.shape[0], nve, _p(tab), _p(fn), level.nnode, _p(xyz), _p(conn),
+                            _p(dof), _p(rhs), 1)
+            ngroups += 1
+    want = mm.neumann_rhs(mm.read_neu(path), order, neumann)
+    assert ngroups >= 1 and np.abs(rhs - want).max() <= 1e-13 * np.abs(want).max()
