@@ -116,6 +116,7 @@ _PROTOS = {
     "b2_mg_set_coarse": (ci, [vp, cd, ci]),
     "b2_mg_set_smoother": (ci, [vp, ci, ci, cd, cd]),
     "b2_schwarz_create": (ci, [vp, vp, i64, vp, vp, i64, vp, vp, vp]),
+    "b2_schwarz_set_subsolver": (ci, [vp, ci]),
     "b2_schwarz_setup": (ci, [vp]),
     "b2_schwarz_apply": (ci, [vp, vp, vp]),
     "b2_schwarz_bytes": (i64, [vp]),
@@ -657,6 +658,10 @@ class Schwarz:
                 self.L.b2_schwarz_destroy(self.h)
         except Exception:
             pass
+
+    def set_subsolver(self, kind):
+        """"lu": exact block solves (dense inverses); "ssor": one SSOR iteration per block (PCSOR default)."""
+        check(self.L.b2_schwarz_set_subsolver(self.h, {"lu": 0, "ssor": 1}[kind]))
 
     def setup(self):
         check(self.L.b2_schwarz_setup(self.h))

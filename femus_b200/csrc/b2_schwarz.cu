@@ -31,6 +31,9 @@ struct b2_schwarz {
   int32_t* group_blocks = nullptr;   // [nblocks] device: blocks in schedule order
   std::vector<int64_t> group_ptr;    // [ngroups+1] host
   int* err = nullptr;             // device: 1 + first block whose pivot vanished, or 0
+  int sub = 0;                    // block solve: 0 = exact (dense inverse), 1 = one SSOR iteration on the block's rows
+  double *tg = nullptr, *dg = nullptr, *zg = nullptr;   // [n] scratch of the SSOR sweep
+  int32_t* mark = nullptr;        // [n]
   bool ready = false;
 };
 
@@ -55,7 +58,7 @@ int b2_schwarz_create(b2_ctx* c, b2_csr* A, int64_t nblocks, const int64_t* blk_
   std::vector<int64_t> inv_ptr((size_t)nblocks + 1, 0);
   for (int64_t b = 0; b < nblocks; b++) {
     const int64_t m = blk_ptr[b + 1] - blk_ptr[b];
-    B2_CHECK(m >= 1 && m <= 4096, "b2_schwarz_create: block %lld has %lld dofs (1..4096 supported)", (long long)b, (long long)m);
+    B2_CHECK(m >= 1, "b2_schwarz_create: block %lld is empty", (long long)b);
     for (int64_t k = blk_ptr[b]; k < blk_ptr[b + 1]; k++) {
       B2_CHECK(blk_dofs[k] >= 0 && blk_dofs[k] < A->nrows, "b2_schwarz_create: block %lld: dof %d outside the operator", (long long)b, (int)blk_dofs[k]);
       B2_CHECK(k == blk_ptr[b] || blk_dofs[k] > blk_dofs[k - 1], "b2_schwarz_create: block %lld: dofs must be sorted and distinct", (long long)b);
@@ -82,19 +85,21 @@ int b2_schwarz_create(b2_ctx* c, b2_csr* A, int64_t nblocks, const int64_t* blk_
   B2_TRY(b2_malloc(c, &s->blk_ptr, (size_t)nblocks + 1));
   B2_TRY(b2_malloc(c, &s->blk_dofs, (size_t)s->ndofs_total));
   B2_TRY(b2_malloc(c, &s->inv_ptr, (size_t)nblocks + 1));
-  B2_TRY(b2_malloc(c, &s->inv, (size_t)s->inv_total));
   B2_TRY(b2_malloc(c, &s->group_blocks, (size_t)nblocks));
   B2_TRY(b2_malloc(c, &s->err, 1));
   B2_TRY(b2_upload(c, s->blk_ptr, blk_ptr, (size_t)nblocks + 1));
   B2_TRY(b2_upload(c, s->blk_dofs, blk_dofs, (size_t)s->ndofs_total));
   B2_TRY(b2_upload(c, s->inv_ptr, inv_ptr.data(), (size_t)nblocks + 1));
   B2_TRY(b2_upload(c, s->group_blocks, group_blocks, (size_t)nblocks));
-  // shared memory of the two kernels: 2 x max_m doubles (<= 64 KB)
-  const int smem = 2 * max_m * (int)sizeof(double);
-  if (smem > 48 * 1024) {
-    B2_CUDA(cudaFuncSetAttribute(schwarz_invert_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    B2_CUDA(cudaFuncSetAttribute(schwarz_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  }
+  return 0;
+}
+
+/* block solve: 0 = exact (MLU_PRECOND on the blocks; dense inverses, blocks of at most 4096 dofs), 1 = one SSOR
+ * iteration (SOR_PRECOND on the blocks, 001_Poisson's own choice; no storage, any block size) */
+int b2_schwarz_set_subsolver(b2_schwarz* s, int kind) {
+  B2_CHECK(s && (kind == 0 || kind == 1), "b2_schwarz_set_subsolver: kind must be 0 (exact) or 1 (SSOR)");
+  if (kind != s->sub) s->ready = false;
+  s->sub = kind;
   return 0;
 }
 
@@ -102,7 +107,27 @@ int b2_schwarz_create(b2_ctx* c, b2_csr* A, int64_t nblocks, const int64_t* blk_
 int b2_schwarz_setup(b2_schwarz* s) {
   B2_CHECK(s, "b2_schwarz_setup: null handle");
   b2_ctx* c = s->ctx;
+  if (s->sub == 1) {              // SSOR works on A's rows: only the scratch vectors are needed
+    const size_t n = (size_t)s->A->nrows;
+    if (!s->mark) {
+      B2_TRY(b2_malloc(c, &s->tg, n));
+      B2_TRY(b2_malloc(c, &s->dg, n));
+      B2_TRY(b2_malloc(c, &s->zg, n));
+      B2_TRY(b2_malloc(c, &s->mark, n));
+      B2_CUDA(cudaMemsetAsync(s->mark, 0xff, n * sizeof(int32_t), c->stream));     // -1: claimed by no block
+    }
+    s->ready = true;
+    return 0;
+  }
+  B2_CHECK(s->max_m <= 4096, "b2_schwarz_setup: a block has %d dofs; exact block solves support at most 4096 (use the SSOR block solve)", s->max_m);
   const int smem = 2 * s->max_m * (int)sizeof(double);
+  if (!s->inv) {
+    B2_TRY(b2_malloc(c, &s->inv, (size_t)s->inv_total));
+    if (smem > 48 * 1024) {       // shared memory of the two kernels: 2 x max_m doubles (<= 64 KB)
+      B2_CUDA(cudaFuncSetAttribute(schwarz_invert_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      B2_CUDA(cudaFuncSetAttribute(schwarz_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    }
+  }
   B2_CUDA(cudaMemsetAsync(s->err, 0, sizeof(int), c->stream));
   B2_LAUNCH(c, schwarz_extract_kernel, b2_grid_for(c, s->nblocks, 1, 8), 256, 0, s->nblocks, s->blk_ptr, s->blk_dofs, s->inv_ptr,
             s->A->rowptr, s->A->col, s->A->val, s->inv);
@@ -125,13 +150,18 @@ int b2_schwarz_apply(b2_schwarz* s, const b2_vec* r, b2_vec* y) {
   B2_CUDA(cudaMemsetAsync(y->d, 0, (size_t)s->A->nrows * sizeof(double), c->stream));
   for (int64_t g = 0; g < s->ngroups; g++) {
     const int64_t g0 = s->group_ptr[g], g1 = s->group_ptr[g + 1];
+    if (s->sub == 1) {
+      B2_LAUNCH(c, schwarz_apply_ssor_kernel, b2_grid_for(c, g1 - g0, 1, 16), kApplyThreads, 0, g0, g1, s->group_blocks, s->blk_ptr, s->blk_dofs,
+                s->A->rowptr, s->A->col, s->A->val, r->d, y->d, s->tg, s->dg, s->zg, s->mark);
+      continue;
+    }
     B2_LAUNCH(c, schwarz_apply_kernel, b2_grid_for(c, g1 - g0, 1, 16), kApplyThreads, smem, g0, g1, s->group_blocks, s->blk_ptr,
               s->blk_dofs, s->inv_ptr, s->inv, s->A->rowptr, s->A->col, s->A->val, r->d, y->d, s->max_m);
   }
   return 0;
 }
 
-int64_t b2_schwarz_bytes(const b2_schwarz* s) { return s ? s->inv_total * (int64_t)sizeof(double) : 0; }
+int64_t b2_schwarz_bytes(const b2_schwarz* s) { return (s && s->inv) ? s->inv_total * (int64_t)sizeof(double) : 0; }
 int64_t b2_schwarz_groups(const b2_schwarz* s) { return s ? s->ngroups : 0; }
 
 int b2_schwarz_destroy(b2_schwarz* s) {
@@ -141,6 +171,10 @@ int b2_schwarz_destroy(b2_schwarz* s) {
   b2_free(c, s->blk_dofs, (size_t)s->ndofs_total);
   b2_free(c, s->inv_ptr, (size_t)s->nblocks + 1);
   b2_free(c, s->inv, (size_t)s->inv_total);
+  b2_free(c, s->tg, (size_t)s->A->nrows);
+  b2_free(c, s->dg, (size_t)s->A->nrows);
+  b2_free(c, s->zg, (size_t)s->A->nrows);
+  b2_free(c, s->mark, (size_t)s->A->nrows);
   b2_free(c, s->group_blocks, (size_t)s->nblocks);
   b2_free(c, s->err, 1);
   delete s;

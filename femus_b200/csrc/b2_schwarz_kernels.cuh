@@ -115,3 +115,73 @@ __global__ void __launch_bounds__(kApplyThreads) schwarz_apply_kernel(int64_t g0
   }
 }
 
+
+// The same sweep with ONE SSOR ITERATION as the block solve (PCSOR's default on the sub-block: local symmetric sweep,
+// omega 1, zero initial guess -- what 001_Poisson's SetPreconditionerFineGrids(SOR_PRECOND) puts on the ASM blocks,
+// LinearEquationSolverPetscAsm.cpp:300-317, PetscPreconditioner.cpp SOR_PRECOND).  No factor storage: the block's
+// rows of A are used as they are.  Gauss-Seidel is sequential in the block's (sorted) dofs, so one warp walks the rows
+// -- lanes over a row's non-zeros -- while the other warps only help with t = (r - A y)[B]; the parallelism is across
+// the blocks of a group.  Scratch per dof in HBM (a block's dofs belong to no other block of its group): tg = t,
+// dg = diagonal, zg = the block solution, mark = the block that last claimed the dof (membership test of a column).
+__global__ void __launch_bounds__(kApplyThreads) schwarz_apply_ssor_kernel(int64_t g0, int64_t g1, const int32_t* __restrict__ group_blocks,
+                                                                            const int64_t* __restrict__ blk_ptr, const int32_t* __restrict__ blk_dofs,
+                                                                            const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                                                                            const double* __restrict__ val, const double* __restrict__ r, double* y,
+                                                                            double* tg, double* dg, double* zg, int32_t* mark) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  for (int64_t q = g0 + blockIdx.x; q < g1; q += gridDim.x) {
+    const int32_t b = group_blocks[q];
+    const int32_t* D = blk_dofs + blk_ptr[b];
+    const int m = (int)(blk_ptr[b + 1] - blk_ptr[b]);
+    for (int i = warp; i < m; i += nwarps) {
+      const int64_t row = D[i];
+      double acc = 0.0, diag = 0.0;
+      for (int64_t k = rowptr[row] + lane; k < rowptr[row + 1]; k += 32) {
+        const int32_t c = col[k];
+        acc = fma(val[k], y[c], acc);
+        if (c == row) diag = val[k];
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        diag += __shfl_xor_sync(0xffffffffu, diag, o);
+      }
+      if (lane == 0) {
+        tg[row] = r[row] - acc;
+        dg[row] = diag;
+        zg[row] = 0.0;
+        mark[row] = b;
+      }
+    }
+    __syncthreads();
+    if (warp == 0) {
+      for (int i = 0; i < m; i++) {                 // forward sweep: z = (D + L)^-1 t
+        const int64_t row = D[i];
+        double s = 0.0;
+        for (int64_t k = rowptr[row] + lane; k < rowptr[row + 1]; k += 32) {
+          const int32_t c = col[k];
+          if (c < row && mark[c] == b) s = fma(val[k], zg[c], s);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) zg[row] = (tg[row] - s) / dg[row];
+        __syncwarp();
+      }
+      for (int i = m - 1; i >= 0; i--) {            // backward sweep from that iterate
+        const int64_t row = D[i];
+        double s = 0.0;
+        for (int64_t k = rowptr[row] + lane; k < rowptr[row + 1]; k += 32) {
+          const int32_t c = col[k];
+          if (c != row && mark[c] == b) s = fma(val[k], zg[c], s);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) zg[row] = (tg[row] - s) / dg[row];
+        __syncwarp();
+      }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < m; i += blockDim.x) y[D[i]] += zg[D[i]];
+    __syncthreads();
+  }
+}

@@ -290,6 +290,12 @@ int b2_mg_level_bounds(const b2_mg* mg, int level, double* emin, double* emax);
  * b2_schwarz_apply: y = M^-1 r.  One rank only (no interface sums). */
 int b2_schwarz_create(b2_ctx* ctx, b2_csr* A, int64_t nblocks, const int64_t* blk_ptr, const int32_t* blk_dofs,
                       int64_t ngroups, const int64_t* group_ptr, const int32_t* group_blocks, b2_schwarz** out);
+/* block solve (call before b2_schwarz_setup): 0 = exact, dense inverses of blocks of at most 4096 dofs (default);
+ * 1 = one SSOR iteration on the block's rows -- PCSOR's default (local symmetric sweep, omega 1, zero guess), the
+ * sub-preconditioner 001_Poisson itself selects with SetPreconditionerFineGrids(SOR_PRECOND) (main.cpp:242,
+ * LinearEquationSolverPetscAsm.cpp:300-317); no storage, any block size: with ONE block holding every element the
+ * level smoother is Richardson + SOR, the application's FEMuS_DEFAULT branch. */
+int b2_schwarz_set_subsolver(b2_schwarz* s, int kind);
 int b2_schwarz_setup(b2_schwarz* s);
 int b2_schwarz_apply(b2_schwarz* s, const b2_vec* r, b2_vec* y);
 int64_t b2_schwarz_bytes(const b2_schwarz* s);      /* HBM held by the block inverses */

@@ -13,7 +13,23 @@ extern "C" {
 // extract + invert + the sweep over the schedule's groups; returns the singular-block flag of the invert kernel
 int emu_schwarz(int64_t n, const int64_t* rowptr, const int32_t* col, const double* val, int64_t nblocks, const int64_t* blk_ptr,
                 const int32_t* blk_dofs, int64_t ngroups, const int64_t* group_ptr, const int32_t* group_blocks, const double* r,
-                double* y, double* inv_out, int threads, int grid) {
+                double* y, double* inv_out, int threads, int grid, int sub) {
+  if (sub == 1) {       // SSOR block solves: scratch vectors only (b2_schwarz_setup with kind 1)
+    std::vector<double> tg((size_t)n, -7.0), dg((size_t)n, -7.0), zg((size_t)n, -7.0);
+    std::vector<int32_t> mark((size_t)n, -1);
+    for (int64_t i = 0; i < n; i++) y[i] = 0.0;
+    for (int64_t g = 0; g < ngroups; g++)
+      emu::launch(schwarz_apply_ssor_kernel, (unsigned)grid, (unsigned)threads, 0, group_ptr[g], group_ptr[g + 1], group_blocks, blk_ptr, blk_dofs,
+                  rowptr, col, val, r, y, tg.data(), dg.data(), zg.data(), mark.data());
+    // a second application on the used scratch must give the same result (stale marks of overlapping blocks)
+    std::vector<double> y2((size_t)n, 0.0);
+    for (int64_t g = 0; g < ngroups; g++)
+      emu::launch(schwarz_apply_ssor_kernel, (unsigned)grid, (unsigned)threads, 0, group_ptr[g], group_ptr[g + 1], group_blocks, blk_ptr, blk_dofs,
+                  rowptr, col, val, r, y2.data(), tg.data(), dg.data(), zg.data(), mark.data());
+    for (int64_t i = 0; i < n; i++)
+      if (y2[i] != y[i]) return -1;
+    return 0;
+  }
   std::vector<int64_t> inv_ptr((size_t)nblocks + 1, 0);
   int max_m = 0;
   for (int64_t b = 0; b < nblocks; b++) {

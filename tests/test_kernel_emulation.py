@@ -25,7 +25,7 @@ def emu(tmp_path_factory):
     assert r.returncode == 0, r.stderr
     L = ctypes.CDLL(so)
     L.emu_schwarz.restype = ctypes.c_int
-    L.emu_schwarz.argtypes = [ctypes.c_int64, vp, vp, vp, ctypes.c_int64, vp, vp, ctypes.c_int64, vp, vp, vp, vp, vp, ctypes.c_int, ctypes.c_int]
+    L.emu_schwarz.argtypes = [ctypes.c_int64, vp, vp, vp, ctypes.c_int64, vp, vp, ctypes.c_int64, vp, vp, vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int]
     L.emu_neumann.restype = None
     L.emu_neumann.argtypes = [ctypes.c_int64, vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp, ctypes.c_int64, vp, vp, vp, vp, ctypes.c_int]
     return L
@@ -35,7 +35,7 @@ def _p(a):
     return a.ctypes.data_as(vp)
 
 
-def _run_schwarz(emu, A, ix, gptr, gblocks, r, threads=64, grid=3):
+def _run_schwarz(emu, A, ix, gptr, gblocks, r, threads=64, grid=3, sub=0):
     rp = np.ascontiguousarray(A.indptr, dtype=np.int64)
     ci = np.ascontiguousarray(A.indices, dtype=np.int32)
     va = np.ascontiguousarray(A.data, dtype=np.float64)
@@ -44,7 +44,7 @@ def _run_schwarz(emu, A, ix, gptr, gblocks, r, threads=64, grid=3):
     y = np.full(A.shape[0], np.nan)
     inv = np.zeros(int(sum(len(b) ** 2 for b in ix.blocks())))
     err = emu.emu_schwarz(A.shape[0], _p(rp), _p(ci), _p(va), ix.nblocks, _p(bp), _p(bd), len(gp) - 1, _p(gp), _p(gb), _p(r), _p(y), _p(inv),
-                          threads, grid)
+                          threads, grid, sub)
     return err, y, inv
 
 
@@ -77,6 +77,31 @@ def test_schwarz_kernels_on_the_emulator(emu, order, nb, schedule):
     assert np.abs(y - want).max() <= 1e-12 * np.abs(want).max()
     if schedule == "levels":        # the reference's own sweep
         assert np.abs(y - O.asm[1].apply(r, range(ix.nblocks))).max() <= 1e-12 * np.abs(want).max()
+
+
+@pytest.mark.parametrize("order,nb,schedule", [("linear", 8, "levels"), ("linear", 5, "colours"), ("biquadratic", 2, "colours"),
+                                               ("linear", 10 ** 6, "colours")])
+def test_schwarz_ssor_kernel_on_the_emulator(emu, order, nb, schedule):
+    """The sweep with one SSOR iteration per block (001_Poisson's SOR_PRECOND sub-preconditioner) against the oracle;
+    applied twice on the same scratch (stale membership marks of overlapping blocks must not matter).  nb = 10^6: ONE
+    block with every element = Richardson + SOR, the application's FEMuS_DEFAULT smoother."""
+    from oracle import mesh_box as mb, mg
+    shape = (2, 2, 2) if order == "linear" else (1, 2, 1)
+    lv = mb.build_hierarchy(*shape, 2)
+    H = hostapi.HostHierarchy(*shape, 2)
+    ix = hostapi.AsmIndex(H.levels[1], order, nb)
+    rp, ci = H.levels[1].sparsity(order)
+    grp, gptr, gblocks = hostapi.asm_schedule(rp, ci, ix.overlap_ptr, ix.overlap, schedule)
+    O = mg.Hierarchy(lv, order, dirichlet_faces=(1, 3, 6), smoother="asm", asm_blocks=[None, ix.blocks()], asm_orders=[None, gblocks],
+                     asm_sub="ssor")
+    A = O.A[1]
+    r = np.random.default_rng(8).standard_normal(A.shape[0])
+    err, y, _ = _run_schwarz(emu, A, ix, gptr, gblocks, r, sub=1)
+    assert err == 0
+    want = O.asm[1].apply(r)
+    assert np.abs(y - want).max() <= 1e-12 * np.abs(want).max()
+    if nb >= 10 ** 6:
+        assert ix.nblocks == 1 and len(gptr) == 2
 
 
 def test_schwarz_invert_kernel_reports_singular_blocks(emu):
