@@ -1,0 +1,80 @@
+"""Timing of the kernels written after round 1's GPU budget was spent (run on a B200 at the start of round 2):
+the element-block smoother (exact and SSOR block solves, coloured sweep) on the finest level of an n^3 HEX27 box
+hierarchy -- ms per application, algorithmic GB/s against the measured HBM peak, V-cycle contraction next to
+Richardson + Jacobi -- and the table-driven assembly kernel on a refined tetrahedral mesh.
+
+    python tools/time_round2.py [n0=8] [levels=4] [order=biquadratic]      # one JSON line per measurement
+"""
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+from femus_b200 import capi, hostapi
+from femus_b200.poisson import PoissonMG
+
+n0 = int(sys.argv[1]) if len(sys.argv) > 1 else 8
+nl = int(sys.argv[2]) if len(sys.argv) > 2 else 4
+order = sys.argv[3] if len(sys.argv) > 3 else "biquadratic"
+peak = None
+try:
+    peak = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json"))).get("hbm_gbs")
+except Exception:
+    pass
+ctx = capi.Context(0)
+
+
+def timed(fn, reps=5, warm=2):
+    for _ in range(warm):
+        fn()
+    ctx.sync()
+    ctx.timer_start()
+    for _ in range(reps):
+        fn()
+    return ctx.timer_stop_ms() / reps
+
+
+for sub in ("lu", "ssor"):
+    pb = PoissonMG(ctx, n0, n0, n0, nl, order, smoother="asm", asm_block_elems=8, asm_schedule="colours", asm_sub=sub, omega=1.0)
+    pb.assemble(); pb.galerkin(); pb.mg_set_levels()
+    top = nl - 1
+    S, ix = pb.schwarz[top], pb.asm_index[top]
+    n = pb.n
+    r, y = ctx.vector(np.sin(np.arange(n) * 0.001)), ctx.vector(n)
+    ms = timed(lambda: S.apply(r, y))
+    A = pb.KK[top]
+    m = np.diff(ix.overlap_ptr)
+    rows_nnz = int(A.nnz * (m.sum() / n))                  # every dof sits in m.sum()/n blocks on average
+    alg = (8 * int((m.astype(np.int64) ** 2).sum()) if sub == "lu" else 0) + 12 * rows_nnz * (1 if sub == "lu" else 3) + 24 * int(m.sum())
+    trace = []
+    for _ in range(4):
+        pb.mg_solve()
+        trace.append(pb.residual_norm())
+    ms_cycle = timed(lambda: pb.mg_solve(), reps=3, warm=1)
+    print(json.dumps({"kernel": "schwarz_apply_" + sub, "workload": f"{n0 * 2 ** (nl - 1)}^3 {order}", "blocks": int(ix.nblocks),
+                      "groups": int(S.ngroups), "ms": ms, "algorithmic_bytes": alg, "GBs": alg / ms / 1e6, "hbm_peak_GBs": peak,
+                      "frac": (alg / ms / 1e6 / peak) if peak else None, "inverse_bytes": S.nbytes, "vcycle_ms": ms_cycle,
+                      "residual_trace": trace}))
+    del pb, S
+
+pb = PoissonMG(ctx, n0, n0, n0, nl, order)
+pb.assemble(); pb.galerkin(); pb.mg_set_levels()
+trace = []
+for _ in range(4):
+    pb.mg_solve()
+    trace.append(pb.residual_norm())
+print(json.dumps({"kernel": "vcycle_richardson_jacobi", "vcycle_ms": timed(lambda: pb.mg_solve(), reps=3, warm=1), "residual_trace": trace}))
+del pb
+
+# table-driven assembly kernel on tetrahedra: the reference's cube_Tet coarse mesh (105 elements) refined
+path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "cube_tet10.neu")
+lev = int(os.environ.get("TET_LEVELS", "5"))
+H = hostapi.HostHierarchy.from_neu(path, lev)
+for fam in ("quadratic", "biquadratic"):
+    pt = PoissonMG(ctx, 0, 0, 0, lev, fam, hier=H)
+    ms = timed(lambda: (pt.RES.zero(), pt.KK[-1].zero(), pt.plans[0][1].poisson(pt.SOL, pt.RES, 1.0, 1.0)))
+    nve = pt.nve
+    print(json.dumps({"kernel": "assemble_general_kernel", "workload": f"tet {fam} {pt.nel} elements", "ms": ms,
+                      "element_dof_updates_per_s": pt.nel * nve / ms * 1e3, "dofs": pt.n}))
+    del pt
