@@ -225,6 +225,31 @@ b2h_asm* b2h_asm_create(const b2h_hier* h, int l, int family, int block_elems, i
     return nullptr;
   }
 }
+b2h_asm* b2h_asm_create_system(const b2h_hier* h, int l, int nvars, const int* families, int nschur, int block_elems, int iproc) {
+  try {
+    if (!h || l < 0 || l >= (int)h->levels.size() || nvars < 1 || !families || block_elems < 1)
+      throw std::invalid_argument("b2h_asm_create_system: bad level, variables or block size");
+    std::unique_ptr<b2h_asm> a(new b2h_asm());
+    const SystemLayout sys(h->levels[l], std::vector<int>(families, families + nvars));
+    a->ix = BuildAsmIndexSystem(h->levels[l], sys, nschur, (unsigned)block_elems, iproc);
+    return a.release();
+  } catch (const std::exception& e) {
+    g_b2h_error = e.what();
+    return nullptr;
+  }
+}
+int b2h_system_offsets(const b2h_hier* h, int l, int nvars, const int* families, int64_t* out) {
+  try {
+    if (!h || l < 0 || l >= (int)h->levels.size() || nvars < 1 || !families || !out) throw std::invalid_argument("b2h_system_offsets: bad arguments");
+    const SystemLayout sys(h->levels[l], std::vector<int>(families, families + nvars));
+    const int np = h->levels[l].nprocs;
+    for (int k = 0; k <= nvars; k++) std::copy(sys.KKoffset[k].begin(), sys.KKoffset[k].end(), out + (size_t)k * np);
+    return 0;
+  } catch (const std::exception& e) {
+    g_b2h_error = e.what();
+    return 1;
+  }
+}
 void b2h_asm_destroy(b2h_asm* a) { delete a; }
 int64_t b2h_asm_nblocks(const b2h_asm* a) { return a->ix.nblocks(); }
 void b2h_asm_block_type_range(const b2h_asm* a, int64_t* out3) { std::copy(a->ix.block_type_range, a->ix.block_type_range + 3, out3); }

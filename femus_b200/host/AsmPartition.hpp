@@ -2,8 +2,10 @@
 // reference hands to PETSc's PCASM, and the schedules the device sweep runs them in.  Reference:
 //   src/06_mesh/00_single_level/02_partitioning/MeshASMPartitioning.cpp:89-148          DoPartition
 //   src/08_algebra.../03_solvers_with_preconditioner/petsc_asm/LinearEquationSolverPetscAsm.cpp:91-262   BuildASMIndex
-// with the settings of applications/001_Poisson ("smoother": "asm", main.cpp:234-250): no Schur variable, so every
-// block is the set of dofs of its own elements (GetElementNearElementSize(iel, 0) == 1).
+// For applications/001_Poisson ("smoother": "asm", main.cpp:234-250) there is one variable and no Schur variable, so
+// every block is the set of dofs of its own elements (GetElementNearElementSize(iel, 0) == 1); systems of several
+// Lagrange variables whose last ones are Schur variables (velocity-pressure Vanka blocks) take the velocities of one
+// layer of near elements and the pressures of the block's own elements.
 //
 // DoPartition: the owned elements of one material class, block_size at a time in element order; classes in the
 // order 4 (solid), 3 (porous), 2 (fluid).  (The reference counts every element that is neither 4 nor 3 into the
@@ -73,17 +75,85 @@ inline void DoPartition(const MeshLevel& L, int iproc, const unsigned block_size
   }
 }
 
-// BuildASMIndex for one non-Schur variable of family `family`, rank iproc; block_elems elements per block in every
-// material class, capped by the level's element count (LinearImplicitSystem::SetElementBlockNumber, :1191-1201)
-inline AsmIndex BuildAsmIndex(const MeshLevel& L, int family, unsigned block_elems, int iproc) {
+// LinearEquation::InitPde (LinearEquation.cpp:211-237): rows of a system of several variables are numbered
+// [rank][variable][dof]; KKoffset[k][p] = first row of variable k on rank p (k = nvars: end of the rank's rows).
+struct SystemLayout {
+  std::vector<int> family;                        // FE family of every variable (0 linear, 1 serendipity, 2 biquadratic)
+  std::vector<std::vector<int64_t>> KKoffset;     // [nvars+1][nprocs]
+  SystemLayout(const MeshLevel& L, const std::vector<int>& fam) : family(fam) {
+    if (fam.empty()) throw std::invalid_argument("SystemLayout: no variable");
+    for (int f : fam)
+      if (f < 0 || f > 2) throw std::invalid_argument("SystemLayout: Lagrange families 0, 1, 2 only");
+    const int nv = (int)fam.size();
+    KKoffset.assign((size_t)nv + 1, std::vector<int64_t>((size_t)L.nprocs, 0));
+    for (int j = 1; j <= nv; j++) KKoffset[j][0] = KKoffset[j - 1][0] + (L.dof_offset[fam[j - 1]][1] - L.dof_offset[fam[j - 1]][0]);
+    for (int i = 1; i < L.nprocs; i++) {
+      KKoffset[0][i] = KKoffset[nv][i - 1];
+      for (int j = 1; j <= nv; j++) KKoffset[j][i] = KKoffset[j - 1][i] + (L.dof_offset[fam[j - 1]][i + 1] - L.dof_offset[fam[j - 1]][i]);
+    }
+  }
+  int nvars() const { return (int)family.size(); }
+  int64_t size() const { return KKoffset.back().back(); }
+  // LinearEquation::GetSystemDof (LinearEquation.cpp:76-85)
+  int64_t system_dof(const MeshLevel& L, int k, int i, int64_t iel) const {
+    const int f = family[k];
+    const int64_t idof = L.GetSolutionDof(i, iel, f);
+    const std::vector<int64_t>& o = L.dof_offset[f];
+    const int isub = (int)(std::upper_bound(o.begin(), o.end(), idof) - o.begin()) - 1;
+    return KKoffset[k][isub] + idof - o[isub];
+  }
+};
+
+// elem::BuildElementNearElement (Elem.cpp:493-526): the element itself, then every other element sharing a vertex
+// with it, ascending; CSR-like (ptr, list) over all elements of the level
+inline void BuildElementNearElement(const MeshLevel& L, std::vector<int64_t>& ptr, std::vector<int32_t>& list) {
+  std::vector<int64_t> vptr((size_t)L.nnode + 1, 0);
+  for (int64_t e = 0; e < L.nel; e++)
+    for (int i = 0; i < ElemTopology::nvert(L.type_of(e)); i++) vptr[L.node(e, i) + 1]++;
+  for (int64_t n = 0; n < L.nnode; n++) vptr[n + 1] += vptr[n];
+  std::vector<int32_t> vlist((size_t)vptr[L.nnode]);
+  std::vector<int64_t> fill(vptr.begin(), vptr.end() - 1);
+  for (int64_t e = 0; e < L.nel; e++)
+    for (int i = 0; i < ElemTopology::nvert(L.type_of(e)); i++) vlist[fill[L.node(e, i)]++] = (int32_t)e;
+  ptr.assign(1, 0);
+  list.clear();
+  std::vector<int32_t> others;
+  for (int64_t e = 0; e < L.nel; e++) {
+    others.clear();
+    for (int i = 0; i < ElemTopology::nvert(L.type_of(e)); i++) {
+      const int32_t nd = L.node(e, i);
+      for (int64_t q = vptr[nd]; q < vptr[nd + 1]; q++)
+        if (vlist[q] != e) others.push_back(vlist[q]);
+    }
+    std::sort(others.begin(), others.end());
+    others.erase(std::unique(others.begin(), others.end()), others.end());
+    list.push_back((int32_t)e);
+    list.insert(list.end(), others.begin(), others.end());
+    ptr.push_back((int64_t)list.size());
+  }
+}
+
+// BuildASMIndex for the system `sys` on rank iproc, the LAST nschur variables being Schur (pressure-like) variables:
+// a block takes the non-Schur dofs of every owned element near its elements (FastVankaBlock == false for Lagrange
+// Schur variables => one layer of near elements; no Schur variable => the elements themselves) and the Schur dofs of
+// its own elements.  block_elems elements per block in every material class, capped by the level's element count
+// (LinearImplicitSystem::SetElementBlockNumber, :1191-1201).
+inline AsmIndex BuildAsmIndexSystem(const MeshLevel& L, const SystemLayout& sys, int nschur, unsigned block_elems, int iproc) {
   if (iproc < 0 || iproc >= L.nprocs) throw std::invalid_argument("BuildAsmIndex: rank out of range");
   if (block_elems == 0) throw std::invalid_argument("BuildAsmIndex: block size 0");
+  const int nv = sys.nvars();
+  if (nschur < 0 || nschur > nv) throw std::invalid_argument("BuildAsmIndex: bad number of Schur variables");
   const unsigned nb = (unsigned)std::min<int64_t>(block_elems, L.nel);
   const unsigned bs[3] = {nb, nb, nb};
   std::vector<std::vector<unsigned>> be;
   AsmIndex out;
   DoPartition(L, iproc, bs, be, out.block_type_range);
-  const int64_t d0 = L.dof_offset[family][iproc], d1 = L.dof_offset[family][iproc + 1], size = d1 - d0;
+  const bool fast = nschur == 0;
+  std::vector<int64_t> near_ptr;
+  std::vector<int32_t> near;
+  if (!fast) BuildElementNearElement(L, near_ptr, near);
+  const int64_t e0 = L.elem_offset[iproc], e1 = L.elem_offset[iproc + 1];
+  const int64_t d0 = sys.KKoffset[0][iproc], size = sys.KKoffset[nv][iproc] - d0;
   std::vector<int64_t> indexa((size_t)size, size), indexb((size_t)size, size);
   std::vector<char> owned((size_t)size, 0);
   std::map<int, bool> ghosts;
@@ -92,36 +162,45 @@ inline AsmIndex BuildAsmIndex(const MeshLevel& L, int family, unsigned block_ele
   out.overlap_ptr.push_back(0);
   std::vector<int32_t> loc, ovl;
   std::vector<char> in_block((size_t)L.nel, 0);
+  auto add = [&](int k, int64_t jel) {
+    const int f = sys.family[k];
+    const int nve = ElemTopology::nve(L.type_of(jel), f);
+    for (int jj = 0; jj < nve; jj++) {
+      const int64_t jdof = L.GetSolutionDof(jj, jel, f);
+      const int64_t kk = sys.system_dof(L, k, jj, jel);
+      if (jdof >= L.dof_offset[f][iproc] && jdof < L.dof_offset[f][iproc + 1]) {
+        if (indexa[kk - d0] == size && !owned[kk - d0]) {
+          owned[kk - d0] = 1;
+          indexa[kk - d0] = (int64_t)loc.size();
+          loc.push_back((int32_t)kk);
+        }
+        if (indexb[kk - d0] == size) {
+          indexb[kk - d0] = (int64_t)ovl.size();
+          ovl.push_back((int32_t)kk);
+        }
+      } else {
+        ghosts[(int)kk] = true;
+      }
+    }
+  };
   for (const std::vector<unsigned>& elems : be) {
     loc.clear();
     ovl.clear();
-    std::vector<unsigned> added;
+    std::vector<int64_t> added;
     for (unsigned iel : elems) {
-      const unsigned jel = iel;                       // near elements with 0 layers: the element itself
-      if (in_block[jel]) continue;
-      in_block[jel] = 1;
-      added.push_back(jel);
-      const int nve = ElemTopology::nve(L.type_of(jel), family);
-      for (int jj = 0; jj < nve; jj++) {
-        const int64_t kk = L.GetSolutionDof(jj, jel, family);      // one variable: system dof == solution dof
-        if (kk >= d0 && kk < d1) {
-          if (indexa[kk - d0] == size && !owned[kk - d0]) {
-            owned[kk - d0] = 1;
-            indexa[kk - d0] = (int64_t)loc.size();
-            loc.push_back((int32_t)kk);
-          }
-          if (indexb[kk - d0] == size) {
-            indexb[kk - d0] = (int64_t)ovl.size();
-            ovl.push_back((int32_t)kk);
-          }
-        } else {
-          ghosts[(int)kk] = true;
-        }
+      const int64_t n0 = fast ? 0 : near_ptr[iel], n1 = fast ? 1 : near_ptr[iel + 1];
+      for (int64_t q = n0; q < n1; q++) {
+        const int64_t jel = fast ? (int64_t)iel : (int64_t)near[q];
+        if (jel < e0 || jel >= e1 || in_block[jel]) continue;
+        in_block[jel] = 1;
+        added.push_back(jel);
+        for (int k = 0; k < nv - nschur; k++) add(k, jel);
       }
+      for (int k = nv - nschur; k < nv; k++) add(k, iel);
     }
     for (int32_t kk : loc) indexa[kk - d0] = size;
     for (int32_t kk : ovl) indexb[kk - d0] = size;
-    for (unsigned jel : added) in_block[jel] = 0;
+    for (int64_t jel : added) in_block[jel] = 0;
     for (const auto& g : ghosts) ovl.push_back((int32_t)g.first);
     ghosts.clear();
     std::sort(loc.begin(), loc.end());
@@ -134,6 +213,11 @@ inline AsmIndex BuildAsmIndex(const MeshLevel& L, int family, unsigned block_ele
     out.overlap_ptr.push_back((int64_t)out.overlap.size());
   }
   return out;
+}
+
+// one Lagrange variable without Schur variables (001_Poisson's "asm" setting)
+inline AsmIndex BuildAsmIndex(const MeshLevel& L, int family, unsigned block_elems, int iproc) {
+  return BuildAsmIndexSystem(L, SystemLayout(L, std::vector<int>(1, family)), 0, block_elems, iproc);
 }
 
 // Schedule of the multiplicative sweep over blocks (sorted dof lists blk_dofs[blk_ptr[b] .. blk_ptr[b+1])) of the

@@ -66,6 +66,8 @@ def _L():
             "b2h_hex_face_nodes": (None, [vp]),
             "b2h_level_boundary_faces": (i64, [vp, ci, vp, vp, vp]),
             "b2h_asm_create": (vp, [vp, ci, ci, ci, ci]),
+            "b2h_asm_create_system": (vp, [vp, ci, ci, vp, ci, ci, ci]),
+            "b2h_system_offsets": (ci, [vp, ci, ci, vp, vp]),
             "b2h_asm_destroy": (None, [vp]),
             "b2h_asm_nblocks": (i64, [vp]),
             "b2h_asm_block_type_range": (None, [vp, vp]),
@@ -352,9 +354,15 @@ class AsmIndex:
     Schur variables (MeshASMPartitioning::DoPartition + LinearEquationSolverPetscAsm::BuildASMIndex): per block
     its elements, the sorted local and overlapping dof sets, as (ptr[nblocks+1], entries) pairs."""
 
-    def __init__(self, level, family, block_elems, iproc=0):
+    def __init__(self, level, family, block_elems, iproc=0, nschur=0):
+        """family: one family name, or a list of them for a system of several variables (rows [rank][variable][dof]),
+        the last `nschur` of which are Schur variables (Vanka blocks of velocity-pressure systems)."""
         L = level.hier.L
-        h = L.b2h_asm_create(level.hier.h, level.l, _fam(family), int(block_elems), int(iproc))
+        if isinstance(family, (list, tuple)):
+            fams = np.array([_fam(f) for f in family], dtype=np.int32)
+            h = L.b2h_asm_create_system(level.hier.h, level.l, len(fams), fams.ctypes.data_as(vp), int(nschur), int(block_elems), int(iproc))
+        else:
+            h = L.b2h_asm_create(level.hier.h, level.l, _fam(family), int(block_elems), int(iproc))
         if not h:
             raise ValueError(L.b2h_last_error().decode())
         try:
@@ -374,6 +382,15 @@ class AsmIndex:
     def blocks(self, which="overlap"):
         ptr, ent = getattr(self, which + "_ptr"), getattr(self, which)
         return [ent[ptr[b]:ptr[b + 1]] for b in range(self.nblocks)]
+
+
+def system_offsets(level, families):
+    """KKoffset[nvars+1][nprocs] of a system of several variables on a level (LinearEquation::InitPde)."""
+    fams = np.array([_fam(f) for f in families], dtype=np.int32)
+    out = np.zeros((len(fams) + 1, level.hier.nprocs), dtype=np.int64)
+    if level.hier.L.b2h_system_offsets(level.hier.h, level.l, len(fams), fams.ctypes.data_as(vp), out.ctypes.data_as(vp)):
+        raise ValueError(level.hier.L.b2h_last_error().decode())
+    return out
 
 
 def asm_schedule(rowptr, col, blk_ptr, blk_dofs, mode="colours"):

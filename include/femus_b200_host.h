@@ -132,6 +132,12 @@ int b2h_elem_face_kind(int type, int f);
  * Writes group_of_block[nblocks], returns the number of groups, -1 on bad arguments. */
 typedef struct b2h_asm b2h_asm;
 b2h_asm* b2h_asm_create(const b2h_hier* h, int l, int family, int block_elems, int iproc);
+/* the same for a system of nvars Lagrange variables (families[k] = 0 / 1 / 2) numbered [rank][variable][dof]
+ * (LinearEquation::InitPde, GetSystemDof, LinearEquation.cpp:76-85, 211-237) whose LAST nschur variables are Schur
+ * (pressure-like) variables: Vanka blocks = non-Schur dofs of one layer of near elements (elem::BuildElementNearElement,
+ * Elem.cpp:493-526) + Schur dofs of the block's own elements.  b2h_system_offsets: KKoffset [nvars+1][nprocs]. */
+b2h_asm* b2h_asm_create_system(const b2h_hier* h, int l, int nvars, const int* families, int nschur, int block_elems, int iproc);
+int b2h_system_offsets(const b2h_hier* h, int l, int nvars, const int* families, int64_t* out);
 void b2h_asm_destroy(b2h_asm* a);
 int64_t b2h_asm_nblocks(const b2h_asm* a);
 void b2h_asm_block_type_range(const b2h_asm* a, int64_t* out3);

@@ -169,3 +169,99 @@ class BlockSmoother:
         for _ in range(nsweeps):
             x = x + scale * self.apply(b - self.A @ x)
         return x
+
+
+# ---- several variables, Schur variables (Vanka blocks of saddle-point systems) -----------------------------------
+def kk_offsets(L, families):
+    """LinearEquation::InitPde (LinearEquation.cpp:211-237): KKoffset[var][rank] of the system rows
+    [rank][variable][dof]; families[k] = FE family index (0 linear, 1 quadratic, 2 biquadratic) of variable k."""
+    nprocs = len(L.elem_offset) - 1
+    nv = len(families)
+    KK = np.zeros((nv + 1, nprocs), dtype=np.int64)
+    for j in range(1, nv + 1):
+        f = families[j - 1]
+        KK[j, 0] = KK[j - 1, 0] + (L.dof_offset[f][1] - L.dof_offset[f][0])
+    for i in range(1, nprocs):
+        KK[0, i] = KK[nv, i - 1]
+        for j in range(1, nv + 1):
+            f = families[j - 1]
+            KK[j, i] = KK[j - 1, i] + (L.dof_offset[f][i + 1] - L.dof_offset[f][i])
+    return KK
+
+
+def system_dof(L, KK, families, k, sol_dof):
+    """LinearEquation::GetSystemDof (LinearEquation.cpp:76-85) of solution dof `sol_dof` of variable k."""
+    f = families[k]
+    isub = int(np.searchsorted(L.dof_offset[f], sol_dof, side="right") - 1)
+    return int(KK[k, isub] + sol_dof - L.dof_offset[f][isub])
+
+
+def near_elements(elem_vertices):
+    """elem::BuildElementNearElement (Elem.cpp:493-526): the element itself, then every other element sharing a
+    vertex with it, ascending.  elem_vertices[e] = vertex nodes of element e."""
+    near_vertex = {}
+    for e, vs in enumerate(elem_vertices):
+        for v in vs:
+            near_vertex.setdefault(int(v), []).append(e)
+    out = []
+    for e, vs in enumerate(elem_vertices):
+        others = set()
+        for v in vs:
+            others.update(near_vertex[int(v)])
+        others.discard(e)
+        out.append([e] + sorted(others))
+    return out
+
+
+def build_asm_index_system(L, elem_sol_dofs, families, nschur, block_elements, near, iproc=0):
+    """LinearEquationSolverPetscAsm::BuildASMIndex (LinearEquationSolverPetscAsm.cpp:91-262) for a system of several
+    Lagrange variables, the last `nschur` of them Schur variables (pressure-like): a block takes the non-Schur dofs
+    of every owned element NEAR its elements (the elements themselves if there is no Schur variable:
+    FastVankaBlock) and the Schur dofs of its own elements.  elem_sol_dofs[k][e] = solution dofs of variable k on
+    element e.  Returns (local_is, overlapping_is) in system numbering, sorted."""
+    nv = len(families)
+    KK = kk_offsets(L, families)
+    e0, e1 = int(L.elem_offset[iproc]), int(L.elem_offset[iproc + 1])
+    dof0 = int(KK[0, iproc])
+    size = int(KK[nv, iproc] - KK[0, iproc])
+    NONE = size
+    indexa, indexb, owned = [NONE] * size, [NONE] * size, [False] * size
+    fast = True if nschur == 0 else False           # Lagrange Schur variable (SolType < 3): not a fast Vanka block
+    non_schur = [True] * (nv - nschur) + [False] * nschur
+    local_is, over_is = [], []
+    for elems in block_elements:
+        loc, ovl, ghosts, inblock = [], [], {}, set()
+
+        def add(k, jel):
+            f = families[k]
+            for jdof in elem_sol_dofs[k][jel]:
+                kk = system_dof(L, KK, families, k, int(jdof))
+                if L.dof_offset[f][iproc] <= jdof < L.dof_offset[f][iproc + 1]:
+                    if indexa[kk - dof0] == NONE and not owned[kk - dof0]:
+                        owned[kk - dof0] = True
+                        indexa[kk - dof0] = len(loc)
+                        loc.append(kk)
+                    if indexb[kk - dof0] == NONE:
+                        indexb[kk - dof0] = len(ovl)
+                        ovl.append(kk)
+                else:
+                    ghosts[kk] = True
+
+        for iel in elems:
+            for jel in (near[iel] if not fast else [iel]):
+                if e0 <= jel < e1 and jel not in inblock:
+                    inblock.add(jel)
+                    for k in range(nv):
+                        if non_schur[k]:
+                            add(k, jel)
+            for k in range(nv):
+                if not non_schur[k]:
+                    add(k, iel)
+        for kk in loc:
+            indexa[kk - dof0] = NONE
+        for kk in ovl:
+            indexb[kk - dof0] = NONE
+        ovl = ovl + sorted(ghosts)
+        local_is.append(np.array(sorted(loc), dtype=np.int64))
+        over_is.append(np.array(sorted(ovl), dtype=np.int64))
+    return local_is, over_is

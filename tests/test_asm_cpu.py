@@ -63,6 +63,35 @@ def test_index_sets_bit_exact_on_unstructured_meshes(name):
                     assert 0 < rng[0] == rng[1] < rng[2]
 
 
+@pytest.mark.parametrize("nprocs", [1, 2])
+def test_vanka_index_sets_of_a_velocity_pressure_system(nprocs):
+    """Three triquadratic velocities + a trilinear pressure numbered [rank][variable][dof] (KKoffset), the pressure a
+    Schur variable: blocks = velocities of one layer of near elements + pressures of the block's own elements
+    (BuildASMIndex with NSchurVar = 1, FastVankaBlock == false); also 0 and 2 Schur variables.  Bit-exact against
+    the oracle's literal loops on every rank."""
+    lv = mb.build_hierarchy(2, 2, 3, 2, nprocs=nprocs)
+    H = hostapi.HostHierarchy(2, 2, 3, 2, nprocs=nprocs)
+    L = lv[1]
+    fams, fi = ["biquadratic"] * 3 + ["linear"], [2, 2, 2, 0]
+    assert np.array_equal(hostapi.system_offsets(H.levels[1], fams), asm.kk_offsets(L, fi))
+    edq, edl = mb.system_dof(L, "biquadratic"), mb.system_dof(L, "linear")
+    near = asm.near_elements(L.conn[:, :8])
+    assert near[0][0] == 0 and near[0][1:] == sorted(near[0][1:])
+    for ip in range(nprocs):
+        for nb in (1, 8, 5):
+            be, _, _, _ = asm.level_blocks(L, edq, 2, nb, ip)
+            for ns in (1, 0, 2):
+                loc, ovl = asm.build_asm_index_system(L, [edq, edq, edq, edl], fi, ns, be, near, ip)
+                ix = hostapi.AsmIndex(H.levels[1], fams, nb, ip, nschur=ns)
+                assert ix.nblocks == len(be)
+                for a, b in zip(ix.blocks("local"), loc):
+                    assert np.array_equal(a, b)
+                for a, b in zip(ix.blocks("overlap"), ovl):
+                    assert np.array_equal(a, b)
+    with pytest.raises(ValueError):
+        hostapi.AsmIndex(H.levels[1], fams, 8, 0, nschur=5)
+
+
 def test_bad_arguments_fail_loudly():
     H = hostapi.HostHierarchy(2, 2, 2, 2)
     with pytest.raises(ValueError):

@@ -104,6 +104,31 @@ def test_schwarz_ssor_kernel_on_the_emulator(emu, order, nb, schedule):
         assert ix.nblocks == 1 and len(gptr) == 2
 
 
+def test_vanka_blocks_of_a_saddle_point_system_on_the_emulator(emu):
+    """Velocity-pressure Vanka blocks (index sets with one Schur variable: velocities of the near elements,
+    pressures of the block's element) of a synthetic Stokes matrix in system numbering: the system dofs put the
+    velocities first, so Gauss-Jordan without pivoting meets the pressure Schur complement last; block inverses
+    and the multiplicative sweep against the oracle."""
+    from oracle import asm, mesh_box as mb
+    from tests import saddle_point as spt
+    L = mb.build_hierarchy(1, 1, 1, 2)[1]
+    A = spt.stokes_matrix(L)
+    H = hostapi.HostHierarchy(1, 1, 1, 2)
+    ix = hostapi.AsmIndex(H.levels[1], spt.FAMILIES, 1, nschur=1)
+    assert ix.nblocks == 8 and all(len(b) == 3 * 125 + 8 for b in ix.blocks())
+    grp, gptr, gblocks = hostapi.asm_schedule(A.indptr, A.indices, ix.overlap_ptr, ix.overlap, "colours")
+    assert len(gptr) - 1 == 8                   # every block holds every velocity: nothing commutes
+    S = asm.BlockSmoother(A, ix.blocks(), order=gblocks)
+    r = np.random.default_rng(9).standard_normal(A.shape[0])
+    err, y, inv = _run_schwarz(emu, A, ix, gptr, gblocks, r, threads=64, grid=2)
+    assert err == 0
+    m = len(ix.blocks()[0])
+    want_inv = np.linalg.inv(S.dense[0])
+    assert np.abs(inv[:m * m].reshape(m, m) - want_inv).max() <= 1e-10 * np.abs(want_inv).max()
+    want = S.apply(r)
+    assert np.abs(y - want).max() <= 1e-10 * np.abs(want).max()
+
+
 def test_schwarz_invert_kernel_reports_singular_blocks(emu):
     import scipy.sparse as sp
     H = hostapi.HostHierarchy(1, 1, 1, 2)

@@ -115,6 +115,27 @@ def test_vcycle_trace_with_ssor_block_solves(ctx, order, nb, schedule):
     del pb
 
 
+def test_vanka_blocks_of_a_saddle_point_system(ctx):
+    """b2_schwarz on velocity-pressure Vanka blocks (host index sets with one Schur variable: blocks of up to 3 x 729 + 27 dofs)
+    of a synthetic Stokes matrix in the reference's system numbering: application against the oracle."""
+    from femus_b200 import capi, hostapi
+    from oracle import asm, mesh_box as mb
+    from tests import saddle_point as spt
+    L = mb.build_hierarchy(2, 2, 2, 2)[1]
+    A = spt.stokes_matrix(L)
+    H = hostapi.HostHierarchy(2, 2, 2, 2)
+    ix = hostapi.AsmIndex(H.levels[1], spt.FAMILIES, 8, nschur=1)
+    grp, gptr, gblocks = hostapi.asm_schedule(A.indptr, A.indices, ix.overlap_ptr, ix.overlap, "colours")
+    dA = ctx.csr_from_scipy(A)
+    S = capi.Schwarz(ctx, dA, ix.overlap_ptr, ix.overlap, gptr, gblocks)
+    S.setup()
+    r = np.random.default_rng(9).standard_normal(A.shape[0])
+    R, Y = ctx.vector(r), ctx.vector(A.shape[0])
+    S.apply(R, Y)
+    want = asm.BlockSmoother(A, ix.blocks(), order=gblocks).apply(r)
+    assert np.abs(Y.get() - want).max() <= 1e-10 * np.abs(want).max()
+
+
 def test_block_smoother_fails_loudly(ctx):
     from femus_b200 import capi, hostapi
     H = hostapi.HostHierarchy(2, 2, 2, 2)
