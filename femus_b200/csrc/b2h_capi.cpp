@@ -4,6 +4,7 @@
 #include <memory>
 #include <string>
 #include "../host/AsmPartition.hpp"
+#include "../host/SystemLayout.hpp"
 #include "../host/BoxMesh.hpp"
 #include "../host/FaceElement.hpp"
 #include "../host/GambitIO.hpp"
@@ -244,6 +245,46 @@ int b2h_system_offsets(const b2h_hier* h, int l, int nvars, const int* families,
     const SystemLayout sys(h->levels[l], std::vector<int>(families, families + nvars));
     const int np = h->levels[l].nprocs;
     for (int k = 0; k <= nvars; k++) std::copy(sys.KKoffset[k].begin(), sys.KKoffset[k].end(), out + (size_t)k * np);
+    return 0;
+  } catch (const std::exception& e) {
+    g_b2h_error = e.what();
+    return 1;
+  }
+}
+void b2h_system_elem_dofs(const b2h_hier* h, int l, int nvars, const int* families, int32_t* out) {
+  const SystemLayout sys(h->levels[l], std::vector<int>(families, families + nvars));
+  const std::vector<int32_t> d = SystemElementDofs(h->levels[l], sys);
+  std::copy(d.begin(), d.end(), out);
+}
+b2h_csr* b2h_system_sparsity_create(const b2h_hier* h, int l, int nvars, const int* families, const uint8_t* pattern) {
+  try {
+    if (!h || l < 0 || l >= (int)h->levels.size() || nvars < 1 || !families) throw std::invalid_argument("b2h_system_sparsity_create: bad arguments");
+    const SystemLayout sys(h->levels[l], std::vector<int>(families, families + nvars));
+    std::unique_ptr<b2h_csr> p(new b2h_csr());
+    p->m = BuildSystemSparsity(h->levels[l], sys, pattern);
+    return p.release();
+  } catch (const std::exception& e) {
+    g_b2h_error = e.what();
+    return nullptr;
+  }
+}
+b2h_csr* b2h_system_prolongator_create(const b2h_hier* h, int lfine, int nvars, const int* families) {
+  try {
+    if (!h || lfine < 1 || lfine >= (int)h->levels.size() || nvars < 1 || !families) throw std::invalid_argument("b2h_system_prolongator_create: bad arguments");
+    std::unique_ptr<b2h_csr> p(new b2h_csr());
+    p->m = BuildSystemProlongator(h->levels[lfine - 1], h->levels[lfine], std::vector<int>(families, families + nvars));
+    return p.release();
+  } catch (const std::exception& e) {
+    g_b2h_error = e.what();
+    return nullptr;
+  }
+}
+int b2h_system_bdc(const b2h_hier* h, int l, int nvars, const int* families, const uint8_t* dirichlet, double* out) {
+  try {
+    if (!h || l < 0 || l >= (int)h->levels.size() || nvars < 1 || !families || !dirichlet || !out) throw std::invalid_argument("b2h_system_bdc: bad arguments");
+    const SystemLayout sys(h->levels[l], std::vector<int>(families, families + nvars));
+    const std::vector<double> b = SystemBdc(h->levels[l], sys, dirichlet);
+    std::copy(b.begin(), b.end(), out);
     return 0;
   } catch (const std::exception& e) {
     g_b2h_error = e.what();

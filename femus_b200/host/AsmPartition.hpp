@@ -27,6 +27,7 @@
 #include <stdexcept>
 #include <vector>
 #include "BoxMesh.hpp"
+#include "SystemLayout.hpp"
 
 namespace femus_b200 {
 
@@ -74,35 +75,6 @@ inline void DoPartition(const MeshLevel& L, int iproc, const unsigned block_size
     }
   }
 }
-
-// LinearEquation::InitPde (LinearEquation.cpp:211-237): rows of a system of several variables are numbered
-// [rank][variable][dof]; KKoffset[k][p] = first row of variable k on rank p (k = nvars: end of the rank's rows).
-struct SystemLayout {
-  std::vector<int> family;                        // FE family of every variable (0 linear, 1 serendipity, 2 biquadratic)
-  std::vector<std::vector<int64_t>> KKoffset;     // [nvars+1][nprocs]
-  SystemLayout(const MeshLevel& L, const std::vector<int>& fam) : family(fam) {
-    if (fam.empty()) throw std::invalid_argument("SystemLayout: no variable");
-    for (int f : fam)
-      if (f < 0 || f > 2) throw std::invalid_argument("SystemLayout: Lagrange families 0, 1, 2 only");
-    const int nv = (int)fam.size();
-    KKoffset.assign((size_t)nv + 1, std::vector<int64_t>((size_t)L.nprocs, 0));
-    for (int j = 1; j <= nv; j++) KKoffset[j][0] = KKoffset[j - 1][0] + (L.dof_offset[fam[j - 1]][1] - L.dof_offset[fam[j - 1]][0]);
-    for (int i = 1; i < L.nprocs; i++) {
-      KKoffset[0][i] = KKoffset[nv][i - 1];
-      for (int j = 1; j <= nv; j++) KKoffset[j][i] = KKoffset[j - 1][i] + (L.dof_offset[fam[j - 1]][i + 1] - L.dof_offset[fam[j - 1]][i]);
-    }
-  }
-  int nvars() const { return (int)family.size(); }
-  int64_t size() const { return KKoffset.back().back(); }
-  // LinearEquation::GetSystemDof (LinearEquation.cpp:76-85)
-  int64_t system_dof(const MeshLevel& L, int k, int i, int64_t iel) const {
-    const int f = family[k];
-    const int64_t idof = L.GetSolutionDof(i, iel, f);
-    const std::vector<int64_t>& o = L.dof_offset[f];
-    const int isub = (int)(std::upper_bound(o.begin(), o.end(), idof) - o.begin()) - 1;
-    return KKoffset[k][isub] + idof - o[isub];
-  }
-};
 
 // elem::BuildElementNearElement (Elem.cpp:493-526): the element itself, then every other element sharing a vertex
 // with it, ascending; CSR-like (ptr, list) over all elements of the level

@@ -68,6 +68,10 @@ def _L():
             "b2h_asm_create": (vp, [vp, ci, ci, ci, ci]),
             "b2h_asm_create_system": (vp, [vp, ci, ci, vp, ci, ci, ci]),
             "b2h_system_offsets": (ci, [vp, ci, ci, vp, vp]),
+            "b2h_system_elem_dofs": (None, [vp, ci, ci, vp, vp]),
+            "b2h_system_sparsity_create": (vp, [vp, ci, ci, vp, vp]),
+            "b2h_system_prolongator_create": (vp, [vp, ci, ci, vp]),
+            "b2h_system_bdc": (ci, [vp, ci, ci, vp, vp, vp]),
             "b2h_asm_destroy": (None, [vp]),
             "b2h_asm_nblocks": (i64, [vp]),
             "b2h_asm_block_type_range": (None, [vp, vp]),
@@ -391,6 +395,57 @@ def system_offsets(level, families):
     if level.hier.L.b2h_system_offsets(level.hier.h, level.l, len(fams), fams.ctypes.data_as(vp), out.ctypes.data_as(vp)):
         raise ValueError(level.hier.L.b2h_last_error().decode())
     return out
+
+
+class SystemOnLevel:
+    """A system of several Lagrange variables on a level, rows [rank][variable][dof] (LinearEquation::InitPde):
+    element dof lists, sparsity pattern, prolongator from the level below, Dirichlet flags -- host side of SURVEY 8f row 3."""
+
+    def __init__(self, level, families):
+        self.level, self.families = level, list(families)
+        self._f = np.array([_fam(f) for f in families], dtype=np.int32)
+        self.offsets = system_offsets(level, families)
+        self.n = int(self.offsets[-1, -1])
+
+    def _csr(self, p, with_values):
+        L = self.level.hier.L
+        if not p:
+            raise ValueError(L.b2h_last_error().decode())
+        n, nnz = int(L.b2h_csr_nrows(p)), int(L.b2h_csr_nnz(p))
+        rp = _view(L.b2h_csr_rowptr(p), (n + 1,), np.int64).copy()
+        col = _view(L.b2h_csr_col(p), (nnz,), np.int32).copy()
+        val = _view(L.b2h_csr_val(p), (nnz,), np.float64).copy() if with_values else None
+        shape = (n, int(L.b2h_csr_ncols(p)))
+        L.b2h_csr_destroy(p)
+        return rp, col, val, shape
+
+    def elem_dofs(self):
+        """[nel][nvars][27] system dofs, -1 padded."""
+        out = np.zeros((self.level.nel, len(self._f), 27), dtype=np.int32)
+        self.level.hier.L.b2h_system_elem_dofs(self.level.hier.h, self.level.l, len(self._f), self._f.ctypes.data_as(vp), out.ctypes.data_as(vp))
+        return out
+
+    def sparsity(self, pattern=None):
+        pat = None if pattern is None else np.ascontiguousarray(pattern, dtype=np.uint8)
+        p = self.level.hier.L.b2h_system_sparsity_create(self.level.hier.h, self.level.l, len(self._f), self._f.ctypes.data_as(vp),
+                                                         pat.ctypes.data_as(vp) if pat is not None else None)
+        rp, col, _, _ = self._csr(p, False)
+        return rp, col
+
+    def prolongator(self):
+        p = self.level.hier.L.b2h_system_prolongator_create(self.level.hier.h, self.level.l, len(self._f), self._f.ctypes.data_as(vp))
+        return self._csr(p, True)
+
+    def bdc(self, dirichlet_faces_per_var):
+        """dirichlet_faces_per_var[k] = boundary sets (1..6) on which variable k is Dirichlet."""
+        flags = np.zeros((len(self._f), 7), dtype=np.uint8)
+        for k, faces in enumerate(dirichlet_faces_per_var):
+            flags[k, list(faces)] = 1
+        out = np.zeros(self.n)
+        if self.level.hier.L.b2h_system_bdc(self.level.hier.h, self.level.l, len(self._f), self._f.ctypes.data_as(vp), flags.ctypes.data_as(vp),
+                                            out.ctypes.data_as(vp)):
+            raise ValueError(self.level.hier.L.b2h_last_error().decode())
+        return out
 
 
 def asm_schedule(rowptr, col, blk_ptr, blk_dofs, mode="colours"):

@@ -138,6 +138,17 @@ b2h_asm* b2h_asm_create(const b2h_hier* h, int l, int family, int block_elems, i
  * Elem.cpp:493-526) + Schur dofs of the block's own elements.  b2h_system_offsets: KKoffset [nvars+1][nprocs]. */
 b2h_asm* b2h_asm_create_system(const b2h_hier* h, int l, int nvars, const int* families, int nschur, int block_elems, int iproc);
 int b2h_system_offsets(const b2h_hier* h, int l, int nvars, const int* families, int64_t* out);
+/* systems of several Lagrange variables (host side), rows [rank][variable][dof]:
+ * b2h_system_elem_dofs: GetSystemDof of every element, [nel][nvars][27] padded with -1;
+ * b2h_system_sparsity_create: LinearEquation::GetSparsityPatternSize (LinearEquation.cpp:407-548), pattern = nvars x
+ *   nvars coupling flags (_SparsityPattern) or NULL for all pairs; a b2h_csr with zero values;
+ * b2h_system_prolongator_create: LinearImplicitSystem::BuildProlongatorMatrix (LinearImplicitSystem.cpp:826-909),
+ *   variable by variable, from level lfine-1 to lfine;
+ * b2h_system_bdc: GenerateBdc of every variable in system numbering, dirichlet[nvars][7] flags of the boundary sets. */
+void b2h_system_elem_dofs(const b2h_hier* h, int l, int nvars, const int* families, int32_t* out);
+b2h_csr* b2h_system_sparsity_create(const b2h_hier* h, int l, int nvars, const int* families, const uint8_t* pattern);
+b2h_csr* b2h_system_prolongator_create(const b2h_hier* h, int lfine, int nvars, const int* families);
+int b2h_system_bdc(const b2h_hier* h, int l, int nvars, const int* families, const uint8_t* dirichlet, double* out);
 void b2h_asm_destroy(b2h_asm* a);
 int64_t b2h_asm_nblocks(const b2h_asm* a);
 void b2h_asm_block_type_range(const b2h_asm* a, int64_t* out3);
