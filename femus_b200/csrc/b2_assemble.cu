@@ -32,6 +32,14 @@ struct b2_mesh {
   int32_t* conn_shadow;  // mesh is uploaded here while the current step still reads xyz / conn
 };
 
+void b2_mesh_view(const b2_mesh* m, b2_ctx** ctx, int64_t* nnode, int64_t* nel, const double** xyz, const int32_t** conn) {
+  *ctx = m->ctx;
+  *nnode = m->nnode;
+  *nel = m->nel;
+  *xyz = m->xyz;
+  *conn = m->conn;
+}
+
 struct b2_asm {
   b2_mesh* mesh;
   b2_csr* A;

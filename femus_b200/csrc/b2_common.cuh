@@ -167,6 +167,7 @@ static inline int b2_grid_for(b2_ctx* c, int64_t work_items, int per_block, int 
 
 // internal cross-TU helpers
 const b2_csr* b2_schwarz_operator(const b2_schwarz* s);
+void b2_mesh_view(const b2_mesh* m, b2_ctx** ctx, int64_t* nnode, int64_t* nel, const double** xyz, const int32_t** conn);
 int b2_csr_alloc(b2_ctx* c, int64_t nrows, int64_t ncols, int64_t nnz, b2_csr** out);
 int b2_csr_finalize(b2_csr* A);   // row statistics -> tpr / max_row, SpMV row chunks
 int b2_csr_build_chunks(b2_csr* A);

@@ -1,0 +1,94 @@
+// Steady Stokes assembly plan: host side of stokes_kernel (b2_stokes_kernel.cuh).  Replaces the assembly callback of
+// the reference's applications/003_NavierStokes/SteadyStokes/main.cpp (AssembleMatrixResNS, :290-598) for Taylor-Hood
+// pairs on meshes of one element type per plan; the system matrix carries the pattern of
+// LinearEquation::GetSparsityPatternSize for the variables U, V, W, P (b2h_system_sparsity_create).
+#include "b2_common.cuh"
+
+struct b2_stokes {
+  b2_ctx* ctx = nullptr;
+  b2_mesh* mesh = nullptr;      // borrowed
+  b2_csr* A = nullptr;          // borrowed
+  int nv = 0, np = 0, ng = 0;
+  int32_t* edof = nullptr;      // [nel][4][27]
+  double *tabv = nullptr, *tabp = nullptr;
+  int64_t nel = 0;
+};
+
+namespace {
+#include "b2_stokes_kernel.cuh"
+size_t stokes_smem(int nv, int np, int ng) { return (size_t)kStokesWarps * (size_t)stokes_warp_doubles_host(nv, np, ng) * sizeof(double); }
+}  // namespace
+
+extern "C" {
+
+int b2_stokes_create(b2_mesh* mesh, b2_csr* A, const int32_t* elem_dofs, int nve_v, int nve_p, int ngauss, const double* dxi,
+                     const double* deta, const double* dzeta, const double* weights, const double* phi_p, b2_stokes** out) {
+  B2_CHECK(mesh && A && elem_dofs && dxi && deta && dzeta && weights && phi_p && out, "b2_stokes_create: null argument");
+  B2_CHECK(nve_v >= 4 && nve_v <= 27 && nve_p >= 1 && nve_p <= 8 && ngauss >= 1 && ngauss <= 64,
+           "b2_stokes_create: nve_v=%d (4..27), nve_p=%d (1..8) or ngauss=%d (1..64) out of range", nve_v, nve_p, ngauss);
+  B2_CHECK(A->nrows == A->ncols, "b2_stokes_create: the system matrix must be square");
+  b2_ctx* c = nullptr;
+  int64_t nnode = 0, nel = 0;
+  const double* xyz = nullptr;
+  const int32_t* conn = nullptr;
+  b2_mesh_view(mesh, &c, &nnode, &nel, &xyz, &conn);
+  // every listed dof must be a row of A and every element coupling a pattern entry: checked on the host against the
+  // dof range here, against the pattern by the caller's construction (b2h_system_sparsity_create)
+  for (int64_t e = 0; e < nel; e++)
+    for (int k = 0; k < 4; k++)
+      for (int i = 0; i < (k < 3 ? nve_v : nve_p); i++) {
+        const int32_t d = elem_dofs[(e * 4 + k) * 27 + i];
+        B2_CHECK(d >= 0 && d < A->nrows, "b2_stokes_create: element %lld variable %d node %d: dof %d outside the system", (long long)e, k, i, (int)d);
+      }
+  b2_stokes* p = new b2_stokes();
+  p->ctx = c;
+  p->mesh = mesh;
+  p->A = A;
+  p->nv = nve_v;
+  p->np = nve_p;
+  p->ng = ngauss;
+  p->nel = nel;
+  *out = p;
+  const size_t nt = (size_t)3 * ngauss * nve_v + ngauss;
+  std::vector<double> tab(nt);
+  std::copy(dxi, dxi + ngauss * nve_v, tab.begin());
+  std::copy(deta, deta + ngauss * nve_v, tab.begin() + ngauss * nve_v);
+  std::copy(dzeta, dzeta + ngauss * nve_v, tab.begin() + 2 * ngauss * nve_v);
+  std::copy(weights, weights + ngauss, tab.begin() + 3 * ngauss * nve_v);
+  B2_TRY(b2_malloc(c, &p->edof, (size_t)nel * 108));
+  B2_TRY(b2_malloc(c, &p->tabv, nt));
+  B2_TRY(b2_malloc(c, &p->tabp, (size_t)ngauss * nve_p));
+  B2_TRY(b2_upload(c, p->edof, elem_dofs, (size_t)nel * 108));
+  B2_TRY(b2_upload(c, p->tabv, tab.data(), nt));
+  B2_TRY(b2_upload(c, p->tabp, phi_p, (size_t)ngauss * nve_p));
+  const size_t smem = stokes_smem(nve_v, nve_p, ngauss);
+  if (smem > 48 * 1024) B2_CUDA(cudaFuncSetAttribute(stokes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  return 0;
+}
+
+/* A += the Stokes element blocks, rhs += the residual F = -B sol at the current solution (sol in system numbering,
+ * NULL = zero; rhs NULL = matrix only).  A and rhs are not zeroed here (the callback calls myKK->zero(), :372). */
+int b2_stokes_assemble(b2_stokes* p, const b2_vec* sol, b2_vec* rhs, double IRe) {
+  B2_CHECK(p, "b2_stokes_assemble: null plan");
+  B2_CHECK((!sol || sol->n >= p->A->nrows) && (!rhs || rhs->n >= p->A->nrows), "b2_stokes_assemble: vector shorter than the system");
+  b2_ctx* c = nullptr;
+  int64_t nnode = 0, nel = 0;
+  const double* xyz = nullptr;
+  const int32_t* conn = nullptr;
+  b2_mesh_view(p->mesh, &c, &nnode, &nel, &xyz, &conn);
+  const size_t smem = stokes_smem(p->nv, p->np, p->ng);
+  B2_LAUNCH(c, stokes_kernel, b2_grid_for(c, nel, kStokesWarps, 3), kStokesWarps * 32, smem, nel, nnode, p->nv, p->np, p->ng, xyz, conn, p->edof,
+            p->tabv, p->tabp, p->A->rowptr, p->A->col, p->A->val, sol ? sol->d : nullptr, rhs ? rhs->d : nullptr, IRe);
+  return 0;
+}
+
+int b2_stokes_destroy(b2_stokes* p) {
+  if (!p) return 0;
+  b2_free(p->ctx, p->edof, (size_t)p->nel * 108);
+  b2_free(p->ctx, p->tabv, (size_t)3 * p->ng * p->nv + p->ng);
+  b2_free(p->ctx, p->tabp, (size_t)p->ng * p->np);
+  delete p;
+  return 0;
+}
+
+}  // extern "C"

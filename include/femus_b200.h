@@ -33,6 +33,7 @@ typedef struct b2_mg b2_mg;
 typedef struct b2_galerkin b2_galerkin;
 typedef struct b2_halo b2_halo;
 typedef struct b2_schwarz b2_schwarz;
+typedef struct b2_stokes b2_stokes;
 
 const char* b2_last_error(void);
 int b2_version(void);
@@ -275,6 +276,20 @@ int b2_mg_set_level_halo(b2_mg* mg, int level, b2_halo* halo);
  * not reproducible); b2_mg_level_bounds returns the interval in use. */
 int b2_mg_set_smoother(b2_mg* mg, int level, int kind, double emin, double emax);
 int b2_mg_level_bounds(const b2_mg* mg, int level, double* emin, double* emax);
+
+/* ---- steady Stokes assembly (first kernel): the callback AssembleMatrixResNS of
+ * applications/003_NavierStokes/SteadyStokes/main.cpp:290-598 for three velocity components of one Lagrange family
+ * (nve_v <= 27 nodes, also the geometry) and a pressure of another (nve_p <= 8) -- Taylor-Hood pairs; the equal-order
+ * stabilisation (alpha != 0, :336-340) is not implemented.  A: the system matrix on the pattern of
+ * LinearEquation::GetSparsityPatternSize for U, V, W, P (b2h_system_sparsity_create); elem_dofs [nel][4][27] =
+ * GetSystemDof per variable (b2h_system_elem_dofs, host array); velocity tables dxi/deta/dzeta [ngauss][nve_v],
+ * weights[ngauss], pressure table phi_p [ngauss][nve_p] of the element type (b2h_elem_tables).
+ * b2_stokes_assemble: A += element blocks (IRe K on the velocity diagonal, -int dphi_i/dx_k phi1_j and its transpose),
+ * rhs += F = -B sol at the current solution in system numbering; neither is zeroed (the callback zeroes KK, :372). */
+int b2_stokes_create(b2_mesh* mesh, b2_csr* A, const int32_t* elem_dofs, int nve_v, int nve_p, int ngauss, const double* dxi,
+                     const double* deta, const double* dzeta, const double* weights, const double* phi_p, b2_stokes** out);
+int b2_stokes_assemble(b2_stokes* p, const b2_vec* sol, b2_vec* rhs, double IRe);
+int b2_stokes_destroy(b2_stokes* p);
 
 /* ---- element-block (ASM / Vanka) smoother: LinearEquationSolverPetscAsm (petsc_asm/LinearEquationSolverPetscAsm.cpp)
  * What the reference sets (:266-340, PetscPreconditioner.cpp:179-184): PCASM, PC_ASM_BASIC, local type

@@ -7,6 +7,9 @@ namespace {
 #include "../../femus_b200/csrc/b2_schwarz_kernels.cuh"
 }
 #include "../../femus_b200/csrc/b2_neumann_kernel.cuh"
+namespace {
+#include "../../femus_b200/csrc/b2_stokes_kernel.cuh"
+}
 
 extern "C" {
 
@@ -56,6 +59,15 @@ void emu_neumann(int64_t nfaces, const int32_t* felem, const int32_t* flocal, co
                  const double* ftab, const int32_t* fnodes, int64_t nnode, const double* xyz, const int32_t* conn, const int32_t* dof,
                  double* rhs, int grid) {
   emu::launch(neumann_kernel, (unsigned)grid, 256u, 0, nfaces, felem, flocal, fvalue, nvf, ngf, nve, ftab, fnodes, nnode, xyz, conn, dof, rhs);
+}
+
+// what b2_stokes_assemble launches: tabv = dxi, deta, dzeta [ng][nv], w[ng]; tabp = phi [ng][np]; edof [nel][4][27]
+void emu_stokes(int64_t nel, int64_t nnode, int nv, int np, int ng, const double* xyz, const int32_t* conn, const int32_t* edof,
+                const double* tabv, const double* tabp, const int64_t* rowptr, const int32_t* col, double* Aval, const double* sol, double* rhs,
+                double IRe, int grid) {
+  const size_t smem = (size_t)kStokesWarps * (size_t)stokes_warp_doubles_host(nv, np, ng) * sizeof(double);
+  emu::launch(stokes_kernel, (unsigned)grid, (unsigned)(kStokesWarps * 32), smem, nel, nnode, nv, np, ng, xyz, conn, edof, tabv, tabp, rowptr, col,
+              Aval, sol, rhs, IRe);
 }
 
 }  // extern "C"

@@ -28,6 +28,9 @@ def emu(tmp_path_factory):
     L.emu_schwarz.argtypes = [ctypes.c_int64, vp, vp, vp, ctypes.c_int64, vp, vp, ctypes.c_int64, vp, vp, vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int]
     L.emu_neumann.restype = None
     L.emu_neumann.argtypes = [ctypes.c_int64, vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp, ctypes.c_int64, vp, vp, vp, vp, ctypes.c_int]
+    L.emu_stokes.restype = None
+    L.emu_stokes.argtypes = [ctypes.c_int64, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp,
+                             ctypes.c_double, ctypes.c_int]
     return L
 
 
@@ -168,3 +171,39 @@ def test_neumann_kernel_on_the_emulator(emu, name, order):
             ngroups += 1
     want = mm.neumann_rhs(mm.read_neu(path), order, neumann)
     assert ngroups >= 1 and np.abs(rhs - want).max() <= 1e-13 * np.abs(want).max()
+
+
+@pytest.mark.parametrize("name,order_v,order_p", [("box", "biquadratic", "linear"), ("cube_tet10", "quadratic", "linear"),
+                                                  ("cube_wedge18", "biquadratic", "linear")])
+def test_stokes_kernel_on_the_emulator(emu, name, order_v, order_p):
+    """stokes_kernel (one warp per element, table-driven) on hexahedra (Q2-Q1, 64 points), tetrahedra (P2-P1, 31
+    points) and wedges (21 / 6 dofs, 52 points): system matrix on the host-built pattern and residual at a random
+    solution against the oracle's restatement of SteadyStokes/main.cpp:290-598."""
+    from oracle import stokes, mesh_box as mb, mesh_mixed as mm, fe_hex, mg
+    fams = [order_v] * 3 + [order_p]
+    if name == "box":
+        H, L, mesh = hostapi.HostHierarchy(2, 1, 2, 1), mb.build_hierarchy(2, 1, 2, 1)[0], mb
+        tables_of = lambda t, o: fe_hex.tables(o)
+    else:
+        path = os.path.join(GOLDEN, name + ".neu")
+        H, L, mesh = hostapi.HostHierarchy.from_neu(path, 1), mm.read_neu(path), mm
+        tables_of = lambda t, o: mm.FE[t].tables(o)
+    level = H.levels[0]
+    S = hostapi.SystemOnLevel(level, fams)
+    rp, ci = S.sparsity()
+    edof = np.ascontiguousarray(S.elem_dofs(), dtype=np.int32)
+    t = level.elem_type
+    tv, tp = hostapi.elem_tables(t, order_v), hostapi.elem_tables(t, order_p)
+    nv, npr, ng = tv[0].shape[1], tp[0].shape[1], tv[4].shape[0]
+    tabv = np.concatenate([tv[1].ravel(), tv[2].ravel(), tv[3].ravel(), tv[4].ravel()])
+    tabp = np.ascontiguousarray(tp[0])
+    sol = np.random.default_rng(11).standard_normal(S.n)
+    val, rhs = np.zeros(len(ci)), np.zeros(S.n)
+    xyz, conn = np.ascontiguousarray(level.xyz), np.ascontiguousarray(level.conn, dtype=np.int32)
+    IRe = 0.37
+    emu.emu_stokes(level.nel, level.nnode, nv, npr, ng, _p(xyz), _p(conn), _p(edof), _p(tabv), _p(tabp), _p(rp), _p(ci), _p(val), _p(sol), _p(rhs),
+                   IRe, 2)
+    Aref, rref = stokes.assemble(L, mesh, order_v, order_p, sol, IRe, tables_of)
+    Aref = mg.on_pattern(Aref, rp, ci)
+    assert np.abs(val - Aref.data).max() <= 1e-12 * np.abs(Aref.data).max()
+    assert np.abs(rhs - rref).max() <= 1e-12 * (np.abs(Aref) @ np.abs(sol)).max()
