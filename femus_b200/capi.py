@@ -123,6 +123,10 @@ _PROTOS = {
     "b2_schwarz_groups": (i64, [vp]),
     "b2_schwarz_destroy": (ci, [vp]),
     "b2_mg_set_level_schwarz": (ci, [vp, ci, vp]),
+    "b2_mg_set_coarse_schwarz": (ci, [vp, vp]),
+    "b2_stokes_create": (ci, [vp, vp, vp, ci, ci, ci, vp, vp, vp, vp, vp, vp]),
+    "b2_stokes_assemble": (ci, [vp, vp, vp, cd]),
+    "b2_stokes_destroy": (ci, [vp]),
     "b2_mg_level_bounds": (ci, [vp, ci, vp, vp]),
     "b2_mg_set_level_halo": (ci, [vp, ci, vp]),
     "b2_halo_create": (ci, [vp, i64, i64, vp, vp, i64, vp, vp, vp]),
@@ -639,6 +643,31 @@ class Assembler:
                                              rhs.h if rhs is not None else None, float(nu), float(fsrc)))
 
 
+class StokesAssembler:
+    """Steady Stokes assembly plan (b2_stokes_*): three velocity components of one family + a pressure of another on a
+    mesh of one element type; elem_dofs [nel][4][27] system dofs, tables of the two families (hostapi.elem_tables)."""
+
+    def __init__(self, mesh, A, elem_dofs, tables_v, tables_p):
+        self.ctx, self.L, self.mesh, self.A = mesh.ctx, mesh.ctx.L, mesh, A
+        ed = _i32(elem_dofs)
+        _, dxi, deta, dzeta, w = [_f64(t) for t in tables_v]
+        phip = _f64(tables_p[0])
+        h = vp()
+        check(self.L.b2_stokes_create(mesh.h, A.h, _ptr(ed), dxi.shape[1], phip.shape[1], dxi.shape[0], _ptr(dxi), _ptr(deta), _ptr(dzeta),
+                                      _ptr(w), _ptr(phip), ctypes.byref(h)))
+        self.h = h
+
+    def __del__(self):
+        try:
+            if self.h and self.ctx.h:
+                self.L.b2_stokes_destroy(self.h)
+        except Exception:
+            pass
+
+    def assemble(self, sol=None, rhs=None, IRe=1.0):
+        check(self.L.b2_stokes_assemble(self.h, sol.h if sol is not None else None, rhs.h if rhs is not None else None, float(IRe)))
+
+
 class Schwarz:
     """Element-block multiplicative Schwarz preconditioner on a device operator (b2_schwarz_*): blocks as
     (blk_ptr, blk_dofs) with sorted dofs, schedule as (group_ptr, group_blocks) -- hostapi.AsmIndex / asm_schedule."""
@@ -711,6 +740,11 @@ class Multigrid:
         """Level smoother = Richardson(omega) + the element-block preconditioner (b2_mg_set_level_schwarz)."""
         self._keep.append(schwarz)
         check(self.L.b2_mg_set_level_schwarz(self.h, level, schwarz.h if schwarz is not None else None))
+
+    def set_coarse_schwarz(self, schwarz):
+        """Direct coarse solve through a one-block exact Schwarz object (b2_mg_set_coarse_schwarz)."""
+        self._keep.append(schwarz)
+        check(self.L.b2_mg_set_coarse_schwarz(self.h, schwarz.h if schwarz is not None else None))
 
     def level_bounds(self, level):
         a, b = cd(), cd()

@@ -34,6 +34,7 @@ struct b2_mg {
   b2_ctx* ctx;
   int nlevels;
   std::vector<b2_mg_level> L;
+  b2_schwarz* coarse_schwarz = nullptr;   // borrowed: exact coarse solve (one block holding every dof) instead of the PCG
   double coarse_rtol = 1e-14;
   int coarse_maxit = 5000;
   int coarse_its = 0;
@@ -311,6 +312,10 @@ int coarse_solve(b2_mg* mg) {
   // r, u = D^-1 r, w = A u, p, s = A p as in Chronopoulos & Gear; mg->z = u, mg->w = w, mg->p = p, mg->q = s.
   b2_mg_level& L = mg->L[0];
   b2_ctx* c = mg->ctx;
+  if (mg->coarse_schwarz) {      // PREONLY + LU of the reference (PetscPreconditioner.cpp:147-160): x = A^-1 b, also for indefinite systems
+    mg->coarse_its = 0;
+    return b2_schwarz_apply(mg->coarse_schwarz, L.b, L.x);
+  }
   const int64_t n = L.A->nrows;
   const int g = vec_grid(c, n);
   int gd = b2_grid_for(c, n, kBlock * 4, 8);
@@ -423,6 +428,11 @@ int b2_mg_set_level(b2_mg* mg, int level, b2_csr* A, b2_csr* P, const int32_t* b
   B2_TRY(b2_csr_diag(A, L.dinv));
   if (L.halo) B2_TRY(b2_halo_sum(L.halo, L.dinv));       // diagonal of the summed operator
   B2_LAUNCH(c, recip_kernel, vec_grid(c, n), kBlock, 0, n, L.dinv->d, L.dinv->d);
+  if (level == 0 && mg->coarse_schwarz) {      // numeric phase of the direct coarse solve on the penalised operator
+    B2_CHECK(!L.halo, "b2_mg_set_level: the direct coarse solve runs on one rank only");
+    B2_CHECK(b2_schwarz_operator(mg->coarse_schwarz) == A, "b2_mg_set_level: the coarse solver was created on another operator");
+    B2_TRY(b2_schwarz_setup(mg->coarse_schwarz));
+  }
   if (L.smoother == 2 && level > 0) {          // numeric phase of the block smoother on the penalised operator
     B2_CHECK(!L.halo, "b2_mg_set_level: the element-block smoother runs on one rank only");
     B2_CHECK(L.schwarz && b2_schwarz_operator(L.schwarz) == A, "b2_mg_set_level: level %d: the block smoother was created on another operator", level);
@@ -472,6 +482,12 @@ int b2_mg_set_level_schwarz(b2_mg* mg, int level, b2_schwarz* s) {
   B2_CHECK(mg && level >= 1 && level < mg->nlevels, "b2_mg_set_level_schwarz: bad level %d (the coarsest level has no smoother)", level);
   mg->L[level].schwarz = s;
   mg->L[level].smoother = s ? 2 : 0;
+  return 0;
+}
+
+int b2_mg_set_coarse_schwarz(b2_mg* mg, b2_schwarz* s) {
+  B2_CHECK(mg, "b2_mg_set_coarse_schwarz: null handle");
+  mg->coarse_schwarz = s;
   return 0;
 }
 

@@ -1,0 +1,83 @@
+"""Harness-side mirror of the reference's driver for the steady Stokes application
+(applications/003_NavierStokes/SteadyStokes/main.cpp: system "Navier-Stokes" with U, V(, W), P; assembly callback
+AssembleMatrixResNS; LinearImplicitSystem::MGsolve with the ASM / Vanka level solver), in three dimensions, expressed
+as calls into the C++ host layer and the device C ABI -- SURVEY 8f row 3, first vertical slice:
+
+    system.init()       per-level system matrices on the multi-variable pattern, system prolongators with the
+                        Dirichlet rows / columns zeroed                       hostapi.SystemOnLevel
+    assembly            b2_stokes_assemble on the finest level                 capi.StokesAssembler
+    Galerkin chain      the general triple product (MatPtAP)                   Csr.ptap
+    level solver        Richardson around velocity-pressure Vanka blocks       hostapi.AsmIndex(nschur=1), capi.Schwarz
+    coarsest level      a direct solve (PREONLY + LU in the reference)         Multigrid.set_coarse_schwarz
+
+No arithmetic happens here: every number is produced by libfemus_b200.so.  One rank, one element type per mesh."""
+import numpy as np
+
+from . import capi, hostapi
+
+
+class StokesMG:
+    def __init__(self, ctx, hier, order_v="biquadratic", order_p="linear", IRe=1.0, velocity_dirichlet=(1, 2, 3, 4, 5, 6),
+                 pressure_dirichlet=(), npre=1, npost=1, omega=1.0, block_elems=1, schedule="colours"):
+        self.ctx, self.hier, self.IRe = ctx, hier, IRe
+        self.fams = [order_v] * 3 + [order_p]
+        lv = hier.levels
+        nl = self.nlevels = len(lv)
+        self.npre, self.npost, self.omega = npre, npost, omega
+        top = lv[-1]
+        if top.elem_type < 0:
+            raise NotImplementedError("the Stokes assembly takes meshes of one element type")
+        self.sys = [hostapi.SystemOnLevel(L, self.fams) for L in lv]
+        self.n = self.sys[-1].n
+        dirichlet = [velocity_dirichlet] * 3 + [pressure_dirichlet]
+        self.bdc = [S.bdc(dirichlet) for S in self.sys]
+        self.bdc_idx = [np.nonzero(b < 1.5)[0].astype(np.int32) for b in self.bdc]
+        self.pattern = [S.sparsity() for S in self.sys]
+        self.KK = [ctx.csr(S.n, S.n, *pat) for S, pat in zip(self.sys, self.pattern)]
+        self.PP = [None] * nl
+        for l in range(1, nl):
+            rp, ci, v, shape = self.sys[l].prolongator()
+            P = ctx.csr(shape[0], shape[1], rp, ci, v)
+            P.zero_rows(self.bdc_idx[l], 0.0)
+            P.zero_cols(self.bdc_idx[l - 1])
+            self.PP[l] = P
+        self.mesh = capi.Mesh(ctx, top.xyz, top.conn)
+        t = top.elem_type
+        self.asm = capi.StokesAssembler(self.mesh, self.KK[-1], self.sys[-1].elem_dofs(), hostapi.elem_tables(t, order_v),
+                                        hostapi.elem_tables(t, order_p))
+        self.RES, self.EPS, self.SOL = ctx.vector(self.n), ctx.vector(self.n), ctx.vector(self.n)
+        self.BDC, self.RESM = ctx.vector(self.bdc[-1]), ctx.vector(self.n)
+        self.mg = capi.Multigrid(ctx, nl)
+        # coarsest level: one block with every dof, exact solve
+        n0 = self.sys[0].n
+        self.coarse = capi.Schwarz(ctx, self.KK[0], np.array([0, n0], dtype=np.int64), np.arange(n0, dtype=np.int32),
+                                   np.array([0, 1], dtype=np.int64), np.zeros(1, dtype=np.int32))
+        self.mg.set_coarse_schwarz(self.coarse)
+        # levels above: Vanka blocks, the pressure being the Schur variable (velocities of the near elements)
+        self.asm_index, self.asm_groups, self.schwarz = [None] * nl, [None] * nl, [None] * nl
+        for l in range(1, nl):
+            ix = hostapi.AsmIndex(lv[l], self.fams, block_elems, nschur=1)
+            grp, gptr, gblocks = hostapi.asm_schedule(*self.pattern[l], ix.overlap_ptr, ix.overlap, schedule)
+            self.asm_index[l], self.asm_groups[l] = ix, grp
+            self.schwarz[l] = capi.Schwarz(ctx, self.KK[l], ix.overlap_ptr, ix.overlap, gptr, gblocks)
+            self.mg.set_level_schwarz(l, self.schwarz[l])
+
+    def assemble(self):
+        self.RES.zero()
+        self.KK[-1].zero()
+        self.asm.assemble(self.SOL, self.RES, self.IRe)
+
+    def galerkin(self):
+        for l in range(self.nlevels - 1, 0, -1):
+            self.KK[l - 1].ptap(self.PP[l], self.KK[l])
+
+    def mg_set_levels(self):
+        for l in range(self.nlevels):
+            self.mg.set_level(l, self.KK[l], self.PP[l], self.bdc_idx[l], self.npre, self.npost, self.omega)
+
+    def mg_solve(self):
+        self.mg.solve(self.RES, self.EPS)
+
+    def residual_norm(self):
+        self.RESM.copy_masked(self.RES, self.BDC, 1.1)
+        return self.RESM.norm(2)

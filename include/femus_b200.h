@@ -321,6 +321,11 @@ int b2_schwarz_destroy(b2_schwarz* s);
  * have been created on the operator handed to b2_mg_set_level for that level; b2_mg_set_level runs its numeric
  * phase after the penalty.  NULL restores the level's previous smoother kind 0. */
 int b2_mg_set_level_schwarz(b2_mg* mg, int level, b2_schwarz* s);
+/* coarsest level: a DIRECT solve, what the reference runs there (PREONLY + LU, PetscPreconditioner.cpp:147-160), in
+ * place of the Jacobi-PCG of b2_mg_set_coarse -- s is a b2_schwarz on the level-0 operator with ONE block holding
+ * every dof and the exact block solve (at most 4096 dofs); required for indefinite (velocity-pressure) systems.  Call
+ * before b2_mg_set_level(0, ...), which runs the numeric phase after the penalty.  NULL: back to the PCG. */
+int b2_mg_set_coarse_schwarz(b2_mg* mg, b2_schwarz* s);
 /* coarse solver: Jacobi-PCG to ||r|| <= rtol ||b|| (the reference: PREONLY + MUMPS LU,
  * PetscPreconditioner.cpp:147-160) */
 int b2_mg_set_coarse(b2_mg* mg, double rtol, int maxit);

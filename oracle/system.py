@@ -72,3 +72,24 @@ def bdc(L, mesh, orders, dirichlet_faces_per_var):
     for k, o in enumerate(orders):
         out[row_map(L, mesh, orders, k)] = mesh.bdc_flags(L, o, dirichlet_faces_per_var[k])
     return out
+
+
+class SystemMesh:
+    """Adapter that lets oracle.mg.Hierarchy run on a system of several variables: the `mesh` module interface
+    (bdc_flags, prolongator, zero_dirichlet, sparsity) for fixed variable families and per-variable Dirichlet sets."""
+
+    def __init__(self, mesh, orders, dirichlet_faces_per_var):
+        self.mesh, self.orders, self.dirichlet = mesh, list(orders), list(dirichlet_faces_per_var)
+
+    def bdc_flags(self, L, order, dirichlet_faces=None):
+        return bdc(L, self.mesh, self.orders, self.dirichlet)
+
+    def prolongator(self, C, F, order):
+        return prolongator(C, F, self.mesh, self.orders)
+
+    def zero_dirichlet(self, P, bdc_f, bdc_c):
+        from . import mesh_box
+        return mesh_box.zero_dirichlet(P, bdc_f, bdc_c)
+
+    def sparsity(self, L, order):
+        return sparsity(L, self.mesh, self.orders)

@@ -1,0 +1,77 @@
+"""GPU parity of the steady Stokes path (first vertical slice): b2_stokes_assemble against the oracle's
+restatement of applications/003_NavierStokes/SteadyStokes/main.cpp:290-598, and the multigrid solve of the system with
+velocity-pressure Vanka blocks and a direct coarse solve against the oracle V-cycle.  Written without a GPU at hand: the
+kernel's source is verified on the CPU emulator (tests/test_kernel_emulation.py); this file is the gate for the device."""
+import os
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-12
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _case(name, nl):
+    from femus_b200 import hostapi
+    from oracle import fe_hex, mesh_box as mb, mesh_mixed as mm
+    if name == "box":
+        return hostapi.HostHierarchy(2, 2, 2, nl), mb.build_hierarchy(2, 2, 2, nl), mb, (lambda t, o: fe_hex.tables(o)), "biquadratic"
+    path = os.path.join(GOLDEN, name + ".neu")
+    return hostapi.HostHierarchy.from_neu(path, nl), mm.build_hierarchy(path, nl), mm, (lambda t, o: mm.FE[t].tables(o)), "quadratic"
+
+
+@pytest.mark.parametrize("name", ["box", "cube_tet10"])
+def test_stokes_assembly_matches_oracle(ctx, name):
+    """System matrix (on the multi-variable pattern, bit-exact structure) and residual at a random solution:
+    Q2-Q1 hexahedra and P2-P1 tetrahedra."""
+    from femus_b200.stokes import StokesMG
+    from oracle import stokes, mg
+    H, lv, mesh, tables_of, ov = _case(name, 1)
+    pb = StokesMG(ctx, H, order_v=ov, IRe=0.37)
+    sol = np.random.default_rng(5).standard_normal(pb.n)
+    pb.SOL.put(sol)
+    pb.assemble()
+    Aref, rref = stokes.assemble(lv[-1], mesh, ov, "linear", sol, 0.37, tables_of)
+    rp, ci = pb.pattern[-1]
+    Aref = mg.on_pattern(Aref, rp, ci)
+    A = pb.KK[-1].to_scipy()
+    assert np.array_equal(A.indptr, rp) and np.array_equal(A.indices, ci)
+    assert np.abs(A.data - Aref.data).max() <= RTOL * np.abs(Aref.data).max()
+    assert np.abs(pb.RES.get() - rref).max() <= RTOL * (np.abs(Aref) @ np.abs(sol)).max()
+    del pb
+
+
+@pytest.mark.parametrize("name,schedule", [("box", "colours"), ("box", "levels")])
+def test_stokes_vcycle_trace_with_vanka_blocks(ctx, name, schedule):
+    """Channel-like problem (velocity Dirichlet on five boundary sets, unit U on the top one, natural outflow on set 2):
+    assembly, Galerkin chain, Vanka smoother (pressure = Schur variable, one element per block), direct coarse solve;
+    six V-cycles against the oracle, which converge by four orders of magnitude.  (Hexahedra only: on the shipped
+    tetrahedral cube the corner elements have every velocity node on the boundary, so the P2-P1 system is singular.)"""
+    from femus_b200.stokes import StokesMG
+    from oracle import stokes, mg, system as osys
+    H, lv, mesh, tables_of, ov = _case(name, 2)
+    fams = [ov] * 3 + ["linear"]
+    walls = (1, 3, 4, 5, 6)
+    pb = StokesMG(ctx, H, order_v=ov, IRe=1.0, velocity_dirichlet=walls, schedule=schedule)
+    sol = np.zeros(pb.n)
+    sol[osys.bdc(lv[-1], mesh, fams, [(6,), (), (), ()]) < 1.5] = 1.0
+    pb.SOL.put(sol)
+    pb.assemble(); pb.galerkin(); pb.mg_set_levels()
+    A, rhs = stokes.assemble(lv[-1], mesh, ov, "linear", sol, 1.0, tables_of)
+    A = mg.on_pattern(A, *pb.pattern[-1])
+    blocks = [None] + [pb.asm_index[l].blocks() for l in range(1, pb.nlevels)]
+    orders = [None] + [np.argsort(pb.asm_groups[l], kind="stable") for l in range(1, pb.nlevels)]
+    O = mg.Hierarchy(lv, None, mesh=osys.SystemMesh(mesh, fams, [walls] * 3 + [()]), A_top=A, rhs=rhs, smoother="asm", asm_blocks=blocks,
+                     asm_orders=orders)
+    got0 = pb.KK[0].to_scipy()
+    assert np.abs(got0.data - O.A[0].data).max() <= 1e-11 * np.abs(O.A[0].data).max()
+    trace_ref, eps_ref = O.mg_solve_trace(6, omega=1.0)
+    trace = []
+    for _ in range(6):
+        pb.mg_solve()
+        trace.append(pb.residual_norm())
+    for a, b in zip(trace, trace_ref):
+        assert abs(a - b) <= 1e-10 * trace_ref[0], (trace, trace_ref)
+    assert trace[-1] < 1e-4 * trace[0]
+    assert np.abs(pb.EPS.get() - eps_ref).max() <= 1e-9 * np.abs(eps_ref).max()
+    del pb
