@@ -11,11 +11,13 @@ struct b2_stokes {
   int nv = 0, np = 0, ng = 0;
   int32_t* edof = nullptr;      // [nel][4][27]
   double *tabv = nullptr, *tabp = nullptr;
+  double* tabns = nullptr;      // phi, dxi, deta, dzeta, w of the velocity element (Navier-Stokes kernel); null without phi_v
   int64_t nel = 0;
 };
 
 namespace {
 #include "b2_stokes_kernel.cuh"
+#include "b2_ns_kernel.cuh"
 size_t stokes_smem(int nv, int np, int ng) { return (size_t)kStokesWarps * (size_t)stokes_warp_doubles_host(nv, np, ng) * sizeof(double); }
 }  // namespace
 
@@ -82,8 +84,46 @@ int b2_stokes_assemble(b2_stokes* p, const b2_vec* sol, b2_vec* rhs, double IRe)
   return 0;
 }
 
+/* the Navier-Stokes twin of b2_stokes_create: additionally the velocity element's phi table [ngauss][nve_v] */
+int b2_ns_create(b2_mesh* mesh, b2_csr* A, const int32_t* elem_dofs, int nve_v, int nve_p, int ngauss, const double* phi_v, const double* dxi,
+                 const double* deta, const double* dzeta, const double* weights, const double* phi_p, b2_stokes** out) {
+  B2_CHECK(phi_v, "b2_ns_create: null argument");
+  B2_TRY(b2_stokes_create(mesh, A, elem_dofs, nve_v, nve_p, ngauss, dxi, deta, dzeta, weights, phi_p, out));
+  b2_stokes* p = *out;
+  const size_t nt = (size_t)4 * ngauss * nve_v + ngauss;
+  std::vector<double> tab(nt);
+  std::copy(phi_v, phi_v + ngauss * nve_v, tab.begin());
+  std::copy(dxi, dxi + ngauss * nve_v, tab.begin() + ngauss * nve_v);
+  std::copy(deta, deta + ngauss * nve_v, tab.begin() + 2 * ngauss * nve_v);
+  std::copy(dzeta, dzeta + ngauss * nve_v, tab.begin() + 3 * ngauss * nve_v);
+  std::copy(weights, weights + ngauss, tab.begin() + 4 * ngauss * nve_v);
+  B2_TRY(b2_malloc(p->ctx, &p->tabns, nt));
+  B2_TRY(b2_upload(p->ctx, p->tabns, tab.data(), nt));
+  const size_t smem = (size_t)ns_cta_doubles_host(nve_v, nve_p, ngauss) * sizeof(double);
+  B2_CHECK(smem <= 227 * 1024, "b2_ns_create: %zu bytes of shared memory per element exceed the SM", smem);
+  if (smem > 48 * 1024) B2_CUDA(cudaFuncSetAttribute(ns_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  return 0;
+}
+
+/* A += the exact Newton Jacobian, rhs += RES = -aRes of the steady Navier-Stokes residual at the current solution
+ * (03_navier_stokes.hpp:305-413); neither is zeroed */
+int b2_ns_assemble(b2_stokes* p, const b2_vec* sol, b2_vec* rhs, double nu) {
+  B2_CHECK(p && p->tabns, "b2_ns_assemble: the plan was not created by b2_ns_create");
+  B2_CHECK((!sol || sol->n >= p->A->nrows) && (!rhs || rhs->n >= p->A->nrows), "b2_ns_assemble: vector shorter than the system");
+  b2_ctx* c = nullptr;
+  int64_t nnode = 0, nel = 0;
+  const double* xyz = nullptr;
+  const int32_t* conn = nullptr;
+  b2_mesh_view(p->mesh, &c, &nnode, &nel, &xyz, &conn);
+  const size_t smem = (size_t)ns_cta_doubles_host(p->nv, p->np, p->ng) * sizeof(double);
+  B2_LAUNCH(c, ns_kernel, b2_grid_for(c, nel, 1, 3), kNsThreads, smem, nel, nnode, p->nv, p->np, p->ng, xyz, conn, p->edof, p->tabns, p->tabp,
+            p->A->rowptr, p->A->col, p->A->val, sol ? sol->d : nullptr, rhs ? rhs->d : nullptr, nu);
+  return 0;
+}
+
 int b2_stokes_destroy(b2_stokes* p) {
   if (!p) return 0;
+  b2_free(p->ctx, p->tabns, (size_t)4 * p->ng * p->nv + p->ng);
   b2_free(p->ctx, p->edof, (size_t)p->nel * 108);
   b2_free(p->ctx, p->tabv, (size_t)3 * p->ng * p->nv + p->ng);
   b2_free(p->ctx, p->tabp, (size_t)p->ng * p->np);

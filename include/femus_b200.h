@@ -290,6 +290,13 @@ int b2_stokes_create(b2_mesh* mesh, b2_csr* A, const int32_t* elem_dofs, int nve
                      const double* deta, const double* dzeta, const double* weights, const double* phi_p, b2_stokes** out);
 int b2_stokes_assemble(b2_stokes* p, const b2_vec* sol, b2_vec* rhs, double IRe);
 int b2_stokes_destroy(b2_stokes* p);
+/* steady Navier-Stokes on the same plan type: the library routine src/08_equations/assemble/03_navier_stokes.hpp
+ * (:305-413): RES = -aRes with aResV[k][i] = int nu grad phi_i . grad u_k + phi_i u . grad u_k - p dphi_i/dx_k,
+ * aResP[i] = -int div u psi_i, and KK += the exact Newton Jacobian d aRes / d sol (the reference records the loop with
+ * adept; here it is written out analytically).  b2_ns_create = b2_stokes_create + the velocity phi table. */
+int b2_ns_create(b2_mesh* mesh, b2_csr* A, const int32_t* elem_dofs, int nve_v, int nve_p, int ngauss, const double* phi_v, const double* dxi,
+                 const double* deta, const double* dzeta, const double* weights, const double* phi_p, b2_stokes** out);
+int b2_ns_assemble(b2_stokes* p, const b2_vec* sol, b2_vec* rhs, double nu);
 
 /* ---- element-block (ASM / Vanka) smoother: LinearEquationSolverPetscAsm (petsc_asm/LinearEquationSolverPetscAsm.cpp)
  * What the reference sets (:266-340, PetscPreconditioner.cpp:179-184): PCASM, PC_ASM_BASIC, local type

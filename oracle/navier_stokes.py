@@ -1,0 +1,79 @@
+"""Oracle (TEST INFRASTRUCTURE ONLY): the steady incompressible Navier-Stokes assembly of the reference's library
+routine, restated with numpy and an ANALYTIC Newton Jacobian.
+
+Restates src/08_equations/assemble/03_navier_stokes.hpp:305-376 (the element loop shared by the Navier-Stokes
+tutorials): per Gauss point of the velocity element, with u, grad u, p evaluated from the current solution,
+    aResV[k][i] += ( nu sum_j dphi_i/dx_j du_k/dx_j + phi_i sum_j u_j du_k/dx_j - p dphi_i/dx_k ) w      (:339-352)
+    aResP[i]    += - div u psi_i w                                                                        (:355-359)
+    RES = -aRes                                                                                            (:379-389)
+    KK += d aRes / d sol   -- the reference records the loop with adept and extracts the exact Jacobian (:391-413);
+                              here it is written out:
+        d aResV[k][i] / d u_l[j] = delta_kl ( nu grad phi_i . grad phi_j + phi_i u . grad phi_j ) w + phi_i phi_j du_k/dx_l w
+        d aResV[k][i] / d p[j]   = - psi_j dphi_i/dx_k w ,   d aResP[i] / d u_l[j] = - psi_i dphi_j/dx_l w ,   d aResP / d p = 0
+PARITY UNPINNED BY THE REFERENCE beyond the FE arithmetic; the Jacobian is checked against finite differences of the
+residual (tests/test_oracle_ns.py).  The boundary-face block of the routine (:200-300) is not restated."""
+import numpy as np
+import scipy.sparse as sp
+
+from . import fe_hex, system as osys
+
+
+def ns_elements(X, U, P, nu, tabs_v, tabs_p):
+    """X[nel,3,nv], U[3][nel,nv], P[nel,np].  Returns aResV[3][nel,nv], aResP[nel,np], D[nel,nv,nv] (the block every
+    velocity component has on its diagonal), N[3][3][nel,nv,nv] (Newton coupling phi_i phi_j du_k/dx_l), G[3][nel,nv,np]."""
+    nel, nv = X.shape[0], tabs_v[0].shape[1]
+    npr = tabs_p[0].shape[1]
+    RV = np.zeros((3, nel, nv))
+    RP = np.zeros((nel, npr))
+    D = np.zeros((nel, nv, nv))
+    N = np.zeros((3, 3, nel, nv, nv))
+    G = np.zeros((3, nel, nv, npr))
+    for ig in range(tabs_v[4].shape[0]):
+        w, phi, g = fe_hex.jacobian(None, X, ig, tabs_v)
+        psi = tabs_p[0][ig]
+        u = np.stack([U[k] @ phi for k in range(3)], axis=1)                         # [nel,3]
+        gu = np.stack([np.einsum("eid,ei->ed", g, U[k]) for k in range(3)], axis=1)     # [nel,k,d]
+        p = P @ psi
+        adv = np.einsum("ej,eij->ei", u, g)                                           # u . grad phi_j  [nel,nv]
+        lap = np.einsum("eid,ejd->eij", g, g)
+        D += (nu * lap + phi[None, :, None] * adv[:, None, :]) * w[:, None, None]
+        mass = phi[:, None] * phi[None, :]
+        for k in range(3):
+            conv = np.einsum("ej,ej->e", u, gu[:, k, :])
+            RV[k] += (nu * np.einsum("eid,ed->ei", g, gu[:, k, :]) + phi[None, :] * conv[:, None] - p[:, None] * g[:, :, k]) * w[:, None]
+            G[k] -= g[:, :, None, k] * psi[None, None, :] * w[:, None, None]
+            for l in range(3):
+                N[k, l] += mass[None, :, :] * (gu[:, k, l] * w)[:, None, None]
+        RP -= psi[None, :] * ((gu[:, 0, 0] + gu[:, 1, 1] + gu[:, 2, 2]) * w)[:, None]
+    return RV, RP, D, N, G
+
+
+def assemble(L, mesh, order_v, order_p, sol, nu, tables_of):
+    """Jacobian (CSR, explicit zeros kept) and RES = -aRes of one level at the solution `sol` (system numbering)."""
+    orders = [order_v] * 3 + [order_p]
+    d = osys.elem_system_dofs(L, mesh, orders)
+    n = sol.shape[0]
+    rows, cols, vals = [], [], []
+    rhs = np.zeros(n)
+    etype = getattr(L, "etype", None)
+    for t in (sorted(set(int(x) for x in etype)) if etype is not None else [0]):
+        sel = [e for e in range(L.nel) if etype is None or etype[e] == t]
+        tv, tp = tables_of(t, order_v), tables_of(t, order_p)
+        nv, npr = tv[0].shape[1], tp[0].shape[1]
+        dv = [np.array([d[k][e] for e in sel]) for k in range(3)]
+        dp = np.array([d[3][e] for e in sel])
+        X = L.xyz[:, L.conn[sel][:, :nv]].transpose(1, 0, 2)
+        RV, RP, D, N, G = ns_elements(X, [sol[dv[k]] for k in range(3)], sol[dp], nu, tv, tp)
+        for k in range(3):
+            for l in range(3):
+                rows.append(np.repeat(dv[k], nv, axis=1).ravel()); cols.append(np.tile(dv[l], (1, nv)).ravel())
+                vals.append((N[k, l] + (D if k == l else 0.0)).ravel())
+            rows.append(np.repeat(dv[k], npr, axis=1).ravel()); cols.append(np.tile(dp, (1, nv)).ravel()); vals.append(G[k].ravel())
+            rows.append(np.repeat(dp, nv, axis=1).ravel()); cols.append(np.tile(dv[k], (1, npr)).ravel())
+            vals.append(G[k].transpose(0, 2, 1).ravel())
+            np.add.at(rhs, dv[k].ravel(), -RV[k].ravel())
+        rows.append(np.repeat(dp, npr, axis=1).ravel()); cols.append(np.tile(dp, (1, npr)).ravel()); vals.append(np.zeros(len(sel) * npr * npr))
+        np.add.at(rhs, dp.ravel(), -RP.ravel())
+    A = sp.coo_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(n, n)).tocsr()
+    A.sort_indices()
+    return A, rhs

@@ -9,6 +9,7 @@ namespace {
 #include "../../femus_b200/csrc/b2_neumann_kernel.cuh"
 namespace {
 #include "../../femus_b200/csrc/b2_stokes_kernel.cuh"
+#include "../../femus_b200/csrc/b2_ns_kernel.cuh"
 }
 
 extern "C" {
@@ -68,6 +69,14 @@ void emu_stokes(int64_t nel, int64_t nnode, int nv, int np, int ng, const double
   const size_t smem = (size_t)kStokesWarps * (size_t)stokes_warp_doubles_host(nv, np, ng) * sizeof(double);
   emu::launch(stokes_kernel, (unsigned)grid, (unsigned)(kStokesWarps * 32), smem, nel, nnode, nv, np, ng, xyz, conn, edof, tabv, tabp, rowptr, col,
               Aval, sol, rhs, IRe);
+}
+
+// what b2_ns_assemble launches: tabv = phi, dxi, deta, dzeta [ng][nv], w[ng]
+void emu_ns(int64_t nel, int64_t nnode, int nv, int np, int ng, const double* xyz, const int32_t* conn, const int32_t* edof, const double* tabv,
+            const double* tabp, const int64_t* rowptr, const int32_t* col, double* Aval, const double* sol, double* rhs, double nu, int grid) {
+  const size_t smem = (size_t)ns_cta_doubles_host(nv, np, ng) * sizeof(double);
+  emu::launch(ns_kernel, (unsigned)grid, (unsigned)kNsThreads, smem, nel, nnode, nv, np, ng, xyz, conn, edof, tabv, tabp, rowptr, col, Aval, sol, rhs,
+              nu);
 }
 
 }  // extern "C"

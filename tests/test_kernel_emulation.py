@@ -31,6 +31,8 @@ def emu(tmp_path_factory):
     L.emu_stokes.restype = None
     L.emu_stokes.argtypes = [ctypes.c_int64, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp,
                              ctypes.c_double, ctypes.c_int]
+    L.emu_ns.restype = None
+    L.emu_ns.argtypes = L.emu_stokes.argtypes
     return L
 
 
@@ -207,3 +209,38 @@ def test_stokes_kernel_on_the_emulator(emu, name, order_v, order_p):
     Aref = mg.on_pattern(Aref, rp, ci)
     assert np.abs(val - Aref.data).max() <= 1e-12 * np.abs(Aref.data).max()
     assert np.abs(rhs - rref).max() <= 1e-12 * (np.abs(Aref) @ np.abs(sol)).max()
+
+
+@pytest.mark.parametrize("name,order_v,order_p", [("box", "biquadratic", "linear"), ("cube_tet10", "quadratic", "linear")])
+def test_navier_stokes_kernel_on_the_emulator(emu, name, order_v, order_p):
+    """ns_kernel (one CTA per element): residual RES = -aRes and the analytic Newton Jacobian at a random solution
+    against the oracle's restatement of 03_navier_stokes.hpp:305-413 (whose Jacobian is checked against finite
+    differences in tests/test_oracle_ns.py)."""
+    from oracle import navier_stokes as ons, mesh_box as mb, mesh_mixed as mm, fe_hex, mg
+    fams = [order_v] * 3 + [order_p]
+    if name == "box":
+        H, L, mesh = hostapi.HostHierarchy(2, 1, 1, 1), mb.build_hierarchy(2, 1, 1, 1)[0], mb
+        tables_of = lambda t, o: fe_hex.tables(o)
+    else:
+        path = os.path.join(GOLDEN, name + ".neu")
+        H, L, mesh = hostapi.HostHierarchy.from_neu(path, 1), mm.read_neu(path), mm
+        tables_of = lambda t, o: mm.FE[t].tables(o)
+    level = H.levels[0]
+    S = hostapi.SystemOnLevel(level, fams)
+    rp, ci = S.sparsity()
+    edof = np.ascontiguousarray(S.elem_dofs(), dtype=np.int32)
+    t = level.elem_type
+    tv, tp = hostapi.elem_tables(t, order_v), hostapi.elem_tables(t, order_p)
+    nv, npr, ng = tv[0].shape[1], tp[0].shape[1], tv[4].shape[0]
+    tabv = np.concatenate([tv[0].ravel(), tv[1].ravel(), tv[2].ravel(), tv[3].ravel(), tv[4].ravel()])
+    tabp = np.ascontiguousarray(tp[0])
+    sol = 0.5 * np.random.default_rng(12).standard_normal(S.n)
+    val, rhs = np.zeros(len(ci)), np.zeros(S.n)
+    xyz, conn = np.ascontiguousarray(level.xyz), np.ascontiguousarray(level.conn, dtype=np.int32)
+    nu = 0.21
+    emu.emu_ns(level.nel, level.nnode, nv, npr, ng, _p(xyz), _p(conn), _p(edof), _p(tabv), _p(tabp), _p(rp), _p(ci), _p(val), _p(sol), _p(rhs), nu,
+               3)
+    Aref, rref = ons.assemble(L, mesh, order_v, order_p, sol, nu, tables_of)
+    Aref = mg.on_pattern(Aref, rp, ci)
+    assert np.abs(val - Aref.data).max() <= 1e-12 * np.abs(Aref.data).max()
+    assert np.abs(rhs - rref).max() <= 1e-12 * np.abs(rref).max()
