@@ -127,6 +127,8 @@ _PROTOS = {
     "b2_stokes_create": (ci, [vp, vp, vp, ci, ci, ci, vp, vp, vp, vp, vp, vp]),
     "b2_stokes_assemble": (ci, [vp, vp, vp, cd]),
     "b2_stokes_destroy": (ci, [vp]),
+    "b2_ns_create": (ci, [vp, vp, vp, ci, ci, ci, vp, vp, vp, vp, vp, vp, vp]),
+    "b2_ns_assemble": (ci, [vp, vp, vp, cd]),
     "b2_mg_level_bounds": (ci, [vp, ci, vp, vp]),
     "b2_mg_set_level_halo": (ci, [vp, ci, vp]),
     "b2_halo_create": (ci, [vp, i64, i64, vp, vp, i64, vp, vp, vp]),
@@ -647,14 +649,19 @@ class StokesAssembler:
     """Steady Stokes assembly plan (b2_stokes_*): three velocity components of one family + a pressure of another on a
     mesh of one element type; elem_dofs [nel][4][27] system dofs, tables of the two families (hostapi.elem_tables)."""
 
-    def __init__(self, mesh, A, elem_dofs, tables_v, tables_p):
+    def __init__(self, mesh, A, elem_dofs, tables_v, tables_p, navier_stokes=False):
+        """navier_stokes: the plan also carries the velocity phi table (b2_ns_create) and offers assemble_ns."""
         self.ctx, self.L, self.mesh, self.A = mesh.ctx, mesh.ctx.L, mesh, A
         ed = _i32(elem_dofs)
-        _, dxi, deta, dzeta, w = [_f64(t) for t in tables_v]
+        phiv, dxi, deta, dzeta, w = [_f64(t) for t in tables_v]
         phip = _f64(tables_p[0])
         h = vp()
-        check(self.L.b2_stokes_create(mesh.h, A.h, _ptr(ed), dxi.shape[1], phip.shape[1], dxi.shape[0], _ptr(dxi), _ptr(deta), _ptr(dzeta),
-                                      _ptr(w), _ptr(phip), ctypes.byref(h)))
+        if navier_stokes:
+            check(self.L.b2_ns_create(mesh.h, A.h, _ptr(ed), dxi.shape[1], phip.shape[1], dxi.shape[0], _ptr(phiv), _ptr(dxi), _ptr(deta),
+                                      _ptr(dzeta), _ptr(w), _ptr(phip), ctypes.byref(h)))
+        else:
+            check(self.L.b2_stokes_create(mesh.h, A.h, _ptr(ed), dxi.shape[1], phip.shape[1], dxi.shape[0], _ptr(dxi), _ptr(deta), _ptr(dzeta),
+                                          _ptr(w), _ptr(phip), ctypes.byref(h)))
         self.h = h
 
     def __del__(self):
@@ -666,6 +673,10 @@ class StokesAssembler:
 
     def assemble(self, sol=None, rhs=None, IRe=1.0):
         check(self.L.b2_stokes_assemble(self.h, sol.h if sol is not None else None, rhs.h if rhs is not None else None, float(IRe)))
+
+    def assemble_ns(self, sol=None, rhs=None, nu=1.0):
+        """Navier-Stokes residual RES = -aRes and exact Newton Jacobian (b2_ns_assemble)."""
+        check(self.L.b2_ns_assemble(self.h, sol.h if sol is not None else None, rhs.h if rhs is not None else None, float(nu)))
 
 
 class Schwarz:

@@ -18,8 +18,10 @@ from . import capi, hostapi
 
 class StokesMG:
     def __init__(self, ctx, hier, order_v="biquadratic", order_p="linear", IRe=1.0, velocity_dirichlet=(1, 2, 3, 4, 5, 6),
-                 pressure_dirichlet=(), npre=1, npost=1, omega=1.0, block_elems=1, schedule="colours"):
-        self.ctx, self.hier, self.IRe = ctx, hier, IRe
+                 pressure_dirichlet=(), npre=1, npost=1, omega=1.0, block_elems=1, schedule="colours", equation="stokes"):
+        """equation: "stokes" (SteadyStokes/main.cpp, IRe = the viscosity factor) or "navier_stokes" (the library routine
+        03_navier_stokes.hpp: Galerkin residual + exact Newton Jacobian, IRe = nu)."""
+        self.ctx, self.hier, self.IRe, self.equation = ctx, hier, IRe, equation
         self.fams = [order_v] * 3 + [order_p]
         lv = hier.levels
         nl = self.nlevels = len(lv)
@@ -44,7 +46,7 @@ class StokesMG:
         self.mesh = capi.Mesh(ctx, top.xyz, top.conn)
         t = top.elem_type
         self.asm = capi.StokesAssembler(self.mesh, self.KK[-1], self.sys[-1].elem_dofs(), hostapi.elem_tables(t, order_v),
-                                        hostapi.elem_tables(t, order_p))
+                                        hostapi.elem_tables(t, order_p), navier_stokes=(equation == "navier_stokes"))
         self.RES, self.EPS, self.SOL = ctx.vector(self.n), ctx.vector(self.n), ctx.vector(self.n)
         self.BDC, self.RESM = ctx.vector(self.bdc[-1]), ctx.vector(self.n)
         self.mg = capi.Multigrid(ctx, nl)
@@ -65,7 +67,10 @@ class StokesMG:
     def assemble(self):
         self.RES.zero()
         self.KK[-1].zero()
-        self.asm.assemble(self.SOL, self.RES, self.IRe)
+        if self.equation == "navier_stokes":
+            self.asm.assemble_ns(self.SOL, self.RES, self.IRe)
+        else:
+            self.asm.assemble(self.SOL, self.RES, self.IRe)
 
     def galerkin(self):
         for l in range(self.nlevels - 1, 0, -1):
@@ -77,6 +82,20 @@ class StokesMG:
 
     def mg_solve(self):
         self.mg.solve(self.RES, self.EPS)
+
+    def newton_step(self, ncycles=1):
+        """One iteration of NonLinearImplicitSystem::solve on the finest level (NonLinearImplicitSystem.cpp:157-361,
+        reduced to its V-cycle path): assemble residual and Jacobian at Sol, Galerkin chain, level setup, `ncycles`
+        MGSolve, Sol += EPS.  Returns ||RES||_2 over the free rows BEFORE the update."""
+        self.EPS.zero()
+        self.assemble()
+        r0 = self.residual_norm()
+        self.galerkin()
+        self.mg_set_levels()
+        for _ in range(ncycles):
+            self.mg_solve()
+        self.SOL.axpy(1.0, self.EPS)
+        return r0
 
     def residual_norm(self):
         self.RESM.copy_masked(self.RES, self.BDC, 1.1)

@@ -75,3 +75,53 @@ def test_stokes_vcycle_trace_with_vanka_blocks(ctx, name, schedule):
     assert trace[-1] < 1e-4 * trace[0]
     assert np.abs(pb.EPS.get() - eps_ref).max() <= 1e-9 * np.abs(eps_ref).max()
     del pb
+
+
+@pytest.mark.parametrize("name", ["box", "cube_tet10"])
+def test_navier_stokes_assembly_matches_oracle(ctx, name):
+    """b2_ns_assemble: residual RES = -aRes and the analytic Newton Jacobian at a random solution against the oracle's
+    restatement of 03_navier_stokes.hpp:305-413 (Jacobian checked against finite differences on the CPU)."""
+    from femus_b200.stokes import StokesMG
+    from oracle import navier_stokes as ons, mg
+    H, lv, mesh, tables_of, ov = _case(name, 1)
+    pb = StokesMG(ctx, H, order_v=ov, IRe=0.21, equation="navier_stokes")
+    sol = 0.5 * np.random.default_rng(6).standard_normal(pb.n)
+    pb.SOL.put(sol)
+    pb.assemble()
+    Aref, rref = ons.assemble(lv[-1], mesh, ov, "linear", sol, 0.21, tables_of)
+    Aref = mg.on_pattern(Aref, *pb.pattern[-1])
+    A = pb.KK[-1].to_scipy()
+    assert np.abs(A.data - Aref.data).max() <= RTOL * np.abs(Aref.data).max()
+    assert np.abs(pb.RES.get() - rref).max() <= RTOL * np.abs(rref).max()
+    del pb
+
+
+def test_navier_stokes_newton_iterations(ctx):
+    """Channel-like problem at nu = 0.1 on a 2-level box: four Newton iterations, each = assembly of residual and
+    Jacobian, Galerkin chain, three V-cycles with Vanka blocks and the direct coarse solve, update; the residual norms
+    before every update against the oracle pipeline run with the same blocks, and quadratic-looking decay."""
+    from femus_b200.stokes import StokesMG
+    from oracle import navier_stokes as ons, mg, system as osys
+    H, lv, mesh, tables_of, ov = _case("box", 2)
+    fams = [ov] * 3 + ["linear"]
+    walls = (1, 3, 4, 5, 6)
+    pb = StokesMG(ctx, H, order_v=ov, IRe=0.1, velocity_dirichlet=walls, equation="navier_stokes")
+    sol = np.zeros(pb.n)
+    sol[osys.bdc(lv[-1], mesh, fams, [(6,), (), (), ()]) < 1.5] = 1.0
+    pb.SOL.put(sol)
+    blocks = [None] + [pb.asm_index[l].blocks() for l in range(1, pb.nlevels)]
+    orders = [None] + [np.argsort(pb.asm_groups[l], kind="stable") for l in range(1, pb.nlevels)]
+    smesh = osys.SystemMesh(mesh, fams, [walls] * 3 + [()])
+    free = smesh.bdc_flags(lv[-1], None) > 1.1
+    got, want = [], []
+    for it in range(4):
+        got.append(pb.newton_step(ncycles=3))
+        A, rhs = ons.assemble(lv[-1], mesh, ov, "linear", sol, 0.1, tables_of)
+        want.append(float(np.linalg.norm(np.where(free, rhs, 0.0))))
+        O = mg.Hierarchy(lv, None, mesh=smesh, A_top=mg.on_pattern(A, *pb.pattern[-1]), rhs=rhs, smoother="asm", asm_blocks=blocks,
+                         asm_orders=orders)
+        _, eps = O.mg_solve_trace(3, omega=1.0)
+        sol = sol + eps
+    for a, b in zip(got, want):
+        assert abs(a - b) <= 1e-9 * want[0], (got, want)
+    assert got[-1] < 1e-3 * got[0]
