@@ -78,3 +78,19 @@ for fam in ("quadratic", "biquadratic"):
     print(json.dumps({"kernel": "assemble_general_kernel", "workload": f"tet {fam} {pt.nel} elements", "ms": ms,
                       "element_dof_updates_per_s": pt.nel * nve / ms * 1e3, "dofs": pt.n}))
     del pt
+
+# Stokes / Navier-Stokes assembly kernels on a Q2-Q1 box (first timing of stokes_kernel / ns_kernel)
+from femus_b200.stokes import StokesMG
+ns0 = int(os.environ.get("STOKES_N0", "8"))
+Hs = hostapi.HostHierarchy(ns0, ns0, ns0, 3)
+for eq in ("stokes", "navier_stokes"):
+    ps = StokesMG(ctx, Hs, IRe=0.1, velocity_dirichlet=(1, 3, 4, 5, 6), equation=eq)
+    ps.SOL.put(0.1 * np.sin(np.arange(ps.n) * 0.01))
+    ms = timed(lambda: ps.assemble())
+    nel = Hs.levels[-1].nel
+    print(json.dumps({"kernel": eq + "_assembly", "workload": f"{ns0 * 4}^3 Q2-Q1, {ps.n} rows", "ms": ms,
+                      "element_dof_updates_per_s": nel * 89 / ms * 1e3}))
+    if eq == "navier_stokes":
+        norms = [ps.newton_step(ncycles=2) for _ in range(3)]
+        print(json.dumps({"kernel": "ns_newton_multigrid", "residuals": norms}))
+    del ps
