@@ -90,7 +90,11 @@ for eq in ("stokes", "navier_stokes"):
     nel = Hs.levels[-1].nel
     print(json.dumps({"kernel": eq + "_assembly", "workload": f"{ns0 * 4}^3 Q2-Q1, {ps.n} rows", "ms": ms,
                       "element_dof_updates_per_s": nel * 89 / ms * 1e3}))
-    if eq == "navier_stokes":
-        norms = [ps.newton_step(ncycles=2) for _ in range(3)]
-        print(json.dumps({"kernel": "ns_newton_multigrid", "residuals": norms}))
     del ps
+# Newton-multigrid on a small hierarchy (the dense Vanka inverses, 8.6 MB per one-element block, bound the size)
+pn = StokesMG(ctx, hostapi.HostHierarchy(2, 2, 2, 3), IRe=0.1, velocity_dirichlet=(1, 3, 4, 5, 6), equation="navier_stokes")
+sol0 = np.zeros(pn.n)
+sol0[pn.sys[-1].bdc([(6,), (), (), ()]) < 1.5] = 1.0
+pn.SOL.put(sol0)
+print(json.dumps({"kernel": "ns_newton_multigrid", "rows": pn.n, "residuals": [pn.newton_step(ncycles=2) for _ in range(4)],
+                  "vanka_inverse_bytes": [s.nbytes for s in pn.schwarz[1:]]}))
