@@ -81,19 +81,22 @@ def build(force=False, verbose=False):
 
 DRIVER_SRC = os.path.join(os.path.dirname(HERE), "tests", "cpp", "poisson_driver.cpp")
 DRIVER = os.path.join(HERE, "poisson_driver")      # in-tree: travels to the GPU box (femus_b200/build/ does not)
+STOKES_DRIVER_SRC = os.path.join(os.path.dirname(HERE), "tests", "cpp", "stokes_driver.cpp")
+STOKES_DRIVER = os.path.join(HERE, "stokes_driver")
 
 
 def build_driver(force=False):
-    """C++ driver of the adapter classes (femus_b200/host/B200*.hpp), linked against the library."""
-    if not os.path.exists(DRIVER_SRC):
-        return None
-    deps = [DRIVER_SRC] + [os.path.join(HERE, "host", f) for f in os.listdir(os.path.join(HERE, "host")) if f.endswith(".hpp")]
-    newest = max(os.path.getmtime(d) for d in deps)
-    if force or not os.path.exists(DRIVER) or os.path.getmtime(DRIVER) < newest:
-        r = subprocess.run(["g++", "-std=c++17", "-O2", "-Wall", "-o", DRIVER, DRIVER_SRC, "-L" + HERE, "-lfemus_b200",
-                            "-Wl,-rpath,$ORIGIN"], capture_output=True, text=True)
-        if r.returncode != 0:
-            raise RuntimeError("adapter driver failed to build:\n" + r.stdout + r.stderr)
+    """C++ drivers of the adapter classes (femus_b200/host/*.hpp), linked against the library."""
+    deps = [os.path.join(HERE, "host", f) for f in os.listdir(os.path.join(HERE, "host")) if f.endswith(".hpp")]
+    for src, exe in ((DRIVER_SRC, DRIVER), (STOKES_DRIVER_SRC, STOKES_DRIVER)):
+        if not os.path.exists(src):
+            continue
+        newest = max(os.path.getmtime(d) for d in deps + [src])
+        if force or not os.path.exists(exe) or os.path.getmtime(exe) < newest:
+            r = subprocess.run(["g++", "-std=c++17", "-O2", "-Wall", "-o", exe, src, "-L" + HERE, "-lfemus_b200",
+                                "-Wl,-rpath,$ORIGIN"], capture_output=True, text=True)
+            if r.returncode != 0:
+                raise RuntimeError("adapter driver failed to build:\n" + r.stdout + r.stderr)
     return DRIVER
 
 

@@ -13,6 +13,7 @@
 // finest KSP, reached by the coarser levels through LinSolver->GetKSP(), LinearEquationSolverPetsc.cpp:230).
 #pragma once
 #include "B200Matrix.hpp"
+#include "SystemLayout.hpp"
 
 namespace femus {
 
@@ -40,7 +41,30 @@ class LinearEquationSolverB200 {
     _bdc = bdc;
     _bdcIndexIsInitialized = false;
   }
+  // The same for a system of several Lagrange variables (InitPde with _SolPdeIndex.size() > 1): rows
+  // [rank][variable][dof] (KKoffset, :211-237), pattern of GetSparsityPatternSize with the coupling table
+  // `pattern` (nvars x nvars, NULL = every pair, :407-548); bdc in system numbering (femus_b200::SystemBdc).
+  // With this the UNCHANGED multi-variable callbacks (add_matrix_blocked of the Jacobian blocks on GetSystemDof
+  // rows) assemble into the device matrix through the staged path, or b2_stokes / b2_ns write it in place.
+  void InitPdeSystem(const femus_b200::MeshLevel& msh, const std::vector<int>& families, const std::vector<double>& bdc,
+                     const uint8_t* pattern = nullptr) {
+    this->DeletePde();
+    const femus_b200::SystemLayout sys(msh, families);
+    const femus_b200::HostCsr pat = femus_b200::BuildSystemSparsity(msh, sys, pattern);
+    const int n = (int)sys.size();
+    if ((size_t)n != bdc.size()) { std::fprintf(stderr, "femus_b200: InitPdeSystem: %zu Dirichlet flags for %d rows\n", bdc.size(), n); std::abort(); }
+    _KK = new B200Matrix;
+    _KK->init_from_csr(n, n, pat.rowptr.data(), pat.col.data(), nullptr);
+    _RES = new B200Vector(n);
+    _EPS = new B200Vector(n);
+    _EPSC = new B200Vector(n);
+    _RESC = new B200Vector(n);
+    _bdc = bdc;
+    _bdcIndexIsInitialized = false;
+  }
   void DeletePde() {
+    if (_coarseSolver) b2_schwarz_destroy(_coarseSolver);
+    _coarseSolver = nullptr;
     delete _KK; delete _RES; delete _EPS; delete _EPSC; delete _RESC;
     _KK = nullptr;
     _RES = _EPS = _EPSC = _RESC = nullptr;
@@ -72,6 +96,10 @@ class LinearEquationSolverB200 {
     if (_mg) b2_mg_destroy(_mg);
     _mg = nullptr;
   }
+  // level 0 only: solve the coarsest system DIRECTLY (the reference's PREONLY + MLU_PRECOND there,
+  // LinearEquationSolverPetsc.hpp:128-151) instead of the Jacobi-PCG -- required for indefinite systems
+  // (velocity-pressure); at most 4096 rows.  Call before MGSetLevel.
+  void SetCoarseDirect(const bool on) { _coarseDirect = on; }
   // MGSetLevel (LinearEquationSolverPetsc.cpp:213-290): called on EVERY level's solver with the
   // finest solver as first argument; PP = prolongator from level-1 (NULL on level 0), RR unused
   // (the reference passes it but restricts with PP^T, :277).
@@ -90,6 +118,17 @@ class LinearEquationSolverB200 {
       P = Pm.handle();
     }
     this->SetLevelSmoother(LinSolver->_mg);
+    if (_level == 0 && _coarseDirect) {
+      if (!_coarseSolver) {
+        const int64_t n = _KK->m();
+        const int64_t bp[2] = {0, n}, gp[2] = {0, 1};
+        std::vector<int32_t> all((size_t)n);
+        for (int64_t i = 0; i < n; i++) all[i] = (int32_t)i;
+        const int32_t gb[1] = {0};
+        B2_ABORT_IF(b2_schwarz_create(B200Context::get(), _KK->handle(), 1, bp, all.data(), 1, gp, gb, &_coarseSolver), "b2_schwarz_create");
+      }
+      B2_ABORT_IF(b2_mg_set_coarse_schwarz(LinSolver->_mg, _coarseSolver), "b2_mg_set_coarse_schwarz");
+    }
     // SetPenalty (:428-436) happens inside: Dirichlet rows -> identity, pattern kept
     B2_ABORT_IF(b2_mg_set_level(LinSolver->_mg, (int)_level, _KK->handle(), P, _bdcIndex.data(), (int64_t)_bdcIndex.size(), (int)npre,
                                 (int)npost, _richardsonScaleFactor),
@@ -131,6 +170,8 @@ class LinearEquationSolverB200 {
   unsigned _level;
 
  private:
+  bool _coarseDirect = false;
+  b2_schwarz* _coarseSolver = nullptr;
   b2_mg* _mg;
   unsigned _levelMax;
   B200SolverType _levelSolverType = RICHARDSON_B200, _mgSolverType = PREONLY_B200;

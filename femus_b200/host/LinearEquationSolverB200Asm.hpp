@@ -5,9 +5,10 @@
 // blocks by MeshASMPartitioning::DoPartition, overlapping index sets, PCASM basic / multiplicative with exact block
 // solves, wrapped by the level's Richardson iteration (b2_schwarz_*, b2_mg_set_level_schwarz).
 //
-// In scope: one Lagrange variable without Schur variables -- SetNumberOfSchurVariables(0), what 001_Poisson sets for
-// "smoother": "asm" (main.cpp:248-249).  The "All"-elements standard ASM (SetElementBlockNumber("All", overlap)) and
-// Schur variables abort.  Stand-alone the mesh of the level (GetMeshFromLinEq() in the reference) is handed in with
+// In scope: Lagrange variables, the last NSchurVar of them Schur variables -- one variable with
+// SetNumberOfSchurVariables(0) is what 001_Poisson sets for "smoother": "asm" (main.cpp:248-249); velocity-pressure
+// systems with the pressure as Schur variable give Vanka blocks.  The "All"-elements standard ASM
+// (SetElementBlockNumber("All", overlap)) aborts.  Stand-alone the mesh of the level (GetMeshFromLinEq() in the reference) is handed in with
 // SetMesh.
 #pragma once
 #include "AsmPartition.hpp"
@@ -21,7 +22,7 @@ enum B200PrecondType { MLU_PRECOND_B200 = 0, SOR_PRECOND_B200 };     // the subs
 class LinearEquationSolverB200Asm : public LinearEquationSolverB200 {
  public:
   LinearEquationSolverB200Asm(const unsigned& igrid)
-      : LinearEquationSolverB200(igrid), _msh(nullptr), _family(0), _schwarz(nullptr), _sweepOrder(1), _NSchurVar(1), _standardASM(true),
+      : LinearEquationSolverB200(igrid), _msh(nullptr), _schwarz(nullptr), _sweepOrder(1), _NSchurVar(1), _standardASM(true),
         _indexIsInitialized(false) {
     _elementBlockNumber[0] = _elementBlockNumber[1] = _elementBlockNumber[2] = 1;
   }
@@ -44,7 +45,13 @@ class LinearEquationSolverB200Asm : public LinearEquationSolverB200 {
   // the level's mesh and the family of the unknown (what GetMeshFromLinEq() / _SolType give the reference)
   void SetMesh(const femus_b200::MeshLevel* msh, const int family) {
     _msh = msh;
-    _family = family;
+    _families.assign(1, family);
+    this->ClearIndex();
+  }
+  // a system of several variables (families in _SolPdeIndex order), the last NSchurVar of them Schur variables
+  void SetMesh(const femus_b200::MeshLevel* msh, const std::vector<int>& families) {
+    _msh = msh;
+    _families = families;
     this->ClearIndex();
   }
   // 0: sweep the blocks in the reference's order (dependency levels), 1: in coloured order (default)
@@ -55,15 +62,16 @@ class LinearEquationSolverB200Asm : public LinearEquationSolverB200 {
  protected:
   void SetLevelSmoother(b2_mg* mg) override {
     if (_level == 0) { LinearEquationSolverB200::SetLevelSmoother(mg); return; }     // the coarsest level is solved, not smoothed
-    if (_standardASM || _NSchurVar != 0 || !_msh) {
-      std::fprintf(stderr, "femus_b200: LinearEquationSolverB200Asm needs SetMesh, SetNumberOfSchurVariables(0) and SetElementBlockNumber(n)\n");
+    if (_standardASM || !_msh || _families.empty() || _NSchurVar > _families.size()) {
+      std::fprintf(stderr, "femus_b200: LinearEquationSolverB200Asm needs SetMesh, SetElementBlockNumber(n) and at most as many Schur variables as variables\n");
       std::abort();
     }
     if (!_indexIsInitialized) {           // BuildASMIndex, once per mesh (the reference's _bdcIndexIsInitialized gate, :42-49)
       using namespace femus_b200;
       try {
-        _index = BuildAsmIndex(*_msh, _family, _elementBlockNumber[2], 0);
-        const HostCsr pat = BuildSparsity(*_msh, _family);
+        const SystemLayout sys(*_msh, _families);
+        _index = BuildAsmIndexSystem(*_msh, sys, (int)_NSchurVar, _elementBlockNumber[2], 0);
+        const HostCsr pat = BuildSystemSparsity(*_msh, sys, nullptr);
         const int64_t nb = _index.nblocks();
         std::vector<int32_t> group((size_t)nb);
         const int64_t ng = AsmSchedule(pat.nrows, pat.rowptr.data(), pat.col.data(), nb, _index.overlap_ptr.data(), _index.overlap.data(),
@@ -95,7 +103,7 @@ class LinearEquationSolverB200Asm : public LinearEquationSolverB200 {
     _indexIsInitialized = false;
   }
   const femus_b200::MeshLevel* _msh;
-  int _family;
+  std::vector<int> _families;
   femus_b200::AsmIndex _index;
   b2_schwarz* _schwarz;
   int _sweepOrder;

@@ -19,7 +19,12 @@ int main() {
   asm_solver.SetNumberOfSchurVariables(0);
   asm_solver.SetElementBlockNumber(8);
   femus::LinearEquationSolverB200* base = &asm_solver;
-  (void)base;
+  base->SetCoarseDirect(true);
+  const femus_b200::MeshLevel box = femus_b200::GenerateCoarseBoxMesh(1, 1, 1, 0., 1., 0., 1., 0., 1., nullptr, 1);
+  const std::vector<int> taylor_hood = {2, 2, 2, 0};          // U, V, W biquadratic, P linear: host-only calls
+  asm_solver.SetMesh(&box, taylor_hood);
+  asm_solver.SetNumberOfSchurVariables(1);
+  if (femus_b200::SystemLayout(box, taylor_hood).size() != 3 * 27 + 8) return 1;
   femus::B200Vector v;        // instantiable => every pure virtual of NumericVector is overridden
   femus::B200Matrix m;        // likewise for SparseMatrix
   femus::NumericVector* nv = &v;
@@ -55,7 +60,7 @@ def test_adapters_are_subclasses_of_the_reference_interfaces(tmp_path):
 def test_driver_builds_and_links():
     from femus_b200 import build
     build.build()
-    assert os.path.exists(build.DRIVER)
+    assert os.path.exists(build.DRIVER) and os.path.exists(build.STOKES_DRIVER)
     out = subprocess.run(["ldd", build.DRIVER], capture_output=True, text=True).stdout
     assert "libfemus_b200.so" in out and "not found" not in out.split("libfemus_b200.so")[1].split("\n")[0]
 

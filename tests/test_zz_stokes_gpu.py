@@ -125,3 +125,38 @@ def test_navier_stokes_newton_iterations(ctx):
     for a, b in zip(got, want):
         assert abs(a - b) <= 1e-9 * want[0], (got, want)
     assert got[-1] < 1e-3 * got[0]
+
+
+def test_cpp_stokes_driver_through_the_adapters():
+    """tests/cpp/stokes_driver.cpp: the multi-variable plugin surface (InitPdeSystem, LinearEquationSolverB200Asm with the
+    pressure as Schur variable, SetCoarseDirect, MGInit / MGSetLevel / MGSolve) reproduces the oracle V-cycle trace."""
+    import re
+    import subprocess
+    from femus_b200 import build, hostapi
+    from oracle import stokes, mg, system as osys, mesh_box as mb, fe_hex
+    ncyc = 4
+    r = subprocess.run([build.STOKES_DRIVER, "2", "2", "2", "2", str(ncyc)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    res = [float(x) for x in re.findall(r"cycle \d+ residual (\S+)", r.stdout)]
+    assert len(res) == ncyc + 1
+    H, lv = hostapi.HostHierarchy(2, 2, 2, 2), mb.build_hierarchy(2, 2, 2, 2)
+    fams = ["biquadratic"] * 3 + ["linear"]
+    walls = (1, 3, 4, 5, 6)
+    S = hostapi.SystemOnLevel(H.levels[-1], fams)
+    rp, ci = S.sparsity()
+    sol = np.zeros(S.n)
+    sol[osys.bdc(lv[-1], mb, fams, [(6,), (), (), ()]) < 1.5] = 1.0
+    A, rhs = stokes.assemble(lv[-1], mb, "biquadratic", "linear", sol, 1.0, lambda t, o: fe_hex.tables(o))
+    ix = hostapi.AsmIndex(H.levels[1], fams, 1, nschur=1)
+    grp, gptr, gblocks = hostapi.asm_schedule(rp, ci, ix.overlap_ptr, ix.overlap, "colours")
+    smesh = osys.SystemMesh(mb, fams, [walls] * 3 + [()])
+    O = mg.Hierarchy(lv, None, mesh=smesh, A_top=mg.on_pattern(A, rp, ci), rhs=rhs, smoother="asm", asm_blocks=[None, ix.blocks()],
+                     asm_orders=[None, gblocks])
+    trace, eps = O.mg_solve_trace(ncyc, omega=1.0)
+    free = smesh.bdc_flags(lv[-1], None) > 1.1
+    r0 = float(np.linalg.norm(np.where(free, rhs, 0.0)))
+    assert abs(res[0] - r0) <= 1e-12 * r0
+    for k in range(ncyc):
+        assert abs(res[k + 1] - trace[k]) <= 1e-9 * r0, (k, res[k + 1], trace[k])
+    m = re.search(r"vanka blocks (\d+) groups (\d+)", r.stdout)
+    assert int(m.group(1)) == ix.nblocks and int(m.group(2)) == len(gptr) - 1
