@@ -700,8 +700,9 @@ class Schwarz:
             pass
 
     def set_subsolver(self, kind):
-        """"lu": exact block solves (dense inverses); "ssor": one SSOR iteration per block (PCSOR default)."""
-        check(self.L.b2_schwarz_set_subsolver(self.h, {"lu": 0, "ssor": 1}[kind]))
+        """"lu": exact block solves (dense inverses); "ssor": one SSOR iteration per block (PCSOR default);
+        "ilu": ILU(0) of every block in its sorted dofs (PCILU default)."""
+        check(self.L.b2_schwarz_set_subsolver(self.h, {"lu": 0, "ssor": 1, "ilu": 2}[kind]))
 
     def setup(self):
         check(self.L.b2_schwarz_setup(self.h))

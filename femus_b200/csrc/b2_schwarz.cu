@@ -31,7 +31,11 @@ struct b2_schwarz {
   int32_t* group_blocks = nullptr;   // [nblocks] device: blocks in schedule order
   std::vector<int64_t> group_ptr;    // [ngroups+1] host
   int* err = nullptr;             // device: 1 + first block whose pivot vanished, or 0
-  int sub = 0;                    // block solve: 0 = exact (dense inverse), 1 = one SSOR iteration on the block's rows
+  int sub = 0;                    // block solve: 0 = exact (dense inverse), 1 = one SSOR iteration on the block's rows, 2 = ILU(0)
+  int64_t* frow = nullptr;        // [ndofs_total] ILU: start of every (block, row)'s factor row
+  double* fac = nullptr;          // [fac_total]   ILU factors on the pattern of the blocks' rows of A
+  int64_t* foff = nullptr;        // [n]           ILU: factor row of the dof in the block that claimed it
+  int64_t fac_total = 0;
   double *tg = nullptr, *dg = nullptr, *zg = nullptr;   // [n] scratch of the SSOR sweep
   int32_t* mark = nullptr;        // [n]
   bool ready = false;
@@ -97,7 +101,7 @@ int b2_schwarz_create(b2_ctx* c, b2_csr* A, int64_t nblocks, const int64_t* blk_
 /* block solve: 0 = exact (MLU_PRECOND on the blocks; dense inverses, blocks of at most 4096 dofs), 1 = one SSOR
  * iteration (SOR_PRECOND on the blocks, 001_Poisson's own choice; no storage, any block size) */
 int b2_schwarz_set_subsolver(b2_schwarz* s, int kind) {
-  B2_CHECK(s && (kind == 0 || kind == 1), "b2_schwarz_set_subsolver: kind must be 0 (exact) or 1 (SSOR)");
+  B2_CHECK(s && kind >= 0 && kind <= 2, "b2_schwarz_set_subsolver: kind must be 0 (exact), 1 (SSOR) or 2 (ILU(0))");
   if (kind != s->sub) s->ready = false;
   s->sub = kind;
   return 0;
@@ -109,13 +113,47 @@ int b2_schwarz_setup(b2_schwarz* s) {
   b2_ctx* c = s->ctx;
   if (s->sub == 1) {              // SSOR works on A's rows: only the scratch vectors are needed
     const size_t n = (size_t)s->A->nrows;
+    if (!s->tg) B2_TRY(b2_malloc(c, &s->tg, n));
+    if (!s->dg) B2_TRY(b2_malloc(c, &s->dg, n));
+    if (!s->zg) B2_TRY(b2_malloc(c, &s->zg, n));
     if (!s->mark) {
-      B2_TRY(b2_malloc(c, &s->tg, n));
-      B2_TRY(b2_malloc(c, &s->dg, n));
-      B2_TRY(b2_malloc(c, &s->zg, n));
       B2_TRY(b2_malloc(c, &s->mark, n));
       B2_CUDA(cudaMemsetAsync(s->mark, 0xff, n * sizeof(int32_t), c->stream));     // -1: claimed by no block
     }
+    s->ready = true;
+    return 0;
+  }
+  if (s->sub == 2) {              // ILU(0) of every block on the pattern of its rows of A, group by group
+    const size_t n = (size_t)s->A->nrows;
+    if (!s->fac) {
+      std::vector<int64_t> rp(n + 1), bp((size_t)s->nblocks + 1);
+      std::vector<int32_t> bd((size_t)s->ndofs_total);
+      B2_TRY(b2_download(c, rp.data(), s->A->rowptr, n + 1));
+      B2_TRY(b2_download(c, bp.data(), s->blk_ptr, (size_t)s->nblocks + 1));
+      B2_TRY(b2_download(c, bd.data(), s->blk_dofs, (size_t)s->ndofs_total));
+      std::vector<int64_t> frow((size_t)s->ndofs_total);
+      int64_t tot = 0;
+      for (int64_t k = 0; k < s->ndofs_total; k++) { frow[k] = tot; tot += rp[bd[k] + 1] - rp[bd[k]]; }
+      s->fac_total = tot;
+      B2_TRY(b2_malloc(c, &s->frow, (size_t)s->ndofs_total));
+      B2_TRY(b2_upload(c, s->frow, frow.data(), (size_t)s->ndofs_total));
+      B2_TRY(b2_malloc(c, &s->fac, (size_t)tot));
+      B2_TRY(b2_malloc(c, &s->foff, n));
+    }
+    if (!s->zg) B2_TRY(b2_malloc(c, &s->zg, n));
+    if (!s->mark) {
+      B2_TRY(b2_malloc(c, &s->mark, n));
+      B2_CUDA(cudaMemsetAsync(s->mark, 0xff, n * sizeof(int32_t), c->stream));
+    }
+    B2_CUDA(cudaMemsetAsync(s->err, 0, sizeof(int), c->stream));
+    for (int64_t g = 0; g < s->ngroups; g++) {
+      const int64_t g0 = s->group_ptr[g], g1 = s->group_ptr[g + 1];
+      B2_LAUNCH(c, schwarz_ilu_factor_kernel, b2_grid_for(c, g1 - g0, 1, 16), kApplyThreads, 0, g0, g1, s->group_blocks, s->blk_ptr, s->blk_dofs,
+                s->frow, s->A->rowptr, s->A->col, s->A->val, s->fac, s->mark, s->foff, s->err);
+    }
+    int err = 0;
+    B2_TRY(b2_download(c, &err, s->err, 1));
+    B2_CHECK(err == 0, "b2_schwarz_setup: ILU(0) of block %d met a zero pivot", err - 1);
     s->ready = true;
     return 0;
   }
@@ -150,6 +188,11 @@ int b2_schwarz_apply(b2_schwarz* s, const b2_vec* r, b2_vec* y) {
   B2_CUDA(cudaMemsetAsync(y->d, 0, (size_t)s->A->nrows * sizeof(double), c->stream));
   for (int64_t g = 0; g < s->ngroups; g++) {
     const int64_t g0 = s->group_ptr[g], g1 = s->group_ptr[g + 1];
+    if (s->sub == 2) {
+      B2_LAUNCH(c, schwarz_apply_ilu_kernel, b2_grid_for(c, g1 - g0, 1, 16), kApplyThreads, 0, g0, g1, s->group_blocks, s->blk_ptr, s->blk_dofs,
+                s->frow, s->A->rowptr, s->A->col, s->A->val, s->fac, r->d, y->d, s->zg, s->mark);
+      continue;
+    }
     if (s->sub == 1) {
       B2_LAUNCH(c, schwarz_apply_ssor_kernel, b2_grid_for(c, g1 - g0, 1, 16), kApplyThreads, 0, g0, g1, s->group_blocks, s->blk_ptr, s->blk_dofs,
                 s->A->rowptr, s->A->col, s->A->val, r->d, y->d, s->tg, s->dg, s->zg, s->mark);
@@ -161,7 +204,10 @@ int b2_schwarz_apply(b2_schwarz* s, const b2_vec* r, b2_vec* y) {
   return 0;
 }
 
-int64_t b2_schwarz_bytes(const b2_schwarz* s) { return (s && s->inv) ? s->inv_total * (int64_t)sizeof(double) : 0; }
+int64_t b2_schwarz_bytes(const b2_schwarz* s) {
+  if (!s) return 0;
+  return ((s->inv ? s->inv_total : 0) + (s->fac ? s->fac_total : 0)) * (int64_t)sizeof(double);
+}
 int64_t b2_schwarz_groups(const b2_schwarz* s) { return s ? s->ngroups : 0; }
 
 int b2_schwarz_destroy(b2_schwarz* s) {
@@ -171,6 +217,9 @@ int b2_schwarz_destroy(b2_schwarz* s) {
   b2_free(c, s->blk_dofs, (size_t)s->ndofs_total);
   b2_free(c, s->inv_ptr, (size_t)s->nblocks + 1);
   b2_free(c, s->inv, (size_t)s->inv_total);
+  b2_free(c, s->frow, (size_t)s->ndofs_total);
+  b2_free(c, s->fac, (size_t)s->fac_total);
+  b2_free(c, s->foff, (size_t)s->A->nrows);
   b2_free(c, s->tg, (size_t)s->A->nrows);
   b2_free(c, s->dg, (size_t)s->A->nrows);
   b2_free(c, s->zg, (size_t)s->A->nrows);

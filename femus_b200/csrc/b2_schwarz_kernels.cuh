@@ -185,3 +185,125 @@ __global__ void __launch_bounds__(kApplyThreads) schwarz_apply_ssor_kernel(int64
     __syncthreads();
   }
 }
+
+// ---- ILU(0) block solves: ILU_PRECOND on the blocks, by far the most common fine-grid preconditioner of the
+// reference's applications (PCILU: levels 0, natural ordering = the block's sorted dofs, PetscPreconditioner.cpp;
+// LinearEquationSolverPetscAsm.cpp:300-317).  The factor of block b lives on the pattern of the block's rows of A:
+// row i of the block (global row r = D[i]) owns len(r) slots at fac[frow[blk_ptr[b] + i] ..), slot q belonging to
+// column col[rowptr[r] + q]; slots of columns outside the block are unused.  One warp per block walks the rows in order
+// (IKJ elimination: for every earlier column k of the row, l_ik = a_ik / u_kk, then a_ij -= l_ik u_kj wherever (k, j) is
+// in the pattern of row k); lanes work across a row's entries.  Per dof scratch as in the SSOR kernel: mark = the
+// block that claimed the dof, foff = where that block keeps the dof's factor row.
+__device__ __forceinline__ int64_t schwarz_bsearch(const int32_t* __restrict__ col, int64_t lo, int64_t hi, int32_t c) {
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (col[mid] < c) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+__global__ void __launch_bounds__(kApplyThreads) schwarz_ilu_factor_kernel(int64_t g0, int64_t g1, const int32_t* __restrict__ group_blocks,
+                                                                            const int64_t* __restrict__ blk_ptr, const int32_t* __restrict__ blk_dofs,
+                                                                            const int64_t* __restrict__ frow, const int64_t* __restrict__ rowptr,
+                                                                            const int32_t* __restrict__ col, const double* __restrict__ val, double* fac,
+                                                                            int32_t* mark, int64_t* foff, int* __restrict__ err) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  for (int64_t q0 = g0 + blockIdx.x; q0 < g1; q0 += gridDim.x) {
+    const int32_t b = group_blocks[q0];
+    const int32_t* D = blk_dofs + blk_ptr[b];
+    const int64_t* F = frow + blk_ptr[b];
+    const int m = (int)(blk_ptr[b + 1] - blk_ptr[b]);
+    for (int i = warp; i < m; i += nwarps) {            // copy the rows, claim the dofs
+      const int64_t r = D[i], rp = rowptr[r], len = rowptr[r + 1] - rp;
+      for (int64_t q = lane; q < len; q += 32) fac[F[i] + q] = val[rp + q];
+      if (lane == 0) { mark[r] = b; foff[r] = F[i]; }
+    }
+    __syncthreads();
+    if (warp == 0) {
+      for (int i = 0; i < m; i++) {
+        const int32_t r = D[i];
+        const int64_t rp = rowptr[r], len = rowptr[r + 1] - rp, fi = F[i];
+        for (int64_t q = 0; q < len; q++) {             // the row's entries in column order: earlier columns are pivots
+          const int32_t k = col[rp + q];
+          if (k >= r) break;
+          if (mark[k] != b) continue;
+          const int64_t kp = rowptr[k], klen = rowptr[k + 1] - kp, fk = foff[k];
+          const int64_t dk = schwarz_bsearch(col, kp, kp + klen, k) - kp;          // the pivot row's diagonal slot
+          const double lik = fac[fi + q] / fac[fk + dk];
+          __syncwarp();
+          if (lane == 0) fac[fi + q] = lik;
+          for (int64_t q2 = q + 1 + lane; q2 < len; q2 += 32) {
+            const int32_t c2 = col[rp + q2];
+            if (mark[c2] != b) continue;
+            const int64_t p = schwarz_bsearch(col, kp, kp + klen, c2);
+            if (p < kp + klen && col[p] == c2) fac[fi + q2] = fma(-lik, fac[fk + (p - kp)], fac[fi + q2]);
+          }
+          __syncwarp();
+        }
+        const int64_t di = schwarz_bsearch(col, rp, rp + len, r) - rp;
+        if (lane == 0 && !(fabs(fac[fi + di]) > 0.0)) atomicCAS(err, 0, b + 1);
+        __syncwarp();
+      }
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(kApplyThreads) schwarz_apply_ilu_kernel(int64_t g0, int64_t g1, const int32_t* __restrict__ group_blocks,
+                                                                           const int64_t* __restrict__ blk_ptr, const int32_t* __restrict__ blk_dofs,
+                                                                           const int64_t* __restrict__ frow, const int64_t* __restrict__ rowptr,
+                                                                           const int32_t* __restrict__ col, const double* __restrict__ val,
+                                                                           const double* __restrict__ fac, const double* __restrict__ r, double* y,
+                                                                           double* zg, int32_t* mark) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  for (int64_t q0 = g0 + blockIdx.x; q0 < g1; q0 += gridDim.x) {
+    const int32_t b = group_blocks[q0];
+    const int32_t* D = blk_dofs + blk_ptr[b];
+    const int64_t* F = frow + blk_ptr[b];
+    const int m = (int)(blk_ptr[b + 1] - blk_ptr[b]);
+    for (int i = warp; i < m; i += nwarps) {            // t = (r - A y)[B] into zg, claim the dofs
+      const int64_t row = D[i];
+      double acc = 0.0;
+      for (int64_t k = rowptr[row] + lane; k < rowptr[row + 1]; k += 32) acc = fma(val[k], y[col[k]], acc);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (lane == 0) { zg[row] = r[row] - acc; mark[row] = b; }
+    }
+    __syncthreads();
+    if (warp == 0) {
+      for (int i = 0; i < m; i++) {                     // L z = t, unit lower triangle
+        const int32_t row = D[i];
+        const int64_t rp = rowptr[row], len = rowptr[row + 1] - rp;
+        double s = 0.0;
+        for (int64_t q = lane; q < len; q += 32) {
+          const int32_t c = col[rp + q];
+          if (c < row && mark[c] == b) s = fma(fac[F[i] + q], zg[c], s);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) zg[row] -= s;
+        __syncwarp();
+      }
+      for (int i = m - 1; i >= 0; i--) {                // U z = z
+        const int32_t row = D[i];
+        const int64_t rp = rowptr[row], len = rowptr[row + 1] - rp;
+        double s = 0.0, d = 0.0;
+        for (int64_t q = lane; q < len; q += 32) {
+          const int32_t c = col[rp + q];
+          if (c == row) d = fac[F[i] + q];
+          else if (c > row && mark[c] == b) s = fma(fac[F[i] + q], zg[c], s);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          s += __shfl_xor_sync(0xffffffffu, s, o);
+          d += __shfl_xor_sync(0xffffffffu, d, o);
+        }
+        if (lane == 0) zg[row] = (zg[row] - s) / d;
+        __syncwarp();
+      }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < m; i += blockDim.x) y[D[i]] += zg[D[i]];
+    __syncthreads();
+  }
+}

@@ -17,7 +17,7 @@
 
 namespace femus {
 
-enum B200PrecondType { MLU_PRECOND_B200 = 0, SOR_PRECOND_B200 };     // the subset of PrecondtypeEnum.hpp the blocks support
+enum B200PrecondType { MLU_PRECOND_B200 = 0, SOR_PRECOND_B200, ILU_PRECOND_B200 };     // the subset of PrecondtypeEnum.hpp the blocks support
 
 class LinearEquationSolverB200Asm : public LinearEquationSolverB200 {
  public:
@@ -40,7 +40,8 @@ class LinearEquationSolverB200Asm : public LinearEquationSolverB200 {
   }
   void SetNumberOfSchurVariables(const unsigned short& NSchurVar) { _NSchurVar = NSchurVar; }
   // LinearEquationSolver::set_preconditioner_type (what SetPreconditionerFineGrids sets, LinearImplicitSystem.cpp:1236-1245):
-  // the solver of every block -- MLU_PRECOND: exact, SOR_PRECOND: one SSOR iteration (001_Poisson, main.cpp:242)
+  // the solver of every block -- MLU_PRECOND: exact, SOR_PRECOND: one SSOR iteration (001_Poisson, main.cpp:242),
+  // ILU_PRECOND: ILU(0) in the block's sorted dofs (the setting of most applications)
   void set_preconditioner_type(const B200PrecondType pt) { _blockPrecond = pt; }
   // the level's mesh and the family of the unknown (what GetMeshFromLinEq() / _SolType give the reference)
   void SetMesh(const femus_b200::MeshLevel* msh, const int family) {
@@ -91,7 +92,7 @@ class LinearEquationSolverB200Asm : public LinearEquationSolverB200 {
       }
       _indexIsInitialized = true;
     }
-    B2_ABORT_IF(b2_schwarz_set_subsolver(_schwarz, _blockPrecond == SOR_PRECOND_B200 ? 1 : 0), "b2_schwarz_set_subsolver");
+    B2_ABORT_IF(b2_schwarz_set_subsolver(_schwarz, _blockPrecond == SOR_PRECOND_B200 ? 1 : (_blockPrecond == ILU_PRECOND_B200 ? 2 : 0)), "b2_schwarz_set_subsolver");
     // SetPreconditioner: the numeric phase runs inside b2_mg_set_level, after the penalty
     B2_ABORT_IF(b2_mg_set_level_schwarz(mg, (int)_level, _schwarz), "b2_mg_set_level_schwarz");
   }

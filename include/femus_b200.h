@@ -312,7 +312,11 @@ int b2_ns_assemble(b2_stokes* p, const b2_vec* sol, b2_vec* rhs, double nu);
  * b2_schwarz_apply: y = M^-1 r.  One rank only (no interface sums). */
 int b2_schwarz_create(b2_ctx* ctx, b2_csr* A, int64_t nblocks, const int64_t* blk_ptr, const int32_t* blk_dofs,
                       int64_t ngroups, const int64_t* group_ptr, const int32_t* group_blocks, b2_schwarz** out);
-/* block solve (call before b2_schwarz_setup): 0 = exact, dense inverses of blocks of at most 4096 dofs (default);
+/* block solve (call before b2_schwarz_setup): 2 = ILU(0) of every block in its sorted dofs -- ILU_PRECOND on the
+ * blocks (PCILU: levels 0, natural ordering), the fine-grid preconditioner most of the reference's applications set;
+ * factors on the pattern of the blocks' rows of A, any block size; with ONE block holding every element the level
+ * smoother is Richardson + ILU(0), i.e. FEMuS_DEFAULT with ILU_PRECOND;
+ * 0 = exact, dense inverses of blocks of at most 4096 dofs (default);
  * 1 = one SSOR iteration on the block's rows -- PCSOR's default (local symmetric sweep, omega 1, zero guess), the
  * sub-preconditioner 001_Poisson itself selects with SetPreconditionerFineGrids(SOR_PRECOND) (main.cpp:242,
  * LinearEquationSolverPetscAsm.cpp:300-317); no storage, any block size: with ONE block holding every element the

@@ -142,11 +142,40 @@ class BlockSmoother:
         self.blocks = [np.asarray(b, dtype=np.int64) for b in blocks]
         self.sub = sub
         self.dense = [self.A[b][:, b].toarray() for b in self.blocks]
+        self._ilu = {}
+
+    def _ilu0(self, i):
+        """ILU(0) of the block in its sorted dofs on the pattern of A[B, B] (PCILU defaults: levels 0, natural
+        ordering): IKJ elimination restricted to the pattern; L (unit) and U share one dense array here."""
+        if i not in self._ilu:
+            b = self.blocks[i]
+            pat = (self.A[b][:, b] != 0).toarray() | (sp.csr_matrix((np.ones(self.A.nnz), self.A.indices, self.A.indptr),
+                                                                      shape=self.A.shape)[b][:, b].toarray() != 0)
+            F = self.dense[i].copy()
+            m = F.shape[0]
+            for r in range(m):
+                cr = np.nonzero(pat[r])[0]
+                for k in cr[cr < r]:
+                    F[r, k] = F[r, k] / F[k, k]
+                    js = cr[cr > k]
+                    js = js[pat[k, js]]
+                    F[r, js] -= F[r, k] * F[k, js]
+            self._ilu[i] = (F, pat)
+        return self._ilu[i]
 
     def _subsolve(self, i, t):
         M = self.dense[i]
         if self.sub == "lu":
             return np.linalg.solve(M, t)
+        if self.sub == "ilu":
+            F, pat = self._ilu0(i)
+            m = len(t)
+            z = t.copy()
+            for r in range(m):
+                z[r] -= (F[r, :r] * pat[r, :r]) @ z[:r]
+            for r in range(m - 1, -1, -1):
+                z[r] = (z[r] - (F[r, r + 1:] * pat[r, r + 1:]) @ z[r + 1:]) / F[r, r]
+            return z
         # PCSOR default: SOR_LOCAL_SYMMETRIC_SWEEP, omega = 1, its = 1, zero initial guess
         z = np.zeros_like(t)
         m = len(t)

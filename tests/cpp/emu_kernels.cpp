@@ -34,6 +34,30 @@ int emu_schwarz(int64_t n, const int64_t* rowptr, const int32_t* col, const doub
       if (y2[i] != y[i]) return -1;
     return 0;
   }
+  if (sub == 2) {       // ILU(0) block solves: factor group by group, then the sweep (twice, on the used scratch)
+    std::vector<int64_t> frow((size_t)blk_ptr[nblocks]);
+    int64_t tot = 0;
+    for (int64_t k = 0; k < blk_ptr[nblocks]; k++) { frow[k] = tot; tot += rowptr[blk_dofs[k] + 1] - rowptr[blk_dofs[k]]; }
+    std::vector<double> fac((size_t)tot, -7.0), zg((size_t)n, -7.0);
+    std::vector<int64_t> foff((size_t)n, -1);
+    std::vector<int32_t> mark((size_t)n, -1);
+    int err = 0;
+    for (int64_t g = 0; g < ngroups; g++)
+      emu::launch(schwarz_ilu_factor_kernel, (unsigned)grid, (unsigned)threads, 0, group_ptr[g], group_ptr[g + 1], group_blocks, blk_ptr, blk_dofs,
+                  (const int64_t*)frow.data(), rowptr, col, val, fac.data(), mark.data(), foff.data(), &err);
+    if (err) return err;
+    std::vector<double> y2((size_t)n, 0.0);
+    for (int pass = 0; pass < 2; pass++) {
+      double* yy = pass ? y2.data() : y;
+      for (int64_t i = 0; i < n; i++) yy[i] = 0.0;
+      for (int64_t g = 0; g < ngroups; g++)
+        emu::launch(schwarz_apply_ilu_kernel, (unsigned)grid, (unsigned)threads, 0, group_ptr[g], group_ptr[g + 1], group_blocks, blk_ptr, blk_dofs,
+                    (const int64_t*)frow.data(), rowptr, col, val, (const double*)fac.data(), r, yy, zg.data(), mark.data());
+    }
+    for (int64_t i = 0; i < n; i++)
+      if (y2[i] != y[i]) return -1;
+    return 0;
+  }
   std::vector<int64_t> inv_ptr((size_t)nblocks + 1, 0);
   int max_m = 0;
   for (int64_t b = 0; b < nblocks; b++) {

@@ -3,12 +3,13 @@
 // on a box mesh, written against B200Vector / B200Matrix / LinearEquationSolverB200 and the host mesh
 // layer.  tests/test_adapters.py runs it on the GPU and checks what it prints against the oracle.
 //
-//   poisson_driver nx ny nz nlevels family(0 linear | 2 biquadratic) ncycles [compat | asm<N> | asmref<N> | asmsor<N>]
+//   poisson_driver nx ny nz nlevels family(0 linear | 2 biquadratic) ncycles [compat | asm<N> | asmref<N> | asmsor<N> | asmilu<N>]
 //
 // "asm<N>" (e.g. asm8) runs the levels through LinearEquationSolverB200Asm: the element-block smoother of
 // "smoother": "asm" (main.cpp:234-250) with N elements per block, Richardson scale 1, coloured sweep; "asmref<N>"
 // sweeps the blocks in the reference's own order; "asmsor<N>" uses one SSOR iteration as the block solve
-// (SetPreconditionerFineGrids(SOR_PRECOND), main.cpp:242) -- asmsor4096 is the application's own "asm" setting.
+// (SetPreconditionerFineGrids(SOR_PRECOND), main.cpp:242) -- asmsor4096 is the application's own "asm" setting;
+// "asmilu<N>" uses ILU(0) (ILU_PRECOND).
 // "compat" additionally rebuilds the finest matrix through the slow plugin path (init with counts,
 // add_matrix_blocked per element, close) from the rows of the device-assembled one and checks that
 // both give the same matrix-vector product.
@@ -29,7 +30,8 @@ int main(int argc, char** argv) {
   const bool use_asm = argc > 7 && std::strncmp(argv[7], "asm", 3) == 0;
   const bool asm_ref = use_asm && std::strncmp(argv[7], "asmref", 6) == 0;
   const bool asm_sor = use_asm && std::strncmp(argv[7], "asmsor", 6) == 0;
-  const int asm_blocks = use_asm ? std::atoi(argv[7] + ((asm_ref || asm_sor) ? 6 : 3)) : 0;
+  const bool asm_ilu = use_asm && std::strncmp(argv[7], "asmilu", 6) == 0;
+  const int asm_blocks = use_asm ? std::atoi(argv[7] + ((asm_ref || asm_sor || asm_ilu) ? 6 : 3)) : 0;
   const bool compat = argc > 7 && !use_asm;
   const int nve = HexElement::nve(family);
 
@@ -50,7 +52,7 @@ int main(int argc, char** argv) {
       s->SetNumberOfSchurVariables(0);
       s->SetElementBlockNumber((unsigned)std::min<int64_t>(asm_blocks, msh[l].nel));      // LinearImplicitSystem.cpp:1198
       s->SetSweepOrder(asm_ref ? 0 : 1);
-      s->set_preconditioner_type(asm_sor ? SOR_PRECOND_B200 : MLU_PRECOND_B200);
+      s->set_preconditioner_type(asm_sor ? SOR_PRECOND_B200 : (asm_ilu ? ILU_PRECOND_B200 : MLU_PRECOND_B200));
       LinSolver.emplace_back(s);
     } else {
       LinSolver.emplace_back(new LinearEquationSolverB200((unsigned)l));

@@ -91,19 +91,21 @@ def test_block_smoother_on_unstructured_meshes(ctx, name, order):
     del pb
 
 
+@pytest.mark.parametrize("sub", ["ssor", "ilu"])
 @pytest.mark.parametrize("order,nb,schedule", [("linear", 8, "colours"), ("biquadratic", 8, "levels"), ("biquadratic", 4096, "colours")])
-def test_vcycle_trace_with_ssor_block_solves(ctx, order, nb, schedule):
+def test_vcycle_trace_with_ssor_block_solves(ctx, order, nb, schedule, sub):
     """The application's own sub-preconditioner: one SSOR iteration per block (SetPreconditionerFineGrids(SOR_PRECOND),
     main.cpp:242).  nb = 4096 = SetElementBlockNumber(4) of main.cpp:249: on these small levels ONE block holds every
-    element and the smoother is Richardson + SOR, what FEMuS_DEFAULT configures too."""
+    element and the smoother is Richardson + SOR, what FEMuS_DEFAULT configures too.  sub = "ilu": ILU(0) block solves
+    (ILU_PRECOND, the setting of most of the reference's applications; one block = Richardson + ILU(0))."""
     from femus_b200.poisson import PoissonMG
     from oracle import mesh_box as mb
-    pb = PoissonMG(ctx, 2, 2, 2, 3, order, smoother="asm", asm_block_elems=nb, asm_schedule=schedule, asm_sub="ssor", omega=1.0,
+    pb = PoissonMG(ctx, 2, 2, 2, 3, order, smoother="asm", asm_block_elems=nb, asm_schedule=schedule, asm_sub=sub, omega=1.0,
                    coarse_rtol=1e-15)
     pb.assemble(); pb.galerkin(); pb.mg_set_levels()
-    O = _oracle(pb, mb.build_hierarchy(2, 2, 2, 3), order, asm_sub="ssor")
+    O = _oracle(pb, mb.build_hierarchy(2, 2, 2, 3), order, asm_sub=sub)
     if nb == 4096:
-        assert pb.asm_index[2].nblocks == 1 and pb.schwarz[2].nbytes == 0
+        assert pb.asm_index[2].nblocks == 1 and (pb.schwarz[2].nbytes == 0 if sub == "ssor" else pb.schwarz[2].nbytes == 8 * pb.KK[2].nnz)
     trace_ref, eps_ref = O.mg_solve_trace(4, omega=1.0)
     trace = []
     for _ in range(4):
@@ -161,7 +163,8 @@ def test_block_smoother_fails_loudly(ctx):
 
 
 @pytest.mark.parametrize("mode,shape,nl,order", [("asm8", (2, 2, 2), 3, "biquadratic"), ("asmref8", (2, 2, 2), 3, "linear"),
-                                                 ("asm5", (3, 2, 2), 2, "linear"), ("asmsor4096", (2, 2, 2), 3, "biquadratic")])
+                                                 ("asm5", (3, 2, 2), 2, "linear"), ("asmsor4096", (2, 2, 2), 3, "biquadratic"),
+                                                 ("asmilu8", (2, 2, 2), 3, "linear")])
 def test_cpp_driver_with_the_asm_level_solver(mode, shape, nl, order):
     """tests/cpp/poisson_driver.cpp through LinearEquationSolverB200Asm (the LinearEquationSolverPetscAsm surface:
     SetNumberOfSchurVariables(0), SetElementBlockNumber(n), MGSetLevel building index sets + preconditioner):
@@ -171,7 +174,7 @@ def test_cpp_driver_with_the_asm_level_solver(mode, shape, nl, order):
     from oracle import mesh_box as mb, mg
     from tests.test_adapters import _run_driver
     fam = {"linear": 0, "biquadratic": 2}[order]
-    nb = int(mode.lstrip("asmrefso"))
+    nb = int(mode.lstrip("asmrefsoilu"))
     ncyc = 3
     out = _run_driver(list(shape) + [nl, fam, ncyc, mode])
     res = [float(x) for x in re.findall(r"cycle \d+ residual (\S+)", out)]
@@ -185,7 +188,7 @@ def test_cpp_driver_with_the_asm_level_solver(mode, shape, nl, order):
         blocks.append(ix.blocks())
         orders.append(gblocks)
     O = mg.Hierarchy(mb.build_hierarchy(*shape, nl), order, smoother="asm", asm_blocks=blocks, asm_orders=orders,
-                     asm_sub="ssor" if "sor" in mode else "lu")
+                     asm_sub="ssor" if "sor" in mode else ("ilu" if "ilu" in mode else "lu"))
     trace, eps = O.mg_solve_trace(ncyc, omega=1.0)
     free = O.bdc[-1] > 1.1
     r0 = float(np.linalg.norm(np.where(free, O.rhs, 0.0)))
