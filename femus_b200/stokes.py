@@ -18,7 +18,8 @@ from . import capi, hostapi
 
 class StokesMG:
     def __init__(self, ctx, hier, order_v="biquadratic", order_p="linear", IRe=1.0, velocity_dirichlet=(1, 2, 3, 4, 5, 6),
-                 pressure_dirichlet=(), npre=1, npost=1, omega=1.0, block_elems=1, schedule="colours", equation="stokes"):
+                 pressure_dirichlet=(), npre=1, npost=1, omega=1.0, block_elems=1, schedule="colours", equation="stokes",
+                 block_sub="lu"):
         """equation: "stokes" (SteadyStokes/main.cpp, IRe = the viscosity factor) or "navier_stokes" (the library routine
         03_navier_stokes.hpp: Galerkin residual + exact Newton Jacobian, IRe = nu)."""
         self.ctx, self.hier, self.IRe, self.equation = ctx, hier, IRe, equation
@@ -62,6 +63,7 @@ class StokesMG:
             grp, gptr, gblocks = hostapi.asm_schedule(*self.pattern[l], ix.overlap_ptr, ix.overlap, schedule)
             self.asm_index[l], self.asm_groups[l] = ix, grp
             self.schwarz[l] = capi.Schwarz(ctx, self.KK[l], ix.overlap_ptr, ix.overlap, gptr, gblocks)
+            self.schwarz[l].set_subsolver(block_sub)     # "lu": exact (MLU_PRECOND), "ilu": ILU(0) in system-dof order (ILU_PRECOND)
             self.mg.set_level_schwarz(l, self.schwarz[l])
 
     def assemble(self):

@@ -41,18 +41,19 @@ def test_stokes_assembly_matches_oracle(ctx, name):
     del pb
 
 
-@pytest.mark.parametrize("name,schedule", [("box", "colours"), ("box", "levels")])
-def test_stokes_vcycle_trace_with_vanka_blocks(ctx, name, schedule):
+@pytest.mark.parametrize("name,schedule,sub", [("box", "colours", "lu"), ("box", "levels", "lu"), ("box", "colours", "ilu")])
+def test_stokes_vcycle_trace_with_vanka_blocks(ctx, name, schedule, sub):
     """Channel-like problem (velocity Dirichlet on five boundary sets, unit U on the top one, natural outflow on set 2):
     assembly, Galerkin chain, Vanka smoother (pressure = Schur variable, one element per block), direct coarse solve;
-    six V-cycles against the oracle, which converge by four orders of magnitude.  (Hexahedra only: on the shipped
+    six V-cycles against the oracle, which converge by four orders of magnitude (sub = "ilu": ILU(0) of the saddle-point
+    blocks in system-dof order, velocities first, instead of their exact inverses).  (Hexahedra only: on the shipped
     tetrahedral cube the corner elements have every velocity node on the boundary, so the P2-P1 system is singular.)"""
     from femus_b200.stokes import StokesMG
     from oracle import stokes, mg, system as osys
     H, lv, mesh, tables_of, ov = _case(name, 2)
     fams = [ov] * 3 + ["linear"]
     walls = (1, 3, 4, 5, 6)
-    pb = StokesMG(ctx, H, order_v=ov, IRe=1.0, velocity_dirichlet=walls, schedule=schedule)
+    pb = StokesMG(ctx, H, order_v=ov, IRe=1.0, velocity_dirichlet=walls, schedule=schedule, block_sub=sub)
     sol = np.zeros(pb.n)
     sol[osys.bdc(lv[-1], mesh, fams, [(6,), (), (), ()]) < 1.5] = 1.0
     pb.SOL.put(sol)
@@ -62,7 +63,7 @@ def test_stokes_vcycle_trace_with_vanka_blocks(ctx, name, schedule):
     blocks = [None] + [pb.asm_index[l].blocks() for l in range(1, pb.nlevels)]
     orders = [None] + [np.argsort(pb.asm_groups[l], kind="stable") for l in range(1, pb.nlevels)]
     O = mg.Hierarchy(lv, None, mesh=osys.SystemMesh(mesh, fams, [walls] * 3 + [()]), A_top=A, rhs=rhs, smoother="asm", asm_blocks=blocks,
-                     asm_orders=orders)
+                     asm_orders=orders, asm_sub=sub)
     got0 = pb.KK[0].to_scipy()
     assert np.abs(got0.data - O.A[0].data).max() <= 1e-11 * np.abs(O.A[0].data).max()
     trace_ref, eps_ref = O.mg_solve_trace(6, omega=1.0)
