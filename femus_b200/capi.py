@@ -124,6 +124,7 @@ _PROTOS = {
     "b2_schwarz_destroy": (ci, [vp]),
     "b2_mg_set_level_schwarz": (ci, [vp, ci, vp]),
     "b2_mg_set_coarse_schwarz": (ci, [vp, vp]),
+    "b2_mg_set_level_ksp": (ci, [vp, ci, ci]),
     "b2_stokes_create": (ci, [vp, vp, vp, ci, ci, ci, vp, vp, vp, vp, vp, vp]),
     "b2_stokes_assemble": (ci, [vp, vp, vp, cd]),
     "b2_stokes_destroy": (ci, [vp]),
@@ -752,6 +753,10 @@ class Multigrid:
         """Level smoother = Richardson(omega) + the element-block preconditioner (b2_mg_set_level_schwarz)."""
         self._keep.append(schwarz)
         check(self.L.b2_mg_set_level_schwarz(self.h, level, schwarz.h if schwarz is not None else None))
+
+    def set_level_ksp(self, level, kind):
+        """Level solver around the level's preconditioner: "richardson" or "gmres" (b2_mg_set_level_ksp)."""
+        check(self.L.b2_mg_set_level_ksp(self.h, level, {"richardson": 0, "gmres": 1}[kind]))
 
     def set_coarse_schwarz(self, schwarz):
         """Direct coarse solve through a one-block exact Schwarz object (b2_mg_set_coarse_schwarz)."""

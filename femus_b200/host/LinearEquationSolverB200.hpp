@@ -18,7 +18,7 @@
 namespace femus {
 
 enum MgSmootherType { FULL = 0, MULTIPLICATIVE, ADDITIVE, KASKADE };      // 00_enums MgTypeEnum.hpp
-enum B200SolverType { RICHARDSON_B200 = 0, CHEBYSHEV_B200, PREONLY_B200 }; // the subset of SolvertypeEnum.hpp in scope
+enum B200SolverType { RICHARDSON_B200 = 0, CHEBYSHEV_B200, PREONLY_B200, GMRES_B200 }; // the subset of SolvertypeEnum.hpp in scope
 
 class LinearEquationSolverB200 {
  public:
@@ -118,6 +118,8 @@ class LinearEquationSolverB200 {
       P = Pm.handle();
     }
     this->SetLevelSmoother(LinSolver->_mg);
+    if (_level > 0)       // KSPSetType of the level: GMRES (the reference's default) or Richardson around the level's preconditioner
+      B2_ABORT_IF(b2_mg_set_level_ksp(LinSolver->_mg, (int)_level, _levelSolverType == GMRES_B200 ? 1 : 0), "b2_mg_set_level_ksp");
     if (_level == 0 && _coarseDirect) {
       if (!_coarseSolver) {
         const int64_t n = _KK->m();

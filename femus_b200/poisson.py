@@ -47,7 +47,7 @@ class PoissonMG:
     def __init__(self, ctx, nx, ny, nz, nlevels, order="biquadratic", bounds=None, npre=1, npost=1, omega=0.5,
                  dirichlet_faces=(1, 2, 3, 4, 5, 6), fsrc=1.0, coarse_rtol=1e-14, hier=None, dist=None, fused=True,
                  neumann=None, smoother="richardson", asm_block_elems=8, asm_schedule="colours",
-                 asm_sub="lu"):
+                 asm_sub="lu", ksp="richardson"):
         self.ctx = ctx
         self.order = order
         self.fam = hostapi.FAMILY[order]
@@ -162,6 +162,13 @@ class PoissonMG:
         elif smoother != "richardson":
             for l in range(1, nlevels):
                 self.mg.set_smoother(l, smoother)
+        # level solver around the Jacobi / element-block preconditioner: SetSolverFineGrids(RICHARDSON | GMRES)
+        self.ksp = ksp
+        if ksp != "richardson":
+            if dist is not None or smoother == "chebyshev":
+                raise NotImplementedError("GMRES as level solver: one rank, Jacobi or element-block preconditioner")
+            for l in range(1, nlevels):
+                self.mg.set_level_ksp(l, ksp)
         # --- distributed layout: interface dofs of every level, ownership; reductions over owned dofs
         self.layout = [None] * nlevels
         self.halo = [None] * nlevels

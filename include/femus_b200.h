@@ -332,6 +332,12 @@ int b2_schwarz_destroy(b2_schwarz* s);
  * have been created on the operator handed to b2_mg_set_level for that level; b2_mg_set_level runs its numeric
  * phase after the penalty.  NULL restores the level's previous smoother kind 0. */
 int b2_mg_set_level_schwarz(b2_mg* mg, int level, b2_schwarz* s);
+/* level solver around the level's preconditioner (Jacobi of kind 0, or the element-block sweep): kind 0 = KSPRICHARDSON
+ * with the scale of b2_mg_set_level, 1 = KSPGMRES -- the reference's DEFAULT level solver (levels >= 1: GMRES +
+ * ILU_PRECOND, LinearEquationSolverPetsc.hpp:128-151; 76 applications call SetSolverFineGrids(GMRES)): left
+ * preconditioning, npre / npost iterations per smoothing call, the preconditioned residual is minimised.  GMRES
+ * around the one-block ILU(0) sweep is the library's default smoother. */
+int b2_mg_set_level_ksp(b2_mg* mg, int level, int kind);
 /* coarsest level: a DIRECT solve, what the reference runs there (PREONLY + LU, PetscPreconditioner.cpp:147-160), in
  * place of the Jacobi-PCG of b2_mg_set_coarse -- s is a b2_schwarz on the level-0 operator with ONE block holding
  * every dof and the exact block solve (at most 4096 dofs); required for indefinite (velocity-pressure) systems.  Call

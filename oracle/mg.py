@@ -69,11 +69,12 @@ class Hierarchy:
 
     def __init__(self, levels, order, fsrc=1.0, dirichlet_faces=(1, 2, 3, 4, 5, 6), A_top=None, rhs=None,
                  coarse_lu=True, ptap=None, neumann=None, smoother="richardson", mesh=None, asm_blocks=None, asm_sub="lu",
-                 asm_orders=None):
+                 asm_orders=None, ksp="richardson"):
         """mesh: the oracle module the levels come from (mesh_box by default, mesh_tet for tetrahedra).
         smoother "asm": asm_blocks[l] = the overlapping index sets of level l >= 1 (oracle.asm.level_blocks),
         asm_orders[l] = the order they are swept in (None: as listed)."""
         self.asm_blocks, self.asm_sub, self.asm_orders = asm_blocks, asm_sub, asm_orders
+        self.ksp = ksp          # "gmres": KSPGMRES (left preconditioning) around the Jacobi / element-block preconditioner
         mb = mesh if mesh is not None else globals()["mb"]
         self.levels = levels
         self.order = order
@@ -142,9 +143,57 @@ class Hierarchy:
             v = self.dinv[l] * (self.A[l] @ (v / nrm))
         return lam
 
+    def pc_apply(self, l, r):
+        return self.asm[l].apply(r) if self.smoother == "asm" else self.dinv[l] * r
+
+    def gmres(self, l, x, b, k):
+        """k iterations of left-preconditioned GMRES from x (PETSc's KSPGMRES defaults; no restart within the call):
+        minimises ||M^-1 (b - A x)|| over x + K_k(M^-1 A, M^-1 r0).  Modified Gram-Schmidt + Givens rotations."""
+        A = self.A[l]
+        z = self.pc_apply(l, b - A @ x)
+        beta = float(np.sqrt(z @ z))
+        if k <= 0 or not beta > 0.0:
+            return x
+        V = [z / beta]
+        H = np.zeros((k + 1, k))
+        cs, sn, g = np.zeros(k), np.zeros(k), np.zeros(k + 1)
+        g[0] = beta
+        m = 0
+        for j in range(k):
+            w = self.pc_apply(l, A @ V[j])
+            for i in range(j + 1):
+                H[i, j] = w @ V[i]
+                w = w - H[i, j] * V[i]
+            hn = float(np.sqrt(w @ w))
+            H[j + 1, j] = hn
+            for i in range(j):
+                a, c = H[i, j], H[i + 1, j]
+                H[i, j], H[i + 1, j] = cs[i] * a + sn[i] * c, -sn[i] * a + cs[i] * c
+            a, c = H[j, j], H[j + 1, j]
+            d = np.sqrt(a * a + c * c)
+            m = j + 1
+            if not d > 0.0:
+                m = j
+                break
+            cs[j], sn[j] = a / d, c / d
+            H[j, j], H[j + 1, j] = d, 0.0
+            g[j + 1] = -sn[j] * g[j]
+            g[j] = cs[j] * g[j]
+            if not hn > 0.0:
+                break
+            V.append(w / hn)
+        y = np.zeros(m)
+        for i in range(m - 1, -1, -1):
+            y[i] = (g[i] - H[i, i + 1:m] @ y[i + 1:]) / H[i, i]
+        for i in range(m):
+            x = x + y[i] * V[i]
+        return x
+
     def smooth(self, l, x, b, nsweeps, omega):
         """KSPRICHARDSON (scale omega) + PCJACOBI: x <- x + omega D^-1 (b - A x); or Chebyshev + Jacobi
         on the stated interval (Saad, alg. 12.1), restarted at every call like a PETSc smoother."""
+        if self.ksp == "gmres" and self.smoother != "chebyshev":
+            return self.gmres(l, x, b, nsweeps)
         if self.smoother == "asm":           # KSPRICHARDSON (scale omega) + PCASM (basic, multiplicative)
             return self.asm[l].richardson(x, b, nsweeps, omega)
         if self.smoother == "chebyshev":

@@ -9,7 +9,8 @@
 // "smoother": "asm" (main.cpp:234-250) with N elements per block, Richardson scale 1, coloured sweep; "asmref<N>"
 // sweeps the blocks in the reference's own order; "asmsor<N>" uses one SSOR iteration as the block solve
 // (SetPreconditionerFineGrids(SOR_PRECOND), main.cpp:242) -- asmsor4096 is the application's own "asm" setting;
-// "asmilu<N>" uses ILU(0) (ILU_PRECOND).
+// "asmilu<N>" uses ILU(0) (ILU_PRECOND); "gmresilu" = GMRES as level solver around ILU(0) of the whole level (one block
+// with every element): the reference's DEFAULT level solver (LinearEquationSolverPetsc.hpp:128-151).
 // "compat" additionally rebuilds the finest matrix through the slow plugin path (init with counts,
 // add_matrix_blocked per element, close) from the rows of the device-assembled one and checks that
 // both give the same matrix-vector product.
@@ -27,11 +28,12 @@ int main(int argc, char** argv) {
   if (argc < 7) { std::fprintf(stderr, "usage: %s nx ny nz nlevels family ncycles [compat]\n", argv[0]); return 2; }
   const int nx = std::atoi(argv[1]), ny = std::atoi(argv[2]), nz = std::atoi(argv[3]), nl = std::atoi(argv[4]);
   const int family = std::atoi(argv[5]), ncycles = std::atoi(argv[6]);
-  const bool use_asm = argc > 7 && std::strncmp(argv[7], "asm", 3) == 0;
+  const bool gmres_ilu = argc > 7 && std::strcmp(argv[7], "gmresilu") == 0;
+  const bool use_asm = argc > 7 && (std::strncmp(argv[7], "asm", 3) == 0 || gmres_ilu);
   const bool asm_ref = use_asm && std::strncmp(argv[7], "asmref", 6) == 0;
   const bool asm_sor = use_asm && std::strncmp(argv[7], "asmsor", 6) == 0;
-  const bool asm_ilu = use_asm && std::strncmp(argv[7], "asmilu", 6) == 0;
-  const int asm_blocks = use_asm ? std::atoi(argv[7] + ((asm_ref || asm_sor || asm_ilu) ? 6 : 3)) : 0;
+  const bool asm_ilu = use_asm && (std::strncmp(argv[7], "asmilu", 6) == 0 || gmres_ilu);
+  const int asm_blocks = gmres_ilu ? (1 << 30) : (use_asm ? std::atoi(argv[7] + ((asm_ref || asm_sor || asm_ilu) ? 6 : 3)) : 0);
   const bool compat = argc > 7 && !use_asm;
   const int nve = HexElement::nve(family);
 
@@ -61,6 +63,7 @@ int main(int argc, char** argv) {
     LinSolver[l]->InitPde((int)msh[l].ndofs(family), msh[l].nel, nve, dof.data(), msh[l].GenerateBdc(family, dirichlet));
     LinSolver[l]->SetTolerances(1.e-10, 1.e-20, 1.e+50, 1, 30);
     LinSolver[l]->SetRichardsonScaleFactor(use_asm ? 1.0 : 0.5);
+    if (gmres_ilu) LinSolver[l]->set_solver_type(GMRES_B200);
   }
   for (int l = 1; l < nl; l++) {      // BuildProlongatorMatrix + ZeroInterpolatorDirichletNodes (:826-909, :1032-1120)
     const HostCsr P = BuildProlongator(msh[l - 1], msh[l], family);

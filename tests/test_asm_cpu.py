@@ -170,3 +170,29 @@ def test_oracle_block_smoother_properties():
     Hs = mg.Hierarchy(lv, "linear", smoother="asm", asm_blocks=[None, ovl], asm_sub="ssor")
     ts, _ = Hs.mg_solve_trace(4, omega=1.0)
     assert ts[-1] < tj[-1]
+
+
+def test_oracle_gmres_level_solver_minimises_the_preconditioned_residual():
+    """oracle.mg.Hierarchy.gmres (KSPGMRES restated: left preconditioning, modified Gram-Schmidt, Givens rotations)
+    returns the least-squares minimiser of ||M^-1 (b - A x)|| over x0 + K_k(M^-1 A, M^-1 r0), for the Jacobi and for the
+    one-block ILU(0) preconditioner (= the reference's default level solver); as a smoother it beats Richardson."""
+    lv = mb.build_hierarchy(2, 2, 2, 2)
+    H = hostapi.HostHierarchy(2, 2, 2, 2)
+    blocks = [None, hostapi.AsmIndex(H.levels[1], "linear", 10 ** 6).blocks()]
+    rng = np.random.default_rng(3)
+    for O in (mg.Hierarchy(lv, "linear", ksp="gmres"), mg.Hierarchy(lv, "linear", smoother="asm", asm_blocks=blocks, asm_sub="ilu", ksp="gmres")):
+        A = O.A[1]
+        b, x0 = rng.standard_normal(A.shape[0]), rng.standard_normal(A.shape[0])
+        for k in (1, 3):
+            xk = O.gmres(1, x0, b, k)
+            z0 = O.pc_apply(1, b - A @ x0)
+            K = [z0]
+            for _ in range(k - 1):
+                K.append(O.pc_apply(1, A @ K[-1]))
+            K = np.array(K).T
+            MAK = np.array([O.pc_apply(1, A @ K[:, j]) for j in range(k)]).T
+            c = np.linalg.lstsq(MAK, z0, rcond=None)[0]
+            assert np.abs(xk - (x0 + K @ c)).max() <= 1e-11 * np.abs(xk).max()
+    tg, _ = mg.Hierarchy(lv, "linear", ksp="gmres").mg_solve_trace(4)
+    tr, _ = mg.Hierarchy(lv, "linear").mg_solve_trace(4)
+    assert tg[-1] < 0.1 * tr[-1]

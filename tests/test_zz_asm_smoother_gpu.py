@@ -138,6 +138,33 @@ def test_vanka_blocks_of_a_saddle_point_system(ctx):
     assert np.abs(Y.get() - want).max() <= 1e-10 * np.abs(want).max()
 
 
+@pytest.mark.parametrize("pc,order,npre", [("jacobi", "biquadratic", 1), ("jacobi", "linear", 3), ("ilu", "linear", 2), ("ilu", "biquadratic", 1),
+                                           ("asm8", "linear", 2)])
+def test_vcycle_trace_with_gmres_level_solver(ctx, pc, order, npre):
+    """KSPGMRES as level solver (left-preconditioned, npre = npost iterations per smoothing call) around Jacobi, around
+    ILU(0) of the whole level -- the reference's DEFAULT level solver, GMRES + ILU_PRECOND -- and around 8-element
+    blocks with exact solves; four V-cycles against the oracle."""
+    from femus_b200.poisson import PoissonMG
+    from oracle import mesh_box as mb, mg
+    kw = {} if pc == "jacobi" else dict(smoother="asm", asm_block_elems=10 ** 6 if pc == "ilu" else 8, asm_sub="ilu" if pc == "ilu" else "lu")
+    pb = PoissonMG(ctx, 2, 2, 2, 3, order, ksp="gmres", npre=npre, npost=npre, coarse_rtol=1e-15, **kw)
+    pb.assemble(); pb.galerkin(); pb.mg_set_levels()
+    lv = mb.build_hierarchy(2, 2, 2, 3)
+    if pc == "jacobi":
+        O = mg.Hierarchy(lv, order, ksp="gmres")
+    else:
+        O = _oracle(pb, lv, order, asm_sub=kw["asm_sub"], ksp="gmres")
+    trace_ref, eps_ref = O.mg_solve_trace(4, npre=npre, npost=npre)
+    trace = []
+    for _ in range(4):
+        pb.mg_solve()
+        trace.append(pb.residual_norm())
+    for a, b in zip(trace, trace_ref):
+        assert abs(a - b) <= 1e-10 * trace_ref[0], (trace, trace_ref)
+    assert np.abs(pb.EPS.get() - eps_ref).max() <= 1e-9 * np.abs(eps_ref).max()
+    del pb
+
+
 def test_block_smoother_fails_loudly(ctx):
     from femus_b200 import capi, hostapi
     H = hostapi.HostHierarchy(2, 2, 2, 2)
@@ -164,7 +191,7 @@ def test_block_smoother_fails_loudly(ctx):
 
 @pytest.mark.parametrize("mode,shape,nl,order", [("asm8", (2, 2, 2), 3, "biquadratic"), ("asmref8", (2, 2, 2), 3, "linear"),
                                                  ("asm5", (3, 2, 2), 2, "linear"), ("asmsor4096", (2, 2, 2), 3, "biquadratic"),
-                                                 ("asmilu8", (2, 2, 2), 3, "linear")])
+                                                 ("asmilu8", (2, 2, 2), 3, "linear"), ("gmresilu", (2, 2, 2), 3, "linear")])
 def test_cpp_driver_with_the_asm_level_solver(mode, shape, nl, order):
     """tests/cpp/poisson_driver.cpp through LinearEquationSolverB200Asm (the LinearEquationSolverPetscAsm surface:
     SetNumberOfSchurVariables(0), SetElementBlockNumber(n), MGSetLevel building index sets + preconditioner):
@@ -174,7 +201,7 @@ def test_cpp_driver_with_the_asm_level_solver(mode, shape, nl, order):
     from oracle import mesh_box as mb, mg
     from tests.test_adapters import _run_driver
     fam = {"linear": 0, "biquadratic": 2}[order]
-    nb = int(mode.lstrip("asmrefsoilu"))
+    nb = 10 ** 6 if mode == "gmresilu" else int(mode.lstrip("asmrefsoilu"))
     ncyc = 3
     out = _run_driver(list(shape) + [nl, fam, ncyc, mode])
     res = [float(x) for x in re.findall(r"cycle \d+ residual (\S+)", out)]
@@ -188,7 +215,7 @@ def test_cpp_driver_with_the_asm_level_solver(mode, shape, nl, order):
         blocks.append(ix.blocks())
         orders.append(gblocks)
     O = mg.Hierarchy(mb.build_hierarchy(*shape, nl), order, smoother="asm", asm_blocks=blocks, asm_orders=orders,
-                     asm_sub="ssor" if "sor" in mode else ("ilu" if "ilu" in mode else "lu"))
+                     asm_sub="ssor" if "sor" in mode else ("ilu" if "ilu" in mode else "lu"), ksp="gmres" if mode == "gmresilu" else "richardson")
     trace, eps = O.mg_solve_trace(ncyc, omega=1.0)
     free = O.bdc[-1] > 1.1
     r0 = float(np.linalg.norm(np.where(free, O.rhs, 0.0)))
