@@ -10,7 +10,8 @@ as calls into the C++ host layer and the device C ABI -- SURVEY 8f row 3, first 
     level solver        Richardson around velocity-pressure Vanka blocks       hostapi.AsmIndex(nschur=1), capi.Schwarz
     coarsest level      a direct solve (PREONLY + LU in the reference)         Multigrid.set_coarse_schwarz
 
-No arithmetic happens here: every number is produced by libfemus_b200.so.  One rank, one element type per mesh."""
+No arithmetic happens here: every number is produced by libfemus_b200.so.  One rank; meshes of several element types
+get one assembly plan per type."""
 import numpy as np
 
 from . import capi, hostapi
@@ -28,8 +29,6 @@ class StokesMG:
         nl = self.nlevels = len(lv)
         self.npre, self.npost, self.omega = npre, npost, omega
         top = lv[-1]
-        if top.elem_type < 0:
-            raise NotImplementedError("the Stokes assembly takes meshes of one element type")
         self.sys = [hostapi.SystemOnLevel(L, self.fams) for L in lv]
         self.n = self.sys[-1].n
         dirichlet = [velocity_dirichlet] * 3 + [pressure_dirichlet]
@@ -44,10 +43,15 @@ class StokesMG:
             P.zero_rows(self.bdc_idx[l], 0.0)
             P.zero_cols(self.bdc_idx[l - 1])
             self.PP[l] = P
-        self.mesh = capi.Mesh(ctx, top.xyz, top.conn)
-        t = top.elem_type
-        self.asm = capi.StokesAssembler(self.mesh, self.KK[-1], self.sys[-1].elem_dofs(), hostapi.elem_tables(t, order_v),
-                                        hostapi.elem_tables(t, order_p), navier_stokes=(equation == "navier_stokes"))
+        # one plan per element type present (the tables are the element type), all accumulating into KK and RES
+        edofs = self.sys[-1].elem_dofs()
+        self.plans = []
+        for t in ([top.elem_type] if top.elem_type >= 0 else sorted(set(top.elem_types.tolist()))):
+            sel = slice(None) if top.elem_type >= 0 else np.nonzero(top.elem_types == t)[0]
+            mesh_t = capi.Mesh(ctx, top.xyz, np.ascontiguousarray(top.conn[sel]))
+            self.plans.append((mesh_t, capi.StokesAssembler(mesh_t, self.KK[-1], np.ascontiguousarray(edofs[sel]), hostapi.elem_tables(t, order_v),
+                                                            hostapi.elem_tables(t, order_p), navier_stokes=(equation == "navier_stokes"))))
+        self.mesh, self.asm = self.plans[0]
         self.RES, self.EPS, self.SOL = ctx.vector(self.n), ctx.vector(self.n), ctx.vector(self.n)
         self.BDC, self.RESM = ctx.vector(self.bdc[-1]), ctx.vector(self.n)
         self.mg = capi.Multigrid(ctx, nl)
@@ -69,10 +73,11 @@ class StokesMG:
     def assemble(self):
         self.RES.zero()
         self.KK[-1].zero()
-        if self.equation == "navier_stokes":
-            self.asm.assemble_ns(self.SOL, self.RES, self.IRe)
-        else:
-            self.asm.assemble(self.SOL, self.RES, self.IRe)
+        for _, plan in self.plans:
+            if self.equation == "navier_stokes":
+                plan.assemble_ns(self.SOL, self.RES, self.IRe)
+            else:
+                plan.assemble(self.SOL, self.RES, self.IRe)
 
     def galerkin(self):
         for l in range(self.nlevels - 1, 0, -1):

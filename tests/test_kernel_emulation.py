@@ -270,3 +270,32 @@ def test_navier_stokes_kernel_on_the_emulator(emu, name, order_v, order_p):
     Aref = mg.on_pattern(Aref, rp, ci)
     assert np.abs(val - Aref.data).max() <= 1e-12 * np.abs(Aref.data).max()
     assert np.abs(rhs - rref).max() <= 1e-12 * np.abs(rref).max()
+
+
+def test_stokes_plans_of_a_mixed_mesh_on_the_emulator(emu):
+    """One launch per element type of the reference's mixed mesh (hexahedra, tetrahedra, wedges; Q2-Q1 / P2-P1 /
+    21-6 dofs), all accumulating into ONE system matrix and residual, as the driver's plans do."""
+    from oracle import stokes, mesh_mixed as mm, mg
+    path = os.path.join(GOLDEN, "cube_mixed.neu")
+    level, L = hostapi.HostHierarchy.from_neu(path, 1).levels[0], mm.read_neu(path)
+    fams = ["biquadratic"] * 3 + ["linear"]
+    S = hostapi.SystemOnLevel(level, fams)
+    rp, ci = S.sparsity()
+    edofs = S.elem_dofs()
+    sol = np.random.default_rng(13).standard_normal(S.n)
+    val, rhs = np.zeros(len(ci)), np.zeros(S.n)
+    xyz = np.ascontiguousarray(level.xyz)
+    for t in sorted(set(level.elem_types.tolist())):
+        sel = np.nonzero(level.elem_types == t)[0]
+        tv, tp = hostapi.elem_tables(t, "biquadratic"), hostapi.elem_tables(t, "linear")
+        nv, npr, ng = tv[0].shape[1], tp[0].shape[1], tv[4].shape[0]
+        tabv = np.concatenate([tv[1].ravel(), tv[2].ravel(), tv[3].ravel(), tv[4].ravel()])
+        tabp = np.ascontiguousarray(tp[0])
+        conn = np.ascontiguousarray(level.conn[sel], dtype=np.int32)
+        edof = np.ascontiguousarray(edofs[sel], dtype=np.int32)
+        emu.emu_stokes(len(sel), level.nnode, nv, npr, ng, _p(xyz), _p(conn), _p(edof), _p(tabv), _p(tabp), _p(rp), _p(ci), _p(val), _p(sol),
+                       _p(rhs), 0.5, 2)
+    Aref, rref = stokes.assemble(L, mm, "biquadratic", "linear", sol, 0.5, lambda t, o: mm.FE[t].tables(o))
+    Aref = mg.on_pattern(Aref, rp, ci)
+    assert np.abs(val - Aref.data).max() <= 1e-12 * np.abs(Aref.data).max()
+    assert np.abs(rhs - rref).max() <= 1e-12 * (np.abs(Aref) @ np.abs(sol)).max()

@@ -161,3 +161,22 @@ def test_cpp_stokes_driver_through_the_adapters():
         assert abs(res[k + 1] - trace[k]) <= 1e-9 * r0, (k, res[k + 1], trace[k])
     m = re.search(r"vanka blocks (\d+) groups (\d+)", r.stdout)
     assert int(m.group(1)) == ix.nblocks and int(m.group(2)) == len(gptr) - 1
+
+
+def test_stokes_assembly_on_the_mixed_mesh(ctx):
+    """One plan per element type (hexahedra, tetrahedra, wedges) accumulating into one system matrix."""
+    from femus_b200 import hostapi
+    from femus_b200.stokes import StokesMG
+    from oracle import stokes, mg, mesh_mixed as mm
+    path = os.path.join(GOLDEN, "cube_mixed.neu")
+    pb = StokesMG(ctx, hostapi.HostHierarchy.from_neu(path, 1), IRe=0.5)
+    assert len(pb.plans) == 3
+    sol = np.random.default_rng(7).standard_normal(pb.n)
+    pb.SOL.put(sol)
+    pb.assemble()
+    Aref, rref = stokes.assemble(mm.read_neu(path), mm, "biquadratic", "linear", sol, 0.5, lambda t, o: mm.FE[t].tables(o))
+    Aref = mg.on_pattern(Aref, *pb.pattern[-1])
+    A = pb.KK[-1].to_scipy()
+    assert np.abs(A.data - Aref.data).max() <= RTOL * np.abs(Aref.data).max()
+    assert np.abs(pb.RES.get() - rref).max() <= RTOL * (np.abs(Aref) @ np.abs(sol)).max()
+    del pb
