@@ -130,6 +130,7 @@ _PROTOS = {
     "b2_stokes_destroy": (ci, [vp]),
     "b2_ns_create": (ci, [vp, vp, vp, ci, ci, ci, vp, vp, vp, vp, vp, vp, vp]),
     "b2_ns_assemble": (ci, [vp, vp, vp, cd]),
+    "b2_ns_pressure_faces": (ci, [vp, i64, vp, vp, vp, ci, ci, vp, vp, vp, vp, vp, vp]),
     "b2_mg_level_bounds": (ci, [vp, ci, vp, vp]),
     "b2_mg_set_level_halo": (ci, [vp, ci, vp]),
     "b2_halo_create": (ci, [vp, i64, i64, vp, vp, i64, vp, vp, vp]),
@@ -674,6 +675,14 @@ class StokesAssembler:
 
     def assemble(self, sol=None, rhs=None, IRe=1.0):
         check(self.L.b2_stokes_assemble(self.h, sol.h if sol is not None else None, rhs.h if rhs is not None else None, float(IRe)))
+
+    def pressure_faces(self, face_elem, face_local, face_value, face_tables, face_nodes, rhs):
+        """Boundary pressure term of the Navier-Stokes residual over faces of one kind (b2_ns_pressure_faces)."""
+        fe, fl, fv = _i32(face_elem), _i32(face_local), _f64(face_value)
+        phi, dxi, deta, w = [_f64(t) for t in face_tables]
+        fn = _i32(face_nodes)
+        check(self.L.b2_ns_pressure_faces(self.h, fe.shape[0], _ptr(fe), _ptr(fl), _ptr(fv), phi.shape[1], phi.shape[0], _ptr(phi), _ptr(dxi),
+                                          _ptr(deta), _ptr(w), _ptr(fn), rhs.h))
 
     def assemble_ns(self, sol=None, rhs=None, nu=1.0):
         """Navier-Stokes residual RES = -aRes and exact Newton Jacobian (b2_ns_assemble)."""

@@ -18,6 +18,7 @@ struct b2_stokes {
 namespace {
 #include "b2_stokes_kernel.cuh"
 #include "b2_ns_kernel.cuh"
+#include "b2_neumann_kernel.cuh"
 size_t stokes_smem(int nv, int np, int ng) { return (size_t)kStokesWarps * (size_t)stokes_warp_doubles_host(nv, np, ng) * sizeof(double); }
 }  // namespace
 
@@ -118,6 +119,57 @@ int b2_ns_assemble(b2_stokes* p, const b2_vec* sol, b2_vec* rhs, double nu) {
   const size_t smem = (size_t)ns_cta_doubles_host(p->nv, p->np, p->ng) * sizeof(double);
   B2_LAUNCH(c, ns_kernel, b2_grid_for(c, nel, 1, 3), kNsThreads, smem, nel, nnode, p->nv, p->np, p->ng, xyz, conn, p->edof, p->tabns, p->tabp,
             p->A->rowptr, p->A->col, p->A->val, sol ? sol->d : nullptr, rhs ? rhs->d : nullptr, nu);
+  return 0;
+}
+
+/* rhs += the boundary pressure term of the Navier-Stokes residual over the listed faces of ONE face kind (tables as in
+ * b2_asm_neumann_faces): RES[U_k dof of face node i] -= int phi_i tau n_k (03_navier_stokes.hpp:196-300) */
+int b2_ns_pressure_faces(b2_stokes* p, int64_t nfaces, const int32_t* face_elem, const int32_t* face_local, const double* face_value, int nvf,
+                         int ngf, const double* phi, const double* dxi, const double* deta, const double* weights, const int32_t* face_nodes,
+                         b2_vec* rhs) {
+  B2_CHECK(p && rhs && phi && dxi && deta && weights && face_nodes && (nfaces == 0 || (face_elem && face_local && face_value)),
+           "b2_ns_pressure_faces: null argument");
+  B2_CHECK(nvf >= 1 && nvf <= 9 && ngf >= 1 && ngf <= 16, "b2_ns_pressure_faces: nvf=%d (1..9) or ngf=%d (1..16) out of range", nvf, ngf);
+  B2_CHECK(rhs->n >= p->A->nrows, "b2_ns_pressure_faces: rhs vector too short");
+  if (nfaces == 0) return 0;
+  b2_ctx* c = nullptr;
+  int64_t nnode = 0, nel = 0;
+  const double* xyz = nullptr;
+  const int32_t* conn = nullptr;
+  b2_mesh_view(p->mesh, &c, &nnode, &nel, &xyz, &conn);
+  for (int64_t k = 0; k < nfaces; k++) {
+    B2_CHECK(face_elem[k] >= 0 && face_elem[k] < nel && face_local[k] >= 0 && face_local[k] < 6, "b2_ns_pressure_faces: face %lld out of range", (long long)k);
+    for (int i = 0; i < nvf; i++) {
+      const int loc = face_nodes[face_local[k] * 9 + i];
+      B2_CHECK(loc >= 0 && loc < p->nv, "b2_ns_pressure_faces: face %lld: face dof %d is local node %d, not one of the %d velocity nodes", (long long)k, i, loc, p->nv);
+    }
+  }
+  int32_t *d_e = nullptr, *d_f = nullptr, *d_fn = nullptr;
+  double *d_v = nullptr, *d_t = nullptr;
+  const size_t nt = (size_t)3 * ngf * nvf + ngf;
+  std::vector<double> tab(nt);
+  std::copy(phi, phi + ngf * nvf, tab.begin());
+  std::copy(dxi, dxi + ngf * nvf, tab.begin() + ngf * nvf);
+  std::copy(deta, deta + ngf * nvf, tab.begin() + 2 * ngf * nvf);
+  std::copy(weights, weights + ngf, tab.begin() + 3 * ngf * nvf);
+  B2_TRY(b2_malloc(c, &d_e, (size_t)nfaces));
+  B2_TRY(b2_malloc(c, &d_f, (size_t)nfaces));
+  B2_TRY(b2_malloc(c, &d_v, (size_t)nfaces));
+  B2_TRY(b2_malloc(c, &d_t, nt));
+  B2_TRY(b2_malloc(c, &d_fn, 54));
+  B2_TRY(b2_upload(c, d_e, face_elem, (size_t)nfaces));
+  B2_TRY(b2_upload(c, d_f, face_local, (size_t)nfaces));
+  B2_TRY(b2_upload(c, d_v, face_value, (size_t)nfaces));
+  B2_TRY(b2_upload(c, d_t, tab.data(), nt));
+  B2_TRY(b2_upload(c, d_fn, face_nodes, 54));
+  B2_LAUNCH(c, pressure_face_kernel, b2_grid_for(c, nfaces * 32, 256, 8), 256, 0, nfaces, d_e, d_f, d_v, nvf, ngf, d_t, d_fn, nnode, xyz, conn,
+            p->edof, rhs->d);
+  B2_CUDA(cudaStreamSynchronize(c->stream));
+  b2_free(c, d_e, (size_t)nfaces);
+  b2_free(c, d_f, (size_t)nfaces);
+  b2_free(c, d_v, (size_t)nfaces);
+  b2_free(c, d_t, nt);
+  b2_free(c, d_fn, 54);
   return 0;
 }
 

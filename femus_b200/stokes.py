@@ -20,9 +20,11 @@ from . import capi, hostapi
 class StokesMG:
     def __init__(self, ctx, hier, order_v="biquadratic", order_p="linear", IRe=1.0, velocity_dirichlet=(1, 2, 3, 4, 5, 6),
                  pressure_dirichlet=(), npre=1, npost=1, omega=1.0, block_elems=1, schedule="colours", equation="stokes",
-                 block_sub="lu"):
+                 block_sub="lu", boundary_pressure=None):
         """equation: "stokes" (SteadyStokes/main.cpp, IRe = the viscosity factor) or "navier_stokes" (the library routine
-        03_navier_stokes.hpp: Galerkin residual + exact Newton Jacobian, IRe = nu)."""
+        03_navier_stokes.hpp: Galerkin residual + exact Newton Jacobian, IRe = nu).  boundary_pressure: {boundary set:
+        prescribed pressure tau} for the faces whose normal velocity is not Dirichlet (the routine's boundary block,
+        :196-300; Navier-Stokes only)."""
         self.ctx, self.hier, self.IRe, self.equation = ctx, hier, IRe, equation
         self.fams = [order_v] * 3 + [order_p]
         lv = hier.levels
@@ -46,11 +48,16 @@ class StokesMG:
         # one plan per element type present (the tables are the element type), all accumulating into KK and RES
         edofs = self.sys[-1].elem_dofs()
         self.plans = []
+        self.pressure_groups = []
         for t in ([top.elem_type] if top.elem_type >= 0 else sorted(set(top.elem_types.tolist()))):
             sel = slice(None) if top.elem_type >= 0 else np.nonzero(top.elem_types == t)[0]
             mesh_t = capi.Mesh(ctx, top.xyz, np.ascontiguousarray(top.conn[sel]))
             self.plans.append((mesh_t, capi.StokesAssembler(mesh_t, self.KK[-1], np.ascontiguousarray(edofs[sel]), hostapi.elem_tables(t, order_v),
                                                             hostapi.elem_tables(t, order_p), navier_stokes=(equation == "navier_stokes"))))
+            if boundary_pressure:
+                from .poisson import neumann_face_groups
+                for faces, tabs, fnodes in neumann_face_groups(top, order_v, dict(boundary_pressure), t, sel):
+                    self.pressure_groups.append((self.plans[-1][1], faces, tabs, fnodes))
         self.mesh, self.asm = self.plans[0]
         self.RES, self.EPS, self.SOL = ctx.vector(self.n), ctx.vector(self.n), ctx.vector(self.n)
         self.BDC, self.RESM = ctx.vector(self.bdc[-1]), ctx.vector(self.n)
@@ -78,6 +85,9 @@ class StokesMG:
                 plan.assemble_ns(self.SOL, self.RES, self.IRe)
             else:
                 plan.assemble(self.SOL, self.RES, self.IRe)
+        if self.equation == "navier_stokes":
+            for plan, faces, tabs, fnodes in self.pressure_groups:
+                plan.pressure_faces(*faces, tabs, fnodes, self.RES)
 
     def galerkin(self):
         for l in range(self.nlevels - 1, 0, -1):

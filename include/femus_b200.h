@@ -297,6 +297,14 @@ int b2_stokes_destroy(b2_stokes* p);
 int b2_ns_create(b2_mesh* mesh, b2_csr* A, const int32_t* elem_dofs, int nve_v, int nve_p, int ngauss, const double* phi_v, const double* dxi,
                  const double* deta, const double* dzeta, const double* weights, const double* phi_p, b2_stokes** out);
 int b2_ns_assemble(b2_stokes* p, const b2_vec* sol, b2_vec* rhs, double nu);
+/* boundary pressure term of the same routine (:196-300): on the listed boundary faces (one face kind per call, tables and
+ * face_nodes as in b2_asm_neumann_faces, velocity family) RES[U_k dof of face node i] -= int phi_i tau n_k, tau = the
+ * prescribed boundary pressure of the face (face_value; the reference evaluates its boundary callback per Gauss point),
+ * n = the unit normal of elem_type_2D::JacobianSur at the Gauss point.  Which faces qualify (normal velocity
+ * component not Dirichlet, :262-266) is the caller's selection. */
+int b2_ns_pressure_faces(b2_stokes* p, int64_t nfaces, const int32_t* face_elem, const int32_t* face_local, const double* face_value, int nvf,
+                         int ngf, const double* phi, const double* dxi, const double* deta, const double* weights, const int32_t* face_nodes,
+                         b2_vec* rhs);
 
 /* ---- element-block (ASM / Vanka) smoother: LinearEquationSolverPetscAsm (petsc_asm/LinearEquationSolverPetscAsm.cpp)
  * What the reference sets (:266-340, PetscPreconditioner.cpp:179-184): PCASM, PC_ASM_BASIC, local type

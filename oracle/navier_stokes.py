@@ -77,3 +77,44 @@ def assemble(L, mesh, order_v, order_p, sol, nu, tables_of):
     A = sp.coo_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(n, n)).tocsr()
     A.sort_indices()
     return A, rhs
+
+
+def pressure_boundary_rhs(L, mesh, order_v, order_p, tau_by_set):
+    """Boundary pressure term (03_navier_stokes.hpp:196-300): for every boundary face whose set index is a key of
+    tau_by_set (the caller's selection of the faces whose normal velocity component is not Dirichlet, :262-266),
+    aResV[k][face node i] += phi_i tau n_k weight_g with the face element of the velocity family and the unit normal of
+    JacobianSur at the Gauss point; returned as the RES contribution (-aRes) in system numbering."""
+    from . import asm, fe_face, mesh_mixed as mm
+    orders = [order_v] * 3 + [order_p]
+    fi = [mesh.FAMILY[o] for o in orders]
+    KK = asm.kk_offsets(L, fi)
+    rhs = np.zeros(int(KK[-1, -1]))
+    etype = getattr(L, "etype", None)
+    tabs = {k: fe_face.tables(k, order_v) for k in ("tri", "quad")}
+    for e in range(L.nel):
+        t = int(etype[e]) if etype is not None else mm.HEX
+        for f in range(mm.NFACES[t]):
+            b = -(int(L.face[e, f]) + 1)
+            if b <= 0 or b not in tau_by_set:
+                continue
+            kind = fe_face.face_kind(mm.FACE_NVERT[t][f])
+            loc = mm.FACE_NODES[t][f][:fe_face.ndofs(kind, order_v)]
+            nodes = L.conn[e, loc]
+            X = L.xyz[:, nodes]
+            sdof = mm.node_dof(L, order_v, nodes) if hasattr(L, "etype") else _box_node_dof(L, mesh, order_v, nodes)
+            for ig in range(tabs[kind][3].shape[0]):
+                wt, phi, nrm = fe_face.jacobian_sur(X, ig, tabs[kind])
+                for k in range(3):
+                    for i, s in enumerate(sdof):
+                        rhs[asm.system_dof(L, KK, fi, k, int(s))] -= phi[i] * float(tau_by_set[b]) * nrm[k] * wt
+    return rhs
+
+
+def _box_node_dof(L, mesh, order, nodes):
+    """solution dof of family `order` of the given nodes on a box level (mesh_box numbering)."""
+    k = mesh.FAMILY[order]
+    nodes = np.asarray(nodes)
+    if k == 2:
+        return nodes.copy()
+    p = np.searchsorted(L.dof_offset[2], nodes, side="right") - 1
+    return (nodes - L.dof_offset[2][p]) + L.dof_offset[k][p]

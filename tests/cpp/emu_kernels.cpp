@@ -103,4 +103,9 @@ void emu_ns(int64_t nel, int64_t nnode, int nv, int np, int ng, const double* xy
               nu);
 }
 
+void emu_pressure_faces(int64_t nfaces, const int32_t* felem, const int32_t* flocal, const double* fvalue, int nvf, int ngf, const double* ftab,
+                        const int32_t* fnodes, int64_t nnode, const double* xyz, const int32_t* conn, const int32_t* edof, double* rhs, int grid) {
+  emu::launch(pressure_face_kernel, (unsigned)grid, 256u, 0, nfaces, felem, flocal, fvalue, nvf, ngf, ftab, fnodes, nnode, xyz, conn, edof, rhs);
+}
+
 }  // extern "C"

@@ -31,6 +31,8 @@ def emu(tmp_path_factory):
     L.emu_stokes.restype = None
     L.emu_stokes.argtypes = [ctypes.c_int64, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp,
                              ctypes.c_double, ctypes.c_int]
+    L.emu_pressure_faces.restype = None
+    L.emu_pressure_faces.argtypes = [ctypes.c_int64, vp, vp, vp, ctypes.c_int, ctypes.c_int, vp, vp, ctypes.c_int64, vp, vp, vp, vp, ctypes.c_int]
     L.emu_ns.restype = None
     L.emu_ns.argtypes = L.emu_stokes.argtypes
     return L
@@ -299,3 +301,31 @@ def test_stokes_plans_of_a_mixed_mesh_on_the_emulator(emu):
     Aref = mg.on_pattern(Aref, rp, ci)
     assert np.abs(val - Aref.data).max() <= 1e-12 * np.abs(Aref.data).max()
     assert np.abs(rhs - rref).max() <= 1e-12 * (np.abs(Aref) @ np.abs(sol)).max()
+
+
+@pytest.mark.parametrize("name,order_v", [("cube_tet10", "quadratic"), ("cube_wedge18", "biquadratic"), ("cube_hex27_2x2x2", "biquadratic")])
+def test_boundary_pressure_kernel_on_the_emulator(emu, name, order_v):
+    """pressure_face_kernel: RES[U_k] -= int phi_i tau n_k over triangular and quadrilateral boundary faces (the boundary
+    block of 03_navier_stokes.hpp:196-300) against the oracle; on a closed surface with constant tau the contributions of
+    every component sum to zero (divergence theorem)."""
+    from femus_b200.poisson import neumann_face_groups
+    from oracle import navier_stokes as ons, mesh_mixed as mm
+    path = os.path.join(GOLDEN, name + ".neu")
+    level, L = hostapi.HostHierarchy.from_neu(path, 1).levels[0], mm.read_neu(path)
+    fams = [order_v] * 3 + ["linear"]
+    S = hostapi.SystemOnLevel(level, fams)
+    edof = np.ascontiguousarray(S.elem_dofs(), dtype=np.int32)
+    xyz, conn = np.ascontiguousarray(level.xyz), np.ascontiguousarray(level.conn, dtype=np.int32)
+    for tau in ({2: 1.5, 5: -0.4}, {b: 1.0 for b in range(1, 7)}):
+        rhs = np.zeros(S.n)
+        for (fe, fl, fv), (phi, dxi, deta, w), fnodes in neumann_face_groups(level, order_v, tau, level.elem_type, slice(None)):
+            tab = np.concatenate([phi.ravel(), dxi.ravel(), deta.ravel(), w.ravel()])
+            fn = np.ascontiguousarray(fnodes, dtype=np.int32)
+            emu.emu_pressure_faces(len(fe), _p(fe), _p(fl), _p(fv), phi.shape[1], phi.shape[0], _p(tab), _p(fn), level.nnode, _p(xyz), _p(conn),
+                                   _p(edof), _p(rhs), 2)
+        want = ons.pressure_boundary_rhs(L, mm, order_v, "linear", tau)
+        assert np.abs(want).max() > 0 and np.abs(rhs - want).max() <= 1e-13 * np.abs(want).max()
+        if len(tau) == 6:
+            nq = level.ndofs(order_v)
+            for k in range(3):
+                assert abs(rhs[k * nq:(k + 1) * nq].sum()) <= 1e-13

@@ -180,3 +180,23 @@ def test_stokes_assembly_on_the_mixed_mesh(ctx):
     assert np.abs(A.data - Aref.data).max() <= RTOL * np.abs(Aref.data).max()
     assert np.abs(pb.RES.get() - rref).max() <= RTOL * (np.abs(Aref) @ np.abs(sol)).max()
     del pb
+
+
+def test_navier_stokes_boundary_pressure_term(ctx):
+    """Pressure-driven channel: prescribed pressures on the open boundary sets 2 (outflow) and 1 (inflow), no-slip
+    elsewhere: the residual at a random solution = volume part + boundary pressure block (03_navier_stokes.hpp:196-300)
+    against the oracle."""
+    from femus_b200 import hostapi
+    from femus_b200.stokes import StokesMG
+    from oracle import navier_stokes as ons, mesh_box as mb, fe_hex
+    tau = {1: 2.0, 2: -0.5}
+    H, lv = hostapi.HostHierarchy(2, 2, 2, 1), mb.build_hierarchy(2, 2, 2, 1)
+    pb = StokesMG(ctx, H, IRe=0.3, velocity_dirichlet=(3, 4, 5, 6), equation="navier_stokes", boundary_pressure=tau)
+    sol = 0.3 * np.random.default_rng(8).standard_normal(pb.n)
+    pb.SOL.put(sol)
+    pb.assemble()
+    _, rref = ons.assemble(lv[-1], mb, "biquadratic", "linear", sol, 0.3, lambda t, o: fe_hex.tables(o))
+    rb = ons.pressure_boundary_rhs(lv[-1], mb, "biquadratic", "linear", tau)
+    assert np.abs(rb).max() > 0
+    assert np.abs(pb.RES.get() - (rref + rb)).max() <= RTOL * np.abs(rref + rb).max()
+    del pb
