@@ -86,16 +86,23 @@ int b2_schwarz_create(b2_ctx* c, b2_csr* A, int64_t nblocks, const int64_t* blk_
   s->max_m = max_m;
   s->group_ptr.assign(group_ptr, group_ptr + ngroups + 1);
   *out = s;
-  B2_TRY(b2_malloc(c, &s->blk_ptr, (size_t)nblocks + 1));
-  B2_TRY(b2_malloc(c, &s->blk_dofs, (size_t)s->ndofs_total));
-  B2_TRY(b2_malloc(c, &s->inv_ptr, (size_t)nblocks + 1));
-  B2_TRY(b2_malloc(c, &s->group_blocks, (size_t)nblocks));
-  B2_TRY(b2_malloc(c, &s->err, 1));
-  B2_TRY(b2_upload(c, s->blk_ptr, blk_ptr, (size_t)nblocks + 1));
-  B2_TRY(b2_upload(c, s->blk_dofs, blk_dofs, (size_t)s->ndofs_total));
-  B2_TRY(b2_upload(c, s->inv_ptr, inv_ptr.data(), (size_t)nblocks + 1));
-  B2_TRY(b2_upload(c, s->group_blocks, group_blocks, (size_t)nblocks));
-  return 0;
+  const int rc = [&]() -> int {
+    B2_TRY(b2_malloc(c, &s->blk_ptr, (size_t)nblocks + 1));
+    B2_TRY(b2_malloc(c, &s->blk_dofs, (size_t)s->ndofs_total));
+    B2_TRY(b2_malloc(c, &s->inv_ptr, (size_t)nblocks + 1));
+    B2_TRY(b2_malloc(c, &s->group_blocks, (size_t)nblocks));
+    B2_TRY(b2_malloc(c, &s->err, 1));
+    B2_TRY(b2_upload(c, s->blk_ptr, blk_ptr, (size_t)nblocks + 1));
+    B2_TRY(b2_upload(c, s->blk_dofs, blk_dofs, (size_t)s->ndofs_total));
+    B2_TRY(b2_upload(c, s->inv_ptr, inv_ptr.data(), (size_t)nblocks + 1));
+    B2_TRY(b2_upload(c, s->group_blocks, group_blocks, (size_t)nblocks));
+    return 0;
+  }();
+  if (rc) {               // nothing half-built is handed out
+    b2_schwarz_destroy(s);
+    *out = nullptr;
+  }
+  return rc;
 }
 
 /* block solve: 0 = exact (MLU_PRECOND on the blocks; dense inverses, blocks of at most 4096 dofs), 1 = one SSOR

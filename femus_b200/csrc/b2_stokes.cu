@@ -58,15 +58,22 @@ int b2_stokes_create(b2_mesh* mesh, b2_csr* A, const int32_t* elem_dofs, int nve
   std::copy(deta, deta + ngauss * nve_v, tab.begin() + ngauss * nve_v);
   std::copy(dzeta, dzeta + ngauss * nve_v, tab.begin() + 2 * ngauss * nve_v);
   std::copy(weights, weights + ngauss, tab.begin() + 3 * ngauss * nve_v);
-  B2_TRY(b2_malloc(c, &p->edof, (size_t)nel * 108));
-  B2_TRY(b2_malloc(c, &p->tabv, nt));
-  B2_TRY(b2_malloc(c, &p->tabp, (size_t)ngauss * nve_p));
-  B2_TRY(b2_upload(c, p->edof, elem_dofs, (size_t)nel * 108));
-  B2_TRY(b2_upload(c, p->tabv, tab.data(), nt));
-  B2_TRY(b2_upload(c, p->tabp, phi_p, (size_t)ngauss * nve_p));
-  const size_t smem = stokes_smem(nve_v, nve_p, ngauss);
-  if (smem > 48 * 1024) B2_CUDA(cudaFuncSetAttribute(stokes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  return 0;
+  const int rc = [&]() -> int {
+    B2_TRY(b2_malloc(c, &p->edof, (size_t)nel * 108));
+    B2_TRY(b2_malloc(c, &p->tabv, nt));
+    B2_TRY(b2_malloc(c, &p->tabp, (size_t)ngauss * nve_p));
+    B2_TRY(b2_upload(c, p->edof, elem_dofs, (size_t)nel * 108));
+    B2_TRY(b2_upload(c, p->tabv, tab.data(), nt));
+    B2_TRY(b2_upload(c, p->tabp, phi_p, (size_t)ngauss * nve_p));
+    const size_t smem = stokes_smem(nve_v, nve_p, ngauss);
+    if (smem > 48 * 1024) B2_CUDA(cudaFuncSetAttribute(stokes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    return 0;
+  }();
+  if (rc) {               // nothing half-built is handed out
+    b2_stokes_destroy(p);
+    *out = nullptr;
+  }
+  return rc;
 }
 
 /* A += the Stokes element blocks, rhs += the residual F = -B sol at the current solution (sol in system numbering,
@@ -91,6 +98,7 @@ int b2_ns_create(b2_mesh* mesh, b2_csr* A, const int32_t* elem_dofs, int nve_v, 
   B2_CHECK(phi_v, "b2_ns_create: null argument");
   B2_TRY(b2_stokes_create(mesh, A, elem_dofs, nve_v, nve_p, ngauss, dxi, deta, dzeta, weights, phi_p, out));
   b2_stokes* p = *out;
+  const int rc = [&]() -> int {
   const size_t nt = (size_t)4 * ngauss * nve_v + ngauss;
   std::vector<double> tab(nt);
   std::copy(phi_v, phi_v + ngauss * nve_v, tab.begin());
@@ -104,6 +112,12 @@ int b2_ns_create(b2_mesh* mesh, b2_csr* A, const int32_t* elem_dofs, int nve_v, 
   B2_CHECK(smem <= 227 * 1024, "b2_ns_create: %zu bytes of shared memory per element exceed the SM", smem);
   if (smem > 48 * 1024) B2_CUDA(cudaFuncSetAttribute(ns_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   return 0;
+  }();
+  if (rc) {
+    b2_stokes_destroy(p);
+    *out = nullptr;
+  }
+  return rc;
 }
 
 /* A += the exact Newton Jacobian, rhs += RES = -aRes of the steady Navier-Stokes residual at the current solution
