@@ -99,19 +99,19 @@ int b2_ns_create(b2_mesh* mesh, b2_csr* A, const int32_t* elem_dofs, int nve_v, 
   B2_TRY(b2_stokes_create(mesh, A, elem_dofs, nve_v, nve_p, ngauss, dxi, deta, dzeta, weights, phi_p, out));
   b2_stokes* p = *out;
   const int rc = [&]() -> int {
-  const size_t nt = (size_t)4 * ngauss * nve_v + ngauss;
-  std::vector<double> tab(nt);
-  std::copy(phi_v, phi_v + ngauss * nve_v, tab.begin());
-  std::copy(dxi, dxi + ngauss * nve_v, tab.begin() + ngauss * nve_v);
-  std::copy(deta, deta + ngauss * nve_v, tab.begin() + 2 * ngauss * nve_v);
-  std::copy(dzeta, dzeta + ngauss * nve_v, tab.begin() + 3 * ngauss * nve_v);
-  std::copy(weights, weights + ngauss, tab.begin() + 4 * ngauss * nve_v);
-  B2_TRY(b2_malloc(p->ctx, &p->tabns, nt));
-  B2_TRY(b2_upload(p->ctx, p->tabns, tab.data(), nt));
-  const size_t smem = (size_t)ns_cta_doubles_host(nve_v, nve_p, ngauss) * sizeof(double);
-  B2_CHECK(smem <= 227 * 1024, "b2_ns_create: %zu bytes of shared memory per element exceed the SM", smem);
-  if (smem > 48 * 1024) B2_CUDA(cudaFuncSetAttribute(ns_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  return 0;
+    const size_t nt = (size_t)4 * ngauss * nve_v + ngauss;
+    std::vector<double> tab(nt);
+    std::copy(phi_v, phi_v + ngauss * nve_v, tab.begin());
+    std::copy(dxi, dxi + ngauss * nve_v, tab.begin() + ngauss * nve_v);
+    std::copy(deta, deta + ngauss * nve_v, tab.begin() + 2 * ngauss * nve_v);
+    std::copy(dzeta, dzeta + ngauss * nve_v, tab.begin() + 3 * ngauss * nve_v);
+    std::copy(weights, weights + ngauss, tab.begin() + 4 * ngauss * nve_v);
+    B2_TRY(b2_malloc(p->ctx, &p->tabns, nt));
+    B2_TRY(b2_upload(p->ctx, p->tabns, tab.data(), nt));
+    const size_t smem = (size_t)ns_cta_doubles_host(nve_v, nve_p, ngauss) * sizeof(double);
+    B2_CHECK(smem <= 227 * 1024, "b2_ns_create: %zu bytes of shared memory per element exceed the SM", smem);
+    if (smem > 48 * 1024) B2_CUDA(cudaFuncSetAttribute(ns_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    return 0;
   }();
   if (rc) {
     b2_stokes_destroy(p);
