@@ -7,7 +7,8 @@ import os
 import numpy as np
 import pytest
 
-pytestmark = pytest.mark.gpu
+# never run on a GPU yet: a kernel that hangs must not hang the box (the thread method ends the process)
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(900, method="thread")]
 RTOL = 1e-12
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
 
