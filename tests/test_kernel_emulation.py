@@ -6,6 +6,7 @@ tests (tests/test_tri_faces_gpu.py, tests/test_zz_asm_smoother_gpu.py) remain th
 import ctypes
 import os
 import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -329,3 +330,36 @@ def test_boundary_pressure_kernel_on_the_emulator(emu, name, order_v):
             nq = level.ndofs(order_v)
             for k in range(3):
                 assert abs(rhs[k * nq:(k + 1) * nq].sum()) <= 1e-13
+
+
+def _libtsan():
+    r = subprocess.run(["gcc", "-print-file-name=libtsan.so"], capture_output=True, text=True)
+    p = r.stdout.strip()
+    return p if r.returncode == 0 and os.path.isabs(p) and os.path.exists(p) else None
+
+
+@pytest.mark.skipif(_libtsan() is None, reason="libtsan not available")
+def test_kernels_are_race_free_under_thread_sanitizer(tmp_path):
+    """The emulator plays every CUDA thread with a host thread and every __syncthreads / __syncwarp with a barrier, so a
+    missing synchronisation in a kernel IS a data race ThreadSanitizer reports.  First the detector is proven on a probe
+    kernel (racy without its barrier, clean with it); then the block-smoother (exact, SSOR, ILU(0)), Stokes,
+    Navier-Stokes, Neumann and boundary-pressure kernels run under it against the oracle without a single report."""
+    cpp = os.path.join(ROOT, "tests", "cpp")
+    probe = str(tmp_path / "probe")
+    r = subprocess.run(["g++", "-std=c++20", "-O1", "-g", "-pthread", "-fsanitize=thread", "-o", probe, os.path.join(cpp, "emu_race_probe.cpp")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    env = dict(os.environ, TSAN_OPTIONS="exitcode=0 report_signal_unsafe=0")
+    racy = subprocess.run([probe], capture_output=True, text=True, env=env)
+    clean = subprocess.run([probe, "sync"], capture_output=True, text=True, env=env)
+    if "FATAL: ThreadSanitizer" in racy.stderr + clean.stderr:
+        pytest.skip("ThreadSanitizer cannot run in this environment: " + (racy.stderr + clean.stderr)[:200])
+    assert "WARNING: ThreadSanitizer: data race" in racy.stderr and "ThreadSanitizer" not in clean.stderr
+    so = str(tmp_path / "libemu_tsan.so")
+    r = subprocess.run(["g++", "-std=c++20", "-O1", "-g", "-pthread", "-shared", "-fPIC", "-fsanitize=thread", "-o", so, os.path.join(cpp, "emu_kernels.cpp")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    env["LD_PRELOAD"] = _libtsan()
+    run = subprocess.run([sys.executable, os.path.join(cpp, "tsan_runner.py"), so], capture_output=True, text=True, env=env, timeout=1500)
+    assert "tsan-run-finished" in run.stdout, run.stdout[-2000:] + run.stderr[-4000:]
+    assert "WARNING: ThreadSanitizer" not in run.stderr, run.stderr[:6000]
