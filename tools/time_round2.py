@@ -35,7 +35,7 @@ def timed(fn, reps=5, warm=2):
     return ctx.timer_stop_ms() / reps
 
 
-for sub in ("lu", "ssor"):
+for sub in ("lu", "ssor", "ilu"):
     pb = PoissonMG(ctx, n0, n0, n0, nl, order, smoother="asm", asm_block_elems=8, asm_schedule="colours", asm_sub=sub, omega=1.0)
     pb.assemble(); pb.galerkin(); pb.mg_set_levels()
     top = nl - 1
@@ -46,7 +46,9 @@ for sub in ("lu", "ssor"):
     A = pb.KK[top]
     m = np.diff(ix.overlap_ptr)
     rows_nnz = int(A.nnz * (m.sum() / n))                  # every dof sits in m.sum()/n blocks on average
-    alg = (8 * int((m.astype(np.int64) ** 2).sum()) if sub == "lu" else 0) + 12 * rows_nnz * (1 if sub == "lu" else 3) + 24 * int(m.sum())
+    # exact: inverse + one pass over the rows; SSOR: three passes over the rows; ILU(0): one pass + the factor twice
+    alg = {"lu": 8 * int((m.astype(np.int64) ** 2).sum()) + 12 * rows_nnz, "ssor": 3 * 12 * rows_nnz, "ilu": 12 * rows_nnz + 2 * 12 * rows_nnz}[sub] \
+        + 24 * int(m.sum())
     trace = []
     for _ in range(4):
         pb.mg_solve()
@@ -58,14 +60,15 @@ for sub in ("lu", "ssor"):
                       "residual_trace": trace}))
     del pb, S
 
-pb = PoissonMG(ctx, n0, n0, n0, nl, order)
-pb.assemble(); pb.galerkin(); pb.mg_set_levels()
-trace = []
-for _ in range(4):
-    pb.mg_solve()
-    trace.append(pb.residual_norm())
-print(json.dumps({"kernel": "vcycle_richardson_jacobi", "vcycle_ms": timed(lambda: pb.mg_solve(), reps=3, warm=1), "residual_trace": trace}))
-del pb
+for ksp in ("richardson", "gmres"):
+    pb = PoissonMG(ctx, n0, n0, n0, nl, order, ksp=ksp)
+    pb.assemble(); pb.galerkin(); pb.mg_set_levels()
+    trace = []
+    for _ in range(4):
+        pb.mg_solve()
+        trace.append(pb.residual_norm())
+    print(json.dumps({"kernel": f"vcycle_{ksp}_jacobi", "vcycle_ms": timed(lambda: pb.mg_solve(), reps=3, warm=1), "residual_trace": trace}))
+    del pb
 
 # table-driven assembly kernel on tetrahedra: the reference's cube_Tet coarse mesh (105 elements) refined
 path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "cube_tet10.neu")
