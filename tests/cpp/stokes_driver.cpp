@@ -4,11 +4,14 @@
 // LinearEquationSolverB200Asm (the LinearEquationSolverPetscAsm surface: Vanka blocks with the pressure as Schur
 // variable) and the host mesh layer.  tests/test_zz_stokes_gpu.py runs it on the GPU against the oracle.
 //
-//   stokes_driver nx ny nz nlevels ncycles
+//   stokes_driver nx ny nz nlevels ncycles [ns]
 //
 // Velocity Dirichlet on the boundary sets 1, 3, 4, 5, 6 (U = 1 on set 6), natural outflow on set 2, IRe = 1.
+// "ns": the steady Navier-Stokes routine (03_navier_stokes.hpp) at nu = 0.1 instead -- every cycle is then one Newton
+// iteration of NonLinearImplicitSystem::solve (residual + exact Jacobian at Sol, three V-cycles, update).
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <memory>
 #include "../../femus_b200/host/LinearEquationSolverB200Asm.hpp"
 
@@ -18,6 +21,8 @@ using namespace femus_b200;
 int main(int argc, char** argv) {
   if (argc < 6) { std::fprintf(stderr, "usage: %s nx ny nz nlevels ncycles\n", argv[0]); return 2; }
   const int nx = std::atoi(argv[1]), ny = std::atoi(argv[2]), nz = std::atoi(argv[3]), nl = std::atoi(argv[4]), ncycles = std::atoi(argv[5]);
+  const bool ns = argc > 6 && std::strcmp(argv[6], "ns") == 0;
+  const int vcycles = ns ? 3 : 1;
   const std::vector<int> families = {BIQUADRATIC, BIQUADRATIC, BIQUADRATIC, LINEAR};       // system "Navier-Stokes": U, V, W, P
 
   std::vector<MeshLevel> msh;
@@ -60,9 +65,14 @@ int main(int argc, char** argv) {
   b2_mesh* dmesh = nullptr;
   b2_stokes* plan = nullptr;
   B2_ABORT_IF(b2_mesh_create(B200Context::get(), top.nnode, top.nel, top.xyz.data(), top.conn.data(), &dmesh), "b2_mesh_create");
-  B2_ABORT_IF(b2_stokes_create(dmesh, fine._KK->handle(), edof.data(), tv.nve, tp.nve, HexElement::NG, tv.dxi.data(), tv.deta.data(),
-                               tv.dzeta.data(), tv.w.data(), tp.phi.data(), &plan),
-              "b2_stokes_create");
+  if (ns)
+    B2_ABORT_IF(b2_ns_create(dmesh, fine._KK->handle(), edof.data(), tv.nve, tp.nve, HexElement::NG, tv.phi.data(), tv.dxi.data(), tv.deta.data(),
+                             tv.dzeta.data(), tv.w.data(), tp.phi.data(), &plan),
+                "b2_ns_create");
+  else
+    B2_ABORT_IF(b2_stokes_create(dmesh, fine._KK->handle(), edof.data(), tv.nve, tp.nve, HexElement::NG, tv.dxi.data(), tv.deta.data(),
+                                 tv.dzeta.data(), tv.w.data(), tp.phi.data(), &plan),
+                "b2_stokes_create");
   B200Vector Sol((int)sys.size());
   {
     const std::vector<double> on_lid = SystemBdc(top, sys, lid);
@@ -77,7 +87,8 @@ int main(int argc, char** argv) {
     fine.SetResZero();
     fine.SetEpsZero();
     fine._KK->zero();
-    B2_ABORT_IF(b2_stokes_assemble(plan, Sol.handle(), fine._RES->handle(), 1.0), "b2_stokes_assemble");
+    if (ns) B2_ABORT_IF(b2_ns_assemble(plan, Sol.handle(), fine._RES->handle(), 0.1), "b2_ns_assemble");
+    else B2_ABORT_IF(b2_stokes_assemble(plan, Sol.handle(), fine._RES->handle(), 1.0), "b2_stokes_assemble");
     fine._KK->touched();
     fine._RES->touched();
     {
@@ -91,7 +102,7 @@ int main(int argc, char** argv) {
     for (int l = nl - 1; l > 0; l--) LinSolver[l - 1]->_KK->matrix_PtAP(*PP[l], *LinSolver[l]->_KK, true);
     fine.MGInit(MULTIPLICATIVE, (unsigned)nl, PREONLY_B200);
     for (int l = 0; l < nl; l++) LinSolver[l]->MGSetLevel(&fine, (unsigned)(nl - 1), vars, l ? PP[l].get() : nullptr, nullptr, 1, 1);
-    fine.MGSolve(true);
+    for (int v = 0; v < vcycles; v++) fine.MGSolve(true);
     fine.MGClear();
     Sol += *fine._EPS;
   }

@@ -201,3 +201,40 @@ def test_navier_stokes_boundary_pressure_term(ctx):
     assert np.abs(rb).max() > 0
     assert np.abs(pb.RES.get() - (rref + rb)).max() <= RTOL * np.abs(rref + rb).max()
     del pb
+
+
+def test_cpp_driver_newton_iterations_of_navier_stokes():
+    """stokes_driver ... ns: b2_ns_assemble through the adapters, one Newton iteration per cycle (three V-cycles each);
+    the residual before every update against the oracle Newton-multigrid pipeline."""
+    import re
+    import subprocess
+    from femus_b200 import build, hostapi
+    from oracle import navier_stokes as ons, mg, system as osys, mesh_box as mb, fe_hex
+    ncyc = 3
+    r = subprocess.run([build.STOKES_DRIVER, "2", "2", "2", "2", str(ncyc), "ns"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    res = [float(x) for x in re.findall(r"cycle \d+ residual (\S+)", r.stdout)]
+    assert len(res) == ncyc + 1
+    H, lv = hostapi.HostHierarchy(2, 2, 2, 2), mb.build_hierarchy(2, 2, 2, 2)
+    fams = ["biquadratic"] * 3 + ["linear"]
+    walls = (1, 3, 4, 5, 6)
+    S = hostapi.SystemOnLevel(H.levels[-1], fams)
+    rp, ci = S.sparsity()
+    ix = hostapi.AsmIndex(H.levels[1], fams, 1, nschur=1)
+    grp, gptr, gblocks = hostapi.asm_schedule(rp, ci, ix.overlap_ptr, ix.overlap, "colours")
+    smesh = osys.SystemMesh(mb, fams, [walls] * 3 + [()])
+    free = smesh.bdc_flags(lv[-1], None) > 1.1
+    sol = np.zeros(S.n)
+    sol[osys.bdc(lv[-1], mb, fams, [(6,), (), (), ()]) < 1.5] = 1.0
+    want = []
+    for it in range(ncyc + 1):
+        A, rhs = ons.assemble(lv[-1], mb, "biquadratic", "linear", sol, 0.1, lambda t, o: fe_hex.tables(o))
+        want.append(float(np.linalg.norm(np.where(free, rhs, 0.0))))
+        if it == ncyc:
+            break
+        O = mg.Hierarchy(lv, None, mesh=smesh, A_top=mg.on_pattern(A, rp, ci), rhs=rhs, smoother="asm", asm_blocks=[None, ix.blocks()],
+                         asm_orders=[None, gblocks])
+        sol = sol + O.mg_solve_trace(3, omega=1.0)[1]
+    for a, b in zip(res, want):
+        assert abs(a - b) <= 1e-9 * want[0], (res, want)
+    assert res[-1] < 1e-3 * res[0]
