@@ -117,6 +117,8 @@ _PROTOS = {
     "b2_mg_set_smoother": (ci, [vp, ci, ci, cd, cd]),
     "b2_schwarz_create": (ci, [vp, vp, i64, vp, vp, i64, vp, vp, vp]),
     "b2_schwarz_set_subsolver": (ci, [vp, ci]),
+    "b2_schwarz_set_row_levels": (ci, [vp, ci]),
+    "b2_schwarz_row_levels": (i64, [vp]),
     "b2_schwarz_setup": (ci, [vp]),
     "b2_schwarz_apply": (ci, [vp, vp, vp]),
     "b2_schwarz_bytes": (i64, [vp]),
@@ -713,6 +715,15 @@ class Schwarz:
         """"lu": exact block solves (dense inverses); "ssor": one SSOR iteration per block (PCSOR default);
         "ilu": ILU(0) of every block in its sorted dofs (PCILU default)."""
         check(self.L.b2_schwarz_set_subsolver(self.h, {"lu": 0, "ssor": 1, "ilu": 2}[kind]))
+
+    def set_row_levels(self, on=True):
+        """SSOR / ILU(0): sort every block's rows into dependency levels and let all warps of the CTA work inside a level
+        (same result bit for bit; for large blocks).  row_levels: the longest chain found by the setup."""
+        check(self.L.b2_schwarz_set_row_levels(self.h, 1 if on else 0))
+
+    @property
+    def row_levels(self):
+        return int(self.L.b2_schwarz_row_levels(self.h))
 
     def setup(self):
         check(self.L.b2_schwarz_setup(self.h))

@@ -17,7 +17,9 @@
 //   schwarz_invert_kernel    in-place Gauss-Jordan without pivoting (blocks of the penalised SPD operator), one CTA
 //                            per block, pivot row / column staged in shared memory
 //   schwarz_apply_kernel     t = (r - A y)[B] (warp per row), z = inv . t (warp per row, coalesced), y[B] += z
+#include <algorithm>
 #include "b2_common.cuh"
+#include "b2_schwarz_levels.hpp"
 
 struct b2_schwarz {
   b2_ctx* ctx = nullptr;
@@ -38,6 +40,12 @@ struct b2_schwarz {
   int64_t fac_total = 0;
   double *tg = nullptr, *dg = nullptr, *zg = nullptr;   // [n] scratch of the SSOR sweep
   int32_t* mark = nullptr;        // [n]
+  // optional dependency levels of every block's rows (b2_schwarz_set_row_levels): forward (lower pattern) / backward
+  bool row_levels = false;
+  int64_t *lvptr_f = nullptr, *lvptr_b = nullptr;       // [nblocks+1] into lvoff_*
+  int32_t *lvoff_f = nullptr, *lvoff_b = nullptr;       // per block: nlev+1 offsets into its row list
+  int32_t *lvrows_f = nullptr, *lvrows_b = nullptr;     // [ndofs_total] local rows of every block sorted by level
+  int64_t lvoff_f_n = 0, lvoff_b_n = 0, max_levels = 0;
   bool ready = false;
 };
 
@@ -114,10 +122,56 @@ int b2_schwarz_set_subsolver(b2_schwarz* s, int kind) {
   return 0;
 }
 
+namespace {
+// dependency levels of the rows of every block in its lower / upper triangular in-block pattern, rows sorted by level
+int build_row_levels(b2_schwarz* s) {
+  b2_ctx* c = s->ctx;
+  const size_t n = (size_t)s->A->nrows;
+  std::vector<int64_t> rp(n + 1), bp((size_t)s->nblocks + 1);
+  std::vector<int32_t> col((size_t)s->A->nnz), bd((size_t)s->ndofs_total);
+  B2_TRY(b2_download(c, rp.data(), s->A->rowptr, n + 1));
+  B2_TRY(b2_download(c, col.data(), s->A->col, (size_t)s->A->nnz));
+  B2_TRY(b2_download(c, bp.data(), s->blk_ptr, (size_t)s->nblocks + 1));
+  B2_TRY(b2_download(c, bd.data(), s->blk_dofs, (size_t)s->ndofs_total));
+  std::vector<int64_t> ptr[2];
+  std::vector<int32_t> off[2], rows[2];
+  s->max_levels = b2_schwarz_row_level_schedule(s->nblocks, bp.data(), bd.data(), rp.data(), col.data(), ptr, off, rows);
+  s->lvoff_f_n = (int64_t)off[0].size();
+  s->lvoff_b_n = (int64_t)off[1].size();
+  B2_TRY(b2_malloc(c, &s->lvptr_f, (size_t)s->nblocks + 1));
+  B2_TRY(b2_malloc(c, &s->lvptr_b, (size_t)s->nblocks + 1));
+  B2_TRY(b2_malloc(c, &s->lvoff_f, off[0].size()));
+  B2_TRY(b2_malloc(c, &s->lvoff_b, off[1].size()));
+  B2_TRY(b2_malloc(c, &s->lvrows_f, (size_t)s->ndofs_total));
+  B2_TRY(b2_malloc(c, &s->lvrows_b, (size_t)s->ndofs_total));
+  B2_TRY(b2_upload(c, s->lvptr_f, ptr[0].data(), (size_t)s->nblocks + 1));
+  B2_TRY(b2_upload(c, s->lvptr_b, ptr[1].data(), (size_t)s->nblocks + 1));
+  B2_TRY(b2_upload(c, s->lvoff_f, off[0].data(), off[0].size()));
+  B2_TRY(b2_upload(c, s->lvoff_b, off[1].data(), off[1].size()));
+  B2_TRY(b2_upload(c, s->lvrows_f, rows[0].data(), (size_t)s->ndofs_total));
+  B2_TRY(b2_upload(c, s->lvrows_b, rows[1].data(), (size_t)s->ndofs_total));
+  return 0;
+}
+}  // namespace
+
+/* the SSOR and ILU(0) block solves walk a block's rows in order (one warp per block).  on != 0: the rows are sorted into
+ * dependency levels of the block's triangular patterns at the next b2_schwarz_setup and every warp of the CTA takes rows
+ * of a level -- the same arithmetic per row, the same result bit for bit; meant for large blocks (the reference's
+ * applications use 8^4 elements per block, or FEMuS_DEFAULT = one block per level).  b2_schwarz_row_levels: the
+ * longest dependency chain found (0 before the setup). */
+int b2_schwarz_set_row_levels(b2_schwarz* s, int on) {
+  B2_CHECK(s, "b2_schwarz_set_row_levels: null handle");
+  if ((on != 0) != s->row_levels) s->ready = false;
+  s->row_levels = on != 0;
+  return 0;
+}
+int64_t b2_schwarz_row_levels(const b2_schwarz* s) { return s ? s->max_levels : 0; }
+
 /* numeric phase: A[B_i,B_i] of the operator's CURRENT values (call it after the penalty rows are set), inverted */
 int b2_schwarz_setup(b2_schwarz* s) {
   B2_CHECK(s, "b2_schwarz_setup: null handle");
   b2_ctx* c = s->ctx;
+  if (s->sub != 0 && s->row_levels && !s->lvrows_f) B2_TRY(build_row_levels(s));
   if (s->sub == 1) {              // SSOR works on A's rows: only the scratch vectors are needed
     const size_t n = (size_t)s->A->nrows;
     if (!s->tg) B2_TRY(b2_malloc(c, &s->tg, n));
@@ -155,8 +209,12 @@ int b2_schwarz_setup(b2_schwarz* s) {
     B2_CUDA(cudaMemsetAsync(s->err, 0, sizeof(int), c->stream));
     for (int64_t g = 0; g < s->ngroups; g++) {
       const int64_t g0 = s->group_ptr[g], g1 = s->group_ptr[g + 1];
-      B2_LAUNCH(c, schwarz_ilu_factor_kernel, b2_grid_for(c, g1 - g0, 1, 16), kApplyThreads, 0, g0, g1, s->group_blocks, s->blk_ptr, s->blk_dofs,
-                s->frow, s->A->rowptr, s->A->col, s->A->val, s->fac, s->mark, s->foff, s->err);
+      if (s->row_levels)
+        B2_LAUNCH(c, schwarz_ilu_factor_kernel<true>, b2_grid_for(c, g1 - g0, 1, 16), kApplyThreads, 0, g0, g1, s->group_blocks, s->blk_ptr,
+                  s->blk_dofs, s->frow, s->A->rowptr, s->A->col, s->A->val, s->fac, s->mark, s->foff, s->err, s->lvptr_f, s->lvoff_f, s->lvrows_f);
+      else
+        B2_LAUNCH(c, schwarz_ilu_factor_kernel<false>, b2_grid_for(c, g1 - g0, 1, 16), kApplyThreads, 0, g0, g1, s->group_blocks, s->blk_ptr,
+                  s->blk_dofs, s->frow, s->A->rowptr, s->A->col, s->A->val, s->fac, s->mark, s->foff, s->err, nullptr, nullptr, nullptr);
     }
     int err = 0;
     B2_TRY(b2_download(c, &err, s->err, 1));
@@ -196,13 +254,25 @@ int b2_schwarz_apply(b2_schwarz* s, const b2_vec* r, b2_vec* y) {
   for (int64_t g = 0; g < s->ngroups; g++) {
     const int64_t g0 = s->group_ptr[g], g1 = s->group_ptr[g + 1];
     if (s->sub == 2) {
-      B2_LAUNCH(c, schwarz_apply_ilu_kernel, b2_grid_for(c, g1 - g0, 1, 16), kApplyThreads, 0, g0, g1, s->group_blocks, s->blk_ptr, s->blk_dofs,
-                s->frow, s->A->rowptr, s->A->col, s->A->val, s->fac, r->d, y->d, s->zg, s->mark);
+      if (s->row_levels)
+        B2_LAUNCH(c, schwarz_apply_ilu_kernel<true>, b2_grid_for(c, g1 - g0, 1, 16), kApplyThreads, 0, g0, g1, s->group_blocks, s->blk_ptr,
+                  s->blk_dofs, s->frow, s->A->rowptr, s->A->col, s->A->val, s->fac, r->d, y->d, s->zg, s->mark, s->lvptr_f, s->lvoff_f, s->lvrows_f,
+                  s->lvptr_b, s->lvoff_b, s->lvrows_b);
+      else
+        B2_LAUNCH(c, schwarz_apply_ilu_kernel<false>, b2_grid_for(c, g1 - g0, 1, 16), kApplyThreads, 0, g0, g1, s->group_blocks, s->blk_ptr,
+                  s->blk_dofs, s->frow, s->A->rowptr, s->A->col, s->A->val, s->fac, r->d, y->d, s->zg, s->mark, nullptr, nullptr, nullptr, nullptr,
+                  nullptr, nullptr);
       continue;
     }
     if (s->sub == 1) {
-      B2_LAUNCH(c, schwarz_apply_ssor_kernel, b2_grid_for(c, g1 - g0, 1, 16), kApplyThreads, 0, g0, g1, s->group_blocks, s->blk_ptr, s->blk_dofs,
-                s->A->rowptr, s->A->col, s->A->val, r->d, y->d, s->tg, s->dg, s->zg, s->mark);
+      if (s->row_levels)
+        B2_LAUNCH(c, schwarz_apply_ssor_kernel<true>, b2_grid_for(c, g1 - g0, 1, 16), kApplyThreads, 0, g0, g1, s->group_blocks, s->blk_ptr,
+                  s->blk_dofs, s->A->rowptr, s->A->col, s->A->val, r->d, y->d, s->tg, s->dg, s->zg, s->mark, s->lvptr_f, s->lvoff_f, s->lvrows_f,
+                  s->lvptr_b, s->lvoff_b, s->lvrows_b);
+      else
+        B2_LAUNCH(c, schwarz_apply_ssor_kernel<false>, b2_grid_for(c, g1 - g0, 1, 16), kApplyThreads, 0, g0, g1, s->group_blocks, s->blk_ptr,
+                  s->blk_dofs, s->A->rowptr, s->A->col, s->A->val, r->d, y->d, s->tg, s->dg, s->zg, s->mark, nullptr, nullptr, nullptr, nullptr,
+                  nullptr, nullptr);
       continue;
     }
     B2_LAUNCH(c, schwarz_apply_kernel, b2_grid_for(c, g1 - g0, 1, 16), kApplyThreads, smem, g0, g1, s->group_blocks, s->blk_ptr,
@@ -224,6 +294,12 @@ int b2_schwarz_destroy(b2_schwarz* s) {
   b2_free(c, s->blk_dofs, (size_t)s->ndofs_total);
   b2_free(c, s->inv_ptr, (size_t)s->nblocks + 1);
   b2_free(c, s->inv, (size_t)s->inv_total);
+  b2_free(c, s->lvptr_f, (size_t)s->nblocks + 1);
+  b2_free(c, s->lvptr_b, (size_t)s->nblocks + 1);
+  b2_free(c, s->lvoff_f, (size_t)s->lvoff_f_n);
+  b2_free(c, s->lvoff_b, (size_t)s->lvoff_b_n);
+  b2_free(c, s->lvrows_f, (size_t)s->ndofs_total);
+  b2_free(c, s->lvrows_b, (size_t)s->ndofs_total);
   b2_free(c, s->frow, (size_t)s->ndofs_total);
   b2_free(c, s->fac, (size_t)s->fac_total);
   b2_free(c, s->foff, (size_t)s->A->nrows);

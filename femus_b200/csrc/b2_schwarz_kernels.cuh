@@ -116,18 +116,77 @@ __global__ void __launch_bounds__(kApplyThreads) schwarz_apply_kernel(int64_t g0
 }
 
 
-// The same sweep with ONE SSOR ITERATION as the block solve (PCSOR's default on the sub-block: local symmetric sweep,
-// omega 1, zero initial guess -- what 001_Poisson's SetPreconditionerFineGrids(SOR_PRECOND) puts on the ASM blocks,
-// LinearEquationSolverPetscAsm.cpp:300-317, PetscPreconditioner.cpp SOR_PRECOND).  No factor storage: the block's
-// rows of A are used as they are.  Gauss-Seidel is sequential in the block's (sorted) dofs, so one warp walks the rows
-// -- lanes over a row's non-zeros -- while the other warps only help with t = (r - A y)[B]; the parallelism is across
-// the blocks of a group.  Scratch per dof in HBM (a block's dofs belong to no other block of its group): tg = t,
-// dg = diagonal, zg = the block solution, mark = the block that last claimed the dof (membership test of a column).
+// ---- block solves that walk the block's rows of A: one SSOR iteration, ILU(0) ------------------------------------
+// Gauss-Seidel and the triangular solves are sequential in the block's (sorted) dofs.  Two ways to run them:
+//   LEV = false  one warp walks the rows in order, lanes over a row's non-zeros; the parallelism is across the
+//                blocks of a group (right for the small blocks of a few elements);
+//   LEV = true   the rows of a block arrive sorted into DEPENDENCY LEVELS of its lower (forward sweeps, ILU
+//                elimination) and upper (backward sweeps) triangular pattern: the rows of a level are independent, so
+//                every warp of the CTA takes rows of the level and the CTA synchronises between levels -- same
+//                arithmetic per row, hence the same result bit for bit (the reference's applications use blocks of
+//                8^4 elements, or one block per level, where the one-warp walk is correct but serial).
+// Per dof scratch in HBM (a block's dofs belong to no other block of its group): mark = the block that last claimed the
+// dof (membership test of a column), zg = the block solution, tg / dg = right-hand side and diagonal (SSOR), foff = where
+// the claiming block keeps the dof's factor row (ILU).
+template <bool LEV, class Body>
+__device__ __forceinline__ void schwarz_rows(bool reverse, int m, const int32_t* __restrict__ rows, const int32_t* __restrict__ off, int nlev,
+                                             Body body) {
+  const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  if (!LEV) {
+    if (warp == 0)
+      for (int ii = 0; ii < m; ii++) {
+        body(reverse ? m - 1 - ii : ii);
+        __syncwarp();
+      }
+    __syncthreads();
+  } else {
+    for (int l = 0; l < nlev; l++) {
+      for (int t = off[l] + warp; t < off[l + 1]; t += nwarps) body(rows[t]);
+      __syncthreads();
+    }
+  }
+}
+
+struct schwarz_ctx {          // what every row body needs
+  int32_t b;
+  const int32_t* D;
+  const int64_t* rowptr;
+  const int32_t* col;
+  const double* val;
+  int32_t* mark;
+  double* zg;
+};
+
+// SSOR (PCSOR's default on the sub-block: local symmetric sweep, omega 1, zero initial guess -- what 001_Poisson's
+// SetPreconditionerFineGrids(SOR_PRECOND) puts on the ASM blocks, LinearEquationSolverPetscAsm.cpp:300-317)
+struct ssor_row {
+  schwarz_ctx c;
+  const double* tg;
+  const double* dg;
+  bool forward;
+  __device__ void operator()(int i) const {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = c.D[i];
+    double s = 0.0;
+    for (int64_t k = c.rowptr[row] + lane; k < c.rowptr[row + 1]; k += 32) {
+      const int32_t cc = c.col[k];
+      if ((forward ? cc < row : cc != row) && c.mark[cc] == c.b) s = fma(c.val[k], c.zg[cc], s);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) c.zg[row] = (tg[row] - s) / dg[row];
+  }
+};
+
+template <bool LEV>
 __global__ void __launch_bounds__(kApplyThreads) schwarz_apply_ssor_kernel(int64_t g0, int64_t g1, const int32_t* __restrict__ group_blocks,
                                                                             const int64_t* __restrict__ blk_ptr, const int32_t* __restrict__ blk_dofs,
                                                                             const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
                                                                             const double* __restrict__ val, const double* __restrict__ r, double* y,
-                                                                            double* tg, double* dg, double* zg, int32_t* mark) {
+                                                                            double* tg, double* dg, double* zg, int32_t* mark,
+                                                                            const int64_t* __restrict__ lvptr_f, const int32_t* __restrict__ lvoff_f,
+                                                                            const int32_t* __restrict__ lvrows_f, const int64_t* __restrict__ lvptr_b,
+                                                                            const int32_t* __restrict__ lvoff_b, const int32_t* __restrict__ lvrows_b) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   for (int64_t q = g0 + blockIdx.x; q < g1; q += gridDim.x) {
     const int32_t b = group_blocks[q];
@@ -154,33 +213,11 @@ __global__ void __launch_bounds__(kApplyThreads) schwarz_apply_ssor_kernel(int64
       }
     }
     __syncthreads();
-    if (warp == 0) {
-      for (int i = 0; i < m; i++) {                 // forward sweep: z = (D + L)^-1 t
-        const int64_t row = D[i];
-        double s = 0.0;
-        for (int64_t k = rowptr[row] + lane; k < rowptr[row + 1]; k += 32) {
-          const int32_t c = col[k];
-          if (c < row && mark[c] == b) s = fma(val[k], zg[c], s);
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (lane == 0) zg[row] = (tg[row] - s) / dg[row];
-        __syncwarp();
-      }
-      for (int i = m - 1; i >= 0; i--) {            // backward sweep from that iterate
-        const int64_t row = D[i];
-        double s = 0.0;
-        for (int64_t k = rowptr[row] + lane; k < rowptr[row + 1]; k += 32) {
-          const int32_t c = col[k];
-          if (c != row && mark[c] == b) s = fma(val[k], zg[c], s);
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (lane == 0) zg[row] = (tg[row] - s) / dg[row];
-        __syncwarp();
-      }
-    }
-    __syncthreads();
+    const schwarz_ctx c{b, D, rowptr, col, val, mark, zg};
+    schwarz_rows<LEV>(false, m, LEV ? lvrows_f + blk_ptr[b] : nullptr, LEV ? lvoff_f + lvptr_f[b] : nullptr,
+                      LEV ? (int)(lvptr_f[b + 1] - lvptr_f[b]) - 1 : 0, ssor_row{c, tg, dg, true});      // z = (D + L)^-1 t
+    schwarz_rows<LEV>(true, m, LEV ? lvrows_b + blk_ptr[b] : nullptr, LEV ? lvoff_b + lvptr_b[b] : nullptr,
+                      LEV ? (int)(lvptr_b[b + 1] - lvptr_b[b]) - 1 : 0, ssor_row{c, tg, dg, false});     // backward sweep from that iterate
     for (int i = threadIdx.x; i < m; i += blockDim.x) y[D[i]] += zg[D[i]];
     __syncthreads();
   }
@@ -190,10 +227,9 @@ __global__ void __launch_bounds__(kApplyThreads) schwarz_apply_ssor_kernel(int64
 // reference's applications (PCILU: levels 0, natural ordering = the block's sorted dofs, PetscPreconditioner.cpp;
 // LinearEquationSolverPetscAsm.cpp:300-317).  The factor of block b lives on the pattern of the block's rows of A:
 // row i of the block (global row r = D[i]) owns len(r) slots at fac[frow[blk_ptr[b] + i] ..), slot q belonging to
-// column col[rowptr[r] + q]; slots of columns outside the block are unused.  One warp per block walks the rows in order
-// (IKJ elimination: for every earlier column k of the row, l_ik = a_ik / u_kk, then a_ij -= l_ik u_kj wherever (k, j) is
-// in the pattern of row k); lanes work across a row's entries.  Per dof scratch as in the SSOR kernel: mark = the
-// block that claimed the dof, foff = where that block keeps the dof's factor row.
+// column col[rowptr[r] + q]; slots of columns outside the block are unused.  IKJ elimination of a row by one warp: for
+// every earlier column k of the row, l_ik = a_ik / u_kk, then a_ij -= l_ik u_kj wherever (k, j) is in the pattern of
+// row k (found by bisection); lanes work across the row's entries.
 __device__ __forceinline__ int64_t schwarz_bsearch(const int32_t* __restrict__ col, int64_t lo, int64_t hi, int32_t c) {
   while (lo < hi) {
     const int64_t mid = (lo + hi) >> 1;
@@ -202,11 +238,45 @@ __device__ __forceinline__ int64_t schwarz_bsearch(const int32_t* __restrict__ c
   return lo;
 }
 
+struct ilu_factor_row {
+  schwarz_ctx c;
+  const int64_t* F;
+  double* fac;
+  const int64_t* foff;
+  int* err;
+  __device__ void operator()(int i) const {
+    const int lane = threadIdx.x & 31;
+    const int32_t r = c.D[i];
+    const int64_t rp = c.rowptr[r], len = c.rowptr[r + 1] - rp, fi = F[i];
+    for (int64_t q = 0; q < len; q++) {             // the row's entries in column order: earlier columns are pivots
+      const int32_t k = c.col[rp + q];
+      if (k >= r) break;
+      if (c.mark[k] != c.b) continue;
+      const int64_t kp = c.rowptr[k], klen = c.rowptr[k + 1] - kp, fk = foff[k];
+      const int64_t dk = schwarz_bsearch(c.col, kp, kp + klen, k) - kp;          // the pivot row's diagonal slot
+      const double lik = fac[fi + q] / fac[fk + dk];
+      __syncwarp();
+      if (lane == 0) fac[fi + q] = lik;
+      for (int64_t q2 = q + 1 + lane; q2 < len; q2 += 32) {
+        const int32_t c2 = c.col[rp + q2];
+        if (c.mark[c2] != c.b) continue;
+        const int64_t p = schwarz_bsearch(c.col, kp, kp + klen, c2);
+        if (p < kp + klen && c.col[p] == c2) fac[fi + q2] = fma(-lik, fac[fk + (p - kp)], fac[fi + q2]);
+      }
+      __syncwarp();
+    }
+    const int64_t di = schwarz_bsearch(c.col, rp, rp + len, r) - rp;
+    if (lane == 0 && !(fabs(fac[fi + di]) > 0.0)) atomicCAS(err, 0, c.b + 1);
+  }
+};
+
+template <bool LEV>
 __global__ void __launch_bounds__(kApplyThreads) schwarz_ilu_factor_kernel(int64_t g0, int64_t g1, const int32_t* __restrict__ group_blocks,
                                                                             const int64_t* __restrict__ blk_ptr, const int32_t* __restrict__ blk_dofs,
                                                                             const int64_t* __restrict__ frow, const int64_t* __restrict__ rowptr,
                                                                             const int32_t* __restrict__ col, const double* __restrict__ val, double* fac,
-                                                                            int32_t* mark, int64_t* foff, int* __restrict__ err) {
+                                                                            int32_t* mark, int64_t* foff, int* err, const int64_t* __restrict__ lvptr_f,
+                                                                            const int32_t* __restrict__ lvoff_f, const int32_t* __restrict__ lvrows_f) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   for (int64_t q0 = g0 + blockIdx.x; q0 < g1; q0 += gridDim.x) {
     const int32_t b = group_blocks[q0];
@@ -219,42 +289,50 @@ __global__ void __launch_bounds__(kApplyThreads) schwarz_ilu_factor_kernel(int64
       if (lane == 0) { mark[r] = b; foff[r] = F[i]; }
     }
     __syncthreads();
-    if (warp == 0) {
-      for (int i = 0; i < m; i++) {
-        const int32_t r = D[i];
-        const int64_t rp = rowptr[r], len = rowptr[r + 1] - rp, fi = F[i];
-        for (int64_t q = 0; q < len; q++) {             // the row's entries in column order: earlier columns are pivots
-          const int32_t k = col[rp + q];
-          if (k >= r) break;
-          if (mark[k] != b) continue;
-          const int64_t kp = rowptr[k], klen = rowptr[k + 1] - kp, fk = foff[k];
-          const int64_t dk = schwarz_bsearch(col, kp, kp + klen, k) - kp;          // the pivot row's diagonal slot
-          const double lik = fac[fi + q] / fac[fk + dk];
-          __syncwarp();
-          if (lane == 0) fac[fi + q] = lik;
-          for (int64_t q2 = q + 1 + lane; q2 < len; q2 += 32) {
-            const int32_t c2 = col[rp + q2];
-            if (mark[c2] != b) continue;
-            const int64_t p = schwarz_bsearch(col, kp, kp + klen, c2);
-            if (p < kp + klen && col[p] == c2) fac[fi + q2] = fma(-lik, fac[fk + (p - kp)], fac[fi + q2]);
-          }
-          __syncwarp();
-        }
-        const int64_t di = schwarz_bsearch(col, rp, rp + len, r) - rp;
-        if (lane == 0 && !(fabs(fac[fi + di]) > 0.0)) atomicCAS(err, 0, b + 1);
-        __syncwarp();
-      }
-    }
-    __syncthreads();
+    const schwarz_ctx c{b, D, rowptr, col, val, mark, nullptr};
+    schwarz_rows<LEV>(false, m, LEV ? lvrows_f + blk_ptr[b] : nullptr, LEV ? lvoff_f + lvptr_f[b] : nullptr,
+                      LEV ? (int)(lvptr_f[b + 1] - lvptr_f[b]) - 1 : 0, ilu_factor_row{c, F, fac, foff, err});
   }
 }
 
+struct ilu_solve_row {
+  schwarz_ctx c;
+  const int64_t* F;
+  const double* fac;
+  bool forward;
+  __device__ void operator()(int i) const {
+    const int lane = threadIdx.x & 31;
+    const int32_t row = c.D[i];
+    const int64_t rp = c.rowptr[row], len = c.rowptr[row + 1] - rp;
+    double s = 0.0, d = 0.0;
+    for (int64_t q = lane; q < len; q += 32) {
+      const int32_t cc = c.col[rp + q];
+      if (forward) {
+        if (cc < row && c.mark[cc] == c.b) s = fma(fac[F[i] + q], c.zg[cc], s);
+      } else {
+        if (cc == row) d = fac[F[i] + q];
+        else if (cc > row && c.mark[cc] == c.b) s = fma(fac[F[i] + q], c.zg[cc], s);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s += __shfl_xor_sync(0xffffffffu, s, o);
+      d += __shfl_xor_sync(0xffffffffu, d, o);
+    }
+    if (lane == 0) c.zg[row] = forward ? c.zg[row] - s : (c.zg[row] - s) / d;      // L z = t (unit diagonal), then U z = z
+  }
+};
+
+template <bool LEV>
 __global__ void __launch_bounds__(kApplyThreads) schwarz_apply_ilu_kernel(int64_t g0, int64_t g1, const int32_t* __restrict__ group_blocks,
                                                                            const int64_t* __restrict__ blk_ptr, const int32_t* __restrict__ blk_dofs,
                                                                            const int64_t* __restrict__ frow, const int64_t* __restrict__ rowptr,
                                                                            const int32_t* __restrict__ col, const double* __restrict__ val,
                                                                            const double* __restrict__ fac, const double* __restrict__ r, double* y,
-                                                                           double* zg, int32_t* mark) {
+                                                                           double* zg, int32_t* mark, const int64_t* __restrict__ lvptr_f,
+                                                                           const int32_t* __restrict__ lvoff_f, const int32_t* __restrict__ lvrows_f,
+                                                                           const int64_t* __restrict__ lvptr_b, const int32_t* __restrict__ lvoff_b,
+                                                                           const int32_t* __restrict__ lvrows_b) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   for (int64_t q0 = g0 + blockIdx.x; q0 < g1; q0 += gridDim.x) {
     const int32_t b = group_blocks[q0];
@@ -270,39 +348,11 @@ __global__ void __launch_bounds__(kApplyThreads) schwarz_apply_ilu_kernel(int64_
       if (lane == 0) { zg[row] = r[row] - acc; mark[row] = b; }
     }
     __syncthreads();
-    if (warp == 0) {
-      for (int i = 0; i < m; i++) {                     // L z = t, unit lower triangle
-        const int32_t row = D[i];
-        const int64_t rp = rowptr[row], len = rowptr[row + 1] - rp;
-        double s = 0.0;
-        for (int64_t q = lane; q < len; q += 32) {
-          const int32_t c = col[rp + q];
-          if (c < row && mark[c] == b) s = fma(fac[F[i] + q], zg[c], s);
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (lane == 0) zg[row] -= s;
-        __syncwarp();
-      }
-      for (int i = m - 1; i >= 0; i--) {                // U z = z
-        const int32_t row = D[i];
-        const int64_t rp = rowptr[row], len = rowptr[row + 1] - rp;
-        double s = 0.0, d = 0.0;
-        for (int64_t q = lane; q < len; q += 32) {
-          const int32_t c = col[rp + q];
-          if (c == row) d = fac[F[i] + q];
-          else if (c > row && mark[c] == b) s = fma(fac[F[i] + q], zg[c], s);
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          s += __shfl_xor_sync(0xffffffffu, s, o);
-          d += __shfl_xor_sync(0xffffffffu, d, o);
-        }
-        if (lane == 0) zg[row] = (zg[row] - s) / d;
-        __syncwarp();
-      }
-    }
-    __syncthreads();
+    const schwarz_ctx c{b, D, rowptr, col, val, mark, zg};
+    schwarz_rows<LEV>(false, m, LEV ? lvrows_f + blk_ptr[b] : nullptr, LEV ? lvoff_f + lvptr_f[b] : nullptr,
+                      LEV ? (int)(lvptr_f[b + 1] - lvptr_f[b]) - 1 : 0, ilu_solve_row{c, F, fac, true});
+    schwarz_rows<LEV>(true, m, LEV ? lvrows_b + blk_ptr[b] : nullptr, LEV ? lvoff_b + lvptr_b[b] : nullptr,
+                      LEV ? (int)(lvptr_b[b + 1] - lvptr_b[b]) - 1 : 0, ilu_solve_row{c, F, fac, false});
     for (int i = threadIdx.x; i < m; i += blockDim.x) y[D[i]] += zg[D[i]];
     __syncthreads();
   }

@@ -47,7 +47,7 @@ class PoissonMG:
     def __init__(self, ctx, nx, ny, nz, nlevels, order="biquadratic", bounds=None, npre=1, npost=1, omega=0.5,
                  dirichlet_faces=(1, 2, 3, 4, 5, 6), fsrc=1.0, coarse_rtol=1e-14, hier=None, dist=None, fused=True,
                  neumann=None, smoother="richardson", asm_block_elems=8, asm_schedule="colours",
-                 asm_sub="lu", ksp="richardson"):
+                 asm_sub="lu", ksp="richardson", asm_row_levels=False):
         self.ctx = ctx
         self.order = order
         self.fam = hostapi.FAMILY[order]
@@ -158,6 +158,8 @@ class PoissonMG:
                 self.asm_index[l], self.asm_groups[l] = ix, grp
                 self.schwarz[l] = capi.Schwarz(ctx, self.KK[l], ix.overlap_ptr, ix.overlap, gptr, gblocks)
                 self.schwarz[l].set_subsolver(asm_sub)      # "lu": MLU_PRECOND on the blocks, "ssor": SOR_PRECOND (main.cpp:242)
+                if asm_row_levels:                          # large blocks: rows of a dependency level in parallel
+                    self.schwarz[l].set_row_levels(True)
                 self.mg.set_level_schwarz(l, self.schwarz[l])
         elif smoother != "richardson":
             for l in range(1, nlevels):

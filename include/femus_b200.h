@@ -330,6 +330,13 @@ int b2_schwarz_create(b2_ctx* ctx, b2_csr* A, int64_t nblocks, const int64_t* bl
  * LinearEquationSolverPetscAsm.cpp:300-317); no storage, any block size: with ONE block holding every element the
  * level smoother is Richardson + SOR, the application's FEMuS_DEFAULT branch. */
 int b2_schwarz_set_subsolver(b2_schwarz* s, int kind);
+/* SSOR / ILU(0) block solves walk a block's rows in order, one warp per block.  on != 0 (before b2_schwarz_setup): the
+ * rows are sorted into dependency levels of the block's triangular patterns and every warp of the CTA takes rows of a
+ * level, the CTA synchronising between levels -- the same arithmetic per row, hence the same result bit for bit; for
+ * large blocks (8^4 elements per block in the reference's applications, one block per level for FEMuS_DEFAULT).
+ * b2_schwarz_row_levels: the longest dependency chain found by the setup. */
+int b2_schwarz_set_row_levels(b2_schwarz* s, int on);
+int64_t b2_schwarz_row_levels(const b2_schwarz* s);
 int b2_schwarz_setup(b2_schwarz* s);
 int b2_schwarz_apply(b2_schwarz* s, const b2_vec* r, b2_vec* y);
 int64_t b2_schwarz_bytes(const b2_schwarz* s);      /* HBM held by the block inverses */

@@ -2,6 +2,7 @@
 // for the CPU thread emulator (cuda_emu.hpp) behind two C entry points that mirror what b2_schwarz_setup /
 // b2_schwarz_apply and b2_asm_neumann_faces launch.  Built and driven by tests/test_kernel_emulation.py.
 #include "cuda_emu.hpp"
+#include "../../femus_b200/csrc/b2_schwarz_levels.hpp"
 
 namespace {
 #include "../../femus_b200/csrc/b2_schwarz_kernels.cuh"
@@ -18,18 +19,31 @@ extern "C" {
 int emu_schwarz(int64_t n, const int64_t* rowptr, const int32_t* col, const double* val, int64_t nblocks, const int64_t* blk_ptr,
                 const int32_t* blk_dofs, int64_t ngroups, const int64_t* group_ptr, const int32_t* group_blocks, const double* r,
                 double* y, double* inv_out, int threads, int grid, int sub) {
+  // sub >= 10: the same block solve with the rows of every block sorted into dependency levels (LEV kernels)
+  const bool lev = sub >= 10;
+  sub %= 10;
+  std::vector<int64_t> lptr[2];
+  std::vector<int32_t> loff[2], lrows[2];
+  if (lev) b2_schwarz_row_level_schedule(nblocks, blk_ptr, blk_dofs, rowptr, col, lptr, loff, lrows);
+  const int64_t *pf = lev ? lptr[0].data() : nullptr, *pb = lev ? lptr[1].data() : nullptr;
+  const int32_t *of = lev ? loff[0].data() : nullptr, *ob = lev ? loff[1].data() : nullptr;
+  const int32_t *rf = lev ? lrows[0].data() : nullptr, *rb = lev ? lrows[1].data() : nullptr;
   if (sub == 1) {       // SSOR block solves: scratch vectors only (b2_schwarz_setup with kind 1)
     std::vector<double> tg((size_t)n, -7.0), dg((size_t)n, -7.0), zg((size_t)n, -7.0);
     std::vector<int32_t> mark((size_t)n, -1);
-    for (int64_t i = 0; i < n; i++) y[i] = 0.0;
-    for (int64_t g = 0; g < ngroups; g++)
-      emu::launch(schwarz_apply_ssor_kernel, (unsigned)grid, (unsigned)threads, 0, group_ptr[g], group_ptr[g + 1], group_blocks, blk_ptr, blk_dofs,
-                  rowptr, col, val, r, y, tg.data(), dg.data(), zg.data(), mark.data());
-    // a second application on the used scratch must give the same result (stale marks of overlapping blocks)
     std::vector<double> y2((size_t)n, 0.0);
-    for (int64_t g = 0; g < ngroups; g++)
-      emu::launch(schwarz_apply_ssor_kernel, (unsigned)grid, (unsigned)threads, 0, group_ptr[g], group_ptr[g + 1], group_blocks, blk_ptr, blk_dofs,
-                  rowptr, col, val, r, y2.data(), tg.data(), dg.data(), zg.data(), mark.data());
+    for (int pass = 0; pass < 2; pass++) {          // twice on the used scratch (stale marks of overlapping blocks)
+      double* yy = pass ? y2.data() : y;
+      for (int64_t i = 0; i < n; i++) yy[i] = 0.0;
+      for (int64_t g = 0; g < ngroups; g++) {
+        if (lev)
+          emu::launch(schwarz_apply_ssor_kernel<true>, (unsigned)grid, (unsigned)threads, 0, group_ptr[g], group_ptr[g + 1], group_blocks, blk_ptr,
+                      blk_dofs, rowptr, col, val, r, yy, tg.data(), dg.data(), zg.data(), mark.data(), pf, of, rf, pb, ob, rb);
+        else
+          emu::launch(schwarz_apply_ssor_kernel<false>, (unsigned)grid, (unsigned)threads, 0, group_ptr[g], group_ptr[g + 1], group_blocks, blk_ptr,
+                      blk_dofs, rowptr, col, val, r, yy, tg.data(), dg.data(), zg.data(), mark.data(), pf, of, rf, pb, ob, rb);
+      }
+    }
     for (int64_t i = 0; i < n; i++)
       if (y2[i] != y[i]) return -1;
     return 0;
@@ -42,17 +56,29 @@ int emu_schwarz(int64_t n, const int64_t* rowptr, const int32_t* col, const doub
     std::vector<int64_t> foff((size_t)n, -1);
     std::vector<int32_t> mark((size_t)n, -1);
     int err = 0;
-    for (int64_t g = 0; g < ngroups; g++)
-      emu::launch(schwarz_ilu_factor_kernel, (unsigned)grid, (unsigned)threads, 0, group_ptr[g], group_ptr[g + 1], group_blocks, blk_ptr, blk_dofs,
-                  (const int64_t*)frow.data(), rowptr, col, val, fac.data(), mark.data(), foff.data(), &err);
+    for (int64_t g = 0; g < ngroups; g++) {
+      if (lev)
+        emu::launch(schwarz_ilu_factor_kernel<true>, (unsigned)grid, (unsigned)threads, 0, group_ptr[g], group_ptr[g + 1], group_blocks, blk_ptr,
+                    blk_dofs, (const int64_t*)frow.data(), rowptr, col, val, fac.data(), mark.data(), foff.data(), &err, pf, of, rf);
+      else
+        emu::launch(schwarz_ilu_factor_kernel<false>, (unsigned)grid, (unsigned)threads, 0, group_ptr[g], group_ptr[g + 1], group_blocks, blk_ptr,
+                    blk_dofs, (const int64_t*)frow.data(), rowptr, col, val, fac.data(), mark.data(), foff.data(), &err, pf, of, rf);
+    }
     if (err) return err;
     std::vector<double> y2((size_t)n, 0.0);
     for (int pass = 0; pass < 2; pass++) {
       double* yy = pass ? y2.data() : y;
       for (int64_t i = 0; i < n; i++) yy[i] = 0.0;
-      for (int64_t g = 0; g < ngroups; g++)
-        emu::launch(schwarz_apply_ilu_kernel, (unsigned)grid, (unsigned)threads, 0, group_ptr[g], group_ptr[g + 1], group_blocks, blk_ptr, blk_dofs,
-                    (const int64_t*)frow.data(), rowptr, col, val, (const double*)fac.data(), r, yy, zg.data(), mark.data());
+      for (int64_t g = 0; g < ngroups; g++) {
+        if (lev)
+          emu::launch(schwarz_apply_ilu_kernel<true>, (unsigned)grid, (unsigned)threads, 0, group_ptr[g], group_ptr[g + 1], group_blocks, blk_ptr,
+                      blk_dofs, (const int64_t*)frow.data(), rowptr, col, val, (const double*)fac.data(), r, yy, zg.data(), mark.data(), pf, of, rf, pb,
+                      ob, rb);
+        else
+          emu::launch(schwarz_apply_ilu_kernel<false>, (unsigned)grid, (unsigned)threads, 0, group_ptr[g], group_ptr[g + 1], group_blocks, blk_ptr,
+                      blk_dofs, (const int64_t*)frow.data(), rowptr, col, val, (const double*)fac.data(), r, yy, zg.data(), mark.data(), pf, of, rf, pb,
+                      ob, rb);
+      }
     }
     for (int64_t i = 0; i < n; i++)
       if (y2[i] != y[i]) return -1;

@@ -163,6 +163,31 @@ def test_schwarz_ilu_kernels_on_the_emulator(emu, order, nb, schedule):
     assert np.abs(want - exact).max() > 1e-6 * np.abs(exact).max()        # incomplete, not exact
 
 
+@pytest.mark.parametrize("sub", ["ssor", "ilu"])
+@pytest.mark.parametrize("order,nb", [("linear", 8), ("linear", 10 ** 6), ("biquadratic", 2)])
+def test_level_scheduled_rows_equal_the_one_warp_walk(emu, sub, order, nb):
+    """b2_schwarz_set_row_levels: the rows of every block sorted into dependency levels of its triangular patterns, all
+    warps of the CTA working inside a level -- the same arithmetic per row, so the result equals the one-warp walk BIT
+    FOR BIT (and the oracle to 1e-12); nb = 10^6: one block with the whole level, the case it is meant for."""
+    from oracle import mesh_box as mb, mg
+    shape = (2, 2, 2) if order == "linear" else (1, 2, 1)
+    lv = mb.build_hierarchy(*shape, 2)
+    H = hostapi.HostHierarchy(*shape, 2)
+    ix = hostapi.AsmIndex(H.levels[1], order, nb)
+    rp, ci = H.levels[1].sparsity(order)
+    grp, gptr, gblocks = hostapi.asm_schedule(rp, ci, ix.overlap_ptr, ix.overlap, "colours")
+    O = mg.Hierarchy(lv, order, dirichlet_faces=(1, 3, 6), smoother="asm", asm_blocks=[None, ix.blocks()], asm_orders=[None, gblocks], asm_sub=sub)
+    A = O.A[1]
+    r = np.random.default_rng(14).standard_normal(A.shape[0])
+    code = {"ssor": 1, "ilu": 2}[sub]
+    err0, y0, _ = _run_schwarz(emu, A, ix, gptr, gblocks, r, sub=code)
+    err1, y1, _ = _run_schwarz(emu, A, ix, gptr, gblocks, r, sub=10 + code, threads=128)
+    assert err0 == 0 and err1 == 0
+    assert np.array_equal(y0, y1)
+    want = O.asm[1].apply(r)
+    assert np.abs(y1 - want).max() <= 1e-12 * np.abs(want).max()
+
+
 def test_schwarz_invert_kernel_reports_singular_blocks(emu):
     import scipy.sparse as sp
     H = hostapi.HostHierarchy(1, 1, 1, 2)

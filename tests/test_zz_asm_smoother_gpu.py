@@ -166,6 +166,25 @@ def test_vcycle_trace_with_gmres_level_solver(ctx, pc, order, npre):
     del pb
 
 
+@pytest.mark.parametrize("sub,nb", [("ilu", 10 ** 6), ("ssor", 10 ** 6), ("ilu", 8)])
+def test_level_scheduled_rows_equal_the_one_warp_walk(ctx, sub, nb):
+    """b2_schwarz_set_row_levels on the device: bit-for-bit the result of the one-warp walk, on 8-element blocks and on
+    ONE block holding the whole level (Richardson + ILU(0) / SOR of FEMuS_DEFAULT)."""
+    from femus_b200.poisson import PoissonMG
+    ys = []
+    for lev in (False, True):
+        pb = PoissonMG(ctx, 2, 2, 2, 3, "biquadratic", smoother="asm", asm_block_elems=nb, asm_sub=sub, asm_row_levels=lev)
+        pb.assemble(); pb.galerkin(); pb.mg_set_levels()
+        n = pb.ndofs[2]
+        R, Y = ctx.vector(np.sin(np.arange(n) * 0.37)), ctx.vector(n)
+        pb.schwarz[2].apply(R, Y)
+        ys.append(Y.get())
+        if lev:
+            assert 1 < pb.schwarz[2].row_levels <= max(len(b) for b in pb.asm_index[2].blocks())
+        del pb
+    assert np.array_equal(ys[0], ys[1])
+
+
 def test_block_smoother_fails_loudly(ctx):
     from femus_b200 import capi, hostapi
     H = hostapi.HostHierarchy(2, 2, 2, 2)
