@@ -10,6 +10,7 @@
 // application and ONE reduction per iteration, and in the sharded run the three scalars of that
 // reduction travel in the same ncclAllReduce as the interface values of the product.
 #include "b2_common.cuh"
+#include "b2_gmres.hpp"
 
 struct b2_mg_level {
   b2_csr* A = nullptr;      // borrowed, penalised in place
@@ -28,7 +29,7 @@ struct b2_mg_level {
   // level solver around the preconditioner of kinds 0 / 2: 0 = Richardson(omega), 1 = GMRES (left-preconditioned,
   // npre / npost iterations, no restart inside a smoothing call) -- KSPGMRES, the reference's default level solver
   int ksp = 0;
-  std::vector<b2_vec*> krylov;     // GMRES basis (max(npre, npost) + 1 vectors) and one work vector
+  std::vector<b2_vec*> krylov;     // GMRES basis (max(npre, npost) vectors) and one work vector
   double emin = 0., emax = 0.;     // bounds in use
   double emin_user = 0., emax_user = 0.;   // emax_user <= 0: estimated at MGSetLevel (power iteration)
   b2_vec* d = nullptr;             // Chebyshev direction
@@ -283,70 +284,7 @@ int pc_apply(b2_mg* mg, b2_mg_level& L, const b2_vec* r, b2_vec* z) {
 // k iterations from the current iterate, x <- x + V y.  Modified Gram-Schmidt + Givens rotations; the iterate is the
 // unique minimiser over x0 + K_k(M^-1 A, M^-1 r0), so it equals PETSc's (classical Gram-Schmidt) up to rounding.
 // Scalars come back to the host (k <= a few iterations per call; one device synchronisation per dot product).
-int smooth_gmres(b2_mg* mg, b2_mg_level& L, int k, bool zero_guess) {
-  b2_ctx* c = mg->ctx;
-  const int64_t n = L.A->nrows;
-  B2_CHECK(!L.halo, "b2_mg: the GMRES level solver runs on one rank only");
-  if (zero_guess) B2_TRY(b2_vec_zero(L.x));
-  if (k <= 0) return 0;
-  while ((int)L.krylov.size() < k + 2) {
-    b2_vec* v = nullptr;
-    B2_TRY(b2_vec_create(c, n, &v));
-    L.krylov.push_back(v);
-  }
-  b2_vec* w = L.krylov[k + 1];
-  const b2_vec* r = L.b;
-  if (!zero_guess) {
-    B2_TRY(level_resid(L, L.b, L.x, L.t));
-    r = L.t;
-  }
-  B2_TRY(pc_apply(mg, L, r, L.krylov[0]));
-  double beta = 0.0;
-  B2_TRY(b2_vec_norm(L.krylov[0], 2, &beta));
-  if (!(beta > 0.0)) return 0;
-  B2_TRY(b2_vec_scale(L.krylov[0], 1.0 / beta));
-  std::vector<double> H((size_t)(k + 1) * k, 0.0), cs(k, 0.0), sn(k, 0.0), g(k + 1, 0.0);
-  g[0] = beta;
-  int m = 0;
-  for (int j = 0; j < k; j++) {
-    B2_TRY(level_spmv(L, L.krylov[j], L.t));
-    B2_TRY(pc_apply(mg, L, L.t, w));
-    for (int i = 0; i <= j; i++) {
-      double h = 0.0;
-      B2_TRY(b2_vec_dot(w, L.krylov[i], &h));
-      H[(size_t)i * k + j] = h;
-      B2_TRY(b2_vec_axpy(w, -h, L.krylov[i]));
-    }
-    double hn = 0.0;
-    B2_TRY(b2_vec_norm(w, 2, &hn));
-    H[(size_t)(j + 1) * k + j] = hn;
-    for (int i = 0; i < j; i++) {          // earlier rotations on the new column
-      const double a = H[(size_t)i * k + j], b = H[(size_t)(i + 1) * k + j];
-      H[(size_t)i * k + j] = cs[i] * a + sn[i] * b;
-      H[(size_t)(i + 1) * k + j] = -sn[i] * a + cs[i] * b;
-    }
-    const double a = H[(size_t)j * k + j], b = H[(size_t)(j + 1) * k + j], d = std::sqrt(a * a + b * b);
-    m = j + 1;
-    if (!(d > 0.0)) { m = j; break; }
-    cs[j] = a / d;
-    sn[j] = b / d;
-    H[(size_t)j * k + j] = d;
-    H[(size_t)(j + 1) * k + j] = 0.0;
-    g[j + 1] = -sn[j] * g[j];
-    g[j] = cs[j] * g[j];
-    if (!(hn > 0.0)) break;                // happy breakdown: the Krylov space is exhausted
-    B2_TRY(b2_vec_copy(L.krylov[j + 1], w));
-    B2_TRY(b2_vec_scale(L.krylov[j + 1], 1.0 / hn));
-  }
-  std::vector<double> y(m, 0.0);
-  for (int i = m - 1; i >= 0; i--) {
-    double t = g[i];
-    for (int j = i + 1; j < m; j++) t -= H[(size_t)i * k + j] * y[j];
-    y[i] = t / H[(size_t)i * k + i];
-  }
-  for (int i = 0; i < m; i++) B2_TRY(b2_vec_axpy(L.x, y[i], L.krylov[i]));
-  return 0;
-}
+int smooth_gmres(b2_mg* mg, b2_mg_level& L, int k, bool zero_guess);
 
 // Richardson(omega) around the element-block preconditioner: x <- x + omega M^-1 (b - A x)
 int smooth_schwarz(b2_mg* mg, b2_mg_level& L, int nsweeps, bool zero_guess) {
@@ -361,6 +299,48 @@ int smooth_schwarz(b2_mg* mg, b2_mg_level& L, int nsweeps, bool zero_guess) {
     B2_TRY(b2_vec_axpy(L.x, L.omega, L.d));
   }
   return 0;
+}
+
+// device-vector operations of the GMRES cycle (b2_gmres.hpp): basis in L.krylov[0..k-1], w = L.krylov[k]
+struct gmres_level_ops {
+  b2_mg* mg;
+  b2_mg_level& L;
+  bool zero_guess;
+  b2_vec* w;
+  int start(double* beta) {
+    const b2_vec* r = L.b;                  // zero guess: r = b
+    if (!zero_guess) {
+      B2_TRY(level_resid(L, L.b, L.x, L.t));
+      r = L.t;
+    }
+    B2_TRY(pc_apply(mg, L, r, L.krylov[0]));
+    return b2_vec_norm(L.krylov[0], 2, beta);
+  }
+  int scale(int j, double a) { return b2_vec_scale(L.krylov[j], a); }
+  int apply(int j) {
+    B2_TRY(level_spmv(L, L.krylov[j], L.t));
+    return pc_apply(mg, L, L.t, w);
+  }
+  int dot_w(int i, double* h) { return b2_vec_dot(w, L.krylov[i], h); }
+  int axpy_w(double a, int i) { return b2_vec_axpy(w, a, L.krylov[i]); }
+  int norm_w(double* n) { return b2_vec_norm(w, 2, n); }
+  int store(int j) { return b2_vec_copy(L.krylov[j], w); }
+  int update_x(double a, int i) { return b2_vec_axpy(L.x, a, L.krylov[i]); }
+};
+
+int smooth_gmres(b2_mg* mg, b2_mg_level& L, int k, bool zero_guess) {
+  b2_ctx* c = mg->ctx;
+  const int64_t n = L.A->nrows;
+  B2_CHECK(!L.halo, "b2_mg: the GMRES level solver runs on one rank only");
+  if (zero_guess) B2_TRY(b2_vec_zero(L.x));
+  if (k <= 0) return 0;
+  while ((int)L.krylov.size() < k + 1) {
+    b2_vec* v = nullptr;
+    B2_TRY(b2_vec_create(c, n, &v));
+    L.krylov.push_back(v);
+  }
+  gmres_level_ops ops{mg, L, zero_guess, L.krylov[k]};
+  return b2_gmres_cycle(ops, k);
 }
 
 int smooth(b2_mg* mg, int l, int nsweeps, bool zero_guess) {

@@ -3,6 +3,7 @@
 // b2_schwarz_apply and b2_asm_neumann_faces launch.  Built and driven by tests/test_kernel_emulation.py.
 #include "cuda_emu.hpp"
 #include "../../femus_b200/csrc/b2_schwarz_levels.hpp"
+#include "../../femus_b200/csrc/b2_gmres.hpp"
 
 namespace {
 #include "../../femus_b200/csrc/b2_schwarz_kernels.cuh"
@@ -13,7 +14,61 @@ namespace {
 #include "../../femus_b200/csrc/b2_ns_kernel.cuh"
 }
 
+// host-vector operations for b2_gmres_cycle: CSR operator, Jacobi preconditioner (what gmres_level_ops does on device vectors)
+struct host_gmres_ops {
+  int64_t n;
+  const int64_t* rowptr;
+  const int32_t* col;
+  const double* val;
+  const double* dinv;
+  const double* b;
+  double* x;
+  bool zero_guess;
+  std::vector<std::vector<double>> v;
+  std::vector<double> w, t;
+  void spmv(const double* in, double* out) const {
+    for (int64_t i = 0; i < n; i++) {
+      double s = 0.0;
+      for (int64_t q = rowptr[i]; q < rowptr[i + 1]; q++) s += val[q] * in[col[q]];
+      out[i] = s;
+    }
+  }
+  int start(double* beta) {
+    if (zero_guess) t.assign(b, b + n);
+    else {
+      spmv(x, t.data());
+      for (int64_t i = 0; i < n; i++) t[i] = b[i] - t[i];
+    }
+    for (int64_t i = 0; i < n; i++) v[0][i] = dinv[i] * t[i];
+    double s = 0.0;
+    for (int64_t i = 0; i < n; i++) s += v[0][i] * v[0][i];
+    *beta = std::sqrt(s);
+    return 0;
+  }
+  int scale(int j, double a) { for (double& e : v[j]) e *= a; return 0; }
+  int apply(int j) {
+    spmv(v[j].data(), t.data());
+    for (int64_t i = 0; i < n; i++) w[i] = dinv[i] * t[i];
+    return 0;
+  }
+  int dot_w(int i, double* h) { double s = 0.0; for (int64_t q = 0; q < n; q++) s += w[q] * v[i][q]; *h = s; return 0; }
+  int axpy_w(double a, int i) { for (int64_t q = 0; q < n; q++) w[q] += a * v[i][q]; return 0; }
+  int norm_w(double* nn) { double s = 0.0; for (double e : w) s += e * e; *nn = std::sqrt(s); return 0; }
+  int store(int j) { v[j] = w; return 0; }
+  int update_x(double a, int i) { for (int64_t q = 0; q < n; q++) x[q] += a * v[i][q]; return 0; }
+};
+
 extern "C" {
+
+// the library's GMRES cycle (b2_gmres.hpp) on host vectors: k iterations from x (zero_guess: from 0)
+int emu_gmres(int64_t n, const int64_t* rowptr, const int32_t* col, const double* val, const double* dinv, const double* b, double* x, int k,
+              int zero_guess) {
+  if (zero_guess)
+    for (int64_t i = 0; i < n; i++) x[i] = 0.0;
+  host_gmres_ops ops{n, rowptr, col, val, dinv, b, x, zero_guess != 0, std::vector<std::vector<double>>(k > 0 ? k : 1, std::vector<double>((size_t)n)),
+                     std::vector<double>((size_t)n), std::vector<double>((size_t)n)};
+  return b2_gmres_cycle(ops, k);
+}
 
 // extract + invert + the sweep over the schedule's groups; returns the singular-block flag of the invert kernel
 int emu_schwarz(int64_t n, const int64_t* rowptr, const int32_t* col, const double* val, int64_t nblocks, const int64_t* blk_ptr,

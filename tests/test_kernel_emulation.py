@@ -34,6 +34,8 @@ def emu(tmp_path_factory):
                              ctypes.c_double, ctypes.c_int]
     L.emu_pressure_faces.restype = None
     L.emu_pressure_faces.argtypes = [ctypes.c_int64, vp, vp, vp, ctypes.c_int, ctypes.c_int, vp, vp, ctypes.c_int64, vp, vp, vp, vp, ctypes.c_int]
+    L.emu_gmres.restype = ctypes.c_int
+    L.emu_gmres.argtypes = [ctypes.c_int64, vp, vp, vp, vp, vp, vp, ctypes.c_int, ctypes.c_int]
     L.emu_ns.restype = None
     L.emu_ns.argtypes = L.emu_stokes.argtypes
     return L
@@ -388,3 +390,31 @@ def test_kernels_are_race_free_under_thread_sanitizer(tmp_path):
     run = subprocess.run([sys.executable, os.path.join(cpp, "tsan_runner.py"), so], capture_output=True, text=True, env=env, timeout=1500)
     assert "tsan-run-finished" in run.stdout, run.stdout[-2000:] + run.stderr[-4000:]
     assert "WARNING: ThreadSanitizer" not in run.stderr, run.stderr[:6000]
+
+
+@pytest.mark.parametrize("k", [1, 2, 4])
+def test_library_gmres_cycle_on_host_vectors(emu, k):
+    """The GMRES cycle of the level solver (femus_b200/csrc/b2_gmres.hpp: the code b2_mg.cu runs on device vectors)
+    instantiated on host vectors with a CSR operator and the Jacobi preconditioner: equal to the oracle's KSPGMRES
+    restatement from a non-zero and from a zero initial guess, and, when the Krylov space is exhausted, exact."""
+    from oracle import mesh_box as mb, mg
+    O = mg.Hierarchy(mb.build_hierarchy(2, 2, 2, 2), "linear", ksp="gmres")
+    A = O.A[1]
+    rp, ci, va = np.ascontiguousarray(A.indptr, dtype=np.int64), np.ascontiguousarray(A.indices, dtype=np.int32), np.ascontiguousarray(A.data)
+    dinv = np.ascontiguousarray(O.dinv[1])
+    rng = np.random.default_rng(15)
+    b, x0 = rng.standard_normal(A.shape[0]), rng.standard_normal(A.shape[0])
+    for zero in (0, 1):
+        x = x0.copy()
+        assert emu.emu_gmres(A.shape[0], _p(rp), _p(ci), _p(va), _p(dinv), _p(b), _p(x), k, zero) == 0
+        want = O.gmres(1, np.zeros_like(x0) if zero else x0, b, k)
+        assert np.abs(x - want).max() <= 1e-12 * np.abs(want).max()
+    # exhausted Krylov space (happy breakdown): a 3 x 3 diagonal operator, 5 iterations asked for -> the exact solution
+    d = np.array([1.0, 2.0, 4.0])
+    rp3, ci3 = np.arange(4, dtype=np.int64), np.arange(3, dtype=np.int32)
+    b3, x3, one = np.array([3.0, -1.0, 0.5]), np.zeros(3), np.ones(3)
+    assert emu.emu_gmres(3, _p(rp3), _p(ci3), _p(d), _p(one), _p(b3), _p(x3), 5, 1) == 0
+    assert np.abs(x3 - b3 / d).max() <= 1e-14
+    # zero right-hand side: nothing to do, no division by zero
+    z3, x3 = np.zeros(3), np.zeros(3)
+    assert emu.emu_gmres(3, _p(rp3), _p(ci3), _p(d), _p(one), _p(z3), _p(x3), 2, 1) == 0 and not x3.any()
