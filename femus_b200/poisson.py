@@ -151,8 +151,13 @@ class PoissonMG:
             # block order exactly, "colours" = the same sweep with the blocks stably sorted by colour
             if dist is not None:
                 raise NotImplementedError("the element-block smoother runs on one rank")
+            # asm_block_elems: elements per block (LinearEquationSolverPetscAsm::SetElementBlockNumber(n); the system-level
+            # SetElementBlockNumber(d) of LinearImplicitSystem.cpp:1191-1201 passes 8^d, capped by the level's element
+            # count); "all": one block with every element of the level, which on one rank is what
+            # SetElementBlockNumber("All", overlap) and FEMuS_DEFAULT amount to (the sub-solver preconditions the level)
+            nb_elems = 2 ** 30 if asm_block_elems == "all" else int(asm_block_elems)
             for l in range(1, nlevels):
-                ix = hostapi.AsmIndex(lv[l], order, asm_block_elems)
+                ix = hostapi.AsmIndex(lv[l], order, nb_elems)
                 rp, ci = lv[l].sparsity(order)
                 grp, gptr, gblocks = hostapi.asm_schedule(rp, ci, ix.overlap_ptr, ix.overlap, asm_schedule)
                 self.asm_index[l], self.asm_groups[l] = ix, grp
