@@ -34,12 +34,15 @@ void b2_set_error(const char* fmt, ...);
   } while (0)
 
 // every kernel launch of the library goes through this macro: counts the launch and checks it
+// (the CPU emulator build of the tests predefines it, tests/cpp/emu_prefix.hpp)
+#ifndef B2_LAUNCH
 #define B2_LAUNCH(ctx, kernel, grid, block, smem, ...)                         \
   do {                                                                         \
     kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);           \
     (ctx)->launches++;                                                         \
     B2_CUDA(cudaGetLastError());                                               \
   } while (0)
+#endif
 
 struct b2_ctx {
   int device = 0;

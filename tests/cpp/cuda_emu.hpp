@@ -80,6 +80,15 @@ inline int atomicCAS(int* p, int expected, int desired) {
   std::atomic_ref<int>(*p).compare_exchange_strong(expected, desired);
   return expected;
 }
+inline unsigned atomicAdd(unsigned* p, unsigned v) { return std::atomic_ref<unsigned>(*p).fetch_add(v); }
+inline int atomicAdd(int* p, int v) { return std::atomic_ref<int>(*p).fetch_add(v); }
+inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
+template <class T>
+inline T __ldcg(const T* p) { return *p; }
+template <class T>
+inline T __ldg(const T* p) { return *p; }
+struct double2 { double x, y; };
+inline double2 make_double2(double x, double y) { return double2{x, y}; }
 using std::fabs;
 using std::fma;
 using std::sqrt;

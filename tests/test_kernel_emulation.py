@@ -418,3 +418,107 @@ def test_library_gmres_cycle_on_host_vectors(emu, k):
     # zero right-hand side: nothing to do, no division by zero
     z3, x3 = np.zeros(3), np.zeros(3)
     assert emu.emu_gmres(3, _p(rp3), _p(ci3), _p(d), _p(one), _p(z3), _p(x3), 2, 1) == 0 and not x3.any()
+
+
+# ---- the multigrid ORCHESTRATION (b2_mg.cu + b2_vec.cu + b2_schwarz.cu) compiled for the emulator ------------------
+@pytest.fixture(scope="module")
+def emu_mg(tmp_path_factory):
+    """b2_vec.cu, b2_schwarz.cu, b2_mg.cu compiled with g++ (-include emu_prefix.hpp: CUDA keywords, B2_LAUNCH ->
+    emu::launch; emu_rt/cuda_runtime.h: stub runtime) + tests/cpp/emu_mg.cpp (plain-CSR stand-ins for the SpMV family)."""
+    d = tmp_path_factory.mktemp("emu_mg")
+    cpp = os.path.join(ROOT, "tests", "cpp")
+    objs = []
+    for src in [os.path.join(ROOT, "femus_b200", "csrc", f) for f in ("b2_vec.cu", "b2_schwarz.cu", "b2_mg.cu")] + [os.path.join(cpp, "emu_mg.cpp")]:
+        obj = str(d / (os.path.basename(src) + ".o"))
+        r = subprocess.run(["g++", "-std=c++20", "-O1", "-pthread", "-fPIC", "-I", os.path.join(cpp, "emu_rt"), "-I", cpp, "-include",
+                            os.path.join(cpp, "emu_prefix.hpp"), "-x", "c++", "-c", src, "-o", obj], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-3000:]
+        objs.append(obj)
+    so = str(d / "libemu_mg.so")
+    r = subprocess.run(["g++", "-shared", "-pthread", "-o", so] + objs, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    L = ctypes.CDLL(so)
+    L.emu_mg_run.restype = ctypes.c_int
+    L.b2_last_error.restype = ctypes.c_char_p
+    return L
+
+
+def _ptr_array(arrays):
+    keep = [None if a is None else np.ascontiguousarray(a) for a in arrays]
+    return (vp * len(keep))(*[None if a is None else a.ctypes.data_as(vp) for a in keep]), keep
+
+
+def _run_emu_mg(L, O, blocks, orders, smoother, sub, ksp, coarse_direct, row_levels, npre, omega, ncycles):
+    nl = len(O.levels)
+    n = np.array([A.shape[0] for A in O.A_raw], dtype=np.int64)
+    As = [A.copy() for A in O.A_raw]
+    for A in As:
+        A.sort_indices()
+    rp, k1 = _ptr_array([A.indptr.astype(np.int64) for A in As])
+    col, k2 = _ptr_array([A.indices.astype(np.int32) for A in As])
+    val, k3 = _ptr_array([A.data.astype(np.float64) for A in As])
+    Ps = [None] + [O.P[l].tocsr() for l in range(1, nl)]
+    prp, k4 = _ptr_array([None if P is None else P.indptr.astype(np.int64) for P in Ps])
+    pcol, k5 = _ptr_array([None if P is None else P.indices.astype(np.int32) for P in Ps])
+    pval, k6 = _ptr_array([None if P is None else P.data.astype(np.float64) for P in Ps])
+    nbdc = np.array([len(b) for b in O.bdc_idx], dtype=np.int64)
+    bdc, k7 = _ptr_array([np.asarray(b, dtype=np.int32) for b in O.bdc_idx])
+    nblk, ngrp = np.zeros(nl, dtype=np.int64), np.zeros(nl, dtype=np.int64)
+    bp, bd, gp, gb = [None] * nl, [None] * nl, [None] * nl, [None] * nl
+    for l in range(1, nl):
+        if blocks is None:
+            continue
+        nblk[l] = len(blocks[l])
+        bp[l] = np.concatenate([[0], np.cumsum([len(b) for b in blocks[l]])]).astype(np.int64)
+        bd[l] = np.concatenate(blocks[l]).astype(np.int32)
+        grp = orders[l]["grp"]
+        ngrp[l] = grp.max() + 1
+        gp[l] = np.concatenate([[0], np.cumsum(np.bincount(grp, minlength=ngrp[l]))]).astype(np.int64)
+        gb[l] = np.argsort(grp, kind="stable").astype(np.int32)
+    bpp, k8 = _ptr_array(bp)
+    bdp, k9 = _ptr_array(bd)
+    gpp, k10 = _ptr_array(gp)
+    gbp, k11 = _ptr_array(gb)
+    res = O.rhs.astype(np.float64).copy()
+    eps = np.zeros_like(res)
+    free = (O.bdc[-1] > 1.1).astype(np.uint8)
+    trace = np.zeros(ncycles)
+    rc = L.emu_mg_run(ctypes.c_int(nl), _p(n), rp, col, val, prp, pcol, pval, _p(nbdc), bdc, ctypes.c_int(smoother), ctypes.c_int(sub), ctypes.c_int(ksp),
+                      ctypes.c_int(coarse_direct), ctypes.c_int(row_levels), _p(nblk), bpp, bdp, _p(ngrp), gpp, gbp, ctypes.c_int(npre), ctypes.c_int(npre),
+                      ctypes.c_double(omega), ctypes.c_int(ncycles), _p(res), _p(eps), _p(free), _p(trace))
+    assert rc == 0, L.b2_last_error().decode()
+    return trace, eps
+
+
+@pytest.mark.parametrize("case", ["jacobi", "gmres_jacobi", "asm_lu", "asm_ilu_levels_gmres", "asm_ssor_direct"])
+def test_multigrid_orchestration_on_the_emulator(emu_mg, case):
+    """MGSetLevel on every level + MGSolve cycles of the REAL b2_mg.cu (penalty, Galerkin-free level setup, V-cycle,
+    residual update), b2_vec.cu and b2_schwarz.cu on the CPU emulator: Richardson + Jacobi, GMRES + Jacobi, Richardson +
+    element blocks (exact), GMRES + ILU(0) blocks with level-scheduled rows, SSOR blocks with the direct coarse solve --
+    residual traces and corrections against the oracle V-cycle."""
+    from oracle import mesh_box as mb, mg
+    lv = mb.build_hierarchy(2, 2, 2, 2)
+    H = hostapi.HostHierarchy(2, 2, 2, 2)
+    order = "linear"
+    cfg = {"jacobi": dict(smoother=0, sub=0, ksp=0, direct=0, rowlev=0, omega=0.5),
+           "gmres_jacobi": dict(smoother=0, sub=0, ksp=1, direct=0, rowlev=0, omega=0.5),
+           "asm_lu": dict(smoother=2, sub=0, ksp=0, direct=0, rowlev=0, omega=1.0),
+           "asm_ilu_levels_gmres": dict(smoother=2, sub=2, ksp=1, direct=0, rowlev=1, omega=1.0),
+           "asm_ssor_direct": dict(smoother=2, sub=1, ksp=0, direct=1, rowlev=0, omega=1.0)}[case]
+    blocks = orders = None
+    kw = {}
+    if cfg["smoother"] == 2:
+        ix = hostapi.AsmIndex(H.levels[1], order, 8)
+        rp, ci = H.levels[1].sparsity(order)
+        grp, gptr, gblocks = hostapi.asm_schedule(rp, ci, ix.overlap_ptr, ix.overlap, "colours")
+        blocks, orders = [None, ix.blocks()], [None, {"grp": grp}]
+        kw = dict(smoother="asm", asm_blocks=blocks, asm_orders=[None, gblocks], asm_sub={0: "lu", 1: "ssor", 2: "ilu"}[cfg["sub"]])
+    O = mg.Hierarchy(lv, order, ksp="gmres" if cfg["ksp"] else "richardson", **kw)
+    npre = 2 if cfg["ksp"] else 1
+    trace, eps = _run_emu_mg(emu_mg, O, blocks, orders, cfg["smoother"], cfg["sub"], cfg["ksp"], cfg["direct"], cfg["rowlev"], npre, cfg["omega"], 3)
+    trace_ref, eps_ref = O.mg_solve_trace(3, npre=npre, npost=npre, omega=cfg["omega"])
+    r0 = float(np.linalg.norm(np.where(O.bdc[-1] > 1.1, O.rhs, 0.0)))           # the scale: the residual before the first cycle
+    for a, b in zip(trace, trace_ref):
+        assert abs(a - b) <= 1e-11 * r0, (trace, trace_ref, r0)
+    assert trace[-1] < 0.5 * r0
+    assert np.abs(eps - eps_ref).max() <= 1e-10 * np.abs(eps_ref).max()
