@@ -522,3 +522,30 @@ def test_multigrid_orchestration_on_the_emulator(emu_mg, case):
         assert abs(a - b) <= 1e-11 * r0, (trace, trace_ref, r0)
     assert trace[-1] < 0.5 * r0
     assert np.abs(eps - eps_ref).max() <= 1e-10 * np.abs(eps_ref).max()
+
+
+def test_stokes_vcycle_orchestration_on_the_emulator(emu_mg):
+    """The velocity-pressure path of b2_mg.cu on the emulator: indefinite level operators (steady Stokes, oracle-assembled,
+    Galerkin coarse operator), Vanka blocks with the pressure as Schur variable and exact block solves by the Gauss-Jordan
+    kernel, DIRECT coarse solve through a one-block Schwarz object; three V-cycles against the oracle (a through-flow
+    channel on a 1 -> 8 element hierarchy: small enough for the emulator, 8 blocks of 383 dofs)."""
+    from oracle import stokes, mesh_box as mb, fe_hex, system as osys, mg
+    lv, H = mb.build_hierarchy(1, 1, 1, 2), hostapi.HostHierarchy(1, 1, 1, 2)
+    fams = ["biquadratic"] * 3 + ["linear"]
+    walls = (3, 4, 5, 6)          # two open boundary sets: the one-element coarse problem stays well posed
+    S = hostapi.SystemOnLevel(H.levels[-1], fams)
+    rp, ci = S.sparsity()
+    sol = np.zeros(S.n)
+    sol[osys.bdc(lv[-1], mb, fams, [(6,), (), (), ()]) < 1.5] = 1.0
+    A, rhs = stokes.assemble(lv[-1], mb, "biquadratic", "linear", sol, 1.0, lambda t, o: fe_hex.tables(o))
+    ix = hostapi.AsmIndex(H.levels[1], fams, 1, nschur=1)
+    grp, gptr, gblocks = hostapi.asm_schedule(rp, ci, ix.overlap_ptr, ix.overlap, "colours")
+    O = mg.Hierarchy(lv, None, mesh=osys.SystemMesh(mb, fams, [walls] * 3 + [()]), A_top=mg.on_pattern(A, rp, ci), rhs=rhs, smoother="asm",
+                     asm_blocks=[None, ix.blocks()], asm_orders=[None, gblocks])
+    trace, eps = _run_emu_mg(emu_mg, O, [None, ix.blocks()], [None, {"grp": grp}], 2, 0, 0, 1, 0, 1, 1.0, 3)
+    trace_ref, eps_ref = O.mg_solve_trace(3, omega=1.0)
+    r0 = float(np.linalg.norm(np.where(O.bdc[-1] > 1.1, O.rhs, 0.0)))
+    for a, b in zip(trace, trace_ref):
+        assert abs(a - b) <= 1e-10 * r0, (trace, trace_ref, r0)
+    assert trace[-1] < 1e-2 * r0
+    assert np.abs(eps - eps_ref).max() <= 1e-9 * np.abs(eps_ref).max()
