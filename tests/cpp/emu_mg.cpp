@@ -36,6 +36,21 @@ int b2_csr_zero_rows_dev(b2_csr* A, const int32_t* rows, int64_t n, double diag,
   return 0;
 }
 
+// the mesh object of b2_assemble.cu, as far as b2_stokes.cu looks at it
+struct b2_mesh {
+  b2_ctx* ctx;
+  int64_t nnode, nel;
+  const double* xyz;
+  const int32_t* conn;
+};
+void b2_mesh_view(const b2_mesh* m, b2_ctx** ctx, int64_t* nnode, int64_t* nel, const double** xyz, const int32_t** conn) {
+  *ctx = m->ctx;
+  *nnode = m->nnode;
+  *nel = m->nel;
+  *xyz = m->xyz;
+  *conn = m->conn;
+}
+
 extern "C" {
 const char* b2_last_error(void) { return g_err.c_str(); }
 int b2_halo_sum(b2_halo*, b2_vec*) { return 0; }
@@ -112,6 +127,41 @@ int b2_csr_transpose(const b2_csr* A, b2_csr** out) {
     }
   *out = make_csr(A->ctx, A->ncols, A->nrows, rp.data(), col.data(), val.data());
   return 0;
+}
+
+// b2_stokes_create / b2_ns_create + assemble (+ the boundary pressure faces) of the real b2_stokes.cu on host arrays:
+// the system matrix values on the pattern (rp, col) and the residual.  ns != 0: the Navier-Stokes routine.
+int emu_stokes_plan(int64_t nnode, int64_t nel, const double* xyz, const int32_t* conn, int64_t n, const int64_t* rp, const int32_t* col,
+                    const int32_t* edof, int nv, int np, int ng, const double* phi_v, const double* dxi, const double* deta, const double* dzeta,
+                    const double* w, const double* phi_p, const double* sol, double coef, int ns, int64_t nfaces, const int32_t* felem,
+                    const int32_t* flocal, const double* fvalue, int nvf, int ngf, const double* fphi, const double* fdxi, const double* fdeta,
+                    const double* fw, const int32_t* fnodes, double* val_out, double* rhs_out) {
+  b2_ctx ctx;
+  ctx.sm_count = 1;
+  b2_mesh mesh{&ctx, nnode, nel, xyz, conn};
+  std::vector<double> zeros((size_t)rp[n], 0.0);
+  b2_csr* A = make_csr(&ctx, n, n, rp, col, zeros.data());
+  auto run = [&]() -> int {
+    b2_stokes* plan = nullptr;
+    if (ns) B2_TRY(b2_ns_create(&mesh, A, edof, nv, np, ng, phi_v, dxi, deta, dzeta, w, phi_p, &plan));
+    else B2_TRY(b2_stokes_create(&mesh, A, edof, nv, np, ng, dxi, deta, dzeta, w, phi_p, &plan));
+    b2_vec *S = nullptr, *R = nullptr;
+    B2_TRY(b2_vec_create(&ctx, n, &S));
+    B2_TRY(b2_vec_create(&ctx, n, &R));
+    B2_TRY(b2_vec_put(S, sol, n));
+    if (ns) B2_TRY(b2_ns_assemble(plan, S, R, coef));
+    else B2_TRY(b2_stokes_assemble(plan, S, R, coef));
+    if (nfaces) B2_TRY(b2_ns_pressure_faces(plan, nfaces, felem, flocal, fvalue, nvf, ngf, fphi, fdxi, fdeta, fw, fnodes, R));
+    B2_TRY(b2_vec_get(R, rhs_out, n));
+    std::memcpy(val_out, A->val, (size_t)rp[n] * sizeof(double));
+    b2_vec_destroy(S);
+    b2_vec_destroy(R);
+    b2_stokes_destroy(plan);
+    return 0;
+  };
+  const int rc = run();
+  b2_csr_destroy(A);
+  return rc;
 }
 
 // One multigrid solve sequence on nlevels levels.  Level l: operator (rp, col, val)[l] (un-penalised), prolongator from

@@ -428,7 +428,7 @@ def emu_mg(tmp_path_factory):
     d = tmp_path_factory.mktemp("emu_mg")
     cpp = os.path.join(ROOT, "tests", "cpp")
     objs = []
-    for src in [os.path.join(ROOT, "femus_b200", "csrc", f) for f in ("b2_vec.cu", "b2_schwarz.cu", "b2_mg.cu")] + [os.path.join(cpp, "emu_mg.cpp")]:
+    for src in [os.path.join(ROOT, "femus_b200", "csrc", f) for f in ("b2_vec.cu", "b2_schwarz.cu", "b2_mg.cu", "b2_stokes.cu")] + [os.path.join(cpp, "emu_mg.cpp")]:
         obj = str(d / (os.path.basename(src) + ".o"))
         r = subprocess.run(["g++", "-std=c++20", "-O1", "-pthread", "-fPIC", "-I", os.path.join(cpp, "emu_rt"), "-I", cpp, "-include",
                             os.path.join(cpp, "emu_prefix.hpp"), "-x", "c++", "-c", src, "-o", obj], capture_output=True, text=True)
@@ -439,6 +439,7 @@ def emu_mg(tmp_path_factory):
     assert r.returncode == 0, r.stderr
     L = ctypes.CDLL(so)
     L.emu_mg_run.restype = ctypes.c_int
+    L.emu_stokes_plan.restype = ctypes.c_int
     L.b2_last_error.restype = ctypes.c_char_p
     return L
 
@@ -549,3 +550,47 @@ def test_stokes_vcycle_orchestration_on_the_emulator(emu_mg):
         assert abs(a - b) <= 1e-10 * r0, (trace, trace_ref, r0)
     assert trace[-1] < 1e-2 * r0
     assert np.abs(eps - eps_ref).max() <= 1e-9 * np.abs(eps_ref).max()
+
+
+@pytest.mark.parametrize("ns", [0, 1])
+def test_stokes_plan_entry_points_on_the_emulator(emu_mg, ns):
+    """b2_stokes_create / b2_ns_create (table packing, shared-memory sizing), b2_stokes_assemble / b2_ns_assemble and
+    b2_ns_pressure_faces of the real b2_stokes.cu, called as the bindings call them, against the oracle (P2-P1 tetrahedra:
+    31 Gauss points, triangular faces with 13)."""
+    from femus_b200.poisson import neumann_face_groups
+    from oracle import stokes, navier_stokes as ons, mesh_mixed as mm, mg
+    path = os.path.join(GOLDEN, "cube_tet10.neu")
+    level, Lm = hostapi.HostHierarchy.from_neu(path, 1).levels[0], mm.read_neu(path)
+    fams = ["quadratic"] * 3 + ["linear"]
+    S = hostapi.SystemOnLevel(level, fams)
+    rp, ci = S.sparsity()
+    edof = np.ascontiguousarray(S.elem_dofs(), dtype=np.int32)
+    t = level.elem_type
+    tv, tp = [np.ascontiguousarray(a) for a in hostapi.elem_tables(t, "quadratic")], [np.ascontiguousarray(a) for a in hostapi.elem_tables(t, "linear")]
+    xyz, conn = np.ascontiguousarray(level.xyz), np.ascontiguousarray(level.conn, dtype=np.int32)
+    sol = 0.4 * np.random.default_rng(16).standard_normal(S.n)
+    tau = {2: 1.5, 5: -0.4}
+    groups = neumann_face_groups(level, "quadratic", tau, t, slice(None)) if ns else []
+    val, rhs = np.zeros(len(ci)), np.zeros(S.n)
+    args = [ctypes.c_int64(level.nnode), ctypes.c_int64(level.nel), _p(xyz), _p(conn), ctypes.c_int64(S.n), _p(rp), _p(ci), _p(edof),
+            ctypes.c_int(tv[0].shape[1]), ctypes.c_int(tp[0].shape[1]), ctypes.c_int(tv[4].shape[0]), _p(tv[0]), _p(tv[1]), _p(tv[2]), _p(tv[3]), _p(tv[4]),
+            _p(tp[0]), _p(sol), ctypes.c_double(0.3), ctypes.c_int(ns)]
+    if groups:
+        (fe, fl, fv), (phi, dxi, deta, w), fnodes = groups[0]
+        fn = np.ascontiguousarray(fnodes, dtype=np.int32)
+        keep = [np.ascontiguousarray(a) for a in (fe, fl, fv, phi, dxi, deta, w)]
+        args += [ctypes.c_int64(len(fe)), _p(keep[0]), _p(keep[1]), _p(keep[2]), ctypes.c_int(phi.shape[1]), ctypes.c_int(phi.shape[0]), _p(keep[3]),
+                 _p(keep[4]), _p(keep[5]), _p(keep[6]), _p(fn)]
+    else:
+        args += [ctypes.c_int64(0), None, None, None, ctypes.c_int(0), ctypes.c_int(0), None, None, None, None, None]
+    rc = emu_mg.emu_stokes_plan(*args, _p(val), _p(rhs))
+    assert rc == 0, emu_mg.b2_last_error().decode()
+    tof = lambda tt, o: mm.FE[tt].tables(o)      # noqa: E731
+    if ns:
+        Aref, rref = ons.assemble(Lm, mm, "quadratic", "linear", sol, 0.3, tof)
+        rref = rref + ons.pressure_boundary_rhs(Lm, mm, "quadratic", "linear", tau)
+    else:
+        Aref, rref = stokes.assemble(Lm, mm, "quadratic", "linear", sol, 0.3, tof)
+    Aref = mg.on_pattern(Aref, rp, ci)
+    assert np.abs(val - Aref.data).max() <= 1e-12 * np.abs(Aref.data).max()
+    assert np.abs(rhs - rref).max() <= 1e-12 * np.abs(rref).max()
