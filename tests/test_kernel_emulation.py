@@ -504,7 +504,7 @@ def _run_emu_mg(L, O, blocks, orders, smoother, sub, ksp, coarse_direct, row_lev
 @pytest.mark.parametrize("case", ["jacobi", "gmres_jacobi", "asm_lu", "asm_ilu_levels_gmres", "asm_ssor_direct"])
 def test_multigrid_orchestration_on_the_emulator(emu_mg, case):
     """MGSetLevel on every level + MGSolve cycles of the REAL b2_mg.cu (penalty, Galerkin-free level setup, V-cycle,
-    residual update), b2_vec.cu and b2_schwarz.cu on the CPU emulator: Richardson + Jacobi, GMRES + Jacobi, Richardson +
+    residual update; two cycles), b2_vec.cu and b2_schwarz.cu on the CPU emulator: Richardson + Jacobi, GMRES + Jacobi, Richardson +
     element blocks (exact), GMRES + ILU(0) blocks with level-scheduled rows, SSOR blocks with the direct coarse solve --
     residual traces and corrections against the oracle V-cycle."""
     from oracle import mesh_box as mb, mg
@@ -526,8 +526,8 @@ def test_multigrid_orchestration_on_the_emulator(emu_mg, case):
         kw = dict(smoother="asm", asm_blocks=blocks, asm_orders=[None, gblocks], asm_sub={0: "lu", 1: "ssor", 2: "ilu"}[cfg["sub"]])
     O = mg.Hierarchy(lv, order, ksp="gmres" if cfg["ksp"] else "richardson", **kw)
     npre = 2 if cfg["ksp"] else 1
-    trace, eps = _run_emu_mg(emu_mg, O, blocks, orders, cfg["smoother"], cfg["sub"], cfg["ksp"], cfg["direct"], cfg["rowlev"], npre, cfg["omega"], 3)
-    trace_ref, eps_ref = O.mg_solve_trace(3, npre=npre, npost=npre, omega=cfg["omega"])
+    trace, eps = _run_emu_mg(emu_mg, O, blocks, orders, cfg["smoother"], cfg["sub"], cfg["ksp"], cfg["direct"], cfg["rowlev"], npre, cfg["omega"], 2)
+    trace_ref, eps_ref = O.mg_solve_trace(2, npre=npre, npost=npre, omega=cfg["omega"])
     r0 = float(np.linalg.norm(np.where(O.bdc[-1] > 1.1, O.rhs, 0.0)))           # the scale: the residual before the first cycle
     for a, b in zip(trace, trace_ref):
         assert abs(a - b) <= 1e-11 * r0, (trace, trace_ref, r0)
@@ -538,7 +538,7 @@ def test_multigrid_orchestration_on_the_emulator(emu_mg, case):
 def test_stokes_vcycle_orchestration_on_the_emulator(emu_mg):
     """The velocity-pressure path of b2_mg.cu on the emulator: indefinite level operators (steady Stokes, oracle-assembled,
     Galerkin coarse operator), Vanka blocks with the pressure as Schur variable and exact block solves by the Gauss-Jordan
-    kernel, DIRECT coarse solve through a one-block Schwarz object; three V-cycles against the oracle (a through-flow
+    kernel, DIRECT coarse solve through a one-block Schwarz object; two V-cycles against the oracle (a through-flow
     channel on a 1 -> 8 element hierarchy: small enough for the emulator, 8 blocks of 383 dofs)."""
     from oracle import stokes, mesh_box as mb, fe_hex, system as osys, mg
     lv, H = mb.build_hierarchy(1, 1, 1, 2), hostapi.HostHierarchy(1, 1, 1, 2)
@@ -553,8 +553,8 @@ def test_stokes_vcycle_orchestration_on_the_emulator(emu_mg):
     grp, gptr, gblocks = hostapi.asm_schedule(rp, ci, ix.overlap_ptr, ix.overlap, "colours")
     O = mg.Hierarchy(lv, None, mesh=osys.SystemMesh(mb, fams, [walls] * 3 + [()]), A_top=mg.on_pattern(A, rp, ci), rhs=rhs, smoother="asm",
                      asm_blocks=[None, ix.blocks()], asm_orders=[None, gblocks])
-    trace, eps = _run_emu_mg(emu_mg, O, [None, ix.blocks()], [None, {"grp": grp}], 2, 0, 0, 1, 0, 1, 1.0, 3)
-    trace_ref, eps_ref = O.mg_solve_trace(3, omega=1.0)
+    trace, eps = _run_emu_mg(emu_mg, O, [None, ix.blocks()], [None, {"grp": grp}], 2, 0, 0, 1, 0, 1, 1.0, 2)
+    trace_ref, eps_ref = O.mg_solve_trace(2, omega=1.0)
     r0 = float(np.linalg.norm(np.where(O.bdc[-1] > 1.1, O.rhs, 0.0)))
     for a, b in zip(trace, trace_ref):
         assert abs(a - b) <= 1e-10 * r0, (trace, trace_ref, r0)
