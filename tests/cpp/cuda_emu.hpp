@@ -40,23 +40,26 @@ void launch(K kernel, unsigned grid, unsigned block, size_t smem_bytes, Args... 
   blockDim.x = block;
   dyn_shared.assign(smem_bytes / sizeof(double) + 1, 0.0);
   const unsigned nwarps = (block + 31) / 32;
-  for (unsigned b = 0; b < grid; b++) {
-    cta_barrier.reset(new std::barrier<>(block));
-    warp_barrier.clear();
-    warp_buf.assign(nwarps, std::vector<double>(32, 0.0));
-    for (unsigned w = 0; w < nwarps; w++) {
-      const unsigned lanes = (w + 1) * 32 <= block ? 32 : block - w * 32;
-      warp_barrier.emplace_back(new std::barrier<>(lanes));
-    }
-    std::vector<std::thread> th;
-    for (unsigned t = 0; t < block; t++)
-      th.emplace_back([=] {
-        threadIdx.x = t;
+  cta_barrier.reset(new std::barrier<>(block));
+  warp_barrier.clear();
+  warp_buf.assign(nwarps, std::vector<double>(32, 0.0));
+  for (unsigned w = 0; w < nwarps; w++) {
+    const unsigned lanes = (w + 1) * 32 <= block ? 32 : block - w * 32;
+    warp_barrier.emplace_back(new std::barrier<>(lanes));
+  }
+  // one host thread per CUDA thread of a CTA, reused for every CTA of the grid: the CTAs run one after the other (the
+  // threads meet at the CTA barrier between two of them), so the static __shared__ storage always belongs to one CTA
+  std::vector<std::thread> th;
+  for (unsigned t = 0; t < block; t++)
+    th.emplace_back([=] {
+      threadIdx.x = t;
+      for (unsigned b = 0; b < grid; b++) {
         blockIdx.x = b;
         kernel(args...);
-      });
-    for (auto& x : th) x.join();
-  }
+        cta_barrier->arrive_and_wait();
+      }
+    });
+  for (auto& x : th) x.join();
 }
 }  // namespace emu
 
