@@ -112,7 +112,8 @@ class Hierarchy:
             Ac = (self.P[l].T @ self.A_raw[l] @ self.P[l]).tocsr()
             self.A_raw[l - 1] = on_pattern(Ac, rp, ci)
         self.A = [penalty_fast(self.A_raw[l], self.bdc_idx[l]) for l in range(nl)]
-        self.dinv = [1.0 / A.diagonal() for A in self.A]
+        with np.errstate(divide="ignore"):          # velocity-pressure systems: zero pressure diagonal (Jacobi is not used there)
+            self.dinv = [1.0 / A.diagonal() for A in self.A]
         self.lu = spla.splu(self.A[0].tocsc()) if self.coarse_lu else None
         self.asm = [None] * nl
         if self.smoother == "asm":          # PCASM sub-matrices are extracted from the penalised level operator
