@@ -131,6 +131,10 @@ struct b2_csr {
   int tpr;           // threads per row of the streaming SpMV kernel (power of two <= 32)
   int max_row;       // longest row
   double last_ms;
+  // bumped by every C-ABI entry point that rewrites values of an EXISTING matrix in place (zero, zero rows / columns,
+  // set rows, add blocks, put values, copy): consumers that cache something derived from the values (the explicit
+  // restriction R = P^T of b2_mg) compare it.  Zero-initialised by b2_csr_alloc (value-initialised struct).
+  uint64_t version;
 };
 
 template <class T>

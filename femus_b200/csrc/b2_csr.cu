@@ -266,6 +266,7 @@ __global__ void zero_rows_owned_kernel(const int64_t* __restrict__ rowptr, const
 }
 int b2_csr_zero_rows_dev(b2_csr* A, const int32_t* d_rows, int64_t n, double diag, const uint8_t* d_owned) {
   if (n == 0) return 0;
+  A->version++;
   b2_ctx* c = A->ctx;
   const int grid = b2_grid_for(c, n * 32, kBlock, 8);
   if (d_owned) B2_LAUNCH(c, zero_rows_owned_kernel, grid, kBlock, 0, A->rowptr, A->col, A->val, d_rows, n, diag, d_owned);
@@ -282,6 +283,7 @@ int b2_csr_alloc(b2_ctx* c, int64_t nrows, int64_t ncols, int64_t nnz, b2_csr** 
   A->tpr = 8;
   A->max_row = 0;
   A->last_ms = 0.;
+  A->version = 0;
   A->diag_pos = nullptr;
   A->chunk_row = nullptr;
   A->dict_ptr = nullptr;
@@ -408,13 +410,18 @@ int b2_csr_get(const b2_csr* A, int64_t* rowptr, int32_t* col, double* vals) {
   if (vals) B2_TRY(b2_download(A->ctx, vals, A->val, (size_t)A->nnz));
   return 0;
 }
-int b2_csr_put_vals(b2_csr* A, const double* vals) { return b2_upload(A->ctx, A->val, vals, (size_t)A->nnz); }
+int b2_csr_put_vals(b2_csr* A, const double* vals) {
+  A->version++;
+  return b2_upload(A->ctx, A->val, vals, (size_t)A->nnz);
+}
 int b2_csr_zero(b2_csr* A) {
+  A->version++;
   B2_CUDA(cudaMemsetAsync(A->val, 0, (size_t)A->nnz * sizeof(double), A->ctx->stream));
   return 0;
 }
 int b2_csr_copy_vals(b2_csr* dst, const b2_csr* src) {
   B2_CHECK(dst->nnz == src->nnz && dst->nrows == src->nrows, "b2_csr_copy_vals: pattern mismatch");
+  dst->version++;
   B2_CUDA(cudaMemcpyAsync(dst->val, src->val, (size_t)src->nnz * sizeof(double), cudaMemcpyDeviceToDevice,
                           dst->ctx->stream));
   return 0;
@@ -423,6 +430,7 @@ int b2_csr_copy_vals(b2_csr* dst, const b2_csr* src) {
 int b2_csr_add_blocks(b2_csr* A, int64_t nblk, int nrow, int ncol, const int32_t* rows, const int32_t* cols,
                       const double* vals) {
   if (nblk == 0) return 0;
+  A->version++;
   b2_ctx* c = A->ctx;
   int32_t *d_r = nullptr, *d_c = nullptr;
   double* d_v = nullptr;
@@ -451,6 +459,7 @@ int b2_csr_add_blocks(b2_csr* A, int64_t nblk, int nrow, int ncol, const int32_t
 int b2_csr_set_rows(b2_csr* A, int64_t nset, const int32_t* rows, const int64_t* ptr, const int32_t* cols,
                     const double* vals) {
   if (nset == 0) return 0;
+  A->version++;
   b2_ctx* c = A->ctx;
   const size_t nv = (size_t)ptr[nset];
   int32_t *d_r = nullptr, *d_c = nullptr;
@@ -482,6 +491,7 @@ int b2_csr_set_rows(b2_csr* A, int64_t nset, const int32_t* rows, const int64_t*
 
 int b2_csr_zero_rows(b2_csr* A, const int32_t* rows, int64_t n, double diag) {
   if (n == 0) return 0;
+  A->version++;
   b2_ctx* c = A->ctx;
   int32_t* d_r = nullptr;
   B2_TRY(b2_malloc(c, &d_r, (size_t)n));
@@ -495,6 +505,7 @@ int b2_csr_zero_rows(b2_csr* A, const int32_t* rows, int64_t n, double diag) {
 
 int b2_csr_zero_cols(b2_csr* A, const int32_t* cols, int64_t n) {
   if (n == 0 || A->nnz == 0) return 0;
+  A->version++;
   b2_ctx* c = A->ctx;
   int32_t* d_c = nullptr;
   unsigned char* mask = nullptr;

@@ -16,6 +16,7 @@ struct b2_mg_level {
   b2_csr* A = nullptr;      // borrowed, penalised in place
   b2_csr* P = nullptr;      // borrowed
   b2_csr* R = nullptr;      // owned: explicit transpose of P
+  uint64_t Pversion = 0;    // P->version R was built from (values of P changed in place => R is rebuilt)
   b2_vec *dinv = nullptr, *x = nullptr, *t = nullptr, *b = nullptr, *r = nullptr;
   int32_t* bdc = nullptr;   // device copy of the Dirichlet row list
   int64_t nbdc = 0;
@@ -458,7 +459,9 @@ int b2_mg_set_level(b2_mg* mg, int level, b2_csr* A, b2_csr* P, const int32_t* b
   B2_CHECK(level == 0 || (P && P->nrows == A->nrows), "b2_mg_set_level: prolongator shape mismatch");
   b2_ctx* c = mg->ctx;
   b2_mg_level& L = mg->L[level];
-  const bool newP = (level > 0) && (L.P != P || !L.R);
+  // PCMGSetRestriction(..., PP) is called at every MGSetLevel (LinearEquationSolverPetsc.cpp:277): the restriction
+  // always matches the prolongator's current values
+  const bool newP = (level > 0) && (L.P != P || !L.R || L.Pversion != P->version);
   L.A = A;
   L.P = level ? P : nullptr;
   L.npre = npre;
@@ -516,6 +519,7 @@ int b2_mg_set_level(b2_mg* mg, int level, b2_csr* A, b2_csr* P, const int32_t* b
   if (newP) {   // the explicit restriction R = P^T is rebuilt only when P changes
     if (L.R) { b2_csr_destroy(L.R); L.R = nullptr; }
     B2_TRY(b2_csr_transpose(P, &L.R));
+    L.Pversion = P->version;
     if (L.halo) B2_TRY(b2_csr_zero_cols_notowned(L.R, L.halo->owned));   // shared fine rows restrict once
   }
   return 0;

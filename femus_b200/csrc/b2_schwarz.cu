@@ -33,6 +33,7 @@ struct b2_schwarz {
   int32_t* group_blocks = nullptr;   // [nblocks] device: blocks in schedule order
   std::vector<int64_t> group_ptr;    // [ngroups+1] host
   int* err = nullptr;             // device: 1 + first block whose pivot vanished, or 0
+  int64_t n = 0;                  // A->nrows at creation (the borrowed operator may be gone when this object is destroyed)
   int sub = 0;                    // block solve: 0 = exact (dense inverse), 1 = one SSOR iteration on the block's rows, 2 = ILU(0)
   int64_t* frow = nullptr;        // [ndofs_total] ILU: start of every (block, row)'s factor row
   double* fac = nullptr;          // [fac_total]   ILU factors on the pattern of the blocks' rows of A
@@ -87,6 +88,7 @@ int b2_schwarz_create(b2_ctx* c, b2_csr* A, int64_t nblocks, const int64_t* blk_
   b2_schwarz* s = new b2_schwarz();
   s->ctx = c;
   s->A = A;
+  s->n = A->nrows;
   s->nblocks = nblocks;
   s->ngroups = ngroups;
   s->ndofs_total = blk_ptr[nblocks];
@@ -224,13 +226,11 @@ int b2_schwarz_setup(b2_schwarz* s) {
   }
   B2_CHECK(s->max_m <= 4096, "b2_schwarz_setup: a block has %d dofs; exact block solves support at most 4096 (use the SSOR block solve)", s->max_m);
   const int smem = 2 * s->max_m * (int)sizeof(double);
-  if (!s->inv) {
-    B2_TRY(b2_malloc(c, &s->inv, (size_t)s->inv_total));
-    if (smem > 48 * 1024) {       // shared memory of the two kernels: 2 x max_m doubles (<= 64 KB)
-      B2_CUDA(cudaFuncSetAttribute(schwarz_invert_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      B2_CUDA(cudaFuncSetAttribute(schwarz_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    }
-  }
+  if (!s->inv) B2_TRY(b2_malloc(c, &s->inv, (size_t)s->inv_total));
+  // shared memory of the two kernels: 2 x max_m doubles.  The attribute belongs to the FUNCTION, not to this object: it is
+  // always the fixed maximum (max_m <= 4096 => 64 KB), so that no other object's setup can lower it under this one
+  B2_CUDA(cudaFuncSetAttribute(schwarz_invert_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 4096 * (int)sizeof(double)));
+  B2_CUDA(cudaFuncSetAttribute(schwarz_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 4096 * (int)sizeof(double)));
   B2_CUDA(cudaMemsetAsync(s->err, 0, sizeof(int), c->stream));
   B2_LAUNCH(c, schwarz_extract_kernel, b2_grid_for(c, s->nblocks, 1, 8), 256, 0, s->nblocks, s->blk_ptr, s->blk_dofs, s->inv_ptr,
             s->A->rowptr, s->A->col, s->A->val, s->inv);
@@ -302,11 +302,11 @@ int b2_schwarz_destroy(b2_schwarz* s) {
   b2_free(c, s->lvrows_b, (size_t)s->ndofs_total);
   b2_free(c, s->frow, (size_t)s->ndofs_total);
   b2_free(c, s->fac, (size_t)s->fac_total);
-  b2_free(c, s->foff, (size_t)s->A->nrows);
-  b2_free(c, s->tg, (size_t)s->A->nrows);
-  b2_free(c, s->dg, (size_t)s->A->nrows);
-  b2_free(c, s->zg, (size_t)s->A->nrows);
-  b2_free(c, s->mark, (size_t)s->A->nrows);
+  b2_free(c, s->foff, (size_t)s->n);
+  b2_free(c, s->tg, (size_t)s->n);
+  b2_free(c, s->dg, (size_t)s->n);
+  b2_free(c, s->zg, (size_t)s->n);
+  b2_free(c, s->mark, (size_t)s->n);
   b2_free(c, s->group_blocks, (size_t)s->nblocks);
   b2_free(c, s->err, 1);
   delete s;

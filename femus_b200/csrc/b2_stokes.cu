@@ -65,8 +65,7 @@ int b2_stokes_create(b2_mesh* mesh, b2_csr* A, const int32_t* elem_dofs, int nve
     B2_TRY(b2_upload(c, p->edof, elem_dofs, (size_t)nel * 108));
     B2_TRY(b2_upload(c, p->tabv, tab.data(), nt));
     B2_TRY(b2_upload(c, p->tabp, phi_p, (size_t)ngauss * nve_p));
-    const size_t smem = stokes_smem(nve_v, nve_p, ngauss);
-    if (smem > 48 * 1024) B2_CUDA(cudaFuncSetAttribute(stokes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B2_CHECK(stokes_smem(nve_v, nve_p, ngauss) <= 227 * 1024, "b2_stokes_create: the element tables exceed the SM's shared memory");
     return 0;
   }();
   if (rc) {               // nothing half-built is handed out
@@ -87,6 +86,8 @@ int b2_stokes_assemble(b2_stokes* p, const b2_vec* sol, b2_vec* rhs, double IRe)
   const int32_t* conn = nullptr;
   b2_mesh_view(p->mesh, &c, &nnode, &nel, &xyz, &conn);
   const size_t smem = stokes_smem(p->nv, p->np, p->ng);
+  // the attribute belongs to the function, not to the plan: set for THIS launch (several plans of a mixed mesh coexist)
+  B2_CUDA(cudaFuncSetAttribute(stokes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024)));
   B2_LAUNCH(c, stokes_kernel, b2_grid_for(c, nel, kStokesWarps, 3), kStokesWarps * 32, smem, nel, nnode, p->nv, p->np, p->ng, xyz, conn, p->edof,
             p->tabv, p->tabp, p->A->rowptr, p->A->col, p->A->val, sol ? sol->d : nullptr, rhs ? rhs->d : nullptr, IRe);
   return 0;
@@ -110,7 +111,6 @@ int b2_ns_create(b2_mesh* mesh, b2_csr* A, const int32_t* elem_dofs, int nve_v, 
     B2_TRY(b2_upload(p->ctx, p->tabns, tab.data(), nt));
     const size_t smem = (size_t)ns_cta_doubles_host(nve_v, nve_p, ngauss) * sizeof(double);
     B2_CHECK(smem <= 227 * 1024, "b2_ns_create: %zu bytes of shared memory per element exceed the SM", smem);
-    if (smem > 48 * 1024) B2_CUDA(cudaFuncSetAttribute(ns_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     return 0;
   }();
   if (rc) {
@@ -131,6 +131,7 @@ int b2_ns_assemble(b2_stokes* p, const b2_vec* sol, b2_vec* rhs, double nu) {
   const int32_t* conn = nullptr;
   b2_mesh_view(p->mesh, &c, &nnode, &nel, &xyz, &conn);
   const size_t smem = (size_t)ns_cta_doubles_host(p->nv, p->np, p->ng) * sizeof(double);
+  B2_CUDA(cudaFuncSetAttribute(ns_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024)));
   B2_LAUNCH(c, ns_kernel, b2_grid_for(c, nel, 1, 3), kNsThreads, smem, nel, nnode, p->nv, p->np, p->ng, xyz, conn, p->edof, p->tabns, p->tabp,
             p->A->rowptr, p->A->col, p->A->val, sol ? sol->d : nullptr, rhs ? rhs->d : nullptr, nu);
   return 0;

@@ -63,6 +63,7 @@ class LinearEquationSolverB200 {
     _bdcIndexIsInitialized = false;
   }
   void DeletePde() {
+    this->OnDeletePde();      // objects that BORROW _KK's handle (the subclass's block smoother) go first
     if (_coarseSolver) b2_schwarz_destroy(_coarseSolver);
     _coarseSolver = nullptr;
     delete _KK; delete _RES; delete _EPS; delete _EPSC; delete _RESC;
@@ -163,6 +164,9 @@ class LinearEquationSolverB200 {
   B200Vector *_RES, *_EPS, *_EPSC, *_RESC;
 
  protected:
+  // called before _KK is deleted (InitPde, InitPdeSystem, DeletePde).  Not reached from this class's destructor (the
+  // subclass part is gone by then): a subclass that overrides it releases its objects in its own destructor as well.
+  virtual void OnDeletePde() {}
   // level smoother: set_solver_type(RICHARDSON) -> Richardson(scale)+Jacobi, set_solver_type(CHEBYSHEV) ->
   // Chebyshev+Jacobi with the backend's stated eigenvalue bounds (KSPSetType switch, :452-536).  The reference's
   // subclasses override SetPreconditioner (LinearEquationSolverPetscAsm.cpp:266); here they override this.

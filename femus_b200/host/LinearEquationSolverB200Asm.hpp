@@ -61,6 +61,7 @@ class LinearEquationSolverB200Asm : public LinearEquationSolverB200 {
   int64_t GroupNumber() const { return _schwarz ? b2_schwarz_groups(_schwarz) : 0; }
 
  protected:
+  void OnDeletePde() override { this->ClearIndex(); }      // the b2_schwarz object borrows _KK->handle()
   void SetLevelSmoother(b2_mg* mg) override {
     if (_level == 0) { LinearEquationSolverB200::SetLevelSmoother(mg); return; }     // the coarsest level is solved, not smoothed
     if (_standardASM || !_msh || _families.empty() || _NSchurVar > _families.size()) {
