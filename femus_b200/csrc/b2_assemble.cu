@@ -55,6 +55,12 @@ struct b2_asm {
   // fused Galerkin plan (b2_asm_poisson_galerkin): per-child element prolongators of the plan `gal`
   const b2_galerkin* gal;
   void* gal_tab;          // device: GalTables<nve>
+  // sum-factorised kernel (b2_assemble_sumfac.cuh): 1-D tables, dofs and slot map in lattice order, Kronecker factors
+  // of the child prolongators; sf_tab == null: the tables are not a 3 x 3 x 3 / 4 x 4 x 4 tensor product (kernel not used)
+  void* sf_tab;           // device: SfTables
+  int32_t* dofL;          // [nel][27]
+  void* lslot;            // [nel][729] uint8 or uint16
+  void* sf_gal;           // device: SfGalTables of the plan `gal`, or null (the child prolongators are not Kronecker products)
 };
 
 // what the fused kernel needs from a Galerkin plan (b2_galerkin.cu)
@@ -104,6 +110,9 @@ struct GalArgs {
   double* Cv;                 // coarse values
   double* emat;               // [nelc][NVE*NVE] record of every coarse element's Galerkin matrix, or null
 };
+
+#include "b2_assemble_sumfac.cuh"
+#include "b2_assemble_sumfac_host.hpp"
 
 template <int NVE>
 struct SmemLayout {
@@ -863,6 +872,100 @@ int build_natural_slots(b2_asm* p) {
   return 0;
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Host side of the sum-factorised kernel (b2_assemble_sumfac.cuh; table factorisation in b2_assemble_sumfac_host.hpp).
+// the stage-3 coefficients live in constant memory: one set per process (every Hex27 / 64-point plan has the same
+// tables; a plan whose tables differ from the loaded set stays on the tensor-core kernel)
+static bool g_sfM_loaded = false;
+static double g_sfM[4][9][4];
+
+template <typename SlotT>
+static int sf_build_slots(b2_asm* p) {
+  b2_ctx* c = p->mesh->ctx;
+  const int64_t total = p->mesh->nel * 729;
+  SlotT* s = nullptr;
+  B2_TRY(b2_malloc(c, &s, (size_t)total));
+  p->lslot = s;
+  int* d_err = nullptr;
+  B2_TRY(b2_malloc(c, &d_err, 1));
+  B2_CUDA(cudaMemsetAsync(d_err, 0, sizeof(int), c->stream));
+  B2_LAUNCH(c, natural_slot_kernel<SlotT>, b2_grid_for(c, total, 256, 8), 256, 0, total, 27, p->dofL, p->A->rowptr, p->A->col, s, d_err);
+  int err = 0;
+  B2_TRY(b2_download(c, &err, d_err, 1));
+  b2_free(c, d_err, 1);
+  B2_CHECK(err == 0, "b2_asm_create: an element couples dofs outside the matrix pattern");
+  return 0;
+}
+
+// called by b2_asm_create for 27 dofs / 64 points; leaves p->sf_tab null when the kernel does not apply
+static int sf_prepare(b2_asm* p, const int32_t* dof, const double* phi, const double* dxi, const double* deta, const double* dzeta, const double* w) {
+  b2_ctx* c = p->mesh->ctx;
+  SfTables T;
+  if (!sf_factor_tables(phi, dxi, deta, dzeta, w, &T)) return 0;
+  if (!g_sfM_loaded) {
+    B2_CUDA(cudaMemcpyToSymbol(c_sfM, T.M, sizeof(T.M)));
+    memcpy(g_sfM, T.M, sizeof(T.M));
+    g_sfM_loaded = true;
+  } else if (memcmp(g_sfM, T.M, sizeof(T.M)) != 0) {
+    return 0;
+  }
+  const int64_t nel = p->mesh->nel;
+  std::vector<int32_t> dl((size_t)nel * 27);
+  for (int64_t e = 0; e < nel; e++)
+    for (int m = 0; m < 27; m++) dl[(size_t)e * 27 + m] = dof[(size_t)e * 27 + T.node_of[m]];
+  B2_TRY(b2_malloc(c, &p->dofL, (size_t)nel * 27));
+  B2_TRY(b2_upload(c, p->dofL, dl.data(), (size_t)nel * 27));
+  if (p->slot_bytes == 1) B2_TRY(sf_build_slots<uint8_t>(p));
+  else B2_TRY(sf_build_slots<uint16_t>(p));
+  SfTables* d_T = nullptr;
+  B2_TRY(b2_malloc(c, &d_T, 1));
+  B2_TRY(b2_upload(c, d_T, &T, 1));
+  p->sf_tab = d_T;
+  return 0;
+}
+
+// Kronecker factors of the 8 child prolongators of the Galerkin plan; leaves p->sf_gal null if they are not products
+static int sf_build_gal(b2_asm* p, const b2_galerkin_view& g) {
+  b2_ctx* c = p->mesh->ctx;
+  if (p->sf_gal) { b2_free(c, (SfGalTables*)p->sf_gal, 1); p->sf_gal = nullptr; }
+  if (!p->sf_tab || g.nc != 27 || g.nf != 125 || p->mesh->nel != 8 * g.nelc) return 0;
+  std::vector<int32_t> hdof(8 * 27), hfd(125);
+  std::vector<double> hp((size_t)125 * 27), Pc((size_t)8 * 27 * 27);
+  B2_TRY(b2_download(c, hdof.data(), p->dof, (size_t)8 * 27));
+  B2_TRY(b2_download(c, hfd.data(), g.fd, (size_t)125));
+  B2_TRY(b2_download(c, hp.data(), g.ploc, (size_t)125 * 27));
+  for (int jn = 0; jn < 8 * 27; jn++) {        // child j, local node n -> its row of the parent's element prolongator
+    int a = -1;
+    for (int t = 0; t < 125; t++)
+      if (hfd[t] == hdof[jn]) { a = t; break; }
+    if (a < 0) return 0;
+    for (int J = 0; J < 27; J++) Pc[(size_t)jn * 27 + J] = hp[(size_t)a * 27 + J];
+  }
+  SfGalTables G;
+  if (!sf_factor_children(Pc.data(), &G)) return 0;
+  SfGalTables* d_G = nullptr;
+  B2_TRY(b2_malloc(c, &d_G, 1));
+  B2_TRY(b2_upload(c, d_G, &G, 1));
+  p->sf_gal = d_G;
+  return 0;
+}
+
+template <typename SlotT, bool GAL, typename CSlotT>
+int launch_assemble_sumfac(b2_asm* p, const SfGalArgs& ga, const b2_vec* u, b2_vec* rhs, double nu, double fsrc) {
+  b2_ctx* c = p->mesh->ctx;
+  b2_prof_scope prof(c, p);
+  auto kern = assemble_q2_sumfac_kernel<SlotT, GAL, CSlotT>;
+  const size_t smem = GAL ? SfSmem::bytes_gal : SfSmem::bytes;
+  B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int64_t nunits = GAL ? p->mesh->nel / 8 : p->mesh->nel;
+  int grid = (int)((nunits + kSfWarps - 1) / kSfWarps);
+  if (grid > c->sm_count) grid = c->sm_count;
+  B2_LAUNCH(c, kern, grid, kSfWarps * 32, smem, p->mesh->nel, p->mesh->nnode, p->mesh->xyz, p->mesh->conn, p->dofL, (const SfTables*)p->sf_tab,
+            (const SlotT*)p->lslot, p->A->rowptr, p->A->val, u ? u->d : nullptr, rhs ? rhs->d : nullptr, nu, fsrc, ga);
+  return 0;
+}
+
 template <typename SlotT, bool GAL, typename CSlotT>
 int launch_assemble_mma(b2_asm* p, const GalArgs& ga, const b2_vec* u, b2_vec* rhs, double nu, double fsrc) {
   b2_ctx* c = p->mesh->ctx;
@@ -1318,6 +1421,10 @@ int b2_asm_create(b2_mesh* m, b2_csr* A, int nve, const int32_t* dof, int ngauss
   p->last_ms = 0.;
   p->gal = nullptr;
   p->gal_tab = nullptr;
+  p->sf_tab = nullptr;
+  p->dofL = nullptr;
+  p->lslot = nullptr;
+  p->sf_gal = nullptr;
   p->general = general;
   B2_TRY(b2_malloc(c, &p->dof, (size_t)m->nel * nve));
   B2_TRY(b2_upload(c, p->dof, dof, (size_t)m->nel * nve));
@@ -1340,6 +1447,7 @@ int b2_asm_create(b2_mesh* m, b2_csr* A, int nve, const int32_t* dof, int ngauss
     if (p->slot_bytes == 1) B2_TRY((build_slots<8, uint8_t>(p)));
     else B2_TRY((build_slots<8, uint16_t>(p)));
   }
+  if (nve == 27 && !general) B2_TRY(sf_prepare(p, dof, phi, dxi, deta, dzeta, weights));
   *out = p;
   return 0;
 }
@@ -1362,6 +1470,13 @@ int b2_asm_destroy(b2_asm* p) {
     if (p->nve == 27) b2_free(c, (GalTables<27>*)p->gal_tab, 1);
     else b2_free(c, (GalTables<8>*)p->gal_tab, 1);
   }
+  b2_free(c, (SfTables*)p->sf_tab, 1);
+  b2_free(c, p->dofL, (size_t)p->mesh->nel * 27);
+  if (p->lslot) {
+    if (p->slot_bytes == 1) b2_free(c, (uint8_t*)p->lslot, (size_t)p->mesh->nel * 729);
+    else b2_free(c, (uint16_t*)p->lslot, (size_t)p->mesh->nel * 729);
+  }
+  b2_free(c, (SfGalTables*)p->sf_gal, 1);
   delete p;
   return 0;
 }
@@ -1377,7 +1492,12 @@ int b2_asm_poisson(b2_asm* p, const b2_vec* u, b2_vec* rhs, double nu, double fs
     if (p->slot_bytes == 1) return launch_assemble_general<uint8_t>(p, u, rhs, nu, fsrc);
     return launch_assemble_general<uint16_t>(p, u, rhs, nu, fsrc);
   }
-  if (p->nve == 27 && p->mesh->ctx->asm_variant == 1) {      // FP64 tensor-core kernel
+  if (p->nve == 27 && p->mesh->ctx->asm_variant == 3 && p->sf_tab) {      // sum-factorised kernel (default)
+    SfGalArgs ga = {};
+    if (p->slot_bytes == 1) return launch_assemble_sumfac<uint8_t, false, uint8_t>(p, ga, u, rhs, nu, fsrc);
+    return launch_assemble_sumfac<uint16_t, false, uint8_t>(p, ga, u, rhs, nu, fsrc);
+  }
+  if (p->nve == 27 && (p->mesh->ctx->asm_variant == 1 || p->mesh->ctx->asm_variant == 3)) {      // FP64 tensor-core kernel
     GalArgs ga = {};
     if (p->slot_bytes == 1) return launch_assemble_mma<uint8_t, false, uint8_t>(p, ga, u, rhs, nu, fsrc);
     return launch_assemble_mma<uint16_t, false, uint8_t>(p, ga, u, rhs, nu, fsrc);
@@ -1410,10 +1530,18 @@ int b2_asm_poisson_galerkin(b2_asm* p, b2_galerkin* gal, const b2_vec* u, b2_vec
     }
     if (p->nve == 27) B2_TRY(build_gal_tables<27>(p, gal, g));
     else B2_TRY(build_gal_tables<8>(p, gal, g));
+    if (p->nve == 27) B2_TRY(sf_build_gal(p, g));
   }
   B2_CUDA(cudaMemsetAsync(g.Ac->val, 0, (size_t)g.Ac->nnz * sizeof(double), c->stream));
   const bool s1 = p->slot_bytes == 1, c1 = g.slot_bytes == 1;
-  if (p->nve == 27 && c->asm_variant == 1) {      // FP64 tensor-core kernel
+  if (p->nve == 27 && c->asm_variant == 3 && p->sf_tab && p->sf_gal) {      // sum-factorised kernel (default)
+    SfGalArgs ga = {(const SfGalTables*)p->sf_gal, g.cd, g.slot, g.fmask, g.cmask, g.Ac->rowptr, g.Ac->val, *g.emat};
+    if (s1 && c1) return launch_assemble_sumfac<uint8_t, true, uint8_t>(p, ga, u, rhs, nu, fsrc);
+    if (s1) return launch_assemble_sumfac<uint8_t, true, uint16_t>(p, ga, u, rhs, nu, fsrc);
+    if (c1) return launch_assemble_sumfac<uint16_t, true, uint8_t>(p, ga, u, rhs, nu, fsrc);
+    return launch_assemble_sumfac<uint16_t, true, uint16_t>(p, ga, u, rhs, nu, fsrc);
+  }
+  if (p->nve == 27 && (c->asm_variant == 1 || c->asm_variant == 3)) {      // FP64 tensor-core kernel
     GalArgs ga = {p->gal_tab, g.cd, g.slot, g.fmask, g.cmask, g.Ac->rowptr, g.Ac->val, *g.emat};
     if (s1 && c1) return launch_assemble_mma<uint8_t, true, uint8_t>(p, ga, u, rhs, nu, fsrc);
     if (s1) return launch_assemble_mma<uint8_t, true, uint16_t>(p, ga, u, rhs, nu, fsrc);

@@ -1,0 +1,376 @@
+// Triquadratic hexahedra (27 dofs, 4 x 4 x 4 Gauss points) by SUM FACTORISATION -- the default assembly kernel of the
+// Hex27 path.  Same arithmetic contract as the tensor-core kernel of b2_assemble.cu (the element loop of
+// applications/001_Poisson/main.cpp:350-602 with elem_type_3D::Jacobian_type, ElemType.hpp:1438-1537, the blocked
+// scatter of PetscMatrix.cpp:699-729 and, fused, the first Galerkin product of LinearImplicitSystem.cpp:347-370), but
+// it uses what the reference's tables ARE: phi_n(g) = l_i1(p_a) l_i2(p_b) l_i3(p_c) for node n at lattice position
+// (i1, i2, i3) and Gauss point g = 16 a + 4 b + c (Hexahedron.cpp:95-163, quadrature_Hexahedron.cpp), so every
+// contraction over nodes or Gauss points splits into three 1-D contractions:
+//   A. J(g) = sum_n dphi_n(g) x_n          3 x 99 FMA per lane instead of 486 (lanes = Gauss points (b, c), two a each)
+//   B. B_ij = sum_{alpha beta} sum_g K_ab(g) d_alpha phi_i(g) d_beta phi_j(g)  with K = w det J^-1 J^-T:
+//        S1[a][b]    = sum_c M3[i3 j3][c] K_ab[a][b][c]
+//        T [j2][a]  += sum_b M2[i2 j2][b] S1[a][b]              (accumulated over the (alpha, beta) of one class)
+//        B[i1 j1 ..] += sum_a M1[i1 j1][a] T[j2][a]             M_d[ij][.] = u_i u_j, u = l or l' as alpha / beta = d
+//      lane = (i2, i3, j3) owns the 27 entries (i1, j1, j2): 1440 FMA per lane and element -- 46 k FMA per element
+//      against 123 k (480 DMMA) + 15 k of the tensor-core formulation; on B200 the FP64 tensor pipe has the SAME peak
+//      as the FP64 CUDA-core pipe (37 TFLOP/s measured), so the flop count, not the pipe, is what matters;
+//   D. fused Galerkin: the child's element prolongator is a Kronecker product A1 x A2 x A3 of 3 x 3 matrices, so
+//      Pc^T B Pc is six passes of 3-vectors through a 3 x 3 matrix, all in registers (lane = row, then column).
+// One warp takes the 8 children of a coarse element one after the other and sums their Galerkin contributions in
+// its own shared-memory tile: no barrier between warps, and the coarse element matrix is summed in a fixed order.
+// The tables handed to b2_asm_create are CHECKED to have this structure (b2_assemble.cu: sf_prepare); if they do
+// not (another rule, another node order) the plan stays on the tensor-core kernel.
+//
+// Kept free of host / runtime calls and of inline PTX so that the same source runs on the CPU thread emulator
+// (tests/cpp/cuda_emu.hpp, tests/test_kernel_emulation.py).  Included inside an anonymous namespace.
+#pragma once
+#ifndef B2_DYN_SHARED
+#define B2_DYN_SHARED(type, name) extern __shared__ type name[]
+#endif
+
+#ifndef B2_SF_WARPS
+#define B2_SF_WARPS 12
+#endif
+constexpr int kSfWarps = B2_SF_WARPS;   // elements in flight per CTA (one CTA per SM; registers bound the count)
+constexpr int kSfNG = 64, kSfNVE = 27;
+
+struct SfTables {                      // built by sf_prepare from the caller's phi / dphi tables
+  double L[3][4];                      // l_i(p_a)
+  double D[3][4];                      // l_i'(p_a)
+  double M[4][9][4];                   // M[2p+q][3i+j][a] = u^p_i(p_a) u^q_j(p_a), u^0 = l, u^1 = l'
+  double w[64];                        // Gauss weights (the reference's 64 truncated literals, NOT a tensor product)
+  int node_of[32];                     // lattice position m = 9 i1 + 3 i2 + i3 -> local node of the reference's order
+};
+struct SfGalTables {
+  double A[8][3][3][3];                // [child][dim d][fine lattice index n_d][coarse lattice index J_d]
+  unsigned short nat2lat[736];         // natural entry I * 27 + J -> lattice entry m(I) * 27 + m(J)
+};
+struct SfGalArgs {
+  const SfGalTables* tab;              // device
+  const int32_t* cd;                   // [nelc][27] coarse dofs (natural order)
+  const void* cslot;                   // [nelc][729] slot of (I, J) inside row cd_I of the coarse matrix (natural order)
+  const uint8_t* fmask;                // fine Dirichlet rows of P (may be null)
+  const uint8_t* cmask;                // coarse Dirichlet columns of P (may be null)
+  const int64_t* Cp;                   // coarse rowptr
+  double* Cv;                          // coarse values
+  double* emat;                        // [nelc][729] record of every coarse element's Galerkin matrix (natural order), or null
+};
+
+// stage-3 coefficients: uniform over the warp and indexed by compile-time constants -> constant-bank operands
+__constant__ double c_sfM[4][9][4];
+
+struct SfSmem {
+  // tables: L, D (12 each), M (144), w (64), A (216, fused Galerkin only) | per warp: X[3][28], U[28], row starts[28],
+  // KB = K[7][64] during the quadrature loop, then the element matrix [27][27]; Dacc [27][27] (fused Galerkin only)
+  static constexpr int tab_doubles = 12 + 12 + 144 + 64;
+  static constexpr int gal_doubles = 216 + 736 / 4;
+  static constexpr int kb_doubles = 736;
+  static constexpr int warp_doubles = 3 * 28 + 28 + 28 + kb_doubles;
+  static constexpr int warp_doubles_gal = warp_doubles + kb_doubles;
+  static constexpr size_t bytes = (size_t)(tab_doubles + kSfWarps * warp_doubles) * sizeof(double);
+  static constexpr size_t bytes_gal = (size_t)(tab_doubles + gal_doubles + kSfWarps * warp_doubles_gal) * sizeof(double);
+};
+
+// one (alpha, beta) term of the stiffness: T[j2][a] += sum_b M2[i2 j2][b] sum_c M3[i3 j3][c] K[a][b][c]
+// (pq2 / pq3 = 2 p + q of dimensions 2 / 3 select which of l, l' the two factors are)
+__device__ __forceinline__ void sf_combo(const double* __restrict__ Kc, const double* __restrict__ m2p, const double* __restrict__ m3p,
+                                         double (&T)[3][4]) {
+  double m3[4], m2[3][4];
+  {
+    const double2 u = *reinterpret_cast<const double2*>(m3p), v = *reinterpret_cast<const double2*>(m3p + 2);
+    m3[0] = u.x; m3[1] = u.y; m3[2] = v.x; m3[3] = v.y;
+  }
+#pragma unroll
+  for (int j2 = 0; j2 < 3; j2++) {
+    const double2 u = *reinterpret_cast<const double2*>(m2p + 4 * j2), v = *reinterpret_cast<const double2*>(m2p + 4 * j2 + 2);
+    m2[j2][0] = u.x; m2[j2][1] = u.y; m2[j2][2] = v.x; m2[j2][3] = v.y;
+  }
+#pragma unroll
+  for (int a = 0; a < 4; a++) {
+    double s[4];
+#pragma unroll
+    for (int b = 0; b < 4; b++) {
+      const double2 k01 = *reinterpret_cast<const double2*>(Kc + a * 16 + b * 4);
+      const double2 k23 = *reinterpret_cast<const double2*>(Kc + a * 16 + b * 4 + 2);
+      s[b] = fma(m3[3], k23.y, fma(m3[2], k23.x, fma(m3[1], k01.y, m3[0] * k01.x)));
+    }
+#pragma unroll
+    for (int j2 = 0; j2 < 3; j2++) T[j2][a] = fma(m2[j2][3], s[3], fma(m2[j2][2], s[2], fma(m2[j2][1], s[1], fma(m2[j2][0], s[0], T[j2][a]))));
+  }
+}
+// the terms of one class (what dimension 1 contributes): `codes` packs, 8 bits per term, K component | pq2 << 3 | pq3 << 5.
+// A real loop: unrolled, the compiler overlaps the terms and runs out of registers.
+template <int PQ1, int NTERMS>
+__device__ __forceinline__ void sf_class(unsigned codes, const double* __restrict__ sK, const double* __restrict__ sM, int i2, int i3j3,
+                                         double (&out)[27]) {
+  double T[3][4];
+#pragma unroll
+  for (int j2 = 0; j2 < 3; j2++)
+#pragma unroll
+    for (int a = 0; a < 4; a++) T[j2][a] = 0.0;
+#pragma unroll 1
+  for (int t = 0; t < NTERMS; t++, codes >>= 8) {
+    const int kc = codes & 7, pq2 = (codes >> 3) & 3, pq3 = (codes >> 5) & 3;
+    sf_combo(sK + kc * kSfNG, sM + (pq2 * 9 + i2 * 3) * 4, sM + (pq3 * 9 + i3j3) * 4, T);
+  }
+#pragma unroll
+  for (int ij = 0; ij < 9; ij++)
+#pragma unroll
+    for (int j2 = 0; j2 < 3; j2++)
+#pragma unroll
+      for (int a = 0; a < 4; a++) out[ij * 3 + j2] = fma(c_sfM[PQ1][ij][a], T[j2][a], out[ij * 3 + j2]);
+}
+#define sf_code(kc, pq2, pq3) ((unsigned)((kc) | ((pq2) << 3) | ((pq3) << 5)))
+// v[n] (n = 0..2 at stride S) -> sum_n v[n] A[n][J]: one 1-D pass of the Kronecker product
+template <int S>
+__device__ __forceinline__ void sf_kron_pass(double (&R)[27], const double* __restrict__ A) {
+  double a[9];
+#pragma unroll
+  for (int t = 0; t < 9; t++) a[t] = A[t];
+#pragma unroll
+  for (int hi = 0; hi < 27; hi += 3 * S)
+#pragma unroll
+    for (int lo = 0; lo < S; lo++) {
+      const double r0 = R[hi + lo], r1 = R[hi + lo + S], r2 = R[hi + lo + 2 * S];
+      R[hi + lo] = fma(r2, a[6], fma(r1, a[3], r0 * a[0]));
+      R[hi + lo + S] = fma(r2, a[7], fma(r1, a[4], r0 * a[1]));
+      R[hi + lo + 2 * S] = fma(r2, a[8], fma(r1, a[5], r0 * a[2]));
+    }
+}
+
+template <typename SlotT, bool GAL, typename CSlotT>
+__global__ void __launch_bounds__(kSfWarps * 32, 1)
+assemble_q2_sumfac_kernel(int64_t nel, int64_t nnode, const double* __restrict__ xyz, const int32_t* __restrict__ conn,
+                          const int32_t* __restrict__ dofL, const SfTables* __restrict__ tabs, const SlotT* __restrict__ lslot,
+                          const int64_t* __restrict__ rowptr, double* __restrict__ Aval, const double* __restrict__ u,
+                          double* __restrict__ rhs, double nu, double fsrc, const SfGalArgs ga) {
+  constexpr int NVE = kSfNVE, NG = kSfNG;
+  B2_DYN_SHARED(double, smem);
+  double* sL = smem;                  // [3][4]
+  double* sD = sL + 12;               // [3][4]
+  double* sM = sD + 12;               // [4][9][4]
+  double* sW = sM + 144;              // [64]
+  double* sA = sW + NG;               // [8][3][9]              (GAL)
+  const unsigned short* sN2L = reinterpret_cast<const unsigned short*>(sA + 216);      // [729] (GAL)
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  double* wbase = smem + SfSmem::tab_doubles + (GAL ? SfSmem::gal_doubles : 0) + wib * (GAL ? SfSmem::warp_doubles_gal : SfSmem::warp_doubles);
+  double* sX = wbase;                                   // [3][28] coordinates, lattice order
+  double* sU = sX + 3 * 28;                             // [28] current solution
+  long long* sRow = reinterpret_cast<long long*>(sU + 28);     // [28] rowptr[dof]
+  double* sK = reinterpret_cast<double*>(sRow + 28);    // [7][64]: K00 K01 K02 K11 K12 K22, w det
+  double* Bs = sK;                                      // [27][27] element matrix (lattice order), reuses sK
+  double* Dacc = sK + SfSmem::kb_doubles;               // [27][27] Galerkin matrix of the coarse element (GAL)
+
+  for (int t = threadIdx.x; t < SfSmem::tab_doubles; t += blockDim.x) smem[t] = reinterpret_cast<const double*>(tabs)[t];
+  if (GAL) {
+    const double* src = reinterpret_cast<const double*>(ga.tab);
+    for (int t = threadIdx.x; t < SfSmem::gal_doubles; t += blockDim.x) sA[t] = src[t];
+  }
+  const int my_node = tabs->node_of[lane < NVE ? lane : 0];
+  __syncthreads();
+
+  // phase A: lane = (a half, b, c); phase B: lane = (i2, i3, j3) (lanes 27..31 shadow lane 26 and store nothing)
+  const int pa_c = lane & 3, pa_b = (lane >> 2) & 3, pa_ah = lane >> 4;
+  const int lb = lane < NVE ? lane : NVE - 1;
+  const int pb_i2 = lb / 9, pb_i3j3 = lb % 9;
+  const int ri1 = lb / 9, ri2 = (lb / 3) % 3, ri3 = lb % 3;      // lattice position of row `lane` (source term)
+
+  const int64_t nunits = GAL ? (nel >> 3) : nel;
+  for (int64_t unit = (int64_t)blockIdx.x * kSfWarps + wib; unit < nunits; unit += (int64_t)gridDim.x * kSfWarps) {
+    if (GAL) {
+      for (int t = lane; t < SfSmem::kb_doubles; t += 32) Dacc[t] = 0.0;
+    }
+#pragma unroll 1
+    for (int child = 0; child < (GAL ? 8 : 1); child++) {
+      const int64_t e = GAL ? unit * 8 + child : unit;
+      // ---- gather (lattice order): coordinates, dofs, current solution, row starts
+      int mydof = 0;
+      if (lane < NVE) {
+        const int64_t nd = conn[e * 27 + my_node];
+        sX[lane] = xyz[nd];
+        sX[28 + lane] = xyz[nnode + nd];
+        sX[56 + lane] = xyz[2 * nnode + nd];
+        mydof = dofL[e * NVE + lane];
+        sU[lane] = u ? u[mydof] : 0.0;
+        sRow[lane] = rowptr[mydof];
+      }
+      __syncwarp();
+
+      // ---- A. geometry at this lane's two Gauss points (a = 2 ah, 2 ah + 1; b; c)
+      {
+        double Lc[3], Dc[3], Lb[3], Db[3];
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+          Lc[i] = sL[i * 4 + pa_c]; Dc[i] = sD[i * 4 + pa_c];
+          Lb[i] = sL[i * 4 + pa_b]; Db[i] = sD[i * 4 + pa_b];
+        }
+        double J[2][3][3];              // [a of the pair][reference direction][coordinate]
+#pragma unroll
+        for (int d = 0; d < 3; d++) {
+          double Z00[3], Z10[3], Z01[3];
+#pragma unroll
+          for (int i1 = 0; i1 < 3; i1++) {
+            double y0[3], y1[3];
+#pragma unroll
+            for (int i2 = 0; i2 < 3; i2++) {
+              const double* x = sX + d * 28 + i1 * 9 + i2 * 3;
+              const double x0 = x[0], x1 = x[1], x2 = x[2];
+              y0[i2] = fma(Lc[2], x2, fma(Lc[1], x1, Lc[0] * x0));
+              y1[i2] = fma(Dc[2], x2, fma(Dc[1], x1, Dc[0] * x0));
+            }
+            Z00[i1] = fma(Lb[2], y0[2], fma(Lb[1], y0[1], Lb[0] * y0[0]));
+            Z10[i1] = fma(Db[2], y0[2], fma(Db[1], y0[1], Db[0] * y0[0]));
+            Z01[i1] = fma(Lb[2], y1[2], fma(Lb[1], y1[1], Lb[0] * y1[0]));
+          }
+#pragma unroll
+          for (int t = 0; t < 2; t++) {
+            const int a = 2 * pa_ah + t;
+            const double La0 = sL[a], La1 = sL[4 + a], La2 = sL[8 + a];
+            const double Da0 = sD[a], Da1 = sD[4 + a], Da2 = sD[8 + a];
+            J[t][0][d] = fma(Da2, Z00[2], fma(Da1, Z00[1], Da0 * Z00[0]));
+            J[t][1][d] = fma(La2, Z10[2], fma(La1, Z10[1], La0 * Z10[0]));
+            J[t][2][d] = fma(La2, Z01[2], fma(La1, Z01[1], La0 * Z01[0]));
+          }
+        }
+#pragma unroll
+        for (int t = 0; t < 2; t++) {
+          const int g = (2 * pa_ah + t) * 16 + pa_b * 4 + pa_c;
+          const double J00 = J[t][0][0], J01 = J[t][0][1], J02 = J[t][0][2];
+          const double J10 = J[t][1][0], J11 = J[t][1][1], J12 = J[t][1][2];
+          const double J20 = J[t][2][0], J21 = J[t][2][1], J22 = J[t][2][2];
+          const double det = J00 * (J11 * J22 - J12 * J21) + J01 * (J12 * J20 - J10 * J22) + J02 * (J10 * J21 - J11 * J20);
+          const double id = 1.0 / det;
+          // JacI[d][a] as ElemType.hpp:1478-1486; grad phi_n [d] = sum_a dphi_n/dxi_a JacI[d][a]
+          const double I00 = (-J12 * J21 + J11 * J22) * id, I01 = (J02 * J21 - J01 * J22) * id, I02 = (-J02 * J11 + J01 * J12) * id;
+          const double I10 = (J12 * J20 - J10 * J22) * id, I11 = (-J02 * J20 + J00 * J22) * id, I12 = (J02 * J10 - J00 * J12) * id;
+          const double I20 = (-J11 * J20 + J10 * J21) * id, I21 = (J01 * J20 - J00 * J21) * id, I22 = (-J01 * J10 + J00 * J11) * id;
+          const double wd = det * sW[g];
+          // K_ab = weight * sum_d JacI[d][a] JacI[d][b]
+          sK[0 * NG + g] = wd * fma(I20, I20, fma(I10, I10, I00 * I00));
+          sK[1 * NG + g] = wd * fma(I20, I21, fma(I10, I11, I00 * I01));
+          sK[2 * NG + g] = wd * fma(I20, I22, fma(I10, I12, I00 * I02));
+          sK[3 * NG + g] = wd * fma(I21, I21, fma(I11, I11, I01 * I01));
+          sK[4 * NG + g] = wd * fma(I21, I22, fma(I11, I12, I01 * I02));
+          sK[5 * NG + g] = wd * fma(I22, I22, fma(I12, I12, I02 * I02));
+          sK[6 * NG + g] = wd;
+        }
+      }
+      __syncwarp();
+
+      // ---- B. stiffness: the nine (alpha, beta) terms grouped by what dimension 1 contributes (class = 2 p1 + q1)
+      double out[27];
+#pragma unroll
+      for (int t = 0; t < 27; t++) out[t] = 0.0;
+      sf_class<3, 1>(sf_code(0, 0, 0), sK, sM, pb_i2, pb_i3j3, out);                                    // (xi, xi)
+      sf_class<2, 2>(sf_code(1, 1, 0) | sf_code(2, 0, 1) << 8, sK, sM, pb_i2, pb_i3j3, out);          // (xi, eta), (xi, zeta)
+      sf_class<1, 2>(sf_code(1, 2, 0) | sf_code(2, 0, 2) << 8, sK, sM, pb_i2, pb_i3j3, out);          // (eta, xi), (zeta, xi)
+      sf_class<0, 4>(sf_code(3, 3, 0) | sf_code(4, 2, 1) << 8 | sf_code(4, 1, 2) << 16 | sf_code(5, 0, 3) << 24, sK, sM, pb_i2, pb_i3j3,
+                     out);                                                                              // (eta | zeta, eta | zeta)
+      // source term of row `lane`: sum_g phi(g) w det = sum_a l_i1(a) sum_b l_i2(b) sum_c l_i3(c) wd[a][b][c]
+      double src = 0.0;
+      if (rhs) {
+        const double* Wd = sK + 6 * NG;
+#pragma unroll
+        for (int a = 0; a < 4; a++) {
+          double ta = 0.0;
+#pragma unroll
+          for (int b = 0; b < 4; b++) {
+            const double2 k01 = *reinterpret_cast<const double2*>(Wd + a * 16 + b * 4);
+            const double2 k23 = *reinterpret_cast<const double2*>(Wd + a * 16 + b * 4 + 2);
+            const double tb = fma(sL[ri3 * 4 + 3], k23.y, fma(sL[ri3 * 4 + 2], k23.x, fma(sL[ri3 * 4 + 1], k01.y, sL[ri3 * 4] * k01.x)));
+            ta = fma(sL[ri2 * 4 + b], tb, ta);
+          }
+          src = fma(sL[ri1 * 4 + a], ta, src);
+        }
+      }
+      __syncwarp();                    // every lane is done with K: the buffer becomes the element matrix
+
+      // ---- C. element matrix -> shared memory (lattice order), scaled by nu
+      if (lane < NVE) {
+        const int ri = (lb / 3) * 27 + lb % 3;          // (3 i2 + i3) * 27 + j3
+#pragma unroll
+        for (int i1 = 0; i1 < 3; i1++)
+#pragma unroll
+          for (int j1 = 0; j1 < 3; j1++)
+#pragma unroll
+            for (int j2 = 0; j2 < 3; j2++) Bs[i1 * 243 + j1 * 9 + j2 * 3 + ri] = nu * out[(i1 * 3 + j1) * 3 + j2];
+      }
+      __syncwarp();
+
+      // ---- residual F_i = fsrc * sum_g phi_i w_g - (B u)_i; with the fused Galerkin product row `lane` stays in registers
+      double R[27];
+      if (GAL || rhs) {
+#pragma unroll
+        for (int j = 0; j < NVE; j++) R[j] = Bs[lb * NVE + j];
+      }
+      if (rhs && lane < NVE) {
+        double s = 0.0;
+#pragma unroll
+        for (int j = 0; j < NVE; j++) s = fma(R[j], sU[j], s);
+        atomicAdd(&rhs[mydof], fsrc * src - s);
+      }
+      // ---- scatter: lattice (i, j) order through the slot map
+      {
+        const SlotT* sl = lslot + (size_t)e * (NVE * NVE);
+        for (int idx = lane; idx < NVE * NVE; idx += 32) {
+          const int i = idx / NVE;
+          atomicAdd(&Aval[sRow[i] + (long long)sl[idx]], Bs[idx]);
+        }
+      }
+      __syncwarp();
+
+      if (GAL) {
+        const double* A1 = sA + (child * 3 + 0) * 9;
+        const double* A2 = sA + (child * 3 + 1) * 9;
+        const double* A3 = sA + (child * 3 + 2) * 9;
+        // rows / columns of Dirichlet fine dofs do not take part in the Galerkin product
+        unsigned mask = 0;
+        if (ga.fmask) {
+          const int fm = lane < NVE ? (int)ga.fmask[mydof] : 0;
+          mask = __ballot_sync(0xffffffffu, fm != 0);
+        }
+        if (mask) {
+          const bool rowdead = (mask >> lb) & 1u;
+#pragma unroll
+          for (int j = 0; j < NVE; j++)
+            if (rowdead || ((mask >> j) & 1u)) R[j] = 0.0;
+        }
+        sf_kron_pass<1>(R, A3);          // T = B Pc, row `lane`: the column index runs over (j1, j2, j3)
+        sf_kron_pass<3>(R, A2);
+        sf_kron_pass<9>(R, A1);
+        if (lane < NVE) {
+#pragma unroll
+          for (int j = 0; j < NVE; j++) Bs[lane * NVE + j] = R[j];
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < NVE; i++) R[i] = Bs[i * NVE + lb];       // column `lane` of T
+        sf_kron_pass<1>(R, A3);          // D = Pc^T T, column `lane`
+        sf_kron_pass<3>(R, A2);
+        sf_kron_pass<9>(R, A1);
+        if (lane < NVE) {
+#pragma unroll
+          for (int i = 0; i < NVE; i++) Dacc[i * NVE + lane] += R[i];
+        }
+        __syncwarp();
+      }
+    }
+    if (GAL) {
+      // ---- the coarse element's Galerkin matrix: record (natural order) and scatter into the coarse operator
+      const int64_t E = unit;
+      const CSlotT* cslot = reinterpret_cast<const CSlotT*>(ga.cslot) + (size_t)E * (NVE * NVE);
+      for (int idx = lane; idx < NVE * NVE; idx += 32) {
+        const double v = Dacc[sN2L[idx]];
+        if (ga.emat) ga.emat[(size_t)E * (NVE * NVE) + idx] = v;
+        if (v == 0.0) continue;
+        const int I = idx / NVE, Jn = idx - I * NVE;
+        const int32_t dI = ga.cd[E * NVE + I];
+        if (ga.cmask) {
+          const int32_t dJ = ga.cd[E * NVE + Jn];
+          if (ga.cmask[dI] || ga.cmask[dJ]) continue;
+        }
+        atomicAdd(&ga.Cv[ga.Cp[dI] + (int64_t)cslot[idx]], v);
+      }
+      __syncwarp();
+    }
+  }
+}

@@ -66,8 +66,9 @@ struct b2_ctx {
   // gathers (B2_SPMV_VARIANT)
   int spmv_variant = 1;
   int spmv_timing = 0;
-  // assembly kernel for triquadratic elements: 1 = FP64 tensor cores (mma.sync m8n8k4), 0 = CUDA-core tiles
-  int asm_variant = 1;     // diagnostic: y = A x prints the consumer phase cycles of CTA 0
+  // assembly kernel for triquadratic elements: 3 = sum factorisation (default; falls back to 1 when the tables are not
+  // tensor products), 1 = FP64 tensor cores (mma.sync m8n8k4), 0 = CUDA-core tiles, 2 = table-driven kernel
+  int asm_variant = 3;
   // multi-GPU
   int nranks = 1, rank = 0;
   void* nccl_comm = nullptr;

@@ -185,7 +185,7 @@ int b2_ctx_set_option(b2_ctx* c, const char* name, int value) {
     return 0;
   }
   if (!strcmp(name, "asm_variant")) {
-    B2_CHECK(value >= 0 && value <= 2, "asm_variant %d (0, 1, 2)", value);
+    B2_CHECK(value >= 0 && value <= 3, "asm_variant %d (0, 1, 2, 3)", value);
     c->asm_variant = value;
     return 0;
   }

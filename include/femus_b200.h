@@ -66,8 +66,9 @@ int b2_ctx_profile_read(b2_ctx* c, const void* handle, int* count, double* total
 int b2_ctx_profile_clear(b2_ctx* c);
 /* tuning knobs: "spmv_variant" = 0 (register-streaming SpMV) | 1 (TMA-staged ring, default) | 2 (staged +
  * software-pipelined gathers); "spmv_timing" = 1 makes y = A x print the consumer phase cycles of CTA 0;
- * "asm_variant" = 1 (triquadratic assembly on the FP64 tensor cores, default) | 0 (CUDA-core register tiles) |
- * 2 (the table-driven kernel of the non-hexahedral families, also for hexahedra) */
+ * "asm_variant" = 3 (triquadratic assembly by sum factorisation, default; plans whose tables are not tensor products
+ * use 1) | 1 (FP64 tensor cores) | 0 (CUDA-core register tiles) | 2 (the table-driven kernel of the non-hexahedral
+ * families, also for hexahedra) */
 int b2_ctx_set_option(b2_ctx* c, const char* name, int value);
 /* measured issue-rate peak of mma.sync.m8n8k4.f64 on this device, TFLOP/s (a few ms of DMMA chains) */
 int b2_ctx_measure_fp64_tensor(b2_ctx* c, double* tflops);

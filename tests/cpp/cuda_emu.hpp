@@ -24,6 +24,7 @@ inline emu_dim3 blockDim, gridDim;
 #define __forceinline__ inline
 #define __restrict__
 #define __launch_bounds__(...)
+#define __constant__
 #define __shared__ static            /* CTAs run one at a time: one static copy per kernel is the CTA's shared memory */
 #define B2_DYN_SHARED(type, name) type* name = reinterpret_cast<type*>(emu::dyn_shared.data())
 
@@ -77,6 +78,16 @@ inline double __shfl_xor_sync(unsigned, double v, int mask) { return emu_shfl(v,
 inline double __shfl_down_sync(unsigned, double v, int delta) {
   const int src = (int)(threadIdx.x & 31) + delta;
   return emu_shfl(v, src < 32 ? src : (int)(threadIdx.x & 31));
+}
+inline unsigned __ballot_sync(unsigned, int pred) {
+  const int w = emu::warp_of(), lane = (int)(threadIdx.x & 31);
+  emu::warp_buf[w][lane] = pred ? 1.0 : 0.0;
+  emu::warp_barrier[w]->arrive_and_wait();
+  unsigned m = 0;
+  for (int l = 0; l < 32; l++)
+    if (emu::warp_buf[w][l] != 0.0) m |= 1u << l;
+  emu::warp_barrier[w]->arrive_and_wait();
+  return m;
 }
 inline double atomicAdd(double* p, double v) { return std::atomic_ref<double>(*p).fetch_add(v); }
 inline int atomicCAS(int* p, int expected, int desired) {

@@ -277,12 +277,12 @@ def distorted(L, amp, seed):
     return out
 
 
-@pytest.fixture(params=[1, 0], ids=["tensorcore", "cudacore"])
+@pytest.fixture(params=[3, 1, 0], ids=["sumfac", "tensorcore", "cudacore"])
 def asm_variant(request, ctx):
-    """Both triquadratic assembly kernels: FP64 tensor cores (default) and CUDA-core register tiles."""
+    """The three triquadratic assembly kernels: sum factorisation (default), FP64 tensor cores, CUDA-core register tiles."""
     ctx.set_option("asm_variant", request.param)
     yield request.param
-    ctx.set_option("asm_variant", 1)
+    ctx.set_option("asm_variant", 3)
 
 
 @pytest.mark.parametrize("order", ["linear", "biquadratic"])

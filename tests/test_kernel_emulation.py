@@ -620,3 +620,85 @@ def test_orchestration_is_race_free_under_thread_sanitizer(tmp_path):
         pytest.skip("ThreadSanitizer cannot run in this environment: " + run.stderr[:200])
     assert "tsan-run-finished" in run.stdout, run.stdout[-2000:] + run.stderr[-4000:]
     assert "WARNING: ThreadSanitizer" not in run.stderr, run.stderr[:6000]
+
+
+# ---- the sum-factorised Hex27 assembly kernel (b2_assemble_sumfac.cuh) -------------------------------------------------
+@pytest.fixture(scope="module")
+def emu_sf(tmp_path_factory):
+    so = str(tmp_path_factory.mktemp("emu_sf") / "libemu_sumfac.so")
+    r = subprocess.run(["g++", "-std=c++20", "-O1", "-pthread", "-shared", "-fPIC", "-o", so, os.path.join(ROOT, "tests", "cpp", "emu_sumfac.cpp")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    L = ctypes.CDLL(so)
+    L.emu_sumfac.restype = ctypes.c_int
+    L.emu_sumfac.argtypes = ([ctypes.c_int64, ctypes.c_int64] + [vp] * 13 + [ctypes.c_double, ctypes.c_double, ctypes.c_int] + [vp] * 8 +
+                             [ctypes.c_int])
+    return L
+
+
+def _distort(L, amp):
+    x, y, z = L.xyz
+    out = L.xyz.copy()
+    out[0] += amp * np.sin(2 * np.pi * y) * np.sin(np.pi * z) * x * (1 - x)
+    out[1] += amp * np.sin(3 * np.pi * z) * np.sin(np.pi * x) * y * (1 - y)
+    out[2] += amp * np.sin(2 * np.pi * x) * np.sin(np.pi * y) * z * (1 - z)
+    return out
+
+
+@pytest.mark.parametrize("amp,gal", [(0.0, 0), (0.07, 0), (0.07, 1)])
+def test_sum_factorised_assembly_on_the_emulator(emu_sf, amp, gal):
+    """assemble_q2_sumfac_kernel (SOURCE of the GPU kernel, on host threads) against the oracle: fine matrix and
+    residual on a distorted 2-level mesh with a non-zero solution; fused: the Galerkin coarse operator P^T A P with
+    the Dirichlet rows / columns of P zeroed, and the recorded coarse element matrices summing to it."""
+    from femus_b200 import hostapi
+    from oracle import fe_hex, mesh_box as mb
+    import scipy.sparse as sp
+    order = "biquadratic"
+    lv = mb.build_hierarchy(1, 2, 1, 2)
+    C, F = lv
+    F.xyz = _distort(F, amp)
+    n, d = mb.ndofs(F, order), np.ascontiguousarray(mb.system_dof(F, order), dtype=np.int32)
+    u = np.random.default_rng(5).standard_normal(n)
+    Aref, rhs_ref = mb.assemble(F, order, u, fsrc=1.5)
+    rp, ci = Aref.indptr.astype(np.int64), Aref.indices.astype(np.int32)
+    val, rhs = np.zeros(Aref.nnz), np.zeros(n)
+    phi, dxi, deta, dzeta, w = [np.ascontiguousarray(t) for t in fe_hex.tables(order)]
+    xyz, conn = np.ascontiguousarray(F.xyz), np.ascontiguousarray(F.conn, dtype=np.int32)
+    null = ctypes.c_void_p(0)
+    args_gal = [null] * 8
+    if gal:
+        nc = mb.ndofs(C, order)
+        cd = np.ascontiguousarray(mb.system_dof(C, order), dtype=np.int32)
+        P = mb.prolongator(C, F, order).tocsr()
+        bf, bc = mb.bdc_flags(F, order) < 1.5, mb.bdc_flags(C, order) < 1.5
+        # child prolongators from the assembled P: Pc[j][n][J] = P[dof of node n of child j of element 0, coarse dof J of element 0]
+        Pd = P.toarray()
+        Pc = np.zeros((8, 27, 27))
+        for j in range(8):
+            Pc[j] = Pd[np.ix_(d[j], cd[0])]
+        Cpat = mb.sparsity(C, order)
+        Cp, Cc = Cpat[0].astype(np.int64), Cpat[1].astype(np.int32)
+        Cv = np.zeros(len(Cc))
+        fmask, cmask = bf.astype(np.uint8), bc.astype(np.uint8)
+        emat = np.zeros((C.nel, 729))
+        args_gal = [_p(cd), _p(Pc), _p(Cp), _p(Cc), _p(Cv), _p(fmask), _p(cmask), _p(emat)]
+    rc = emu_sf.emu_sumfac(F.nel, F.nnode, _p(xyz), _p(conn), _p(d), _p(phi), _p(dxi), _p(deta), _p(dzeta), _p(w), _p(rp), _p(ci), _p(val), _p(u), _p(rhs),
+                           1.0, 1.5, gal, *args_gal, 2)
+    assert rc == 0
+    assert np.abs(val - Aref.data).max() <= 1e-12 * np.abs(Aref.data).max()
+    mag = np.abs(Aref) @ np.abs(u) + np.abs(rhs_ref)
+    assert np.all(np.abs(rhs - rhs_ref) <= 1e-12 * mag.max())
+    if gal:
+        Pz = mb.zero_dirichlet(P, mb.bdc_flags(F, order), mb.bdc_flags(C, order))
+        want = (Pz.T @ Aref @ Pz).toarray()
+        got = sp.csr_matrix((Cv, Cc, Cp), shape=(nc, nc)).toarray()
+        assert np.abs(got - want).max() <= 1e-12 * np.abs(want).max()
+        # the recorded element matrices: un-masked on the coarse side, they sum to P^T A P with only the FINE Dirichlet rows zeroed
+        Pf = P.copy().tolil()
+        Pf[np.nonzero(bf)[0], :] = 0
+        Pf = Pf.tocsr()
+        want_e = (Pf.T @ Aref @ Pf).toarray()
+        acc = np.zeros((nc, nc))
+        for E in range(C.nel):
+            np.add.at(acc, (cd[E][:, None], cd[E][None, :]), emat[E].reshape(27, 27))
+        assert np.abs(acc - want_e).max() <= 1e-12 * np.abs(want_e).max()

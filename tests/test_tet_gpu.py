@@ -111,7 +111,7 @@ def test_general_kernel_on_hexahedra(ctx, order):
         U, R = ctx.vector(u), ctx.vector(n)
         asm.poisson(U, R, nu=1.0, fsrc=0.7)
     finally:
-        ctx.set_option("asm_variant", 1)
+        ctx.set_option("asm_variant", 3)
     got = A.to_scipy()
     assert np.array_equal(got.indices, Aref.indices)
     assert np.abs(got.data - Aref.data).max() <= RTOL * np.abs(Aref.data).max()
