@@ -905,6 +905,7 @@ static int sf_prepare(b2_asm* p, const int32_t* dof, const double* phi, const do
   if (!sf_factor_tables(phi, dxi, deta, dzeta, w, &T)) return 0;
   if (!g_sfM_loaded) {
     B2_CUDA(cudaMemcpyToSymbol(c_sfM, T.M, sizeof(T.M)));
+    B2_CUDA(cudaMemcpyToSymbol(c_sfU, T.L, sizeof(T.L) + sizeof(T.D)));      // L then D, contiguous in SfTables
     memcpy(g_sfM, T.M, sizeof(T.M));
     g_sfM_loaded = true;
   } else if (memcmp(g_sfM, T.M, sizeof(T.M)) != 0) {
@@ -951,19 +952,24 @@ static int sf_build_gal(b2_asm* p, const b2_galerkin_view& g) {
   return 0;
 }
 
-template <typename SlotT, bool GAL, typename CSlotT>
-int launch_assemble_sumfac(b2_asm* p, const SfGalArgs& ga, const b2_vec* u, b2_vec* rhs, double nu, double fsrc) {
+template <int WARPS, typename SlotT, bool GAL, typename CSlotT>
+int launch_assemble_sumfac_w(b2_asm* p, const SfGalArgs& ga, const b2_vec* u, b2_vec* rhs, double nu, double fsrc) {
   b2_ctx* c = p->mesh->ctx;
   b2_prof_scope prof(c, p);
-  auto kern = assemble_q2_sumfac_kernel<SlotT, GAL, CSlotT>;
-  const size_t smem = GAL ? SfSmem::bytes_gal : SfSmem::bytes;
+  auto kern = assemble_q2_sumfac_kernel<WARPS, SlotT, GAL, CSlotT>;
+  const size_t smem = GAL ? SfSmem<WARPS>::bytes_gal : SfSmem<WARPS>::bytes;
   B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t nunits = GAL ? p->mesh->nel / 8 : p->mesh->nel;
-  int grid = (int)((nunits + kSfWarps - 1) / kSfWarps);
+  int grid = (int)((nunits + WARPS - 1) / WARPS);
   if (grid > c->sm_count) grid = c->sm_count;
-  B2_LAUNCH(c, kern, grid, kSfWarps * 32, smem, p->mesh->nel, p->mesh->nnode, p->mesh->xyz, p->mesh->conn, p->dofL, (const SfTables*)p->sf_tab,
+  B2_LAUNCH(c, kern, grid, WARPS * 32, smem, p->mesh->nel, p->mesh->nnode, p->mesh->xyz, p->mesh->conn, p->dofL, (const SfTables*)p->sf_tab,
             (const SlotT*)p->lslot, p->A->rowptr, p->A->val, u ? u->d : nullptr, rhs ? rhs->d : nullptr, nu, fsrc, ga);
   return 0;
+}
+template <typename SlotT, bool GAL, typename CSlotT>
+int launch_assemble_sumfac(b2_asm* p, const SfGalArgs& ga, const b2_vec* u, b2_vec* rhs, double nu, double fsrc) {
+  if (p->mesh->ctx->asm_warps == 16) return launch_assemble_sumfac_w<16, SlotT, GAL, CSlotT>(p, ga, u, rhs, nu, fsrc);
+  return launch_assemble_sumfac_w<kSfWarpsDefault, SlotT, GAL, CSlotT>(p, ga, u, rhs, nu, fsrc);
 }
 
 template <typename SlotT, bool GAL, typename CSlotT>

@@ -7,12 +7,17 @@
 // contraction over nodes or Gauss points splits into three 1-D contractions:
 //   A. J(g) = sum_n dphi_n(g) x_n          3 x 99 FMA per lane instead of 486 (lanes = Gauss points (b, c), two a each)
 //   B. B_ij = sum_{alpha beta} sum_g K_ab(g) d_alpha phi_i(g) d_beta phi_j(g)  with K = w det J^-1 J^-T:
-//        S1[a][b]    = sum_c M3[i3 j3][c] K_ab[a][b][c]
-//        T [j2][a]  += sum_b M2[i2 j2][b] S1[a][b]              (accumulated over the (alpha, beta) of one class)
+//        S1[i3 j3][a][b] = sum_c M3[i3 j3][c] K_ab[a][b][c]     lanes = Gauss points (a, b): every K value is read ONCE,
+//                                                              the coefficients are constant-bank operands; S1 goes
+//                                                              through shared memory (4 terms per round, two rounds)
+//        T [j2][a]  += sum_b M2[i2 j2][b] S1[i3 j3][a][b]       (accumulated over the (alpha, beta) of one class)
 //        B[i1 j1 ..] += sum_a M1[i1 j1][a] T[j2][a]             M_d[ij][.] = u_i u_j, u = l or l' as alpha / beta = d
-//      lane = (i2, i3, j3) owns the 27 entries (i1, j1, j2): 1440 FMA per lane and element -- 46 k FMA per element
+//      lane = (i2, i3, j3) owns the 27 entries (i1, j1, j2): ~1300 FMA per lane and element -- 41 k FMA per element
 //      against 123 k (480 DMMA) + 15 k of the tensor-core formulation; on B200 the FP64 tensor pipe has the SAME peak
-//      as the FP64 CUDA-core pipe (37 TFLOP/s measured), so the flop count, not the pipe, is what matters;
+//      as the FP64 CUDA-core pipe (37 TFLOP/s measured), so the flop count, not the pipe, is what matters.  (First
+//      version: every lane contracted all 64 points itself, 1440 FMA -- and 9 x 64 broadcast K loads per lane; a
+//      shared-memory load costs register-writeback bandwidth per LANE, broadcast or not: ncu showed the l1tex data
+//      pipe at 88 %, 1150 of 1480 wavefronts per element from those loads.)
 //   D. fused Galerkin: the child's element prolongator is a Kronecker product A1 x A2 x A3 of 3 x 3 matrices, so
 //      Pc^T B Pc is six passes of 3-vectors through a 3 x 3 matrix, all in registers (lane = row, then column).
 // One warp takes the 8 children of a coarse element one after the other and sums their Galerkin contributions in
@@ -27,10 +32,9 @@
 #define B2_DYN_SHARED(type, name) extern __shared__ type name[]
 #endif
 
-#ifndef B2_SF_WARPS
-#define B2_SF_WARPS 12
-#endif
-constexpr int kSfWarps = B2_SF_WARPS;   // elements in flight per CTA (one CTA per SM; registers bound the count)
+// WARPS = elements in flight per CTA (one CTA per SM): 12 (168 registers per thread) or 16 (128, a few spills);
+// both are built, "asm_warps" of b2_ctx_set_option / B2_SF_WARPS picks one
+constexpr int kSfWarpsDefault = 12;
 constexpr int kSfNG = 64, kSfNVE = 27;
 
 struct SfTables {                      // built by sf_prepare from the caller's phi / dphi tables
@@ -55,63 +59,53 @@ struct SfGalArgs {
   double* emat;                        // [nelc][729] record of every coarse element's Galerkin matrix (natural order), or null
 };
 
-// stage-3 coefficients: uniform over the warp and indexed by compile-time constants -> constant-bank operands
+// coefficients that are uniform over the warp and indexed by compile-time constants -> constant-bank operands:
+// c_sfM (stages 1 and 3), c_sfU[p][j][b] = u^p_j(p_b) (stage 2: M2[i2 j2][b] = u^p_i2(b) u^q_j2(b), the i2 factor is a
+// per-lane register constant)
 __constant__ double c_sfM[4][9][4];
+__constant__ double c_sfU[2][3][4];
 
+template <int WARPS>
 struct SfSmem {
   // tables: L, D (12 each), M (144), w (64), A (216, fused Galerkin only) | per warp: X[3][28], U[28], row starts[28],
-  // KB = K[7][64] during the quadrature loop, then the element matrix [27][27]; Dacc [27][27] (fused Galerkin only)
+  // KB = K[7][64] + S1[4][9][16] during the quadrature loop, then the element matrix [27][27]; Dacc [27][27] (fused
+  // Galerkin only)
   static constexpr int tab_doubles = 12 + 12 + 144 + 64;
   static constexpr int gal_doubles = 216 + 736 / 4;
-  static constexpr int kb_doubles = 736;
+  static constexpr int s1_doubles = 4 * 9 * 16;        // S1 of the four terms of a round: [term][i3 j3][a b]
+  static constexpr int kb_doubles = 7 * 64 + s1_doubles;   // K, S1; later the element matrix (729)
+  static constexpr int dacc_doubles = 736;
   static constexpr int warp_doubles = 3 * 28 + 28 + 28 + kb_doubles;
-  static constexpr int warp_doubles_gal = warp_doubles + kb_doubles;
-  static constexpr size_t bytes = (size_t)(tab_doubles + kSfWarps * warp_doubles) * sizeof(double);
-  static constexpr size_t bytes_gal = (size_t)(tab_doubles + gal_doubles + kSfWarps * warp_doubles_gal) * sizeof(double);
+  static constexpr int warp_doubles_gal = warp_doubles + dacc_doubles;
+  static constexpr size_t bytes = (size_t)(tab_doubles + WARPS * warp_doubles) * sizeof(double);
+  static constexpr size_t bytes_gal = (size_t)(tab_doubles + gal_doubles + WARPS * warp_doubles_gal) * sizeof(double);
 };
 
-// one (alpha, beta) term of the stiffness: T[j2][a] += sum_b M2[i2 j2][b] sum_c M3[i3 j3][c] K[a][b][c]
-// (pq2 / pq3 = 2 p + q of dimensions 2 / 3 select which of l, l' the two factors are)
-__device__ __forceinline__ void sf_combo(const double* __restrict__ Kc, const double* __restrict__ m2p, const double* __restrict__ m3p,
-                                         double (&T)[3][4]) {
-  double m3[4], m2[3][4];
-  {
-    const double2 u = *reinterpret_cast<const double2*>(m3p), v = *reinterpret_cast<const double2*>(m3p + 2);
-    m3[0] = u.x; m3[1] = u.y; m3[2] = v.x; m3[3] = v.y;
-  }
+// stage 1 of one term, lanes 0..15 = Gauss points (a, b): S1[i3 j3][a b] = sum_c M3[i3 j3][c] K[a][b][c]
+template <int PQ3>
+__device__ __forceinline__ void sf_stage1(const double* __restrict__ Kc, double* __restrict__ S1, int ab) {
+  const double2 k01 = *reinterpret_cast<const double2*>(Kc + ab * 4);
+  const double2 k23 = *reinterpret_cast<const double2*>(Kc + ab * 4 + 2);
 #pragma unroll
-  for (int j2 = 0; j2 < 3; j2++) {
-    const double2 u = *reinterpret_cast<const double2*>(m2p + 4 * j2), v = *reinterpret_cast<const double2*>(m2p + 4 * j2 + 2);
-    m2[j2][0] = u.x; m2[j2][1] = u.y; m2[j2][2] = v.x; m2[j2][3] = v.y;
-  }
+  for (int ij = 0; ij < 9; ij++)
+    S1[ij * 16 + ab] = fma(c_sfM[PQ3][ij][3], k23.y, fma(c_sfM[PQ3][ij][2], k23.x, fma(c_sfM[PQ3][ij][1], k01.y, c_sfM[PQ3][ij][0] * k01.x)));
+}
+// stage 2 of one term, lane = (i2, i3, j3): T[j2][a] += sum_b u^P2_i2(b) u^Q2_j2(b) S1[i3 j3][a][b]
+template <int P2, int Q2>
+__device__ __forceinline__ void sf_stage2(const double* __restrict__ S1, const double (&ui2)[2][4], double (&T)[3][4]) {
 #pragma unroll
   for (int a = 0; a < 4; a++) {
-    double s[4];
+    const double2 s01 = *reinterpret_cast<const double2*>(S1 + a * 4);
+    const double2 s23 = *reinterpret_cast<const double2*>(S1 + a * 4 + 2);
+    const double s0 = ui2[P2][0] * s01.x, s1 = ui2[P2][1] * s01.y, s2 = ui2[P2][2] * s23.x, s3 = ui2[P2][3] * s23.y;
 #pragma unroll
-    for (int b = 0; b < 4; b++) {
-      const double2 k01 = *reinterpret_cast<const double2*>(Kc + a * 16 + b * 4);
-      const double2 k23 = *reinterpret_cast<const double2*>(Kc + a * 16 + b * 4 + 2);
-      s[b] = fma(m3[3], k23.y, fma(m3[2], k23.x, fma(m3[1], k01.y, m3[0] * k01.x)));
-    }
-#pragma unroll
-    for (int j2 = 0; j2 < 3; j2++) T[j2][a] = fma(m2[j2][3], s[3], fma(m2[j2][2], s[2], fma(m2[j2][1], s[1], fma(m2[j2][0], s[0], T[j2][a]))));
+    for (int j2 = 0; j2 < 3; j2++)
+      T[j2][a] = fma(c_sfU[Q2][j2][3], s3, fma(c_sfU[Q2][j2][2], s2, fma(c_sfU[Q2][j2][1], s1, fma(c_sfU[Q2][j2][0], s0, T[j2][a]))));
   }
 }
-// the terms of one class (what dimension 1 contributes): `codes` packs, 8 bits per term, K component | pq2 << 3 | pq3 << 5.
-// A real loop: unrolled, the compiler overlaps the terms and runs out of registers.
-template <int PQ1, int NTERMS>
-__device__ __forceinline__ void sf_class(unsigned codes, const double* __restrict__ sK, const double* __restrict__ sM, int i2, int i3j3,
-                                         double (&out)[27]) {
-  double T[3][4];
-#pragma unroll
-  for (int j2 = 0; j2 < 3; j2++)
-#pragma unroll
-    for (int a = 0; a < 4; a++) T[j2][a] = 0.0;
-#pragma unroll 1
-  for (int t = 0; t < NTERMS; t++, codes >>= 8) {
-    const int kc = codes & 7, pq2 = (codes >> 3) & 3, pq3 = (codes >> 5) & 3;
-    sf_combo(sK + kc * kSfNG, sM + (pq2 * 9 + i2 * 3) * 4, sM + (pq3 * 9 + i3j3) * 4, T);
-  }
+// stage 3 of one class: out[(3 i1 + j1) * 3 + j2] += sum_a M1[i1 j1][a] T[j2][a]
+template <int PQ1>
+__device__ __forceinline__ void sf_stage3(const double (&T)[3][4], double (&out)[27]) {
 #pragma unroll
   for (int ij = 0; ij < 9; ij++)
 #pragma unroll
@@ -119,7 +113,12 @@ __device__ __forceinline__ void sf_class(unsigned codes, const double* __restric
 #pragma unroll
       for (int a = 0; a < 4; a++) out[ij * 3 + j2] = fma(c_sfM[PQ1][ij][a], T[j2][a], out[ij * 3 + j2]);
 }
-#define sf_code(kc, pq2, pq3) ((unsigned)((kc) | ((pq2) << 3) | ((pq3) << 5)))
+__device__ __forceinline__ void sf_zero(double (&T)[3][4]) {
+#pragma unroll
+  for (int j2 = 0; j2 < 3; j2++)
+#pragma unroll
+    for (int a = 0; a < 4; a++) T[j2][a] = 0.0;
+}
 // v[n] (n = 0..2 at stride S) -> sum_n v[n] A[n][J]: one 1-D pass of the Kronecker product
 template <int S>
 __device__ __forceinline__ void sf_kron_pass(double (&R)[27], const double* __restrict__ A) {
@@ -137,13 +136,14 @@ __device__ __forceinline__ void sf_kron_pass(double (&R)[27], const double* __re
     }
 }
 
-template <typename SlotT, bool GAL, typename CSlotT>
-__global__ void __launch_bounds__(kSfWarps * 32, 1)
+template <int WARPS, typename SlotT, bool GAL, typename CSlotT>
+__global__ void __launch_bounds__(WARPS * 32, 1)
 assemble_q2_sumfac_kernel(int64_t nel, int64_t nnode, const double* __restrict__ xyz, const int32_t* __restrict__ conn,
                           const int32_t* __restrict__ dofL, const SfTables* __restrict__ tabs, const SlotT* __restrict__ lslot,
                           const int64_t* __restrict__ rowptr, double* __restrict__ Aval, const double* __restrict__ u,
                           double* __restrict__ rhs, double nu, double fsrc, const SfGalArgs ga) {
   constexpr int NVE = kSfNVE, NG = kSfNG;
+  using Smem = SfSmem<WARPS>;
   B2_DYN_SHARED(double, smem);
   double* sL = smem;                  // [3][4]
   double* sD = sL + 12;               // [3][4]
@@ -152,18 +152,19 @@ assemble_q2_sumfac_kernel(int64_t nel, int64_t nnode, const double* __restrict__
   double* sA = sW + NG;               // [8][3][9]              (GAL)
   const unsigned short* sN2L = reinterpret_cast<const unsigned short*>(sA + 216);      // [729] (GAL)
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  double* wbase = smem + SfSmem::tab_doubles + (GAL ? SfSmem::gal_doubles : 0) + wib * (GAL ? SfSmem::warp_doubles_gal : SfSmem::warp_doubles);
+  double* wbase = smem + Smem::tab_doubles + (GAL ? Smem::gal_doubles : 0) + wib * (GAL ? Smem::warp_doubles_gal : Smem::warp_doubles);
   double* sX = wbase;                                   // [3][28] coordinates, lattice order
   double* sU = sX + 3 * 28;                             // [28] current solution
   long long* sRow = reinterpret_cast<long long*>(sU + 28);     // [28] rowptr[dof]
   double* sK = reinterpret_cast<double*>(sRow + 28);    // [7][64]: K00 K01 K02 K11 K12 K22, w det
-  double* Bs = sK;                                      // [27][27] element matrix (lattice order), reuses sK
-  double* Dacc = sK + SfSmem::kb_doubles;               // [27][27] Galerkin matrix of the coarse element (GAL)
+  double* sS1 = sK + 7 * NG;                            // [4][9][16] stage-1 sums of the four terms of a round
+  double* Bs = sK;                                      // [27][27] element matrix (lattice order), reuses sK / sS1
+  double* Dacc = sK + Smem::kb_doubles;               // [27][27] Galerkin matrix of the coarse element (GAL)
 
-  for (int t = threadIdx.x; t < SfSmem::tab_doubles; t += blockDim.x) smem[t] = reinterpret_cast<const double*>(tabs)[t];
+  for (int t = threadIdx.x; t < Smem::tab_doubles; t += blockDim.x) smem[t] = reinterpret_cast<const double*>(tabs)[t];
   if (GAL) {
     const double* src = reinterpret_cast<const double*>(ga.tab);
-    for (int t = threadIdx.x; t < SfSmem::gal_doubles; t += blockDim.x) sA[t] = src[t];
+    for (int t = threadIdx.x; t < Smem::gal_doubles; t += blockDim.x) sA[t] = src[t];
   }
   const int my_node = tabs->node_of[lane < NVE ? lane : 0];
   __syncthreads();
@@ -173,11 +174,17 @@ assemble_q2_sumfac_kernel(int64_t nel, int64_t nnode, const double* __restrict__
   const int lb = lane < NVE ? lane : NVE - 1;
   const int pb_i2 = lb / 9, pb_i3j3 = lb % 9;
   const int ri1 = lb / 9, ri2 = (lb / 3) % 3, ri3 = lb % 3;      // lattice position of row `lane` (source term)
+  double ui2[2][4];                                              // u^p_i2(p_b) of this lane's i2 (stage 2)
+#pragma unroll
+  for (int b = 0; b < 4; b++) {
+    ui2[0][b] = sL[pb_i2 * 4 + b];
+    ui2[1][b] = sD[pb_i2 * 4 + b];
+  }
 
   const int64_t nunits = GAL ? (nel >> 3) : nel;
-  for (int64_t unit = (int64_t)blockIdx.x * kSfWarps + wib; unit < nunits; unit += (int64_t)gridDim.x * kSfWarps) {
+  for (int64_t unit = (int64_t)blockIdx.x * WARPS + wib; unit < nunits; unit += (int64_t)gridDim.x * WARPS) {
     if (GAL) {
-      for (int t = lane; t < SfSmem::kb_doubles; t += 32) Dacc[t] = 0.0;
+      for (int t = lane; t < Smem::dacc_doubles; t += 32) Dacc[t] = 0.0;
     }
 #pragma unroll 1
     for (int child = 0; child < (GAL ? 8 : 1); child++) {
@@ -260,11 +267,44 @@ assemble_q2_sumfac_kernel(int64_t nel, int64_t nnode, const double* __restrict__
       double out[27];
 #pragma unroll
       for (int t = 0; t < 27; t++) out[t] = 0.0;
-      sf_class<3, 1>(sf_code(0, 0, 0), sK, sM, pb_i2, pb_i3j3, out);                                    // (xi, xi)
-      sf_class<2, 2>(sf_code(1, 1, 0) | sf_code(2, 0, 1) << 8, sK, sM, pb_i2, pb_i3j3, out);          // (xi, eta), (xi, zeta)
-      sf_class<1, 2>(sf_code(1, 2, 0) | sf_code(2, 0, 2) << 8, sK, sM, pb_i2, pb_i3j3, out);          // (eta, xi), (zeta, xi)
-      sf_class<0, 4>(sf_code(3, 3, 0) | sf_code(4, 2, 1) << 8 | sf_code(4, 1, 2) << 16 | sf_code(5, 0, 3) << 24, sK, sM, pb_i2, pb_i3j3,
-                     out);                                                                              // (eta | zeta, eta | zeta)
+      {
+        double T[3][4];
+        const double* S = sS1 + pb_i3j3 * 16;
+        // round 1: the terms with xi on either side.  Stage-1 sums: (K00, l l), (K01, l l), (K02, l l'), (K02, l' l)
+        if (lane < 16) {
+          sf_stage1<0>(sK + 0 * NG, sS1 + 0 * 144, lane);
+          sf_stage1<0>(sK + 1 * NG, sS1 + 1 * 144, lane);
+          sf_stage1<1>(sK + 2 * NG, sS1 + 2 * 144, lane);
+          sf_stage1<2>(sK + 2 * NG, sS1 + 3 * 144, lane);
+        }
+        __syncwarp();
+        sf_zero(T);                                   // class (1,1): (xi, xi)
+        sf_stage2<0, 0>(S + 0 * 144, ui2, T);
+        sf_stage3<3>(T, out);
+        sf_zero(T);                                   // class (1,0): (xi, eta), (xi, zeta)
+        sf_stage2<0, 1>(S + 1 * 144, ui2, T);
+        sf_stage2<0, 0>(S + 2 * 144, ui2, T);
+        sf_stage3<2>(T, out);
+        sf_zero(T);                                   // class (0,1): (eta, xi), (zeta, xi)
+        sf_stage2<1, 0>(S + 1 * 144, ui2, T);
+        sf_stage2<0, 0>(S + 3 * 144, ui2, T);
+        sf_stage3<1>(T, out);
+        __syncwarp();
+        // round 2, class (0,0): (eta, eta), (eta, zeta), (zeta, eta), (zeta, zeta)
+        if (lane < 16) {
+          sf_stage1<0>(sK + 3 * NG, sS1 + 0 * 144, lane);
+          sf_stage1<1>(sK + 4 * NG, sS1 + 1 * 144, lane);
+          sf_stage1<2>(sK + 4 * NG, sS1 + 2 * 144, lane);
+          sf_stage1<3>(sK + 5 * NG, sS1 + 3 * 144, lane);
+        }
+        __syncwarp();
+        sf_zero(T);
+        sf_stage2<1, 1>(S + 0 * 144, ui2, T);
+        sf_stage2<1, 0>(S + 1 * 144, ui2, T);
+        sf_stage2<0, 1>(S + 2 * 144, ui2, T);
+        sf_stage2<0, 0>(S + 3 * 144, ui2, T);
+        sf_stage3<0>(T, out);
+      }
       // source term of row `lane`: sum_g phi(g) w det = sum_a l_i1(a) sum_b l_i2(b) sum_c l_i3(c) wd[a][b][c]
       double src = 0.0;
       if (rhs) {

@@ -69,6 +69,7 @@ struct b2_ctx {
   // assembly kernel for triquadratic elements: 3 = sum factorisation (default; falls back to 1 when the tables are not
   // tensor products), 1 = FP64 tensor cores (mma.sync m8n8k4), 0 = CUDA-core tiles, 2 = table-driven kernel
   int asm_variant = 3;
+  int asm_warps = 12;      // warps per CTA of the sum-factorised kernel: 12 or 16
   // multi-GPU
   int nranks = 1, rank = 0;
   void* nccl_comm = nullptr;

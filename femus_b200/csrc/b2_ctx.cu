@@ -78,6 +78,7 @@ int b2_ctx_create(int device, b2_ctx** out) {
   c->sm_count = prop.multiProcessorCount;
   if (const char* v = getenv("B2_SPMV_VARIANT")) c->spmv_variant = atoi(v);
   if (const char* v = getenv("B2_ASM_VARIANT")) c->asm_variant = atoi(v);
+  if (const char* v = getenv("B2_SF_WARPS")) c->asm_warps = atoi(v) == 16 ? 16 : 12;
   B2_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   B2_CUDA(cudaEventCreate(&c->ev0));
   B2_CUDA(cudaEventCreate(&c->ev1));
@@ -182,6 +183,11 @@ int b2_ctx_set_option(b2_ctx* c, const char* name, int value) {
   if (!strcmp(name, "spmv_variant")) {
     B2_CHECK(value >= 0 && value <= 2, "spmv_variant %d (0, 1, 2)", value);
     c->spmv_variant = value;
+    return 0;
+  }
+  if (!strcmp(name, "asm_warps")) {
+    B2_CHECK(value == 12 || value == 16, "asm_warps %d (12, 16)", value);
+    c->asm_warps = value;
     return 0;
   }
   if (!strcmp(name, "asm_variant")) {

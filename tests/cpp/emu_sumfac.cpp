@@ -30,6 +30,7 @@ int emu_sumfac(int64_t nel, int64_t nnode, const double* xyz, const int32_t* con
   SfTables T;
   if (!sf_factor_tables(phi, dxi, deta, dzeta, w, &T)) return 1;
   std::memcpy(c_sfM, T.M, sizeof(T.M));
+  std::memcpy(c_sfU, T.L, sizeof(T.L) + sizeof(T.D));
   std::vector<int32_t> dofL((size_t)nel * 27);
   std::vector<uint16_t> lslot((size_t)nel * 729);
   for (int64_t e = 0; e < nel; e++) {
@@ -56,10 +57,10 @@ int emu_sumfac(int64_t nel, int64_t nnode, const double* xyz, const int32_t* con
           cslot[E * 729 + I * 27 + J] = (uint16_t)s;
         }
     ga = SfGalArgs{&G, cd, cslot.data(), fmask, cmask, Cp, Cv, emat};
-    emu::launch(assemble_q2_sumfac_kernel<uint16_t, true, uint16_t>, (unsigned)grid, (unsigned)(kSfWarps * 32), SfSmem::bytes_gal, nel, nnode, xyz, conn,
+    emu::launch(assemble_q2_sumfac_kernel<kSfWarpsDefault, uint16_t, true, uint16_t>, (unsigned)grid, (unsigned)(kSfWarpsDefault * 32), SfSmem<kSfWarpsDefault>::bytes_gal, nel, nnode, xyz, conn,
                 (const int32_t*)dofL.data(), (const SfTables*)&T, (const uint16_t*)lslot.data(), rowptr, Aval, u, rhs, nu, fsrc, ga);
   } else {
-    emu::launch(assemble_q2_sumfac_kernel<uint16_t, false, uint16_t>, (unsigned)grid, (unsigned)(kSfWarps * 32), SfSmem::bytes, nel, nnode, xyz, conn,
+    emu::launch(assemble_q2_sumfac_kernel<kSfWarpsDefault, uint16_t, false, uint16_t>, (unsigned)grid, (unsigned)(kSfWarpsDefault * 32), SfSmem<kSfWarpsDefault>::bytes, nel, nnode, xyz, conn,
                 (const int32_t*)dofL.data(), (const SfTables*)&T, (const uint16_t*)lslot.data(), rowptr, Aval, u, rhs, nu, fsrc, ga);
   }
   return 0;
