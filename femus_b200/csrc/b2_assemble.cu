@@ -968,7 +968,9 @@ int launch_assemble_sumfac_w(b2_asm* p, const SfGalArgs& ga, const b2_vec* u, b2
 }
 template <typename SlotT, bool GAL, typename CSlotT>
 int launch_assemble_sumfac(b2_asm* p, const SfGalArgs& ga, const b2_vec* u, b2_vec* rhs, double nu, double fsrc) {
-  if (p->mesh->ctx->asm_warps == 16) return launch_assemble_sumfac_w<16, SlotT, GAL, CSlotT>(p, ga, u, rhs, nu, fsrc);
+  // 16 warps: only where the CTA's shared memory fits the SM (not with the fused Galerkin tile)
+  if (p->mesh->ctx->asm_warps == 16 && (GAL ? SfSmem<16>::bytes_gal : SfSmem<16>::bytes) <= (size_t)227 * 1024)
+    return launch_assemble_sumfac_w<16, SlotT, GAL, CSlotT>(p, ga, u, rhs, nu, fsrc);
   return launch_assemble_sumfac_w<kSfWarpsDefault, SlotT, GAL, CSlotT>(p, ga, u, rhs, nu, fsrc);
 }
 

@@ -45,8 +45,14 @@ struct SfTables {                      // built by sf_prepare from the caller's 
   int node_of[32];                     // lattice position m = 9 i1 + 3 i2 + i3 -> local node of the reference's order
 };
 struct SfGalTables {
-  double A[8][3][3][3];                // [child][dim d][fine lattice index n_d][coarse lattice index J_d]
+  // 1-D factors of the child prolongators.  Refining a quadratic 1-D element, a child's three nodes take
+  //   lower child: (v0, a v0 + b v1 + c v2, v1)      upper child: (v1, c v0 + b v1 + a v2, v2)
+  // from the parent's (v0, v1, v2) -- (a, b, c) = (3/8, 3/4, -1/8) for Lagrange polynomials; sf_factor_children
+  // checks that every factor has one of these two forms, so a pass costs 3 instead of 9 multiply-adds per triple
+  double abc[4];                       // a, b, c, (unused)
+  int hi[8][4];                        // [child][dim d]: 1 = upper child in that dimension
   unsigned short nat2lat[736];         // natural entry I * 27 + J -> lattice entry m(I) * 27 + m(J)
+  double A[8][3][3][3];                // [child][dim d][fine lattice index n_d][coarse lattice index J_d] (host-side check only)
 };
 struct SfGalArgs {
   const SfGalTables* tab;              // device
@@ -68,15 +74,16 @@ __constant__ double c_sfU[2][3][4];
 template <int WARPS>
 struct SfSmem {
   // tables: L, D (12 each), M (144), w (64), A (216, fused Galerkin only) | per warp: X[3][28], U[28], row starts[28],
-  // KB = K[7][64] + S1[4][9][16] during the quadrature loop, then the element matrix [27][27]; Dacc [27][27] (fused
+  // KB = K[7][64] + S1[4][9][18] during the quadrature loop, then the element matrix [27][27]; Dacc [27][27] (fused
   // Galerkin only)
   static constexpr int tab_doubles = 12 + 12 + 144 + 64;
-  static constexpr int gal_doubles = 216 + 736 / 4;
-  static constexpr int s1_doubles = 4 * 9 * 16;        // S1 of the four terms of a round: [term][i3 j3][a b]
+  static constexpr int gal_doubles = 4 + 16 + 736 / 4;      // abc, hi flags, nat2lat
+  static constexpr int s1_doubles = 4 * 9 * 18;        // S1 of the four terms of a round: [term][i3 j3][a b], rows padded to 18
+                                                       // (stride 16 puts the 9 rows a quarter-warp reads on the same banks)
   static constexpr int kb_doubles = 7 * 64 + s1_doubles;   // K, S1; later the element matrix (729)
   static constexpr int dacc_doubles = 736;
   static constexpr int warp_doubles = 3 * 28 + 28 + 28 + kb_doubles;
-  static constexpr int warp_doubles_gal = warp_doubles + dacc_doubles;
+  static constexpr int warp_doubles_gal = warp_doubles + dacc_doubles + 28;      // + row starts of the coarse dofs
   static constexpr size_t bytes = (size_t)(tab_doubles + WARPS * warp_doubles) * sizeof(double);
   static constexpr size_t bytes_gal = (size_t)(tab_doubles + gal_doubles + WARPS * warp_doubles_gal) * sizeof(double);
 };
@@ -88,7 +95,7 @@ __device__ __forceinline__ void sf_stage1(const double* __restrict__ Kc, double*
   const double2 k23 = *reinterpret_cast<const double2*>(Kc + ab * 4 + 2);
 #pragma unroll
   for (int ij = 0; ij < 9; ij++)
-    S1[ij * 16 + ab] = fma(c_sfM[PQ3][ij][3], k23.y, fma(c_sfM[PQ3][ij][2], k23.x, fma(c_sfM[PQ3][ij][1], k01.y, c_sfM[PQ3][ij][0] * k01.x)));
+    S1[ij * 18 + ab] = fma(c_sfM[PQ3][ij][3], k23.y, fma(c_sfM[PQ3][ij][2], k23.x, fma(c_sfM[PQ3][ij][1], k01.y, c_sfM[PQ3][ij][0] * k01.x)));
 }
 // stage 2 of one term, lane = (i2, i3, j3): T[j2][a] += sum_b u^P2_i2(b) u^Q2_j2(b) S1[i3 j3][a][b]
 template <int P2, int Q2>
@@ -119,21 +126,31 @@ __device__ __forceinline__ void sf_zero(double (&T)[3][4]) {
 #pragma unroll
     for (int a = 0; a < 4; a++) T[j2][a] = 0.0;
 }
-// v[n] (n = 0..2 at stride S) -> sum_n v[n] A[n][J]: one 1-D pass of the Kronecker product
+// one 1-D pass of the Kronecker product on the triples (v0, v1, v2) at stride S: v -> v A with A the transposed
+// lower / upper child factor (see SfGalTables)
 template <int S>
-__device__ __forceinline__ void sf_kron_pass(double (&R)[27], const double* __restrict__ A) {
-  double a[9];
+__device__ __forceinline__ void sf_kron_pass(double (&R)[27], bool hi, double a, double b, double c) {
+  if (hi) {
 #pragma unroll
-  for (int t = 0; t < 9; t++) a[t] = A[t];
+    for (int h = 0; h < 27; h += 3 * S)
 #pragma unroll
-  for (int hi = 0; hi < 27; hi += 3 * S)
+      for (int lo = 0; lo < S; lo++) {
+        const double r0 = R[h + lo], r1 = R[h + lo + S], r2 = R[h + lo + 2 * S];
+        R[h + lo] = c * r1;
+        R[h + lo + S] = fma(b, r1, r0);
+        R[h + lo + 2 * S] = fma(a, r1, r2);
+      }
+  } else {
 #pragma unroll
-    for (int lo = 0; lo < S; lo++) {
-      const double r0 = R[hi + lo], r1 = R[hi + lo + S], r2 = R[hi + lo + 2 * S];
-      R[hi + lo] = fma(r2, a[6], fma(r1, a[3], r0 * a[0]));
-      R[hi + lo + S] = fma(r2, a[7], fma(r1, a[4], r0 * a[1]));
-      R[hi + lo + 2 * S] = fma(r2, a[8], fma(r1, a[5], r0 * a[2]));
-    }
+    for (int h = 0; h < 27; h += 3 * S)
+#pragma unroll
+      for (int lo = 0; lo < S; lo++) {
+        const double r0 = R[h + lo], r1 = R[h + lo + S], r2 = R[h + lo + 2 * S];
+        R[h + lo] = fma(a, r1, r0);
+        R[h + lo + S] = fma(b, r1, r2);
+        R[h + lo + 2 * S] = c * r1;
+      }
+  }
 }
 
 template <int WARPS, typename SlotT, bool GAL, typename CSlotT>
@@ -149,17 +166,19 @@ assemble_q2_sumfac_kernel(int64_t nel, int64_t nnode, const double* __restrict__
   double* sD = sL + 12;               // [3][4]
   double* sM = sD + 12;               // [4][9][4]
   double* sW = sM + 144;              // [64]
-  double* sA = sW + NG;               // [8][3][9]              (GAL)
-  const unsigned short* sN2L = reinterpret_cast<const unsigned short*>(sA + 216);      // [729] (GAL)
+  double* sA = sW + NG;               // a, b, c, -; then int hi[8][4]; then nat2lat  (GAL)
+  const int* sHi = reinterpret_cast<const int*>(sA + 4);
+  const unsigned short* sN2L = reinterpret_cast<const unsigned short*>(sA + 4 + 16);      // [729] (GAL)
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   double* wbase = smem + Smem::tab_doubles + (GAL ? Smem::gal_doubles : 0) + wib * (GAL ? Smem::warp_doubles_gal : Smem::warp_doubles);
   double* sX = wbase;                                   // [3][28] coordinates, lattice order
   double* sU = sX + 3 * 28;                             // [28] current solution
   long long* sRow = reinterpret_cast<long long*>(sU + 28);     // [28] rowptr[dof]
   double* sK = reinterpret_cast<double*>(sRow + 28);    // [7][64]: K00 K01 K02 K11 K12 K22, w det
-  double* sS1 = sK + 7 * NG;                            // [4][9][16] stage-1 sums of the four terms of a round
+  double* sS1 = sK + 7 * NG;                            // [4][9][18] stage-1 sums of the four terms of a round
   double* Bs = sK;                                      // [27][27] element matrix (lattice order), reuses sK / sS1
   double* Dacc = sK + Smem::kb_doubles;               // [27][27] Galerkin matrix of the coarse element (GAL)
+  long long* sCRow = reinterpret_cast<long long*>(Dacc + Smem::dacc_doubles);      // [28] Cp[coarse dof] (GAL)
 
   for (int t = threadIdx.x; t < Smem::tab_doubles; t += blockDim.x) smem[t] = reinterpret_cast<const double*>(tabs)[t];
   if (GAL) {
@@ -182,23 +201,50 @@ assemble_q2_sumfac_kernel(int64_t nel, int64_t nnode, const double* __restrict__
   }
 
   const int64_t nunits = GAL ? (nel >> 3) : nel;
-  for (int64_t unit = (int64_t)blockIdx.x * WARPS + wib; unit < nunits; unit += (int64_t)gridDim.x * WARPS) {
+  const int64_t ustride = (int64_t)gridDim.x * WARPS;
+  // node id and dof of the NEXT element are fetched one element ahead (the coordinate / solution / row-start loads
+  // that depend on them then start without waiting for this first level of the gather)
+  int64_t nd_pf = 0;
+  int dof_pf = 0;
+  {
+    const int64_t u0 = (int64_t)blockIdx.x * WARPS + wib;
+    if (u0 < nunits && lane < NVE) {
+      const int64_t e0 = GAL ? u0 * 8 : u0;
+      nd_pf = conn[e0 * 27 + my_node];
+      dof_pf = dofL[e0 * NVE + lane];
+    }
+  }
+  for (int64_t unit = (int64_t)blockIdx.x * WARPS + wib; unit < nunits; unit += ustride) {
+    unsigned cmaskbits = 0;            // coarse Dirichlet dofs of this coarse element (natural order), one bit per dof
     if (GAL) {
       for (int t = lane; t < Smem::dacc_doubles; t += 32) Dacc[t] = 0.0;
+      int cm = 0;
+      if (lane < NVE) {
+        const int32_t dI = ga.cd[unit * NVE + lane];
+        sCRow[lane] = ga.Cp[dI];
+        cm = ga.cmask ? (int)ga.cmask[dI] : 0;
+      }
+      cmaskbits = __ballot_sync(0xffffffffu, cm != 0);
     }
 #pragma unroll 1
     for (int child = 0; child < (GAL ? 8 : 1); child++) {
       const int64_t e = GAL ? unit * 8 + child : unit;
       // ---- gather (lattice order): coordinates, dofs, current solution, row starts
-      int mydof = 0;
+      int mydof = 0, fm = 0;
       if (lane < NVE) {
-        const int64_t nd = conn[e * 27 + my_node];
+        const int64_t nd = nd_pf;
+        mydof = dof_pf;
+        const int64_t en = (GAL && child < 7) ? e + 1 : (GAL ? (unit + ustride) * 8 : unit + ustride);
+        if (en < nel) {
+          nd_pf = conn[en * 27 + my_node];
+          dof_pf = dofL[en * NVE + lane];
+        }
         sX[lane] = xyz[nd];
         sX[28 + lane] = xyz[nnode + nd];
         sX[56 + lane] = xyz[2 * nnode + nd];
-        mydof = dofL[e * NVE + lane];
         sU[lane] = u ? u[mydof] : 0.0;
         sRow[lane] = rowptr[mydof];
+        if (GAL && ga.fmask) fm = (int)ga.fmask[mydof];      // used after the element matrix is formed
       }
       __syncwarp();
 
@@ -269,40 +315,40 @@ assemble_q2_sumfac_kernel(int64_t nel, int64_t nnode, const double* __restrict__
       for (int t = 0; t < 27; t++) out[t] = 0.0;
       {
         double T[3][4];
-        const double* S = sS1 + pb_i3j3 * 16;
+        const double* S = sS1 + pb_i3j3 * 18;
         // round 1: the terms with xi on either side.  Stage-1 sums: (K00, l l), (K01, l l), (K02, l l'), (K02, l' l)
         if (lane < 16) {
-          sf_stage1<0>(sK + 0 * NG, sS1 + 0 * 144, lane);
-          sf_stage1<0>(sK + 1 * NG, sS1 + 1 * 144, lane);
-          sf_stage1<1>(sK + 2 * NG, sS1 + 2 * 144, lane);
-          sf_stage1<2>(sK + 2 * NG, sS1 + 3 * 144, lane);
+          sf_stage1<0>(sK + 0 * NG, sS1 + 0 * 162, lane);
+          sf_stage1<0>(sK + 1 * NG, sS1 + 1 * 162, lane);
+          sf_stage1<1>(sK + 2 * NG, sS1 + 2 * 162, lane);
+          sf_stage1<2>(sK + 2 * NG, sS1 + 3 * 162, lane);
         }
         __syncwarp();
         sf_zero(T);                                   // class (1,1): (xi, xi)
-        sf_stage2<0, 0>(S + 0 * 144, ui2, T);
+        sf_stage2<0, 0>(S + 0 * 162, ui2, T);
         sf_stage3<3>(T, out);
         sf_zero(T);                                   // class (1,0): (xi, eta), (xi, zeta)
-        sf_stage2<0, 1>(S + 1 * 144, ui2, T);
-        sf_stage2<0, 0>(S + 2 * 144, ui2, T);
+        sf_stage2<0, 1>(S + 1 * 162, ui2, T);
+        sf_stage2<0, 0>(S + 2 * 162, ui2, T);
         sf_stage3<2>(T, out);
         sf_zero(T);                                   // class (0,1): (eta, xi), (zeta, xi)
-        sf_stage2<1, 0>(S + 1 * 144, ui2, T);
-        sf_stage2<0, 0>(S + 3 * 144, ui2, T);
+        sf_stage2<1, 0>(S + 1 * 162, ui2, T);
+        sf_stage2<0, 0>(S + 3 * 162, ui2, T);
         sf_stage3<1>(T, out);
         __syncwarp();
         // round 2, class (0,0): (eta, eta), (eta, zeta), (zeta, eta), (zeta, zeta)
         if (lane < 16) {
-          sf_stage1<0>(sK + 3 * NG, sS1 + 0 * 144, lane);
-          sf_stage1<1>(sK + 4 * NG, sS1 + 1 * 144, lane);
-          sf_stage1<2>(sK + 4 * NG, sS1 + 2 * 144, lane);
-          sf_stage1<3>(sK + 5 * NG, sS1 + 3 * 144, lane);
+          sf_stage1<0>(sK + 3 * NG, sS1 + 0 * 162, lane);
+          sf_stage1<1>(sK + 4 * NG, sS1 + 1 * 162, lane);
+          sf_stage1<2>(sK + 4 * NG, sS1 + 2 * 162, lane);
+          sf_stage1<3>(sK + 5 * NG, sS1 + 3 * 162, lane);
         }
         __syncwarp();
         sf_zero(T);
-        sf_stage2<1, 1>(S + 0 * 144, ui2, T);
-        sf_stage2<1, 0>(S + 1 * 144, ui2, T);
-        sf_stage2<0, 1>(S + 2 * 144, ui2, T);
-        sf_stage2<0, 0>(S + 3 * 144, ui2, T);
+        sf_stage2<1, 1>(S + 0 * 162, ui2, T);
+        sf_stage2<1, 0>(S + 1 * 162, ui2, T);
+        sf_stage2<0, 1>(S + 2 * 162, ui2, T);
+        sf_stage2<0, 0>(S + 3 * 162, ui2, T);
         sf_stage3<0>(T, out);
       }
       // source term of row `lane`: sum_g phi(g) w det = sum_a l_i1(a) sum_b l_i2(b) sum_c l_i3(c) wd[a][b][c]
@@ -359,24 +405,19 @@ assemble_q2_sumfac_kernel(int64_t nel, int64_t nnode, const double* __restrict__
       __syncwarp();
 
       if (GAL) {
-        const double* A1 = sA + (child * 3 + 0) * 9;
-        const double* A2 = sA + (child * 3 + 1) * 9;
-        const double* A3 = sA + (child * 3 + 2) * 9;
+        const double ka = sA[0], kb = sA[1], kc = sA[2];
+        const bool hi1 = sHi[child * 4 + 0] != 0, hi2 = sHi[child * 4 + 1] != 0, hi3 = sHi[child * 4 + 2] != 0;
         // rows / columns of Dirichlet fine dofs do not take part in the Galerkin product
-        unsigned mask = 0;
-        if (ga.fmask) {
-          const int fm = lane < NVE ? (int)ga.fmask[mydof] : 0;
-          mask = __ballot_sync(0xffffffffu, fm != 0);
-        }
+        const unsigned mask = __ballot_sync(0xffffffffu, fm != 0);
         if (mask) {
           const bool rowdead = (mask >> lb) & 1u;
 #pragma unroll
           for (int j = 0; j < NVE; j++)
             if (rowdead || ((mask >> j) & 1u)) R[j] = 0.0;
         }
-        sf_kron_pass<1>(R, A3);          // T = B Pc, row `lane`: the column index runs over (j1, j2, j3)
-        sf_kron_pass<3>(R, A2);
-        sf_kron_pass<9>(R, A1);
+        sf_kron_pass<1>(R, hi3, ka, kb, kc);          // T = B Pc, row `lane`: the column index runs over (j1, j2, j3)
+        sf_kron_pass<3>(R, hi2, ka, kb, kc);
+        sf_kron_pass<9>(R, hi1, ka, kb, kc);
         if (lane < NVE) {
 #pragma unroll
           for (int j = 0; j < NVE; j++) Bs[lane * NVE + j] = R[j];
@@ -384,9 +425,9 @@ assemble_q2_sumfac_kernel(int64_t nel, int64_t nnode, const double* __restrict__
         __syncwarp();
 #pragma unroll
         for (int i = 0; i < NVE; i++) R[i] = Bs[i * NVE + lb];       // column `lane` of T
-        sf_kron_pass<1>(R, A3);          // D = Pc^T T, column `lane`
-        sf_kron_pass<3>(R, A2);
-        sf_kron_pass<9>(R, A1);
+        sf_kron_pass<1>(R, hi3, ka, kb, kc);          // D = Pc^T T, column `lane`
+        sf_kron_pass<3>(R, hi2, ka, kb, kc);
+        sf_kron_pass<9>(R, hi1, ka, kb, kc);
         if (lane < NVE) {
 #pragma unroll
           for (int i = 0; i < NVE; i++) Dacc[i * NVE + lane] += R[i];
@@ -403,12 +444,8 @@ assemble_q2_sumfac_kernel(int64_t nel, int64_t nnode, const double* __restrict__
         if (ga.emat) ga.emat[(size_t)E * (NVE * NVE) + idx] = v;
         if (v == 0.0) continue;
         const int I = idx / NVE, Jn = idx - I * NVE;
-        const int32_t dI = ga.cd[E * NVE + I];
-        if (ga.cmask) {
-          const int32_t dJ = ga.cd[E * NVE + Jn];
-          if (ga.cmask[dI] || ga.cmask[dJ]) continue;
-        }
-        atomicAdd(&ga.Cv[ga.Cp[dI] + (int64_t)cslot[idx]], v);
+        if (((cmaskbits >> I) | (cmaskbits >> Jn)) & 1u) continue;
+        atomicAdd(&ga.Cv[sCRow[I] + (long long)cslot[idx]], v);
       }
       __syncwarp();
     }

@@ -79,6 +79,19 @@ static inline bool sf_factor_children(const double* Pc, SfGalTables* G) {
         if (!(fabs(want - P(m, M)) <= 1e-15)) return false;
       }
   }
+  // every factor must be the lower- or upper-child form of SfGalTables, with the same (a, b, c)
+  bool have = false;
+  for (int j = 0; j < 8; j++)
+    for (int d = 0; d < 3; d++) {
+      const double (*A)[3] = G->A[j][d];
+      const bool lo = A[0][0] == 1.0 && A[0][1] == 0.0 && A[0][2] == 0.0 && A[2][0] == 0.0 && A[2][1] == 1.0 && A[2][2] == 0.0;
+      const bool up = A[0][0] == 0.0 && A[0][1] == 1.0 && A[0][2] == 0.0 && A[2][0] == 0.0 && A[2][1] == 0.0 && A[2][2] == 1.0;
+      if (!lo && !up) return false;
+      const double abc[3] = {lo ? A[1][0] : A[1][2], A[1][1], lo ? A[1][2] : A[1][0]};
+      if (!have) { G->abc[0] = abc[0]; G->abc[1] = abc[1]; G->abc[2] = abc[2]; have = true; }
+      else if (abc[0] != G->abc[0] || abc[1] != G->abc[1] || abc[2] != G->abc[2]) return false;
+      G->hi[j][d] = up ? 1 : 0;
+    }
   for (int I = 0; I < 27; I++)
     for (int J = 0; J < 27; J++) G->nat2lat[I * 27 + J] = (unsigned short)(sf_lattice_of(I) * 27 + sf_lattice_of(J));
   return true;

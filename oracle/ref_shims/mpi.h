@@ -42,6 +42,11 @@ typedef struct { int MPI_SOURCE, MPI_TAG, MPI_ERROR; } MPI_Status;
 #define MPI_SUM 1
 #define MPI_MIN 2
 #define MPI_MAX 3
+#define MPI_BAND 4
+#define MPI_BOR 5
+#define MPI_LAND 6
+#define MPI_LOR 7
+#define MPI_PROD 8
 
 #ifdef __cplusplus
 extern "C" {
