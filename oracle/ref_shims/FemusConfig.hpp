@@ -9,6 +9,7 @@
 #define __femus_FemusConfig_hpp__
 #include <climits>
 #include <cstdlib>
+#include <iostream>
 #define FEMTTU_VERSION_MAJOR 1
 #define FEMTTU_VERSION_MINOR 0
 #define HAVE_MPI
@@ -16,6 +17,8 @@
 #define HAVE_JSONCPP
 #define HAVE_ADEPT
 #define HAVE_B64
+#define HAVE_METIS
+#define HAVE_HDF5
 #undef LSOLVER
 #define LSOLVER PETSC_SOLVERS
 #define FEMTTU_DETECTED_PETSC_VERSION_MAJOR 3
@@ -47,6 +50,12 @@ typedef double PetscReal;
 #define CHKERRABORT(comm, ierr) do { if (ierr) abort(); } while (0)
 static inline int PetscInitialize(int*, char***, const char*, const char*) { return 0; }
 static inline int PetscFinalize() { return 0; }
+typedef void* PetscViewer;
+#define PETSCVIEWERASCII "ascii"
+static inline int PetscViewerCreate(int, PetscViewer*) { return 0; }
+static inline int PetscViewerSetType(PetscViewer, const char*) { return 0; }
+static inline int PetscViewerFileSetName(PetscViewer, const char*) { return 0; }
+static inline int PetscLogView(PetscViewer) { return 0; }
 namespace femus {
 class FieldSplitTree;      // FieldSplitTree.hpp is PETSc code; the base solver interface only passes pointers to it
 }
