@@ -10,6 +10,9 @@
 #include <climits>
 #include <cstdlib>
 #include <iostream>
+#include <cmath>
+using std::isnan;      // the reference calls isnan(double) unqualified (petsc.h drags <math.h> in)
+using std::isinf;
 #define FEMTTU_VERSION_MAJOR 1
 #define FEMTTU_VERSION_MINOR 0
 #define HAVE_MPI
@@ -18,6 +21,7 @@
 #define HAVE_ADEPT
 #define HAVE_B64
 #define HAVE_METIS
+#define HAVE_FPARSER
 #define HAVE_HDF5
 #undef LSOLVER
 #define LSOLVER PETSC_SOLVERS

@@ -1,1 +1,7 @@
-// TEST INFRASTRUCTURE: empty stand-in (uq.cpp is not part of the oracle build)
+// TEST INFRASTRUCTURE: stand-in for <boost/random.hpp>.  The reference's uq sources only need the standard headers the
+// real one drags in (no boost random generator is on the oracle's path).
+#pragma once
+#include <math.h>
+#include <cmath>
+#include <cstring>
+#include <iostream>
