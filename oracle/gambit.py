@@ -4,7 +4,8 @@ permutation), :83 (face permutation), :92-352 (sections), followed by the refere
 renumbering (mesh_box._renumber, Mesh.cpp:517-559).  Fixture: tests/golden/cube_hex27_2x2x2.neu holds the
 nodes, elements and boundary sets of the reference's applications/001_Poisson/input/cube_Hex.neu,
 re-serialised by tests/golden/make_neu_fixture.py.  Tetrahedral files: oracle/mesh_tet.py.
-PARITY UNPINNED BY THE REFERENCE beyond the file format itself (no expected numbering is shipped)."""
+The numbering this reader produces equals the reference's own (tests/test_reference_pin.py, cube_hex case, through the
+product's reader, which tests/test_host_mesh.py holds equal to this one)."""
 import numpy as np
 
 from . import mesh_box as mb

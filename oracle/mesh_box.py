@@ -1,8 +1,10 @@
 """Oracle (TEST INFRASTRUCTURE ONLY): structured HEX27 box meshes, FEMuS node/dof numbering,
 uniform refinement, Dirichlet flags, system sparsity and prolongators, restated with numpy.
 
-PARITY UNPINNED BY THE REFERENCE: the reference needs PETSc+MPI to run this part and ships no
-golden vectors for it.  Each function cites what it restates
+PARITY PINNED TO REFERENCE OUTPUT (round 2): the reference's own sources, compiled unmodified on the single-process host
+backend of oracle/ref_build and run here (applications/001_Poisson/main.cpp), produced tests/golden/ref_poisson_*.npz
+(tests/golden/make_ref_golden.py); tests/test_reference_pin.py compares this module with them -- integers bit-exact,
+values and printed residual norms to the stated tolerances.  Each function cites what it restates
 (paths relative to /root/reference/src):
 
   06_mesh/00_single_level/01_input/02_from_implemented_code/MeshGeneration.cpp:790-849   box nodes

@@ -3,8 +3,11 @@ Gambit neutral files: FEMuS node/dof numbering, the face and centre nodes the fi
 refinement, Dirichlet flags, sparsity, Poisson assembly and prolongators, restated with numpy/scipy and plain
 Python loops over ragged element lists (small meshes only).
 
-PARITY UNPINNED BY THE REFERENCE beyond the FE arithmetic (fe_hex / fe_tet / fe_wedge, pinned to the compiled
-reference): the reference needs PETSc+MPI to run this part and ships no expected numbering.
+PARITY PINNED TO REFERENCE OUTPUT (round 2): the reference's own sources, compiled unmodified on the single-process host
+backend of oracle/ref_build and run here (applications/001_Poisson/main.cpp), produced tests/golden/ref_poisson_*.npz
+(tests/golden/make_ref_golden.py); tests/test_reference_pin.py compares this module with them -- integers bit-exact,
+values and printed residual norms to the stated tolerances.  (The FE arithmetic, fe_hex / fe_tet / fe_wedge, is pinned to the compiled
+reference as well.)
 Restates (paths relative to /root/reference/src):
   06_mesh/00_single_level/01_input/01_from_external_file/GambitIO.cpp:56-85, 92-352   file sections, permutations
   06_mesh/00_single_level/00_definition/Mesh.cpp:105-125, 1207-1333   AddBiquadraticNodesNotInMeshFile

@@ -2,8 +2,8 @@
 numbering, the face and centre nodes the file lacks, uniform 1 -> 8 refinement, Dirichlet flags, sparsity,
 Poisson assembly and prolongators, restated with numpy/scipy and plain loops (small meshes).
 
-PARITY UNPINNED BY THE REFERENCE beyond the FE arithmetic (fe_tet.py, pinned to the compiled reference):
-the reference needs PETSc+MPI to run this part and ships no expected numbering.
+PARITY: equal to oracle/mesh_mixed.py on tetrahedral files (tests/test_host_mesh.py), which tests/test_reference_pin.py pins
+to the reference's own output (tests/golden/ref_poisson_cube_tet_*.npz); FE arithmetic pinned to the compiled reference.
 Restates (paths relative to /root/reference/src):
   06_mesh/00_single_level/01_input/01_from_external_file/GambitIO.cpp:56-85, 92-352   file sections, permutations
   06_mesh/00_single_level/00_definition/Mesh.cpp:105-125, 1207-1333   AddBiquadraticNodesNotInMeshFile

@@ -1,9 +1,12 @@
 """Oracle (TEST INFRASTRUCTURE ONLY): the multigrid solve the reference CONFIGURES in PETSc,
 restated with scipy.sparse in fp64.
 
-PARITY UNPINNED BY THE REFERENCE (arithmetic lives in PETSc 3.20.2, pinned at
-contrib/scripts/install_petsc.sh:12, not installed here; the reference holds no golden vectors
-for it).  Restates, with paths relative to /root/reference/src:
+PARITY: the operators (assembled matrix, prolongators with Dirichlet rows / columns zeroed, Galerkin chain,
+Dirichlet rows) and the residual norms of six V-cycles with the application's own smoother (Richardson 0.5 + SOR,
+main.cpp:239-242) are pinned to REFERENCE OUTPUT (tests/golden/ref_poisson_*.npz, tests/test_reference_pin.py): the
+reference's unmodified sources run here on the host backend of oracle/ref_build.  The cycle arithmetic itself lives
+in PETSc 3.20.2 (contrib/scripts/install_petsc.sh:12, absent): in that run it is the host backend's C++ restatement
+of PCMG, an implementation independent of this one; the two agree to the 7 digits the reference prints.  Restates, with paths relative to /root/reference/src:
 
   08_equations/00_stationary/LinearImplicitSystem.cpp:347-370     Galerkin chain A_{l-1} = P^T A_l P
   08_algebra.../LinearEquationSolverPetsc.cpp:53-90, 428-436      BuildBdcIndex, SetPenalty

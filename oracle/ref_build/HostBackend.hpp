@@ -20,6 +20,8 @@
 #include <fstream>
 #include <map>
 #include <memory>
+#include <string>
+#include <type_traits>
 #include <vector>
 
 #include "NumericVector.hpp"
@@ -415,6 +417,7 @@ class HostLinearEquationSolver : public LinearEquationSolver {
     HostLinearEquationSolver* top = static_cast<HostLinearEquationSolver*>(LinSolver);
     if (top->_hier.size() != (size_t)levelMax + 1) { std::fprintf(stderr, "oracle host backend: MGSetLevel before MGInit\n"); std::abort(); }
     if (!_bdcIndexIsInitialized) this->BuildBdcIndex(variable_to_be_solved);
+    if (const char* dir = std::getenv("FEMUS_REF_DUMP")) this->dump_level(dir, PP);      // before the penalty: the assembled / Galerkin operator
     _KK->mat_zero_rows(_bdcIndex, 1.0);                 // SetPenalty (:428-436)
     if (_level > 0 && (this->_levelSolverType != RICHARDSON ||
                        (this->preconditioner_type() != JACOBI_PRECOND && this->preconditioner_type() != SOR_PRECOND))) {
@@ -431,6 +434,10 @@ class HostLinearEquationSolver : public LinearEquationSolver {
   // one multiplicative V-cycle as outer PREONLY (:294-353): ZerosBoundaryResiduals; EPSC = V(RES); RESC = KK EPSC; RES -= RESC; EPS += EPSC
   void MGSolve(const bool) override {
     HostVector& RES = static_cast<HostVector&>(*_RES);
+    if (const char* dir = std::getenv("FEMUS_REF_DUMP")) {
+      if (!_resDumped) dump_array(dir, "RES", RES.data());          // the assembled residual of the first cycle
+      _resDumped = true;
+    }
     for (int i : _bdcIndex) RES.data()[i] = 0.0;
     std::vector<double> x;
     vcycle((int)_level, RES.data(), x);
@@ -441,6 +448,79 @@ class HostLinearEquationSolver : public LinearEquationSolver {
   }
 
  private:
+  // ---- reference output for the golden fixtures (tests/golden/make_ref_golden.py): one raw little-endian file per array,
+  // <dir>/L<level>_<name>.<i4|i8|f8>, everything read out of the reference's own objects
+  template <class T>
+  void dump_array(const char* dir, const char* name, const std::vector<T>& a) const {
+    const char* suffix = sizeof(T) == 8 ? (std::is_floating_point<T>::value ? "f8" : "i8") : "i4";
+    const std::string path = std::string(dir) + "/L" + std::to_string(_level) + "_" + name + "." + suffix;
+    std::ofstream f(path, std::ios::binary);
+    f.write(reinterpret_cast<const char*>(a.data()), (std::streamsize)(a.size() * sizeof(T)));
+  }
+  void dump_csr(const char* dir, const char* name, const HostMatrix& A) const {
+    std::vector<long long> rp(1, 0);
+    std::vector<int> col;
+    std::vector<double> val;
+    for (const auto& r : A.rows()) {
+      for (const auto& e : r) { col.push_back(e.first); val.push_back(e.second); }
+      rp.push_back((long long)col.size());
+    }
+    dump_array(dir, (std::string(name) + "_rowptr").c_str(), rp);
+    dump_array(dir, (std::string(name) + "_col").c_str(), col);
+    dump_array(dir, (std::string(name) + "_val").c_str(), val);
+    dump_array(dir, (std::string(name) + "_shape").c_str(), std::vector<int>{A.m(), A.n()});
+  }
+  void dump_level(const char* dir, SparseMatrix* PP) const {
+    const Mesh* msh = GetMeshFromLinEq();
+    const unsigned nel = msh->GetNumberOfElements(), nnode = msh->GetNumberOfNodes();
+    std::vector<int> conn((size_t)nel * 27, -1), etype(nel), faces((size_t)nel * 6, 0), sysdof, info;
+    for (unsigned iel = 0; iel < nel; iel++) {
+      etype[iel] = msh->GetElementType(iel);
+      const unsigned nn = msh->GetMeshElements()->GetElementDofNumber(iel, 2);
+      for (unsigned j = 0; j < nn; j++) conn[(size_t)iel * 27 + j] = (int)msh->GetMeshElements()->GetElementDofIndex(iel, j);
+      for (unsigned f = 0; f < msh->GetMeshElements()->GetElementFaceNumber(iel); f++) faces[(size_t)iel * 6 + f] = msh->GetMeshElements()->GetFaceElementIndex(iel, f);
+    }
+    std::vector<double> xyz((size_t)3 * nnode, 0.0);
+    for (unsigned d = 0; d < msh->GetDimension(); d++)
+      for (unsigned i = 0; i < nnode; i++) xyz[(size_t)d * nnode + i] = (*msh->GetTopology()->_Sol[d])(i);
+    std::vector<int> dofoff;
+    for (int k = 0; k < 3; k++)
+      for (unsigned p = 0; p <= n_processors(); p++) dofoff.push_back((int)msh->_dofOffset[k][p]);
+    // system dofs of every element and variable: [variable][element][27] (-1 padded)
+    for (unsigned k = 0; k < _SolPdeIndex.size(); k++) {
+      const unsigned indexSol = _SolPdeIndex[k], soltype = _SolType[indexSol];
+      for (unsigned iel = 0; iel < nel; iel++) {
+        const unsigned nve = msh->GetMeshElements()->GetElementDofNumber(iel, soltype);
+        for (unsigned j = 0; j < 27; j++) sysdof.push_back(j < nve ? (int)GetSystemDof(indexSol, k, j, iel) : -1);
+      }
+    }
+    std::vector<int> kkoff;
+    for (const auto& row : KKoffset)
+      for (unsigned v : row) kkoff.push_back((int)v);
+    std::vector<double> bdc;
+    for (unsigned k = 0; k < _SolPdeIndex.size(); k++) {
+      const NumericVector& b = *(*_Bdc)[_SolPdeIndex[k]];
+      for (int i = 0; i < b.size(); i++) bdc.push_back(b(i));
+    }
+    info = {(int)nel, (int)nnode, (int)msh->GetDimension(), (int)_SolPdeIndex.size(), (int)_SolType[_SolPdeIndex[0]], (int)n_processors()};
+    dump_array(dir, "info", info);
+    dump_array(dir, "conn", conn);
+    dump_array(dir, "etype", etype);
+    dump_array(dir, "face_index", faces);
+    dump_array(dir, "xyz", xyz);
+    dump_array(dir, "dofOffset", dofoff);
+    dump_array(dir, "sysdof", sysdof);
+    dump_array(dir, "KKoffset", kkoff);
+    dump_array(dir, "Bdc", bdc);
+    dump_array(dir, "bdcIndex", _bdcIndex);
+    const HostMatrix& KK = HostMatrix::cast(*_KK);
+    dump_array(dir, "n_nz", KK.n_nz());
+    dump_array(dir, "n_oz", KK.n_oz());
+    dump_csr(dir, "KK", KK);
+    if (PP) dump_csr(dir, "PP", HostMatrix::cast(*PP));
+  }
+  bool _resDumped = false;
+
   // x = V-cycle(b) from a zero guess on level l of the hierarchy this (finest) solver owns
   void vcycle(const int l, const std::vector<double>& b, std::vector<double>& x) const {
     const HostLinearEquationSolver* L = _hier[l];
