@@ -35,6 +35,8 @@ _PROTOS = {
     "b2_timer_stop_ms": (ci, [vp, vp]),
     "b2_ctx_flush_l2": (ci, [vp]),
     "b2_ctx_measure_fp64_tensor": (ci, [vp, vp]),
+    "b2_ctx_measure_fp64_fma": (ci, [vp, vp]),
+    "b2_asm_kernel_name": (ctypes.c_char_p, [vp]),
     "b2_ctx_set_option": (ci, [vp, ctypes.c_char_p, ci]),
     "b2_ctx_profile": (ci, [vp, ci]),
     "b2_ctx_profile_only": (ci, [vp, vp]),
@@ -253,6 +255,12 @@ class Context:
         """Measured fp64 tensor-core (DMMA) peak of this device in TFLOP/s."""
         t = cd()
         check(self.L.b2_ctx_measure_fp64_tensor(self.h, ctypes.byref(t)))
+        return t.value
+
+    def measure_fp64_fma(self):
+        """Measured fp64 CUDA-core (DFMA) issue-rate peak of this device in TFLOP/s."""
+        t = cd()
+        check(self.L.b2_ctx_measure_fp64_fma(self.h, ctypes.byref(t)))
         return t.value
 
     def set_option(self, name, value):

@@ -52,6 +52,7 @@ struct b2_asm {
   int slot_bytes;  // 1 or 2
   size_t slot_count, nslot_count;
   double last_ms;
+  const char* last_kernel = "";      // name of the kernel the last b2_asm_poisson* call launched
   // fused Galerkin plan (b2_asm_poisson_galerkin): per-child element prolongators of the plan `gal`
   const b2_galerkin* gal;
   void* gal_tab;          // device: GalTables<nve>
@@ -1271,6 +1272,22 @@ __global__ void __launch_bounds__(512) dmma_probe_kernel(int iters, double* out)
   if (s == -1.0) out[0] = s;      // never true: keeps the chains alive
 }
 
+// fp64 CUDA-core issue-rate probe: every thread keeps 8 independent DFMA chains busy
+__global__ void __launch_bounds__(512) dfma_probe_kernel(int iters, double* out) {
+  double c[8];
+#pragma unroll
+  for (int t = 0; t < 8; t++) c[t] = 1e-3 * t;
+  const double a = 1.0 + 1e-9 * threadIdx.x, b = 1e-9 * threadIdx.x;
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int t = 0; t < 8; t++) c[t] = fma(c[t], a, b);
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int t = 0; t < 8; t++) s += c[t];
+  if (s == -1.0) out[0] = s;      // never true: keeps the chains alive
+}
+
 extern "C" {
 
 /* rhs += Neumann integrals over the listed boundary faces (host arrays: element, local face, flux value) of ONE
@@ -1356,6 +1373,31 @@ int b2_ctx_measure_fp64_tensor(b2_ctx* c, double* tflops) {
   cudaEventDestroy(e1);
   b2_free(c, d, 1);
   const double flop = (double)grid * 16.0 * iters * 8.0 * 512.0;     // warps x iterations x chains x (8x8x4 FMA = 512 flop)
+  *tflops = flop / (ms * 1e-3) / 1e12;
+  return 0;
+}
+
+/* measured issue-rate peak of DFMA on this device, TFLOP/s (2 flop per lane and instruction) */
+int b2_ctx_measure_fp64_fma(b2_ctx* c, double* tflops) {
+  B2_CHECK(c && tflops, "b2_ctx_measure_fp64_fma: null argument");
+  double* d = nullptr;
+  B2_TRY(b2_malloc(c, &d, 1));
+  const int iters = 20000, grid = c->sm_count * 2;
+  dfma_probe_kernel<<<grid, 512, 0, c->stream>>>(2000, d);       // warm-up
+  cudaEvent_t e0, e1;
+  B2_CUDA(cudaEventCreate(&e0));
+  B2_CUDA(cudaEventCreate(&e1));
+  B2_CUDA(cudaEventRecord(e0, c->stream));
+  dfma_probe_kernel<<<grid, 512, 0, c->stream>>>(iters, d);
+  c->launches += 2;
+  B2_CUDA(cudaEventRecord(e1, c->stream));
+  B2_CUDA(cudaEventSynchronize(e1));
+  float ms = 0.f;
+  B2_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  b2_free(c, d, 1);
+  const double flop = (double)grid * 512.0 * iters * 8.0 * 2.0;     // threads x iterations x chains x 2
   *tflops = flop / (ms * 1e-3) / 1e12;
   return 0;
 }
@@ -1493,6 +1535,7 @@ int b2_asm_poisson(b2_asm* p, const b2_vec* u, b2_vec* rhs, double nu, double fs
   B2_CHECK(!u || u->n >= p->A->nrows, "b2_asm_poisson: solution vector too short");
   B2_CHECK(!rhs || rhs->n >= p->A->nrows, "b2_asm_poisson: rhs vector too short");
   if (p->general || p->mesh->ctx->asm_variant == 2) {       // table-driven kernel (any family)
+    p->last_kernel = "assemble_general_kernel";
     if (!p->nslot) {
       if (p->slot_bytes == 1) B2_TRY(build_natural_slots<uint8_t>(p));
       else B2_TRY(build_natural_slots<uint16_t>(p));
@@ -1502,14 +1545,17 @@ int b2_asm_poisson(b2_asm* p, const b2_vec* u, b2_vec* rhs, double nu, double fs
   }
   if (p->nve == 27 && p->mesh->ctx->asm_variant == 3 && p->sf_tab) {      // sum-factorised kernel (default)
     SfGalArgs ga = {};
+    p->last_kernel = "assemble_q2_sumfac_kernel";
     if (p->slot_bytes == 1) return launch_assemble_sumfac<uint8_t, false, uint8_t>(p, ga, u, rhs, nu, fsrc);
     return launch_assemble_sumfac<uint16_t, false, uint8_t>(p, ga, u, rhs, nu, fsrc);
   }
   if (p->nve == 27 && (p->mesh->ctx->asm_variant == 1 || p->mesh->ctx->asm_variant == 3)) {      // FP64 tensor-core kernel
     GalArgs ga = {};
+    p->last_kernel = "assemble_q2_mma_kernel";
     if (p->slot_bytes == 1) return launch_assemble_mma<uint8_t, false, uint8_t>(p, ga, u, rhs, nu, fsrc);
     return launch_assemble_mma<uint16_t, false, uint8_t>(p, ga, u, rhs, nu, fsrc);
   }
+  p->last_kernel = "assemble_poisson_kernel";
   if (p->nve == 27) {
     if (!p->slot) {      // first use of the CUDA-core kernel on this plan
       if (p->slot_bytes == 1) B2_TRY((build_slots<27, uint8_t>(p)));
@@ -1544,6 +1590,7 @@ int b2_asm_poisson_galerkin(b2_asm* p, b2_galerkin* gal, const b2_vec* u, b2_vec
   const bool s1 = p->slot_bytes == 1, c1 = g.slot_bytes == 1;
   if (p->nve == 27 && c->asm_variant == 3 && p->sf_tab && p->sf_gal) {      // sum-factorised kernel (default)
     SfGalArgs ga = {(const SfGalTables*)p->sf_gal, g.cd, g.slot, g.fmask, g.cmask, g.Ac->rowptr, g.Ac->val, *g.emat};
+    p->last_kernel = "assemble_q2_sumfac_kernel<fused Galerkin>";
     if (s1 && c1) return launch_assemble_sumfac<uint8_t, true, uint8_t>(p, ga, u, rhs, nu, fsrc);
     if (s1) return launch_assemble_sumfac<uint8_t, true, uint16_t>(p, ga, u, rhs, nu, fsrc);
     if (c1) return launch_assemble_sumfac<uint16_t, true, uint8_t>(p, ga, u, rhs, nu, fsrc);
@@ -1551,11 +1598,13 @@ int b2_asm_poisson_galerkin(b2_asm* p, b2_galerkin* gal, const b2_vec* u, b2_vec
   }
   if (p->nve == 27 && (c->asm_variant == 1 || c->asm_variant == 3)) {      // FP64 tensor-core kernel
     GalArgs ga = {p->gal_tab, g.cd, g.slot, g.fmask, g.cmask, g.Ac->rowptr, g.Ac->val, *g.emat};
+    p->last_kernel = "assemble_q2_mma_kernel<fused Galerkin>";
     if (s1 && c1) return launch_assemble_mma<uint8_t, true, uint8_t>(p, ga, u, rhs, nu, fsrc);
     if (s1) return launch_assemble_mma<uint8_t, true, uint16_t>(p, ga, u, rhs, nu, fsrc);
     if (c1) return launch_assemble_mma<uint16_t, true, uint8_t>(p, ga, u, rhs, nu, fsrc);
     return launch_assemble_mma<uint16_t, true, uint16_t>(p, ga, u, rhs, nu, fsrc);
   }
+  p->last_kernel = "assemble_poisson_galerkin_kernel";
   if (p->nve == 27) {
     if (!p->slot) {
       if (s1) B2_TRY((build_slots<27, uint8_t>(p)));
@@ -1571,6 +1620,9 @@ int b2_asm_poisson_galerkin(b2_asm* p, b2_galerkin* gal, const b2_vec* u, b2_vec
   if (c1) return launch_assemble_gal<8, uint16_t, uint8_t>(p, g, u, rhs, nu, fsrc);
   return launch_assemble_gal<8, uint16_t, uint16_t>(p, g, u, rhs, nu, fsrc);
 }
+/* name of the kernel the last b2_asm_poisson / b2_asm_poisson_galerkin call on this plan launched (bench.py labels
+ * its roofline with it) */
+const char* b2_asm_kernel_name(const b2_asm* p) { return p ? p->last_kernel : ""; }
 /* record the Galerkin element matrices of gal's coarse elements whenever gal is applied by the fused
  * assembly or from element matrices (needed by b2_galerkin_apply_from_elements of the next plan) */
 int b2_galerkin_record_elements(b2_galerkin* gal, int on) {

@@ -297,9 +297,43 @@ int b2_vec_minmax(const b2_vec* x, double* mn, double* mx) {
   return 0;
 }
 
+// Entries arrive in CALL ORDER, duplicates allowed, with the meaning of VecSetValues (PetscVector.hpp:595-612): for
+// INSERT the last value given for an index stays, for ADD the contributions of an index are summed in the order
+// given.  A device scatter has no order, so duplicates are combined here, on the host arrays, before the upload.
 static int indexed_op(b2_vec* v, const int32_t* idx, const double* vals, int64_t n, int mode, double a) {
   if (n == 0) return 0;
   b2_ctx* c = v->ctx;
+  std::vector<int32_t> u_idx;
+  std::vector<double> u_val;
+  if (vals) {
+    bool dup = false;
+    {
+      std::vector<uint8_t> seen((size_t)v->n, 0);
+      for (int64_t k = 0; k < n; k++) {
+        B2_CHECK(idx[k] >= 0 && idx[k] < v->n, "indexed vector access: index %d outside [0, %lld)", idx[k], (long long)v->n);
+        if (seen[idx[k]]) { dup = true; break; }
+        seen[idx[k]] = 1;
+      }
+    }
+    if (dup) {
+      std::vector<int64_t> slot((size_t)v->n, -1);
+      for (int64_t k = 0; k < n; k++) {
+        int64_t& s = slot[idx[k]];
+        if (s < 0) {
+          s = (int64_t)u_idx.size();
+          u_idx.push_back(idx[k]);
+          u_val.push_back(vals[k]);
+        } else if (mode == 0) {
+          u_val[(size_t)s] = vals[k];
+        } else {
+          u_val[(size_t)s] += vals[k];
+        }
+      }
+      idx = u_idx.data();
+      vals = u_val.data();
+      n = (int64_t)u_idx.size();
+    }
+  }
   int32_t* d_idx = nullptr;
   double* d_vals = nullptr;
   B2_TRY(b2_malloc(c, &d_idx, (size_t)n));

@@ -16,6 +16,9 @@
 #ifndef B2_WITH_FEMUS_HEADERS
 #define B2_WITH_FEMUS_HEADERS
 #endif
+#include <fstream>
+#include <string>
+#include <type_traits>
 #include "B200Matrix.hpp"
 #include "LinearEquationSolver.hpp"
 #include "Mesh.hpp"
@@ -68,6 +71,7 @@ class LinearEquationSolverB200Ref : public LinearEquationSolver {
     LinearEquationSolverB200Ref* top = static_cast<LinearEquationSolverB200Ref*>(LinSolver);
     if (!top->_mg || levelMax + 1 != top->_levelMax) { std::fprintf(stderr, "femus_b200: MGSetLevel: MGInit was not called on the finest solver\n"); std::abort(); }
     if (!_bdcIndexIsInitialized) this->BuildBdcIndex(variable_to_be_solved);
+    if (const char* dir = std::getenv("FEMUS_REF_DUMP")) this->dump_level(dir, PP);      // before the penalty, like the oracle's host backend
     this->configure_level(top->_mg, (int)_level, PP, npre, npost);
   }
   // one multiplicative V-cycle as outer PREONLY (:294-353): ZerosBoundaryResiduals; EPSC = V(RES); RESC = KK EPSC; RES -= RESC; EPS += EPSC
@@ -76,9 +80,16 @@ class LinearEquationSolverB200Ref : public LinearEquationSolver {
     B200Vector &RES = static_cast<B200Vector&>(*_RES), &EPS = static_cast<B200Vector&>(*_EPS);
     RES.close();
     EPS.close();
+    const char* dir = _dumped ? nullptr : std::getenv("FEMUS_REF_DUMP");
+    if (dir) dump_vector(dir, "RES", RES);
     B2_ABORT_IF(b2_mg_solve(_mg, RES.handle(), EPS.handle()), "b2_mg_solve");
     RES.touched();
     EPS.touched();
+    if (dir) {
+      dump_vector(dir, "RES_after", RES);
+      dump_vector(dir, "EPS_after", EPS);
+    }
+    _dumped = true;
   }
   // one level, no multigrid: penalty + the solve of that level (a one-level hierarchy: its level 0 is solved)
   void Solve(const std::vector<unsigned>& variable_to_be_solved, const bool&) override {
@@ -92,6 +103,31 @@ class LinearEquationSolverB200Ref : public LinearEquationSolver {
   }
 
  private:
+  // ---- diagnostics: the arrays of oracle/ref_build/HostBackend.hpp's dump, read back from the device objects
+  template <class T>
+  void dump_array(const char* dir, const std::string& name, const std::vector<T>& a) const {
+    const char* suffix = sizeof(T) == 8 ? (std::is_floating_point<T>::value ? "f8" : "i8") : "i4";
+    std::ofstream f(std::string(dir) + "/L" + std::to_string(_level) + "_" + name + "." + suffix, std::ios::binary);
+    f.write(reinterpret_cast<const char*>(a.data()), (std::streamsize)(a.size() * sizeof(T)));
+  }
+  void dump_vector(const char* dir, const char* name, const NumericVector& v) const {
+    std::vector<double> a((size_t)v.size());
+    for (int i = 0; i < v.size(); i++) a[(size_t)i] = v(i);
+    dump_array(dir, name, a);
+  }
+  void dump_csr(const char* dir, const std::string& name, const B200Matrix& A) const {
+    dump_array(dir, name + "_rowptr", A.host_rowptr());
+    dump_array(dir, name + "_col", A.host_col());
+    dump_array(dir, name + "_val", A.host_val());
+    dump_array(dir, name + "_shape", std::vector<int>{A.m(), A.n()});
+  }
+  void dump_level(const char* dir, SparseMatrix* PP) const {
+    dump_csr(dir, "KK", B200Matrix::cast(*_KK));
+    if (PP) dump_csr(dir, "PP", B200Matrix::cast(*PP));
+    dump_array(dir, "bdcIndex", _bdcIndex);
+  }
+  bool _dumped = false;
+
   void configure_level(b2_mg* mg, const int level, SparseMatrix* PP, const unsigned npre, const unsigned npost) {
     B200Matrix& KK = static_cast<B200Matrix&>(*_KK);
     KK.close();

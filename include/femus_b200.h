@@ -72,6 +72,8 @@ int b2_ctx_profile_clear(b2_ctx* c);
 int b2_ctx_set_option(b2_ctx* c, const char* name, int value);
 /* measured issue-rate peak of mma.sync.m8n8k4.f64 on this device, TFLOP/s (a few ms of DMMA chains) */
 int b2_ctx_measure_fp64_tensor(b2_ctx* c, double* tflops);
+/* the same for DFMA on the CUDA cores (the pipe of the sum-factorised assembly kernel) */
+int b2_ctx_measure_fp64_fma(b2_ctx* c, double* tflops);
 /* write 256 MiB of device memory (> L2 size) to evict the L2 between timed iterations */
 int b2_ctx_flush_l2(b2_ctx* c);
 
@@ -111,7 +113,9 @@ int b2_vec_norm(const b2_vec* x, int kind /*1: l1, 2: l2, 0: linf*/, double* out
 int b2_vec_sum(const b2_vec* x, double* out);                          /* sum         VecSum */
 int b2_vec_minmax(const b2_vec* x, double* mn, double* mx);            /* min/max     PetscVector.hpp:777-796 */
 /* staged set()/add() of PetscVector (VecSetValues INSERT/ADD, PetscVector.cpp:96-141) flushed as
- * one batch: idx/vals are host arrays. */
+ * one batch: idx/vals are host arrays in CALL ORDER; an index may repeat -- the last value set stays, added
+ * values are summed in the order given (what VecSetValues does on local entries; MultiLevelSolution::GenerateBdc
+ * relies on it: set(j, 2.) ... set(idof, 1.) ... set(idof, 0.) on one vector before close()). */
 int b2_vec_set_indexed(b2_vec* v, const int32_t* idx, const double* vals, int64_t n);
 int b2_vec_add_indexed(b2_vec* v, const int32_t* idx, const double* vals, int64_t n);
 int b2_vec_fill_indexed(b2_vec* v, const int32_t* idx, int64_t n, double a); /* ZerosBoundaryResiduals LinearEquationSolverPetsc.cpp:417-424 */
@@ -251,6 +255,8 @@ int b2_asm_neumann_faces(b2_asm* p, int64_t nfaces, const int32_t* face_elem, co
  * the fine matrix.  gal must have been created on this plan's matrix; Ac is overwritten, A is not zeroed.
  * Fails (no fallback) if the fine elements are not the children 8*E+j of gal's coarse elements. */
 int b2_asm_poisson_galerkin(b2_asm* p, b2_galerkin* gal, const b2_vec* u, b2_vec* rhs, double nu, double fsrc);
+/* name of the kernel the last b2_asm_poisson / b2_asm_poisson_galerkin call on this plan launched (measurement aid) */
+const char* b2_asm_kernel_name(const b2_asm* p);
 /* Element-matrix Galerkin chain for the levels below: with recording on, applying `gal` through
  * b2_asm_poisson_galerkin (or through b2_galerkin_apply_from_elements) also stores the nc x nc
  * Galerkin matrix D_E of each of its coarse elements; the next-coarser plan then forms

@@ -72,6 +72,22 @@ def test_vector_indexed(ctx):
     x[idx] = 0.0
     assert relerr(X.get(), x) < 1e-14
     assert np.array_equal(X.get_indexed(idx2), X.get()[idx2])
+    # duplicates in CALL ORDER (VecSetValues): the last value set stays -- MultiLevelSolution::GenerateBdc writes 2., then
+    # 1., then 0. to one entry before close() (MultiLevelSolution.cpp:737-835); sums of a zeroed entry are bit-exact
+    idx3 = rng.integers(0, n, 4000).astype(np.int32)
+    v3 = rng.standard_normal(4000)
+    x = rng.standard_normal(n)
+    X = ctx.vector(x)
+    X.set_indexed(idx3, v3)
+    for i, a in zip(idx3, v3):
+        x[i] = a
+    assert np.array_equal(X.get(), x)
+    X.zero()
+    X.add_indexed(idx3, v3)
+    x[:] = 0.0
+    for i, a in zip(idx3, v3):
+        x[i] += a
+    assert np.array_equal(X.get(), x)
 
 
 def test_empty_vector(ctx):
