@@ -159,6 +159,7 @@ def run_cpu_sample(n0, nlevels, order, steps, warmup):
         "assembly_ms": float(np.mean([r["assembly"] for r in rs])) * 1e3,
         "galerkin_setup_ms": float(np.mean([r["galerkin_setup"] for r in rs])) * 1e3,
         "vcycle_ms": float(np.mean([r["vcycle"] for r in rs])) * 1e3,
+        "resnorm": rs[-1]["resnorm"],
     }
     return out
 
@@ -171,6 +172,26 @@ def workload_for(ngpus, n0, nlevels):
     return n0 * mul[0], n0 * mul[1], n0 * mul[2]
 
 
+def bounds_for(nx, ny, nz):
+    """The domain grows with the box so that the elements stay cubes at every N (unit cube at N=1 and N=8)."""
+    m = float(min(nx, ny, nz))
+    return (0.0, nx / m, 0.0, ny / m, 0.0, nz / m)
+
+
+def ncu_capture(kernel, workload_key):
+    """Per-launch DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum) and pipe figures of `kernel` from the
+    committed ncu --set full capture of this workload (profiles/ncu_kernels.json, written by tools/ncu_raw_extract.py
+    from the .ncu-rep; nothing is typed in by hand).  None when no capture of this kernel / workload is on file."""
+    try:
+        db = json.load(open(os.path.join(ROOT, "profiles", "ncu_kernels.json")))
+    except Exception:
+        return None
+    for rec in db.get("kernels", []):
+        if rec.get("workload") == workload_key and rec.get("kernel") == kernel:
+            return rec
+    return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -180,7 +201,7 @@ def main():
     ap.add_argument("--n0", type=int, default=16, help="coarsest-level elements per side per GPU")
     ap.add_argument("--levels", type=int, default=4)
     ap.add_argument("--order", default="biquadratic", choices=["linear", "biquadratic"])
-    ap.add_argument("--cpu-n0", type=int, default=4, help="coarsest-level size of the CPU baseline sample")
+    ap.add_argument("--cpu-n0", type=int, default=8, help="coarsest-level size of the CPU sample (8: 64^3 elements with 4 levels)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     W = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -194,6 +215,7 @@ def main():
     workload = (f"3D Poisson, {'Hex27' if nve == 27 else 'Hex8 (Q1 on Hex27 geometry)'}, {nx * f}x{ny * f}x{nz * f} elements, "
                 f"{args.levels}-level geometric MG V-cycle (Richardson 0.5 + Jacobi, 1 pre / 1 post, coarse Jacobi-PCG), fp64")
     config = {"workload": workload, "coarse_box": [nx, ny, nz], "levels": args.levels, "fe_order": args.order,
+              "domain": list(bounds_for(nx, ny, nz)),
               "partition": "single GPU" if args.gpus == 1 else f"z-slabs over {args.gpus} GPUs",
               "l2": "inputs larger than L2 (finest CSR >> 126 MB); no flush needed"}
 
@@ -202,10 +224,13 @@ def main():
         if rank != 0:
             return 0
         r = run_cpu_sample(args.cpu_n0, args.levels, args.order, max(args.steps, 1), args.warmup)
+        fs = args.cpu_n0 * f
+        config = dict(config, reference_sample=f"every step of this arm is a BOUNDED SAMPLE of the workload: {fs}x{fs}x{fs} elements "
+                      f"({r['sample'].split(':')[0]}), not {nx * f}x{ny * f}x{nz * f}; DOF/s is per finest-level dof of the sample")
         line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
-                "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}, "residual_after_one_vcycle": r["resnorm"],
                 "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "assembly_elem_dof_per_s": r["assembly_elem_dof_per_s"], "assembly_ms": r["assembly_ms"],
                 "galerkin_setup_ms": r["galerkin_setup_ms"], "vcycle_ms": r["vcycle_ms"], "gpu_launches": 0}
@@ -253,7 +278,7 @@ def main():
         return float(t.item())
 
     t_setup = time.time()
-    pb = PoissonMG(ctx, nx, ny, nz, args.levels, args.order, dist=dist_arg)
+    pb = PoissonMG(ctx, nx, ny, nz, args.levels, args.order, bounds=bounds_for(nx, ny, nz), dist=dist_arg)
     ctx.sync()
     t_setup = time.time() - t_setup
     top = pb.hier.levels[-1]
@@ -366,52 +391,69 @@ def main():
     ms_step = ms_total / args.steps
     value = n / (ms_step * 1e-3)
     e2e_value = n / (ms_e2e / args.steps * 1e-3)
-    # ---- roofline of the dominant kernel: finest-level CSR SpMV family (3 launches per step:
-    # 2 x r = b - A x, 1 x Jacobi sweep); algorithmic bytes per launch, BASELINE.md section 4
+    # ---- rooflines.  `roofline` = the kernel with the largest share of the step (the fused assembly); the finest-level
+    # SpMV family of the V-cycle is reported next to it as `roofline_spmv`.
     peak, peak_src = measured_peaks()
+    wl_key = f"{args.order}:{nx * f}x{ny * f}x{nz * f}:{args.levels}lev:n{args.gpus}"
+    # (1) SpMV family on the finest CSR (3 launches per step: 2 x r = b - A x, 1 x Jacobi sweep); algorithmic bytes per
+    # launch as SURVEY section 8(d) defines them
     b_y = pb.spmv_bytes(-1)
     bytes_per_launch = (2 * (b_y + 8 * n_loc) + (b_y + 24 * n_loc)) / 3.0 if world == 1 else b_y + 16 * n_loc
     ach = bytes_per_launch / (ms_sp / max(nsp, 1) * 1e-3) / 1e9 if nsp else None
-    # DRAM traffic per launch of the same kernel from the ncu --set full capture of this round
-    # (profiles/r1_ncu_summary.md: dram__bytes_read.sum + dram__bytes_write.sum, mean of resid x2 + Jacobi x1)
-    traffic = 12.77e9 if (world == 1 and args.n0 == 16 and args.levels == 4 and args.order == "biquadratic") else None
-    roofline = {"bound": "hbm", "kernel": "spmv_tma_kernel on the finest-level CSR (2 x r = b - A x, 1 x Jacobi sweep per step)",
-                "achieved": ach, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-                "frac": (ach / peak) if ach else None, "traffic": traffic,
-                "algorithmic_bytes_per_launch": bytes_per_launch, "launches_timed": nsp,
-                "avg_launch_ms": ms_sp / max(nsp, 1), "share_of_step": ms_sp / ms_total_local}
+    cap = ncu_capture("spmv_tma_kernel", wl_key)
+    roofline_spmv = {"bound": "hbm", "kernel": "spmv_tma_kernel on the finest-level CSR (2 x r = b - A x, 1 x Jacobi sweep per step)",
+                     "achieved": ach, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+                     "frac": (ach / peak) if ach else None,
+                     "traffic": cap["dram_bytes_per_launch"] if cap else None,
+                     "traffic_source": cap["source"] if cap else None,
+                     "algorithmic_bytes_per_launch": bytes_per_launch, "launches_timed": nsp,
+                     "avg_launch_ms": ms_sp / max(nsp, 1), "share_of_step": ms_sp / ms_total_local}
     if world > 1:
-        roofline["kernel"] = "spmv_tma_kernel on rank 0's finest-level partial CSR (weighted resid x3 per step)"
-    # the kernel with the largest share of the step is the (fused) assembly: FP64 tensor-core / shared-memory
-    # bound, not HBM bound.  Algorithmic work per Q2 element: 4.5e5 flop, 7020 B.
+        roofline_spmv["kernel"] = "spmv_tma_kernel on rank 0's finest-level partial CSR (weighted resid x3 per step)"
+    # (2) the assembly kernel (fused with the finest Galerkin product).  SURVEY section 8(d): algorithmic work per Q2
+    # element 4.5e5 flop (the element loop as the reference writes it: 64 Gauss points x (Jacobian, gradients, 27 x 27
+    # x 8 stiffness, residual)) and 7020 B (972 read + 6048 written); reported as flop/s against the chip's fp64 peak,
+    # MEASURED in this run by two issue-rate probes (chains of independent DFMA / of mma.sync.m8n8k4.f64 on every SM,
+    # a few ms each: b2_ctx_measure_fp64_fma / _tensor; MEASURED_PEAKS.json carries no fp64 figure), with the HBM view
+    # beside it.  The sum-factorised kernel performs the same contraction with ~1/5 of the multiply-adds, so the
+    # algorithmic figure can exceed the pipe peak; `executed` is what the kernel really issues (ncu instruction counts).
     nel_loc = pb.nel
-    dmma_peak = ctx.measure_fp64_tensor()       # in-run microbenchmark: DMMA.8x8x4 chains on every SM
+    kname = ctx.L.b2_asm_kernel_name(pb.asm.h).decode()
+    dmma_peak = ctx.measure_fp64_tensor()
+    dfma_peak = ctx.measure_fp64_fma()
+    on_tensor = "mma" in kname
+    fp64_peak = dmma_peak if on_tensor else dfma_peak
     flop_el = 4.5e5 if nve == 27 else 4.5e5 * (8 * 8) / (27 * 27)
     bytes_el = (27 * 3 * 8 + 27 * 4 + nve * 8) + (nve * nve + nve) * 8
-    asm_roof = {"kernel": "assemble_q2_mma_kernel (assembly fused with the finest Galerkin product)" if nve == 27
-                else "assemble_poisson_kernel", "avg_launch_ms": asm_kernel_ms, "share_of_step": asm_kernel_ms / ms_step,
-                "bound": "tensor", "unit": "TFLOP/s", "achieved": nel_loc * flop_el / (asm_kernel_ms * 1e-3) / 1e12,
-                "peak": 40.0, "peak_source": "nominal B200 fp64 (MEASURED_PEAKS.json carries no fp64 figure)",
-                "peak_measured_dmma": dmma_peak,
-                "peak_measured_note": "mma.sync.m8n8k4.f64 issue-rate probe run inside bench.py (b2_ctx_measure_fp64_tensor); "
-                                      "the kernel issues 480 DMMA = 2.46e5 flop per Q2 element (upper tiles of the symmetric "
-                                      "element matrix), the algorithmic figure counts the full 27x27 matrix",
-                "dmma_flop_per_launch": nel_loc * 480 * 512.0 if nve == 27 else None,
-                "algorithmic_flop_per_launch": nel_loc * flop_el,
-                "hbm_view": {"algorithmic_bytes_per_launch": nel_loc * bytes_el,
+    cap = ncu_capture(kname, wl_key)
+    ach_tf = nel_loc * flop_el / (asm_kernel_ms * 1e-3) / 1e12
+    roofline = {"bound": "tensor" if on_tensor else "fp64 (CUDA-core DFMA pipe; the kernel has no tensor-core or HBM bound: "
+                         "see hbm_view)",
+                "kernel": kname + " (element assembly fused with the finest Galerkin product; one launch per step)",
+                "achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach_tf / fp64_peak,
+                "peak_source": "measured in this run: issue-rate probe of " + ("mma.sync.m8n8k4.f64" if on_tensor else "DFMA") +
+                               f" chains on every SM (DFMA {dfma_peak:.1f}, DMMA {dmma_peak:.1f} TFLOP/s)",
+                "algorithmic_flop_per_launch": nel_loc * flop_el, "algorithmic_flop_per_element": flop_el,
+                "avg_launch_ms": asm_kernel_ms, "share_of_step": asm_kernel_ms / ms_step,
+                "traffic": cap["dram_bytes_per_launch"] if cap else None,
+                "traffic_source": cap["source"] if cap else None,
+                "hbm_view": {"algorithmic_bytes_per_launch": nel_loc * bytes_el, "algorithmic_bytes_per_element": bytes_el,
                              "achieved_gbs": nel_loc * bytes_el / (asm_kernel_ms * 1e-3) / 1e9, "peak_gbs": peak,
-                             "traffic": 28.25e9 if traffic else None},
-                "limiters_ncu": "l1tex data pipe (shared-memory wavefronts) 66-69 %, fp64 tensor pipe 33-44 % (profiles/r1_ncu_summary.md)"}
-    asm_roof["frac"] = asm_roof["achieved"] / asm_roof["peak"]
-    if nve == 27 and dmma_peak > 0:
-        asm_roof["frac_of_measured_dmma_peak"] = nel_loc * 480 * 512.0 / (asm_kernel_ms * 1e-3) / 1e12 / dmma_peak
+                             "frac": nel_loc * bytes_el / (asm_kernel_ms * 1e-3) / 1e9 / peak}}
+    if cap:
+        for k in ("fp64_pipe_pct", "l1tex_data_pipe_pct", "issue_active_pct", "registers_per_thread", "dfma_flop_per_launch"):
+            if k in cap:
+                roofline.setdefault("ncu", {})[k] = cap[k]
+        if cap.get("dfma_flop_per_launch"):
+            roofline["executed_flop_per_launch"] = cap["dfma_flop_per_launch"]
+            roofline["frac_executed"] = cap["dfma_flop_per_launch"] / (asm_kernel_ms * 1e-3) / 1e12 / fp64_peak
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": W,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": config,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "roofline_assembly": asm_roof,
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "roofline_spmv": roofline_spmv,
             "assembly_elem_dof_per_s": nel * nve / (phases["assembly"] * 1e-3),
             "spmv_gbs": ach, "phases_ms": phases, "finest_dofs": n, "finest_nnz": Afine.nnz, "elements": nel,
             "setup_s": t_setup, "residual_trace": trace, "coarse_pcg_iterations": pb.mg.coarse_iterations(),
@@ -423,7 +465,16 @@ def main():
             return 0
     if not args.no_cpu_baseline and world == 1:
         try:
-            line["cpu_baseline"] = {k: v for k, v in run_cpu_sample(args.cpu_n0, args.levels, args.order, 2, 1).items()}
+            cb = run_cpu_sample(args.cpu_n0, args.levels, args.order, 1, 1)
+            line["cpu_baseline"] = {k: v for k, v in cb.items() if k != "resnorm"}
+            # in-run parity: the SAME sample through the GPU path (assembly, Galerkin chain, level setup, one V-cycle from
+            # a zero guess) against the CPU run's residual norm after that cycle
+            ps = PoissonMG(ctx, args.cpu_n0, args.cpu_n0, args.cpu_n0, args.levels, args.order)
+            ps.step()
+            g = ps.RES.norm(2)
+            line["parity"] = {"what": "||RES||_2 after assembly + one V-cycle on the CPU baseline's sample, GPU path vs CPU reference path",
+                              "gpu": g, "cpu": cb["resnorm"], "rel_err": abs(g - cb["resnorm"]) / cb["resnorm"], "tol": 1e-10}
+            del ps
         except Exception as e:      # the baseline is reported, never required for the GPU number
             line["cpu_baseline"] = {"error": repr(e)}
     print(json.dumps(line))

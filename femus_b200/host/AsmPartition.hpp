@@ -38,41 +38,26 @@ struct AsmIndex {
   int64_t nblocks() const { return (int64_t)elem_ptr.size() - 1; }
 };
 
-// MeshASMPartitioning::DoPartition for rank iproc
+// The element blocks of rank iproc (what MeshASMPartitioning::DoPartition produces): the rank's elements are split
+// by material class -- solid (4) first, then porous (3), then fluid (2) -- keeping element order inside a class (a
+// stable partition), and every class is cut into consecutive chunks of its block size, the last chunk ragged.
+// block_type_range[k] = number of blocks up to and including class k.
 inline void DoPartition(const MeshLevel& L, int iproc, const unsigned block_size[3], std::vector<std::vector<unsigned>>& block_elements,
                         int64_t block_type_range[3]) {
-  const unsigned e0 = (unsigned)L.elem_offset[iproc], e1 = (unsigned)L.elem_offset[iproc + 1];
-  const unsigned flag_block[3] = {4, 3, 2};
-  auto material = [&](unsigned iel) -> unsigned { return L.material.empty() ? 2u : (unsigned)L.material[iel]; };
-  unsigned counter[3] = {0, 0, 0};
-  for (unsigned iel = e0; iel < e1; iel++) {
-    const unsigned m = material(iel);
-    if (m == flag_block[0]) counter[0]++;
-    else if (m == flag_block[1]) counter[1]++;
-    else if (m != flag_block[2]) throw std::invalid_argument("DoPartition: element material must be 2, 3 or 4");
+  static const int kClassOfMaterial[5] = {-1, -1, 2, 1, 0};      // material 4 -> class 0, 3 -> 1, 2 -> 2
+  std::vector<unsigned> members[3];
+  for (int64_t iel = L.elem_offset[iproc]; iel < L.elem_offset[iproc + 1]; iel++) {
+    const int m = L.material.empty() ? 2 : (int)L.material[iel];
+    if (m < 2 || m > 4) throw std::invalid_argument("DoPartition: element material must be 2, 3 or 4");
+    members[kClassOfMaterial[m]].push_back((unsigned)iel);
   }
-  counter[2] = (e1 - e0) - counter[0] - counter[1];
   block_elements.clear();
-  unsigned block_start = 0;
-  for (int im = 0; im < 3; im++) {
-    if (counter[im] != 0) {
-      if (block_size[im] == 0) throw std::invalid_argument("DoPartition: block size 0");
-      const unsigned rem = counter[im] % block_size[im];
-      const unsigned blocks = rem == 0 ? counter[im] / block_size[im] : counter[im] / block_size[im] + 1;
-      block_elements.resize(block_start + blocks);
-      for (unsigned i = 0; i < blocks; i++) block_elements[block_start + i].resize(block_size[im]);
-      if (rem != 0) block_elements[block_start + blocks - 1].resize(rem);
-      unsigned c = 0;
-      for (unsigned iel = e0; iel < e1; iel++)
-        if (material(iel) == flag_block[im]) {
-          block_elements[block_start + c / block_size[im]][c % block_size[im]] = iel;
-          c++;
-        }
-      block_type_range[im] = block_start + blocks;
-      block_start += blocks;
-    } else {
-      block_type_range[im] = block_start;
-    }
+  for (int k = 0; k < 3; k++) {
+    const std::vector<unsigned>& e = members[k];
+    if (!e.empty() && block_size[k] == 0) throw std::invalid_argument("DoPartition: block size 0");
+    for (size_t first = 0; first < e.size(); first += block_size[k])
+      block_elements.emplace_back(e.begin() + (std::ptrdiff_t)first, e.begin() + (std::ptrdiff_t)std::min(e.size(), first + block_size[k]));
+    block_type_range[k] = (int64_t)block_elements.size();
   }
 }
 

@@ -592,6 +592,28 @@ def test_full_size_properties(ctx):
     del pb
 
 
+@pytest.mark.gpu
+def test_more_than_2_to_31_nonzeros_on_one_gpu(ctx):
+    """north_star's single-GPU target (256^3 Hex27) implies 64-bit entry offsets on one device: 192^3 elements, 57 M
+    dofs, 1537^3 = 3.63e9 non-zeros (93 GB of device memory) through the fused assembly, the Galerkin chain, level
+    setup and 45 V-cycles, checked by the size-independent properties of test_full_size_properties
+    (tools/big_run.py; first run on B200: profiles/r2_big_run_192cube_3.6e9_nnz.json)."""
+    import gc
+    import importlib.util
+    import os
+    import torch
+    gc.collect()
+    free, _ = torch.cuda.mem_get_info(0)
+    if free < 110e9:
+        pytest.skip(f"needs 110 GB of free device memory, {free / 1e9:.0f} GB are free")
+    spec = importlib.util.spec_from_file_location("big_run", os.path.join(os.path.dirname(os.path.dirname(__file__)), "tools", "big_run.py"))
+    big = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(big)
+    out = big.run(ctx, 24)
+    assert out["nnz"] == 1537 ** 3 > 2 ** 31
+    gc.collect()
+
+
 NEU = __import__("os").path.join(__import__("os").path.dirname(__file__), "golden", "cube_hex27_2x2x2.neu")
 
 
@@ -650,3 +672,80 @@ def test_neu_mesh_multilevel_solution_equals_box_solution(ctx):
     got = pb.EPS.get()
     assert np.abs(got - xo[perm]).max() <= 1e-9 * np.abs(xo).max()
     del pb
+
+
+# ------------------------------------------------------------------------------ BASELINE sizes against the oracle
+def _oracle_system(lv, order, nthreads=None):
+    """Finest matrix and right-hand side of the oracle at sizes its numpy loops would take minutes for: the element
+    loop by the compiled reference FE kernel (oracle/_ref) where that was built, else the numpy restatement."""
+    import os
+    from oracle import ref
+    top = lv[-1]
+    n = mb.ndofs(top, order)
+    if ref.available():
+        rp, ci = mb.sparsity(top, order)
+        vals, rhs, _ = ref.RefHex(order).assemble_csr(top.conn, mb.system_dof(top, order), top.xyz, np.zeros(n), rp, ci, 1.0,
+                                                      nthreads or os.cpu_count() or 1)
+        return sp.csr_matrix((vals, ci, rp), shape=(n, n)), rhs
+    return mb.assemble(top, order)
+
+
+def test_baseline_config1_32cube_hex8_one_level(ctx):
+    """BASELINE configs[0] at its FULL size: applications/001_Poisson on the 3-D unit box, 32^3 elements, trilinear
+    (Hex8) unknown, ONE level -- 35 937 dofs.  Dof -> row map and CSR structure bit-exact, matrix entries and the
+    right-hand side to 1e-12 against the oracle, MGSolve on one level (the reference: PREONLY + LU) against the solution
+    of the oracle's penalised system, and the residual after it at round-off level."""
+    import scipy.sparse.linalg as spla
+    from femus_b200.poisson import PoissonMG
+    lv = mb.build_hierarchy(32, 32, 32, 1)
+    pb = PoissonMG(ctx, 32, 32, 32, 1, "linear", coarse_rtol=1e-15)
+    assert pb.n == 33 ** 3
+    assert np.array_equal(pb.dofs[-1], mb.system_dof(lv[-1], "linear"))                 # dof -> row map
+    rp, ci = mb.sparsity(lv[-1], "linear")
+    pb.assemble()
+    got = pb.KK[-1].to_scipy()
+    assert np.array_equal(got.indptr, rp) and np.array_equal(got.indices, ci)            # CSR structure
+    Aref, rhs = _oracle_system(lv, "linear")
+    Aref.sort_indices()
+    assert np.abs(got.data - Aref.data).max() <= RTOL * np.abs(Aref.data).max()
+    assert np.abs(pb.RES.get() - rhs).max() <= RTOL * np.abs(rhs).max()
+    pb.mg_set_levels()
+    pb.mg_solve()
+    H = mg.Hierarchy(lv, "linear", A_top=Aref, rhs=rhs, coarse_lu=False)
+    assert np.array_equal(pb.bdc_idx[-1], H.bdc_idx[-1])
+    b = rhs.copy()
+    b[H.bdc_idx[-1]] = 0.0
+    # (a sparse LU of 36 k dofs in natural 3-D ordering takes half a minute: the oracle's solve is scipy's CG run to round-off)
+    xref, info = spla.cg(H.A[-1], b, rtol=1e-15, atol=0.0, maxiter=5000, M=sp.diags(1.0 / H.A[-1].diagonal()))
+    assert info == 0 and np.linalg.norm(b - H.A[-1] @ xref) <= 1e-13 * np.linalg.norm(b)
+    assert np.abs(pb.EPS.get() - xref).max() <= 1e-11 * np.abs(xref).max()
+    assert pb.residual_norm() <= 1e-12 * np.linalg.norm(b)
+
+
+def test_baseline_config2_sample_32cube_hex27_4_levels_against_the_cpu_port(ctx):
+    """BASELINE configs[1] (Hex27, 4-level V-cycle) on the sample bench.py's CPU arm runs: 32^3 elements, 274 625 dofs.
+    Every level operator after the Galerkin chain + penalty and the residual norms of 4 V-cycles against the oracle
+    (oracle/mg.Hierarchy for the operators, the OpenMP C port oracle/cpu_port for the cycles), 1e-12 relative."""
+    import os
+    from femus_b200.poisson import PoissonMG
+    from oracle import cpu_port
+    nt = os.cpu_count() or 1
+    lv = mb.build_hierarchy(4, 4, 4, 4)
+    Aref, rhs = _oracle_system(lv, "biquadratic", nt)
+    H = mg.Hierarchy(lv, "biquadratic", A_top=Aref, rhs=rhs, coarse_lu=False, ptap=lambda P, Af, prp, pci: cpu_port.ptap(P, Af, prp, pci, nt))
+    pb = PoissonMG(ctx, 4, 4, 4, 4, "biquadratic")
+    pb.assemble(); pb.galerkin(); pb.mg_set_levels()
+    for l in range(4):
+        got, ref = pb.KK[l].to_scipy(), H.A[l]
+        ref.sort_indices()
+        assert np.array_equal(got.indptr, ref.indptr) and np.array_equal(got.indices, ref.indices)
+        assert np.abs(got.data - ref.data).max() <= RTOL * np.abs(ref.data).max(), l
+    M = cpu_port.PortMG(H, nt)
+    res, eps = rhs.copy(), np.zeros(pb.n)
+    free = H.bdc[-1] > 1.1
+    for _ in range(4):
+        res, eps = M.mg_solve(res, eps)
+        pb.mg_solve()
+        a, b = pb.residual_norm(), float(np.linalg.norm(res[free]))
+        assert abs(a - b) <= 1e-11 * float(np.linalg.norm(rhs[free])), (a, b)
+    assert np.abs(pb.EPS.get() - eps).max() <= 1e-10 * np.abs(eps).max()
