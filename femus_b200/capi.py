@@ -71,6 +71,10 @@ _PROTOS = {
     "b2_vec_norm": (ci, [vp, ci, vp]),
     "b2_vec_sum": (ci, [vp, vp]),
     "b2_vec_minmax": (ci, [vp, vp, vp]),
+    "b2_vec_abs": (ci, [vp]),
+    "b2_csr_matmat": (ci, [vp, vp, vp]),
+    "b2_csr_axpy": (ci, [vp, cd, vp]),
+    "b2_csr_pattern_contains": (ci, [vp, vp, vp]),
     "b2_vec_set_indexed": (ci, [vp, vp, vp, i64]),
     "b2_vec_add_indexed": (ci, [vp, vp, vp, i64]),
     "b2_vec_fill_indexed": (ci, [vp, vp, i64, cd]),
@@ -388,6 +392,9 @@ class Vector:
         check(self.L.b2_vec_minmax(self.h, ctypes.byref(a), ctypes.byref(b)))
         return a.value, b.value
 
+    def abs(self):
+        check(self.L.b2_vec_abs(self.h))
+
     def set_indexed(self, idx, vals):
         idx, vals = _i32(idx), _f64(vals)
         check(self.L.b2_vec_set_indexed(self.h, _ptr(idx), _ptr(vals), idx.shape[0]))
@@ -497,6 +504,21 @@ class Csr:
         h = vp()
         check(self.L.b2_csr_transpose(self.h, ctypes.byref(h)))
         return Csr(self.ctx, h)
+
+    def matmat(self, B):
+        """self * B as a new matrix (b2_csr_matmat)."""
+        h = vp()
+        check(self.L.b2_csr_matmat(self.h, B.h, ctypes.byref(h)))
+        return Csr(self.ctx, h)
+
+    def axpy(self, a, X):
+        """self += a X, the pattern of X inside the pattern of self (b2_csr_axpy)."""
+        check(self.L.b2_csr_axpy(self.h, float(a), X.h))
+
+    def pattern_contains(self, X):
+        r = ci()
+        check(self.L.b2_csr_pattern_contains(self.h, X.h, ctypes.byref(r)))
+        return bool(r.value)
 
     def spmv(self, x, y):
         check(self.L.b2_csr_spmv(self.h, x.h, y.h))

@@ -7,7 +7,7 @@ namespace {
 
 constexpr int kBlock = 256;
 
-enum VecOp { OP_FILL, OP_AXPY, OP_AYPX, OP_SCALE, OP_SHIFT, OP_PMULT, OP_COPY_MASKED };
+enum VecOp { OP_FILL, OP_AXPY, OP_AYPX, OP_SCALE, OP_SHIFT, OP_PMULT, OP_COPY_MASKED, OP_ABS };
 
 template <int OP>
 __device__ __forceinline__ double vec_apply(double y, double x, double z, double a) {
@@ -16,6 +16,7 @@ __device__ __forceinline__ double vec_apply(double y, double x, double z, double
   if (OP == OP_AYPX) return fma(a, y, x);
   if (OP == OP_SCALE) return a * y;
   if (OP == OP_SHIFT) return y + a;
+  if (OP == OP_ABS) return fabs(y);
   if (OP == OP_PMULT) return x * z;
   if (OP == OP_COPY_MASKED) return z > a ? x : 0.0;
   return y;
@@ -238,6 +239,7 @@ int b2_vec_aypx(b2_vec* y, double a, const b2_vec* x) {
 }
 int b2_vec_scale(b2_vec* v, double a) { return launch_map<OP_SCALE>(v, nullptr, nullptr, a); }
 int b2_vec_add_scalar(b2_vec* v, double a) { return launch_map<OP_SHIFT>(v, nullptr, nullptr, a); }
+int b2_vec_abs(b2_vec* v) { return launch_map<OP_ABS>(v, nullptr, nullptr, 0.); }
 int b2_vec_pointwise_mult(b2_vec* w, const b2_vec* x, const b2_vec* y) {
   B2_CHECK(w->n == x->n && w->n == y->n, "b2_vec_pointwise_mult: size mismatch");
   return launch_map<OP_PMULT>(w, x, y, 0.);

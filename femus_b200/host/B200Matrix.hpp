@@ -26,6 +26,8 @@ class B200Matrix : public SparseMatrix {
   static std::unique_ptr<SparseMatrix> build() { return std::unique_ptr<SparseMatrix>(new B200Matrix); }
 
   b2_csr* handle() const { return _A; }
+  // changes whenever the device matrix behind this object is REPLACED (new pattern): who borrows the handle compares it
+  uint64_t generation() const { return _gen; }
   void touched() const { _mirror_ok = false; }      // device values were written behind our back (fused assembly)
 
   // ---- pattern ------------------------------------------------------------------------------
@@ -52,12 +54,14 @@ class B200Matrix : public SparseMatrix {
     this->clear();
     set_dims(m, m);
     B2_ABORT_IF(b2_csr_create_from_elements(B200Context::get(), m, nel, nve, dof, &_A), "b2_csr_create_from_elements");
+    new_generation();
     _frozen = _closed = _is_initialized = true;
   }
   void init_from_csr(const int m, const int n, const int64_t* rowptr, const int32_t* col, const double* vals) {
     this->clear();
     set_dims(m, n);
     B2_ABORT_IF(b2_csr_create(B200Context::get(), m, n, rowptr, col, vals, &_A), "b2_csr_create");
+    new_generation();
     _frozen = _closed = _is_initialized = true;
   }
   void update_sparsity_pattern_old(const Graph&) override { B2_NOT_ON_PATH("update_sparsity_pattern_old"); }
@@ -115,31 +119,99 @@ class B200Matrix : public SparseMatrix {
   bool closed() const override { return _closed; }
 
   // ---- algebra -------------------------------------------------------------------------------------
-  // this = P^T A P (MatPtAP, PetscMatrix.cpp:733-751).  With a pattern already in place (the coarse
-  // element-coupling pattern, or reuse == true) only the numeric phase runs, on the device; otherwise
-  // the pattern of the product is first formed on the host from the patterns of P and A.
+  // this = P^T A P (MatPtAP, PetscMatrix.cpp:733-751).  reuse (MAT_REUSE_MATRIX): only the numeric phase, onto the pattern
+  // in place (the coarse element-coupling pattern or an earlier product).  Otherwise, as MAT_INITIAL_MATRIX, the matrix is
+  // rebuilt with the pattern of the product -- in an F-cycle the same level matrix is first an assembled (AMR-constrained)
+  // operator and later a Galerkin product with a larger pattern (LinearImplicitSystem.cpp:347-370): P^T (A P) by two
+  // general products on the device.
   void matrix_PtAP(const SparseMatrix& mat_P, const SparseMatrix& mat_A, const bool& reuse) override {
     const B200Matrix& P = cast(mat_P);
     const B200Matrix& A = cast(mat_A);
     P.close();
     A.close();
-    if (!_frozen || (!reuse && (_m != P._n || _n != P._n))) symbolic_ptap(P, A);
-    B2_ABORT_IF(b2_csr_ptap(P._A, A._A, _A), "b2_csr_ptap");
-    _closed = true;
+    if (reuse && _frozen && _m == P._n && _n == P._n) {
+      drop_staging();
+      B2_ABORT_IF(b2_csr_ptap(P._A, A._A, _A), "b2_csr_ptap");
+      _closed = true;
+      touched();
+      return;
+    }
+    b2_csr *Pt = nullptr, *AP = nullptr, *C = nullptr;
+    B2_ABORT_IF(b2_csr_transpose(P._A, &Pt), "b2_csr_transpose");
+    B2_ABORT_IF(b2_csr_matmat(A._A, P._A, &AP), "b2_csr_matmat");
+    B2_ABORT_IF(b2_csr_matmat(Pt, AP, &C), "b2_csr_matmat");
+    b2_csr_destroy(AP);
+    b2_csr_destroy(Pt);
+    adopt(C, P._n, P._n);
+  }
+  // this = A B C (MatMatMatMult, PetscMatrix.cpp:833-856: KK <- RRamr KKamr PPamr on a non-homogeneous level,
+  // LinearImplicitSystem.cpp:336-341): two general products on the device; with reuse the pattern is the same by construction
+  void matrix_ABC(const SparseMatrix& mat_A, const SparseMatrix& mat_B, const SparseMatrix& mat_C, const bool&) override {
+    const B200Matrix &A = cast(mat_A), &B = cast(mat_B), &C = cast(mat_C);
+    A.close();
+    B.close();
+    C.close();
+    b2_csr *BC = nullptr, *ABC = nullptr;
+    B2_ABORT_IF(b2_csr_matmat(B._A, C._A, &BC), "b2_csr_matmat");
+    B2_ABORT_IF(b2_csr_matmat(A._A, BC, &ABC), "b2_csr_matmat");
+    b2_csr_destroy(BC);
+    adopt(ABC, A._m, C._n);
+  }
+  // this = this A / this = A this (MatMatMult, PetscMatrix.cpp:858-896: _PP[ig] <- _PP[ig] _PPamr[ig-1], LinearImplicitSystem.cpp:255-258)
+  void matrix_RightMatMult(const SparseMatrix& mat_A) override {
+    const B200Matrix& A = cast(mat_A);
+    A.close();
+    this->close();
+    b2_csr* C = nullptr;
+    B2_ABORT_IF(b2_csr_matmat(_A, A._A, &C), "b2_csr_matmat");
+    adopt(C, _m, A._n);
+  }
+  void matrix_LeftMatMult(const SparseMatrix& mat_A) override {
+    const B200Matrix& A = cast(mat_A);
+    A.close();
+    this->close();
+    b2_csr* C = nullptr;
+    B2_ABORT_IF(b2_csr_matmat(A._A, _A, &C), "b2_csr_matmat");
+    adopt(C, A._m, _n);
+  }
+  // this += a X (MatAXPY, PetscMatrix.cpp: matrix_add / add).  X inside this pattern: in place on the device; otherwise the
+  // union pattern is formed on the host first (DIFFERENT_NONZERO_PATTERN)
+  void matrix_add(const double a, SparseMatrix& X_in, const char[]) override { this->add(a, X_in); }
+  void add(const double a, SparseMatrix& X_in) override {
+    const B200Matrix& X = cast(X_in);
+    X.close();
+    this->close();
+    int inside = 0;
+    B2_ABORT_IF(b2_csr_pattern_contains(_A, X._A, &inside), "b2_csr_pattern_contains");
+    if (!inside) {
+      const std::vector<int64_t> rp = host_rowptr(), xrp = X.host_rowptr();
+      const std::vector<int32_t> ci = host_col(), xci = X.host_col();
+      const std::vector<double> v = host_val();
+      std::vector<int64_t> urp((size_t)_m + 1, 0);
+      std::vector<int32_t> uci;
+      std::vector<double> uv;
+      for (int i = 0; i < _m; i++) {
+        int64_t p = rp[i], q = xrp[i];
+        while (p < rp[i + 1] || q < xrp[i + 1]) {
+          const bool take_x = p == rp[i + 1] || (q < xrp[i + 1] && xci[q] < ci[p]);
+          if (take_x) { uci.push_back(xci[q++]); uv.push_back(0.0); }
+          else { if (q < xrp[i + 1] && xci[q] == ci[p]) q++; uci.push_back(ci[p]); uv.push_back(v[p++]); }
+        }
+        urp[i + 1] = (int64_t)uci.size();
+      }
+      const int m = _m, n = _n;
+      this->init_from_csr(m, n, urp.data(), uci.data(), uv.data());
+    }
+    B2_ABORT_IF(b2_csr_axpy(_A, a, X._A), "b2_csr_axpy");
     touched();
   }
-  void matrix_ABC(const SparseMatrix&, const SparseMatrix&, const SparseMatrix&, const bool&) override { B2_NOT_ON_PATH("matrix_ABC"); }
-  void matrix_RightMatMult(const SparseMatrix&) override { B2_NOT_ON_PATH("matrix_RightMatMult"); }
-  void matrix_LeftMatMult(const SparseMatrix&) override { B2_NOT_ON_PATH("matrix_LeftMatMult"); }
-  void matrix_add(const double, SparseMatrix&, const char[]) override { B2_NOT_ON_PATH("matrix_add"); }
-  void add(const double, SparseMatrix&) override { B2_NOT_ON_PATH("add(c, B)"); }
   void get_transpose(SparseMatrix& dest) const override {
     this->close();
     B200Matrix& T = dynamic_cast<B200Matrix&>(dest);
-    T.clear();
-    T.set_dims(_n, _m);
-    B2_ABORT_IF(b2_csr_transpose(_A, &T._A), "b2_csr_transpose");
-    T._frozen = T._closed = T._is_initialized = true;
+    b2_csr* At = nullptr;
+    B2_ABORT_IF(b2_csr_transpose(_A, &At), "b2_csr_transpose");
+    const int m = _m, n = _n;       // dest may be this matrix (LinearImplicitSystem.cpp:1025 transposes _PPamr in place)
+    T.adopt(At, n, m);
   }
   void get_diagonal(NumericVector& dest) const override {
     this->close();
@@ -163,12 +235,40 @@ class B200Matrix : public SparseMatrix {
     value.resize(index.size());
     for (size_t k = 0; k < index.size(); k++) value[k] = (*this)(index[k], index[k]);
   }
-  void matrix_set_diagonal_values(NumericVector&) override { B2_NOT_ON_PATH("matrix_set_diagonal_values"); }
-  void matrix_set_diagonal_values(const std::vector<int>&, const double&) override { B2_NOT_ON_PATH("matrix_set_diagonal_values"); }
-  void matrix_set_diagonal_values(const std::vector<int>&, const std::vector<double>&) override { B2_NOT_ON_PATH("matrix_set_diagonal_values"); }
-  void matrix_set_off_diagonal_values_blocked(const std::vector<int>&, const std::vector<int>&, const double&) override { B2_NOT_ON_PATH("matrix_set_off_diagonal_values_blocked"); }
-  void matrix_set_off_diagonal_values_blocked(const std::vector<int>&, const std::vector<int>&, const std::vector<double>&) override { B2_NOT_ON_PATH("matrix_set_off_diagonal_values_blocked"); }
-  void RemoveZeroEntries(double&) override { B2_NOT_ON_PATH("RemoveZeroEntries"); }
+  // MatDiagonalSet / MatSetValues(INSERT) on single entries (PetscMatrix.cpp:911-952): staged like every other insertion
+  void matrix_set_diagonal_values(NumericVector& D) override {
+    std::vector<double> d;
+    D.localize(d);
+    for (int i = 0; i < _m && i < (int)d.size(); i++) this->set(i, i, d[i]);
+  }
+  void matrix_set_diagonal_values(const std::vector<int>& index, const double& value) override {
+    for (int i : index) this->set(i, i, value);
+  }
+  void matrix_set_diagonal_values(const std::vector<int>& index, const std::vector<double>& value) override {
+    for (size_t k = 0; k < index.size(); k++) this->set(index[k], index[k], value[k]);
+  }
+  void matrix_set_off_diagonal_values_blocked(const std::vector<int>& rows, const std::vector<int>& cols, const double& value) override {
+    for (size_t k = 0; k < rows.size(); k++) this->set(rows[k], cols[k], value);
+  }
+  void matrix_set_off_diagonal_values_blocked(const std::vector<int>& rows, const std::vector<int>& cols, const std::vector<double>& value) override {
+    for (size_t k = 0; k < rows.size(); k++) this->set(rows[k], cols[k], value[k]);
+  }
+  // rebuild the matrix without the entries of magnitude <= tolerance (PetscMatrix.cpp:755-830)
+  void RemoveZeroEntries(double& tolerance) override {
+    const std::vector<int64_t> rp = host_rowptr();
+    const std::vector<int32_t> ci = host_col();
+    const std::vector<double> v = host_val();
+    std::vector<int64_t> nrp((size_t)_m + 1, 0);
+    std::vector<int32_t> nci;
+    std::vector<double> nv;
+    for (int i = 0; i < _m; i++) {
+      for (int64_t k = rp[i]; k < rp[i + 1]; k++)
+        if (std::fabs(v[k]) > tolerance) { nci.push_back(ci[k]); nv.push_back(v[k]); }
+      nrp[i + 1] = (int64_t)nci.size();
+    }
+    const int m = _m, n = _n;
+    this->init_from_csr(m, n, nrp.data(), nci.data(), nv.data());
+  }
 
   // ---- inspection (host mirror of the CSR, refreshed on demand) ----------------------------------
   int m() const override { return _m; }
@@ -228,6 +328,18 @@ class B200Matrix : public SparseMatrix {
   }
 
  private:
+  // take ownership of a finished device matrix (the previous one, its staging and its mirror go)
+  void adopt(b2_csr* A, int m, int n) {
+    this->clear();
+    set_dims(m, n);
+    _A = A;
+    new_generation();
+    _frozen = _closed = _is_initialized = true;
+  }
+  void new_generation() {
+    static uint64_t counter = 0;
+    _gen = ++counter;
+  }
   struct Row {      // unsorted (column, value) pairs of one row while the pattern is still open
     std::vector<int32_t> col;
     std::vector<double> val;
@@ -276,6 +388,7 @@ class B200Matrix : public SparseMatrix {
         for (size_t k = 0; k < perm.size(); k++) { col[rp[i] + k] = r.col[perm[k]]; val[rp[i] + k] = r.val[perm[k]]; }
       }
       B2_ABORT_IF(b2_csr_create(B200Context::get(), _m, _n, rp.data(), col.data(), val.data(), &_A), "b2_csr_create");
+      new_generation();
       _rows.clear();
       _rows.shrink_to_fit();
       _frozen = true;
@@ -294,32 +407,6 @@ class B200Matrix : public SparseMatrix {
     _closed = true;
     touched();
   }
-  // pattern of P^T A P from the host copies of the two patterns (row-wise products with a marker array)
-  void symbolic_ptap(const B200Matrix& P, const B200Matrix& A) {
-    const std::vector<int64_t>& prp = P.host_rowptr();
-    const std::vector<int32_t>& pc = P.host_col();
-    const std::vector<int64_t>& arp = A.host_rowptr();
-    const std::vector<int32_t>& ac = A.host_col();
-    const int nf = P._m, ncoarse = P._n;
-    std::vector<std::vector<int32_t>> ap((size_t)nf);         // pattern of A P, row by row
-    std::vector<int> mark((size_t)ncoarse, -1);
-    for (int i = 0; i < nf; i++)
-      for (int64_t k = arp[i]; k < arp[i + 1]; k++)
-        for (int64_t q = prp[ac[k]]; q < prp[ac[k] + 1]; q++)
-          if (mark[pc[q]] != i) { mark[pc[q]] = i; ap[i].push_back(pc[q]); }
-    std::vector<std::vector<int32_t>> c((size_t)ncoarse);     // rows of P^T (A P): scatter row i of AP to rows pc[q]
-    for (int i = 0; i < nf; i++)
-      for (int64_t q = prp[i]; q < prp[i + 1]; q++) c[pc[q]].insert(c[pc[q]].end(), ap[i].begin(), ap[i].end());
-    std::vector<int64_t> rp((size_t)ncoarse + 1, 0);
-    for (int I = 0; I < ncoarse; I++) {
-      std::sort(c[I].begin(), c[I].end());
-      c[I].erase(std::unique(c[I].begin(), c[I].end()), c[I].end());
-      rp[I + 1] = rp[I] + (int64_t)c[I].size();
-    }
-    std::vector<int32_t> col((size_t)rp[ncoarse]);
-    for (int I = 0; I < ncoarse; I++) std::copy(c[I].begin(), c[I].end(), col.begin() + rp[I]);
-    this->init_from_csr(ncoarse, ncoarse, rp.data(), col.data(), nullptr);
-  }
   void refresh_mirror() const {
     this->close();
     if (_mirror_ok) return;
@@ -333,6 +420,7 @@ class B200Matrix : public SparseMatrix {
 
   struct Blocks { std::vector<int32_t> rows, cols; std::vector<double> vals; };
   b2_csr* _A;
+  uint64_t _gen = 0;
   bool _frozen, _closed;
   std::vector<Row> _rows;
   std::map<std::pair<int, int>, Blocks> _blk;

@@ -175,7 +175,7 @@ class B200Vector : public NumericVector {
   void add(const NumericVector& V) override { this->add(1., V); }
   void add(const double a, const NumericVector& V) override { B2_ABORT_IF(b2_vec_axpy(_v, a, dev(V)), "b2_vec_axpy"); touched(); }
   void scale(const double factor) override { B2_ABORT_IF(b2_vec_scale(_v, factor), "b2_vec_scale"); touched(); }
-  void abs() override { B2_NOT_ON_PATH("abs"); }
+  void abs() override { B2_ABORT_IF(b2_vec_abs(_v), "b2_vec_abs"); touched(); }
   void pointwise_mult(const NumericVector& a, const NumericVector& b) override {
     B2_ABORT_IF(b2_vec_pointwise_mult(_v, dev(a), dev(b)), "b2_vec_pointwise_mult");
     touched();

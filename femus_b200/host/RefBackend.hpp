@@ -3,8 +3,8 @@
 // SparseMatrix.cpp:42-63, LinearEquationSolver.cpp:40-74).  With this header pre-included (-include) into those three
 // translation units, the reference's UNMODIFIED sources and applications (applications/001_Poisson/main.cpp) run on
 // libfemus_b200.so: every vector / matrix / solver object the application touches is a device object behind the
-// reference's own abstract interfaces.  femus_b200/ref_build.py builds exactly that (single rank, the reference's MPI /
-// PETSc headers replaced by the single-process shims of oracle/ref_shims -- build plumbing, no arithmetic).
+// reference's own abstract interfaces.  tests/ref_apps_build.py builds exactly that (single rank, the reference's MPI /
+// PETSc headers replaced by the single-process shims of the test build -- build plumbing, no arithmetic).
 //
 // LinearEquationSolverB200Ref derives from the reference's LinearEquationSolver (LinearEquationSolver.hpp:55) and
 // implements its pure virtuals on b2_mg_*: MGInit / MGSetLevel / MGSolve / Solve as LinearEquationSolverPetsc.cpp:185-353
@@ -71,7 +71,7 @@ class LinearEquationSolverB200Ref : public LinearEquationSolver {
     LinearEquationSolverB200Ref* top = static_cast<LinearEquationSolverB200Ref*>(LinSolver);
     if (!top->_mg || levelMax + 1 != top->_levelMax) { std::fprintf(stderr, "femus_b200: MGSetLevel: MGInit was not called on the finest solver\n"); std::abort(); }
     if (!_bdcIndexIsInitialized) this->BuildBdcIndex(variable_to_be_solved);
-    if (const char* dir = std::getenv("FEMUS_REF_DUMP")) this->dump_level(dir, PP);      // before the penalty, like the oracle's host backend
+    if (const char* dir = std::getenv("FEMUS_REF_DUMP")) this->dump_level(dir, PP);      // before the penalty
     this->configure_level(top->_mg, (int)_level, PP, npre, npost);
   }
   // one multiplicative V-cycle as outer PREONLY (:294-353): ZerosBoundaryResiduals; EPSC = V(RES); RESC = KK EPSC; RES -= RESC; EPS += EPSC
@@ -103,7 +103,7 @@ class LinearEquationSolverB200Ref : public LinearEquationSolver {
   }
 
  private:
-  // ---- diagnostics: the arrays of oracle/ref_build/HostBackend.hpp's dump, read back from the device objects
+  // ---- diagnostics (tools/ref_app_diag.py): level operators, prolongators and vectors read back from the device objects
   template <class T>
   void dump_array(const char* dir, const std::string& name, const std::vector<T>& a) const {
     const char* suffix = sizeof(T) == 8 ? (std::is_floating_point<T>::value ? "f8" : "i8") : "i4";
@@ -144,7 +144,9 @@ class LinearEquationSolverB200Ref : public LinearEquationSolver {
       if (pc == JACOBI_PRECOND) {
         B2_ABORT_IF(b2_mg_set_smoother(mg, level, 0, 0., 0.), "b2_mg_set_smoother");
       } else if (pc == SOR_PRECOND) {          // PCSOR on the level = the SSOR sweep of ONE block holding every dof
+        if (_sweep && _sweepGen != KK.generation()) { b2_schwarz_destroy(_sweep); _sweep = nullptr; }      // the level matrix was rebuilt (F-cycle)
         if (!_sweep) {
+          _sweepGen = KK.generation();
           const int64_t bp[2] = {0, n}, gp[2] = {0, 1};
           std::vector<int32_t> all((size_t)n);
           for (int64_t i = 0; i < n; i++) all[(size_t)i] = (int32_t)i;
@@ -159,7 +161,9 @@ class LinearEquationSolverB200Ref : public LinearEquationSolver {
         std::abort();
       }
     } else if (n <= 4096) {                    // exact coarse solve, like the reference's LU
+      if (_coarse && _coarseGen != KK.generation()) { b2_schwarz_destroy(_coarse); _coarse = nullptr; }
       if (!_coarse) {
+        _coarseGen = KK.generation();
         const int64_t bp[2] = {0, n}, gp[2] = {0, 1};
         std::vector<int32_t> all((size_t)n);
         for (int64_t i = 0; i < n; i++) all[(size_t)i] = (int32_t)i;
@@ -179,6 +183,7 @@ class LinearEquationSolverB200Ref : public LinearEquationSolver {
   b2_mg* _mg;
   unsigned _levelMax;
   b2_schwarz *_sweep, *_coarse;
+  uint64_t _sweepGen = 0, _coarseGen = 0;      // generation of the level matrix the two block objects were created on
   std::vector<int32_t> _bdcIndex;
   bool _bdcIndexIsInitialized;
 };

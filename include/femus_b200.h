@@ -106,6 +106,7 @@ int b2_vec_copy(b2_vec* dst, const b2_vec* src);                       /* operat
 int b2_vec_axpy(b2_vec* y, double a, const b2_vec* x);                 /* add(a,V)    VecAXPY          :303 */
 int b2_vec_aypx(b2_vec* y, double a, const b2_vec* x);                 /* y = x + a y VecAYPX */
 int b2_vec_scale(b2_vec* v, double a);                                 /* scale       VecScale         :378 */
+int b2_vec_abs(b2_vec* v);                                             /* abs         VecAbs           :387 */
 int b2_vec_add_scalar(b2_vec* v, double a);                            /* add(double) VecShift         :283 */
 int b2_vec_pointwise_mult(b2_vec* w, const b2_vec* x, const b2_vec* y);/* pointwise_mult               :782 */
 int b2_vec_dot(const b2_vec* x, const b2_vec* y, double* out);         /* dot         VecDot           :399 */
@@ -186,6 +187,13 @@ int b2_csr_jacobi_sweep(const b2_csr* A, const b2_vec* dinv, const b2_vec* b, co
 /* matrix_PtAP (PetscMatrix.cpp:733-751): C = P^T A P, numeric phase onto C's existing pattern
  * (the coarse element-coupling pattern). */
 int b2_csr_ptap(const b2_csr* P, const b2_csr* A, b2_csr* C);
+/* General products and sums of the AMR path (b2_matmat.cu).  C = A B as a NEW matrix the caller owns: matrix_RightMatMult /
+ * matrix_LeftMatMult (MatMatMult, PetscMatrix.cpp:766-790; _PP[ig] <- _PP[ig] * _PPamr[ig-1], LinearImplicitSystem.cpp:255-258)
+ * and, applied twice, matrix_ABC (MatMatMatMult, :755-764).  Structural zeros are kept; run-to-run bit-identical. */
+int b2_csr_matmat(const b2_csr* A, const b2_csr* B, b2_csr** C);
+/* Y += a X for a pattern of X inside the pattern of Y (matrix_add / add: MatAXPY, PetscMatrix.cpp:793-812); fails otherwise */
+int b2_csr_axpy(b2_csr* Y, double a, const b2_csr* X);
+int b2_csr_pattern_contains(const b2_csr* Y, const b2_csr* X, int* contained);
 double b2_csr_last_kernel_ms(const b2_csr* A);
 /* Fast path of matrix_PtAP for the geometric prolongators of BuildProlongatorMatrix
  * (LinearImplicitSystem.cpp:826-909, Dirichlet rows/columns zeroed by :1032-1120): the product is

@@ -8,6 +8,7 @@ oracle/_ref/ -- no copy of any reference source enters this repository, the refe
     ref_dump                oracle/ref_build/ref_dump.cpp: mesh -> numbering -> sparsity -> prolongators -> Dirichlet flags
                             -> assembled system, through the reference's classes, written as .npz-ready text
     ref_poisson_host        applications/001_Poisson/main.cpp, UNMODIFIED, on the host backend
+    ref_amr_poisson_host    tests/cpp/ref_amr_poisson.cpp: selectively refined meshes through the reference's AMR path
 
     python -m oracle.ref_build.build [--force]
 """
@@ -94,13 +95,14 @@ def build(ref="/root/reference", force=False):
             os.unlink(LIB)
         subprocess.run(["ar", "rcs", LIB] + objs, check=True)
     fl = flags(ref)
-    exes = {"ref_dump": os.path.join(HERE, "ref_dump.cpp"), "ref_poisson_host": os.path.join(ref, "applications/001_Poisson/main.cpp")}
+    exes = {"ref_dump": os.path.join(HERE, "ref_dump.cpp"), "ref_poisson_host": os.path.join(ref, "applications/001_Poisson/main.cpp"),
+            "ref_amr_poisson_host": os.path.join(os.path.dirname(ORACLE), "tests", "cpp", "ref_amr_poisson.cpp")}
     for name, src in exes.items():
         if not os.path.exists(src):
             continue
         exe = os.path.join(OUT, name)
         if force or changed or not os.path.exists(exe) or os.path.getmtime(exe) < max(os.path.getmtime(src), os.path.getmtime(backend)):
-            r = subprocess.run(["g++"] + fl + ["-include", backend, src, "-o", exe, LIB, "-lpthread"], capture_output=True, text=True)
+            r = subprocess.run(["g++"] + fl + ["-I" + ref, "-include", backend, src, "-o", exe, LIB, "-lpthread"], capture_output=True, text=True)
             if r.returncode:
                 raise RuntimeError(f"link of {name} failed:\n{r.stderr[-4000:]}")
     return OUT

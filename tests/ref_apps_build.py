@@ -1,19 +1,23 @@
-"""The reference's UNMODIFIED application applications/001_Poisson/main.cpp on the femus_b200 backend:
+"""TEST INFRASTRUCTURE (it compiles reference objects shared with the oracle's host build).  The reference's UNMODIFIED application applications/001_Poisson/main.cpp on the femus_b200 backend:
 
     femus_b200/ref_poisson_b200    main.cpp + the reference's own mesh / solution / system sources (compiled where they
                                    lie under /root/reference, objects shared with oracle/ref_build) + the three factory
                                    translation units compiled with femus_b200/host/RefBackend.hpp pre-included, linked
                                    against libfemus_b200.so
 
-Built in the container that has /root/reference (python -m femus_b200.ref_build); the binary is in-tree (git-ignored,
+    femus_b200/ref_amr_poisson_b200    tests/cpp/ref_amr_poisson.cpp the same way: selectively refined meshes through the
+                                   reference's own AMR path (hanging-node constraint matrices, non-homogeneous levels)
+
+Built in the container that has /root/reference (python tests/ref_apps_build.py); the binary is in-tree (git-ignored,
 like the library) so that it travels to the GPU box, where tests/test_zz_reference_app_gpu.py runs it."""
 import os
 import subprocess
 import sys
 
-HERE = os.path.dirname(os.path.abspath(__file__))
-ROOT = os.path.dirname(HERE)
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HERE = os.path.join(ROOT, "femus_b200")       # the binaries sit next to libfemus_b200.so (rpath $ORIGIN)
 EXE = os.path.join(HERE, "ref_poisson_b200")
+AMR_EXE = os.path.join(HERE, "ref_amr_poisson_b200")
 
 
 def build(ref="/root/reference", force=False):
@@ -41,11 +45,13 @@ def build(ref="/root/reference", force=False):
             objs.append(o2)
         else:
             objs.append(o)
-    main = os.path.join(ref, "applications/001_Poisson/main.cpp")
-    r = subprocess.run(["g++"] + fl + ["-include", backend, main, "-o", EXE] + objs + ["-L" + HERE, "-lfemus_b200", "-Wl,-rpath,$ORIGIN", "-lpthread"],
-                       capture_output=True, text=True)
-    if r.returncode:
-        raise RuntimeError(f"link of ref_poisson_b200 failed:\n{r.stderr[-4000:]}")
+    apps = {EXE: os.path.join(ref, "applications/001_Poisson/main.cpp"),            # the reference's application, unmodified
+            AMR_EXE: os.path.join(ROOT, "tests", "cpp", "ref_amr_poisson.cpp")}      # the reference's AMR path (see the file header)
+    for exe, main in apps.items():
+        r = subprocess.run(["g++"] + fl + ["-I" + ref, "-include", backend, main, "-o", exe] + objs + ["-L" + HERE, "-lfemus_b200", "-Wl,-rpath,$ORIGIN", "-lpthread"],
+                           capture_output=True, text=True)
+        if r.returncode:
+            raise RuntimeError(f"link of {os.path.basename(exe)} failed:\n{r.stderr[-4000:]}")
     return EXE
 
 

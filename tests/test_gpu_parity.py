@@ -437,6 +437,36 @@ def test_ptap_matches_oracle(ctx, order):
         assert np.abs(got.data - ref.data).max() <= RTOL * np.abs(ref.data).max()
 
 
+@pytest.mark.parametrize("shape", [(40, 30, 50, 0.2), (1, 1, 1, 1.0), (300, 257, 129, 0.03), (64, 64, 64, 0.0)])
+def test_matmat_and_axpy_match_scipy(ctx, shape):
+    """General products / sums of the AMR path (matrix_RightMatMult, matrix_LeftMatMult, matrix_ABC, matrix_add):
+    structure identical to scipy's (structural zeros kept), values to round-off, run-to-run bit-identical."""
+    m, k, n, dens = shape
+    rng = np.random.default_rng(m + n)
+    A, B = random_csr(rng, m, k, dens), random_csr(rng, k, n, dens)
+    dA, dB = ctx.csr_from_scipy(A), ctx.csr_from_scipy(B)
+    C = dA.matmat(dB)
+    got = C.to_scipy()
+    # scipy drops nothing structurally either: pattern of the product of the patterns
+    ref = (A @ B).tocsr()
+    pat = (abs(A).sign() @ abs(B).sign()).tocsr()
+    pat.sort_indices()
+    assert got.shape == ref.shape and np.array_equal(got.indptr, pat.indptr) and np.array_equal(got.indices, pat.indices)
+    assert abs(got - ref).max() <= 1e-14 * max(abs(ref).max(), 1e-300) if ref.nnz else got.nnz == 0
+    again = dA.matmat(dB).to_scipy()
+    assert np.array_equal(again.data, got.data)
+    if m == k == n:
+        # Y += a X: the pattern of X inside the pattern of Y
+        Y = (A + B).tocsr()
+        Y.sort_indices()
+        dY = ctx.csr_from_scipy(Y)
+        assert dY.pattern_contains(dA) and not ctx.csr_from_scipy(sp.csr_matrix((m, m))).pattern_contains(ctx.csr_from_scipy(sp.eye(m, format="csr")))
+        dY.axpy(-0.5, dA)
+        assert abs(dY.to_scipy() - (Y - 0.5 * A)).max() <= 1e-15 * max(abs(Y).max(), 1.0)
+        with pytest.raises(capi.B2Error):
+            ctx.csr_from_scipy(sp.csr_matrix((m, m))).axpy(1.0, ctx.csr_from_scipy(sp.eye(m, format="csr")))
+
+
 @pytest.mark.parametrize("order", ["linear", "biquadratic"])
 @pytest.mark.parametrize("shape", [(2, 2, 3), (1, 1, 1), (3, 1, 2)])
 def test_galerkin_element_gather_matches_oracle(ctx, order, shape):

@@ -1,7 +1,7 @@
 """GPU: the reference's UNMODIFIED application applications/001_Poisson/main.cpp, compiled with the reference's own
 mesh / solution / system sources, running on libfemus_b200.so: every NumericVector / SparseMatrix /
 LinearEquationSolver the application touches is a device object of this backend behind the reference's factories
-(femus_b200/host/RefBackend.hpp, femus_b200/ref_build.py).  The residual norms the reference prints after every
+(femus_b200/host/RefBackend.hpp, tests/ref_apps_build.py).  The residual norms the reference prints after every
 V-cycle (LinearImplicitSystem.cpp:426) must equal, to the 7 digits printed, what the SAME application printed on the
 host backend of the oracle build (tests/golden/ref_poisson_*.npz).  The binary is built where /root/reference exists
 (__graft_entry__.build()) and travels in-tree."""
@@ -23,7 +23,7 @@ EXE = os.path.join(ROOT, "femus_b200", "ref_poisson_b200")
 @pytest.mark.parametrize("case", ["box222_q2_3lev", "box222_q1_3lev", "box324_q2_2lev_neumann", "cube_hex_q2_2lev", "cube_tet_q2_2lev", "cube_mixed_q2_2lev"])
 def test_unmodified_reference_application_on_the_b200_backend(case, tmp_path):
     if not os.path.exists(EXE):
-        pytest.fail("femus_b200/ref_poisson_b200 is missing: build it with `python -m femus_b200.ref_build` where /root/reference exists")
+        pytest.fail("femus_b200/ref_poisson_b200 is missing: build it with `python tests/ref_apps_build.py` where /root/reference exists")
     g = np.load(os.path.join(GOLDEN, f"ref_poisson_{case}.npz"))
     work = str(tmp_path)
     os.makedirs(os.path.join(work, "input"))
