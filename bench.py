@@ -203,6 +203,7 @@ def main():
     ap.add_argument("--order", default="biquadratic", choices=["linear", "biquadratic"])
     ap.add_argument("--cpu-n0", type=int, default=8, help="coarsest-level size of the CPU sample (8: 64^3 elements with 4 levels)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--halo", default="peer", choices=["peer", "nccl"], help="interface sums: peer-memory exchange or packed ncclAllReduce")
     args = ap.parse_args()
     W = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -217,6 +218,8 @@ def main():
     config = {"workload": workload, "coarse_box": [nx, ny, nz], "levels": args.levels, "fe_order": args.order,
               "domain": list(bounds_for(nx, ny, nz)),
               "partition": "single GPU" if args.gpus == 1 else f"z-slabs over {args.gpus} GPUs",
+              "interface_sums": None if args.gpus == 1 else ("peer-memory exchange over NVLink (remote stores + flags)" if args.halo == "peer"
+                                                               else "packed ncclAllReduce"),
               "l2": "inputs larger than L2 (finest CSR >> 126 MB); no flush needed"}
 
     # ------------------------------------------------------------------ reference arm (CPU)
@@ -278,7 +281,7 @@ def main():
         return float(t.item())
 
     t_setup = time.time()
-    pb = PoissonMG(ctx, nx, ny, nz, args.levels, args.order, bounds=bounds_for(nx, ny, nz), dist=dist_arg)
+    pb = PoissonMG(ctx, nx, ny, nz, args.levels, args.order, bounds=bounds_for(nx, ny, nz), dist=dist_arg, peer=args.halo == "peer")
     ctx.sync()
     t_setup = time.time() - t_setup
     top = pb.hier.levels[-1]
@@ -365,6 +368,23 @@ def main():
                 kernel_ms.setdefault("assembly", []).append(msk / max(nk, 1))
         phases[name] = float(np.median(ts))
     asm_kernel_ms = float(np.median(kernel_ms["assembly"]))
+    if world > 1 and args.halo == "peer":      # the same V-cycle with the interface sums as a packed ncclAllReduce, for comparison
+        ctx.set_option("halo_peer", 0)
+        ts = []
+        for _ in range(3):
+            barrier()
+            ctx.timer_start()
+            pb.mg_solve()
+            ts.append(max_over_ranks(ctx.timer_stop_ms()))
+        phases["vcycle_with_nccl_allreduce"] = float(np.median(ts))
+        ctx.set_option("halo_peer", 1)
+        ts = []
+        for _ in range(3):
+            barrier()
+            ctx.timer_start()
+            pb.mg_solve()
+            ts.append(max_over_ranks(ctx.timer_stop_ms()))
+        phases["vcycle_max_over_ranks"] = float(np.median(ts))
     # ---- end-to-end: host buffers in, host buffers out
     upload_next()
     for k in range(2):

@@ -72,6 +72,10 @@ _PROTOS = {
     "b2_vec_sum": (ci, [vp, vp]),
     "b2_vec_minmax": (ci, [vp, vp, vp]),
     "b2_vec_abs": (ci, [vp]),
+    "b2_ctx_peer_export": (ci, [vp, i64, vp]),
+    "b2_ctx_peer_open": (ci, [vp, vp]),
+    "b2_ctx_peer_error": (ci, [vp, vp]),
+    "b2_halo_set_exchange": (ci, [vp, ci, vp, vp, vp, vp, vp, vp]),
     "b2_csr_matmat": (ci, [vp, vp, vp]),
     "b2_csr_axpy": (ci, [vp, cd, vp]),
     "b2_csr_pattern_contains": (ci, [vp, vp, vp]),
@@ -222,6 +226,18 @@ class Context:
     def comm_init(self, nranks, rank, uid_bytes):
         buf = (ctypes.c_char * 128).from_buffer_copy(uid_bytes)
         check(self.L.b2_ctx_comm_init(self.h, nranks, rank, buf))
+
+    def peer_init(self, slot_doubles, allgather):
+        """Peer-memory exchange over NVLink: export this rank's inbox, gather the IPC handles, open every rank's."""
+        buf = (ctypes.c_char * 64)()
+        check(self.L.b2_ctx_peer_export(self.h, int(slot_doubles), buf))
+        handles = b"".join(allgather(bytes(buf)))
+        check(self.L.b2_ctx_peer_open(self.h, (ctypes.c_char * len(handles)).from_buffer_copy(handles)))
+
+    def peer_error(self):
+        e = ci()
+        check(self.L.b2_ctx_peer_error(self.h, ctypes.byref(e)))
+        return bool(e.value)
 
     @staticmethod
     def nccl_unique_id():
@@ -557,6 +573,12 @@ class Halo:
 
     def sum(self, v):
         check(self.L.b2_halo_sum(self.h, v.h))
+
+    def set_exchange(self, share_rank, send_ptr, send_dof, hold_ptr, hold_rank, hold_pos):
+        share_rank, send_dof, hold_rank, hold_pos = _i32(share_rank), _i32(send_dof), _i32(hold_rank), _i32(hold_pos)
+        send_ptr, hold_ptr = np.ascontiguousarray(send_ptr, dtype=np.int64), np.ascontiguousarray(hold_ptr, dtype=np.int64)
+        check(self.L.b2_halo_set_exchange(self.h, share_rank.shape[0], _ptr(share_rank), _ptr(send_ptr), _ptr(send_dof), _ptr(hold_ptr),
+                                          _ptr(hold_rank), _ptr(hold_pos)))
 
     def owned_count(self):
         return int(self.L.b2_halo_owned_count(self.h))

@@ -73,6 +73,18 @@ struct b2_ctx {
   // multi-GPU
   int nranks = 1, rank = 0;
   void* nccl_comm = nullptr;
+  // peer-memory exchange over NVLink / NVSwitch (b2_halo.cu): one block of device memory per rank, opened by every
+  // other rank of the node through CUDA IPC.  Layout: [flags: nranks x 8 B, padded to 4 KiB][inbox: 2 (parity) x
+  // nranks (sender) x peer_slot doubles].  peer_base[r] = rank r's block as seen from this process (own: local pointer).
+  void* peer_local = nullptr;
+  void** peer_base = nullptr;           // host array [nranks]
+  void** d_peer_base = nullptr;         // the same on the device
+  int64_t peer_slot = 0;                // doubles per (parity, sender) slot: 8 scalars + interface values
+  unsigned long long peer_epoch = 0;    // exchanges done so far (identical on every rank: SPMD call sequence)
+  unsigned int* peer_counter = nullptr; // last-block-done counter of the push kernel
+  int* peer_err = nullptr;              // device: set when a wait timed out
+  int coarse_persistent = 1;            // 1: iteration loop of the coarse PCG as one cooperative kernel (b2_cg.cu), 0: host-driven loop
+  int halo_peer = 1;                    // 1: interface sums through the peer-memory exchange when it is set up; 0: packed ncclAllReduce
   // optional per-launch event timing of the SpMV family / assembly (b2_ctx_profile)
   bool profiling = false;
   const void* prof_only = nullptr;   // when set, only launches tagged with this handle are timed
@@ -114,6 +126,17 @@ struct b2_halo {
   uint8_t* owned;      // [n_local] 1 if this rank owns the dof
   double* invmult;     // [n_local] 1 / (number of ranks holding the dof)
   int64_t n_owned;
+  // peer-memory exchange (b2_halo_set_exchange): what goes to every rank sharing dofs with this one, and for every
+  // interface entry its holders in ascending rank order (the sum is taken in that order on every holder)
+  int nshare = 0;
+  int32_t* share_rank = nullptr;   // [nshare] (device)
+  int64_t* send_ptr = nullptr;     // [nshare+1]
+  int32_t* send_dof = nullptr;     // [send_ptr[nshare]] local dofs in the order the receiver expects
+  int64_t n_send = 0;
+  int64_t* hold_ptr = nullptr;     // [n_if+1]
+  int32_t* hold_rank = nullptr;    // [hold_ptr[n_if]] holder ranks, ascending, this rank included
+  int32_t* hold_pos = nullptr;     // position of the value in that holder's message to this rank (unused for this rank)
+  int64_t n_hold = 0;
 };
 
 struct b2_csr {

@@ -100,6 +100,15 @@ int b2_ctx_destroy(b2_ctx* c) {
   if (!c) return 0;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
+  if (c->peer_base) {
+    for (int r = 0; r < c->nranks; r++)
+      if (r != c->rank && c->peer_base[r]) cudaIpcCloseMemHandle(c->peer_base[r]);
+    delete[] c->peer_base;
+    b2_free(c, c->d_peer_base, (size_t)c->nranks);
+    b2_free(c, c->peer_counter, 1);
+    b2_free(c, c->peer_err, 1);
+  }
+  if (c->peer_local) cudaFree(c->peer_local);
   if (c->nccl_comm && g_nccl.destroy) ((int (*)(void*))g_nccl.destroy)(c->nccl_comm);
   b2_free(c, c->red_partial, (size_t)kRedBlocks * 2);
   b2_free(c, c->red_result, 8);
@@ -114,6 +123,51 @@ int b2_ctx_destroy(b2_ctx* c) {
   if (c->ev_free) cudaEventDestroy(c->ev_free);
   if (c->ev_marked) cudaEventDestroy(c->ev_marked);
   delete c;
+  return 0;
+}
+
+/* Peer-memory exchange, step 1: allocate this rank's block (flags + double-buffered inbox with `slot_doubles` doubles per
+ * sender) and export its CUDA IPC handle (64 bytes) for the launcher to all-gather. */
+int b2_ctx_peer_export(b2_ctx* c, int64_t slot_doubles, void* handle64) {
+  B2_CHECK(c && handle64 && slot_doubles >= 8, "b2_ctx_peer_export: bad arguments");
+  B2_CHECK(c->nranks > 1, "b2_ctx_peer_export: communicator not initialised (b2_ctx_comm_init first)");
+  B2_CHECK(!c->peer_local, "b2_ctx_peer_export: already exported");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+  const size_t bytes = 4096 + (size_t)2 * c->nranks * (size_t)slot_doubles * sizeof(double);
+  B2_CUDA(cudaMalloc(&c->peer_local, bytes));
+  c->bytes += (int64_t)bytes;
+  B2_CUDA(cudaMemset(c->peer_local, 0, bytes));
+  c->peer_slot = slot_doubles;
+  cudaIpcMemHandle_t h;
+  B2_CUDA(cudaIpcGetMemHandle(&h, c->peer_local));
+  memcpy(handle64, &h, 64);
+  return 0;
+}
+/* step 2: open the blocks of all ranks (handles[nranks][64], gathered in rank order) */
+int b2_ctx_peer_open(b2_ctx* c, const void* handles) {
+  B2_CHECK(c && handles && c->peer_local && !c->peer_base, "b2_ctx_peer_open: export first, open once");
+  c->peer_base = new void*[c->nranks];
+  for (int r = 0; r < c->nranks; r++) {
+    if (r == c->rank) { c->peer_base[r] = c->peer_local; continue; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, (const char*)handles + (size_t)r * 64, 64);
+    cudaError_t e = cudaIpcOpenMemHandle(&c->peer_base[r], h, cudaIpcMemLazyEnablePeerAccess);
+    B2_CHECK(e == cudaSuccess, "cudaIpcOpenMemHandle(rank %d): %s", r, cudaGetErrorString(e));
+  }
+  B2_TRY(b2_malloc(c, &c->d_peer_base, (size_t)c->nranks));
+  B2_TRY(b2_upload(c, c->d_peer_base, c->peer_base, (size_t)c->nranks));
+  B2_TRY(b2_malloc(c, &c->peer_counter, 1));
+  B2_TRY(b2_malloc(c, &c->peer_err, 1));
+  B2_CUDA(cudaMemsetAsync(c->peer_counter, 0, sizeof(unsigned int), c->stream));
+  B2_CUDA(cudaMemsetAsync(c->peer_err, 0, sizeof(int), c->stream));
+  B2_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+/* 1 when a wait of the peer-memory exchange timed out since the last call (a rank stopped taking part) */
+int b2_ctx_peer_error(b2_ctx* c, int* err) {
+  *err = 0;
+  if (!c->peer_err) return 0;
+  B2_TRY(b2_download(c, err, c->peer_err, 1));
   return 0;
 }
 
@@ -183,6 +237,14 @@ int b2_ctx_set_option(b2_ctx* c, const char* name, int value) {
   if (!strcmp(name, "spmv_variant")) {
     B2_CHECK(value >= 0 && value <= 2, "spmv_variant %d (0, 1, 2)", value);
     c->spmv_variant = value;
+    return 0;
+  }
+  if (!strcmp(name, "coarse_persistent")) {      // 1: coarse PCG loop in one cooperative kernel (default), 0: host-driven loop
+    c->coarse_persistent = value ? 1 : 0;
+    return 0;
+  }
+  if (!strcmp(name, "halo_peer")) {      // 1: interface sums through peer memory (default once set up), 0: packed ncclAllReduce
+    c->halo_peer = value ? 1 : 0;
     return 0;
   }
   if (!strcmp(name, "asm_warps")) {

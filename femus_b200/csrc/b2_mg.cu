@@ -51,6 +51,10 @@ struct b2_mg {
   unsigned int* dot_counter = nullptr;
 };
 
+int b2_cg_persistent(b2_ctx* c, const b2_csr* A, const double* dinv, const double* b, const uint8_t* owned, const b2_halo* halo,
+                     double* x, double* r, double* u, double* p, double* s, double* w, double* partial, int partial_blocks,
+                     double* out4, double rtol, int maxit, int* its, int* ran);      // b2_cg.cu
+
 namespace {
 
 constexpr int kBlock = 256;
@@ -395,6 +399,15 @@ int coarse_solve(b2_mg* mg) {
   double h[4];
   double bb = 0.0;
   mg->coarse_its = 0;
+  if (c->coarse_persistent) {      // the whole iteration loop in one cooperative kernel (b2_cg.cu)
+    int ran = 0, its = 0;
+    B2_TRY(b2_cg_persistent(c, L.A, L.dinv->d, L.b->d, own, L.halo, L.x->d, L.r->d, mg->z->d, mg->p->d, mg->q->d, mg->w->d, mg->dot_partial,
+                            kRedBlocks, sc, mg->coarse_rtol, mg->coarse_maxit, &its, &ran));
+    if (ran) {
+      mg->coarse_its = its;
+      return 0;
+    }
+  }
   const int check_every = 8;
   int bank = 0;
   for (int it = 0; it <= mg->coarse_maxit; it++) {

@@ -47,7 +47,7 @@ class PoissonMG:
     def __init__(self, ctx, nx, ny, nz, nlevels, order="biquadratic", bounds=None, npre=1, npost=1, omega=0.5,
                  dirichlet_faces=(1, 2, 3, 4, 5, 6), fsrc=1.0, coarse_rtol=1e-14, hier=None, dist=None, fused=True,
                  neumann=None, smoother="richardson", asm_block_elems=8, asm_schedule="colours",
-                 asm_sub="lu", ksp="richardson", asm_row_levels=False):
+                 asm_sub="lu", ksp="richardson", asm_row_levels=False, peer=True):
         self.ctx = ctx
         self.order = order
         self.fam = hostapi.FAMILY[order]
@@ -183,9 +183,20 @@ class PoissonMG:
         if dist is not None:
             rank, world, gather = dist
             for l in range(nlevels):
-                lay = distlayout.level_layout(lv[l], self.ndofs[l], rank, gather)
-                self.layout[l] = lay
+                self.layout[l] = distlayout.level_layout(lv[l], self.ndofs[l], rank, gather)
+            # interface sums through peer memory (NVLink / NVSwitch stores + flags) instead of a packed ncclAllReduce:
+            # one inbox block per rank, sized for the largest message of the run, opened by every rank (once per context)
+            if peer and getattr(ctx, "peer_slot", None) is None:
+                need = max([int(np.diff(lay.exchange[1]).max()) if lay.exchange[1].shape[0] > 1 else 0 for lay in self.layout])
+                ctx.peer_slot = max(max(gather(need)) + 8, 1 << 16)
+                ctx.peer_init(ctx.peer_slot, gather)
+            for l in range(nlevels):
+                lay = self.layout[l]
                 self.halo[l] = capi.Halo(ctx, lay.n_local, lay.idx, lay.pos, lay.n_packed, lay.owned, lay.mult)
+                if peer:
+                    if lay.exchange[1].shape[0] > 1 and int(np.diff(lay.exchange[1]).max()) + 8 > ctx.peer_slot:
+                        raise ValueError("the peer inbox of this context is too small for this mesh")
+                    self.halo[l].set_exchange(*lay.exchange)
                 self.mg.set_level_halo(l, self.halo[l])
             self.n_global = int(sum(gather(self.layout[-1].n_owned)))
             for v in (self.RES, self.EPS, self.SOL, self.RESM):

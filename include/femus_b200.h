@@ -136,6 +136,17 @@ int b2_vec_copy_masked(b2_vec* dst, const b2_vec* src, const b2_vec* mask, doubl
 int b2_halo_create(b2_ctx* c, int64_t n_local, int64_t n_if, const int32_t* local_idx, const int32_t* packed_pos,
                    int64_t n_packed, const uint8_t* owned, const uint8_t* mult, b2_halo** out);
 int b2_halo_destroy(b2_halo* h);
+/* Peer-memory form of the interface sum: remote stores into the sharing ranks' inboxes over NVLink / NVSwitch and a flag
+ * per rank instead of pack -> ncclAllReduce -> unpack (b2_halo.cu).  Setup: every rank exports its inbox block
+ * (b2_ctx_peer_export), the launcher all-gathers the 64-byte handles, every rank opens them (b2_ctx_peer_open), then each
+ * layout gets its per-peer send lists and per-entry holder lists (b2_halo_set_exchange; femus_b200/dist.py derives them
+ * from the gathered lattice keys).  Sums are taken in ascending rank order on every holder: all copies of a dof agree
+ * bit for bit, as after an allreduce.  Option "halo_peer" 0 keeps the NCCL form. */
+int b2_ctx_peer_export(b2_ctx* c, int64_t slot_doubles, void* handle64);
+int b2_ctx_peer_open(b2_ctx* c, const void* handles /* [nranks][64] */);
+int b2_ctx_peer_error(b2_ctx* c, int* err);
+int b2_halo_set_exchange(b2_halo* h, int nshare, const int32_t* share_rank, const int64_t* send_ptr, const int32_t* send_dof,
+                         const int64_t* hold_ptr, const int32_t* hold_rank, const int32_t* hold_pos);
 int64_t b2_halo_owned_count(const b2_halo* h);
 int64_t b2_halo_interface_count(const b2_halo* h);
 /* v[interface] <- sum over the ranks holding each dof (pack, ncclAllReduce over NVLink, unpack) */

@@ -21,6 +21,13 @@ void b2_set_error(const char* fmt, ...) {
 int b2_allreduce_op(b2_ctx*, double*, int64_t, int) { return 0; }
 int b2_allreduce_sum(b2_ctx*, double*, int64_t) { return 0; }
 int b2_halo_sum_scalars(b2_halo*, b2_vec*, double*, int) { return 0; }
+// the cooperative coarse-PCG kernel (b2_cg.cu) has no emulated form: the host-driven loop of b2_mg.cu runs instead
+int b2_cg_persistent(b2_ctx*, const b2_csr*, const double*, const double*, const uint8_t*, const b2_halo*, double*, double*, double*, double*,
+                     double*, double*, double*, int, double*, double, int, int* its, int* ran) {
+  *its = 0;
+  *ran = 0;
+  return 0;
+}
 int b2_csr_zero_cols_notowned(b2_csr*, const uint8_t*) { return 0; }
 int b2_csr_resid_w(const b2_csr* A, const double* b, const double* w, const double* x, double* r) {
   for (int64_t i = 0; i < A->nrows; i++) {

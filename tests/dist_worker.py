@@ -19,7 +19,7 @@ def init_gloo(rank, world, port):
     return dist
 
 
-def run_gpu_rank(rank, world, port, box, nlevels, order, ncycles, out_path):
+def run_gpu_rank(rank, world, port, box, nlevels, order, ncycles, out_path, peer=True):
     import torch
     dist = init_gloo(rank, world, port)
     from femus_b200 import capi
@@ -31,7 +31,7 @@ def run_gpu_rank(rank, world, port, box, nlevels, order, ncycles, out_path):
     dist.broadcast_object_list(uid, src=0)
     ctx.comm_init(world, rank, uid[0])
     gather = torch_allgather()
-    pb = PoissonMG(ctx, *box, nlevels, order, dist=(rank, world, gather), coarse_rtol=1e-15)
+    pb = PoissonMG(ctx, *box, nlevels, order, dist=(rank, world, gather), coarse_rtol=1e-15, peer=peer)
     pb.step()
     trace = [pb.residual_norm()]
     for _ in range(ncycles - 1):
@@ -47,6 +47,7 @@ def run_gpu_rank(rank, world, port, box, nlevels, order, ncycles, out_path):
         A = pb.KK[l].to_scipy().tocoo()
         k = pb.hier.levels[l].lattice_key(np.arange(pb.ndofs[l]))
         mats.append((k[A.row], k[A.col], A.data))
+    assert not ctx.peer_error(), "a wait of the peer-memory exchange timed out"
     allr = gather((keys, eps, trace, mats, pb.mg.coarse_iterations(), ctx.launches()))
     if rank == 0:
         np.save(out_path, np.array(allr, dtype=object), allow_pickle=True)

@@ -53,6 +53,69 @@ def test_layout_ownership_matches_reference_offsets(order):
         assert np.all(claims == 2) and np.all(owners == 1)
 
 
+def _synthetic_layouts(P, n_local, seed):
+    """Ranks holding random subsets of a common key space (up to 4 holders per key): the exchange lists do not assume slabs."""
+    rng = np.random.default_rng(seed)
+    nkeys = 40
+    holders = [rng.choice(P, size=rng.integers(2, min(P, 4) + 1), replace=False) for _ in range(nkeys)]
+    nodes, keys = [], []
+    for r in range(P):
+        k = np.array([K for K in range(nkeys) if r in holders[K]], dtype=np.int64)
+        k = k[rng.permutation(k.shape[0])]                 # every rank lists its interface entries in its own order
+        keys.append(k * 7 + 3)
+        nodes.append(rng.choice(n_local, size=k.shape[0], replace=False).astype(np.int64))
+    return nodes, keys
+
+
+@pytest.mark.parametrize("case", ["slabs", "synthetic"])
+def test_peer_exchange_lists_reproduce_the_packed_interface_sum(case):
+    """b2_halo_set_exchange's inputs (femus_b200.dist.exchange_lists): emulate the messages rank by rank and sum every
+    interface entry over its holders in ascending rank order -- the result must be the packed all-reduce's, and equal
+    on all holders of a dof bit for bit."""
+    if case == "slabs":
+        box, nl, P, order = (2, 2, 4), 2, 4, "biquadratic"
+        H = [hostapi.HostHierarchy(*box, nl, nprocs=P, local_rank=r) for r in range(P)]
+        l = nl - 1
+        nd = [H[r].levels[l].ndofs(order) for r in range(P)]
+        nodes = [H[r].levels[l].interface_nodes() for r in range(P)]
+        nodes = [nodes[r][nodes[r] < nd[r]] for r in range(P)]
+        keys = [H[r].levels[l].lattice_key(nodes[r]) for r in range(P)]
+    else:
+        P = 5
+        nd = [60] * P
+        nodes, keys = _synthetic_layouts(P, 60, 3)
+    ex = [distlayout.exchange_lists(nodes[r], keys, r) for r in range(P)]
+    rng = np.random.default_rng(1)
+    v = [rng.standard_normal(nd[r]) for r in range(P)]
+    # messages: sender -> receiver -> values
+    msg = [{} for _ in range(P)]
+    for r in range(P):
+        share, sptr, sdof = ex[r][0], ex[r][1], ex[r][2]
+        for s, q in enumerate(share):
+            msg[q][r] = v[r][sdof[sptr[s]:sptr[s + 1]]]
+        assert sorted(share) == list(share) and r not in share
+    # reference: sum over holders through the union of keys
+    union = np.unique(np.concatenate(keys))
+    total = np.zeros(union.shape[0])
+    for r in range(P):
+        np.add.at(total, np.searchsorted(union, keys[r]), v[r][nodes[r]])
+    got_by_key = {}
+    for r in range(P):
+        hptr, hrank, hpos = ex[r][3], ex[r][4], ex[r][5]
+        assert hptr.shape[0] == nodes[r].shape[0] + 1
+        for k in range(nodes[r].shape[0]):
+            hs = hrank[hptr[k]:hptr[k + 1]]
+            assert np.all(np.diff(hs) > 0) and r in hs                       # ascending, this rank included
+            s = None
+            for q, pos in zip(hs, hpos[hptr[k]:hptr[k + 1]]):
+                a = v[r][nodes[r][k]] if q == r else msg[r][q][pos]
+                s = a if s is None else s + a
+            K = int(keys[r][k])
+            assert abs(s - total[np.searchsorted(union, K)]) <= 1e-14 * max(1.0, abs(s))
+            assert got_by_key.setdefault(K, s) == s                           # bit-identical on every holder
+    assert len(got_by_key) == union.shape[0]
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))

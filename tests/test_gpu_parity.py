@@ -550,6 +550,33 @@ def test_vcycle_residual_trace(ctx, order, shape, nl):
     assert np.abs(eps.get() - eps_ref).max() <= 1e-11 * np.abs(eps_ref).max()
 
 
+@pytest.mark.parametrize("order,n0", [("biquadratic", 3), ("linear", 12)])
+def test_coarse_pcg_persistent_kernel_equals_the_host_driven_loop(ctx, order, n0):
+    """The coarse Jacobi-PCG as one cooperative kernel (b2_cg.cu: grid-wide barriers between the phases of an iteration)
+    against the host-driven loop of five launches per iteration (option coarse_persistent = 0): same solution to
+    round-off, a residual at the tolerance, run-to-run bit-identical, and the V-cycle traces of both against the oracle."""
+    from femus_b200.poisson import PoissonMG
+    pb = PoissonMG(ctx, n0, n0, n0, 2, order, coarse_rtol=1e-14)
+    pb.assemble(); pb.galerkin(); pb.mg_set_levels()
+    res0 = pb.RES.get()              # (the assembly sums with atomics: the SAME assembled system goes through every mode)
+    sols, its = [], []
+    for mode in (1, 1, 0):
+        ctx.set_option("coarse_persistent", mode)
+        pb.RES.put(res0)
+        pb.EPS.zero()
+        pb.mg_solve()
+        sols.append(pb.EPS.get())
+        its.append(pb.mg.coarse_iterations())
+    ctx.set_option("coarse_persistent", 1)
+    assert np.array_equal(sols[0], sols[1])                                    # deterministic reductions
+    assert np.abs(sols[0] - sols[2]).max() <= 1e-12 * np.abs(sols[2]).max()
+    assert its[0] >= 5 and its[2] - 8 <= its[0] <= its[2]                        # the host loop looks at the residual every 8th iteration
+    lv = mb.build_hierarchy(n0, n0, n0, 2)
+    H = mg.Hierarchy(lv, order)
+    trace_ref, eps_ref = H.mg_solve_trace(1)
+    assert np.abs(sols[0] - eps_ref).max() <= 1e-11 * np.abs(eps_ref).max()
+
+
 def test_single_level_is_a_direct_solve(ctx):
     """BASELINE config 1 (1 level): MGSolve degenerates to the coarse solver (reference: LU)."""
     lv = mb.build_hierarchy(4, 4, 4, 1)

@@ -1,5 +1,5 @@
-"""Multi-GPU parity: the z-slab sharded run (one rank per GPU, partial matrices, interface sums by
-ncclAllReduce inside the library) against the serial CPU oracle on the same mesh.  Needs >= 2 GPUs."""
+"""Multi-GPU parity: the z-slab sharded run (one rank per GPU, partial matrices, interface sums through peer memory
+over NVLink, or by ncclAllReduce, inside the library) against the serial CPU oracle on the same mesh.  Needs >= 2 GPUs."""
 import os
 import socket
 import tempfile
@@ -23,9 +23,10 @@ def ngpus():
     return torch.cuda.device_count()
 
 
+@pytest.mark.parametrize("peer", [True, False], ids=["peer_memory", "nccl_allreduce"])
 @pytest.mark.parametrize("order,box,nl,world", [("biquadratic", (2, 2, 4), 3, 2), ("linear", (2, 3, 4), 3, 2),
                                                  ("biquadratic", (2, 2, 4), 2, 4)])
-def test_sharded_vcycle_matches_serial_oracle(order, box, nl, world):
+def test_sharded_vcycle_matches_serial_oracle(order, box, nl, world, peer):
     if ngpus() < world:
         pytest.skip(f"needs {world} GPUs")
     import torch.multiprocessing as mp
@@ -36,7 +37,7 @@ def test_sharded_vcycle_matches_serial_oracle(order, box, nl, world):
     ncyc = 4
     with tempfile.TemporaryDirectory() as td:
         out = os.path.join(td, "res.npy")
-        mp.spawn(dist_worker.run_gpu_rank, args=(world, free_port(), box, nl, order, ncyc, out), nprocs=world, join=True)
+        mp.spawn(dist_worker.run_gpu_rank, args=(world, free_port(), box, nl, order, ncyc, out, peer), nprocs=world, join=True)
         res = np.load(out, allow_pickle=True)
     # serial oracle; global dof <-> lattice key through the host layer (bit-identical numbering)
     lv = mb.build_hierarchy(*box, nl)
