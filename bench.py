@@ -368,6 +368,14 @@ def main():
                 kernel_ms.setdefault("assembly", []).append(msk / max(nk, 1))
         phases[name] = float(np.median(ts))
     asm_kernel_ms = float(np.median(kernel_ms["assembly"]))
+    # V-cycle by level and phase (events around every phase; one extra cycle)
+    pb.mg.set_timing(True)
+    pb.mg_solve()
+    tv = pb.mg.get_timing(args.levels)
+    pb.mg.set_timing(False)
+    vcycle_phases = {f"level{l}": {k: round(float(tv[l][j]), 4) for j, k in enumerate(("pre_smooth", "residual", "restrict", "coarse_solve",
+                                                                                  "prolong", "post_smooth")) if tv[l][j] > 0}
+                     for l in range(args.levels)}
     if world > 1 and args.halo == "peer":      # the same V-cycle with the interface sums as a packed ncclAllReduce, for comparison
         ctx.set_option("halo_peer", 0)
         ts = []
@@ -475,7 +483,7 @@ def main():
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "roofline_spmv": roofline_spmv,
             "assembly_elem_dof_per_s": nel * nve / (phases["assembly"] * 1e-3),
-            "spmv_gbs": ach, "phases_ms": phases, "finest_dofs": n, "finest_nnz": Afine.nnz, "elements": nel,
+            "spmv_gbs": ach, "phases_ms": phases, "vcycle_phases_ms": vcycle_phases, "finest_dofs": n, "finest_nnz": Afine.nnz, "elements": nel,
             "setup_s": t_setup, "residual_trace": trace, "coarse_pcg_iterations": pb.mg.coarse_iterations(),
             "device_bytes": ctx.bytes_in_use(), "dofs_per_rank": n_loc}
     if world > 1:

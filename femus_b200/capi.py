@@ -72,10 +72,12 @@ _PROTOS = {
     "b2_vec_sum": (ci, [vp, vp]),
     "b2_vec_minmax": (ci, [vp, vp, vp]),
     "b2_vec_abs": (ci, [vp]),
+    "b2_mg_set_timing": (ci, [vp, ci]),
+    "b2_mg_get_timing": (ci, [vp, vp]),
     "b2_ctx_peer_export": (ci, [vp, i64, vp]),
     "b2_ctx_peer_open": (ci, [vp, vp]),
     "b2_ctx_peer_error": (ci, [vp, vp]),
-    "b2_halo_set_exchange": (ci, [vp, ci, vp, vp, vp, vp, vp, vp]),
+    "b2_halo_set_exchange": (ci, [vp, vp, vp, vp, vp]),
     "b2_csr_matmat": (ci, [vp, vp, vp]),
     "b2_csr_axpy": (ci, [vp, cd, vp]),
     "b2_csr_pattern_contains": (ci, [vp, vp, vp]),
@@ -227,10 +229,10 @@ class Context:
         buf = (ctypes.c_char * 128).from_buffer_copy(uid_bytes)
         check(self.L.b2_ctx_comm_init(self.h, nranks, rank, buf))
 
-    def peer_init(self, slot_doubles, allgather):
+    def peer_init(self, slot_cells, allgather):
         """Peer-memory exchange over NVLink: export this rank's inbox, gather the IPC handles, open every rank's."""
         buf = (ctypes.c_char * 64)()
-        check(self.L.b2_ctx_peer_export(self.h, int(slot_doubles), buf))
+        check(self.L.b2_ctx_peer_export(self.h, int(slot_cells), buf))
         handles = b"".join(allgather(bytes(buf)))
         check(self.L.b2_ctx_peer_open(self.h, (ctypes.c_char * len(handles)).from_buffer_copy(handles)))
 
@@ -574,11 +576,10 @@ class Halo:
     def sum(self, v):
         check(self.L.b2_halo_sum(self.h, v.h))
 
-    def set_exchange(self, share_rank, send_ptr, send_dof, hold_ptr, hold_rank, hold_pos):
-        share_rank, send_dof, hold_rank, hold_pos = _i32(share_rank), _i32(send_dof), _i32(hold_rank), _i32(hold_pos)
-        send_ptr, hold_ptr = np.ascontiguousarray(send_ptr, dtype=np.int64), np.ascontiguousarray(hold_ptr, dtype=np.int64)
-        check(self.L.b2_halo_set_exchange(self.h, share_rank.shape[0], _ptr(share_rank), _ptr(send_ptr), _ptr(send_dof), _ptr(hold_ptr),
-                                          _ptr(hold_rank), _ptr(hold_pos)))
+    def set_exchange(self, hold_ptr, hold_rank, hold_pos, hold_spos):
+        hold_rank, hold_pos, hold_spos = _i32(hold_rank), _i32(hold_pos), _i32(hold_spos)
+        hold_ptr = np.ascontiguousarray(hold_ptr, dtype=np.int64)
+        check(self.L.b2_halo_set_exchange(self.h, _ptr(hold_ptr), _ptr(hold_rank), _ptr(hold_pos), _ptr(hold_spos)))
 
     def owned_count(self):
         return int(self.L.b2_halo_owned_count(self.h))
@@ -798,6 +799,7 @@ class Multigrid:
         h = vp()
         check(self.L.b2_mg_create(ctx.h, nlevels, ctypes.byref(h)))
         self.h = h
+        self.nlevels = nlevels
         self._keep = []
 
     def __del__(self):
@@ -851,3 +853,13 @@ class Multigrid:
 
     def coarse_iterations(self):
         return int(self.L.b2_mg_coarse_iterations(self.h))
+
+    def set_timing(self, on=True):
+        check(self.L.b2_mg_set_timing(self.h, 1 if on else 0))
+
+    def get_timing(self, nlevels):
+        """ms[level][phase] since the last call; phases: pre-smoothing, residual, restriction, coarse solve, prolongation,
+        post-smoothing (b2_mg_get_timing)."""
+        out = np.zeros((nlevels, 6))
+        check(self.L.b2_mg_get_timing(self.h, _ptr(out)))
+        return out

@@ -4,8 +4,8 @@
 // interface sum, update) on a problem of 10^4 - 10^5 dofs: ~25 us per iteration of pure launch latency on one GPU,
 // ~45 us with the interface exchange, 80 - 150 iterations per V-cycle.  Here the whole iteration -- CSR product, the
 // three dot products, the interface sum with the other ranks through peer memory, the vector update and the
-// convergence test -- runs inside one kernel; iterations are separated by grid-wide barriers (2 on one rank, 4 with
-// the exchange), the scalars never leave the chip.
+// convergence test -- runs inside one kernel; iterations are separated by grid-wide barriers (2 on one rank, 3 with
+// the exchange, which itself needs none), the scalars never leave the chip.
 //
 // Same recurrence as the host loop (single-reduction Chronopoulos-Gear PCG, b2_mg.cu): w = A u; gamma = (r,u),
 // delta = (w,u), rr = (r,r) in one reduction; beta = gamma / gamma_old; alpha = gamma / (delta - beta gamma / alpha_old);
@@ -14,14 +14,13 @@
 // equal on all ranks.  The convergence test runs every iteration (the host loop looks every 8th).
 #include <cooperative_groups.h>
 #include "b2_common.cuh"
+#include "b2_peer.cuh"
 
 namespace cg = cooperative_groups;
 
 namespace {
 
-constexpr int kCgBlock = 256;
-constexpr int kFlagBytes = 4096;      // layout of a rank's peer block: b2_halo.cu
-constexpr int kPeerScal = 8;
+constexpr int kCgBlock = 1024;     // few, large blocks: the grid-wide barrier costs per block, the product wants every thread slot of the SM
 
 struct CgArgs {
   int64_t n;
@@ -33,52 +32,64 @@ struct CgArgs {
   const uint8_t* owned;       // null: every entry is owned
   double *x, *r, *u, *p, *s, *w;
   double* partial;            // [gridDim][4]
-  double* out;                // [4]: iterations, rr, bb, abort flag
+  double* out;                // [4]: iterations, rr, bb
+  double* trace;              // null, or [5]: cycles of the phases of iteration 5 seen by thread 0 (product, barrier, totals / exchange, update, barrier)
   double rtol2;
   int maxit;
   // interface exchange (nranks == 1: none)
   int nranks, me;
-  void* const* bases;         // device array [nranks]: every rank's peer block
-  void* base;                 // this rank's block
+  void* const* bases;         // device array [nranks]: every rank's inbox
+  void* base;                 // this rank's inbox
   int64_t slot;
   unsigned long long epoch0;  // exchanges done before this solve
-  int nshare;
-  const int32_t* share_rank;
-  const int64_t* send_ptr;
-  const int32_t* send_dof;
   int64_t n_if;
   const int32_t* idx;
   const int64_t* hold_ptr;
   const int32_t* hold_rank;
   const int32_t* hold_pos;
+  const int32_t* hold_spos;
+  int* err;
 };
 
-__device__ __forceinline__ double* slot_ptr(void* base, int64_t slot, int nranks, int parity, int sender) {
-  return reinterpret_cast<double*>(reinterpret_cast<char*>(base) + kFlagBytes) + ((int64_t)parity * nranks + sender) * slot;
-}
-
-__global__ void __launch_bounds__(kCgBlock) cg_persistent_kernel(const CgArgs a) {
+__global__ void __launch_bounds__(kCgBlock, 1) cg_persistent_kernel(const CgArgs a) {
   cg::grid_group grid = cg::this_grid();
   __shared__ double sh[kCgBlock / 32][4];
   __shared__ double tot[4];
   __shared__ int s_abort;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, gthreads = (int64_t)gridDim.x * blockDim.x;
-  const int sub = lane & 7;                                   // 8 lanes per row
-  const int64_t grow = gtid >> 3, nrows_step = gthreads >> 3;
+  const int sub = lane & 3;                                   // 4 lanes per row
+  const int64_t grow = gtid >> 2, nrows_step = gthreads >> 2;
   double gamma_old = 0.0, alpha_old = 0.0, bb = 0.0;
   int it = 0;
   int aborted = 0;
   for (;; it++) {
     // ---- w = A u on this rank's rows; partial sums of (r,u) | owned, (w,u) | all, (r,r) | owned (, (b,b) | owned)
+    long long tk[6];
+    const bool tr = a.trace && it == 5 && gtid == 0;
+    if (tr) tk[0] = clock64();
     double acc[4] = {0., 0., 0., 0.};
-    // (the four rows of a warp leave the loop together: the shuffles below name all 32 lanes)
-    for (int64_t i0 = grow - (lane >> 3); i0 < a.n; i0 += nrows_step) {
-      const int64_t i = i0 + (lane >> 3);
+    // (the eight rows of a warp leave the loop together: the shuffles below name all 32 lanes)
+    for (int64_t i0 = grow - (lane >> 2); i0 < a.n; i0 += nrows_step) {
+      const int64_t i = i0 + (lane >> 2);
       double t = 0.0;
-      if (i < a.n)
-        for (int64_t q = a.rowptr[i] + sub; q < a.rowptr[i + 1]; q += 8) t = fma(a.val[q], a.u[a.col[q]], t);
-      t += __shfl_xor_sync(0xffffffffu, t, 4);
+      if (i < a.n) {
+        // latency-bound (a few 10^4 rows, everything in L2): eight independent (value, column) loads and eight gathers
+        // in flight per lane instead of one dependent chain
+        const int64_t q1 = a.rowptr[i + 1];
+        int64_t q = a.rowptr[i] + sub;
+        for (; q + 28 < q1; q += 32) {
+          int32_t cc[8];
+          double vv[8], uu[8];
+#pragma unroll
+          for (int k = 0; k < 8; k++) { cc[k] = a.col[q + 4 * k]; vv[k] = a.val[q + 4 * k]; }
+#pragma unroll
+          for (int k = 0; k < 8; k++) uu[k] = a.u[cc[k]];
+#pragma unroll
+          for (int k = 0; k < 8; k++) t = fma(vv[k], uu[k], t);
+        }
+        for (; q < q1; q += 4) t = fma(a.val[q], a.u[a.col[q]], t);
+      }
       t += __shfl_xor_sync(0xffffffffu, t, 2);
       t += __shfl_xor_sync(0xffffffffu, t, 1);
       if (sub == 0 && i < a.n) {
@@ -105,7 +116,9 @@ __global__ void __launch_bounds__(kCgBlock) cg_persistent_kernel(const CgArgs a)
       for (int ww = 0; ww < kCgBlock / 32; ww++) t += sh[ww][threadIdx.x];
       a.partial[4 * blockIdx.x + threadIdx.x] = t;
     }
+    if (tr) tk[1] = clock64();
     grid.sync();
+    if (tr) tk[2] = clock64();
     // ---- this rank's totals: every block sums the partials of all blocks in the same order
     if (wib == 0) {
       double t[4] = {0., 0., 0., 0.};
@@ -120,58 +133,47 @@ __global__ void __launch_bounds__(kCgBlock) cg_persistent_kernel(const CgArgs a)
     }
     __syncthreads();
     if (a.nranks > 1) {
-      // ---- interface sum of w and global sums of the scalars through peer memory (see b2_halo.cu)
+      // ---- interface sum of w and global sums of the scalars through peer memory (cells and protocol: b2_halo.cu): the
+      // thread that owns an interface entry sends its value to the other holders, waits for theirs, sums in rank order
       const unsigned long long epoch = a.epoch0 + (unsigned long long)it + 1ull;
       const int parity = (int)(epoch & 1ull);
-      for (int sidx = 0; sidx < a.nshare; sidx++) {
-        double* dst = slot_ptr(a.bases[a.share_rank[sidx]], a.slot, a.nranks, parity, a.me) + kPeerScal;
-        const int64_t s0 = a.send_ptr[sidx], s1 = a.send_ptr[sidx + 1];
-        for (int64_t k = s0 + gtid; k < s1; k += gthreads) dst[k - s0] = a.w[a.send_dof[k]];
-      }
+      const unsigned flag = b2_peer_flag(epoch);
       if (blockIdx.x == 0 && threadIdx.x < 4)
-        for (int r = 0; r < a.nranks; r++) slot_ptr(a.bases[r], a.slot, a.nranks, parity, a.me)[threadIdx.x] = tot[threadIdx.x];
-      __threadfence_system();
-      grid.sync();
-      if (blockIdx.x == 0 && threadIdx.x < a.nranks) {
-        __threadfence_system();
-        reinterpret_cast<volatile unsigned long long*>(a.bases[threadIdx.x])[a.me] = epoch;
+        for (int r = 0; r < a.nranks; r++)
+          if (r != a.me) b2_peer_store(b2_peer_cell(a.bases[r], a.slot, a.nranks, parity, a.me, threadIdx.x), tot[threadIdx.x], flag);
+      for (int64_t k = gtid; k < a.n_if; k += gthreads) {
+        const int32_t d = a.idx[k];
+        const double own = a.w[d];
+        const int64_t h0 = a.hold_ptr[k], h1 = a.hold_ptr[k + 1];
+        for (int64_t q = h0; q < h1; q++)
+          if (a.hold_rank[q] != a.me)
+            b2_peer_store(b2_peer_cell(a.bases[a.hold_rank[q]], a.slot, a.nranks, parity, a.me, kPeerScal + a.hold_spos[q]), own, flag);
+        double t = 0.0;
+        for (int64_t q = h0; q < h1; q++) {
+          const int r = a.hold_rank[q];
+          const double v = r == a.me ? own : b2_peer_wait(b2_peer_cell(a.base, a.slot, a.nranks, parity, r, kPeerScal + a.hold_pos[q]), flag, a.err);
+          t = q == h0 ? v : t + v;
+        }
+        a.w[d] = t;
       }
-      if (threadIdx.x == 0) {
-        volatile unsigned long long* flags = reinterpret_cast<volatile unsigned long long*>(a.base);
-        const long long t_start = clock64();
-        int bad = 0;
-        for (int r = 0; r < a.nranks && !bad; r++)
-          while (flags[r] < epoch)
-            if (clock64() - t_start > 20000000000ll) { bad = 1; break; }       // ~10 s: a rank stopped taking part
-        if (bad) a.out[3] = 1.0;
-        __threadfence_system();
-      }
-      __syncthreads();
+      __syncthreads();      // (block 0: the local totals were read for sending before they are replaced)
       if (threadIdx.x < 4) {
+        const double mine = tot[threadIdx.x];
         double t = 0.0;
         for (int r = 0; r < a.nranks; r++) {
-          const double v = __ldcv(slot_ptr(a.base, a.slot, a.nranks, parity, r) + threadIdx.x);
+          const double v = r == a.me ? mine : b2_peer_wait(b2_peer_cell(a.base, a.slot, a.nranks, parity, r, threadIdx.x), flag, a.err);
           t = r == 0 ? v : t + v;
         }
         tot[threadIdx.x] = t;
       }
-      for (int64_t k = gtid; k < a.n_if; k += gthreads) {
-        const int32_t d = a.idx[k];
-        double t = 0.0;
-        for (int64_t q = a.hold_ptr[k]; q < a.hold_ptr[k + 1]; q++) {
-          const int r = a.hold_rank[q];
-          const double v = r == a.me ? a.w[d] : __ldcv(slot_ptr(a.base, a.slot, a.nranks, parity, r) + kPeerScal + a.hold_pos[q]);
-          t = q == a.hold_ptr[k] ? v : t + v;
-        }
-        a.w[d] = t;
-      }
       grid.sync();
-      if (threadIdx.x == 0) s_abort = __ldcg(&a.out[3]) != 0.0;
+      if (threadIdx.x == 0) s_abort = *reinterpret_cast<volatile int*>(a.err) != 0;
       __syncthreads();
       aborted = s_abort;
     } else {
       __syncthreads();
     }
+    if (tr) tk[3] = clock64();
     const double gn = tot[0], delta = tot[1], rr = tot[2];
     if (it == 0) bb = tot[3];
     if (aborted || bb == 0.0 || !(rr > a.rtol2 * bb) || it == a.maxit) {
@@ -203,7 +205,12 @@ __global__ void __launch_bounds__(kCgBlock) cg_persistent_kernel(const CgArgs a)
       a.r[i] = ri;
       a.u[i] = a.dinv[i] * ri;
     }
+    if (tr) tk[4] = clock64();
     grid.sync();
+    if (tr) {
+      tk[5] = clock64();
+      for (int k = 0; k < 5; k++) a.trace[k] = (double)(tk[k + 1] - tk[k]);
+    }
   }
 }
 
@@ -224,9 +231,8 @@ int b2_cg_persistent(b2_ctx* c, const b2_csr* A, const double* dinv, const doubl
   int per_sm = 0;
   B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cg_persistent_kernel, kCgBlock, 0));
   if (per_sm < 1) return 0;
-  if (per_sm > 2) per_sm = 2;
   int grid = c->sm_count * per_sm;
-  const int64_t want = (A->nrows * 8 + kCgBlock - 1) / kCgBlock;      // 8 lanes per row
+  const int64_t want = (A->nrows * 4 + kCgBlock - 1) / kCgBlock;      // 4 lanes per row
   if (grid > want) grid = (int)(want > 0 ? want : 1);
   if (grid > partial_blocks) grid = partial_blocks;
   CgArgs a = {};
@@ -240,6 +246,7 @@ int b2_cg_persistent(b2_ctx* c, const b2_csr* A, const double* dinv, const doubl
   a.x = x; a.r = r; a.u = u; a.p = p; a.s = s; a.w = w;
   a.partial = partial;
   a.out = out4;
+  a.trace = getenv("B2_CG_TRACE") ? out4 + 8 : nullptr;
   a.rtol2 = rtol * rtol;
   a.maxit = maxit;
   a.nranks = c->nranks;
@@ -249,15 +256,13 @@ int b2_cg_persistent(b2_ctx* c, const b2_csr* A, const double* dinv, const doubl
     a.base = c->peer_local;
     a.slot = c->peer_slot;
     a.epoch0 = c->peer_epoch;
-    a.nshare = halo->nshare;
-    a.share_rank = halo->share_rank;
-    a.send_ptr = halo->send_ptr;
-    a.send_dof = halo->send_dof;
     a.n_if = halo->n_if;
     a.idx = halo->idx;
     a.hold_ptr = halo->hold_ptr;
     a.hold_rank = halo->hold_rank;
     a.hold_pos = halo->hold_pos;
+    a.hold_spos = halo->hold_spos;
+    a.err = c->peer_err;
   }
   B2_CUDA(cudaMemsetAsync(out4, 0, 4 * sizeof(double), c->stream));
   void* params[] = {(void*)&a};
@@ -266,8 +271,18 @@ int b2_cg_persistent(b2_ctx* c, const b2_csr* A, const double* dinv, const doubl
   double h[4];
   B2_TRY(b2_download(c, h, out4, 4));      // synchronises: the exchange counter of the host must follow the kernel's
   *its = (int)h[0];
+  if (a.trace) {
+    double t[5];
+    B2_TRY(b2_download(c, t, a.trace, 5));
+    fprintf(stderr, "b2_cg_persistent: n %lld nnz %lld grid %d x %d, %d iterations; cycles of iteration 5: product %.0f barrier %.0f totals/exchange %.0f update %.0f barrier %.0f\n",
+            (long long)A->nrows, (long long)A->nnz, grid, kCgBlock, *its, t[0], t[1], t[2], t[3], t[4]);
+  }
   if (c->nranks > 1) c->peer_epoch += (unsigned long long)*its + 1ull;
-  B2_CHECK(h[3] == 0.0, "coarse PCG: a wait of the peer-memory exchange timed out (a rank stopped taking part)");
+  if (c->nranks > 1) {
+    int perr = 0;
+    B2_TRY(b2_download(c, &perr, c->peer_err, 1));
+    B2_CHECK(!perr, "coarse PCG: a wait of the peer-memory exchange timed out (a rank stopped taking part)");
+  }
   *ran = 1;
   return 0;
 }

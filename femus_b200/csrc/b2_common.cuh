@@ -73,15 +73,14 @@ struct b2_ctx {
   // multi-GPU
   int nranks = 1, rank = 0;
   void* nccl_comm = nullptr;
-  // peer-memory exchange over NVLink / NVSwitch (b2_halo.cu): one block of device memory per rank, opened by every
-  // other rank of the node through CUDA IPC.  Layout: [flags: nranks x 8 B, padded to 4 KiB][inbox: 2 (parity) x
-  // nranks (sender) x peer_slot doubles].  peer_base[r] = rank r's block as seen from this process (own: local pointer).
+  // peer-memory exchange over NVLink / NVSwitch (b2_halo.cu): one inbox per rank, opened by every other rank of the node
+  // through CUDA IPC.  Layout: 2 (parity of the exchange number) x nranks (sender) x peer_slot cells of 16 bytes
+  // {low word, flag, high word, flag}; peer_base[r] = rank r's inbox as seen from this process (own: local pointer).
   void* peer_local = nullptr;
   void** peer_base = nullptr;           // host array [nranks]
   void** d_peer_base = nullptr;         // the same on the device
-  int64_t peer_slot = 0;                // doubles per (parity, sender) slot: 8 scalars + interface values
+  int64_t peer_slot = 0;                // cells per (parity, sender): 8 scalars + interface values
   unsigned long long peer_epoch = 0;    // exchanges done so far (identical on every rank: SPMD call sequence)
-  unsigned int* peer_counter = nullptr; // last-block-done counter of the push kernel
   int* peer_err = nullptr;              // device: set when a wait timed out
   int coarse_persistent = 1;            // 1: iteration loop of the coarse PCG as one cooperative kernel (b2_cg.cu), 0: host-driven loop
   int halo_peer = 1;                    // 1: interface sums through the peer-memory exchange when it is set up; 0: packed ncclAllReduce
@@ -126,16 +125,13 @@ struct b2_halo {
   uint8_t* owned;      // [n_local] 1 if this rank owns the dof
   double* invmult;     // [n_local] 1 / (number of ranks holding the dof)
   int64_t n_owned;
-  // peer-memory exchange (b2_halo_set_exchange): what goes to every rank sharing dofs with this one, and for every
-  // interface entry its holders in ascending rank order (the sum is taken in that order on every holder)
-  int nshare = 0;
-  int32_t* share_rank = nullptr;   // [nshare] (device)
-  int64_t* send_ptr = nullptr;     // [nshare+1]
-  int32_t* send_dof = nullptr;     // [send_ptr[nshare]] local dofs in the order the receiver expects
-  int64_t n_send = 0;
+  // peer-memory exchange (b2_halo_set_exchange): for every interface entry its holders in ascending rank order (the sum
+  // is taken in that order on every holder), where each holder's value arrives in this rank's inbox and where this
+  // rank's value goes in the holder's
   int64_t* hold_ptr = nullptr;     // [n_if+1]
   int32_t* hold_rank = nullptr;    // [hold_ptr[n_if]] holder ranks, ascending, this rank included
-  int32_t* hold_pos = nullptr;     // position of the value in that holder's message to this rank (unused for this rank)
+  int32_t* hold_pos = nullptr;     // cell of the holder's value in its message to this rank (unused for this rank)
+  int32_t* hold_spos = nullptr;    // cell of this rank's value in its message to the holder
   int64_t n_hold = 0;
 };
 

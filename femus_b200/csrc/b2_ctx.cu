@@ -105,7 +105,6 @@ int b2_ctx_destroy(b2_ctx* c) {
       if (r != c->rank && c->peer_base[r]) cudaIpcCloseMemHandle(c->peer_base[r]);
     delete[] c->peer_base;
     b2_free(c, c->d_peer_base, (size_t)c->nranks);
-    b2_free(c, c->peer_counter, 1);
     b2_free(c, c->peer_err, 1);
   }
   if (c->peer_local) cudaFree(c->peer_local);
@@ -126,14 +125,15 @@ int b2_ctx_destroy(b2_ctx* c) {
   return 0;
 }
 
-/* Peer-memory exchange, step 1: allocate this rank's block (flags + double-buffered inbox with `slot_doubles` doubles per
- * sender) and export its CUDA IPC handle (64 bytes) for the launcher to all-gather. */
-int b2_ctx_peer_export(b2_ctx* c, int64_t slot_doubles, void* handle64) {
-  B2_CHECK(c && handle64 && slot_doubles >= 8, "b2_ctx_peer_export: bad arguments");
+/* Peer-memory exchange, step 1: allocate this rank's inbox (double buffered, `slot_cells` 16-byte cells per sender: 8
+ * for scalars + the longest message) and export its CUDA IPC handle (64 bytes) for the launcher to all-gather. */
+int b2_ctx_peer_export(b2_ctx* c, int64_t slot_cells, void* handle64) {
+  const int64_t slot_doubles = slot_cells;
+  B2_CHECK(c && handle64 && slot_cells >= 8, "b2_ctx_peer_export: bad arguments");
   B2_CHECK(c->nranks > 1, "b2_ctx_peer_export: communicator not initialised (b2_ctx_comm_init first)");
   B2_CHECK(!c->peer_local, "b2_ctx_peer_export: already exported");
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
-  const size_t bytes = 4096 + (size_t)2 * c->nranks * (size_t)slot_doubles * sizeof(double);
+  const size_t bytes = (size_t)2 * c->nranks * (size_t)slot_doubles * 16;
   B2_CUDA(cudaMalloc(&c->peer_local, bytes));
   c->bytes += (int64_t)bytes;
   B2_CUDA(cudaMemset(c->peer_local, 0, bytes));
@@ -156,9 +156,7 @@ int b2_ctx_peer_open(b2_ctx* c, const void* handles) {
   }
   B2_TRY(b2_malloc(c, &c->d_peer_base, (size_t)c->nranks));
   B2_TRY(b2_upload(c, c->d_peer_base, c->peer_base, (size_t)c->nranks));
-  B2_TRY(b2_malloc(c, &c->peer_counter, 1));
   B2_TRY(b2_malloc(c, &c->peer_err, 1));
-  B2_CUDA(cudaMemsetAsync(c->peer_counter, 0, sizeof(unsigned int), c->stream));
   B2_CUDA(cudaMemsetAsync(c->peer_err, 0, sizeof(int), c->stream));
   B2_CUDA(cudaStreamSynchronize(c->stream));
   return 0;

@@ -13,6 +13,7 @@
 // send buffer that is zero elsewhere, one ncclAllReduce(sum) over NVLink/NVSwitch completes them,
 // and the rank reads back its own positions.
 #include "b2_common.cuh"
+#include "b2_peer.cuh"
 
 namespace {
 constexpr int kBlock = 256;
@@ -50,81 +51,46 @@ __global__ void halo_invmult_kernel(int64_t n, const uint8_t* __restrict__ mult,
 }
 
 // ---- peer-memory exchange ------------------------------------------------------------------------------------
-// One interface sum = two kernels on the library stream, no NCCL call:
-//   push: this rank's values go straight into the inboxes of the ranks that share them (remote stores over NVLink),
-//         its scalars into the inbox of every rank; after a system-scope fence the LAST block to finish raises this
-//         rank's flag (= the exchange number) in every rank's memory;
-//   pull: waits until every rank's flag has reached the exchange number, then forms every interface entry as the sum
-//         over its holders in ascending rank order (own value read in place) -- all holders of a dof compute the same
-//         bits -- and the scalars as the sum over all ranks in rank order.
-// The inbox is double buffered by the parity of the exchange number; a rank can be at most one exchange ahead of
-// another (its pull waits for everybody's push), so a slot is never overwritten before it was read.
-constexpr int kFlagBytes = 4096;
-constexpr int kPeerScal = 8;
-
-__device__ __forceinline__ double* peer_slot_ptr(void* base, int64_t slot, int nranks, int parity, int sender) {
-  return reinterpret_cast<double*>(reinterpret_cast<char*>(base) + kFlagBytes) + ((int64_t)parity * nranks + sender) * slot;
-}
-
-__global__ void peer_push_kernel(void* const* __restrict__ bases, int nranks, int me, int64_t slot, unsigned long long epoch,
-                                 int nshare, const int32_t* __restrict__ share_rank, const int64_t* __restrict__ send_ptr,
-                                 const int32_t* __restrict__ send_dof, const double* __restrict__ v,
-                                 const double* __restrict__ scal, int nscal, unsigned int* __restrict__ counter) {
+// One interface sum = ONE kernel, no NCCL call, no fence: the thread that owns an interface entry stores its value
+// straight into the inbox of every other rank holding that dof (remote stores over NVLink / NVSwitch), then waits for
+// their values in its own inbox and sums over the holders in ascending rank order (own value in place) -- all holders
+// of a dof compute the same bits.  A value travels as a 16-byte cell {low word, flag, high word, flag} with flag = the
+// exchange number (the "LL" protocol of NCCL: 8-byte stores are atomic, so a half is either old or complete, and the
+// receiver simply re-reads until both flags match).  Scalars (dot products of the coarse solver) ride in the first 8
+// cells of every slot, from every rank to every rank, summed in rank order.  Slots are double buffered by the parity
+// of the exchange number: a rank cannot finish exchange e + 1 before every sharing rank has finished e.
+__global__ void peer_ll_kernel(void* const* __restrict__ bases, void* base, int nranks, int me, int64_t slot, unsigned long long epoch,
+                               int64_t n_if, const int32_t* __restrict__ idx, const int64_t* __restrict__ hold_ptr,
+                               const int32_t* __restrict__ hold_rank, const int32_t* __restrict__ hold_pos,
+                               const int32_t* __restrict__ hold_spos, double* __restrict__ v, double* __restrict__ scal, int nscal,
+                               int* __restrict__ err) {
   const int parity = (int)(epoch & 1ull);
+  const unsigned flag = b2_peer_flag(epoch);
   const int64_t t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
-  for (int s = 0; s < nshare; s++) {
-    double* dst = peer_slot_ptr(bases[share_rank[s]], slot, nranks, parity, me) + kPeerScal;
-    const int64_t a = send_ptr[s], b = send_ptr[s + 1];
-    for (int64_t k = a + t0; k < b; k += stride) dst[k - a] = v[send_dof[k]];
+  if (blockIdx.x == 0 && threadIdx.x < nscal) {
+    const double mine = scal[threadIdx.x];
+    for (int r = 0; r < nranks; r++)
+      if (r != me) b2_peer_store(b2_peer_cell(bases[r], slot, nranks, parity, me, threadIdx.x), mine, flag);
   }
-  if (blockIdx.x == 0 && threadIdx.x < nscal)
-    for (int r = 0; r < nranks; r++) peer_slot_ptr(bases[r], slot, nranks, parity, me)[threadIdx.x] = scal[threadIdx.x];
-  __threadfence_system();
-  __shared__ bool last;
-  __syncthreads();
-  if (threadIdx.x == 0) last = atomicAdd(counter, 1u) == gridDim.x - 1;
-  __syncthreads();
-  if (last) {
-    __threadfence_system();
-    for (int r = threadIdx.x; r < nranks; r += blockDim.x)
-      reinterpret_cast<volatile unsigned long long*>(bases[r])[me] = epoch;
-    if (threadIdx.x == 0) *counter = 0;
-  }
-}
-
-__global__ void peer_pull_kernel(void* base, int nranks, int me, int64_t slot, unsigned long long epoch, int64_t n_if,
-                                 const int32_t* __restrict__ idx, const int64_t* __restrict__ hold_ptr,
-                                 const int32_t* __restrict__ hold_rank, const int32_t* __restrict__ hold_pos,
-                                 double* __restrict__ v, double* __restrict__ scal, int nscal, int* __restrict__ err) {
-  const int parity = (int)(epoch & 1ull);
-  __shared__ int bad;
-  if (threadIdx.x == 0) {
-    bad = 0;
-    volatile unsigned long long* flags = reinterpret_cast<volatile unsigned long long*>(base);
-    const long long t_start = clock64();
-    for (int r = 0; r < nranks && !bad; r++)
-      while (flags[r] < epoch) {
-        if (clock64() - t_start > 20000000000ll) { bad = 1; *err = 1; break; }      // ~10 s: a rank died; leave instead of hanging
-      }
-    __threadfence_system();
-  }
-  __syncthreads();
-  if (bad) return;
-  const int64_t t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t k = t0; k < n_if; k += stride) {
     const int32_t d = idx[k];
+    const double own = v[d];
+    const int64_t h0 = hold_ptr[k], h1 = hold_ptr[k + 1];
+    for (int64_t q = h0; q < h1; q++)
+      if (hold_rank[q] != me) b2_peer_store(b2_peer_cell(bases[hold_rank[q]], slot, nranks, parity, me, kPeerScal + hold_spos[q]), own, flag);
     double s = 0.0;
-    for (int64_t q = hold_ptr[k]; q < hold_ptr[k + 1]; q++) {
+    for (int64_t q = h0; q < h1; q++) {
       const int r = hold_rank[q];
-      const double a = r == me ? v[d] : __ldcv(peer_slot_ptr(base, slot, nranks, parity, r) + kPeerScal + hold_pos[q]);
-      s = q == hold_ptr[k] ? a : s + a;
+      const double a = r == me ? own : b2_peer_wait(b2_peer_cell(base, slot, nranks, parity, r, kPeerScal + hold_pos[q]), flag, err);
+      s = q == h0 ? a : s + a;
     }
     v[d] = s;
   }
   if (blockIdx.x == 0 && threadIdx.x < nscal) {
+    const double mine = scal[threadIdx.x];
     double s = 0.0;
     for (int r = 0; r < nranks; r++) {
-      const double a = __ldcv(peer_slot_ptr(base, slot, nranks, parity, r) + threadIdx.x);
+      const double a = r == me ? mine : b2_peer_wait(b2_peer_cell(base, slot, nranks, parity, r, threadIdx.x), flag, err);
       s = r == 0 ? a : s + a;
     }
     scal[threadIdx.x] = s;
@@ -136,12 +102,9 @@ bool use_peer(const b2_halo* h) { return h->ctx->halo_peer && h->ctx->peer_base 
 int peer_exchange(b2_halo* h, b2_vec* v, double* d_scal, int nscal) {
   b2_ctx* c = h->ctx;
   const unsigned long long epoch = ++c->peer_epoch;
-  int64_t work = h->n_send > h->n_if ? h->n_send : h->n_if;
-  int grid = b2_grid_for(c, work > 0 ? work : 1, kBlock, 2);
-  B2_LAUNCH(c, peer_push_kernel, grid, kBlock, 0, (void* const*)c->d_peer_base, c->nranks, c->rank, c->peer_slot, epoch, h->nshare, h->share_rank,
-            h->send_ptr, h->send_dof, v->d, d_scal, nscal, c->peer_counter);
-  B2_LAUNCH(c, peer_pull_kernel, grid, kBlock, 0, c->peer_local, c->nranks, c->rank, c->peer_slot, epoch, h->n_if, h->idx, h->hold_ptr, h->hold_rank,
-            h->hold_pos, v->d, d_scal, nscal, c->peer_err);
+  const int grid = b2_grid_for(c, h->n_if > 0 ? h->n_if : 1, kBlock, 4);
+  B2_LAUNCH(c, peer_ll_kernel, grid, kBlock, 0, (void* const*)c->d_peer_base, c->peer_local, c->nranks, c->rank, c->peer_slot, epoch, h->n_if,
+            h->idx, h->hold_ptr, h->hold_rank, h->hold_pos, h->hold_spos, v->d, d_scal, nscal, c->peer_err);
   return 0;
 }
 
@@ -201,12 +164,10 @@ int b2_halo_destroy(b2_halo* h) {
   b2_free(c, h->owned, (size_t)h->n_local);
   b2_free(c, h->invmult, (size_t)h->n_local + 4);
   if (h->hold_ptr) {
-    b2_free(c, h->share_rank, (size_t)h->nshare);
-    b2_free(c, h->send_ptr, (size_t)h->nshare + 1);
-    b2_free(c, h->send_dof, (size_t)h->n_send);
     b2_free(c, h->hold_ptr, (size_t)h->n_if + 1);
     b2_free(c, h->hold_rank, (size_t)h->n_hold);
     b2_free(c, h->hold_pos, (size_t)h->n_hold);
+    b2_free(c, h->hold_spos, (size_t)h->n_hold);
   }
   delete h;
   return 0;
@@ -245,38 +206,33 @@ int b2_halo_sum_scalars(b2_halo* h, b2_vec* v, double* d_scal, int nscal) {
 
 extern "C" {
 
-/* Peer-memory form of the interface sum (needs b2_ctx_peer_open): for each of the nshare ranks sharing dofs with this
- * one the local dofs whose values it receives (in the order both sides derive from the gathered lattice keys), and
- * for every interface entry k (order of local_idx at creation) its holders in ascending rank order, this rank
- * included, with the position of the value in that holder's message to this rank. */
-int b2_halo_set_exchange(b2_halo* h, int nshare, const int32_t* share_rank, const int64_t* send_ptr, const int32_t* send_dof,
-                         const int64_t* hold_ptr, const int32_t* hold_rank, const int32_t* hold_pos) {
-  B2_CHECK(h && nshare >= 0 && send_ptr && hold_ptr, "b2_halo_set_exchange: bad arguments");
+/* Peer-memory form of the interface sum (needs b2_ctx_peer_open): for every interface entry k (order of local_idx at
+ * creation) its holders in ascending rank order, this rank included; for each holder the cell of ITS value in its
+ * message to this rank (hold_pos) and the cell of THIS rank's value in its message to the holder (hold_spos).  A
+ * message rank q -> rank r lists, in q's entry order, the entries of q that r also holds. */
+int b2_halo_set_exchange(b2_halo* h, const int64_t* hold_ptr, const int32_t* hold_rank, const int32_t* hold_pos, const int32_t* hold_spos) {
+  B2_CHECK(h && hold_ptr && (h->n_if == 0 || (hold_rank && hold_pos && hold_spos)), "b2_halo_set_exchange: bad arguments");
   B2_CHECK(!h->hold_ptr, "b2_halo_set_exchange: already set");
   b2_ctx* c = h->ctx;
-  const int64_t ns = send_ptr[nshare], nh = hold_ptr[h->n_if];
-  for (int s = 0; s < nshare; s++) {
-    B2_CHECK(share_rank[s] >= 0 && share_rank[s] < c->nranks && share_rank[s] != c->rank, "b2_halo_set_exchange: bad peer rank %d", share_rank[s]);
-    B2_CHECK(send_ptr[s + 1] - send_ptr[s] + kPeerScal <= c->peer_slot || !c->peer_base, "b2_halo_set_exchange: message of %lld values exceeds the inbox slot (%lld)",
-             (long long)(send_ptr[s + 1] - send_ptr[s]), (long long)c->peer_slot);
+  const int64_t nh = hold_ptr[h->n_if];
+  for (int64_t q = 0; q < nh; q++) {
+    B2_CHECK(hold_rank[q] >= 0 && hold_rank[q] < c->nranks, "b2_halo_set_exchange: holder rank out of range");
+    if (hold_rank[q] == c->rank) continue;
+    B2_CHECK(hold_pos[q] >= 0 && hold_spos[q] >= 0, "b2_halo_set_exchange: negative message position");
+    B2_CHECK(!c->peer_base || (hold_pos[q] + kPeerScal < c->peer_slot && hold_spos[q] + kPeerScal < c->peer_slot),
+             "b2_halo_set_exchange: message position %d / %d beyond the inbox slot (%lld cells)", hold_pos[q], hold_spos[q], (long long)c->peer_slot);
   }
-  for (int64_t k = 0; k < ns; k++) B2_CHECK(send_dof[k] >= 0 && send_dof[k] < h->n_local, "b2_halo_set_exchange: send dof out of range");
-  for (int64_t q = 0; q < nh; q++) B2_CHECK(hold_rank[q] >= 0 && hold_rank[q] < c->nranks, "b2_halo_set_exchange: holder rank out of range");
-  h->nshare = nshare;
-  h->n_send = ns;
   h->n_hold = nh;
-  B2_TRY(b2_malloc(c, &h->share_rank, (size_t)nshare));
-  B2_TRY(b2_malloc(c, &h->send_ptr, (size_t)nshare + 1));
-  B2_TRY(b2_malloc(c, &h->send_dof, (size_t)ns));
   B2_TRY(b2_malloc(c, &h->hold_ptr, (size_t)h->n_if + 1));
   B2_TRY(b2_malloc(c, &h->hold_rank, (size_t)nh));
   B2_TRY(b2_malloc(c, &h->hold_pos, (size_t)nh));
-  if (nshare) B2_TRY(b2_upload(c, h->share_rank, share_rank, (size_t)nshare));
-  B2_TRY(b2_upload(c, h->send_ptr, send_ptr, (size_t)nshare + 1));
-  if (ns) B2_TRY(b2_upload(c, h->send_dof, send_dof, (size_t)ns));
+  B2_TRY(b2_malloc(c, &h->hold_spos, (size_t)nh));
   B2_TRY(b2_upload(c, h->hold_ptr, hold_ptr, (size_t)h->n_if + 1));
-  if (nh) B2_TRY(b2_upload(c, h->hold_rank, hold_rank, (size_t)nh));
-  if (nh) B2_TRY(b2_upload(c, h->hold_pos, hold_pos, (size_t)nh));
+  if (nh) {
+    B2_TRY(b2_upload(c, h->hold_rank, hold_rank, (size_t)nh));
+    B2_TRY(b2_upload(c, h->hold_pos, hold_pos, (size_t)nh));
+    B2_TRY(b2_upload(c, h->hold_spos, hold_spos, (size_t)nh));
+  }
   return 0;
 }
 

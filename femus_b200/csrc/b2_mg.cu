@@ -49,6 +49,22 @@ struct b2_mg {
   double* scal = nullptr;   // [16]: 0 gamma_new (r.u), 1 delta (w.u), 2 rr, 3 bb | 8 gamma, 9 alpha, 10 beta
   double* dot_partial = nullptr;      // [kRedBlocks][4]
   unsigned int* dot_counter = nullptr;
+  // optional per-phase device timing of the cycles (b2_mg_set_timing): events around every phase of every level
+  bool timing = false;
+  struct Stamp { int level, phase; cudaEvent_t e0, e1; };
+  std::vector<Stamp> stamps;
+};
+
+// brackets one phase of one level with events when timing is on (phases: 0 pre-smoothing, 1 residual, 2 restriction,
+// 3 coarse solve, 4 prolongation, 5 post-smoothing)
+struct b2_mg_phase {
+  b2_mg* mg; int level, phase; cudaEvent_t e0 = nullptr, e1 = nullptr;
+  b2_mg_phase(b2_mg* m, int l, int p) : mg(m), level(l), phase(p) {
+    if (mg->timing) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, mg->ctx->stream); }
+  }
+  ~b2_mg_phase() {
+    if (e0) { cudaEventRecord(e1, mg->ctx->stream); mg->stamps.push_back({level, phase, e0, e1}); }
+  }
 };
 
 int b2_cg_persistent(b2_ctx* c, const b2_csr* A, const double* dinv, const double* b, const uint8_t* owned, const b2_halo* halo,
@@ -433,15 +449,33 @@ int coarse_solve(b2_mg* mg) {
 int vcycle(b2_mg* mg, int l) {
   // solves (approximately) A_l x_l = b_l, zero initial guess; operands are the level work vectors
   b2_mg_level& L = mg->L[l];
-  if (l == 0) return coarse_solve(mg);
-  B2_TRY(smooth(mg, l, L.npre, true));
-  B2_TRY(level_resid(L, L.b, L.x, L.r));
+  if (l == 0) {
+    b2_mg_phase ph(mg, 0, 3);
+    return coarse_solve(mg);
+  }
+  {
+    b2_mg_phase ph(mg, l, 0);
+    B2_TRY(smooth(mg, l, L.npre, true));
+  }
+  {
+    b2_mg_phase ph(mg, l, 1);
+    B2_TRY(level_resid(L, L.b, L.x, L.r));
+  }
   b2_mg_level& C = mg->L[l - 1];
-  B2_TRY(b2_csr_spmv(L.R, L.r, C.b));        // R = P^T restricted to the fine rows this rank owns
-  if (C.halo) B2_TRY(b2_halo_sum(C.halo, C.b));
+  {
+    b2_mg_phase ph(mg, l, 2);
+    B2_TRY(b2_csr_spmv(L.R, L.r, C.b));        // R = P^T restricted to the fine rows this rank owns
+    if (C.halo) B2_TRY(b2_halo_sum(C.halo, C.b));
+  }
   B2_TRY(vcycle(mg, l - 1));
-  B2_TRY(b2_csr_spmv_add(L.P, C.x, L.x));
-  B2_TRY(smooth(mg, l, L.npost, false));
+  {
+    b2_mg_phase ph(mg, l, 4);
+    B2_TRY(b2_csr_spmv_add(L.P, C.x, L.x));
+  }
+  {
+    b2_mg_phase ph(mg, l, 5);
+    B2_TRY(smooth(mg, l, L.npost, false));
+  }
   return 0;
 }
 
@@ -617,6 +651,26 @@ int b2_mg_solve(b2_mg* mg, b2_vec* res, b2_vec* eps) {
 }
 
 int b2_mg_coarse_iterations(const b2_mg* mg) { return mg->coarse_its; }
+
+/* per-phase device timing of the cycles run from now on (on = 1); b2_mg_get_timing sums what was recorded since the last
+ * call into ms[nlevels][6] (phases: pre-smoothing, residual, restriction, coarse solve, prolongation, post-smoothing) */
+int b2_mg_set_timing(b2_mg* mg, int on) {
+  mg->timing = on != 0;
+  return 0;
+}
+int b2_mg_get_timing(b2_mg* mg, double* ms) {
+  B2_CUDA(cudaStreamSynchronize(mg->ctx->stream));
+  for (int k = 0; k < mg->nlevels * 6; k++) ms[k] = 0.0;
+  for (auto& st : mg->stamps) {
+    float t = 0.f;
+    cudaEventElapsedTime(&t, st.e0, st.e1);
+    ms[st.level * 6 + st.phase] += (double)t;
+    cudaEventDestroy(st.e0);
+    cudaEventDestroy(st.e1);
+  }
+  mg->stamps.clear();
+  return 0;
+}
 
 int b2_mg_destroy(b2_mg* mg) {
   if (!mg) return 0;

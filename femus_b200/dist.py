@@ -15,7 +15,7 @@ class LevelLayout:
     """Interface layout of one level for one FE family on one rank."""
 
     def __init__(self, n_local, idx, pos, n_packed, owned, mult, exchange=None):
-        # exchange: (share_rank, send_ptr, send_dof, hold_ptr, hold_rank, hold_pos) of the peer-memory form of the sum
+        # exchange: (hold_ptr, hold_rank, hold_pos, hold_spos, longest message) of the peer-memory form of the sum
         self.exchange = exchange
         self.n_local = n_local
         self.idx = idx                  # int32 [n_if] local dofs on the interface
@@ -55,36 +55,37 @@ def exchange_lists(nodes, all_keys, rank):
     """Peer-memory form of the interface sum (b2_halo_set_exchange).  all_keys[q] = lattice keys of rank q's interface
     entries in ITS entry order.  The message q -> r carries, in q's entry order, the values of q's entries whose key r
     also holds; so both sides know every position without talking to each other.  Returns
-      share_rank [nshare], send_ptr [nshare+1], send_dof: local dofs of this rank's messages, peer after peer;
-      hold_ptr [n_if+1], hold_rank, hold_pos: per entry its holders in ascending rank order (this rank included,
-      position -1) and where each holder's value sits in that holder's message to this rank."""
+      hold_ptr [n_if+1], hold_rank, hold_pos, hold_spos: per entry its holders in ascending rank order (this rank
+      included, positions -1), where each holder's value sits in that holder's message to this rank and where this
+      rank's value sits in its message to the holder;  longest: the longest message this rank sends or receives."""
     mine = all_keys[rank]
     n_if = mine.shape[0]
-    share_rank, send_ptr, send_dof = [], [0], []
-    hk, hr, hp = [np.arange(n_if, dtype=np.int64)], [np.full(n_if, rank, dtype=np.int64)], [np.full(n_if, -1, dtype=np.int64)]
+    hk = [np.arange(n_if, dtype=np.int64)]
+    hr = [np.full(n_if, rank, dtype=np.int64)]
+    hp = [np.full(n_if, -1, dtype=np.int64)]
+    hs = [np.full(n_if, -1, dtype=np.int64)]
+    longest = 0
     for q, kq in enumerate(all_keys):
         if q == rank or kq.shape[0] == 0 or n_if == 0:
             continue
         to_q = np.isin(mine, kq)                    # my entries that q holds: my message to q, in my entry order
         if not to_q.any():
             continue
-        share_rank.append(q)
-        send_dof.append(nodes[to_q])
-        send_ptr.append(send_ptr[-1] + int(to_q.sum()))
         from_q = kq[np.isin(kq, mine)]              # q's message to me, in q's entry order
         order = np.argsort(from_q, kind="stable")
         where = order[np.searchsorted(from_q[order], mine[to_q])]
         hk.append(np.nonzero(to_q)[0].astype(np.int64))
         hr.append(np.full(where.shape[0], q, dtype=np.int64))
         hp.append(where.astype(np.int64))
-    hk, hr, hp = np.concatenate(hk), np.concatenate(hr), np.concatenate(hp)
+        hs.append(np.arange(where.shape[0], dtype=np.int64))
+        longest = max(longest, int(where.shape[0]))
+    hk, hr, hp, hs = np.concatenate(hk), np.concatenate(hr), np.concatenate(hp), np.concatenate(hs)
     o = np.lexsort((hr, hk))                        # by entry, then by holder rank
-    hk, hr, hp = hk[o], hr[o], hp[o]
+    hk, hr, hp, hs = hk[o], hr[o], hp[o], hs[o]
     hold_ptr = np.zeros(n_if + 1, dtype=np.int64)
     np.add.at(hold_ptr, hk + 1, 1)
     hold_ptr = np.cumsum(hold_ptr)
-    return (np.array(share_rank, dtype=np.int32), np.array(send_ptr, dtype=np.int64),
-            (np.concatenate(send_dof) if send_dof else np.zeros(0)).astype(np.int32), hold_ptr, hr.astype(np.int32), hp.astype(np.int32))
+    return hold_ptr, hr.astype(np.int32), hp.astype(np.int32), hs.astype(np.int32), longest
 
 
 def torch_allgather():

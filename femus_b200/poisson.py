@@ -187,16 +187,16 @@ class PoissonMG:
             # interface sums through peer memory (NVLink / NVSwitch stores + flags) instead of a packed ncclAllReduce:
             # one inbox block per rank, sized for the largest message of the run, opened by every rank (once per context)
             if peer and getattr(ctx, "peer_slot", None) is None:
-                need = max([int(np.diff(lay.exchange[1]).max()) if lay.exchange[1].shape[0] > 1 else 0 for lay in self.layout])
+                need = max(lay.exchange[4] for lay in self.layout)
                 ctx.peer_slot = max(max(gather(need)) + 8, 1 << 16)
                 ctx.peer_init(ctx.peer_slot, gather)
             for l in range(nlevels):
                 lay = self.layout[l]
                 self.halo[l] = capi.Halo(ctx, lay.n_local, lay.idx, lay.pos, lay.n_packed, lay.owned, lay.mult)
                 if peer:
-                    if lay.exchange[1].shape[0] > 1 and int(np.diff(lay.exchange[1]).max()) + 8 > ctx.peer_slot:
+                    if lay.exchange[4] + 8 > ctx.peer_slot:
                         raise ValueError("the peer inbox of this context is too small for this mesh")
-                    self.halo[l].set_exchange(*lay.exchange)
+                    self.halo[l].set_exchange(*lay.exchange[:4])
                 self.mg.set_level_halo(l, self.halo[l])
             self.n_global = int(sum(gather(self.layout[-1].n_owned)))
             for v in (self.RES, self.EPS, self.SOL, self.RESM):

@@ -136,17 +136,18 @@ int b2_vec_copy_masked(b2_vec* dst, const b2_vec* src, const b2_vec* mask, doubl
 int b2_halo_create(b2_ctx* c, int64_t n_local, int64_t n_if, const int32_t* local_idx, const int32_t* packed_pos,
                    int64_t n_packed, const uint8_t* owned, const uint8_t* mult, b2_halo** out);
 int b2_halo_destroy(b2_halo* h);
-/* Peer-memory form of the interface sum: remote stores into the sharing ranks' inboxes over NVLink / NVSwitch and a flag
- * per rank instead of pack -> ncclAllReduce -> unpack (b2_halo.cu).  Setup: every rank exports its inbox block
- * (b2_ctx_peer_export), the launcher all-gathers the 64-byte handles, every rank opens them (b2_ctx_peer_open), then each
- * layout gets its per-peer send lists and per-entry holder lists (b2_halo_set_exchange; femus_b200/dist.py derives them
- * from the gathered lattice keys).  Sums are taken in ascending rank order on every holder: all copies of a dof agree
- * bit for bit, as after an allreduce.  Option "halo_peer" 0 keeps the NCCL form. */
-int b2_ctx_peer_export(b2_ctx* c, int64_t slot_doubles, void* handle64);
+/* Peer-memory form of the interface sum: ONE kernel instead of pack -> ncclAllReduce -> unpack (b2_halo.cu).  The thread
+ * that owns an interface entry stores its value into the inbox of every other holder (remote stores over NVLink /
+ * NVSwitch, 16-byte cells carrying the exchange number as their flag), waits for the holders' values in its own inbox
+ * and sums in ascending rank order: all copies of a dof agree bit for bit, as after an allreduce; no fence, no collective.
+ * Setup: every rank exports its inbox (b2_ctx_peer_export), the launcher all-gathers the 64-byte CUDA IPC handles, every
+ * rank opens them (b2_ctx_peer_open); each layout then gets its per-entry holder lists (b2_halo_set_exchange;
+ * femus_b200/dist.py derives them from the gathered lattice keys).  Option "halo_peer" 0 keeps the NCCL form.  The
+ * coarse PCG runs the same exchange inside its persistent kernel (b2_cg.cu). */
+int b2_ctx_peer_export(b2_ctx* c, int64_t slot_cells, void* handle64);
 int b2_ctx_peer_open(b2_ctx* c, const void* handles /* [nranks][64] */);
 int b2_ctx_peer_error(b2_ctx* c, int* err);
-int b2_halo_set_exchange(b2_halo* h, int nshare, const int32_t* share_rank, const int64_t* send_ptr, const int32_t* send_dof,
-                         const int64_t* hold_ptr, const int32_t* hold_rank, const int32_t* hold_pos);
+int b2_halo_set_exchange(b2_halo* h, const int64_t* hold_ptr, const int32_t* hold_rank, const int32_t* hold_pos, const int32_t* hold_spos);
 int64_t b2_halo_owned_count(const b2_halo* h);
 int64_t b2_halo_interface_count(const b2_halo* h);
 /* v[interface] <- sum over the ranks holding each dof (pack, ncclAllReduce over NVLink, unpack) */
@@ -295,6 +296,10 @@ int b2_mg_set_level(b2_mg* mg, int level, b2_csr* A, b2_csr* P, const int32_t* b
 /* distributed run: layout of the level's vectors; A is then this rank's partial operator (sum over
  * its own elements), P its local prolongator.  Call before b2_mg_set_level. */
 int b2_mg_set_level_halo(b2_mg* mg, int level, b2_halo* halo);
+/* per-phase device timing of the cycles (measurement aid): ms[nlevels][6] = pre-smoothing, residual, restriction, coarse
+ * solve, prolongation, post-smoothing, summed over the cycles since the last call */
+int b2_mg_set_timing(b2_mg* mg, int on);
+int b2_mg_get_timing(b2_mg* mg, double* ms);
 /* smoother of a level (call before b2_mg_set_level): kind 0 = Richardson(omega)+Jacobi, 1 = Chebyshev+Jacobi
  * (KSPCHEBYSHEV + PCJACOBI, LinearEquationSolverPetsc.cpp:452-536) on [emin, emax] of D^-1 A.  emax <= 0:
  * the bounds are OUR OWN stated ones -- [0.1, 1.1] x the largest eigenvalue found by 10 power iterations

@@ -87,13 +87,16 @@ def test_peer_exchange_lists_reproduce_the_packed_interface_sum(case):
     ex = [distlayout.exchange_lists(nodes[r], keys, r) for r in range(P)]
     rng = np.random.default_rng(1)
     v = [rng.standard_normal(nd[r]) for r in range(P)]
-    # messages: sender -> receiver -> values
+    # messages: every rank writes its value of entry k into cell hold_spos of its message to each other holder
     msg = [{} for _ in range(P)]
     for r in range(P):
-        share, sptr, sdof = ex[r][0], ex[r][1], ex[r][2]
-        for s, q in enumerate(share):
-            msg[q][r] = v[r][sdof[sptr[s]:sptr[s + 1]]]
-        assert sorted(share) == list(share) and r not in share
+        hptr, hrank, hpos, hspos, longest = ex[r]
+        for k in range(nodes[r].shape[0]):
+            for q, sp_ in zip(hrank[hptr[k]:hptr[k + 1]], hspos[hptr[k]:hptr[k + 1]]):
+                if q != r:
+                    cell = msg[q].setdefault(r, {})
+                    assert sp_ not in cell and 0 <= sp_ < longest               # one value per cell, inside the slot
+                    cell[int(sp_)] = v[r][nodes[r][k]]
     # reference: sum over holders through the union of keys
     union = np.unique(np.concatenate(keys))
     total = np.zeros(union.shape[0])
@@ -101,14 +104,14 @@ def test_peer_exchange_lists_reproduce_the_packed_interface_sum(case):
         np.add.at(total, np.searchsorted(union, keys[r]), v[r][nodes[r]])
     got_by_key = {}
     for r in range(P):
-        hptr, hrank, hpos = ex[r][3], ex[r][4], ex[r][5]
+        hptr, hrank, hpos = ex[r][0], ex[r][1], ex[r][2]
         assert hptr.shape[0] == nodes[r].shape[0] + 1
         for k in range(nodes[r].shape[0]):
             hs = hrank[hptr[k]:hptr[k + 1]]
             assert np.all(np.diff(hs) > 0) and r in hs                       # ascending, this rank included
             s = None
             for q, pos in zip(hs, hpos[hptr[k]:hptr[k + 1]]):
-                a = v[r][nodes[r][k]] if q == r else msg[r][q][pos]
+                a = v[r][nodes[r][k]] if q == r else msg[r][q][int(pos)]
                 s = a if s is None else s + a
             K = int(keys[r][k])
             assert abs(s - total[np.searchsorted(union, K)]) <= 1e-14 * max(1.0, abs(s))
