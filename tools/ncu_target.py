@@ -44,6 +44,8 @@ if nl > 1:
     xc = ctx.vector(np.sin(np.arange(P.shape[1]) * 0.001))
     yf = ctx.vector(P.shape[0])
     R = P.transpose()
+if "vcycle" in what:
+    pb.assemble(); pb.galerkin(); pb.mg_set_levels()
 ctx.sync()
 
 cudart.cudaProfilerStart()
@@ -66,6 +68,8 @@ if "spmv" in what:
 if "pr" in what and nl > 1:
     P.spmv(xc, yf)
     R.spmv(yf, xc)
+if "vcycle" in what:      # every kernel of one V-cycle, the persistent coarse PCG among them
+    pb.mg_solve()
 ctx.sync()
 cudart.cudaProfilerStop()
 print("ncu target done; launches", ctx.launches())
