@@ -28,6 +28,7 @@ class B200Matrix : public SparseMatrix {
   b2_csr* handle() const { return _A; }
   // changes whenever the device matrix behind this object is REPLACED (new pattern): who borrows the handle compares it
   uint64_t generation() const { return _gen; }
+  bool frozen() const { return _frozen; }      // the pattern is on the device
   void touched() const { _mirror_ok = false; }      // device values were written behind our back (fused assembly)
 
   // ---- pattern ------------------------------------------------------------------------------

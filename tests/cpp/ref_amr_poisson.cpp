@@ -7,13 +7,20 @@
 // boundary function are those of applications/001_Poisson/main.cpp, compiled in place (its main() is renamed away),
 // the refinement criterion is the shrinking circle of applications/MGAMR/ex5/ex5.cpp:49-70 around the box centre.
 //
-//   ref_amr_poisson <nx> <uniform levels> <selective levels> <V|F> <jacobi|sor> [cycles]
+//   ref_amr_poisson <nx> <uniform levels> <selective levels> <V|F> <jacobi|sor> [cycles] [device]
+//
+// "device" (B200 build only): the element loop itself runs on the GPU -- femus::AssemblePoissonB200
+// (femus_b200/host/RefAssemble.hpp, the replacement callback of INTEGRATION.md section 5) is registered instead of
+// 001_Poisson's callback; everything else stays the reference's code.
 //
 // prints the reference's own "Linear Res L2norm" lines (LinearImplicitSystem.cpp:426).  Test infrastructure: the host
 // backend run generates tests/golden/ref_amr_*.npz, the B200 backend run is compared with it on the GPU.
 #define main femus_001_poisson_main_unused
 #include "applications/001_Poisson/main.cpp"
 #undef main
+#ifdef B2_REF_DEVICE_ASSEMBLY
+#include "RefAssemble.hpp"
+#endif
 
 static bool RefineInsideShrinkingCircle(const std::vector<double>& x, const int& /*elemgroupnumber*/, const int& level) {
   const double radius = 0.25 / level;
@@ -29,6 +36,7 @@ int main(int argc, char** argv) {
   const bool fcycle = argv[4][0] == 'F';
   const bool sor = std::string(argv[5]) == "sor";
   const unsigned cycles = argc > 6 ? std::atoi(argv[6]) : 6;
+  const bool device = argc > 7 && std::string(argv[7]) == "device";
 
   FemusInit init(argc, argv, MPI_COMM_WORLD);
   Files files;
@@ -53,6 +61,15 @@ int main(int argc, char** argv) {
   LinearImplicitSystem& system = ml_prob.add_system<LinearImplicitSystem>("Poisson");
   system.AddSolutionToSystemPDE("Sol");
   system.SetAssembleFunction(AssemblePoissonMatrixandRhs);
+  if (device) {
+#ifdef B2_REF_DEVICE_ASSEMBLY
+    system.SetAssembleFunction(femus::AssemblePoissonB200);      // nu = 1, f = 1: what fpsource and main.cpp:391-413 say in 3-D
+    std::cout << " element loop: femus::AssemblePoissonB200 (device)" << std::endl;
+#else
+    std::cerr << "this build has no device assembly" << std::endl;
+    return 1;
+#endif
+  }
   system.SetMaxNumberOfLinearIterations(cycles);
   system.SetAbsoluteLinearConvergenceTolerance(1.e-30);
   system.SetMgType(fcycle ? F_CYCLE : V_CYCLE);

@@ -48,7 +48,7 @@ def build(ref="/root/reference", force=False):
     apps = {EXE: os.path.join(ref, "applications/001_Poisson/main.cpp"),            # the reference's application, unmodified
             AMR_EXE: os.path.join(ROOT, "tests", "cpp", "ref_amr_poisson.cpp")}      # the reference's AMR path (see the file header)
     for exe, main in apps.items():
-        r = subprocess.run(["g++"] + fl + ["-I" + ref, "-include", backend, main, "-o", exe] + objs + ["-L" + HERE, "-lfemus_b200", "-Wl,-rpath,$ORIGIN", "-lpthread"],
+        r = subprocess.run(["g++"] + fl + ["-I" + ref, "-DB2_REF_DEVICE_ASSEMBLY", "-include", backend, main, "-o", exe] + objs + ["-L" + HERE, "-lfemus_b200", "-Wl,-rpath,$ORIGIN", "-lpthread"],
                            capture_output=True, text=True)
         if r.returncode:
             raise RuntimeError(f"link of {os.path.basename(exe)} failed:\n{r.stderr[-4000:]}")

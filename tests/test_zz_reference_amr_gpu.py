@@ -23,8 +23,13 @@ sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
 GOLD = json.load(open(os.path.join(ROOT, "tests", "golden", "ref_amr_poisson.json")))
 
 
+@pytest.mark.parametrize("assembly", ["reference_callback", "device_callback"])
 @pytest.mark.parametrize("case", sorted(GOLD))
-def test_reference_amr_path_on_the_b200_backend(case, tmp_path):
+def test_reference_amr_path_on_the_b200_backend(case, assembly, tmp_path):
+    """assembly = "device_callback": the element loop itself runs on the GPU too -- femus::AssemblePoissonB200
+    (femus_b200/host/RefAssemble.hpp: plans built from the reference's own Mesh / elem_type / boundary-function objects,
+    b2_asm_poisson + b2_asm_neumann_faces on every level, the selectively refined ones included) is registered in place
+    of 001_Poisson's callback; the golden numbers stay those of the reference's callback on the host backend."""
     if not os.path.exists(EXE):
         pytest.fail("femus_b200/ref_amr_poisson_b200 is missing: build it with `python tests/ref_apps_build.py` where /root/reference exists")
     from make_ref_amr_golden import parse
@@ -32,8 +37,10 @@ def test_reference_amr_path_on_the_b200_backend(case, tmp_path):
     os.makedirs(tmp_path / "input")
     os.makedirs(tmp_path / "output")
     env = dict(os.environ, GLIBC_TUNABLES="glibc.malloc.tcache_count=0")
-    r = subprocess.run([EXE] + g["args"], cwd=str(tmp_path), env=env, capture_output=True, text=True, timeout=800)
+    args = g["args"] + (["device"] if assembly == "device_callback" else [])
+    r = subprocess.run([EXE] + args, cwd=str(tmp_path), env=env, capture_output=True, text=True, timeout=800)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert ("femus::AssemblePoissonB200 (device)" in r.stdout) == (assembly == "device_callback")
     out = parse(r.stdout)
     assert out["elements"] == g["elements"]                                   # the selectively refined hierarchy itself
     assert [l[0] for l in out["levels"]] == [l[0] for l in g["levels"]]      # dofs per level
