@@ -72,6 +72,7 @@ _PROTOS = {
     "b2_vec_sum": (ci, [vp, vp]),
     "b2_vec_minmax": (ci, [vp, vp, vp]),
     "b2_vec_abs": (ci, [vp]),
+    "b2_mg_set_level_nullspace": (ci, [vp, ci, vp]),
     "b2_mg_set_timing": (ci, [vp, ci]),
     "b2_mg_get_timing": (ci, [vp, vp]),
     "b2_ctx_peer_export": (ci, [vp, i64, vp]),
@@ -853,6 +854,10 @@ class Multigrid:
 
     def coarse_iterations(self):
         return int(self.L.b2_mg_coarse_iterations(self.h))
+
+    def set_level_nullspace(self, level, nvec):
+        """nvec: Vector spanning the null space of the level operator (copied and normalised), or None."""
+        check(self.L.b2_mg_set_level_nullspace(self.h, level, nvec.h if nvec is not None else None))
 
     def set_timing(self, on=True):
         check(self.L.b2_mg_set_timing(self.h, 1 if on else 0))

@@ -34,6 +34,9 @@ struct b2_mg_level {
   double emin = 0., emax = 0.;     // bounds in use
   double emin_user = 0., emax_user = 0.;   // emax_user <= 0: estimated at MGSetLevel (power iteration)
   b2_vec* d = nullptr;             // Chebyshev direction
+  // null space of the level operator (MatSetNullSpace / MatSetTransposeNullSpace, LinearEquationSolverPetsc.cpp:357-414):
+  // one normalised vector (the constant pressure of an enclosed flow), owned; bproj = the smoother's projected right-hand side
+  b2_vec *nullvec = nullptr, *bproj = nullptr;
 };
 
 struct b2_mg {
@@ -364,10 +367,36 @@ int smooth_gmres(b2_mg* mg, b2_mg_level& L, int k, bool zero_guess) {
   return b2_gmres_cycle(ops, k);
 }
 
+// Richardson(omega) around the level's preconditioner on an operator with a null space, as KSPSolve does it once
+// MatSetNullSpace / MatSetTransposeNullSpace are set: the right-hand side is projected (a copy: the cycle's residual keeps
+// the original), and so is every preconditioned residual: b' = b - (n.b) n; x <- x + omega (I - n n^T) M^-1 (b' - A x)
+int smooth_nullspace(b2_mg* mg, b2_mg_level& L, int nsweeps, bool zero_guess) {
+  B2_CHECK(L.ksp == 0 && L.smoother != 1, "a level with a null space is smoothed by Richardson around Jacobi or the element blocks");
+  if (zero_guess) B2_TRY(b2_vec_zero(L.x));
+  if (nsweeps <= 0) return 0;
+  double s = 0.0;
+  B2_TRY(b2_vec_copy(L.bproj, L.b));
+  B2_TRY(b2_vec_dot(L.nullvec, L.bproj, &s));
+  B2_TRY(b2_vec_axpy(L.bproj, -s, L.nullvec));
+  for (int k = 0; k < nsweeps; k++) {
+    const b2_vec* r = L.bproj;
+    if (!(zero_guess && k == 0)) {
+      B2_TRY(level_resid(L, L.bproj, L.x, L.t));
+      r = L.t;
+    }
+    B2_TRY(pc_apply(mg, L, r, L.d));
+    B2_TRY(b2_vec_dot(L.nullvec, L.d, &s));
+    B2_TRY(b2_vec_axpy(L.d, -s, L.nullvec));
+    B2_TRY(b2_vec_axpy(L.x, L.omega, L.d));
+  }
+  return 0;
+}
+
 int smooth(b2_mg* mg, int l, int nsweeps, bool zero_guess) {
   b2_mg_level& L = mg->L[l];
   b2_ctx* c = mg->ctx;
   const int64_t n = L.A->nrows;
+  if (L.nullvec) return smooth_nullspace(mg, L, nsweeps, zero_guess);
   if (L.smoother == 1) return smooth_chebyshev(mg, L, nsweeps, zero_guess);
   if (L.ksp == 1) return smooth_gmres(mg, L, nsweeps, zero_guess);
   if (L.smoother == 2) return smooth_schwarz(mg, L, nsweeps, zero_guess);
@@ -551,6 +580,11 @@ int b2_mg_set_level(b2_mg* mg, int level, b2_csr* A, b2_csr* P, const int32_t* b
     if (!L.d) B2_TRY(b2_vec_create(c, n, &L.d));
     B2_TRY(b2_schwarz_setup(L.schwarz));
   }
+  if (L.nullvec && level > 0) {
+    B2_CHECK(L.nullvec->n == n, "b2_mg_set_level: the null-space vector of level %d has %lld entries, the operator %lld rows", level,
+             (long long)L.nullvec->n, (long long)n);
+    if (!L.d) B2_TRY(b2_vec_create(c, n, &L.d));
+  }
   if (L.smoother == 1 && level > 0) {
     if (!L.d) B2_TRY(b2_vec_create(c, n, &L.d));
     if (L.emax_user <= 0.0) {                       // our own stated bounds: [0.1, 1.1] x power-iteration estimate
@@ -595,6 +629,26 @@ int b2_mg_set_level_schwarz(b2_mg* mg, int level, b2_schwarz* s) {
   B2_CHECK(mg && level >= 1 && level < mg->nlevels, "b2_mg_set_level_schwarz: bad level %d (the coarsest level has no smoother)", level);
   mg->L[level].schwarz = s;
   mg->L[level].smoother = s ? 2 : 0;
+  return 0;
+}
+
+/* Null space of the operator of one level >= 1 (RemoveNullSpace, LinearEquationSolverPetsc.cpp:357-414: levels above the
+ * coarsest; the base vector of GetNullSpaceBase is 1 on the free dofs of the flagged variable, normalised): the level's
+ * smoother projects its right-hand side and every preconditioned residual onto the complement.  nvec is copied and
+ * normalised; NULL removes the setting. */
+int b2_mg_set_level_nullspace(b2_mg* mg, int level, const b2_vec* nvec) {
+  B2_CHECK(mg && level >= 1 && level < mg->nlevels, "b2_mg_set_level_nullspace: bad level %d (levels above the coarsest)", level);
+  b2_mg_level& L = mg->L[level];
+  if (L.nullvec) { b2_vec_destroy(L.nullvec); L.nullvec = nullptr; }
+  if (L.bproj) { b2_vec_destroy(L.bproj); L.bproj = nullptr; }
+  if (!nvec) return 0;
+  double nn = 0.0;
+  B2_TRY(b2_vec_dot(nvec, nvec, &nn));
+  B2_CHECK(nn > 0.0, "b2_mg_set_level_nullspace: zero vector");
+  B2_TRY(b2_vec_create(mg->ctx, nvec->n, &L.nullvec));
+  B2_TRY(b2_vec_create(mg->ctx, nvec->n, &L.bproj));
+  B2_TRY(b2_vec_copy(L.nullvec, nvec));
+  B2_TRY(b2_vec_scale(L.nullvec, 1.0 / sqrt(nn)));
   return 0;
 }
 
@@ -683,6 +737,8 @@ int b2_mg_destroy(b2_mg* mg) {
     b2_vec_destroy(L.b);
     b2_vec_destroy(L.r);
     b2_vec_destroy(L.d);
+    b2_vec_destroy(L.nullvec);
+    b2_vec_destroy(L.bproj);
     for (b2_vec* v : L.krylov) b2_vec_destroy(v);
     if (L.R) b2_csr_destroy(L.R);
     if (L.bdc) b2_free(c, L.bdc, (size_t)L.nbdc);

@@ -14,8 +14,8 @@
 // 2x2x2 block of HEX27 elements = 125 KB).  The apply kernel is HBM-bound on those inverses: per block m^2 x 8 B of
 // inverse + the block's CSR rows (12 B per non-zero) in, m x 8 B out.
 //   schwarz_extract_kernel   A[B,B] -> dense (binary search of every column in the block's sorted dof list)
-//   schwarz_invert_kernel    in-place Gauss-Jordan without pivoting (blocks of the penalised SPD operator), one CTA
-//                            per block, pivot row / column staged in shared memory
+//   schwarz_invert_kernel    in-place Gauss-Jordan with partial pivoting, one CTA per block, pivot row / column staged
+//                            in shared memory
 //   schwarz_apply_kernel     t = (r - A y)[B] (warp per row), z = inv . t (warp per row, coalesced), y[B] += z
 #include <algorithm>
 #include "b2_common.cuh"
@@ -229,16 +229,16 @@ int b2_schwarz_setup(b2_schwarz* s) {
   if (!s->inv) B2_TRY(b2_malloc(c, &s->inv, (size_t)s->inv_total));
   // shared memory of the two kernels: 2 x max_m doubles.  The attribute belongs to the FUNCTION, not to this object: it is
   // always the fixed maximum (max_m <= 4096 => 64 KB), so that no other object's setup can lower it under this one
-  B2_CUDA(cudaFuncSetAttribute(schwarz_invert_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 4096 * (int)sizeof(double)));
+  B2_CUDA(cudaFuncSetAttribute(schwarz_invert_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 4096 * (int)sizeof(double) + 4096 * (int)sizeof(int)));
   B2_CUDA(cudaFuncSetAttribute(schwarz_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 4096 * (int)sizeof(double)));
   B2_CUDA(cudaMemsetAsync(s->err, 0, sizeof(int), c->stream));
   B2_LAUNCH(c, schwarz_extract_kernel, b2_grid_for(c, s->nblocks, 1, 8), 256, 0, s->nblocks, s->blk_ptr, s->blk_dofs, s->inv_ptr,
             s->A->rowptr, s->A->col, s->A->val, s->inv);
-  B2_LAUNCH(c, schwarz_invert_kernel, b2_grid_for(c, s->nblocks, 1, 4), kInvertThreads, smem, s->nblocks, s->blk_ptr, s->inv_ptr, s->inv,
-            s->max_m, s->err);
+  B2_LAUNCH(c, schwarz_invert_kernel, b2_grid_for(c, s->nblocks, 1, 4), kInvertThreads, smem + s->max_m * (int)sizeof(int), s->nblocks, s->blk_ptr,
+            s->inv_ptr, s->inv, s->max_m, s->err);
   int err = 0;
   B2_TRY(b2_download(c, &err, s->err, 1));
-  B2_CHECK(err == 0, "b2_schwarz_setup: block %d is singular (zero pivot without pivoting)", err - 1);
+  B2_CHECK(err == 0, "b2_schwarz_setup: block %d is singular (zero pivot column)", err - 1);
   s->ready = true;
   return 0;
 }

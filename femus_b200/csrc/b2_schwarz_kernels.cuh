@@ -35,23 +35,67 @@ __global__ void schwarz_extract_kernel(int64_t nblocks, const int64_t* __restric
   }
 }
 
-// In-place Gauss-Jordan: for every pivot k, row k is scaled by 1/pivot (its k-th entry becomes 1/pivot, the image of
-// the identity column) and every other row i gets  M[i][j] = (j == k ? 0 : M[i][j]) - M[i][k] * rowk[j].
+// In-place Gauss-Jordan with partial (row) pivoting: at step k the row with the largest entry of column k among the rows
+// not used yet is swapped into place (the reference's exact block solve is an LU with pivoting, MLU_PRECOND; a
+// velocity-pressure block can be regular and still meet an exactly zero Schur pivot); row k is scaled by 1/pivot (its k-th
+// entry becomes 1/pivot, the image of the identity column) and every other row i gets
+// M[i][j] = (j == k ? 0 : M[i][j]) - M[i][k] * rowk[j]; the row swaps are undone at the end as column swaps in reverse
+// order.  Ties go to the lowest row, so the result does not depend on the number of threads.
+// Shared memory: 2 * max_m doubles + max_m ints (dynamic) + the reduction scratch below.
+constexpr int kInvertMaxThreads = 1024;
 __global__ void __launch_bounds__(kInvertThreads) schwarz_invert_kernel(int64_t nblocks, const int64_t* __restrict__ blk_ptr,
                                                                          const int64_t* __restrict__ inv_ptr, double* __restrict__ inv,
                                                                          int max_m, int* __restrict__ err) {
   B2_DYN_SHARED(double, sh);
+  __shared__ double red_v[kInvertMaxThreads];
+  __shared__ int red_i[kInvertMaxThreads];
   double* rowk = sh;
   double* colk = sh + max_m;
+  int* perm = reinterpret_cast<int*>(sh + 2 * max_m);
   for (int64_t b = blockIdx.x; b < nblocks; b += gridDim.x) {
     const int m = (int)(blk_ptr[b + 1] - blk_ptr[b]);
     double* M = inv + inv_ptr[b];
-    __syncthreads();                       // the extract launch finished; rowk / colk of the previous block are free
+    __syncthreads();                       // the extract launch finished; the buffers of the previous block are free
     for (int k = 0; k < m; k++) {
-      for (int i = threadIdx.x; i < m; i += blockDim.x) {
-        colk[i] = M[(int64_t)i * m + k];
-        rowk[i] = M[(int64_t)k * m + i];
+      for (int i = threadIdx.x; i < m; i += blockDim.x) colk[i] = M[(int64_t)i * m + k];
+      __syncthreads();
+      // pivot row: largest |M[i][k]|, i >= k, lowest i on ties
+      double bv = -1.0;
+      int bi = k;
+      for (int i = k + (int)threadIdx.x; i < m; i += blockDim.x) {
+        const double a = fabs(colk[i]);
+        if (a > bv) { bv = a; bi = i; }
       }
+      red_v[threadIdx.x] = bv;
+      red_i[threadIdx.x] = bi;
+      __syncthreads();
+      for (int off = 1; off < (int)blockDim.x; off <<= 1) {
+        if ((threadIdx.x & (2 * off - 1)) == 0 && threadIdx.x + off < blockDim.x) {
+          const double ov = red_v[threadIdx.x + off];
+          const int oi = red_i[threadIdx.x + off];
+          if (ov > red_v[threadIdx.x] || (ov == red_v[threadIdx.x] && oi < red_i[threadIdx.x])) {
+            red_v[threadIdx.x] = ov;
+            red_i[threadIdx.x] = oi;
+          }
+        }
+        __syncthreads();
+      }
+      const int r = red_i[0];
+      if (threadIdx.x == 0) perm[k] = r;
+      if (r != k) {
+        for (int j = threadIdx.x; j < m; j += blockDim.x) {
+          const double t = M[(int64_t)k * m + j];
+          M[(int64_t)k * m + j] = M[(int64_t)r * m + j];
+          M[(int64_t)r * m + j] = t;
+        }
+        if (threadIdx.x == 0) {
+          const double t = colk[k];
+          colk[k] = colk[r];
+          colk[r] = t;
+        }
+      }
+      __syncthreads();
+      for (int i = threadIdx.x; i < m; i += blockDim.x) rowk[i] = M[(int64_t)k * m + i];
       __syncthreads();
       const double piv = colk[k];
       if (threadIdx.x == 0 && !(fabs(piv) > 0.0)) atomicCAS(err, 0, (int)(b < 0x7ffffffe ? b + 1 : 0x7fffffff));
@@ -70,6 +114,16 @@ __global__ void __launch_bounds__(kInvertThreads) schwarz_invert_kernel(int64_t 
         const double old = (j == k) ? 0.0 : M[e];
         M[e] = fma(-colk[i], rowk[j], old);
       }
+      __syncthreads();
+    }
+    for (int k = m - 1; k >= 0; k--) {     // (P A)^-1 P: the row swaps become column swaps, last one first
+      const int r = perm[k];
+      if (r != k)
+        for (int i = threadIdx.x; i < m; i += blockDim.x) {
+          const double t = M[(int64_t)i * m + k];
+          M[(int64_t)i * m + k] = M[(int64_t)i * m + r];
+          M[(int64_t)i * m + r] = t;
+        }
       __syncthreads();
     }
   }

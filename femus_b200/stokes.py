@@ -20,11 +20,14 @@ from . import capi, hostapi
 class StokesMG:
     def __init__(self, ctx, hier, order_v="biquadratic", order_p="linear", IRe=1.0, velocity_dirichlet=(1, 2, 3, 4, 5, 6),
                  pressure_dirichlet=(), npre=1, npost=1, omega=1.0, block_elems=1, schedule="colours", equation="stokes",
-                 block_sub="lu", boundary_pressure=None):
+                 block_sub="lu", boundary_pressure=None, fix_pressure_at_one_point=False):
         """equation: "stokes" (SteadyStokes/main.cpp, IRe = the viscosity factor) or "navier_stokes" (the library routine
         03_navier_stokes.hpp: Galerkin residual + exact Newton Jacobian, IRe = nu).  boundary_pressure: {boundary set:
         prescribed pressure tau} for the faces whose normal velocity is not Dirichlet (the routine's boundary block,
-        :196-300; Navier-Stokes only)."""
+        :196-300; Navier-Stokes only).  fix_pressure_at_one_point: MultiLevelSolution::FixSolutionAtOnePoint("P") for
+        enclosed flows (every velocity Dirichlet: the pressure is defined up to a constant) -- the first pressure dof of the
+        COARSEST level becomes a Dirichlet row (MultiLevelSolution.cpp:826-830), and on the levels above the constant
+        pressure is removed as the null space of the operator (RemoveNullSpace, LinearEquationSolverPetsc.cpp:357-414)."""
         self.ctx, self.hier, self.IRe, self.equation = ctx, hier, IRe, equation
         self.fams = [order_v] * 3 + [order_p]
         lv = hier.levels
@@ -35,6 +38,9 @@ class StokesMG:
         self.n = self.sys[-1].n
         dirichlet = [velocity_dirichlet] * 3 + [pressure_dirichlet]
         self.bdc = [S.bdc(dirichlet) for S in self.sys]
+        self.fix_pressure = fix_pressure_at_one_point
+        if fix_pressure_at_one_point:
+            self.bdc[0][int(self.sys[0].offsets[3, 0])] = 0.0
         self.bdc_idx = [np.nonzero(b < 1.5)[0].astype(np.int32) for b in self.bdc]
         self.pattern = [S.sparsity() for S in self.sys]
         self.KK = [ctx.csr(S.n, S.n, *pat) for S, pat in zip(self.sys, self.pattern)]
@@ -76,6 +82,14 @@ class StokesMG:
             self.schwarz[l] = capi.Schwarz(ctx, self.KK[l], ix.overlap_ptr, ix.overlap, gptr, gblocks)
             self.schwarz[l].set_subsolver(block_sub)     # "lu": exact (MLU_PRECOND), "ilu": ILU(0) in system-dof order (ILU_PRECOND)
             self.mg.set_level_schwarz(l, self.schwarz[l])
+            if fix_pressure_at_one_point:                 # GetNullSpaceBase: 1 on the pressure dofs with Bdc > 1.9
+                self.mg.set_level_nullspace(l, ctx.vector(self.nullspace_base(l)))
+
+    def nullspace_base(self, l):
+        nv = np.zeros(self.sys[l].n)
+        p0, p1 = int(self.sys[l].offsets[3, 0]), int(self.sys[l].offsets[4, 0])
+        nv[p0:p1] = self.bdc[l][p0:p1] > 1.9
+        return nv
 
     def assemble(self):
         self.RES.zero()

@@ -296,6 +296,11 @@ int b2_mg_set_level(b2_mg* mg, int level, b2_csr* A, b2_csr* P, const int32_t* b
 /* distributed run: layout of the level's vectors; A is then this rank's partial operator (sum over
  * its own elements), P its local prolongator.  Call before b2_mg_set_level. */
 int b2_mg_set_level_halo(b2_mg* mg, int level, b2_halo* halo);
+/* Null space of a level operator (RemoveNullSpace / GetNullSpaceBase, LinearEquationSolverPetsc.cpp:357-414: levels above
+ * the coarsest; MatSetNullSpace + MatSetTransposeNullSpace): nvec (copied, normalised) spans it -- 1 on the free dofs of the
+ * variable flagged by MultiLevelSolution::FixSolutionAtOnePoint, e.g. the pressure of an enclosed flow.  The level's
+ * Richardson smoother then projects its right-hand side and every preconditioned residual, as KSPSolve does.  NULL unsets. */
+int b2_mg_set_level_nullspace(b2_mg* mg, int level, const b2_vec* nvec);
 /* per-phase device timing of the cycles (measurement aid): ms[nlevels][6] = pre-smoothing, residual, restriction, coarse
  * solve, prolongation, post-smoothing, summed over the cycles since the last call */
 int b2_mg_set_timing(b2_mg* mg, int on);

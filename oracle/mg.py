@@ -72,11 +72,14 @@ class Hierarchy:
 
     def __init__(self, levels, order, fsrc=1.0, dirichlet_faces=(1, 2, 3, 4, 5, 6), A_top=None, rhs=None,
                  coarse_lu=True, ptap=None, neumann=None, smoother="richardson", mesh=None, asm_blocks=None, asm_sub="lu",
-                 asm_orders=None, ksp="richardson"):
+                 asm_orders=None, ksp="richardson", nullspace=None):
         """mesh: the oracle module the levels come from (mesh_box by default, mesh_tet for tetrahedra).
         smoother "asm": asm_blocks[l] = the overlapping index sets of level l >= 1 (oracle.asm.level_blocks),
         asm_orders[l] = the order they are swept in (None: as listed)."""
         self.asm_blocks, self.asm_sub, self.asm_orders = asm_blocks, asm_sub, asm_orders
+        # nullspace[l]: vector spanning the null space of the level-l operator, l >= 1 (RemoveNullSpace,
+        # LinearEquationSolverPetsc.cpp:357-414), or None
+        self.nullspace = nullspace
         self.ksp = ksp          # "gmres": KSPGMRES (left preconditioning) around the Jacobi / element-block preconditioner
         mb = mesh if mesh is not None else globals()["mb"]
         self.levels = levels
@@ -196,6 +199,16 @@ class Hierarchy:
     def smooth(self, l, x, b, nsweeps, omega):
         """KSPRICHARDSON (scale omega) + PCJACOBI: x <- x + omega D^-1 (b - A x); or Chebyshev + Jacobi
         on the stated interval (Saad, alg. 12.1), restarted at every call like a PETSc smoother."""
+        if self.nullspace is not None and self.nullspace[l] is not None:
+            # KSPSolve with MatSetNullSpace + MatSetTransposeNullSpace: the right-hand side is projected (a copy), and so
+            # is every preconditioned residual (KSP_PCApply -> KSP_RemoveNullSpace); Richardson around the preconditioner
+            assert self.ksp == "richardson" and self.smoother != "chebyshev"
+            nv = self.nullspace[l] / np.linalg.norm(self.nullspace[l])
+            bp = b - (nv @ b) * nv
+            for _ in range(nsweeps):
+                z = self.pc_apply(l, bp - self.A[l] @ x)
+                x = x + omega * (z - (nv @ z) * nv)
+            return x
         if self.ksp == "gmres" and self.smoother != "chebyshev":
             return self.gmres(l, x, b, nsweeps)
         if self.smoother == "asm":           # KSPRICHARDSON (scale omega) + PCASM (basic, multiplicative)

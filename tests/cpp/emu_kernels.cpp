@@ -151,8 +151,8 @@ int emu_schwarz(int64_t n, const int64_t* rowptr, const int32_t* col, const doub
   const size_t smem = 2 * (size_t)max_m * sizeof(double);
   emu::launch(schwarz_extract_kernel, (unsigned)grid, (unsigned)threads, 0, nblocks, blk_ptr, blk_dofs, inv_ptr.data(), rowptr, col, val,
               inv.data());
-  emu::launch(schwarz_invert_kernel, (unsigned)grid, (unsigned)threads, smem, nblocks, blk_ptr, (const int64_t*)inv_ptr.data(), inv.data(),
-              max_m, &err);
+  emu::launch(schwarz_invert_kernel, (unsigned)grid, (unsigned)threads, smem + (size_t)max_m * sizeof(int), nblocks, blk_ptr,
+              (const int64_t*)inv_ptr.data(), inv.data(), max_m, &err);
   for (int64_t i = 0; i < n; i++) y[i] = 0.0;
   for (int64_t g = 0; g < ngroups; g++)
     emu::launch(schwarz_apply_kernel, (unsigned)grid, (unsigned)threads, smem, group_ptr[g], group_ptr[g + 1], group_blocks, blk_ptr, blk_dofs,

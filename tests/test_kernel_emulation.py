@@ -117,7 +117,7 @@ def test_schwarz_ssor_kernel_on_the_emulator(emu, order, nb, schedule):
 def test_vanka_blocks_of_a_saddle_point_system_on_the_emulator(emu):
     """Velocity-pressure Vanka blocks (index sets with one Schur variable: velocities of the near elements,
     pressures of the block's element) of a synthetic Stokes matrix in system numbering: the system dofs put the
-    velocities first, so Gauss-Jordan without pivoting meets the pressure Schur complement last; block inverses
+    velocities first, the pressure Schur complement last (the Gauss-Jordan inverse pivots on rows); block inverses
     and the multiplicative sweep against the oracle."""
     from oracle import asm, mesh_box as mb
     from tests import saddle_point as spt

@@ -238,3 +238,58 @@ def test_cpp_driver_newton_iterations_of_navier_stokes():
     for a, b in zip(res, want):
         assert abs(a - b) <= 1e-9 * want[0], (res, want)
     assert res[-1] < 1e-3 * res[0]
+
+
+@pytest.mark.parametrize("name,ov", [("box", "biquadratic")])
+def test_lid_driven_cavity_with_vanka_blocks_and_pressure_null_space(ctx, name, ov):
+    """BASELINE configs[3] as a parity case: steady Navier-Stokes in an ENCLOSED cavity (every velocity Dirichlet, the lid
+    moving), two levels, velocity-pressure Vanka blocks as level smoother, Q2-Q1 hexahedra.  (Not on the shipped
+    tetrahedral cube: with every wall Dirichlet its 105-element coarse level is discretely singular even with the pressure
+    pinned -- a Taylor-Hood mesh with tetrahedra that have no interior vertex: smallest singular value 3e-17 of 2.1 -- so
+    the reference's LU on level 0 has nothing to solve there; Tet10 assembly and V-cycles are covered by the tests above
+    and tests/test_tet_gpu.py.)  The pressure is defined up to a constant:
+    MultiLevelSolution::FixSolutionAtOnePoint("P") pins its first dof on the coarsest level
+    (MultiLevelSolution.cpp:826-830) and removes the constant pressure as null space of the operators above
+    (RemoveNullSpace, LinearEquationSolverPetsc.cpp:357-414: right-hand side and every preconditioned residual of the
+    level smoother projected).  Newton iterations on the device against the oracle pipeline with the same blocks."""
+    from femus_b200.stokes import StokesMG
+    from oracle import navier_stokes as ons, mg, system as osys
+    H, lv, mesh, tables_of, _ = _case(name, 2)
+    fams = [ov] * 3 + ["linear"]
+    walls = (1, 2, 3, 4, 5, 6)
+    nu = 0.5
+    pb = StokesMG(ctx, H, order_v=ov, IRe=nu, velocity_dirichlet=walls, equation="navier_stokes", fix_pressure_at_one_point=True)
+    # the lid: unit x-velocity on the dofs of boundary set 6 that are on no other wall
+    lid = osys.bdc(lv[-1], mesh, fams, [(6,), (), (), ()]) < 1.5
+    other = osys.bdc(lv[-1], mesh, fams, [(1, 2, 3, 4, 5), (), (), ()]) < 1.5
+    sol = np.zeros(pb.n)
+    sol[lid & ~other] = 1.0
+    pb.SOL.put(sol)
+    blocks = [None] + [pb.asm_index[l].blocks() for l in range(1, pb.nlevels)]
+    orders = [None] + [np.argsort(pb.asm_groups[l], kind="stable") for l in range(1, pb.nlevels)]
+
+    class Cavity(osys.SystemMesh):           # FixSolutionAtOnePoint: the first pressure dof of level 0 is a Dirichlet row
+        def bdc_flags(self, L, order, dirichlet_faces=None):
+            b = osys.SystemMesh.bdc_flags(self, L, order, dirichlet_faces)
+            if L is lv[0]:
+                b[int(pb.sys[0].offsets[3, 0])] = 0.0
+            return b
+    smesh = Cavity(mesh, fams, [walls] * 3 + [()])
+    assert np.array_equal(np.nonzero(smesh.bdc_flags(lv[0], None) < 1.5)[0], pb.bdc_idx[0])
+    nulls = [None] + [pb.nullspace_base(l) for l in range(1, pb.nlevels)]
+    free = smesh.bdc_flags(lv[-1], None) > 1.1
+    got, want = [], []
+    for it in range(4):
+        got.append(pb.newton_step(ncycles=4))
+        A, rhs = ons.assemble(lv[-1], mesh, ov, "linear", sol, nu, tables_of)
+        want.append(float(np.linalg.norm(np.where(free, rhs, 0.0))))
+        O = mg.Hierarchy(lv, None, mesh=smesh, A_top=mg.on_pattern(A, *pb.pattern[-1]), rhs=rhs, smoother="asm", asm_blocks=blocks,
+                         asm_orders=orders, nullspace=nulls)
+        # the constant pressure IS the null space of the penalised finest operator
+        assert np.abs(O.A[-1] @ nulls[-1]).max() <= 1e-12 * np.abs(O.A[-1].data).max()
+        _, eps = O.mg_solve_trace(4, omega=1.0)
+        sol = sol + eps
+    for a, b in zip(got, want):
+        assert abs(a - b) <= 1e-8 * want[0], (got, want)
+    assert got[-1] < 1e-2 * got[0], got
+    del pb
