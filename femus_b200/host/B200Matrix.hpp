@@ -16,6 +16,10 @@
 #include <algorithm>
 #include <map>
 #include "B200Vector.hpp"
+#ifdef B2_WITH_FEMUS_HEADERS
+#include "DenseMatrix.hpp"
+#include "Graph.hpp"
+#endif
 
 namespace femus {
 
@@ -65,11 +69,31 @@ class B200Matrix : public SparseMatrix {
     new_generation();
     _frozen = _closed = _is_initialized = true;
   }
-  void update_sparsity_pattern_old(const Graph&) override { B2_NOT_ON_PATH("update_sparsity_pattern_old"); }
-  void update_sparsity_pattern(const Graph&) override { B2_NOT_ON_PATH("update_sparsity_pattern(Graph)"); }
-  void update_sparsity_pattern(int, int, int, int, const std::vector<int>, const std::vector<int>) override {
-    B2_NOT_ON_PATH("update_sparsity_pattern(counts)");
+  // re-initialisation from per-row counts (PetscMatrix.cpp:206-298): the same staged start as init()
+  void update_sparsity_pattern(int m, int n, int m_l, int n_l, const std::vector<int> n_oz, const std::vector<int> n_nz) override {
+    this->init(m, n, m_l, n_l, n_nz, n_oz);
   }
+#ifdef B2_WITH_FEMUS_HEADERS
+  // a Graph carries the columns themselves (every row: its columns, then the off-diagonal count, PetscMatrix.cpp:301-320):
+  // the exact pattern goes to the device at once
+  void update_sparsity_pattern(const Graph& g) override {
+    std::vector<int64_t> rp((size_t)g._m + 1, 0);
+    std::vector<int32_t> col;
+    for (unsigned i = 0; i < g._m; i++) {
+      const size_t len = g[i].empty() ? 0 : g[i].size() - 1;
+      std::vector<int32_t> c(g[i].begin(), g[i].begin() + (std::ptrdiff_t)len);
+      std::sort(c.begin(), c.end());
+      c.erase(std::unique(c.begin(), c.end()), c.end());
+      col.insert(col.end(), c.begin(), c.end());
+      rp[i + 1] = (int64_t)col.size();
+    }
+    this->init_from_csr((int)g._m, (int)g._n, rp.data(), col.data(), nullptr);
+  }
+  void update_sparsity_pattern_old(const Graph& g) override { this->update_sparsity_pattern(g); }
+#else
+  void update_sparsity_pattern_old(const Graph&) override { B2_NOT_ON_PATH("update_sparsity_pattern_old (needs the FEMuS Graph class)"); }
+  void update_sparsity_pattern(const Graph&) override { B2_NOT_ON_PATH("update_sparsity_pattern(Graph) (needs the FEMuS Graph class)"); }
+#endif
 
   // ---- staged element access --------------------------------------------------------------------
   void set(const int i, const int j, const double value) override {
@@ -104,8 +128,17 @@ class B200Matrix : public SparseMatrix {
     for (int k = 0; k < ncols; k++) { _ins_cols.push_back(cols[k]); _ins_vals.push_back(values[k]); }
     _ins_ptr.push_back((int64_t)_ins_cols.size());
   }
-  void add_matrix(const DenseMatrix&, const std::vector<unsigned int>&, const std::vector<unsigned int>&) override { B2_NOT_ON_PATH("add_matrix(DenseMatrix)"); }
-  void add_matrix(const DenseMatrix&, const std::vector<unsigned int>&) override { B2_NOT_ON_PATH("add_matrix(DenseMatrix)"); }
+#ifdef B2_WITH_FEMUS_HEADERS
+  // MatSetValues(ADD_VALUES) of a dense element matrix (PetscMatrix.cpp:678-696), staged like add_matrix_blocked
+  void add_matrix(const DenseMatrix& dm, const std::vector<unsigned int>& rows, const std::vector<unsigned int>& cols) override {
+    add_block(dm.get_values().data(), reinterpret_cast<const int*>(rows.data()), (int)rows.size(), reinterpret_cast<const int*>(cols.data()),
+              (int)cols.size());
+  }
+  void add_matrix(const DenseMatrix& dm, const std::vector<unsigned int>& dof_indices) override { this->add_matrix(dm, dof_indices, dof_indices); }
+#else
+  void add_matrix(const DenseMatrix&, const std::vector<unsigned int>&, const std::vector<unsigned int>&) override { B2_NOT_ON_PATH("add_matrix(DenseMatrix) (needs the FEMuS DenseMatrix class)"); }
+  void add_matrix(const DenseMatrix&, const std::vector<unsigned int>&) override { B2_NOT_ON_PATH("add_matrix(DenseMatrix) (needs the FEMuS DenseMatrix class)"); }
+#endif
   void zero() override {
     if (_frozen) {
       drop_staging();

@@ -19,6 +19,8 @@
 #ifdef B2_WITH_FEMUS_HEADERS
 #include "NumericVector.hpp"
 #include "SparseMatrix.hpp"
+#include "DenseVector.hpp"
+#include "DenseSubvector.hpp"
 #else
 #include "femus_iface/AlgebraBase.hpp"
 #endif
@@ -129,9 +131,21 @@ class B200Vector : public NumericVector {
   void insert(const NumericVector& V, const std::vector<int>& dof) override {
     for (size_t k = 0; k < dof.size(); k++) stage(1, dof[k], V((int)k));
   }
-  void insert(const DenseVector&, const std::vector<int>&) override { B2_NOT_ON_PATH("insert(DenseVector)"); }
-  void insert(const DenseSubVector&, const std::vector<int>&) override { B2_NOT_ON_PATH("insert(DenseSubVector)"); }
-  void add_vector(const DenseVector&, const std::vector<unsigned int>&) override { B2_NOT_ON_PATH("add_vector(DenseVector)"); }
+#ifdef B2_WITH_FEMUS_HEADERS
+  void insert(const DenseVector& V, const std::vector<int>& dof) override {      // PetscVector.cpp:347-359
+    for (size_t k = 0; k < dof.size(); k++) stage(1, dof[k], V((unsigned)k));
+  }
+  void insert(const DenseSubVector& V, const std::vector<int>& dof) override {
+    for (size_t k = 0; k < dof.size(); k++) stage(1, dof[k], V((unsigned)k));
+  }
+  void add_vector(const DenseVector& V, const std::vector<unsigned int>& dof) override {      // PetscVector.cpp:197-201
+    for (size_t k = 0; k < dof.size(); k++) stage(2, (int)dof[k], V((unsigned)k));
+  }
+#else
+  void insert(const DenseVector&, const std::vector<int>&) override { B2_NOT_ON_PATH("insert(DenseVector) (needs the FEMuS dense classes)"); }
+  void insert(const DenseSubVector&, const std::vector<int>&) override { B2_NOT_ON_PATH("insert(DenseSubVector) (needs the FEMuS dense classes)"); }
+  void add_vector(const DenseVector&, const std::vector<unsigned int>&) override { B2_NOT_ON_PATH("add_vector(DenseVector) (needs the FEMuS dense classes)"); }
+#endif
   void close() override {
     if (!_stage_idx.empty()) {
       const int64_t n = (int64_t)_stage_idx.size();
