@@ -50,7 +50,8 @@ def test_adapters_are_subclasses_of_the_reference_interfaces(tmp_path):
     """Compiled against /root/reference's NumericVector.hpp and SparseMatrix.hpp (not copies): every
     pure virtual of the two interfaces is overridden with the reference's exact signature."""
     inc = ["-DB2_WITH_FEMUS_HEADERS", "-I", os.path.join(ROOT, "femus_b200/host/femus_iface/shim"),
-           "-I", os.path.join(REF, "03_algebra/00_vectors"), "-I", os.path.join(REF, "03_algebra/01_matrices")]
+           "-I", os.path.join(REF, "03_algebra/00_vectors"), "-I", os.path.join(REF, "03_algebra/01_matrices"),
+           "-I", os.path.join(REF, "03_algebra_dense/00_vectors"), "-I", os.path.join(REF, "03_algebra_dense/01_matrices")]
     for top in ("00_enums", "00_utils"):
         for d, _, _ in os.walk(os.path.join(REF, top)):
             inc += ["-I", d]
