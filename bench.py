@@ -455,8 +455,9 @@ def main():
     bytes_el = (27 * 3 * 8 + 27 * 4 + nve * 8) + (nve * nve + nve) * 8
     cap = ncu_capture(kname, wl_key)
     ach_tf = nel_loc * flop_el / (asm_kernel_ms * 1e-3) / 1e12
-    roofline = {"bound": "tensor" if on_tensor else "fp64 (CUDA-core DFMA pipe; the kernel has no tensor-core or HBM bound: "
-                         "see hbm_view)",
+    roofline = {"bound": "tensor" if on_tensor else "fp64",
+                "bound_note": None if on_tensor else "FP64 FMA pipe of the CUDA cores (same peak as the FP64 tensor pipe on B200); neither "
+                                                     "tensor-core nor HBM bound: see hbm_view",
                 "kernel": kname + " (element assembly fused with the finest Galerkin product; one launch per step)",
                 "achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach_tf / fp64_peak,
                 "peak_source": "measured in this run: issue-rate probe of " + ("mma.sync.m8n8k4.f64" if on_tensor else "DFMA") +
