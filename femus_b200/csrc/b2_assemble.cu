@@ -60,7 +60,7 @@ struct b2_asm {
   // of the child prolongators; sf_tab == null: the tables are not a 3 x 3 x 3 / 4 x 4 x 4 tensor product (kernel not used)
   void* sf_tab;           // device: SfTables
   int32_t* dofL;          // [nel][27]
-  void* lslot;            // [nel][729] uint8 or uint16
+  void* lslot;            // [nel][736] uint8 or uint16 (729 entries in lattice order + padding)
   void* sf_gal;           // device: SfGalTables of the plan `gal`, or null (the child prolongators are not Kronecker products)
 };
 
@@ -670,7 +670,7 @@ assemble_q2_mma_kernel(int64_t nel, int64_t nnode, const double* __restrict__ xy
 // element -> CSR slot map in natural (i, j) order
 template <typename SlotT>
 __global__ void natural_slot_kernel(int64_t total, int nve, const int32_t* __restrict__ dof, const int64_t* __restrict__ rowptr,
-                                    const int32_t* __restrict__ col, SlotT* __restrict__ slot, int* err) {
+                                    const int32_t* __restrict__ col, SlotT* __restrict__ slot, int* err, int out_stride = 0) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int nn = nve * nve;
   for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
@@ -686,7 +686,7 @@ __global__ void natural_slot_kernel(int64_t total, int nve, const int32_t* __res
       else hi = mid;
     }
     if (lo >= en || col[lo] != c) atomicExch(err, 1);
-    slot[t] = (SlotT)(lo - s);
+    slot[out_stride ? e * out_stride + idx : t] = (SlotT)(lo - s);
   }
 }
 
@@ -886,12 +886,13 @@ static int sf_build_slots(b2_asm* p) {
   b2_ctx* c = p->mesh->ctx;
   const int64_t total = p->mesh->nel * 729;
   SlotT* s = nullptr;
-  B2_TRY(b2_malloc(c, &s, (size_t)total));
+  B2_TRY(b2_malloc(c, &s, (size_t)p->mesh->nel * kSfSlotStride));      // 729 entries per element, padded to 16-byte multiples
+  B2_CUDA(cudaMemsetAsync(s, 0, (size_t)p->mesh->nel * kSfSlotStride * sizeof(SlotT), c->stream));
   p->lslot = s;
   int* d_err = nullptr;
   B2_TRY(b2_malloc(c, &d_err, 1));
   B2_CUDA(cudaMemsetAsync(d_err, 0, sizeof(int), c->stream));
-  B2_LAUNCH(c, natural_slot_kernel<SlotT>, b2_grid_for(c, total, 256, 8), 256, 0, total, 27, p->dofL, p->A->rowptr, p->A->col, s, d_err);
+  B2_LAUNCH(c, natural_slot_kernel<SlotT>, b2_grid_for(c, total, 256, 8), 256, 0, total, 27, p->dofL, p->A->rowptr, p->A->col, s, d_err, kSfSlotStride);
   int err = 0;
   B2_TRY(b2_download(c, &err, d_err, 1));
   b2_free(c, d_err, 1);
@@ -1523,8 +1524,8 @@ int b2_asm_destroy(b2_asm* p) {
   b2_free(c, (SfTables*)p->sf_tab, 1);
   b2_free(c, p->dofL, (size_t)p->mesh->nel * 27);
   if (p->lslot) {
-    if (p->slot_bytes == 1) b2_free(c, (uint8_t*)p->lslot, (size_t)p->mesh->nel * 729);
-    else b2_free(c, (uint16_t*)p->lslot, (size_t)p->mesh->nel * 729);
+    if (p->slot_bytes == 1) b2_free(c, (uint8_t*)p->lslot, (size_t)p->mesh->nel * kSfSlotStride);
+    else b2_free(c, (uint16_t*)p->lslot, (size_t)p->mesh->nel * kSfSlotStride);
   }
   b2_free(c, (SfGalTables*)p->sf_gal, 1);
   delete p;

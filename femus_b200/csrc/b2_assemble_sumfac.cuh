@@ -36,6 +36,8 @@
 // both are built, "asm_warps" of b2_ctx_set_option / B2_SF_WARPS picks one
 constexpr int kSfWarpsDefault = 12;
 constexpr int kSfNG = 64, kSfNVE = 27;
+// slot map of one element: 729 entries padded to 736 so that every element starts on a 16-byte boundary (vector loads)
+constexpr int kSfSlotStride = 736;
 
 struct SfTables {                      // built by sf_prepare from the caller's phi / dphi tables
   double L[3][4];                      // l_i(p_a)
@@ -74,15 +76,16 @@ __constant__ double c_sfU[2][3][4];
 template <int WARPS>
 struct SfSmem {
   // tables: L, D (12 each), M (144), w (64), A (216, fused Galerkin only) | per warp: X[3][28], U[28], row starts[28],
-  // KB = K[7][64] + S1[4][9][18] during the quadrature loop, then the element matrix [27][27]; Dacc [27][27] (fused
-  // Galerkin only)
+  // KB = K[7][64] + S1[4][9][18] during the quadrature loop, then the element matrix [27][27]; the element's slot map
+  // [736]; Dacc [27][27] (fused Galerkin only)
   static constexpr int tab_doubles = 12 + 12 + 144 + 64;
   static constexpr int gal_doubles = 4 + 16 + 736 / 4;      // abc, hi flags, nat2lat
   static constexpr int s1_doubles = 4 * 9 * 18;        // S1 of the four terms of a round: [term][i3 j3][a b], rows padded to 18
                                                        // (stride 16 puts the 9 rows a quarter-warp reads on the same banks)
   static constexpr int kb_doubles = 7 * 64 + s1_doubles;   // K, S1; later the element matrix (729)
   static constexpr int dacc_doubles = 736;
-  static constexpr int warp_doubles = 3 * 28 + 28 + 28 + kb_doubles;
+  static constexpr int slot_doubles = kSfSlotStride * 2 / 8;      // this element's slot map, staged early (16-bit entries at most)
+  static constexpr int warp_doubles = 3 * 28 + 28 + 28 + kb_doubles + slot_doubles;
   static constexpr int warp_doubles_gal = warp_doubles + dacc_doubles + 28;      // + row starts of the coarse dofs
   static constexpr size_t bytes = (size_t)(tab_doubles + WARPS * warp_doubles) * sizeof(double);
   static constexpr size_t bytes_gal = (size_t)(tab_doubles + gal_doubles + WARPS * warp_doubles_gal) * sizeof(double);
@@ -177,7 +180,8 @@ assemble_q2_sumfac_kernel(int64_t nel, int64_t nnode, const double* __restrict__
   double* sK = reinterpret_cast<double*>(sRow + 28);    // [7][64]: K00 K01 K02 K11 K12 K22, w det
   double* sS1 = sK + 7 * NG;                            // [4][9][18] stage-1 sums of the four terms of a round
   double* Bs = sK;                                      // [27][27] element matrix (lattice order), reuses sK / sS1
-  double* Dacc = sK + Smem::kb_doubles;               // [27][27] Galerkin matrix of the coarse element (GAL)
+  SlotT* sSlot = reinterpret_cast<SlotT*>(sK + Smem::kb_doubles);      // [736] slot map of the current element
+  double* Dacc = sK + Smem::kb_doubles + Smem::slot_doubles;      // [27][27] Galerkin matrix of the coarse element (GAL)
   long long* sCRow = reinterpret_cast<long long*>(Dacc + Smem::dacc_doubles);      // [28] Cp[coarse dof] (GAL)
 
   for (int t = threadIdx.x; t < Smem::tab_doubles; t += blockDim.x) smem[t] = reinterpret_cast<const double*>(tabs)[t];
@@ -230,6 +234,17 @@ assemble_q2_sumfac_kernel(int64_t nel, int64_t nnode, const double* __restrict__
     for (int child = 0; child < (GAL ? 8 : 1); child++) {
       const int64_t e = GAL ? unit * 8 + child : unit;
       // ---- gather (lattice order): coordinates, dofs, current solution, row starts
+      // the element's slot map feeds the addresses of the scatter at the END of the element: its 16-byte pieces are
+      // requested now, sit in registers while the geometry is computed (whose register demand is far below the
+      // stiffness stages') and go to shared memory after phase A -- the scatter then never waits for global memory
+      constexpr int SLOT_VECS = kSfSlotStride * (int)sizeof(SlotT) / 16, SLOT_LOADS = (SLOT_VECS + 31) / 32;
+      double2 sv[SLOT_LOADS];
+      {
+        const double2* src = reinterpret_cast<const double2*>(lslot + (size_t)e * kSfSlotStride);
+#pragma unroll
+        for (int q = 0; q < SLOT_LOADS; q++)
+          if (lane + 32 * q < SLOT_VECS) sv[q] = src[lane + 32 * q];
+      }
       int mydof = 0, fm = 0;
       if (lane < NVE) {
         const int64_t nd = nd_pf;
@@ -306,6 +321,12 @@ assemble_q2_sumfac_kernel(int64_t nel, int64_t nnode, const double* __restrict__
           sK[5 * NG + g] = wd * fma(I22, I22, fma(I12, I12, I02 * I02));
           sK[6 * NG + g] = wd;
         }
+      }
+      {
+        double2* dst = reinterpret_cast<double2*>(sSlot);
+#pragma unroll
+        for (int q = 0; q < SLOT_LOADS; q++)
+          if (lane + 32 * q < SLOT_VECS) dst[lane + 32 * q] = sv[q];
       }
       __syncwarp();
 
@@ -396,10 +417,9 @@ assemble_q2_sumfac_kernel(int64_t nel, int64_t nnode, const double* __restrict__
       }
       // ---- scatter: lattice (i, j) order through the slot map
       {
-        const SlotT* sl = lslot + (size_t)e * (NVE * NVE);
         for (int idx = lane; idx < NVE * NVE; idx += 32) {
           const int i = idx / NVE;
-          atomicAdd(&Aval[sRow[i] + (long long)sl[idx]], Bs[idx]);
+          atomicAdd(&Aval[sRow[i] + (long long)sSlot[idx]], Bs[idx]);
         }
       }
       __syncwarp();

@@ -32,14 +32,14 @@ int emu_sumfac(int64_t nel, int64_t nnode, const double* xyz, const int32_t* con
   std::memcpy(c_sfM, T.M, sizeof(T.M));
   std::memcpy(c_sfU, T.L, sizeof(T.L) + sizeof(T.D));
   std::vector<int32_t> dofL((size_t)nel * 27);
-  std::vector<uint16_t> lslot((size_t)nel * 729);
+  std::vector<uint16_t> lslot((size_t)nel * kSfSlotStride, 0);
   for (int64_t e = 0; e < nel; e++) {
     for (int m = 0; m < 27; m++) dofL[e * 27 + m] = dof[e * 27 + T.node_of[m]];
     for (int i = 0; i < 27; i++)
       for (int j = 0; j < 27; j++) {
         const int s = slot_of(rowptr, col, dofL[e * 27 + i], dofL[e * 27 + j]);
         if (s < 0) return 2;
-        lslot[e * 729 + i * 27 + j] = (uint16_t)s;
+        lslot[e * kSfSlotStride + i * 27 + j] = (uint16_t)s;
       }
   }
   SfGalArgs ga = {};
