@@ -19,6 +19,7 @@ struct b2_mg_level {
   uint64_t Pversion = 0;    // P->version R was built from (values of P changed in place => R is rebuilt)
   b2_vec *dinv = nullptr, *x = nullptr, *t = nullptr, *b = nullptr, *r = nullptr;
   int32_t* bdc = nullptr;   // device copy of the Dirichlet row list
+  std::vector<int32_t> bdc_host;      // what it holds
   int64_t nbdc = 0;
   b2_halo* halo = nullptr;  // borrowed: distributed layout of this level's vectors (null: single rank)
   int npre = 1, npost = 1;
@@ -557,15 +558,21 @@ int b2_mg_set_level(b2_mg* mg, int level, b2_csr* A, b2_csr* P, const int32_t* b
       B2_TRY(b2_vec_create(c, n, &mg->w));
     }
   }
-  if (L.bdc) { b2_free(c, L.bdc, (size_t)L.nbdc); L.bdc = nullptr; }
-  L.nbdc = nbdc;
   B2_CHECK(!L.halo || L.halo->n_local == n, "b2_mg_set_level: layout of level %d has %lld dofs, operator %lld", level,
            (long long)(L.halo ? L.halo->n_local : 0), (long long)n);
-  if (nbdc) {
+  // the Dirichlet row list rarely changes between two MGSetLevel calls: keep the device copy (a cudaFree here would wait
+  // for every stream of the device, e.g. for the next step's inputs still uploading on the copy stream)
+  const bool same_bdc = L.bdc_host.size() == (size_t)nbdc && (nbdc == 0 || memcmp(L.bdc_host.data(), bdc_idx, (size_t)nbdc * sizeof(int32_t)) == 0);
+  if (!same_bdc) {
+    if (L.bdc) { b2_free(c, L.bdc, (size_t)L.nbdc); L.bdc = nullptr; }
+    L.bdc_host.assign(bdc_idx, bdc_idx + nbdc);
+  }
+  L.nbdc = nbdc;
+  if (nbdc && !same_bdc) {
     B2_TRY(b2_malloc(c, &L.bdc, (size_t)nbdc));
     B2_TRY(b2_upload(c, L.bdc, bdc_idx, (size_t)nbdc));
-    B2_TRY(b2_csr_zero_rows_dev(A, L.bdc, nbdc, 1.0, owned(L)));     // SetPenalty
   }
+  if (nbdc) B2_TRY(b2_csr_zero_rows_dev(A, L.bdc, nbdc, 1.0, owned(L)));     // SetPenalty
   B2_TRY(b2_csr_diag(A, L.dinv));
   if (L.halo) B2_TRY(b2_halo_sum(L.halo, L.dinv));       // diagonal of the summed operator
   B2_LAUNCH(c, recip_kernel, vec_grid(c, n), kBlock, 0, n, L.dinv->d, L.dinv->d);

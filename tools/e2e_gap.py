@@ -29,7 +29,7 @@ def upload_next():
     ctx.mark_copies()
 
 
-def run(K, upload, download, scalar):
+def run(K, upload, download, scalar, order="scalar_first"):
     for _ in range(3):
         pb.step()
     ctx.sync()
@@ -56,15 +56,28 @@ def run(K, upload, download, scalar):
         t0 = time.perf_counter()
         pb.step()
         t_host += time.perf_counter() - t0
+        if scalar and order == "scalar_first":
+            pb.residual_norm()
         if download:
             pb.EPS.fetch(h_eps.data_ptr(), n)
-        if scalar:
+        if scalar and order != "scalar_first":
             pb.residual_norm()
     ctx.join_copies()
     ms = ctx.timer_stop_ms()
     return ms / K, t_host / K * 1e3
 
 
-for up, down, sc in ((0, 0, 0), (0, 0, 1), (0, 1, 1), (1, 0, 1), (1, 1, 1), (1, 1, 0)):
-    ms, host = run(6, up, down, sc)
-    print(json.dumps({"upload": up, "download": down, "scalar_per_step": sc, "ms_per_step": ms, "host_enqueue_ms_per_step": host}))
+# the host -> device link itself: the step's inputs (coordinates + connectivity + solution) from pinned memory, alone
+ctx.sync()
+t0 = time.perf_counter()
+for _ in range(3):
+    upload_next()
+    ctx.join_copies()
+    ctx.sync()
+dt = (time.perf_counter() - t0) / 3
+nbytes = h_xyz.numel() * 8 + h_conn.numel() * 4 + n * 8
+print(json.dumps({"h2d_bytes": nbytes, "h2d_ms_alone": dt * 1e3, "h2d_GBs": nbytes / dt / 1e9}))
+for up, down, sc, order in ((0, 0, 0, ""), (0, 0, 1, ""), (0, 1, 1, "download_first"), (0, 1, 1, "scalar_first"), (1, 0, 1, ""),
+                            (1, 1, 1, "download_first"), (1, 1, 1, "scalar_first"), (1, 1, 0, "")):
+    ms, host = run(6, up, down, sc, order)
+    print(json.dumps({"upload": up, "download": down, "scalar_per_step": sc, "order": order, "ms_per_step": ms, "host_enqueue_ms_per_step": host}))
