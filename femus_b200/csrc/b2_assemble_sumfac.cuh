@@ -471,3 +471,101 @@ assemble_q2_sumfac_kernel(int64_t nel, int64_t nnode, const double* __restrict__
     }
   }
 }
+
+// ---- Galerkin product of a COARSER level pair from the recorded element matrices, through the same Kronecker factors:
+// A_{l-1} = sum_E Pc(E)^T D_E Pc(E) with D_E the Galerkin element matrix of element E of level l (natural order, as the
+// fused kernel above and this kernel record them).  One warp takes the 8 children of a coarser element one after the
+// other: load D (5.8 KB, coalesced) into the lattice order, six 1-D passes in registers (2 x 3 x 27 triples per lane
+// instead of 2 x 125 x 27 multiply-adds of the column-list form), sum in the warp's own tile, scatter + record once.
+constexpr int kSfChainWarps = 12;
+template <int WARPS>
+struct SfChainSmem {
+  static constexpr int gal_doubles = 4 + 16 + 736 / 4;      // abc, hi flags, nat2lat (as SfSmem)
+  static constexpr int warp_doubles = 736 + 736 + 28 + 16;  // B, Dacc, row starts of the coarse dofs, lattice -> natural node (ints)
+  static constexpr size_t bytes = (size_t)(gal_doubles + WARPS * warp_doubles) * sizeof(double);
+};
+
+template <int WARPS, typename CSlotT>
+__global__ void __launch_bounds__(WARPS * 32, 1)
+galerkin_chain_sumfac_kernel(int64_t nelc, const double* __restrict__ emat_in, const int32_t* __restrict__ dof_in, const SfGalArgs ga) {
+  constexpr int NVE = kSfNVE;
+  using Smem = SfChainSmem<WARPS>;
+  B2_DYN_SHARED(double, smem);
+  double* sA = smem;                  // a, b, c, -; then int hi[8][4]; then nat2lat
+  const int* sHi = reinterpret_cast<const int*>(sA + 4);
+  const unsigned short* sN2L = reinterpret_cast<const unsigned short*>(sA + 4 + 16);
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  double* wbase = smem + Smem::gal_doubles + wib * Smem::warp_doubles;
+  double* Bs = wbase;                                   // [27][27] lattice order
+  double* Dacc = Bs + 736;                              // [27][27] lattice order
+  long long* sCRow = reinterpret_cast<long long*>(Dacc + 736);      // [28]
+  int* sNodeAt = reinterpret_cast<int*>(sCRow + 28);    // [27] natural node at lattice position m
+  {
+    const double* src = reinterpret_cast<const double*>(ga.tab);
+    for (int t = threadIdx.x; t < Smem::gal_doubles; t += blockDim.x) sA[t] = src[t];
+  }
+  __syncthreads();
+  if (lane < NVE) sNodeAt[sN2L[lane * NVE] / NVE] = lane;      // nat2lat[I * 27 + J] = lattice(I) * 27 + lattice(J), lattice(J) < 27
+  __syncwarp();
+  const int lb = lane < NVE ? lane : NVE - 1;
+  const double ka = sA[0], kb = sA[1], kc = sA[2];
+  for (int64_t unit = (int64_t)blockIdx.x * WARPS + wib; unit < nelc; unit += (int64_t)gridDim.x * WARPS) {
+    for (int t = lane; t < 736; t += 32) Dacc[t] = 0.0;
+    int cm = 0;
+    if (lane < NVE) {
+      const int32_t dI = ga.cd[unit * NVE + lane];
+      sCRow[lane] = ga.Cp[dI];
+      cm = ga.cmask ? (int)ga.cmask[dI] : 0;
+    }
+    const unsigned cmaskbits = __ballot_sync(0xffffffffu, cm != 0);
+#pragma unroll 1
+    for (int child = 0; child < 8; child++) {
+      const int64_t e = unit * 8 + child;
+      const double* De = emat_in + (size_t)e * (NVE * NVE);
+      for (int idx = lane; idx < NVE * NVE; idx += 32) Bs[sN2L[idx]] = De[idx];
+      int fm = 0;
+      if (ga.fmask && lane < NVE) fm = (int)ga.fmask[dof_in[e * NVE + sNodeAt[lane]]];
+      const unsigned mask = __ballot_sync(0xffffffffu, fm != 0);      // this level's Dirichlet dofs, lattice order
+      __syncwarp();
+      const bool hi1 = sHi[child * 4 + 0] != 0, hi2 = sHi[child * 4 + 1] != 0, hi3 = sHi[child * 4 + 2] != 0;
+      double R[27];
+#pragma unroll
+      for (int j = 0; j < NVE; j++) R[j] = Bs[lb * NVE + j];
+      if (mask) {
+        const bool rowdead = (mask >> lb) & 1u;
+#pragma unroll
+        for (int j = 0; j < NVE; j++)
+          if (rowdead || ((mask >> j) & 1u)) R[j] = 0.0;
+      }
+      sf_kron_pass<1>(R, hi3, ka, kb, kc);
+      sf_kron_pass<3>(R, hi2, ka, kb, kc);
+      sf_kron_pass<9>(R, hi1, ka, kb, kc);
+      __syncwarp();
+      if (lane < NVE) {
+#pragma unroll
+        for (int j = 0; j < NVE; j++) Bs[lane * NVE + j] = R[j];
+      }
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < NVE; i++) R[i] = Bs[i * NVE + lb];
+      sf_kron_pass<1>(R, hi3, ka, kb, kc);
+      sf_kron_pass<3>(R, hi2, ka, kb, kc);
+      sf_kron_pass<9>(R, hi1, ka, kb, kc);
+      if (lane < NVE) {
+#pragma unroll
+        for (int i = 0; i < NVE; i++) Dacc[i * NVE + lane] += R[i];
+      }
+      __syncwarp();
+    }
+    const CSlotT* cslot = reinterpret_cast<const CSlotT*>(ga.cslot) + (size_t)unit * (NVE * NVE);
+    for (int idx = lane; idx < NVE * NVE; idx += 32) {
+      const double v = Dacc[sN2L[idx]];
+      if (ga.emat) ga.emat[(size_t)unit * (NVE * NVE) + idx] = v;
+      if (v == 0.0) continue;
+      const int I = idx / NVE, Jn = idx - I * NVE;
+      if (((cmaskbits >> I) | (cmaskbits >> Jn)) & 1u) continue;
+      atomicAdd(&ga.Cv[sCRow[I] + (long long)cslot[idx]], v);
+    }
+    __syncwarp();
+  }
+}

@@ -45,6 +45,8 @@ struct b2_galerkin {
   double* emat;     // [nelc][nc*nc] or null
   void* chain_tab;  // per-child prolongator tables for b2_galerkin_apply_from_elements, or null
   int chain_tab_nve;
+  void* chain_sf;   // Kronecker factors of the same prolongators (sum-factorised chain kernel), or null
+  int chain_sf_tried;
 };
 
 namespace {
@@ -330,12 +332,14 @@ struct b2_galerkin_view {
   double** emat;        // storage slots owned by the plan (element-matrix chain)
   void** chain_tab;
   int* chain_tab_nve;
+  void** chain_sf;
+  int* chain_sf_tried;
 };
 int b2_galerkin_get_view(const b2_galerkin* g, b2_galerkin_view* v) {
   B2_CHECK(g && v, "b2_galerkin_get_view: null argument");
   b2_galerkin* m = const_cast<b2_galerkin*>(g);
   *v = b2_galerkin_view{g->Af, g->Ac, g->nelc, g->nf, g->nc, g->fd, g->cd, g->ploc, g->fmask, g->cmask, g->slot, g->slot_bytes,
-                        &m->emat, &m->chain_tab, &m->chain_tab_nve};
+                        &m->emat, &m->chain_tab, &m->chain_tab_nve, &m->chain_sf, &m->chain_sf_tried};
   return 0;
 }
 
@@ -391,6 +395,8 @@ int b2_galerkin_create(b2_csr* Af, b2_csr* Ac, int64_t nelc, int nf, int nc, con
   g->emat = nullptr;
   g->chain_tab = nullptr;
   g->chain_tab_nve = 0;
+  g->chain_sf = nullptr;
+  g->chain_sf_tried = 0;
   if (fine_mask) {
     B2_TRY(b2_malloc(c, &g->fmask, (size_t)Af->nrows));
     B2_TRY(b2_upload(c, g->fmask, fine_mask, (size_t)Af->nrows));
@@ -434,6 +440,7 @@ int b2_galerkin_destroy(b2_galerkin* g) {
   const size_t ns = (size_t)g->nelc * g->nc * g->nc;
   if (g->emat) b2_free(c, g->emat, ns);
   if (g->chain_tab) { cudaFree(g->chain_tab); }
+  if (g->chain_sf) { cudaFree(g->chain_sf); }
   if (g->slot_bytes == 1) b2_free(c, (uint8_t*)g->slot, ns);
   else b2_free(c, (uint16_t*)g->slot, ns);
   delete g;
