@@ -96,6 +96,61 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------
+class HostMemoryNearGpu:
+    """Places the pinned host buffers of the end-to-end leg on the NUMA node of this rank's GPU: on a two-socket box
+    eight ranks pulling 6 GB per step through one socket's memory controllers (first touch puts every rank's pages
+    where its process happens to run) is what limits the end-to-end leg at N = 8.  set_mempolicy(MPOL_PREFERRED) around
+    the allocations, restored afterwards; reports what it found / did (containers may forbid the call)."""
+    SYS_set_mempolicy = 238          # x86_64
+    MPOL_DEFAULT, MPOL_PREFERRED = 0, 1
+
+    def __init__(self, torch, local_rank):
+        self.info = {"gpu_numa_node": None, "nodes": None, "policy": "default"}
+        self.node = None
+        try:
+            nodes = [int(d[4:]) for d in os.listdir("/sys/devices/system/node") if d.startswith("node") and d[4:].isdigit()]
+            self.info["nodes"] = len(nodes)
+            p = torch.cuda.get_device_properties(local_rank)
+            bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+            node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
+            self.info["gpu_numa_node"] = node
+            if node >= 0 and len(nodes) > 1 and node in nodes:
+                self.node = node
+        except Exception as e:          # no sysfs / no pci ids: leave the default policy
+            self.info["policy"] = f"default ({type(e).__name__})"
+
+    def _set(self, mode, node):
+        import ctypes
+        libc = ctypes.CDLL(None, use_errno=True)
+        if mode == self.MPOL_DEFAULT:
+            rc = libc.syscall(self.SYS_set_mempolicy, mode, None, 0)
+        else:
+            mask = (ctypes.c_ulong * 16)()
+            mask[node // 64] = 1 << (node % 64)
+            rc = libc.syscall(self.SYS_set_mempolicy, mode, mask, 16 * 64 + 1)
+        if rc != 0:
+            raise OSError(ctypes.get_errno(), os.strerror(ctypes.get_errno()))
+
+    def __enter__(self):
+        if self.node is not None:
+            try:
+                self._set(self.MPOL_PREFERRED, self.node)
+                self.info["policy"] = "preferred"
+            except Exception as e:
+                self.info["policy"] = f"default (set_mempolicy: {e})"
+                self.node = None
+        return self
+
+    def __exit__(self, *a):
+        if self.node is not None:
+            try:
+                self._set(self.MPOL_DEFAULT, 0)
+            except Exception:
+                pass
+        return False
+
+
+# ---------------------------------------------------------------------------------------------
 def cpu_reference_problem(n0, nlevels, order, nthreads):
     """Setup (untimed) of the CPU sample, what system.init() does once: oracle meshes, patterns,
     prolongators with their Dirichlet rows/columns zeroed, Dirichlet index lists."""
@@ -292,9 +347,12 @@ def main():
     def pinned(a):
         t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
         return t
-    h_xyz, h_conn = pinned(top.xyz), pinned(top.conn)
-    h_sol = torch.zeros(n_loc, dtype=torch.float64).pin_memory()
-    h_eps = torch.zeros(n_loc, dtype=torch.float64).pin_memory()
+    near = HostMemoryNearGpu(torch, local_rank)
+    with near:
+        h_xyz, h_conn = pinned(top.xyz), pinned(top.conn)
+        h_sol = torch.zeros(n_loc, dtype=torch.float64).pin_memory()
+        h_eps = torch.zeros(n_loc, dtype=torch.float64).pin_memory()
+    config["host_buffers"] = dict(near.info, cpus=len(os.sched_getaffinity(0)))
     h2d = sum_over_ranks(h_xyz.numel() * 8 + h_conn.numel() * 4 + n_loc * 8)
     d2h = sum_over_ranks(n_loc * 8 + 8)
 

@@ -12,6 +12,8 @@ struct b2_stokes {
   int32_t* edof = nullptr;      // [nel][4][27]
   double *tabv = nullptr, *tabp = nullptr;
   double* tabns = nullptr;      // phi, dxi, deta, dzeta, w of the velocity element (Navier-Stokes kernel); null without phi_v
+  unsigned short* slot = nullptr;     // [nel][3 nv nv + 6 nv np] position of every element coupling inside its CSR row
+  unsigned short* slot_ns = nullptr;  // [nel][9 nv nv + 6 nv np] the same for the ten blocks of the Newton Jacobian
   int64_t nel = 0;
 };
 
@@ -20,6 +22,29 @@ namespace {
 #include "b2_ns_kernel.cuh"
 #include "b2_neumann_kernel.cuh"
 size_t stokes_smem(int nv, int np, int ng) { return (size_t)kStokesWarps * (size_t)stokes_warp_doubles_host(nv, np, ng) * sizeof(double); }
+
+// element -> CSR slot map of a plan (ns: the nine velocity blocks of the Newton Jacobian instead of the three diagonals);
+// fails loudly when an element coupling is not an entry of the pattern
+int build_slot_map(b2_stokes* p, bool ns) {
+  b2_ctx* c = p->ctx;
+  const size_t per = ns ? (size_t)ns_slots_per_element(p->nv, p->np) : (size_t)stokes_slots_per_element(p->nv, p->np);
+  const size_t total = (size_t)p->nel * per;
+  unsigned short** dst = ns ? &p->slot_ns : &p->slot;
+  B2_TRY(b2_malloc(c, dst, total));
+  int* d_err = nullptr;
+  B2_TRY(b2_malloc(c, &d_err, 1));
+  int h_err = 0;
+  B2_TRY(b2_upload(c, d_err, &h_err, 1));
+  const int grid = b2_grid_for(c, (int64_t)total, 256, 8);
+  if (ns) B2_LAUNCH(c, ns_slot_kernel, grid, 256, 0, p->nel, p->nv, p->np, p->edof, p->A->rowptr, p->A->col, *dst, d_err);
+  else B2_LAUNCH(c, stokes_slot_kernel, grid, 256, 0, p->nel, p->nv, p->np, p->edof, p->A->rowptr, p->A->col, *dst, d_err);
+  const int rc = b2_download(c, &h_err, d_err, 1);
+  b2_free(c, d_err, 1);
+  if (rc) return rc;
+  B2_CHECK(h_err != 1, "b2_%s_create: an element coupling is not an entry of the system matrix's pattern", ns ? "ns" : "stokes");
+  B2_CHECK(h_err != 2, "b2_%s_create: a row of the system matrix is longer than 65536 entries", ns ? "ns" : "stokes");
+  return 0;
+}
 }  // namespace
 
 extern "C" {
@@ -35,8 +60,8 @@ int b2_stokes_create(b2_mesh* mesh, b2_csr* A, const int32_t* elem_dofs, int nve
   const double* xyz = nullptr;
   const int32_t* conn = nullptr;
   b2_mesh_view(mesh, &c, &nnode, &nel, &xyz, &conn);
-  // every listed dof must be a row of A and every element coupling a pattern entry: checked on the host against the
-  // dof range here, against the pattern by the caller's construction (b2h_system_sparsity_create)
+  // every listed dof must be a row of A (checked here on the host) and every element coupling a pattern entry
+  // (checked on the device while the slot map is built)
   for (int64_t e = 0; e < nel; e++)
     for (int k = 0; k < 4; k++)
       for (int i = 0; i < (k < 3 ? nve_v : nve_p); i++) {
@@ -66,6 +91,7 @@ int b2_stokes_create(b2_mesh* mesh, b2_csr* A, const int32_t* elem_dofs, int nve
     B2_TRY(b2_upload(c, p->tabv, tab.data(), nt));
     B2_TRY(b2_upload(c, p->tabp, phi_p, (size_t)ngauss * nve_p));
     B2_CHECK(stokes_smem(nve_v, nve_p, ngauss) <= 227 * 1024, "b2_stokes_create: the element tables exceed the SM's shared memory");
+    B2_TRY(build_slot_map(p, false));
     return 0;
   }();
   if (rc) {               // nothing half-built is handed out
@@ -88,8 +114,10 @@ int b2_stokes_assemble(b2_stokes* p, const b2_vec* sol, b2_vec* rhs, double IRe)
   const size_t smem = stokes_smem(p->nv, p->np, p->ng);
   // the attribute belongs to the function, not to the plan: set for THIS launch (several plans of a mixed mesh coexist)
   B2_CUDA(cudaFuncSetAttribute(stokes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024)));
-  B2_LAUNCH(c, stokes_kernel, b2_grid_for(c, nel, kStokesWarps, 3), kStokesWarps * 32, smem, nel, nnode, p->nv, p->np, p->ng, xyz, conn, p->edof,
-            p->tabv, p->tabp, p->A->rowptr, p->A->col, p->A->val, sol ? sol->d : nullptr, rhs ? rhs->d : nullptr, IRe);
+  int per_sm = (int)((size_t)220 * 1024 / (smem + 1024));      // CTAs one SM's shared memory holds
+  per_sm = per_sm < 1 ? 1 : (per_sm > 3 ? 3 : per_sm);
+  B2_LAUNCH(c, stokes_kernel, b2_grid_for(c, nel, kStokesWarps, per_sm), kStokesWarps * 32, smem, nel, nnode, p->nv, p->np, p->ng, xyz, conn, p->edof,
+            p->tabv, p->tabp, p->A->rowptr, p->slot, p->A->val, sol ? sol->d : nullptr, rhs ? rhs->d : nullptr, IRe);
   return 0;
 }
 
@@ -111,6 +139,8 @@ int b2_ns_create(b2_mesh* mesh, b2_csr* A, const int32_t* elem_dofs, int nve_v, 
     B2_TRY(b2_upload(p->ctx, p->tabns, tab.data(), nt));
     const size_t smem = (size_t)ns_cta_doubles_host(nve_v, nve_p, ngauss) * sizeof(double);
     B2_CHECK(smem <= 227 * 1024, "b2_ns_create: %zu bytes of shared memory per element exceed the SM", smem);
+    B2_CHECK(ns_threads(nve_v, nve_p) <= kNsMaxThreads, "b2_ns_create: %d threads per element exceed the kernel's bound", ns_threads(nve_v, nve_p));
+    B2_TRY(build_slot_map(p, true));
     return 0;
   }();
   if (rc) {
@@ -132,8 +162,9 @@ int b2_ns_assemble(b2_stokes* p, const b2_vec* sol, b2_vec* rhs, double nu) {
   b2_mesh_view(p->mesh, &c, &nnode, &nel, &xyz, &conn);
   const size_t smem = (size_t)ns_cta_doubles_host(p->nv, p->np, p->ng) * sizeof(double);
   B2_CUDA(cudaFuncSetAttribute(ns_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024)));
-  B2_LAUNCH(c, ns_kernel, b2_grid_for(c, nel, 1, 3), kNsThreads, smem, nel, nnode, p->nv, p->np, p->ng, xyz, conn, p->edof, p->tabns, p->tabp,
-            p->A->rowptr, p->A->col, p->A->val, sol ? sol->d : nullptr, rhs ? rhs->d : nullptr, nu);
+  const int threads = ns_threads(p->nv, p->np);
+  B2_LAUNCH(c, ns_kernel, b2_grid_for(c, nel, 1, 1024 / threads), threads, smem, nel, nnode, p->nv, p->np, p->ng, xyz, conn, p->edof, p->tabns,
+            p->tabp, p->A->rowptr, p->slot_ns, p->A->val, sol ? sol->d : nullptr, rhs ? rhs->d : nullptr, nu);
   return 0;
 }
 
@@ -191,6 +222,8 @@ int b2_ns_pressure_faces(b2_stokes* p, int64_t nfaces, const int32_t* face_elem,
 int b2_stokes_destroy(b2_stokes* p) {
   if (!p) return 0;
   b2_free(p->ctx, p->tabns, (size_t)4 * p->ng * p->nv + p->ng);
+  b2_free(p->ctx, p->slot, (size_t)p->nel * stokes_slots_per_element(p->nv, p->np));
+  b2_free(p->ctx, p->slot_ns, (size_t)p->nel * ns_slots_per_element(p->nv, p->np));
   b2_free(p->ctx, p->edof, (size_t)p->nel * 108);
   b2_free(p->ctx, p->tabv, (size_t)3 * p->ng * p->nv + p->ng);
   b2_free(p->ctx, p->tabp, (size_t)p->ng * p->np);

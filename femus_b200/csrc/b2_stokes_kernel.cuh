@@ -13,36 +13,70 @@
 //
 // One warp per element, table-driven like assemble_general_kernel (any element type: nv <= 27 velocity nodes,
 // np <= 8 pressure nodes, ng <= 64 points).  Phase A: lanes = Gauss points (J, det, J^-1).  Phase B: per Gauss point
-// the nv physical gradients go to shared memory and lane l accumulates the entries l, l + 32, ... of K and G_0..2 in
-// the warp's shared accumulator (nv^2 + 3 nv np doubles; owned entries, no conflicts).  Phase C: residual from the
-// element blocks, then fp64 atomicAdd scatter; the position of a column inside its CSR row is found by bisection
-// (first correct path: a slot map as in the Poisson kernels is the obvious next step).
+// the nv physical gradients (and the np pressure functions) go to a double-buffered shared tile and lane l accumulates
+// the entries l, l + 32, ... of K and, from the next multiple of 32 on, of G_0..2 IN REGISTERS (44 at most; the
+// (i, j) of an owned entry is decoded once per warp, every register row is of one kind: no divergence, no divisions
+// and no shared-memory accumulators in the loop).  Phase C: blocks to shared memory, residual from the element blocks,
+// fp64 atomicAdd scatter through a precomputed element -> CSR slot map (stokes_slot_kernel, once per plan): lanes run
+// along a row of the element block, so the atomics of one instruction fall into the same CSR row.
 #pragma once
 #ifndef B2_DYN_SHARED
 #define B2_DYN_SHARED(type, name) extern __shared__ type name[]
 #endif
 
 constexpr int kStokesWarps = 4;
+constexpr int kStokesAcc = ((27 * 27 + 31) / 32) + ((3 * 27 * 8 + 31) / 32);      // 23 rows of K + 21 rows of G_k
 
-#define B2_STOKES_WARP_DOUBLES(nv, np, ng) (3 * 32 + 3 * 32 + 10 * (ng) + 3 * 32 + 8 + (nv) * (nv) + 3 * (nv) * (np))   /* X, G, Geo, U, P, K, G_k */
+/* per warp: X[3][32], G[2][3][32], Psi[2][8], Geo[10][ng], U[3][32], P[8], row starts [4][32] (int64), dofs [4][32] (int32),
+ * blocks K | G_k [nv nv + 3 nv np] */
+#define B2_STOKES_WARP_DOUBLES(nv, np, ng) (96 + 192 + 16 + 10 * (ng) + 96 + 8 + 128 + 64 + (nv) * (nv) + 3 * (nv) * (np))
 __device__ __forceinline__ int stokes_warp_doubles(int nv, int np, int ng) { return B2_STOKES_WARP_DOUBLES(nv, np, ng); }
 inline int stokes_warp_doubles_host(int nv, int np, int ng) { return B2_STOKES_WARP_DOUBLES(nv, np, ng); }
+/* slots per element: K on the three velocity diagonals [3][nv nv], then G_k in the velocity rows and its transpose in
+ * the pressure rows [2][3 nv np] */
+__host__ __device__ __forceinline__ int stokes_slots_per_element(int nv, int np) { return 3 * nv * nv + 6 * nv * np; }
 
-__device__ __forceinline__ int64_t stokes_find(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, int32_t row, int32_t c) {
-  int64_t lo = rowptr[row], hi = rowptr[row + 1];
-  while (lo < hi) {
-    const int64_t mid = (lo + hi) >> 1;
-    if (col[mid] < c) lo = mid + 1; else hi = mid;
+// position of every element coupling inside its CSR row, once per plan.  t < 3 nK: (k, i, j) of K on diagonal k;
+// then (k, i, j) of G_k in row (U_k, i), column (P, j); then the transposed entry.  err: 1 = coupling not in the pattern,
+// 2 = position does not fit 16 bits
+__global__ void stokes_slot_kernel(int64_t nel, int nv, int np, const int32_t* __restrict__ edof, const int64_t* __restrict__ rowptr,
+                                   const int32_t* __restrict__ col, unsigned short* __restrict__ slot, int* err) {
+  const int nK = nv * nv, nG = nv * np, S = 3 * nK + 6 * nG;
+  const int64_t total = nel * (int64_t)S;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t el = t / S;
+    const int r = (int)(t - el * S);
+    const int32_t* ed = edof + el * 108;
+    int32_t row, c;
+    if (r < 3 * nK) {
+      const int k = r / nK, q = r - k * nK, i = q / nv, j = q - i * nv;
+      row = ed[27 * k + i];
+      c = ed[27 * k + j];
+    } else {
+      const int tr = (r - 3 * nK) / (3 * nG), q = (r - 3 * nK) - tr * 3 * nG, k = q / nG, rr = q - k * nG, i = rr / np, j = rr - i * np;
+      const int32_t du = ed[27 * k + i], dp = ed[81 + j];
+      row = tr ? dp : du;
+      c = tr ? du : dp;
+    }
+    const int64_t s0 = rowptr[row];
+    int64_t lo = s0, hi = rowptr[row + 1];
+    const int64_t end = hi;
+    while (lo < hi) {
+      const int64_t mid = (lo + hi) >> 1;
+      if (col[mid] < c) lo = mid + 1; else hi = mid;
+    }
+    if (lo >= end || col[lo] != c) *err = 1;
+    else if (lo - s0 > 65535) *err = 2;
+    slot[t] = (unsigned short)(lo - s0);
   }
-  return lo;          // the pattern holds every element coupling: col[lo] == c
 }
 
 // tabv: dxi, deta, dzeta [ng][nv], w[ng] of the velocity element; tabp: phi [ng][np] of the pressure element;
-// edof: [nel][4][27] system dofs (U, V, W, P), -1 padded
+// edof: [nel][4][27] system dofs (U, V, W, P), -1 padded; slot: [nel][stokes_slots_per_element]
 __global__ void __launch_bounds__(kStokesWarps * 32)
 stokes_kernel(int64_t nel, int64_t nnode, int nv, int np, int ng, const double* __restrict__ xyz, const int32_t* __restrict__ conn,
               const int32_t* __restrict__ edof, const double* __restrict__ tabv, const double* __restrict__ tabp,
-              const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, double* Aval, const double* __restrict__ sol,
+              const int64_t* __restrict__ rowptr, const unsigned short* __restrict__ slot, double* Aval, const double* __restrict__ sol,
               double* rhs, double IRe) {
   B2_DYN_SHARED(double, smem);
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -51,13 +85,33 @@ stokes_kernel(int64_t nel, int64_t nnode, int nv, int np, int ng, const double* 
   const double* t_dz = t_dy + ng * nv;
   const double* t_w = t_dz + ng * nv;
   double* sX = smem + wib * stokes_warp_doubles(nv, np, ng);      // [3][32]
-  double* sG = sX + 96;                                           // [3][32] physical gradients at the current point
-  double* sGeo = sG + 96;                                         // [10][ng]
+  double* sG = sX + 96;                                           // [2][3][32] physical gradients at the current point
+  double* sPsi = sG + 192;                                        // [2][8]
+  double* sGeo = sPsi + 16;                                       // [10][ng]
   double* sU = sGeo + 10 * ng;                                    // [3][32]
   double* sP = sU + 96;                                           // [8]
-  double* sK = sP + 8;                                            // [nv][nv]
+  int64_t* sRow = reinterpret_cast<int64_t*>(sP + 8);             // [4][32] first slot of the row of (variable, node)
+  int32_t* sDof = reinterpret_cast<int32_t*>(sRow + 128);         // [4][32]
+  double* sK = reinterpret_cast<double*>(sDof + 128);             // [nv][nv]
   double* sGk = sK + nv * nv;                                     // [3][nv][np]
-  const int nK = nv * nv, nG = nv * np, nacc = nK + 3 * nG;
+  const int nK = nv * nv, nG = nv * np;
+  const int nKp = (nK + 31) & ~31;                                // the G rows start at a multiple of 32
+
+  // the entries this lane owns, decoded once: K rows i * 32 + j; G rows (k * 32 + i) * 8 + j; two per register
+  unsigned pk[kStokesAcc / 2];
+#pragma unroll
+  for (int q = 0; q < kStokesAcc; q++) {
+    const int e = lane + 32 * q;
+    unsigned v = 0;
+    if (e < nK) {
+      const int i = e / nv;
+      v = (unsigned)(i * 32 + (e - i * nv));
+    } else if (e >= nKp && e - nKp < 3 * nG) {
+      const int r = e - nKp, k = r / nG, rr = r - k * nG, i = rr / np;
+      v = (unsigned)((k * 32 + i) * 8 + (rr - i * np));
+    }
+    if (q & 1) pk[q >> 1] |= v << 16; else pk[q >> 1] = v;
+  }
 
   for (int64_t el = (int64_t)blockIdx.x * kStokesWarps + wib; el < nel; el += (int64_t)gridDim.x * kStokesWarps) {
     const int32_t* ed = edof + el * 108;
@@ -66,10 +120,19 @@ stokes_kernel(int64_t nel, int64_t nnode, int nv, int np, int ng, const double* 
       sX[lane] = xyz[nd];
       sX[32 + lane] = xyz[nnode + nd];
       sX[64 + lane] = xyz[2 * nnode + nd];
-      for (int k = 0; k < 3; k++) sU[32 * k + lane] = sol ? sol[ed[27 * k + lane]] : 0.0;
+      for (int k = 0; k < 3; k++) {
+        const int32_t d = ed[27 * k + lane];
+        sDof[32 * k + lane] = d;
+        sRow[32 * k + lane] = rowptr[d];
+        sU[32 * k + lane] = sol ? sol[d] : 0.0;
+      }
     }
-    if (lane < np) sP[lane] = sol ? sol[ed[81 + lane]] : 0.0;
-    for (int e = lane; e < nacc; e += 32) sK[e] = 0.0;             // sK and sGk are contiguous
+    if (lane < np) {
+      const int32_t d = ed[81 + lane];
+      sDof[96 + lane] = d;
+      sRow[96 + lane] = rowptr[d];
+      sP[lane] = sol ? sol[d] : 0.0;
+    }
     __syncwarp();
 
     // ---- A. geometry at the Gauss points owned by this lane (Jacobian_type, ElemType.hpp:1438-1537)
@@ -97,30 +160,43 @@ stokes_kernel(int64_t nel, int64_t nnode, int nv, int np, int ng, const double* 
     }
     __syncwarp();
 
-    // ---- B. element blocks K and G_0..2
+    // ---- B. element blocks K and G_0..2, entries lane + 32 q in registers
+    double acc[kStokesAcc];
+#pragma unroll
+    for (int q = 0; q < kStokesAcc; q++) acc[q] = 0.0;
     for (int g = 0; g < ng; g++) {
+      double* G = sG + (g & 1) * 96;
+      double* Psi = sPsi + (g & 1) * 8;
       if (lane < nv) {
         const double a = t_dx[g * nv + lane], b = t_dy[g * nv + lane], c = t_dz[g * nv + lane];
-        sG[lane] = fma(c, sGeo[2 * ng + g], fma(b, sGeo[1 * ng + g], a * sGeo[0 * ng + g]));
-        sG[32 + lane] = fma(c, sGeo[5 * ng + g], fma(b, sGeo[4 * ng + g], a * sGeo[3 * ng + g]));
-        sG[64 + lane] = fma(c, sGeo[8 * ng + g], fma(b, sGeo[7 * ng + g], a * sGeo[6 * ng + g]));
+        G[lane] = fma(c, sGeo[2 * ng + g], fma(b, sGeo[1 * ng + g], a * sGeo[0 * ng + g]));
+        G[32 + lane] = fma(c, sGeo[5 * ng + g], fma(b, sGeo[4 * ng + g], a * sGeo[3 * ng + g]));
+        G[64 + lane] = fma(c, sGeo[8 * ng + g], fma(b, sGeo[7 * ng + g], a * sGeo[6 * ng + g]));
       }
+      if (lane < np) Psi[lane] = tabp[g * np + lane];
       __syncwarp();
       const double wg = sGeo[9 * ng + g];
-      for (int e = lane; e < nacc; e += 32) {
-        if (e < nK) {
-          const int i = e / nv, j = e - i * nv;
-          const double d = fma(sG[64 + i], sG[64 + j], fma(sG[32 + i], sG[32 + j], sG[i] * sG[j]));
-          sK[e] = fma(d, wg, sK[e]);
-        } else {
-          const int q = e - nK, k = q / nG, r = q - k * nG, i = r / np, j = r - i * np;
-          sK[e] = fma(-sG[32 * k + i] * tabp[g * np + j], wg, sK[e]);
+#pragma unroll
+      for (int q = 0; q < kStokesAcc; q++) {
+        const unsigned v = (q & 1) ? pk[q >> 1] >> 16 : pk[q >> 1] & 0xffffu;
+        if (32 * q < nKp) {                      // warp-uniform: a register row of K
+          const int i = v >> 5, j = v & 31;
+          const double d = fma(G[64 + i], G[64 + j], fma(G[32 + i], G[32 + j], G[i] * G[j]));
+          acc[q] = fma(d, wg, acc[q]);
+        } else if (32 * q < nKp + 3 * nG) {      // a register row of G_k
+          acc[q] = fma(-G[v >> 3] * Psi[v & 7], wg, acc[q]);
         }
       }
-      __syncwarp();
     }
 
-    // ---- C. residual F = -B sol, then the scatter
+    // ---- C. blocks to shared memory, residual F = -B sol, scatter through the slot map
+#pragma unroll
+    for (int q = 0; q < kStokesAcc; q++) {
+      const int e = lane + 32 * q;
+      if (e < nK) sK[e] = acc[q];
+      else if (e >= nKp && e - nKp < 3 * nG) sGk[e - nKp] = acc[q];
+    }
+    __syncwarp();
     if (rhs) {
       for (int q = lane; q < 3 * nv + np; q += 32) {
         double f = 0.0;
@@ -130,30 +206,30 @@ stokes_kernel(int64_t nel, int64_t nnode, int nv, int np, int ng, const double* 
           for (int j = 0; j < nv; j++) s = fma(sK[i * nv + j], sU[32 * k + j], s);
           f = -IRe * s;
           for (int j = 0; j < np; j++) f = fma(-sGk[(k * nv + i) * np + j], sP[j], f);
-          atomicAdd(&rhs[ed[27 * k + i]], f);
+          atomicAdd(&rhs[sDof[32 * k + i]], f);
         } else {
           const int i = q - 3 * nv;
           for (int k = 0; k < 3; k++)
             for (int j = 0; j < nv; j++) f = fma(-sGk[(k * nv + j) * np + i], sU[32 * k + j], f);
-          atomicAdd(&rhs[ed[81 + i]], f);
+          atomicAdd(&rhs[sDof[96 + i]], f);
         }
       }
     }
-    for (int e = lane; e < nacc; e += 32) {
+    const unsigned short* sl = slot + (size_t)el * stokes_slots_per_element(nv, np);
+#pragma unroll
+    for (int q = 0; q < kStokesAcc; q++) {
+      const unsigned v = (q & 1) ? pk[q >> 1] >> 16 : pk[q >> 1] & 0xffffu;
+      const int e = lane + 32 * q;
       if (e < nK) {
-        const int i = e / nv, j = e - i * nv;
-        const double v = IRe * sK[e];
-        for (int k = 0; k < 3; k++) {
-          const int32_t r = ed[27 * k + i];
-          atomicAdd(&Aval[stokes_find(rowptr, col, r, ed[27 * k + j])], v);
-        }
-      } else {
-        const int q = e - nK, k = q / nG, rr = q - k * nG, i = rr / np, j = rr - i * np;
-        const int32_t ru = ed[27 * k + i], rp = ed[81 + j];
-        atomicAdd(&Aval[stokes_find(rowptr, col, ru, rp)], sK[e]);
-        atomicAdd(&Aval[stokes_find(rowptr, col, rp, ru)], sK[e]);
+        const int i = v >> 5;
+        const double val = IRe * acc[q];
+        for (int k = 0; k < 3; k++) atomicAdd(&Aval[sRow[32 * k + i] + (int64_t)sl[k * nK + e]], val);
+      } else if (e >= nKp && e - nKp < 3 * nG) {
+        const int r = e - nKp;
+        atomicAdd(&Aval[sRow[v >> 3] + (int64_t)sl[3 * nK + r]], acc[q]);              // row (U_k, i): v >> 3 = 32 k + i
+        atomicAdd(&Aval[sRow[96 + (v & 7)] + (int64_t)sl[3 * nK + 3 * nG + r]], acc[q]);   // row (P, j)
       }
     }
-    __syncwarp();
+    __syncwarp();      // the next element overwrites X, U, P, dofs, Geo, the blocks
   }
 }

@@ -172,16 +172,24 @@ void emu_stokes(int64_t nel, int64_t nnode, int nv, int np, int ng, const double
                 const double* tabv, const double* tabp, const int64_t* rowptr, const int32_t* col, double* Aval, const double* sol, double* rhs,
                 double IRe, int grid) {
   const size_t smem = (size_t)kStokesWarps * (size_t)stokes_warp_doubles_host(nv, np, ng) * sizeof(double);
-  emu::launch(stokes_kernel, (unsigned)grid, (unsigned)(kStokesWarps * 32), smem, nel, nnode, nv, np, ng, xyz, conn, edof, tabv, tabp, rowptr, col,
-              Aval, sol, rhs, IRe);
+  std::vector<unsigned short> slot((size_t)nel * stokes_slots_per_element(nv, np));
+  int err = 0;
+  emu::launch(stokes_slot_kernel, 2u, 64u, 0, nel, nv, np, edof, rowptr, col, slot.data(), &err);
+  if (err) std::abort();
+  emu::launch(stokes_kernel, (unsigned)grid, (unsigned)(kStokesWarps * 32), smem, nel, nnode, nv, np, ng, xyz, conn, edof, tabv, tabp, rowptr,
+              (const unsigned short*)slot.data(), Aval, sol, rhs, IRe);
 }
 
 // what b2_ns_assemble launches: tabv = phi, dxi, deta, dzeta [ng][nv], w[ng]
 void emu_ns(int64_t nel, int64_t nnode, int nv, int np, int ng, const double* xyz, const int32_t* conn, const int32_t* edof, const double* tabv,
             const double* tabp, const int64_t* rowptr, const int32_t* col, double* Aval, const double* sol, double* rhs, double nu, int grid) {
   const size_t smem = (size_t)ns_cta_doubles_host(nv, np, ng) * sizeof(double);
-  emu::launch(ns_kernel, (unsigned)grid, (unsigned)kNsThreads, smem, nel, nnode, nv, np, ng, xyz, conn, edof, tabv, tabp, rowptr, col, Aval, sol, rhs,
-              nu);
+  std::vector<unsigned short> slot((size_t)nel * ns_slots_per_element(nv, np));
+  int err = 0;
+  emu::launch(ns_slot_kernel, 2u, 64u, 0, nel, nv, np, edof, rowptr, col, slot.data(), &err);
+  if (err) std::abort();
+  emu::launch(ns_kernel, (unsigned)grid, (unsigned)ns_threads(nv, np), smem, nel, nnode, nv, np, ng, xyz, conn, edof, tabv, tabp, rowptr,
+              (const unsigned short*)slot.data(), Aval, sol, rhs, nu);
 }
 
 void emu_pressure_faces(int64_t nfaces, const int32_t* felem, const int32_t* flocal, const double* fvalue, int nvf, int ngf, const double* ftab,
