@@ -77,7 +77,7 @@ __global__ void ns_slot_kernel(int64_t nel, int nv, int np, const int32_t* __res
 
 // tabv: phi, dxi, deta, dzeta [ng][nv], w[ng] of the velocity element; tabp: psi [ng][np]; edof [nel][4][27];
 // slot [nel][ns_slots_per_element]; launched with ns_threads(nv, np) threads
-__global__ void __launch_bounds__(kNsMaxThreads)
+__global__ void __launch_bounds__(kNsMaxThreads, 2)
 ns_kernel(int64_t nel, int64_t nnode, int nv, int np, int ng, const double* __restrict__ xyz, const int32_t* __restrict__ conn,
           const int32_t* __restrict__ edof, const double* __restrict__ tabv, const double* __restrict__ tabp,
           const int64_t* __restrict__ rowptr, const unsigned short* __restrict__ slot, double* Aval, const double* __restrict__ sol, double* rhs,

@@ -35,7 +35,8 @@ struct b2_schwarz {
   int* err = nullptr;             // device: 1 + first block whose pivot vanished, or 0
   int64_t n = 0;                  // A->nrows at creation (the borrowed operator may be gone when this object is destroyed)
   int sub = 0;                    // block solve: 0 = exact (dense inverse), 1 = one SSOR iteration on the block's rows, 2 = ILU(0)
-  int64_t* frow = nullptr;        // [ndofs_total] ILU: start of every (block, row)'s factor row
+  int64_t* frow = nullptr;        // [ndofs_total+1] start of every (block, row)'s row of factor values / local indices
+  unsigned short* lidx = nullptr; // [fac_total] staged walk: position of every row entry's column in its block's dof list (b2_schwarz_walk.cuh)
   double* fac = nullptr;          // [fac_total]   ILU factors on the pattern of the blocks' rows of A
   int64_t* foff = nullptr;        // [n]           ILU: factor row of the dof in the block that claimed it
   int64_t fac_total = 0;
@@ -53,10 +54,63 @@ struct b2_schwarz {
 namespace {
 
 #include "b2_schwarz_kernels.cuh"
+#include "b2_schwarz_walk.cuh"
+
+// the row-walking block solves run staged (b2_schwarz_walk.cuh) unless the rows are level-scheduled or a block is too large
+bool staged_walk(const b2_schwarz* s) { return s->sub != 0 && !s->row_levels && s->max_m <= kWalkMaxM; }
+
+// rows of the blocks laid end to end: frow[k] = first slot of block row k (k over blk_dofs), frow[ndofs_total] = total
+int build_frow(b2_schwarz* s) {
+  if (s->frow) return 0;
+  b2_ctx* c = s->ctx;
+  const size_t n = (size_t)s->A->nrows;
+  std::vector<int64_t> rp(n + 1);
+  std::vector<int32_t> bd((size_t)s->ndofs_total);
+  B2_TRY(b2_download(c, rp.data(), s->A->rowptr, n + 1));
+  B2_TRY(b2_download(c, bd.data(), s->blk_dofs, (size_t)s->ndofs_total));
+  std::vector<int64_t> frow((size_t)s->ndofs_total + 1);
+  int64_t tot = 0;
+  for (int64_t k = 0; k < s->ndofs_total; k++) { frow[k] = tot; tot += rp[bd[k] + 1] - rp[bd[k]]; }
+  frow[(size_t)s->ndofs_total] = tot;
+  s->fac_total = tot;
+  B2_TRY(b2_malloc(c, &s->frow, (size_t)s->ndofs_total + 1));
+  B2_TRY(b2_upload(c, s->frow, frow.data(), (size_t)s->ndofs_total + 1));
+  return 0;
+}
+// local indices of the staged walk (pattern only: built once)
+int build_lidx(b2_schwarz* s) {
+  if (s->lidx) return 0;
+  b2_ctx* c = s->ctx;
+  B2_TRY(build_frow(s));
+  B2_TRY(b2_malloc(c, &s->lidx, (size_t)s->fac_total));
+  B2_LAUNCH(c, schwarz_lidx_kernel, b2_grid_for(c, s->nblocks, 1, 8), 256, 0, s->nblocks, s->blk_ptr, s->blk_dofs, s->frow, s->A->rowptr,
+            s->A->col, s->lidx);
+  return 0;
+}
+// grid / CTA size / shared memory of a staged-walk launch over one group
+template <class K>
+int walk_launch_shape(b2_schwarz* s, K kern, int64_t nblk, int* grid, int* threads, size_t* smem) {
+  b2_ctx* c = s->ctx;
+  *smem = walk_smem_bytes(s->max_m);
+  // the attribute belongs to the function: always the fixed maximum, so that no other object's launch can lower it
+  B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)walk_smem_bytes(kWalkMaxM)));
+  *threads = nblk >= 8 * (int64_t)c->sm_count ? 64 : (nblk >= 4 * (int64_t)c->sm_count ? 128 : kApplyThreads);
+  int per_sm = 1;
+  B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, *threads, *smem));
+  *grid = b2_grid_for(c, nblk, 1, per_sm < 1 ? 1 : per_sm);
+  return 0;
+}
 
 }  // namespace
 
 const b2_csr* b2_schwarz_operator(const b2_schwarz* s) { return s ? s->A : nullptr; }
+
+// Row-walking block solves without row levels: ONE warp sweeps a block (the other warps of the CTA only help with the
+// block's residual), so when a group has many blocks small CTAs put more sweeping warps on an SM (32 resident CTAs of
+// 64 threads instead of 8 of 256)
+static inline int walk_threads(const b2_ctx* c, int64_t nblocks_in_group) {
+  return nblocks_in_group >= 8 * (int64_t)c->sm_count ? 64 : (nblocks_in_group >= 4 * (int64_t)c->sm_count ? 128 : kApplyThreads);
+}
 
 extern "C" {
 
@@ -174,7 +228,12 @@ int b2_schwarz_setup(b2_schwarz* s) {
   B2_CHECK(s, "b2_schwarz_setup: null handle");
   b2_ctx* c = s->ctx;
   if (s->sub != 0 && s->row_levels && !s->lvrows_f) B2_TRY(build_row_levels(s));
-  if (s->sub == 1) {              // SSOR works on A's rows: only the scratch vectors are needed
+  if (s->sub == 1 && staged_walk(s)) {      // SSOR works on A's rows: only the local indices are needed
+    B2_TRY(build_lidx(s));
+    s->ready = true;
+    return 0;
+  }
+  if (s->sub == 1) {              // plain / level-scheduled walk: scratch vectors
     const size_t n = (size_t)s->A->nrows;
     if (!s->tg) B2_TRY(b2_malloc(c, &s->tg, n));
     if (!s->dg) B2_TRY(b2_malloc(c, &s->dg, n));
@@ -188,21 +247,26 @@ int b2_schwarz_setup(b2_schwarz* s) {
   }
   if (s->sub == 2) {              // ILU(0) of every block on the pattern of its rows of A, group by group
     const size_t n = (size_t)s->A->nrows;
-    if (!s->fac) {
-      std::vector<int64_t> rp(n + 1), bp((size_t)s->nblocks + 1);
-      std::vector<int32_t> bd((size_t)s->ndofs_total);
-      B2_TRY(b2_download(c, rp.data(), s->A->rowptr, n + 1));
-      B2_TRY(b2_download(c, bp.data(), s->blk_ptr, (size_t)s->nblocks + 1));
-      B2_TRY(b2_download(c, bd.data(), s->blk_dofs, (size_t)s->ndofs_total));
-      std::vector<int64_t> frow((size_t)s->ndofs_total);
-      int64_t tot = 0;
-      for (int64_t k = 0; k < s->ndofs_total; k++) { frow[k] = tot; tot += rp[bd[k] + 1] - rp[bd[k]]; }
-      s->fac_total = tot;
-      B2_TRY(b2_malloc(c, &s->frow, (size_t)s->ndofs_total));
-      B2_TRY(b2_upload(c, s->frow, frow.data(), (size_t)s->ndofs_total));
-      B2_TRY(b2_malloc(c, &s->fac, (size_t)tot));
-      B2_TRY(b2_malloc(c, &s->foff, n));
+    B2_TRY(build_frow(s));
+    if (!s->fac) B2_TRY(b2_malloc(c, &s->fac, (size_t)s->fac_total));
+    if (staged_walk(s)) {
+      B2_TRY(build_lidx(s));
+      B2_CUDA(cudaMemsetAsync(s->err, 0, sizeof(int), c->stream));
+      for (int64_t g = 0; g < s->ngroups; g++) {
+        const int64_t g0 = s->group_ptr[g], g1 = s->group_ptr[g + 1];
+        int grid = 1, threads = 64;
+        size_t smem = 0;
+        B2_TRY(walk_launch_shape(s, schwarz_walk_ilu_factor_kernel, g1 - g0, &grid, &threads, &smem));
+        B2_LAUNCH(c, schwarz_walk_ilu_factor_kernel, grid, threads, smem, g0, g1, s->group_blocks, s->blk_ptr, s->blk_dofs, s->frow, s->lidx,
+                  s->A->rowptr, s->A->val, s->fac, s->err, s->max_m);
+      }
+      int err = 0;
+      B2_TRY(b2_download(c, &err, s->err, 1));
+      B2_CHECK(err == 0, "b2_schwarz_setup: ILU(0) of block %d met a zero pivot", err - 1);
+      s->ready = true;
+      return 0;
     }
+    if (!s->foff) B2_TRY(b2_malloc(c, &s->foff, n));
     if (!s->zg) B2_TRY(b2_malloc(c, &s->zg, n));
     if (!s->mark) {
       B2_TRY(b2_malloc(c, &s->mark, n));
@@ -215,7 +279,7 @@ int b2_schwarz_setup(b2_schwarz* s) {
         B2_LAUNCH(c, schwarz_ilu_factor_kernel<true>, b2_grid_for(c, g1 - g0, 1, 16), kApplyThreads, 0, g0, g1, s->group_blocks, s->blk_ptr,
                   s->blk_dofs, s->frow, s->A->rowptr, s->A->col, s->A->val, s->fac, s->mark, s->foff, s->err, s->lvptr_f, s->lvoff_f, s->lvrows_f);
       else
-        B2_LAUNCH(c, schwarz_ilu_factor_kernel<false>, b2_grid_for(c, g1 - g0, 1, 16), kApplyThreads, 0, g0, g1, s->group_blocks, s->blk_ptr,
+        B2_LAUNCH(c, schwarz_ilu_factor_kernel<false>, b2_grid_for(c, g1 - g0, 1, 2048 / walk_threads(c, g1 - g0)), walk_threads(c, g1 - g0), 0, g0, g1, s->group_blocks, s->blk_ptr,
                   s->blk_dofs, s->frow, s->A->rowptr, s->A->col, s->A->val, s->fac, s->mark, s->foff, s->err, nullptr, nullptr, nullptr);
     }
     int err = 0;
@@ -253,13 +317,27 @@ int b2_schwarz_apply(b2_schwarz* s, const b2_vec* r, b2_vec* y) {
   B2_CUDA(cudaMemsetAsync(y->d, 0, (size_t)s->A->nrows * sizeof(double), c->stream));
   for (int64_t g = 0; g < s->ngroups; g++) {
     const int64_t g0 = s->group_ptr[g], g1 = s->group_ptr[g + 1];
+    if (staged_walk(s)) {
+      int grid = 1, threads = 64;
+      size_t wsm = 0;
+      if (s->sub == 2) {
+        B2_TRY(walk_launch_shape(s, schwarz_walk_apply_kernel<true>, g1 - g0, &grid, &threads, &wsm));
+        B2_LAUNCH(c, schwarz_walk_apply_kernel<true>, grid, threads, wsm, g0, g1, s->group_blocks, s->blk_ptr, s->blk_dofs, s->frow, s->lidx,
+                  s->A->rowptr, s->A->col, s->A->val, s->fac, r->d, y->d, s->max_m);
+      } else {
+        B2_TRY(walk_launch_shape(s, schwarz_walk_apply_kernel<false>, g1 - g0, &grid, &threads, &wsm));
+        B2_LAUNCH(c, schwarz_walk_apply_kernel<false>, grid, threads, wsm, g0, g1, s->group_blocks, s->blk_ptr, s->blk_dofs, s->frow, s->lidx,
+                  s->A->rowptr, s->A->col, s->A->val, (const double*)nullptr, r->d, y->d, s->max_m);
+      }
+      continue;
+    }
     if (s->sub == 2) {
       if (s->row_levels)
         B2_LAUNCH(c, schwarz_apply_ilu_kernel<true>, b2_grid_for(c, g1 - g0, 1, 16), kApplyThreads, 0, g0, g1, s->group_blocks, s->blk_ptr,
                   s->blk_dofs, s->frow, s->A->rowptr, s->A->col, s->A->val, s->fac, r->d, y->d, s->zg, s->mark, s->lvptr_f, s->lvoff_f, s->lvrows_f,
                   s->lvptr_b, s->lvoff_b, s->lvrows_b);
       else
-        B2_LAUNCH(c, schwarz_apply_ilu_kernel<false>, b2_grid_for(c, g1 - g0, 1, 16), kApplyThreads, 0, g0, g1, s->group_blocks, s->blk_ptr,
+        B2_LAUNCH(c, schwarz_apply_ilu_kernel<false>, b2_grid_for(c, g1 - g0, 1, 2048 / walk_threads(c, g1 - g0)), walk_threads(c, g1 - g0), 0, g0, g1, s->group_blocks, s->blk_ptr,
                   s->blk_dofs, s->frow, s->A->rowptr, s->A->col, s->A->val, s->fac, r->d, y->d, s->zg, s->mark, nullptr, nullptr, nullptr, nullptr,
                   nullptr, nullptr);
       continue;
@@ -270,7 +348,7 @@ int b2_schwarz_apply(b2_schwarz* s, const b2_vec* r, b2_vec* y) {
                   s->blk_dofs, s->A->rowptr, s->A->col, s->A->val, r->d, y->d, s->tg, s->dg, s->zg, s->mark, s->lvptr_f, s->lvoff_f, s->lvrows_f,
                   s->lvptr_b, s->lvoff_b, s->lvrows_b);
       else
-        B2_LAUNCH(c, schwarz_apply_ssor_kernel<false>, b2_grid_for(c, g1 - g0, 1, 16), kApplyThreads, 0, g0, g1, s->group_blocks, s->blk_ptr,
+        B2_LAUNCH(c, schwarz_apply_ssor_kernel<false>, b2_grid_for(c, g1 - g0, 1, 2048 / walk_threads(c, g1 - g0)), walk_threads(c, g1 - g0), 0, g0, g1, s->group_blocks, s->blk_ptr,
                   s->blk_dofs, s->A->rowptr, s->A->col, s->A->val, r->d, y->d, s->tg, s->dg, s->zg, s->mark, nullptr, nullptr, nullptr, nullptr,
                   nullptr, nullptr);
       continue;
@@ -283,7 +361,7 @@ int b2_schwarz_apply(b2_schwarz* s, const b2_vec* r, b2_vec* y) {
 
 int64_t b2_schwarz_bytes(const b2_schwarz* s) {
   if (!s) return 0;
-  return ((s->inv ? s->inv_total : 0) + (s->fac ? s->fac_total : 0)) * (int64_t)sizeof(double);
+  return ((s->inv ? s->inv_total : 0) + (s->fac ? s->fac_total : 0)) * (int64_t)sizeof(double) + (s->lidx ? s->fac_total : 0) * (int64_t)sizeof(unsigned short);
 }
 int64_t b2_schwarz_groups(const b2_schwarz* s) { return s ? s->ngroups : 0; }
 
@@ -300,7 +378,8 @@ int b2_schwarz_destroy(b2_schwarz* s) {
   b2_free(c, s->lvoff_b, (size_t)s->lvoff_b_n);
   b2_free(c, s->lvrows_f, (size_t)s->ndofs_total);
   b2_free(c, s->lvrows_b, (size_t)s->ndofs_total);
-  b2_free(c, s->frow, (size_t)s->ndofs_total);
+  b2_free(c, s->frow, (size_t)s->ndofs_total + 1);
+  b2_free(c, s->lidx, (size_t)s->fac_total);
   b2_free(c, s->fac, (size_t)s->fac_total);
   b2_free(c, s->foff, (size_t)s->n);
   b2_free(c, s->tg, (size_t)s->n);

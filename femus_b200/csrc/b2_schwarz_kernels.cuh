@@ -7,6 +7,7 @@
 #endif
 
 constexpr int kApplyThreads = 256;
+constexpr int kRowBatch = 8;         // row entries per lane in flight in the row-walking block solves
 constexpr int kInvertThreads = 512;
 
 __global__ void schwarz_extract_kernel(int64_t nblocks, const int64_t* __restrict__ blk_ptr, const int32_t* __restrict__ blk_dofs,
@@ -218,13 +219,33 @@ struct ssor_row {
   const double* tg;
   const double* dg;
   bool forward;
+  // Entry k of the row belongs to lane (k - row start) % 32 and is added in ascending k: the arithmetic of the plain
+  // strided loop.  Eight entries per lane are in flight at a time and nothing branches: column, membership mark and
+  // block solution are three dependent loads per BATCH instead of three per entry (the sweep is a chain of such rows).
   __device__ void operator()(int i) const {
     const int lane = threadIdx.x & 31;
     const int64_t row = c.D[i];
+    const int64_t k1 = c.rowptr[row + 1];
     double s = 0.0;
-    for (int64_t k = c.rowptr[row] + lane; k < c.rowptr[row + 1]; k += 32) {
-      const int32_t cc = c.col[k];
-      if ((forward ? cc < row : cc != row) && c.mark[cc] == c.b) s = fma(c.val[k], c.zg[cc], s);
+    for (int64_t kb = c.rowptr[row] + lane; kb < k1; kb += 32 * kRowBatch) {
+      int32_t cc[kRowBatch];
+      double v[kRowBatch], z[kRowBatch];
+      bool use[kRowBatch];
+#pragma unroll
+      for (int j = 0; j < kRowBatch; j++) {
+        const int64_t k = kb + 32 * j;
+        const bool ok = k < k1;
+        cc[j] = ok ? c.col[k] : (int32_t)row;
+        v[j] = ok ? c.val[k] : 0.0;
+        use[j] = forward ? cc[j] < row : cc[j] != row;
+      }
+#pragma unroll
+      for (int j = 0; j < kRowBatch; j++) use[j] = use[j] && c.mark[use[j] ? cc[j] : (int32_t)row] == c.b;
+#pragma unroll
+      for (int j = 0; j < kRowBatch; j++) z[j] = use[j] ? c.zg[cc[j]] : 0.0;      // only members are read: no stray reads of other blocks' dofs
+#pragma unroll
+      for (int j = 0; j < kRowBatch; j++)
+        if (use[j]) s = fma(v[j], z[j], s);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
@@ -354,19 +375,33 @@ struct ilu_solve_row {
   const int64_t* F;
   const double* fac;
   bool forward;
+  // same batching as ssor_row: entry q of the row belongs to lane q % 32, added in ascending q, nothing branches
   __device__ void operator()(int i) const {
     const int lane = threadIdx.x & 31;
     const int32_t row = c.D[i];
     const int64_t rp = c.rowptr[row], len = c.rowptr[row + 1] - rp;
+    const double* f = fac + F[i];
     double s = 0.0, d = 0.0;
-    for (int64_t q = lane; q < len; q += 32) {
-      const int32_t cc = c.col[rp + q];
-      if (forward) {
-        if (cc < row && c.mark[cc] == c.b) s = fma(fac[F[i] + q], c.zg[cc], s);
-      } else {
-        if (cc == row) d = fac[F[i] + q];
-        else if (cc > row && c.mark[cc] == c.b) s = fma(fac[F[i] + q], c.zg[cc], s);
+    for (int64_t qb = lane; qb < len; qb += 32 * kRowBatch) {
+      int32_t cc[kRowBatch];
+      double v[kRowBatch], z[kRowBatch];
+      bool use[kRowBatch];
+#pragma unroll
+      for (int j = 0; j < kRowBatch; j++) {
+        const int64_t q = qb + 32 * j;
+        const bool ok = q < len;
+        cc[j] = ok ? c.col[rp + q] : row;
+        v[j] = ok ? f[q] : 0.0;
+        use[j] = forward ? cc[j] < row : cc[j] > row;
+        if (!forward && ok && cc[j] == row) d = v[j];
       }
+#pragma unroll
+      for (int j = 0; j < kRowBatch; j++) use[j] = use[j] && c.mark[use[j] ? cc[j] : row] == c.b;
+#pragma unroll
+      for (int j = 0; j < kRowBatch; j++) z[j] = use[j] ? c.zg[cc[j]] : 0.0;
+#pragma unroll
+      for (int j = 0; j < kRowBatch; j++)
+        if (use[j]) s = fma(v[j], z[j], s);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {

@@ -113,10 +113,12 @@ int b2_stokes_assemble(b2_stokes* p, const b2_vec* sol, b2_vec* rhs, double IRe)
   b2_mesh_view(p->mesh, &c, &nnode, &nel, &xyz, &conn);
   const size_t smem = stokes_smem(p->nv, p->np, p->ng);
   // the attribute belongs to the function, not to the plan: set for THIS launch (several plans of a mixed mesh coexist)
-  B2_CUDA(cudaFuncSetAttribute(stokes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024)));
-  int per_sm = (int)((size_t)220 * 1024 / (smem + 1024));      // CTAs one SM's shared memory holds
-  per_sm = per_sm < 1 ? 1 : (per_sm > 3 ? 3 : per_sm);
-  B2_LAUNCH(c, stokes_kernel, b2_grid_for(c, nel, kStokesWarps, per_sm), kStokesWarps * 32, smem, nel, nnode, p->nv, p->np, p->ng, xyz, conn, p->edof,
+  const stokes_kernel_t kern = stokes_kernel_for(p->nv, p->np);
+  B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024)));
+  int per_sm = 1;      // resident CTAs by registers and shared memory
+  B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kStokesWarps * 32, smem));
+  per_sm = per_sm < 1 ? 1 : per_sm;
+  B2_LAUNCH(c, kern, b2_grid_for(c, nel, kStokesWarps, per_sm), kStokesWarps * 32, smem, nel, nnode, p->nv, p->np, p->ng, xyz, conn, p->edof,
             p->tabv, p->tabp, p->A->rowptr, p->slot, p->A->val, sol ? sol->d : nullptr, rhs ? rhs->d : nullptr, IRe);
   return 0;
 }
@@ -163,7 +165,10 @@ int b2_ns_assemble(b2_stokes* p, const b2_vec* sol, b2_vec* rhs, double nu) {
   const size_t smem = (size_t)ns_cta_doubles_host(p->nv, p->np, p->ng) * sizeof(double);
   B2_CUDA(cudaFuncSetAttribute(ns_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024)));
   const int threads = ns_threads(p->nv, p->np);
-  B2_LAUNCH(c, ns_kernel, b2_grid_for(c, nel, 1, 1024 / threads), threads, smem, nel, nnode, p->nv, p->np, p->ng, xyz, conn, p->edof, p->tabns,
+  int per_sm = 1;      // resident CTAs by registers and shared memory
+  B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ns_kernel, threads, smem));
+  per_sm = per_sm < 1 ? 1 : per_sm;
+  B2_LAUNCH(c, ns_kernel, b2_grid_for(c, nel, 1, per_sm), threads, smem, nel, nnode, p->nv, p->np, p->ng, xyz, conn, p->edof, p->tabns,
             p->tabp, p->A->rowptr, p->slot_ns, p->A->val, sol ? sol->d : nullptr, rhs ? rhs->d : nullptr, nu);
   return 0;
 }

@@ -12,20 +12,21 @@
 // belong to the pattern; nothing is added there.
 //
 // One warp per element, table-driven like assemble_general_kernel (any element type: nv <= 27 velocity nodes,
-// np <= 8 pressure nodes, ng <= 64 points).  Phase A: lanes = Gauss points (J, det, J^-1).  Phase B: per Gauss point
-// the nv physical gradients (and the np pressure functions) go to a double-buffered shared tile and lane l accumulates
-// the entries l, l + 32, ... of K and, from the next multiple of 32 on, of G_0..2 IN REGISTERS (44 at most; the
-// (i, j) of an owned entry is decoded once per warp, every register row is of one kind: no divergence, no divisions
-// and no shared-memory accumulators in the loop).  Phase C: blocks to shared memory, residual from the element blocks,
-// fp64 atomicAdd scatter through a precomputed element -> CSR slot map (stokes_slot_kernel, once per plan): lanes run
-// along a row of the element block, so the atomics of one instruction fall into the same CSR row.
+// np <= 8 pressure nodes, ng <= 64 points).  Phase A: lanes = Gauss points (J, det, J^-1).  Phase B: lane j computes the
+// physical gradient of ITS velocity function at the point, keeps it in registers and publishes it in a double-buffered
+// shared tile; it owns COLUMN j of K (row i needs the three broadcast loads of function i's gradient and three fused
+// multiply-adds) and ROW j of G_0..2 (one broadcast load of psi per entry): nv + 3 np accumulators in registers, no index
+// decoding, no shared-memory accumulators, every row independent of the others.  The row counts are template parameters
+// (one instantiation per Taylor-Hood pair of the reference's element families, a guarded one for anything else), so the
+// loops unroll without branches.  Phase C: blocks to shared memory, residual from the element blocks, fp64 atomicAdd
+// scatter through a precomputed element -> CSR slot map (stokes_slot_kernel, once per plan): lanes run along a row of
+// the element block, so the atomics of one instruction fall into the same CSR row.
 #pragma once
 #ifndef B2_DYN_SHARED
 #define B2_DYN_SHARED(type, name) extern __shared__ type name[]
 #endif
 
 constexpr int kStokesWarps = 4;
-constexpr int kStokesAcc = ((27 * 27 + 31) / 32) + ((3 * 27 * 8 + 31) / 32);      // 23 rows of K + 21 rows of G_k
 
 /* per warp: X[3][32], G[2][3][32], Psi[2][8], Geo[10][ng], U[3][32], P[8], row starts [4][32] (int64), dofs [4][32] (int32),
  * blocks K | G_k [nv nv + 3 nv np] */
@@ -72,7 +73,9 @@ __global__ void stokes_slot_kernel(int64_t nel, int nv, int np, const int32_t* _
 }
 
 // tabv: dxi, deta, dzeta [ng][nv], w[ng] of the velocity element; tabp: phi [ng][np] of the pressure element;
-// edof: [nel][4][27] system dofs (U, V, W, P), -1 padded; slot: [nel][stokes_slots_per_element]
+// edof: [nel][4][27] system dofs (U, V, W, P), -1 padded; slot: [nel][stokes_slots_per_element].
+// NV, NP: compile-time nv, np (GUARD = false), or their upper bounds with the rows beyond nv / np skipped (GUARD = true)
+template <int NV, int NP, bool GUARD>
 __global__ void __launch_bounds__(kStokesWarps * 32)
 stokes_kernel(int64_t nel, int64_t nnode, int nv, int np, int ng, const double* __restrict__ xyz, const int32_t* __restrict__ conn,
               const int32_t* __restrict__ edof, const double* __restrict__ tabv, const double* __restrict__ tabp,
@@ -95,27 +98,11 @@ stokes_kernel(int64_t nel, int64_t nnode, int nv, int np, int ng, const double* 
   double* sK = reinterpret_cast<double*>(sDof + 128);             // [nv][nv]
   double* sGk = sK + nv * nv;                                     // [3][nv][np]
   const int nK = nv * nv, nG = nv * np;
-  const int nKp = (nK + 31) & ~31;                                // the G rows start at a multiple of 32
-
-  // the entries this lane owns, decoded once: K rows i * 32 + j; G rows (k * 32 + i) * 8 + j; two per register
-  unsigned pk[kStokesAcc / 2];
-#pragma unroll
-  for (int q = 0; q < kStokesAcc; q++) {
-    const int e = lane + 32 * q;
-    unsigned v = 0;
-    if (e < nK) {
-      const int i = e / nv;
-      v = (unsigned)(i * 32 + (e - i * nv));
-    } else if (e >= nKp && e - nKp < 3 * nG) {
-      const int r = e - nKp, k = r / nG, rr = r - k * nG, i = rr / np;
-      v = (unsigned)((k * 32 + i) * 8 + (rr - i * np));
-    }
-    if (q & 1) pk[q >> 1] |= v << 16; else pk[q >> 1] = v;
-  }
+  const bool mine = lane < nv;                                    // this lane owns a velocity function
 
   for (int64_t el = (int64_t)blockIdx.x * kStokesWarps + wib; el < nel; el += (int64_t)gridDim.x * kStokesWarps) {
     const int32_t* ed = edof + el * 108;
-    if (lane < nv) {
+    if (mine) {
       const int64_t nd = conn[el * 27 + lane];
       sX[lane] = xyz[nd];
       sX[32 + lane] = xyz[nnode + nd];
@@ -160,41 +147,55 @@ stokes_kernel(int64_t nel, int64_t nnode, int nv, int np, int ng, const double* 
     }
     __syncwarp();
 
-    // ---- B. element blocks K and G_0..2, entries lane + 32 q in registers
-    double acc[kStokesAcc];
+    // ---- B. lane j: column j of K (aK[i] = K[i][j]) and row j of G_0..2 (aG[k][q] = G_k[j][q]) in registers
+    double aK[NV], aG[3][NP];
 #pragma unroll
-    for (int q = 0; q < kStokesAcc; q++) acc[q] = 0.0;
+    for (int i = 0; i < NV; i++) aK[i] = 0.0;
+#pragma unroll
+    for (int k = 0; k < 3; k++)
+#pragma unroll
+      for (int q = 0; q < NP; q++) aG[k][q] = 0.0;
     for (int g = 0; g < ng; g++) {
       double* G = sG + (g & 1) * 96;
       double* Psi = sPsi + (g & 1) * 8;
-      if (lane < nv) {
+      double gx = 0.0, gy = 0.0, gz = 0.0;
+      if (mine) {
         const double a = t_dx[g * nv + lane], b = t_dy[g * nv + lane], c = t_dz[g * nv + lane];
-        G[lane] = fma(c, sGeo[2 * ng + g], fma(b, sGeo[1 * ng + g], a * sGeo[0 * ng + g]));
-        G[32 + lane] = fma(c, sGeo[5 * ng + g], fma(b, sGeo[4 * ng + g], a * sGeo[3 * ng + g]));
-        G[64 + lane] = fma(c, sGeo[8 * ng + g], fma(b, sGeo[7 * ng + g], a * sGeo[6 * ng + g]));
+        gx = fma(c, sGeo[2 * ng + g], fma(b, sGeo[1 * ng + g], a * sGeo[0 * ng + g]));
+        gy = fma(c, sGeo[5 * ng + g], fma(b, sGeo[4 * ng + g], a * sGeo[3 * ng + g]));
+        gz = fma(c, sGeo[8 * ng + g], fma(b, sGeo[7 * ng + g], a * sGeo[6 * ng + g]));
+        G[lane] = gx;
+        G[32 + lane] = gy;
+        G[64 + lane] = gz;
       }
       if (lane < np) Psi[lane] = tabp[g * np + lane];
       __syncwarp();
       const double wg = sGeo[9 * ng + g];
+      const double wx = gx * wg, wy = gy * wg, wz = gz * wg;      // this lane's gradient times the weight
 #pragma unroll
-      for (int q = 0; q < kStokesAcc; q++) {
-        const unsigned v = (q & 1) ? pk[q >> 1] >> 16 : pk[q >> 1] & 0xffffu;
-        if (32 * q < nKp) {                      // warp-uniform: a register row of K
-          const int i = v >> 5, j = v & 31;
-          const double d = fma(G[64 + i], G[64 + j], fma(G[32 + i], G[32 + j], G[i] * G[j]));
-          acc[q] = fma(d, wg, acc[q]);
-        } else if (32 * q < nKp + 3 * nG) {      // a register row of G_k
-          acc[q] = fma(-G[v >> 3] * Psi[v & 7], wg, acc[q]);
+      for (int i = 0; i < NV; i++)
+        if (!GUARD || i < nv) aK[i] = fma(G[64 + i], wz, fma(G[32 + i], wy, fma(G[i], wx, aK[i])));
+#pragma unroll
+      for (int q = 0; q < NP; q++)
+        if (!GUARD || q < np) {
+          const double ps = Psi[q];
+          aG[0][q] = fma(-wx, ps, aG[0][q]);
+          aG[1][q] = fma(-wy, ps, aG[1][q]);
+          aG[2][q] = fma(-wz, ps, aG[2][q]);
         }
-      }
     }
 
-    // ---- C. blocks to shared memory, residual F = -B sol, scatter through the slot map
+    // ---- C. blocks to shared memory (K is symmetric in exact arithmetic; stored as computed: K[i][j] by lane j),
+    // residual F = -B sol, scatter through the slot map
+    if (mine) {
 #pragma unroll
-    for (int q = 0; q < kStokesAcc; q++) {
-      const int e = lane + 32 * q;
-      if (e < nK) sK[e] = acc[q];
-      else if (e >= nKp && e - nKp < 3 * nG) sGk[e - nKp] = acc[q];
+      for (int i = 0; i < NV; i++)
+        if (!GUARD || i < nv) sK[i * nv + lane] = aK[i];
+#pragma unroll
+      for (int k = 0; k < 3; k++)
+#pragma unroll
+        for (int q = 0; q < NP; q++)
+          if (!GUARD || q < np) sGk[(k * nv + lane) * np + q] = aG[k][q];
     }
     __syncwarp();
     if (rhs) {
@@ -216,20 +217,30 @@ stokes_kernel(int64_t nel, int64_t nnode, int nv, int np, int ng, const double* 
       }
     }
     const unsigned short* sl = slot + (size_t)el * stokes_slots_per_element(nv, np);
-#pragma unroll
-    for (int q = 0; q < kStokesAcc; q++) {
-      const unsigned v = (q & 1) ? pk[q >> 1] >> 16 : pk[q >> 1] & 0xffffu;
-      const int e = lane + 32 * q;
-      if (e < nK) {
-        const int i = v >> 5;
-        const double val = IRe * acc[q];
-        for (int k = 0; k < 3; k++) atomicAdd(&Aval[sRow[32 * k + i] + (int64_t)sl[k * nK + e]], val);
-      } else if (e >= nKp && e - nKp < 3 * nG) {
-        const int r = e - nKp;
-        atomicAdd(&Aval[sRow[v >> 3] + (int64_t)sl[3 * nK + r]], acc[q]);              // row (U_k, i): v >> 3 = 32 k + i
-        atomicAdd(&Aval[sRow[96 + (v & 7)] + (int64_t)sl[3 * nK + 3 * nG + r]], acc[q]);   // row (P, j)
-      }
+    const int dv = GUARD ? nv : NV, dp = GUARD ? np : NP;         // compile-time divisors where the pair is known
+    for (int e = lane; e < nK; e += 32) {
+      const int i = e / dv;
+      const double val = IRe * sK[e];
+      for (int k = 0; k < 3; k++) atomicAdd(&Aval[sRow[32 * k + i] + (int64_t)sl[k * nK + e]], val);
+    }
+    for (int r = lane; r < 3 * nG; r += 32) {
+      const int ki = r / dp, j = r - ki * dp, k = ki / dv, i = ki - k * dv;      // r = (k nv + i) np + j
+      const double val = sGk[r];
+      atomicAdd(&Aval[sRow[32 * k + i] + (int64_t)sl[3 * nK + r]], val);              // row (U_k, i), column (P, j)
+      atomicAdd(&Aval[sRow[96 + j] + (int64_t)sl[3 * nK + 3 * nG + r]], val);         // row (P, j), column (U_k, i)
     }
     __syncwarp();      // the next element overwrites X, U, P, dofs, Geo, the blocks
   }
+}
+
+// the Taylor-Hood pairs of the reference's element families (hexahedra 20 / 27 + 8, tetrahedra 10 / 15 + 4, wedges
+// 15 / 21 + 6) get their own instantiation; anything else within nv <= 27, np <= 8 runs the guarded one
+#define B2_STOKES_PAIRS(X) X(27, 8) X(20, 8) X(10, 4) X(15, 4) X(21, 6) X(15, 6)
+typedef void (*stokes_kernel_t)(int64_t, int64_t, int, int, int, const double*, const int32_t*, const int32_t*, const double*, const double*,
+                                const int64_t*, const unsigned short*, double*, const double*, double*, double);
+inline stokes_kernel_t stokes_kernel_for(int nv, int np) {
+#define B2_STOKES_CASE(V, P) if (nv == V && np == P) return stokes_kernel<V, P, false>;
+  B2_STOKES_PAIRS(B2_STOKES_CASE)
+#undef B2_STOKES_CASE
+  return stokes_kernel<27, 8, true>;
 }

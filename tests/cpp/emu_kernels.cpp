@@ -176,7 +176,7 @@ void emu_stokes(int64_t nel, int64_t nnode, int nv, int np, int ng, const double
   int err = 0;
   emu::launch(stokes_slot_kernel, 2u, 64u, 0, nel, nv, np, edof, rowptr, col, slot.data(), &err);
   if (err) std::abort();
-  emu::launch(stokes_kernel, (unsigned)grid, (unsigned)(kStokesWarps * 32), smem, nel, nnode, nv, np, ng, xyz, conn, edof, tabv, tabp, rowptr,
+  emu::launch(stokes_kernel_for(nv, np), (unsigned)grid, (unsigned)(kStokesWarps * 32), smem, nel, nnode, nv, np, ng, xyz, conn, edof, tabv, tabp, rowptr,
               (const unsigned short*)slot.data(), Aval, sol, rhs, IRe);
 }
 

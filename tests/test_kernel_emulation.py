@@ -606,6 +606,37 @@ def test_stokes_plan_entry_points_on_the_emulator(emu_mg, ns):
     assert np.abs(rhs - rref).max() <= 1e-12 * np.abs(rref).max()
 
 
+@pytest.mark.parametrize("ns", [0, 1])
+def test_stokes_plan_rejects_a_pattern_without_an_element_coupling(emu_mg, ns):
+    """The element -> CSR slot map is built at plan creation; an element coupling that is not an entry of the system
+    matrix's pattern (here: one velocity-pressure entry removed from the pattern) makes b2_stokes_create / b2_ns_create
+    fail loudly instead of scattering into a neighbouring slot."""
+    path = os.path.join(GOLDEN, "cube_tet10.neu")
+    level = hostapi.HostHierarchy.from_neu(path, 1).levels[0]
+    fams = ["quadratic"] * 3 + ["linear"]
+    S = hostapi.SystemOnLevel(level, fams)
+    rp, ci = S.sparsity()
+    edof = np.ascontiguousarray(S.elem_dofs(), dtype=np.int32)
+    row, c = int(edof[0, 0, 0]), int(edof[0, 3, 1])                 # (U dof of node 0, P dof of node 1) of element 0
+    k = rp[row] + int(np.searchsorted(ci[rp[row]:rp[row + 1]], c))
+    assert ci[k] == c
+    ci2 = np.ascontiguousarray(np.delete(ci, k))
+    rp2 = rp.copy()
+    rp2[row + 1:] -= 1
+    t = level.elem_type
+    tv, tp = [np.ascontiguousarray(a) for a in hostapi.elem_tables(t, "quadratic")], [np.ascontiguousarray(a) for a in hostapi.elem_tables(t, "linear")]
+    xyz, conn = np.ascontiguousarray(level.xyz), np.ascontiguousarray(level.conn, dtype=np.int32)
+    sol, val, rhs = np.zeros(S.n), np.zeros(len(ci2)), np.zeros(S.n)
+    args = [ctypes.c_int64(level.nnode), ctypes.c_int64(level.nel), _p(xyz), _p(conn), ctypes.c_int64(S.n), _p(rp2), _p(ci2), _p(edof),
+            ctypes.c_int(tv[0].shape[1]), ctypes.c_int(tp[0].shape[1]), ctypes.c_int(tv[4].shape[0]), _p(tv[0]), _p(tv[1]), _p(tv[2]), _p(tv[3]), _p(tv[4]),
+            _p(tp[0]), _p(sol), ctypes.c_double(0.3), ctypes.c_int(ns),
+            ctypes.c_int64(0), None, None, None, ctypes.c_int(0), ctypes.c_int(0), None, None, None, None, None]
+    rc = emu_mg.emu_stokes_plan(*args, _p(val), _p(rhs))
+    assert rc != 0
+    assert "not an entry of the system matrix's pattern" in emu_mg.b2_last_error().decode()
+    assert not val.any()
+
+
 @pytest.mark.skipif(_libtsan() is None, reason="libtsan not available")
 def test_orchestration_is_race_free_under_thread_sanitizer(tmp_path):
     """b2_vec.cu (two-level reductions with a ticket counter), b2_schwarz.cu, b2_mg.cu, b2_stokes.cu built with
