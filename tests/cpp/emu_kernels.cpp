@@ -7,6 +7,7 @@
 
 namespace {
 #include "../../femus_b200/csrc/b2_schwarz_kernels.cuh"
+#include "../../femus_b200/csrc/b2_schwarz_walk.cuh"
 }
 #include "../../femus_b200/csrc/b2_neumann_kernel.cuh"
 namespace {
@@ -74,6 +75,44 @@ int emu_gmres(int64_t n, const int64_t* rowptr, const int32_t* col, const double
 int emu_schwarz(int64_t n, const int64_t* rowptr, const int32_t* col, const double* val, int64_t nblocks, const int64_t* blk_ptr,
                 const int32_t* blk_dofs, int64_t ngroups, const int64_t* group_ptr, const int32_t* group_blocks, const double* r,
                 double* y, double* inv_out, int threads, int grid, int sub) {
+  // sub >= 20: the staged row walk (b2_schwarz_walk.cuh: local indices, block vectors in shared memory, map-based ILU)
+  if (sub >= 20) {
+    const bool ilu = sub % 10 == 2;
+    const int64_t nd = blk_ptr[nblocks];
+    std::vector<int64_t> frow((size_t)nd + 1);
+    int64_t tot = 0;
+    int max_m = 0;
+    for (int64_t k = 0; k < nd; k++) { frow[k] = tot; tot += rowptr[blk_dofs[k] + 1] - rowptr[blk_dofs[k]]; }
+    frow[(size_t)nd] = tot;
+    for (int64_t b = 0; b < nblocks; b++) max_m = std::max<int>(max_m, (int)(blk_ptr[b + 1] - blk_ptr[b]));
+    std::vector<unsigned short> lidx((size_t)tot, 0x7777);
+    std::vector<double> fac(ilu ? (size_t)tot : 1, -7.0);
+    emu::launch(schwarz_lidx_kernel, (unsigned)grid, (unsigned)threads, 0, nblocks, blk_ptr, blk_dofs, (const int64_t*)frow.data(), rowptr, col,
+                lidx.data());
+    const size_t smem = walk_smem_bytes(max_m);
+    int err = 0;
+    if (ilu)
+      for (int64_t g = 0; g < ngroups; g++)
+        emu::launch(schwarz_walk_ilu_factor_kernel, (unsigned)grid, (unsigned)threads, smem, group_ptr[g], group_ptr[g + 1], group_blocks, blk_ptr,
+                    blk_dofs, (const int64_t*)frow.data(), (const unsigned short*)lidx.data(), rowptr, val, fac.data(), &err, max_m);
+    if (err) return err;
+    std::vector<double> y2((size_t)n, 0.0);
+    for (int pass = 0; pass < 2; pass++) {          // twice: nothing may survive in the shared arrays between applications
+      double* yy = pass ? y2.data() : y;
+      for (int64_t i = 0; i < n; i++) yy[i] = 0.0;
+      for (int64_t g = 0; g < ngroups; g++) {
+        if (ilu)
+          emu::launch(schwarz_walk_apply_kernel<true>, (unsigned)grid, (unsigned)threads, smem, group_ptr[g], group_ptr[g + 1], group_blocks, blk_ptr,
+                      blk_dofs, (const int64_t*)frow.data(), (const unsigned short*)lidx.data(), rowptr, col, val, (const double*)fac.data(), r, yy, max_m);
+        else
+          emu::launch(schwarz_walk_apply_kernel<false>, (unsigned)grid, (unsigned)threads, smem, group_ptr[g], group_ptr[g + 1], group_blocks, blk_ptr,
+                      blk_dofs, (const int64_t*)frow.data(), (const unsigned short*)lidx.data(), rowptr, col, val, (const double*)nullptr, r, yy, max_m);
+      }
+    }
+    for (int64_t i = 0; i < n; i++)
+      if (y2[i] != y[i]) return -1;
+    return 0;
+  }
   // sub >= 10: the same block solve with the rows of every block sorted into dependency levels (LEV kernels)
   const bool lev = sub >= 10;
   sub %= 10;

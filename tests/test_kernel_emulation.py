@@ -64,8 +64,7 @@ def test_schwarz_kernels_on_the_emulator(emu, order, nb, schedule):
     """extract -> Gauss-Jordan inverse -> one launch per group, on the penalised level-1 operator of a 2x2x2 box:
     block inverses against numpy, the sweep against the oracle's PCASM restatement in the same block order;
     3 CTAs of 64 threads, so every CTA strides over several blocks of a group."""
-    from oracle import mesh_box as mb, mg
-    shape = (2, 2, 2) if order == "linear" else (1, 2, 1)
+    from oracle import mesh_box as mb, mg      # the 4 x 4 x 4 Q2 case has rows of 343 entries: longer than one batch of the walks
     lv = mb.build_hierarchy(*shape, 2)
     H = hostapi.HostHierarchy(*shape, 2)
     ix = hostapi.AsmIndex(H.levels[1], order, nb)
@@ -95,8 +94,7 @@ def test_schwarz_ssor_kernel_on_the_emulator(emu, order, nb, schedule):
     """The sweep with one SSOR iteration per block (001_Poisson's SOR_PRECOND sub-preconditioner) against the oracle;
     applied twice on the same scratch (stale membership marks of overlapping blocks must not matter).  nb = 10^6: ONE
     block with every element = Richardson + SOR, the application's FEMuS_DEFAULT smoother."""
-    from oracle import mesh_box as mb, mg
-    shape = (2, 2, 2) if order == "linear" else (1, 2, 1)
+    from oracle import mesh_box as mb, mg      # the 4 x 4 x 4 Q2 case has rows of 343 entries: longer than one batch of the walks
     lv = mb.build_hierarchy(*shape, 2)
     H = hostapi.HostHierarchy(*shape, 2)
     ix = hostapi.AsmIndex(H.levels[1], order, nb)
@@ -146,8 +144,7 @@ def test_schwarz_ilu_kernels_on_the_emulator(emu, order, nb, schedule):
     by group and the sweep against the oracle's IKJ ILU(0) on the pattern of A[B, B]; one block with every element =
     Richardson + ILU(0), FEMuS_DEFAULT with ILU_PRECOND.  With a single dof per row coupling (exact pattern) ILU(0) of a
     tridiagonal-like block would be exact; here it is a genuine incomplete factorisation."""
-    from oracle import mesh_box as mb, mg
-    shape = (2, 2, 2) if order == "linear" else (1, 2, 1)
+    from oracle import mesh_box as mb, mg      # the 4 x 4 x 4 Q2 case has rows of 343 entries: longer than one batch of the walks
     lv = mb.build_hierarchy(*shape, 2)
     H = hostapi.HostHierarchy(*shape, 2)
     ix = hostapi.AsmIndex(H.levels[1], order, nb)
@@ -166,13 +163,15 @@ def test_schwarz_ilu_kernels_on_the_emulator(emu, order, nb, schedule):
 
 
 @pytest.mark.parametrize("sub", ["ssor", "ilu"])
-@pytest.mark.parametrize("order,nb", [("linear", 8), ("linear", 10 ** 6), ("biquadratic", 2)])
-def test_level_scheduled_rows_equal_the_one_warp_walk(emu, sub, order, nb):
+@pytest.mark.parametrize("order,nb,shape", [("linear", 8, (2, 2, 2)), ("linear", 10 ** 6, (2, 2, 2)), ("biquadratic", 2, (1, 2, 1)),
+                                            ("biquadratic", 8, (2, 2, 2))])
+def test_level_scheduled_rows_equal_the_one_warp_walk(emu, sub, order, nb, shape):
     """b2_schwarz_set_row_levels: the rows of every block sorted into dependency levels of its triangular patterns, all
     warps of the CTA working inside a level -- the same arithmetic per row, so the result equals the one-warp walk BIT
-    FOR BIT (and the oracle to 1e-12); nb = 10^6: one block with the whole level, the case it is meant for."""
-    from oracle import mesh_box as mb, mg
-    shape = (2, 2, 2) if order == "linear" else (1, 2, 1)
+    FOR BIT (and the oracle to 1e-12); nb = 10^6: one block with the whole level, the case it is meant for.  The staged
+    walk of b2_schwarz_walk.cuh (local indices, shared-memory block vectors, next row prefetched, map-based ILU(0)
+    factorisation) is the third variant of the same arithmetic."""
+    from oracle import mesh_box as mb, mg      # the 4 x 4 x 4 Q2 case has rows of 343 entries: longer than one batch of the walks
     lv = mb.build_hierarchy(*shape, 2)
     H = hostapi.HostHierarchy(*shape, 2)
     ix = hostapi.AsmIndex(H.levels[1], order, nb)
@@ -188,6 +187,10 @@ def test_level_scheduled_rows_equal_the_one_warp_walk(emu, sub, order, nb):
     assert np.array_equal(y0, y1)
     want = O.asm[1].apply(r)
     assert np.abs(y1 - want).max() <= 1e-12 * np.abs(want).max()
+    # the staged walk (what the library runs without row levels): 64-thread CTAs as the library launches them
+    err2, y2, _ = _run_schwarz(emu, A, ix, gptr, gblocks, r, sub=20 + code, threads=64)
+    assert err2 == 0
+    assert np.array_equal(y0, y2)
 
 
 def test_schwarz_invert_kernel_reports_singular_blocks(emu):
