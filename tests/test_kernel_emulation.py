@@ -64,7 +64,8 @@ def test_schwarz_kernels_on_the_emulator(emu, order, nb, schedule):
     """extract -> Gauss-Jordan inverse -> one launch per group, on the penalised level-1 operator of a 2x2x2 box:
     block inverses against numpy, the sweep against the oracle's PCASM restatement in the same block order;
     3 CTAs of 64 threads, so every CTA strides over several blocks of a group."""
-    from oracle import mesh_box as mb, mg      # the 4 x 4 x 4 Q2 case has rows of 343 entries: longer than one batch of the walks
+    from oracle import mesh_box as mb, mg
+    shape = (2, 2, 2) if order == "linear" else (1, 2, 1)
     lv = mb.build_hierarchy(*shape, 2)
     H = hostapi.HostHierarchy(*shape, 2)
     ix = hostapi.AsmIndex(H.levels[1], order, nb)
@@ -94,7 +95,8 @@ def test_schwarz_ssor_kernel_on_the_emulator(emu, order, nb, schedule):
     """The sweep with one SSOR iteration per block (001_Poisson's SOR_PRECOND sub-preconditioner) against the oracle;
     applied twice on the same scratch (stale membership marks of overlapping blocks must not matter).  nb = 10^6: ONE
     block with every element = Richardson + SOR, the application's FEMuS_DEFAULT smoother."""
-    from oracle import mesh_box as mb, mg      # the 4 x 4 x 4 Q2 case has rows of 343 entries: longer than one batch of the walks
+    from oracle import mesh_box as mb, mg
+    shape = (2, 2, 2) if order == "linear" else (1, 2, 1)
     lv = mb.build_hierarchy(*shape, 2)
     H = hostapi.HostHierarchy(*shape, 2)
     ix = hostapi.AsmIndex(H.levels[1], order, nb)
@@ -144,7 +146,8 @@ def test_schwarz_ilu_kernels_on_the_emulator(emu, order, nb, schedule):
     by group and the sweep against the oracle's IKJ ILU(0) on the pattern of A[B, B]; one block with every element =
     Richardson + ILU(0), FEMuS_DEFAULT with ILU_PRECOND.  With a single dof per row coupling (exact pattern) ILU(0) of a
     tridiagonal-like block would be exact; here it is a genuine incomplete factorisation."""
-    from oracle import mesh_box as mb, mg      # the 4 x 4 x 4 Q2 case has rows of 343 entries: longer than one batch of the walks
+    from oracle import mesh_box as mb, mg
+    shape = (2, 2, 2) if order == "linear" else (1, 2, 1)
     lv = mb.build_hierarchy(*shape, 2)
     H = hostapi.HostHierarchy(*shape, 2)
     ix = hostapi.AsmIndex(H.levels[1], order, nb)
