@@ -320,6 +320,8 @@ int b2_mg_level_bounds(const b2_mg* mg, int level, double* emin, double* emax);
  * LinearEquation::GetSparsityPatternSize for U, V, W, P (b2h_system_sparsity_create); elem_dofs [nel][4][27] =
  * GetSystemDof per variable (b2h_system_elem_dofs, host array); velocity tables dxi/deta/dzeta [ngauss][nve_v],
  * weights[ngauss], pressure table phi_p [ngauss][nve_p] of the element type (b2h_elem_tables).
+ * b2_stokes_create also builds the element -> CSR slot map of the plan and FAILS if an element coupling is not an
+ * entry of A's pattern (or a row of A is longer than 65536 entries).
  * b2_stokes_assemble: A += element blocks (IRe K on the velocity diagonal, -int dphi_i/dx_k phi1_j and its transpose),
  * rhs += F = -B sol at the current solution in system numbering; neither is zeroed (the callback zeroes KK, :372). */
 int b2_stokes_create(b2_mesh* mesh, b2_csr* A, const int32_t* elem_dofs, int nve_v, int nve_p, int ngauss, const double* dxi,
