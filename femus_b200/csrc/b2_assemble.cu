@@ -41,8 +41,10 @@ void b2_mesh_view(const b2_mesh* m, b2_ctx** ctx, int64_t* nnode, int64_t* nel, 
 }
 
 struct b2_asm {
-  b2_mesh* mesh;
-  b2_csr* A;
+  b2_mesh* mesh;   // borrowed
+  b2_csr* A;       // borrowed
+  b2_ctx* ctx = nullptr;   // the borrowed objects may be gone when the plan is destroyed: what b2_asm_destroy needs is kept here
+  int64_t nel = 0;
   int nve, ngauss;
   bool general;    // not a hexahedron with the 64-point rule: table-driven kernel
   int32_t* dof;    // [nel][nve]
@@ -1475,6 +1477,8 @@ int b2_asm_create(b2_mesh* m, b2_csr* A, int nve, const int32_t* dof, int ngauss
   b2_asm* p = new b2_asm();
   p->mesh = m;
   p->A = A;
+  p->ctx = c;
+  p->nel = m->nel;
   p->nve = nve;
   p->ngauss = ngauss;
   p->last_ms = 0.;
@@ -1513,9 +1517,9 @@ int b2_asm_create(b2_mesh* m, b2_csr* A, int nve, const int32_t* dof, int ngauss
 
 int b2_asm_destroy(b2_asm* p) {
   if (!p) return 0;
-  b2_ctx* c = p->mesh->ctx;
+  b2_ctx* c = p->ctx;      // never through the borrowed mesh / matrix (they may have been destroyed first)
   cudaStreamSynchronize(c->stream);
-  b2_free(c, p->dof, (size_t)p->mesh->nel * p->nve);
+  b2_free(c, p->dof, (size_t)p->nel * p->nve);
   b2_free(c, p->tab, (size_t)4 * p->ngauss * p->nve + p->ngauss);
   if (p->slot) {
     if (p->slot_bytes == 1) b2_free(c, (uint8_t*)p->slot, p->slot_count);
@@ -1530,10 +1534,10 @@ int b2_asm_destroy(b2_asm* p) {
     else b2_free(c, (GalTables<8>*)p->gal_tab, 1);
   }
   b2_free(c, (SfTables*)p->sf_tab, 1);
-  b2_free(c, p->dofL, (size_t)p->mesh->nel * 27);
+  b2_free(c, p->dofL, (size_t)p->nel * 27);
   if (p->lslot) {
-    if (p->slot_bytes == 1) b2_free(c, (uint8_t*)p->lslot, (size_t)p->mesh->nel * kSfSlotStride);
-    else b2_free(c, (uint16_t*)p->lslot, (size_t)p->mesh->nel * kSfSlotStride);
+    if (p->slot_bytes == 1) b2_free(c, (uint8_t*)p->lslot, (size_t)p->nel * kSfSlotStride);
+    else b2_free(c, (uint16_t*)p->lslot, (size_t)p->nel * kSfSlotStride);
   }
   b2_free(c, (SfGalTables*)p->sf_gal, 1);
   delete p;

@@ -25,7 +25,8 @@
 
 struct b2_galerkin {
   b2_ctx* ctx;
-  b2_csr *Af, *Ac;
+  b2_csr *Af, *Ac;  // borrowed
+  int64_t nrows_f = 0, nrows_c = 0;   // sizes of the masks (the borrowed matrices may be gone at destruction)
   int64_t nelc;
   int nf, nc, pnnz;
   int32_t* fd;      // [nelc][nf] fine dofs in lattice order
@@ -398,10 +399,12 @@ int b2_galerkin_create(b2_csr* Af, b2_csr* Ac, int64_t nelc, int nf, int nc, con
   g->chain_sf = nullptr;
   g->chain_sf_tried = 0;
   if (fine_mask) {
+    g->nrows_f = Af->nrows;
     B2_TRY(b2_malloc(c, &g->fmask, (size_t)Af->nrows));
     B2_TRY(b2_upload(c, g->fmask, fine_mask, (size_t)Af->nrows));
   }
   if (coarse_mask) {
+    g->nrows_c = Ac->nrows;
     B2_TRY(b2_malloc(c, &g->cmask, (size_t)Ac->nrows));
     B2_TRY(b2_upload(c, g->cmask, coarse_mask, (size_t)Ac->nrows));
   }
@@ -435,8 +438,8 @@ int b2_galerkin_destroy(b2_galerkin* g) {
   b2_free(c, g->pv, (size_t)g->pnnz);
   b2_free(c, g->fent, (size_t)g->nf);
   b2_free(c, g->val, (size_t)g->nelc * 27);
-  if (g->fmask) b2_free(c, g->fmask, (size_t)g->Af->nrows);
-  if (g->cmask) b2_free(c, g->cmask, (size_t)g->Ac->nrows);
+  if (g->fmask) b2_free(c, g->fmask, (size_t)g->nrows_f);
+  if (g->cmask) b2_free(c, g->cmask, (size_t)g->nrows_c);
   const size_t ns = (size_t)g->nelc * g->nc * g->nc;
   if (g->emat) b2_free(c, g->emat, ns);
   if (g->chain_tab) { cudaFree(g->chain_tab); }
