@@ -94,7 +94,9 @@ int walk_launch_shape(b2_schwarz* s, K kern, int64_t nblk, int* grid, int* threa
   *smem = walk_smem_bytes(s->max_m);
   // the attribute belongs to the function: always the fixed maximum, so that no other object's launch can lower it
   B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)walk_smem_bytes(kWalkMaxM)));
-  *threads = nblk >= 8 * (int64_t)c->sm_count ? 64 : (nblk >= 4 * (int64_t)c->sm_count ? 128 : kApplyThreads);
+  // one warp sweeps a block; the other warps of the CTA only help with the block's residual.  Many blocks: the smallest
+  // CTAs put the most sweeping warps on an SM (registers allow ~25 one-warp CTAs, 12 of two warps)
+  *threads = nblk >= 16 * (int64_t)c->sm_count ? 32 : (nblk >= 8 * (int64_t)c->sm_count ? 64 : (nblk >= 4 * (int64_t)c->sm_count ? 128 : kApplyThreads));
   int per_sm = 1;
   B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, *threads, *smem));
   *grid = b2_grid_for(c, nblk, 1, per_sm < 1 ? 1 : per_sm);
