@@ -1127,7 +1127,10 @@ struct GenSmem {
   static size_t bytes(int nve, int ng) { return (size_t)(4 * ng * nve + ng + kGenWarps * warp_doubles(nve, ng)) * sizeof(double); }
 };
 
-template <typename SlotT>
+// NROWS = ceil(nve^2 / 32) register rows known at compile time (the loops over the entries unroll WITHOUT guards: with
+// run-time guards, warp-uniform as they are, the compiler keeps every row in its own basic block and every row exposes
+// its load -> multiply-add latency), or 0 = any nve <= 27 behind guards
+template <typename SlotT, int NROWS>
 __global__ void __launch_bounds__(kGenWarps * 32)
 assemble_general_kernel(int64_t nel, int64_t nnode, int nve, int ng, const double* __restrict__ xyz,
                         const int32_t* __restrict__ conn, const int32_t* __restrict__ dof, const double* __restrict__ tab,
@@ -1152,10 +1155,11 @@ assemble_general_kernel(int64_t nel, int64_t nnode, int nve, int ng, const doubl
   __syncthreads();
 
   const int nn = nve * nve;
+  constexpr int NACC = NROWS ? NROWS : kGenAcc;
   // (i, j) of the entries this lane owns, packed i * 32 + j
-  int ij[kGenAcc];
+  int ij[NACC];
 #pragma unroll
-  for (int k = 0; k < kGenAcc; k++) {
+  for (int k = 0; k < NACC; k++) {
     const int e = lane + 32 * k;
     const int i = e < nn ? e / nve : 0;
     ij[k] = i * 32 + (e < nn ? e - i * nve : 0);
@@ -1202,9 +1206,9 @@ assemble_general_kernel(int64_t nel, int64_t nnode, int nve, int ng, const doubl
     __syncwarp();
 
     // ---- B. element matrix, entries lane + 32 k in registers
-    double acc[kGenAcc];
+    double acc[NACC];
 #pragma unroll
-    for (int k = 0; k < kGenAcc; k++) acc[k] = 0.0;
+    for (int k = 0; k < NACC; k++) acc[k] = 0.0;
     for (int g = 0; g < ng; g++) {
       double* G = sG + (g & 1) * 96;
       if (lane < nve) {
@@ -1216,8 +1220,8 @@ assemble_general_kernel(int64_t nel, int64_t nnode, int nve, int ng, const doubl
       __syncwarp();
       const double wg = sGeo[9 * ng + g];
 #pragma unroll
-      for (int k = 0; k < kGenAcc; k++) {
-        if (32 * k < nn) {      // warp-uniform: skips the unused register rows of small elements
+      for (int k = 0; k < NACC; k++) {
+        if (NROWS || 32 * k < nn) {      // generic instantiation only: skips the unused register rows of small elements
           const int i = ij[k] >> 5, j = ij[k] & 31;
           const double d = fma(G[64 + i], G[64 + j], fma(G[32 + i], G[32 + j], G[i] * G[j]));
           acc[k] = fma(d, wg, acc[k]);
@@ -1227,7 +1231,7 @@ assemble_general_kernel(int64_t nel, int64_t nnode, int nve, int ng, const doubl
 
     // ---- C. element matrix to shared memory, residual, scatter
 #pragma unroll
-    for (int k = 0; k < kGenAcc; k++) {
+    for (int k = 0; k < NACC; k++) {
       const int e = lane + 32 * k;
       if (e < nn) sB[e] = acc[k];
     }
@@ -1240,7 +1244,7 @@ assemble_general_kernel(int64_t nel, int64_t nnode, int nve, int ng, const doubl
     }
     const SlotT* sl = slot + (size_t)el * nn;
 #pragma unroll
-    for (int k = 0; k < kGenAcc; k++) {
+    for (int k = 0; k < NACC; k++) {
       const int e = lane + 32 * k;
       if (e < nn) atomicAdd(&Aval[rowptr[sDof[ij[k] >> 5]] + (int64_t)sl[e]], nu * acc[k]);
     }
@@ -1248,20 +1252,36 @@ assemble_general_kernel(int64_t nel, int64_t nnode, int nve, int ng, const doubl
   }
 }
 
-template <typename SlotT>
-int launch_assemble_general(b2_asm* p, const b2_vec* u, b2_vec* rhs, double nu, double fsrc) {
+template <typename SlotT, int NROWS>
+int launch_assemble_general_n(b2_asm* p, const b2_vec* u, b2_vec* rhs, double nu, double fsrc) {
   b2_ctx* c = p->mesh->ctx;
   b2_prof_scope prof(c, p);
-  auto kern = assemble_general_kernel<SlotT>;
+  auto kern = assemble_general_kernel<SlotT, NROWS>;
   const size_t smem = GenSmem::bytes(p->nve, p->ngauss);
   B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int per_sm = (int)((size_t)220 * 1024 / (smem + 1024));      // CTAs one SM's shared memory holds
-  per_sm = per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm);
+  int per_sm = 1;      // resident CTAs by registers and shared memory
+  B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kGenWarps * 32, smem));
+  per_sm = per_sm < 1 ? 1 : per_sm;
   const int grid = b2_grid_for(c, p->mesh->nel, kGenWarps, per_sm);
   B2_LAUNCH(c, kern, grid, kGenWarps * 32, smem, p->mesh->nel, p->mesh->nnode, p->nve, p->ngauss, p->mesh->xyz, p->mesh->conn,
             p->dof, p->tab, (const SlotT*)p->nslot, p->A->rowptr, p->A->val, u ? u->d : nullptr, rhs ? rhs->d : nullptr, nu,
             fsrc);
   return 0;
+}
+// one instantiation per register-row count of the reference's 3-D Lagrange families (4 / 10 / 15 tetrahedra, 6 / 15 / 21
+// wedges, 8 / 20 / 27 hexahedra: 1, 4, 8, 2, 8, 14, 2, 13, 23 rows), the guarded one for anything else
+template <typename SlotT>
+int launch_assemble_general(b2_asm* p, const b2_vec* u, b2_vec* rhs, double nu, double fsrc) {
+  switch ((p->nve * p->nve + 31) / 32) {
+    case 1: return launch_assemble_general_n<SlotT, 1>(p, u, rhs, nu, fsrc);
+    case 2: return launch_assemble_general_n<SlotT, 2>(p, u, rhs, nu, fsrc);
+    case 4: return launch_assemble_general_n<SlotT, 4>(p, u, rhs, nu, fsrc);
+    case 8: return launch_assemble_general_n<SlotT, 8>(p, u, rhs, nu, fsrc);
+    case 13: return launch_assemble_general_n<SlotT, 13>(p, u, rhs, nu, fsrc);
+    case 14: return launch_assemble_general_n<SlotT, 14>(p, u, rhs, nu, fsrc);
+    case 23: return launch_assemble_general_n<SlotT, 23>(p, u, rhs, nu, fsrc);
+    default: return launch_assemble_general_n<SlotT, 0>(p, u, rhs, nu, fsrc);
+  }
 }
 }  // namespace
 
