@@ -77,6 +77,9 @@ __global__ void ns_slot_kernel(int64_t nel, int nv, int np, const int32_t* __res
 
 // tabv: phi, dxi, deta, dzeta [ng][nv], w[ng] of the velocity element; tabp: psi [ng][np]; edof [nel][4][27];
 // slot [nel][ns_slots_per_element]; launched with ns_threads(nv, np) threads
+// RP, RG: pairs / G entries per thread known at compile time (the accumulation loops unroll without guards: threads
+// beyond the block compute on entry 0 and scatter nothing), or 0, 0 = the guarded instantiation for any nv, np
+template <int RP, int RG>
 __global__ void __launch_bounds__(kNsMaxThreads, 2)
 ns_kernel(int64_t nel, int64_t nnode, int nv, int np, int ng, const double* __restrict__ xyz, const int32_t* __restrict__ conn,
           const int32_t* __restrict__ edof, const double* __restrict__ tabv, const double* __restrict__ tabp,
@@ -101,16 +104,17 @@ ns_kernel(int64_t nel, int64_t nnode, int nv, int np, int ng, const double* __re
   int32_t* sDof = reinterpret_cast<int32_t*>(sRow + 128);       // [4][32]
   const int nK = nv * nv, nG = nv * np;
 
+  constexpr int NPAIR = RP ? RP : kNsPairs, NGACC = RP ? RG : kNsGacc;
   // the pairs / G entries this thread owns, decoded once
-  int pi[kNsPairs], pj[kNsPairs], gk[kNsGacc], gi[kNsGacc], gj[kNsGacc];
+  int pi[NPAIR], pj[NPAIR], gk[NGACC], gi[NGACC], gj[NGACC];
 #pragma unroll
-  for (int r = 0; r < kNsPairs; r++) {
+  for (int r = 0; r < NPAIR; r++) {
     const int p = tid + r * T;
     pi[r] = p < nK ? p / nv : 0;
     pj[r] = p < nK ? p - pi[r] * nv : 0;
   }
 #pragma unroll
-  for (int r = 0; r < kNsGacc; r++) {
+  for (int r = 0; r < NGACC; r++) {
     const int e = tid + r * T;
     const int k = e < 3 * nG ? e / nG : 0, rr = e < 3 * nG ? e - k * nG : 0;
     gk[r] = k;
@@ -200,15 +204,15 @@ ns_kernel(int64_t nel, int64_t nnode, int nv, int np, int ng, const double* __re
     __syncthreads();
 
     // ---- B. Gauss point loop: accumulators in registers
-    double aD[kNsPairs], aN[kNsPairs][9], aG[kNsGacc], aRes = 0.0;
+    double aD[NPAIR], aN[NPAIR][9], aG[NGACC], aRes = 0.0;
 #pragma unroll
-    for (int r = 0; r < kNsPairs; r++) {
+    for (int r = 0; r < NPAIR; r++) {
       aD[r] = 0.0;
 #pragma unroll
       for (int kl = 0; kl < 9; kl++) aN[r][kl] = 0.0;
     }
 #pragma unroll
-    for (int r = 0; r < kNsGacc; r++) aG[r] = 0.0;
+    for (int r = 0; r < NGACC; r++) aG[r] = 0.0;
     for (int g = 0; g < ng; g++) {
       const double* G = sG + (g & 1) * 96;
       const double* Phi = sPhi + (g & 1) * 32;
@@ -230,8 +234,8 @@ ns_kernel(int64_t nel, int64_t nnode, int nv, int np, int ng, const double* __re
       const double wg = sGeo[9 * ng + g];
       const double u0 = Q[0], u1 = Q[1], u2 = Q[2];
 #pragma unroll
-      for (int r = 0; r < kNsPairs; r++) {
-        if (r * T < nK) {            // uniform over the CTA
+      for (int r = 0; r < NPAIR; r++) {
+        if (RP || r * T < nK) {      // guarded instantiation only (uniform over the CTA)
           const int i = pi[r], j = pj[r];
           const double lap = fma(G[64 + i], G[64 + j], fma(G[32 + i], G[32 + j], G[i] * G[j]));
           const double adv = fma(u2, G[64 + j], fma(u1, G[32 + j], u0 * G[j]));
@@ -242,8 +246,8 @@ ns_kernel(int64_t nel, int64_t nnode, int nv, int np, int ng, const double* __re
         }
       }
 #pragma unroll
-      for (int r = 0; r < kNsGacc; r++)
-        if (r * T < 3 * nG) aG[r] = fma(-G[32 * gk[r] + gi[r]] * Psi[gj[r]], wg, aG[r]);
+      for (int r = 0; r < NGACC; r++)
+        if (RP || r * T < 3 * nG) aG[r] = fma(-G[32 * gk[r] + gi[r]] * Psi[gj[r]], wg, aG[r]);
       if (tid < 3 * nv) {
         const double* gu = Q + 3 + 3 * rk;
         const double conv = fma(u2, gu[2], fma(u1, gu[1], u0 * gu[0]));
@@ -259,7 +263,7 @@ ns_kernel(int64_t nel, int64_t nnode, int nv, int np, int ng, const double* __re
     if (rhs && tid < 3 * nv + np) atomicAdd(&rhs[sDof[32 * rk + ri]], -aRes);
     const unsigned short* sl = slot + (size_t)el * ns_slots_per_element(nv, np);
 #pragma unroll
-    for (int r = 0; r < kNsPairs; r++) {
+    for (int r = 0; r < NPAIR; r++) {
       const int p = tid + r * T;
       if (p < nK) {
 #pragma unroll
@@ -271,7 +275,7 @@ ns_kernel(int64_t nel, int64_t nnode, int nv, int np, int ng, const double* __re
       }
     }
 #pragma unroll
-    for (int r = 0; r < kNsGacc; r++) {
+    for (int r = 0; r < NGACC; r++) {
       const int e = tid + r * T;
       if (e < 3 * nG) {
         atomicAdd(&Aval[sRow[32 * gk[r] + gi[r]] + (int64_t)sl[9 * nK + e]], aG[r]);
@@ -280,4 +284,16 @@ ns_kernel(int64_t nel, int64_t nnode, int nv, int np, int ng, const double* __re
     }
     __syncthreads();      // the next element overwrites X, U, P, dofs, Geo, Q
   }
+}
+
+// per-thread counts of the Taylor-Hood pairs of the reference's element families with ns_threads() threads: (3, 3) for
+// 27 + 8 / 20 + 8 / 21 + 6 / 15 + 6, (3, 2) for 15 + 4, (2, 2) for 10 + 4; anything else runs the guarded instantiation
+typedef void (*ns_kernel_t)(int64_t, int64_t, int, int, int, const double*, const int32_t*, const int32_t*, const double*, const double*,
+                            const int64_t*, const unsigned short*, double*, const double*, double*, double);
+inline ns_kernel_t ns_kernel_for(int nv, int np) {
+  const int T = ns_threads(nv, np), rp = (nv * nv + T - 1) / T, rg = (3 * nv * np + T - 1) / T;
+  if (rp == 3 && rg == 3) return ns_kernel<3, 3>;
+  if (rp == 3 && rg == 2) return ns_kernel<3, 2>;
+  if (rp == 2 && rg == 2) return ns_kernel<2, 2>;
+  return ns_kernel<0, 0>;
 }

@@ -163,12 +163,13 @@ int b2_ns_assemble(b2_stokes* p, const b2_vec* sol, b2_vec* rhs, double nu) {
   const int32_t* conn = nullptr;
   b2_mesh_view(p->mesh, &c, &nnode, &nel, &xyz, &conn);
   const size_t smem = (size_t)ns_cta_doubles_host(p->nv, p->np, p->ng) * sizeof(double);
-  B2_CUDA(cudaFuncSetAttribute(ns_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024)));
   const int threads = ns_threads(p->nv, p->np);
+  const ns_kernel_t kern = ns_kernel_for(p->nv, p->np);
+  B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024)));
   int per_sm = 1;      // resident CTAs by registers and shared memory
-  B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ns_kernel, threads, smem));
+  B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
   per_sm = per_sm < 1 ? 1 : per_sm;
-  B2_LAUNCH(c, ns_kernel, b2_grid_for(c, nel, 1, per_sm), threads, smem, nel, nnode, p->nv, p->np, p->ng, xyz, conn, p->edof, p->tabns,
+  B2_LAUNCH(c, kern, b2_grid_for(c, nel, 1, per_sm), threads, smem, nel, nnode, p->nv, p->np, p->ng, xyz, conn, p->edof, p->tabns,
             p->tabp, p->A->rowptr, p->slot_ns, p->A->val, sol ? sol->d : nullptr, rhs ? rhs->d : nullptr, nu);
   return 0;
 }

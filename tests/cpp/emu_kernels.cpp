@@ -227,7 +227,7 @@ void emu_ns(int64_t nel, int64_t nnode, int nv, int np, int ng, const double* xy
   int err = 0;
   emu::launch(ns_slot_kernel, 2u, 64u, 0, nel, nv, np, edof, rowptr, col, slot.data(), &err);
   if (err) std::abort();
-  emu::launch(ns_kernel, (unsigned)grid, (unsigned)ns_threads(nv, np), smem, nel, nnode, nv, np, ng, xyz, conn, edof, tabv, tabp, rowptr,
+  emu::launch(ns_kernel_for(nv, np), (unsigned)grid, (unsigned)ns_threads(nv, np), smem, nel, nnode, nv, np, ng, xyz, conn, edof, tabv, tabp, rowptr,
               (const unsigned short*)slot.data(), Aval, sol, rhs, nu);
 }
 
