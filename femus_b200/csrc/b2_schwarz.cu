@@ -322,15 +322,10 @@ int b2_schwarz_apply(b2_schwarz* s, const b2_vec* r, b2_vec* y) {
     if (staged_walk(s)) {
       int grid = 1, threads = 64;
       size_t wsm = 0;
-      if (s->sub == 2) {
-        B2_TRY(walk_launch_shape(s, schwarz_walk_apply_kernel<true>, g1 - g0, &grid, &threads, &wsm));
-        B2_LAUNCH(c, schwarz_walk_apply_kernel<true>, grid, threads, wsm, g0, g1, s->group_blocks, s->blk_ptr, s->blk_dofs, s->frow, s->lidx,
-                  s->A->rowptr, s->A->col, s->A->val, s->fac, r->d, y->d, s->max_m);
-      } else {
-        B2_TRY(walk_launch_shape(s, schwarz_walk_apply_kernel<false>, g1 - g0, &grid, &threads, &wsm));
-        B2_LAUNCH(c, schwarz_walk_apply_kernel<false>, grid, threads, wsm, g0, g1, s->group_blocks, s->blk_ptr, s->blk_dofs, s->frow, s->lidx,
-                  s->A->rowptr, s->A->col, s->A->val, (const double*)nullptr, r->d, y->d, s->max_m);
-      }
+      const walk_apply_kernel_t kern = s->sub == 2 ? schwarz_walk_apply_kernel_for<true>(s->A->max_row) : schwarz_walk_apply_kernel_for<false>(s->A->max_row);
+      B2_TRY(walk_launch_shape(s, kern, g1 - g0, &grid, &threads, &wsm));
+      B2_LAUNCH(c, kern, grid, threads, wsm, g0, g1, s->group_blocks, s->blk_ptr, s->blk_dofs, s->frow, s->lidx, s->A->rowptr, s->A->col, s->A->val,
+                s->sub == 2 ? (const double*)s->fac : (const double*)nullptr, r->d, y->d, s->max_m);
       continue;
     }
     if (s->sub == 2) {

@@ -9,8 +9,8 @@
 //     entry q in the block's sorted dof list, 0xffff outside the block (schwarz_lidx_kernel): membership and position in
 //     one 16-bit load that does not depend on the sweep;
 //   * the block's right-hand side, diagonal and solution live in the CTA's shared memory;
-//   * the first kRowBatch x 32 entries (local index, value) of the NEXT row are requested before the current row is
-//     reduced, so the global latency of a row hides behind the row before it.
+//   * the first batch of entries (local index, value) of the NEXT row is requested before the current row is reduced,
+//     so the global latency of a row hides behind the row before it.
 // The arithmetic of a row is that of the plain walk -- entry q belongs to lane q % 32, members are added in ascending
 // q, butterfly reduction, (t - s) / d by lane 0 -- so both walks and the level-scheduled rows agree bit for bit.
 #pragma once
@@ -43,14 +43,18 @@ __global__ void schwarz_lidx_kernel(int64_t nblocks, const int64_t* __restrict__
   }
 }
 
-// first batch of a row: entry lane + 32 j, j < kRowBatch
+// a batch of a row: entry lane + 32 j, j < NB.  NB is a template parameter of the walk: the smallest of 1, 2, 4, 8 whose
+// batch holds the longest row of the operator (27 entries for trilinear, 125 for triquadratic hexahedra), so that the usual
+// row is ONE batch without empty slots -- the slots are the instructions of a row visit
+template <int NB>
 struct walk_batch {
-  int l[kRowBatch];
-  double v[kRowBatch];
+  int l[NB];
+  double v[NB];
 };
-__device__ __forceinline__ void walk_load(walk_batch& B, const unsigned short* __restrict__ lx, const double* __restrict__ v, int len, int lane) {
+template <int NB>
+__device__ __forceinline__ void walk_load(walk_batch<NB>& B, const unsigned short* __restrict__ lx, const double* __restrict__ v, int len, int lane) {
 #pragma unroll
-  for (int j = 0; j < kRowBatch; j++) {
+  for (int j = 0; j < NB; j++) {
     const int q = lane + 32 * j;
     const bool ok = q < len;
     B.l[j] = ok ? (int)lx[q] : (int)kNotInBlock;
@@ -61,11 +65,11 @@ __device__ __forceinline__ void walk_load(walk_batch& B, const unsigned short* _
 // One sweep over the rows of a block by ONE warp.  KIND 0: SSOR forward (members l < i), 1: SSOR backward (l != i),
 // 2: ILU forward (l < i, unit diagonal), 3: ILU backward (l > i, diagonal from the row).  lx / vals: the block's rows
 // of local indices / values, row i at F[i] - F[0] resp. at vrow(i); z, t, d in shared memory.
-template <int KIND, class VRow>
+template <int KIND, int NB, class VRow>
 __device__ __forceinline__ void walk_sweep(int m, const int64_t* F, const unsigned short* __restrict__ lidx, VRow vrow, double* z,
                                            const double* t, const double* d, int lane) {
   constexpr bool reverse = KIND == 1 || KIND == 3;
-  walk_batch cur, nxt;
+  walk_batch<NB> cur, nxt;
   {
     const int i0 = reverse ? m - 1 : 0;
     walk_load(cur, lidx + F[i0], vrow(i0), (int)(F[i0 + 1] - F[i0]), lane);
@@ -80,20 +84,20 @@ __device__ __forceinline__ void walk_sweep(int m, const int64_t* F, const unsign
     }
     double s = 0.0, dd = 0.0;
 #pragma unroll
-    for (int j = 0; j < kRowBatch; j++) {
+    for (int j = 0; j < NB; j++) {
       const int l = cur.l[j];
       const bool use = l != (int)kNotInBlock && (KIND == 0 || KIND == 2 ? l < i : (KIND == 1 ? l != i : l > i));
       if (KIND == 3 && l == i) dd = cur.v[j];
       if (use) s = fma(cur.v[j], z[l], s);
     }
-    if (len > 32 * kRowBatch) {            // the rare rows longer than one batch
+    if (len > 32 * NB) {                   // rows longer than one batch (only when the longest row exceeds 256 entries)
       const unsigned short* lx = lidx + F[i];
       const double* v = vrow(i);
-      for (int qb = 32 * kRowBatch; qb < len; qb += 32 * kRowBatch) {
-        walk_batch more;
+      for (int qb = 32 * NB; qb < len; qb += 32 * NB) {
+        walk_batch<NB> more;
         walk_load(more, lx + qb, v + qb, len - qb, lane);
 #pragma unroll
-        for (int j = 0; j < kRowBatch; j++) {
+        for (int j = 0; j < NB; j++) {
           const int l = more.l[j];
           const bool use = l != (int)kNotInBlock && (KIND == 0 || KIND == 2 ? l < i : (KIND == 1 ? l != i : l > i));
           if (KIND == 3 && l == i) dd = more.v[j];
@@ -126,7 +130,7 @@ struct walk_smem {
 };
 
 // y[B] += (one SSOR iteration | the ILU(0) solve) of (r - A y)[B], one CTA per block of the group
-template <bool ILU>
+template <bool ILU, int NB>
 __global__ void __launch_bounds__(kApplyThreads) schwarz_walk_apply_kernel(int64_t g0, int64_t g1, const int32_t* __restrict__ group_blocks,
                                                                             const int64_t* __restrict__ blk_ptr, const int32_t* __restrict__ blk_dofs,
                                                                             const int64_t* __restrict__ frow, const unsigned short* __restrict__ lidx,
@@ -166,17 +170,28 @@ __global__ void __launch_bounds__(kApplyThreads) schwarz_walk_apply_kernel(int64
     if (warp == 0) {
       if (ILU) {
         auto vrow = [&](int i) { return fac + S.F[i]; };
-        walk_sweep<2>(m, S.F, lidx, vrow, S.z, S.t, S.d, lane);      // L z = t (unit diagonal)
-        walk_sweep<3>(m, S.F, lidx, vrow, S.z, S.t, S.d, lane);      // U z = z
+        walk_sweep<2, NB>(m, S.F, lidx, vrow, S.z, S.t, S.d, lane);      // L z = t (unit diagonal)
+        walk_sweep<3, NB>(m, S.F, lidx, vrow, S.z, S.t, S.d, lane);      // U z = z
       } else {
         auto vrow = [&](int i) { return val + S.rs[i]; };
-        walk_sweep<0>(m, S.F, lidx, vrow, S.z, S.t, S.d, lane);      // z = (D + L)^-1 t
-        walk_sweep<1>(m, S.F, lidx, vrow, S.z, S.t, S.d, lane);      // backward sweep from that iterate
+        walk_sweep<0, NB>(m, S.F, lidx, vrow, S.z, S.t, S.d, lane);      // z = (D + L)^-1 t
+        walk_sweep<1, NB>(m, S.F, lidx, vrow, S.z, S.t, S.d, lane);      // backward sweep from that iterate
       }
     }
     __syncthreads();
     for (int i = threadIdx.x; i < m; i += blockDim.x) y[D[i]] += S.z[i];
   }
+}
+
+// the instantiation for an operator whose longest row has max_row entries
+typedef void (*walk_apply_kernel_t)(int64_t, int64_t, const int32_t*, const int64_t*, const int32_t*, const int64_t*, const unsigned short*,
+                                    const int64_t*, const int32_t*, const double*, const double*, const double*, double*, int);
+template <bool ILU>
+inline walk_apply_kernel_t schwarz_walk_apply_kernel_for(int max_row) {
+  if (max_row <= 32) return schwarz_walk_apply_kernel<ILU, 1>;
+  if (max_row <= 64) return schwarz_walk_apply_kernel<ILU, 2>;
+  if (max_row <= 128) return schwarz_walk_apply_kernel<ILU, 4>;
+  return schwarz_walk_apply_kernel<ILU, 8>;
 }
 
 // ILU(0) of every block of the group on the pattern of its rows of A, IKJ order by one warp: row i's slots are

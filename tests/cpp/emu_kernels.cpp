@@ -101,12 +101,12 @@ int emu_schwarz(int64_t n, const int64_t* rowptr, const int32_t* col, const doub
       double* yy = pass ? y2.data() : y;
       for (int64_t i = 0; i < n; i++) yy[i] = 0.0;
       for (int64_t g = 0; g < ngroups; g++) {
-        if (ilu)
-          emu::launch(schwarz_walk_apply_kernel<true>, (unsigned)grid, (unsigned)threads, smem, group_ptr[g], group_ptr[g + 1], group_blocks, blk_ptr,
-                      blk_dofs, (const int64_t*)frow.data(), (const unsigned short*)lidx.data(), rowptr, col, val, (const double*)fac.data(), r, yy, max_m);
-        else
-          emu::launch(schwarz_walk_apply_kernel<false>, (unsigned)grid, (unsigned)threads, smem, group_ptr[g], group_ptr[g + 1], group_blocks, blk_ptr,
-                      blk_dofs, (const int64_t*)frow.data(), (const unsigned short*)lidx.data(), rowptr, col, val, (const double*)nullptr, r, yy, max_m);
+        int max_row = 0;
+        for (int64_t i = 0; i < n; i++) max_row = std::max<int>(max_row, (int)(rowptr[i + 1] - rowptr[i]));
+        const walk_apply_kernel_t kern = ilu ? schwarz_walk_apply_kernel_for<true>(max_row) : schwarz_walk_apply_kernel_for<false>(max_row);
+        emu::launch(kern, (unsigned)grid, (unsigned)threads, smem, group_ptr[g], group_ptr[g + 1], group_blocks, blk_ptr, blk_dofs,
+                    (const int64_t*)frow.data(), (const unsigned short*)lidx.data(), rowptr, col, val, ilu ? (const double*)fac.data() : (const double*)nullptr,
+                    r, yy, max_m);
       }
     }
     for (int64_t i = 0; i < n; i++)
