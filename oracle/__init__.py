@@ -12,7 +12,11 @@ Two halves:
   local prolongators).
 * a numpy / scipy restatement of everything that needs PETSc+MPI in the reference (box mesh,
   renumbering, refinement, dof maps, Dirichlet flags, sparsity, assembly, prolongators, Galerkin
-  operators, V-cycle).  **Parity of that half is unpinned by the reference**: the reference ships
-  no golden vectors for a 3-D hex Poisson problem and cannot be executed without PETSc
-  (SURVEY.md section 4 and 8c); each function cites the file:line it restates.
+  operators, V-cycle; systems of several variables, Stokes / Navier-Stokes element loops).  The reference ships no
+  golden vectors for these and its build needs PETSc + MPI, but its OWN sources compile here on a single-process host
+  backend (:mod:`oracle.ref_build`): the reference's unmodified 001_Poisson, and drivers that compile its Stokes callback
+  and its Navier-Stokes library routine in place, generated tests/golden/ref_poisson_*.npz and ref_stokes_*.npz, which
+  pin this half (tests/test_reference_pin.py, tests/test_reference_pin_stokes.py).  What stays unpinned is PETSc's own
+  numerics (PCASM / ILU(0) / GMRES / MUMPS: :mod:`oracle.asm` restates their published algorithms); each function cites
+  the file:line it restates.
 """

@@ -10,8 +10,11 @@ tutorials): per Gauss point of the velocity element, with u, grad u, p evaluated
                               here it is written out:
         d aResV[k][i] / d u_l[j] = delta_kl ( nu grad phi_i . grad phi_j + phi_i u . grad phi_j ) w + phi_i phi_j du_k/dx_l w
         d aResV[k][i] / d p[j]   = - psi_j dphi_i/dx_k w ,   d aResP[i] / d u_l[j] = - psi_i dphi_j/dx_l w ,   d aResP / d p = 0
-PARITY UNPINNED BY THE REFERENCE beyond the FE arithmetic; the Jacobian is checked against finite differences of the
-residual (tests/test_oracle_ns.py).  The boundary-face block of the routine (:200-300) is not restated."""
+PINNED TO THE REFERENCE ITSELF (round 2): femus::AssembleNavierStokes_AD, run by the reference's own classes on the host
+backend of oracle/ref_build (tests/cpp/ref_stokes.cpp "ns"), produced tests/golden/ref_stokes_ns_*.npz -- the residual,
+the Jacobian ADEPT recorded and the boundary pressure block; assemble() + pressure_boundary_rhs() reproduce them to 1e-12
+(tests/test_reference_pin_stokes.py).  The Jacobian is also checked against finite differences of the residual
+(tests/test_oracle_ns.py)."""
 import numpy as np
 import scipy.sparse as sp
 

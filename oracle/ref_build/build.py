@@ -9,6 +9,8 @@ oracle/_ref/ -- no copy of any reference source enters this repository, the refe
                             -> assembled system, through the reference's classes, written as .npz-ready text
     ref_poisson_host        applications/001_Poisson/main.cpp, UNMODIFIED, on the host backend
     ref_amr_poisson_host    tests/cpp/ref_amr_poisson.cpp: selectively refined meshes through the reference's AMR path
+    ref_stokes_host         tests/cpp/ref_stokes.cpp: a Taylor-Hood system U, V, W, P with the assembly callback of
+                            applications/003_NavierStokes/SteadyStokes/main.cpp compiled in place
 
     python -m oracle.ref_build.build [--force]
 """
@@ -96,7 +98,8 @@ def build(ref="/root/reference", force=False):
         subprocess.run(["ar", "rcs", LIB] + objs, check=True)
     fl = flags(ref)
     exes = {"ref_dump": os.path.join(HERE, "ref_dump.cpp"), "ref_poisson_host": os.path.join(ref, "applications/001_Poisson/main.cpp"),
-            "ref_amr_poisson_host": os.path.join(os.path.dirname(ORACLE), "tests", "cpp", "ref_amr_poisson.cpp")}
+            "ref_amr_poisson_host": os.path.join(os.path.dirname(ORACLE), "tests", "cpp", "ref_amr_poisson.cpp"),
+            "ref_stokes_host": os.path.join(os.path.dirname(ORACLE), "tests", "cpp", "ref_stokes.cpp")}
     for name, src in exes.items():
         if not os.path.exists(src):
             continue

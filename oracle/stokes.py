@@ -11,8 +11,11 @@ velocity family's nodes, :448-450; pressure functions phi1 = the pressure elemen
     B[p][p]       -= hk^2 / (4 IRe) alpha ...   with alpha = 0 unless both families are linear (:336-340, 541-552):
                      zero VALUES for Taylor-Hood pairs, but the block is added, so it belongs to the pattern
 and scatters them with add_matrix_blocked / add_vector_blocked into the system rows [rank][variable][dof] (:575-590).
-PARITY UNPINNED BY THE REFERENCE beyond the FE arithmetic (tables / Jacobian pinned to the compiled reference): the
-application needs PETSc + MPI to run.  Equal-order linear pairs (alpha != 0) are not restated."""
+PINNED TO THE REFERENCE ITSELF (round 2): the callback, compiled in place from the reference's unmodified main.cpp and run
+by the reference's own classes on the host backend of oracle/ref_build (tests/cpp/ref_stokes.cpp), produced
+tests/golden/ref_stokes_*.npz -- pattern of the assembled matrix, its values, the residual at given fields, the Galerkin
+operator below; assemble() reproduces them to 1e-13 (tests/test_reference_pin_stokes.py).  Equal-order linear pairs
+(alpha != 0) are not restated."""
 import numpy as np
 import scipy.sparse as sp
 

@@ -2,7 +2,10 @@
 [rank][variable][dof], element dof lists, sparsity pattern, prolongator, Dirichlet flags -- restated with numpy / scipy
 on top of the single-variable oracles (mesh_box, mesh_mixed), whose per-family results it only re-indexes.
 
-PARITY UNPINNED BY THE REFERENCE (needs PETSc + MPI to run; no expected values shipped).  Restates (paths relative to
+PINNED TO THE REFERENCE ITSELF (round 2): system dofs of every variable, KKoffset, sparsity counts, Dirichlet flags per
+variable and the system prolongator of a Taylor-Hood system are reference output in tests/golden/ref_stokes_*.npz
+(tests/cpp/ref_stokes.cpp on the host backend of oracle/ref_build) and reproduced bit-exactly
+(tests/test_reference_pin_stokes.py).  Restates (paths relative to
 /root/reference/src/08_algebra.../03_solvers_with_preconditioner and src/08_equations/00_stationary):
   LinearEquation.cpp:76-85, 211-237     GetSystemDof, KKoffset                       (oracle/asm.py: kk_offsets, system_dof)
   LinearEquation.cpp:407-548            GetSparsityPatternSize: every element couples variable i with variable j

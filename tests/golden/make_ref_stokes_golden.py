@@ -1,0 +1,60 @@
+"""Generate tests/golden/ref_stokes_*.npz from the REFERENCE ITSELF: tests/cpp/ref_stokes.cpp -- a Taylor-Hood system
+U, V, W (SECOND) + P (FIRST) on a HEX27 box, driven through the reference's own MultiLevelMesh / MultiLevelSolution /
+LinearImplicitSystem classes with the assembly callback of applications/003_NavierStokes/SteadyStokes/main.cpp
+(AssembleMatrixResSteadyStokes, :290-598) compiled in place -- on the single-process host backend of oracle/ref_build
+(no PETSc / MPI).  Every integer (system dofs of every variable, KKoffset, sparsity counts and pattern, prolongator
+structure, Dirichlet flags per variable from the application's own SetBoundaryCondition) and every value (assembled
+matrix, Galerkin operator, prolongator, assembled residual at the initial fields of ref_stokes.cpp) is reference output.
+The "ns" case swaps in the library routine femus::AssembleNavierStokes_AD (03_navier_stokes.hpp:21-413) on a
+NonLinearImplicitSystem: residual of the Galerkin form, the Jacobian adept recorded, the boundary pressure block.
+
+Run in the build container (needs /root/reference):   python tests/golden/make_ref_stokes_golden.py"""
+import os
+import re
+import shutil
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+from oracle.ref_build import build as rb  # noqa: E402
+
+CASES = {"box211_q2q1_2lev": (2, 1, 1, 2), "ns_box211_q2q1_2lev": (2, 1, 1, 2, "ns")}
+
+
+def run_case(name, args):
+    exe = os.path.join(rb.OUT, "ref_stokes_host")
+    work = tempfile.mkdtemp(prefix="refstokes_")
+    try:
+        for d in ("input", "output", "dump"):
+            os.makedirs(os.path.join(work, d))
+        env = dict(os.environ, FEMUS_REF_DUMP=os.path.join(work, "dump"), GLIBC_TUNABLES="glibc.malloc.tcache_count=0")
+        r = subprocess.run([exe] + [str(a) for a in args], cwd=work, env=env, capture_output=True, text=True, timeout=3600)
+        if r.returncode:
+            raise RuntimeError(f"{name}: reference run failed ({r.returncode})\n{r.stdout[-2000:]}\n{r.stderr[-2000:]}")
+        ire = float(re.search(r"IReynolds\s+([0-9.eE+-]+)", r.stdout).group(1))
+        out = {"box": np.array(args[:3]), "nlevels": np.array(args[3]), "IReynolds": np.array(ire)}      # "ns": the routine's nu = 1
+        dt = {"i4": np.int32, "i8": np.int64, "f8": np.float64}
+        for f in sorted(os.listdir(os.path.join(work, "dump"))):
+            m = re.match(r"L(\d+)_(\w+)\.(i4|i8|f8)$", f)
+            out[f"L{int(m.group(1))}_{m.group(2)}"] = np.fromfile(os.path.join(work, "dump", f), dtype=dt[m.group(3)])
+        return out
+    finally:
+        shutil.rmtree(work, ignore_errors=True)
+
+
+def main():
+    rb.build()
+    for name, args in CASES.items():
+        out = run_case(name, args)
+        path = os.path.join(HERE, f"ref_stokes_{name}.npz")
+        np.savez_compressed(path, **out)
+        print(f"{name}: {len(out)} arrays, {os.path.getsize(path) / 1024:.0f} KiB")
+
+
+if __name__ == "__main__":
+    main()

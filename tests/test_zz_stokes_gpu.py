@@ -293,3 +293,30 @@ def test_lid_driven_cavity_with_vanka_blocks_and_pressure_null_space(ctx, name, 
         assert abs(a - b) <= 1e-8 * want[0], (got, want)
     assert got[-1] < 1e-2 * got[0], got
     del pb
+
+
+@pytest.mark.parametrize("eq", ["stokes", "navier_stokes"])
+def test_assembly_matches_the_reference_output(ctx, eq):
+    """The device kernels against REFERENCE OUTPUT, without the oracle in between: tests/golden/ref_stokes_*.npz hold the
+    matrix and the residual the reference's own classes assembled for a Taylor-Hood system on a 2 x 1 x 1 box refined once
+    -- AssembleMatrixResSteadyStokes of applications/003_NavierStokes/SteadyStokes/main.cpp, resp. the library routine
+    AssembleNavierStokes_AD (Jacobian recorded by adept, boundary pressure 0.75 on boundary set 2) -- at the fields the
+    fixture carries (tests/cpp/ref_stokes.cpp, tests/golden/make_ref_stokes_golden.py)."""
+    import scipy.sparse as sp
+    from femus_b200 import hostapi
+    from femus_b200.stokes import StokesMG
+    ns = eq == "navier_stokes"
+    g = np.load(os.path.join(GOLDEN, "ref_stokes_ns_box211_q2q1_2lev.npz" if ns else "ref_stokes_box211_q2q1_2lev.npz"))
+    box, nl = tuple(int(v) for v in g["box"]), int(g["nlevels"])
+    top = nl - 1
+    pb = StokesMG(ctx, hostapi.HostHierarchy(*box, nl), IRe=float(g["IReynolds"]), equation=eq, boundary_pressure={2: 0.75} if ns else None)
+    sol = np.concatenate([g[f"L{top}_SOL_{v}"] for v in "UVWP"])          # one rank: system rows = [variable][dof]
+    assert sol.shape[0] == pb.n
+    pb.SOL.put(sol)
+    pb.assemble()
+    Ar = sp.csr_matrix((g[f"L{top}_KK_val"], g[f"L{top}_KK_col"], g[f"L{top}_KK_rowptr"]), shape=(pb.n, pb.n))
+    A = pb.KK[-1].to_scipy()             # on the full coupling pattern: the entries the reference's callback never touches stay zero
+    assert abs(A - Ar).max() <= RTOL * np.abs(Ar.data).max()
+    res = g[f"L{top}_RES"]
+    assert np.abs(pb.RES.get() - res).max() <= RTOL * np.abs(res).max()
+    del pb
