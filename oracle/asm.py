@@ -2,8 +2,11 @@
 numpy and plain loops for ONE Lagrange variable (the Poisson system of applications/001_Poisson with
 "smoother": "asm": SetNumberOfSchurVariables(0), SetElementBlockNumber(n), main.cpp:234-250).
 
-PARITY UNPINNED BY THE REFERENCE: the smoother needs PETSc (PCASM) to run and the reference ships no expected
-index sets or residuals for it; what is restated is (paths relative to /root/reference/src)
+PARITY: the element blocks (DoPartition, with the material flags in the reference's element order on refined boxes and
+on the mixed mesh with three material groups) are PINNED to the reference's own output (tests/cpp/ref_partition.cpp on
+the host backend of oracle/ref_build -> tests/golden/ref_partition.json, tests/test_asm_cpu.py).  BuildASMIndex and the
+application of the smoother stay UNPINNED: they live in the PETSc solver classes (PCASM), which cannot be built here, and
+the reference ships no expected index sets or residuals for them.  What is restated (paths relative to /root/reference/src)
   06_mesh/00_single_level/02_partitioning/MeshASMPartitioning.cpp:89-148      DoPartition: consecutive owned
       elements of one material, block_size at a time; materials in the order 4 (solid), 3 (porous), 2 (fluid)
   08_algebra.../03_solvers_with_preconditioner/petsc_asm/LinearEquationSolverPetscAsm.cpp:91-262   BuildASMIndex:

@@ -11,6 +11,7 @@ oracle/_ref/ -- no copy of any reference source enters this repository, the refe
     ref_amr_poisson_host    tests/cpp/ref_amr_poisson.cpp: selectively refined meshes through the reference's AMR path
     ref_stokes_host         tests/cpp/ref_stokes.cpp: a Taylor-Hood system U, V, W, P with the assembly callback of
                             applications/003_NavierStokes/SteadyStokes/main.cpp compiled in place
+    ref_partition_host      tests/cpp/ref_partition.cpp: MeshASMPartitioning::DoPartition on every level, printed
 
     python -m oracle.ref_build.build [--force]
 """
@@ -99,7 +100,8 @@ def build(ref="/root/reference", force=False):
     fl = flags(ref)
     exes = {"ref_dump": os.path.join(HERE, "ref_dump.cpp"), "ref_poisson_host": os.path.join(ref, "applications/001_Poisson/main.cpp"),
             "ref_amr_poisson_host": os.path.join(os.path.dirname(ORACLE), "tests", "cpp", "ref_amr_poisson.cpp"),
-            "ref_stokes_host": os.path.join(os.path.dirname(ORACLE), "tests", "cpp", "ref_stokes.cpp")}
+            "ref_stokes_host": os.path.join(os.path.dirname(ORACLE), "tests", "cpp", "ref_stokes.cpp"),
+            "ref_partition_host": os.path.join(os.path.dirname(ORACLE), "tests", "cpp", "ref_partition.cpp")}
     for name, src in exes.items():
         if not os.path.exists(src):
             continue

@@ -47,8 +47,38 @@ def run_case(name, args):
         shutil.rmtree(work, ignore_errors=True)
 
 
+PARTITION_CASES = {"box322_3lev": ["box", 3, 2, 2, 3, 1, 3, 8, 1000000],
+                   "cube_mixed_3groups_2lev": ["file", "input/cube_mixed_3groups.neu", 2, 1, 3, 8]}
+
+
+def run_partition(args):
+    """MeshASMPartitioning::DoPartition on every level (tests/cpp/ref_partition.cpp) -> dict"""
+    import json
+    exe = os.path.join(rb.OUT, "ref_partition_host")
+    work = tempfile.mkdtemp(prefix="refpart_")
+    try:
+        for d in ("input", "output"):
+            os.makedirs(os.path.join(work, d))
+        for f in os.listdir(HERE):
+            if f.endswith(".neu"):
+                shutil.copy(os.path.join(HERE, f), os.path.join(work, "input", f))
+        env = dict(os.environ, GLIBC_TUNABLES="glibc.malloc.tcache_count=0")
+        r = subprocess.run([exe] + [str(a) for a in args], cwd=work, env=env, capture_output=True, text=True, timeout=3600)
+        if r.returncode:
+            raise RuntimeError(f"reference run failed ({r.returncode})\n{r.stdout[-2000:]}\n{r.stderr[-2000:]}")
+        line = [ln for ln in r.stdout.splitlines() if ln.startswith("REF_PARTITION_JSON ")][-1]
+        return dict(json.loads(line[len("REF_PARTITION_JSON "):]), args=[str(a) for a in args])
+    finally:
+        shutil.rmtree(work, ignore_errors=True)
+
+
 def main():
+    import json
     rb.build()
+    parts = {name: run_partition(args) for name, args in PARTITION_CASES.items()}
+    with open(os.path.join(HERE, "ref_partition.json"), "w") as f:
+        json.dump(parts, f, separators=(",", ":"))
+    print("ref_partition.json:", {k: [lv["nel"] for lv in v["levels"]] for k, v in parts.items()})
     for name, args in CASES.items():
         out = run_case(name, args)
         path = os.path.join(HERE, f"ref_stokes_{name}.npz")

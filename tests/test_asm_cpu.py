@@ -196,3 +196,36 @@ def test_oracle_gmres_level_solver_minimises_the_preconditioned_residual():
     tg, _ = mg.Hierarchy(lv, "linear", ksp="gmres").mg_solve_trace(4)
     tr, _ = mg.Hierarchy(lv, "linear").mg_solve_trace(4)
     assert tg[-1] < 0.1 * tr[-1]
+
+
+@pytest.mark.parametrize("case", ["box322_3lev", "cube_mixed_3groups_2lev"])
+def test_element_blocks_match_the_reference(case):
+    """REFERENCE OUTPUT: tests/golden/ref_partition.json holds what the reference's own MeshASMPartitioning::DoPartition
+    returned on every level of a refined HEX27 box and of the mixed mesh with three material groups (7 solid + 13 fluid
+    coarse elements), for several block sizes, with every element's material flag in the reference's element order
+    (tests/cpp/ref_partition.cpp on the host backend of oracle/ref_build; tests/golden/make_ref_stokes_golden.py).  The
+    oracle's restatement and the product's host layer (AsmPartition.hpp) reproduce element blocks and block type ranges
+    bit-exactly -- with the element numbering of the refined levels, which is what the blocks are made of."""
+    import json
+    ref = json.load(open(os.path.join(GOLDEN, "ref_partition.json")))[case]
+    if case.startswith("box"):
+        n, nl = [int(v) for v in ref["args"][1:4]], int(ref["args"][4])
+        H, lv = hostapi.HostHierarchy(*n, nl), mb.build_hierarchy(*n, nl)
+    else:
+        path, nl = os.path.join(GOLDEN, os.path.basename(ref["args"][1])), int(ref["args"][2])
+        H, lv = hostapi.HostHierarchy.from_neu(path, nl), mm.build_hierarchy(path, nl)
+    assert len(ref["levels"]) == nl
+    for l, R in enumerate(ref["levels"]):
+        assert R["nel"] == lv[l].nel
+        material = getattr(lv[l], "material", None)
+        if material is None or len(material) == 0:
+            material = np.full(lv[l].nel, 2)
+        assert np.array_equal(R["material"], material), f"level {l}: material flags in element order"
+        for part in R["partitions"]:
+            bs = part["block_size"]
+            be, rng = asm.do_partition(material, lv[l].elem_offset, 0, (bs, bs, bs))
+            assert [list(map(int, b)) for b in be] == part["blocks"] and list(rng) == part["block_type_range"], f"oracle: level {l} block size {bs}"
+            ix = hostapi.AsmIndex(H.levels[l], "linear", min(bs, lv[l].nel))        # LinearImplicitSystem.cpp:1198 clamps the block size
+            want = part["blocks"]
+            assert [b.tolist() for b in ix.blocks("elem")] == want, f"host layer: level {l} block size {bs}"
+            assert ix.block_type_range.tolist() == part["block_type_range"]
