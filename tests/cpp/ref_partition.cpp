@@ -40,6 +40,15 @@ int main(int argc, char** argv) {
     const unsigned nel = msh->GetNumberOfElements();
     std::cout << (l ? ", " : "") << "{\"nel\": " << nel << ", \"material\": [";
     for (unsigned e = 0; e < nel; e++) std::cout << (e ? "," : "") << msh->GetElementMaterial(e);
+    // one layer of near elements of every element (elem::BuildElementNearElement, Elem.cpp:493-526): what a Vanka block
+    // takes its velocity dofs from
+    std::cout << "], \"near\": [";
+    for (unsigned e = 0; e < nel; e++) {
+      std::cout << (e ? "," : "") << "[";
+      const unsigned nn = msh->GetMeshElements()->GetElementNearElementSize(e, 1);
+      for (unsigned j = 0; j < nn; j++) std::cout << (j ? "," : "") << msh->GetMeshElements()->GetElementNearElement(e, j);
+      std::cout << "]";
+    }
     std::cout << "], \"partitions\": [";
     for (int k = a; k < argc; k++) {
       const unsigned bs = std::atoi(argv[k]);

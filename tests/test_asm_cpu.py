@@ -205,7 +205,9 @@ def test_element_blocks_match_the_reference(case):
     coarse elements), for several block sizes, with every element's material flag in the reference's element order
     (tests/cpp/ref_partition.cpp on the host backend of oracle/ref_build; tests/golden/make_ref_stokes_golden.py).  The
     oracle's restatement and the product's host layer (AsmPartition.hpp) reproduce element blocks and block type ranges
-    bit-exactly -- with the element numbering of the refined levels, which is what the blocks are made of."""
+    bit-exactly -- with the element numbering of the refined levels, which is what the blocks are made of -- and the
+    oracle the reference's near-element lists (elem::BuildElementNearElement), from which Vanka blocks take their
+    velocity dofs."""
     import json
     ref = json.load(open(os.path.join(GOLDEN, "ref_partition.json")))[case]
     if case.startswith("box"):
@@ -221,6 +223,12 @@ def test_element_blocks_match_the_reference(case):
         if material is None or len(material) == 0:
             material = np.full(lv[l].nel, 2)
         assert np.array_equal(R["material"], material), f"level {l}: material flags in element order"
+        # one layer of near elements (elem::BuildElementNearElement): the element itself, then its vertex neighbours ascending
+        if case.startswith("box"):
+            verts = lv[l].conn[:, :8]
+        else:
+            verts = [lv[l].conn[e, :mm.NVE[int(lv[l].etype[e])][0]] for e in range(lv[l].nel)]
+        assert [list(map(int, x)) for x in asm.near_elements(verts)] == R["near"], f"level {l}: near elements"
         for part in R["partitions"]:
             bs = part["block_size"]
             be, rng = asm.do_partition(material, lv[l].elem_offset, 0, (bs, bs, bs))
