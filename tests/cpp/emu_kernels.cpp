@@ -215,7 +215,10 @@ void emu_stokes(int64_t nel, int64_t nnode, int nv, int np, int ng, const double
   int err = 0;
   emu::launch(stokes_slot_kernel, 2u, 64u, 0, nel, nv, np, edof, rowptr, col, slot.data(), &err);
   if (err) std::abort();
-  emu::launch(stokes_kernel_for(nv, np), (unsigned)grid, (unsigned)(kStokesWarps * 32), smem, nel, nnode, nv, np, ng, xyz, conn, edof, tabv, tabp, rowptr,
+  // grid < 0: the guarded instantiation (what any other (nv, np) pair runs) on -grid CTAs
+  const stokes_kernel_t kern = grid < 0 ? stokes_kernel<27, 8, true> : stokes_kernel_for(nv, np);
+  if (grid < 0) grid = -grid;
+  emu::launch(kern, (unsigned)grid, (unsigned)(kStokesWarps * 32), smem, nel, nnode, nv, np, ng, xyz, conn, edof, tabv, tabp, rowptr,
               (const unsigned short*)slot.data(), Aval, sol, rhs, IRe);
 }
 
@@ -227,7 +230,9 @@ void emu_ns(int64_t nel, int64_t nnode, int nv, int np, int ng, const double* xy
   int err = 0;
   emu::launch(ns_slot_kernel, 2u, 64u, 0, nel, nv, np, edof, rowptr, col, slot.data(), &err);
   if (err) std::abort();
-  emu::launch(ns_kernel_for(nv, np), (unsigned)grid, (unsigned)ns_threads(nv, np), smem, nel, nnode, nv, np, ng, xyz, conn, edof, tabv, tabp, rowptr,
+  const ns_kernel_t kern = grid < 0 ? ns_kernel<0, 0> : ns_kernel_for(nv, np);      // grid < 0: the guarded instantiation
+  if (grid < 0) grid = -grid;
+  emu::launch(kern, (unsigned)grid, (unsigned)ns_threads(nv, np), smem, nel, nnode, nv, np, ng, xyz, conn, edof, tabv, tabp, rowptr,
               (const unsigned short*)slot.data(), Aval, sol, rhs, nu);
 }
 

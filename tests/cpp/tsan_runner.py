@@ -26,7 +26,7 @@ T.test_schwarz_kernels_on_the_emulator(L, "linear", 8, "colours")
 T.test_schwarz_ilu_kernels_on_the_emulator(L, "linear", 5, "colours")
 T.test_level_scheduled_rows_equal_the_one_warp_walk(L, "ssor", "linear", 8, (2, 2, 2))
 T.test_level_scheduled_rows_equal_the_one_warp_walk(L, "ilu", "linear", 8, (2, 2, 2))
-T.test_stokes_kernel_on_the_emulator(L, "cube_tet10", "quadratic", "linear")
-T.test_navier_stokes_kernel_on_the_emulator(L, "box", "biquadratic", "linear")
+T.test_stokes_kernel_on_the_emulator(L, "cube_tet10", "quadratic", "linear", False)
+T.test_navier_stokes_kernel_on_the_emulator(L, "box", "biquadratic", "linear", False)
 T.test_boundary_pressure_kernel_on_the_emulator(L, "cube_tet10", "quadratic")
 print("tsan-run-finished")

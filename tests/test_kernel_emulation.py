@@ -237,12 +237,14 @@ def test_neumann_kernel_on_the_emulator(emu, name, order):
     assert ngroups >= 1 and np.abs(rhs - want).max() <= 1e-13 * np.abs(want).max()
 
 
+@pytest.mark.parametrize("guarded", [False, True], ids=["pair_instantiation", "guarded_instantiation"])
 @pytest.mark.parametrize("name,order_v,order_p", [("box", "biquadratic", "linear"), ("cube_tet10", "quadratic", "linear"),
                                                   ("cube_wedge18", "biquadratic", "linear")])
-def test_stokes_kernel_on_the_emulator(emu, name, order_v, order_p):
+def test_stokes_kernel_on_the_emulator(emu, name, order_v, order_p, guarded):
     """stokes_kernel (one warp per element, table-driven) on hexahedra (Q2-Q1, 64 points), tetrahedra (P2-P1, 31
     points) and wedges (21 / 6 dofs, 52 points): system matrix on the host-built pattern and residual at a random
-    solution against the oracle's restatement of SteadyStokes/main.cpp:290-598."""
+    solution against the oracle's restatement of SteadyStokes/main.cpp:290-598.  Both the instantiation of the element
+    pair and the guarded one that any other (nv, np) would run."""
     from oracle import stokes, mesh_box as mb, mesh_mixed as mm, fe_hex, mg
     fams = [order_v] * 3 + [order_p]
     if name == "box":
@@ -266,18 +268,20 @@ def test_stokes_kernel_on_the_emulator(emu, name, order_v, order_p):
     xyz, conn = np.ascontiguousarray(level.xyz), np.ascontiguousarray(level.conn, dtype=np.int32)
     IRe = 0.37
     emu.emu_stokes(level.nel, level.nnode, nv, npr, ng, _p(xyz), _p(conn), _p(edof), _p(tabv), _p(tabp), _p(rp), _p(ci), _p(val), _p(sol), _p(rhs),
-                   IRe, 2)
+                   IRe, -2 if guarded else 2)
     Aref, rref = stokes.assemble(L, mesh, order_v, order_p, sol, IRe, tables_of)
     Aref = mg.on_pattern(Aref, rp, ci)
     assert np.abs(val - Aref.data).max() <= 1e-12 * np.abs(Aref.data).max()
     assert np.abs(rhs - rref).max() <= 1e-12 * (np.abs(Aref) @ np.abs(sol)).max()
 
 
+@pytest.mark.parametrize("guarded", [False, True], ids=["pair_instantiation", "guarded_instantiation"])
 @pytest.mark.parametrize("name,order_v,order_p", [("box", "biquadratic", "linear"), ("cube_tet10", "quadratic", "linear")])
-def test_navier_stokes_kernel_on_the_emulator(emu, name, order_v, order_p):
+def test_navier_stokes_kernel_on_the_emulator(emu, name, order_v, order_p, guarded):
     """ns_kernel (one CTA per element): residual RES = -aRes and the analytic Newton Jacobian at a random solution
     against the oracle's restatement of 03_navier_stokes.hpp:305-413 (whose Jacobian is checked against finite
-    differences in tests/test_oracle_ns.py)."""
+    differences in tests/test_oracle_ns.py and against the reference's adept Jacobian in tests/test_reference_pin_stokes.py).
+    Both the instantiation with compile-time pair counts and the guarded one."""
     from oracle import navier_stokes as ons, mesh_box as mb, mesh_mixed as mm, fe_hex, mg
     fams = [order_v] * 3 + [order_p]
     if name == "box":
@@ -301,7 +305,7 @@ def test_navier_stokes_kernel_on_the_emulator(emu, name, order_v, order_p):
     xyz, conn = np.ascontiguousarray(level.xyz), np.ascontiguousarray(level.conn, dtype=np.int32)
     nu = 0.21
     emu.emu_ns(level.nel, level.nnode, nv, npr, ng, _p(xyz), _p(conn), _p(edof), _p(tabv), _p(tabp), _p(rp), _p(ci), _p(val), _p(sol), _p(rhs), nu,
-               3)
+               -3 if guarded else 3)
     Aref, rref = ons.assemble(L, mesh, order_v, order_p, sol, nu, tables_of)
     Aref = mg.on_pattern(Aref, rp, ci)
     assert np.abs(val - Aref.data).max() <= 1e-12 * np.abs(Aref.data).max()
