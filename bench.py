@@ -560,10 +560,16 @@ def main():
             # in-run parity: the SAME sample through the GPU path (assembly, Galerkin chain, level setup, one V-cycle from
             # a zero guess) against the CPU run's residual norm after that cycle
             ps = PoissonMG(ctx, args.cpu_n0, args.cpu_n0, args.cpu_n0, args.levels, args.order)
-            ps.step()
+            ps.EPS.zero()
+            ps.assemble()
+            r0 = ps.RES.norm(2)              # the residual the cycle starts from: the scale of the comparison (as in the parity tests)
+            ps.galerkin()
+            ps.mg_set_levels()
+            ps.mg_solve()
             g = ps.RES.norm(2)
-            line["parity"] = {"what": "||RES||_2 after assembly + one V-cycle on the CPU baseline's sample, GPU path vs CPU reference path",
-                              "gpu": g, "cpu": cb["resnorm"], "rel_err": abs(g - cb["resnorm"]) / cb["resnorm"], "tol": 1e-10}
+            line["parity"] = {"what": "||RES||_2 after assembly + one V-cycle on the CPU baseline's sample, GPU path vs CPU reference path; "
+                                      "rel_err = |gpu - cpu| / ||RES||_2 before the cycle",
+                              "gpu": g, "cpu": cb["resnorm"], "residual_before_the_cycle": r0, "rel_err": abs(g - cb["resnorm"]) / r0, "tol": 1e-10}
             del ps
         except Exception as e:      # the baseline is reported, never required for the GPU number
             line["cpu_baseline"] = {"error": repr(e)}
