@@ -166,8 +166,7 @@ def test_schwarz_ilu_kernels_on_the_emulator(emu, order, nb, schedule):
 
 
 @pytest.mark.parametrize("sub", ["ssor", "ilu"])
-@pytest.mark.parametrize("order,nb,shape", [("linear", 8, (2, 2, 2)), ("linear", 10 ** 6, (2, 2, 2)), ("biquadratic", 2, (1, 2, 1)),
-                                            ("biquadratic", 8, (2, 2, 2))])
+@pytest.mark.parametrize("order,nb,shape", [("linear", 8, (2, 2, 2)), ("linear", 10 ** 6, (2, 2, 2)), ("biquadratic", 8, (2, 2, 2))])
 def test_level_scheduled_rows_equal_the_one_warp_walk(emu, sub, order, nb, shape):
     """b2_schwarz_set_row_levels: the rows of every block sorted into dependency levels of its triangular patterns, all
     warps of the CTA working inside a level -- the same arithmetic per row, so the result equals the one-warp walk BIT
