@@ -8,7 +8,7 @@
 // with all couplings (GetSparsityPatternSize), Dirichlet flags per variable from the application's own
 // SetBoundaryCondition (GenerateBdc), prolongators variable by variable (BuildProlongatorMatrix), the element loop.
 //
-//   ref_stokes <nx> <ny> <nz> <levels> [ns]
+//   ref_stokes <nx> <ny> <nz> <levels> [ns [fix]]
 //
 // "ns": the system is the NonLinearImplicitSystem "NS" and the callback the reference's library routine
 // femus::AssembleNavierStokes_AD (src/08_equations/assemble/03_navier_stokes.hpp:21-413: Galerkin residual with nu = 1,
@@ -32,6 +32,14 @@ static bool SetBoundaryConditionNS(const MultiLevelProblem*, const std::vector<d
   const bool dirichlet = SetBoundaryCondition(x, name, value, facename, time);
   if (!strcmp(name, "P") && facename == 2) value = 0.75;
   return dirichlet;
+}
+
+// an enclosed flow (lid-driven cavity): every velocity component Dirichlet (U = 1 on boundary set 6), the pressure natural
+// everywhere -- defined up to a constant, hence FixSolutionAtOnePoint("P")
+static bool SetBoundaryConditionEnclosed(const MultiLevelProblem*, const std::vector<double>&, const char name[], double& value, const int facename,
+                                         const double) {
+  value = (!strcmp(name, "U") && facename == 6) ? 1. : 0.;
+  return strcmp(name, "P") != 0;
 }
 
 static double InitU(const std::vector<double>& x) { return 0.3 * x[1] * (1.0 - x[2]) + 0.1 * x[0] * x[0]; }
@@ -66,8 +74,14 @@ int main(int argc, char** argv) {
   ml_sol.Initialize("P", InitP);
   const bool ns = argc > 5 && std::string(argv[5]) == "ns";
   MultiLevelProblem ml_prob(&ml_sol);
+  const bool fix = argc > 6 && std::string(argv[6]) == "fix";      // MultiLevelSolution::FixSolutionAtOnePoint("P"), as the enclosed-flow tutorials do
   if (ns) {
-    ml_sol.AttachSetBoundaryConditionFunction(SetBoundaryConditionNS);
+    if (fix) {
+      ml_sol.AttachSetBoundaryConditionFunction(SetBoundaryConditionEnclosed);
+      ml_sol.FixSolutionAtOnePoint("P");
+    } else {
+      ml_sol.AttachSetBoundaryConditionFunction(SetBoundaryConditionNS);
+    }
     ml_sol.GenerateBdc("All", "Steady", &ml_prob);
   } else {
     ml_sol.AttachSetBoundaryConditionFunction(SetBoundaryCondition);      // SteadyStokes's own

@@ -24,6 +24,8 @@ sys.path.insert(0, ROOT)
 from oracle.ref_build import build as rb  # noqa: E402
 
 CASES = {"box211_q2q1_2lev": (2, 1, 1, 2), "ns_box211_q2q1_2lev": (2, 1, 1, 2, "ns")}
+# Dirichlet flags only: the same system with MultiLevelSolution::FixSolutionAtOnePoint("P") (which level, which dof)
+BDC_CASES = {"ns_fix_box211_q2q1_3lev": (2, 1, 1, 3, "ns", "fix")}
 
 
 def run_case(name, args):
@@ -75,6 +77,11 @@ def run_partition(args):
 def main():
     import json
     rb.build()
+    for name, args in BDC_CASES.items():
+        out = run_case(name, args)
+        keep = {k: v for k, v in out.items() if k.endswith(("_Bdc", "_bdcIndex", "_KKoffset")) or k in ("box", "nlevels")}
+        np.savez_compressed(os.path.join(HERE, f"ref_stokes_{name}_bdc.npz"), **keep)
+        print(f"{name}: Dirichlet flags of {len(keep)} arrays")
     parts = {name: run_partition(args) for name, args in PARTITION_CASES.items()}
     with open(os.path.join(HERE, "ref_partition.json"), "w") as f:
         json.dump(parts, f, separators=(",", ":"))

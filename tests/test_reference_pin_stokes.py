@@ -135,3 +135,26 @@ def test_navier_stokes_routine_matches_the_reference():
     P = csr(g, f"L{top}_PP")
     G = (P.T @ Ao @ P).tocsr()
     assert abs(csr(g, f"L{top - 1}_KK") - G).max() <= 1e-12 * abs(G).max()
+
+
+def test_pressure_pinned_at_one_point_matches_the_reference():
+    """MultiLevelSolution::FixSolutionAtOnePoint("P") on an enclosed flow (every velocity Dirichlet, pressure natural), run by
+    the reference itself on three levels: the FIRST pressure dof of the COARSEST level becomes a Dirichlet row (flag 0),
+    nothing changes on the levels above (MultiLevelSolution.cpp:826-830) -- the rule StokesMG(fix_pressure_at_one_point)
+    applies (femus_b200/stokes.py), with the constant removed as the operators' null space above."""
+    from femus_b200 import hostapi
+    from oracle import mesh_box as mb, system as osys
+    g = np.load(os.path.join(GOLDEN, "ref_stokes_ns_fix_box211_q2q1_3lev_bdc.npz"))
+    box, nl = tuple(int(v) for v in g["box"]), int(g["nlevels"])
+    enclosed = [(1, 2, 3, 4, 5, 6)] * 3 + [()]
+    lv, H = mb.build_hierarchy(*box, nl), hostapi.HostHierarchy(*box, nl)
+    for l in range(nl):
+        S = hostapi.SystemOnLevel(H.levels[l], ORDERS)
+        want = S.bdc(enclosed)
+        assert np.array_equal(want, osys.bdc(lv[l], mb, ORDERS, enclosed))
+        if l == 0:
+            p0 = int(g["L0_KKoffset"][3])
+            assert p0 == int(S.offsets[3, 0]) and want[p0] == 2.0
+            want[p0] = 0.0                      # what stokes.py does: self.bdc[0][offsets[3, 0]] = 0.0
+        assert np.array_equal(g[f"L{l}_Bdc"], want), f"level {l}"
+        assert np.array_equal(g[f"L{l}_bdcIndex"], np.nonzero(want < 1.5)[0])
