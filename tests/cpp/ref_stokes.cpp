@@ -8,7 +8,7 @@
 // with all couplings (GetSparsityPatternSize), Dirichlet flags per variable from the application's own
 // SetBoundaryCondition (GenerateBdc), prolongators variable by variable (BuildProlongatorMatrix), the element loop.
 //
-//   ref_stokes <nx> <ny> <nz> <levels> [ns [fix]]
+//   ref_stokes <nx> <ny> <nz> <levels> [ns [fix|-] [newton <n>]]
 //
 // "ns": the system is the NonLinearImplicitSystem "NS" and the callback the reference's library routine
 // femus::AssembleNavierStokes_AD (src/08_equations/assemble/03_navier_stokes.hpp:21-413: Galerkin residual with nu = 1,
@@ -99,7 +99,13 @@ int main(int argc, char** argv) {
   LinearImplicitSystem* sys = nullptr;
   if (ns) {
     NonLinearImplicitSystem& nls = ml_prob.add_system<NonLinearImplicitSystem>("NS");
-    nls.SetMaxNumberOfNonLinearIterations(1);
+    // "newton <n>" after "ns": n Newton iterations (on ONE level the linear solves are the host backend's exact LU, so the
+    // "Nonlinear Eps_l2norm" lines the reference prints are the Newton updates themselves); otherwise one, for the dump
+    unsigned newton = 1;
+    for (int k = 6; k + 1 < argc; k++)
+      if (std::string(argv[k]) == "newton") newton = std::atoi(argv[k + 1]);
+    nls.SetMaxNumberOfNonLinearIterations(newton);
+    nls.SetNonLinearConvergenceTolerance(1.e-30);
     sys = &nls;
   } else {
     sys = &ml_prob.add_system<LinearImplicitSystem>("Stokes");

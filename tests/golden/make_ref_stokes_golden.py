@@ -28,7 +28,7 @@ CASES = {"box211_q2q1_2lev": (2, 1, 1, 2), "ns_box211_q2q1_2lev": (2, 1, 1, 2, "
 BDC_CASES = {"ns_fix_box211_q2q1_3lev": (2, 1, 1, 3, "ns", "fix")}
 
 
-def run_case(name, args):
+def run_case(name, args, newton=False):
     exe = os.path.join(rb.OUT, "ref_stokes_host")
     work = tempfile.mkdtemp(prefix="refstokes_")
     try:
@@ -40,6 +40,11 @@ def run_case(name, args):
             raise RuntimeError(f"{name}: reference run failed ({r.returncode})\n{r.stdout[-2000:]}\n{r.stderr[-2000:]}")
         ire = float(re.search(r"IReynolds\s+([0-9.eE+-]+)", r.stdout).group(1))
         out = {"box": np.array(args[:3]), "nlevels": np.array(args[3]), "IReynolds": np.array(ire)}      # "ns": the routine's nu = 1
+        if newton:      # per Newton iteration and variable (U, V, W, P): ||Eps||_2 and ||Sol||_2 as printed (NonLinearImplicitSystem.cpp:137)
+            rows = re.findall(r"Nonlinear Eps_l2norm/Sol_l2norm (\w)=\s*[0-9.eE+-]+\s*\*\* Eps_l2norm=\s*([0-9.eE+-]+)\s*\*\* Sol_l2norm=\s*([0-9.eE+-]+)", r.stdout)
+            assert len(rows) % 4 == 0 and [v for v, _, _ in rows[:4]] == ["U", "V", "W", "P"]
+            out["newton_eps_l2"] = np.array([float(e) for _, e, _ in rows]).reshape(-1, 4)
+            out["newton_sol_l2"] = np.array([float(s) for _, _, s in rows]).reshape(-1, 4)
         dt = {"i4": np.int32, "i8": np.int64, "f8": np.float64}
         for f in sorted(os.listdir(os.path.join(work, "dump"))):
             m = re.match(r"L(\d+)_(\w+)\.(i4|i8|f8)$", f)
@@ -48,6 +53,10 @@ def run_case(name, args):
     finally:
         shutil.rmtree(work, ignore_errors=True)
 
+
+# the reference's own Newton loop (NonLinearImplicitSystem::MGsolve) on ONE level, where every linear solve is the host
+# backend's exact LU: the "Nonlinear Eps_l2norm" lines it prints are the Newton updates
+NEWTON_CASES = {"ns_newton_box221_q2q1_1lev": (2, 2, 1, 1, "ns", "-", "newton", 5)}
 
 PARTITION_CASES = {"box322_3lev": ["box", 3, 2, 2, 3, 1, 3, 8, 1000000],
                    "cube_mixed_3groups_2lev": ["file", "input/cube_mixed_3groups.neu", 2, 1, 3, 8]}
@@ -77,6 +86,12 @@ def run_partition(args):
 def main():
     import json
     rb.build()
+    for name, args in NEWTON_CASES.items():
+        out = run_case(name, args, newton=True)
+        top = int(args[3]) - 1
+        keep = {k: v for k, v in out.items() if k.startswith(("newton_", f"L{top}_SOL_", f"L{top}_Bdc", f"L{top}_KKoffset")) or k in ("box", "nlevels", "IReynolds")}
+        np.savez_compressed(os.path.join(HERE, f"ref_stokes_{name}.npz"), **keep)
+        print(f"{name}: Newton updates (U)", keep["newton_eps_l2"][:, 0])
     for name, args in BDC_CASES.items():
         out = run_case(name, args)
         keep = {k: v for k, v in out.items() if k.endswith(("_Bdc", "_bdcIndex", "_KKoffset")) or k in ("box", "nlevels")}

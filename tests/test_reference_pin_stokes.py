@@ -158,3 +158,41 @@ def test_pressure_pinned_at_one_point_matches_the_reference():
             want[p0] = 0.0                      # what stokes.py does: self.bdc[0][offsets[3, 0]] = 0.0
         assert np.array_equal(g[f"L{l}_Bdc"], want), f"level {l}"
         assert np.array_equal(g[f"L{l}_bdcIndex"], np.nonzero(want < 1.5)[0])
+
+
+def test_newton_iteration_matches_the_reference():
+    """The reference's OWN Newton loop (NonLinearImplicitSystem::MGsolve, NonLinearImplicitSystem.cpp:157-361) around its
+    library routine, on one level, where every linear solve is the host backend's exact LU: the norms of the update and of
+    the solution it prints per variable after every iteration (:137; 7 digits) against the oracle's loop -- assemble
+    residual and ANALYTIC Jacobian at Sol, Dirichlet rows to the identity with zero residual (SetPenalty,
+    ZerosBoundaryResiduals), exact solve, Sol += Eps.  Quadratic convergence: 0.68 -> 3.8e-3 -> 1.5e-7 -> round-off."""
+    import scipy.sparse.linalg as spla
+    from oracle import fe_hex, mesh_box as mb, navier_stokes as ons, system as osys
+    g = np.load(os.path.join(GOLDEN, "ref_stokes_ns_newton_box221_q2q1_1lev.npz"))
+    box, nl = tuple(int(v) for v in g["box"]), int(g["nlevels"])
+    assert nl == 1
+    L = mb.build_hierarchy(*box, 1)[0]
+    kk = g["L0_KKoffset"]
+    n = int(kk[-1])
+    bdc = g["L0_Bdc"]
+    assert np.array_equal(bdc, osys.bdc(L, mb, ORDERS, DIRICHLET))
+    sol = np.concatenate([g[f"L0_SOL_{v}"] for v in "UVWP"])
+    fixed = bdc < 1.5
+    eps_ref, sol_ref = g["newton_eps_l2"], g["newton_sol_l2"]
+    assert eps_ref.shape[0] >= 4
+    for it in range(eps_ref.shape[0]):
+        A, rhs = ons.assemble(L, mb, "biquadratic", "linear", sol, 1.0, lambda t, o: fe_hex.tables(o))
+        rhs = rhs + ons.pressure_boundary_rhs(L, mb, "biquadratic", "linear", {2: 0.75})
+        A = A.tolil()
+        for i in np.nonzero(fixed)[0]:
+            A.rows[i], A.data[i] = [int(i)], [1.0]
+        rhs[fixed] = 0.0
+        eps = spla.spsolve(A.tocsc(), rhs)
+        sol = sol + eps
+        for k in range(4):
+            e, s = np.linalg.norm(eps[kk[k]:kk[k + 1]]), np.linalg.norm(sol[kk[k]:kk[k + 1]])
+            if eps_ref[it, k] > 1e-10:          # the last iteration is round-off on both sides
+                assert abs(e - eps_ref[it, k]) <= 2e-6 * eps_ref[it, k], (it, k, e, eps_ref[it, k])
+            else:
+                assert e < 1e-10
+            assert abs(s - sol_ref[it, k]) <= 2e-6 * sol_ref[it, k], (it, k, s, sol_ref[it, k])
